@@ -1,0 +1,183 @@
+/*
+ * tdnnf_nas_b200.h -- C ABI of the B200-native (sm_100a) training hot path of TDNN-F_NAS.
+ *
+ * This is the drop-in boundary: the entry points below are what the six reference nnet3
+ * components (and the chain denominator) call IN PLACE OF the CuMatrix/CuVector methods
+ * they call in the reference.  Plain pointers and sizes only; every function returns an
+ * int status (0 = ok) and never throws; memory is caller-owned except the opaque handles;
+ * nothing here synchronises the host with the device unless the comment says so.
+ *
+ * Conventions
+ *   - All matrices are row-major fp32 (Kaldi BaseFloat) given as (device pointer, rows,
+ *     cols, stride-in-elements), exactly a CuMatrixBase view.  stride >= cols.
+ *   - Kernels run on the context's stream (tdnnf_ctx_set_stream).
+ *   - Citations "ref: file:line" are into the reference tree (skhu101/TDNN-F_NAS):
+ *       tdnn.cc   = src/nnet3/nnet-tdnn-component.cc
+ *       simple.cc = src/nnet3/nnet-simple-component.cc
+ *       norm.cc   = src/nnet3/nnet-normalize-component.cc
+ *     "kaldi:" citations are into upstream kaldi-asr/kaldi (not shipped with the reference).
+ */
+#ifndef TDNNF_NAS_B200_H_
+#define TDNNF_NAS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDNNF_OK 0
+#define TDNNF_ERR_INVALID 1  /* bad argument (the reference would KALDI_ASSERT / KALDI_ERR) */
+#define TDNNF_ERR_CUDA 2     /* a CUDA runtime / driver call failed                         */
+#define TDNNF_ERR_NOMEM 3
+#define TDNNF_ERR_UNSUPPORTED 4
+
+#define TDNNF_MAX_OFFSETS 16
+
+typedef struct tdnnf_ctx tdnnf_ctx;
+typedef struct tdnnf_den_graph tdnnf_den_graph;
+typedef struct tdnnf_den_comp tdnnf_den_comp;
+
+/* ------------------------------------------------------------------ context ---------- */
+/* Message of the last failing call on this host thread (never NULL). */
+const char* tdnnf_last_error(void);
+/* ABI version: major*1000 + minor. */
+int tdnnf_abi_version(void);
+
+/* Create a context on CUDA device `device` (replaces Kaldi's CuDevice singleton for this
+ * path).  Fails with TDNNF_ERR_CUDA when there is no sm_100 device: there is NO CPU path. */
+int tdnnf_ctx_create(int device, tdnnf_ctx** out);
+int tdnnf_ctx_destroy(tdnnf_ctx* ctx);
+/* stream: a cudaStream_t passed as void* (NULL = legacy default stream). */
+int tdnnf_ctx_set_stream(tdnnf_ctx* ctx, void* stream);
+/* Pre-size the internal scratch arena (bf16 operand planes) so later calls never grow it. */
+int tdnnf_ctx_reserve(tdnnf_ctx* ctx, uint64_t bytes);
+/* Number of kernels this context has launched so far (for gpu_launches accounting). */
+uint64_t tdnnf_ctx_launch_count(const tdnnf_ctx* ctx);
+
+/* ------------------------------------------------------------------ TdnnDARTSV3 ------- */
+/* mode flags of TdnnDARTSV3Component (ref: conv.h:243-257) */
+#define TDNNF_DARTS_USE_GUMBEL 1
+#define TDNNF_DARTS_FREE_SELECT 2
+#define TDNNF_DARTS_UNIFORM_SAMPLE 4
+#define TDNNF_DARTS_USE_ENTROPY 8
+#define TDNNF_DARTS_UPDATE_ALPHA 16
+
+/* Mixing coefficients (ref: tdnn.cc:250-289; replaces SetRandUniform/ApplyLog/Scale/AddVec/
+ * ApplySoftMax/ApplyFloor/ApplyExp/InvertElements and the per-element .Max() host syncs).
+ *   alpha        device, n log-weights (bias_params_[0..n))
+ *   u_gumbel     HOST, n uniforms in (0,1) for the Gumbel noise (used iff USE_GUMBEL)
+ *   u_uniform    the single uniform draw of uniform-sample mode (used iff UNIFORM_SAMPLE)
+ *   share_index  offset slot that is always passed with weight 1 (ref: tdnn.cc:230-241)
+ *   coef         device out, n: the memo the reference returns from Propagate
+ *   weff         device out, n: effective GEMM weight per offset (0 => offset skipped)
+ * Randomness is injected by the caller so that every data-parallel rank draws identical
+ * noise; nothing is copied back to the host. */
+int tdnnf_darts_coef(tdnnf_ctx* ctx, const float* alpha, int n, int flags, float temperature,
+                     const float* u_gumbel, float u_uniform, int share_index, float* coef, float* weff);
+
+/* Effective weights from an existing memo (Backprop recomputes them, ref: tdnn.cc:352-364). */
+int tdnnf_darts_weff_from_coef(tdnnf_ctx* ctx, const float* coef, int n, int flags, int share_index,
+                               float* weff);
+
+/* Propagate GEMMs (ref: tdnn.cc:230-241, 292-328; replaces CopyRowsFromVec/SetZero and the n
+ * AddMatMat calls on GetInputPart views, tdnn.cc:806-820).
+ *   out[k,:] = (bias_tail or 0 or out[k,:]) + sum_i weff[i] * in[row_offsets[i]+k*row_stride,:] * W_i^T
+ *   W: out_dim x (n*in_dim), W_i = columns [i*in_dim,(i+1)*in_dim)
+ *   bias_mode: 0 = out is accumulated into (kPropagateAdds), 1 = out overwritten starting from
+ *              zero, 2 = out overwritten starting from the broadcast `bias` (out_dim, device). */
+int tdnnf_darts_propagate(tdnnf_ctx* ctx, const float* in, int in_rows, int in_dim, int in_stride,
+                          float* out, int out_rows, int out_dim, int out_stride, const float* W,
+                          int w_stride, const float* bias, int bias_mode, const float* weff, int n,
+                          const int32_t* row_offsets, int row_stride);
+
+/* Backprop to the input (ref: tdnn.cc:366-416; kBackpropAdds):
+ *   in_deriv[row_offsets[i]+k*row_stride,:] += weff[i] * out_deriv[k,:] * W_i   for all i,k */
+int tdnnf_darts_backprop_data(tdnnf_ctx* ctx, const float* out_deriv, int out_rows, int out_dim,
+                              int od_stride, float* in_deriv, int in_rows, int in_dim, int id_stride,
+                              const float* W, int w_stride, const float* weff, int n,
+                              const int32_t* row_offsets, int row_stride);
+
+/* Parameter gradients (ref: tdnn.cc:482-539, 607-624 without the two PreconditionDirections
+ * calls, i.e. in_scale = out_scale = 1; replaces the R x (n*D_in+1) in_value_temp, the n extra
+ * AddMatMat+AddMatMatElements+Sum() and the final AddMatMat / AddMatVec):
+ *   dW_i   += lr * weff[i] * out_deriv^T * X_i            (X_i = the offset-i input view)
+ *   dbias  += lr * colsum(out_deriv)                      (dbias may be NULL)
+ *   s[i]    = sum((X_i W_i^T) .* out_deriv) = <out_deriv^T X_i, W_i>   (s may be NULL; overwritten)
+ *   W_model: the model's weights (for s), dW: the delta component's weights. */
+int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value, int in_rows, int in_dim,
+                                int in_stride, const float* out_deriv, int out_rows, int out_dim,
+                                int od_stride, const float* W_model, int w_stride, float* dW,
+                                int dw_stride, float* dbias, const float* weff, int n,
+                                const int32_t* row_offsets, int row_stride, float lr, float* s);
+
+/* Architecture-weight update (ref: tdnn.cc:541-590): accumulates the softmax / sigmoid
+ * Jacobian products of s into dalpha, then applies the x5 / xlr / x10000 scalings to the WHOLE
+ * dalpha range exactly as the reference does.  All pointers device, n entries. */
+int tdnnf_darts_alpha_update(tdnnf_ctx* ctx, const float* s, const float* coef, int n, int flags,
+                             float temperature, int share_index, float lr, float* dalpha);
+
+/* ------------------------------------------------------------------ mixing components - */
+/* {Gumbel}SoftmaxFlopsComponent::Propagate (ref: simple.cc:10088-10113, 9968-9981):
+ *   out = max(softmax_row((in + G) * inv_temp), 1e-20),  G_j = -log(-log u[j]) (u HOST, cols
+ *   entries, one draw per COLUMN shared by all rows) or G = 0 when u == NULL. */
+int tdnnf_softmax_flops_fwd(tdnnf_ctx* ctx, const float* in, int rows, int cols, int in_stride, float* out,
+                            int out_stride, const float* u, float inv_temp);
+/* {Gumbel}SoftmaxFlopsComponent::Backprop (ref: simple.cc:10116-10158, 9984-10020):
+ *   e = out_deriv + penalty * f,  f = (-25,-50,-80,-100,-120,-160,-200,-240) on columns 0..7
+ *   in_deriv = (p .* e - p * (p . e)) * inv_temp;  penalty = scale / (rows_for_norm * cols).
+ *   write_back_e != 0 reproduces the reference's mutation of out_deriv (it writes through a
+ *   const reference); in_deriv may alias out_deriv (kBackpropInPlace).  cols must be >= 8. */
+int tdnnf_softmax_flops_bwd(tdnnf_ctx* ctx, const float* out_value, int ov_stride, float* out_deriv,
+                            int od_stride, float* in_deriv, int id_stride, int rows, int cols, float penalty,
+                            float inv_temp, int write_back_e);
+/* CopyNComponent (ref: simple.cc:4843-4867; AddMatBlocks): fwd out[:, b*in_cols + j] += scale*in[:, j];
+ * bwd in_deriv[:, j] += scale * sum_b out_deriv[:, b*in_cols + j]. */
+int tdnnf_copyn_fwd(tdnnf_ctx* ctx, const float* in, int rows, int in_cols, int in_stride, float* out,
+                    int out_cols, int out_stride, float scale);
+int tdnnf_copyn_bwd(tdnnf_ctx* ctx, const float* out_deriv, int rows, int out_cols, int od_stride,
+                    float* in_deriv, int in_cols, int id_stride, float scale);
+/* OnehotFunctionComponent::Propagate (ref: simple.cc:9504-9519): every row of out becomes the
+ * one-hot of the slot i with i/dim <= u < (i+1)/dim (float compares); u injected by the caller. */
+int tdnnf_onehot_fwd(tdnnf_ctx* ctx, float* out, int rows, int dim, int out_stride, float u);
+/* vec[j] += scale * sum_rows mat[:, j]   (AddRowSumMat; ref: simple.cc:9544-9548, tdnn.cc:614) */
+int tdnnf_add_row_sum(tdnnf_ctx* ctx, const float* mat, int rows, int cols, int stride, float scale,
+                      float* vec);
+/* BatchNormTestComponent (ref: norm.cc:843-877, 879-922; CopyFromMat+MulColsVec+AddVecToRows):
+ *   fwd: out = in .* scale + offset ; bwd: in_deriv = out_deriv .* scale.  In-place allowed.
+ *   scale/offset: device vectors of `cols` entries; offset NULL => none. */
+int tdnnf_scale_offset_rows(tdnnf_ctx* ctx, const float* in, int rows, int cols, int in_stride, float* out,
+                            int out_stride, const float* scale, const float* offset);
+/* ElementwiseProductComponent (ref: simple.cc:256-299): in is rows x (2*out_cols);
+ * fwd: out = in[:, :D] .* in[:, D:]; bwd: in_deriv[:, :D] = od .* in[:, D:], in_deriv[:, D:] = od .* in[:, :D] */
+int tdnnf_elementwise_product_fwd(tdnnf_ctx* ctx, const float* in, int rows, int out_cols, int in_stride,
+                                  float* out, int out_stride);
+int tdnnf_elementwise_product_bwd(tdnnf_ctx* ctx, const float* in, int in_stride, const float* out_deriv,
+                                  int od_stride, float* in_deriv, int id_stride, int rows, int out_cols);
+
+/* ------------------------------------------------------------------ chain denominator - */
+/* DenominatorGraph (kaldi: chain/chain-den-graph.{h,cc}).  Host arrays, copied to the device.
+ *   fwd_ranges / bwd_ranges: num_states pairs [begin,end) into `transitions` (forward list
+ *   first, then backward list), transitions: {prob, pdf_id, hmm_state} as three parallel arrays. */
+int tdnnf_den_graph_create(tdnnf_ctx* ctx, int num_states, int num_pdfs, int num_transitions,
+                           const int32_t* fwd_ranges, const int32_t* bwd_ranges, const float* trans_prob,
+                           const int32_t* trans_pdf, const int32_t* trans_state, const float* initial_probs,
+                           tdnnf_den_graph** out);
+int tdnnf_den_graph_destroy(tdnnf_den_graph* g);
+
+/* DenominatorComputation (kaldi: chain/chain-denominator.{h,cc}).  nnet_output is
+ * (frames_per_seq*num_seqs) x num_pdfs with row = t*num_seqs + s. */
+int tdnnf_den_create(tdnnf_ctx* ctx, const tdnnf_den_graph* g, int num_seqs, int frames_per_seq,
+                     float leaky_hmm_coefficient, tdnnf_den_comp** out);
+int tdnnf_den_destroy(tdnnf_den_comp* c);
+/* Forward(): returns the total log-prob summed over sequences in *logprob (HOST; this call
+ * synchronises the stream -- the reference returns the scalar the same way). */
+int tdnnf_den_forward(tdnnf_den_comp* c, const float* nnet_output, int stride, float* logprob);
+/* Backward(deriv_weight, &nnet_output_deriv): nnet_output_deriv += deriv_weight * posterior.
+ * *ok (HOST) = 0 when the t=0 alpha.beta check fails (the reference's return value).  Syncs. */
+int tdnnf_den_backward(tdnnf_den_comp* c, float deriv_weight, float* nnet_output_deriv, int stride, int* ok);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDNNF_NAS_B200_H_ */

@@ -1,0 +1,298 @@
+"""ctypes binding of the C ABI (include/tdnnf_nas_b200.h) for Python callers.
+
+torch is used only for device memory and streams: every wrapper passes raw device pointers,
+sizes and strides to the shared library.  There is no fallback: if the library is missing or a
+call fails, a RuntimeError carrying tdnnf_last_error() is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libtdnnf_nas_b200.so")
+
+USE_GUMBEL, FREE_SELECT, UNIFORM_SAMPLE, USE_ENTROPY, UPDATE_ALPHA = 1, 2, 4, 8, 16
+
+_lib = None
+
+c_float_p = C.POINTER(C.c_float)
+c_int_p = C.POINTER(C.c_int32)
+vp = C.c_void_p
+
+
+def _declare(lib):
+    def sig(name, argtypes, restype=C.c_int):
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+
+    i, f = C.c_int, C.c_float
+    sig("tdnnf_last_error", [], C.c_char_p)
+    sig("tdnnf_abi_version", [])
+    sig("tdnnf_ctx_create", [i, C.POINTER(vp)])
+    sig("tdnnf_ctx_destroy", [vp])
+    sig("tdnnf_ctx_set_stream", [vp, vp])
+    sig("tdnnf_ctx_reserve", [vp, C.c_uint64])
+    sig("tdnnf_ctx_launch_count", [vp], C.c_uint64)
+    sig("tdnnf_darts_coef", [vp, vp, i, i, f, c_float_p, f, i, vp, vp])
+    sig("tdnnf_darts_weff_from_coef", [vp, vp, i, i, i, vp])
+    sig("tdnnf_darts_propagate", [vp, vp, i, i, i, vp, i, i, i, vp, i, vp, i, vp, i, c_int_p, i])
+    sig("tdnnf_darts_backprop_data", [vp, vp, i, i, i, vp, i, i, i, vp, i, vp, i, c_int_p, i])
+    sig("tdnnf_darts_backprop_params", [vp, vp, i, i, i, vp, i, i, i, vp, i, vp, i, vp, vp, i, c_int_p, i, f, vp])
+    sig("tdnnf_darts_alpha_update", [vp, vp, vp, i, i, f, i, f, vp])
+    sig("tdnnf_softmax_flops_fwd", [vp, vp, i, i, i, vp, i, c_float_p, f])
+    sig("tdnnf_softmax_flops_bwd", [vp, vp, i, vp, i, vp, i, i, i, f, f, i])
+    sig("tdnnf_copyn_fwd", [vp, vp, i, i, i, vp, i, i, f])
+    sig("tdnnf_copyn_bwd", [vp, vp, i, i, i, vp, i, i, f])
+    sig("tdnnf_onehot_fwd", [vp, vp, i, i, i, f])
+    sig("tdnnf_add_row_sum", [vp, vp, i, i, i, f, vp])
+    sig("tdnnf_scale_offset_rows", [vp, vp, i, i, i, vp, i, vp, vp])
+    sig("tdnnf_elementwise_product_fwd", [vp, vp, i, i, i, vp, i])
+    sig("tdnnf_elementwise_product_bwd", [vp, vp, i, vp, i, vp, i, i, i])
+    sig("tdnnf_den_graph_create", [vp, i, i, i, c_int_p, c_int_p, c_float_p, c_int_p, c_int_p, c_float_p, C.POINTER(vp)])
+    sig("tdnnf_den_graph_destroy", [vp])
+    sig("tdnnf_den_create", [vp, vp, i, i, f, C.POINTER(vp)])
+    sig("tdnnf_den_destroy", [vp])
+    sig("tdnnf_den_forward", [vp, vp, i, c_float_p])
+    sig("tdnnf_den_backward", [vp, f, vp, i, c_int_p])
+
+
+def load():
+    """Load the shared library (raises if it has not been built: there is no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python tdnn-f_nas_b200/build.py` "
+                "(the product has no CPU or PyTorch fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+class TdnnfError(RuntimeError):
+    pass
+
+
+def check(rc: int):
+    if rc != 0:
+        raise TdnnfError(f"tdnnf error {rc}: {load().tdnnf_last_error().decode()}")
+
+
+def _ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _mat(t):
+    """(ptr, rows, cols, stride) of a 2-D fp32 CUDA tensor whose last dim is contiguous."""
+    import torch
+
+    assert t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1, "need a row-major fp32 CUDA matrix"
+    return t.data_ptr(), t.shape[0], t.shape[1], t.stride(0)
+
+
+def _fhost(a: Optional[Sequence[float]]):
+    if a is None:
+        return None
+    arr = (C.c_float * len(a))(*[float(x) for x in a])
+    return arr
+
+
+def _ihost(a: Sequence[int]):
+    return (C.c_int32 * len(a))(*[int(x) for x in a])
+
+
+class Context:
+    """RAII wrapper of tdnnf_ctx bound to a CUDA device and (optionally) a torch stream."""
+
+    def __init__(self, device: int = 0, stream=None):
+        lib = load()
+        h = vp()
+        check(lib.tdnnf_ctx_create(device, C.byref(h)))
+        self.h = h
+        self.device = device
+        if stream is not None:
+            self.set_stream(stream)
+
+    def set_stream(self, stream):
+        check(load().tdnnf_ctx_set_stream(self.h, vp(stream.cuda_stream if hasattr(stream, "cuda_stream") else stream)))
+
+    def use_current_stream(self):
+        import torch
+
+        self.set_stream(torch.cuda.current_stream(self.device))
+
+    def reserve(self, nbytes: int):
+        check(load().tdnnf_ctx_reserve(self.h, nbytes))
+
+    @property
+    def launches(self) -> int:
+        return int(load().tdnnf_ctx_launch_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            load().tdnnf_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ DARTS
+    def darts_coef(self, alpha, flags, temperature, u_gumbel, u_uniform, share_index, coef, weff):
+        n = alpha.numel()
+        check(load().tdnnf_darts_coef(self.h, _ptr(alpha), n, flags, temperature, _fhost(u_gumbel), u_uniform,
+                                      share_index, _ptr(coef), _ptr(weff)))
+
+    def darts_weff_from_coef(self, coef, flags, share_index, weff):
+        check(load().tdnnf_darts_weff_from_coef(self.h, _ptr(coef), coef.numel(), flags, share_index, _ptr(weff)))
+
+    def darts_propagate(self, x, out, W, bias, bias_mode, weff, row_offsets, row_stride):
+        xp, xr, xc, xs = _mat(x)
+        op, orr, oc, os_ = _mat(out)
+        wp, wr, wc, ws = _mat(W)
+        n = len(row_offsets)
+        assert wr == oc and wc == n * xc
+        check(load().tdnnf_darts_propagate(self.h, xp, xr, xc, xs, op, orr, oc, os_, wp, ws, _ptr(bias), bias_mode,
+                                           _ptr(weff), n, _ihost(row_offsets), row_stride))
+
+    def darts_backprop_data(self, out_deriv, in_deriv, W, weff, row_offsets, row_stride):
+        dp, dr, dc, ds = _mat(out_deriv)
+        ip, ir, ic, is_ = _mat(in_deriv)
+        wp, wr, wc, ws = _mat(W)
+        n = len(row_offsets)
+        assert wr == dc and wc == n * ic
+        check(load().tdnnf_darts_backprop_data(self.h, dp, dr, dc, ds, ip, ir, ic, is_, wp, ws, _ptr(weff), n,
+                                               _ihost(row_offsets), row_stride))
+
+    def darts_backprop_params(self, x, out_deriv, W_model, dW, dbias, weff, row_offsets, row_stride, lr, s=None):
+        xp, xr, xc, xs = _mat(x)
+        dp, dr, dc, ds = _mat(out_deriv)
+        gp, gr, gc, gs = _mat(dW)
+        n = len(row_offsets)
+        wptr, wstride = (0, 0)
+        if W_model is not None:
+            wptr, _, _, wstride = _mat(W_model)
+        check(load().tdnnf_darts_backprop_params(self.h, xp, xr, xc, xs, dp, dr, dc, ds, wptr, wstride, gp, gs,
+                                                 _ptr(dbias), _ptr(weff), n, _ihost(row_offsets), row_stride, lr,
+                                                 _ptr(s)))
+
+    def darts_alpha_update(self, s, coef, flags, temperature, share_index, lr, dalpha):
+        check(load().tdnnf_darts_alpha_update(self.h, _ptr(s), _ptr(coef), coef.numel(), flags, temperature,
+                                              share_index, lr, _ptr(dalpha)))
+
+    # ------------------------------------------------------------------ mixing components
+    def softmax_flops_fwd(self, x, out, u=None, inv_temp=1.0):
+        xp, r, c, xs = _mat(x)
+        op, _, _, os_ = _mat(out)
+        check(load().tdnnf_softmax_flops_fwd(self.h, xp, r, c, xs, op, os_, _fhost(u), inv_temp))
+
+    def softmax_flops_bwd(self, out_value, out_deriv, in_deriv, penalty, inv_temp=1.0, write_back_e=1):
+        vp_, r, c, vs = _mat(out_value)
+        dp, _, _, ds = _mat(out_deriv)
+        ip, _, _, is_ = _mat(in_deriv)
+        check(load().tdnnf_softmax_flops_bwd(self.h, vp_, vs, dp, ds, ip, is_, r, c, penalty, inv_temp, write_back_e))
+
+    def copyn_fwd(self, x, out, scale):
+        xp, r, c, xs = _mat(x)
+        op, _, oc, os_ = _mat(out)
+        check(load().tdnnf_copyn_fwd(self.h, xp, r, c, xs, op, oc, os_, scale))
+
+    def copyn_bwd(self, out_deriv, in_deriv, scale):
+        dp, r, oc, ds = _mat(out_deriv)
+        ip, _, ic, is_ = _mat(in_deriv)
+        check(load().tdnnf_copyn_bwd(self.h, dp, r, oc, ds, ip, ic, is_, scale))
+
+    def onehot_fwd(self, out, u):
+        op, r, c, os_ = _mat(out)
+        check(load().tdnnf_onehot_fwd(self.h, op, r, c, os_, u))
+
+    def add_row_sum(self, mat, scale, vec):
+        mp, r, c, ms = _mat(mat)
+        check(load().tdnnf_add_row_sum(self.h, mp, r, c, ms, scale, _ptr(vec)))
+
+    def scale_offset_rows(self, x, out, scale, offset=None):
+        xp, r, c, xs = _mat(x)
+        op, _, _, os_ = _mat(out)
+        check(load().tdnnf_scale_offset_rows(self.h, xp, r, c, xs, op, os_, _ptr(scale), _ptr(offset)))
+
+    def elementwise_product_fwd(self, x, out):
+        xp, r, c, xs = _mat(x)
+        op, _, oc, os_ = _mat(out)
+        check(load().tdnnf_elementwise_product_fwd(self.h, xp, r, oc, xs, op, os_))
+
+    def elementwise_product_bwd(self, x, out_deriv, in_deriv):
+        xp, r, c, xs = _mat(x)
+        dp, _, oc, ds = _mat(out_deriv)
+        ip, _, _, is_ = _mat(in_deriv)
+        check(load().tdnnf_elementwise_product_bwd(self.h, xp, xs, dp, ds, ip, is_, r, oc))
+
+
+class DenGraph:
+    """DenominatorGraph on the device.  Arrays are host (numpy) as in the C ABI."""
+
+    def __init__(self, ctx: Context, graph: dict):
+        import numpy as np
+
+        self.ctx = ctx
+        self.num_states = int(graph["num_states"])
+        self.num_pdfs = int(graph["num_pdfs"])
+        fr = np.ascontiguousarray(graph["fwd_ranges"], dtype=np.int32)
+        br = np.ascontiguousarray(graph["bwd_ranges"], dtype=np.int32)
+        pr = np.ascontiguousarray(graph["prob"], dtype=np.float32)
+        pd = np.ascontiguousarray(graph["pdf"], dtype=np.int32)
+        st = np.ascontiguousarray(graph["state"], dtype=np.int32)
+        init = np.ascontiguousarray(graph["init"], dtype=np.float32)
+        self.num_transitions = len(pr)
+        h = vp()
+        check(load().tdnnf_den_graph_create(
+            ctx.h, self.num_states, self.num_pdfs, len(pr), fr.ctypes.data_as(c_int_p), br.ctypes.data_as(c_int_p),
+            pr.ctypes.data_as(c_float_p), pd.ctypes.data_as(c_int_p), st.ctypes.data_as(c_int_p),
+            init.ctypes.data_as(c_float_p), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            load().tdnnf_den_graph_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DenominatorComputation:
+    def __init__(self, ctx: Context, graph: DenGraph, num_seqs: int, frames_per_seq: int, leaky: float):
+        self.ctx, self.graph = ctx, graph
+        h = vp()
+        check(load().tdnnf_den_create(ctx.h, graph.h, num_seqs, frames_per_seq, leaky, C.byref(h)))
+        self.h = h
+
+    def forward(self, nnet_output) -> float:
+        p, r, c, s = _mat(nnet_output)
+        lp = C.c_float(0)
+        check(load().tdnnf_den_forward(self.h, p, s, C.byref(lp)))
+        return float(lp.value)
+
+    def backward(self, deriv_weight: float, nnet_output_deriv) -> bool:
+        p, r, c, s = _mat(nnet_output_deriv)
+        ok = C.c_int32(0)
+        check(load().tdnnf_den_backward(self.h, deriv_weight, p, s, C.byref(ok)))
+        return bool(ok.value)
+
+    def close(self):
+        if getattr(self, "h", None):
+            load().tdnnf_den_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

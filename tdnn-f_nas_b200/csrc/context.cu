@@ -1,0 +1,107 @@
+// Context, error reporting and scratch arena of the C ABI.
+#include <cstdio>
+#include <string>
+
+#include "context.h"
+
+namespace tdnnf {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+}  // namespace tdnnf
+
+using namespace tdnnf;
+
+void* tdnnf_ctx::ws_alloc(size_t bytes) {
+  bytes = (bytes + 1023) & ~size_t(1023);
+  if (ws_off + bytes > ws_bytes) {
+    set_error("internal: scratch arena overflow (ws_reserve was not called with the full size)");
+    return nullptr;
+  }
+  void* p = ws + ws_off;
+  ws_off += bytes;
+  return p;
+}
+
+int tdnnf_ctx::ws_reserve(size_t bytes) {
+  bytes = ((bytes + 1023) & ~size_t(1023)) + 4096;
+  if (bytes <= ws_bytes) return TDNNF_OK;
+  // Growing: earlier kernels on the stream may still read the old arena.
+  TDNNF_CUDA_OK(cudaStreamSynchronize(stream));
+  if (ws) TDNNF_CUDA_OK(cudaFree(ws));
+  ws = nullptr;
+  ws_bytes = 0;
+  size_t want = bytes + bytes / 4;  // head-room so that slightly larger minibatches do not regrow
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ws), want);
+  if (e != cudaSuccess) {
+    want = bytes;
+    e = cudaMalloc(reinterpret_cast<void**>(&ws), want);
+  }
+  if (e != cudaSuccess) return fail(TDNNF_ERR_NOMEM, std::string("cudaMalloc of scratch arena failed: ") + cudaGetErrorString(e));
+  ws_bytes = want;
+  return TDNNF_OK;
+}
+
+extern "C" const char* tdnnf_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int tdnnf_abi_version(void) { return 1000; }
+
+extern "C" int tdnnf_ctx_create(int device, tdnnf_ctx** out) {
+  TDNNF_REQUIRE(out != nullptr, "null out pointer");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(TDNNF_ERR_CUDA, std::string("no CUDA device available (there is no CPU path): ") +
+                                    (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  TDNNF_REQUIRE(device >= 0 && device < count, "device index out of range");
+  TDNNF_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  TDNNF_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(TDNNF_ERR_UNSUPPORTED, "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                           "; this library contains sm_100a code only");
+  tdnnf_ctx* ctx = new tdnnf_ctx();
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    delete ctx;
+    return fail(TDNNF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  }
+  ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  *out = ctx;
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_ctx_destroy(tdnnf_ctx* ctx) {
+  if (!ctx) return TDNNF_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->ws) cudaFree(ctx->ws);
+  delete ctx;
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_ctx_set_stream(tdnnf_ctx* ctx, void* stream) {
+  TDNNF_REQUIRE(ctx != nullptr, "null context");
+  ctx->stream = static_cast<cudaStream_t>(stream);
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_ctx_reserve(tdnnf_ctx* ctx, uint64_t bytes) {
+  TDNNF_REQUIRE(ctx != nullptr, "null context");
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+  return ctx->ws_reserve((size_t)bytes);
+}
+
+extern "C" uint64_t tdnnf_ctx_launch_count(const tdnnf_ctx* ctx) { return ctx ? ctx->launches : 0; }

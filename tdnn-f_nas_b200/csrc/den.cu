@@ -1,0 +1,514 @@
+// LF-MMI denominator forward-backward (kaldi: chain/chain-denominator.{h,cc}, chain-den-graph.{h,cc},
+// chain-kernels.cu -- upstream Kaldi, not shipped with the reference; restated from SURVEY.md App. B).
+//
+// Layout in HBM (all fp32, the sequence index s is always the contiguous one):
+//   E     [T][P][S]      exp(clamp(nnet_output, -30, 30)), transposed once per call
+//   alpha [T+1][N][S]    un-"dashed" alpha; tot[T+1][S] holds sum_h alpha(t,h,s)  (Kaldi keeps
+//                        alpha-dash plus the sums in S trailing columns; alpha-dash is re-formed on
+//                        read as alpha + leaky*init[h]*tot, which saves a full pass per frame)
+//   betad [2][N][S]      beta-dash ping-pong; bsum[2][S] = sum_g init[g]*betad(g,s)
+//   gamma [T][P][S]      occupation probabilities, transposed-added into nnet_output_deriv at the end
+// Arithmetic is Kaldi's: probability domain, every frame divided by the previous frame's total.
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "context.h"
+
+using namespace tdnnf;
+
+struct tdnnf_den_graph {
+  tdnnf_ctx* ctx = nullptr;
+  int num_states = 0, num_pdfs = 0, num_transitions = 0;
+  int2* fwd_ranges = nullptr;   // device [N]
+  int2* bwd_ranges = nullptr;   // device [N]
+  float4* trans = nullptr;      // device [A]: {prob, pdf (as int bits), state (as int bits), unused}
+  float* init = nullptr;        // device [N]
+  float init_sum = 0.f;         // sum_h init[h] (host copy, fp32 sequential sum)
+};
+
+struct tdnnf_den_comp {
+  tdnnf_ctx* ctx = nullptr;
+  const tdnnf_den_graph* g = nullptr;
+  int S = 0, T = 0;
+  float leaky = 0.f;
+  float* E = nullptr;
+  float* alpha = nullptr;
+  float* tot = nullptr;     // [(T+1)][S]
+  float* betad = nullptr;   // [2][N][S]
+  float* bsum = nullptr;    // [2][S]
+  float* gamma = nullptr;   // [T][P][S]
+  float* tot_prob = nullptr;  // [S]
+  double* scalars = nullptr;  // [2]: logprob, alpha.beta check
+  bool forward_done = false;
+};
+
+namespace {
+
+template <int V>
+struct Vec;
+template <>
+struct Vec<1> {
+  float v[1];
+  __device__ static Vec load(const float* p) { Vec r; r.v[0] = *p; return r; }
+  __device__ void store(float* p) const { *p = v[0]; }
+};
+template <>
+struct Vec<2> {
+  float v[2];
+  __device__ static Vec load(const float* p) { const float2 t = *reinterpret_cast<const float2*>(p); Vec r; r.v[0] = t.x; r.v[1] = t.y; return r; }
+  __device__ void store(float* p) const { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+};
+template <>
+struct Vec<4> {
+  float v[4];
+  __device__ static Vec load(const float* p) { const float4 t = *reinterpret_cast<const float4*>(p); Vec r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r; }
+  __device__ void store(float* p) const { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+
+template <int V>
+__device__ __forceinline__ void red_add_vec(float* p, const float (&x)[V]) {
+  if constexpr (V == 4) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
+  } else if constexpr (V == 2) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(x[0]), "f"(x[1]) : "memory");
+  } else {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(x[0]) : "memory");
+  }
+}
+
+constexpr int kDenThreads = 256;
+constexpr int kStatesPerBlock = 64;
+
+// E[t][p][s] = exp(clamp(x[t*S+s][p])) : 32x32 tiled transpose per frame.
+__global__ void den_exp_transpose_kernel(const float* __restrict__ x, long long ld, int S, int P, float* __restrict__ E) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z;
+  const int p0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int s = s0 + i, p = p0 + threadIdx.x;
+    float v = 0.f;
+    if (s < S && p < P) v = expf(fminf(fmaxf(x[((long long)t * S + s) * ld + p], -30.f), 30.f));
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int p = p0 + i, s = s0 + threadIdx.x;
+    if (s < S && p < P) E[((long long)t * P + p) * S + s] = tile[threadIdx.x][i];
+  }
+}
+
+// alpha(0,h,s) = init[h]; tot(0,s) = sum_h init[h]
+__global__ void den_alpha_first_kernel(const float* __restrict__ init, int N, int S, float init_sum,
+                                       float* __restrict__ alpha0, float* __restrict__ tot0) {
+  const long long total = (long long)N * S;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    alpha0[i] = init[i / S];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < S; i += (long long)gridDim.x * blockDim.x)
+    tot0[i] = init_sum;
+}
+
+// One forward frame.  Thread = (state h, V consecutive sequences); lanes run along s, so every
+// arc is two coalesced row reads (alpha(t-1,g,:) and E(t-1,pdf,:)) plus broadcast scalars.
+template <int V>
+__global__ void __launch_bounds__(kDenThreads)
+den_alpha_frame_kernel(const int2* __restrict__ bwd_ranges, const float4* __restrict__ trans,
+                       const float* __restrict__ init, int N, int S, float leaky, const float* __restrict__ alpha_prev,
+                       const float* __restrict__ tot_prev, const float* __restrict__ E_prev,
+                       float* __restrict__ alpha_cur, float* __restrict__ tot_cur) {
+  const int SV = S / V;
+  const int tps = kDenThreads / SV;  // states processed concurrently by the block (SV <= 256 divides 256 or not: see host)
+  const int sv = threadIdx.x % SV;
+  const int hl = threadIdx.x / SV;
+  const int s = sv * V;
+  const bool active = hl < tps;
+  float lt[V], inv[V], part[V];
+  {
+    const Vec<V> tp = Vec<V>::load(tot_prev + s);
+#pragma unroll
+    for (int j = 0; j < V; ++j) { lt[j] = leaky * tp.v[j]; inv[j] = 1.0f / tp.v[j]; part[j] = 0.f; }
+  }
+  const int h_begin = blockIdx.x * kStatesPerBlock;
+  const int h_end = min(h_begin + kStatesPerBlock, N);
+  if (active) {
+    for (int h = h_begin + hl; h < h_end; h += tps) {
+      const int2 rg = bwd_ranges[h];
+      float acc[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] = 0.f;
+      for (int a = rg.x; a < rg.y; ++a) {
+        const float4 tr = trans[a];
+        const int pdf = __float_as_int(tr.y), g = __float_as_int(tr.z);
+        const float ig = init[g];
+        const Vec<V> al = Vec<V>::load(alpha_prev + (long long)g * S + s);
+        const Vec<V> e = Vec<V>::load(E_prev + (long long)pdf * S + s);
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] += ((al.v[j] + ig * lt[j]) * tr.x) * e.v[j];
+      }
+      Vec<V> o;
+#pragma unroll
+      for (int j = 0; j < V; ++j) { o.v[j] = acc[j] * inv[j]; part[j] += o.v[j]; }
+      o.store(alpha_cur + (long long)h * S + s);
+    }
+  }
+  // block reduction of the per-sequence totals over the states of this block
+  __shared__ float red[kDenThreads * V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) red[threadIdx.x * V + j] = active ? part[j] : 0.f;
+  __syncthreads();
+  if (threadIdx.x < SV) {
+    float sum[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) sum[j] = 0.f;
+    for (int k = 0; k < tps; ++k)
+#pragma unroll
+      for (int j = 0; j < V; ++j) sum[j] += red[(k * SV + threadIdx.x) * V + j];
+    red_add_vec<V>(tot_cur + s, sum);
+  }
+}
+
+// tot_prob[s] = sum_h alpha'(T,h,s) = tot(T,s) * (1 + leaky*sum(init));  logprob = sum_s log tot_prob + sum_{t<T,s} log tot(t,s)
+// Also seeds the backward pass: betad(T,h,s) = 1/tot_prob[s]  =>  bsum(T,s) = sum(init)/tot_prob[s].
+__global__ void den_loglike_kernel(const float* __restrict__ tot, int T, int S, float leaky, float init_sum,
+                                   float* __restrict__ tot_prob, double* __restrict__ scalars) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const float tp = tot[(long long)T * S + s] + leaky * init_sum * tot[(long long)T * S + s];
+    tot_prob[s] = tp;
+    acc += (double)logf(tp);
+  }
+  for (long long i = threadIdx.x; i < (long long)T * S; i += blockDim.x) acc += (double)logf(tot[i]);
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) scalars[0] = red[0];
+}
+
+__global__ void den_beta_last_kernel(const float* __restrict__ tot_prob, int N, int S, float init_sum,
+                                     float* __restrict__ betad, float* __restrict__ bsum) {
+  const long long total = (long long)N * S;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    betad[i] = 1.0f / tot_prob[i % S];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < S; i += (long long)gridDim.x * blockDim.x)
+    bsum[i] = init_sum / tot_prob[i];
+}
+
+// One backward frame (kaldi: BetaDashGeneralFrame + Beta): thread = (source state h, V sequences).
+//   vf = p * beta(t+1,g,s) * E(t,pdf,s);  gamma(t,pdf,s) += vf * alpha'(t,h,s)/tot(t,s);  betad(t,h,s) = sum vf / tot(t,s)
+template <int V>
+__global__ void __launch_bounds__(kDenThreads)
+den_beta_frame_kernel(const int2* __restrict__ fwd_ranges, const float4* __restrict__ trans,
+                      const float* __restrict__ init, int N, int S, float leaky, const float* __restrict__ alpha_t,
+                      const float* __restrict__ tot_t, const float* __restrict__ E_t,
+                      const float* __restrict__ betad_next, const float* __restrict__ bsum_next,
+                      float* __restrict__ betad_cur, float* __restrict__ bsum_cur, float* __restrict__ gamma_t,
+                      double* __restrict__ check /* null unless t == 0 */) {
+  const int SV = S / V;
+  const int tps = kDenThreads / SV;
+  const int sv = threadIdx.x % SV;
+  const int hl = threadIdx.x / SV;
+  const int s = sv * V;
+  const bool active = hl < tps;
+  float lt[V], inv[V], lb[V], part[V], chk[V];
+  {
+    const Vec<V> tp = Vec<V>::load(tot_t + s);
+    const Vec<V> bs = Vec<V>::load(bsum_next + s);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      lt[j] = leaky * tp.v[j];
+      inv[j] = 1.0f / tp.v[j];
+      lb[j] = leaky * bs.v[j];
+      part[j] = 0.f;
+      chk[j] = 0.f;
+    }
+  }
+  const int h_begin = blockIdx.x * kStatesPerBlock;
+  const int h_end = min(h_begin + kStatesPerBlock, N);
+  if (active) {
+    for (int h = h_begin + hl; h < h_end; h += tps) {
+      const int2 rg = fwd_ranges[h];
+      const float ih = init[h];
+      const Vec<V> al = Vec<V>::load(alpha_t + (long long)h * S + s);
+      float occ[V], totv[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) { occ[j] = (al.v[j] + ih * lt[j]) * inv[j]; totv[j] = 0.f; }
+      for (int a = rg.x; a < rg.y; ++a) {
+        const float4 tr = trans[a];
+        const int pdf = __float_as_int(tr.y), g = __float_as_int(tr.z);
+        const Vec<V> b = Vec<V>::load(betad_next + (long long)g * S + s);
+        const Vec<V> e = Vec<V>::load(E_t + (long long)pdf * S + s);
+        float op[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const float vf = (tr.x * (b.v[j] + lb[j])) * e.v[j];
+          totv[j] += vf;
+          op[j] = vf * occ[j];
+        }
+        red_add_vec<V>(gamma_t + (long long)pdf * S + s, op);
+      }
+      Vec<V> o;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        o.v[j] = totv[j] * inv[j];
+        part[j] += ih * o.v[j];
+        chk[j] += (al.v[j] + ih * lt[j]) * o.v[j];  // alpha'(t,h,s) * betad(t,h,s)
+      }
+      o.store(betad_cur + (long long)h * S + s);
+    }
+  }
+  __shared__ float red[kDenThreads * V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) red[threadIdx.x * V + j] = active ? part[j] : 0.f;
+  __syncthreads();
+  if (threadIdx.x < SV) {
+    float sum[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) sum[j] = 0.f;
+    for (int k = 0; k < tps; ++k)
+#pragma unroll
+      for (int j = 0; j < V; ++j) sum[j] += red[(k * SV + threadIdx.x) * V + j];
+    red_add_vec<V>(bsum_cur + s, sum);
+  }
+  if (check != nullptr) {
+    __syncthreads();
+    float c = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) c += active ? chk[j] : 0.f;
+    red[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = kDenThreads / 2; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(check, (double)red[0]);
+  }
+}
+
+// nnet_output_deriv[t*S+s][p] += w * gamma[t][p][s]   (32x32 tiled transpose-add)
+__global__ void den_deriv_transpose_add_kernel(const float* __restrict__ gamma, int S, int P, float w,
+                                               float* __restrict__ deriv, long long ld) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z;
+  const int p0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int p = p0 + i, s = s0 + threadIdx.x;
+    tile[i][threadIdx.x] = (s < S && p < P) ? gamma[((long long)t * P + p) * S + s] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int s = s0 + i, p = p0 + threadIdx.x;
+    if (s < S && p < P) deriv[((long long)t * S + s) * ld + p] += w * tile[threadIdx.x][i];
+  }
+}
+
+int pick_vec(int S) {
+  if (S % 4 == 0 && S >= 64) return 4;
+  if (S % 2 == 0 && S >= 32) return 2;
+  return 1;
+}
+
+}  // namespace
+
+extern "C" int tdnnf_den_graph_create(tdnnf_ctx* ctx, int num_states, int num_pdfs, int num_transitions,
+                                      const int32_t* fwd_ranges, const int32_t* bwd_ranges, const float* trans_prob,
+                                      const int32_t* trans_pdf, const int32_t* trans_state, const float* initial_probs,
+                                      tdnnf_den_graph** out) {
+  TDNNF_REQUIRE(ctx && fwd_ranges && bwd_ranges && trans_prob && trans_pdf && trans_state && initial_probs && out,
+                "null argument");
+  TDNNF_REQUIRE(num_states > 0 && num_pdfs > 0 && num_transitions > 0, "empty graph");
+  for (int h = 0; h < num_states; ++h) {
+    TDNNF_REQUIRE(fwd_ranges[2 * h] >= 0 && fwd_ranges[2 * h] <= fwd_ranges[2 * h + 1] &&
+                      fwd_ranges[2 * h + 1] <= num_transitions && bwd_ranges[2 * h] >= 0 &&
+                      bwd_ranges[2 * h] <= bwd_ranges[2 * h + 1] && bwd_ranges[2 * h + 1] <= num_transitions,
+                  "transition range out of bounds");
+  }
+  for (int a = 0; a < num_transitions; ++a)
+    TDNNF_REQUIRE(trans_pdf[a] >= 0 && trans_pdf[a] < num_pdfs && trans_state[a] >= 0 && trans_state[a] < num_states,
+                  "transition pdf-id / hmm-state out of range");
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+  tdnnf_den_graph* g = new tdnnf_den_graph();
+  g->ctx = ctx;
+  g->num_states = num_states;
+  g->num_pdfs = num_pdfs;
+  g->num_transitions = num_transitions;
+  std::vector<float4> tr(num_transitions);
+  for (int a = 0; a < num_transitions; ++a) {
+    tr[a].x = trans_prob[a];
+    memcpy(&tr[a].y, &trans_pdf[a], 4);
+    memcpy(&tr[a].z, &trans_state[a], 4);
+    tr[a].w = 0.f;
+  }
+  float isum = 0.f;
+  for (int h = 0; h < num_states; ++h) isum += initial_probs[h];
+  g->init_sum = isum;
+  cudaError_t e = cudaSuccess;
+  auto up = [&](void** dst, const void* src, size_t bytes) {
+    if (e != cudaSuccess) return;
+    e = cudaMalloc(dst, bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+  };
+  up(reinterpret_cast<void**>(&g->fwd_ranges), fwd_ranges, sizeof(int2) * num_states);
+  up(reinterpret_cast<void**>(&g->bwd_ranges), bwd_ranges, sizeof(int2) * num_states);
+  up(reinterpret_cast<void**>(&g->trans), tr.data(), sizeof(float4) * num_transitions);
+  up(reinterpret_cast<void**>(&g->init), initial_probs, sizeof(float) * num_states);
+  if (e != cudaSuccess) {
+    tdnnf_den_graph_destroy(g);
+    return fail(TDNNF_ERR_CUDA, std::string("den graph upload failed: ") + cudaGetErrorString(e));
+  }
+  *out = g;
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_den_graph_destroy(tdnnf_den_graph* g) {
+  if (!g) return TDNNF_OK;
+  cudaFree(g->fwd_ranges);
+  cudaFree(g->bwd_ranges);
+  cudaFree(g->trans);
+  cudaFree(g->init);
+  delete g;
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_den_create(tdnnf_ctx* ctx, const tdnnf_den_graph* g, int num_seqs, int frames_per_seq,
+                                float leaky_hmm_coefficient, tdnnf_den_comp** out) {
+  TDNNF_REQUIRE(ctx && g && out, "null argument");
+  TDNNF_REQUIRE(num_seqs > 0 && frames_per_seq > 0, "empty minibatch");
+  TDNNF_REQUIRE(num_seqs <= 1024, "num_seqs > 1024 is not supported");
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+  tdnnf_den_comp* c = new tdnnf_den_comp();
+  c->ctx = ctx;
+  c->g = g;
+  c->S = num_seqs;
+  c->T = frames_per_seq;
+  c->leaky = leaky_hmm_coefficient;
+  const size_t N = g->num_states, P = g->num_pdfs, S = num_seqs, T = frames_per_seq;
+  cudaError_t e = cudaSuccess;
+  auto al = [&](void** p, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+  };
+  al(reinterpret_cast<void**>(&c->E), sizeof(float) * T * P * S);
+  al(reinterpret_cast<void**>(&c->alpha), sizeof(float) * (T + 1) * N * S);
+  al(reinterpret_cast<void**>(&c->tot), sizeof(float) * (T + 1) * S);
+  al(reinterpret_cast<void**>(&c->betad), sizeof(float) * 2 * N * S);
+  al(reinterpret_cast<void**>(&c->bsum), sizeof(float) * 2 * S);
+  al(reinterpret_cast<void**>(&c->gamma), sizeof(float) * T * P * S);
+  al(reinterpret_cast<void**>(&c->tot_prob), sizeof(float) * S);
+  al(reinterpret_cast<void**>(&c->scalars), sizeof(double) * 2);
+  if (e != cudaSuccess) {
+    tdnnf_den_destroy(c);
+    return fail(TDNNF_ERR_NOMEM, std::string("denominator workspace allocation failed: ") + cudaGetErrorString(e));
+  }
+  *out = c;
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_den_destroy(tdnnf_den_comp* c) {
+  if (!c) return TDNNF_OK;
+  cudaFree(c->E);
+  cudaFree(c->alpha);
+  cudaFree(c->tot);
+  cudaFree(c->betad);
+  cudaFree(c->bsum);
+  cudaFree(c->gamma);
+  cudaFree(c->tot_prob);
+  cudaFree(c->scalars);
+  delete c;
+  return TDNNF_OK;
+}
+
+#define DEN_LAUNCH_CHECK(ctx)            \
+  do {                                   \
+    (ctx)->launches++;                   \
+    TDNNF_CUDA_OK(cudaGetLastError());   \
+  } while (0)
+
+extern "C" int tdnnf_den_forward(tdnnf_den_comp* c, const float* nnet_output, int stride, float* logprob) {
+  TDNNF_REQUIRE(c && nnet_output && logprob, "null argument");
+  const tdnnf_den_graph* g = c->g;
+  tdnnf_ctx* ctx = c->ctx;
+  const int N = g->num_states, P = g->num_pdfs, S = c->S, T = c->T;
+  TDNNF_REQUIRE(stride >= P, "stride < num_pdfs");
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  den_exp_transpose_kernel<<<dim3((P + 31) / 32, (S + 31) / 32, T), dim3(32, 8), 0, st>>>(nnet_output, stride, S, P, c->E);
+  DEN_LAUNCH_CHECK(ctx);
+  TDNNF_CUDA_OK(cudaMemsetAsync(c->tot, 0, sizeof(float) * (size_t)(T + 1) * S, st));
+  den_alpha_first_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(g->init, N, S, g->init_sum, c->alpha, c->tot);
+  DEN_LAUNCH_CHECK(ctx);
+  const int V = pick_vec(S);
+  const int blocks = (N + kStatesPerBlock - 1) / kStatesPerBlock;
+  TDNNF_REQUIRE(S / V <= kDenThreads, "num_seqs too large for the frame kernels");
+  for (int t = 1; t <= T; ++t) {
+    const float* ap = c->alpha + (size_t)(t - 1) * N * S;
+    float* ac = c->alpha + (size_t)t * N * S;
+    const float* tp = c->tot + (size_t)(t - 1) * S;
+    float* tc = c->tot + (size_t)t * S;
+    const float* Ep = c->E + (size_t)(t - 1) * P * S;
+    if (V == 4)
+      den_alpha_frame_kernel<4><<<blocks, kDenThreads, 0, st>>>(g->bwd_ranges, g->trans, g->init, N, S, c->leaky, ap, tp, Ep, ac, tc);
+    else if (V == 2)
+      den_alpha_frame_kernel<2><<<blocks, kDenThreads, 0, st>>>(g->bwd_ranges, g->trans, g->init, N, S, c->leaky, ap, tp, Ep, ac, tc);
+    else
+      den_alpha_frame_kernel<1><<<blocks, kDenThreads, 0, st>>>(g->bwd_ranges, g->trans, g->init, N, S, c->leaky, ap, tp, Ep, ac, tc);
+    DEN_LAUNCH_CHECK(ctx);
+  }
+  den_loglike_kernel<<<1, 256, 0, st>>>(c->tot, T, S, c->leaky, g->init_sum, c->tot_prob, c->scalars);
+  DEN_LAUNCH_CHECK(ctx);
+  double lp = 0.0;
+  TDNNF_CUDA_OK(cudaMemcpyAsync(&lp, c->scalars, sizeof(double), cudaMemcpyDeviceToHost, st));
+  TDNNF_CUDA_OK(cudaStreamSynchronize(st));
+  *logprob = (float)lp;
+  c->forward_done = true;
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_den_backward(tdnnf_den_comp* c, float deriv_weight, float* nnet_output_deriv, int stride, int* ok) {
+  TDNNF_REQUIRE(c && nnet_output_deriv && ok, "null argument");
+  TDNNF_REQUIRE(c->forward_done, "Backward() called before Forward()");
+  const tdnnf_den_graph* g = c->g;
+  tdnnf_ctx* ctx = c->ctx;
+  const int N = g->num_states, P = g->num_pdfs, S = c->S, T = c->T;
+  TDNNF_REQUIRE(stride >= P, "stride < num_pdfs");
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  TDNNF_CUDA_OK(cudaMemsetAsync(c->gamma, 0, sizeof(float) * (size_t)T * P * S, st));
+  TDNNF_CUDA_OK(cudaMemsetAsync(c->scalars + 1, 0, sizeof(double), st));
+  den_beta_last_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(c->tot_prob, N, S, g->init_sum, c->betad + (size_t)(T & 1) * N * S,
+                                                         c->bsum + (size_t)(T & 1) * S);
+  DEN_LAUNCH_CHECK(ctx);
+  const int V = pick_vec(S);
+  const int blocks = (N + kStatesPerBlock - 1) / kStatesPerBlock;
+  for (int t = T - 1; t >= 0; --t) {
+    const float* bn = c->betad + (size_t)((t + 1) & 1) * N * S;
+    const float* sn = c->bsum + (size_t)((t + 1) & 1) * S;
+    float* bc = c->betad + (size_t)(t & 1) * N * S;
+    float* sc = c->bsum + (size_t)(t & 1) * S;
+    TDNNF_CUDA_OK(cudaMemsetAsync(sc, 0, sizeof(float) * S, st));
+    const float* at = c->alpha + (size_t)t * N * S;
+    const float* tt = c->tot + (size_t)t * S;
+    const float* Et = c->E + (size_t)t * P * S;
+    float* gt = c->gamma + (size_t)t * P * S;
+    double* chk = (t == 0) ? c->scalars + 1 : nullptr;
+    if (V == 4)
+      den_beta_frame_kernel<4><<<blocks, kDenThreads, 0, st>>>(g->fwd_ranges, g->trans, g->init, N, S, c->leaky, at, tt, Et, bn, sn, bc, sc, gt, chk);
+    else if (V == 2)
+      den_beta_frame_kernel<2><<<blocks, kDenThreads, 0, st>>>(g->fwd_ranges, g->trans, g->init, N, S, c->leaky, at, tt, Et, bn, sn, bc, sc, gt, chk);
+    else
+      den_beta_frame_kernel<1><<<blocks, kDenThreads, 0, st>>>(g->fwd_ranges, g->trans, g->init, N, S, c->leaky, at, tt, Et, bn, sn, bc, sc, gt, chk);
+    DEN_LAUNCH_CHECK(ctx);
+  }
+  den_deriv_transpose_add_kernel<<<dim3((P + 31) / 32, (S + 31) / 32, T), dim3(32, 8), 0, st>>>(c->gamma, S, P, deriv_weight,
+                                                                                               nnet_output_deriv, stride);
+  DEN_LAUNCH_CHECK(ctx);
+  double chk = 0.0;
+  TDNNF_CUDA_OK(cudaMemcpyAsync(&chk, c->scalars + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
+  TDNNF_CUDA_OK(cudaStreamSynchronize(st));
+  // kaldi: BetaGeneralFrameDebug at t == 0: |sum alpha'.betad - num_sequences| > 2  =>  ok_ = false
+  *ok = (chk == chk && fabs(chk - (double)S) <= 2.0) ? 1 : 0;
+  return TDNNF_OK;
+}

@@ -1,0 +1,461 @@
+// Host side of the TdnnDARTSV3 GEMMs: operand-plane pre-pass kernels, TMA tensor maps, the
+// work decomposition and the C-ABI entry points tdnnf_darts_{propagate,backprop_data,backprop_params}.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "context.h"
+#include "splice_gemm.cuh"
+
+namespace tdnnf {
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline int ceil_div(int x, int m) { return (x + m - 1) / m; }
+
+// ------------------------------------------------------------------------------------------
+// Pre-pass 1: fp32 rows -> bf16 hi/lo planes with K (the column index) contiguous.
+//   dst[plane][c][q][k]  (pitch Kpad, zero padded) =
+//        scale[c] * src[(q*r + c*c_row_mul) * ld + c*c_col_mul + k]      k < D, source row < R
+// X planes of Propagate (c = row % r), out_deriv planes of Backprop (r = 1) and the per-offset
+// weight planes (c = offset, c_col_mul = D_in, scale = weff) all go through here.
+// ------------------------------------------------------------------------------------------
+__global__ void split_rows_kernel(const float* __restrict__ src, int R, int D, long long ld, int r, int groups,
+                                  int c_row_mul, int c_col_mul, const float* __restrict__ scale, int Q, int Kpad,
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const int kvec = Kpad >> 3;
+  const long long total = (long long)groups * Q * kvec;
+  const bool aligned = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((c_col_mul & 3) == 0);
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int kv = (int)(idx % kvec);
+    const long long rowidx = idx / kvec;
+    const int q = (int)(rowidx % Q);
+    const int c = (int)(rowidx / Q);
+    const long long srow = (long long)q * r + (long long)c * c_row_mul;
+    const int k0 = kv * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (srow < R && k0 < D) {
+      const float* s = src + srow * ld + (long long)c * c_col_mul + k0;
+      if (aligned && k0 + 8 <= D) {
+        const float4 a = *reinterpret_cast<const float4*>(s);
+        const float4 b = *reinterpret_cast<const float4*>(s + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (k0 + j < D) v[j] = s[j];
+      }
+      if (scale != nullptr) {
+        const float sc = scale[c];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= sc;
+      }
+    }
+    __align__(16) __nv_bfloat16 h[8];
+    __align__(16) __nv_bfloat16 l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      h[j] = __float2bfloat16_rn(v[j]);
+      l[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h[j]));
+    }
+    const long long o = rowidx * Kpad + k0;
+    *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Pre-pass 2: fp32 rows -> TRANSPOSED bf16 hi/lo planes (the row index becomes K, contiguous).
+//   dst[plane][c][j][q]  (pitch Qp, zero padded) =
+//        scale[c] * src[(q*r + c*c_row_mul) * ld + c*c_col_mul + j]      j < J, q < Q, source row < R
+// X^T / out_deriv^T planes of the parameter gradient and the W_i^T planes of the data gradient.
+// ------------------------------------------------------------------------------------------
+__global__ void split_transpose_kernel(const float* __restrict__ src, int R, int J, long long ld, int r,
+                                       int c_row_mul, int c_col_mul, const float* __restrict__ scale, int Q, int Qp,
+                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  __shared__ float tile[64][33];
+  const int c = blockIdx.z;
+  const int q0 = blockIdx.x * 64;
+  const int j0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // (32, 8)
+  const float sc = scale ? scale[c] : 1.0f;
+  for (int qq = ty; qq < 64; qq += 8) {
+    const int q = q0 + qq;
+    const long long srow = (long long)q * r + (long long)c * c_row_mul;
+    float v = 0.f;
+    if (q < Q && srow < R && j0 + tx < J) v = sc * src[srow * ld + (long long)c * c_col_mul + j0 + tx];
+    tile[qq][tx] = v;
+  }
+  __syncthreads();
+  for (int jj = ty; jj < 32; jj += 8) {
+    const int j = j0 + jj;
+    if (j >= J) continue;
+    const int q = q0 + 2 * tx;
+    if (q >= Qp) continue;  // Qp is even
+    const float a = tile[2 * tx][jj], b = tile[2 * tx + 1][jj];
+    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+    const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
+    const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+    const long long o = ((long long)c * J + j) * Qp + q;
+    __nv_bfloat162 h2, l2;
+    h2.x = ah; h2.y = bh;
+    l2.x = al; l2.y = bl;
+    *reinterpret_cast<__nv_bfloat162*>(hi + o) = h2;
+    *reinterpret_cast<__nv_bfloat162*>(lo + o) = l2;
+  }
+}
+
+// out[r, :] = bias (or 0) for all rows: the starting value when Propagate is split along K.
+__global__ void init_rows_kernel(float* __restrict__ out, int rows, int cols, long long ld,
+                                 const float* __restrict__ bias) {
+  const long long total = (long long)rows * cols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cols);
+    const long long r = idx / cols;
+    out[r * ld + c] = bias ? bias[c] : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+struct Planes {
+  __nv_bfloat16* base = nullptr;  // hi plane; lo plane follows at base + plane_elems
+  long long plane_elems = 0;
+  int K = 0;       // valid extent of the contiguous dimension (TMA zero-fills beyond it)
+  int Kpitch = 0;  // pitch in elements (multiple of 8)
+  int rows = 0;    // rows per group
+  int groups = 0;
+};
+
+static size_t planes_bytes(int groups, int rows, int Kpitch) {
+  size_t b = (size_t)2 * groups * rows * Kpitch * sizeof(__nv_bfloat16);
+  return (b + 1023) & ~size_t(1023);
+}
+
+static int make_map(tdnnf_ctx* ctx, const Planes& pl, int box_rows, CUtensorMap* out) {
+  cuuint64_t dims[4] = {(cuuint64_t)pl.K, (cuuint64_t)pl.rows, (cuuint64_t)pl.groups, 2};
+  cuuint64_t strides[3] = {(cuuint64_t)pl.Kpitch * 2, (cuuint64_t)pl.rows * pl.Kpitch * 2,
+                           (cuuint64_t)pl.plane_elems * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)box_rows, 1, 2};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = ctx->encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, pl.base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(TDNNF_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+  return TDNNF_OK;
+}
+
+static int launch_split_rows(tdnnf_ctx* ctx, const float* src, int R, int D, long long ld, int r, int groups,
+                             int c_row_mul, int c_col_mul, const float* scale, int Q, int Kpad, Planes* pl) {
+  pl->plane_elems = (long long)groups * Q * Kpad;
+  pl->K = Kpad;
+  pl->Kpitch = Kpad;
+  pl->rows = Q;
+  pl->groups = groups;
+  pl->base = static_cast<__nv_bfloat16*>(ctx->ws_alloc(planes_bytes(groups, Q, Kpad)));
+  if (!pl->base) return TDNNF_ERR_NOMEM;
+  const long long total = (long long)groups * Q * (Kpad >> 3);
+  const int threads = 256;
+  const int blocks = (int)std::min<long long>((total + threads - 1) / threads, (long long)ctx->num_sms * 16);
+  split_rows_kernel<<<std::max(blocks, 1), threads, 0, ctx->stream>>>(src, R, D, ld, r, groups, c_row_mul, c_col_mul,
+                                                                      scale, Q, Kpad, pl->base,
+                                                                      pl->base + pl->plane_elems);
+  ctx->launches++;
+  TDNNF_CUDA_OK(cudaGetLastError());
+  return TDNNF_OK;
+}
+
+static int launch_split_transpose(tdnnf_ctx* ctx, const float* src, int R, int J, long long ld, int r, int groups,
+                                  int c_row_mul, int c_col_mul, const float* scale, int Q, int Qp, int Kvalid,
+                                  Planes* pl) {
+  pl->plane_elems = (long long)groups * J * Qp;
+  pl->K = Kvalid;
+  pl->Kpitch = Qp;
+  pl->rows = J;
+  pl->groups = groups;
+  pl->base = static_cast<__nv_bfloat16*>(ctx->ws_alloc(planes_bytes(groups, J, Qp)));
+  if (!pl->base) return TDNNF_ERR_NOMEM;
+  dim3 grid(ceil_div(Qp, 64), ceil_div(J, 32), groups), block(32, 8);
+  split_transpose_kernel<<<grid, block, 0, ctx->stream>>>(src, R, J, ld, r, c_row_mul, c_col_mul, scale, Q, Qp,
+                                                          pl->base, pl->base + pl->plane_elems);
+  ctx->launches++;
+  TDNNF_CUDA_OK(cudaGetLastError());
+  return TDNNF_OK;
+}
+
+// Split-K factor: fill the SMs in whole waves without starving a unit of K iterations.
+static int choose_splits(int tiles, int iters_per_tile, int num_sms) {
+  int best = 1;
+  double best_score = -1.0;
+  for (int s = 1; s <= 8; ++s) {
+    if (s > 1 && iters_per_tile / s < 8) break;
+    const double units = (double)tiles * s;
+    const double waves = std::ceil(units / num_sms);
+    const double eff = units / (waves * num_sms);
+    const double score = eff - 0.012 * (s - 1);
+    if (score > best_score + 1e-9) {
+      best_score = score;
+      best = s;
+    }
+  }
+  return best;
+}
+
+template <int BN>
+static int launch_gemm_bn(tdnnf_ctx* ctx, const Planes& A, const Planes& B, const GemmParams& p) {
+  CUtensorMap tmA, tmB;
+  int rc = make_map(ctx, A, kBM, &tmA);
+  if (rc) return rc;
+  rc = make_map(ctx, B, BN, &tmB);
+  if (rc) return rc;
+  auto kern = splice_gemm_kernel<BN>;
+  static bool attr_set = false;  // per template instance
+  if (!attr_set) {
+    TDNNF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmemBytes));
+    attr_set = true;
+  }
+  const int units = p.c_tiles * p.m_tiles * p.n_tiles * p.splits;
+  if (units <= 0) return TDNNF_OK;
+  const int grid = std::min(units, ctx->num_sms);
+  kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, ctx->stream>>>(tmA, tmB, p);
+  ctx->launches++;
+  TDNNF_CUDA_OK(cudaGetLastError());
+  return TDNNF_OK;
+}
+
+static int pick_bn(int n) {
+  if (n <= 32) return 32;
+  if (n <= 64) return 64;
+  if (n % 160 == 0) return 160;
+  if (n % 128 == 0 || n > 160) return 128;
+  if (n <= 128) return 128;
+  return 160;
+}
+
+static int launch_gemm(tdnnf_ctx* ctx, int bn, const Planes& A, const Planes& B, const GemmParams& p) {
+  switch (bn) {
+    case 32: return launch_gemm_bn<32>(ctx, A, B, p);
+    case 64: return launch_gemm_bn<64>(ctx, A, B, p);
+    case 128: return launch_gemm_bn<128>(ctx, A, B, p);
+    case 160: return launch_gemm_bn<160>(ctx, A, B, p);
+    default: return fail(TDNNF_ERR_INVALID, "unsupported BN");
+  }
+}
+
+static int check_offsets(int n, const int32_t* row_offsets, int row_stride, int out_rows, int in_rows) {
+  TDNNF_REQUIRE(n >= 1 && n <= TDNNF_MAX_OFFSETS, "number of time offsets must be in [1,16]");
+  TDNNF_REQUIRE(row_stride >= 1 && row_stride <= kMaxSeg, "row_stride must be in [1,16]");
+  for (int i = 0; i < n; ++i) {
+    // same condition as the KALDI_ASSERT in GetInputPart (ref: tdnn.cc:811-813)
+    TDNNF_REQUIRE(row_offsets[i] >= 0 &&
+                      (long long)in_rows >= (long long)row_offsets[i] + (long long)row_stride * out_rows - (row_stride - 1),
+                  "row offset / stride view does not fit in the input matrix");
+  }
+  return TDNNF_OK;
+}
+
+}  // namespace tdnnf
+
+using namespace tdnnf;
+
+extern "C" int tdnnf_darts_propagate(tdnnf_ctx* ctx, const float* in, int in_rows, int in_dim, int in_stride,
+                                     float* out, int out_rows, int out_dim, int out_stride, const float* W,
+                                     int w_stride, const float* bias, int bias_mode, const float* weff, int n,
+                                     const int32_t* row_offsets, int row_stride) {
+  TDNNF_REQUIRE(ctx && in && out && W && weff && row_offsets, "null argument");
+  TDNNF_REQUIRE(in_rows > 0 && in_dim > 0 && out_rows > 0 && out_dim > 0, "empty matrix");
+  TDNNF_REQUIRE(in_stride >= in_dim && out_stride >= out_dim && w_stride >= n * in_dim, "stride < cols");
+  TDNNF_REQUIRE(bias_mode >= 0 && bias_mode <= 2 && (bias_mode != 2 || bias), "bad bias_mode");
+  int rc = check_offsets(n, row_offsets, row_stride, out_rows, in_rows);
+  if (rc) return rc;
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+
+  const int r = row_stride;
+  const int Q = ceil_div(in_rows, r);
+  const int Kpad = round_up(in_dim, kBK);
+  ctx->ws_reset();
+  rc = ctx->ws_reserve(planes_bytes(r, Q, Kpad) + planes_bytes(n, out_dim, Kpad));
+  if (rc) return rc;
+  Planes A, B;
+  rc = launch_split_rows(ctx, in, in_rows, in_dim, in_stride, r, r, 1, 0, nullptr, Q, Kpad, &A);
+  if (rc) return rc;
+  rc = launch_split_rows(ctx, W, out_dim, in_dim, w_stride, 1, n, 0, in_dim, weff, out_dim, Kpad, &B);
+  if (rc) return rc;
+
+  const int bn = pick_bn(out_dim);
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.m_tiles = ceil_div(out_rows, kBM);
+  p.n_tiles = ceil_div(out_dim, bn);
+  p.c_tiles = 1;
+  p.kb_per_seg = Kpad / kBK;
+  p.nseg = n;
+  for (int i = 0; i < n; ++i) {
+    p.seg_a_m[i] = row_offsets[i] / r;
+    p.seg_a_c[i] = row_offsets[i] % r;
+    p.seg_b_c[i] = i;
+    p.seg_cmatch[i] = -1;
+  }
+  p.m_valid[0] = out_rows;
+  p.n_valid = out_dim;
+  p.seg_weight = weff;
+  p.splits = choose_splits(p.m_tiles * p.n_tiles, n * p.kb_per_seg, ctx->num_sms);
+  p.out = out;
+  p.out_ld = out_stride;
+  p.row_mul = 1;
+  p.alpha = 1.0f;
+  if (p.splits > 1) {
+    if (bias_mode != 0) {
+      const long long total = (long long)out_rows * out_dim;
+      const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 16);
+      init_rows_kernel<<<blocks, 256, 0, ctx->stream>>>(out, out_rows, out_dim, out_stride,
+                                                        bias_mode == 2 ? bias : nullptr);
+      ctx->launches++;
+      TDNNF_CUDA_OK(cudaGetLastError());
+    }
+    p.accumulate = 1;
+    p.atomic = 1;
+  } else {
+    p.accumulate = (bias_mode == 0);
+    p.bias = (bias_mode == 2) ? bias : nullptr;
+  }
+  return launch_gemm(ctx, bn, A, B, p);
+}
+
+extern "C" int tdnnf_darts_backprop_data(tdnnf_ctx* ctx, const float* out_deriv, int out_rows, int out_dim,
+                                         int od_stride, float* in_deriv, int in_rows, int in_dim, int id_stride,
+                                         const float* W, int w_stride, const float* weff, int n,
+                                         const int32_t* row_offsets, int row_stride) {
+  TDNNF_REQUIRE(ctx && out_deriv && in_deriv && W && weff && row_offsets, "null argument");
+  TDNNF_REQUIRE(in_rows > 0 && in_dim > 0 && out_rows > 0 && out_dim > 0, "empty matrix");
+  TDNNF_REQUIRE(id_stride >= in_dim && od_stride >= out_dim && w_stride >= n * in_dim, "stride < cols");
+  int rc = check_offsets(n, row_offsets, row_stride, out_rows, in_rows);
+  if (rc) return rc;
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+
+  const int r = row_stride;
+  const int Kpad = round_up(out_dim, kBK);
+  ctx->ws_reset();
+  rc = ctx->ws_reserve(planes_bytes(1, out_rows, Kpad) + planes_bytes(n, in_dim, Kpad));
+  if (rc) return rc;
+  Planes A, B;
+  rc = launch_split_rows(ctx, out_deriv, out_rows, out_dim, od_stride, 1, 1, 0, 0, nullptr, out_rows, Kpad, &A);
+  if (rc) return rc;
+  // B planes: [i][d][o] = weff[i] * W[o][i*in_dim + d]
+  rc = launch_split_transpose(ctx, W, out_dim, in_dim, w_stride, 1, n, 0, in_dim, weff, out_dim, Kpad, Kpad, &B);
+  if (rc) return rc;
+
+  const int bn = pick_bn(in_dim);
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int Qin = ceil_div(in_rows, r);
+  p.m_tiles = ceil_div(Qin, kBM);
+  p.n_tiles = ceil_div(in_dim, bn);
+  p.c_tiles = r;
+  p.kb_per_seg = Kpad / kBK;
+  p.nseg = n;
+  for (int i = 0; i < n; ++i) {
+    p.seg_a_m[i] = -(row_offsets[i] / r);
+    p.seg_b_c[i] = i;
+    p.seg_cmatch[i] = row_offsets[i] % r;
+  }
+  for (int c = 0; c < r; ++c) p.m_valid[c] = (in_rows - c + r - 1) / r;
+  p.n_valid = in_dim;
+  p.seg_weight = weff;
+  p.splits = choose_splits(p.m_tiles * p.n_tiles * r, std::max(1, n / r) * p.kb_per_seg, ctx->num_sms);
+  p.out = in_deriv;
+  p.out_ld = id_stride;
+  p.row_mul = r;
+  p.row_cadd = 1;
+  p.accumulate = 1;
+  p.atomic = p.splits > 1;
+  p.alpha = 1.0f;
+  return launch_gemm(ctx, bn, A, B, p);
+}
+
+extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value, int in_rows, int in_dim,
+                                           int in_stride, const float* out_deriv, int out_rows, int out_dim,
+                                           int od_stride, const float* W_model, int w_stride, float* dW,
+                                           int dw_stride, float* dbias, const float* weff, int n,
+                                           const int32_t* row_offsets, int row_stride, float lr, float* s) {
+  TDNNF_REQUIRE(ctx && in_value && out_deriv && dW && weff && row_offsets, "null argument");
+  TDNNF_REQUIRE(in_rows > 0 && in_dim > 0 && out_rows > 0 && out_dim > 0, "empty matrix");
+  TDNNF_REQUIRE(in_stride >= in_dim && od_stride >= out_dim && dw_stride >= n * in_dim, "stride < cols");
+  TDNNF_REQUIRE(s == nullptr || (W_model != nullptr && w_stride >= n * in_dim), "s requires W_model");
+  int rc = check_offsets(n, row_offsets, row_stride, out_rows, in_rows);
+  if (rc) return rc;
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+
+  const int r = row_stride;
+  const int Q = ceil_div(in_rows, r);
+  const int Qp = round_up(Q, 8);
+  const int Rp = round_up(out_rows, 8);
+  ctx->ws_reset();
+  rc = ctx->ws_reserve(planes_bytes(r, in_dim, Qp) + planes_bytes(1, out_dim, Rp));
+  if (rc) return rc;
+  Planes XT, ODT;
+  rc = launch_split_transpose(ctx, in_value, in_rows, in_dim, in_stride, r, r, 1, 0, nullptr, Q, Qp, Q, &XT);
+  if (rc) return rc;
+  rc = launch_split_transpose(ctx, out_deriv, out_rows, out_dim, od_stride, 1, 1, 0, 0, nullptr, out_rows, Rp,
+                              out_rows, &ODT);
+  if (rc) return rc;
+  if (s) TDNNF_CUDA_OK(cudaMemsetAsync(s, 0, sizeof(float) * n, ctx->stream));
+
+  auto waste = [](int x) { return (double)round_up(x, kBM) / x; };
+  const bool m_is_in = waste(in_dim) <= waste(out_dim);  // which dimension rides the 128-row MMA M
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.c_tiles = n;
+  p.kb_per_seg = ceil_div(out_rows, kBK);
+  p.nseg = n;
+  p.seg_weight = weff;  // weff[i] == 0 (unsampled offset): X~ block is zero, nothing to add (ref: tdnn.cc:509-513)
+  p.out = dW;
+  p.out_ld = dw_stride;
+  p.accumulate = 1;
+  p.alpha = lr;
+  p.c_scale = weff;
+  p.dot_ref = s ? W_model : nullptr;
+  p.dot_ld = w_stride;
+  p.dot_out = s;
+  int bn;
+  if (m_is_in) {
+    // acc[d, o] = sum_k X_i^T[d, k] * OD^T[o, k]  ->  dW[o, i*in_dim + d]   (transposed store)
+    bn = pick_bn(out_dim);
+    p.m_tiles = ceil_div(in_dim, kBM);
+    p.n_tiles = ceil_div(out_dim, bn);
+    for (int i = 0; i < n; ++i) {
+      p.seg_a_k[i] = row_offsets[i] / r;
+      p.seg_a_c[i] = row_offsets[i] % r;
+      p.seg_cmatch[i] = i;
+      p.m_valid[i] = in_dim;
+    }
+    p.n_valid = out_dim;
+    p.transposed = 1;
+    p.row_mul = 1;
+    p.row_cadd = in_dim;
+  } else {
+    // acc[o, d] = sum_k OD^T[o, k] * X_i^T[d, k]  ->  dW[o, i*in_dim + d]   (row-major store)
+    bn = pick_bn(in_dim);
+    p.m_tiles = ceil_div(out_dim, kBM);
+    p.n_tiles = ceil_div(in_dim, bn);
+    for (int i = 0; i < n; ++i) {
+      p.seg_b_k[i] = row_offsets[i] / r;
+      p.seg_b_c[i] = row_offsets[i] % r;
+      p.seg_cmatch[i] = i;
+      p.m_valid[i] = out_dim;
+    }
+    p.n_valid = in_dim;
+    p.row_mul = 1;
+    p.col_cadd = in_dim;
+  }
+  p.splits = choose_splits(p.m_tiles * p.n_tiles * n, p.kb_per_seg, ctx->num_sms);
+  p.atomic = p.splits > 1;
+  rc = m_is_in ? launch_gemm(ctx, bn, XT, ODT, p) : launch_gemm(ctx, bn, ODT, XT, p);
+  if (rc) return rc;
+  if (dbias) return tdnnf_add_row_sum(ctx, out_deriv, out_rows, out_dim, od_stride, lr, dbias);
+  return TDNNF_OK;
+}

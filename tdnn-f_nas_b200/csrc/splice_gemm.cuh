@@ -1,0 +1,371 @@
+// Segment GEMM on sm_100a: the one tensor-core kernel behind TdnnDARTSV3Component's
+// Propagate / Backprop / parameter-gradient GEMMs (ref: tdnn.cc:292-328, 366-416, 482-539, 619-624).
+//
+//   acc[m, n] = sum over segments g (matching the tile's group c), sum over k:
+//                  A[plane][g.a_c][m0 + m + g.a_m][k + g.a_k] * B[plane'][g.b_c][n0 + n + g.b_n][k + g.b_k]
+//
+// A and B are bf16 "hi/lo" operand planes (x = hi + lo + O(2^-18 x)); each K block issues the
+// three products hi*hi, hi*lo, lo*hi into one fp32 TMEM accumulator, which restores ~fp32
+// accuracy (Kaldi computes in fp32) at bf16 tensor-core rate.  Operands arrive through two 4-D
+// TMA tensor maps (k, row, group, plane) with 128-byte swizzle; out-of-range rows / k are zero
+// filled by TMA, which is what implements the splice boundaries of the data-gradient.
+//
+// Warp roles (192 threads, 1 CTA / SM, persistent over work units):
+//   warp 0   TMA producer            (one lane)
+//   warp 1   tcgen05.mma issuer      (one lane) + TMEM allocator
+//   warp 2-5 epilogue: tcgen05.ld -> registers -> scaled store / red.add / dot-product reduce
+// Two TMEM accumulator buffers let the epilogue of unit j overlap the MMAs of unit j+1.
+#pragma once
+#include "ptx.cuh"
+
+namespace tdnnf {
+
+constexpr int kMaxSeg = 16;
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kGemmThreads = 192;
+constexpr int kAccCols = 256;  // TMEM columns per accumulator buffer
+
+struct GemmParams {
+  int m_tiles, n_tiles, c_tiles, splits;
+  int kb_per_seg;  // K blocks (of 64) per segment
+  int nseg;
+  int seg_a_k[kMaxSeg], seg_a_m[kMaxSeg], seg_a_c[kMaxSeg];
+  int seg_b_k[kMaxSeg], seg_b_n[kMaxSeg], seg_b_c[kMaxSeg];
+  int seg_cmatch[kMaxSeg];  // segment applies to tiles of group c == cmatch (-1: every group)
+  int m_valid[kMaxSeg];     // valid accumulator rows per group c
+  int n_valid;
+  const float* seg_weight;  // device [nseg] or null: a segment whose weight is 0 is skipped
+  // epilogue
+  float* out;
+  long long out_ld;
+  int row_mul, row_cadd;  // R = m*row_mul + c*row_cadd
+  int col_cadd;           // C = n + c*col_cadd
+  int transposed;         // element index = transposed ? C*ld + R : R*ld + C
+  int accumulate;         // 1: out += v ; 0: out = v
+  int atomic;             // 1: use red.global.add (split-K or shared outputs)
+  const float* bias;      // [n_valid] added by split 0 only, or null
+  float alpha;            // v = alpha * c_scale[c] * acc (+ bias)
+  const float* c_scale;   // device [c_tiles] or null
+  const float* dot_ref;   // optional: dot_out[c] += sum(acc * dot_ref[index'])  (un-scaled acc;
+  long long dot_ld;       //           index' uses dot_ld in place of out_ld)
+  float* dot_out;
+};
+
+struct GemmSmemMeta {
+  int seg_a_k[kMaxSeg], seg_a_m[kMaxSeg], seg_a_c[kMaxSeg];
+  int seg_b_k[kMaxSeg], seg_b_n[kMaxSeg], seg_b_c[kMaxSeg];
+  int list[kMaxSeg][kMaxSeg];  // per group c: active matching segments
+  int cnt[kMaxSeg];
+  int m_valid[kMaxSeg];
+  float c_scale[kMaxSeg];
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = 2 * kBM * kBK * 2;  // hi + lo
+  static constexpr int kBBytes = 2 * BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kMetaBytes = 2048 + (int)sizeof(GemmSmemMeta);
+  static constexpr int kStages = (232448 - 1024 - kMetaBytes) / kStageBytes >= 4
+                                     ? 4
+                                     : (232448 - 1024 - kMetaBytes) / kStageBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kMetaBytes + 1024;
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N must be a multiple of 16 in [16,256]");
+  static_assert(kStages >= 2, "need at least a double buffer");
+};
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
+                                            int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar)), "r"(c0),
+        "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+struct UnitCoord {
+  int c, m_t, n_t, split;
+  int it0, it1;
+};
+
+__device__ __forceinline__ UnitCoord decode_unit(int u, const GemmParams& p, const GemmSmemMeta* meta) {
+  UnitCoord uc;
+  uc.n_t = u % p.n_tiles;
+  u /= p.n_tiles;
+  uc.split = u % p.splits;
+  u /= p.splits;
+  uc.m_t = u % p.m_tiles;
+  uc.c = u / p.m_tiles;
+  const long long total = (long long)meta->cnt[uc.c] * p.kb_per_seg;
+  uc.it0 = (int)((total * uc.split) / p.splits);
+  uc.it1 = (int)((total * (uc.split + 1)) / p.splits);
+  return uc;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tiles = smem;
+  uint8_t* meta_base = smem + kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(meta_base);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  GemmSmemMeta* meta = reinterpret_cast<GemmSmemMeta*>(meta_base + 2048);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- one-time setup
+  for (int i = threadIdx.x; i < kMaxSeg; i += blockDim.x) {
+    meta->seg_a_k[i] = p.seg_a_k[i];
+    meta->seg_a_m[i] = p.seg_a_m[i];
+    meta->seg_a_c[i] = p.seg_a_c[i];
+    meta->seg_b_k[i] = p.seg_b_k[i];
+    meta->seg_b_n[i] = p.seg_b_n[i];
+    meta->seg_b_c[i] = p.seg_b_c[i];
+    meta->m_valid[i] = p.m_valid[i];
+    meta->c_scale[i] = (p.c_scale != nullptr && i < p.c_tiles) ? p.c_scale[i] : 1.0f;
+    // active segment list of group c = i
+    int n = 0;
+    if (i < p.c_tiles) {
+      for (int g = 0; g < p.nseg; ++g) {
+        const bool active = (p.seg_weight == nullptr) || (p.seg_weight[g] != 0.0f);
+        if (active && (p.seg_cmatch[g] < 0 || p.seg_cmatch[g] == i)) meta->list[i][n++] = g;
+      }
+    }
+    meta->cnt[i] = n;
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&tmem_full[b], 1);
+      ptx::mbar_init(&tmem_empty[b], 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr, 2 * kAccCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int total_units = p.c_tiles * p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0) {
+    // ================================================= TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const UnitCoord uc = decode_unit(u, p, meta);
+        int j = uc.it0 / p.kb_per_seg, kb = uc.it0 % p.kb_per_seg;
+        for (int it = uc.it0; it < uc.it1; ++it) {
+          const int g = meta->list[uc.c][j];
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          uint8_t* sa = tiles + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          tma_load_4d(sa, &tmA, &full_bar[stage], kb * kBK + meta->seg_a_k[g], uc.m_t * kBM + meta->seg_a_m[g],
+                      meta->seg_a_c[g], 0);
+          tma_load_4d(sb, &tmB, &full_bar[stage], kb * kBK + meta->seg_b_k[g], uc.n_t * BN + meta->seg_b_n[g],
+                      meta->seg_b_c[g], 0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++kb == p.kb_per_seg) { kb = 0; ++j; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================= MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc_buf = 0;
+      uint32_t acc_phase = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const UnitCoord uc = decode_unit(u, p, meta);
+        if (uc.it1 <= uc.it0) continue;
+        ptx::mbar_wait(&tmem_empty[acc_buf], acc_phase ^ 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc_buf * kAccCols;
+        for (int it = uc.it0; it < uc.it1; ++it) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t sa = ptx::smem_u32(tiles + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t a_hi = ptx::umma_desc_k_sw128(sa);
+          const uint64_t a_lo = ptx::umma_desc_k_sw128(sa + kBM * kBK * 2);
+          const uint64_t b_hi = ptx::umma_desc_k_sw128(sb);
+          const uint64_t b_lo = ptx::umma_desc_k_sw128(sb + BN * kBK * 2);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);  // 16 bf16 = 32 B = 2 x 16 B units inside the swizzle atom
+            ptx::umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, (it > uc.it0 || k > 0) ? 1u : 0u);
+            ptx::umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+            ptx::umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+          }
+          ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tmem_full[acc_buf]);
+        acc_buf ^= 1;
+        if (acc_buf == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ================================================= epilogue (warps 2..5)
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    int acc_buf = 0;
+    uint32_t acc_phase = 0;
+    const bool vec_ok = (!p.transposed) && ((p.out_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
+                        ((p.col_cadd & 3) == 0);
+    const bool dot_vec_ok = p.dot_ref != nullptr && ((reinterpret_cast<uintptr_t>(p.dot_ref) & 15) == 0) &&
+                            ((p.dot_ld & 3) == 0) && ((p.col_cadd & 3) == 0);
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const UnitCoord uc = decode_unit(u, p, meta);
+      const bool has_acc = uc.it1 > uc.it0;
+      if (!has_acc && p.accumulate) continue;  // nothing to add
+      if (has_acc) {
+        ptx::mbar_wait(&tmem_full[acc_buf], acc_phase);
+        ptx::tc_fence_after_sync();
+      }
+      const int m = uc.m_t * kBM + quarter * 32 + lane;
+      const bool row_ok = m < meta->m_valid[uc.c];
+      const long long R = (long long)m * p.row_mul + (long long)uc.c * p.row_cadd;
+      const float scale = p.alpha * meta->c_scale[uc.c];
+      const bool add_bias = (p.bias != nullptr) && (uc.split == 0);
+      float dot = 0.f;
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 16; ++chunk) {
+        uint32_t v[16];
+        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
+        if (has_acc) {
+          ptx::tmem_ld_32x16(tmem_base + acc_buf * kAccCols + ((uint32_t)(quarter * 32) << 16) + chunk * 16, v);
+          ptx::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0u;
+        }
+        const int n0 = uc.n_t * BN + chunk * 16;
+        if (row_ok && n0 < p.n_valid) {
+        const long long C0 = (long long)n0 + (long long)uc.c * p.col_cadd;
+        const bool full = (n0 + 16 <= p.n_valid);
+        if (!p.transposed) {
+          float* dst = p.out + R * p.out_ld + C0;
+          if (p.dot_ref != nullptr) {
+            const float* ref = p.dot_ref + R * p.dot_ld + C0;
+            if (full && dot_vec_ok) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 r4 = *reinterpret_cast<const float4*>(ref + j);
+                dot += __uint_as_float(v[j]) * r4.x + __uint_as_float(v[j + 1]) * r4.y +
+                       __uint_as_float(v[j + 2]) * r4.z + __uint_as_float(v[j + 3]) * r4.w;
+              }
+            } else {
+              for (int j = 0; j < 16; ++j)
+                if (n0 + j < p.n_valid) dot += __uint_as_float(v[j]) * ref[j];
+            }
+          }
+          if (full && vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              float4 o;
+              o.x = scale * __uint_as_float(v[j]);
+              o.y = scale * __uint_as_float(v[j + 1]);
+              o.z = scale * __uint_as_float(v[j + 2]);
+              o.w = scale * __uint_as_float(v[j + 3]);
+              if (add_bias) {
+                const float4 b4 = *reinterpret_cast<const float4*>(p.bias + n0 + j);  // n0 % 16 == 0
+                o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+              }
+              if (p.atomic) {
+                red_add_v4_f32(dst + j, o.x, o.y, o.z, o.w);
+              } else {
+                if (p.accumulate) {
+                  const float4 prev = *reinterpret_cast<const float4*>(dst + j);
+                  o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
+                }
+                *reinterpret_cast<float4*>(dst + j) = o;
+              }
+            }
+          } else {
+            for (int j = 0; j < 16; ++j) {
+              if (n0 + j >= p.n_valid) break;
+              float o = scale * __uint_as_float(v[j]);
+              if (add_bias) o += p.bias[n0 + j];
+              if (p.atomic) red_add_f32(dst + j, o);
+              else if (p.accumulate) dst[j] += o;
+              else dst[j] = o;
+            }
+          }
+        } else {
+          // transposed: consecutive lanes (rows m) are consecutive addresses -> coalesced per register
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (n0 + j < p.n_valid) {
+              const long long idx = (C0 + j) * p.out_ld + R;
+              const float a = __uint_as_float(v[j]);
+              if (p.dot_ref != nullptr) dot += a * p.dot_ref[(C0 + j) * p.dot_ld + R];
+              float o = scale * a;
+              if (add_bias) o += p.bias[n0 + j];
+              if (p.atomic) red_add_f32(p.out + idx, o);
+              else if (p.accumulate) p.out[idx] += o;
+              else p.out[idx] = o;
+            }
+          }
+        }
+        }  // row_ok && n0 < n_valid
+      }
+      __syncwarp();
+      if (p.dot_ref != nullptr) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+        if (lane == 0 && dot != 0.f) atomicAdd(p.dot_out + uc.c, dot);
+      }
+      if (has_acc) {
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc_buf]);
+        acc_buf ^= 1;
+        if (acc_buf == 0) acc_phase ^= 1;
+      }
+    }
+  }
+
+  // ---- teardown
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, 2 * kAccCols);
+  }
+}
+
+}  // namespace tdnnf
