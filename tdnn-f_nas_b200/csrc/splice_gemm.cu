@@ -71,11 +71,16 @@ __global__ void split_rows_kernel(const float* __restrict__ src, int R, int D, l
 // ------------------------------------------------------------------------------------------
 // Pre-pass 2: fp32 rows -> TRANSPOSED bf16 hi/lo planes (the row index becomes K, contiguous).
 //   dst[plane][c][j][q]  (pitch Qp, zero padded) =
-//        scale[c] * src[(q*r + c*c_row_mul) * ld + c*c_col_mul + j]      j < J, q < Q, source row < R
+//        scale[c] * src[(q*r + c*c_row_mul + c_row_off[c]) * ld + c*c_col_mul + j]   j < J, q < Q, source row < R
 // X^T / out_deriv^T planes of the parameter gradient and the W_i^T planes of the data gradient.
 // ------------------------------------------------------------------------------------------
+struct GroupRowOffsets {
+  int v[kMaxSeg];
+};
+
 __global__ void split_transpose_kernel(const float* __restrict__ src, int R, int J, long long ld, int r,
-                                       int c_row_mul, int c_col_mul, const float* __restrict__ scale, int Q, int Qp,
+                                       int c_row_mul, int c_col_mul, GroupRowOffsets c_row_off,
+                                       const float* __restrict__ scale, int Q, int Qp,
                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   __shared__ float tile[64][33];
   const int c = blockIdx.z;
@@ -85,7 +90,7 @@ __global__ void split_transpose_kernel(const float* __restrict__ src, int R, int
   const float sc = scale ? scale[c] : 1.0f;
   for (int qq = ty; qq < 64; qq += 8) {
     const int q = q0 + qq;
-    const long long srow = (long long)q * r + (long long)c * c_row_mul;
+    const long long srow = (long long)q * r + (long long)c * c_row_mul + c_row_off.v[c];
     float v = 0.f;
     if (q < Q && srow < R && j0 + tx < J) v = sc * src[srow * ld + (long long)c * c_col_mul + j0 + tx];
     tile[qq][tx] = v;
@@ -171,7 +176,7 @@ static int launch_split_rows(tdnnf_ctx* ctx, const float* src, int R, int D, lon
 
 static int launch_split_transpose(tdnnf_ctx* ctx, const float* src, int R, int J, long long ld, int r, int groups,
                                   int c_row_mul, int c_col_mul, const float* scale, int Q, int Qp, int Kvalid,
-                                  Planes* pl) {
+                                  Planes* pl, const int32_t* group_row_offsets = nullptr) {
   pl->plane_elems = (long long)groups * J * Qp;
   pl->K = Kvalid;
   pl->Kpitch = Qp;
@@ -180,7 +185,9 @@ static int launch_split_transpose(tdnnf_ctx* ctx, const float* src, int R, int J
   pl->base = static_cast<__nv_bfloat16*>(ctx->ws_alloc(planes_bytes(groups, J, Qp)));
   if (!pl->base) return TDNNF_ERR_NOMEM;
   dim3 grid(ceil_div(Qp, 64), ceil_div(J, 32), groups), block(32, 8);
-  split_transpose_kernel<<<grid, block, 0, ctx->stream>>>(src, R, J, ld, r, c_row_mul, c_col_mul, scale, Q, Qp,
+  GroupRowOffsets gro;
+  for (int i = 0; i < kMaxSeg; ++i) gro.v[i] = (group_row_offsets && i < groups) ? group_row_offsets[i] : 0;
+  split_transpose_kernel<<<grid, block, 0, ctx->stream>>>(src, R, J, ld, r, c_row_mul, c_col_mul, gro, scale, Q, Qp,
                                                           pl->base, pl->base + pl->plane_elems);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
@@ -394,11 +401,22 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
   const int Q = ceil_div(in_rows, r);
   const int Qp = round_up(Q, 8);
   const int Rp = round_up(out_rows, 8);
+  // TMA needs the start of every box row 16-byte aligned: with K = the (de-interleaved) row index,
+  // the per-offset K shift row_offsets[i]/r must be a multiple of 8 bf16.  True whenever the number
+  // of sequences is a multiple of 8 (the recipes use 64/128); otherwise each offset gets its own
+  // pre-shifted X^T plane group (n x the pre-pass traffic, same GEMM).
+  bool shifts_aligned = true;
+  for (int i = 0; i < n; ++i) shifts_aligned = shifts_aligned && ((row_offsets[i] / r) % 8 == 0);
   ctx->ws_reset();
-  rc = ctx->ws_reserve(planes_bytes(r, in_dim, Qp) + planes_bytes(1, out_dim, Rp));
+  rc = ctx->ws_reserve((shifts_aligned ? planes_bytes(r, in_dim, Qp) : planes_bytes(n, in_dim, Rp)) +
+                       planes_bytes(1, out_dim, Rp));
   if (rc) return rc;
   Planes XT, ODT;
-  rc = launch_split_transpose(ctx, in_value, in_rows, in_dim, in_stride, r, r, 1, 0, nullptr, Q, Qp, Q, &XT);
+  if (shifts_aligned)
+    rc = launch_split_transpose(ctx, in_value, in_rows, in_dim, in_stride, r, r, 1, 0, nullptr, Q, Qp, Q, &XT);
+  else
+    rc = launch_split_transpose(ctx, in_value, in_rows, in_dim, in_stride, r, n, 0, 0, nullptr, out_rows, Rp,
+                                out_rows, &XT, row_offsets);
   if (rc) return rc;
   rc = launch_split_transpose(ctx, out_deriv, out_rows, out_dim, od_stride, 1, 1, 0, 0, nullptr, out_rows, Rp,
                               out_rows, &ODT);
@@ -428,8 +446,8 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
     p.m_tiles = ceil_div(in_dim, kBM);
     p.n_tiles = ceil_div(out_dim, bn);
     for (int i = 0; i < n; ++i) {
-      p.seg_a_k[i] = row_offsets[i] / r;
-      p.seg_a_c[i] = row_offsets[i] % r;
+      p.seg_a_k[i] = shifts_aligned ? row_offsets[i] / r : 0;
+      p.seg_a_c[i] = shifts_aligned ? row_offsets[i] % r : i;
       p.seg_cmatch[i] = i;
       p.m_valid[i] = in_dim;
     }
@@ -443,8 +461,8 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
     p.m_tiles = ceil_div(out_dim, kBM);
     p.n_tiles = ceil_div(in_dim, bn);
     for (int i = 0; i < n; ++i) {
-      p.seg_b_k[i] = row_offsets[i] / r;
-      p.seg_b_c[i] = row_offsets[i] % r;
+      p.seg_b_k[i] = shifts_aligned ? row_offsets[i] / r : 0;
+      p.seg_b_c[i] = shifts_aligned ? row_offsets[i] % r : i;
       p.seg_cmatch[i] = i;
       p.m_valid[i] = out_dim;
     }

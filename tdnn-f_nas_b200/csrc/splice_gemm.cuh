@@ -300,9 +300,9 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               o.y = scale * __uint_as_float(v[j + 1]);
               o.z = scale * __uint_as_float(v[j + 2]);
               o.w = scale * __uint_as_float(v[j + 3]);
-              if (add_bias) {
-                const float4 b4 = *reinterpret_cast<const float4*>(p.bias + n0 + j);  // n0 % 16 == 0
-                o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+              if (add_bias) {  // the bias tail starts n floats into bias_params_: not 16-byte aligned in general
+                const float* bj = p.bias + n0 + j;
+                o.x += __ldg(bj); o.y += __ldg(bj + 1); o.z += __ldg(bj + 2); o.w += __ldg(bj + 3);
               }
               if (p.atomic) {
                 red_add_v4_f32(dst + j, o.x, o.y, o.z, o.w);
