@@ -155,6 +155,55 @@ int tdnnf_elementwise_product_fwd(tdnnf_ctx* ctx, const float* in, int rows, int
 int tdnnf_elementwise_product_bwd(tdnnf_ctx* ctx, const float* in, int in_stride, const float* out_deriv,
                                   int od_stride, float* in_deriv, int id_stride, int rows, int out_cols);
 
+
+/* ------------------------------------------------------------------ whole-parameter ops -- */
+/* The CuMatrix/CuVector calls inside Scale / Add / DotProduct / PerturbParams / Vectorize of the
+ * updatable components (ref: tdnn.cc:907-979, simple.cc:9606-9642): strided fp32 matrices; a
+ * vector is a 1 x n matrix. */
+int tdnnf_mat_set(tdnnf_ctx* ctx, float* a, int rows, int cols, int stride, float value);
+int tdnnf_mat_scale(tdnnf_ctx* ctx, float* a, int rows, int cols, int stride, float scale);
+/* out[r, :] = vec for every row (CopyRowsFromVec; ref: simple.cc:2606, 9518, tdnn.cc:234). */
+int tdnnf_copy_rows_from_vec(tdnnf_ctx* ctx, const float* vec, float* out, int rows, int cols, int stride);
+/* dst += alpha * src */
+int tdnnf_mat_axpy(tdnnf_ctx* ctx, float alpha, const float* src, int src_stride, float* dst, int dst_stride,
+                   int rows, int cols);
+/* *result (HOST) = sum(a .* b); synchronises the stream (TraceMatMat(a, b, kTrans) / VecVec). */
+int tdnnf_mat_dot(tdnnf_ctx* ctx, const float* a, int a_stride, const float* b, int b_stride, int rows, int cols,
+                  float* result);
+/* Same, but the result stays on the device (double accumulator): result_dev[0] += sum(a .* b). */
+int tdnnf_mat_dot_dev(tdnnf_ctx* ctx, const float* a, int a_stride, const float* b, int b_stride, int rows,
+                      int cols, double* result_dev);
+
+/* ------------------------------------------------------------------ stock TDNN-F neighbours - */
+/* The stock components that sit between the NAS components in a TDNN-F block, so
+ * that a whole supernet step runs on this library: RectifiedLinearComponent without self-repair,
+ * the bypass Sum(Scale(s, a), b), and BatchNormComponent in training mode
+ * (ref: norm.cc:401-465, 467-549, 551-589). */
+int tdnnf_relu_fwd(tdnnf_ctx* ctx, const float* in, int rows, int cols, int in_stride, float* out, int out_stride);
+/* in_deriv = out_deriv .* (out_value > 0) */
+int tdnnf_relu_bwd(tdnnf_ctx* ctx, const float* out_value, int ov_stride, const float* out_deriv, int od_stride,
+                   float* in_deriv, int id_stride, int rows, int cols);
+/* dst[r, :] = src[row_map[r], :] (row_map device int32, -1 => zero row): CuMatrix::CopyRows, the
+ * row gather nnet3 inserts where ReorderIndexes changed a component's input order. */
+int tdnnf_copy_rows(tdnnf_ctx* ctx, const float* src, int src_stride, float* dst, int dst_stride, int dst_rows, int cols,
+                    const int32_t* row_map);
+/* dst[row_map[r], :] += alpha * src[r, :] for r < src_rows (row_map entries unique or -1): the transpose of
+ * tdnnf_copy_rows (CuMatrix::AddToRows). */
+int tdnnf_add_to_rows(tdnnf_ctx* ctx, float alpha, const float* src, int src_stride, int src_rows, int cols, float* dst,
+                      int dst_stride, const int32_t* row_map);
+/* out = a * alpha + b * beta   (out may alias a or b) */
+int tdnnf_add_scaled(tdnnf_ctx* ctx, const float* a, int a_stride, float alpha, const float* b, int b_stride,
+                     float beta, float* out, int out_stride, int rows, int cols);
+/* BatchNorm, training mode.  memo: device, 5 x cols (rows: mean, uvar, scale, -, -) as in the reference.
+ *   fwd:  mean/var over rows; scale = target_rms * (var + eps)^-0.5; out = (in - mean) .* scale
+ *   bwd:  x' = scale .* (z' - mean(z')) + z .* var_deriv_mod,
+ *         var_deriv_mod = -1/target_rms^2 * mean(z' .* z) .* scale      (ref: norm.cc:392-398) */
+int tdnnf_batchnorm_train_fwd(tdnnf_ctx* ctx, const float* in, int rows, int cols, int in_stride, float* out,
+                              int out_stride, float epsilon, float target_rms, float* memo);
+int tdnnf_batchnorm_train_bwd(tdnnf_ctx* ctx, const float* out_value, int ov_stride, const float* out_deriv,
+                              int od_stride, float* in_deriv, int id_stride, int rows, int cols, float target_rms,
+                              const float* memo);
+
 /* ------------------------------------------------------------------ chain denominator - */
 /* DenominatorGraph (kaldi: chain/chain-den-graph.{h,cc}).  Host arrays, copied to the device.
  *   fwd_ranges / bwd_ranges: num_states pairs [begin,end) into `transitions` (forward list

@@ -1,0 +1,95 @@
+/*
+ * tdnnf_nnet3.h -- C handle API over the nnet3 component mirror (tdnn-f_nas_b200/csrc/nnet3).
+ *
+ * What a non-C++ host needs to drive the reference's components the way NnetComputer does
+ * (ref: SURVEY.md section 8b; kaldi nnet3/nnet-computation.cc kPropagate / kBackprop):
+ * create from a config line or a model stream, PrecomputeIndexes, Propagate -> memo,
+ * Backprop(memo, to_update), Write, the UpdatableComponent whole-parameter ops and the
+ * `nnet3-copy --edits` directives.  A C++ host uses csrc/nnet3/components.h directly.
+ *
+ * Every function returns 0 on success; on failure the KALDI_ERR / KALDI_ASSERT / kernel message is
+ * available from tdnnf_nnet3_last_error().  Strings and index arrays returned through `char**` /
+ * `int32_t**` are malloc'd: release them with tdnnf_nnet3_free().  Indexes are (n, t, x) triples.
+ */
+#ifndef TDNNF_NNET3_H_
+#define TDNNF_NNET3_H_
+
+#include <stdint.h>
+
+#include "tdnnf_nas_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* tdnnf_nnet3_last_error(void);
+void tdnnf_nnet3_free(void* p);
+
+/* The "CuDevice" of the mirror: the context the components launch on (per host thread). */
+int tdnnf_nnet3_set_context(tdnnf_ctx* ctx);
+/* Counter-based host RNG behind SetRandUniform / RandInt: same seed + counter => same draws on every rank. */
+int tdnnf_nnet3_set_rand_seed(uint64_t seed);
+int tdnnf_nnet3_set_rand_counter(uint64_t counter);
+uint64_t tdnnf_nnet3_get_rand_counter(void);
+float tdnnf_nnet3_rand_uniform(void);
+/* Data-parallel world size: the FLOPs penalty is normalised by rows * world_size. */
+int tdnnf_nnet3_set_dp_world_size(int world_size);
+/* Re-enable the reference's per-minibatch "log_alpha" stdout print (ref: tdnn.cc:571, simple.cc:2640). */
+int tdnnf_nnet3_set_print_log_alpha(int enable);
+
+/* Component::NewComponentOfType + InitFromConfig (ref: itf.cc:126-293, tdnn.cc:109-212, ...). */
+int tdnnf_nnet3_component_new(const char* type, const char* config_line, void** out);
+int tdnnf_nnet3_tdnn_darts_for_indexing(const int32_t* time_offsets, int n, void** out);
+/* Component::ReadNew / Write on memory buffers, text or binary (ref: itf.cc:106-124, tdnn.cc:659-761, ...). */
+int tdnnf_nnet3_component_read(const char* data, uint64_t len, int binary, void** out);
+int tdnnf_nnet3_component_write(const void* comp, int binary, char** out, uint64_t* len);
+int tdnnf_nnet3_component_copy(const void* comp, void** out);
+int tdnnf_nnet3_component_delete(void* comp);
+int tdnnf_nnet3_component_info(const void* comp, char** out);
+int tdnnf_nnet3_component_type(const void* comp, char** out);
+int tdnnf_nnet3_component_dims(const void* comp, int* input_dim, int* output_dim, int* properties);
+
+/* Index methods (ref: tdnn.cc:628-657, 763-905). */
+int tdnnf_nnet3_precompute_indexes(const void* comp, const int32_t* in_idx, int n_in, const int32_t* out_idx, int n_out,
+                                   int need_backprop, void** out);
+int tdnnf_nnet3_indexes_delete(void* idx);
+int tdnnf_nnet3_indexes_write(const void* idx, int binary, char** out, uint64_t* len);
+int tdnnf_nnet3_indexes_read(const char* data, uint64_t len, int binary, void** out);
+int tdnnf_nnet3_reorder_indexes(const void* comp, const int32_t* in_idx, int n_in, const int32_t* out_idx, int n_out,
+                                int32_t** new_in, int* new_n_in, int32_t** new_out, int* new_n_out);
+int tdnnf_nnet3_get_input_indexes(const void* comp, int n, int t, int x, int32_t** out, int* n_out);
+int tdnnf_nnet3_is_computable(const void* comp, int n, int t, int x, const int32_t* avail, int n_avail, int* result);
+
+/* Propagate / Backprop / DeleteMemo on device matrices given as (pointer, rows, cols, stride). */
+int tdnnf_nnet3_propagate(const void* comp, const void* indexes, const float* in, int in_rows, int in_cols, int in_stride,
+                          float* out, int out_rows, int out_cols, int out_stride, void** memo);
+int tdnnf_nnet3_backprop(const void* comp, const void* indexes, const float* in_value, int in_rows, int in_cols,
+                         int in_stride, const float* out_value, int ov_stride, const float* out_deriv, int out_rows,
+                         int out_cols, int od_stride, void* memo, void* to_update, float* in_deriv, int id_stride);
+int tdnnf_nnet3_delete_memo(const void* comp, void* memo);
+
+/* UpdatableComponent surface (ref: tdnn.cc:907-979, simple.cc:9606-9681, itf.cc:313-431). */
+int tdnnf_nnet3_scale(void* comp, float scale);
+int tdnnf_nnet3_add(void* comp, float alpha, const void* other);
+int tdnnf_nnet3_dot_product(void* comp, const void* other, float* result);
+int tdnnf_nnet3_num_parameters(void* comp, int* n);
+int tdnnf_nnet3_vectorize(void* comp, float* params, int n);
+int tdnnf_nnet3_unvectorize(void* comp, const float* params, int n);
+int tdnnf_nnet3_perturb_params(void* comp, float stddev);
+int tdnnf_nnet3_set_learning_rate(void* comp, float underlying_lrate);
+int tdnnf_nnet3_set_actual_learning_rate(void* comp, float lrate);
+int tdnnf_nnet3_get_learning_rate(void* comp, float* lrate);
+int tdnnf_nnet3_set_test_mode(void* comp, int test_mode);
+int tdnnf_nnet3_temp_proportion(const void* comp, float* value);
+/* Device parameter buffers (<= 2) of an updatable component, for the all-reduce of the deltas. */
+int tdnnf_nnet3_param_buffers(void* comp, float** ptrs, int* rows, int* cols, int* strides, int* count);
+int tdnnf_nnet3_bn_test_set_stats(void* comp, int dim, int block_dim, float epsilon, float target_rms, double count,
+                                  const double* sum, const double* sumsq);
+
+/* ReadEditConfig subset: set-temperature-proportion, set-learning-rate{,-factor} (ref: utils.cc:1166-1415). */
+int tdnnf_nnet3_apply_edits(const char* edits, const char** names, void** comps, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDNNF_NNET3_H_ */

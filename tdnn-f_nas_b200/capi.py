@@ -51,6 +51,18 @@ def _declare(lib):
     sig("tdnnf_scale_offset_rows", [vp, vp, i, i, i, vp, i, vp, vp])
     sig("tdnnf_elementwise_product_fwd", [vp, vp, i, i, i, vp, i])
     sig("tdnnf_elementwise_product_bwd", [vp, vp, i, vp, i, vp, i, i, i])
+    sig("tdnnf_mat_set", [vp, vp, i, i, i, f])
+    sig("tdnnf_mat_scale", [vp, vp, i, i, i, f])
+    sig("tdnnf_mat_axpy", [vp, f, vp, i, vp, i, i, i])
+    sig("tdnnf_mat_dot", [vp, vp, i, vp, i, i, i, c_float_p])
+    sig("tdnnf_copy_rows_from_vec", [vp, vp, vp, i, i, i])
+    sig("tdnnf_copy_rows", [vp, vp, i, vp, i, i, i, vp])
+    sig("tdnnf_add_to_rows", [vp, f, vp, i, i, i, vp, i, vp])
+    sig("tdnnf_relu_fwd", [vp, vp, i, i, i, vp, i])
+    sig("tdnnf_relu_bwd", [vp, vp, i, vp, i, vp, i, i, i])
+    sig("tdnnf_add_scaled", [vp, vp, i, f, vp, i, f, vp, i, i, i])
+    sig("tdnnf_batchnorm_train_fwd", [vp, vp, i, i, i, vp, i, f, f, vp])
+    sig("tdnnf_batchnorm_train_bwd", [vp, vp, i, vp, i, vp, i, i, i, f, vp])
     sig("tdnnf_den_graph_create", [vp, i, i, i, c_int_p, c_int_p, c_float_p, c_int_p, c_int_p, c_float_p, C.POINTER(vp)])
     sig("tdnnf_den_graph_destroy", [vp])
     sig("tdnnf_den_create", [vp, vp, i, i, f, C.POINTER(vp)])
@@ -230,6 +242,66 @@ class Context:
         dp, _, oc, ds = _mat(out_deriv)
         ip, _, _, is_ = _mat(in_deriv)
         check(load().tdnnf_elementwise_product_bwd(self.h, xp, xs, dp, ds, ip, is_, r, oc))
+
+
+    # ------------------------------------------------------------------ parameter ops / neighbours
+    def mat_set(self, a, value):
+        p, r, c, s = _mat(a)
+        check(load().tdnnf_mat_set(self.h, p, r, c, s, value))
+
+    def mat_scale(self, a, scale):
+        p, r, c, s = _mat(a)
+        check(load().tdnnf_mat_scale(self.h, p, r, c, s, scale))
+
+    def mat_axpy(self, alpha, src, dst):
+        sp, r, c, ss = _mat(src)
+        dp, _, _, ds = _mat(dst)
+        check(load().tdnnf_mat_axpy(self.h, alpha, sp, ss, dp, ds, r, c))
+
+    def mat_dot(self, a, b) -> float:
+        ap, r, c, as_ = _mat(a)
+        bp, _, _, bs = _mat(b)
+        out = C.c_float(0)
+        check(load().tdnnf_mat_dot(self.h, ap, as_, bp, bs, r, c, C.byref(out)))
+        return float(out.value)
+
+    def copy_rows(self, src, dst, row_map):
+        sp, _, c, ss = _mat(src)
+        dp, r, _, ds = _mat(dst)
+        check(load().tdnnf_copy_rows(self.h, sp, ss, dp, ds, r, c, row_map.data_ptr()))
+
+    def add_to_rows(self, alpha, src, dst, row_map):
+        sp, r, c, ss = _mat(src)
+        dp, _, _, ds = _mat(dst)
+        check(load().tdnnf_add_to_rows(self.h, alpha, sp, ss, r, c, dp, ds, row_map.data_ptr()))
+
+    def relu_fwd(self, x, out):
+        xp, r, c, xs = _mat(x)
+        op, _, _, os_ = _mat(out)
+        check(load().tdnnf_relu_fwd(self.h, xp, r, c, xs, op, os_))
+
+    def relu_bwd(self, out_value, out_deriv, in_deriv):
+        vp_, r, c, vs = _mat(out_value)
+        dp, _, _, ds = _mat(out_deriv)
+        ip, _, _, is_ = _mat(in_deriv)
+        check(load().tdnnf_relu_bwd(self.h, vp_, vs, dp, ds, ip, is_, r, c))
+
+    def add_scaled(self, a, alpha, b, beta, out):
+        ap, r, c, as_ = _mat(a)
+        bp, _, _, bs = _mat(b)
+        op, _, _, os_ = _mat(out)
+        check(load().tdnnf_add_scaled(self.h, ap, as_, alpha, bp, bs, beta, op, os_, r, c))
+
+    def batchnorm_train_fwd(self, x, out, memo, epsilon=1e-3, target_rms=1.0):
+        xp, r, c, xs = _mat(x)
+        op, _, _, os_ = _mat(out)
+        check(load().tdnnf_batchnorm_train_fwd(self.h, xp, r, c, xs, op, os_, epsilon, target_rms, memo.data_ptr()))
+
+    def batchnorm_train_bwd(self, out_value, out_deriv, in_deriv, memo, target_rms=1.0):
+        vp_, r, c, vs = _mat(out_value)
+        dp, _, _, ds = _mat(out_deriv)
+        ip, _, _, is_ = _mat(in_deriv)
+        check(load().tdnnf_batchnorm_train_bwd(self.h, vp_, vs, dp, ds, ip, is_, r, c, target_rms, memo.data_ptr()))
 
 
 class DenGraph:

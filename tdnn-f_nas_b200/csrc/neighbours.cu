@@ -1,0 +1,348 @@
+// Whole-parameter ops of the updatable components and the stock TDNN-F neighbours (ReLU, bypass
+// sum, BatchNorm training mode).  All bandwidth-bound, one fused pass each.
+#include "context.h"
+
+using namespace tdnnf;
+
+namespace {
+
+inline int grid_for(long long total, int threads, int num_sms) {
+  long long b = (total + threads - 1) / threads;
+  long long cap = (long long)num_sms * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+#define ELEMWISE_LOOP(total)                                                                      \
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < (total);           \
+       idx += (long long)gridDim.x * blockDim.x)
+
+__global__ void mat_set_kernel(float* a, int rows, int cols, long long stride, float v) {
+  ELEMWISE_LOOP((long long)rows * cols) a[(idx / cols) * stride + idx % cols] = v;
+}
+__global__ void copy_rows_from_vec_kernel(const float* __restrict__ vec, float* __restrict__ out, int rows, int cols,
+                                          long long stride) {
+  ELEMWISE_LOOP((long long)rows * cols) out[(idx / cols) * stride + idx % cols] = vec[idx % cols];
+}
+__global__ void copy_rows_kernel(const float* __restrict__ src, long long ss, float* __restrict__ dst, long long ds,
+                                 int rows, int cols, const int32_t* __restrict__ map) {
+  ELEMWISE_LOOP((long long)rows * cols) {
+    const long long r = idx / cols;
+    const int c = (int)(idx % cols);
+    const int m = map[r];
+    dst[r * ds + c] = m >= 0 ? src[(long long)m * ss + c] : 0.f;
+  }
+}
+__global__ void add_to_rows_kernel(float alpha, const float* __restrict__ src, long long ss, int rows, int cols,
+                                   float* __restrict__ dst, long long ds, const int32_t* __restrict__ map) {
+  ELEMWISE_LOOP((long long)rows * cols) {
+    const long long r = idx / cols;
+    const int c = (int)(idx % cols);
+    const int m = map[r];
+    if (m >= 0) dst[(long long)m * ds + c] += alpha * src[r * ss + c];
+  }
+}
+__global__ void mat_scale_kernel(float* a, int rows, int cols, long long stride, float s) {
+  ELEMWISE_LOOP((long long)rows * cols) a[(idx / cols) * stride + idx % cols] *= s;
+}
+__global__ void mat_axpy_kernel(float alpha, const float* __restrict__ src, long long ss, float* __restrict__ dst,
+                                long long ds, int rows, int cols) {
+  ELEMWISE_LOOP((long long)rows * cols) {
+    const long long r = idx / cols;
+    const int c = (int)(idx % cols);
+    dst[r * ds + c] += alpha * src[r * ss + c];
+  }
+}
+__global__ void mat_dot_kernel(const float* __restrict__ a, long long as, const float* __restrict__ b, long long bs,
+                               int rows, int cols, double* __restrict__ result) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  ELEMWISE_LOOP((long long)rows * cols) {
+    const long long r = idx / cols;
+    const int c = (int)(idx % cols);
+    acc += (double)a[r * as + c] * (double)b[r * bs + c];
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(result, red[0]);
+}
+
+__global__ void relu_fwd_kernel(const float* __restrict__ in, int rows, int cols, long long is, float* __restrict__ out,
+                                long long os, bool vec) {
+  if (vec) {
+    const int c4 = cols >> 2;
+    ELEMWISE_LOOP((long long)rows * c4) {
+      const long long r = idx / c4;
+      const int c = (int)(idx % c4) * 4;
+      float4 x = *reinterpret_cast<const float4*>(in + r * is + c);
+      x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+      *reinterpret_cast<float4*>(out + r * os + c) = x;
+    }
+  } else {
+    ELEMWISE_LOOP((long long)rows * cols) {
+      const long long r = idx / cols;
+      const int c = (int)(idx % cols);
+      out[r * os + c] = fmaxf(in[r * is + c], 0.f);
+    }
+  }
+}
+__global__ void relu_bwd_kernel(const float* __restrict__ ov, long long vs, const float* __restrict__ od, long long ds,
+                                float* __restrict__ id, long long is, int rows, int cols, bool vec) {
+  if (vec) {
+    const int c4 = cols >> 2;
+    ELEMWISE_LOOP((long long)rows * c4) {
+      const long long r = idx / c4;
+      const int c = (int)(idx % c4) * 4;
+      const float4 v = *reinterpret_cast<const float4*>(ov + r * vs + c);
+      float4 g = *reinterpret_cast<const float4*>(od + r * ds + c);
+      g.x = v.x > 0.f ? g.x : 0.f; g.y = v.y > 0.f ? g.y : 0.f; g.z = v.z > 0.f ? g.z : 0.f; g.w = v.w > 0.f ? g.w : 0.f;
+      *reinterpret_cast<float4*>(id + r * is + c) = g;
+    }
+  } else {
+    ELEMWISE_LOOP((long long)rows * cols) {
+      const long long r = idx / cols;
+      const int c = (int)(idx % cols);
+      id[r * is + c] = ov[r * vs + c] > 0.f ? od[r * ds + c] : 0.f;
+    }
+  }
+}
+__global__ void add_scaled_kernel(const float* a, long long as, float alpha, const float* b, long long bs, float beta,
+                                  float* out, long long os, int rows, int cols, bool vec) {
+  if (vec) {
+    const int c4 = cols >> 2;
+    ELEMWISE_LOOP((long long)rows * c4) {
+      const long long r = idx / c4;
+      const int c = (int)(idx % c4) * 4;
+      const float4 x = *reinterpret_cast<const float4*>(a + r * as + c);
+      const float4 y = *reinterpret_cast<const float4*>(b + r * bs + c);
+      *reinterpret_cast<float4*>(out + r * os + c) =
+          make_float4(alpha * x.x + beta * y.x, alpha * x.y + beta * y.y, alpha * x.z + beta * y.z, alpha * x.w + beta * y.w);
+    }
+  } else {
+    ELEMWISE_LOOP((long long)rows * cols) {
+      const long long r = idx / cols;
+      const int c = (int)(idx % cols);
+      out[r * os + c] = alpha * a[r * as + c] + beta * b[r * bs + c];
+    }
+  }
+}
+
+// Column statistics: sums[0][c] += sum_r f(r,c), sums[1][c] += sum_r g(r,c).  Block = (32 cols, 8 row lanes).
+//   MODE 0: f = x, g = x*x                       (BatchNorm forward statistics)
+//   MODE 1: f = z' (od), g = z' * z (od * ov)    (BatchNorm backward statistics)
+template <int MODE>
+__global__ void col_stats_kernel(const float* __restrict__ a, long long as, const float* __restrict__ b, long long bs,
+                                 int rows, int cols, float* __restrict__ sums /* 2 x cols */) {
+  __shared__ float red0[8][33], red1[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  float s0 = 0.f, s1 = 0.f;
+  if (col < cols) {
+    for (long long r = blockIdx.y * 8 + threadIdx.y; r < rows; r += (long long)gridDim.y * 8) {
+      const float x = a[r * as + col];
+      if (MODE == 0) { s0 += x; s1 += x * x; }
+      else { s0 += x; s1 += x * b[r * bs + col]; }
+    }
+  }
+  red0[threadIdx.y][threadIdx.x] = s0;
+  red1[threadIdx.y][threadIdx.x] = s1;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < cols) {
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { t0 += red0[i][threadIdx.x]; t1 += red1[i][threadIdx.x]; }
+    atomicAdd(sums + col, t0);
+    atomicAdd(sums + cols + col, t1);
+  }
+}
+
+// memo rows: 0 mean, 1 uvar, 2 scale ; rows 3,4 scratch sums
+__global__ void bn_finalize_fwd_kernel(float* memo, int cols, int rows, float eps, float target_rms) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const float mean = memo[3 * cols + c] / rows;
+  float var = memo[4 * cols + c] / rows - mean * mean;
+  var = fmaxf(var, 0.f);
+  memo[c] = mean;
+  memo[cols + c] = var;
+  memo[2 * cols + c] = target_rms * powf(var + eps, -0.5f);
+}
+__global__ void bn_apply_fwd_kernel(const float* __restrict__ in, long long is, float* __restrict__ out, long long os,
+                                    int rows, int cols, const float* __restrict__ memo) {
+  ELEMWISE_LOOP((long long)rows * cols) {
+    const long long r = idx / cols;
+    const int c = (int)(idx % cols);
+    out[r * os + c] = (in[r * is + c] - memo[c]) * memo[2 * cols + c];
+  }
+}
+__global__ void bn_apply_bwd_kernel(const float* __restrict__ ov, long long vs, const float* __restrict__ od,
+                                    long long ds, float* __restrict__ id, long long is, int rows, int cols,
+                                    float target_rms, const float* __restrict__ memo, const float* __restrict__ sums) {
+  ELEMWISE_LOOP((long long)rows * cols) {
+    const long long r = idx / cols;
+    const int c = (int)(idx % cols);
+    const float scale = memo[2 * cols + c];
+    const float mean_od = sums[c] / rows;
+    const float var_deriv_mod = -1.0f / (target_rms * target_rms) * (sums[cols + c] / rows) * scale;
+    id[r * is + c] = scale * (od[r * ds + c] - mean_od) + ov[r * vs + c] * var_deriv_mod;
+  }
+}
+
+bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+#define LAUNCH_CHECK(ctx)              \
+  do {                                 \
+    (ctx)->launches++;                 \
+    TDNNF_CUDA_OK(cudaGetLastError()); \
+  } while (0)
+#define PROLOGUE(cond, msg)                       \
+  TDNNF_REQUIRE(ctx != nullptr, "null context");  \
+  TDNNF_REQUIRE(cond, msg);                       \
+  if (rows == 0 || cols == 0) return TDNNF_OK;    \
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device))
+
+extern "C" int tdnnf_mat_set(tdnnf_ctx* ctx, float* a, int rows, int cols, int stride, float value) {
+  PROLOGUE(a && rows >= 0 && cols >= 0 && stride >= cols, "bad matrix");
+  mat_set_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(a, rows, cols, stride, value);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+extern "C" int tdnnf_copy_rows_from_vec(tdnnf_ctx* ctx, const float* vec, float* out, int rows, int cols, int stride) {
+  PROLOGUE(vec && out && rows >= 0 && cols >= 0 && stride >= cols, "bad matrix");
+  copy_rows_from_vec_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(vec, out, rows, cols,
+                                                                                                         stride);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+extern "C" int tdnnf_copy_rows(tdnnf_ctx* ctx, const float* src, int src_stride, float* dst, int dst_stride, int rows,
+                               int cols, const int32_t* row_map) {
+  PROLOGUE(src && dst && row_map && src_stride >= cols && dst_stride >= cols, "bad matrix");
+  copy_rows_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(src, src_stride, dst, dst_stride,
+                                                                                                 rows, cols, row_map);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+extern "C" int tdnnf_add_to_rows(tdnnf_ctx* ctx, float alpha, const float* src, int src_stride, int rows, int cols,
+                                 float* dst, int dst_stride, const int32_t* row_map) {
+  PROLOGUE(src && dst && row_map && src_stride >= cols && dst_stride >= cols, "bad matrix");
+  add_to_rows_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(alpha, src, src_stride, rows,
+                                                                                                   cols, dst, dst_stride, row_map);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+extern "C" int tdnnf_mat_scale(tdnnf_ctx* ctx, float* a, int rows, int cols, int stride, float scale) {
+  PROLOGUE(a && rows >= 0 && cols >= 0 && stride >= cols, "bad matrix");
+  mat_scale_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(a, rows, cols, stride, scale);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+extern "C" int tdnnf_mat_axpy(tdnnf_ctx* ctx, float alpha, const float* src, int src_stride, float* dst,
+                              int dst_stride, int rows, int cols) {
+  PROLOGUE(src && dst && src_stride >= cols && dst_stride >= cols, "bad matrix");
+  mat_axpy_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(alpha, src, src_stride, dst,
+                                                                                                dst_stride, rows, cols);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+extern "C" int tdnnf_mat_dot_dev(tdnnf_ctx* ctx, const float* a, int a_stride, const float* b, int b_stride, int rows,
+                                 int cols, double* result_dev) {
+  PROLOGUE(a && b && result_dev && a_stride >= cols && b_stride >= cols, "bad matrix");
+  mat_dot_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(a, a_stride, b, b_stride, rows,
+                                                                                               cols, result_dev);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+extern "C" int tdnnf_mat_dot(tdnnf_ctx* ctx, const float* a, int a_stride, const float* b, int b_stride, int rows,
+                             int cols, float* result) {
+  TDNNF_REQUIRE(ctx && result, "null argument");
+  *result = 0.f;
+  if (rows == 0 || cols == 0) return TDNNF_OK;
+  ctx->ws_reset();
+  int rc = ctx->ws_reserve(64);
+  if (rc) return rc;
+  double* acc = static_cast<double*>(ctx->ws_alloc(sizeof(double)));
+  if (!acc) return TDNNF_ERR_NOMEM;
+  TDNNF_CUDA_OK(cudaMemsetAsync(acc, 0, sizeof(double), ctx->stream));
+  rc = tdnnf_mat_dot_dev(ctx, a, a_stride, b, b_stride, rows, cols, acc);
+  if (rc) return rc;
+  double h = 0.0;
+  TDNNF_CUDA_OK(cudaMemcpyAsync(&h, acc, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  TDNNF_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  *result = (float)h;
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_relu_fwd(tdnnf_ctx* ctx, const float* in, int rows, int cols, int in_stride, float* out,
+                              int out_stride) {
+  PROLOGUE(in && out && in_stride >= cols && out_stride >= cols, "bad matrix");
+  const bool vec = cols % 4 == 0 && in_stride % 4 == 0 && out_stride % 4 == 0 && al16(in) && al16(out);
+  relu_fwd_kernel<<<grid_for((long long)rows * cols / (vec ? 4 : 1), 256, ctx->num_sms), 256, 0, ctx->stream>>>(
+      in, rows, cols, in_stride, out, out_stride, vec);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+extern "C" int tdnnf_relu_bwd(tdnnf_ctx* ctx, const float* out_value, int ov_stride, const float* out_deriv,
+                              int od_stride, float* in_deriv, int id_stride, int rows, int cols) {
+  PROLOGUE(out_value && out_deriv && in_deriv && ov_stride >= cols && od_stride >= cols && id_stride >= cols, "bad matrix");
+  const bool vec = cols % 4 == 0 && ov_stride % 4 == 0 && od_stride % 4 == 0 && id_stride % 4 == 0 && al16(out_value) &&
+                   al16(out_deriv) && al16(in_deriv);
+  relu_bwd_kernel<<<grid_for((long long)rows * cols / (vec ? 4 : 1), 256, ctx->num_sms), 256, 0, ctx->stream>>>(
+      out_value, ov_stride, out_deriv, od_stride, in_deriv, id_stride, rows, cols, vec);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+extern "C" int tdnnf_add_scaled(tdnnf_ctx* ctx, const float* a, int a_stride, float alpha, const float* b, int b_stride,
+                                float beta, float* out, int out_stride, int rows, int cols) {
+  PROLOGUE(a && b && out && a_stride >= cols && b_stride >= cols && out_stride >= cols, "bad matrix");
+  const bool vec = cols % 4 == 0 && a_stride % 4 == 0 && b_stride % 4 == 0 && out_stride % 4 == 0 && al16(a) && al16(b) &&
+                   al16(out);
+  add_scaled_kernel<<<grid_for((long long)rows * cols / (vec ? 4 : 1), 256, ctx->num_sms), 256, 0, ctx->stream>>>(
+      a, a_stride, alpha, b, b_stride, beta, out, out_stride, rows, cols, vec);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_batchnorm_train_fwd(tdnnf_ctx* ctx, const float* in, int rows, int cols, int in_stride, float* out,
+                                         int out_stride, float epsilon, float target_rms, float* memo) {
+  PROLOGUE(in && out && memo && in_stride >= cols && out_stride >= cols, "bad matrix");
+  TDNNF_CUDA_OK(cudaMemsetAsync(memo + 3 * (size_t)cols, 0, sizeof(float) * 2 * cols, ctx->stream));
+  int gy = (rows + 255) / 256;
+  if (gy > 128) gy = 128;
+  col_stats_kernel<0><<<dim3((cols + 31) / 32, gy), dim3(32, 8), 0, ctx->stream>>>(in, in_stride, nullptr, 0, rows, cols,
+                                                                                memo + 3 * (size_t)cols);
+  LAUNCH_CHECK(ctx);
+  bn_finalize_fwd_kernel<<<(cols + 255) / 256, 256, 0, ctx->stream>>>(memo, cols, rows, epsilon, target_rms);
+  LAUNCH_CHECK(ctx);
+  bn_apply_fwd_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(in, in_stride, out,
+                                                                                                    out_stride, rows, cols, memo);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_batchnorm_train_bwd(tdnnf_ctx* ctx, const float* out_value, int ov_stride, const float* out_deriv,
+                                         int od_stride, float* in_deriv, int id_stride, int rows, int cols,
+                                         float target_rms, const float* memo) {
+  PROLOGUE(out_value && out_deriv && in_deriv && memo && ov_stride >= cols && od_stride >= cols && id_stride >= cols,
+           "bad matrix");
+  ctx->ws_reset();
+  int rc = ctx->ws_reserve(sizeof(float) * 2 * cols);
+  if (rc) return rc;
+  float* sums = static_cast<float*>(ctx->ws_alloc(sizeof(float) * 2 * cols));
+  if (!sums) return TDNNF_ERR_NOMEM;
+  TDNNF_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * cols, ctx->stream));
+  int gy = (rows + 255) / 256;
+  if (gy > 128) gy = 128;
+  col_stats_kernel<1><<<dim3((cols + 31) / 32, gy), dim3(32, 8), 0, ctx->stream>>>(out_deriv, od_stride, out_value, ov_stride,
+                                                                                rows, cols, sums);
+  LAUNCH_CHECK(ctx);
+  bn_apply_bwd_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
+      out_value, ov_stride, out_deriv, od_stride, in_deriv, id_stride, rows, cols, target_rms, memo, sums);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}

@@ -1,0 +1,1199 @@
+// Method bodies of the NAS components (see components.h).  Each body follows the reference method
+// it replaces (cited), with the CuMatrix calls swapped for the C-ABI kernels.
+#include "components.h"
+
+#include <cmath>
+#include <cstring>
+#include <iomanip>
+
+namespace tdnnf {
+namespace nnet3 {
+
+double ShimRandGauss();  // shim.cc
+
+static int32 g_dp_world = 1;
+static bool g_print_log_alpha = false;
+void SetDataParallelWorldSize(int32 g) { KALDI_ASSERT(g >= 1); g_dp_world = g; }
+int32 GetDataParallelWorldSize() { return g_dp_world; }
+void SetPrintLogAlpha(bool b) { g_print_log_alpha = b; }
+
+static void PrintLogAlpha(const BaseFloat* dev, int32 n) {
+  std::vector<BaseFloat> h(n);
+  CuVector tmp(n);
+  CheckStatus(tdnnf_mat_axpy(CurrentContext(), 1.0f, dev, n, tmp.Data(), n, 1, n));
+  h = tmp.ToHost();
+  std::cout << "log_alpha  [ ";
+  for (BaseFloat x : h) std::cout << x << " ";
+  std::cout << "]\n" << std::endl;
+}
+
+static std::vector<BaseFloat> RandnVector(size_t n, BaseFloat stddev, BaseFloat mean) {
+  std::vector<BaseFloat> v(n);
+  for (size_t i = 0; i < n; ++i) v[i] = (BaseFloat)(ShimRandGauss() * stddev + mean);
+  return v;
+}
+
+// =====================================================================================
+// TdnnDARTSV3Component
+// =====================================================================================
+TdnnDARTSV3Component::TdnnDARTSV3Component()  // tdnn.cc:38-40
+    : test_mode_(false), use_gumbel_(true), use_entropy_(true), free_select_(true), update_alpha_(true),
+      update_theta_(true), uniform_sample_(true), temp_proportion_(1.0), orthonormal_constraint_(0.0),
+      use_natural_gradient_(true) {}
+
+TdnnDARTSV3Component::TdnnDARTSV3Component(const TdnnDARTSV3Component& other)  // tdnn.cc:43-61
+    : UpdatableComponent(other), test_mode_(other.test_mode_), use_gumbel_(other.use_gumbel_),
+      use_entropy_(other.use_entropy_), free_select_(other.free_select_), update_alpha_(other.update_alpha_),
+      update_theta_(other.update_theta_), uniform_sample_(other.uniform_sample_),
+      temp_proportion_(other.temp_proportion_), time_offsets_(other.time_offsets_),
+      linear_params_(other.linear_params_), bias_params_(other.bias_params_),
+      orthonormal_constraint_(other.orthonormal_constraint_), use_natural_gradient_(other.use_natural_gradient_),
+      preconditioner_in_(other.preconditioner_in_), preconditioner_out_(other.preconditioner_out_) {
+  Check();
+}
+
+TdnnDARTSV3Component* TdnnDARTSV3Component::NewForIndexing(const std::vector<int32>& time_offsets) {
+  TdnnDARTSV3Component* c = new TdnnDARTSV3Component();
+  c->time_offsets_ = time_offsets;
+  return c;
+}
+
+void TdnnDARTSV3Component::Check() const {  // tdnn.cc:64-73
+  KALDI_ASSERT(linear_params_.NumRows() > 0 && !time_offsets_.empty() &&
+               std::set<int32>(time_offsets_.begin(), time_offsets_.end()).size() == time_offsets_.size() &&
+               linear_params_.NumCols() % time_offsets_.size() == 0 &&
+               (bias_params_.Dim() == 0 ||
+                bias_params_.Dim() == linear_params_.NumRows() + (int32)time_offsets_.size()));
+  KALDI_ASSERT(time_offsets_.size() <= TDNNF_MAX_OFFSETS);
+}
+
+std::string TdnnDARTSV3Component::Info() const {  // tdnn.cc:75-106
+  std::ostringstream stream;
+  stream << UpdatableComponent::Info();
+  if (orthonormal_constraint_ != 0.0) stream << ", orthonormal-constraint=" << orthonormal_constraint_;
+  stream << ", time-offsets=";
+  for (size_t i = 0; i < time_offsets_.size(); i++) {
+    if (i != 0) stream << ',';
+    stream << time_offsets_[i];
+  }
+  PrintParameterStats(stream, "linear-params", linear_params_, false);
+  if (bias_params_.Dim() == 0) stream << ", has-bias=false";
+  else PrintParameterStats(stream, "bias", bias_params_, true);
+  if (!use_natural_gradient_) {
+    stream << ", use-natural-gradient=false";
+  } else {
+    stream << ", rank-in=" << preconditioner_in_.GetRank() << ", rank-out=" << preconditioner_out_.GetRank()
+           << ", num-samples-history=" << preconditioner_in_.GetNumSamplesHistory()
+           << ", update-period=" << preconditioner_in_.GetUpdatePeriod() << ", alpha-in=" << preconditioner_in_.GetAlpha()
+           << ", alpha-out=" << preconditioner_out_.GetAlpha();
+  }
+  return stream.str();
+}
+
+void TdnnDARTSV3Component::InitFromConfig(ConfigLine* cfl) {  // tdnn.cc:109-212
+  InitLearningRatesFromConfig(cfl);
+  std::string time_offsets;
+  int32 input_dim = -1, output_dim = -1;
+  bool ok = cfl->GetValue("time-offsets", &time_offsets) && cfl->GetValue("input-dim", &input_dim) &&
+            cfl->GetValue("output-dim", &output_dim);
+  if (!ok || input_dim <= 0 || output_dim <= 0 || !SplitStringToIntegers(time_offsets, ",", false, &time_offsets_) ||
+      time_offsets_.empty()) {
+    KALDI_ERR << "Bad initializer: there is a problem with time-offsets, input-dim or output-dim (not defined?): "
+              << cfl->WholeLine();
+  }
+  if (std::set<int32>(time_offsets_.begin(), time_offsets_.end()).size() != time_offsets_.size())
+    KALDI_ERR << "Bad initializer: repeated time-offsets: " << cfl->WholeLine();
+  if (time_offsets_.size() > TDNNF_MAX_OFFSETS)
+    KALDI_ERR << "Bad initializer: more than " << TDNNF_MAX_OFFSETS << " time-offsets: " << cfl->WholeLine();
+
+  orthonormal_constraint_ = 0.0;
+  BaseFloat param_stddev = -1, bias_mean = 0.0, bias_stddev = 1.0;
+  bool use_bias = true;
+  cfl->GetValue("param-stddev", &param_stddev);
+  cfl->GetValue("bias-stddev", &bias_stddev);
+  cfl->GetValue("bias-mean", &bias_mean);
+  cfl->GetValue("use-bias", &use_bias);
+  cfl->GetValue("orthonormal-constraint", &orthonormal_constraint_);
+  if (param_stddev < 0.0) param_stddev = 1.0 / std::sqrt((double)input_dim * time_offsets_.size());
+
+  // the C++ defaults when a key is omitted are all TRUE (tdnn.cc:150-156, quirk Q15)
+  use_gumbel_ = true;
+  temp_proportion_ = 1.0;
+  use_entropy_ = true;
+  free_select_ = true;
+  update_alpha_ = true;
+  update_theta_ = true;
+  uniform_sample_ = true;
+  cfl->GetValue("use-gumbel", &use_gumbel_);
+  cfl->GetValue("use-entropy", &use_entropy_);
+  cfl->GetValue("free-select", &free_select_);
+  cfl->GetValue("update-alpha", &update_alpha_);
+  cfl->GetValue("update-theta", &update_theta_);
+  cfl->GetValue("uniform-sample", &uniform_sample_);
+  cfl->GetValue("Temp-Proportion", &temp_proportion_);
+
+  const int32 n = (int32)time_offsets_.size();
+  Matrix<BaseFloat> lin(output_dim, input_dim * n);
+  lin.v = RandnVector(lin.v.size(), param_stddev, 0.0);
+  linear_params_.CopyFromHost(lin);
+  if (use_bias) {
+    std::vector<BaseFloat> b = RandnVector(output_dim + n, bias_stddev, bias_mean);
+    for (int32 i = 0; i < n; ++i) b[i] = 0.0;  // the architecture log-weights start at 0 (tdnn.cc:176)
+    bias_params_.CopyFromHost(b);
+  } else {
+    bias_params_.Resize(0);
+  }
+
+  use_natural_gradient_ = true;
+  int32 rank_out = -1, rank_in = -1;
+  BaseFloat alpha_out = 4.0, alpha_in = 4.0, num_samples_history = 2000.0;
+  cfl->GetValue("use-natural-gradient", &use_natural_gradient_);
+  cfl->GetValue("rank-in", &rank_in);
+  cfl->GetValue("rank-out", &rank_out);
+  cfl->GetValue("alpha-in", &alpha_in);
+  cfl->GetValue("alpha-out", &alpha_out);
+  cfl->GetValue("num-samples-history", &num_samples_history);
+  int32 spliced_input_dim = input_dim * n;
+  if (rank_in < 0) rank_in = std::min<int32>(20, (spliced_input_dim + 1) / 2);
+  preconditioner_in_.SetRank(rank_in);
+  if (rank_out < 0) rank_out = std::min<int32>(80, (output_dim + 1) / 2);
+  preconditioner_out_.SetRank(rank_out);
+  preconditioner_in_.SetNumSamplesHistory(num_samples_history);
+  preconditioner_out_.SetNumSamplesHistory(num_samples_history);
+  preconditioner_in_.SetAlpha(alpha_in);
+  preconditioner_out_.SetAlpha(alpha_out);
+  preconditioner_in_.SetUpdatePeriod(4);
+  preconditioner_out_.SetUpdatePeriod(4);
+  // note: like the reference, no HasUnusedValues() check is made here.
+}
+
+int32 TdnnDARTSV3Component::Flags() const {
+  return (use_gumbel_ ? TDNNF_DARTS_USE_GUMBEL : 0) | (free_select_ ? TDNNF_DARTS_FREE_SELECT : 0) |
+         (uniform_sample_ ? TDNNF_DARTS_UNIFORM_SAMPLE : 0) | (use_entropy_ ? TDNNF_DARTS_USE_ENTROPY : 0) |
+         (update_alpha_ ? TDNNF_DARTS_UPDATE_ALPHA : 0);
+}
+
+int32 TdnnDARTSV3Component::ShareOffsetIndex() const {  // tdnn.cc:227-241, 356-364
+  const int32 n = (int32)time_offsets_.size();
+  if (n >= 2 && time_offsets_[1] > 0) return 0;
+  if (n >= 2 && time_offsets_[1] < 0) return n - 1;
+  // the reference reads share_offset_index uninitialised here: undefined behaviour
+  KALDI_ERR << "TdnnDARTSV3Component: share_offset_index is undefined in the reference when there is a single "
+               "time offset or time_offsets[1] == 0";
+  return -1;
+}
+
+void* TdnnDARTSV3Component::Propagate(const ComponentPrecomputedIndexes* indexes_in, const CuMatrixBase<BaseFloat>& in,
+                                      CuMatrixBase<BaseFloat>* out) const {  // tdnn.cc:214-333
+  const PrecomputedIndexes* indexes = dynamic_cast<const PrecomputedIndexes*>(indexes_in);
+  KALDI_ASSERT(indexes != NULL);
+  KALDI_ASSERT(indexes->row_offsets.size() == time_offsets_.size());
+  const int32 num_offsets = (int32)time_offsets_.size();
+  KALDI_ASSERT(in.NumCols() == InputDim() && out->NumCols() == OutputDim());
+  // bias_params_.Range(0, num_offsets) on an empty vector asserts in the reference (quirk Q3)
+  if (bias_params_.Dim() == 0)
+    KALDI_ERR << "TdnnDARTSV3Component needs use-bias=true: the architecture weights live in bias_params_ (tdnn.cc:253)";
+  const int32 share_offset_index = ShareOffsetIndex();
+  // out->CopyRowsFromVec(bias tail) when the shared slot is the first one; out->SetZero() (bias NOT added) otherwise
+  const int bias_mode = (time_offsets_[1] > 0) ? 2 : 1;
+
+  // randomness: same draws, same order as the reference (n Gumbel uniforms, then the one-hot uniform)
+  float u_gumbel[TDNNF_MAX_OFFSETS];
+  float u_uniform = 0.f;
+  if (use_gumbel_)
+    for (int32 i = 0; i < num_offsets; i++) u_gumbel[i] = RandUniformOpen();
+  if (uniform_sample_) u_uniform = RandUniformOpen();
+
+  Memo* memo = new Memo();
+  memo->coef.Resize(num_offsets);
+  memo->weff.Resize(num_offsets);
+  tdnnf_ctx* ctx = CurrentContext();
+  CheckStatus(tdnnf_darts_coef(ctx, bias_params_.Data(), num_offsets, Flags(), temp_proportion_,
+                               use_gumbel_ ? u_gumbel : NULL, u_uniform, share_offset_index, memo->coef.Data(),
+                               memo->weff.Data()));
+  CheckStatus(tdnnf_darts_propagate(ctx, in.Data(), in.NumRows(), in.NumCols(), in.Stride(), out->Data(), out->NumRows(),
+                                    out->NumCols(), out->Stride(), linear_params_.Data(), linear_params_.Stride(),
+                                    bias_params_.Data() + num_offsets, bias_mode, memo->weff.Data(), num_offsets,
+                                    indexes->row_offsets.data(), indexes->row_stride));
+  return memo;
+}
+
+void TdnnDARTSV3Component::DeleteMemo(void* memo) const {
+  // the reference deletes its CuVector through a CuMatrix* cast (conv.h:147-149, quirk Q6): fixed here
+  delete static_cast<Memo*>(memo);
+}
+
+void TdnnDARTSV3Component::Backprop(const std::string& debug_info, const ComponentPrecomputedIndexes* indexes_in,
+                                    const CuMatrixBase<BaseFloat>& in_value, const CuMatrixBase<BaseFloat>&,
+                                    const CuMatrixBase<BaseFloat>& out_deriv, void* memo_in, Component* to_update_in,
+                                    CuMatrixBase<BaseFloat>* in_deriv) const {  // tdnn.cc:335-431
+  const PrecomputedIndexes* indexes = dynamic_cast<const PrecomputedIndexes*>(indexes_in);
+  KALDI_ASSERT(indexes != NULL && indexes->row_offsets.size() == time_offsets_.size());
+  KALDI_ASSERT(memo_in != NULL);
+  const Memo* memo = static_cast<const Memo*>(memo_in);
+  const int32 num_offsets = (int32)time_offsets_.size();
+  const int32 share_offset_index = ShareOffsetIndex();
+  tdnnf_ctx* ctx = CurrentContext();
+  if (in_deriv != NULL) {
+    CheckStatus(tdnnf_darts_backprop_data(ctx, out_deriv.Data(), out_deriv.NumRows(), out_deriv.NumCols(),
+                                          out_deriv.Stride(), in_deriv->Data(), in_deriv->NumRows(), in_deriv->NumCols(),
+                                          in_deriv->Stride(), linear_params_.Data(), linear_params_.Stride(),
+                                          memo->weff.Data(), num_offsets, indexes->row_offsets.data(),
+                                          indexes->row_stride));
+  }
+  if (to_update_in != NULL) {
+    TdnnDARTSV3Component* to_update = dynamic_cast<TdnnDARTSV3Component*>(to_update_in);
+    KALDI_ASSERT(to_update != NULL);
+    if (to_update->learning_rate_ == 0.0) return;
+    if (to_update->is_gradient_ || !to_update->use_natural_gradient_)
+      to_update->UpdateSimple(*indexes, in_value, out_deriv);
+    else
+      to_update->UpdateNaturalGradient(*indexes, in_value, out_deriv, linear_params_, *memo, share_offset_index, Flags(),
+                                       temp_proportion_);
+  }
+}
+
+void TdnnDARTSV3Component::UpdateSimple(const PrecomputedIndexes&, const CuMatrixBase<BaseFloat>&,
+                                        const CuMatrixBase<BaseFloat>& out_deriv) {  // tdnn.cc:433-455
+  // bias_params_.AddRowSumMat(learning_rate_, out_deriv): dim n + D_out vs D_out columns -> the
+  // reference asserts here whenever a bias exists (and one must exist): quirk Q4.
+  if (bias_params_.Dim() != 0) KALDI_ASSERT(bias_params_.Dim() == out_deriv.NumCols());
+  KALDI_ERR << "TdnnDARTSV3Component::UpdateSimple is unreachable in the reference";
+}
+
+void TdnnDARTSV3Component::UpdateNaturalGradient(const PrecomputedIndexes& indexes,
+                                                 const CuMatrixBase<BaseFloat>& in_value,
+                                                 const CuMatrixBase<BaseFloat>& out_deriv,
+                                                 const CuMatrix& linear_params_temp_, const Memo& memo,
+                                                 int32 share_offset_index_temp_, int32 model_flags,
+                                                 BaseFloat temp_proportion_temp_) {  // tdnn.cc:457-626
+  // `this` is the delta component (to_update); the model's parameters / flags arrive as arguments.
+  const int32 num_offsets = (int32)time_offsets_.size();
+  KALDI_ASSERT(bias_params_.Dim() == linear_params_.NumRows() + num_offsets);
+  tdnnf_ctx* ctx = CurrentContext();
+  // "scale" from the two PreconditionDirections calls (tdnn.cc:598-604)
+  const BaseFloat in_scale = preconditioner_in_.PreconditionDirectionsScale(),
+                  out_scale = preconditioner_out_.PreconditionDirectionsScale();
+  const BaseFloat local_lrate = in_scale * out_scale * learning_rate_;
+  const bool want_s = !(model_flags & TDNNF_DARTS_UNIFORM_SAMPLE);
+  CuVector s(num_offsets);
+  // linear_params_ += local_lrate * out_deriv^T * [w_1 X_1 | ... | w_n X_n]      (tdnn.cc:619-624)
+  // bias tail     += local_lrate * colsum(out_deriv)                             (tdnn.cc:607-617)
+  // s_i = sum((X_i W_i^T) .* out_deriv), the out_temp.Sum() of tdnn.cc:506-507, 538-539, as an epilogue
+  CheckStatus(tdnnf_darts_backprop_params(
+      ctx, in_value.Data(), in_value.NumRows(), in_value.NumCols(), in_value.Stride(), out_deriv.Data(), out_deriv.NumRows(),
+      out_deriv.NumCols(), out_deriv.Stride(), linear_params_temp_.Data(), linear_params_temp_.Stride(), linear_params_.Data(),
+      linear_params_.Stride(), bias_params_.Data() + num_offsets, memo.weff.Data(), num_offsets, indexes.row_offsets.data(),
+      indexes.row_stride, local_lrate, want_s ? s.Data() : NULL));
+  // architecture weights: Jacobian products + the x5 / xlr / x10000 scalings       (tdnn.cc:541-590)
+  CheckStatus(tdnnf_darts_alpha_update(ctx, s.Data(), memo.coef.Data(), num_offsets, model_flags, temp_proportion_temp_,
+                                       share_offset_index_temp_, learning_rate_, bias_params_.Data()));
+  if (g_print_log_alpha) PrintLogAlpha(bias_params_.Data(), num_offsets);  // tdnn.cc:571 (prints the MODEL's alpha there)
+}
+
+void TdnnDARTSV3Component::ReorderIndexes(std::vector<Index>* input_indexes, std::vector<Index>* output_indexes) const {
+  using namespace time_height_convolution;  // tdnn.cc:628-657
+  ConvolutionComputationIo io;
+  GetComputationIo(*input_indexes, *output_indexes, &io);
+  ModifyComputationIo(&io);
+  std::vector<Index> modified_input_indexes, modified_output_indexes;
+  GetIndexesForComputation(io, *input_indexes, *output_indexes, &modified_input_indexes, &modified_output_indexes);
+  input_indexes->swap(modified_input_indexes);
+  output_indexes->swap(modified_output_indexes);
+}
+
+void TdnnDARTSV3Component::Write(std::ostream& os, bool binary) const {  // tdnn.cc:659-700
+  WriteUpdatableCommon(os, binary);
+  WriteToken(os, binary, "<use-gumbel>");
+  WriteBasicType(os, binary, use_gumbel_);
+  WriteToken(os, binary, "<use-entropy>");
+  WriteBasicType(os, binary, use_entropy_);
+  WriteToken(os, binary, "<free-select>");
+  WriteBasicType(os, binary, free_select_);
+  WriteToken(os, binary, "<update-alpha>");
+  WriteBasicType(os, binary, update_alpha_);
+  WriteToken(os, binary, "<update-theta>");
+  WriteBasicType(os, binary, update_theta_);
+  WriteToken(os, binary, "<uniform-sample>");
+  WriteBasicType(os, binary, uniform_sample_);
+  WriteToken(os, binary, "<Temp-Proportion>");
+  WriteBasicType(os, binary, temp_proportion_);
+  WriteToken(os, binary, "<TimeOffsets>");
+  WriteIntegerVector(os, binary, time_offsets_);
+  WriteToken(os, binary, "<LinearParams>");
+  linear_params_.Write(os, binary);
+  WriteToken(os, binary, "<BiasParams>");
+  bias_params_.Write(os, binary);
+  WriteToken(os, binary, "<OrthonormalConstraint>");
+  WriteBasicType(os, binary, orthonormal_constraint_);
+  WriteToken(os, binary, "<UseNaturalGradient>");
+  WriteBasicType(os, binary, use_natural_gradient_);
+  int32 rank_in = preconditioner_in_.GetRank(), rank_out = preconditioner_out_.GetRank();
+  BaseFloat alpha_in = preconditioner_in_.GetAlpha(), alpha_out = preconditioner_out_.GetAlpha(),
+            num_samples_history = preconditioner_in_.GetNumSamplesHistory();
+  WriteToken(os, binary, "<NumSamplesHistory>");
+  WriteBasicType(os, binary, num_samples_history);
+  WriteToken(os, binary, "<AlphaInOut>");
+  WriteBasicType(os, binary, alpha_in);
+  WriteBasicType(os, binary, alpha_out);
+  WriteToken(os, binary, "<RankInOut>");
+  WriteBasicType(os, binary, rank_in);
+  WriteBasicType(os, binary, rank_out);
+  WriteToken(os, binary, "</TdnnDARTSV3Component>");
+}
+
+void TdnnDARTSV3Component::Read(std::istream& is, bool binary) {  // tdnn.cc:702-761
+  std::string token = ReadUpdatableCommon(is, binary);
+  ExpectToken(is, binary, "<use-gumbel>");
+  ReadBasicType(is, binary, &use_gumbel_);
+  ExpectToken(is, binary, "<use-entropy>");
+  ReadBasicType(is, binary, &use_entropy_);
+  ExpectToken(is, binary, "<free-select>");
+  ReadBasicType(is, binary, &free_select_);
+  ExpectToken(is, binary, "<update-alpha>");
+  ReadBasicType(is, binary, &update_alpha_);
+  ExpectToken(is, binary, "<update-theta>");
+  ReadBasicType(is, binary, &update_theta_);
+  ExpectToken(is, binary, "<uniform-sample>");
+  ReadBasicType(is, binary, &uniform_sample_);
+  ExpectToken(is, binary, "<Temp-Proportion>");
+  ReadBasicType(is, binary, &temp_proportion_);
+  ExpectToken(is, binary, "<TimeOffsets>");
+  ReadIntegerVector(is, binary, &time_offsets_);
+  ExpectToken(is, binary, "<LinearParams>");
+  linear_params_.Read(is, binary);
+  ExpectToken(is, binary, "<BiasParams>");
+  bias_params_.Read(is, binary);
+  ExpectToken(is, binary, "<OrthonormalConstraint>");
+  ReadBasicType(is, binary, &orthonormal_constraint_);
+  ExpectToken(is, binary, "<UseNaturalGradient>");
+  ReadBasicType(is, binary, &use_natural_gradient_);
+  int32 rank_in, rank_out;
+  BaseFloat alpha_in, alpha_out, num_samples_history;
+  ExpectToken(is, binary, "<NumSamplesHistory>");
+  ReadBasicType(is, binary, &num_samples_history);
+  {
+    std::string token;
+    ReadToken(is, binary, &token);
+    if (token == "<AlphaInOut>") {
+      ReadBasicType(is, binary, &alpha_in);
+      ReadBasicType(is, binary, &alpha_out);
+    } else {
+      KALDI_ASSERT(token == "<Alpha>");
+      ReadBasicType(is, binary, &alpha_in);
+      alpha_out = alpha_in;
+    }
+  }
+  preconditioner_in_.SetAlpha(alpha_in);
+  preconditioner_out_.SetAlpha(alpha_out);
+  ExpectToken(is, binary, "<RankInOut>");
+  ReadBasicType(is, binary, &rank_in);
+  ReadBasicType(is, binary, &rank_out);
+  preconditioner_in_.SetRank(rank_in);
+  preconditioner_out_.SetRank(rank_out);
+  preconditioner_in_.SetNumSamplesHistory(num_samples_history);
+  preconditioner_out_.SetNumSamplesHistory(num_samples_history);
+  preconditioner_in_.SetUpdatePeriod(4);
+  preconditioner_out_.SetUpdatePeriod(4);
+  ExpectToken(is, binary, "</TdnnDARTSV3Component>");
+  Check();
+}
+
+void TdnnDARTSV3Component::GetInputIndexes(const MiscComputationInfo&, const Index& output_index,
+                                           std::vector<Index>* desired_indexes) const {  // tdnn.cc:763-775
+  KALDI_ASSERT(output_index.t != kNoTime);
+  size_t size = time_offsets_.size();
+  desired_indexes->resize(size);
+  for (size_t i = 0; i < size; i++) {
+    (*desired_indexes)[i].n = output_index.n;
+    (*desired_indexes)[i].t = output_index.t + time_offsets_[i];
+    (*desired_indexes)[i].x = output_index.x;
+  }
+}
+
+bool TdnnDARTSV3Component::IsComputable(const MiscComputationInfo&, const Index& output_index,
+                                        const IndexSet& input_index_set, std::vector<Index>* used_inputs) const {
+  KALDI_ASSERT(output_index.t != kNoTime);  // tdnn.cc:778-803
+  size_t size = time_offsets_.size();
+  Index index(output_index);
+  if (used_inputs != NULL) {
+    used_inputs->clear();
+    used_inputs->reserve(size);
+  }
+  for (size_t i = 0; i < size; i++) {
+    index.t = output_index.t + time_offsets_[i];
+    if (input_index_set(index)) {
+      if (used_inputs != NULL) used_inputs->push_back(index);
+    } else {
+      return false;
+    }
+  }
+  return true;
+}
+
+void TdnnDARTSV3Component::ModifyComputationIo(time_height_convolution::ConvolutionComputationIo* io) {
+  if (io->t_step_out == 0) {  // tdnn.cc:822-844
+    if (io->t_step_in == 0) io->t_step_in = 1;
+    io->t_step_out = io->t_step_in;
+  }
+  KALDI_ASSERT(io->t_step_out % io->t_step_in == 0);
+  io->reorder_t_in = io->t_step_out / io->t_step_in;
+  int32 n = io->reorder_t_in;
+  io->num_t_in = n * ((io->num_t_in + n - 1) / n);
+}
+
+ComponentPrecomputedIndexes* TdnnDARTSV3Component::PrecomputeIndexes(const MiscComputationInfo&,
+                                                                     const std::vector<Index>& input_indexes,
+                                                                     const std::vector<Index>& output_indexes,
+                                                                     bool) const {  // tdnn.cc:846-905
+  using namespace time_height_convolution;
+  ConvolutionComputationIo io;
+  GetComputationIo(input_indexes, output_indexes, &io);
+  ModifyComputationIo(&io);
+  if (RandInt(0, 10) == 0) {
+    std::vector<Index> modified_input_indexes, modified_output_indexes;
+    GetIndexesForComputation(io, input_indexes, output_indexes, &modified_input_indexes, &modified_output_indexes);
+    KALDI_ASSERT(modified_input_indexes == input_indexes && modified_output_indexes == output_indexes);
+  }
+  PrecomputedIndexes* ans = new PrecomputedIndexes();
+  ans->row_stride = io.reorder_t_in;
+  int32 num_offsets = (int32)time_offsets_.size();
+  ans->row_offsets.resize(num_offsets);
+  for (int32 i = 0; i < num_offsets; i++) {
+    int32 time_offset = time_offsets_[i], required_input_t = io.start_t_out + time_offset,
+          input_t = (required_input_t - io.start_t_in) / io.t_step_in;
+    KALDI_ASSERT(required_input_t == io.start_t_in + io.t_step_in * input_t);
+    int32 n = io.reorder_t_in, input_t_multiple = n * (input_t / n), input_t_remainder = input_t % n;
+    int32 input_row_offset = input_t_multiple * io.num_images + input_t_remainder;
+    ans->row_offsets[i] = input_row_offset;
+  }
+  return ans;
+}
+
+void TdnnDARTSV3Component::Scale(BaseFloat scale) {  // tdnn.cc:907-915 (includes the alpha entries, quirk Q5)
+  if (scale == 0.0) {
+    linear_params_.SetZero();
+    bias_params_.SetZero();
+  } else {
+    linear_params_.Scale(scale);
+    bias_params_.Scale(scale);
+  }
+}
+void TdnnDARTSV3Component::Add(BaseFloat alpha, const Component& other_in) {  // tdnn.cc:917-925
+  const TdnnDARTSV3Component* other = dynamic_cast<const TdnnDARTSV3Component*>(&other_in);
+  KALDI_ASSERT(other != NULL);
+  linear_params_.AddMat(alpha, other->linear_params_);
+  if (bias_params_.Dim() != 0) bias_params_.AddVec(alpha, other->bias_params_);
+}
+void TdnnDARTSV3Component::PerturbParams(BaseFloat stddev) {  // tdnn.cc:927-938
+  CuMatrix temp_mat(linear_params_.NumRows(), linear_params_.NumCols());
+  Matrix<BaseFloat> h(linear_params_.NumRows(), linear_params_.NumCols());
+  h.v = RandnVector(h.v.size(), 1.0, 0.0);
+  temp_mat.CopyFromHost(h);
+  linear_params_.AddMat(stddev, temp_mat);
+  if (bias_params_.Dim() != 0) {
+    CuVector temp_vec;
+    temp_vec.CopyFromHost(RandnVector(bias_params_.Dim(), 1.0, 0.0));
+    bias_params_.AddVec(stddev, temp_vec);
+  }
+}
+BaseFloat TdnnDARTSV3Component::DotProduct(const UpdatableComponent& other_in) const {  // tdnn.cc:940-949
+  const TdnnDARTSV3Component* other = dynamic_cast<const TdnnDARTSV3Component*>(&other_in);
+  KALDI_ASSERT(other != NULL);
+  BaseFloat ans = TraceMatMatTrans(linear_params_, other->linear_params_);
+  if (bias_params_.Dim() != 0) ans += VecVec(bias_params_, other->bias_params_);
+  return ans;
+}
+int32 TdnnDARTSV3Component::NumParameters() const {  // tdnn.cc:951-955
+  return linear_params_.NumRows() * linear_params_.NumCols() + bias_params_.Dim();
+}
+void TdnnDARTSV3Component::Vectorize(std::vector<BaseFloat>* params) const {  // tdnn.cc:957-966
+  const Matrix<BaseFloat> lin = linear_params_.ToHost();
+  const std::vector<BaseFloat> b = bias_params_.ToHost();
+  params->clear();
+  params->insert(params->end(), lin.v.begin(), lin.v.end());
+  params->insert(params->end(), b.begin(), b.end());
+}
+void TdnnDARTSV3Component::UnVectorize(const std::vector<BaseFloat>& params) {  // tdnn.cc:968-977
+  KALDI_ASSERT((int32)params.size() == NumParameters());
+  Matrix<BaseFloat> lin(linear_params_.NumRows(), linear_params_.NumCols());
+  std::copy(params.begin(), params.begin() + lin.v.size(), lin.v.begin());
+  linear_params_.CopyFromHost(lin);
+  if (bias_params_.Dim() != 0)
+    bias_params_.CopyFromHost(std::vector<BaseFloat>(params.begin() + lin.v.size(), params.end()));
+}
+void TdnnDARTSV3Component::FreezeNaturalGradient(bool freeze) {
+  preconditioner_in_.Freeze(freeze);
+  preconditioner_out_.Freeze(freeze);
+}
+TdnnDARTSV3Component::PrecomputedIndexes* TdnnDARTSV3Component::PrecomputedIndexes::Copy() const {
+  return new PrecomputedIndexes(*this);
+}
+void TdnnDARTSV3Component::PrecomputedIndexes::Write(std::ostream& os, bool binary) const {  // tdnn.cc:986-994
+  WriteToken(os, binary, "<TdnnDARTSV3ComponentPrecomputedIndexes>");
+  WriteToken(os, binary, "<RowStride>");
+  WriteBasicType(os, binary, row_stride);
+  WriteToken(os, binary, "<RowOffsets>");
+  WriteIntegerVector(os, binary, row_offsets);
+  WriteToken(os, binary, "</TdnnDARTSV3ComponentPrecomputedIndexes>");
+}
+void TdnnDARTSV3Component::PrecomputedIndexes::Read(std::istream& is, bool binary) {  // tdnn.cc:996-1005
+  ExpectOneOrTwoTokens(is, binary, "<TdnnDARTSV3ComponentPrecomputedIndexes>", "<RowStride>");
+  ReadBasicType(is, binary, &row_stride);
+  ExpectToken(is, binary, "<RowOffsets>");
+  ReadIntegerVector(is, binary, &row_offsets);
+  ExpectToken(is, binary, "</TdnnDARTSV3ComponentPrecomputedIndexes>");
+}
+void TdnnDARTSV3Component::ConsolidateMemory() {  // tdnn.cc:1007-1012
+  OnlineNaturalGradient temp_in(preconditioner_in_);
+  preconditioner_in_.Swap(&temp_in);
+  OnlineNaturalGradient temp_out(preconditioner_out_);
+  preconditioner_out_.Swap(&temp_out);
+}
+
+// =====================================================================================
+// SoftmaxFlopsComponent / GumbelSoftmaxFlopsComponent
+// =====================================================================================
+void SoftmaxFlopsComponent::InitFromConfig(ConfigLine* cfl) {  // simple.cc:9947-9959 (validation commented out there)
+  int32 dim = 0;
+  BaseFloat scale = 1.0;
+  bool ok = cfl->GetValue("dim", &dim) && cfl->GetValue("scale", &scale);
+  (void)ok;
+  Init(dim, scale);
+}
+std::string SoftmaxFlopsComponent::Info() const {
+  std::ostringstream stream;
+  stream << Type() << ", dim=" << dim_ << ", scale=" << scale_;
+  return stream.str();
+}
+void* SoftmaxFlopsComponent::Propagate(const ComponentPrecomputedIndexes*, const CuMatrixBase<BaseFloat>& in,
+                                       CuMatrixBase<BaseFloat>* out) const {  // simple.cc:9968-9981
+  KALDI_ASSERT(SameDim(in, *out));
+  CheckStatus(tdnnf_softmax_flops_fwd(CurrentContext(), in.Data(), in.NumRows(), in.NumCols(), in.Stride(), out->Data(),
+                                      out->Stride(), NULL, 1.0f));
+  return NULL;
+}
+static void SoftmaxFlopsBackprop(BaseFloat scale, BaseFloat inv_temp, const CuMatrixBase<BaseFloat>& out_value,
+                                 const CuMatrixBase<BaseFloat>& out_deriv, CuMatrixBase<BaseFloat>* in_deriv) {
+  if (in_deriv == NULL) return;
+  KALDI_ASSERT(SameDim(out_value, out_deriv) && SameDim(out_value, *in_deriv));
+  // scale_/out_deriv.NumRows()/out_deriv.NumCols() (simple.cc:10154), rows taken globally under data parallelism
+  const BaseFloat penalty = scale / ((BaseFloat)out_deriv.NumRows() * GetDataParallelWorldSize()) / out_deriv.NumCols();
+  // the reference writes the penalty into out_deriv through a const reference (quirk Q9): reproduced
+  CheckStatus(tdnnf_softmax_flops_bwd(CurrentContext(), out_value.Data(), out_value.Stride(),
+                                      const_cast<BaseFloat*>(out_deriv.Data()), out_deriv.Stride(), in_deriv->Data(),
+                                      in_deriv->Stride(), out_deriv.NumRows(), out_deriv.NumCols(), penalty, inv_temp, 1));
+}
+void SoftmaxFlopsComponent::Backprop(const std::string&, const ComponentPrecomputedIndexes*, const CuMatrixBase<BaseFloat>&,
+                                     const CuMatrixBase<BaseFloat>& out_value, const CuMatrixBase<BaseFloat>& out_deriv,
+                                     void*, Component*, CuMatrixBase<BaseFloat>* in_deriv) const {  // simple.cc:9984-10020
+  SoftmaxFlopsBackprop(scale_, 1.0f, out_value, out_deriv, in_deriv);
+}
+void SoftmaxFlopsComponent::Read(std::istream& is, bool binary) {  // simple.cc:10022-10035
+  std::string token;
+  ReadToken(is, binary, &token);
+  if (token == "<SoftmaxFlopsComponent>") ReadToken(is, binary, &token);
+  KALDI_ASSERT(token == "<Dim>");
+  ReadBasicType(is, binary, &dim_);
+  ReadToken(is, binary, &token);
+  KALDI_ASSERT(token == "<Scale>");
+  ReadBasicType(is, binary, &scale_);
+  ReadToken(is, binary, &token);
+  KALDI_ASSERT(token == "</SoftmaxFlopsComponent>");
+}
+void SoftmaxFlopsComponent::Write(std::ostream& os, bool binary) const {  // simple.cc:10037-10044
+  WriteToken(os, binary, "<SoftmaxFlopsComponent>");
+  WriteToken(os, binary, "<Dim>");
+  WriteBasicType(os, binary, dim_);
+  WriteToken(os, binary, "<Scale>");
+  WriteBasicType(os, binary, scale_);
+  WriteToken(os, binary, "</SoftmaxFlopsComponent>");
+}
+
+void GumbelSoftmaxFlopsComponent::InitFromConfig(ConfigLine* cfl) {  // simple.cc:10064-10078
+  int32 dim = 0;
+  BaseFloat scale = 1.0;
+  BaseFloat temp_proportion = 0.0;
+  bool ok = cfl->GetValue("dim", &dim) && cfl->GetValue("scale", &scale) && cfl->GetValue("temp-proportion", &temp_proportion);
+  (void)ok;
+  Init(dim, scale, temp_proportion);
+}
+std::string GumbelSoftmaxFlopsComponent::Info() const {
+  std::ostringstream stream;
+  stream << Type() << ", dim=" << dim_ << ", scale=" << scale_ << ", temp-proportion=" << temp_proportion_;
+  return stream.str();
+}
+void* GumbelSoftmaxFlopsComponent::Propagate(const ComponentPrecomputedIndexes*, const CuMatrixBase<BaseFloat>& in,
+                                             CuMatrixBase<BaseFloat>* out) const {  // simple.cc:10088-10113
+  KALDI_ASSERT(SameDim(in, *out));
+  std::vector<float> u(in.NumCols());
+  for (int32 j = 0; j < in.NumCols(); ++j) u[j] = RandUniformOpen();  // rand_.SetRandUniform(): one draw per column
+  CheckStatus(tdnnf_softmax_flops_fwd(CurrentContext(), in.Data(), in.NumRows(), in.NumCols(), in.Stride(), out->Data(),
+                                      out->Stride(), u.data(), 1.0f / temp_proportion_));
+  return NULL;
+}
+void GumbelSoftmaxFlopsComponent::Backprop(const std::string&, const ComponentPrecomputedIndexes*,
+                                           const CuMatrixBase<BaseFloat>&, const CuMatrixBase<BaseFloat>& out_value,
+                                           const CuMatrixBase<BaseFloat>& out_deriv, void*, Component*,
+                                           CuMatrixBase<BaseFloat>* in_deriv) const {  // simple.cc:10116-10158
+  SoftmaxFlopsBackprop(scale_, 1.0f / temp_proportion_, out_value, out_deriv, in_deriv);
+}
+void GumbelSoftmaxFlopsComponent::Read(std::istream& is, bool binary) {  // simple.cc:10160-10176
+  std::string token;
+  ReadToken(is, binary, &token);
+  if (token == "<GumbelSoftmaxFlopsComponent>") ReadToken(is, binary, &token);
+  KALDI_ASSERT(token == "<Dim>");
+  ReadBasicType(is, binary, &dim_);
+  ReadToken(is, binary, &token);
+  KALDI_ASSERT(token == "<Scale>");
+  ReadBasicType(is, binary, &scale_);
+  ReadToken(is, binary, &token);
+  KALDI_ASSERT(token == "<TempProportion>");
+  ReadBasicType(is, binary, &temp_proportion_);
+  ReadToken(is, binary, &token);
+  KALDI_ASSERT(token == "</GumbelSoftmaxFlopsComponent>");
+}
+void GumbelSoftmaxFlopsComponent::Write(std::ostream& os, bool binary) const {  // simple.cc:10178-10187
+  WriteToken(os, binary, "<GumbelSoftmaxFlopsComponent>");
+  WriteToken(os, binary, "<Dim>");
+  WriteBasicType(os, binary, dim_);
+  WriteToken(os, binary, "<Scale>");
+  WriteBasicType(os, binary, scale_);
+  WriteToken(os, binary, "<TempProportion>");
+  WriteBasicType(os, binary, temp_proportion_);
+  WriteToken(os, binary, "</GumbelSoftmaxFlopsComponent>");
+}
+
+// =====================================================================================
+// CopyNComponent
+// =====================================================================================
+void CopyNComponent::InitFromConfig(ConfigLine* cfl) {  // simple.cc:4799-4812
+  scale_ = 1.0;
+  bool ok = cfl->GetValue("input-dim", &input_dim_) && cfl->GetValue("output-dim", &output_dim_);
+  if (!ok) KALDI_ERR << "input-dim and output-dim must both be provided.";
+  if (input_dim_ <= 0 || output_dim_ % input_dim_ != 0)
+    KALDI_ERR << "Invalid values input-dim=" << input_dim_ << " output-dim=" << output_dim_;
+  cfl->GetValue("scale", &scale_);
+  if (cfl->HasUnusedValues()) KALDI_ERR << "Could not process these elements in initializer: " << cfl->UnusedValues();
+}
+void CopyNComponent::Read(std::istream& is, bool binary) {  // simple.cc:4814-4822
+  ExpectOneOrTwoTokens(is, binary, "<CopyNComponent>", "<InputDim>");
+  ReadBasicType(is, binary, &input_dim_);
+  ExpectToken(is, binary, "<OutputDim>");
+  ReadBasicType(is, binary, &output_dim_);
+  ExpectToken(is, binary, "<Scale>");
+  ReadBasicType(is, binary, &scale_);
+  ExpectToken(is, binary, "</CopyNComponent>");
+}
+void CopyNComponent::Write(std::ostream& os, bool binary) const {  // simple.cc:4824-4833
+  WriteToken(os, binary, "<CopyNComponent>");
+  WriteToken(os, binary, "<InputDim>");
+  WriteBasicType(os, binary, input_dim_);
+  WriteToken(os, binary, "<OutputDim>");
+  WriteBasicType(os, binary, output_dim_);
+  WriteToken(os, binary, "<Scale>");
+  WriteBasicType(os, binary, scale_);
+  WriteToken(os, binary, "</CopyNComponent>");
+}
+std::string CopyNComponent::Info() const {
+  std::ostringstream stream;
+  stream << Type() << ", input-dim=" << input_dim_ << ", output-dim=" << output_dim_ << ", scale=" << scale_;
+  return stream.str();
+}
+void* CopyNComponent::Propagate(const ComponentPrecomputedIndexes*, const CuMatrixBase<BaseFloat>& in,
+                                CuMatrixBase<BaseFloat>* out) const {  // simple.cc:4843-4852
+  KALDI_ASSERT(out->NumRows() == in.NumRows() && out->NumCols() == output_dim_ && in.NumCols() == input_dim_);
+  CheckStatus(tdnnf_copyn_fwd(CurrentContext(), in.Data(), in.NumRows(), in.NumCols(), in.Stride(), out->Data(),
+                              out->NumCols(), out->Stride(), scale_));
+  return NULL;
+}
+void CopyNComponent::Backprop(const std::string&, const ComponentPrecomputedIndexes*, const CuMatrixBase<BaseFloat>&,
+                              const CuMatrixBase<BaseFloat>&, const CuMatrixBase<BaseFloat>& out_deriv, void*, Component*,
+                              CuMatrixBase<BaseFloat>* in_deriv) const {  // simple.cc:4854-4867
+  if (in_deriv)
+    CheckStatus(tdnnf_copyn_bwd(CurrentContext(), out_deriv.Data(), out_deriv.NumRows(), out_deriv.NumCols(),
+                                out_deriv.Stride(), in_deriv->Data(), in_deriv->NumCols(), in_deriv->Stride(), scale_));
+}
+
+// =====================================================================================
+// OnehotFunctionComponent / ConstantFunctionComponent
+// =====================================================================================
+std::string VectorFunctionComponentBase::Info() const {  // simple.cc:9482-9492
+  std::ostringstream stream;
+  stream << UpdatableComponent::Info() << ", " << Type() << ", input-dim=" << InputDim() << ", output-dim=" << OutputDim()
+         << ", is-updatable=" << std::boolalpha << is_updatable_ << ", use-natural-gradient=" << std::boolalpha
+         << use_natural_gradient_;
+  PrintParameterStats(stream, "output", output_, true);
+  return stream.str();
+}
+void* OnehotFunctionComponent::Propagate(const ComponentPrecomputedIndexes*, const CuMatrixBase<BaseFloat>&,
+                                         CuMatrixBase<BaseFloat>* out) const {  // simple.cc:9504-9519
+  KALDI_ASSERT(out->NumCols() == output_.Dim());
+  const float u = RandUniformOpen();  // uniform_.SetRandUniform(): one draw per minibatch; the input is ignored
+  CheckStatus(tdnnf_onehot_fwd(CurrentContext(), out->Data(), out->NumRows(), out->NumCols(), out->Stride(), u));
+  return NULL;
+}
+void* ConstantFunctionComponent::Propagate(const ComponentPrecomputedIndexes*, const CuMatrixBase<BaseFloat>&,
+                                           CuMatrixBase<BaseFloat>* out) const {  // simple.cc:2602-2608
+  KALDI_ASSERT(out->NumCols() == output_.Dim());
+  CheckStatus(tdnnf_copy_rows_from_vec(CurrentContext(), output_.Data(), out->Data(), out->NumRows(), out->NumCols(),
+                                       out->Stride()));
+  return NULL;
+}
+void VectorFunctionComponentBase::Backprop(const std::string&, const ComponentPrecomputedIndexes*,
+                                           const CuMatrixBase<BaseFloat>&, const CuMatrixBase<BaseFloat>&,
+                                           const CuMatrixBase<BaseFloat>& out_deriv, void*, Component* to_update_in,
+                                           CuMatrixBase<BaseFloat>*) const {  // simple.cc:9521-9552, 2610-2642
+  // in_deriv is untouched: kBackpropAdds and the output does not depend on the input.
+  if (to_update_in) {
+    VectorFunctionComponentBase* to_update = dynamic_cast<VectorFunctionComponentBase*>(to_update_in);
+    KALDI_ASSERT(to_update != NULL);
+    if (to_update->is_updatable_) {
+      KALDI_ASSERT(out_deriv.NumCols() == to_update->output_.Dim());
+      BaseFloat factor;
+      if (to_update->use_natural_gradient_ && !to_update->is_gradient_)
+        factor = to_update->preconditioner_.PreconditionDirectionsScale() * to_update->learning_rate_;
+      else
+        factor = to_update->PlainUpdateFactor() * to_update->learning_rate_;
+      CheckStatus(tdnnf_add_row_sum(CurrentContext(), out_deriv.Data(), out_deriv.NumRows(), out_deriv.NumCols(),
+                                    out_deriv.Stride(), factor, to_update->output_.Data()));
+    }
+    if (PrintsLogAlpha() && g_print_log_alpha) PrintLogAlpha(output_.Data(), output_.Dim());
+  }
+}
+void VectorFunctionComponentBase::Read(std::istream& is, bool binary) {  // simple.cc:9554-9591 (no MaxChange/L2 branch)
+  std::string token;
+  ReadToken(is, binary, &token);
+  if (token == "<" + Type() + ">") ReadToken(is, binary, &token);
+  if (token == "<LearningRateFactor>") { ReadBasicType(is, binary, &learning_rate_factor_); ReadToken(is, binary, &token); }
+  else learning_rate_factor_ = 1.0;
+  if (token == "<IsGradient>") { ReadBasicType(is, binary, &is_gradient_); ReadToken(is, binary, &token); }
+  else is_gradient_ = false;
+  if (token == "<LearningRate>") { ReadBasicType(is, binary, &learning_rate_); ReadToken(is, binary, &token); }
+  else learning_rate_ = 0.001;
+  if (token == "<InputDim>") ReadBasicType(is, binary, &input_dim_);
+  else KALDI_ERR << "Expected token <InputDim>, got " << token;
+  ExpectToken(is, binary, "<Output>");
+  output_.Read(is, binary);
+  ExpectToken(is, binary, "<IsUpdatable>");
+  ReadBasicType(is, binary, &is_updatable_);
+  ExpectToken(is, binary, "<UseNaturalGradient>");
+  ReadBasicType(is, binary, &use_natural_gradient_);
+  ExpectToken(is, binary, "</" + Type() + ">");
+}
+void VectorFunctionComponentBase::Write(std::ostream& os, bool binary) const {  // simple.cc:9593-9604
+  WriteUpdatableCommon(os, binary);
+  WriteToken(os, binary, "<InputDim>");
+  WriteBasicType(os, binary, input_dim_);
+  WriteToken(os, binary, "<Output>");
+  output_.Write(os, binary);
+  WriteToken(os, binary, "<IsUpdatable>");
+  WriteBasicType(os, binary, is_updatable_);
+  WriteToken(os, binary, "<UseNaturalGradient>");
+  WriteBasicType(os, binary, use_natural_gradient_);
+  WriteToken(os, binary, "</" + Type() + ">");
+}
+void VectorFunctionComponentBase::Scale(BaseFloat scale) {  // simple.cc:9610-9618
+  if (is_updatable_) {
+    if (scale == 0.0) output_.SetZero();
+    else output_.Scale(scale);
+  }
+}
+void VectorFunctionComponentBase::Add(BaseFloat alpha, const Component& other_in) {  // simple.cc:9620-9627
+  if (is_updatable_) {
+    const VectorFunctionComponentBase* other = dynamic_cast<const VectorFunctionComponentBase*>(&other_in);
+    KALDI_ASSERT(other != NULL);
+    output_.AddVec(alpha, other->output_);
+  }
+}
+void VectorFunctionComponentBase::PerturbParams(BaseFloat stddev) {  // simple.cc:9629-9633
+  CuVector temp_output;
+  temp_output.CopyFromHost(RandnVector(output_.Dim(), 1.0, 0.0));
+  output_.AddVec(stddev, temp_output);
+}
+BaseFloat VectorFunctionComponentBase::DotProduct(const UpdatableComponent& other_in) const {  // simple.cc:9635-9642
+  KALDI_ASSERT(is_updatable_);
+  const VectorFunctionComponentBase* other = dynamic_cast<const VectorFunctionComponentBase*>(&other_in);
+  KALDI_ASSERT(other != NULL);
+  return VecVec(output_, other->output_);
+}
+void VectorFunctionComponentBase::InitFromConfig(ConfigLine* cfl) {  // simple.cc:9644-9663
+  int32 output_dim = 0;
+  InitLearningRatesFromConfig(cfl);
+  bool ok = cfl->GetValue("output-dim", &output_dim) && cfl->GetValue("input-dim", &input_dim_);
+  cfl->GetValue("is-updatable", &is_updatable_);
+  cfl->GetValue("use-natural-gradient", &use_natural_gradient_);
+  BaseFloat output_mean = 0.0, output_stddev = 0.0;
+  cfl->GetValue("output-mean", &output_mean);
+  cfl->GetValue("output-stddev", &output_stddev);
+  if (!ok || cfl->HasUnusedValues() || input_dim_ <= 0 || output_dim <= 0) KALDI_ERR << "Bad initializer " << cfl->WholeLine();
+  output_.CopyFromHost(RandnVector(output_dim, output_stddev, output_mean));
+}
+int32 VectorFunctionComponentBase::NumParameters() const {
+  KALDI_ASSERT(is_updatable_);
+  return output_.Dim();
+}
+void VectorFunctionComponentBase::Vectorize(std::vector<BaseFloat>* params) const { *params = output_.ToHost(); }
+void VectorFunctionComponentBase::UnVectorize(const std::vector<BaseFloat>& params) {
+  KALDI_ASSERT((int32)params.size() == output_.Dim());
+  output_.CopyFromHost(params);
+}
+void VectorFunctionComponentBase::ConsolidateMemory() {
+  OnlineNaturalGradient temp(preconditioner_);
+  preconditioner_.Swap(&temp);
+}
+
+// =====================================================================================
+// ElementwiseProductComponent
+// =====================================================================================
+void ElementwiseProductComponent::Init(int32 input_dim, int32 output_dim) {  // simple.cc:237-243
+  input_dim_ = input_dim;
+  output_dim_ = output_dim;
+  KALDI_ASSERT(input_dim_ > 0 && output_dim_ >= 0);
+  KALDI_ASSERT(input_dim_ > output_dim_);
+  KALDI_ASSERT(input_dim_ % output_dim_ == 0);
+}
+void ElementwiseProductComponent::InitFromConfig(ConfigLine* cfl) {  // simple.cc:245-254
+  int32 input_dim = 0, output_dim = 0;
+  bool ok = cfl->GetValue("output-dim", &output_dim) && cfl->GetValue("input-dim", &input_dim);
+  if (!ok || cfl->HasUnusedValues() || output_dim <= 0)
+    KALDI_ERR << "Invalid initializer for layer of type " << Type() << ": \"" << cfl->WholeLine() << "\"";
+  Init(input_dim, output_dim);
+}
+void* ElementwiseProductComponent::Propagate(const ComponentPrecomputedIndexes*, const CuMatrixBase<BaseFloat>& in,
+                                             CuMatrixBase<BaseFloat>* out) const {  // simple.cc:256-272
+  KALDI_ASSERT(in.NumCols() == input_dim_);
+  if (input_dim_ != 2 * output_dim_)
+    KALDI_ERR << "ElementwiseProductComponent: only the two-input form used by the NAS recipes is implemented";
+  CheckStatus(tdnnf_elementwise_product_fwd(CurrentContext(), in.Data(), in.NumRows(), output_dim_, in.Stride(), out->Data(),
+                                            out->Stride()));
+  return NULL;
+}
+void ElementwiseProductComponent::Backprop(const std::string&, const ComponentPrecomputedIndexes*,
+                                           const CuMatrixBase<BaseFloat>& in_value, const CuMatrixBase<BaseFloat>&,
+                                           const CuMatrixBase<BaseFloat>& out_deriv, void*, Component*,
+                                           CuMatrixBase<BaseFloat>* in_deriv) const {  // simple.cc:274-299
+  if (!in_deriv) return;
+  if (input_dim_ != 2 * output_dim_)
+    KALDI_ERR << "ElementwiseProductComponent: only the two-input form used by the NAS recipes is implemented";
+  CheckStatus(tdnnf_elementwise_product_bwd(CurrentContext(), in_value.Data(), in_value.Stride(), out_deriv.Data(),
+                                            out_deriv.Stride(), in_deriv->Data(), in_deriv->Stride(), in_value.NumRows(),
+                                            output_dim_));
+}
+void ElementwiseProductComponent::Read(std::istream& is, bool binary) {
+  ExpectOneOrTwoTokens(is, binary, "<ElementwiseProductComponent>", "<InputDim>");
+  ReadBasicType(is, binary, &input_dim_);
+  ExpectToken(is, binary, "<OutputDim>");
+  ReadBasicType(is, binary, &output_dim_);
+  ExpectToken(is, binary, "</ElementwiseProductComponent>");
+}
+void ElementwiseProductComponent::Write(std::ostream& os, bool binary) const {
+  WriteToken(os, binary, "<ElementwiseProductComponent>");
+  WriteToken(os, binary, "<InputDim>");
+  WriteBasicType(os, binary, input_dim_);
+  WriteToken(os, binary, "<OutputDim>");
+  WriteBasicType(os, binary, output_dim_);
+  WriteToken(os, binary, "</ElementwiseProductComponent>");
+}
+
+// =====================================================================================
+// BatchNormTestComponent
+// =====================================================================================
+void BatchNormTestComponent::ComputeDerived() {  // norm.cc:680-713
+  if (dim_ == 0) return;
+  if (count_ == 0.0) {
+    KaldiWarn("Test-mode is set but there is no data count.  Creating random counts.  This only makes sense in "
+              "unit-tests (or compute_prob_*.0.log).  If you see this elsewhere, something is very wrong.");
+    count_ = 1.0;
+    stats_sum_.assign(block_dim_, 0.0);
+    stats_sumsq_.assign(block_dim_, 0.0);
+    for (int32 i = 0; i < block_dim_; ++i) {
+      stats_sum_[i] = ShimRandGauss();
+      stats_sumsq_[i] = ShimRandGauss();
+      stats_sumsq_[i] += stats_sum_[i] * stats_sum_[i];
+    }
+  }
+  std::vector<BaseFloat> offset(block_dim_), scale(block_dim_);
+  for (int32 i = 0; i < block_dim_; ++i) {
+    BaseFloat off = (BaseFloat)stats_sum_[i];  // offset_.CopyFromVec(stats_sum_)
+    off *= (BaseFloat)(-1.0 / count_);         // now -mean
+    BaseFloat sc = (BaseFloat)stats_sumsq_[i];
+    sc *= (BaseFloat)(1.0 / count_);
+    sc += -1.0f * off * off;                   // variance
+    sc = std::max(sc, 0.0f);                   // ApplyFloor(0.0)
+    sc += epsilon_;
+    sc = std::pow(sc, -0.5f);
+    sc *= target_rms_;
+    off *= sc;                                 // -(scale * mean)
+    scale[i] = sc;
+    offset[i] = off;
+  }
+  offset_.CopyFromHost(offset);
+  scale_.CopyFromHost(scale);
+}
+void BatchNormTestComponent::SetTestMode(bool test_mode) {  // norm.cc:715-718
+  test_mode_ = test_mode;
+  ComputeDerived();
+}
+void BatchNormTestComponent::Check() const {  // norm.cc:720-723
+  KALDI_ASSERT(dim_ > 0 && block_dim_ > 0 && dim_ % block_dim_ == 0 && epsilon_ > 0.0 && target_rms_ > 0.0);
+}
+BatchNormTestComponent::BatchNormTestComponent(const BatchNormTestComponent& other)  // norm.cc:725-732
+    : dim_(other.dim_), block_dim_(other.block_dim_), epsilon_(other.epsilon_), target_rms_(other.target_rms_),
+      test_mode_(other.test_mode_), count_(other.count_), stats_sum_(other.stats_sum_), stats_sumsq_(other.stats_sumsq_) {
+  ComputeDerived();
+  Check();
+}
+void BatchNormTestComponent::SetStats(int32 dim, int32 block_dim, BaseFloat epsilon, BaseFloat target_rms, double count,
+                                      const std::vector<double>& sum, const std::vector<double>& sumsq) {
+  dim_ = dim;
+  block_dim_ = block_dim;
+  epsilon_ = epsilon;
+  target_rms_ = target_rms;
+  count_ = count;
+  stats_sum_ = sum;
+  stats_sumsq_ = sumsq;
+  KALDI_ASSERT((int32)sum.size() == block_dim && (int32)sumsq.size() == block_dim);
+  Check();
+  ComputeDerived();
+}
+std::string BatchNormTestComponent::Info() const {  // norm.cc:735-755
+  std::ostringstream stream;
+  stream << Type() << ", dim=" << dim_ << ", block-dim=" << block_dim_ << ", epsilon=" << epsilon_
+         << ", target-rms=" << target_rms_ << ", count=" << count_ << ", test-mode=" << (test_mode_ ? "true" : "false");
+  if (count_ > 0) {
+    std::vector<BaseFloat> mean(block_dim_), var(block_dim_);
+    for (int32 i = 0; i < block_dim_; ++i) {
+      mean[i] = (BaseFloat)(stats_sum_[i] / count_);
+      var[i] = std::sqrt(std::max<BaseFloat>(0.0f, (BaseFloat)(stats_sumsq_[i] / count_) - mean[i] * mean[i]));
+    }
+    stream << ", data-mean=" << SummarizeVector(mean) << ", data-stddev=" << SummarizeVector(var);
+  }
+  return stream.str();
+}
+void BatchNormTestComponent::InitFromConfig(ConfigLine*) {}  // norm.cc:757-759 (empty in the reference)
+
+void* BatchNormTestComponent::Propagate(const ComponentPrecomputedIndexes*, const CuMatrixBase<BaseFloat>& in,
+                                        CuMatrixBase<BaseFloat>* out) const {  // norm.cc:843-877
+  KALDI_ASSERT(SameDim(in, *out) && (in.NumCols() == dim_ || in.NumCols() == block_dim_));
+  int32 rows = in.NumRows(), cols = in.NumCols(), in_stride = in.Stride(), out_stride = out->Stride();
+  if (in.NumCols() != block_dim_) {
+    KALDI_ASSERT(in.Stride() == in.NumCols() && out->Stride() == out->NumCols());
+    int32 ratio = dim_ / block_dim_;
+    rows = rows * ratio;
+    cols = cols / ratio;
+    in_stride = out_stride = cols;
+  }
+  if (!test_mode_) {
+    // the reference falls off the end of a non-void function here (quirk Q8): undefined behaviour
+    KALDI_ERR << "BatchNormTestComponent::Propagate is only defined in test mode (norm.cc:863-877)";
+  }
+  if (offset_.Dim() != block_dim_) {
+    if (count_ == 0) KALDI_ERR << "Test mode set in BatchNormTestComponent, but no stats.";
+    else KALDI_ERR << "Code error in BatchNormTestComponent";
+  }
+  CheckStatus(tdnnf_scale_offset_rows(CurrentContext(), in.Data(), rows, cols, in_stride, out->Data(), out_stride,
+                                      scale_.Data(), offset_.Data()));
+  return NULL;
+}
+void BatchNormTestComponent::Backprop(const std::string&, const ComponentPrecomputedIndexes*, const CuMatrixBase<BaseFloat>&,
+                                      const CuMatrixBase<BaseFloat>& out_value, const CuMatrixBase<BaseFloat>& out_deriv,
+                                      void*, Component*, CuMatrixBase<BaseFloat>* in_deriv) const {  // norm.cc:879-922
+  KALDI_ASSERT(in_deriv != NULL);
+  KALDI_ASSERT(SameDim(out_value, out_deriv) && SameDim(out_value, *in_deriv) &&
+               (out_value.NumCols() == dim_ || out_value.NumCols() == block_dim_));
+  int32 rows = out_deriv.NumRows(), cols = out_deriv.NumCols(), od_stride = out_deriv.Stride(), id_stride = in_deriv->Stride();
+  if (out_value.NumCols() != block_dim_) {
+    KALDI_ASSERT(out_value.Stride() == out_value.NumCols() && out_deriv.Stride() == out_deriv.NumCols() &&
+                 in_deriv->Stride() == in_deriv->NumCols());
+    int32 ratio = dim_ / block_dim_;
+    rows = rows * ratio;
+    cols = cols / ratio;
+    od_stride = id_stride = cols;
+  }
+  if (!test_mode_) KALDI_ERR << "BatchNormTestComponent::Backprop is only defined in test mode (norm.cc:910-921)";
+  KALDI_ASSERT(offset_.Dim() == block_dim_);
+  CheckStatus(tdnnf_scale_offset_rows(CurrentContext(), out_deriv.Data(), rows, cols, od_stride, in_deriv->Data(), id_stride,
+                                      scale_.Data(), NULL));
+}
+void BatchNormTestComponent::Read(std::istream& is, bool binary) {  // norm.cc:931-954
+  ExpectOneOrTwoTokens(is, binary, "<BatchNormTestComponent>", "<Dim>");
+  ReadBasicType(is, binary, &dim_);
+  ExpectToken(is, binary, "<BlockDim>");
+  ReadBasicType(is, binary, &block_dim_);
+  ExpectToken(is, binary, "<Epsilon>");
+  ReadBasicType(is, binary, &epsilon_);
+  ExpectToken(is, binary, "<TargetRms>");
+  ReadBasicType(is, binary, &target_rms_);
+  ExpectToken(is, binary, "<TestMode>");
+  ReadBasicType(is, binary, &test_mode_);
+  ExpectToken(is, binary, "<Count>");
+  ReadBasicType(is, binary, &count_);
+  ExpectToken(is, binary, "<StatsMean>");
+  Vector<double> mean, var;
+  mean.Read(is, binary);
+  ExpectToken(is, binary, "<StatsVar>");
+  var.Read(is, binary);
+  KALDI_ASSERT(mean.Dim() == var.Dim());
+  stats_sum_ = mean.v;
+  stats_sumsq_ = var.v;
+  for (size_t i = 0; i < stats_sum_.size(); ++i) {
+    stats_sumsq_[i] += stats_sum_[i] * stats_sum_[i];  // AddVecVec(1.0, stats_sum_, stats_sum_, 1.0)
+    stats_sum_[i] *= count_;
+    stats_sumsq_[i] *= count_;
+  }
+  ExpectToken(is, binary, "</BatchNormTestComponent>");
+  ComputeDerived();
+  Check();
+}
+void BatchNormTestComponent::Write(std::ostream& os, bool binary) const {  // norm.cc:956-982
+  Check();
+  WriteToken(os, binary, "<BatchNormTestComponent>");
+  WriteToken(os, binary, "<Dim>");
+  WriteBasicType(os, binary, dim_);
+  WriteToken(os, binary, "<BlockDim>");
+  WriteBasicType(os, binary, block_dim_);
+  WriteToken(os, binary, "<Epsilon>");
+  WriteBasicType(os, binary, epsilon_);
+  WriteToken(os, binary, "<TargetRms>");
+  WriteBasicType(os, binary, target_rms_);
+  WriteToken(os, binary, "<TestMode>");
+  WriteBasicType(os, binary, test_mode_);
+  WriteToken(os, binary, "<Count>");
+  WriteBasicType(os, binary, count_);
+  Vector<BaseFloat> mean((int32)stats_sum_.size()), var((int32)stats_sumsq_.size());
+  for (size_t i = 0; i < stats_sum_.size(); ++i) {
+    mean.v[i] = (BaseFloat)stats_sum_[i];
+    var.v[i] = (BaseFloat)stats_sumsq_[i];
+    if (count_ != 0) {
+      mean.v[i] *= (BaseFloat)(1.0 / count_);
+      var.v[i] *= (BaseFloat)(1.0 / count_);
+      var.v[i] += -1.0f * mean.v[i] * mean.v[i];
+    }
+  }
+  WriteToken(os, binary, "<StatsMean>");
+  mean.Write(os, binary);
+  WriteToken(os, binary, "<StatsVar>");
+  var.Write(os, binary);
+  WriteToken(os, binary, "</BatchNormTestComponent>");
+}
+void BatchNormTestComponent::Scale(BaseFloat scale) {  // norm.cc:984-994
+  if (scale == 0) {
+    count_ = 0.0;
+    std::fill(stats_sum_.begin(), stats_sum_.end(), 0.0);
+    std::fill(stats_sumsq_.begin(), stats_sumsq_.end(), 0.0);
+  } else {
+    count_ *= scale;
+    for (double& x : stats_sum_) x *= scale;
+    for (double& x : stats_sumsq_) x *= scale;
+  }
+}
+void BatchNormTestComponent::Add(BaseFloat alpha, const Component& other_in) {  // norm.cc:997-1006
+  const BatchNormTestComponent* other = dynamic_cast<const BatchNormTestComponent*>(&other_in);
+  KALDI_ASSERT(other != NULL);
+  count_ += alpha * other->count_;
+  for (size_t i = 0; i < stats_sum_.size(); ++i) {
+    stats_sum_[i] += alpha * other->stats_sum_[i];
+    stats_sumsq_[i] += alpha * other->stats_sumsq_[i];
+  }
+  ComputeDerived();
+}
+
+// =====================================================================================
+// factories (itf.cc:56-293: the registrations the README adds) and edit directives
+// =====================================================================================
+Component* Component::NewComponentOfType(const std::string& component_type) {
+  Component* ans = NULL;
+  if (component_type == "TdnnDARTSV3Component") ans = new TdnnDARTSV3Component();                    // itf.cc:88-89
+  else if (component_type == "CopyNComponent") ans = new CopyNComponent();                           // itf.cc:202-203
+  else if (component_type == "BatchNormTestComponent") ans = new BatchNormTestComponent();           // itf.cc:226-227
+  else if (component_type == "OnehotFunctionComponent") ans = new OnehotFunctionComponent();         // itf.cc:250-251
+  else if (component_type == "SoftmaxFlopsComponent") ans = new SoftmaxFlopsComponent();             // itf.cc:262-263
+  else if (component_type == "GumbelSoftmaxFlopsComponent") ans = new GumbelSoftmaxFlopsComponent(); // itf.cc:270-273
+  else if (component_type == "ConstantFunctionComponent") ans = new ConstantFunctionComponent();
+  else if (component_type == "ElementwiseProductComponent") ans = new ElementwiseProductComponent();
+  if (ans != NULL) KALDI_ASSERT(component_type == ans->Type());
+  return ans;
+}
+ComponentPrecomputedIndexes* ComponentPrecomputedIndexes::NewComponentPrecomputedIndexesOfType(const std::string& cpi_type) {
+  ComponentPrecomputedIndexes* ans = NULL;
+  if (cpi_type == "TdnnDARTSV3ComponentPrecomputedIndexes") ans = new TdnnDARTSV3Component::PrecomputedIndexes();  // itf.cc:66-67
+  if (ans != NULL) KALDI_ASSERT(cpi_type == ans->Type());
+  return ans;
+}
+
+bool NameMatchesPattern(const char* name, const char* pattern) {  // kaldi nnet-parse.cc
+  if (*pattern == '*') return NameMatchesPattern(name, pattern + 1) || (*name != '\0' && NameMatchesPattern(name + 1, pattern));
+  else if (*name == *pattern) return (*name == '\0' || NameMatchesPattern(name + 1, pattern + 1));
+  else return false;
+}
+
+void ReadEditConfig(std::istream& edit_config_is, const std::vector<std::string>& names,
+                    const std::vector<Component*>& components) {  // utils.cc:1166-1415 (subset)
+  KALDI_ASSERT(names.size() == components.size());
+  std::string line;
+  while (std::getline(edit_config_is, line)) {
+    // ReadConfigLines: strip comments and surrounding space, skip empty lines; directives may also be ';' separated
+    size_t start = 0;
+    while (start <= line.size()) {
+      size_t semi = line.find(';', start);
+      std::string piece = line.substr(start, semi == std::string::npos ? std::string::npos : semi - start);
+      start = (semi == std::string::npos) ? line.size() + 1 : semi + 1;
+      size_t hash = piece.find('#');
+      if (hash != std::string::npos) piece = piece.substr(0, hash);
+      size_t b = piece.find_first_not_of(" \t\r"), e = piece.find_last_not_of(" \t\r");
+      if (b == std::string::npos) continue;
+      piece = piece.substr(b, e - b + 1);
+      ConfigLine config_line;
+      if (!config_line.ParseLine(piece)) KALDI_ERR << "Error parsing config line: " << piece;
+      const std::string& directive = config_line.FirstToken();
+      if (directive == "set-temperature-proportion") {  // utils.cc:1352-1405
+        std::string name_pattern = "*";
+        config_line.GetValue("name", &name_pattern);
+        BaseFloat proportion = -1.0;
+        if (!config_line.GetValue("proportion", &proportion))
+          KALDI_ERR << "In edits-config, expected proportion to be set in line: " << config_line.WholeLine();
+        int32 num_temp_proportions_set = 0;
+        for (size_t c = 0; c < components.size(); c++) {
+          if (NameMatchesPattern(names[c].c_str(), name_pattern.c_str())) {
+            if (TdnnDARTSV3Component* t = dynamic_cast<TdnnDARTSV3Component*>(components[c])) {
+              t->SetTempProportion(proportion);
+              num_temp_proportions_set++;
+            } else if (GumbelSoftmaxFlopsComponent* g = dynamic_cast<GumbelSoftmaxFlopsComponent*>(components[c])) {
+              g->SetTempProportion(proportion);
+              num_temp_proportions_set++;
+            }
+          }
+        }
+        KaldiLog("Set temp proportions for " + std::to_string(num_temp_proportions_set) + " components.");
+      } else if (directive == "set-learning-rate" || directive == "set-learning-rate-factor") {
+        std::string name_pattern = "*";
+        config_line.GetValue("name", &name_pattern);
+        const bool is_factor = directive == "set-learning-rate-factor";
+        BaseFloat value = -1;
+        if (!config_line.GetValue(is_factor ? "learning-rate-factor" : "learning-rate", &value))
+          KALDI_ERR << "In edits-config, expected " << (is_factor ? "learning-rate-factor" : "learning-rate")
+                    << " to be set in line: " << config_line.WholeLine();
+        int32 num_set = 0;
+        for (size_t c = 0; c < components.size(); c++) {
+          if (NameMatchesPattern(names[c].c_str(), name_pattern.c_str())) {
+            if (UpdatableComponent* u = dynamic_cast<UpdatableComponent*>(components[c])) {
+              if (is_factor) u->SetLearningRateFactor(value);
+              else u->SetUnderlyingLearningRate(value);
+              num_set++;
+            }
+          }
+        }
+        KaldiLog("Set " + directive.substr(4) + " for " + std::to_string(num_set) + " components.");
+      } else {
+        KALDI_ERR << "Directive '" << directive << "' is not currently supported (reading edit-config).";
+      }
+      if (config_line.HasUnusedValues())
+        KALDI_ERR << "Could not interpret '" << config_line.UnusedValues() << "' in edit config line "
+                  << config_line.WholeLine();
+    }
+  }
+}
+
+}  // namespace nnet3
+}  // namespace tdnnf

@@ -1,0 +1,375 @@
+// The reference's NAS components with their nnet3 Component interface intact (same class names,
+// virtuals, Properties() flags, config keys and on-disk tokens), re-hosted on the C ABI of
+// include/tdnnf_nas_b200.h: every CuMatrix/CuVector call of the reference's method bodies is
+// replaced by one fused sm_100a kernel call.  Citations are into /root/reference:
+//   conv.h = src/nnet3/nnet-convolutional-component.h, tdnn.cc = src/nnet3/nnet-tdnn-component.cc,
+//   simple.{h,cc} = src/nnet3/nnet-simple-component.{h,cc}, norm.{h,cc} = src/nnet3/nnet-normalize-component.{h,cc}
+#pragma once
+#include "shim.h"
+
+namespace tdnnf {
+namespace nnet3 {
+
+// Configuration holder for OnlineNaturalGradient (kaldi: nnet3/natural-gradient-online.h).  The
+// preconditioner itself is SURVEY.md "next" row N1; see natural_gradient.cc for what is done now.
+class OnlineNaturalGradient {
+ public:
+  OnlineNaturalGradient() : rank_(40), update_period_(1), num_samples_history_(2000.0), alpha_(4.0), frozen_(false) {}
+  void SetRank(int32 rank) { rank_ = rank; }
+  void SetUpdatePeriod(int32 update_period) { update_period_ = update_period; }
+  void SetNumSamplesHistory(BaseFloat h) { num_samples_history_ = h; }
+  void SetAlpha(BaseFloat alpha) { alpha_ = alpha; }
+  int32 GetRank() const { return rank_; }
+  int32 GetUpdatePeriod() const { return update_period_; }
+  BaseFloat GetNumSamplesHistory() const { return num_samples_history_; }
+  BaseFloat GetAlpha() const { return alpha_; }
+  void Freeze(bool frozen) { frozen_ = frozen; }
+  void Swap(OnlineNaturalGradient* other) { std::swap(*this, *other); }
+  // Returns the scale the caller multiplies into the learning rate.  Currently the identity
+  // preconditioner (scale 1, directions untouched) with a one-time warning; see natural_gradient.cc.
+  BaseFloat PreconditionDirectionsScale() const;
+ private:
+  int32 rank_, update_period_;
+  BaseFloat num_samples_history_, alpha_;
+  bool frozen_;
+};
+
+// Data-parallel world size used to normalise the FLOPs penalty by the GLOBAL row count
+// (the reference divides by its local rows, simple.cc:10154; summed over G ranks that
+// would count the penalty G times).  Default 1 = the reference's arithmetic.
+void SetDataParallelWorldSize(int32 g);
+int32 GetDataParallelWorldSize();
+// The reference prints "log_alpha [ ... ]" to stdout every minibatch per component (tdnn.cc:571,
+// simple.cc:2640), which costs a device->host sync each time; off by default here.
+void SetPrintLogAlpha(bool b);
+
+// ------------------------------------------------------------------ TdnnDARTSV3Component (conv.h:112-332)
+class TdnnDARTSV3Component : public UpdatableComponent {
+ public:
+  TdnnDARTSV3Component();
+  TdnnDARTSV3Component(const TdnnDARTSV3Component& other);
+  virtual int32 InputDim() const { return linear_params_.NumCols() / static_cast<int32>(time_offsets_.size()); }
+  virtual int32 OutputDim() const { return linear_params_.NumRows(); }
+  virtual std::string Info() const;
+  virtual void InitFromConfig(ConfigLine* cfl);
+  virtual std::string Type() const { return "TdnnDARTSV3Component"; }
+  virtual int32 Properties() const {
+    return kUpdatableComponent | kReordersIndexes | kBackpropAdds | (bias_params_.Dim() == 0 ? kPropagateAdds : 0) |
+           kBackpropNeedsInput | kUsesMemo;
+  }
+  virtual void* Propagate(const ComponentPrecomputedIndexes* indexes, const CuMatrixBase<BaseFloat>& in,
+                          CuMatrixBase<BaseFloat>* out) const;
+  virtual void Backprop(const std::string& debug_info, const ComponentPrecomputedIndexes* indexes,
+                        const CuMatrixBase<BaseFloat>& in_value, const CuMatrixBase<BaseFloat>& out_value,
+                        const CuMatrixBase<BaseFloat>& out_deriv, void* memo, Component* to_update,
+                        CuMatrixBase<BaseFloat>* in_deriv) const;
+  virtual void DeleteMemo(void* memo) const;
+  virtual void Read(std::istream& is, bool binary);
+  virtual void Write(std::ostream& os, bool binary) const;
+  virtual Component* Copy() const { return new TdnnDARTSV3Component(*this); }
+  virtual void ReorderIndexes(std::vector<Index>* input_indexes, std::vector<Index>* output_indexes) const;
+  virtual void GetInputIndexes(const MiscComputationInfo& misc_info, const Index& output_index,
+                               std::vector<Index>* desired_indexes) const;
+  virtual bool IsComputable(const MiscComputationInfo& misc_info, const Index& output_index,
+                            const IndexSet& input_index_set, std::vector<Index>* used_inputs) const;
+  virtual ComponentPrecomputedIndexes* PrecomputeIndexes(const MiscComputationInfo& misc_info,
+                                                         const std::vector<Index>& input_indexes,
+                                                         const std::vector<Index>& output_indexes,
+                                                         bool need_backprop) const;
+  virtual void Scale(BaseFloat scale);
+  virtual void Add(BaseFloat alpha, const Component& other);
+  virtual void PerturbParams(BaseFloat stddev);
+  virtual BaseFloat DotProduct(const UpdatableComponent& other) const;
+  virtual int32 NumParameters() const;
+  virtual void Vectorize(std::vector<BaseFloat>* params) const;
+  virtual void UnVectorize(const std::vector<BaseFloat>& params);
+  virtual void FreezeNaturalGradient(bool freeze);
+
+  class PrecomputedIndexes : public ComponentPrecomputedIndexes {
+   public:
+    PrecomputedIndexes() {}
+    PrecomputedIndexes(const PrecomputedIndexes& other) : row_stride(other.row_stride), row_offsets(other.row_offsets) {}
+    virtual PrecomputedIndexes* Copy() const;
+    virtual void Write(std::ostream& os, bool binary) const;
+    virtual void Read(std::istream& os, bool binary);
+    virtual std::string Type() const { return "TdnnDARTSV3ComponentPrecomputedIndexes"; }
+    virtual ~PrecomputedIndexes() {}
+    int32 row_stride;
+    std::vector<int32> row_offsets;
+  };
+
+  CuMatrix& LinearParams() { return linear_params_; }
+  CuVector& BiasParams() { return bias_params_; }
+  const CuMatrix& LinearParams() const { return linear_params_; }
+  const CuVector& BiasParams() const { return bias_params_; }
+  BaseFloat OrthonormalConstraint() const { return orthonormal_constraint_; }
+  void ConsolidateMemory();
+  void SetTempProportion(BaseFloat p) { temp_proportion_ = p; }
+  BaseFloat TempProportion() const { return temp_proportion_; }
+  void SetTestMode(bool test_mode) { test_mode_ = test_mode; }
+  bool test_mode_;  // public, unused -- as in the reference (conv.h:241)
+  // A parameter-less instance that only knows its time offsets: enough for the index methods
+  // (ReorderIndexes, PrecomputeIndexes, GetInputIndexes, IsComputable), which need no device.
+  static TdnnDARTSV3Component* NewForIndexing(const std::vector<int32>& time_offsets);
+
+  // The memo returned by Propagate: the mixing coefficients (what the reference keeps) plus the
+  // effective GEMM weights derived from them; both stay on the device.
+  struct Memo {
+    CuVector coef, weff;
+  };
+
+ private:
+  int32 Flags() const;
+  // share_offset_index of tdnn.cc:227-241; KALDI_ERR where the reference reads it uninitialised.
+  int32 ShareOffsetIndex() const;
+  static void ModifyComputationIo(time_height_convolution::ConvolutionComputationIo* io);
+  void Check() const;
+  void UpdateNaturalGradient(const PrecomputedIndexes& indexes, const CuMatrixBase<BaseFloat>& in_value,
+                             const CuMatrixBase<BaseFloat>& out_deriv, const CuMatrix& linear_params_temp_,
+                             const Memo& memo, int32 share_offset_index_temp_, int32 model_flags,
+                             BaseFloat temp_proportion_temp_);
+  void UpdateSimple(const PrecomputedIndexes& indexes, const CuMatrixBase<BaseFloat>& in_value,
+                    const CuMatrixBase<BaseFloat>& out_deriv);
+
+  bool use_gumbel_, use_entropy_, free_select_, update_alpha_, update_theta_, uniform_sample_;
+  BaseFloat temp_proportion_;
+  std::vector<int32> time_offsets_;
+  CuMatrix linear_params_;
+  CuVector bias_params_;
+  BaseFloat orthonormal_constraint_;
+  bool use_natural_gradient_;
+  OnlineNaturalGradient preconditioner_in_, preconditioner_out_;
+};
+
+// ------------------------------------------------------------------ {Gumbel}SoftmaxFlopsComponent (simple.h:2924-3040)
+class SoftmaxFlopsComponent : public RandomComponent {
+ public:
+  SoftmaxFlopsComponent() : dim_(0), scale_(1.0) {}
+  SoftmaxFlopsComponent(const SoftmaxFlopsComponent& other) : RandomComponent(other), dim_(other.dim_), scale_(other.scale_) {}
+  void Init(int32 dim, BaseFloat scale) { scale_ = scale; dim_ = dim; }
+  virtual int32 Properties() const {
+    return kBackpropInPlace | kSimpleComponent | kBackpropNeedsInput | kBackpropNeedsOutput | kRandomComponent;
+  }
+  virtual std::string Type() const { return "SoftmaxFlopsComponent"; }
+  virtual void InitFromConfig(ConfigLine* cfl);
+  virtual int32 InputDim() const { return dim_; }
+  virtual int32 OutputDim() const { return dim_; }
+  virtual void Read(std::istream& is, bool binary);
+  virtual void Write(std::ostream& os, bool binary) const;
+  virtual void* Propagate(const ComponentPrecomputedIndexes* indexes, const CuMatrixBase<BaseFloat>& in,
+                          CuMatrixBase<BaseFloat>* out) const;
+  virtual void Backprop(const std::string& debug_info, const ComponentPrecomputedIndexes* indexes,
+                        const CuMatrixBase<BaseFloat>& in_value, const CuMatrixBase<BaseFloat>& out_value,
+                        const CuMatrixBase<BaseFloat>& out_deriv, void* memo, Component* to_update,
+                        CuMatrixBase<BaseFloat>* in_deriv) const;
+  virtual Component* Copy() const { return new SoftmaxFlopsComponent(*this); }
+  virtual std::string Info() const;
+ private:
+  int32 dim_;
+  BaseFloat scale_;
+};
+
+class GumbelSoftmaxFlopsComponent : public RandomComponent {
+ public:
+  GumbelSoftmaxFlopsComponent() : dim_(0), scale_(1.0), temp_proportion_(0.0) {}
+  GumbelSoftmaxFlopsComponent(const GumbelSoftmaxFlopsComponent& other)
+      : RandomComponent(other), dim_(other.dim_), scale_(other.scale_), temp_proportion_(other.temp_proportion_) {}
+  void Init(int32 dim, BaseFloat scale, BaseFloat temp_proportion) { temp_proportion_ = temp_proportion; scale_ = scale; dim_ = dim; }
+  virtual int32 Properties() const {
+    return kBackpropInPlace | kSimpleComponent | kBackpropNeedsInput | kBackpropNeedsOutput | kRandomComponent;
+  }
+  virtual std::string Type() const { return "GumbelSoftmaxFlopsComponent"; }
+  virtual void InitFromConfig(ConfigLine* cfl);
+  virtual int32 InputDim() const { return dim_; }
+  virtual int32 OutputDim() const { return dim_; }
+  virtual void Read(std::istream& is, bool binary);
+  virtual void Write(std::ostream& os, bool binary) const;
+  virtual void* Propagate(const ComponentPrecomputedIndexes* indexes, const CuMatrixBase<BaseFloat>& in,
+                          CuMatrixBase<BaseFloat>* out) const;
+  virtual void Backprop(const std::string& debug_info, const ComponentPrecomputedIndexes* indexes,
+                        const CuMatrixBase<BaseFloat>& in_value, const CuMatrixBase<BaseFloat>& out_value,
+                        const CuMatrixBase<BaseFloat>& out_deriv, void* memo, Component* to_update,
+                        CuMatrixBase<BaseFloat>* in_deriv) const;
+  virtual Component* Copy() const { return new GumbelSoftmaxFlopsComponent(*this); }
+  virtual std::string Info() const;
+  void SetTempProportion(BaseFloat p) { temp_proportion_ = p; }
+  BaseFloat TempProportion() const { return temp_proportion_; }
+ private:
+  int32 dim_;
+  BaseFloat scale_;
+  BaseFloat temp_proportion_;
+};
+
+// ------------------------------------------------------------------ CopyNComponent (simple.h:2119-2150)
+class CopyNComponent : public Component {
+ public:
+  CopyNComponent() : input_dim_(0), output_dim_(0), scale_(1.0) {}
+  CopyNComponent(const CopyNComponent& other) : input_dim_(other.input_dim_), output_dim_(other.output_dim_), scale_(other.scale_) {}
+  virtual int32 Properties() const { return kSimpleComponent | kPropagateAdds | kBackpropAdds; }
+  virtual std::string Type() const { return "CopyNComponent"; }
+  virtual void InitFromConfig(ConfigLine* cfl);
+  virtual int32 InputDim() const { return input_dim_; }
+  virtual int32 OutputDim() const { return output_dim_; }
+  virtual void Read(std::istream& is, bool binary);
+  virtual void Write(std::ostream& os, bool binary) const;
+  virtual void* Propagate(const ComponentPrecomputedIndexes* indexes, const CuMatrixBase<BaseFloat>& in,
+                          CuMatrixBase<BaseFloat>* out) const;
+  virtual void Backprop(const std::string& debug_info, const ComponentPrecomputedIndexes* indexes,
+                        const CuMatrixBase<BaseFloat>& in_value, const CuMatrixBase<BaseFloat>& out_value,
+                        const CuMatrixBase<BaseFloat>& out_deriv, void* memo, Component* to_update,
+                        CuMatrixBase<BaseFloat>* in_deriv) const;
+  virtual Component* Copy() const { return new CopyNComponent(*this); }
+  virtual std::string Info() const;
+ private:
+  int32 input_dim_, output_dim_;
+  BaseFloat scale_;
+};
+
+// ------------------------------------------------------------------ Onehot / Constant function (simple.h:2734-2794)
+// OnehotFunctionComponent and the reference's modified ConstantFunctionComponent share everything
+// except Propagate, the non-natural-gradient learning-rate factor (x5 for Constant, simple.cc:2636) and
+// the log_alpha print (simple.cc:2640).
+class VectorFunctionComponentBase : public UpdatableComponent {
+ public:
+  VectorFunctionComponentBase() : UpdatableComponent(), input_dim_(-1), is_updatable_(true), use_natural_gradient_(true) {}
+  VectorFunctionComponentBase(const VectorFunctionComponentBase& other)
+      : UpdatableComponent(other), input_dim_(other.input_dim_), output_(other.output_),
+        is_updatable_(other.is_updatable_), use_natural_gradient_(other.use_natural_gradient_),
+        preconditioner_(other.preconditioner_) {}
+  virtual int32 InputDim() const { return input_dim_; }
+  virtual int32 OutputDim() const { return output_.Dim(); }
+  virtual std::string Info() const;
+  virtual void InitFromConfig(ConfigLine* cfl);
+  virtual int32 Properties() const {
+    return kSimpleComponent | (is_updatable_ ? kUpdatableComponent : 0) |
+           (InputDim() == OutputDim() ? kPropagateInPlace : 0) | kBackpropAdds;
+  }
+  virtual void Backprop(const std::string& debug_info, const ComponentPrecomputedIndexes* indexes,
+                        const CuMatrixBase<BaseFloat>& in_value, const CuMatrixBase<BaseFloat>& out_value,
+                        const CuMatrixBase<BaseFloat>& out_deriv, void* memo, Component* to_update,
+                        CuMatrixBase<BaseFloat>* in_deriv) const;
+  virtual void Read(std::istream& is, bool binary);
+  virtual void Write(std::ostream& os, bool binary) const;
+  virtual void Scale(BaseFloat scale);
+  virtual void Add(BaseFloat alpha, const Component& other);
+  virtual void PerturbParams(BaseFloat stddev);
+  virtual BaseFloat DotProduct(const UpdatableComponent& other) const;
+  virtual int32 NumParameters() const;
+  virtual void Vectorize(std::vector<BaseFloat>* params) const;
+  virtual void UnVectorize(const std::vector<BaseFloat>& params);
+  virtual void ConsolidateMemory();
+  CuVector& Output() { return output_; }
+  const CuVector& Output() const { return output_; }
+ protected:
+  virtual BaseFloat PlainUpdateFactor() const = 0;  // multiplies learning_rate_ when NG is off
+  virtual bool PrintsLogAlpha() const = 0;
+  int32 input_dim_;
+  CuVector output_;
+  bool is_updatable_;
+  bool use_natural_gradient_;
+  OnlineNaturalGradient preconditioner_;
+};
+
+class OnehotFunctionComponent : public VectorFunctionComponentBase {
+ public:
+  OnehotFunctionComponent() {}
+  OnehotFunctionComponent(const OnehotFunctionComponent& other) : VectorFunctionComponentBase(other) {}
+  virtual std::string Type() const { return "OnehotFunctionComponent"; }
+  virtual void* Propagate(const ComponentPrecomputedIndexes* indexes, const CuMatrixBase<BaseFloat>& in,
+                          CuMatrixBase<BaseFloat>* out) const;
+  virtual Component* Copy() const { return new OnehotFunctionComponent(*this); }
+ protected:
+  virtual BaseFloat PlainUpdateFactor() const { return 1.0; }  // simple.cc:9547
+  virtual bool PrintsLogAlpha() const { return false; }
+};
+
+class ConstantFunctionComponent : public VectorFunctionComponentBase {
+ public:
+  ConstantFunctionComponent() {}
+  ConstantFunctionComponent(const ConstantFunctionComponent& other) : VectorFunctionComponentBase(other) {}
+  virtual std::string Type() const { return "ConstantFunctionComponent"; }
+  virtual void* Propagate(const ComponentPrecomputedIndexes* indexes, const CuMatrixBase<BaseFloat>& in,
+                          CuMatrixBase<BaseFloat>* out) const;
+  virtual Component* Copy() const { return new ConstantFunctionComponent(*this); }
+ protected:
+  virtual BaseFloat PlainUpdateFactor() const { return 5.0; }  // simple.cc:2636 (the reference's silent modification)
+  virtual bool PrintsLogAlpha() const { return true; }         // simple.cc:2640
+};
+
+// ------------------------------------------------------------------ ElementwiseProductComponent (simple.cc:237-299)
+class ElementwiseProductComponent : public Component {
+ public:
+  ElementwiseProductComponent() : input_dim_(0), output_dim_(0) {}
+  void Init(int32 input_dim, int32 output_dim);
+  virtual int32 Properties() const { return kSimpleComponent | kBackpropNeedsInput; }
+  virtual std::string Type() const { return "ElementwiseProductComponent"; }
+  virtual void InitFromConfig(ConfigLine* cfl);
+  virtual int32 InputDim() const { return input_dim_; }
+  virtual int32 OutputDim() const { return output_dim_; }
+  virtual void Read(std::istream& is, bool binary);
+  virtual void Write(std::ostream& os, bool binary) const;
+  virtual void* Propagate(const ComponentPrecomputedIndexes* indexes, const CuMatrixBase<BaseFloat>& in,
+                          CuMatrixBase<BaseFloat>* out) const;
+  virtual void Backprop(const std::string& debug_info, const ComponentPrecomputedIndexes* indexes,
+                        const CuMatrixBase<BaseFloat>& in_value, const CuMatrixBase<BaseFloat>& out_value,
+                        const CuMatrixBase<BaseFloat>& out_deriv, void* memo, Component* to_update,
+                        CuMatrixBase<BaseFloat>* in_deriv) const;
+  virtual Component* Copy() const { return new ElementwiseProductComponent(*this); }
+ private:
+  int32 input_dim_, output_dim_;
+};
+
+// ------------------------------------------------------------------ BatchNormTestComponent (norm.h:336-471)
+class BatchNormTestComponent : public Component {
+ public:
+  BatchNormTestComponent() : dim_(0), block_dim_(0), epsilon_(1.0e-03), target_rms_(1.0), test_mode_(false), count_(0) {}
+  BatchNormTestComponent(const BatchNormTestComponent& other);
+  virtual int32 InputDim() const { return dim_; }
+  virtual int32 OutputDim() const { return dim_; }
+  virtual std::string Info() const;
+  virtual void InitFromConfig(ConfigLine* cfl);  // empty in the reference (norm.cc:757-759)
+  virtual std::string Type() const { return "BatchNormTestComponent"; }
+  virtual int32 Properties() const {
+    return kSimpleComponent | kBackpropNeedsOutput | kPropagateInPlace | kBackpropInPlace |
+           (block_dim_ < dim_ ? kInputContiguous | kOutputContiguous : 0);
+  }
+  virtual void* Propagate(const ComponentPrecomputedIndexes* indexes, const CuMatrixBase<BaseFloat>& in,
+                          CuMatrixBase<BaseFloat>* out) const;
+  virtual void Backprop(const std::string& debug_info, const ComponentPrecomputedIndexes* indexes,
+                        const CuMatrixBase<BaseFloat>& in_value, const CuMatrixBase<BaseFloat>& out_value,
+                        const CuMatrixBase<BaseFloat>& out_deriv, void* memo, Component* to_update,
+                        CuMatrixBase<BaseFloat>* in_deriv) const;
+  virtual void Read(std::istream& is, bool binary);
+  virtual void Write(std::ostream& os, bool binary) const;
+  virtual Component* Copy() const { return new BatchNormTestComponent(*this); }
+  virtual void Scale(BaseFloat scale);
+  virtual void Add(BaseFloat alpha, const Component& other);
+  virtual void ZeroStats() {}                                                                  // norm.cc:1008-1010
+  virtual void StoreStats(const CuMatrixBase<BaseFloat>&, const CuMatrixBase<BaseFloat>&, void*) {}  // norm.cc:924-929
+  void SetTestMode(bool test_mode);
+  const CuVector& Offset() const { return offset_; }
+  const CuVector& ScaleVec() const { return scale_; }
+  // test hook: install statistics directly (the reference only gets them through Read()).
+  void SetStats(int32 dim, int32 block_dim, BaseFloat epsilon, BaseFloat target_rms, double count,
+                const std::vector<double>& sum, const std::vector<double>& sumsq);
+ private:
+  void Check() const;
+  void ComputeDerived();
+  int32 dim_, block_dim_;
+  BaseFloat epsilon_, target_rms_;
+  bool test_mode_;
+  double count_;
+  std::vector<double> stats_sum_, stats_sumsq_;  // CuVector<double> in the reference; tiny, host side here
+  CuVector offset_, scale_;
+};
+
+// ------------------------------------------------------------------ edit directives (utils.cc:1166-1415)
+// The subset of ReadEditConfig this path needs: set-temperature-proportion (utils.cc:1352-1405)
+// plus set-learning-rate / set-learning-rate-factor for the recipes' model surgery.
+// `names[i]` is the component name of components[i]; name patterns use '*' wildcards as in Kaldi.
+void ReadEditConfig(std::istream& config_file, const std::vector<std::string>& names,
+                    const std::vector<Component*>& components);
+bool NameMatchesPattern(const char* name, const char* pattern);
+
+}  // namespace nnet3
+}  // namespace tdnnf

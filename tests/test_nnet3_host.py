@@ -1,0 +1,136 @@
+"""CPU tests of the host logic: index handling (bit-exact against an independent restatement),
+PrecomputedIndexes I/O, the edit directive's error behaviour, the temperature schedule, and that the
+shared library loads and exports every symbol include/*.h declares.  No compute calls (no GPU)."""
+import os
+import re
+import random
+
+import pytest
+
+from tests import index_ref as IR
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from tdnnf_nas_b200 import capi
+
+    lib = capi.load()
+    header = ""
+    for h in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        header += open(os.path.join(ROOT, "include", h)).read()
+    names = sorted(set(re.findall(r"\b(tdnnf_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) > 70
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.tdnnf_abi_version() == 1000
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+
+    from tdnnf_nas_b200 import capi
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(capi.TdnnfError, match="no CPU path"):
+        capi.Context(0)
+
+
+def _grid(S, t_in, t_out, xs=(0,)):
+    inp = [(n, t, x) for t in t_in for x in xs for n in range(S)]
+    out = [(n, t, x) for t in t_out for x in xs for n in range(S)]
+    return inp, out
+
+
+CASES = [
+    ([0, 1, 2, 3, 4, 5, 6], 4, range(0, 20), range(0, 14)),
+    ([-6, -5, -4, -3, -2, -1, 0], 3, range(-6, 10), range(0, 10)),
+    ([0, 1, 2, 3, 4, 5, 6], 5, range(0, 21), range(0, 15, 3)),      # frame-subsampled output: reorder_t_in = 3
+    ([-3, 0, 3], 2, range(-3, 16, 3), range(0, 13, 3)),             # input on a stride-3 grid
+    ([0, 2], 1, range(0, 5), [0]),                                  # a single output frame (t_step_out == 0)
+    ([0, 1, 2], 2, range(0, 8), range(0, 6, 2)),                    # needs num_t_in rounded up
+]
+
+
+@pytest.mark.parametrize("offsets,S,t_in,t_out", CASES)
+def test_precompute_and_reorder_indexes_bit_exact(offsets, S, t_in, t_out):
+    from tdnnf_nas_b200 import nnet3
+
+    comp = nnet3.Component.tdnn_darts_for_indexing(offsets)
+    inp, out = _grid(S, list(t_in), list(t_out))
+    rnd = random.Random(S)
+    inp_s, out_s = inp[:], out[:]
+    rnd.shuffle(inp_s)
+    rnd.shuffle(out_s)
+    # ReorderIndexes on shuffled indexes -> the regular order the kernels assume
+    ri, ro = comp.reorder_indexes(inp_s, out_s)
+    ei, eo = IR.reorder_indexes(inp_s, out_s)
+    assert ri == ei and ro == eo
+    # PrecomputeIndexes on the regular order
+    nnet3.set_rand_seed(1)
+    for _ in range(12):  # the 1-in-11 spot check (tdnn.cc:859-870) is exercised too
+        pi = comp.precompute_indexes(ri, ro)
+        assert pi.row_stride_and_offsets() == tuple(IR.precompute_indexes(offsets, ri, ro))
+    # text and binary round trip of the PrecomputedIndexes
+    for binary in (False, True):
+        data = pi.write(binary)
+        head = b"<TdnnDARTSV3ComponentPrecomputedIndexes> <RowStride> "
+        assert data.startswith(head)
+        back = nnet3.PrecomputedIndexes.read(data, binary)
+        assert back.write(binary) == data
+
+
+def test_reorder_inserts_blanks_for_missing_indexes():
+    from tdnnf_nas_b200 import nnet3
+
+    comp = nnet3.Component.tdnn_darts_for_indexing([0, 1])
+    inp, out = _grid(2, [0, 1, 2, 4], [0, 1, 3])   # t=3 missing from the input, t=2 from the output
+    ri, ro = comp.reorder_indexes(inp, out)
+    assert (ri, ro) == IR.reorder_indexes(inp, out)
+    assert any(t == nnet3.kNoTime for (_, t, _) in ri) and any(t == nnet3.kNoTime for (_, t, _) in ro)
+
+
+def test_get_input_indexes_and_is_computable():
+    from tdnnf_nas_b200 import nnet3
+
+    comp = nnet3.Component.tdnn_darts_for_indexing([-2, 0, 3])
+    assert comp.get_input_indexes(5, 10, 1) == [(5, 8, 1), (5, 10, 1), (5, 13, 1)]
+    avail = [(5, 8, 1), (5, 10, 1), (5, 13, 1)]
+    assert comp.is_computable(5, 10, 1, avail)
+    assert not comp.is_computable(5, 10, 1, avail[:2])
+    assert not comp.is_computable(4, 10, 1, avail)
+    with pytest.raises(nnet3.Nnet3Error):  # KALDI_ASSERT(output_index.t != kNoTime), tdnn.cc:767
+        comp.get_input_indexes(0, nnet3.kNoTime, 0)
+
+
+def test_edit_directive_errors():
+    from tdnnf_nas_b200 import nnet3
+
+    # missing proportion -> KALDI_ERR (utils.cc:1358-1361)
+    with pytest.raises(nnet3.Nnet3Error, match="expected proportion"):
+        nnet3.apply_edits("set-temperature-proportion name=*", [])
+    with pytest.raises(nnet3.Nnet3Error, match="not currently supported"):
+        nnet3.apply_edits("frobnicate name=*", [])
+    with pytest.raises(nnet3.Nnet3Error, match="Could not interpret"):
+        nnet3.apply_edits("set-temperature-proportion name=* proportion=0.5 bogus=1", [])
+    nnet3.apply_edits("set-temperature-proportion name=tdnnf* proportion=0.5; set-temperature-proportion proportion=0.1", [])
+
+
+def test_temperature_schedule_matches_reference_formula():
+    from tdnnf_nas_b200 import nnet3
+
+    # temperature_schedule.py:51 : T = (1 - f) * (1 - 0.03) + 0.03
+    assert nnet3.temperature_for_iteration(0, 10) == pytest.approx(1.0)
+    assert nnet3.temperature_for_iteration(10, 10) == pytest.approx(0.03)
+    assert nnet3.temperature_for_iteration(5, 10) == pytest.approx(0.515)
+    assert nnet3.temperature_edit_string(5, 10) == "set-temperature-proportion name=* proportion=0.515"
+
+
+def test_unknown_component_type_fails():
+    from tdnnf_nas_b200 import nnet3
+
+    with pytest.raises(nnet3.Nnet3Error, match="Unknown component type"):
+        nnet3.Component.new("NoSuchComponent", "dim=3")
+    with pytest.raises(nnet3.Nnet3Error):
+        nnet3.Component.read(b"<NoSuchComponent> <Dim> 3 </NoSuchComponent> ", False)
