@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- the driver-facing benchmark (see the task contract).
+
+  python bench.py --gpus N --steps K --warmup W            our arm: DARTS TDNN-F supernet training step
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU arithmetic (oracle) on host cores
+
+Metric (BASELINE.json): supernet training frames/sec (input frames = chunks x frames_per_eg consumed per
+second; forward + LF-MMI denominator forward-backward + backward + delta reduction + parameter step), on the
+context-offset search supernet of configs[2] with 64 chunks x 150 frames PER GPU (weak scaling).
+One JSON line on stdout from rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "TDNN-F DARTS supernet train frames/sec"
+UNIT = "frames/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"], bf16_tflops_sustained=p["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    power_w_max=max(pw) if pw else None, samples=len(sm), reasons=sorted(reasons))
+
+
+# ------------------------------------------------------------------ CPU baseline (the oracle, timed)
+def cpu_baseline_sample(cfg, repeats: int = 1):
+    """Times the oracle on a bounded sample of the workload and extrapolates to frames/sec.
+    Sample: one TDNN-F block (TdnnDARTSV3 1536->160 and 160->1536, 7 offsets; Propagate + Backprop incl. the
+    parameter/alpha update) at 64 sequences x 32 output frames, plus the denominator forward-backward on the
+    bench graph with 4 sequences x T frames.  Extrapolation: GEMM time scales with algorithmic FLOPs, the
+    denominator with the number of sequences."""
+    import numpy as np
+
+    from oracle import oracle as O
+    from tdnnf_nas_b200 import synth
+
+    g = np.random.default_rng(1)
+    n, D, B, S = cfg.num_offsets, cfg.dim, cfg.bottleneck, 64
+    t_out = 32
+    flags = O.USE_GUMBEL | O.UPDATE_ALPHA if cfg.mode == "search" else O.UNIFORM_SAMPLE
+    n_eff = n if cfg.mode == "search" else 2
+
+    def comp(din, dout, offsets):
+        rs, ro = synth.regular_row_offsets(offsets, min(offsets), 0, S, 1, 1)
+        in_rows, out_rows = (t_out + n - 1) * S, t_out * S
+        x = g.standard_normal((in_rows, din)).astype(np.float32)
+        W = (g.standard_normal((dout, n * din)) / np.sqrt(n * din)).astype(np.float32)
+        bp = g.standard_normal(n + dout).astype(np.float32)
+        od = (g.standard_normal((out_rows, dout)) / out_rows).astype(np.float32)
+        return dict(offsets=offsets, x=x, W=W, bp=bp, od=od, ro=ro, out_rows=out_rows,
+                    flops=3 * 2.0 * out_rows * n_eff * din * dout)
+
+    comps = [comp(D, B, list(range(-(n - 1), 1))), comp(B, D, list(range(n)))]
+    ug = g.uniform(0.1, 0.9, n).astype(np.float32)
+    graph = synth.make_den_graph(cfg.den_states, cfg.num_pdfs, cfg.den_out_degree, seed=5)
+    T, S_den = cfg.frames_per_eg // cfg.frame_subsampling, 4
+    xo = g.standard_normal((T * S_den, cfg.num_pdfs)).astype(np.float32)
+    t_gemm = t_den = 0.0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for c in comps:
+            out, coef = O.tdnn_propagate(c["offsets"], flags, 0.5, c["W"], c["bp"], c["x"], c["out_rows"], c["ro"], 1, ug, 0.3)
+            O.tdnn_backprop(c["offsets"], flags, 0.5, c["W"], c["x"], c["od"], coef, c["ro"], 1, 1e-3,
+                            in_deriv=np.zeros_like(c["x"]), dW=np.zeros_like(c["W"]), dbias=np.zeros_like(c["bp"]))
+        t1 = time.perf_counter()
+        O.den_forward_backward(graph, xo, S_den, T, cfg.leaky_hmm, deriv_weight=-1.0)
+        t2 = time.perf_counter()
+        t_gemm += t1 - t0
+        t_den += t2 - t1
+    t_gemm /= repeats
+    t_den /= repeats
+    return dict(t_gemm=t_gemm, t_den=t_den, sample_flops=sum(c["flops"] for c in comps), den_seqs=S_den,
+                cores=O.num_threads(),
+                sample=("oracle (CPU restatement, OpenMP): 1 TDNN-F block (TdnnDARTSV3 1536->160 + 160->1536, 7 offsets) "
+                        "Propagate+Backprop+update at 64 seq x 32 frames, + denominator fwd-bwd on the bench graph at "
+                        f"{S_den} seq x {T} frames; extrapolated to the full step by algorithmic GEMM FLOPs and by sequences"))
+
+
+def cpu_frames_per_sec(cfg, sample, total_flops, frames_per_step):
+    step_s = sample["t_gemm"] * total_flops / sample["sample_flops"] + sample["t_den"] * cfg.num_seqs / sample["den_seqs"]
+    return frames_per_step / step_s, step_s
+
+
+def supernet_flops(cfg):
+    """Algorithmic DARTS GEMM FLOPs per step without building the net (same formula as Supernet.algorithmic_flops)."""
+    T = cfg.frames_per_eg // cfg.frame_subsampling
+    w = cfg.num_offsets - 1
+    n_eff = cfg.num_offsets if cfg.mode == "search" else 2
+    rows_aff = [T]
+    rows_lin = [cfg.frame_subsampling * (T - 1) + 1 + w]
+    for _ in range(cfg.num_blocks - 1):
+        rows_aff.append(rows_lin[-1] + w)
+        rows_lin.append(rows_aff[-1] + w)
+    return sum(3 * 2.0 * (rl + ra) * cfg.num_seqs * n_eff * cfg.dim * cfg.bottleneck for rl, ra in zip(rows_lin, rows_aff))
+
+
+# ------------------------------------------------------------------ arms
+def run_reference(args, cfg, rank, world):
+    if rank != 0:
+        return
+    frames = cfg.num_seqs * cfg.frames_per_eg
+    flops = supernet_flops(cfg)
+    for _ in range(args.warmup):
+        cpu_baseline_sample(cfg)
+    t0 = time.perf_counter()
+    acc = dict(t_gemm=0.0, t_den=0.0)
+    s = None
+    for _ in range(args.steps):
+        s = cpu_baseline_sample(cfg)
+        acc["t_gemm"] += s["t_gemm"]
+        acc["t_den"] += s["t_den"]
+    wall = time.perf_counter() - t0
+    s["t_gemm"], s["t_den"] = acc["t_gemm"] / args.steps, acc["t_den"] / args.steps
+    fps, step_s = cpu_frames_per_sec(cfg, s, flops, frames)
+    line = dict(impl="reference", metric=METRIC, value=fps, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=step_s * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", config=workload_config(cfg, args.gpus),
+                cpu_baseline=dict(value=fps, unit=UNIT, cores=s["cores"], kind="port", sample=s["sample"]),
+                e2e=dict(value=fps, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                note=("the reference (a patch set on upstream Kaldi) cannot be built here; this arm times the in-repo CPU "
+                      f"oracle on one host ({s['cores']} threads); measured sample wall {wall / args.steps:.2f} s/step; "
+                      "it is a single-host number and does not scale with --gpus"))
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(cfg, gpus):
+    return dict(workload=("context-offset DARTS TDNN-F supernet, search stage (BASELINE.json configs[2]): 14 x "
+                          "{TdnnDARTSV3 1536->160 offsets -6..0, TdnnDARTSV3 160->1536 offsets 0..6, ReLU, BatchNormTest, "
+                          "bypass 0.66}, tdnn1 220->1536, prefinal 256/1536, output 6008; LF-MMI denominator fwd-bwd on a "
+                          f"synthetic {cfg.den_states}-state den graph"),
+                mode=cfg.mode, chunks_per_gpu=cfg.num_seqs, frames_per_eg=cfg.frames_per_eg, global_chunks=cfg.num_seqs * gpus,
+                num_pdfs=cfg.num_pdfs, den_states=cfg.den_states, parallelism=f"dp{gpus}",
+                cache="per-step working set (~14 GB of activations) exceeds the 126 MB L2: no explicit flush needed",
+                not_included="numerator graph (synthetic single-path alignment), natural gradient (identity), max-change/L2")
+
+
+def run_ours(args, cfg, rank, world, local_rank):
+    import torch
+
+    from tdnnf_nas_b200.supernet import Supernet
+
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        pg = dist.group.WORLD
+    net = Supernet(cfg, device=local_rank, rank=rank, world_size=world, process_group=pg)
+    dev = net.dev
+    host_inputs = [net.make_input(i).pin_memory() for i in range(2)]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(n_steps, with_copy):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = net.ctx.launches
+        e0.record()
+        last = None
+        for i in range(n_steps):
+            last = net.step(host_inputs[i % 2] if with_copy else None)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, net.ctx.launches - launches0, last
+
+    net.x.copy_(host_inputs[0])
+    for i in range(args.warmup):
+        net.step(host_inputs[i % 2])
+    # ---- device-resident number (`value`)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches, objf = timed(args.steps, with_copy=False)
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- end-to-end number (`e2e`): pinned host input copied in and the objective read back every step
+    ms_e2e, _, _ = timed(args.steps, with_copy=True)
+    # ---- roofline of the dominant kernel: per-launch CUDA events around every tensor-core GEMM of 2 more steps
+    net.ctx.gemm_timing_enable(True)
+    net.step(None)
+    net.step(None)
+    gemm_ms, gemm_flops, gemm_launches = net.ctx.gemm_timing_read()
+    net.ctx.gemm_timing_enable(False)
+    barrier()
+    if rank != 0:
+        net.close()
+        return
+    peaks = load_peaks()
+    frames_all = net.frames_per_step * world
+    value = frames_all * args.steps / (ms_dev / 1e3)
+    e2e = frames_all * args.steps / (ms_e2e / 1e3)
+    achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    peak = peaks["bf16_tflops_sustained"]
+    step_ms = ms_dev / args.steps
+    cpu = cpu_baseline_sample(cfg)
+    cpu_fps, _ = cpu_frames_per_sec(cfg, cpu, net.algorithmic_flops(), net.frames_per_step)
+    line = dict(
+        metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=step_ms,
+        higher_is_better=True, scaling="weak", vs_baseline=None,
+        dtype="f32 (bf16 hi/lo split operands, 3 tensor-core products, fp32 accumulate)", data="synthetic",
+        config=workload_config(cfg, world), clocks=clocks,
+        e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=int(net.x.numel() * 4), d2h_bytes_per_step=12,
+                 ms_per_step=ms_e2e / args.steps),
+        gpu_launches=int(launches),
+        roofline=dict(bound="tensor", kernel="splice_gemm_kernel (tcgen05, all TdnnDARTSV3 fwd/dgrad/wgrad GEMMs)",
+                      achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=None,
+                      peak_source=peaks["source"] + ", bf16 sustained",
+                      achieved_raw_bf16=3 * achieved, frac_raw_bf16=3 * achieved / peak,
+                      launches_timed=gemm_launches, gemm_ms_per_step=gemm_ms / 2, gemm_share_of_step=(gemm_ms / 2) / step_ms,
+                      note=("achieved = algorithmic fp32-equivalent FLOPs (2MNK, one pass) / CUDA-event time of the GEMM launches; "
+                            "each K block issues 3 bf16 MMAs (hi*hi, hi*lo, lo*hi), so the tensor pipe runs at 3x this rate")),
+        cpu_baseline=dict(value=cpu_fps, unit=UNIT, cores=cpu["cores"], kind="port", sample=cpu["sample"]),
+        objf_per_frame=objf, den_arcs=net.den_arcs)
+    print(json.dumps(line), flush=True)
+    net.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="search", choices=["search", "pretrain"])
+    ap.add_argument("--den-states", type=int, default=16384)
+    ap.add_argument("--blocks", type=int, default=14)
+    ap.add_argument("--chunks", type=int, default=64)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from tdnnf_nas_b200.supernet import SupernetConfig
+
+    cfg = SupernetConfig(mode=args.mode, den_states=args.den_states, num_blocks=args.blocks, num_seqs=args.chunks)
+    if args.impl == "reference":
+        if args.steps > 3:
+            args.steps = 3  # each step is ~10 s of CPU work: keep the whole run within a few minutes
+        args.warmup = min(args.warmup, 1)
+        run_reference(args, cfg, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+    run_ours(args, cfg, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -54,6 +54,12 @@ int tdnnf_ctx_set_stream(tdnnf_ctx* ctx, void* stream);
 int tdnnf_ctx_reserve(tdnnf_ctx* ctx, uint64_t bytes);
 /* Number of kernels this context has launched so far (for gpu_launches accounting). */
 uint64_t tdnnf_ctx_launch_count(const tdnnf_ctx* ctx);
+/* Roofline instrumentation: while enabled, every tensor-core GEMM launch is bracketed by CUDA events on
+ * the context's stream and its algorithmic FLOPs (2*M*N*K over the un-padded operands, one pass: the
+ * bf16 hi/lo split is NOT counted) are recorded.  tdnnf_ctx_gemm_timing_read synchronises the stream and
+ * returns the sums since enabling, then clears them. */
+int tdnnf_ctx_gemm_timing_enable(tdnnf_ctx* ctx, int enable);
+int tdnnf_ctx_gemm_timing_read(tdnnf_ctx* ctx, double* total_ms, double* total_flops, uint64_t* launches);
 
 /* ------------------------------------------------------------------ TdnnDARTSV3 ------- */
 /* mode flags of TdnnDARTSV3Component (ref: conv.h:243-257) */

@@ -36,6 +36,8 @@ def _declare(lib):
     sig("tdnnf_ctx_set_stream", [vp, vp])
     sig("tdnnf_ctx_reserve", [vp, C.c_uint64])
     sig("tdnnf_ctx_launch_count", [vp], C.c_uint64)
+    sig("tdnnf_ctx_gemm_timing_enable", [vp, i])
+    sig("tdnnf_ctx_gemm_timing_read", [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)])
     sig("tdnnf_darts_coef", [vp, vp, i, i, f, c_float_p, f, i, vp, vp])
     sig("tdnnf_darts_weff_from_coef", [vp, vp, i, i, i, vp])
     sig("tdnnf_darts_propagate", [vp, vp, i, i, i, vp, i, i, i, vp, i, vp, i, vp, i, c_int_p, i])
@@ -55,6 +57,7 @@ def _declare(lib):
     sig("tdnnf_mat_scale", [vp, vp, i, i, i, f])
     sig("tdnnf_mat_axpy", [vp, f, vp, i, vp, i, i, i])
     sig("tdnnf_mat_dot", [vp, vp, i, vp, i, i, i, c_float_p])
+    sig("tdnnf_mat_dot_dev", [vp, vp, i, vp, i, i, i, vp])
     sig("tdnnf_copy_rows_from_vec", [vp, vp, vp, i, i, i])
     sig("tdnnf_copy_rows", [vp, vp, i, vp, i, i, i, vp])
     sig("tdnnf_add_to_rows", [vp, f, vp, i, i, i, vp, i, vp])
@@ -142,6 +145,15 @@ class Context:
     @property
     def launches(self) -> int:
         return int(load().tdnnf_ctx_launch_count(self.h))
+
+    def gemm_timing_enable(self, on: bool):
+        check(load().tdnnf_ctx_gemm_timing_enable(self.h, int(on)))
+
+    def gemm_timing_read(self):
+        """(total_ms, total_algorithmic_flops, launches) of the tensor-core GEMM launches since enabling."""
+        ms, fl, n = C.c_double(), C.c_double(), C.c_uint64()
+        check(load().tdnnf_ctx_gemm_timing_read(self.h, C.byref(ms), C.byref(fl), C.byref(n)))
+        return ms.value, fl.value, int(n.value)
 
     def close(self):
         if getattr(self, "h", None):

@@ -105,3 +105,29 @@ extern "C" int tdnnf_ctx_reserve(tdnnf_ctx* ctx, uint64_t bytes) {
 }
 
 extern "C" uint64_t tdnnf_ctx_launch_count(const tdnnf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int tdnnf_ctx_gemm_timing_enable(tdnnf_ctx* ctx, int enable) {
+  TDNNF_REQUIRE(ctx != nullptr, "null context");
+  ctx->gemm_timing = enable != 0;
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_ctx_gemm_timing_read(tdnnf_ctx* ctx, double* total_ms, double* total_flops, uint64_t* launches) {
+  TDNNF_REQUIRE(ctx && total_ms && total_flops && launches, "null argument");
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+  TDNNF_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  double ms = 0.0, fl = 0.0;
+  for (auto& t : ctx->gemm_events) {
+    float e = 0.f;
+    TDNNF_CUDA_OK(cudaEventElapsedTime(&e, t.start, t.stop));
+    ms += e;
+    fl += t.flops;
+    cudaEventDestroy(t.start);
+    cudaEventDestroy(t.stop);
+  }
+  *total_ms = ms;
+  *total_flops = fl;
+  *launches = ctx->gemm_events.size();
+  ctx->gemm_events.clear();
+  return TDNNF_OK;
+}

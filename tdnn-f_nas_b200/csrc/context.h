@@ -5,6 +5,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <string>
+#include <vector>
 
 #include "../../include/tdnnf_nas_b200.h"
 
@@ -45,6 +46,13 @@ struct tdnnf_ctx {
   size_t ws_off = 0;
   // counters for bench.py's gpu_launches claim
   unsigned long long launches = 0;
+  // optional per-GEMM-launch event timing (roofline instrumentation)
+  bool gemm_timing = false;
+  struct GemmTiming {
+    cudaEvent_t start, stop;
+    double flops;
+  };
+  std::vector<GemmTiming> gemm_events;
 
   void ws_reset() { ws_off = 0; }
   // Returns nullptr on failure (error string set).

@@ -213,7 +213,7 @@ static int choose_splits(int tiles, int iters_per_tile, int num_sms) {
 }
 
 template <int BN>
-static int launch_gemm_bn(tdnnf_ctx* ctx, const Planes& A, const Planes& B, const GemmParams& p) {
+static int launch_gemm_bn(tdnnf_ctx* ctx, const Planes& A, const Planes& B, const GemmParams& p, double algorithmic_flops) {
   CUtensorMap tmA, tmB;
   int rc = make_map(ctx, A, kBM, &tmA);
   if (rc) return rc;
@@ -228,9 +228,20 @@ static int launch_gemm_bn(tdnnf_ctx* ctx, const Planes& A, const Planes& B, cons
   const int units = p.c_tiles * p.m_tiles * p.n_tiles * p.splits;
   if (units <= 0) return TDNNF_OK;
   const int grid = std::min(units, ctx->num_sms);
+  tdnnf_ctx::GemmTiming tm;
+  if (ctx->gemm_timing) {
+    TDNNF_CUDA_OK(cudaEventCreate(&tm.start));
+    TDNNF_CUDA_OK(cudaEventCreate(&tm.stop));
+    tm.flops = algorithmic_flops;
+    TDNNF_CUDA_OK(cudaEventRecord(tm.start, ctx->stream));
+  }
   kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, ctx->stream>>>(tmA, tmB, p);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
+  if (ctx->gemm_timing) {
+    TDNNF_CUDA_OK(cudaEventRecord(tm.stop, ctx->stream));
+    ctx->gemm_events.push_back(tm);
+  }
   return TDNNF_OK;
 }
 
@@ -243,12 +254,12 @@ static int pick_bn(int n) {
   return 160;
 }
 
-static int launch_gemm(tdnnf_ctx* ctx, int bn, const Planes& A, const Planes& B, const GemmParams& p) {
+static int launch_gemm(tdnnf_ctx* ctx, int bn, const Planes& A, const Planes& B, const GemmParams& p, double algorithmic_flops) {
   switch (bn) {
-    case 32: return launch_gemm_bn<32>(ctx, A, B, p);
-    case 64: return launch_gemm_bn<64>(ctx, A, B, p);
-    case 128: return launch_gemm_bn<128>(ctx, A, B, p);
-    case 160: return launch_gemm_bn<160>(ctx, A, B, p);
+    case 32: return launch_gemm_bn<32>(ctx, A, B, p, algorithmic_flops);
+    case 64: return launch_gemm_bn<64>(ctx, A, B, p, algorithmic_flops);
+    case 128: return launch_gemm_bn<128>(ctx, A, B, p, algorithmic_flops);
+    case 160: return launch_gemm_bn<160>(ctx, A, B, p, algorithmic_flops);
     default: return fail(TDNNF_ERR_INVALID, "unsupported BN");
   }
 }
@@ -330,7 +341,8 @@ extern "C" int tdnnf_darts_propagate(tdnnf_ctx* ctx, const float* in, int in_row
     p.accumulate = (bias_mode == 0);
     p.bias = (bias_mode == 2) ? bias : nullptr;
   }
-  return launch_gemm(ctx, bn, A, B, p);
+  // all n offsets counted: in uniform-sample mode the skipped offsets make this an upper bound
+  return launch_gemm(ctx, bn, A, B, p, 2.0 * out_rows * (double)out_dim * in_dim * n);
 }
 
 extern "C" int tdnnf_darts_backprop_data(tdnnf_ctx* ctx, const float* out_deriv, int out_rows, int out_dim,
@@ -381,7 +393,7 @@ extern "C" int tdnnf_darts_backprop_data(tdnnf_ctx* ctx, const float* out_deriv,
   p.accumulate = 1;
   p.atomic = p.splits > 1;
   p.alpha = 1.0f;
-  return launch_gemm(ctx, bn, A, B, p);
+  return launch_gemm(ctx, bn, A, B, p, 2.0 * out_rows * (double)out_dim * in_dim * n);
 }
 
 extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value, int in_rows, int in_dim,
@@ -472,7 +484,8 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
   }
   p.splits = choose_splits(p.m_tiles * p.n_tiles * n, p.kb_per_seg, ctx->num_sms);
   p.atomic = p.splits > 1;
-  rc = m_is_in ? launch_gemm(ctx, bn, XT, ODT, p) : launch_gemm(ctx, bn, ODT, XT, p);
+  const double wflops = 2.0 * out_rows * (double)out_dim * in_dim * n;
+  rc = m_is_in ? launch_gemm(ctx, bn, XT, ODT, p, wflops) : launch_gemm(ctx, bn, ODT, XT, p, wflops);
   if (rc) return rc;
   if (dbias) return tdnnf_add_row_sum(ctx, out_deriv, out_rows, out_dim, od_stride, lr, dbias);
   return TDNNF_OK;

@@ -1,0 +1,528 @@
+"""The context-offset DARTS TDNN-F supernet of run_TDNN_DARTSV3_fbk_stride_{pretrain,cvupdate}.sh
+(BASELINE.json configs[2]) as one training step on this library: forward, LF-MMI denominator
+forward-backward, backward, data-parallel reduction of the deltas and the parameter step.
+
+What runs where:
+  * the 2 x 14 TdnnDARTSV3Component instances, BatchNormTestComponent (search mode) -> the nnet3
+    component mirror (csrc/nnet3) exactly as NnetComputer would call them;
+  * ReLU / BatchNorm-train / bypass sum / the stock affine layers around them (tdnn1, prefinal,
+    output: "N4" neighbours) -> the same kernels through the C ABI (a stock TdnnComponent is the
+    DARTS GEMM with one offset and weight 1);
+  * DenominatorComputation -> den kernels; the numerator is a synthetic single-path alignment
+    (SURVEY "next" row N3 is not built), natural gradient is the identity (N1), max-change / L2 /
+    orthonormal constraint are not applied (N2), dropout-proportion is 0.0 as in the recipe.
+torch is device memory, the H2D copy, streams and torch.distributed; every kernel is ours except the
+3 200-element numerator gather/scatter.
+
+The step is compiled once into flat lists of pre-bound C calls so the per-step Python cost is a loop.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from functools import partial
+from typing import List, Optional
+
+import numpy as np
+
+from . import capi, nnet3, parallel, synth
+
+
+@dataclass
+class SupernetConfig:
+    num_seqs: int = 64              # chunks per minibatch per GPU (--trainer.num-chunk-per-minibatch 64)
+    frames_per_eg: int = 150
+    frame_subsampling: int = 3
+    feat_dim: int = 220             # Append(-1,0,1) of 40-dim fbank + 100-dim i-vector, after the fixed LDA
+    dim: int = 1536
+    bottleneck: int = 160
+    num_blocks: int = 14            # tdnnf2 .. tdnnf15
+    num_offsets: int = 7            # offset_len: left context -6..0, right context 0..6
+    prefinal_small: int = 256
+    num_pdfs: int = 6008
+    den_states: int = 16384
+    den_out_degree: float = 16.0
+    leaky_hmm: float = 0.1
+    bypass_scale: float = 0.66
+    mode: str = "search"            # "search": use-gumbel, update-alpha, BatchNormTest; "pretrain": uniform-sample
+    learning_rate: float = 2.5e-4
+    darts_lr_factor: float = 1.0e-4  # <LearningRateFactor> set by the cvupdate recipe's sed (search mode only)
+    max_change: float = 0.75         # per-component max-change (xconfig default of the tdnnf layers)
+    max_param_change: float = 2.0    # --trainer.max-param-change (global)
+    seed: int = 20221 + 3
+
+
+class _Plan:
+    """A flat list of zero-argument C calls; run() checks every status."""
+
+    def __init__(self):
+        self.calls = []
+
+    def add(self, kind: str, fn, *args):
+        self.calls.append((kind, partial(fn, *args)))
+
+    def run(self):
+        for kind, call in self.calls:
+            rc = call()
+            if rc != 0:
+                lib = capi.load()
+                msg = lib.tdnnf_nnet3_last_error() if kind == "nnet3" else lib.tdnnf_last_error()
+                raise RuntimeError(f"supernet step failed in a {kind} call: {msg.decode()}")
+
+
+def _m(t):
+    p, r, c, s = capi._mat(t)
+    return C.c_void_p(p), r, c, s
+
+
+class Supernet:
+    def __init__(self, cfg: SupernetConfig, device: int = 0, rank: int = 0, world_size: int = 1,
+                 process_group=None):
+        import torch
+
+        self.cfg, self.rank, self.world, self.pg = cfg, rank, world_size, process_group
+        self.dev = torch.device("cuda", device)
+        torch.cuda.set_device(self.dev)
+        self.ctx = capi.Context(device)
+        self.ctx.use_current_stream()
+        nnet3.set_context(self.ctx)
+        nnet3.set_rand_seed(cfg.seed)          # identical on every rank: same Gumbel noise / one-hot choices
+        nnet3.set_dp_world_size(world_size)
+        self.lib = capi.load()
+        self._build()
+
+    # ------------------------------------------------------------------ construction
+    def _frames(self):
+        cfg = self.cfg
+        T = cfg.frames_per_eg // cfg.frame_subsampling
+        ctx_w = cfg.num_offsets - 1
+        sub = cfg.frame_subsampling
+        out_t = [sub * i for i in range(T)]
+        L = cfg.num_blocks
+        # per block: t-lists of the linear output (= affine input) and affine output (= block output)
+        aff_t: List[List[int]] = [None] * L
+        lin_t: List[List[int]] = [None] * L
+        aff_t[L - 1] = out_t
+        lin_t[L - 1] = list(range(out_t[0], out_t[-1] + ctx_w + 1))
+        for b in range(L - 2, -1, -1):
+            lo, hi = lin_t[b + 1][0] - ctx_w, lin_t[b + 1][-1]
+            aff_t[b] = list(range(lo, hi + 1))
+            lin_t[b] = list(range(lo, hi + ctx_w + 1))
+        in_t = list(range(lin_t[0][0] - ctx_w, lin_t[0][-1] + 1))  # tdnn1 output frames
+        return T, out_t, lin_t, aff_t, in_t
+
+    def _build(self):
+        import torch
+
+        cfg, dev, ctx = self.cfg, self.dev, self.ctx
+        S, D, B, n = cfg.num_seqs, cfg.dim, cfg.bottleneck, cfg.num_offsets
+        T, out_t, lin_t, aff_t, in_t = self._frames()
+        self.T, self.in_frames = T, len(in_t)
+        g = synth.rng(3, stream=1)
+        zeros = lambda r, c: torch.zeros((r, c), device=dev, dtype=torch.float32)
+        randn = lambda r, c, s: torch.from_numpy((g.standard_normal((r, c)) * s).astype(np.float32)).to(dev)
+        self.keep = []  # tensors / ctypes arrays that must outlive the plans
+
+        search = cfg.mode == "search"
+        flags_cfg = ("use-gumbel=true use-entropy=false free-select=false update-alpha=true update-theta=false uniform-sample=false"
+                     if search else
+                     "use-gumbel=false use-entropy=false free-select=false update-alpha=false update-theta=true uniform-sample=true")
+        lrf = cfg.darts_lr_factor if search else 1.0
+
+        def grid(ts):
+            return [(s, t, 0) for t in ts for s in range(S)]
+
+        # ---------------- stock affine layers (weights as plain device matrices)
+        def affine_params(din, dout, bias=True, zero=False):
+            W = zeros(dout, din) if zero else randn(dout, din, 1.0 / np.sqrt(din))
+            b = (torch.zeros(dout, device=dev) if zero else randn(1, dout, 0.1)[0]) if bias else None
+            dW = zeros(dout, din)
+            db = torch.zeros(dout, device=dev) if bias else None
+            return dict(W=W, b=b, dW=dW, db=db)
+
+        self.one = torch.ones(1, device=dev)
+        self.zero_off = (C.c_int32 * 1)(0)
+        self.stock = dict(tdnn1=affine_params(cfg.feat_dim, D), prefinal_l=affine_params(D, cfg.prefinal_small, False),
+                          pc_affine=affine_params(cfg.prefinal_small, D), pc_linear=affine_params(D, cfg.prefinal_small, False),
+                          output=affine_params(cfg.prefinal_small, cfg.num_pdfs, zero=True))  # output-layer: param-stddev=0
+
+        # ---------------- frozen batch-norm (BatchNormTestComponent) or train-mode batch-norm
+        def make_bn(dim):
+            # memo of the train-mode kernels.  In search mode these are replaced, after one calibration
+            # forward pass, by BatchNormTestComponents carrying the measured statistics -- the synthetic
+            # stand-in for "pretrain the supernet, then sed BatchNormComponent -> BatchNormTestComponent".
+            return torch.zeros(5 * dim, device=dev)
+
+        # ---------------- DARTS blocks
+        left = ",".join(str(i) for i in range(-(n - 1), 1))
+        right = ",".join(str(i) for i in range(n))
+        self.blocks = []
+        for b in range(cfg.num_blocks):
+            common = f"learning-rate={cfg.learning_rate * lrf} learning-rate-factor={lrf} {flags_cfg} use-bias=true"
+            lin = nnet3.Component.new("TdnnDARTSV3Component", f"input-dim={D} output-dim={B} time-offsets={left} {common}")
+            aff = nnet3.Component.new("TdnnDARTSV3Component", f"input-dim={B} output-dim={D} time-offsets={right} {common}")
+            prev_t = in_t if b == 0 else aff_t[b - 1]
+            # linear: input = previous block output (t-major), output = lin_t[b]
+            li_in, li_out = lin.reorder_indexes(grid(prev_t), grid(lin_t[b]))
+            assert li_in == grid(prev_t) and li_out == grid(lin_t[b])
+            lin_idx = lin.precompute_indexes(li_in, li_out)
+            # affine: ReorderIndexes may ask for the blocked (reorder_t_in = subsampling) input order
+            ai_in, ai_out = aff.reorder_indexes(grid(lin_t[b]), grid(aff_t[b]))
+            assert ai_out == grid(aff_t[b])
+            aff_idx = aff.precompute_indexes(ai_in, ai_out)
+            reorder = None
+            if ai_in != grid(lin_t[b]):
+                pos = {ix: r for r, ix in enumerate(grid(lin_t[b]))}
+                fwd_map = np.array([pos.get(ix, -1) for ix in ai_in], dtype=np.int32)      # blocked row <- t-major row
+                inv_map = np.full(len(pos), -1, dtype=np.int32)
+                for r, m in enumerate(fwd_map):
+                    if m >= 0:
+                        inv_map[m] = r
+                reorder = dict(fwd=torch.from_numpy(fwd_map).to(dev), inv=torch.from_numpy(inv_map).to(dev),
+                               rows=len(ai_in))
+            # bypass: rows of the previous block output that line up with this block's output frames
+            if b == 0:
+                bypass = None  # tdnnf2's bypass input is tdnn1 (dim matches): Sum(Scale(0.66, tdnn1), .)
+            prev_pos = {ix: r for r, ix in enumerate(grid(prev_t))}
+            by_rows = np.array([prev_pos[ix] for ix in grid(aff_t[b])], dtype=np.int32)
+            contiguous = bool(np.all(np.diff(by_rows) == 1))
+            bypass = dict(offset=int(by_rows[0]), contiguous=contiguous,
+                          map=None if contiguous else torch.from_numpy(by_rows).to(dev))
+            rows_lin, rows_aff, rows_prev = len(lin_t[b]) * S, len(aff_t[b]) * S, len(prev_t) * S
+            blk = dict(lin=lin, aff=aff, lin_idx=lin_idx, aff_idx=aff_idx, reorder=reorder, bypass=bypass,
+                       lin_delta=lin.copy(), aff_delta=aff.copy(), bn=make_bn(D),
+                       lin_out=zeros(rows_lin, B), aff_in=zeros(reorder["rows"], B) if reorder else None,
+                       aff_out=zeros(rows_aff, D), relu=zeros(rows_aff, D), bn_out=zeros(rows_aff, D), out=zeros(rows_aff, D),
+                       d_out=zeros(rows_aff, D), d_aff=zeros(rows_aff, D), d_aff_in=zeros(reorder["rows"], B) if reorder else None,
+                       d_lin=zeros(rows_lin, B), byp_tmp=None if contiguous else zeros(rows_aff, D),
+                       memo_lin=C.c_void_p(), memo_aff=C.c_void_p(), rows_prev=rows_prev)
+            blk["lin_delta"].scale(0.0)
+            blk["aff_delta"].scale(0.0)
+            self.blocks.append(blk)
+
+        rows_in, rows_T = len(in_t) * S, T * S
+        self.rows_in = rows_in
+        self.x = zeros(rows_in, cfg.feat_dim)
+        self.x_host = torch.zeros((rows_in, cfg.feat_dim), dtype=torch.float32).pin_memory()
+        self.t1 = dict(aff=zeros(rows_in, D), relu=zeros(rows_in, D), out=zeros(rows_in, D), bn=make_bn(D),
+                       d_out=zeros(rows_in, D), d_aff=zeros(rows_in, D))
+        P, Ssm = cfg.num_pdfs, cfg.prefinal_small
+        self.head = dict(pl=zeros(rows_T, Ssm), pa=zeros(rows_T, D), pr=zeros(rows_T, D), pb=zeros(rows_T, D),
+                         pli=zeros(rows_T, Ssm), pb2=zeros(rows_T, Ssm), out=zeros(rows_T, P), bn1=make_bn(D), bn2=make_bn(Ssm),
+                         d_out=zeros(rows_T, P), d_pb2=zeros(rows_T, Ssm), d_pli=zeros(rows_T, Ssm), d_pb=zeros(rows_T, D),
+                         d_pa=zeros(rows_T, D), d_pl=zeros(rows_T, Ssm))
+        # ---------------- denominator graph + synthetic numerator alignment
+        graph = synth.make_den_graph(cfg.den_states, P, cfg.den_out_degree, seed=5)
+        self.den_arcs = graph["num_arcs"]
+        self.den_graph = capi.DenGraph(ctx, graph)
+        self.den = capi.DenominatorComputation(ctx, self.den_graph, S, T, cfg.leaky_hmm)
+        ali = synth.rng(3, stream=2 + self.rank).integers(0, P, size=rows_T)
+        self.num_index = torch.from_numpy(np.arange(rows_T) * P + ali).to(dev)
+        self.num_weight = torch.ones(rows_T, device=dev)
+        self._compile()
+        if search:
+            self._freeze_batchnorm()
+            self._compile()
+
+    def _freeze_batchnorm(self):
+        """Calibration pass: one forward with train-mode batch-norm on a synthetic minibatch, then every
+        batch-norm becomes a BatchNormTestComponent holding those statistics (test mode)."""
+        import torch
+
+        self.x.copy_(self.make_input(-1).to(self.dev))
+        self.fwd_plan.run()
+        torch.cuda.synchronize(self.dev)
+        for blk in self.blocks:
+            self.lib.tdnnf_nnet3_delete_memo(blk["lin"].h, blk["memo_lin"])
+            self.lib.tdnnf_nnet3_delete_memo(blk["aff"].h, blk["memo_aff"])
+
+        def freeze(memo, dim, count):
+            m = memo.cpu().numpy().astype(np.float64)
+            mean, var = m[:dim], m[dim:2 * dim]
+            bn = nnet3.Component.new("BatchNormTestComponent", "")
+            bn.bn_test_set_stats(dim, dim, 1e-3, 1.0, float(count), mean * count, (var + mean * mean) * count)
+            bn.set_test_mode(True)
+            return bn
+
+        self.t1["bn"] = freeze(self.t1["bn"], self.cfg.dim, self.t1["aff"].shape[0])
+        for blk in self.blocks:
+            blk["bn"] = freeze(blk["bn"], self.cfg.dim, blk["aff_out"].shape[0])
+        self.head["bn1"] = freeze(self.head["bn1"], self.cfg.dim, self.head["pa"].shape[0])
+        self.head["bn2"] = freeze(self.head["bn2"], self.cfg.prefinal_small, self.head["pli"].shape[0])
+
+    # ------------------------------------------------------------------ the step as pre-bound calls
+    def _affine_fwd(self, plan, x, p, out):
+        lib, h = self.lib, self.ctx.h
+        xp, xr, xc, xs = _m(x)
+        op, orr, oc, os_ = _m(out)
+        wp, _, _, ws = _m(p["W"])
+        b = p["b"]
+        plan.add("abi", lib.tdnnf_darts_propagate, h, xp, xr, xc, xs, op, orr, oc, os_, wp, ws,
+                 C.c_void_p(b.data_ptr()) if b is not None else None, 2 if b is not None else 1,
+                 C.c_void_p(self.one.data_ptr()), 1, self.zero_off, 1)
+
+    def _affine_bwd(self, plan, x, p, d_out, d_in, lr):
+        lib, h = self.lib, self.ctx.h
+        xp, xr, xc, xs = _m(x)
+        dp, dr, dc, ds = _m(d_out)
+        wp, _, _, ws = _m(p["W"])
+        gp, _, _, gs = _m(p["dW"])
+        one = C.c_void_p(self.one.data_ptr())
+        if d_in is not None:
+            ip, ir, ic, is_ = _m(d_in)
+            plan.add("abi", lib.tdnnf_mat_set, h, ip, ir, ic, is_, 0.0)
+            plan.add("abi", lib.tdnnf_darts_backprop_data, h, dp, dr, dc, ds, ip, ir, ic, is_, wp, ws, one, 1, self.zero_off, 1)
+        plan.add("abi", lib.tdnnf_darts_backprop_params, h, xp, xr, xc, xs, dp, dr, dc, ds, None, 0, gp, gs,
+                 C.c_void_p(p["db"].data_ptr()) if p["db"] is not None else None, one, 1, self.zero_off, 1, lr, None)
+
+    def _bn_fwd(self, plan, bn, x, out):
+        lib, h = self.lib, self.ctx.h
+        xp, xr, xc, xs = _m(x)
+        op, _, _, os_ = _m(out)
+        if isinstance(bn, nnet3.Component):
+            plan.add("nnet3", lib.tdnnf_nnet3_propagate, bn.h, None, xp, xr, xc, xs, op, xr, xc, os_, None)
+        else:
+            plan.add("abi", lib.tdnnf_batchnorm_train_fwd, h, xp, xr, xc, xs, op, os_, 1e-3, 1.0, C.c_void_p(bn.data_ptr()))
+
+    def _bn_bwd(self, plan, bn, out_value, d_out, d_in):
+        lib, h = self.lib, self.ctx.h
+        vp_, r, c, vs = _m(out_value)
+        dp, _, _, ds = _m(d_out)
+        ip, _, _, is_ = _m(d_in)
+        if isinstance(bn, nnet3.Component):
+            plan.add("nnet3", lib.tdnnf_nnet3_backprop, bn.h, None, None, r, c, 0, vp_, vs, dp, r, c, ds, None, None, ip, is_)
+        else:
+            plan.add("abi", lib.tdnnf_batchnorm_train_bwd, h, vp_, vs, dp, ds, ip, is_, r, c, 1.0, C.c_void_p(bn.data_ptr()))
+
+    def _compile(self):
+        cfg, lib, h = self.cfg, self.lib, self.ctx.h
+        lr = cfg.learning_rate
+        fwd, bwd, upd = _Plan(), _Plan(), _Plan()
+        st, t1, hd = self.stock, self.t1, self.head
+        # ---- forward
+        self._affine_fwd(fwd, self.x, st["tdnn1"], t1["aff"])
+        fwd.add("abi", lib.tdnnf_relu_fwd, h, *_m(t1["aff"]), _m(t1["relu"])[0], _m(t1["relu"])[3])
+        self._bn_fwd(fwd, t1["bn"], t1["relu"], t1["out"])
+        prev = t1["out"]
+        for blk in self.blocks:
+            pp, pr, pc, ps = _m(prev)
+            lp, lr_, lc, ls = _m(blk["lin_out"])
+            fwd.add("nnet3", lib.tdnnf_nnet3_propagate, blk["lin"].h, blk["lin_idx"].h, pp, pr, pc, ps, lp, lr_, lc, ls,
+                    C.byref(blk["memo_lin"]))
+            a_in = blk["lin_out"]
+            if blk["reorder"]:
+                ip, ir, ic, is_ = _m(blk["aff_in"])
+                fwd.add("abi", lib.tdnnf_copy_rows, h, lp, ls, ip, is_, ir, ic, C.c_void_p(blk["reorder"]["fwd"].data_ptr()))
+                a_in = blk["aff_in"]
+            ap, ar, ac, as_ = _m(a_in)
+            op, orr, oc, os_ = _m(blk["aff_out"])
+            fwd.add("nnet3", lib.tdnnf_nnet3_propagate, blk["aff"].h, blk["aff_idx"].h, ap, ar, ac, as_, op, orr, oc, os_,
+                    C.byref(blk["memo_aff"]))
+            fwd.add("abi", lib.tdnnf_relu_fwd, h, op, orr, oc, os_, _m(blk["relu"])[0], _m(blk["relu"])[3])
+            self._bn_fwd(fwd, blk["bn"], blk["relu"], blk["bn_out"])
+            # noop = Sum(Scale(0.66, prev[rows]), batchnorm)
+            byp = blk["bypass"]
+            if byp["contiguous"]:
+                src = prev[byp["offset"]: byp["offset"] + orr]
+            else:
+                fwd.add("abi", lib.tdnnf_copy_rows, h, pp, ps, _m(blk["byp_tmp"])[0], _m(blk["byp_tmp"])[3], orr, oc,
+                        C.c_void_p(byp["map"].data_ptr()))
+                src = blk["byp_tmp"]
+            self.keep.append(src)
+            fwd.add("abi", lib.tdnnf_add_scaled, h, _m(src)[0], _m(src)[3], cfg.bypass_scale, _m(blk["bn_out"])[0],
+                    _m(blk["bn_out"])[3], 1.0, _m(blk["out"])[0], _m(blk["out"])[3], orr, oc)
+            prev = blk["out"]
+        self._affine_fwd(fwd, prev, st["prefinal_l"], hd["pl"])
+        self._affine_fwd(fwd, hd["pl"], st["pc_affine"], hd["pa"])
+        fwd.add("abi", lib.tdnnf_relu_fwd, h, *_m(hd["pa"]), _m(hd["pr"])[0], _m(hd["pr"])[3])
+        self._bn_fwd(fwd, hd["bn1"], hd["pr"], hd["pb"])
+        self._affine_fwd(fwd, hd["pb"], st["pc_linear"], hd["pli"])
+        self._bn_fwd(fwd, hd["bn2"], hd["pli"], hd["pb2"])
+        self._affine_fwd(fwd, hd["pb2"], st["output"], hd["out"])
+
+        # ---- backward (d_out of the output layer is filled by the objective)
+        self._affine_bwd(bwd, hd["pb2"], st["output"], hd["d_out"], hd["d_pb2"], lr)
+        self._bn_bwd(bwd, hd["bn2"], hd["pb2"], hd["d_pb2"], hd["d_pb2"])
+        self._affine_bwd(bwd, hd["pb"], st["pc_linear"], hd["d_pb2"], hd["d_pb"], lr)
+        self._bn_bwd(bwd, hd["bn1"], hd["pb"], hd["d_pb"], hd["d_pb"])
+        bwd.add("abi", lib.tdnnf_relu_bwd, h, _m(hd["pr"])[0], _m(hd["pr"])[3], _m(hd["d_pb"])[0], _m(hd["d_pb"])[3],
+                _m(hd["d_pa"])[0], _m(hd["d_pa"])[3], hd["pr"].shape[0], hd["pr"].shape[1])
+        self._affine_bwd(bwd, hd["pl"], st["pc_affine"], hd["d_pa"], hd["d_pl"], lr)
+        last = self.blocks[-1]
+        self._affine_bwd(bwd, last["out"], st["prefinal_l"], hd["d_pl"], last["d_out"], lr)
+        for bi in range(len(self.blocks) - 1, -1, -1):
+            blk = self.blocks[bi]
+            prev_out = self.blocks[bi - 1]["out"] if bi > 0 else t1["out"]
+            d_prev = self.blocks[bi - 1]["d_out"] if bi > 0 else t1["d_out"]
+            dp_, dr, dc, ds = _m(blk["d_out"])
+            qp, qr, qc, qs = _m(d_prev)
+            # d_prev = 0 everywhere, then the bypass term on the matching rows
+            bwd.add("abi", lib.tdnnf_mat_set, h, qp, qr, qc, qs, 0.0)
+            byp = blk["bypass"]
+            if byp["contiguous"]:
+                dst = d_prev[byp["offset"]: byp["offset"] + dr]
+                self.keep.append(dst)
+                bwd.add("abi", lib.tdnnf_mat_axpy, h, cfg.bypass_scale, dp_, ds, _m(dst)[0], _m(dst)[3], dr, dc)
+            else:
+                bwd.add("abi", lib.tdnnf_add_to_rows, h, cfg.bypass_scale, dp_, ds, dr, dc, qp, qs, C.c_void_p(byp["map"].data_ptr()))
+            # batchnorm, relu
+            self._bn_bwd(bwd, blk["bn"], blk["bn_out"], blk["d_out"], blk["d_aff"])
+            bwd.add("abi", lib.tdnnf_relu_bwd, h, _m(blk["relu"])[0], _m(blk["relu"])[3], _m(blk["d_aff"])[0], _m(blk["d_aff"])[3],
+                    _m(blk["d_aff"])[0], _m(blk["d_aff"])[3], dr, dc)
+            # affine DARTS: in_deriv (kBackpropAdds) must start from zero
+            a_in = blk["aff_in"] if blk["reorder"] else blk["lin_out"]
+            d_ain = blk["d_aff_in"] if blk["reorder"] else blk["d_lin"]
+            ip, ir, ic, is_ = _m(a_in)
+            gp, gr, gc, gs = _m(d_ain)
+            bwd.add("abi", lib.tdnnf_mat_set, h, gp, gr, gc, gs, 0.0)
+            bwd.add("nnet3", lib.tdnnf_nnet3_backprop, blk["aff"].h, blk["aff_idx"].h, ip, ir, ic, is_, None, 0,
+                    _m(blk["d_aff"])[0], dr, dc, _m(blk["d_aff"])[3], blk["memo_aff"], blk["aff_delta"].h, gp, gs)
+            bwd.add("nnet3", lib.tdnnf_nnet3_delete_memo, blk["aff"].h, blk["memo_aff"])
+            if blk["reorder"]:
+                lp, lr_, lc, ls = _m(blk["d_lin"])
+                bwd.add("abi", lib.tdnnf_copy_rows, h, gp, gs, lp, ls, lr_, lc, C.c_void_p(blk["reorder"]["inv"].data_ptr()))
+            # linear DARTS: accumulates into d_prev on top of the bypass term
+            pp, pr, pc, ps = _m(prev_out)
+            lp, lr_, lc, ls = _m(blk["d_lin"])
+            bwd.add("nnet3", lib.tdnnf_nnet3_backprop, blk["lin"].h, blk["lin_idx"].h, pp, pr, pc, ps, None, 0, lp, lr_, lc, ls,
+                    blk["memo_lin"], blk["lin_delta"].h, qp, qs)
+            bwd.add("nnet3", lib.tdnnf_nnet3_delete_memo, blk["lin"].h, blk["memo_lin"])
+        self._bn_bwd(bwd, t1["bn"], t1["out"], t1["d_out"], t1["d_out"])
+        bwd.add("abi", lib.tdnnf_relu_bwd, h, _m(t1["relu"])[0], _m(t1["relu"])[3], _m(t1["d_out"])[0], _m(t1["d_out"])[3],
+                _m(t1["d_aff"])[0], _m(t1["d_aff"])[3], t1["relu"].shape[0], t1["relu"].shape[1])
+        self._affine_bwd(bwd, self.x, st["tdnn1"], t1["d_aff"], None, lr)
+
+        # ---- parameter step (UpdateNnetWithMaxChange, utils.cc:2085-2175): squared norms of every delta on the
+        # device, ONE read-back, Kaldi's per-component / global max-change factors on the host, scaled Add.
+        import torch
+
+        self.updatables = []  # (kind, model, delta, max_change)
+        for blk in self.blocks:
+            self.updatables.append(("comp", blk["lin"], blk["lin_delta"], cfg.max_change))
+            self.updatables.append(("comp", blk["aff"], blk["aff_delta"], cfg.max_change))
+        for name, p in st.items():
+            self.updatables.append(("stock", p, None, 1.5 if name == "output" else cfg.max_change))
+        self.dots = torch.zeros(len(self.updatables), dtype=torch.float64, device=self.dev)
+        for i, (kind, m, d, _) in enumerate(self.updatables):
+            slot = C.c_void_p(self.dots.data_ptr() + 8 * i)
+            if kind == "comp":
+                for ptr, rows, cols, stride in d.param_buffers():
+                    upd.add("abi", lib.tdnnf_mat_dot_dev, h, C.c_void_p(ptr), stride, C.c_void_p(ptr), stride, rows, cols, slot)
+            else:
+                gp, gr, gc, gs = _m(m["dW"])
+                upd.add("abi", lib.tdnnf_mat_dot_dev, h, gp, gs, gp, gs, gr, gc, slot)
+                if m["db"] is not None:
+                    n = m["db"].numel()
+                    dbp = C.c_void_p(m["db"].data_ptr())
+                    upd.add("abi", lib.tdnnf_mat_dot_dev, h, dbp, n, dbp, n, 1, n, slot)
+        self.fwd_plan, self.bwd_plan, self.upd_plan = fwd, bwd, upd
+        # delta buffers as torch views for the all-reduce
+        self.delta_views = self._delta_views() if self.world > 1 else []
+
+    def _delta_views(self):
+        import torch
+
+        class _Arr:
+            def __init__(self, ptr, nelem):
+                self.__cuda_array_interface__ = dict(shape=(nelem,), typestr="<f4", data=(ptr, False), version=2, strides=None)
+
+        views = []
+        for blk in self.blocks:
+            for d in (blk["lin_delta"], blk["aff_delta"]):
+                for ptr, rows, cols, stride in d.param_buffers():
+                    views.append(torch.as_tensor(_Arr(ptr, rows * stride), device=self.dev))
+        for p in self.stock.values():
+            views.append(p["dW"].view(-1))
+            if p["db"] is not None:
+                views.append(p["db"])
+        return views
+
+    # ------------------------------------------------------------------ public API
+    @property
+    def frames_per_step(self) -> int:
+        """Input frames consumed per step per GPU (chunks x frames_per_eg): the unit of the headline metric."""
+        return self.cfg.num_seqs * self.cfg.frames_per_eg
+
+    def algorithmic_flops(self) -> float:
+        """fwd + dgrad + wgrad FLOPs of the TdnnDARTSV3 GEMMs per step (n_eff = n in search mode)."""
+        cfg = self.cfg
+        n_eff = cfg.num_offsets if cfg.mode == "search" else 2
+        tot = 0.0
+        for blk in self.blocks:
+            tot += 3 * 2.0 * blk["lin_out"].shape[0] * n_eff * cfg.dim * cfg.bottleneck
+            tot += 3 * 2.0 * blk["aff_out"].shape[0] * n_eff * cfg.bottleneck * cfg.dim
+        return tot
+
+    def make_input(self, step: int = 0):
+        """Synthetic egs for this rank: N(0,1) features, different per rank (its shard of the minibatch)."""
+        import torch
+
+        g = synth.rng(3, stream=100 + self.rank * 1000 + step)
+        return torch.from_numpy(g.standard_normal((self.rows_in, self.cfg.feat_dim)).astype(np.float32))
+
+    def step(self, x_host=None, apply_update: bool = True) -> float:
+        """One training step.  x_host: pinned host tensor (rows_in x feat_dim) or None to reuse device input.
+        Returns the LF-MMI objective per output frame (numerator - denominator) of this rank."""
+        import torch
+
+        if x_host is not None:
+            self.x.copy_(x_host, non_blocking=True)
+        self.fwd_plan.run()
+        out, d_out = self.head["out"], self.head["d_out"]
+        self.ctx.mat_set(d_out, 0.0)
+        den_logprob = self.den.forward(out)                       # synchronises (returns a host scalar, like Kaldi)
+        ok = self.den.backward(-1.0, d_out)
+        # synthetic single-path numerator (row-wise gather / scatter of T*S elements; torch, not a hot kernel)
+        num_logprob = out.view(-1).index_select(0, self.num_index).sum()
+        d_out.view(-1).index_add_(0, self.num_index, self.num_weight)
+        if not ok:
+            d_out.zero_()
+        self.bwd_plan.run()
+        if self.world > 1:
+            parallel.allreduce_deltas(self.delta_views, self.pg)
+        if apply_update:
+            self._update_with_max_change()
+        objf = (float(num_logprob) - den_logprob) / (self.T * self.cfg.num_seqs)
+        return objf if ok else -10.0
+
+    def _update_with_max_change(self, scale: float = 1.0, max_change_scale: float = 1.0):
+        """UpdateNnetWithMaxChange + ScaleNnet(momentum=0) (utils.cc:2085-2175, common.py:877-878)."""
+        cfg, lib, h = self.cfg, self.lib, self.ctx.h
+        self.dots.zero_()
+        self.upd_plan.run()
+        dots = self.dots.cpu().numpy()  # the step's second (and last) host sync
+        factors = np.ones(len(dots))
+        param_delta_squared = 0.0
+        for i, (_, _, _, mc) in enumerate(self.updatables):
+            norm = float(np.sqrt(dots[i])) * abs(scale)
+            if mc != 0.0 and norm > mc * max_change_scale:
+                factors[i] = mc * max_change_scale / norm
+            param_delta_squared += factors[i] ** 2 * dots[i]
+        param_delta = float(np.sqrt(param_delta_squared)) * abs(scale)
+        if cfg.max_param_change != 0.0 and param_delta > cfg.max_param_change * max_change_scale:
+            if not np.isfinite(param_delta):
+                factors[:] = 0.0  # "Infinite parameter change, will not apply."
+            else:
+                scale *= cfg.max_param_change * max_change_scale / param_delta
+        self.last_max_change_factors = factors * scale
+        for f, (kind, m, d, _) in zip(self.last_max_change_factors, self.updatables):
+            f = float(f)
+            if kind == "comp":
+                if lib.tdnnf_nnet3_add(m.h, C.c_float(f), d.h) != 0 or lib.tdnnf_nnet3_scale(d.h, C.c_float(0.0)) != 0:
+                    self._raise_nnet3()
+            else:
+                self.ctx.mat_axpy(f, m["dW"], m["W"])
+                self.ctx.mat_set(m["dW"], 0.0)
+                if m["b"] is not None:
+                    self.ctx.mat_axpy(f, m["db"].view(1, -1), m["b"].view(1, -1))
+                    self.ctx.mat_set(m["db"].view(1, -1), 0.0)
+
+    def _raise_nnet3(self):
+        raise RuntimeError(self.lib.tdnnf_nnet3_last_error().decode())
+
+    def close(self):
+        import torch
+
+        torch.cuda.synchronize(self.dev)
+        self.den.close()
+        self.den_graph.close()

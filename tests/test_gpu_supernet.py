@@ -1,0 +1,38 @@
+"""GPU test of the supernet training step (the bench workload, at a small size)."""
+import math
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("mode", ["search", "pretrain"])
+def test_supernet_step_runs_and_learns(mode):
+    import torch
+
+    from tdnnf_nas_b200.supernet import Supernet, SupernetConfig
+
+    cfg = SupernetConfig(num_seqs=8, frames_per_eg=30, dim=128, bottleneck=32, num_blocks=3, prefinal_small=64,
+                         num_pdfs=200, den_states=300, den_out_degree=6.0, mode=mode, learning_rate=2e-3)
+    net = Supernet(cfg)
+    x = net.make_input(0).pin_memory()
+    launches0 = net.ctx.launches
+    objfs = [net.step(x) for _ in range(8)]
+    assert net.ctx.launches > launches0
+    assert all(math.isfinite(o) for o in objfs), objfs
+    # zero-initialised output layer: the first objective is num - den with all-zero outputs, i.e. -log-partition per frame
+    assert objfs[0] < 0
+    # ascending the LF-MMI objective on a fixed minibatch must improve it
+    assert objfs[-1] > objfs[0], objfs
+    # last block is frame-subsampled: its affine takes the blocked (reorder_t_in = 3) input order
+    assert net.blocks[-1]["reorder"] is not None and net.blocks[0]["reorder"] is None
+    if mode == "search":
+        from tdnnf_nas_b200 import nnet3
+
+        assert isinstance(net.blocks[0]["bn"], nnet3.Component) and net.blocks[0]["bn"].type() == "BatchNormTestComponent"
+        # alpha moved (update-alpha=true), and identically-seeded noise keeps it finite
+        v = net.blocks[0]["lin"].vectorize()
+        n = cfg.num_offsets
+        alpha = v[cfg.bottleneck * n * cfg.dim: cfg.bottleneck * n * cfg.dim + n]
+        assert all(math.isfinite(float(a)) for a in alpha) and any(abs(float(a)) > 0 for a in alpha)
+    net.close()
