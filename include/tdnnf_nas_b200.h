@@ -200,6 +200,18 @@ int tdnnf_add_to_rows(tdnnf_ctx* ctx, float alpha, const float* src, int src_str
 /* out = a * alpha + b * beta   (out may alias a or b) */
 int tdnnf_add_scaled(tdnnf_ctx* ctx, const float* a, int a_stride, float alpha, const float* b, int b_stride,
                      float beta, float* out, int out_stride, int rows, int cols);
+/* Fused tail of a TDNN-F block in the search stage: ReLU -> BatchNormTest (scale/offset) -> bypass sum, one
+ * pass instead of three (and no intermediate matrices):
+ *   fwd: out = relu(x) .* scale + offset + bypass_scale * prev
+ *   bwd: d_x = (x > 0) ? d_out .* scale : 0 ;  d_prev = bypass_scale * d_out   (d_prev overwritten)
+ * Equivalent to RectifiedLinearComponent + BatchNormTestComponent (ref: norm.cc:843-922) +
+ * Sum(Scale(bypass_scale, prev), .) evaluated separately. */
+int tdnnf_relu_scale_offset_bypass_fwd(tdnnf_ctx* ctx, const float* x, int rows, int cols, int x_stride,
+                                       const float* scale, const float* offset, const float* prev, int prev_stride,
+                                       float bypass_scale, float* out, int out_stride);
+int tdnnf_relu_scale_offset_bypass_bwd(tdnnf_ctx* ctx, const float* d_out, int do_stride, const float* x, int x_stride,
+                                       const float* scale, float bypass_scale, float* d_x, int dx_stride, float* d_prev,
+                                       int dp_stride, int rows, int cols);
 /* BatchNorm, training mode.  memo: device, 5 x cols (rows: mean, uvar, scale, -, -) as in the reference.
  *   fwd:  mean/var over rows; scale = target_rms * (var + eps)^-0.5; out = (in - mean) .* scale
  *   bwd:  x' = scale .* (z' - mean(z')) + z .* var_deriv_mod,

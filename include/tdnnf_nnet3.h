@@ -86,6 +86,9 @@ int tdnnf_nnet3_param_buffers(void* comp, float** ptrs, int* rows, int* cols, in
 int tdnnf_nnet3_bn_test_set_stats(void* comp, int dim, int block_dim, float epsilon, float target_rms, double count,
                                   const double* sum, const double* sumsq);
 
+/* Device pointers of BatchNormTestComponent's derived scale_ / offset_ vectors (ref: norm.cc:680-713). */
+int tdnnf_nnet3_bn_test_scale_offset(const void* comp, const float** scale, const float** offset, int* dim);
+
 /* ReadEditConfig subset: set-temperature-proportion, set-learning-rate{,-factor} (ref: utils.cc:1166-1415). */
 int tdnnf_nnet3_apply_edits(const char* edits, const char** names, void** comps, int n);
 

@@ -64,6 +64,8 @@ def _declare(lib):
     sig("tdnnf_relu_fwd", [vp, vp, i, i, i, vp, i])
     sig("tdnnf_relu_bwd", [vp, vp, i, vp, i, vp, i, i, i])
     sig("tdnnf_add_scaled", [vp, vp, i, f, vp, i, f, vp, i, i, i])
+    sig("tdnnf_relu_scale_offset_bypass_fwd", [vp, vp, i, i, i, vp, vp, vp, i, f, vp, i])
+    sig("tdnnf_relu_scale_offset_bypass_bwd", [vp, vp, i, vp, i, vp, f, vp, i, vp, i, i, i])
     sig("tdnnf_batchnorm_train_fwd", [vp, vp, i, i, i, vp, i, f, f, vp])
     sig("tdnnf_batchnorm_train_bwd", [vp, vp, i, vp, i, vp, i, i, i, f, vp])
     sig("tdnnf_den_graph_create", [vp, i, i, i, c_int_p, c_int_p, c_float_p, c_int_p, c_int_p, c_float_p, C.POINTER(vp)])
@@ -303,6 +305,21 @@ class Context:
         bp, _, _, bs = _mat(b)
         op, _, _, os_ = _mat(out)
         check(load().tdnnf_add_scaled(self.h, ap, as_, alpha, bp, bs, beta, op, os_, r, c))
+
+    def relu_scale_offset_bypass_fwd(self, x, scale, offset, prev, bypass_scale, out):
+        xp, r, c, xs = _mat(x)
+        pp, _, _, ps = _mat(prev)
+        op, _, _, os_ = _mat(out)
+        check(load().tdnnf_relu_scale_offset_bypass_fwd(self.h, xp, r, c, xs, _ptr(scale), _ptr(offset), pp, ps,
+                                                        bypass_scale, op, os_))
+
+    def relu_scale_offset_bypass_bwd(self, d_out, x, scale, bypass_scale, d_x, d_prev):
+        dp, r, c, ds = _mat(d_out)
+        xp, _, _, xs = _mat(x)
+        gp, _, _, gs = _mat(d_x)
+        pp, _, _, ps = _mat(d_prev)
+        check(load().tdnnf_relu_scale_offset_bypass_bwd(self.h, dp, ds, xp, xs, _ptr(scale), bypass_scale, gp, gs, pp,
+                                                        ps, r, c))
 
     def batchnorm_train_fwd(self, x, out, memo, epsilon=1e-3, target_rms=1.0):
         xp, r, c, xs = _mat(x)

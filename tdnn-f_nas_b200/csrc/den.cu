@@ -23,7 +23,7 @@ struct tdnnf_den_graph {
   int num_states = 0, num_pdfs = 0, num_transitions = 0;
   int2* fwd_ranges = nullptr;   // device [N]
   int2* bwd_ranges = nullptr;   // device [N]
-  float4* trans = nullptr;      // device [A]: {prob, pdf (as int bits), state (as int bits), unused}
+  float4* trans = nullptr;      // device [A]: {prob, pdf (as int bits), state (as int bits), init[state]}
   float* init = nullptr;        // device [N]
   float init_sum = 0.f;         // sum_h init[h] (host copy, fp32 sequential sum)
 };
@@ -79,7 +79,7 @@ __device__ __forceinline__ void red_add_vec(float* p, const float (&x)[V]) {
 }
 
 constexpr int kDenThreads = 256;
-constexpr int kStatesPerBlock = 64;
+constexpr int kStatesPerBlock = 32;
 
 // E[t][p][s] = exp(clamp(x[t*S+s][p])) : 32x32 tiled transpose per frame.
 __global__ void den_exp_transpose_kernel(const float* __restrict__ x, long long ld, int S, int P, float* __restrict__ E) {
@@ -137,14 +137,23 @@ den_alpha_frame_kernel(const int2* __restrict__ bwd_ranges, const float4* __rest
       float acc[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) acc[j] = 0.f;
-      for (int a = rg.x; a < rg.y; ++a) {
-        const float4 tr = trans[a];
-        const int pdf = __float_as_int(tr.y), g = __float_as_int(tr.z);
-        const float ig = init[g];
-        const Vec<V> al = Vec<V>::load(alpha_prev + (long long)g * S + s);
-        const Vec<V> e = Vec<V>::load(E_prev + (long long)pdf * S + s);
+      // arcs in groups of 4: all transition records first, then all row gathers, then the FMAs, so that
+      // 8 independent L2 reads are in flight per thread instead of a dependent chain
+      for (int a = rg.x; a < rg.y; a += 4) {
+        float4 tr[4];
+        Vec<V> al[4], e[4];
 #pragma unroll
-        for (int j = 0; j < V; ++j) acc[j] += ((al.v[j] + ig * lt[j]) * tr.x) * e.v[j];
+        for (int u = 0; u < 4; ++u) tr[u] = (a + u < rg.y) ? trans[a + u] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int pdf = __float_as_int(tr[u].y), g = __float_as_int(tr[u].z);  // (0,0) for the padding arcs: valid rows, weight 0
+          al[u] = Vec<V>::load(alpha_prev + (long long)g * S + s);
+          e[u] = Vec<V>::load(E_prev + (long long)pdf * S + s);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int j = 0; j < V; ++j) acc[j] += ((al[u].v[j] + tr[u].w * lt[j]) * tr[u].x) * e[u].v[j];
       }
       Vec<V> o;
 #pragma unroll
@@ -237,19 +246,31 @@ den_beta_frame_kernel(const int2* __restrict__ fwd_ranges, const float4* __restr
       float occ[V], totv[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) { occ[j] = (al.v[j] + ih * lt[j]) * inv[j]; totv[j] = 0.f; }
-      for (int a = rg.x; a < rg.y; ++a) {
-        const float4 tr = trans[a];
-        const int pdf = __float_as_int(tr.y), g = __float_as_int(tr.z);
-        const Vec<V> b = Vec<V>::load(betad_next + (long long)g * S + s);
-        const Vec<V> e = Vec<V>::load(E_t + (long long)pdf * S + s);
-        float op[V];
+      for (int a = rg.x; a < rg.y; a += 4) {
+        float4 tr[4];
+        Vec<V> b[4], e[4];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-          const float vf = (tr.x * (b.v[j] + lb[j])) * e.v[j];
-          totv[j] += vf;
-          op[j] = vf * occ[j];
+        for (int u = 0; u < 4; ++u) tr[u] = (a + u < rg.y) ? trans[a + u] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int pdf = __float_as_int(tr[u].y), g = __float_as_int(tr[u].z);
+          b[u] = Vec<V>::load(betad_next + (long long)g * S + s);
+          e[u] = Vec<V>::load(E_t + (long long)pdf * S + s);
         }
-        red_add_vec<V>(gamma_t + (long long)pdf * S + s, op);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (a + u < rg.y) {
+            const int pdf = __float_as_int(tr[u].y);
+            float op[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              const float vf = (tr[u].x * (b[u].v[j] + lb[j])) * e[u].v[j];
+              totv[j] += vf;
+              op[j] = vf * occ[j];
+            }
+            red_add_vec<V>(gamma_t + (long long)pdf * S + s, op);
+          }
+        }
       }
       Vec<V> o;
 #pragma unroll
@@ -341,7 +362,7 @@ extern "C" int tdnnf_den_graph_create(tdnnf_ctx* ctx, int num_states, int num_pd
     tr[a].x = trans_prob[a];
     memcpy(&tr[a].y, &trans_pdf[a], 4);
     memcpy(&tr[a].z, &trans_state[a], 4);
-    tr[a].w = 0.f;
+    tr[a].w = initial_probs[trans_state[a]];  // saves a dependent load per arc in the forward recursion
   }
   float isum = 0.f;
   for (int h = 0; h < num_states; ++h) isum += initial_probs[h];

@@ -192,6 +192,41 @@ __global__ void bn_apply_bwd_kernel(const float* __restrict__ ov, long long vs, 
   }
 }
 
+__global__ void tail_fwd_kernel(const float* __restrict__ x, long long xs, const float* __restrict__ scale,
+                                const float* __restrict__ offset, const float* __restrict__ prev, long long ps, float bs,
+                                float* __restrict__ out, long long os, int rows, int cols) {
+  const int c4 = cols >> 2;
+  ELEMWISE_LOOP((long long)rows * c4) {
+    const long long r = idx / c4;
+    const int c = (int)(idx % c4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + r * xs + c);
+    const float4 s = *reinterpret_cast<const float4*>(scale + c);
+    const float4 o = *reinterpret_cast<const float4*>(offset + c);
+    const float4 p = *reinterpret_cast<const float4*>(prev + r * ps + c);
+    float4 y;
+    y.x = fmaxf(v.x, 0.f) * s.x + o.x + bs * p.x;
+    y.y = fmaxf(v.y, 0.f) * s.y + o.y + bs * p.y;
+    y.z = fmaxf(v.z, 0.f) * s.z + o.z + bs * p.z;
+    y.w = fmaxf(v.w, 0.f) * s.w + o.w + bs * p.w;
+    *reinterpret_cast<float4*>(out + r * os + c) = y;
+  }
+}
+__global__ void tail_bwd_kernel(const float* __restrict__ dout, long long dos, const float* __restrict__ x, long long xs,
+                                const float* __restrict__ scale, float bs, float* __restrict__ dx, long long dxs,
+                                float* __restrict__ dprev, long long dps, int rows, int cols) {
+  const int c4 = cols >> 2;
+  ELEMWISE_LOOP((long long)rows * c4) {
+    const long long r = idx / c4;
+    const int c = (int)(idx % c4) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(dout + r * dos + c);
+    const float4 v = *reinterpret_cast<const float4*>(x + r * xs + c);
+    const float4 s = *reinterpret_cast<const float4*>(scale + c);
+    *reinterpret_cast<float4*>(dx + r * dxs + c) =
+        make_float4(v.x > 0.f ? g.x * s.x : 0.f, v.y > 0.f ? g.y * s.y : 0.f, v.z > 0.f ? g.z * s.z : 0.f, v.w > 0.f ? g.w * s.w : 0.f);
+    *reinterpret_cast<float4*>(dprev + r * dps + c) = make_float4(bs * g.x, bs * g.y, bs * g.z, bs * g.w);
+  }
+}
+
 bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
@@ -343,6 +378,33 @@ extern "C" int tdnnf_batchnorm_train_bwd(tdnnf_ctx* ctx, const float* out_value,
   LAUNCH_CHECK(ctx);
   bn_apply_bwd_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
       out_value, ov_stride, out_deriv, od_stride, in_deriv, id_stride, rows, cols, target_rms, memo, sums);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_relu_scale_offset_bypass_fwd(tdnnf_ctx* ctx, const float* x, int rows, int cols, int x_stride,
+                                                  const float* scale, const float* offset, const float* prev,
+                                                  int prev_stride, float bypass_scale, float* out, int out_stride) {
+  PROLOGUE(x && scale && offset && prev && out && x_stride >= cols && prev_stride >= cols && out_stride >= cols, "bad matrix");
+  TDNNF_REQUIRE(cols % 4 == 0 && x_stride % 4 == 0 && prev_stride % 4 == 0 && out_stride % 4 == 0 && al16(x) && al16(prev) &&
+                    al16(out) && al16(scale) && al16(offset),
+                "fused tail needs 16-byte aligned rows (cols and strides multiples of 4)");
+  tail_fwd_kernel<<<grid_for((long long)rows * cols / 4, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
+      x, x_stride, scale, offset, prev, prev_stride, bypass_scale, out, out_stride, rows, cols);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_relu_scale_offset_bypass_bwd(tdnnf_ctx* ctx, const float* d_out, int do_stride, const float* x,
+                                                  int x_stride, const float* scale, float bypass_scale, float* d_x,
+                                                  int dx_stride, float* d_prev, int dp_stride, int rows, int cols) {
+  PROLOGUE(d_out && x && scale && d_x && d_prev && do_stride >= cols && x_stride >= cols && dx_stride >= cols && dp_stride >= cols,
+           "bad matrix");
+  TDNNF_REQUIRE(cols % 4 == 0 && do_stride % 4 == 0 && x_stride % 4 == 0 && dx_stride % 4 == 0 && dp_stride % 4 == 0 &&
+                    al16(d_out) && al16(x) && al16(d_x) && al16(d_prev) && al16(scale),
+                "fused tail needs 16-byte aligned rows (cols and strides multiples of 4)");
+  tail_bwd_kernel<<<grid_for((long long)rows * cols / 4, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
+      d_out, do_stride, x, x_stride, scale, bypass_scale, d_x, dx_stride, d_prev, dp_stride, rows, cols);
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }

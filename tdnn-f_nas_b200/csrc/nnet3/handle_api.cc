@@ -261,6 +261,17 @@ int tdnnf_nnet3_bn_test_set_stats(void* comp, int dim, int block_dim, float epsi
   API_END
 }
 
+// Device pointers of a BatchNormTestComponent's derived scale_ / offset_ (block_dim entries each).
+int tdnnf_nnet3_bn_test_scale_offset(const void* comp, const float** scale, const float** offset, int* dim) {
+  API_BEGIN
+  const BatchNormTestComponent* b = dynamic_cast<const BatchNormTestComponent*>(static_cast<const Component*>(comp));
+  if (!b) KALDI_ERR << "not a BatchNormTestComponent";
+  *scale = b->ScaleVec().Data();
+  *offset = b->Offset().Data();
+  *dim = b->ScaleVec().Dim();
+  API_END
+}
+
 // ReadEditConfig over a list of (name, component): the `nnet3-copy --edits=...` step of train.py:524-532.
 int tdnnf_nnet3_apply_edits(const char* edits, const char** names, void** comps, int n) {
   API_BEGIN

@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "context.h"
@@ -78,39 +79,58 @@ struct GroupRowOffsets {
   int v[kMaxSeg];
 };
 
-__global__ void split_transpose_kernel(const float* __restrict__ src, int R, int J, long long ld, int r,
-                                       int c_row_mul, int c_col_mul, GroupRowOffsets c_row_off,
-                                       const float* __restrict__ scale, int Q, int Qp,
-                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-  __shared__ float tile[64][33];
+__global__ void __launch_bounds__(256)
+split_transpose_kernel(const float* __restrict__ src, int R, int J, long long ld, int r, int c_row_mul, int c_col_mul,
+                       GroupRowOffsets c_row_off, const float* __restrict__ scale, int Q, int Qp,
+                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  // 64 (q) x 64 (j) tile: 256-byte coalesced float4 reads along j, 128-byte (8 x bf16 per lane) writes along q.
+  __shared__ float tile[64][65];
   const int c = blockIdx.z;
   const int q0 = blockIdx.x * 64;
-  const int j0 = blockIdx.y * 32;
-  const int tx = threadIdx.x, ty = threadIdx.y;  // (32, 8)
+  const int j0 = blockIdx.y * 64;
+  const int t = threadIdx.x;
   const float sc = scale ? scale[c] : 1.0f;
-  for (int qq = ty; qq < 64; qq += 8) {
+  const long long col0 = (long long)c * c_col_mul + j0;
+  const bool vec = ((ld & 3) == 0) && ((col0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (j0 + 64 <= J);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int qq = (t >> 4) + 16 * i, j4 = (t & 15) * 4;
     const int q = q0 + qq;
     const long long srow = (long long)q * r + (long long)c * c_row_mul + c_row_off.v[c];
-    float v = 0.f;
-    if (q < Q && srow < R && j0 + tx < J) v = sc * src[srow * ld + (long long)c * c_col_mul + j0 + tx];
-    tile[qq][tx] = v;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < Q && srow < R) {
+      const float* sp = src + srow * ld + col0 + j4;
+      if (vec) {
+        v = *reinterpret_cast<const float4*>(sp);
+      } else {
+        if (j0 + j4 + 0 < J) v.x = sp[0];
+        if (j0 + j4 + 1 < J) v.y = sp[1];
+        if (j0 + j4 + 2 < J) v.z = sp[2];
+        if (j0 + j4 + 3 < J) v.w = sp[3];
+      }
+    }
+    tile[qq][j4 + 0] = sc * v.x;
+    tile[qq][j4 + 1] = sc * v.y;
+    tile[qq][j4 + 2] = sc * v.z;
+    tile[qq][j4 + 3] = sc * v.w;
   }
   __syncthreads();
-  for (int jj = ty; jj < 32; jj += 8) {
-    const int j = j0 + jj;
-    if (j >= J) continue;
-    const int q = q0 + 2 * tx;
-    if (q >= Qp) continue;  // Qp is even
-    const float a = tile[2 * tx][jj], b = tile[2 * tx + 1][jj];
-    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-    const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
-    const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int jj = (t >> 3) + 32 * i, qc = (t & 7) * 8;
+    const int j = j0 + jj, q = q0 + qc;
+    if (j >= J || q >= Qp) continue;  // Qp is a multiple of 8
+    __align__(16) __nv_bfloat16 h[8];
+    __align__(16) __nv_bfloat16 l[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float a = tile[qc + k][jj];
+      h[k] = __float2bfloat16_rn(a);
+      l[k] = __float2bfloat16_rn(a - __bfloat162float(h[k]));
+    }
     const long long o = ((long long)c * J + j) * Qp + q;
-    __nv_bfloat162 h2, l2;
-    h2.x = ah; h2.y = bh;
-    l2.x = al; l2.y = bl;
-    *reinterpret_cast<__nv_bfloat162*>(hi + o) = h2;
-    *reinterpret_cast<__nv_bfloat162*>(lo + o) = l2;
+    *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(l);
   }
 }
 
@@ -184,7 +204,7 @@ static int launch_split_transpose(tdnnf_ctx* ctx, const float* src, int R, int J
   pl->groups = groups;
   pl->base = static_cast<__nv_bfloat16*>(ctx->ws_alloc(planes_bytes(groups, J, Qp)));
   if (!pl->base) return TDNNF_ERR_NOMEM;
-  dim3 grid(ceil_div(Qp, 64), ceil_div(J, 32), groups), block(32, 8);
+  dim3 grid(ceil_div(Qp, 64), ceil_div(J, 64), groups), block(256);
   GroupRowOffsets gro;
   for (int i = 0; i < kMaxSeg; ++i) gro.v[i] = (group_row_offsets && i < groups) ? group_row_offsets[i] : 0;
   split_transpose_kernel<<<grid, block, 0, ctx->stream>>>(src, R, J, ld, r, c_row_mul, c_col_mul, gro, scale, Q, Qp,
@@ -246,9 +266,14 @@ static int launch_gemm_bn(tdnnf_ctx* ctx, const Planes& A, const Planes& B, cons
 }
 
 static int pick_bn(int n) {
+  static const int wide = [] {  // experiment knob: TDNNF_BN_WIDE=128|256 for outputs that are multiples of 256
+    const char* e = getenv("TDNNF_BN_WIDE");
+    return e ? atoi(e) : 128;
+  }();
   if (n <= 32) return 32;
   if (n <= 64) return 64;
   if (n % 160 == 0) return 160;
+  if (n % 256 == 0 && wide == 256) return 256;
   if (n % 128 == 0 || n > 160) return 128;
   if (n <= 128) return 128;
   return 160;
@@ -260,6 +285,7 @@ static int launch_gemm(tdnnf_ctx* ctx, int bn, const Planes& A, const Planes& B,
     case 64: return launch_gemm_bn<64>(ctx, A, B, p, algorithmic_flops);
     case 128: return launch_gemm_bn<128>(ctx, A, B, p, algorithmic_flops);
     case 160: return launch_gemm_bn<160>(ctx, A, B, p, algorithmic_flops);
+    case 256: return launch_gemm_bn<256>(ctx, A, B, p, algorithmic_flops);
     default: return fail(TDNNF_ERR_INVALID, "unsupported BN");
   }
 }

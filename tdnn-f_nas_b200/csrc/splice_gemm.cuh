@@ -86,12 +86,13 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// No "memory" clobber on purpose: the reductions are fire-and-forget and nothing in the thread reads the
+// locations back, so the compiler may hoist independent loads (dot_ref, bias) above them.
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
-  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v));
 }
 __device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
-               : "memory");
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d));
 }
 
 struct UnitCoord {
@@ -100,13 +101,17 @@ struct UnitCoord {
 };
 
 __device__ __forceinline__ UnitCoord decode_unit(int u, const GemmParams& p, const GemmSmemMeta* meta) {
+  // Order: group c fastest, then n-tile, then k-split, then m-tile.  Units that run at the same time on
+  // different SMs then share operand tiles through L2: the 7 offsets of a parameter-gradient tile read the
+  // same activation rows (shifted by one K block) and the n-tiles of a wide output share the A tile.  (With
+  // c slowest every wave re-streamed the ~130 MB of operand planes from HBM in 128-byte pieces.)
   UnitCoord uc;
+  uc.c = u % p.c_tiles;
+  u /= p.c_tiles;
   uc.n_t = u % p.n_tiles;
   u /= p.n_tiles;
   uc.split = u % p.splits;
-  u /= p.splits;
-  uc.m_t = u % p.m_tiles;
-  uc.c = u / p.m_tiles;
+  uc.m_t = u / p.splits;
   const long long total = (long long)meta->cnt[uc.c] * p.kb_per_seg;
   uc.it0 = (int)((total * uc.split) / p.splits);
   uc.it1 = (int)((total * (uc.split + 1)) / p.splits);
@@ -264,83 +269,97 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll 1
       for (int chunk = 0; chunk < BN / 16; ++chunk) {
         uint32_t v[16];
+        float ref[16];
         __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
-        if (has_acc) {
+        const int n0 = uc.n_t * BN + chunk * 16;
+        const bool live = row_ok && n0 < p.n_valid;
+        const long long C0 = (long long)n0 + (long long)uc.c * p.col_cadd;
+        const bool full = (n0 + 16 <= p.n_valid);
+        if (has_acc)
           ptx::tmem_ld_32x16(tmem_base + acc_buf * kAccCols + ((uint32_t)(quarter * 32) << 16) + chunk * 16, v);
+        // the dot_ref reads are issued before waiting for TMEM so that their L2 latency overlaps the load
+        if (p.dot_ref != nullptr && live) {
+          if (!p.transposed) {
+            const float* rp = p.dot_ref + R * p.dot_ld + C0;
+            if (full && dot_vec_ok) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
+                ref[j] = r4.x; ref[j + 1] = r4.y; ref[j + 2] = r4.z; ref[j + 3] = r4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) ref[j] = (n0 + j < p.n_valid) ? rp[j] : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ref[j] = (n0 + j < p.n_valid) ? p.dot_ref[(C0 + j) * p.dot_ld + R] : 0.f;
+          }
+        }
+        if (has_acc) {
           ptx::tmem_ld_wait();
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = 0u;
         }
-        const int n0 = uc.n_t * BN + chunk * 16;
-        if (row_ok && n0 < p.n_valid) {
-        const long long C0 = (long long)n0 + (long long)uc.c * p.col_cadd;
-        const bool full = (n0 + 16 <= p.n_valid);
-        if (!p.transposed) {
-          float* dst = p.out + R * p.out_ld + C0;
+        if (live) {
           if (p.dot_ref != nullptr) {
-            const float* ref = p.dot_ref + R * p.dot_ld + C0;
-            if (full && dot_vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dot += __uint_as_float(v[j]) * ref[j];
+          }
+          if (!p.transposed) {
+            float* dst = p.out + R * p.out_ld + C0;
+            if (full && vec_ok) {
+              float4 prev[4];
+              if (!p.atomic && p.accumulate) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) prev[j] = *reinterpret_cast<const float4*>(dst + 4 * j);
+              }
 #pragma unroll
               for (int j = 0; j < 16; j += 4) {
-                const float4 r4 = *reinterpret_cast<const float4*>(ref + j);
-                dot += __uint_as_float(v[j]) * r4.x + __uint_as_float(v[j + 1]) * r4.y +
-                       __uint_as_float(v[j + 2]) * r4.z + __uint_as_float(v[j + 3]) * r4.w;
+                float4 o;
+                o.x = scale * __uint_as_float(v[j]);
+                o.y = scale * __uint_as_float(v[j + 1]);
+                o.z = scale * __uint_as_float(v[j + 2]);
+                o.w = scale * __uint_as_float(v[j + 3]);
+                if (add_bias) {  // the bias tail starts n floats into bias_params_: not 16-byte aligned in general
+                  const float* bj = p.bias + n0 + j;
+                  o.x += __ldg(bj); o.y += __ldg(bj + 1); o.z += __ldg(bj + 2); o.w += __ldg(bj + 3);
+                }
+                if (p.atomic) {
+                  red_add_v4_f32(dst + j, o.x, o.y, o.z, o.w);
+                } else {
+                  if (p.accumulate) {
+                    o.x += prev[j >> 2].x; o.y += prev[j >> 2].y; o.z += prev[j >> 2].z; o.w += prev[j >> 2].w;
+                  }
+                  *reinterpret_cast<float4*>(dst + j) = o;
+                }
               }
             } else {
-              for (int j = 0; j < 16; ++j)
-                if (n0 + j < p.n_valid) dot += __uint_as_float(v[j]) * ref[j];
-            }
-          }
-          if (full && vec_ok) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              float4 o;
-              o.x = scale * __uint_as_float(v[j]);
-              o.y = scale * __uint_as_float(v[j + 1]);
-              o.z = scale * __uint_as_float(v[j + 2]);
-              o.w = scale * __uint_as_float(v[j + 3]);
-              if (add_bias) {  // the bias tail starts n floats into bias_params_: not 16-byte aligned in general
-                const float* bj = p.bias + n0 + j;
-                o.x += __ldg(bj); o.y += __ldg(bj + 1); o.z += __ldg(bj + 2); o.w += __ldg(bj + 3);
-              }
-              if (p.atomic) {
-                red_add_v4_f32(dst + j, o.x, o.y, o.z, o.w);
-              } else {
-                if (p.accumulate) {
-                  const float4 prev = *reinterpret_cast<const float4*>(dst + j);
-                  o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
-                }
-                *reinterpret_cast<float4*>(dst + j) = o;
+              for (int j = 0; j < 16; ++j) {
+                if (n0 + j >= p.n_valid) break;
+                float o = scale * __uint_as_float(v[j]);
+                if (add_bias) o += p.bias[n0 + j];
+                if (p.atomic) red_add_f32(dst + j, o);
+                else if (p.accumulate) dst[j] += o;
+                else dst[j] = o;
               }
             }
           } else {
-            for (int j = 0; j < 16; ++j) {
-              if (n0 + j >= p.n_valid) break;
-              float o = scale * __uint_as_float(v[j]);
-              if (add_bias) o += p.bias[n0 + j];
-              if (p.atomic) red_add_f32(dst + j, o);
-              else if (p.accumulate) dst[j] += o;
-              else dst[j] = o;
-            }
-          }
-        } else {
-          // transposed: consecutive lanes (rows m) are consecutive addresses -> coalesced per register
+            // transposed: consecutive lanes (rows m) are consecutive addresses -> coalesced per register
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (n0 + j < p.n_valid) {
-              const long long idx = (C0 + j) * p.out_ld + R;
-              const float a = __uint_as_float(v[j]);
-              if (p.dot_ref != nullptr) dot += a * p.dot_ref[(C0 + j) * p.dot_ld + R];
-              float o = scale * a;
-              if (add_bias) o += p.bias[n0 + j];
-              if (p.atomic) red_add_f32(p.out + idx, o);
-              else if (p.accumulate) p.out[idx] += o;
-              else p.out[idx] = o;
+            for (int j = 0; j < 16; ++j) {
+              if (n0 + j < p.n_valid) {
+                const long long idx = (C0 + j) * p.out_ld + R;
+                float o = scale * __uint_as_float(v[j]);
+                if (add_bias) o += p.bias[n0 + j];
+                if (p.atomic) red_add_f32(p.out + idx, o);
+                else if (p.accumulate) p.out[idx] += o;
+                else p.out[idx] = o;
+              }
             }
           }
         }
-        }  // row_ok && n0 < n_valid
       }
       __syncwarp();
       if (p.dot_ref != nullptr) {

@@ -303,6 +303,12 @@ class Component:
                                                     C.c_double(count), a.ctypes.data_as(C.POINTER(C.c_double)),
                                                     b.ctypes.data_as(C.POINTER(C.c_double))))
 
+    def bn_test_scale_offset(self):
+        """(scale_ptr, offset_ptr, dim): device pointers of a BatchNormTestComponent's derived vectors."""
+        sp, op, dim = C.c_void_p(), C.c_void_p(), C.c_int()
+        _check(_lib().tdnnf_nnet3_bn_test_scale_offset(self.h, C.byref(sp), C.byref(op), C.byref(dim)))
+        return sp.value, op.value, dim.value
+
     def __del__(self):
         try:
             if self.h:

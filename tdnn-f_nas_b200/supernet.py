@@ -49,6 +49,7 @@ class SupernetConfig:
     darts_lr_factor: float = 1.0e-4  # <LearningRateFactor> set by the cvupdate recipe's sed (search mode only)
     max_change: float = 0.75         # per-component max-change (xconfig default of the tdnnf layers)
     max_param_change: float = 2.0    # --trainer.max-param-change (global)
+    fuse_tail: bool = True           # search mode: ReLU + BatchNormTest + bypass as one pass (else three components)
     seed: int = 20221 + 3
 
 
@@ -318,9 +319,8 @@ class Supernet:
             op, orr, oc, os_ = _m(blk["aff_out"])
             fwd.add("nnet3", lib.tdnnf_nnet3_propagate, blk["aff"].h, blk["aff_idx"].h, ap, ar, ac, as_, op, orr, oc, os_,
                     C.byref(blk["memo_aff"]))
-            fwd.add("abi", lib.tdnnf_relu_fwd, h, op, orr, oc, os_, _m(blk["relu"])[0], _m(blk["relu"])[3])
-            self._bn_fwd(fwd, blk["bn"], blk["relu"], blk["bn_out"])
-            # noop = Sum(Scale(0.66, prev[rows]), batchnorm)
+            fused = cfg.fuse_tail and isinstance(blk["bn"], nnet3.Component)
+            # noop = Sum(Scale(0.66, prev[rows]), batchnorm(relu(affine)))
             byp = blk["bypass"]
             if byp["contiguous"]:
                 src = prev[byp["offset"]: byp["offset"] + orr]
@@ -329,8 +329,15 @@ class Supernet:
                         C.c_void_p(byp["map"].data_ptr()))
                 src = blk["byp_tmp"]
             self.keep.append(src)
-            fwd.add("abi", lib.tdnnf_add_scaled, h, _m(src)[0], _m(src)[3], cfg.bypass_scale, _m(blk["bn_out"])[0],
-                    _m(blk["bn_out"])[3], 1.0, _m(blk["out"])[0], _m(blk["out"])[3], orr, oc)
+            if fused:
+                sp, ofp, _ = blk["bn"].bn_test_scale_offset()
+                fwd.add("abi", lib.tdnnf_relu_scale_offset_bypass_fwd, h, op, orr, oc, os_, C.c_void_p(sp), C.c_void_p(ofp),
+                        _m(src)[0], _m(src)[3], cfg.bypass_scale, _m(blk["out"])[0], _m(blk["out"])[3])
+            else:
+                fwd.add("abi", lib.tdnnf_relu_fwd, h, op, orr, oc, os_, _m(blk["relu"])[0], _m(blk["relu"])[3])
+                self._bn_fwd(fwd, blk["bn"], blk["relu"], blk["bn_out"])
+                fwd.add("abi", lib.tdnnf_add_scaled, h, _m(src)[0], _m(src)[3], cfg.bypass_scale, _m(blk["bn_out"])[0],
+                        _m(blk["bn_out"])[3], 1.0, _m(blk["out"])[0], _m(blk["out"])[3], orr, oc)
             prev = blk["out"]
         self._affine_fwd(fwd, prev, st["prefinal_l"], hd["pl"])
         self._affine_fwd(fwd, hd["pl"], st["pc_affine"], hd["pa"])
@@ -356,19 +363,40 @@ class Supernet:
             d_prev = self.blocks[bi - 1]["d_out"] if bi > 0 else t1["d_out"]
             dp_, dr, dc, ds = _m(blk["d_out"])
             qp, qr, qc, qs = _m(d_prev)
-            # d_prev = 0 everywhere, then the bypass term on the matching rows
-            bwd.add("abi", lib.tdnnf_mat_set, h, qp, qr, qc, qs, 0.0)
+            fused = cfg.fuse_tail and isinstance(blk["bn"], nnet3.Component)
             byp = blk["bypass"]
-            if byp["contiguous"]:
-                dst = d_prev[byp["offset"]: byp["offset"] + dr]
+            if fused and byp["contiguous"]:
+                # zero only the halo rows of d_prev; the fused kernel overwrites the matching rows with the bypass term
+                off = byp["offset"]
+                for lo_, hi_ in ((0, off), (off + dr, qr)):
+                    if hi_ > lo_:
+                        halo = d_prev[lo_:hi_]
+                        self.keep.append(halo)
+                        bwd.add("abi", lib.tdnnf_mat_set, h, _m(halo)[0], hi_ - lo_, qc, _m(halo)[3], 0.0)
+                dst = d_prev[off: off + dr]
                 self.keep.append(dst)
-                bwd.add("abi", lib.tdnnf_mat_axpy, h, cfg.bypass_scale, dp_, ds, _m(dst)[0], _m(dst)[3], dr, dc)
+                sp, _, _ = blk["bn"].bn_test_scale_offset()
+                bwd.add("abi", lib.tdnnf_relu_scale_offset_bypass_bwd, h, dp_, ds, _m(blk["aff_out"])[0], _m(blk["aff_out"])[3],
+                        C.c_void_p(sp), cfg.bypass_scale, _m(blk["d_aff"])[0], _m(blk["d_aff"])[3], _m(dst)[0], _m(dst)[3], dr, dc)
             else:
-                bwd.add("abi", lib.tdnnf_add_to_rows, h, cfg.bypass_scale, dp_, ds, dr, dc, qp, qs, C.c_void_p(byp["map"].data_ptr()))
-            # batchnorm, relu
-            self._bn_bwd(bwd, blk["bn"], blk["bn_out"], blk["d_out"], blk["d_aff"])
-            bwd.add("abi", lib.tdnnf_relu_bwd, h, _m(blk["relu"])[0], _m(blk["relu"])[3], _m(blk["d_aff"])[0], _m(blk["d_aff"])[3],
-                    _m(blk["d_aff"])[0], _m(blk["d_aff"])[3], dr, dc)
+                # d_prev = 0 everywhere, then the bypass term on the matching rows
+                bwd.add("abi", lib.tdnnf_mat_set, h, qp, qr, qc, qs, 0.0)
+                if byp["contiguous"]:
+                    dst = d_prev[byp["offset"]: byp["offset"] + dr]
+                    self.keep.append(dst)
+                    bwd.add("abi", lib.tdnnf_mat_axpy, h, cfg.bypass_scale, dp_, ds, _m(dst)[0], _m(dst)[3], dr, dc)
+                else:
+                    bwd.add("abi", lib.tdnnf_add_to_rows, h, cfg.bypass_scale, dp_, ds, dr, dc, qp, qs, C.c_void_p(byp["map"].data_ptr()))
+                if fused:
+                    sp, _, _ = blk["bn"].bn_test_scale_offset()
+                    scratch = blk["bn_out"]  # d_prev of the non-contiguous (last) block is handled above; discard the kernel's copy
+                    bwd.add("abi", lib.tdnnf_relu_scale_offset_bypass_bwd, h, dp_, ds, _m(blk["aff_out"])[0], _m(blk["aff_out"])[3],
+                            C.c_void_p(sp), 0.0, _m(blk["d_aff"])[0], _m(blk["d_aff"])[3], _m(scratch)[0], _m(scratch)[3], dr, dc)
+                else:
+                    # batchnorm, relu
+                    self._bn_bwd(bwd, blk["bn"], blk["bn_out"], blk["d_out"], blk["d_aff"])
+                    bwd.add("abi", lib.tdnnf_relu_bwd, h, _m(blk["relu"])[0], _m(blk["relu"])[3], _m(blk["d_aff"])[0], _m(blk["d_aff"])[3],
+                            _m(blk["d_aff"])[0], _m(blk["d_aff"])[3], dr, dc)
             # affine DARTS: in_deriv (kBackpropAdds) must start from zero
             a_in = blk["aff_in"] if blk["reorder"] else blk["lin_out"]
             d_ain = blk["d_aff_in"] if blk["reorder"] else blk["d_lin"]

@@ -36,3 +36,20 @@ def test_supernet_step_runs_and_learns(mode):
         alpha = v[cfg.bottleneck * n * cfg.dim: cfg.bottleneck * n * cfg.dim + n]
         assert all(math.isfinite(float(a)) for a in alpha) and any(abs(float(a)) > 0 for a in alpha)
     net.close()
+
+
+def test_fused_tail_matches_component_path():
+    """The fused ReLU+BatchNormTest+bypass pass must give the same training trajectory as the three components."""
+    from tdnnf_nas_b200.supernet import Supernet, SupernetConfig
+
+    objfs = []
+    for fuse in (False, True):
+        cfg = SupernetConfig(num_seqs=8, frames_per_eg=30, dim=128, bottleneck=32, num_blocks=3, prefinal_small=64,
+                             num_pdfs=200, den_states=300, den_out_degree=6.0, mode="search", learning_rate=2e-3,
+                             fuse_tail=fuse)
+        net = Supernet(cfg)
+        x = net.make_input(0).pin_memory()
+        objfs.append([net.step(x) for _ in range(4)])
+        net.close()
+    for a, b in zip(*objfs):
+        assert abs(a - b) <= 1e-4 * abs(a) + 1e-6, objfs
