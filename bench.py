@@ -23,6 +23,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "TDNN-F DARTS supernet train frames/sec"
+# dram__bytes_read.sum + dram__bytes_write.sum per splice_gemm_kernel launch, from the committed `ncu --set full`
+# capture (profiles/r01_summary.md).  A tensor-bound kernel: this is context, not the roofline numerator.
+NCU_GEMM_TRAFFIC_BYTES = 108.8e6
 UNIT = "frames/s"
 
 
@@ -87,7 +90,7 @@ class ClockSampler:
 def cpu_baseline_sample(cfg, repeats: int = 1):
     """Times the oracle on a bounded sample of the workload and extrapolates to frames/sec.
     Sample: one TDNN-F block (TdnnDARTSV3 1536->160 and 160->1536, 7 offsets; Propagate + Backprop incl. the
-    parameter/alpha update) at 64 sequences x 32 output frames, plus the denominator forward-backward on the
+    parameter/alpha update) at 64 sequences x 96 output frames, plus the denominator forward-backward on the
     bench graph with 4 sequences x T frames.  Extrapolation: GEMM time scales with algorithmic FLOPs, the
     denominator with the number of sequences."""
     import numpy as np
@@ -97,7 +100,7 @@ def cpu_baseline_sample(cfg, repeats: int = 1):
 
     g = np.random.default_rng(1)
     n, D, B, S = cfg.num_offsets, cfg.dim, cfg.bottleneck, 64
-    t_out = 32
+    t_out = 96
     flags = O.USE_GUMBEL | O.UPDATE_ALPHA if cfg.mode == "search" else O.UNIFORM_SAMPLE
     n_eff = n if cfg.mode == "search" else 2
 
@@ -114,7 +117,7 @@ def cpu_baseline_sample(cfg, repeats: int = 1):
     comps = [comp(D, B, list(range(-(n - 1), 1))), comp(B, D, list(range(n)))]
     ug = g.uniform(0.1, 0.9, n).astype(np.float32)
     graph = synth.make_den_graph(cfg.den_states, cfg.num_pdfs, cfg.den_out_degree, seed=5)
-    T, S_den = cfg.frames_per_eg // cfg.frame_subsampling, 4
+    T, S_den = cfg.frames_per_eg // cfg.frame_subsampling, 8
     xo = g.standard_normal((T * S_den, cfg.num_pdfs)).astype(np.float32)
     t_gemm = t_den = 0.0
     for _ in range(repeats):
@@ -133,7 +136,7 @@ def cpu_baseline_sample(cfg, repeats: int = 1):
     return dict(t_gemm=t_gemm, t_den=t_den, sample_flops=sum(c["flops"] for c in comps), den_seqs=S_den,
                 cores=O.num_threads(),
                 sample=("oracle (CPU restatement, OpenMP): 1 TDNN-F block (TdnnDARTSV3 1536->160 + 160->1536, 7 offsets) "
-                        "Propagate+Backprop+update at 64 seq x 32 frames, + denominator fwd-bwd on the bench graph at "
+                        "Propagate+Backprop+update at 64 seq x 96 frames (plain OpenMP/AVX2 loops: no BLAS in the image), + denominator fwd-bwd on the bench graph at "
                         f"{S_den} seq x {T} frames; extrapolated to the full step by algorithmic GEMM FLOPs and by sequences"))
 
 
@@ -271,7 +274,8 @@ def run_ours(args, cfg, rank, world, local_rank):
                  ms_per_step=ms_e2e / args.steps),
         gpu_launches=int(launches),
         roofline=dict(bound="tensor", kernel="splice_gemm_kernel (tcgen05, all TdnnDARTSV3 fwd/dgrad/wgrad GEMMs)",
-                      achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=None,
+                      achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=NCU_GEMM_TRAFFIC_BYTES,
+                      traffic_source="profiles/r01_summary.md: mean dram__bytes_read+write over the 6 captured launches",
                       peak_source=peaks["source"] + ", bf16 sustained",
                       achieved_raw_bf16=3 * achieved, frac_raw_bf16=3 * achieved / peak,
                       launches_timed=gemm_launches, gemm_ms_per_step=gemm_ms / 2, gemm_share_of_step=(gemm_ms / 2) / step_ms,

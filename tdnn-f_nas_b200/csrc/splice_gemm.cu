@@ -268,7 +268,7 @@ static int launch_gemm_bn(tdnnf_ctx* ctx, const Planes& A, const Planes& B, cons
 static int pick_bn(int n) {
   static const int wide = [] {  // experiment knob: TDNNF_BN_WIDE=128|256 for outputs that are multiples of 256
     const char* e = getenv("TDNNF_BN_WIDE");
-    return e ? atoi(e) : 128;
+    return e ? atoi(e) : 256;
   }();
   if (n <= 32) return 32;
   if (n <= 64) return 64;
@@ -337,6 +337,7 @@ extern "C" int tdnnf_darts_propagate(tdnnf_ctx* ctx, const float* in, int in_row
   p.n_tiles = ceil_div(out_dim, bn);
   p.c_tiles = 1;
   p.kb_per_seg = Kpad / kBK;
+  p.kb_last_steps = ceil_div(in_dim - (p.kb_per_seg - 1) * kBK, 16);
   p.nseg = n;
   for (int i = 0; i < n; ++i) {
     p.seg_a_m[i] = row_offsets[i] / r;
@@ -402,6 +403,7 @@ extern "C" int tdnnf_darts_backprop_data(tdnnf_ctx* ctx, const float* out_deriv,
   p.n_tiles = ceil_div(in_dim, bn);
   p.c_tiles = r;
   p.kb_per_seg = Kpad / kBK;
+  p.kb_last_steps = ceil_div(out_dim - (p.kb_per_seg - 1) * kBK, 16);
   p.nseg = n;
   for (int i = 0; i < n; ++i) {
     p.seg_a_m[i] = -(row_offsets[i] / r);
@@ -467,6 +469,7 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
   memset(&p, 0, sizeof(p));
   p.c_tiles = n;
   p.kb_per_seg = ceil_div(out_rows, kBK);
+  p.kb_last_steps = ceil_div(out_rows - (p.kb_per_seg - 1) * kBK, 16);
   p.nseg = n;
   p.seg_weight = weff;  // weff[i] == 0 (unsampled offset): X~ block is zero, nothing to add (ref: tdnn.cc:509-513)
   p.out = dW;

@@ -29,6 +29,7 @@ constexpr int kAccCols = 256;  // TMEM columns per accumulator buffer
 struct GemmParams {
   int m_tiles, n_tiles, c_tiles, splits;
   int kb_per_seg;  // K blocks (of 64) per segment
+  int kb_last_steps;  // 16-wide MMA steps that hold data in the LAST K block of a segment (1..4): zero padding is skipped
   int nseg;
   int seg_a_k[kMaxSeg], seg_a_m[kMaxSeg], seg_a_c[kMaxSeg];
   int seg_b_k[kMaxSeg], seg_b_n[kMaxSeg], seg_b_c[kMaxSeg];
@@ -219,7 +220,10 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         ptx::mbar_wait(&tmem_empty[acc_buf], acc_phase ^ 1);
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc_buf * kAccCols;
+        int kb = uc.it0 % p.kb_per_seg;
         for (int it = uc.it0; it < uc.it1; ++it) {
+          const int ksteps = (kb == p.kb_per_seg - 1) ? p.kb_last_steps : kBK / 16;
+          if (++kb == p.kb_per_seg) kb = 0;
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after_sync();
           const uint32_t sa = ptx::smem_u32(tiles + stage * Cfg::kStageBytes);
@@ -230,6 +234,7 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint64_t b_lo = ptx::umma_desc_k_sw128(sb + BN * kBK * 2);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
+            if (k >= ksteps) break;
             const uint64_t adv = (uint64_t)(k * 2);  // 16 bf16 = 32 B = 2 x 16 B units inside the swizzle atom
             ptx::umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, (it > uc.it0 || k > 0) ? 1u : 0u);
             ptx::umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
