@@ -195,7 +195,7 @@ def workload_config(cfg, gpus):
                 mode=cfg.mode, chunks_per_gpu=cfg.num_seqs, frames_per_eg=cfg.frames_per_eg, global_chunks=cfg.num_seqs * gpus,
                 num_pdfs=cfg.num_pdfs, den_states=cfg.den_states, parallelism=f"dp{gpus}",
                 cache="per-step working set (~14 GB of activations) exceeds the 126 MB L2: no explicit flush needed",
-                not_included="numerator graph (synthetic single-path alignment), natural gradient (identity), max-change/L2")
+                not_included="natural gradient (identity preconditioner), L2 / orthonormal constraint, xent branch, dropout (proportion 0)")
 
 
 def run_ours(args, cfg, rank, world, local_rank):
@@ -255,6 +255,7 @@ def run_ours(args, cfg, rank, world, local_rank):
     barrier()
     if rank != 0:
         net.close()
+        torch.distributed.destroy_process_group()
         return
     peaks = load_peaks()
     frames_all = net.frames_per_step * world
@@ -285,6 +286,8 @@ def run_ours(args, cfg, rank, world, local_rank):
         objf_per_frame=objf, den_arcs=net.den_arcs)
     print(json.dumps(line), flush=True)
     net.close()
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 def main():

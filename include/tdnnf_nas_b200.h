@@ -244,6 +244,27 @@ int tdnnf_den_forward(tdnnf_den_comp* c, const float* nnet_output, int stride, f
  * *ok (HOST) = 0 when the t=0 alpha.beta check fails (the reference's return value).  Syncs. */
 int tdnnf_den_backward(tdnnf_den_comp* c, float deriv_weight, float* nnet_output_deriv, int stride, int* ok);
 
+/* ------------------------------------------------------------------ chain numerator ---- */
+/* GenericNumeratorComputation (kaldi: chain/chain-generic-numerator.{h,cc}; SURVEY "next" row N3): log-domain
+ * forward-backward over one small FST per sequence (the unconstrained / e2e supervision the recipes train
+ * with, `--constrained false`).  Every arc consumes one frame and carries (pdf-id, log transition prob).
+ * Host arrays, copied to the device:
+ *   state_offsets[num_seqs+1]        states of sequence s are [state_offsets[s], state_offsets[s+1]); the first is the start state
+ *   fwd_ranges / bwd_ranges          per global state, [begin,end) into the arc arrays (arcs leaving / entering the state)
+ *   arc_state                        the OTHER end of the arc as a global state index (destination in the forward list, source in the backward list)
+ *   final_logprob[num_states]        log final probability, -inf (<= -1e30) when not final */
+typedef struct tdnnf_num_graph tdnnf_num_graph;
+int tdnnf_num_graph_create(tdnnf_ctx* ctx, int num_seqs, const int32_t* state_offsets, int num_arcs,
+                           const int32_t* fwd_ranges, const int32_t* bwd_ranges, const float* arc_logprob,
+                           const int32_t* arc_pdf, const int32_t* arc_state, const float* final_logprob,
+                           tdnnf_num_graph** out);
+int tdnnf_num_graph_destroy(tdnnf_num_graph* g);
+/* total log-prob summed over sequences in *logprob (HOST; synchronises).  If nnet_output_deriv != NULL:
+ * nnet_output_deriv[t*num_seqs+s, pdf] += deriv_weight * posterior.  *ok = 0 if any sequence has no path. */
+int tdnnf_num_forward_backward(tdnnf_ctx* ctx, const tdnnf_num_graph* g, const float* nnet_output, int stride,
+                               int frames_per_seq, float deriv_weight, float* nnet_output_deriv, int deriv_stride,
+                               float* logprob, int* ok);
+
 #ifdef __cplusplus
 }
 #endif

@@ -566,4 +566,60 @@ float orc_den_forward_backward(int N, int P, const int* fwd_ranges, const int* b
   return logprob;
 }
 
+// ------------------------------------------------------------------ chain numerator (generic, per-sequence FST)
+// kaldi chain-generic-numerator.cc (CPU, log domain), restated in float64: alpha(0,start)=0;
+// alpha(t+1,dst) = logsum_arcs alpha(t,src) + w + x(t,pdf); total = logsum_h alpha(T,h) + final(h);
+// posterior(arc,t) = exp(alpha(t,src) + w + x(t,pdf) + beta(t+1,dst) - total).
+// Arrays as in tdnnf_num_graph_create (only the forward arc list is used here).  Returns the summed log-prob;
+// *ok = 0 if some sequence has no complete path (its derivative is then left untouched).
+double orc_num_forward_backward(int S, const int* state_offsets, const int* fwd_ranges, const float* arc_logprob,
+                                const int* arc_pdf, const int* arc_state, const float* final_logprob,
+                                const float* nnet_output, int no_stride, int T, float deriv_weight, float* deriv,
+                                int d_stride, int* ok) {
+  const double kZero = -1.0e30;
+  auto log_add = [&](double a, double b) {
+    if (a < b) std::swap(a, b);
+    if (b <= kZero) return a;
+    return a + log1p(exp(b - a));
+  };
+  double total_all = 0.0;
+  *ok = 1;
+  for (int s = 0; s < S; ++s) {
+    const int s0 = state_offsets[s], ns = state_offsets[s + 1] - s0;
+    std::vector<double> alpha((size_t)(T + 1) * ns, kZero), beta((size_t)(T + 1) * ns, kZero);
+    alpha[0] = 0.0;
+    for (int t = 0; t < T; ++t)
+      for (int h = 0; h < ns; ++h) {
+        const double a = alpha[(size_t)t * ns + h];
+        if (a <= kZero) continue;
+        for (int e = fwd_ranges[2 * (s0 + h)]; e < fwd_ranges[2 * (s0 + h) + 1]; ++e) {
+          double& d = alpha[(size_t)(t + 1) * ns + (arc_state[e] - s0)];
+          d = log_add(d, a + arc_logprob[e] + nnet_output[((size_t)t * S + s) * no_stride + arc_pdf[e]]);
+        }
+      }
+    double tot = kZero;
+    for (int h = 0; h < ns; ++h) {
+      beta[(size_t)T * ns + h] = final_logprob[s0 + h] > kZero ? final_logprob[s0 + h] : kZero;
+      if (final_logprob[s0 + h] > kZero && alpha[(size_t)T * ns + h] > kZero) tot = log_add(tot, alpha[(size_t)T * ns + h] + final_logprob[s0 + h]);
+    }
+    if (tot <= kZero) { *ok = 0; continue; }
+    total_all += tot;
+    if (!deriv) continue;
+    for (int t = T - 1; t >= 0; --t)
+      for (int h = 0; h < ns; ++h) {
+        double acc = kZero;
+        for (int e = fwd_ranges[2 * (s0 + h)]; e < fwd_ranges[2 * (s0 + h) + 1]; ++e) {
+          const double b = beta[(size_t)(t + 1) * ns + (arc_state[e] - s0)];
+          if (b <= kZero) continue;
+          const double v = arc_logprob[e] + nnet_output[((size_t)t * S + s) * no_stride + arc_pdf[e]] + b;
+          acc = log_add(acc, v);
+          const double a = alpha[(size_t)t * ns + h];
+          if (a > kZero) deriv[((size_t)t * S + s) * d_stride + arc_pdf[e]] += deriv_weight * (float)exp(a + v - tot);
+        }
+        beta[(size_t)t * ns + h] = acc;
+      }
+  }
+  return total_all;
+}
+
 }  // extern "C"

@@ -32,6 +32,7 @@ def lib():
         build()
         _lib = C.CDLL(LIB)
         _lib.orc_den_forward_backward.restype = C.c_float
+        _lib.orc_num_forward_backward.restype = C.c_double
     return _lib
 
 
@@ -203,3 +204,21 @@ def den_forward_backward(graph, nnet_output, S, T, leaky, deriv_weight=None):
         _stride(nnet_output), C.c_float(0.0 if deriv_weight is None else deriv_weight),
         None if deriv is None else _f(deriv), 0 if deriv is None else _stride(deriv), C.byref(ok))
     return float(lp), deriv, bool(ok.value)
+
+
+def num_forward_backward(graph, nnet_output, T, deriv_weight=None):
+    """graph: dict from synth.make_num_graphs.  Returns (logprob, deriv or None, ok)."""
+    S = graph["num_seqs"]
+    so = np.ascontiguousarray(graph["state_offsets"], dtype=np.int32)
+    fr = np.ascontiguousarray(graph["fwd_ranges"], dtype=np.int32)
+    lp = np.ascontiguousarray(graph["arc_logprob"], dtype=np.float32)
+    pd = np.ascontiguousarray(graph["arc_pdf"], dtype=np.int32)
+    st = np.ascontiguousarray(graph["arc_state"], dtype=np.int32)
+    fl = np.ascontiguousarray(graph["final_logprob"], dtype=np.float32)
+    ok = C.c_int(1)
+    deriv = None if deriv_weight is None else np.zeros_like(nnet_output)
+    tot = lib().orc_num_forward_backward(S, _i(so), _i(fr), _f(lp), _i(pd), _i(st), _f(fl), _f(nnet_output),
+                                         _stride(nnet_output), T, C.c_float(deriv_weight or 0.0),
+                                         None if deriv is None else _f(deriv), 0 if deriv is None else _stride(deriv),
+                                         C.byref(ok))
+    return float(tot), deriv, bool(ok.value)

@@ -68,6 +68,9 @@ def _declare(lib):
     sig("tdnnf_relu_scale_offset_bypass_bwd", [vp, vp, i, vp, i, vp, f, vp, i, vp, i, i, i])
     sig("tdnnf_batchnorm_train_fwd", [vp, vp, i, i, i, vp, i, f, f, vp])
     sig("tdnnf_batchnorm_train_bwd", [vp, vp, i, vp, i, vp, i, i, i, f, vp])
+    sig("tdnnf_num_graph_create", [vp, i, c_int_p, i, c_int_p, c_int_p, c_float_p, c_int_p, c_int_p, c_float_p, C.POINTER(vp)])
+    sig("tdnnf_num_graph_destroy", [vp])
+    sig("tdnnf_num_forward_backward", [vp, vp, vp, i, i, f, vp, i, c_float_p, c_int_p])
     sig("tdnnf_den_graph_create", [vp, i, i, i, c_int_p, c_int_p, c_float_p, c_int_p, c_int_p, c_float_p, C.POINTER(vp)])
     sig("tdnnf_den_graph_destroy", [vp])
     sig("tdnnf_den_create", [vp, vp, i, i, f, C.POINTER(vp)])
@@ -390,6 +393,45 @@ class DenominatorComputation:
     def close(self):
         if getattr(self, "h", None):
             load().tdnnf_den_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class NumeratorGraph:
+    """Per-sequence numerator FSTs on the device + GenericNumeratorComputation::ForwardBackward."""
+
+    def __init__(self, ctx: Context, graph: dict):
+        import numpy as np
+
+        self.ctx = ctx
+        a = lambda k, dt: np.ascontiguousarray(graph[k], dtype=dt)
+        so, fr, br = a("state_offsets", np.int32), a("fwd_ranges", np.int32), a("bwd_ranges", np.int32)
+        lp, pd, st, fl = a("arc_logprob", np.float32), a("arc_pdf", np.int32), a("arc_state", np.int32), a("final_logprob", np.float32)
+        self.num_seqs = int(graph["num_seqs"])
+        h = vp()
+        check(load().tdnnf_num_graph_create(ctx.h, self.num_seqs, so.ctypes.data_as(c_int_p), int(graph["num_arcs"]),
+                                            fr.ctypes.data_as(c_int_p), br.ctypes.data_as(c_int_p), lp.ctypes.data_as(c_float_p),
+                                            pd.ctypes.data_as(c_int_p), st.ctypes.data_as(c_int_p), fl.ctypes.data_as(c_float_p),
+                                            C.byref(h)))
+        self.h = h
+
+    def forward_backward(self, nnet_output, frames_per_seq: int, deriv_weight: float = 1.0, nnet_output_deriv=None):
+        """Returns (logprob, ok); adds deriv_weight * posteriors into nnet_output_deriv if given."""
+        p, r, c, s = _mat(nnet_output)
+        dp, ds = (0, 0) if nnet_output_deriv is None else (_mat(nnet_output_deriv)[0], _mat(nnet_output_deriv)[3])
+        lp, ok = C.c_float(0), C.c_int32(0)
+        check(load().tdnnf_num_forward_backward(self.ctx.h, self.h, p, s, frames_per_seq, deriv_weight, dp, ds, C.byref(lp),
+                                                C.byref(ok)))
+        return float(lp.value), bool(ok.value)
+
+    def close(self):
+        if getattr(self, "h", None):
+            load().tdnnf_num_graph_destroy(self.h)
             self.h = None
 
     def __del__(self):

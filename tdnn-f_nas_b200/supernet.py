@@ -8,11 +8,10 @@ What runs where:
   * ReLU / BatchNorm-train / bypass sum / the stock affine layers around them (tdnn1, prefinal,
     output: "N4" neighbours) -> the same kernels through the C ABI (a stock TdnnComponent is the
     DARTS GEMM with one offset and weight 1);
-  * DenominatorComputation -> den kernels; the numerator is a synthetic single-path alignment
-    (SURVEY "next" row N3 is not built), natural gradient is the identity (N1), max-change / L2 /
-    orthonormal constraint are not applied (N2), dropout-proportion is 0.0 as in the recipe.
-torch is device memory, the H2D copy, streams and torch.distributed; every kernel is ours except the
-3 200-element numerator gather/scatter.
+  * ComputeChainObjfAndDeriv (chain.py) -> den kernels + the generic (per-sequence FST) numerator kernel;
+    natural gradient is the identity (N1); UpdateNnetWithMaxChange is applied (host logic, one read-back);
+    L2 / orthonormal constraint are not (N2); dropout-proportion is 0.0 as in the recipe; no xent branch.
+torch is device memory, the H2D copy, streams and torch.distributed; every kernel launched is ours.
 
 The step is compiled once into flat lists of pre-bound C calls so the per-step Python cost is a loop.
 """
@@ -25,7 +24,7 @@ from typing import List, Optional
 
 import numpy as np
 
-from . import capi, nnet3, parallel, synth
+from . import capi, chain, nnet3, parallel, synth
 
 
 @dataclass
@@ -61,6 +60,13 @@ class _Plan:
 
     def add(self, kind: str, fn, *args):
         self.calls.append((kind, partial(fn, *args)))
+
+    def add_py(self, fn):
+        """A Python callable (returns None) interleaved with the C calls, e.g. launching an async all-reduce."""
+        def call():
+            fn()
+            return 0
+        self.calls.append(("py", call))
 
     def run(self):
         for kind, call in self.calls:
@@ -216,10 +222,10 @@ class Supernet:
         graph = synth.make_den_graph(cfg.den_states, P, cfg.den_out_degree, seed=5)
         self.den_arcs = graph["num_arcs"]
         self.den_graph = capi.DenGraph(ctx, graph)
-        self.den = capi.DenominatorComputation(ctx, self.den_graph, S, T, cfg.leaky_hmm)
-        ali = synth.rng(3, stream=2 + self.rank).integers(0, P, size=rows_T)
-        self.num_index = torch.from_numpy(np.arange(rows_T) * P + ali).to(dev)
-        self.num_weight = torch.ones(rows_T, device=dev)
+        # per-sequence numerator FSTs of this rank's shard (unconstrained supervision, `--constrained false`)
+        self.num_graph = capi.NumeratorGraph(ctx, synth.make_num_graphs(S, P, T, seed=60 + self.rank))
+        self.objective = chain.ChainObjective(ctx, self.den_graph, self.num_graph, S, T,
+                                              chain.ChainTrainingOptions(leaky_hmm_coefficient=cfg.leaky_hmm))
         self._compile()
         if search:
             self._freeze_batchnorm()
@@ -415,6 +421,8 @@ class Supernet:
             bwd.add("nnet3", lib.tdnnf_nnet3_backprop, blk["lin"].h, blk["lin_idx"].h, pp, pr, pc, ps, None, 0, lp, lr_, lc, ls,
                     blk["memo_lin"], blk["lin_delta"].h, qp, qs)
             bwd.add("nnet3", lib.tdnnf_nnet3_delete_memo, blk["lin"].h, blk["memo_lin"])
+            if self.world > 1:  # this block's deltas are final: reduce them while the earlier blocks still run
+                bwd.add_py(partial(self._launch_allreduce, self._views_of([blk["aff_delta"], blk["lin_delta"]])))
         self._bn_bwd(bwd, t1["bn"], t1["out"], t1["d_out"], t1["d_out"])
         bwd.add("abi", lib.tdnnf_relu_bwd, h, _m(t1["relu"])[0], _m(t1["relu"])[3], _m(t1["d_out"])[0], _m(t1["d_out"])[3],
                 _m(t1["d_aff"])[0], _m(t1["d_aff"])[3], t1["relu"].shape[0], t1["relu"].shape[1])
@@ -443,11 +451,18 @@ class Supernet:
                     n = m["db"].numel()
                     dbp = C.c_void_p(m["db"].data_ptr())
                     upd.add("abi", lib.tdnnf_mat_dot_dev, h, dbp, n, dbp, n, 1, n, slot)
+        if self.world > 1:  # the stock layers' deltas (head layers finish first, tdnn1 last): one more bucket
+            stock_views = []
+            for p in st.values():
+                stock_views.append(p["dW"].view(-1))
+                if p["db"] is not None:
+                    stock_views.append(p["db"])
+            bwd.add_py(partial(self._launch_allreduce, stock_views))
         self.fwd_plan, self.bwd_plan, self.upd_plan = fwd, bwd, upd
-        # delta buffers as torch views for the all-reduce
-        self.delta_views = self._delta_views() if self.world > 1 else []
+        self.pending = []
 
-    def _delta_views(self):
+    def _views_of(self, deltas):
+        """The parameter buffers of delta components as flat torch views (pitch padding included: it is zero)."""
         import torch
 
         class _Arr:
@@ -455,15 +470,13 @@ class Supernet:
                 self.__cuda_array_interface__ = dict(shape=(nelem,), typestr="<f4", data=(ptr, False), version=2, strides=None)
 
         views = []
-        for blk in self.blocks:
-            for d in (blk["lin_delta"], blk["aff_delta"]):
-                for ptr, rows, cols, stride in d.param_buffers():
-                    views.append(torch.as_tensor(_Arr(ptr, rows * stride), device=self.dev))
-        for p in self.stock.values():
-            views.append(p["dW"].view(-1))
-            if p["db"] is not None:
-                views.append(p["db"])
+        for d in deltas:
+            for ptr, rows, cols, stride in d.param_buffers():
+                views.append(torch.as_tensor(_Arr(ptr, rows * stride), device=self.dev))
         return views
+
+    def _launch_allreduce(self, views):
+        self.pending += parallel.allreduce_deltas(views, self.pg, async_op=True)
 
     # ------------------------------------------------------------------ public API
     @property
@@ -496,22 +509,15 @@ class Supernet:
         if x_host is not None:
             self.x.copy_(x_host, non_blocking=True)
         self.fwd_plan.run()
-        out, d_out = self.head["out"], self.head["d_out"]
-        self.ctx.mat_set(d_out, 0.0)
-        den_logprob = self.den.forward(out)                       # synchronises (returns a host scalar, like Kaldi)
-        ok = self.den.backward(-1.0, d_out)
-        # synthetic single-path numerator (row-wise gather / scatter of T*S elements; torch, not a hot kernel)
-        num_logprob = out.view(-1).index_select(0, self.num_index).sum()
-        d_out.view(-1).index_add_(0, self.num_index, self.num_weight)
-        if not ok:
-            d_out.zero_()
+        # ComputeChainObjfAndDeriv: denominator fwd-bwd, numerator fwd-bwd, objf = num - den (host scalars, like Kaldi)
+        objf, _, weight = self.objective.compute(self.head["out"], self.head["d_out"])
         self.bwd_plan.run()
-        if self.world > 1:
-            parallel.allreduce_deltas(self.delta_views, self.pg)
+        for w in self.pending:  # all-reduces launched bucket by bucket during the backward pass
+            w.wait()
+        self.pending = []
         if apply_update:
             self._update_with_max_change()
-        objf = (float(num_logprob) - den_logprob) / (self.T * self.cfg.num_seqs)
-        return objf if ok else -10.0
+        return objf / weight
 
     def _update_with_max_change(self, scale: float = 1.0, max_change_scale: float = 1.0):
         """UpdateNnetWithMaxChange + ScaleNnet(momentum=0) (utils.cc:2085-2175, common.py:877-878)."""
@@ -552,5 +558,6 @@ class Supernet:
         import torch
 
         torch.cuda.synchronize(self.dev)
-        self.den.close()
+        self.objective.close()
+        self.num_graph.close()
         self.den_graph.close()

@@ -66,3 +66,43 @@ def regular_row_offsets(time_offsets, start_t_in: int, start_t_out: int, num_ima
         input_t = (start_t_out + off - start_t_in) // t_step_in
         offs.append(n * (input_t // n) * num_images + input_t % n)
     return n, offs
+
+
+def make_num_graphs(num_seqs: int, num_pdfs: int, frames: int, seed: int = 6, min_phones: int = 3, max_phones: int = 12) -> dict:
+    """Synthetic unconstrained numerator supervision: per sequence a left-to-right FST over a random "phone" string
+    with the chain topology (one forward pdf consumed on entering a phone, then a self-loop pdf), plus an optional
+    alternative pronunciation branch so that the FST is not a single path.  Arc lists are given twice (grouped by
+    source = forward list, then by destination = backward list) as tdnnf_num_graph_create expects."""
+    g = rng(seed)
+    state_offsets = [0]
+    src, dst, pdf, lp, final = [], [], [], [], []
+    for _ in range(num_seqs):
+        k = int(g.integers(min_phones, min(max_phones, frames) + 1))
+        base = state_offsets[-1]
+        ns = k + 1
+        f = np.full(ns, -1.0e30, dtype=np.float32)
+        f[k] = 0.0
+        for j in range(k):
+            fwd_pdf, loop_pdf = int(g.integers(0, num_pdfs)), int(g.integers(0, num_pdfs))
+            src += [base + j, base + j + 1]
+            dst += [base + j + 1, base + j + 1]
+            pdf += [fwd_pdf, loop_pdf]
+            lp += [float(np.log(0.5)), float(np.log(0.5))]
+            if g.uniform() < 0.3:  # alternative phone on the same transition
+                src.append(base + j)
+                dst.append(base + j + 1)
+                pdf.append(int(g.integers(0, num_pdfs)))
+                lp.append(float(np.log(0.25)))
+        final.append(f)
+        state_offsets.append(base + ns)
+    src, dst = np.array(src), np.array(dst)
+    pdf, lp = np.array(pdf, dtype=np.int32), np.array(lp, dtype=np.float32)
+    N, A = state_offsets[-1], len(src)
+    of = np.argsort(src, kind="stable")
+    ob = np.argsort(dst, kind="stable")
+    fb = np.concatenate([[0], np.cumsum(np.bincount(src, minlength=N))])
+    bb = np.concatenate([[0], np.cumsum(np.bincount(dst, minlength=N))]) + A
+    return dict(num_seqs=num_seqs, state_offsets=np.array(state_offsets, dtype=np.int32), num_arcs=A,
+                fwd_ranges=np.stack([fb[:-1], fb[1:]], 1).astype(np.int32), bwd_ranges=np.stack([bb[:-1], bb[1:]], 1).astype(np.int32),
+                arc_logprob=np.concatenate([lp[of], lp[ob]]), arc_pdf=np.concatenate([pdf[of], pdf[ob]]),
+                arc_state=np.concatenate([dst[of], src[ob]]).astype(np.int32), final_logprob=np.concatenate(final))

@@ -63,3 +63,61 @@ def test_den_invariants_large(ctx):
     x2[: S] += 0.5
     lp2, _, _ = _run_gpu(ctx, graph, x2, S, T, 0.1, -1.0)
     assert abs((lp2 - lp) - 0.5 * S) < 1e-3 * abs(lp) + 1e-2
+
+
+@pytest.mark.parametrize("S,P,T", [(4, 9, 6), (64, 300, 50), (7, 40, 17)])
+def test_numerator_parity(ctx, S, P, T):
+    import torch
+
+    from oracle import oracle as O
+    from tdnnf_nas_b200 import capi, synth
+
+    graph = synth.make_num_graphs(S, P, T, seed=S)
+    g = np.random.default_rng(S)
+    x = (g.standard_normal((T * S, P)) * 2).astype(np.float32)
+    lp_ref, d_ref, ok_ref = O.num_forward_backward(graph, x, T, deriv_weight=1.0)
+    ng = capi.NumeratorGraph(ctx, graph)
+    xd = torch.from_numpy(x).cuda()
+    deriv = torch.zeros_like(xd)
+    lp, ok = ng.forward_backward(xd, T, 1.0, deriv)
+    assert ok and ok_ref
+    assert abs(lp - lp_ref) <= 1e-4 * abs(lp_ref)
+    assert rel_err(deriv.cpu().numpy(), d_ref) < 1e-3
+    np.testing.assert_allclose(deriv.cpu().numpy().sum(1), 1.0, rtol=1e-3)
+    ng.close()
+
+
+def test_chain_objf_and_deriv(ctx):
+    """ComputeChainObjfAndDeriv (chain.py) == oracle numerator - oracle denominator, derivative included; the
+    failure path (no numerator path) returns -10 per frame with a zero derivative, as in Kaldi."""
+    import torch
+
+    from oracle import oracle as O
+    from tdnnf_nas_b200 import capi, chain, synth
+
+    S, P, T, N = 16, 60, 12, 200
+    dgraph = synth.make_den_graph(N, P, 5.0, seed=4)
+    ngraph = synth.make_num_graphs(S, P, T, seed=8)
+    g = np.random.default_rng(2)
+    x = g.standard_normal((T * S, P)).astype(np.float32)
+    den_lp, den_d, _ = O.den_forward_backward(dgraph, x, S, T, 0.1, deriv_weight=-1.0)
+    num_lp, num_d, _ = O.num_forward_backward(ngraph, x, T, deriv_weight=1.0)
+    dg, ng = capi.DenGraph(ctx, dgraph), capi.NumeratorGraph(ctx, ngraph)
+    obj = chain.ChainObjective(ctx, dg, ng, S, T, chain.ChainTrainingOptions(l2_regularize=1e-3))
+    xd = torch.from_numpy(x).cuda()
+    deriv = torch.full_like(xd, 3.0)
+    objf, l2, weight = obj.compute(xd, deriv)
+    assert weight == S * T
+    assert objf == pytest.approx(num_lp - den_lp, rel=1e-4)
+    assert l2 == pytest.approx(-0.5 * 1e-3 * float((x.astype(np.float64) ** 2).sum()), rel=1e-4)
+    assert rel_err(deriv.cpu().numpy(), num_d + den_d - 1e-3 * x) < 1e-3
+    # T shorter than the phone strings: no numerator path
+    bad = capi.NumeratorGraph(ctx, synth.make_num_graphs(S, P, T, seed=8, min_phones=T, max_phones=T))
+    obj2 = chain.ChainObjective(ctx, dg, bad, S, 4)
+    x2 = torch.from_numpy(x[: 4 * S].copy()).cuda()
+    d2 = torch.full_like(x2, 3.0)
+    objf2, _, w2 = obj2.compute(x2, d2)
+    assert objf2 == -10.0 * w2 and torch.all(d2 == 0)
+    for o in (obj, obj2):
+        o.close()
+    ng.close(); bad.close(); dg.close()
