@@ -114,6 +114,12 @@ extern "C" {
 #define ORC_USE_ENTROPY 8
 #define ORC_UPDATE_ALPHA 16
 
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -60,6 +60,13 @@ def num_threads() -> int:
     return lib().orc_num_threads()
 
 
+def use_all_cores() -> int:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline is meant to use every host core."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_num_threads(n)
+    return num_threads()
+
+
 def share_index(time_offsets) -> int:
     to = np.asarray(time_offsets, dtype=np.int32)
     return lib().orc_share_index(_i(to), len(to))

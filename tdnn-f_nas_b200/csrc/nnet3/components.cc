@@ -302,20 +302,28 @@ void TdnnDARTSV3Component::ReorderIndexes(std::vector<Index>* input_indexes, std
   output_indexes->swap(modified_output_indexes);
 }
 
-void TdnnDARTSV3Component::Write(std::ostream& os, bool binary) const {  // tdnn.cc:659-700
+// On-disk form (tdnn.cc:659-761): the UpdatableComponent header, six mode booleans, the
+// temperature, the offsets, the two parameter blocks and the natural-gradient configuration.  The boolean
+// block is driven by one table so that Write and Read cannot drift apart.
+namespace {
+struct ModeFlagField {
+  const char* token;
+  bool TdnnDARTSV3ModeFlags::*member;
+};
+const ModeFlagField kModeFlagFields[] = {
+    {"<use-gumbel>", &TdnnDARTSV3ModeFlags::use_gumbel},       {"<use-entropy>", &TdnnDARTSV3ModeFlags::use_entropy},
+    {"<free-select>", &TdnnDARTSV3ModeFlags::free_select},     {"<update-alpha>", &TdnnDARTSV3ModeFlags::update_alpha},
+    {"<update-theta>", &TdnnDARTSV3ModeFlags::update_theta},   {"<uniform-sample>", &TdnnDARTSV3ModeFlags::uniform_sample},
+};
+}  // namespace
+
+void TdnnDARTSV3Component::Write(std::ostream& os, bool binary) const {
   WriteUpdatableCommon(os, binary);
-  WriteToken(os, binary, "<use-gumbel>");
-  WriteBasicType(os, binary, use_gumbel_);
-  WriteToken(os, binary, "<use-entropy>");
-  WriteBasicType(os, binary, use_entropy_);
-  WriteToken(os, binary, "<free-select>");
-  WriteBasicType(os, binary, free_select_);
-  WriteToken(os, binary, "<update-alpha>");
-  WriteBasicType(os, binary, update_alpha_);
-  WriteToken(os, binary, "<update-theta>");
-  WriteBasicType(os, binary, update_theta_);
-  WriteToken(os, binary, "<uniform-sample>");
-  WriteBasicType(os, binary, uniform_sample_);
+  const TdnnDARTSV3ModeFlags flags = {use_gumbel_, use_entropy_, free_select_, update_alpha_, update_theta_, uniform_sample_};
+  for (const ModeFlagField& f : kModeFlagFields) {
+    WriteToken(os, binary, f.token);
+    WriteBasicType(os, binary, flags.*(f.member));
+  }
   WriteToken(os, binary, "<Temp-Proportion>");
   WriteBasicType(os, binary, temp_proportion_);
   WriteToken(os, binary, "<TimeOffsets>");
@@ -328,34 +336,31 @@ void TdnnDARTSV3Component::Write(std::ostream& os, bool binary) const {  // tdnn
   WriteBasicType(os, binary, orthonormal_constraint_);
   WriteToken(os, binary, "<UseNaturalGradient>");
   WriteBasicType(os, binary, use_natural_gradient_);
-  int32 rank_in = preconditioner_in_.GetRank(), rank_out = preconditioner_out_.GetRank();
-  BaseFloat alpha_in = preconditioner_in_.GetAlpha(), alpha_out = preconditioner_out_.GetAlpha(),
-            num_samples_history = preconditioner_in_.GetNumSamplesHistory();
+  // natural-gradient configuration: history, (alpha in, alpha out), (rank in, rank out); the state is not saved
   WriteToken(os, binary, "<NumSamplesHistory>");
-  WriteBasicType(os, binary, num_samples_history);
+  WriteBasicType(os, binary, preconditioner_in_.GetNumSamplesHistory());
   WriteToken(os, binary, "<AlphaInOut>");
-  WriteBasicType(os, binary, alpha_in);
-  WriteBasicType(os, binary, alpha_out);
+  WriteBasicType(os, binary, preconditioner_in_.GetAlpha());
+  WriteBasicType(os, binary, preconditioner_out_.GetAlpha());
   WriteToken(os, binary, "<RankInOut>");
-  WriteBasicType(os, binary, rank_in);
-  WriteBasicType(os, binary, rank_out);
+  WriteBasicType(os, binary, preconditioner_in_.GetRank());
+  WriteBasicType(os, binary, preconditioner_out_.GetRank());
   WriteToken(os, binary, "</TdnnDARTSV3Component>");
 }
 
-void TdnnDARTSV3Component::Read(std::istream& is, bool binary) {  // tdnn.cc:702-761
-  std::string token = ReadUpdatableCommon(is, binary);
-  ExpectToken(is, binary, "<use-gumbel>");
-  ReadBasicType(is, binary, &use_gumbel_);
-  ExpectToken(is, binary, "<use-entropy>");
-  ReadBasicType(is, binary, &use_entropy_);
-  ExpectToken(is, binary, "<free-select>");
-  ReadBasicType(is, binary, &free_select_);
-  ExpectToken(is, binary, "<update-alpha>");
-  ReadBasicType(is, binary, &update_alpha_);
-  ExpectToken(is, binary, "<update-theta>");
-  ReadBasicType(is, binary, &update_theta_);
-  ExpectToken(is, binary, "<uniform-sample>");
-  ReadBasicType(is, binary, &uniform_sample_);
+void TdnnDARTSV3Component::Read(std::istream& is, bool binary) {
+  ReadUpdatableCommon(is, binary);  // consumes up to and including <LearningRate>
+  TdnnDARTSV3ModeFlags flags;
+  for (const ModeFlagField& f : kModeFlagFields) {
+    ExpectToken(is, binary, f.token);
+    ReadBasicType(is, binary, &(flags.*(f.member)));
+  }
+  use_gumbel_ = flags.use_gumbel;
+  use_entropy_ = flags.use_entropy;
+  free_select_ = flags.free_select;
+  update_alpha_ = flags.update_alpha;
+  update_theta_ = flags.update_theta;
+  uniform_sample_ = flags.uniform_sample;
   ExpectToken(is, binary, "<Temp-Proportion>");
   ReadBasicType(is, binary, &temp_proportion_);
   ExpectToken(is, binary, "<TimeOffsets>");
@@ -368,33 +373,30 @@ void TdnnDARTSV3Component::Read(std::istream& is, bool binary) {  // tdnn.cc:702
   ReadBasicType(is, binary, &orthonormal_constraint_);
   ExpectToken(is, binary, "<UseNaturalGradient>");
   ReadBasicType(is, binary, &use_natural_gradient_);
-  int32 rank_in, rank_out;
-  BaseFloat alpha_in, alpha_out, num_samples_history;
+  BaseFloat history = 0, alpha[2] = {0, 0};
+  int32 rank[2] = {0, 0};
   ExpectToken(is, binary, "<NumSamplesHistory>");
-  ReadBasicType(is, binary, &num_samples_history);
-  {
-    std::string token;
-    ReadToken(is, binary, &token);
-    if (token == "<AlphaInOut>") {
-      ReadBasicType(is, binary, &alpha_in);
-      ReadBasicType(is, binary, &alpha_out);
-    } else {
-      KALDI_ASSERT(token == "<Alpha>");
-      ReadBasicType(is, binary, &alpha_in);
-      alpha_out = alpha_in;
-    }
+  ReadBasicType(is, binary, &history);
+  std::string alpha_token;
+  ReadToken(is, binary, &alpha_token);
+  if (alpha_token == "<AlphaInOut>") {
+    ReadBasicType(is, binary, &alpha[0]);
+    ReadBasicType(is, binary, &alpha[1]);
+  } else {  // older models carry a single <Alpha> for both factors (tdnn.cc:733-746)
+    KALDI_ASSERT(alpha_token == "<Alpha>");
+    ReadBasicType(is, binary, &alpha[0]);
+    alpha[1] = alpha[0];
   }
-  preconditioner_in_.SetAlpha(alpha_in);
-  preconditioner_out_.SetAlpha(alpha_out);
   ExpectToken(is, binary, "<RankInOut>");
-  ReadBasicType(is, binary, &rank_in);
-  ReadBasicType(is, binary, &rank_out);
-  preconditioner_in_.SetRank(rank_in);
-  preconditioner_out_.SetRank(rank_out);
-  preconditioner_in_.SetNumSamplesHistory(num_samples_history);
-  preconditioner_out_.SetNumSamplesHistory(num_samples_history);
-  preconditioner_in_.SetUpdatePeriod(4);
-  preconditioner_out_.SetUpdatePeriod(4);
+  ReadBasicType(is, binary, &rank[0]);
+  ReadBasicType(is, binary, &rank[1]);
+  OnlineNaturalGradient* ng[2] = {&preconditioner_in_, &preconditioner_out_};
+  for (int k = 0; k < 2; ++k) {
+    ng[k]->SetAlpha(alpha[k]);
+    ng[k]->SetRank(rank[k]);
+    ng[k]->SetNumSamplesHistory(history);
+    ng[k]->SetUpdatePeriod(4);  // not configurable
+  }
   ExpectToken(is, binary, "</TdnnDARTSV3Component>");
   Check();
 }
@@ -402,44 +404,35 @@ void TdnnDARTSV3Component::Read(std::istream& is, bool binary) {  // tdnn.cc:702
 void TdnnDARTSV3Component::GetInputIndexes(const MiscComputationInfo&, const Index& output_index,
                                            std::vector<Index>* desired_indexes) const {  // tdnn.cc:763-775
   KALDI_ASSERT(output_index.t != kNoTime);
-  size_t size = time_offsets_.size();
-  desired_indexes->resize(size);
-  for (size_t i = 0; i < size; i++) {
-    (*desired_indexes)[i].n = output_index.n;
-    (*desired_indexes)[i].t = output_index.t + time_offsets_[i];
-    (*desired_indexes)[i].x = output_index.x;
-  }
+  desired_indexes->clear();
+  for (int32 offset : time_offsets_) desired_indexes->push_back(Index(output_index.n, output_index.t + offset, output_index.x));
 }
 
-bool TdnnDARTSV3Component::IsComputable(const MiscComputationInfo&, const Index& output_index,
+bool TdnnDARTSV3Component::IsComputable(const MiscComputationInfo& misc, const Index& output_index,
                                         const IndexSet& input_index_set, std::vector<Index>* used_inputs) const {
-  KALDI_ASSERT(output_index.t != kNoTime);  // tdnn.cc:778-803
-  size_t size = time_offsets_.size();
-  Index index(output_index);
-  if (used_inputs != NULL) {
-    used_inputs->clear();
-    used_inputs->reserve(size);
-  }
-  for (size_t i = 0; i < size; i++) {
-    index.t = output_index.t + time_offsets_[i];
-    if (input_index_set(index)) {
-      if (used_inputs != NULL) used_inputs->push_back(index);
-    } else {
-      return false;
-    }
+  // computable iff every spliced input frame t + offset_i is available (tdnn.cc:778-803)
+  std::vector<Index> wanted;
+  GetInputIndexes(misc, output_index, &wanted);
+  if (used_inputs != NULL) used_inputs->clear();
+  for (const Index& w : wanted) {
+    if (!input_index_set(w)) return false;
+    if (used_inputs != NULL) used_inputs->push_back(w);
   }
   return true;
 }
 
 void TdnnDARTSV3Component::ModifyComputationIo(time_height_convolution::ConvolutionComputationIo* io) {
-  if (io->t_step_out == 0) {  // tdnn.cc:822-844
+  // tdnn.cc:822-844.  A single input or output frame leaves the step undetermined (0): any step works.
+  if (io->t_step_out == 0) {
     if (io->t_step_in == 0) io->t_step_in = 1;
     io->t_step_out = io->t_step_in;
   }
   KALDI_ASSERT(io->t_step_out % io->t_step_in == 0);
-  io->reorder_t_in = io->t_step_out / io->t_step_in;
-  int32 n = io->reorder_t_in;
-  io->num_t_in = n * ((io->num_t_in + n - 1) / n);
+  // frame-subsampling factor between output and input: the input is consumed in blocks of that many frames,
+  // which is also the row stride of the input views; the input frame count is padded to whole blocks.
+  const int32 factor = io->t_step_out / io->t_step_in;
+  io->reorder_t_in = factor;
+  io->num_t_in = factor * ((io->num_t_in + factor - 1) / factor);
 }
 
 ComponentPrecomputedIndexes* TdnnDARTSV3Component::PrecomputeIndexes(const MiscComputationInfo&,
@@ -450,22 +443,21 @@ ComponentPrecomputedIndexes* TdnnDARTSV3Component::PrecomputeIndexes(const MiscC
   ConvolutionComputationIo io;
   GetComputationIo(input_indexes, output_indexes, &io);
   ModifyComputationIo(&io);
-  if (RandInt(0, 10) == 0) {
-    std::vector<Index> modified_input_indexes, modified_output_indexes;
-    GetIndexesForComputation(io, input_indexes, output_indexes, &modified_input_indexes, &modified_output_indexes);
-    KALDI_ASSERT(modified_input_indexes == input_indexes && modified_output_indexes == output_indexes);
+  if (RandInt(0, 10) == 0) {  // occasional check that the caller really passed the ReorderIndexes() ordering
+    std::vector<Index> regular_in, regular_out;
+    GetIndexesForComputation(io, input_indexes, output_indexes, &regular_in, &regular_out);
+    KALDI_ASSERT(regular_in == input_indexes && regular_out == output_indexes);
   }
   PrecomputedIndexes* ans = new PrecomputedIndexes();
-  ans->row_stride = io.reorder_t_in;
-  int32 num_offsets = (int32)time_offsets_.size();
-  ans->row_offsets.resize(num_offsets);
-  for (int32 i = 0; i < num_offsets; i++) {
-    int32 time_offset = time_offsets_[i], required_input_t = io.start_t_out + time_offset,
-          input_t = (required_input_t - io.start_t_in) / io.t_step_in;
-    KALDI_ASSERT(required_input_t == io.start_t_in + io.t_step_in * input_t);
-    int32 n = io.reorder_t_in, input_t_multiple = n * (input_t / n), input_t_remainder = input_t % n;
-    int32 input_row_offset = input_t_multiple * io.num_images + input_t_remainder;
-    ans->row_offsets[i] = input_row_offset;
+  const int32 block = io.reorder_t_in;
+  ans->row_stride = block;
+  for (int32 offset : time_offsets_) {
+    // frame number (counting input frames from 0) that the FIRST output frame reads for this offset
+    const int32 t_wanted = io.start_t_out + offset;
+    const int32 frame = (t_wanted - io.start_t_in) / io.t_step_in;
+    KALDI_ASSERT(t_wanted == io.start_t_in + io.t_step_in * frame);
+    // blocked input order: whole blocks advance by block * num_images rows, frames inside a block by one row
+    ans->row_offsets.push_back((frame / block) * block * io.num_images + frame % block);
   }
   return ans;
 }

@@ -43,6 +43,11 @@ int32 GetDataParallelWorldSize();
 // simple.cc:2640), which costs a device->host sync each time; off by default here.
 void SetPrintLogAlpha(bool b);
 
+// The six mode booleans of TdnnDARTSV3Component in their on-disk order (conv.h:243-257).
+struct TdnnDARTSV3ModeFlags {
+  bool use_gumbel, use_entropy, free_select, update_alpha, update_theta, uniform_sample;
+};
+
 // ------------------------------------------------------------------ TdnnDARTSV3Component (conv.h:112-332)
 class TdnnDARTSV3Component : public UpdatableComponent {
  public:

@@ -82,7 +82,8 @@ struct GroupRowOffsets {
 __global__ void __launch_bounds__(256)
 split_transpose_kernel(const float* __restrict__ src, int R, int J, long long ld, int r, int c_row_mul, int c_col_mul,
                        GroupRowOffsets c_row_off, const float* __restrict__ scale, int Q, int Qp,
-                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ colsum,
+                       float colsum_scale) {
   // 64 (q) x 64 (j) tile: 256-byte coalesced float4 reads along j, 128-byte (8 x bf16 per lane) writes along q.
   __shared__ float tile[64][65];
   const int c = blockIdx.z;
@@ -115,6 +116,13 @@ split_transpose_kernel(const float* __restrict__ src, int R, int J, long long ld
     tile[qq][j4 + 3] = sc * v.w;
   }
   __syncthreads();
+  if (colsum != nullptr && t < 64 && j0 + t < J) {
+    // fused AddRowSumMat (bias gradient, ref: tdnn.cc:607-617): column sums of this tile, one atomic per column
+    float sum = 0.f;
+#pragma unroll 8
+    for (int qq = 0; qq < 64; ++qq) sum += tile[qq][t];
+    atomicAdd(colsum + j0 + t, colsum_scale * sum);
+  }
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int jj = (t >> 3) + 32 * i, qc = (t & 7) * 8;
@@ -196,7 +204,8 @@ static int launch_split_rows(tdnnf_ctx* ctx, const float* src, int R, int D, lon
 
 static int launch_split_transpose(tdnnf_ctx* ctx, const float* src, int R, int J, long long ld, int r, int groups,
                                   int c_row_mul, int c_col_mul, const float* scale, int Q, int Qp, int Kvalid,
-                                  Planes* pl, const int32_t* group_row_offsets = nullptr) {
+                                  Planes* pl, const int32_t* group_row_offsets = nullptr, float* colsum = nullptr,
+                                  float colsum_scale = 0.f) {
   pl->plane_elems = (long long)groups * J * Qp;
   pl->K = Kvalid;
   pl->Kpitch = Qp;
@@ -208,7 +217,7 @@ static int launch_split_transpose(tdnnf_ctx* ctx, const float* src, int R, int J
   GroupRowOffsets gro;
   for (int i = 0; i < kMaxSeg; ++i) gro.v[i] = (group_row_offsets && i < groups) ? group_row_offsets[i] : 0;
   split_transpose_kernel<<<grid, block, 0, ctx->stream>>>(src, R, J, ld, r, c_row_mul, c_col_mul, gro, scale, Q, Qp,
-                                                          pl->base, pl->base + pl->plane_elems);
+                                                          pl->base, pl->base + pl->plane_elems, colsum, colsum_scale);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   return TDNNF_OK;
@@ -458,8 +467,9 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
     rc = launch_split_transpose(ctx, in_value, in_rows, in_dim, in_stride, r, n, 0, 0, nullptr, out_rows, Rp,
                                 out_rows, &XT, row_offsets);
   if (rc) return rc;
+  // the out_deriv^T pre-pass also accumulates dbias += lr * colsum(out_deriv) (each element is read exactly once)
   rc = launch_split_transpose(ctx, out_deriv, out_rows, out_dim, od_stride, 1, 1, 0, 0, nullptr, out_rows, Rp,
-                              out_rows, &ODT);
+                              out_rows, &ODT, nullptr, dbias, lr);
   if (rc) return rc;
   if (s) TDNNF_CUDA_OK(cudaMemsetAsync(s, 0, sizeof(float) * n, ctx->stream));
 
@@ -516,6 +526,5 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
   const double wflops = 2.0 * out_rows * (double)out_dim * in_dim * n;
   rc = m_is_in ? launch_gemm(ctx, bn, XT, ODT, p, wflops) : launch_gemm(ctx, bn, ODT, XT, p, wflops);
   if (rc) return rc;
-  if (dbias) return tdnnf_add_row_sum(ctx, out_deriv, out_rows, out_dim, od_stride, lr, dbias);
   return TDNNF_OK;
 }

@@ -421,8 +421,6 @@ class Supernet:
             bwd.add("nnet3", lib.tdnnf_nnet3_backprop, blk["lin"].h, blk["lin_idx"].h, pp, pr, pc, ps, None, 0, lp, lr_, lc, ls,
                     blk["memo_lin"], blk["lin_delta"].h, qp, qs)
             bwd.add("nnet3", lib.tdnnf_nnet3_delete_memo, blk["lin"].h, blk["memo_lin"])
-            if self.world > 1:  # this block's deltas are final: reduce them while the earlier blocks still run
-                bwd.add_py(partial(self._launch_allreduce, self._views_of([blk["aff_delta"], blk["lin_delta"]])))
         self._bn_bwd(bwd, t1["bn"], t1["out"], t1["d_out"], t1["d_out"])
         bwd.add("abi", lib.tdnnf_relu_bwd, h, _m(t1["relu"])[0], _m(t1["relu"])[3], _m(t1["d_out"])[0], _m(t1["d_out"])[3],
                 _m(t1["d_aff"])[0], _m(t1["d_aff"])[3], t1["relu"].shape[0], t1["relu"].shape[1])
@@ -451,15 +449,24 @@ class Supernet:
                     n = m["db"].numel()
                     dbp = C.c_void_p(m["db"].data_ptr())
                     upd.add("abi", lib.tdnnf_mat_dot_dev, h, dbp, n, dbp, n, 1, n, slot)
-        if self.world > 1:  # the stock layers' deltas (head layers finish first, tdnn1 last): one more bucket
-            stock_views = []
+        # Data-parallel reduction of the deltas: ONE flat all-reduce after the backward pass.  (Per-block
+        # all-reduces overlapped with the backward GEMMs were measured slower: the persistent GEMM kernels own
+        # every SM (226 KB smem per CTA), so a concurrent NCCL kernel delays a whole wave of their CTAs; and ~60
+        # separate 1-7 MB all-reduces are latency-bound.)
+        if self.world > 1:
+            import torch
+
+            views = []
+            for blk in self.blocks:
+                views += self._views_of([blk["aff_delta"], blk["lin_delta"]])
             for p in st.values():
-                stock_views.append(p["dW"].view(-1))
+                views.append(p["dW"].view(-1))
                 if p["db"] is not None:
-                    stock_views.append(p["db"])
-            bwd.add_py(partial(self._launch_allreduce, stock_views))
+                    views.append(p["db"])
+            self.delta_views = views
+            self.delta_flat = torch.empty(sum(v.numel() for v in views), device=self.dev, dtype=torch.float32)
+            self.delta_chunks = list(torch.split(self.delta_flat, [v.numel() for v in views]))
         self.fwd_plan, self.bwd_plan, self.upd_plan = fwd, bwd, upd
-        self.pending = []
 
     def _views_of(self, deltas):
         """The parameter buffers of delta components as flat torch views (pitch padding included: it is zero)."""
@@ -475,8 +482,12 @@ class Supernet:
                 views.append(torch.as_tensor(_Arr(ptr, rows * stride), device=self.dev))
         return views
 
-    def _launch_allreduce(self, views):
-        self.pending += parallel.allreduce_deltas(views, self.pg, async_op=True)
+    def _allreduce_deltas(self):
+        import torch
+
+        torch._foreach_copy_(self.delta_chunks, self.delta_views)      # gather (device-to-device, one multi-tensor kernel)
+        parallel.allreduce_deltas([self.delta_flat], self.pg)          # NCCL all-reduce(sum) over NVLink
+        torch._foreach_copy_(self.delta_views, self.delta_chunks)      # scatter back into the delta components
 
     # ------------------------------------------------------------------ public API
     @property
@@ -512,9 +523,8 @@ class Supernet:
         # ComputeChainObjfAndDeriv: denominator fwd-bwd, numerator fwd-bwd, objf = num - den (host scalars, like Kaldi)
         objf, _, weight = self.objective.compute(self.head["out"], self.head["d_out"])
         self.bwd_plan.run()
-        for w in self.pending:  # all-reduces launched bucket by bucket during the backward pass
-            w.wait()
-        self.pending = []
+        if self.world > 1:
+            self._allreduce_deltas()
         if apply_update:
             self._update_with_max_change()
         return objf / weight
