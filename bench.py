@@ -159,6 +159,19 @@ def supernet_flops(cfg):
     return sum(3 * 2.0 * (rl + ra) * cfg.num_seqs * n_eff * cfg.dim * cfg.bottleneck for rl, ra in zip(rows_lin, rows_aff))
 
 
+def den_report(cfg, arcs, den_ms, peaks):
+    """Denominator fwd-bwd roofline figures: algorithmic HBM bytes and the L2 gather bytes that
+    actually bound the recursion (two 4-byte row gathers per arc, sequence and frame, both directions)."""
+    S, T, N, P = cfg.num_seqs, cfg.frames_per_eg // cfg.frame_subsampling, cfg.den_states, cfg.num_pdfs
+    alg = 4.0 * S * (2 * (T + 1) * (N + 1) + 3 * P * T) + 12.0 * arcs * 2
+    gather = 8.0 * arcs * S * T * 2
+    gbs = alg / den_ms / 1e6
+    return dict(ms=den_ms, states=N, arcs=arcs, seqs=S, frames=T, algorithmic_bytes=alg, achieved_GBps=gbs,
+                hbm_peak_GBps=peaks["hbm_gbs"], frac_of_hbm=gbs / peaks["hbm_gbs"], l2_gather_bytes=gather,
+                l2_gather_GBps=gather / den_ms / 1e6,
+                note="bound by L2 row gathers (8 B per arc, sequence and frame), ~25x the algorithmic HBM bytes")
+
+
 # ------------------------------------------------------------------ arms
 def run_reference(args, cfg, rank, world):
     if rank != 0:
@@ -253,6 +266,19 @@ def run_ours(args, cfg, rank, world, local_rank):
     net.step(None)
     gemm_ms, gemm_flops, gemm_launches = net.ctx.gemm_timing_read()
     net.ctx.gemm_timing_enable(False)
+    # ---- the denominator forward-backward on its own (second half of BASELINE.json's metric): CUDA events around
+    # DenominatorComputation::Forward + Backward on the step's (T*S) x P output; algorithmic bytes per SURVEY 8d
+    den_reps = 5
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    net.objective.den.forward(net.head["out"])
+    torch.cuda.synchronize(dev)
+    d0.record()
+    for _ in range(den_reps):
+        net.objective.den.forward(net.head["out"])
+        net.objective.den.backward(-1.0, net.head["d_out"])
+    d1.record()
+    torch.cuda.synchronize(dev)
+    den_ms = d0.elapsed_time(d1) / den_reps
     barrier()
     if rank != 0:
         net.close()
@@ -286,6 +312,7 @@ def run_ours(args, cfg, rank, world, local_rank):
                       launches_timed=gemm_launches, gemm_ms_per_step=gemm_ms / 2, gemm_share_of_step=(gemm_ms / 2) / step_ms,
                       note=("achieved = algorithmic fp32-equivalent FLOPs (2MNK, one pass) / CUDA-event time of the GEMM launches; "
                             "each K block issues 3 bf16 MMAs (hi*hi, hi*lo, lo*hi), so the tensor pipe runs at 3x this rate")),
+        den=den_report(cfg, net.den_arcs, den_ms, peaks),
         cpu_baseline=cpu_line, objf_per_frame=objf, den_arcs=net.den_arcs)
     print(json.dumps(line), flush=True)
     net.close()
