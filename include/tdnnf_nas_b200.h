@@ -50,6 +50,12 @@ int tdnnf_ctx_create(int device, tdnnf_ctx** out);
 int tdnnf_ctx_destroy(tdnnf_ctx* ctx);
 /* stream: a cudaStream_t passed as void* (NULL = legacy default stream). */
 int tdnnf_ctx_set_stream(tdnnf_ctx* ctx, void* stream);
+int tdnnf_ctx_get_stream(tdnnf_ctx* ctx, void** stream);
+/* Operand precision of the tensor-core GEMMs behind tdnnf_darts_{propagate,backprop_data,backprop_params}:
+ * every fp32 operand is split into `planes` bf16 planes.  2 (default): x = hi + lo to ~2^-17, three products
+ * per K step, results within ~5e-6 of fp32.  3: hi + mid + lo to 2^-24, six products, fp32-level results at
+ * twice the tensor-pipe time -- used by the natural-gradient update, whose eigen-problem amplifies rounding. */
+int tdnnf_ctx_set_gemm_planes(tdnnf_ctx* ctx, int planes);
 /* Pre-size the internal scratch arena (bf16 operand planes) so later calls never grow it. */
 int tdnnf_ctx_reserve(tdnnf_ctx* ctx, uint64_t bytes);
 /* Number of kernels this context has launched so far (for gpu_launches accounting). */
@@ -221,6 +227,27 @@ int tdnnf_batchnorm_train_fwd(tdnnf_ctx* ctx, const float* in, int rows, int col
 int tdnnf_batchnorm_train_bwd(tdnnf_ctx* ctx, const float* out_value, int ov_stride, const float* out_deriv,
                               int od_stride, float* in_deriv, int id_stride, int rows, int cols, float target_rms,
                               const float* memo);
+
+/* ------------------------------------------------------------------ natural gradient --- */
+/* Device-side pieces of OnlineNaturalGradient::PreconditionDirections (kaldi: nnet3/natural-gradient-online.cc;
+ * called at ref tdnn.cc:598-599 and simple.cc:9542) that are not GEMMs.  The GEMM-shaped pieces (H = X W^T,
+ * J = H^T X, L = H^T H, K = J J^T, W_{t+1} = A B) go through tdnnf_darts_{propagate,backprop_data,backprop_params}
+ * (with one offset they are plain products), so the spliced input [w_1 X_1 | ... | w_n X_n | 1] of
+ * tdnn.cc:476-514 is never materialised.
+ *
+ * sumsq[i] (device double[n], overwritten) = sum over the rows of view i of ||row||^2, view i = rows
+ * row_offsets[i] + k*row_stride, k < out_rows (GetInputPart, ref tdnn.cc:806-820); n = 1, offset 0, stride 1
+ * gives ||in||_F^2.  This is TraceMatMat(X, X, kTrans) of the spliced matrix once weighted by w_i^2. */
+int tdnnf_darts_view_sumsq(tdnnf_ctx* ctx, const float* in, int in_rows, int in_dim, int in_stride, int out_rows,
+                           int n, const int32_t* row_offsets, int row_stride, double* sumsq);
+/* out3 (device float[3]) = { tr(X X^T), tr(Xhat Xhat^T), sqrt(ratio) } for Xhat = X - (X W^T) W, from
+ * sumsq (above), the block weights weff (device [n] or NULL = 1), ones_rows (= row count when X carries the
+ * appended column of ones, else 0), L = (X W^T)^T (X W^T) and W W^T (rank x rank).  No host sync. */
+int tdnnf_ng_scale(tdnnf_ctx* ctx, const double* sumsq, const float* weff, int n, float ones_rows, const float* L,
+                   int l_stride, const float* WWt, int w_stride, int rank, float* out3);
+/* dst += alpha * (*factor1_dev) * (*factor2_dev) * src   (device scalars, either may be NULL = 1) */
+int tdnnf_mat_axpy_dev(tdnnf_ctx* ctx, float alpha, const float* factor1_dev, const float* factor2_dev,
+                       const float* src, int src_stride, float* dst, int dst_stride, int rows, int cols);
 
 /* ------------------------------------------------------------------ chain denominator - */
 /* DenominatorGraph (kaldi: chain/chain-den-graph.{h,cc}).  Host arrays, copied to the device.

@@ -89,6 +89,22 @@ int tdnnf_nnet3_bn_test_set_stats(void* comp, int dim, int block_dim, float epsi
 /* Device pointers of BatchNormTestComponent's derived scale_ / offset_ vectors (ref: norm.cc:680-713). */
 int tdnnf_nnet3_bn_test_scale_offset(const void* comp, const float** scale, const float** offset, int* dim);
 
+/* OnlineNaturalGradient (kaldi: nnet3/natural-gradient-online.h) as a standalone object: what the components
+ * own as preconditioner_in_ / preconditioner_out_ / preconditioner_ (ref: conv.h:324-327, simple.h:2790). */
+int tdnnf_nnet3_ng_new(int rank, int update_period, float num_samples_history, float alpha, void** out);
+int tdnnf_nnet3_ng_delete(void* ng);
+int tdnnf_nnet3_ng_freeze(void* ng, int frozen);
+/* PreconditionDirections(&X, &scale): X (device, rows x cols) is overwritten; *scale on the host (one sync). */
+int tdnnf_nnet3_ng_precondition(void* ng, float* x, int rows, int cols, int stride, float* scale);
+/* State read-back: t, rank, dim, rho; d (host, rank floats) and W (host, rank x dim, dense) may be NULL. */
+int tdnnf_nnet3_ng_state(void* ng, int* t, int* rank, int* dim, float* rho, float* d, float* W, int* num_reorthogonalized);
+/* The preconditioners of a TdnnDARTSV3Component (which = 0: preconditioner_in_, 1: preconditioner_out_) or of an
+ * Onehot/ConstantFunction component (which = 0); the pointer is owned by the component. */
+int tdnnf_nnet3_component_ng(void* comp, int which, void** ng);
+/* Diagnostic switch: with 1, every PreconditionDirections call is the identity with scale 1, i.e. the components
+ * accumulate the un-preconditioned gradient (what the first-level parity tests pin). */
+int tdnnf_nnet3_set_ng_identity(int enable);
+
 /* ReadEditConfig subset: set-temperature-proportion, set-learning-rate{,-factor} (ref: utils.cc:1166-1415). */
 int tdnnf_nnet3_apply_edits(const char* edits, const char** names, void** comps, int n);
 

@@ -15,14 +15,16 @@
 // (tests/test_oracle_*.py).  The denominator follows upstream kaldi chain-denominator.cc
 // (CPU code path) as summarised in SURVEY.md Appendix B.
 //
-// The two OnlineNaturalGradient::PreconditionDirections calls (tdnn.cc:598-599) are taken as
-// the identity with in_scale = out_scale = 1 (the "raw gradient" path of BASELINE.md section 3).
+// The two OnlineNaturalGradient::PreconditionDirections calls (tdnn.cc:598-599) follow upstream Kaldi's
+// natural-gradient-online.cc as restated in oracle_ng.inc (orc_tdnn_backprop_ng); orc_tdnn_backprop is
+// the same with both preconditioners = identity (the "raw gradient" path of BASELINE.md section 3).
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <numeric>
 #include <vector>
 
 #ifdef _OPENMP
@@ -105,6 +107,8 @@ Mat GetInputPart(const Mat& input, int num_output_rows, int row_stride, int row_
 }
 
 }  // namespace
+
+#include "oracle_ng.inc"
 
 extern "C" {
 
@@ -220,16 +224,17 @@ int orc_tdnn_propagate(const int* time_offsets, int n, int flags, float temp_pro
   return 0;
 }
 
-// TdnnDARTSV3Component::Backprop + UpdateNaturalGradient, tdnn.cc:335-431, 457-626, with the
-// PreconditionDirections calls replaced by the identity (scale 1).
+// TdnnDARTSV3Component::Backprop + UpdateNaturalGradient, tdnn.cc:335-431, 457-626.
 //   in_deriv   may be NULL; it is ADDED to (kBackpropAdds)
 //   dW / dbias are the delta component's linear_params_ / bias_params_ (n + out_dim); NULL => no update
 //   s_out      (optional, n): the raw inner products out_temp.Sum() per offset (0 where not computed)
-int orc_tdnn_backprop(const int* time_offsets, int n, int flags, float temp_proportion, const float* W, int w_stride,
-                      const float* in_value, int in_rows, int in_dim, int in_stride, const float* out_deriv,
-                      int out_rows, int out_dim, int od_stride, const float* coef_memo, const int* row_offsets,
-                      int row_stride, float* in_deriv, int id_stride, float learning_rate, float* dW, int dw_stride,
-                      float* dbias, float* s_out) {
+//   ng_in / ng_out  (optional, orc_ng_create handles): preconditioner_in_ / preconditioner_out_ of the delta
+//              component; NULL = the identity with scale 1 (the un-preconditioned gradient).
+int orc_tdnn_backprop_ng(const int* time_offsets, int n, int flags, float temp_proportion, const float* W, int w_stride,
+                         const float* in_value, int in_rows, int in_dim, int in_stride, const float* out_deriv,
+                         int out_rows, int out_dim, int od_stride, const float* coef_memo, const int* row_offsets,
+                         int row_stride, float* in_deriv, int id_stride, float learning_rate, float* dW, int dw_stride,
+                         float* dbias, float* s_out, void* ng_in, void* ng_out, float* scales_out) {
   Mat in_m{const_cast<float*>(in_value), in_rows, in_dim, in_stride};
   Mat od{const_cast<float*>(out_deriv), out_rows, out_dim, od_stride};
   Mat lin{const_cast<float*>(W), out_dim, n * in_dim, w_stride};
@@ -311,19 +316,36 @@ int orc_tdnn_backprop(const int* time_offsets, int n, int flags, float temp_prop
   if (flags & ORC_UPDATE_ALPHA)                                  // tdnn.cc:588-590
     for (int i = 0; i < n; ++i) dbias[i] *= 10000;
 
-  // PreconditionDirections == identity, in_scale = out_scale = 1
-  const BaseFloat local_lrate = 1.0f * learning_rate;
+  // CuMatrix<BaseFloat> out_deriv_temp(out_deriv); the two PreconditionDirections calls   tdnn.cc:592-604
+  OwnedMat out_deriv_temp(out_rows, out_dim);
+  for (int r = 0; r < out_rows; ++r) memcpy(&out_deriv_temp.m(r, 0), &od(r, 0), sizeof(float) * out_dim);
+  BaseFloat in_scale = 1.0f, out_scale = 1.0f;
+  if (ng_in) NgPrecondition(static_cast<OrcNG*>(ng_in), in_value_temp.m, &in_scale);
+  if (ng_out) NgPrecondition(static_cast<OrcNG*>(ng_out), out_deriv_temp.m, &out_scale);
+  if (scales_out) { scales_out[0] = in_scale; scales_out[1] = out_scale; }
+  const BaseFloat scale = in_scale * out_scale, local_lrate = scale * learning_rate;
   // bias tail: AddMatVec(local_lrate, out_deriv_temp, kTrans, precon_ones, 1.0)   tdnn.cc:607-617
   for (int c = 0; c < out_dim; ++c) {
     double sum = 0.0;
-    for (int r = 0; r < out_rows; ++r) sum += (double)od(r, c) * (double)in_value_temp.m(r, spliced);
+    for (int r = 0; r < out_rows; ++r) sum += (double)out_deriv_temp.m(r, c) * (double)in_value_temp.m(r, spliced);
     dbias[n + c] += local_lrate * (BaseFloat)sum;
   }
   // linear_params_.AddMatMat(local_lrate, out_deriv_temp, kTrans, in_value_precon_part, kNoTrans, 1.0)   tdnn.cc:619-624
   Mat dlin{dW, out_dim, spliced, dw_stride};
   Mat precon = in_value_temp.m.Range(0, out_rows, 0, spliced);
-  AddMatMat(dlin, local_lrate, od, kTrans, precon, kNoTrans, 1.0f);
+  AddMatMat(dlin, local_lrate, out_deriv_temp.m, kTrans, precon, kNoTrans, 1.0f);
   return 0;
+}
+
+// The same with both preconditioners = identity (the raw-gradient form the first parity tests pin).
+int orc_tdnn_backprop(const int* time_offsets, int n, int flags, float temp_proportion, const float* W, int w_stride,
+                      const float* in_value, int in_rows, int in_dim, int in_stride, const float* out_deriv,
+                      int out_rows, int out_dim, int od_stride, const float* coef_memo, const int* row_offsets,
+                      int row_stride, float* in_deriv, int id_stride, float learning_rate, float* dW, int dw_stride,
+                      float* dbias, float* s_out) {
+  return orc_tdnn_backprop_ng(time_offsets, n, flags, temp_proportion, W, w_stride, in_value, in_rows, in_dim, in_stride,
+                              out_deriv, out_rows, out_dim, od_stride, coef_memo, row_offsets, row_stride, in_deriv,
+                              id_stride, learning_rate, dW, dw_stride, dbias, s_out, nullptr, nullptr, nullptr);
 }
 
 // ------------------------------------------------------------------ {Gumbel}SoftmaxFlops

@@ -19,8 +19,8 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(HERE, "oracle.cc")
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+    srcs = [os.path.join(HERE, f) for f in ("oracle.cc", "oracle_ng.inc")]
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(f) for f in srcs):
         subprocess.run(["make", "-C", HERE, "-B" if force else "-s", "_build/liboracle.so"], check=True,
                        capture_output=True)
     return LIB
@@ -33,6 +33,7 @@ def lib():
         _lib = C.CDLL(LIB)
         _lib.orc_den_forward_backward.restype = C.c_float
         _lib.orc_num_forward_backward.restype = C.c_double
+        _lib.orc_ng_create.restype = C.c_void_p
     return _lib
 
 
@@ -102,9 +103,42 @@ def tdnn_propagate(time_offsets, flags, temp, W, bias_params, x, out_rows, row_o
     return out, coef
 
 
+class NaturalGradient:
+    """OnlineNaturalGradient state (oracle_ng.inc): precondition(X) overwrites X and returns the scale."""
+
+    def __init__(self, rank=40, update_period=1, num_samples_history=2000.0, alpha=4.0):
+        self.h = C.c_void_p(lib().orc_ng_create(rank, update_period, C.c_float(num_samples_history), C.c_float(alpha)))
+
+    def precondition(self, X):
+        scale = C.c_float(0.0)
+        lib().orc_ng_precondition(self.h, _f(X), X.shape[0], X.shape[1], _stride(X), C.byref(scale))
+        return float(scale.value)
+
+    def freeze(self, frozen=True):
+        lib().orc_ng_freeze(self.h, int(frozen))
+
+    def state(self):
+        t, rank, D, nre, nfl = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        rho = C.c_float()
+        lib().orc_ng_state(self.h, C.byref(t), C.byref(rank), C.byref(D), C.byref(rho), None, None, C.byref(nre), C.byref(nfl))
+        d = np.zeros(max(rank.value, 0), dtype=np.float32)
+        W = np.zeros((max(rank.value, 0), max(D.value, 0)), dtype=np.float32)
+        if t.value > 0 and rank.value > 0:
+            lib().orc_ng_state(self.h, None, None, None, None, _f(d), _f(W), None, None)
+        return dict(t=t.value, rank=rank.value, D=D.value, rho=float(rho.value), d=d, W=W, num_reorth=nre.value,
+                    num_floored=nfl.value)
+
+    def __del__(self):
+        try:
+            lib().orc_ng_destroy(self.h)
+        except Exception:
+            pass
+
+
 def tdnn_backprop(time_offsets, flags, temp, W, x, out_deriv, coef, row_offsets, row_stride, lr,
-                  in_deriv=None, dW=None, dbias=None):
-    """in_deriv (added to), dW, dbias (n+out_dim; added to) are modified in place.  Returns raw s (n,)."""
+                  in_deriv=None, dW=None, dbias=None, ng_in=None, ng_out=None, scales=None):
+    """in_deriv (added to), dW, dbias (n+out_dim; added to) are modified in place.  Returns raw s (n,).
+    ng_in / ng_out: NaturalGradient objects (None = identity); scales: optional float32[2] <- (in_scale, out_scale)."""
     to = np.asarray(time_offsets, dtype=np.int32)
     n = len(to)
     out_dim = W.shape[0]
@@ -112,11 +146,13 @@ def tdnn_backprop(time_offsets, flags, temp, W, x, out_deriv, coef, row_offsets,
     ro = np.asarray(row_offsets, dtype=np.int32)
     s = np.zeros(n, dtype=np.float32)
     coef = np.ascontiguousarray(coef, dtype=np.float32)
-    rc = lib().orc_tdnn_backprop(
+    rc = lib().orc_tdnn_backprop_ng(
         _i(to), n, flags, C.c_float(temp), _f(W), _stride(W), _f(x), x.shape[0], in_dim, _stride(x), _f(out_deriv),
         out_deriv.shape[0], out_dim, _stride(out_deriv), _f(coef), _i(ro), row_stride,
         None if in_deriv is None else _f(in_deriv), 0 if in_deriv is None else _stride(in_deriv), C.c_float(lr),
-        None if dW is None else _f(dW), 0 if dW is None else _stride(dW), None if dbias is None else _f(dbias), _f(s))
+        None if dW is None else _f(dW), 0 if dW is None else _stride(dW), None if dbias is None else _f(dbias), _f(s),
+        None if ng_in is None else ng_in.h, None if ng_out is None else ng_out.h,
+        None if scales is None else _f(scales))
     if rc != 0:
         raise RuntimeError(f"oracle: reference behaviour undefined here (rc={rc})")
     return s

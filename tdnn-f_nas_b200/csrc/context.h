@@ -32,6 +32,11 @@ int fail(int code, const std::string& msg);
 
 }  // namespace tdnnf
 
+// per-offset row offsets passed by value to kernels
+struct TdnnfOffsets {
+  int v[TDNNF_MAX_OFFSETS];
+};
+
 // The opaque context of the C ABI.  One per (host thread, device); owns the stream the
 // kernels are launched on and a grow-only scratch arena for operand planes.
 struct tdnnf_ctx {
@@ -44,6 +49,8 @@ struct tdnnf_ctx {
   char* ws = nullptr;
   size_t ws_bytes = 0;
   size_t ws_off = 0;
+  // operand planes of the tensor-core GEMMs: 2 = bf16 hi/lo (three products), 3 = hi/mid/lo (six products)
+  int gemm_planes = 2;
   // counters for bench.py's gpu_launches claim
   unsigned long long launches = 0;
   // optional per-GEMM-launch event timing (roofline instrumentation)

@@ -271,20 +271,82 @@ void TdnnDARTSV3Component::UpdateNaturalGradient(const PrecomputedIndexes& index
   const int32 num_offsets = (int32)time_offsets_.size();
   KALDI_ASSERT(bias_params_.Dim() == linear_params_.NumRows() + num_offsets);
   tdnnf_ctx* ctx = CurrentContext();
-  // "scale" from the two PreconditionDirections calls (tdnn.cc:598-604)
-  const BaseFloat in_scale = preconditioner_in_.PreconditionDirectionsScale(),
-                  out_scale = preconditioner_out_.PreconditionDirectionsScale();
-  const BaseFloat local_lrate = in_scale * out_scale * learning_rate_;
+  const int32 num_rows = out_deriv.NumRows(), input_dim = in_value.NumCols(), output_dim = out_deriv.NumCols(),
+              spliced_input_dim = num_offsets * input_dim, augmented_input_dim = spliced_input_dim + 1;
   const bool want_s = !(model_flags & TDNNF_DARTS_UNIFORM_SAMPLE);
   CuVector s(num_offsets);
-  // linear_params_ += local_lrate * out_deriv^T * [w_1 X_1 | ... | w_n X_n]      (tdnn.cc:619-624)
-  // bias tail     += local_lrate * colsum(out_deriv)                             (tdnn.cc:607-617)
-  // s_i = sum((X_i W_i^T) .* out_deriv), the out_temp.Sum() of tdnn.cc:506-507, 538-539, as an epilogue
+  if (ng_consts_.Dim() == 0) {
+    ng_consts_.Resize(2);
+    ng_consts_.CopyFromHost(std::vector<BaseFloat>{1.0f, -1.0f});
+  }
+  const BaseFloat *one = ng_consts_.Data(), *minus_one = ng_consts_.Data() + 1;
+  const int32 zero_offset[1] = {0};
+
+  // The two PreconditionDirections calls (tdnn.cc:598-599).  in_value_temp = [w_1 X_1 | ... | w_n X_n | 1]
+  // (tdnn.cc:476-514) and the copy of out_deriv stay implicit: each call updates its Fisher estimate and
+  // returns (W, H = X W^T, scale on the device); see natural_gradient.cc.
+  NgOperand x_in;
+  x_in.data = in_value.Data();
+  x_in.rows = in_value.NumRows();
+  x_in.cols = input_dim;
+  x_in.stride = in_value.Stride();
+  x_in.num_rows = num_rows;
+  x_in.n = num_offsets;
+  x_in.row_offsets = indexes.row_offsets.data();
+  x_in.row_stride = indexes.row_stride;
+  x_in.weff = memo.weff.Data();
+  x_in.ones_col = true;
+  NgProjection p_in, p_out;
+  preconditioner_in_.PreconditionImplicit(x_in, &p_in);
+  preconditioner_out_.PreconditionImplicit(NgOperand::Plain(out_deriv), &p_out);
+
+  // G = out_deriv^T [w_1 X_1 | ... | w_n X_n | 1]  (D_out x (n D_in + 1)), the un-preconditioned gradient, with
+  // s_i = sum((X_i W_i^T) .* out_deriv), the out_temp.Sum() of tdnn.cc:506-507, 538-539, as an epilogue reduction.
+  if (ng_grad_.NumRows() != output_dim || ng_grad_.NumCols() != augmented_input_dim)
+    ng_grad_.Resize(output_dim, augmented_input_dim);
+  ng_grad_.SetZero();
+  if (ng_colsum_.Dim() != output_dim) ng_colsum_.Resize(output_dim);
+  ng_colsum_.SetZero();
   CheckStatus(tdnnf_darts_backprop_params(
       ctx, in_value.Data(), in_value.NumRows(), in_value.NumCols(), in_value.Stride(), out_deriv.Data(), out_deriv.NumRows(),
-      out_deriv.NumCols(), out_deriv.Stride(), linear_params_temp_.Data(), linear_params_temp_.Stride(), linear_params_.Data(),
-      linear_params_.Stride(), bias_params_.Data() + num_offsets, memo.weff.Data(), num_offsets, indexes.row_offsets.data(),
-      indexes.row_stride, local_lrate, want_s ? s.Data() : NULL));
+      out_deriv.NumCols(), out_deriv.Stride(), linear_params_temp_.Data(), linear_params_temp_.Stride(), ng_grad_.Data(),
+      ng_grad_.Stride(), ng_colsum_.Data(), memo.weff.Data(), num_offsets, indexes.row_offsets.data(), indexes.row_stride, 1.0f,
+      want_s ? s.Data() : NULL));
+  CheckStatus(tdnnf_mat_axpy(ctx, 1.0f, ng_colsum_.Data(), 1, ng_grad_.Data() + spliced_input_dim, ng_grad_.Stride(),
+                             output_dim, 1));
+  // out_deriv_hat^T X_hat = (I - W_o^T W_o) [ G - (out_deriv^T H_in) W_in ]: both projections are applied to the
+  // D_out x D gradient (rank-r corrections) instead of to the R x D operands.
+  if (!p_in.identity) {
+    const int32 r = p_in.rank;
+    if (ng_g1_.NumRows() != output_dim || ng_g1_.NumCols() != r) ng_g1_.Resize(output_dim, r);
+    ng_g1_.SetZero();
+    CheckStatus(tdnnf_darts_backprop_params(ctx, p_in.H->Data(), num_rows, r, p_in.H->Stride(), out_deriv.Data(), num_rows,
+                                            output_dim, out_deriv.Stride(), NULL, 0, ng_g1_.Data(), ng_g1_.Stride(), NULL, one,
+                                            1, zero_offset, 1, 1.0f, NULL));
+    CheckStatus(tdnnf_darts_backprop_data(ctx, ng_g1_.Data(), output_dim, r, ng_g1_.Stride(), ng_grad_.Data(), output_dim,
+                                          augmented_input_dim, ng_grad_.Stride(), p_in.W->Data(), p_in.W->Stride(), minus_one,
+                                          1, zero_offset, 1));
+  }
+  if (!p_out.identity) {
+    const int32 q = p_out.rank;
+    if (ng_t_.NumRows() != q || ng_t_.NumCols() != augmented_input_dim) ng_t_.Resize(q, augmented_input_dim);
+    ng_t_.SetZero();
+    // T = W_o G
+    CheckStatus(tdnnf_darts_backprop_data(ctx, p_out.W->Data(), q, output_dim, p_out.W->Stride(), ng_t_.Data(), q,
+                                          augmented_input_dim, ng_t_.Stride(), ng_grad_.Data(), ng_grad_.Stride(), one, 1,
+                                          zero_offset, 1));
+    // G -= W_o^T T
+    CheckStatus(tdnnf_darts_backprop_params(ctx, ng_t_.Data(), q, augmented_input_dim, ng_t_.Stride(), p_out.W->Data(), q,
+                                            output_dim, p_out.W->Stride(), NULL, 0, ng_grad_.Data(), ng_grad_.Stride(), NULL,
+                                            one, 1, zero_offset, 1, -1.0f, NULL));
+  }
+  // local_lrate = in_scale * out_scale * learning_rate_ (tdnn.cc:600-604), the scales read on the device:
+  //   linear_params_ += local_lrate * out_deriv_hat^T X_hat[:, :n D_in]            (tdnn.cc:619-624)
+  //   bias tail      += local_lrate * out_deriv_hat^T precon_ones                  (tdnn.cc:607-617)
+  CheckStatus(tdnnf_mat_axpy_dev(ctx, learning_rate_, p_in.scale_dev, p_out.scale_dev, ng_grad_.Data(), ng_grad_.Stride(),
+                                 linear_params_.Data(), linear_params_.Stride(), output_dim, spliced_input_dim));
+  CheckStatus(tdnnf_mat_axpy_dev(ctx, learning_rate_, p_in.scale_dev, p_out.scale_dev, ng_grad_.Data() + spliced_input_dim,
+                                 ng_grad_.Stride(), bias_params_.Data() + num_offsets, 1, output_dim, 1));
   // architecture weights: Jacobian products + the x5 / xlr / x10000 scalings       (tdnn.cc:541-590)
   CheckStatus(tdnnf_darts_alpha_update(ctx, s.Data(), memo.coef.Data(), num_offsets, model_flags, temp_proportion_temp_,
                                        share_offset_index_temp_, learning_rate_, bias_params_.Data()));
@@ -742,13 +804,25 @@ void VectorFunctionComponentBase::Backprop(const std::string&, const ComponentPr
     KALDI_ASSERT(to_update != NULL);
     if (to_update->is_updatable_) {
       KALDI_ASSERT(out_deriv.NumCols() == to_update->output_.Dim());
-      BaseFloat factor;
-      if (to_update->use_natural_gradient_ && !to_update->is_gradient_)
-        factor = to_update->preconditioner_.PreconditionDirectionsScale() * to_update->learning_rate_;
-      else
-        factor = to_update->PlainUpdateFactor() * to_update->learning_rate_;
-      CheckStatus(tdnnf_add_row_sum(CurrentContext(), out_deriv.Data(), out_deriv.NumRows(), out_deriv.NumCols(),
-                                    out_deriv.Stride(), factor, to_update->output_.Data()));
+      if (to_update->use_natural_gradient_ && !to_update->is_gradient_ && !NaturalGradientIdentity()) {
+        // CuMatrix out_deriv_copy(out_deriv); PreconditionDirections(&out_deriv_copy, &scale);
+        // output_.AddRowSumMat(scale * learning_rate_, out_deriv_copy)          (simple.cc:9539-9546, 2628-2635)
+        CuMatrix& copy = to_update->out_deriv_copy_;
+        if (copy.NumRows() != out_deriv.NumRows() || copy.NumCols() != out_deriv.NumCols())
+          copy.Resize(out_deriv.NumRows(), out_deriv.NumCols());
+        copy.SetZero();
+        CheckStatus(tdnnf_mat_axpy(CurrentContext(), 1.0f, out_deriv.Data(), out_deriv.Stride(), copy.Data(), copy.Stride(),
+                                   copy.NumRows(), copy.NumCols()));
+        BaseFloat scale = 1.0;
+        to_update->preconditioner_.PreconditionDirections(&copy, &scale);
+        CheckStatus(tdnnf_add_row_sum(CurrentContext(), copy.Data(), copy.NumRows(), copy.NumCols(), copy.Stride(),
+                                      scale * to_update->learning_rate_, to_update->output_.Data()));
+      } else {
+        const bool ng_path = to_update->use_natural_gradient_ && !to_update->is_gradient_;  // identity preconditioner
+        const BaseFloat factor = (ng_path ? 1.0f : to_update->PlainUpdateFactor()) * to_update->learning_rate_;
+        CheckStatus(tdnnf_add_row_sum(CurrentContext(), out_deriv.Data(), out_deriv.NumRows(), out_deriv.NumCols(),
+                                      out_deriv.Stride(), factor, to_update->output_.Data()));
+      }
     }
     if (PrintsLogAlpha() && g_print_log_alpha) PrintLogAlpha(output_.Data(), output_.Dim());
   }

@@ -10,11 +10,37 @@
 namespace tdnnf {
 namespace nnet3 {
 
-// Configuration holder for OnlineNaturalGradient (kaldi: nnet3/natural-gradient-online.h).  The
-// preconditioner itself is SURVEY.md "next" row N1; see natural_gradient.cc for what is done now.
+// X as a preconditioner sees it, WITHOUT materialising it: the splice [w_1 X_1 | ... | w_n X_n | 1] of a device
+// matrix (views as in GetInputPart, ref tdnn.cc:806-820), or a plain matrix (n = 1, no weights, no ones).
+struct NgOperand {
+  const BaseFloat* data;      // device matrix the views are taken from
+  int32 rows, cols, stride;
+  int32 num_rows;             // N: rows of X (= rows of every view)
+  int32 n;                    // number of views
+  const int32* row_offsets;   // host, n entries
+  int32 row_stride;
+  const BaseFloat* weff;      // device, n block weights (may be NULL only when n == 1: weight 1)
+  bool ones_col;              // X carries an appended column of ones
+  int32 Dim() const { return n * cols + (ones_col ? 1 : 0); }
+  static NgOperand Plain(const CuMatrixBase<BaseFloat>& m);
+};
+
+// What a preconditioning call hands back: X_hat = X - H W and the device-resident scale.
+struct NgProjection {
+  bool identity;               // dimension 1 / rank 0: X_hat = X, scale 1
+  int32 rank;
+  const CuMatrix* W;           // W_t (rank x Dim) the projection was taken with
+  const CuMatrix* H;           // X W_t^T (N x rank)
+  const BaseFloat* scale_dev;  // device scalar sqrt(tr(X X^T) / tr(X_hat X_hat^T))
+};
+
+// OnlineNaturalGradient (kaldi: nnet3/natural-gradient-online.h); see natural_gradient.cc.
 class OnlineNaturalGradient {
  public:
-  OnlineNaturalGradient() : rank_(40), update_period_(1), num_samples_history_(2000.0), alpha_(4.0), frozen_(false) {}
+  OnlineNaturalGradient();
+  OnlineNaturalGradient(const OnlineNaturalGradient& other);
+  OnlineNaturalGradient& operator=(const OnlineNaturalGradient& other);
+  ~OnlineNaturalGradient();
   void SetRank(int32 rank) { rank_ = rank; }
   void SetUpdatePeriod(int32 update_period) { update_period_ = update_period; }
   void SetNumSamplesHistory(BaseFloat h) { num_samples_history_ = h; }
@@ -24,14 +50,44 @@ class OnlineNaturalGradient {
   BaseFloat GetNumSamplesHistory() const { return num_samples_history_; }
   BaseFloat GetAlpha() const { return alpha_; }
   void Freeze(bool frozen) { frozen_ = frozen; }
-  void Swap(OnlineNaturalGradient* other) { std::swap(*this, *other); }
-  // Returns the scale the caller multiplies into the learning rate.  Currently the identity
-  // preconditioner (scale 1, directions untouched) with a one-time warning; see natural_gradient.cc.
-  BaseFloat PreconditionDirectionsScale() const;
+  void Swap(OnlineNaturalGradient* other);
+  // The upstream call: X_t <- X_hat_t, *scale on the host (synchronises the stream once).
+  void PreconditionDirections(CuMatrixBase<BaseFloat>* X_t, BaseFloat* scale);
+  // The same update of the Fisher estimate with X (and X_hat) left implicit and no host sync.
+  void PreconditionImplicit(const NgOperand& X, NgProjection* out);
+  // State read-back (finishes a pending update first): for tests and diagnostics.
+  void GetState(int32* t, BaseFloat* rho, std::vector<BaseFloat>* d, Matrix<BaseFloat>* W);
+  int32 NumReorthogonalized() const { return num_reorthogonalized_; }
+  void FreeScratch();
+
  private:
+  struct Pending;
+  BaseFloat Eta(int32 N) const;
+  bool Updating() const;
+  void InitDefault(int32 D);
+  void Init(const NgOperand& X);
+  void Step(const NgOperand& X, bool updating);
+  void FinishPendingUpdate();
+  void Reorthogonalize();
+  void RefreshDerived();
+  void EnsureConsts();
+
   int32 rank_, update_period_;
-  BaseFloat num_samples_history_, alpha_;
+  BaseFloat num_samples_history_, alpha_, epsilon_, delta_;
   bool frozen_;
+  int32 t_;
+  BaseFloat rho_t_;
+  std::vector<BaseFloat> d_t_;
+  int32 num_reorthogonalized_;
+  CuMatrix W_t_;     // rank x D
+  CuMatrix WWt_;     // rank x rank
+  CuVector w_last_;  // last column of W_t (weights of the column of ones), contiguous
+  CuVector consts_;  // {1, -1} on the device
+  // scratch, sized on first use
+  CuMatrix H_, J_, L_, K_, A_, AC_, W_next_;
+  CuVector scal_, tmp_r_;
+  double* sumsq_ = nullptr;
+  Pending* pending_;
 };
 
 // Data-parallel world size used to normalise the FLOPs penalty by the GLOBAL row count
@@ -42,6 +98,9 @@ int32 GetDataParallelWorldSize();
 // The reference prints "log_alpha [ ... ]" to stdout every minibatch per component (tdnn.cc:571,
 // simple.cc:2640), which costs a device->host sync each time; off by default here.
 void SetPrintLogAlpha(bool b);
+// Diagnostic: PreconditionDirections == identity with scale 1 (the un-preconditioned gradient).
+void SetNaturalGradientIdentity(bool b);
+bool NaturalGradientIdentity();
 
 // The six mode booleans of TdnnDARTSV3Component in their on-disk order (conv.h:243-257).
 struct TdnnDARTSV3ModeFlags {
@@ -108,6 +167,8 @@ class TdnnDARTSV3Component : public UpdatableComponent {
   const CuMatrix& LinearParams() const { return linear_params_; }
   const CuVector& BiasParams() const { return bias_params_; }
   BaseFloat OrthonormalConstraint() const { return orthonormal_constraint_; }
+  OnlineNaturalGradient& PreconditionerIn() { return preconditioner_in_; }
+  OnlineNaturalGradient& PreconditionerOut() { return preconditioner_out_; }
   void ConsolidateMemory();
   void SetTempProportion(BaseFloat p) { temp_proportion_ = p; }
   BaseFloat TempProportion() const { return temp_proportion_; }
@@ -144,6 +205,9 @@ class TdnnDARTSV3Component : public UpdatableComponent {
   BaseFloat orthonormal_constraint_;
   bool use_natural_gradient_;
   OnlineNaturalGradient preconditioner_in_, preconditioner_out_;
+  // scratch of UpdateNaturalGradient (sized on first use; not part of the model)
+  CuMatrix ng_grad_, ng_g1_, ng_t_;
+  CuVector ng_colsum_, ng_consts_;
 };
 
 // ------------------------------------------------------------------ {Gumbel}SoftmaxFlopsComponent (simple.h:2924-3040)
@@ -265,6 +329,7 @@ class VectorFunctionComponentBase : public UpdatableComponent {
   virtual void ConsolidateMemory();
   CuVector& Output() { return output_; }
   const CuVector& Output() const { return output_; }
+  OnlineNaturalGradient& Preconditioner() { return preconditioner_; }
  protected:
   virtual BaseFloat PlainUpdateFactor() const = 0;  // multiplies learning_rate_ when NG is off
   virtual bool PrintsLogAlpha() const = 0;
@@ -273,6 +338,7 @@ class VectorFunctionComponentBase : public UpdatableComponent {
   bool is_updatable_;
   bool use_natural_gradient_;
   OnlineNaturalGradient preconditioner_;
+  CuMatrix out_deriv_copy_;  // scratch of Backprop (the reference's out_deriv_copy)
 };
 
 class OnehotFunctionComponent : public VectorFunctionComponentBase {

@@ -55,6 +55,57 @@ uint64_t tdnnf_nnet3_get_rand_counter(void) { return GetRandCounter(); }
 float tdnnf_nnet3_rand_uniform(void) { return RandUniformOpen(); }
 int tdnnf_nnet3_set_dp_world_size(int g) { API_BEGIN SetDataParallelWorldSize(g); API_END }
 int tdnnf_nnet3_set_print_log_alpha(int b) { API_BEGIN SetPrintLogAlpha(b != 0); API_END }
+int tdnnf_nnet3_set_ng_identity(int b) { API_BEGIN SetNaturalGradientIdentity(b != 0); API_END }
+
+int tdnnf_nnet3_ng_new(int rank, int update_period, float num_samples_history, float alpha, void** out) {
+  API_BEGIN
+  OnlineNaturalGradient* ng = new OnlineNaturalGradient();
+  ng->SetRank(rank);
+  ng->SetUpdatePeriod(update_period);
+  ng->SetNumSamplesHistory(num_samples_history);
+  ng->SetAlpha(alpha);
+  *out = ng;
+  API_END
+}
+int tdnnf_nnet3_ng_delete(void* ng) { API_BEGIN delete static_cast<OnlineNaturalGradient*>(ng); API_END }
+int tdnnf_nnet3_ng_freeze(void* ng, int frozen) { API_BEGIN static_cast<OnlineNaturalGradient*>(ng)->Freeze(frozen != 0); API_END }
+int tdnnf_nnet3_ng_precondition(void* ng, float* x, int rows, int cols, int stride, float* scale) {
+  API_BEGIN
+  CuSubMatrix<BaseFloat> X(x, rows, cols, stride);
+  BaseFloat s = 1.0;
+  static_cast<OnlineNaturalGradient*>(ng)->PreconditionDirections(&X, &s);
+  if (scale) *scale = s;
+  API_END
+}
+int tdnnf_nnet3_ng_state(void* ng_in, int* t, int* rank, int* dim, float* rho, float* d, float* W, int* num_reorth) {
+  API_BEGIN
+  OnlineNaturalGradient* ng = static_cast<OnlineNaturalGradient*>(ng_in);
+  int32 tt;
+  BaseFloat r;
+  std::vector<BaseFloat> dv;
+  Matrix<BaseFloat> Wm;
+  ng->GetState(&tt, &r, &dv, (W || dim) ? &Wm : NULL);
+  if (t) *t = tt;
+  if (rank) *rank = ng->GetRank();
+  if (dim) *dim = Wm.cols;
+  if (rho) *rho = r;
+  if (d) std::copy(dv.begin(), dv.end(), d);
+  if (W) std::copy(Wm.v.begin(), Wm.v.end(), W);
+  if (num_reorth) *num_reorth = ng->NumReorthogonalized();
+  API_END
+}
+int tdnnf_nnet3_component_ng(void* comp, int which, void** ng) {
+  API_BEGIN
+  Component* c = static_cast<Component*>(comp);
+  if (TdnnDARTSV3Component* t = dynamic_cast<TdnnDARTSV3Component*>(c)) {
+    *ng = which == 0 ? &t->PreconditionerIn() : &t->PreconditionerOut();
+  } else if (VectorFunctionComponentBase* v = dynamic_cast<VectorFunctionComponentBase*>(c)) {
+    *ng = &v->Preconditioner();
+  } else {
+    KALDI_ERR << "component " << c->Type() << " has no natural-gradient preconditioner";
+  }
+  API_END
+}
 
 // NewComponentOfType + InitFromConfig ("key=value ..." line as in an nnet3 config file)
 int tdnnf_nnet3_component_new(const char* type, const char* config_line, void** out) {

@@ -144,6 +144,12 @@ class CuMatrix : public CuMatrixBase<BaseFloat> {
   CuMatrix& operator=(const CuMatrix& o);
   ~CuMatrix();
   void Resize(int32 rows, int32 cols);  // zero-filled
+  void Swap(CuMatrix* o) {
+    std::swap(data_, o->data_);
+    std::swap(num_rows_, o->num_rows_);
+    std::swap(num_cols_, o->num_cols_);
+    std::swap(stride_, o->stride_);
+  }
   void CopyFromHost(const Matrix<BaseFloat>& h);
   Matrix<BaseFloat> ToHost() const;
   void SetZero();

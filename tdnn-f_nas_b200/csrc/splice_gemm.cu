@@ -23,7 +23,8 @@ static inline int ceil_div(int x, int m) { return (x + m - 1) / m; }
 // ------------------------------------------------------------------------------------------
 __global__ void split_rows_kernel(const float* __restrict__ src, int R, int D, long long ld, int r, int groups,
                                   int c_row_mul, int c_col_mul, const float* __restrict__ scale, int Q, int Kpad,
-                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                  __nv_bfloat16* __restrict__ lo2) {
   const int kvec = Kpad >> 3;
   const long long total = (long long)groups * Q * kvec;
   const bool aligned = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((c_col_mul & 3) == 0);
@@ -58,14 +59,18 @@ __global__ void split_rows_kernel(const float* __restrict__ src, int R, int D, l
     }
     __align__(16) __nv_bfloat16 h[8];
     __align__(16) __nv_bfloat16 l[8];
+    __align__(16) __nv_bfloat16 l2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       h[j] = __float2bfloat16_rn(v[j]);
-      l[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h[j]));
+      const float r1 = v[j] - __bfloat162float(h[j]);
+      l[j] = __float2bfloat16_rn(r1);
+      l2[j] = __float2bfloat16_rn(r1 - __bfloat162float(l[j]));
     }
     const long long o = rowidx * Kpad + k0;
     *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(h);
     *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(l);
+    if (lo2 != nullptr) *reinterpret_cast<uint4*>(lo2 + o) = *reinterpret_cast<const uint4*>(l2);
   }
 }
 
@@ -82,8 +87,8 @@ struct GroupRowOffsets {
 __global__ void __launch_bounds__(256)
 split_transpose_kernel(const float* __restrict__ src, int R, int J, long long ld, int r, int c_row_mul, int c_col_mul,
                        GroupRowOffsets c_row_off, const float* __restrict__ scale, int Q, int Qp,
-                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ colsum,
-                       float colsum_scale) {
+                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, __nv_bfloat16* __restrict__ lo2,
+                       float* __restrict__ colsum, float colsum_scale) {
   // 64 (q) x 64 (j) tile: 256-byte coalesced float4 reads along j, 128-byte (8 x bf16 per lane) writes along q.
   __shared__ float tile[64][65];
   const int c = blockIdx.z;
@@ -130,15 +135,19 @@ split_transpose_kernel(const float* __restrict__ src, int R, int J, long long ld
     if (j >= J || q >= Qp) continue;  // Qp is a multiple of 8
     __align__(16) __nv_bfloat16 h[8];
     __align__(16) __nv_bfloat16 l[8];
+    __align__(16) __nv_bfloat16 l2[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float a = tile[qc + k][jj];
       h[k] = __float2bfloat16_rn(a);
-      l[k] = __float2bfloat16_rn(a - __bfloat162float(h[k]));
+      const float r1 = a - __bfloat162float(h[k]);
+      l[k] = __float2bfloat16_rn(r1);
+      l2[k] = __float2bfloat16_rn(r1 - __bfloat162float(l[k]));
     }
     const long long o = ((long long)c * J + j) * Qp + q;
     *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(h);
     *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(l);
+    if (lo2 != nullptr) *reinterpret_cast<uint4*>(lo2 + o) = *reinterpret_cast<const uint4*>(l2);
   }
 }
 
@@ -162,18 +171,19 @@ struct Planes {
   int Kpitch = 0;  // pitch in elements (multiple of 8)
   int rows = 0;    // rows per group
   int groups = 0;
+  int np = 2;      // planes (2: hi, lo; 3: hi, mid, lo)
 };
 
-static size_t planes_bytes(int groups, int rows, int Kpitch) {
-  size_t b = (size_t)2 * groups * rows * Kpitch * sizeof(__nv_bfloat16);
+static size_t planes_bytes(int np, int groups, int rows, int Kpitch) {
+  size_t b = (size_t)np * groups * rows * Kpitch * sizeof(__nv_bfloat16);
   return (b + 1023) & ~size_t(1023);
 }
 
 static int make_map(tdnnf_ctx* ctx, const Planes& pl, int box_rows, CUtensorMap* out) {
-  cuuint64_t dims[4] = {(cuuint64_t)pl.K, (cuuint64_t)pl.rows, (cuuint64_t)pl.groups, 2};
+  cuuint64_t dims[4] = {(cuuint64_t)pl.K, (cuuint64_t)pl.rows, (cuuint64_t)pl.groups, (cuuint64_t)pl.np};
   cuuint64_t strides[3] = {(cuuint64_t)pl.Kpitch * 2, (cuuint64_t)pl.rows * pl.Kpitch * 2,
                            (cuuint64_t)pl.plane_elems * 2};
-  cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)box_rows, 1, 2};
+  cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)box_rows, 1, (cuuint32_t)pl.np};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = ctx->encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, pl.base, dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -189,14 +199,16 @@ static int launch_split_rows(tdnnf_ctx* ctx, const float* src, int R, int D, lon
   pl->Kpitch = Kpad;
   pl->rows = Q;
   pl->groups = groups;
-  pl->base = static_cast<__nv_bfloat16*>(ctx->ws_alloc(planes_bytes(groups, Q, Kpad)));
+  pl->np = ctx->gemm_planes;
+  pl->base = static_cast<__nv_bfloat16*>(ctx->ws_alloc(planes_bytes(pl->np, groups, Q, Kpad)));
   if (!pl->base) return TDNNF_ERR_NOMEM;
   const long long total = (long long)groups * Q * (Kpad >> 3);
   const int threads = 256;
   const int blocks = (int)std::min<long long>((total + threads - 1) / threads, (long long)ctx->num_sms * 16);
   split_rows_kernel<<<std::max(blocks, 1), threads, 0, ctx->stream>>>(src, R, D, ld, r, groups, c_row_mul, c_col_mul,
                                                                       scale, Q, Kpad, pl->base,
-                                                                      pl->base + pl->plane_elems);
+                                                                      pl->base + pl->plane_elems,
+                                                                      pl->np == 3 ? pl->base + 2 * pl->plane_elems : nullptr);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   return TDNNF_OK;
@@ -211,13 +223,16 @@ static int launch_split_transpose(tdnnf_ctx* ctx, const float* src, int R, int J
   pl->Kpitch = Qp;
   pl->rows = J;
   pl->groups = groups;
-  pl->base = static_cast<__nv_bfloat16*>(ctx->ws_alloc(planes_bytes(groups, J, Qp)));
+  pl->np = ctx->gemm_planes;
+  pl->base = static_cast<__nv_bfloat16*>(ctx->ws_alloc(planes_bytes(pl->np, groups, J, Qp)));
   if (!pl->base) return TDNNF_ERR_NOMEM;
   dim3 grid(ceil_div(Qp, 64), ceil_div(J, 64), groups), block(256);
   GroupRowOffsets gro;
   for (int i = 0; i < kMaxSeg; ++i) gro.v[i] = (group_row_offsets && i < groups) ? group_row_offsets[i] : 0;
   split_transpose_kernel<<<grid, block, 0, ctx->stream>>>(src, R, J, ld, r, c_row_mul, c_col_mul, gro, scale, Q, Qp,
-                                                          pl->base, pl->base + pl->plane_elems, colsum, colsum_scale);
+                                                          pl->base, pl->base + pl->plane_elems,
+                                                          pl->np == 3 ? pl->base + 2 * pl->plane_elems : nullptr, colsum,
+                                                          colsum_scale);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   return TDNNF_OK;
@@ -241,17 +256,17 @@ static int choose_splits(int tiles, int iters_per_tile, int num_sms) {
   return best;
 }
 
-template <int BN>
+template <int BN, int NP>
 static int launch_gemm_bn(tdnnf_ctx* ctx, const Planes& A, const Planes& B, const GemmParams& p, double algorithmic_flops) {
   CUtensorMap tmA, tmB;
   int rc = make_map(ctx, A, kBM, &tmA);
   if (rc) return rc;
   rc = make_map(ctx, B, BN, &tmB);
   if (rc) return rc;
-  auto kern = splice_gemm_kernel<BN>;
+  auto kern = splice_gemm_kernel<BN, NP>;
   static bool attr_set = false;  // per template instance
   if (!attr_set) {
-    TDNNF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::kSmemBytes));
+    TDNNF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, NP>::kSmemBytes));
     attr_set = true;
   }
   const int units = p.c_tiles * p.m_tiles * p.n_tiles * p.splits;
@@ -264,7 +279,7 @@ static int launch_gemm_bn(tdnnf_ctx* ctx, const Planes& A, const Planes& B, cons
     tm.flops = algorithmic_flops;
     TDNNF_CUDA_OK(cudaEventRecord(tm.start, ctx->stream));
   }
-  kern<<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, ctx->stream>>>(tmA, tmB, p);
+  kern<<<grid, kGemmThreads, GemmCfg<BN, NP>::kSmemBytes, ctx->stream>>>(tmA, tmB, p);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   if (ctx->gemm_timing) {
@@ -274,7 +289,13 @@ static int launch_gemm_bn(tdnnf_ctx* ctx, const Planes& A, const Planes& B, cons
   return TDNNF_OK;
 }
 
-static int pick_bn(int n) {
+static int pick_bn(int n, int np = 2) {
+  if (np == 3) {  // six products: keep two smem stages (BN <= 160)
+    if (n <= 32) return 32;
+    if (n <= 64) return 64;
+    if (n % 160 == 0) return 160;
+    return 128;
+  }
   static const int wide = [] {  // experiment knob: TDNNF_BN_WIDE=128|256 for outputs that are multiples of 256
     const char* e = getenv("TDNNF_BN_WIDE");
     return e ? atoi(e) : 256;
@@ -289,12 +310,22 @@ static int pick_bn(int n) {
 }
 
 static int launch_gemm(tdnnf_ctx* ctx, int bn, const Planes& A, const Planes& B, const GemmParams& p, double algorithmic_flops) {
+  if (A.np != B.np) return fail(TDNNF_ERR_INVALID, "operand plane counts differ");
+  if (A.np == 3) {
+    switch (bn) {
+      case 32: return launch_gemm_bn<32, 3>(ctx, A, B, p, algorithmic_flops);
+      case 64: return launch_gemm_bn<64, 3>(ctx, A, B, p, algorithmic_flops);
+      case 128: return launch_gemm_bn<128, 3>(ctx, A, B, p, algorithmic_flops);
+      case 160: return launch_gemm_bn<160, 3>(ctx, A, B, p, algorithmic_flops);
+      default: return fail(TDNNF_ERR_INVALID, "unsupported BN for 3-plane operands");
+    }
+  }
   switch (bn) {
-    case 32: return launch_gemm_bn<32>(ctx, A, B, p, algorithmic_flops);
-    case 64: return launch_gemm_bn<64>(ctx, A, B, p, algorithmic_flops);
-    case 128: return launch_gemm_bn<128>(ctx, A, B, p, algorithmic_flops);
-    case 160: return launch_gemm_bn<160>(ctx, A, B, p, algorithmic_flops);
-    case 256: return launch_gemm_bn<256>(ctx, A, B, p, algorithmic_flops);
+    case 32: return launch_gemm_bn<32, 2>(ctx, A, B, p, algorithmic_flops);
+    case 64: return launch_gemm_bn<64, 2>(ctx, A, B, p, algorithmic_flops);
+    case 128: return launch_gemm_bn<128, 2>(ctx, A, B, p, algorithmic_flops);
+    case 160: return launch_gemm_bn<160, 2>(ctx, A, B, p, algorithmic_flops);
+    case 256: return launch_gemm_bn<256, 2>(ctx, A, B, p, algorithmic_flops);
     default: return fail(TDNNF_ERR_INVALID, "unsupported BN");
   }
 }
@@ -331,7 +362,7 @@ extern "C" int tdnnf_darts_propagate(tdnnf_ctx* ctx, const float* in, int in_row
   const int Q = ceil_div(in_rows, r);
   const int Kpad = round_up(in_dim, kBK);
   ctx->ws_reset();
-  rc = ctx->ws_reserve(planes_bytes(r, Q, Kpad) + planes_bytes(n, out_dim, Kpad));
+  rc = ctx->ws_reserve(planes_bytes(ctx->gemm_planes, r, Q, Kpad) + planes_bytes(ctx->gemm_planes, n, out_dim, Kpad));
   if (rc) return rc;
   Planes A, B;
   rc = launch_split_rows(ctx, in, in_rows, in_dim, in_stride, r, r, 1, 0, nullptr, Q, Kpad, &A);
@@ -339,7 +370,7 @@ extern "C" int tdnnf_darts_propagate(tdnnf_ctx* ctx, const float* in, int in_row
   rc = launch_split_rows(ctx, W, out_dim, in_dim, w_stride, 1, n, 0, in_dim, weff, out_dim, Kpad, &B);
   if (rc) return rc;
 
-  const int bn = pick_bn(out_dim);
+  const int bn = pick_bn(out_dim, ctx->gemm_planes);
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.m_tiles = ceil_div(out_rows, kBM);
@@ -395,7 +426,7 @@ extern "C" int tdnnf_darts_backprop_data(tdnnf_ctx* ctx, const float* out_deriv,
   const int r = row_stride;
   const int Kpad = round_up(out_dim, kBK);
   ctx->ws_reset();
-  rc = ctx->ws_reserve(planes_bytes(1, out_rows, Kpad) + planes_bytes(n, in_dim, Kpad));
+  rc = ctx->ws_reserve(planes_bytes(ctx->gemm_planes, 1, out_rows, Kpad) + planes_bytes(ctx->gemm_planes, n, in_dim, Kpad));
   if (rc) return rc;
   Planes A, B;
   rc = launch_split_rows(ctx, out_deriv, out_rows, out_dim, od_stride, 1, 1, 0, 0, nullptr, out_rows, Kpad, &A);
@@ -404,7 +435,7 @@ extern "C" int tdnnf_darts_backprop_data(tdnnf_ctx* ctx, const float* out_deriv,
   rc = launch_split_transpose(ctx, W, out_dim, in_dim, w_stride, 1, n, 0, in_dim, weff, out_dim, Kpad, Kpad, &B);
   if (rc) return rc;
 
-  const int bn = pick_bn(in_dim);
+  const int bn = pick_bn(in_dim, ctx->gemm_planes);
   GemmParams p;
   memset(&p, 0, sizeof(p));
   const int Qin = ceil_div(in_rows, r);
@@ -457,8 +488,8 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
   bool shifts_aligned = true;
   for (int i = 0; i < n; ++i) shifts_aligned = shifts_aligned && ((row_offsets[i] / r) % 8 == 0);
   ctx->ws_reset();
-  rc = ctx->ws_reserve((shifts_aligned ? planes_bytes(r, in_dim, Qp) : planes_bytes(n, in_dim, Rp)) +
-                       planes_bytes(1, out_dim, Rp));
+  rc = ctx->ws_reserve((shifts_aligned ? planes_bytes(ctx->gemm_planes, r, in_dim, Qp) : planes_bytes(ctx->gemm_planes, n, in_dim, Rp)) +
+                       planes_bytes(ctx->gemm_planes, 1, out_dim, Rp));
   if (rc) return rc;
   Planes XT, ODT;
   if (shifts_aligned)
@@ -493,7 +524,7 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
   int bn;
   if (m_is_in) {
     // acc[d, o] = sum_k X_i^T[d, k] * OD^T[o, k]  ->  dW[o, i*in_dim + d]   (transposed store)
-    bn = pick_bn(out_dim);
+    bn = pick_bn(out_dim, ctx->gemm_planes);
     p.m_tiles = ceil_div(in_dim, kBM);
     p.n_tiles = ceil_div(out_dim, bn);
     for (int i = 0; i < n; ++i) {
@@ -508,7 +539,7 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
     p.row_cadd = in_dim;
   } else {
     // acc[o, d] = sum_k OD^T[o, k] * X_i^T[d, k]  ->  dW[o, i*in_dim + d]   (row-major store)
-    bn = pick_bn(in_dim);
+    bn = pick_bn(in_dim, ctx->gemm_planes);
     p.m_tiles = ceil_div(out_dim, kBM);
     p.n_tiles = ceil_div(in_dim, bn);
     for (int i = 0; i < n; ++i) {
@@ -526,5 +557,11 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
   const double wflops = 2.0 * out_rows * (double)out_dim * in_dim * n;
   rc = m_is_in ? launch_gemm(ctx, bn, XT, ODT, p, wflops) : launch_gemm(ctx, bn, ODT, XT, p, wflops);
   if (rc) return rc;
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_ctx_set_gemm_planes(tdnnf_ctx* ctx, int planes) {
+  TDNNF_REQUIRE(ctx && (planes == 2 || planes == 3), "planes must be 2 or 3");
+  ctx->gemm_planes = planes;
   return TDNNF_OK;
 }

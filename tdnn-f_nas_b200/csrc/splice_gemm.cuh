@@ -62,10 +62,12 @@ struct GemmSmemMeta {
   float c_scale[kMaxSeg];
 };
 
-template <int BN>
+// NP = operand planes per matrix: 2 (hi, lo: x to ~2^-17, three products per K step) or 3 (hi, mid, lo: x to
+// 2^-24, six products) -- the latter for the natural-gradient update whose eigen-problem amplifies rounding.
+template <int BN, int NP>
 struct GemmCfg {
-  static constexpr int kABytes = 2 * kBM * kBK * 2;  // hi + lo
-  static constexpr int kBBytes = 2 * BN * kBK * 2;
+  static constexpr int kABytes = NP * kBM * kBK * 2;
+  static constexpr int kBBytes = NP * BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kMetaBytes = 2048 + (int)sizeof(GemmSmemMeta);
   static constexpr int kStages = (232448 - 1024 - kMetaBytes) / kStageBytes >= 4
@@ -119,11 +121,11 @@ __device__ __forceinline__ UnitCoord decode_unit(int u, const GemmParams& p, con
   return uc;
 }
 
-template <int BN>
+template <int BN, int NP>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, NP>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -232,13 +234,25 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint64_t a_lo = ptx::umma_desc_k_sw128(sa + kBM * kBK * 2);
           const uint64_t b_hi = ptx::umma_desc_k_sw128(sb);
           const uint64_t b_lo = ptx::umma_desc_k_sw128(sb + BN * kBK * 2);
+          const uint64_t a_l2 = ptx::umma_desc_k_sw128(sa + (NP - 1) * kBM * kBK * 2);  // third plane (NP == 3)
+          const uint64_t b_l2 = ptx::umma_desc_k_sw128(sb + (NP - 1) * BN * kBK * 2);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             if (k >= ksteps) break;
             const uint64_t adv = (uint64_t)(k * 2);  // 16 bf16 = 32 B = 2 x 16 B units inside the swizzle atom
-            ptx::umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, (it > uc.it0 || k > 0) ? 1u : 0u);
-            ptx::umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-            ptx::umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+            if (NP == 3) {
+              // smallest products first: (lo, hi) and (mid, mid) are ~2^-16 of (hi, hi); (mid, lo), (lo, lo) < 2^-24 dropped
+              ptx::umma_bf16(d_tmem, a_l2 + adv, b_hi + adv, idesc, (it > uc.it0 || k > 0) ? 1u : 0u);
+              ptx::umma_bf16(d_tmem, a_hi + adv, b_l2 + adv, idesc, 1u);
+              ptx::umma_bf16(d_tmem, a_lo + adv, b_lo + adv, idesc, 1u);
+              ptx::umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+              ptx::umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+              ptx::umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+            } else {
+              ptx::umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, (it > uc.it0 || k > 0) ? 1u : 0u);
+              ptx::umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+              ptx::umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+            }
           }
           ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1; }

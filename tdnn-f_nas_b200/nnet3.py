@@ -78,6 +78,56 @@ def set_print_log_alpha(flag: bool):
     _check(_lib().tdnnf_nnet3_set_print_log_alpha(int(flag)))
 
 
+def set_ng_identity(flag: bool):
+    """Diagnostic: every PreconditionDirections call becomes the identity with scale 1 (raw gradient)."""
+    _check(_lib().tdnnf_nnet3_set_ng_identity(int(flag)))
+
+
+class NaturalGradient:
+    """OnlineNaturalGradient (kaldi natural-gradient-online.h): standalone, or borrowed from a component."""
+
+    def __init__(self, rank=40, update_period=1, num_samples_history=2000.0, alpha=4.0, _borrowed=None):
+        self.owned = _borrowed is None
+        if self.owned:
+            self.h = vp()
+            _check(_lib().tdnnf_nnet3_ng_new(rank, update_period, C.c_float(num_samples_history), C.c_float(alpha),
+                                             C.byref(self.h)))
+        else:
+            self.h = _borrowed
+
+    def precondition(self, x) -> float:
+        """x: torch CUDA float32 matrix, overwritten by the preconditioned directions; returns the scale."""
+        p, r, c, s = capi._mat(x)
+        scale = C.c_float(1.0)
+        _check(_lib().tdnnf_nnet3_ng_precondition(self.h, vp(p), r, c, s, C.byref(scale)))
+        return float(scale.value)
+
+    def freeze(self, frozen=True):
+        _check(_lib().tdnnf_nnet3_ng_freeze(self.h, int(frozen)))
+
+    def state(self):
+        import numpy as np
+
+        t, rank, dim, nre = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        rho = C.c_float()
+        _check(_lib().tdnnf_nnet3_ng_state(self.h, C.byref(t), C.byref(rank), C.byref(dim), C.byref(rho), None, None,
+                                           C.byref(nre)))
+        d = np.zeros(max(rank.value, 0), dtype=np.float32)
+        W = np.zeros((max(rank.value, 0), max(dim.value, 0)), dtype=np.float32)
+        if dim.value > 0:
+            _check(_lib().tdnnf_nnet3_ng_state(self.h, None, None, None, None, d.ctypes.data_as(C.POINTER(C.c_float)),
+                                               W.ctypes.data_as(C.POINTER(C.c_float)), None))
+        return dict(t=t.value, rank=rank.value, D=dim.value, rho=float(rho.value), d=d, W=W, num_reorth=nre.value)
+
+    def __del__(self):
+        try:
+            if self.owned and self.h:
+                _lib().tdnnf_nnet3_ng_delete(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
 def _idx_array(indexes: Sequence[Tuple[int, int, int]]):
     flat = []
     for n, t, x in indexes:
@@ -285,6 +335,14 @@ class Component:
         r = C.c_float()
         _check(_lib().tdnnf_nnet3_temp_proportion(self.h, C.byref(r)))
         return r.value
+
+    def preconditioner(self, which: int = 0) -> "NaturalGradient":
+        """preconditioner_in_ (0) / preconditioner_out_ (1) of a TdnnDARTSV3Component, or preconditioner_ (0)."""
+        h = vp()
+        _check(_lib().tdnnf_nnet3_component_ng(self.h, which, C.byref(h)))
+        ng = NaturalGradient(_borrowed=h)
+        ng._keepalive = self
+        return ng
 
     def param_buffers(self):
         """[(device_ptr, rows, cols, stride), ...] of the parameter buffers (for the delta all-reduce)."""

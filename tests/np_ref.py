@@ -88,3 +88,101 @@ def backprop(W, x, od, row_offsets, row_stride, w, c, flags, T, share, lr):
     if flags & UPDATE_ALPHA:
         mul *= 10000
     return ind, dW, dbias, s, dalpha * mul
+
+
+class NaturalGradientF64:
+    """Independent float64 restatement of Kaldi's OnlineNaturalGradient, written from the equations of the
+    method (F_t ~ R_t^T D_t R_t + rho_t I, W_t = E_t^{1/2} R_t, Z_t eigen-update), numpy.linalg.eigh for the
+    eigenproblem.  A second opinion on oracle/oracle_ng.inc (which follows the upstream code structure in fp32)."""
+
+    def __init__(self, rank=40, update_period=1, num_samples_history=2000.0, alpha=4.0):
+        self.rank, self.update_period, self.nsh, self.alpha = rank, update_period, num_samples_history, alpha
+        self.eps, self.delta, self.t, self.frozen = 1e-10, 5e-4, 0, False
+        self.W = self.d = self.rho = None
+
+    def _eta(self, N):
+        return min(0.9, 1.0 - np.exp(-N / self.nsh))
+
+    def _e(self, d, rho, D):
+        beta = rho * (1 + self.alpha) + self.alpha * d.sum() / D
+        return 1.0 / (beta / d + 1.0)
+
+    def _init_default(self, D):
+        if self.rank >= D:
+            self.rank = D - 1
+        R = self.rank
+        self.rho, self.d = self.eps, np.full(R, self.eps)
+        Rm = np.zeros((R, D))
+        for r in range(R):
+            cols = np.arange(r, D, R)
+            Rm[r, cols] = 1.0
+            Rm[r, cols[0]] = 1.1
+            Rm[r] /= np.linalg.norm(Rm[r])
+        self.W = Rm * np.sqrt(1.0 / (2.0 + (D + R) * self.alpha / D))
+
+    def _updating(self):
+        return (not self.frozen) and (self.t <= 10 or (self.t - 10) % self.update_period == 0)
+
+    def precondition(self, X):
+        """Returns (X_hat, scale)."""
+        X = np.asarray(X, dtype=np.float64)
+        N, D = X.shape
+        if D == 1:
+            return X, 1.0
+        if self.t == 0:
+            self._init_default(D)
+            if N > self.rank:
+                saved = self.t
+                self.t = 1
+                fr, self.frozen = self.frozen, False
+                for _ in range(3):
+                    self._step(X)
+                    self.t += 1
+                self.t, self.frozen = saved, fr
+        Xh = self._step(X)
+        self.t += 1
+        ip, fp = (X * X).sum(), (Xh * Xh).sum()
+        return Xh, (1.0 if ip <= 0 else float(np.sqrt(ip / fp)))
+
+    def _step(self, X):
+        N, D = X.shape
+        R, W, d, rho, eta = self.rank, self.W, self.d, self.rho, self._eta(X.shape[0])
+        H = X @ W.T
+        Xh = X - H @ W
+        if not self._updating():
+            return Xh
+        J = H.T @ X
+        L, K = H.T @ H, J @ J.T
+        e = self._e(d, rho, D)
+        ise = 1.0 / np.sqrt(e)
+        dr = d + rho
+        etaN, eta1 = eta / N, 1.0 - eta
+        Lt = ise[:, None] * L * ise[None, :]
+        Z = etaN ** 2 * ise[:, None] * K * ise[None, :] + etaN * eta1 * (Lt * dr[None, :] + dr[:, None] * Lt) \
+            + np.diag(eta1 ** 2 * dr ** 2)
+        c, U = np.linalg.eigh(0.5 * (Z + Z.T))
+        order = np.argsort(-np.abs(c))
+        c, U = c[order], U[:, order]
+        reorth = c[0] > 1e6 * c[-1]
+        floor = (rho * (1 - eta)) ** 2
+        if (c < floor).any():
+            reorth = True
+        c = np.maximum(c, floor)
+        sc = np.sqrt(c)
+        rho1 = (etaN * (X * X).sum() + eta1 * (D * rho + d.sum()) - sc.sum()) / (D - R)
+        d1 = sc - rho1
+        fl = max(self.eps, self.delta * sc.max())
+        rho1, d1 = max(rho1, fl), np.maximum(d1, fl)
+        e1 = self._e(d1, rho1, D)
+        B = J + (eta1 / etaN) * dr[:, None] * W
+        A = etaN * (np.sqrt(e1) / sc)[:, None] * U.T * ise[None, :]
+        W1 = A @ B
+        if reorth:
+            # R_{t+1} = E^{-1/2} W_{t+1} should have orthonormal rows: restore it (Cholesky form)
+            Rm = W1 / np.sqrt(e1)[:, None]
+            O = Rm @ Rm.T
+            if np.abs(O - np.eye(R)).max() > 1e-3:
+                Ci = np.linalg.inv(np.linalg.cholesky(O))
+                W1 = np.sqrt(e1)[:, None] * (Ci @ Rm)
+        self.W, self.d, self.rho = W1, d1, rho1
+        return Xh

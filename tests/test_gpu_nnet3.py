@@ -14,7 +14,9 @@ def nn(ctx):
 
     nnet3.set_context(ctx)
     nnet3.set_rand_seed(777)
-    return nnet3
+    nnet3.set_ng_identity(False)
+    yield nnet3
+    nnet3.set_ng_identity(False)
 
 
 def _grid(S, t_in, t_out):
@@ -34,11 +36,15 @@ def _params(comp, n, din, dout):
     ("use-gumbel=false use-entropy=true free-select=true update-alpha=false update-theta=true uniform-sample=false", 2 | 8),
 ])
 @pytest.mark.parametrize("offsets,subsample", [(list(range(0, 7)), 1), (list(range(-6, 1)), 1), (list(range(0, 7)), 3)])
-def test_tdnn_darts_component_vs_oracle(nn, mode_cfg, flags, offsets, subsample):
+@pytest.mark.parametrize("natural_gradient", [False, True], ids=["raw", "ng"])
+def test_tdnn_darts_component_vs_oracle(nn, mode_cfg, flags, offsets, subsample, natural_gradient):
     import torch
 
     from oracle import oracle as O
 
+    # "raw": both preconditioners forced to the identity (the un-preconditioned gradient G and s_i);
+    # "ng": OnlineNaturalGradient as in the reference (rank-in 20; rank-out min(80, (D_out+1)/2) = 24, tdnn.cc:196-201)
+    nn.set_ng_identity(not natural_gradient)
     n, din, dout, S = len(offsets), 64, 48, 8
     cfg = f"input-dim={din} output-dim={dout} time-offsets={','.join(map(str, offsets))} learning-rate=0.02 {mode_cfg}"
     comp = nn.Component.new("TdnnDARTSV3Component", cfg)
@@ -86,8 +92,10 @@ def test_tdnn_darts_component_vs_oracle(nn, mode_cfg, flags, offsets, subsample)
     ind_ref = np.zeros_like(x)
     dW_ref = np.zeros_like(W)
     db_ref = np.zeros(n + dout, np.float32)
+    ng_in = O.NaturalGradient(20, 4, 2000.0, 4.0) if natural_gradient else None
+    ng_out = O.NaturalGradient(24, 4, 2000.0, 4.0) if natural_gradient else None
     O.tdnn_backprop(offsets, flags, temp, W, x, od, coef_ref, row_offsets, row_stride, delta.learning_rate(),
-                    in_deriv=ind_ref, dW=dW_ref, dbias=db_ref)
+                    in_deriv=ind_ref, dW=dW_ref, dbias=db_ref, ng_in=ng_in, ng_out=ng_out)
     dW, db = _params(delta, n, din, dout)
     assert rel_err(in_deriv.cpu().numpy(), ind_ref) < 1e-3
     assert rel_err(dW, dW_ref) < 1e-3
