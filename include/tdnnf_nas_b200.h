@@ -56,6 +56,14 @@ int tdnnf_ctx_get_stream(tdnnf_ctx* ctx, void** stream);
  * per K step, results within ~5e-6 of fp32.  3: hi + mid + lo to 2^-24, six products, fp32-level results at
  * twice the tensor-pipe time -- used by the natural-gradient update, whose eigen-problem amplifies rounding. */
 int tdnnf_ctx_set_gemm_planes(tdnnf_ctx* ctx, int planes);
+/* Operand-plane cache.  Between begin and end, the bf16 operand planes built from one of the `num_sources` (<= 8)
+ * registered device matrices (matched by base pointer, shape and stride) are kept and reused by later
+ * tdnnf_darts_* calls that need the same matrix in the same form.  TdnnDARTSV3Component::Backprop (ref: tdnn.cc:335-431
+ * and 457-626) reads in_value and out_deriv 3-4 times each: data gradient, the two PreconditionDirections calls, the
+ * parameter gradient.  The caller promises the registered matrices are not written inside the scope.  Scopes do not nest. */
+int tdnnf_ctx_operand_cache_begin(tdnnf_ctx* ctx, const float* const* sources, int num_sources);
+int tdnnf_ctx_operand_cache_end(tdnnf_ctx* ctx);
+int tdnnf_ctx_operand_cache_stats(const tdnnf_ctx* ctx, uint64_t* hits, uint64_t* misses);
 /* Pre-size the internal scratch arena (bf16 operand planes) so later calls never grow it. */
 int tdnnf_ctx_reserve(tdnnf_ctx* ctx, uint64_t bytes);
 /* Number of kernels this context has launched so far (for gpu_launches accounting). */

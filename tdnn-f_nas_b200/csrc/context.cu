@@ -1,4 +1,5 @@
 // Context, error reporting and scratch arena of the C ABI.
+#include <algorithm>
 #include <cstdio>
 #include <string>
 
@@ -49,6 +50,61 @@ int tdnnf_ctx::ws_reserve(size_t bytes) {
   return TDNNF_OK;
 }
 
+int tdnnf_ctx::cws_reserve(size_t bytes) {
+  if (!cache_on) return TDNNF_OK;
+  bytes = ((bytes + 1023) & ~size_t(1023)) + 8192;
+  if (cws_off + bytes <= cws_bytes) return TDNNF_OK;
+  // Growing: kernels on the stream may still read cached planes, and the cached planes move.
+  TDNNF_CUDA_OK(cudaStreamSynchronize(stream));
+  cache.clear();
+  const size_t want = std::max(cws_off + bytes, cws_bytes) * 2;
+  if (cws) TDNNF_CUDA_OK(cudaFree(cws));
+  cws = nullptr;
+  cws_bytes = cws_off = 0;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&cws), want);
+  if (e != cudaSuccess) return fail(TDNNF_ERR_NOMEM, std::string("cudaMalloc of the operand cache failed: ") + cudaGetErrorString(e));
+  cws_bytes = want;
+  return TDNNF_OK;
+}
+
+void* tdnnf_ctx::cws_alloc(size_t bytes) {
+  bytes = (bytes + 1023) & ~size_t(1023);
+  if (cws_off + bytes > cws_bytes) {
+    set_error("internal: operand cache overflow (cws_reserve was not called with the full size)");
+    return nullptr;
+  }
+  void* p = cws + cws_off;
+  cws_off += bytes;
+  return p;
+}
+
+extern "C" int tdnnf_ctx_operand_cache_begin(tdnnf_ctx* ctx, const float* const* sources, int num_sources) {
+  TDNNF_REQUIRE(ctx != nullptr && (num_sources == 0 || sources != nullptr), "null argument");
+  TDNNF_REQUIRE(num_sources >= 0 && num_sources <= 8, "at most 8 cached sources");
+  TDNNF_REQUIRE(!ctx->cache_on, "operand cache scopes do not nest");
+  ctx->cache_on = true;
+  ctx->cache.clear();
+  ctx->cws_off = 0;
+  ctx->cache_srcs.assign(sources, sources + num_sources);
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_ctx_operand_cache_end(tdnnf_ctx* ctx) {
+  TDNNF_REQUIRE(ctx != nullptr, "null context");
+  ctx->cache_on = false;
+  ctx->cache.clear();
+  ctx->cache_srcs.clear();
+  ctx->cws_off = 0;
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_ctx_operand_cache_stats(const tdnnf_ctx* ctx, uint64_t* hits, uint64_t* misses) {
+  TDNNF_REQUIRE(ctx && hits && misses, "null argument");
+  *hits = ctx->cache_hits;
+  *misses = ctx->cache_misses;
+  return TDNNF_OK;
+}
+
 extern "C" const char* tdnnf_last_error(void) { return g_last_error.c_str(); }
 
 extern "C" int tdnnf_abi_version(void) { return 1000; }
@@ -88,6 +144,7 @@ extern "C" int tdnnf_ctx_destroy(tdnnf_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->cws) cudaFree(ctx->cws);
   delete ctx;
   return TDNNF_OK;
 }

@@ -65,4 +65,38 @@ struct tdnnf_ctx {
   // Returns nullptr on failure (error string set).
   void* ws_alloc(size_t bytes);
   int ws_reserve(size_t bytes);
+
+  // Operand-plane cache (tdnnf_ctx_operand_cache_begin/end): inside a scope the planes built from a REGISTERED
+  // source matrix are kept in a second arena and reused by later calls that split the same matrix the same way
+  // (Backprop splits in_value / out_deriv for the data gradient, the two natural-gradient projections and the
+  // parameter gradient).  The caller promises that registered sources do not change inside the scope.
+  struct PlaneCacheEntry {
+    int kind;  // 0: rows, 1: transposed
+    const float* src;
+    int R, D;
+    long long ld;
+    int r, groups, c_row_mul, c_col_mul;
+    const float* scale;
+    int Q, pitch;
+    int offs[16];
+    int np;
+    void* base;
+    long long plane_elems;
+  };
+  bool cache_on = false;
+  std::vector<const float*> cache_srcs;
+  std::vector<PlaneCacheEntry> cache;
+  char* cws = nullptr;
+  size_t cws_bytes = 0, cws_off = 0;
+  unsigned long long cache_hits = 0, cache_misses = 0;
+  bool cache_registered(const float* p) const {
+    if (!cache_on) return false;
+    for (const float* q : cache_srcs)
+      if (q == p) return true;
+    return false;
+  }
+  // Makes room for `bytes` more cached planes; called at the top of a public call, before any plane of that call
+  // exists (growing drops every cached plane).
+  int cws_reserve(size_t bytes);
+  void* cws_alloc(size_t bytes);
 };

@@ -59,23 +59,32 @@ view_sumsq_kernel(const float* __restrict__ in, int in_rows, int in_dim, long lo
 __global__ void ng_scale_kernel(const double* __restrict__ sumsq, const float* __restrict__ weff, int n, float ones_rows,
                                 const float* __restrict__ L, int l_ld, const float* __restrict__ WWt, int w_ld, int r,
                                 float* __restrict__ out) {
-  __shared__ double red_tr[256], red_dot[256];
+  // 1024 threads, row-strided: every thread has ~r*r/1024 independent loads in flight (the single-block version with a
+  // dependent idx/r loop took 17 us at r = 80, all of it load latency)
+  __shared__ double red_tr[32], red_dot[32];
   double tr = 0.0, dot = 0.0;
-  for (int idx = threadIdx.x; idx < r * r; idx += blockDim.x) {
-    const int i = idx / r, j = idx % r;
-    const double l = L[(long long)i * l_ld + j];
-    if (i == j) tr += l;
-    dot += l * (double)WWt[(long long)i * w_ld + j];
-  }
-  red_tr[threadIdx.x] = tr;
-  red_dot[threadIdx.x] = dot;
-  __syncthreads();
-  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-    if (threadIdx.x < s) {
-      red_tr[threadIdx.x] += red_tr[threadIdx.x + s];
-      red_dot[threadIdx.x] += red_dot[threadIdx.x + s];
+  for (int i = threadIdx.x / 32; i < r; i += blockDim.x / 32) {
+    for (int j = threadIdx.x % 32; j < r; j += 32) {
+      const double l = L[(long long)i * l_ld + j];
+      if (i == j) tr += l;
+      dot += l * (double)WWt[(long long)i * w_ld + j];
     }
-    __syncthreads();
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tr += __shfl_xor_sync(0xffffffffu, tr, o);
+    dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red_tr[threadIdx.x >> 5] = tr;
+    red_dot[threadIdx.x >> 5] = dot;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      red_tr[0] += red_tr[w];
+      red_dot[0] += red_dot[w];
+    }
   }
   if (threadIdx.x == 0) {
     double initial = (double)ones_rows;
@@ -127,7 +136,7 @@ extern "C" int tdnnf_ng_scale(tdnnf_ctx* ctx, const double* sumsq, const float* 
   TDNNF_REQUIRE(ctx && sumsq && L && WWt && out3, "null argument");
   TDNNF_REQUIRE(n >= 1 && n <= TDNNF_MAX_OFFSETS && rank >= 1 && l_stride >= rank && w_stride >= rank, "bad argument");
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
-  ng_scale_kernel<<<1, 256, 0, ctx->stream>>>(sumsq, weff, n, ones_rows, L, l_stride, WWt, w_stride, rank, out3);
+  ng_scale_kernel<<<1, 1024, 0, ctx->stream>>>(sumsq, weff, n, ones_rows, L, l_stride, WWt, w_stride, rank, out3);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   return TDNNF_OK;

@@ -234,6 +234,16 @@ void TdnnDARTSV3Component::Backprop(const std::string& debug_info, const Compone
   const int32 num_offsets = (int32)time_offsets_.size();
   const int32 share_offset_index = ShareOffsetIndex();
   tdnnf_ctx* ctx = CurrentContext();
+  // in_value and out_deriv are read-only for the whole call: their operand planes are built once and shared by
+  // the data gradient, the two preconditioners and the parameter gradient.
+  struct OperandCacheScope {
+    tdnnf_ctx* ctx;
+    OperandCacheScope(tdnnf_ctx* c, const BaseFloat* a, const BaseFloat* b) : ctx(c) {
+      const float* srcs[2] = {a, b};
+      CheckStatus(tdnnf_ctx_operand_cache_begin(ctx, srcs, 2));
+    }
+    ~OperandCacheScope() { tdnnf_ctx_operand_cache_end(ctx); }
+  } cache_scope(ctx, in_value.Data(), out_deriv.Data());
   if (in_deriv != NULL) {
     CheckStatus(tdnnf_darts_backprop_data(ctx, out_deriv.Data(), out_deriv.NumRows(), out_deriv.NumCols(),
                                           out_deriv.Stride(), in_deriv->Data(), in_deriv->NumRows(), in_deriv->NumCols(),

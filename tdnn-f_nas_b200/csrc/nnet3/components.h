@@ -68,6 +68,7 @@ class OnlineNaturalGradient {
   void Init(const NgOperand& X);
   void Step(const NgOperand& X, bool updating);
   void FinishPendingUpdate();
+  void HostHalfOfUpdate(int32 D);
   void Reorthogonalize();
   void RefreshDerived();
   void EnsureConsts();

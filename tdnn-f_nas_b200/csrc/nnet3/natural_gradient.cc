@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <future>
 
 #include "components.h"
 
@@ -183,7 +184,19 @@ struct OnlineNaturalGradient::Pending {
   cudaEvent_t ready = nullptr;     // L, K and the traces have arrived
   cudaEvent_t uploaded = nullptr;  // the device has consumed A, A diag(c)
   bool upload_in_flight = false;
+  // The host half of the update runs on a worker thread (it waits for `ready`, then solves the R x R
+  // eigenproblem) while the caller keeps launching the rest of the backward pass; FinishPendingUpdate joins it.
+  std::future<void> host_half;
+  std::vector<BaseFloat> d_t1;
+  BaseFloat rho_t1 = 0.f;
+  bool must_reorthogonalize = false;
+  void Join() {
+    if (host_half.valid()) host_half.get();
+  }
   ~Pending() {
+    if (host_half.valid()) {
+      try { host_half.get(); } catch (...) {}
+    }
     if (host) cudaFreeHost(host);
     if (ready) cudaEventDestroy(ready);
     if (uploaded) cudaEventDestroy(uploaded);
@@ -204,6 +217,7 @@ OnlineNaturalGradient::OnlineNaturalGradient(const OnlineNaturalGradient& other)
 OnlineNaturalGradient& OnlineNaturalGradient::operator=(const OnlineNaturalGradient& other) {
   if (this == &other) return *this;
   const_cast<OnlineNaturalGradient&>(other).FinishPendingUpdate();
+  pending_->Join();  // a worker of ours may still read the state overwritten below
   pending_->active = false;
   rank_ = other.rank_;
   update_period_ = other.update_period_;
@@ -365,16 +379,21 @@ void OnlineNaturalGradient::Step(const NgOperand& X, bool updating) {
   CudaCheck(cudaEventRecord(pending_->ready, st), "cudaEventRecord");
   pending_->active = true;
   pending_->N = N;
+  int device = 0;
+  CudaCheck(cudaGetDevice(&device), "cudaGetDevice");
+  const int32 D_total = D;
+  pending_->host_half = std::async(std::launch::async, [this, device, D_total] {
+    CudaCheck(cudaSetDevice(device), "cudaSetDevice");
+    HostHalfOfUpdate(D_total);
+  });
 }
 
 // The host half of PreconditionDirectionsInternal (ComputeZt, the eigenproblem, the floors, rho_{t+1},
-// D_{t+1}, ComputeWt1's coefficient matrices) followed by W_{t+1} = A_t (J_t + diag(c) W_t) on the device.
-void OnlineNaturalGradient::FinishPendingUpdate() {
-  if (!pending_->active) return;
-  pending_->active = false;
-  FullPrecisionGemms full(true);
+// D_{t+1}, ComputeWt1's coefficient matrices): worker thread, reads only the pinned buffer and the (t)-state,
+// writes A_t, A_t diag(c) into the pinned buffer and (d_{t+1}, rho_{t+1}) into Pending.
+void OnlineNaturalGradient::HostHalfOfUpdate(int32 D) {
   CudaCheck(cudaEventSynchronize(pending_->ready), "cudaEventSynchronize");
-  const int32 R = rank_, D = W_t_.NumCols(), N = pending_->N;
+  const int32 R = rank_, N = pending_->N;
   const float* Lh = pending_->host;
   const float* Kh = pending_->host + (size_t)R * R;
   const BaseFloat tr_X_Xt = pending_->host[(size_t)2 * R * R];
@@ -437,7 +456,7 @@ void OnlineNaturalGradient::FinishPendingUpdate() {
   KALDI_ASSERT(beta_t1 > 0.0);
   std::vector<BaseFloat> sqrt_e_t1, inv_sqrt_e_t1;
   FisherE(d_t1, beta_t1, &sqrt_e_t1, &inv_sqrt_e_t1);
-  // staged in pinned memory and uploaded on the stream: no device-wide sync
+  // staged in pinned memory (the previous upload from this staging area must have been consumed)
   if (pending_->upload_in_flight) CudaCheck(cudaEventSynchronize(pending_->uploaded), "cudaEventSynchronize");
   float* A = pending_->host + (size_t)2 * R * R + 4;
   float* AC = A + (size_t)R * R;
@@ -449,6 +468,20 @@ void OnlineNaturalGradient::FinishPendingUpdate() {
       AC[(size_t)i * R + j] = A[(size_t)i * R + j] * ((1.0f - eta) / (eta / N) * (d_t[j] + rho_t));
     }
   }
+  pending_->d_t1 = d_t1;
+  pending_->rho_t1 = rho_t1;
+  pending_->must_reorthogonalize = must_reorthogonalize;
+}
+
+// The device half: W_{t+1} = A_t (J_t + diag(c) W_t), uploaded on the stream (no device-wide sync).
+void OnlineNaturalGradient::FinishPendingUpdate() {
+  if (!pending_->active) return;
+  pending_->active = false;
+  pending_->Join();
+  FullPrecisionGemms full(true);
+  const int32 R = rank_, D = W_t_.NumCols();
+  const float* A = pending_->host + (size_t)2 * R * R + 4;
+  const float* AC = A + (size_t)R * R;
   EnsureConsts();
   EnsureSize(&A_, R, R);
   EnsureSize(&AC_, R, R);
@@ -467,10 +500,10 @@ void OnlineNaturalGradient::FinishPendingUpdate() {
   ProductAB(A_, J_, consts_.Data(), &W_next_);
   ProductAB(AC_, W_t_, consts_.Data(), &W_next_);
   W_t_.Swap(&W_next_);
-  d_t_ = d_t1;
-  rho_t_ = rho_t1;
+  d_t_ = pending_->d_t1;
+  rho_t_ = pending_->rho_t1;
   RefreshDerived();
-  if (must_reorthogonalize) Reorthogonalize();
+  if (pending_->must_reorthogonalize) Reorthogonalize();
 }
 
 // ReorthogonalizeRt1: O = E^{-1/2} W W^T E^{-1/2} should be the unit matrix; if not, W <- E^{1/2} C^{-1} E^{-1/2} W

@@ -192,6 +192,46 @@ static int make_map(tdnnf_ctx* ctx, const Planes& pl, int box_rows, CUtensorMap*
   return TDNNF_OK;
 }
 
+// Cache lookup / insertion for planes of a registered source (see tdnnf_ctx_operand_cache_begin).
+static tdnnf_ctx::PlaneCacheEntry make_key(int kind, const float* src, int R, int D, long long ld, int r, int groups,
+                                           int c_row_mul, int c_col_mul, const float* scale, int Q, int pitch,
+                                           const int32_t* offs) {
+  tdnnf_ctx::PlaneCacheEntry k;
+  memset(&k, 0, sizeof(k));
+  k.kind = kind;
+  k.src = src;
+  k.R = R;
+  k.D = D;
+  k.ld = ld;
+  k.r = r;
+  k.groups = groups;
+  k.c_row_mul = groups > 1 ? c_row_mul : 0;  // group index is always 0: the multipliers do not matter
+  k.c_col_mul = groups > 1 ? c_col_mul : 0;
+  k.scale = scale;
+  k.Q = Q;
+  k.pitch = pitch;
+  for (int i = 0; i < kMaxSeg; ++i) k.offs[i] = (offs && i < groups) ? offs[i] : 0;
+  return k;
+}
+
+static tdnnf_ctx::PlaneCacheEntry* cache_find(tdnnf_ctx* ctx, const tdnnf_ctx::PlaneCacheEntry& k) {
+  for (auto& e : ctx->cache) {
+    if (e.kind == k.kind && e.src == k.src && e.R == k.R && e.D == k.D && e.ld == k.ld && e.r == k.r &&
+        e.groups == k.groups && e.c_row_mul == k.c_row_mul && e.c_col_mul == k.c_col_mul && e.scale == k.scale &&
+        e.Q == k.Q && e.pitch == k.pitch && memcmp(e.offs, k.offs, sizeof(k.offs)) == 0)
+      return &e;
+  }
+  return nullptr;
+}
+
+static void cache_store(tdnnf_ctx* ctx, tdnnf_ctx::PlaneCacheEntry k, const Planes& pl) {
+  k.np = pl.np;
+  k.base = pl.base;
+  k.plane_elems = pl.plane_elems;
+  if (tdnnf_ctx::PlaneCacheEntry* e = cache_find(ctx, k)) *e = k;
+  else ctx->cache.push_back(k);
+}
+
 static int launch_split_rows(tdnnf_ctx* ctx, const float* src, int R, int D, long long ld, int r, int groups,
                              int c_row_mul, int c_col_mul, const float* scale, int Q, int Kpad, Planes* pl) {
   pl->plane_elems = (long long)groups * Q * Kpad;
@@ -200,7 +240,20 @@ static int launch_split_rows(tdnnf_ctx* ctx, const float* src, int R, int D, lon
   pl->rows = Q;
   pl->groups = groups;
   pl->np = ctx->gemm_planes;
-  pl->base = static_cast<__nv_bfloat16*>(ctx->ws_alloc(planes_bytes(pl->np, groups, Q, Kpad)));
+  const bool cacheable = ctx->cache_registered(src);
+  tdnnf_ctx::PlaneCacheEntry key;
+  if (cacheable) {
+    key = make_key(0, src, R, D, ld, r, groups, c_row_mul, c_col_mul, scale, Q, Kpad, nullptr);
+    const tdnnf_ctx::PlaneCacheEntry* e = cache_find(ctx, key);
+    if (e && e->np >= pl->np) {  // the first np planes of a 3-plane split ARE the 2-plane split
+      pl->base = static_cast<__nv_bfloat16*>(e->base);
+      ctx->cache_hits++;
+      return TDNNF_OK;
+    }
+    ctx->cache_misses++;
+  }
+  const size_t bytes = planes_bytes(pl->np, groups, Q, Kpad);
+  pl->base = static_cast<__nv_bfloat16*>(cacheable ? ctx->cws_alloc(bytes) : ctx->ws_alloc(bytes));
   if (!pl->base) return TDNNF_ERR_NOMEM;
   const long long total = (long long)groups * Q * (Kpad >> 3);
   const int threads = 256;
@@ -211,6 +264,7 @@ static int launch_split_rows(tdnnf_ctx* ctx, const float* src, int R, int D, lon
                                                                       pl->np == 3 ? pl->base + 2 * pl->plane_elems : nullptr);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
+  if (cacheable) cache_store(ctx, key, *pl);
   return TDNNF_OK;
 }
 
@@ -224,7 +278,21 @@ static int launch_split_transpose(tdnnf_ctx* ctx, const float* src, int R, int J
   pl->rows = J;
   pl->groups = groups;
   pl->np = ctx->gemm_planes;
-  pl->base = static_cast<__nv_bfloat16*>(ctx->ws_alloc(planes_bytes(pl->np, groups, J, Qp)));
+  const bool cacheable = ctx->cache_registered(src);
+  tdnnf_ctx::PlaneCacheEntry key;
+  if (cacheable) {
+    key = make_key(1, src, R, J, ld, r, groups, c_row_mul, c_col_mul, scale, Q, Qp, group_row_offsets);
+    const tdnnf_ctx::PlaneCacheEntry* e = cache_find(ctx, key);
+    // a request that also wants the fused column sums must run the kernel
+    if (colsum == nullptr && e && e->np >= pl->np) {
+      pl->base = static_cast<__nv_bfloat16*>(e->base);
+      ctx->cache_hits++;
+      return TDNNF_OK;
+    }
+    ctx->cache_misses++;
+  }
+  const size_t bytes = planes_bytes(pl->np, groups, J, Qp);
+  pl->base = static_cast<__nv_bfloat16*>(cacheable ? ctx->cws_alloc(bytes) : ctx->ws_alloc(bytes));
   if (!pl->base) return TDNNF_ERR_NOMEM;
   dim3 grid(ceil_div(Qp, 64), ceil_div(J, 64), groups), block(256);
   GroupRowOffsets gro;
@@ -235,11 +303,16 @@ static int launch_split_transpose(tdnnf_ctx* ctx, const float* src, int R, int J
                                                           colsum_scale);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
+  if (cacheable) cache_store(ctx, key, *pl);
   return TDNNF_OK;
 }
 
 // Split-K factor: fill the SMs in whole waves without starving a unit of K iterations.
 static int choose_splits(int tiles, int iters_per_tile, int num_sms) {
+  // Skinny outputs (the natural-gradient Gram matrices H^T H, J J^T: one or two tiles, K = all rows): even 8 splits
+  // leave most SMs idle, and the epilogue of an r x r tile is nothing, so spread K over every SM.  (Measured
+  // before: 56 single-CTA launches of 130-175 us each per step.)
+  if (tiles * 8 < num_sms) return std::max(1, std::min(num_sms / tiles, iters_per_tile / 2));
   int best = 1;
   double best_score = -1.0;
   for (int s = 1; s <= 8; ++s) {
@@ -364,6 +437,8 @@ extern "C" int tdnnf_darts_propagate(tdnnf_ctx* ctx, const float* in, int in_row
   ctx->ws_reset();
   rc = ctx->ws_reserve(planes_bytes(ctx->gemm_planes, r, Q, Kpad) + planes_bytes(ctx->gemm_planes, n, out_dim, Kpad));
   if (rc) return rc;
+  rc = ctx->cws_reserve(planes_bytes(ctx->gemm_planes, r, Q, Kpad) + planes_bytes(ctx->gemm_planes, n, out_dim, Kpad));
+  if (rc) return rc;
   Planes A, B;
   rc = launch_split_rows(ctx, in, in_rows, in_dim, in_stride, r, r, 1, 0, nullptr, Q, Kpad, &A);
   if (rc) return rc;
@@ -428,6 +503,8 @@ extern "C" int tdnnf_darts_backprop_data(tdnnf_ctx* ctx, const float* out_deriv,
   ctx->ws_reset();
   rc = ctx->ws_reserve(planes_bytes(ctx->gemm_planes, 1, out_rows, Kpad) + planes_bytes(ctx->gemm_planes, n, in_dim, Kpad));
   if (rc) return rc;
+  rc = ctx->cws_reserve(planes_bytes(ctx->gemm_planes, 1, out_rows, Kpad) + planes_bytes(ctx->gemm_planes, n, in_dim, Kpad));
+  if (rc) return rc;
   Planes A, B;
   rc = launch_split_rows(ctx, out_deriv, out_rows, out_dim, od_stride, 1, 1, 0, 0, nullptr, out_rows, Kpad, &A);
   if (rc) return rc;
@@ -488,8 +565,11 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
   bool shifts_aligned = true;
   for (int i = 0; i < n; ++i) shifts_aligned = shifts_aligned && ((row_offsets[i] / r) % 8 == 0);
   ctx->ws_reset();
-  rc = ctx->ws_reserve((shifts_aligned ? planes_bytes(ctx->gemm_planes, r, in_dim, Qp) : planes_bytes(ctx->gemm_planes, n, in_dim, Rp)) +
-                       planes_bytes(ctx->gemm_planes, 1, out_dim, Rp));
+  const size_t need = (shifts_aligned ? planes_bytes(ctx->gemm_planes, r, in_dim, Qp) : planes_bytes(ctx->gemm_planes, n, in_dim, Rp)) +
+                      planes_bytes(ctx->gemm_planes, 1, out_dim, Rp);
+  rc = ctx->ws_reserve(need);
+  if (rc) return rc;
+  rc = ctx->cws_reserve(need);
   if (rc) return rc;
   Planes XT, ODT;
   if (shifts_aligned)
