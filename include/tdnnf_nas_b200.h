@@ -56,6 +56,13 @@ int tdnnf_ctx_get_stream(tdnnf_ctx* ctx, void** stream);
  * per K step, results within ~5e-6 of fp32.  3: hi + mid + lo to 2^-24, six products, fp32-level results at
  * twice the tensor-pipe time -- used by the natural-gradient update, whose eigen-problem amplifies rounding. */
 int tdnnf_ctx_set_gemm_planes(tdnnf_ctx* ctx, int planes);
+/* Precision of the parameter-gradient GEMM (north-star tolerance: gradients 1e-3, forward 1e-4).
+ * fast = 0 (default): three bf16 products per K step (~5e-6).
+ * fast = 1: tdnnf_darts_backprop_params runs ONE product: both operands as one fp16 plane, scaled into the fp16
+ *           range by an exact power of two of their max magnitude (measured 2.9e-4).  The data gradient keeps three
+ *           products (its error would accumulate down the layers); tdnnf_darts_propagate is never affected; neither
+ *           is anything run with 3 planes (the natural-gradient update). */
+int tdnnf_ctx_set_gradient_mode(tdnnf_ctx* ctx, int fast);
 /* Operand-plane cache.  Between begin and end, the bf16 operand planes built from one of the `num_sources` (<= 8)
  * registered device matrices (matched by base pointer, shape and stride) are kept and reused by later
  * tdnnf_darts_* calls that need the same matrix in the same form.  TdnnDARTSV3Component::Backprop (ref: tdnn.cc:335-431
@@ -74,6 +81,11 @@ uint64_t tdnnf_ctx_launch_count(const tdnnf_ctx* ctx);
  * returns the sums since enabling, then clears them. */
 int tdnnf_ctx_gemm_timing_enable(tdnnf_ctx* ctx, int enable);
 int tdnnf_ctx_gemm_timing_read(tdnnf_ctx* ctx, double* total_ms, double* total_flops, uint64_t* launches);
+/* The same, split by size: launches with at least `min_flops` algorithmic FLOPs go into total_* (tensor_pipe_flops =
+ * sum of FLOPs x products per K step actually issued: 1, 2, 3 or 6), the rest (skinny natural-gradient products)
+ * into other_*. */
+int tdnnf_ctx_gemm_timing_read_ex(tdnnf_ctx* ctx, double min_flops, double* total_ms, double* total_flops,
+                                  double* tensor_pipe_flops, uint64_t* launches, double* other_ms, uint64_t* other_launches);
 
 /* ------------------------------------------------------------------ TdnnDARTSV3 ------- */
 /* mode flags of TdnnDARTSV3Component (ref: conv.h:243-257) */
@@ -253,6 +265,18 @@ int tdnnf_darts_view_sumsq(tdnnf_ctx* ctx, const float* in, int in_rows, int in_
  * appended column of ones, else 0), L = (X W^T)^T (X W^T) and W W^T (rank x rank).  No host sync. */
 int tdnnf_ng_scale(tdnnf_ctx* ctx, const double* sumsq, const float* weff, int n, float ones_rows, const float* L,
                    int l_stride, const float* WWt, int w_stride, int rank, float* out3);
+/* Inside an operand-cache scope: *rowsq = device array of per-row sums of squares of the registered matrix `source`
+ * (`rows` rows), produced as a by-product of its first row-major operand split in this scope, or NULL if there was none. */
+int tdnnf_ctx_operand_rowsq(tdnnf_ctx* ctx, const float* source, int rows, const float** rowsq);
+/* The device half of one OnlineNaturalGradient step after H = X W^T, in two launches and one pass over H (rank <= 128):
+ *   L (rank x rank, overwritten) = H^T H in fp32 FMAs (kaldi: L_t = H_t^T H_t), and
+ *   out3 = { tr(X X^T), tr(Xhat Xhat^T), scale } as tdnnf_ng_scale.
+ * tr(X X^T) comes from sumsq[n]: with rowsq != NULL (tdnnf_ctx_operand_rowsq) sumsq is first overwritten by the per-view
+ * sums of rowsq (view i = rows row_offsets[i] + k*row_stride, k < rows); with rowsq == NULL it must already hold what
+ * tdnnf_darts_view_sumsq computes. */
+int tdnnf_ng_gram_scale(tdnnf_ctx* ctx, const float* H, int rows, int rank, int h_stride, float* L, int l_stride,
+                        const float* WWt, int w_stride, const float* rowsq, double* sumsq, int in_rows, int n,
+                        const int32_t* row_offsets, int row_stride, const float* weff, float ones_rows, float* out3);
 /* dst += alpha * (*factor1_dev) * (*factor2_dev) * src   (device scalars, either may be NULL = 1) */
 int tdnnf_mat_axpy_dev(tdnnf_ctx* ctx, float alpha, const float* factor1_dev, const float* factor2_dev,
                        const float* src, int src_stride, float* dst, int dst_stride, int rows, int cols);

@@ -36,6 +36,9 @@ float tdnnf_nnet3_rand_uniform(void);
 int tdnnf_nnet3_set_dp_world_size(int world_size);
 /* Re-enable the reference's per-minibatch "log_alpha" stdout print (ref: tdnn.cc:571, simple.cc:2640). */
 int tdnnf_nnet3_set_print_log_alpha(int enable);
+/* Parameter-gradient GEMM of TdnnDARTSV3Component::Backprop with one fp16 product (tdnnf_ctx_set_gradient_mode).
+ * Default 0: the natural-gradient projection amplifies its 2.9e-4 error beyond the 1e-3 tolerance (measured). */
+int tdnnf_nnet3_set_fast_gradients(int enable);
 
 /* Component::NewComponentOfType + InitFromConfig (ref: itf.cc:126-293, tdnn.cc:109-212, ...). */
 int tdnnf_nnet3_component_new(const char* type, const char* config_line, void** out);

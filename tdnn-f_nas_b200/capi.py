@@ -38,6 +38,12 @@ def _declare(lib):
     sig("tdnnf_ctx_launch_count", [vp], C.c_uint64)
     sig("tdnnf_ctx_gemm_timing_enable", [vp, i])
     sig("tdnnf_ctx_gemm_timing_read", [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)])
+    sig("tdnnf_ctx_gemm_timing_read_ex", [vp, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                          C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_uint64)])
+    sig("tdnnf_ctx_set_gradient_mode", [vp, i])
+    sig("tdnnf_ctx_operand_cache_begin", [vp, C.POINTER(C.c_void_p), i])
+    sig("tdnnf_ctx_operand_cache_end", [vp])
+    sig("tdnnf_ctx_operand_cache_stats", [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)])
     sig("tdnnf_darts_coef", [vp, vp, i, i, f, c_float_p, f, i, vp, vp])
     sig("tdnnf_darts_weff_from_coef", [vp, vp, i, i, i, vp])
     sig("tdnnf_darts_propagate", [vp, vp, i, i, i, vp, i, i, i, vp, i, vp, i, vp, i, c_int_p, i])
@@ -159,6 +165,25 @@ class Context:
         ms, fl, n = C.c_double(), C.c_double(), C.c_uint64()
         check(load().tdnnf_ctx_gemm_timing_read(self.h, C.byref(ms), C.byref(fl), C.byref(n)))
         return ms.value, fl.value, int(n.value)
+
+    def gemm_timing_read_ex(self, min_flops: float):
+        """Split by size: dict(ms, flops, pipe_flops, launches) of the launches with >= min_flops algorithmic FLOPs
+        (pipe_flops counts every tensor-core product issued) and (other_ms, other_launches) of the rest."""
+        ms, fl, raw, oms = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+        n, on = C.c_uint64(), C.c_uint64()
+        check(load().tdnnf_ctx_gemm_timing_read_ex(self.h, float(min_flops), C.byref(ms), C.byref(fl), C.byref(raw), C.byref(n),
+                                                   C.byref(oms), C.byref(on)))
+        return dict(ms=ms.value, flops=fl.value, pipe_flops=raw.value, launches=int(n.value), other_ms=oms.value,
+                    other_launches=int(on.value))
+
+    def set_gradient_mode(self, fast: bool):
+        """fast: data gradient with two tensor-core products, parameter gradient with one (see the header)."""
+        check(load().tdnnf_ctx_set_gradient_mode(self.h, int(fast)))
+
+    def operand_cache_stats(self):
+        h, m = C.c_uint64(), C.c_uint64()
+        check(load().tdnnf_ctx_operand_cache_stats(self.h, C.byref(h), C.byref(m)))
+        return int(h.value), int(m.value)
 
     def close(self):
         if getattr(self, "h", None):

@@ -82,6 +82,11 @@ extern "C" int tdnnf_ctx_operand_cache_begin(tdnnf_ctx* ctx, const float* const*
   TDNNF_REQUIRE(ctx != nullptr && (num_sources == 0 || sources != nullptr), "null argument");
   TDNNF_REQUIRE(num_sources >= 0 && num_sources <= 8, "at most 8 cached sources");
   TDNNF_REQUIRE(!ctx->cache_on, "operand cache scopes do not nest");
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+  if (!ctx->absmax_dev) TDNNF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ctx->absmax_dev), sizeof(float) * 8));
+  TDNNF_CUDA_OK(cudaMemsetAsync(ctx->absmax_dev, 0, sizeof(float) * 8, ctx->stream));
+  for (bool& v : ctx->absmax_valid) v = false;
+  for (bool& v : ctx->rowsq_valid) v = false;
   ctx->cache_on = true;
   ctx->cache.clear();
   ctx->cws_off = 0;
@@ -94,6 +99,7 @@ extern "C" int tdnnf_ctx_operand_cache_end(tdnnf_ctx* ctx) {
   ctx->cache_on = false;
   ctx->cache.clear();
   ctx->cache_srcs.clear();
+  for (bool& v : ctx->rowsq_valid) v = false;
   ctx->cws_off = 0;
   return TDNNF_OK;
 }
@@ -145,6 +151,10 @@ extern "C" int tdnnf_ctx_destroy(tdnnf_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->cws) cudaFree(ctx->cws);
+  if (ctx->absmax_dev) cudaFree(ctx->absmax_dev);
+  if (ctx->ng_scratch) cudaFree(ctx->ng_scratch);
+  for (float* p : ctx->rowsq_dev)
+    if (p) cudaFree(p);
   delete ctx;
   return TDNNF_OK;
 }
@@ -185,6 +195,39 @@ extern "C" int tdnnf_ctx_gemm_timing_read(tdnnf_ctx* ctx, double* total_ms, doub
   *total_ms = ms;
   *total_flops = fl;
   *launches = ctx->gemm_events.size();
+  ctx->gemm_events.clear();
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_ctx_gemm_timing_read_ex(tdnnf_ctx* ctx, double min_flops, double* total_ms, double* total_flops,
+                                             double* tensor_pipe_flops, uint64_t* launches, double* other_ms,
+                                             uint64_t* other_launches) {
+  TDNNF_REQUIRE(ctx && total_ms && total_flops && tensor_pipe_flops && launches && other_ms && other_launches, "null argument");
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+  TDNNF_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  double ms = 0.0, fl = 0.0, raw = 0.0, oms = 0.0;
+  uint64_t n = 0, on = 0;
+  for (auto& t : ctx->gemm_events) {
+    float e = 0.f;
+    TDNNF_CUDA_OK(cudaEventElapsedTime(&e, t.start, t.stop));
+    if (t.flops >= min_flops) {
+      ms += e;
+      fl += t.flops;
+      raw += t.flops * t.products;
+      n++;
+    } else {
+      oms += e;
+      on++;
+    }
+    cudaEventDestroy(t.start);
+    cudaEventDestroy(t.stop);
+  }
+  *total_ms = ms;
+  *total_flops = fl;
+  *tensor_pipe_flops = raw;
+  *launches = n;
+  *other_ms = oms;
+  *other_launches = on;
   ctx->gemm_events.clear();
   return TDNNF_OK;
 }

@@ -58,6 +58,7 @@ struct tdnnf_ctx {
   struct GemmTiming {
     cudaEvent_t start, stop;
     double flops;
+    int products;  // tensor-core products per K step of this launch (1, 2, 3 or 6)
   };
   std::vector<GemmTiming> gemm_events;
 
@@ -72,6 +73,7 @@ struct tdnnf_ctx {
   // parameter gradient).  The caller promises that registered sources do not change inside the scope.
   struct PlaneCacheEntry {
     int kind;  // 0: rows, 1: transposed
+    int fp16;  // 1: one scaled fp16 plane, 0: bf16 hi/lo(/lo2) planes
     const float* src;
     int R, D;
     long long ld;
@@ -95,6 +97,25 @@ struct tdnnf_ctx {
       if (q == p) return true;
     return false;
   }
+  int cache_source_index(const float* p) const {
+    if (!cache_on) return -1;
+    for (size_t i = 0; i < cache_srcs.size(); ++i)
+      if (cache_srcs[i] == p) return (int)i;
+    return -1;
+  }
+  // max |x| of each registered source (device floats), filled by the first row split or by absmax_kernel
+  float* absmax_dev = nullptr;
+  bool absmax_valid[8] = {false, false, false, false, false, false, false, false};
+  // per-row sums of squares of each registered source (device floats), by-product of its first row split
+  float* rowsq_dev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t rowsq_cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int rowsq_rows[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bool rowsq_valid[8] = {false, false, false, false, false, false, false, false};
+  // scratch of tdnnf_ng_gram_scale: {double acc[2], uint counter, pad to 64 B, per-CTA partial Gram matrices}
+  char* ng_scratch = nullptr;
+  size_t ng_scratch_bytes = 0;
+  // parameter-gradient GEMM precision: false = three bf16 products; true = one fp16 x fp16 product (power-of-two scaled)
+  bool grad_fast = false;
   // Makes room for `bytes` more cached planes; called at the top of a public call, before any plane of that call
   // exists (growing drops every cached plane).
   int cws_reserve(size_t bytes);

@@ -2,6 +2,8 @@
 // ref tdnn.cc:598-599, simple.cc:9542) that are not GEMMs: the trace of X~ X~^T over the spliced input
 // WITHOUT materialising X~ (the reference builds the R x (n*D_in+1) matrix in_value_temp, tdnn.cc:476-514),
 // the "scale" factor kept on the device (no host sync), and an axpy whose coefficient lives on the device.
+#include <algorithm>
+
 #include "context.h"
 
 using namespace tdnnf;
@@ -99,6 +101,145 @@ __global__ void ng_scale_kernel(const double* __restrict__ sumsq, const float* _
   }
 }
 
+// L (r x r) += H^T H for a tall skinny H (N x r, r <= 16*TB): the Gram matrix of the natural-gradient projection
+// (kaldi: L_t = H_t^T H_t), in plain fp32 FMAs.  Thread (ti, tj) of a 16 x 16 block owns the TB x TB outputs
+// (ti*TB.., tj*TB..); rows are staged through shared memory 32 at a time; one red.add per output per CTA.
+// Replaces {zero L, two transposed operand splits of H, a split-K tensor-core GEMM}: HBM-bound on reading H once.
+template <int TB>
+__global__ void __launch_bounds__(256) ng_gram_kernel(const float* __restrict__ H, int N, int r, long long ld,
+                                                      float* __restrict__ partials,
+                                                      const float* __restrict__ rowsq, int in_rows, int n, TdnnfOffsets offs,
+                                                      int row_stride, double* __restrict__ sumsq) {
+  constexpr int kRows = 32;
+  constexpr int W = 16 * TB;
+  __shared__ float tile[kRows][W + 1];
+  // optional second job: sumsq[i] += sum over the rows of view i of rowsq[row] (view i = rows offs[i] + k*row_stride,
+  // k < N): tr(X X^T) of the spliced operand from the per-row sums of squares the operand split left behind
+  if (rowsq != nullptr) {
+    double local[TDNNF_MAX_OFFSETS];
+#pragma unroll
+    for (int i = 0; i < TDNNF_MAX_OFFSETS; ++i) local[i] = 0.0;
+    for (int row = blockIdx.x * 256 + threadIdx.x; row < in_rows; row += gridDim.x * 256) {
+      const float sq = rowsq[row];
+#pragma unroll
+      for (int i = 0; i < TDNNF_MAX_OFFSETS; ++i) {
+        if (i < n) {
+          const int d = row - offs.v[i];
+          const bool in_view = row_stride == 1 ? (d >= 0 && d < N) : (d >= 0 && d % row_stride == 0 && d / row_stride < N);
+          if (in_view) local[i] += (double)sq;
+        }
+      }
+    }
+    __shared__ double view_sum[TDNNF_MAX_OFFSETS];
+    if (threadIdx.x < TDNNF_MAX_OFFSETS) view_sum[threadIdx.x] = 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < TDNNF_MAX_OFFSETS; ++i) {
+      if (i < n) {
+        double v = local[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&view_sum[i], v);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < n && view_sum[threadIdx.x] != 0.0) atomicAdd(&sumsq[threadIdx.x], view_sum[threadIdx.x]);
+  }
+  const int ti = threadIdx.x / 16, tj = threadIdx.x % 16;
+  float acc[TB][TB];
+#pragma unroll
+  for (int a = 0; a < TB; ++a)
+#pragma unroll
+    for (int b = 0; b < TB; ++b) acc[a][b] = 0.f;
+  for (long long row0 = (long long)blockIdx.x * kRows; row0 < N; row0 += (long long)gridDim.x * kRows) {
+    for (int idx = threadIdx.x; idx < kRows * W; idx += 256) {
+      const int rr = idx / W, c = idx % W;
+      tile[rr][c] = (row0 + rr < N && c < r) ? H[(row0 + rr) * ld + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int rr = 0; rr < kRows; ++rr) {
+      float a[TB], b[TB];
+#pragma unroll
+      for (int k = 0; k < TB; ++k) {
+        a[k] = tile[rr][ti * TB + k];
+        b[k] = tile[rr][tj * TB + k];
+      }
+#pragma unroll
+      for (int x = 0; x < TB; ++x)
+#pragma unroll
+        for (int y = 0; y < TB; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
+    }
+    __syncthreads();
+  }
+  // per-CTA partial (no atomics: rank^2 same-address red.adds from every CTA serialise in L2, measured 37 us at
+  // rank 80 from 117 CTAs); ng_gram_finish_kernel sums the partials
+  float* mine = partials + (size_t)blockIdx.x * r * r;
+#pragma unroll
+  for (int x = 0; x < TB; ++x)
+#pragma unroll
+    for (int y = 0; y < TB; ++y) {
+      const int i = ti * TB + x, j = tj * TB + y;
+      if (i < r && j < r) mine[i * r + j] = acc[x][y];
+    }
+}
+
+// L[i][j] = sum of the per-CTA partials; tr(L) and <L, W W^T> reduced across CTAs in double; the last CTA to finish
+// turns them into out[0..2] = {tr(X X^T), tr(X^ X^^T), scale} exactly as ng_scale_kernel, and re-arms the scratch.
+__global__ void __launch_bounds__(256) ng_gram_finish_kernel(const float* __restrict__ partials, int nblk, int r,
+                                                             float* __restrict__ L, long long l_ld,
+                                                             const float* __restrict__ WWt, long long w_ld,
+                                                             const double* __restrict__ sumsq, const float* __restrict__ weff,
+                                                             int n, float ones_rows, double* __restrict__ acc /* [2] */,
+                                                             unsigned int* __restrict__ counter, float* __restrict__ out) {
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  double tr = 0.0, dot = 0.0;
+  if (e < r * r) {
+    float sum = 0.f;
+    for (int b = 0; b < nblk; ++b) sum += partials[(size_t)b * r * r + e];
+    const int i = e / r, j = e % r;
+    L[i * l_ld + j] = sum;
+    if (i == j) tr = (double)sum;
+    dot = (double)sum * (double)WWt[i * w_ld + j];
+  }
+  __shared__ double red_tr[8], red_dot[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tr += __shfl_xor_sync(0xffffffffu, tr, o);
+    dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red_tr[threadIdx.x >> 5] = tr;
+    red_dot[threadIdx.x >> 5] = dot;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      red_tr[0] += red_tr[w];
+      red_dot[0] += red_dot[w];
+    }
+    atomicAdd(&acc[0], red_tr[0]);
+    atomicAdd(&acc[1], red_dot[0]);
+    __threadfence();
+    if (atomicAdd(counter, 1u) == gridDim.x - 1) {
+      __threadfence();
+      const double t = atomicAdd(&acc[0], 0.0), d = atomicAdd(&acc[1], 0.0);  // read through L2
+      double initial = (double)ones_rows;
+      for (int i = 0; i < n; ++i) {
+        const double w = weff ? (double)weff[i] : 1.0;
+        initial += w * w * sumsq[i];
+      }
+      const double fin = initial - 2.0 * t + d;
+      out[0] = (float)initial;
+      out[1] = (float)fin;
+      out[2] = (initial <= 0.0 || !(fin > 0.0)) ? 1.0f : (float)sqrt(initial / fin);
+      acc[0] = 0.0;
+      acc[1] = 0.0;
+      *counter = 0u;
+    }
+  }
+}
+
 __global__ void mat_axpy_dev_kernel(float alpha, const float* __restrict__ f1, const float* __restrict__ f2,
                                     const float* __restrict__ src, long long ss, float* __restrict__ dst, long long ds,
                                     int rows, int cols) {
@@ -137,6 +278,56 @@ extern "C" int tdnnf_ng_scale(tdnnf_ctx* ctx, const double* sumsq, const float* 
   TDNNF_REQUIRE(n >= 1 && n <= TDNNF_MAX_OFFSETS && rank >= 1 && l_stride >= rank && w_stride >= rank, "bad argument");
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
   ng_scale_kernel<<<1, 1024, 0, ctx->stream>>>(sumsq, weff, n, ones_rows, L, l_stride, WWt, w_stride, rank, out3);
+  ctx->launches++;
+  TDNNF_CUDA_OK(cudaGetLastError());
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_ng_gram_scale(tdnnf_ctx* ctx, const float* H, int rows, int rank, int h_stride, float* L,
+                                   int l_stride, const float* WWt, int w_stride, const float* rowsq, double* sumsq,
+                                   int in_rows, int n, const int32_t* row_offsets, int row_stride, const float* weff,
+                                   float ones_rows, float* out3) {
+  TDNNF_REQUIRE(ctx && H && L && WWt && sumsq && out3, "null argument");
+  TDNNF_REQUIRE(rows > 0 && rank >= 1 && rank <= 128 && h_stride >= rank && l_stride >= rank && w_stride >= rank,
+                "bad argument (rank <= 128)");
+  TDNNF_REQUIRE(n >= 1 && n <= TDNNF_MAX_OFFSETS, "bad number of views");
+  TDNNF_REQUIRE(rowsq == nullptr || (row_offsets && row_stride >= 1 && in_rows > 0), "bad view description");
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+  const int blocks = std::max(1, std::min((rows + 63) / 64, ctx->num_sms));
+  const size_t need = (size_t)blocks * rank * rank * sizeof(float) + 64;
+  if (ctx->ng_scratch_bytes < need) {
+    if (ctx->ng_scratch) TDNNF_CUDA_OK(cudaFree(ctx->ng_scratch));  // waits for kernels still using it
+    ctx->ng_scratch = nullptr;
+    ctx->ng_scratch_bytes = 0;
+    const size_t want = std::max(need, (size_t)ctx->num_sms * 128 * 128 * sizeof(float) + 64);
+    TDNNF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ctx->ng_scratch), want));
+    TDNNF_CUDA_OK(cudaMemsetAsync(ctx->ng_scratch, 0, 64, ctx->stream));  // {acc[2], counter}: self re-arming afterwards
+    ctx->ng_scratch_bytes = want;
+  }
+  double* acc = reinterpret_cast<double*>(ctx->ng_scratch);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(ctx->ng_scratch + 16);
+  float* partials = reinterpret_cast<float*>(ctx->ng_scratch + 64);
+  TdnnfOffsets offs;
+  for (int i = 0; i < TDNNF_MAX_OFFSETS; ++i) offs.v[i] = (rowsq && i < n) ? row_offsets[i] : 0;
+  if (rowsq) TDNNF_CUDA_OK(cudaMemsetAsync(sumsq, 0, sizeof(double) * n, ctx->stream));
+  const int tb = (rank + 15) / 16;
+  auto launch = [&](auto kern) {
+    kern<<<blocks, 256, 0, ctx->stream>>>(H, rows, rank, h_stride, partials, rowsq, in_rows, n, offs, row_stride, sumsq);
+  };
+  switch (tb) {
+    case 1: launch(ng_gram_kernel<1>); break;
+    case 2: launch(ng_gram_kernel<2>); break;
+    case 3: launch(ng_gram_kernel<3>); break;
+    case 4: launch(ng_gram_kernel<4>); break;
+    case 5: launch(ng_gram_kernel<5>); break;
+    case 6: launch(ng_gram_kernel<6>); break;
+    case 7: launch(ng_gram_kernel<7>); break;
+    default: launch(ng_gram_kernel<8>); break;
+  }
+  ctx->launches++;
+  TDNNF_CUDA_OK(cudaGetLastError());
+  ng_gram_finish_kernel<<<(rank * rank + 255) / 256, 256, 0, ctx->stream>>>(partials, blocks, rank, L, l_stride, WWt, w_stride,
+                                                                           sumsq, weff, n, ones_rows, acc, counter, out3);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   return TDNNF_OK;

@@ -99,6 +99,9 @@ int32 GetDataParallelWorldSize();
 // The reference prints "log_alpha [ ... ]" to stdout every minibatch per component (tdnn.cc:571,
 // simple.cc:2640), which costs a device->host sync each time; off by default here.
 void SetPrintLogAlpha(bool b);
+// One fp16 tensor-core product in the parameter-gradient GEMM of TdnnDARTSV3Component (default: off, see components.cc).
+void SetFastGradients(bool b);
+bool FastGradients();
 // Diagnostic: PreconditionDirections == identity with scale 1 (the un-preconditioned gradient).
 void SetNaturalGradientIdentity(bool b);
 bool NaturalGradientIdentity();

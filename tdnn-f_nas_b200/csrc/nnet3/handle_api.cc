@@ -55,6 +55,7 @@ uint64_t tdnnf_nnet3_get_rand_counter(void) { return GetRandCounter(); }
 float tdnnf_nnet3_rand_uniform(void) { return RandUniformOpen(); }
 int tdnnf_nnet3_set_dp_world_size(int g) { API_BEGIN SetDataParallelWorldSize(g); API_END }
 int tdnnf_nnet3_set_print_log_alpha(int b) { API_BEGIN SetPrintLogAlpha(b != 0); API_END }
+int tdnnf_nnet3_set_fast_gradients(int b) { API_BEGIN SetFastGradients(b != 0); API_END }
 int tdnnf_nnet3_set_ng_identity(int b) { API_BEGIN SetNaturalGradientIdentity(b != 0); API_END }
 
 int tdnnf_nnet3_ng_new(int rank, int update_period, float num_samples_history, float alpha, void** out) {

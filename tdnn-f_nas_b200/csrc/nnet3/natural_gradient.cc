@@ -25,8 +25,14 @@
 
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
+#include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <functional>
 #include <future>
+#include <mutex>
+#include <thread>
 
 #include "components.h"
 
@@ -38,6 +44,57 @@ namespace {
 void CudaCheck(cudaError_t e, const char* what) {
   if (e != cudaSuccess) KALDI_ERR << what << ": " << cudaGetErrorString(e);
 }
+
+// A few long-lived host threads for the eigen-updates (one task per preconditioner per refresh: 56 per step of the
+// bench supernet, ~1-3 ms each).  Long-lived rather than one std::async thread per task: each new thread that touches
+// CUDA pays a per-thread runtime initialisation, and tools that instrument CUDA calls see a stable set of threads.
+class HostWorkers {
+ public:
+  static HostWorkers& Get() {
+    static HostWorkers* w = new HostWorkers();  // leaked on purpose: no join during static destruction
+    return *w;
+  }
+  std::future<void> Run(std::function<void()> fn) {
+    std::packaged_task<void()> task(std::move(fn));
+    std::future<void> fut = task.get_future();
+    if (threads_.empty()) {  // TDNNF_NG_ASYNC=0: on the calling thread, now
+      task();
+      return fut;
+    }
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      queue_.push_back(std::move(task));
+    }
+    cv_.notify_one();
+    return fut;
+  }
+
+ private:
+  HostWorkers() {
+    const char* e = getenv("TDNNF_NG_ASYNC");
+    int n = 4;
+    if (e) n = atoi(e);
+    n = std::max(0, std::min(n, 16));
+    for (int i = 0; i < n; ++i) threads_.emplace_back([this] { Loop(); });
+    for (std::thread& t : threads_) t.detach();
+  }
+  void Loop() {
+    for (;;) {
+      std::packaged_task<void()> task;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [this] { return !queue_.empty(); });
+        task = std::move(queue_.front());
+        queue_.pop_front();
+      }
+      task();
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<std::packaged_task<void()>> queue_;
+  std::vector<std::thread> threads_;
+};
 
 cudaStream_t Stream() {
   void* s = nullptr;
@@ -333,16 +390,26 @@ void OnlineNaturalGradient::Step(const NgOperand& X, bool updating) {
   CheckStatus(tdnnf_darts_propagate(ctx, X.data, X.rows, X.cols, X.stride, H_.Data(), N, R, H_.Stride(), W_t_.Data(),
                                     W_t_.Stride(), X.ones_col ? w_last_.Data() : NULL, X.ones_col ? 2 : 1, weff, X.n,
                                     X.row_offsets, X.row_stride));
-  // L_t = H_t^T H_t
+  // L_t = H_t^T H_t and tr(X X^T).  Inside Backprop's operand-cache scope the per-row sums of squares of X came with
+  // the operand split of the H product above, and one launch does both (fp32 FMAs, one pass over H); otherwise the
+  // trace takes one pass over X, and ranks beyond 128 go through the tensor-core GEMM.
   EnsureSize(&L_, R, R);
-  L_.SetZero();
-  ProductAtB(H_, H_, 1.0f, one, &L_);
-  // tr(X X^T), tr(X_hat X_hat^T), scale -- all on the device
   if (sumsq_ == nullptr) CudaCheck(cudaMalloc(reinterpret_cast<void**>(&sumsq_), sizeof(double) * TDNNF_MAX_OFFSETS), "cudaMalloc");
   if (scal_.Dim() != 4) scal_.Resize(4);
-  CheckStatus(tdnnf_darts_view_sumsq(ctx, X.data, X.rows, X.cols, X.stride, N, X.n, X.row_offsets, X.row_stride, sumsq_));
-  CheckStatus(tdnnf_ng_scale(ctx, sumsq_, X.weff, X.n, X.ones_col ? (float)N : 0.f, L_.Data(), L_.Stride(), WWt_.Data(),
-                             WWt_.Stride(), R, scal_.Data()));
+  const float* rowsq = NULL;
+  CheckStatus(tdnnf_ctx_operand_rowsq(ctx, X.data, X.rows, &rowsq));
+  if (rowsq == NULL || R > 128)
+    CheckStatus(tdnnf_darts_view_sumsq(ctx, X.data, X.rows, X.cols, X.stride, N, X.n, X.row_offsets, X.row_stride, sumsq_));
+  if (R > 128) {
+    L_.SetZero();
+    ProductAtB(H_, H_, 1.0f, one, &L_);
+    CheckStatus(tdnnf_ng_scale(ctx, sumsq_, X.weff, X.n, X.ones_col ? (float)N : 0.f, L_.Data(), L_.Stride(), WWt_.Data(),
+                               WWt_.Stride(), R, scal_.Data()));
+  } else {
+    CheckStatus(tdnnf_ng_gram_scale(ctx, H_.Data(), N, R, H_.Stride(), L_.Data(), L_.Stride(), WWt_.Data(), WWt_.Stride(),
+                                    rowsq, sumsq_, X.rows, X.n, X.row_offsets, X.row_stride, X.weff,
+                                    X.ones_col ? (float)N : 0.f, scal_.Data()));
+  }
   if (!updating) return;
   // J_t = H_t^T X_t   (block i scaled by w_i, last column = column sums of H)
   EnsureSize(&J_, R, D);
@@ -382,7 +449,8 @@ void OnlineNaturalGradient::Step(const NgOperand& X, bool updating) {
   int device = 0;
   CudaCheck(cudaGetDevice(&device), "cudaGetDevice");
   const int32 D_total = D;
-  pending_->host_half = std::async(std::launch::async, [this, device, D_total] {
+  // worker threads (TDNNF_NG_ASYNC=<n>, default 4; 0 = on the calling thread, synchronously)
+  pending_->host_half = HostWorkers::Get().Run([this, device, D_total] {
     CudaCheck(cudaSetDevice(device), "cudaSetDevice");
     HostHalfOfUpdate(D_total);
   });

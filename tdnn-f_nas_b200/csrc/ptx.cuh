@@ -190,5 +190,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// The same with the A / B formats given separately (0 = fp16, 1 = bf16): kind::f16 mixes them freely.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N, uint32_t a_fmt, uint32_t b_fmt) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
 }  // namespace ptx
 }  // namespace tdnnf

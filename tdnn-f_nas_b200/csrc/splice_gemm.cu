@@ -1,6 +1,7 @@
 // Host side of the TdnnDARTSV3 GEMMs: operand-plane pre-pass kernels, TMA tensor maps, the
 // work decomposition and the C-ABI entry points tdnnf_darts_{propagate,backprop_data,backprop_params}.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -21,15 +22,26 @@ static inline int ceil_div(int x, int m) { return (x + m - 1) / m; }
 // X planes of Propagate (c = row % r), out_deriv planes of Backprop (r = 1) and the per-offset
 // weight planes (c = offset, c_col_mul = D_in, scale = weff) all go through here.
 // ------------------------------------------------------------------------------------------
+// fp16 != 0: ONE fp16 plane, x * pow2_scale(*absmax_in) (absmax_in null: unscaled), written to `hi`.
+// By-products of reading every element once (either may be null):
+//   absmax_out  max |x| (ordered as an int: values are >= 0)
+//   rowsq       rowsq[source row] += sum of squares of that row (segmented warp reduction, one red.add per run of
+//               lanes on the same row) -- the natural-gradient tr(X X^T) without another pass over X
 __global__ void split_rows_kernel(const float* __restrict__ src, int R, int D, long long ld, int r, int groups,
                                   int c_row_mul, int c_col_mul, const float* __restrict__ scale, int Q, int Kpad,
                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                  __nv_bfloat16* __restrict__ lo2) {
+                                  __nv_bfloat16* __restrict__ lo2, int fp16, const float* __restrict__ absmax_in,
+                                  float* __restrict__ absmax_out, float* __restrict__ rowsq) {
   const int kvec = Kpad >> 3;
   const long long total = (long long)groups * Q * kvec;
+  const long long total_up = (total + 31) & ~31LL;  // warp-uniform trip count (the by-products use shuffles)
   const bool aligned = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((c_col_mul & 3) == 0);
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+  const float s16 = (fp16 && absmax_in) ? pow2_scale(*absmax_in) : 1.0f;
+  const int lane = threadIdx.x & 31;
+  float amax = 0.f;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total_up;
        idx += (long long)gridDim.x * blockDim.x) {
+    const bool valid = idx < total;
     const int kv = (int)(idx % kvec);
     const long long rowidx = idx / kvec;
     const int q = (int)(rowidx % Q);
@@ -39,7 +51,8 @@ __global__ void split_rows_kernel(const float* __restrict__ src, int R, int D, l
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    if (srow < R && k0 < D) {
+    const bool live = valid && srow < R && k0 < D;
+    if (live) {
       const float* s = src + srow * ld + (long long)c * c_col_mul + k0;
       if (aligned && k0 + 8 <= D) {
         const float4 a = *reinterpret_cast<const float4*>(s);
@@ -57,6 +70,33 @@ __global__ void split_rows_kernel(const float* __restrict__ src, int R, int D, l
         for (int j = 0; j < 8; ++j) v[j] *= sc;
       }
     }
+    if (absmax_out != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(v[j]));
+    }
+    if (rowsq != nullptr) {
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sq = fmaf(v[j], v[j], sq);
+      const long long key = live ? srow : -1 - (long long)lane;  // dead lanes: singleton runs, nothing to add
+      const long long prev = __shfl_up_sync(0xffffffffu, key, 1);
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float other = __shfl_down_sync(0xffffffffu, sq, o);
+        const long long okey = __shfl_down_sync(0xffffffffu, key, o);
+        if (lane + o < 32 && okey == key) sq += other;
+      }
+      if (live && (lane == 0 || prev != key)) atomicAdd(rowsq + srow, sq);
+    }
+    if (!valid) continue;
+    const long long o = rowidx * Kpad + k0;
+    if (fp16) {
+      __align__(16) __half h[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h[j] = __float2half_rn(v[j] * s16);
+      *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(h);
+      continue;
+    }
     __align__(16) __nv_bfloat16 h[8];
     __align__(16) __nv_bfloat16 l[8];
     __align__(16) __nv_bfloat16 l2[8];
@@ -67,11 +107,26 @@ __global__ void split_rows_kernel(const float* __restrict__ src, int R, int D, l
       l[j] = __float2bfloat16_rn(r1);
       l2[j] = __float2bfloat16_rn(r1 - __bfloat162float(l[j]));
     }
-    const long long o = rowidx * Kpad + k0;
     *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(h);
     *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(l);
     if (lo2 != nullptr) *reinterpret_cast<uint4*>(lo2 + o) = *reinterpret_cast<const uint4*>(l2);
   }
+  if (absmax_out != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (lane == 0 && amax > 0.f) atomicMax(reinterpret_cast<int*>(absmax_out), __float_as_int(amax));
+  }
+}
+
+// max |x| over a matrix (for operands that were not row-split earlier in the cache scope).
+__global__ void absmax_kernel(const float* __restrict__ src, int R, int D, long long ld, float* __restrict__ absmax_out) {
+  float amax = 0.f;
+  const long long total = (long long)R * D;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+    amax = fmaxf(amax, fabsf(src[(idx / D) * ld + idx % D]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(reinterpret_cast<int*>(absmax_out), __float_as_int(amax));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -88,7 +143,7 @@ __global__ void __launch_bounds__(256)
 split_transpose_kernel(const float* __restrict__ src, int R, int J, long long ld, int r, int c_row_mul, int c_col_mul,
                        GroupRowOffsets c_row_off, const float* __restrict__ scale, int Q, int Qp,
                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, __nv_bfloat16* __restrict__ lo2,
-                       float* __restrict__ colsum, float colsum_scale) {
+                       float* __restrict__ colsum, float colsum_scale, int fp16, const float* __restrict__ absmax_in) {
   // 64 (q) x 64 (j) tile: 256-byte coalesced float4 reads along j, 128-byte (8 x bf16 per lane) writes along q.
   __shared__ float tile[64][65];
   const int c = blockIdx.z;
@@ -133,6 +188,15 @@ split_transpose_kernel(const float* __restrict__ src, int R, int J, long long ld
     const int jj = (t >> 3) + 32 * i, qc = (t & 7) * 8;
     const int j = j0 + jj, q = q0 + qc;
     if (j >= J || q >= Qp) continue;  // Qp is a multiple of 8
+    const long long o = ((long long)c * J + j) * Qp + q;
+    if (fp16) {  // one fp16 plane, scaled into the fp16 range by a power of two
+      const float s16 = absmax_in ? pow2_scale(*absmax_in) : 1.0f;
+      __align__(16) __half hh[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) hh[k] = __float2half_rn(tile[qc + k][jj] * s16);
+      *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(hh);
+      continue;
+    }
     __align__(16) __nv_bfloat16 h[8];
     __align__(16) __nv_bfloat16 l[8];
     __align__(16) __nv_bfloat16 l2[8];
@@ -144,7 +208,6 @@ split_transpose_kernel(const float* __restrict__ src, int R, int J, long long ld
       l[k] = __float2bfloat16_rn(r1);
       l2[k] = __float2bfloat16_rn(r1 - __bfloat162float(l[k]));
     }
-    const long long o = ((long long)c * J + j) * Qp + q;
     *reinterpret_cast<uint4*>(hi + o) = *reinterpret_cast<const uint4*>(h);
     *reinterpret_cast<uint4*>(lo + o) = *reinterpret_cast<const uint4*>(l);
     if (lo2 != nullptr) *reinterpret_cast<uint4*>(lo2 + o) = *reinterpret_cast<const uint4*>(l2);
@@ -195,10 +258,11 @@ static int make_map(tdnnf_ctx* ctx, const Planes& pl, int box_rows, CUtensorMap*
 // Cache lookup / insertion for planes of a registered source (see tdnnf_ctx_operand_cache_begin).
 static tdnnf_ctx::PlaneCacheEntry make_key(int kind, const float* src, int R, int D, long long ld, int r, int groups,
                                            int c_row_mul, int c_col_mul, const float* scale, int Q, int pitch,
-                                           const int32_t* offs) {
+                                           const int32_t* offs, int fp16) {
   tdnnf_ctx::PlaneCacheEntry k;
   memset(&k, 0, sizeof(k));
   k.kind = kind;
+  k.fp16 = fp16;
   k.src = src;
   k.R = R;
   k.D = D;
@@ -216,7 +280,7 @@ static tdnnf_ctx::PlaneCacheEntry make_key(int kind, const float* src, int R, in
 
 static tdnnf_ctx::PlaneCacheEntry* cache_find(tdnnf_ctx* ctx, const tdnnf_ctx::PlaneCacheEntry& k) {
   for (auto& e : ctx->cache) {
-    if (e.kind == k.kind && e.src == k.src && e.R == k.R && e.D == k.D && e.ld == k.ld && e.r == k.r &&
+    if (e.kind == k.kind && e.fp16 == k.fp16 && e.src == k.src && e.R == k.R && e.D == k.D && e.ld == k.ld && e.r == k.r &&
         e.groups == k.groups && e.c_row_mul == k.c_row_mul && e.c_col_mul == k.c_col_mul && e.scale == k.scale &&
         e.Q == k.Q && e.pitch == k.pitch && memcmp(e.offs, k.offs, sizeof(k.offs)) == 0)
       return &e;
@@ -232,18 +296,48 @@ static void cache_store(tdnnf_ctx* ctx, tdnnf_ctx::PlaneCacheEntry k, const Plan
   else ctx->cache.push_back(k);
 }
 
+// Device-resident max |x| of a source matrix, for the power-of-two scaling of single-plane fp16 operands.
+// Registered sources of the open cache scope have a slot that a row split fills as a by-product; anything else
+// gets a scratch slot and one absmax_kernel pass.
+static int get_absmax(tdnnf_ctx* ctx, const float* src, int R, int D, long long ld, const float** out) {
+  const int idx = ctx->cache_source_index(src);
+  float* slot = nullptr;
+  if (idx >= 0) {
+    if (ctx->absmax_valid[idx]) {
+      *out = ctx->absmax_dev + idx;
+      return TDNNF_OK;
+    }
+    slot = ctx->absmax_dev + idx;  // zeroed by tdnnf_ctx_operand_cache_begin
+    ctx->absmax_valid[idx] = true;
+  } else {
+    slot = static_cast<float*>(ctx->ws_alloc(1024));
+    if (!slot) return TDNNF_ERR_NOMEM;
+    TDNNF_CUDA_OK(cudaMemsetAsync(slot, 0, sizeof(float), ctx->stream));
+  }
+  const long long total = (long long)R * D;
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((total + 1023) / 1024, (long long)ctx->num_sms * 8));
+  absmax_kernel<<<blocks, 256, 0, ctx->stream>>>(src, R, D, ld, slot);
+  ctx->launches++;
+  TDNNF_CUDA_OK(cudaGetLastError());
+  *out = slot;
+  return TDNNF_OK;
+}
+
+// np: 0 = the context's bf16 plane count (2 or 3); 1 = one fp16 plane scaled by pow2_scale(*absmax_in) (null: unscaled)
 static int launch_split_rows(tdnnf_ctx* ctx, const float* src, int R, int D, long long ld, int r, int groups,
-                             int c_row_mul, int c_col_mul, const float* scale, int Q, int Kpad, Planes* pl) {
+                             int c_row_mul, int c_col_mul, const float* scale, int Q, int Kpad, Planes* pl, int np = 0,
+                             const float* absmax_in = nullptr) {
   pl->plane_elems = (long long)groups * Q * Kpad;
   pl->K = Kpad;
   pl->Kpitch = Kpad;
   pl->rows = Q;
   pl->groups = groups;
-  pl->np = ctx->gemm_planes;
+  pl->np = np ? np : ctx->gemm_planes;
+  const int fp16 = pl->np == 1;
   const bool cacheable = ctx->cache_registered(src);
   tdnnf_ctx::PlaneCacheEntry key;
   if (cacheable) {
-    key = make_key(0, src, R, D, ld, r, groups, c_row_mul, c_col_mul, scale, Q, Kpad, nullptr);
+    key = make_key(0, src, R, D, ld, r, groups, c_row_mul, c_col_mul, scale, Q, Kpad, nullptr, fp16);
     const tdnnf_ctx::PlaneCacheEntry* e = cache_find(ctx, key);
     if (e && e->np >= pl->np) {  // the first np planes of a 3-plane split ARE the 2-plane split
       pl->base = static_cast<__nv_bfloat16*>(e->base);
@@ -251,6 +345,31 @@ static int launch_split_rows(tdnnf_ctx* ctx, const float* src, int R, int D, lon
       return TDNNF_OK;
     }
     ctx->cache_misses++;
+  }
+  // The first row split of a registered source also produces its per-row sums of squares (for the natural-gradient
+  // trace) and, in fast-gradient mode, its absmax: every element is read here anyway.
+  float* absmax_out = nullptr;
+  float* rowsq = nullptr;
+  const int sidx = ctx->cache_source_index(src);
+  if (sidx >= 0 && scale == nullptr && !fp16) {
+    if (ctx->grad_fast && !ctx->absmax_valid[sidx]) {
+      absmax_out = ctx->absmax_dev + sidx;
+      ctx->absmax_valid[sidx] = true;
+    }
+    if (!ctx->rowsq_valid[sidx]) {
+      if (ctx->rowsq_cap[sidx] < (size_t)R) {
+        // grow-only; cudaFree waits for earlier kernels that may still read the old array
+        if (ctx->rowsq_dev[sidx]) TDNNF_CUDA_OK(cudaFree(ctx->rowsq_dev[sidx]));
+        ctx->rowsq_dev[sidx] = nullptr;
+        ctx->rowsq_cap[sidx] = 0;
+        TDNNF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ctx->rowsq_dev[sidx]), sizeof(float) * (size_t)R * 2));
+        ctx->rowsq_cap[sidx] = (size_t)R * 2;
+      }
+      rowsq = ctx->rowsq_dev[sidx];
+      TDNNF_CUDA_OK(cudaMemsetAsync(rowsq, 0, sizeof(float) * (size_t)R, ctx->stream));
+      ctx->rowsq_valid[sidx] = true;
+      ctx->rowsq_rows[sidx] = R;
+    }
   }
   const size_t bytes = planes_bytes(pl->np, groups, Q, Kpad);
   pl->base = static_cast<__nv_bfloat16*>(cacheable ? ctx->cws_alloc(bytes) : ctx->ws_alloc(bytes));
@@ -261,7 +380,8 @@ static int launch_split_rows(tdnnf_ctx* ctx, const float* src, int R, int D, lon
   split_rows_kernel<<<std::max(blocks, 1), threads, 0, ctx->stream>>>(src, R, D, ld, r, groups, c_row_mul, c_col_mul,
                                                                       scale, Q, Kpad, pl->base,
                                                                       pl->base + pl->plane_elems,
-                                                                      pl->np == 3 ? pl->base + 2 * pl->plane_elems : nullptr);
+                                                                      pl->np == 3 ? pl->base + 2 * pl->plane_elems : nullptr,
+                                                                      fp16, absmax_in, absmax_out, rowsq);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   if (cacheable) cache_store(ctx, key, *pl);
@@ -271,17 +391,18 @@ static int launch_split_rows(tdnnf_ctx* ctx, const float* src, int R, int D, lon
 static int launch_split_transpose(tdnnf_ctx* ctx, const float* src, int R, int J, long long ld, int r, int groups,
                                   int c_row_mul, int c_col_mul, const float* scale, int Q, int Qp, int Kvalid,
                                   Planes* pl, const int32_t* group_row_offsets = nullptr, float* colsum = nullptr,
-                                  float colsum_scale = 0.f) {
+                                  float colsum_scale = 0.f, int np = 0, const float* absmax_in = nullptr) {
   pl->plane_elems = (long long)groups * J * Qp;
   pl->K = Kvalid;
   pl->Kpitch = Qp;
   pl->rows = J;
   pl->groups = groups;
-  pl->np = ctx->gemm_planes;
+  pl->np = np ? np : ctx->gemm_planes;
+  const int fp16 = pl->np == 1;
   const bool cacheable = ctx->cache_registered(src);
   tdnnf_ctx::PlaneCacheEntry key;
   if (cacheable) {
-    key = make_key(1, src, R, J, ld, r, groups, c_row_mul, c_col_mul, scale, Q, Qp, group_row_offsets);
+    key = make_key(1, src, R, J, ld, r, groups, c_row_mul, c_col_mul, scale, Q, Qp, group_row_offsets, fp16);
     const tdnnf_ctx::PlaneCacheEntry* e = cache_find(ctx, key);
     // a request that also wants the fused column sums must run the kernel
     if (colsum == nullptr && e && e->np >= pl->np) {
@@ -300,7 +421,7 @@ static int launch_split_transpose(tdnnf_ctx* ctx, const float* src, int R, int J
   split_transpose_kernel<<<grid, block, 0, ctx->stream>>>(src, R, J, ld, r, c_row_mul, c_col_mul, gro, scale, Q, Qp,
                                                           pl->base, pl->base + pl->plane_elems,
                                                           pl->np == 3 ? pl->base + 2 * pl->plane_elems : nullptr, colsum,
-                                                          colsum_scale);
+                                                          colsum_scale, fp16, absmax_in);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   if (cacheable) cache_store(ctx, key, *pl);
@@ -329,17 +450,17 @@ static int choose_splits(int tiles, int iters_per_tile, int num_sms) {
   return best;
 }
 
-template <int BN, int NP>
+template <int BN, int NPA, int NPB>
 static int launch_gemm_bn(tdnnf_ctx* ctx, const Planes& A, const Planes& B, const GemmParams& p, double algorithmic_flops) {
   CUtensorMap tmA, tmB;
   int rc = make_map(ctx, A, kBM, &tmA);
   if (rc) return rc;
   rc = make_map(ctx, B, BN, &tmB);
   if (rc) return rc;
-  auto kern = splice_gemm_kernel<BN, NP>;
+  auto kern = splice_gemm_kernel<BN, NPA, NPB>;
   static bool attr_set = false;  // per template instance
   if (!attr_set) {
-    TDNNF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, NP>::kSmemBytes));
+    TDNNF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, NPA, NPB>::kSmemBytes));
     attr_set = true;
   }
   const int units = p.c_tiles * p.m_tiles * p.n_tiles * p.splits;
@@ -350,9 +471,10 @@ static int launch_gemm_bn(tdnnf_ctx* ctx, const Planes& A, const Planes& B, cons
     TDNNF_CUDA_OK(cudaEventCreate(&tm.start));
     TDNNF_CUDA_OK(cudaEventCreate(&tm.stop));
     tm.flops = algorithmic_flops;
+    tm.products = (NPA == 3) ? 6 : (NPA == 2 && NPB == 2 ? 3 : NPA * NPB);
     TDNNF_CUDA_OK(cudaEventRecord(tm.start, ctx->stream));
   }
-  kern<<<grid, kGemmThreads, GemmCfg<BN, NP>::kSmemBytes, ctx->stream>>>(tmA, tmB, p);
+  kern<<<grid, kGemmThreads, GemmCfg<BN, NPA, NPB>::kSmemBytes, ctx->stream>>>(tmA, tmB, p);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   if (ctx->gemm_timing) {
@@ -382,25 +504,25 @@ static int pick_bn(int n, int np = 2) {
   return 160;
 }
 
-static int launch_gemm(tdnnf_ctx* ctx, int bn, const Planes& A, const Planes& B, const GemmParams& p, double algorithmic_flops) {
-  if (A.np != B.np) return fail(TDNNF_ERR_INVALID, "operand plane counts differ");
-  if (A.np == 3) {
-    switch (bn) {
-      case 32: return launch_gemm_bn<32, 3>(ctx, A, B, p, algorithmic_flops);
-      case 64: return launch_gemm_bn<64, 3>(ctx, A, B, p, algorithmic_flops);
-      case 128: return launch_gemm_bn<128, 3>(ctx, A, B, p, algorithmic_flops);
-      case 160: return launch_gemm_bn<160, 3>(ctx, A, B, p, algorithmic_flops);
-      default: return fail(TDNNF_ERR_INVALID, "unsupported BN for 3-plane operands");
-    }
-  }
+template <int NPA, int NPB>
+static int launch_gemm_np(tdnnf_ctx* ctx, int bn, const Planes& A, const Planes& B, const GemmParams& p, double fl) {
   switch (bn) {
-    case 32: return launch_gemm_bn<32, 2>(ctx, A, B, p, algorithmic_flops);
-    case 64: return launch_gemm_bn<64, 2>(ctx, A, B, p, algorithmic_flops);
-    case 128: return launch_gemm_bn<128, 2>(ctx, A, B, p, algorithmic_flops);
-    case 160: return launch_gemm_bn<160, 2>(ctx, A, B, p, algorithmic_flops);
-    case 256: return launch_gemm_bn<256, 2>(ctx, A, B, p, algorithmic_flops);
+    case 32: return launch_gemm_bn<32, NPA, NPB>(ctx, A, B, p, fl);
+    case 64: return launch_gemm_bn<64, NPA, NPB>(ctx, A, B, p, fl);
+    case 128: return launch_gemm_bn<128, NPA, NPB>(ctx, A, B, p, fl);
+    case 160: return launch_gemm_bn<160, NPA, NPB>(ctx, A, B, p, fl);
+    case 256:
+      if constexpr (NPA == 3) return fail(TDNNF_ERR_INVALID, "unsupported BN for 3-plane operands");
+      else return launch_gemm_bn<256, NPA, NPB>(ctx, A, B, p, fl);
     default: return fail(TDNNF_ERR_INVALID, "unsupported BN");
   }
+}
+
+static int launch_gemm(tdnnf_ctx* ctx, int bn, const Planes& A, const Planes& B, const GemmParams& p, double algorithmic_flops) {
+  if (A.np == 3 && B.np == 3) return launch_gemm_np<3, 3>(ctx, bn, A, B, p, algorithmic_flops);
+  if (A.np == 2 && B.np == 2) return launch_gemm_np<2, 2>(ctx, bn, A, B, p, algorithmic_flops);
+  if (A.np == 1 && B.np == 1) return launch_gemm_np<1, 1>(ctx, bn, A, B, p, algorithmic_flops);
+  return fail(TDNNF_ERR_INVALID, "unsupported operand plane combination");
 }
 
 static int check_offsets(int n, const int32_t* row_offsets, int row_stride, int out_rows, int in_rows) {
@@ -567,20 +689,32 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
   ctx->ws_reset();
   const size_t need = (shifts_aligned ? planes_bytes(ctx->gemm_planes, r, in_dim, Qp) : planes_bytes(ctx->gemm_planes, n, in_dim, Rp)) +
                       planes_bytes(ctx->gemm_planes, 1, out_dim, Rp);
-  rc = ctx->ws_reserve(need);
+  rc = ctx->ws_reserve(need + 4096);
   if (rc) return rc;
   rc = ctx->cws_reserve(need);
   if (rc) return rc;
+  // Gradient mode "fast": both operands as ONE fp16 plane each, scaled into the fp16 range by a power of two
+  // taken from their device-resident absmax (exact to undo in the epilogue): one product instead of three.
+  const bool fast = ctx->grad_fast && ctx->gemm_planes == 2;
+  const float *amax_x = nullptr, *amax_od = nullptr;
+  if (fast) {
+    rc = get_absmax(ctx, in_value, in_rows, in_dim, in_stride, &amax_x);
+    if (rc) return rc;
+    rc = get_absmax(ctx, out_deriv, out_rows, out_dim, od_stride, &amax_od);
+    if (rc) return rc;
+  }
+  const int gnp = fast ? 1 : 0;
   Planes XT, ODT;
   if (shifts_aligned)
-    rc = launch_split_transpose(ctx, in_value, in_rows, in_dim, in_stride, r, r, 1, 0, nullptr, Q, Qp, Q, &XT);
+    rc = launch_split_transpose(ctx, in_value, in_rows, in_dim, in_stride, r, r, 1, 0, nullptr, Q, Qp, Q, &XT, nullptr,
+                                nullptr, 0.f, gnp, amax_x);
   else
     rc = launch_split_transpose(ctx, in_value, in_rows, in_dim, in_stride, r, n, 0, 0, nullptr, out_rows, Rp,
-                                out_rows, &XT, row_offsets);
+                                out_rows, &XT, row_offsets, nullptr, 0.f, gnp, amax_x);
   if (rc) return rc;
   // the out_deriv^T pre-pass also accumulates dbias += lr * colsum(out_deriv) (each element is read exactly once)
   rc = launch_split_transpose(ctx, out_deriv, out_rows, out_dim, od_stride, 1, 1, 0, 0, nullptr, out_rows, Rp,
-                              out_rows, &ODT, nullptr, dbias, lr);
+                              out_rows, &ODT, nullptr, dbias, lr, gnp, amax_od);
   if (rc) return rc;
   if (s) TDNNF_CUDA_OK(cudaMemsetAsync(s, 0, sizeof(float) * n, ctx->stream));
 
@@ -601,6 +735,8 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
   p.dot_ref = s ? W_model : nullptr;
   p.dot_ld = w_stride;
   p.dot_out = s;
+  p.absmax_a = m_is_in ? amax_x : amax_od;
+  p.absmax_b = m_is_in ? amax_od : amax_x;
   int bn;
   if (m_is_in) {
     // acc[d, o] = sum_k X_i^T[d, k] * OD^T[o, k]  ->  dW[o, i*in_dim + d]   (transposed store)
@@ -643,5 +779,19 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
 extern "C" int tdnnf_ctx_set_gemm_planes(tdnnf_ctx* ctx, int planes) {
   TDNNF_REQUIRE(ctx && (planes == 2 || planes == 3), "planes must be 2 or 3");
   ctx->gemm_planes = planes;
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_ctx_set_gradient_mode(tdnnf_ctx* ctx, int fast) {
+  TDNNF_REQUIRE(ctx != nullptr, "null context");
+  ctx->grad_fast = fast != 0;
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_ctx_operand_rowsq(tdnnf_ctx* ctx, const float* source, int rows, const float** rowsq) {
+  TDNNF_REQUIRE(ctx && source && rowsq, "null argument");
+  *rowsq = nullptr;
+  const int idx = ctx->cache_source_index(source);
+  if (idx >= 0 && ctx->rowsq_valid[idx] && ctx->rowsq_rows[idx] == rows) *rowsq = ctx->rowsq_dev[idx];
   return TDNNF_OK;
 }

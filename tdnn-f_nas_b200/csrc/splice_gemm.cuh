@@ -51,7 +51,22 @@ struct GemmParams {
   const float* dot_ref;   // optional: dot_out[c] += sum(acc * dot_ref[index'])  (un-scaled acc;
   long long dot_ld;       //           index' uses dot_ld in place of out_ld)
   float* dot_out;
+  // single-plane fp16 operands are stored as x * pow2_scale(absmax): the device-resident absmax of each such
+  // operand (null: not scaled) lets the epilogue undo it, v *= 1 / (pow2_scale(*absmax_a) * pow2_scale(*absmax_b))
+  const float* absmax_a;
+  const float* absmax_b;
 };
+
+// Power-of-two factor that brings a tensor whose largest magnitude is `absmax` into [2^14, 2^15): the top of the
+// fp16 range, so that elements down to 2^-29 * absmax stay normal.  Exact to apply and to undo.
+__host__ __device__ __forceinline__ float pow2_scale(float absmax) {
+  if (!(absmax > 0.f) || absmax > 3.0e38f) return 1.0f;
+  int e;
+  frexpf(absmax, &e);  // absmax = m * 2^e, m in [0.5, 1)
+  int k = 15 - e;
+  k = k > 120 ? 120 : (k < -120 ? -120 : k);
+  return ldexpf(1.0f, k);
+}
 
 struct GemmSmemMeta {
   int seg_a_k[kMaxSeg], seg_a_m[kMaxSeg], seg_a_c[kMaxSeg];
@@ -62,12 +77,17 @@ struct GemmSmemMeta {
   float c_scale[kMaxSeg];
 };
 
-// NP = operand planes per matrix: 2 (hi, lo: x to ~2^-17, three products per K step) or 3 (hi, mid, lo: x to
-// 2^-24, six products) -- the latter for the natural-gradient update whose eigen-problem amplifies rounding.
-template <int BN, int NP>
+// NPA / NPB = planes of the A / B operand.  Plane formats and products per K step:
+//   (2,2)  bf16 hi/lo each (x to ~2^-17): hi*hi + hi*lo + lo*hi, three products -- Propagate (1e-4 tolerance)
+//   (3,3)  bf16 hi/mid/lo (x to 2^-24): six products -- the natural-gradient update, whose eigen-problem amplifies rounding
+//   (1,1)  ONE fp16 plane each (x to 2^-11), scaled by a power of two into the fp16 range: one product -- the
+//          parameter gradient (1e-3 tolerance; measured 2.9e-4)
+// (Mixing a bf16 operand with an fp16 one in one kind::f16 MMA -- which would give a two-product data gradient --
+// is rejected by the hardware: "illegal instruction", measured on B200.)
+template <int BN, int NPA, int NPB>
 struct GemmCfg {
-  static constexpr int kABytes = NP * kBM * kBK * 2;
-  static constexpr int kBBytes = NP * BN * kBK * 2;
+  static constexpr int kABytes = NPA * kBM * kBK * 2;
+  static constexpr int kBBytes = NPB * BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kMetaBytes = 2048 + (int)sizeof(GemmSmemMeta);
   static constexpr int kStages = (232448 - 1024 - kMetaBytes) / kStageBytes >= 4
@@ -76,6 +96,7 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kMetaBytes + 1024;
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N must be a multiple of 16 in [16,256]");
   static_assert(kStages >= 2, "need at least a double buffer");
+  static_assert(NPA == NPB && NPA >= 1 && NPA <= 3, "unsupported plane combination");
 };
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
@@ -121,11 +142,11 @@ __device__ __forceinline__ UnitCoord decode_unit(int u, const GemmParams& p, con
   return uc;
 }
 
-template <int BN, int NP>
+template <int BN, int NPA, int NPB>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN, NP>;
+  using Cfg = GemmCfg<BN, NPA, NPB>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -211,7 +232,8 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else if (warp == 1) {
     // ================================================= MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(kBM, BN);
+      // single-plane operands are fp16 (format 0), multi-plane operands are bf16 (format 1)
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(kBM, BN, NPA == 1 ? 0u : 1u, NPB == 1 ? 0u : 1u);
       int stage = 0;
       uint32_t phase = 0;
       int acc_buf = 0;
@@ -231,27 +253,30 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint32_t sa = ptx::smem_u32(tiles + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
           const uint64_t a_hi = ptx::umma_desc_k_sw128(sa);
-          const uint64_t a_lo = ptx::umma_desc_k_sw128(sa + kBM * kBK * 2);
+          const uint64_t a_lo = ptx::umma_desc_k_sw128(sa + (NPA > 1 ? 1 : 0) * kBM * kBK * 2);
           const uint64_t b_hi = ptx::umma_desc_k_sw128(sb);
-          const uint64_t b_lo = ptx::umma_desc_k_sw128(sb + BN * kBK * 2);
-          const uint64_t a_l2 = ptx::umma_desc_k_sw128(sa + (NP - 1) * kBM * kBK * 2);  // third plane (NP == 3)
-          const uint64_t b_l2 = ptx::umma_desc_k_sw128(sb + (NP - 1) * BN * kBK * 2);
+          const uint64_t b_lo = ptx::umma_desc_k_sw128(sb + (NPB > 1 ? 1 : 0) * BN * kBK * 2);
+          const uint64_t a_l2 = ptx::umma_desc_k_sw128(sa + (NPA - 1) * kBM * kBK * 2);  // third plane (NP == 3)
+          const uint64_t b_l2 = ptx::umma_desc_k_sw128(sb + (NPB - 1) * BN * kBK * 2);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             if (k >= ksteps) break;
-            const uint64_t adv = (uint64_t)(k * 2);  // 16 bf16 = 32 B = 2 x 16 B units inside the swizzle atom
-            if (NP == 3) {
+            const uint64_t adv = (uint64_t)(k * 2);  // 16 elements = 32 B = 2 x 16 B units inside the swizzle atom
+            const uint32_t first = (it > uc.it0 || k > 0) ? 1u : 0u;
+            if (NPA == 3) {
               // smallest products first: (lo, hi) and (mid, mid) are ~2^-16 of (hi, hi); (mid, lo), (lo, lo) < 2^-24 dropped
-              ptx::umma_bf16(d_tmem, a_l2 + adv, b_hi + adv, idesc, (it > uc.it0 || k > 0) ? 1u : 0u);
+              ptx::umma_bf16(d_tmem, a_l2 + adv, b_hi + adv, idesc, first);
               ptx::umma_bf16(d_tmem, a_hi + adv, b_l2 + adv, idesc, 1u);
               ptx::umma_bf16(d_tmem, a_lo + adv, b_lo + adv, idesc, 1u);
               ptx::umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
               ptx::umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
               ptx::umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
-            } else {
-              ptx::umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, (it > uc.it0 || k > 0) ? 1u : 0u);
+            } else if (NPA == 2 && NPB == 2) {
+              ptx::umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, first);
               ptx::umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
               ptx::umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+            } else {  // (1,1)
+              ptx::umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, first);
             }
           }
           ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
@@ -269,6 +294,8 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint32_t acc_phase = 0;
     const bool vec_ok = (!p.transposed) && ((p.out_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
                         ((p.col_cadd & 3) == 0);
+    // undo the power-of-two scaling of single-plane fp16 operands (exact)
+    const float descale = 1.0f / ((p.absmax_a ? pow2_scale(*p.absmax_a) : 1.0f) * (p.absmax_b ? pow2_scale(*p.absmax_b) : 1.0f));
     const bool dot_vec_ok = p.dot_ref != nullptr && ((reinterpret_cast<uintptr_t>(p.dot_ref) & 15) == 0) &&
                             ((p.dot_ld & 3) == 0) && ((p.col_cadd & 3) == 0);
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
@@ -282,7 +309,7 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int m = uc.m_t * kBM + quarter * 32 + lane;
       const bool row_ok = m < meta->m_valid[uc.c];
       const long long R = (long long)m * p.row_mul + (long long)uc.c * p.row_cadd;
-      const float scale = p.alpha * meta->c_scale[uc.c];
+      const float scale = p.alpha * meta->c_scale[uc.c] * descale;
       const bool add_bias = (p.bias != nullptr) && (uc.split == 0);
       float dot = 0.f;
 #pragma unroll 1
@@ -324,7 +351,7 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (live) {
           if (p.dot_ref != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) dot += __uint_as_float(v[j]) * ref[j];
+            for (int j = 0; j < 16; ++j) dot += __uint_as_float(v[j]) * ref[j];  // descaled once per unit below
           }
           if (!p.transposed) {
             float* dst = p.out + R * p.out_ld + C0;
@@ -372,8 +399,9 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const long long idx = (C0 + j) * p.out_ld + R;
                 float o = scale * __uint_as_float(v[j]);
                 if (add_bias) o += p.bias[n0 + j];
-                if (p.atomic) red_add_f32(p.out + idx, o);
-                else if (p.accumulate) p.out[idx] += o;
+                // accumulate always goes through red.add: a plain `+=` here is a chain of BN dependent
+                // load-add-store round trips to L2 (~0.6 us each) per thread
+                if (p.atomic || p.accumulate) red_add_f32(p.out + idx, o);
                 else p.out[idx] = o;
               }
             }
@@ -384,7 +412,7 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (p.dot_ref != nullptr) {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
-        if (lane == 0 && dot != 0.f) atomicAdd(p.dot_out + uc.c, dot);
+        if (lane == 0 && dot != 0.f) atomicAdd(p.dot_out + uc.c, dot * descale);
       }
       if (has_acc) {
         ptx::tc_fence_before_sync();

@@ -78,6 +78,12 @@ def set_print_log_alpha(flag: bool):
     _check(_lib().tdnnf_nnet3_set_print_log_alpha(int(flag)))
 
 
+def set_fast_gradients(flag: bool):
+    """TdnnDARTSV3Component parameter-gradient GEMM with one fp16 product instead of three bf16 ones.  Default False:
+    with natural gradient the projection amplifies the 2.9e-4 error beyond the 1e-3 tolerance."""
+    _check(_lib().tdnnf_nnet3_set_fast_gradients(int(flag)))
+
+
 def set_ng_identity(flag: bool):
     """Diagnostic: every PreconditionDirections call becomes the identity with scale 1 (raw gradient)."""
     _check(_lib().tdnnf_nnet3_set_ng_identity(int(flag)))

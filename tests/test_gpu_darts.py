@@ -54,9 +54,12 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("grad_fast", [False, True], ids=["grad3x", "gradfast"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 @pytest.mark.parametrize("mode", list(MODES))
-def test_propagate_backprop_parity(ctx, case, mode):
+def test_propagate_backprop_parity(ctx, case, mode, grad_fast):
+    """grad_fast: the parameter gradient with ONE tensor-core product (fp16 x fp16, both operands scaled by an exact
+    power of two) instead of three bf16 ones -- same 1e-3 tolerance (tdnnf_ctx_set_gradient_mode)."""
     import torch
 
     from oracle import oracle as O
@@ -109,11 +112,15 @@ def test_propagate_backprop_parity(ctx, case, mode):
     in_deriv.copy_(torch.from_numpy(in_deriv0))
     weff2 = torch.zeros(n, device="cuda")
     ctx.darts_weff_from_coef(coef, flags, share, weff2)
-    ctx.darts_backprop_data(od, in_deriv, W, weff2, d["row_offsets"], row_stride)
-    dW = torch.zeros((out_dim, n * in_dim), device="cuda")
-    dbias = torch.zeros(n + out_dim, device="cuda")
-    s = torch.zeros(n, device="cuda")
-    ctx.darts_backprop_params(x, od, W, dW, dbias[n:], weff2, d["row_offsets"], row_stride, lr, s)
+    ctx.set_gradient_mode(grad_fast)
+    try:
+        ctx.darts_backprop_data(od, in_deriv, W, weff2, d["row_offsets"], row_stride)
+        dW = torch.zeros((out_dim, n * in_dim), device="cuda")
+        dbias = torch.zeros(n + out_dim, device="cuda")
+        s = torch.zeros(n, device="cuda")
+        ctx.darts_backprop_params(x, od, W, dW, dbias[n:], weff2, d["row_offsets"], row_stride, lr, s)
+    finally:
+        ctx.set_gradient_mode(False)
     ctx.darts_alpha_update(s, coef, fl_upd, temp, share, lr, dbias[:n])
     torch.cuda.synchronize()
     assert torch.equal(weff, weff2)
@@ -131,6 +138,45 @@ def test_propagate_backprop_parity(ctx, case, mode):
         assert np.abs(dbias[:n].cpu().numpy() - dbias_ref[:n]).max() / scale < 5 * GRAD_TOL
     else:
         assert np.all(dbias[:n].cpu().numpy() == 0)
+
+
+@pytest.mark.parametrize("x_scale,od_scale", [(1.0, 1.0), (3.0e4, 1.0e-12), (1.0e-9, 1.0e7)])
+def test_fast_gradients_dynamic_range(ctx, x_scale, od_scale):
+    """The one-product parameter gradient stores both operands as fp16 after an exact power-of-two scaling taken
+    from their max magnitude: activations of 3e4 (near the fp16 maximum unscaled) and derivatives of 1e-12 (far
+    below the smallest fp16 subnormal unscaled) must give the same relative accuracy as O(1) data."""
+    import torch
+
+    from oracle import oracle as O
+
+    n, in_dim, out_dim, S, t_out, offsets = 3, 96, 80, 8, 40, [0, 2, 5]
+    d = _setup(n, in_dim, out_dim, S, t_out, offsets, 1, seed=11)
+    x = (d["x"] * x_scale).astype(np.float32)
+    od = (d["od"] * od_scale).astype(np.float32)
+    coef = np.array([1.0, 0.3, 0.7], np.float32)
+    dW_ref = np.zeros((out_dim, n * in_dim), np.float64)
+    for i in range(n):
+        xi = x[d["row_offsets"][i]: d["row_offsets"][i] + d["out_rows"]].astype(np.float64)
+        dW_ref[:, i * in_dim:(i + 1) * in_dim] = coef[i] * (od.astype(np.float64).T @ xi)
+    in_ref = np.zeros((d["in_rows"], in_dim), np.float64)
+    for i in range(n):
+        Wi = d["W"][:, i * in_dim:(i + 1) * in_dim].astype(np.float64)
+        in_ref[d["row_offsets"][i]: d["row_offsets"][i] + d["out_rows"]] += coef[i] * (od.astype(np.float64) @ Wi)
+    weff = torch.from_numpy(coef).cuda()
+    dW = torch.zeros((out_dim, n * in_dim), device="cuda")
+    dbias = torch.zeros(out_dim, device="cuda")
+    in_deriv = torch.zeros((d["in_rows"], in_dim), device="cuda")
+    ctx.set_gradient_mode(True)
+    try:
+        ctx.darts_backprop_data(torch.from_numpy(od).cuda(), in_deriv, to_cuda_view(d["W"]), weff, d["row_offsets"], 1)
+        ctx.darts_backprop_params(torch.from_numpy(x).cuda(), torch.from_numpy(od).cuda(), None, dW, dbias, weff,
+                                  d["row_offsets"], 1, 1.0, None)
+    finally:
+        ctx.set_gradient_mode(False)
+    torch.cuda.synchronize()
+    assert rel_err(dW.cpu().numpy(), dW_ref) < GRAD_TOL
+    assert rel_err(in_deriv.cpu().numpy(), in_ref) < GRAD_TOL
+    assert rel_err(dbias.cpu().numpy(), od.astype(np.float64).sum(0)) < 1e-5
 
 
 def test_propagate_adds_mode(ctx):

@@ -127,6 +127,7 @@ def test_darts_natural_gradient_update_over_steps(nn, mode_cfg, flags, din, dout
         sc = np.abs(db_ref[:n]).max()
         if sc > 0:
             assert np.abs(db[:n] - db_ref[:n]).max() / sc < 5e-3
+    print(f"worst delta rel err over 13 steps: {worst:.2e}")
     # the preconditioners' own state stayed in step with the oracle's
     for which, orc in ((0, ng_in), (1, ng_out)):
         sg, so = delta.preconditioner(which).state(), orc.state()
