@@ -5,9 +5,13 @@
   python bench.py --impl reference --gpus N --steps K ...  the reference's CPU arithmetic (oracle) on host cores
 
 Metric (BASELINE.json): supernet training frames/sec (input frames = chunks x frames_per_eg consumed per
-second; forward + LF-MMI denominator forward-backward + backward + delta reduction + parameter step), on the
-context-offset search supernet of configs[2] with 64 chunks x 150 frames PER GPU (weak scaling).
-One JSON line on stdout from rank 0.
+second; forward + LF-MMI numerator/denominator forward-backward + backward with the natural-gradient update of
+every TdnnDARTSV3Component + delta reduction + max-change parameter step), on the context-offset search supernet
+of configs[2] with 64 chunks x 150 frames PER GPU (weak scaling).  One JSON line on stdout from rank 0.
+
+OnlineNaturalGradient refreshes its Fisher estimate on each of its first 10 calls and then on every 4th
+(update_period 4): NG_SETTLE_STEPS untimed steps run before the W warm-up steps so that the K timed steps sample
+the steady state (K = 10 holds 2-3 refresh steps, as a long run does on average).
 """
 from __future__ import annotations
 
@@ -27,6 +31,10 @@ METRIC = "TDNN-F DARTS supernet train frames/sec"
 # capture (profiles/r01_summary.md).  A tensor-bound kernel: this is context, not the roofline numerator.
 NCU_GEMM_TRAFFIC_BYTES = 108.8e6
 UNIT = "frames/s"
+NG_SETTLE_STEPS = 12
+# launches with fewer algorithmic FLOPs than this are the skinny natural-gradient products (H = X W^T with 20-80
+# columns: <= 8.5 GFLOP; rank-r corrections), not the TdnnDARTSV3 Propagate / Backprop GEMMs (>= 11 GFLOP at this config)
+MAIN_GEMM_MIN_FLOPS = 1.0e10
 
 
 def load_peaks():
@@ -137,7 +145,8 @@ def cpu_baseline_sample(cfg, repeats: int = 1):
     return dict(t_gemm=t_gemm, t_den=t_den, sample_flops=sum(c["flops"] for c in comps), den_seqs=S_den,
                 cores=O.num_threads(),
                 sample=("oracle (CPU restatement, OpenMP): 1 TDNN-F block (TdnnDARTSV3 1536->160 + 160->1536, 7 offsets) "
-                        "Propagate+Backprop+update at 64 seq x 96 frames (plain OpenMP/AVX2 loops: no BLAS in the image), + denominator fwd-bwd on the bench graph at "
+                        "Propagate+Backprop+update at 64 seq x 96 frames (plain OpenMP/AVX2 loops: no BLAS in the image; "
+                        "natural-gradient preconditioning NOT included, which favours this baseline), + denominator fwd-bwd on the bench graph at "
                         f"{S_den} seq x {T} frames; extrapolated to the full step by algorithmic GEMM FLOPs and by sequences"))
 
 
@@ -209,7 +218,10 @@ def workload_config(cfg, gpus):
                 mode=cfg.mode, chunks_per_gpu=cfg.num_seqs, frames_per_eg=cfg.frames_per_eg, global_chunks=cfg.num_seqs * gpus,
                 num_pdfs=cfg.num_pdfs, den_states=cfg.den_states, parallelism=f"dp{gpus}",
                 cache="per-step working set (~14 GB of activations) exceeds the 126 MB L2: no explicit flush needed",
-                not_included="natural gradient (identity preconditioner), L2 / orthonormal constraint, xent branch, dropout (proportion 0)")
+                included=("natural-gradient update (OnlineNaturalGradient rank 20/80, update period 4) of all 28 TdnnDARTSV3 "
+                          "components, LF-MMI numerator (per-sequence FST) and denominator, UpdateNnetWithMaxChange"),
+                ng_settle_steps=NG_SETTLE_STEPS,
+                not_included="L2 regularisation, xent branch, dropout (proportion 0 in the recipe); the orthonormal constraint does not cover TdnnDARTSV3 (utils.cc:1047-1061)")
 
 
 def run_ours(args, cfg, rank, world, local_rank):
@@ -250,7 +262,7 @@ def run_ours(args, cfg, rank, world, local_rank):
         return ms, net.ctx.launches - launches0, last
 
     net.x.copy_(host_inputs[0])
-    for i in range(args.warmup):
+    for i in range(NG_SETTLE_STEPS + args.warmup):
         net.step(host_inputs[i % 2])
     # ---- device-resident number (`value`)
     sampler = ClockSampler(local_rank)
@@ -262,9 +274,10 @@ def run_ours(args, cfg, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
     # ---- roofline of the dominant kernel: per-launch CUDA events around every tensor-core GEMM of 2 more steps
     net.ctx.gemm_timing_enable(True)
-    net.step(None)
-    net.step(None)
-    gemm_ms, gemm_flops, gemm_launches = net.ctx.gemm_timing_read()
+    ROOF_STEPS = 4  # one natural-gradient period
+    for _ in range(ROOF_STEPS):
+        net.step(None)
+    gt = net.ctx.gemm_timing_read_ex(MAIN_GEMM_MIN_FLOPS)
     net.ctx.gemm_timing_enable(False)
     # ---- the denominator forward-backward on its own (second half of BASELINE.json's metric): CUDA events around
     # DenominatorComputation::Forward + Backward on the step's (T*S) x P output; algorithmic bytes per SURVEY 8d
@@ -288,7 +301,8 @@ def run_ours(args, cfg, rank, world, local_rank):
     frames_all = net.frames_per_step * world
     value = frames_all * args.steps / (ms_dev / 1e3)
     e2e = frames_all * args.steps / (ms_e2e / 1e3)
-    achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    achieved = gt["flops"] / (gt["ms"] / 1e3) / 1e12 if gt["ms"] > 0 else 0.0
+    achieved_pipe = gt["pipe_flops"] / (gt["ms"] / 1e3) / 1e12 if gt["ms"] > 0 else 0.0
     peak = peaks["bf16_tflops_sustained"]
     step_ms = ms_dev / args.steps
     cpu_line = None
@@ -304,14 +318,19 @@ def run_ours(args, cfg, rank, world, local_rank):
         e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=int(net.x.numel() * 4), d2h_bytes_per_step=12,
                  ms_per_step=ms_e2e / args.steps),
         gpu_launches=int(launches),
-        roofline=dict(bound="tensor", kernel="splice_gemm_kernel (tcgen05, all TdnnDARTSV3 fwd/dgrad/wgrad GEMMs)",
+        roofline=dict(bound="tensor", kernel="splice_gemm_kernel (tcgen05, the TdnnDARTSV3 Propagate / data-gradient / parameter-gradient GEMMs)",
                       achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=NCU_GEMM_TRAFFIC_BYTES,
-                      traffic_source="profiles/r01_summary.md: mean dram__bytes_read+write over the 6 captured launches",
+                      traffic_source="profiles/r01_summary.md: mean dram__bytes_read+write per launch of the ncu --set full capture",
                       peak_source=peaks["source"] + ", bf16 sustained",
-                      achieved_raw_bf16=3 * achieved, frac_raw_bf16=3 * achieved / peak,
-                      launches_timed=gemm_launches, gemm_ms_per_step=gemm_ms / 2, gemm_share_of_step=(gemm_ms / 2) / step_ms,
-                      note=("achieved = algorithmic fp32-equivalent FLOPs (2MNK, one pass) / CUDA-event time of the GEMM launches; "
-                            "each K block issues 3 bf16 MMAs (hi*hi, hi*lo, lo*hi), so the tensor pipe runs at 3x this rate")),
+                      achieved_tensor_pipe=achieved_pipe, frac_tensor_pipe=achieved_pipe / peak,
+                      launches_timed=gt["launches"], steps_timed=ROOF_STEPS, gemm_ms_per_step=gt["ms"] / ROOF_STEPS,
+                      gemm_share_of_step=(gt["ms"] / ROOF_STEPS) / step_ms,
+                      skinny_ng_gemm_launches=gt["other_launches"], skinny_ng_gemm_ms_per_step=gt["other_ms"] / ROOF_STEPS,
+                      note=("achieved = algorithmic fp32-equivalent FLOPs (2MNK over un-padded operands, one pass) / CUDA-event "
+                            "time, over every launch with >= 10 GFLOP (the TdnnDARTSV3 GEMMs); fp32-level accuracy comes from "
+                            "bf16 hi/lo operand planes and 3 tensor-core products per K step, so the tensor pipe itself runs at "
+                            "achieved_tensor_pipe (counts each product issued); launches below 10 GFLOP are the skinny "
+                            "natural-gradient products, timed separately")),
         den=den_report(cfg, net.den_arcs, den_ms, peaks),
         cpu_baseline=cpu_line, objf_per_frame=objf, den_arcs=net.den_arcs)
     print(json.dumps(line), flush=True)
