@@ -46,6 +46,23 @@ def test_den_parity(ctx, N, P, S, T, deg):
     np.testing.assert_allclose(-d.sum(axis=1), 1.0, rtol=2e-3)
 
 
+@pytest.mark.parametrize("N,P,S,T,deg", [(300, 50, 32, 9, 6.0), (1000, 300, 128, 7, 16.0), (257, 33, 21, 4, 5.0)])
+def test_den_resident_path_parity(ctx, monkeypatch, N, P, S, T, deg):
+    """The opt-in cluster-resident kernels (TDNNF_DEN_RESIDENT=1; V = 4 / 4 / 1 sequences per cluster here)."""
+    from oracle import oracle as O
+    from tdnnf_nas_b200 import synth
+
+    monkeypatch.setenv("TDNNF_DEN_RESIDENT", "1")
+    graph = synth.make_den_graph(N, P, deg, seed=N)
+    g = np.random.default_rng(N + S)
+    x = np.clip(g.standard_normal((T * S, P)) * 2.0, -30, 30).astype(np.float32)
+    lp_ref, d_ref, ok_ref = O.den_forward_backward(graph, x, S, T, 0.1, deriv_weight=-1.0)
+    lp, d, ok = _run_gpu(ctx, graph, x, S, T, 0.1, -1.0)
+    assert ok and ok_ref
+    assert abs(lp - lp_ref) <= 1e-4 * abs(lp_ref), (lp, lp_ref)
+    assert rel_err(d, d_ref) < 1e-3
+
+
 def test_den_invariants_large(ctx):
     """Switchboard-shaped sizes the oracle would take minutes on: check invariants instead."""
     from tdnnf_nas_b200 import synth
