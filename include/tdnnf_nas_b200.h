@@ -271,9 +271,8 @@ int tdnnf_ctx_operand_rowsq(tdnnf_ctx* ctx, const float* source, int rows, const
 /* The device half of one OnlineNaturalGradient step after H = X W^T, in two launches and one pass over H (rank <= 128):
  *   L (rank x rank, overwritten) = H^T H in fp32 FMAs (kaldi: L_t = H_t^T H_t), and
  *   out3 = { tr(X X^T), tr(Xhat Xhat^T), scale } as tdnnf_ng_scale.
- * tr(X X^T) comes from sumsq[n]: with rowsq != NULL (tdnnf_ctx_operand_rowsq) sumsq is first overwritten by the per-view
- * sums of rowsq (view i = rows row_offsets[i] + k*row_stride, k < rows); with rowsq == NULL it must already hold what
- * tdnnf_darts_view_sumsq computes. */
+ * tr(X X^T): with rowsq != NULL (tdnnf_ctx_operand_rowsq) from the per-view sums of rowsq (view i = rows row_offsets[i] +
+ * k*row_stride, k < rows; sumsq is not used); with rowsq == NULL from sumsq[n] as tdnnf_darts_view_sumsq computes it. */
 int tdnnf_ng_gram_scale(tdnnf_ctx* ctx, const float* H, int rows, int rank, int h_stride, float* L, int l_stride,
                         const float* WWt, int w_stride, const float* rowsq, double* sumsq, int in_rows, int n,
                         const int32_t* row_offsets, int row_stride, const float* weff, float ones_rows, float* out3);

@@ -113,8 +113,9 @@ __global__ void __launch_bounds__(256) ng_gram_kernel(const float* __restrict__ 
   constexpr int kRows = 32;
   constexpr int W = 16 * TB;
   __shared__ float tile[kRows][W + 1];
-  // optional second job: sumsq[i] += sum over the rows of view i of rowsq[row] (view i = rows offs[i] + k*row_stride,
-  // k < N): tr(X X^T) of the spliced operand from the per-row sums of squares the operand split left behind
+  // optional second job: this CTA's share of sum over the rows of view i of rowsq[row] (view i = rows offs[i] +
+  // k*row_stride, k < N) -> sumsq[blockIdx.x][i]: tr(X X^T) of the spliced operand from the per-row sums of squares
+  // the operand split left behind
   if (rowsq != nullptr) {
     double local[TDNNF_MAX_OFFSETS];
 #pragma unroll
@@ -130,20 +131,22 @@ __global__ void __launch_bounds__(256) ng_gram_kernel(const float* __restrict__ 
         }
       }
     }
-    __shared__ double view_sum[TDNNF_MAX_OFFSETS];
-    if (threadIdx.x < TDNNF_MAX_OFFSETS) view_sum[threadIdx.x] = 0.0;
-    __syncthreads();
+    // block reduction (warp shuffles, then 8 warps through shared memory); the per-CTA result goes to
+    // view_partials[blockIdx.x][i] -- same-address double atomics from every CTA serialise in L2
+    __shared__ double view_red[8][TDNNF_MAX_OFFSETS];
 #pragma unroll
     for (int i = 0; i < TDNNF_MAX_OFFSETS; ++i) {
-      if (i < n) {
-        double v = local[i];
+      double v = i < n ? local[i] : 0.0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&view_sum[i], v);
-      }
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0) view_red[threadIdx.x >> 5][i] = v;
     }
     __syncthreads();
-    if (threadIdx.x < n && view_sum[threadIdx.x] != 0.0) atomicAdd(&sumsq[threadIdx.x], view_sum[threadIdx.x]);
+    if (threadIdx.x < TDNNF_MAX_OFFSETS) {
+      double v = 0.0;
+      for (int w = 0; w < 8; ++w) v += view_red[w][threadIdx.x];
+      sumsq[(size_t)blockIdx.x * TDNNF_MAX_OFFSETS + threadIdx.x] = v;
+    }
   }
   const int ti = threadIdx.x / 16, tj = threadIdx.x % 16;
   float acc[TB][TB];
@@ -186,57 +189,85 @@ __global__ void __launch_bounds__(256) ng_gram_kernel(const float* __restrict__ 
 
 // L[i][j] = sum of the per-CTA partials; tr(L) and <L, W W^T> reduced across CTAs in double; the last CTA to finish
 // turns them into out[0..2] = {tr(X X^T), tr(X^ X^^T), scale} exactly as ng_scale_kernel, and re-arms the scratch.
-__global__ void __launch_bounds__(256) ng_gram_finish_kernel(const float* __restrict__ partials, int nblk, int r,
-                                                             float* __restrict__ L, long long l_ld,
-                                                             const float* __restrict__ WWt, long long w_ld,
-                                                             const double* __restrict__ sumsq, const float* __restrict__ weff,
-                                                             int n, float ones_rows, double* __restrict__ acc /* [2] */,
-                                                             unsigned int* __restrict__ counter, float* __restrict__ out) {
-  const int e = blockIdx.x * 256 + threadIdx.x;
-  double tr = 0.0, dot = 0.0;
+// 1024 threads = 128 consecutive elements x 8 slices of the partials: coalesced, and only nblk/8 loads per thread.
+__global__ void __launch_bounds__(1024) ng_gram_finish_kernel(const float* __restrict__ partials, int nblk, int r,
+                                                              float* __restrict__ L, long long l_ld,
+                                                              const float* __restrict__ WWt, long long w_ld,
+                                                              const double* __restrict__ sumsq,
+                                                              const double* __restrict__ view_partials /* [nblk][16] or null */,
+                                                              const float* __restrict__ weff, int n, float ones_rows,
+                                                              double* __restrict__ acc /* [2] */,
+                                                              unsigned int* __restrict__ counter, float* __restrict__ out) {
+  __shared__ float red[8][128];
+  __shared__ double red_tr[4], red_dot[4];
+  __shared__ double view_sum[TDNNF_MAX_OFFSETS];
+  __shared__ bool last;
+  const int col = threadIdx.x & 127, slice = threadIdx.x >> 7;
+  const int e = blockIdx.x * 128 + col;
+  float sum = 0.f;
   if (e < r * r) {
-    float sum = 0.f;
-    for (int b = 0; b < nblk; ++b) sum += partials[(size_t)b * r * r + e];
-    const int i = e / r, j = e % r;
-    L[i * l_ld + j] = sum;
-    if (i == j) tr = (double)sum;
-    dot = (double)sum * (double)WWt[i * w_ld + j];
+#pragma unroll 4
+    for (int b = slice; b < nblk; b += 8) sum += partials[(size_t)b * r * r + e];
   }
-  __shared__ double red_tr[8], red_dot[8];
+  red[slice][col] = sum;
+  __syncthreads();
+  if (slice == 0) {
+    double tr = 0.0, dot = 0.0;
+    if (e < r * r) {
+      float tot = 0.f;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    tr += __shfl_xor_sync(0xffffffffu, tr, o);
-    dot += __shfl_xor_sync(0xffffffffu, dot, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    red_tr[threadIdx.x >> 5] = tr;
-    red_dot[threadIdx.x >> 5] = dot;
+      for (int k = 0; k < 8; ++k) tot += red[k][col];
+      const int i = e / r, j = e % r;
+      L[i * l_ld + j] = tot;
+      if (i == j) tr = (double)tot;
+      dot = (double)tot * (double)WWt[i * w_ld + j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      tr += __shfl_xor_sync(0xffffffffu, tr, o);
+      dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      red_tr[threadIdx.x >> 5] = tr;
+      red_dot[threadIdx.x >> 5] = dot;
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) {
-      red_tr[0] += red_tr[w];
-      red_dot[0] += red_dot[w];
-    }
-    atomicAdd(&acc[0], red_tr[0]);
-    atomicAdd(&acc[1], red_dot[0]);
+    atomicAdd(&acc[0], red_tr[0] + red_tr[1] + red_tr[2] + red_tr[3]);
+    atomicAdd(&acc[1], red_dot[0] + red_dot[1] + red_dot[2] + red_dot[3]);
     __threadfence();
-    if (atomicAdd(counter, 1u) == gridDim.x - 1) {
-      __threadfence();
-      const double t = atomicAdd(&acc[0], 0.0), d = atomicAdd(&acc[1], 0.0);  // read through L2
-      double initial = (double)ones_rows;
-      for (int i = 0; i < n; ++i) {
-        const double w = weff ? (double)weff[i] : 1.0;
-        initial += w * w * sumsq[i];
-      }
-      const double fin = initial - 2.0 * t + d;
-      out[0] = (float)initial;
-      out[1] = (float)fin;
-      out[2] = (initial <= 0.0 || !(fin > 0.0)) ? 1.0f : (float)sqrt(initial / fin);
-      acc[0] = 0.0;
-      acc[1] = 0.0;
-      *counter = 0u;
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  // the last CTA: view sums (from the per-CTA partials if given), then the three scalars
+  if (threadIdx.x < TDNNF_MAX_OFFSETS) view_sum[threadIdx.x] = 0.0;
+  __syncthreads();
+  if (view_partials != nullptr) {
+    const int i = threadIdx.x & 15;
+    double v = 0.0;
+    for (int b = threadIdx.x >> 4; b < nblk; b += 64) v += view_partials[(size_t)b * TDNNF_MAX_OFFSETS + i];
+    if (i < n && v != 0.0) atomicAdd(&view_sum[i], v);
+  } else if (threadIdx.x < n) {
+    view_sum[threadIdx.x] = sumsq[threadIdx.x];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const double t = atomicAdd(&acc[0], 0.0), d = atomicAdd(&acc[1], 0.0);  // read through L2
+    double initial = (double)ones_rows;
+    for (int i = 0; i < n; ++i) {
+      const double w = weff ? (double)weff[i] : 1.0;
+      initial += w * w * view_sum[i];
     }
+    const double fin = initial - 2.0 * t + d;
+    out[0] = (float)initial;
+    out[1] = (float)fin;
+    out[2] = (initial <= 0.0 || !(fin > 0.0)) ? 1.0f : (float)sqrt(initial / fin);
+    acc[0] = 0.0;
+    acc[1] = 0.0;
+    *counter = 0u;
   }
 }
 
@@ -287,32 +318,34 @@ extern "C" int tdnnf_ng_gram_scale(tdnnf_ctx* ctx, const float* H, int rows, int
                                    int l_stride, const float* WWt, int w_stride, const float* rowsq, double* sumsq,
                                    int in_rows, int n, const int32_t* row_offsets, int row_stride, const float* weff,
                                    float ones_rows, float* out3) {
-  TDNNF_REQUIRE(ctx && H && L && WWt && sumsq && out3, "null argument");
+  TDNNF_REQUIRE(ctx && H && L && WWt && out3 && (rowsq || sumsq), "null argument");
   TDNNF_REQUIRE(rows > 0 && rank >= 1 && rank <= 128 && h_stride >= rank && l_stride >= rank && w_stride >= rank,
                 "bad argument (rank <= 128)");
   TDNNF_REQUIRE(n >= 1 && n <= TDNNF_MAX_OFFSETS, "bad number of views");
   TDNNF_REQUIRE(rowsq == nullptr || (row_offsets && row_stride >= 1 && in_rows > 0), "bad view description");
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
   const int blocks = std::max(1, std::min((rows + 63) / 64, ctx->num_sms));
-  const size_t need = (size_t)blocks * rank * rank * sizeof(float) + 64;
+  // scratch: [0,16) acc[2] doubles, [16,20) counter, [64, 64 + 128*blocks) per-CTA view sums, then the partial Gram matrices
+  const size_t view_bytes = (size_t)ctx->num_sms * TDNNF_MAX_OFFSETS * sizeof(double);
+  const size_t need = 64 + view_bytes + (size_t)blocks * rank * rank * sizeof(float);
   if (ctx->ng_scratch_bytes < need) {
     if (ctx->ng_scratch) TDNNF_CUDA_OK(cudaFree(ctx->ng_scratch));  // waits for kernels still using it
     ctx->ng_scratch = nullptr;
     ctx->ng_scratch_bytes = 0;
-    const size_t want = std::max(need, (size_t)ctx->num_sms * 128 * 128 * sizeof(float) + 64);
+    const size_t want = std::max(need, 64 + view_bytes + (size_t)ctx->num_sms * 128 * 128 * sizeof(float));
     TDNNF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ctx->ng_scratch), want));
     TDNNF_CUDA_OK(cudaMemsetAsync(ctx->ng_scratch, 0, 64, ctx->stream));  // {acc[2], counter}: self re-arming afterwards
     ctx->ng_scratch_bytes = want;
   }
   double* acc = reinterpret_cast<double*>(ctx->ng_scratch);
   unsigned int* counter = reinterpret_cast<unsigned int*>(ctx->ng_scratch + 16);
-  float* partials = reinterpret_cast<float*>(ctx->ng_scratch + 64);
+  double* view_partials = reinterpret_cast<double*>(ctx->ng_scratch + 64);
+  float* partials = reinterpret_cast<float*>(ctx->ng_scratch + 64 + view_bytes);
   TdnnfOffsets offs;
   for (int i = 0; i < TDNNF_MAX_OFFSETS; ++i) offs.v[i] = (rowsq && i < n) ? row_offsets[i] : 0;
-  if (rowsq) TDNNF_CUDA_OK(cudaMemsetAsync(sumsq, 0, sizeof(double) * n, ctx->stream));
   const int tb = (rank + 15) / 16;
   auto launch = [&](auto kern) {
-    kern<<<blocks, 256, 0, ctx->stream>>>(H, rows, rank, h_stride, partials, rowsq, in_rows, n, offs, row_stride, sumsq);
+    kern<<<blocks, 256, 0, ctx->stream>>>(H, rows, rank, h_stride, partials, rowsq, in_rows, n, offs, row_stride, view_partials);
   };
   switch (tb) {
     case 1: launch(ng_gram_kernel<1>); break;
@@ -326,8 +359,9 @@ extern "C" int tdnnf_ng_gram_scale(tdnnf_ctx* ctx, const float* H, int rows, int
   }
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
-  ng_gram_finish_kernel<<<(rank * rank + 255) / 256, 256, 0, ctx->stream>>>(partials, blocks, rank, L, l_stride, WWt, w_stride,
-                                                                           sumsq, weff, n, ones_rows, acc, counter, out3);
+  ng_gram_finish_kernel<<<(rank * rank + 127) / 128, 1024, 0, ctx->stream>>>(partials, blocks, rank, L, l_stride, WWt, w_stride, sumsq,
+                                                                            rowsq ? view_partials : nullptr, weff, n, ones_rows, acc,
+                                                                            counter, out3);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   return TDNNF_OK;

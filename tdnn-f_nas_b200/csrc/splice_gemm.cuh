@@ -213,7 +213,12 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
         const UnitCoord uc = decode_unit(u, p, meta);
-        int j = uc.it0 / p.kb_per_seg, kb = uc.it0 % p.kb_per_seg;
+        // Iteration order: K block outer, segment (time offset) inner.  Offset i of m-tile m and offset i-2 of m-tile
+        // m+1 read the SAME activation rows; with the segment outer they did so 2*kb_per_seg iterations apart, and
+        // with one unit per SM (no split-K) the ~225 MB streamed in between pushed them out of the 126 MB L2:
+        // ncu showed 774 MB of DRAM reads for a 144 MB operand.  Now the reuse distance is 2 iterations.
+        const int cnt = max(meta->cnt[uc.c], 1);
+        int kb = uc.it0 / cnt, j = uc.it0 % cnt;
         for (int it = uc.it0; it < uc.it1; ++it) {
           const int g = meta->list[uc.c][j];
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -225,7 +230,7 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           tma_load_4d(sb, &tmB, &full_bar[stage], kb * kBK + meta->seg_b_k[g], uc.n_t * BN + meta->seg_b_n[g],
                       meta->seg_b_c[g], 0);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
-          if (++kb == p.kb_per_seg) { kb = 0; ++j; }
+          if (++j == cnt) { j = 0; ++kb; }
         }
       }
     }
@@ -244,10 +249,11 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         ptx::mbar_wait(&tmem_empty[acc_buf], acc_phase ^ 1);
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc_buf * kAccCols;
-        int kb = uc.it0 % p.kb_per_seg;
+        const int cnt = max(meta->cnt[uc.c], 1);
+        int kb = uc.it0 / cnt, j = uc.it0 % cnt;  // same order as the producer: K block outer, segment inner
         for (int it = uc.it0; it < uc.it1; ++it) {
           const int ksteps = (kb == p.kb_per_seg - 1) ? p.kb_last_steps : kBK / 16;
-          if (++kb == p.kb_per_seg) kb = 0;
+          if (++j == cnt) { j = 0; ++kb; }
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after_sync();
           const uint32_t sa = ptx::smem_u32(tiles + stage * Cfg::kStageBytes);
