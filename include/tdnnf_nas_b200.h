@@ -123,6 +123,13 @@ int tdnnf_darts_propagate(tdnnf_ctx* ctx, const float* in, int in_rows, int in_d
                           int w_stride, const float* bias, int bias_mode, const float* weff, int n,
                           const int32_t* row_offsets, int row_stride);
 
+/* out (out_rows x rank) = [w_1 X_1 | ... | w_n X_n] W^T (+ bias[rank]) for a skinny W (rank x n*in_dim): the same
+ * result as tdnnf_darts_propagate(..., out_dim = rank), organised for small rank: one un-spliced GEMM over the input
+ * rows, then a gather-sum over the offsets.  Used for H = X W_t^T of OnlineNaturalGradient on the spliced input
+ * (the reference materialises that input: in_value_temp, nnet-tdnn-component.cc:476-514). */
+int tdnnf_darts_project(tdnnf_ctx* ctx, const float* in, int in_rows, int in_dim, int in_stride, float* out, int out_rows,
+                        int rank, int out_stride, const float* W, int w_stride, const float* bias, const float* weff, int n,
+                        const int32_t* row_offsets, int row_stride);
 /* Backprop to the input (ref: tdnn.cc:366-416; kBackpropAdds):
  *   in_deriv[row_offsets[i]+k*row_stride,:] += weff[i] * out_deriv[k,:] * W_i   for all i,k */
 int tdnnf_darts_backprop_data(tdnnf_ctx* ctx, const float* out_deriv, int out_rows, int out_dim,

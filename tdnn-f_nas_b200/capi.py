@@ -41,12 +41,14 @@ def _declare(lib):
     sig("tdnnf_ctx_gemm_timing_read_ex", [vp, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                           C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_uint64)])
     sig("tdnnf_ctx_set_gradient_mode", [vp, i])
+    sig("tdnnf_ctx_set_gemm_planes", [vp, i])
     sig("tdnnf_ctx_operand_cache_begin", [vp, C.POINTER(C.c_void_p), i])
     sig("tdnnf_ctx_operand_cache_end", [vp])
     sig("tdnnf_ctx_operand_cache_stats", [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)])
     sig("tdnnf_darts_coef", [vp, vp, i, i, f, c_float_p, f, i, vp, vp])
     sig("tdnnf_darts_weff_from_coef", [vp, vp, i, i, i, vp])
     sig("tdnnf_darts_propagate", [vp, vp, i, i, i, vp, i, i, i, vp, i, vp, i, vp, i, c_int_p, i])
+    sig("tdnnf_darts_project", [vp, vp, i, i, i, vp, i, i, i, vp, i, vp, vp, i, c_int_p, i])
     sig("tdnnf_darts_backprop_data", [vp, vp, i, i, i, vp, i, i, i, vp, i, vp, i, c_int_p, i])
     sig("tdnnf_darts_backprop_params", [vp, vp, i, i, i, vp, i, i, i, vp, i, vp, i, vp, vp, i, c_int_p, i, f, vp])
     sig("tdnnf_darts_alpha_update", [vp, vp, vp, i, i, f, i, f, vp])
@@ -176,6 +178,10 @@ class Context:
         return dict(ms=ms.value, flops=fl.value, pipe_flops=raw.value, launches=int(n.value), other_ms=oms.value,
                     other_launches=int(on.value))
 
+    def set_gemm_planes(self, planes: int):
+        """2 = bf16 hi/lo operand planes (three products), 3 = hi/mid/lo (six products, fp32-level)."""
+        check(load().tdnnf_ctx_set_gemm_planes(self.h, int(planes)))
+
     def set_gradient_mode(self, fast: bool):
         """fast: data gradient with two tensor-core products, parameter gradient with one (see the header)."""
         check(load().tdnnf_ctx_set_gradient_mode(self.h, int(fast)))
@@ -213,6 +219,16 @@ class Context:
         assert wr == oc and wc == n * xc
         check(load().tdnnf_darts_propagate(self.h, xp, xr, xc, xs, op, orr, oc, os_, wp, ws, _ptr(bias), bias_mode,
                                            _ptr(weff), n, _ihost(row_offsets), row_stride))
+
+    def darts_project(self, x, out, W, bias, weff, row_offsets, row_stride):
+        """out = [w_1 X_1 | ... | w_n X_n] W[:, :n*in_dim]^T (+ bias): skinny-W form of darts_propagate."""
+        xp, xr, xc, xs = _mat(x)
+        op, orr, oc, os_ = _mat(out)
+        wp, wr, wc, ws = _mat(W)
+        n = len(row_offsets)
+        assert wr == oc and wc >= n * xc
+        check(load().tdnnf_darts_project(self.h, xp, xr, xc, xs, op, orr, oc, os_, wp, ws, _ptr(bias), _ptr(weff), n,
+                                         _ihost(row_offsets), row_stride))
 
     def darts_backprop_data(self, out_deriv, in_deriv, W, weff, row_offsets, row_stride):
         dp, dr, dc, ds = _mat(out_deriv)

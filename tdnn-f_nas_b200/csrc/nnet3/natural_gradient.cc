@@ -387,9 +387,14 @@ void OnlineNaturalGradient::Step(const NgOperand& X, bool updating) {
   FullPrecisionGemms full(updating);
   // H_t = X_t W_t^T
   EnsureSize(&H_, N, R);
-  CheckStatus(tdnnf_darts_propagate(ctx, X.data, X.rows, X.cols, X.stride, H_.Data(), N, R, H_.Stride(), W_t_.Data(),
-                                    W_t_.Stride(), X.ones_col ? w_last_.Data() : NULL, X.ones_col ? 2 : 1, weff, X.n,
-                                    X.row_offsets, X.row_stride));
+  if (X.n > 1) {  // spliced operand, skinny W: one un-spliced GEMM + gather-sum over the offsets
+    CheckStatus(tdnnf_darts_project(ctx, X.data, X.rows, X.cols, X.stride, H_.Data(), N, R, H_.Stride(), W_t_.Data(),
+                                    W_t_.Stride(), X.ones_col ? w_last_.Data() : NULL, weff, X.n, X.row_offsets, X.row_stride));
+  } else {
+    CheckStatus(tdnnf_darts_propagate(ctx, X.data, X.rows, X.cols, X.stride, H_.Data(), N, R, H_.Stride(), W_t_.Data(),
+                                      W_t_.Stride(), X.ones_col ? w_last_.Data() : NULL, X.ones_col ? 2 : 1, weff, X.n,
+                                      X.row_offsets, X.row_stride));
+  }
   // L_t = H_t^T H_t and tr(X X^T).  Inside Backprop's operand-cache scope the per-row sums of squares of X came with
   // the operand split of the H product above, and one launch does both (fp32 FMAs, one pass over H); otherwise the
   // trace takes one pass over X, and ranks beyond 128 go through the tensor-core GEMM.

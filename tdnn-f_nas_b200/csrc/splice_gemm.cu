@@ -226,6 +226,21 @@ __global__ void init_rows_kernel(float* __restrict__ out, int rows, int cols, lo
   }
 }
 
+// out[q, j] = bias[j] + sum_i Y[(offs[i] + q*row_stride), i*rank + j]     (tdnnf_darts_project, second stage)
+__global__ void project_gather_kernel(const float* __restrict__ Y, long long y_ld, int out_rows, int rank, int n,
+                                      GroupRowOffsets offs, int row_stride, const float* __restrict__ bias,
+                                      float* __restrict__ out, long long out_ld) {
+  const long long total = (long long)out_rows * rank;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % rank);
+    const long long q = idx / rank;
+    float acc = bias ? bias[j] : 0.f;
+    for (int i = 0; i < n; ++i) acc += Y[(offs.v[i] + q * row_stride) * y_ld + i * rank + j];
+    out[q * out_ld + j] = acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 struct Planes {
   __nv_bfloat16* base = nullptr;  // hi plane; lo plane follows at base + plane_elems
@@ -488,7 +503,7 @@ static int pick_bn(int n, int np = 2) {
   if (np == 3) {  // six products: keep two smem stages (BN <= 160)
     if (n <= 32) return 32;
     if (n <= 64) return 64;
-    if (n % 160 == 0) return 160;
+    if (n % 160 == 0 || (n > 128 && n <= 160)) return 160;
     return 128;
   }
   static const int wide = [] {  // experiment knob: TDNNF_BN_WIDE=128|256 for outputs that are multiples of 256
@@ -607,6 +622,81 @@ extern "C" int tdnnf_darts_propagate(tdnnf_ctx* ctx, const float* in, int in_row
   }
   // all n offsets counted: in uniform-sample mode the skipped offsets make this an upper bound
   return launch_gemm(ctx, bn, A, B, p, 2.0 * out_rows * (double)out_dim * in_dim * n);
+}
+
+// out = [w_1 X_1 | ... | w_n X_n | 1] W^T for a SKINNY W (rank rows): the H = X W_t^T product of OnlineNaturalGradient
+// on the spliced input.  tdnnf_darts_propagate would stream the activation planes once per offset (n x the operand
+// through L2 into a 32-column tile: bandwidth-bound); here ONE un-spliced GEMM Y = X [W_1^T | ... | W_n^T]
+// (in_rows x n*rank, every activation tile fetched once) is followed by a gather-sum over the offsets.
+extern "C" int tdnnf_darts_project(tdnnf_ctx* ctx, const float* in, int in_rows, int in_dim, int in_stride, float* out,
+                                   int out_rows, int rank, int out_stride, const float* W, int w_stride, const float* bias,
+                                   const float* weff, int n, const int32_t* row_offsets, int row_stride) {
+  TDNNF_REQUIRE(ctx && in && out && W && weff && row_offsets, "null argument");
+  TDNNF_REQUIRE(in_rows > 0 && in_dim > 0 && out_rows > 0 && rank > 0, "empty matrix");
+  TDNNF_REQUIRE(in_stride >= in_dim && out_stride >= rank && w_stride >= n * in_dim, "stride < cols");
+  int rc = check_offsets(n, row_offsets, row_stride, out_rows, in_rows);
+  if (rc) return rc;
+  const int ncols = n * rank;
+  if (ncols > 256)  // wider than one N tile: the spliced GEMM reads the operand as often
+    return tdnnf_darts_propagate(ctx, in, in_rows, in_dim, in_stride, out, out_rows, rank, out_stride, W, w_stride, bias,
+                                 bias ? 2 : 1, weff, n, row_offsets, row_stride);
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+  const int r = row_stride;
+  const int Q = ceil_div(in_rows, r);
+  const int Kpad = round_up(in_dim, kBK);
+  const size_t y_bytes = ((size_t)in_rows * ncols * sizeof(float) + 1023) & ~size_t(1023);
+  const size_t need = planes_bytes(ctx->gemm_planes, r, Q, Kpad) + planes_bytes(ctx->gemm_planes, n, rank, Kpad);
+  ctx->ws_reset();
+  rc = ctx->ws_reserve(need + y_bytes);
+  if (rc) return rc;
+  rc = ctx->cws_reserve(need);
+  if (rc) return rc;
+  Planes A, B;
+  rc = launch_split_rows(ctx, in, in_rows, in_dim, in_stride, r, r, 1, 0, nullptr, Q, Kpad, &A);
+  if (rc) return rc;
+  rc = launch_split_rows(ctx, W, rank, in_dim, w_stride, 1, n, 0, in_dim, weff, rank, Kpad, &B);
+  if (rc) return rc;
+  B.rows = ncols;  // [offset][rank rows][K] is contiguous: one group of n*rank rows
+  B.groups = 1;
+  float* Y = static_cast<float*>(ctx->ws_alloc(y_bytes));
+  if (!Y) return TDNNF_ERR_NOMEM;
+
+  const int bn = pick_bn(ncols, ctx->gemm_planes);
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.m_tiles = ceil_div(Q, kBM);
+  p.n_tiles = ceil_div(ncols, bn);
+  p.c_tiles = r;
+  p.kb_per_seg = Kpad / kBK;
+  p.kb_last_steps = ceil_div(in_dim - (p.kb_per_seg - 1) * kBK, 16);
+  p.nseg = r;
+  for (int c = 0; c < r; ++c) {
+    p.seg_a_c[c] = c;
+    p.seg_cmatch[c] = c;
+    p.m_valid[c] = (in_rows - c + r - 1) / r;
+  }
+  p.n_valid = ncols;
+  p.splits = choose_splits(p.m_tiles * p.n_tiles * r, p.kb_per_seg, ctx->num_sms);
+  p.out = Y;
+  p.out_ld = ncols;
+  p.row_mul = r;
+  p.row_cadd = 1;
+  p.alpha = 1.0f;
+  if (p.splits > 1) {
+    TDNNF_CUDA_OK(cudaMemsetAsync(Y, 0, (size_t)in_rows * ncols * sizeof(float), ctx->stream));
+    p.accumulate = 1;
+    p.atomic = 1;
+  }
+  rc = launch_gemm(ctx, bn, A, B, p, 2.0 * in_rows * (double)ncols * in_dim);
+  if (rc) return rc;
+  GroupRowOffsets offs;
+  for (int i = 0; i < kMaxSeg; ++i) offs.v[i] = i < n ? row_offsets[i] : 0;
+  const long long total = (long long)out_rows * rank;
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 16));
+  project_gather_kernel<<<blocks, 256, 0, ctx->stream>>>(Y, ncols, out_rows, rank, n, offs, r, bias, out, out_stride);
+  ctx->launches++;
+  TDNNF_CUDA_OK(cudaGetLastError());
+  return TDNNF_OK;
 }
 
 extern "C" int tdnnf_darts_backprop_data(tdnnf_ctx* ctx, const float* out_deriv, int out_rows, int out_dim,

@@ -179,6 +179,40 @@ def test_fast_gradients_dynamic_range(ctx, x_scale, od_scale):
     assert rel_err(dbias.cpu().numpy(), od.astype(np.float64).sum(0)) < 1e-5
 
 
+@pytest.mark.parametrize("n,in_dim,rank,S,t_out,offsets,row_stride,planes", [
+    (7, 1536, 20, 8, 24, list(range(-6, 1)), 1, 2), (7, 160, 20, 8, 24, list(range(0, 7)), 1, 3),
+    (7, 96, 12, 5, 17, list(range(0, 7)), 3, 2), (3, 52, 80, 3, 19, [0, 1, 4], 1, 2), (3, 52, 80, 3, 19, [0, 1, 4], 1, 3),
+    (7, 64, 40, 4, 20, list(range(0, 7)), 1, 2)])
+def test_project_matches_spliced_product(ctx, n, in_dim, rank, S, t_out, offsets, row_stride, planes):
+    """tdnnf_darts_project (one un-spliced GEMM + gather over the offsets; the natural-gradient H = X W^T) against
+    float64 numpy on the materialised spliced input [w_1 X_1 | ... | w_n X_n | 1]; the last case (n*rank = 280 > 256)
+    takes the fall-back through tdnnf_darts_propagate."""
+    import torch
+
+    d = _setup(n, in_dim, rank, S, t_out, offsets, row_stride, seed=n * in_dim + rank)
+    g = d["rng"]
+    W = (g.standard_normal((rank, n * in_dim + 1)) * 0.1).astype(np.float32)
+    weff = g.uniform(0.1, 1.0, n).astype(np.float32)
+    x64 = d["x"].astype(np.float64)
+    ref = np.tile(W[:, -1].astype(np.float64), (d["out_rows"], 1))
+    for i in range(n):
+        rows = d["row_offsets"][i] + row_stride * np.arange(d["out_rows"])
+        ref += weff[i] * (x64[rows] @ W[:, i * in_dim:(i + 1) * in_dim].astype(np.float64).T)
+    out = torch.full((d["out_rows"], rank), 3.0, device="cuda")
+    ctx.reserve(64 << 20)
+    junk = torch.full((16 << 20,), float("nan"), device="cuda")  # whatever the scratch arena hands out must not leak into Y
+    del junk
+    ctx.set_gemm_planes(planes)
+    try:
+        ctx.darts_project(to_cuda_view(d["x"]), out, torch.from_numpy(W).cuda(), torch.from_numpy(W[:, -1].copy()).cuda(),
+                          torch.from_numpy(weff).cuda(), d["row_offsets"], row_stride)
+    finally:
+        ctx.set_gemm_planes(2)
+    torch.cuda.synchronize()
+    e = rel_err(out.cpu().numpy(), ref)
+    assert e < (6e-6 if planes == 3 else 2e-5), e  # 3 planes: fp32 accumulation over K is what is left
+
+
 def test_propagate_adds_mode(ctx):
     """bias_mode 0 (kPropagateAdds, conv.h:130-134): out is accumulated into."""
     import torch
