@@ -362,11 +362,6 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (!p.transposed) {
             float* dst = p.out + R * p.out_ld + C0;
             if (full && vec_ok) {
-              float4 prev[4];
-              if (!p.atomic && p.accumulate) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) prev[j] = *reinterpret_cast<const float4*>(dst + 4 * j);
-              }
 #pragma unroll
               for (int j = 0; j < 16; j += 4) {
                 float4 o;
@@ -378,22 +373,17 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                   const float* bj = p.bias + n0 + j;
                   o.x += __ldg(bj); o.y += __ldg(bj + 1); o.z += __ldg(bj + 2); o.w += __ldg(bj + 3);
                 }
-                if (p.atomic) {
-                  red_add_v4_f32(dst + j, o.x, o.y, o.z, o.w);
-                } else {
-                  if (p.accumulate) {
-                    o.x += prev[j >> 2].x; o.y += prev[j >> 2].y; o.z += prev[j >> 2].z; o.w += prev[j >> 2].w;
-                  }
-                  *reinterpret_cast<float4*>(dst + j) = o;
-                }
+                // accumulation is always a fire-and-forget red.add (L2 does the read-modify-write): loading the old
+                // value first puts an L2 round trip per 16 columns on the epilogue's critical path
+                if (p.atomic || p.accumulate) red_add_v4_f32(dst + j, o.x, o.y, o.z, o.w);
+                else *reinterpret_cast<float4*>(dst + j) = o;
               }
             } else {
               for (int j = 0; j < 16; ++j) {
                 if (n0 + j >= p.n_valid) break;
                 float o = scale * __uint_as_float(v[j]);
                 if (add_bias) o += p.bias[n0 + j];
-                if (p.atomic) red_add_f32(dst + j, o);
-                else if (p.accumulate) dst[j] += o;
+                if (p.atomic || p.accumulate) red_add_f32(dst + j, o);
                 else dst[j] = o;
               }
             }
