@@ -254,6 +254,9 @@ int tdnnf_batchnorm_train_fwd(tdnnf_ctx* ctx, const float* in, int rows, int col
 int tdnnf_batchnorm_train_bwd(tdnnf_ctx* ctx, const float* out_value, int ov_stride, const float* out_deriv,
                               int od_stride, float* in_deriv, int id_stride, int rows, int cols, float target_rms,
                               const float* memo);
+/* BatchNormComponent::StoreStats (ref: norm.cc:551-589): stats[0:cols] += num_frames * mean, stats[cols:2cols] +=
+ * num_frames * uvar (device doubles, as the reference's CuVector<double>), mean / uvar = rows 0 / 1 of memo. */
+int tdnnf_batchnorm_accumulate_stats(tdnnf_ctx* ctx, const float* memo, int cols, float num_frames, double* stats);
 
 /* ------------------------------------------------------------------ natural gradient --- */
 /* Device-side pieces of OnlineNaturalGradient::PreconditionDirections (kaldi: nnet3/natural-gradient-online.cc;

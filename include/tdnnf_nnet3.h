@@ -70,6 +70,12 @@ int tdnnf_nnet3_backprop(const void* comp, const void* indexes, const float* in_
                          int in_stride, const float* out_value, int ov_stride, const float* out_deriv, int out_rows,
                          int out_cols, int od_stride, void* memo, void* to_update, float* in_deriv, int id_stride);
 int tdnnf_nnet3_delete_memo(const void* comp, void* memo);
+/* Component::StoreStats / ZeroStats (components with kStoresStats: BatchNormComponent in training mode, ref
+ * nnet-normalize-component.cc:551-589, 668-678); in_value may be NULL.  tdnnf_nnet3_bn_count: its frame count. */
+int tdnnf_nnet3_store_stats(void* comp, const float* in_value, int in_rows, int in_cols, int in_stride, const float* out_value,
+                            int out_rows, int out_cols, int ov_stride, void* memo);
+int tdnnf_nnet3_zero_stats(void* comp);
+int tdnnf_nnet3_bn_count(const void* comp, double* count);
 
 /* UpdatableComponent surface (ref: tdnn.cc:907-979, simple.cc:9606-9681, itf.cc:313-431). */
 int tdnnf_nnet3_scale(void* comp, float scale);

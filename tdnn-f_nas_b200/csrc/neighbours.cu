@@ -165,10 +165,11 @@ __global__ void bn_finalize_fwd_kernel(float* memo, int cols, int rows, float ep
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
   const float mean = memo[3 * cols + c] / rows;
-  float var = memo[4 * cols + c] / rows - mean * mean;
+  const float uvar = memo[4 * cols + c] / rows;  // row 1 = the UNCENTRED second moment, as the reference's memo
+  float var = uvar - mean * mean;                //   (uvar.AddDiagMat2, norm.cc:432): StoreStats accumulates it
   var = fmaxf(var, 0.f);
   memo[c] = mean;
-  memo[cols + c] = var;
+  memo[cols + c] = uvar;
   memo[2 * cols + c] = target_rms * powf(var + eps, -0.5f);
 }
 __global__ void bn_apply_fwd_kernel(const float* __restrict__ in, long long is, float* __restrict__ out, long long os,
@@ -378,6 +379,23 @@ extern "C" int tdnnf_batchnorm_train_bwd(tdnnf_ctx* ctx, const float* out_value,
   LAUNCH_CHECK(ctx);
   bn_apply_bwd_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
       out_value, ov_stride, out_deriv, od_stride, in_deriv, id_stride, rows, cols, target_rms, memo, sums);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+
+// stats[i] += num_frames * mean[i], stats[cols + i] += num_frames * uvar[i]   (BatchNormComponent::StoreStats, norm.cc:583-588)
+__global__ void bn_accumulate_stats_kernel(const float* __restrict__ memo, int cols, float num_frames, double* __restrict__ stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cols) {
+    stats[i] += (double)num_frames * (double)memo[i];
+    stats[cols + i] += (double)num_frames * (double)memo[cols + i];
+  }
+}
+
+extern "C" int tdnnf_batchnorm_accumulate_stats(tdnnf_ctx* ctx, const float* memo, int cols, float num_frames, double* stats) {
+  const int rows = 1;
+  PROLOGUE(memo && stats && cols > 0, "bad argument");
+  bn_accumulate_stats_kernel<<<(cols + 255) / 256, 256, 0, ctx->stream>>>(memo, cols, num_frames, stats);
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }

@@ -1,5 +1,7 @@
 // Method bodies of the NAS components (see components.h).  Each body follows the reference method
 // it replaces (cited), with the CuMatrix calls swapped for the C-ABI kernels.
+#include <cuda_runtime.h>
+
 #include "components.h"
 
 #include <cmath>
@@ -1113,7 +1115,7 @@ void BatchNormTestComponent::Backprop(const std::string&, const ComponentPrecomp
                                       scale_.Data(), NULL));
 }
 void BatchNormTestComponent::Read(std::istream& is, bool binary) {  // norm.cc:931-954
-  ExpectOneOrTwoTokens(is, binary, "<BatchNormTestComponent>", "<Dim>");
+  ExpectOneOrTwoTokens(is, binary, std::string("<") + Token() + ">", "<Dim>");
   ReadBasicType(is, binary, &dim_);
   ExpectToken(is, binary, "<BlockDim>");
   ReadBasicType(is, binary, &block_dim_);
@@ -1138,13 +1140,13 @@ void BatchNormTestComponent::Read(std::istream& is, bool binary) {  // norm.cc:9
     stats_sum_[i] *= count_;
     stats_sumsq_[i] *= count_;
   }
-  ExpectToken(is, binary, "</BatchNormTestComponent>");
+  ExpectToken(is, binary, std::string("</") + Token() + ">");
   ComputeDerived();
   Check();
 }
 void BatchNormTestComponent::Write(std::ostream& os, bool binary) const {  // norm.cc:956-982
   Check();
-  WriteToken(os, binary, "<BatchNormTestComponent>");
+  WriteToken(os, binary, std::string("<") + Token() + ">");
   WriteToken(os, binary, "<Dim>");
   WriteBasicType(os, binary, dim_);
   WriteToken(os, binary, "<BlockDim>");
@@ -1171,7 +1173,7 @@ void BatchNormTestComponent::Write(std::ostream& os, bool binary) const {  // no
   mean.Write(os, binary);
   WriteToken(os, binary, "<StatsVar>");
   var.Write(os, binary);
-  WriteToken(os, binary, "</BatchNormTestComponent>");
+  WriteToken(os, binary, std::string("</") + Token() + ">");
 }
 void BatchNormTestComponent::Scale(BaseFloat scale) {  // norm.cc:984-994
   if (scale == 0) {
@@ -1195,6 +1197,211 @@ void BatchNormTestComponent::Add(BaseFloat alpha, const Component& other_in) {  
   ComputeDerived();
 }
 
+
+// =====================================================================================
+// BatchNormComponent (training mode; norm.cc:209-680)
+// =====================================================================================
+BatchNormComponent::BatchNormComponent() : d_stats_(NULL), pending_count_(0.0) {}
+
+BatchNormComponent::BatchNormComponent(const BatchNormComponent& other)  // norm.cc:259-266
+    : BatchNormTestComponent(), d_stats_(NULL), pending_count_(0.0) {
+  other.FlushStats();
+  dim_ = other.dim_;
+  block_dim_ = other.block_dim_;
+  epsilon_ = other.epsilon_;
+  target_rms_ = other.target_rms_;
+  test_mode_ = other.test_mode_;
+  count_ = other.count_;
+  stats_sum_ = other.stats_sum_;
+  stats_sumsq_ = other.stats_sumsq_;
+  ComputeDerivedBn();
+  Check();
+}
+
+BatchNormComponent::~BatchNormComponent() {
+  if (d_stats_) cudaFree(d_stats_);
+}
+
+void BatchNormComponent::ComputeDerivedBn() {  // norm.cc:209-247
+  if (!test_mode_) {
+    offset_.Resize(0);
+    scale_.Resize(0);
+    return;
+  }
+  ComputeDerived();
+}
+
+void BatchNormComponent::FlushStats() const {
+  if (pending_count_ == 0.0 || d_stats_ == NULL) return;
+  BatchNormComponent* self = const_cast<BatchNormComponent*>(this);
+  std::vector<double> host(2 * (size_t)block_dim_);
+  void* st = NULL;
+  CheckStatus(tdnnf_ctx_get_stream(CurrentContext(), &st));
+  if (cudaMemcpyAsync(host.data(), d_stats_, sizeof(double) * host.size(), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(st)) != cudaSuccess ||
+      cudaMemsetAsync(d_stats_, 0, sizeof(double) * host.size(), static_cast<cudaStream_t>(st)) != cudaSuccess ||
+      cudaStreamSynchronize(static_cast<cudaStream_t>(st)) != cudaSuccess)
+    KALDI_ERR << "BatchNormComponent: reading the accumulated statistics failed";
+  if ((int32)self->stats_sum_.size() != block_dim_) {
+    self->stats_sum_.assign(block_dim_, 0.0);
+    self->stats_sumsq_.assign(block_dim_, 0.0);
+  }
+  for (int32 i = 0; i < block_dim_; ++i) {
+    self->stats_sum_[i] += host[i];
+    self->stats_sumsq_[i] += host[block_dim_ + i];
+  }
+  self->count_ += pending_count_;
+  pending_count_ = 0.0;
+}
+
+double BatchNormComponent::Count() const {
+  FlushStats();
+  return count_;
+}
+
+std::string BatchNormComponent::Info() const {
+  FlushStats();
+  return BatchNormTestComponent::Info();
+}
+
+void BatchNormComponent::InitFromConfig(ConfigLine* cfl) {  // norm.cc:289-317
+  dim_ = -1;
+  block_dim_ = -1;
+  epsilon_ = 1.0e-03;
+  target_rms_ = 1.0;
+  test_mode_ = false;
+  bool ok = cfl->GetValue("dim", &dim_);
+  cfl->GetValue("block-dim", &block_dim_);
+  cfl->GetValue("epsilon", &epsilon_);
+  cfl->GetValue("target-rms", &target_rms_);
+  cfl->GetValue("test-mode", &test_mode_);
+  if (!ok || dim_ <= 0) KALDI_ERR << "BatchNormComponent must have 'dim' specified, and > 0";
+  if (block_dim_ == -1) block_dim_ = dim_;
+  if (!(block_dim_ > 0 && dim_ % block_dim_ == 0 && epsilon_ > 0 && target_rms_ > 0))
+    KALDI_ERR << "Invalid configuration in BatchNormComponent.";
+  if (cfl->HasUnusedValues()) KALDI_ERR << "Could not process these elements in initializer: " << cfl->UnusedValues();
+  count_ = 0;
+  pending_count_ = 0.0;
+  stats_sum_.assign(block_dim_, 0.0);
+  stats_sumsq_.assign(block_dim_, 0.0);
+  if (test_mode_) ComputeDerivedBn();
+}
+
+void BatchNormComponent::SetTestMode(bool test_mode) {  // norm.cc:249-252
+  FlushStats();
+  test_mode_ = test_mode;
+  ComputeDerivedBn();
+}
+
+void* BatchNormComponent::Propagate(const ComponentPrecomputedIndexes* indexes, const CuMatrixBase<BaseFloat>& in,
+                                    CuMatrixBase<BaseFloat>* out) const {  // norm.cc:401-465
+  if (test_mode_) return BatchNormTestComponent::Propagate(indexes, in, out);
+  KALDI_ASSERT(SameDim(in, *out) && (in.NumCols() == dim_ || in.NumCols() == block_dim_));
+  int32 rows = in.NumRows(), cols = in.NumCols(), in_stride = in.Stride(), out_stride = out->Stride();
+  if (in.NumCols() != block_dim_) {  // the reference recurses on a reshaped view
+    KALDI_ASSERT(in.Stride() == in.NumCols() && out->Stride() == out->NumCols());
+    const int32 ratio = dim_ / block_dim_;
+    rows *= ratio;
+    cols /= ratio;
+    in_stride = out_stride = cols;
+  }
+  Memo* memo = new Memo;
+  memo->num_frames = rows;
+  memo->mean_uvar_scale.Resize(5 * cols);
+  // mean, uvar, scale = (max(uvar - mean^2, 0) + eps)^-0.5 * target_rms, out = (in - mean) .* scale: one call
+  CheckStatus(tdnnf_batchnorm_train_fwd(CurrentContext(), in.Data(), rows, cols, in_stride, out->Data(), out_stride, epsilon_,
+                                        target_rms_, memo->mean_uvar_scale.Data()));
+  return memo;
+}
+
+void BatchNormComponent::Backprop(const std::string& debug_info, const ComponentPrecomputedIndexes* indexes,
+                                  const CuMatrixBase<BaseFloat>& in_value, const CuMatrixBase<BaseFloat>& out_value,
+                                  const CuMatrixBase<BaseFloat>& out_deriv, void* memo_in, Component* to_update,
+                                  CuMatrixBase<BaseFloat>* in_deriv) const {  // norm.cc:467-549
+  if (test_mode_) {
+    BatchNormTestComponent::Backprop(debug_info, indexes, in_value, out_value, out_deriv, memo_in, to_update, in_deriv);
+    return;
+  }
+  KALDI_ASSERT(in_deriv != NULL);
+  KALDI_ASSERT(SameDim(out_value, out_deriv) && SameDim(out_value, *in_deriv) &&
+               (out_value.NumCols() == dim_ || out_value.NumCols() == block_dim_));
+  int32 rows = out_value.NumRows(), cols = out_value.NumCols(), ov_stride = out_value.Stride(),
+        od_stride = out_deriv.Stride(), id_stride = in_deriv->Stride();
+  if (out_value.NumCols() != block_dim_) {
+    KALDI_ASSERT(out_value.Stride() == out_value.NumCols() && out_deriv.Stride() == out_deriv.NumCols() &&
+                 in_deriv->Stride() == in_deriv->NumCols());
+    const int32 ratio = dim_ / block_dim_;
+    rows *= ratio;
+    cols /= ratio;
+    ov_stride = od_stride = id_stride = cols;
+  }
+  Memo* memo = static_cast<Memo*>(memo_in);
+  KALDI_ASSERT(memo != NULL && "memo not passed into backprop");
+  KALDI_ASSERT(rows == memo->num_frames);
+  CheckStatus(tdnnf_batchnorm_train_bwd(CurrentContext(), out_value.Data(), ov_stride, out_deriv.Data(), od_stride,
+                                        in_deriv->Data(), id_stride, rows, cols, target_rms_, memo->mean_uvar_scale.Data()));
+}
+
+void BatchNormComponent::StoreStats(const CuMatrixBase<BaseFloat>&, const CuMatrixBase<BaseFloat>& out_value,
+                                    void* memo_in) {  // norm.cc:551-589
+  KALDI_ASSERT(!test_mode_);
+  KALDI_ASSERT(out_value.NumCols() == dim_ || out_value.NumCols() == block_dim_);
+  int32 rows = out_value.NumRows();
+  if (out_value.NumCols() != block_dim_) rows *= dim_ / block_dim_;
+  Memo* memo = static_cast<Memo*>(memo_in);
+  KALDI_ASSERT(memo != NULL && rows == memo->num_frames && memo->num_frames > 0);
+  if (d_stats_ == NULL) {
+    if (cudaMalloc(reinterpret_cast<void**>(&d_stats_), sizeof(double) * 2 * block_dim_) != cudaSuccess ||
+        cudaMemset(d_stats_, 0, sizeof(double) * 2 * block_dim_) != cudaSuccess)
+      KALDI_ERR << "BatchNormComponent: cudaMalloc of the statistics failed";
+  }
+  // stats_sum_ += num_frames * mean, stats_sumsq_ += num_frames * uvar, count_ += num_frames -- on the device
+  CheckStatus(tdnnf_batchnorm_accumulate_stats(CurrentContext(), memo->mean_uvar_scale.Data(), block_dim_,
+                                               (float)memo->num_frames, d_stats_));
+  pending_count_ += memo->num_frames;
+}
+
+void BatchNormComponent::ZeroStats() {  // norm.cc:668-678: not in test mode (the stats are the transform there)
+  if (!test_mode_) {
+    FlushStats();
+    count_ = 0.0;
+    std::fill(stats_sum_.begin(), stats_sum_.end(), 0.0);
+    std::fill(stats_sumsq_.begin(), stats_sumsq_.end(), 0.0);
+  }
+}
+
+void BatchNormComponent::Read(std::istream& is, bool binary) {  // norm.cc:591-614
+  pending_count_ = 0.0;
+  BatchNormTestComponent::Read(is, binary);  // same fields; ends with the test component's ComputeDerived
+  ComputeDerivedBn();
+}
+
+void BatchNormComponent::Write(std::ostream& os, bool binary) const {  // norm.cc:616-642
+  FlushStats();
+  BatchNormTestComponent::Write(os, binary);
+}
+
+void BatchNormComponent::Scale(BaseFloat scale) {  // norm.cc:644-654
+  FlushStats();
+  BatchNormTestComponent::Scale(scale);
+}
+
+void BatchNormComponent::Add(BaseFloat alpha, const Component& other_in) {  // norm.cc:657-666
+  const BatchNormComponent* other = dynamic_cast<const BatchNormComponent*>(&other_in);
+  KALDI_ASSERT(other != NULL);
+  FlushStats();
+  other->FlushStats();
+  count_ += alpha * other->count_;
+  if (stats_sum_.size() != other->stats_sum_.size()) {
+    stats_sum_.assign(other->stats_sum_.size(), 0.0);
+    stats_sumsq_.assign(other->stats_sumsq_.size(), 0.0);
+  }
+  for (size_t i = 0; i < stats_sum_.size(); ++i) {
+    stats_sum_[i] += alpha * other->stats_sum_[i];
+    stats_sumsq_[i] += alpha * other->stats_sumsq_[i];
+  }
+  ComputeDerivedBn();
+}
+
 // =====================================================================================
 // factories (itf.cc:56-293: the registrations the README adds) and edit directives
 // =====================================================================================
@@ -1203,6 +1410,7 @@ Component* Component::NewComponentOfType(const std::string& component_type) {
   if (component_type == "TdnnDARTSV3Component") ans = new TdnnDARTSV3Component();                    // itf.cc:88-89
   else if (component_type == "CopyNComponent") ans = new CopyNComponent();                           // itf.cc:202-203
   else if (component_type == "BatchNormTestComponent") ans = new BatchNormTestComponent();           // itf.cc:226-227
+  else if (component_type == "BatchNormComponent") ans = new BatchNormComponent();                   // itf.cc (stock)
   else if (component_type == "OnehotFunctionComponent") ans = new OnehotFunctionComponent();         // itf.cc:250-251
   else if (component_type == "SoftmaxFlopsComponent") ans = new SoftmaxFlopsComponent();             // itf.cc:262-263
   else if (component_type == "GumbelSoftmaxFlopsComponent") ans = new GumbelSoftmaxFlopsComponent(); // itf.cc:270-273

@@ -427,7 +427,8 @@ class BatchNormTestComponent : public Component {
   // test hook: install statistics directly (the reference only gets them through Read()).
   void SetStats(int32 dim, int32 block_dim, BaseFloat epsilon, BaseFloat target_rms, double count,
                 const std::vector<double>& sum, const std::vector<double>& sumsq);
- private:
+ protected:
+  virtual const char* Token() const { return "BatchNormTestComponent"; }  // on-disk name (Read / Write)
   void Check() const;
   void ComputeDerived();
   int32 dim_, block_dim_;
@@ -436,6 +437,54 @@ class BatchNormTestComponent : public Component {
   double count_;
   std::vector<double> stats_sum_, stats_sumsq_;  // CuVector<double> in the reference; tiny, host side here
   CuVector offset_, scale_;
+};
+
+// ------------------------------------------------------------------ BatchNormComponent (norm.h:150-262, norm.cc:209-680)
+// The stock component of the supernet PRETRAIN stage (the search stage `sed`s it into BatchNormTestComponent):
+// training mode normalises with the minibatch statistics (Memo 5 x block_dim: mean, uvar, scale, var_deriv_mod,
+// temp), StoreStats accumulates them; test mode is the same affine map as BatchNormTestComponent.  Shares the
+// statistics, derived vectors and on-disk layout with BatchNormTestComponent (only the token differs).
+class BatchNormComponent : public BatchNormTestComponent {
+ public:
+  struct Memo {
+    int32 num_frames;
+    CuVector mean_uvar_scale;  // 5 x block_dim, rows contiguous: mean, uvar, scale, var_deriv_mod, temp
+  };
+  BatchNormComponent();
+  BatchNormComponent(const BatchNormComponent& other);
+  virtual ~BatchNormComponent();
+  virtual std::string Info() const;
+  virtual void InitFromConfig(ConfigLine* cfl);  // norm.cc:289-317
+  virtual std::string Type() const { return "BatchNormComponent"; }
+  virtual int32 Properties() const {
+    return kSimpleComponent | kBackpropNeedsOutput | kPropagateInPlace | kBackpropInPlace |
+           (block_dim_ < dim_ ? kInputContiguous | kOutputContiguous : 0) | (test_mode_ ? 0 : kUsesMemo | kStoresStats);
+  }
+  virtual void* Propagate(const ComponentPrecomputedIndexes* indexes, const CuMatrixBase<BaseFloat>& in,
+                          CuMatrixBase<BaseFloat>* out) const;
+  virtual void Backprop(const std::string& debug_info, const ComponentPrecomputedIndexes* indexes,
+                        const CuMatrixBase<BaseFloat>& in_value, const CuMatrixBase<BaseFloat>& out_value,
+                        const CuMatrixBase<BaseFloat>& out_deriv, void* memo, Component* to_update,
+                        CuMatrixBase<BaseFloat>* in_deriv) const;
+  virtual void StoreStats(const CuMatrixBase<BaseFloat>& in_value, const CuMatrixBase<BaseFloat>& out_value, void* memo);
+  virtual void ZeroStats();
+  virtual void DeleteMemo(void* memo) const { delete static_cast<Memo*>(memo); }
+  virtual void Read(std::istream& is, bool binary);
+  virtual void Write(std::ostream& os, bool binary) const;
+  virtual Component* Copy() const { return new BatchNormComponent(*this); }
+  virtual void Scale(BaseFloat scale);
+  virtual void Add(BaseFloat alpha, const Component& other);
+  void SetTestMode(bool test_mode);
+  double Count() const;
+
+ protected:
+  virtual const char* Token() const { return "BatchNormComponent"; }
+  void ComputeDerivedBn();  // norm.cc:209-247: empty vectors outside test mode
+  // StoreStats accumulates on the device (no host sync per minibatch); the host copies are brought up to date
+  // whenever they are read.
+  void FlushStats() const;
+  mutable double* d_stats_;        // device [2 * block_dim]: sum, sumsq accumulated since the last flush
+  mutable double pending_count_;
 };
 
 // ------------------------------------------------------------------ edit directives (utils.cc:1166-1415)

@@ -237,6 +237,23 @@ int tdnnf_nnet3_backprop(const void* comp, const void* indexes, const float* in_
   API_END
 }
 int tdnnf_nnet3_delete_memo(const void* comp, void* memo) { API_BEGIN static_cast<const Component*>(comp)->DeleteMemo(memo); API_END }
+// Component::StoreStats / ZeroStats (kStoresStats components: BatchNormComponent in training mode)
+int tdnnf_nnet3_store_stats(void* comp, const float* in_value, int in_rows, int in_cols, int in_stride, const float* out_value,
+                            int out_rows, int out_cols, int ov_stride, void* memo) {
+  API_BEGIN
+  CuMatrixBase<BaseFloat> in_v = View(in_value, in_value ? in_rows : 0, in_value ? in_cols : 0, in_stride),
+                          ov_v = View(out_value, out_rows, out_cols, ov_stride);
+  static_cast<Component*>(comp)->StoreStats(in_v, ov_v, memo);
+  API_END
+}
+int tdnnf_nnet3_zero_stats(void* comp) { API_BEGIN static_cast<Component*>(comp)->ZeroStats(); API_END }
+int tdnnf_nnet3_bn_count(const void* comp, double* count) {
+  API_BEGIN
+  const BatchNormComponent* b = dynamic_cast<const BatchNormComponent*>(static_cast<const Component*>(comp));
+  if (!b) KALDI_ERR << "not a BatchNormComponent";
+  *count = b->Count();
+  API_END
+}
 
 // ---- UpdatableComponent surface
 static UpdatableComponent* Upd(void* comp) {
@@ -274,7 +291,8 @@ int tdnnf_nnet3_get_learning_rate(void* comp, float* lrate) { API_BEGIN *lrate =
 int tdnnf_nnet3_set_test_mode(void* comp, int test_mode) {
   API_BEGIN
   Component* c = static_cast<Component*>(comp);
-  if (BatchNormTestComponent* b = dynamic_cast<BatchNormTestComponent*>(c)) b->SetTestMode(test_mode != 0);
+  if (BatchNormComponent* bn = dynamic_cast<BatchNormComponent*>(c)) bn->SetTestMode(test_mode != 0);
+  else if (BatchNormTestComponent* b = dynamic_cast<BatchNormTestComponent*>(c)) b->SetTestMode(test_mode != 0);
   else if (RandomComponent* r = dynamic_cast<RandomComponent*>(c)) r->SetTestMode(test_mode != 0);
   else if (TdnnDARTSV3Component* t = dynamic_cast<TdnnDARTSV3Component*>(c)) t->SetTestMode(test_mode != 0);
   API_END

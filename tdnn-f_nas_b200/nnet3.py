@@ -285,6 +285,20 @@ class Component:
         _check(_lib().tdnnf_nnet3_backprop(self.h, indexes.h if indexes else None, vp(ivp), ir, ic, ivs, vp(ovp), ovs,
                                            vp(dp), dr, dc, ds, memo, to_update.h if to_update else None, vp(idp), ids))
 
+    def store_stats(self, in_value, out_value, memo):
+        """Component::StoreStats (BatchNormComponent in training mode accumulates its minibatch statistics)."""
+        ivp, ir, ic, ivs = (0, 0, 0, 0) if in_value is None else capi._mat(in_value)
+        op, orr, oc, os_ = capi._mat(out_value)
+        _check(_lib().tdnnf_nnet3_store_stats(self.h, vp(ivp), ir, ic, ivs, vp(op), orr, oc, os_, memo))
+
+    def zero_stats(self):
+        _check(_lib().tdnnf_nnet3_zero_stats(self.h))
+
+    def bn_count(self) -> float:
+        c = C.c_double()
+        _check(_lib().tdnnf_nnet3_bn_count(self.h, C.byref(c)))
+        return c.value
+
     def delete_memo(self, memo):
         if memo is not None:
             _check(_lib().tdnnf_nnet3_delete_memo(self.h, memo))

@@ -282,3 +282,77 @@ def test_batchnorm_test_component_from_model_text(nn):
     bn.set_test_mode(False)
     with pytest.raises(nn.Nnet3Error, match="test mode"):
         bn.propagate(None, xd, xd)
+
+
+@pytest.mark.parametrize("D,block,R", [(96, 96, 200), (64, 16, 50)])
+def test_batchnorm_component_training_mode(nn, D, block, R):
+    """BatchNormComponent (nnet-normalize-component.cc:401-589): training-mode Propagate / Backprop against float64 numpy
+    of the BATCHNORM_MATH comment (:321-398), StoreStats over two minibatches, the on-disk statistics, test mode, and
+    equality with BatchNormTestComponent once the model text is `sed`-ed as the search recipe does."""
+    import torch
+
+    g = np.random.default_rng(D + R)
+    eps, rms = 1e-3, 0.7
+    bn = nn.Component.new("BatchNormComponent", f"dim={D} block-dim={block} epsilon={eps} target-rms={rms}")
+    ratio = D // block
+    pooled_sum, pooled_sumsq, count = np.zeros(block), np.zeros(block), 0
+    for step in range(2):
+        x = (g.standard_normal((R, D)) * (1 + step) + 0.3).astype(np.float32)
+        zp = g.standard_normal((R, D)).astype(np.float32)
+        xr, zpr = x.astype(np.float64).reshape(R * ratio, block), zp.astype(np.float64).reshape(R * ratio, block)
+        mean, uvar = xr.mean(0), (xr ** 2).mean(0)
+        scale = rms * (np.maximum(uvar - mean ** 2, 0) + eps) ** -0.5
+        z = (xr - mean) * scale
+        vdm = -1.0 / (rms * rms) * (zpr * z).mean(0) * scale
+        xp = scale * (zpr - zpr.mean(0)) + z * vdm
+        xd = torch.from_numpy(x).cuda()
+        out = torch.empty_like(xd)
+        memo = bn.propagate(None, xd, out)
+        assert memo is not None
+        assert rel_err(out.cpu().numpy(), z.reshape(R, D)) < 1e-5
+        bn.store_stats(None, out, memo)
+        ind = torch.from_numpy(zp).cuda()  # in place (kBackpropInPlace)
+        bn.backprop(None, None, out, ind, memo, None, ind)
+        bn.delete_memo(memo)
+        assert rel_err(ind.cpu().numpy(), xp.reshape(R, D)) < 1e-4
+        pooled_sum += xr.sum(0)
+        pooled_sumsq += (xr ** 2).sum(0)
+        count += R * ratio
+    assert bn.bn_count() == count
+    txt = bn.write(False).decode()
+    mean_txt = np.array(txt.split("<StatsMean>")[1].split("[")[1].split("]")[0].split(), dtype=np.float64)
+    var_txt = np.array(txt.split("<StatsVar>")[1].split("[")[1].split("]")[0].split(), dtype=np.float64)
+    pm = pooled_sum / count
+    np.testing.assert_allclose(mean_txt, pm, rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(var_txt, pooled_sumsq / count - pm ** 2, rtol=2e-4)
+    # a copy carries the statistics; Scale(0) clears them; Add restores
+    cp = bn.copy()
+    assert cp.bn_count() == count
+    cp.scale(0.0)
+    assert cp.bn_count() == 0
+    cp.add(1.0, bn)
+    assert cp.bn_count() == count
+    # test mode: the affine map from the pooled statistics, no memo, no kStoresStats
+    bn.set_test_mode(True)
+    assert bn.properties() & (nn.kUsesMemo | nn.kStoresStats) == 0
+    x = g.standard_normal((R, D)).astype(np.float32)
+    xd = torch.from_numpy(x).cuda()
+    out = torch.empty_like(xd)
+    assert bn.propagate(None, xd, out) is None
+    sc = rms * (np.maximum(pooled_sumsq / count - pm ** 2, 0) + eps) ** -0.5
+    ref = ((x.astype(np.float64).reshape(R * ratio, block) - pm) * sc).reshape(R, D)
+    assert rel_err(out.cpu().numpy(), ref) < 1e-4
+    # `sed s/BatchNormComponent/BatchNormTestComponent/` on the text model (the search-stage recipe) gives the same map
+    test_comp = nn.Component.read(bn.write(False).replace(b"BatchNormComponent", b"BatchNormTestComponent"), False)
+    assert test_comp.type() == "BatchNormTestComponent"
+    out2 = torch.empty_like(xd)
+    test_comp.propagate(None, xd, out2)
+    assert rel_err(out2.cpu().numpy(), out.cpu().numpy()) < 1e-5  # the text form rounds the statistics to ~7 digits
+    # round trip of the component itself; ZeroStats is a no-op in test mode (norm.cc:668-678)
+    back = nn.Component.read(bn.write(True), True)
+    assert back.type() == "BatchNormComponent" and back.write(False) == bn.write(False)
+    bn.zero_stats()
+    assert bn.bn_count() == count
+    bn.set_test_mode(False)
+    bn.zero_stats()
+    assert bn.bn_count() == 0

@@ -134,3 +134,25 @@ def test_unknown_component_type_fails():
         nnet3.Component.new("NoSuchComponent", "dim=3")
     with pytest.raises(nnet3.Nnet3Error):
         nnet3.Component.read(b"<NoSuchComponent> <Dim> 3 </NoSuchComponent> ", False)
+
+
+def test_batchnorm_component_config_and_text_form():
+    """BatchNormComponent (the stock component the search stage `sed`s into BatchNormTestComponent): config keys,
+    Properties() and the on-disk token stream of nnet-normalize-component.cc:289-317, 616-642.  Training mode holds no
+    device state, so this runs without a GPU."""
+    from tdnnf_nas_b200 import nnet3
+
+    bn = nnet3.Component.new("BatchNormComponent", "dim=12 block-dim=4 epsilon=0.01 target-rms=0.5")
+    assert bn.type() == "BatchNormComponent" and bn.input_dim() == 12 and bn.output_dim() == 12
+    assert bn.properties() == (nnet3.kSimpleComponent | nnet3.kBackpropNeedsOutput | nnet3.kPropagateInPlace |
+                               nnet3.kBackpropInPlace | nnet3.kInputContiguous | nnet3.kOutputContiguous |
+                               nnet3.kUsesMemo | nnet3.kStoresStats)
+    txt = bn.write(False)
+    assert txt.startswith(b"<BatchNormComponent> <Dim> 12 <BlockDim> 4 <Epsilon> 0.01 <TargetRms> 0.5 <TestMode> F <Count> 0 <StatsMean>")
+    assert txt.rstrip().endswith(b"</BatchNormComponent>")
+    full = nnet3.Component.new("BatchNormComponent", "dim=8")
+    assert full.properties() & (nnet3.kInputContiguous | nnet3.kOutputContiguous) == 0
+    assert "test-mode=false" in full.info() and "block-dim=8" in full.info()
+    for bad in ("block-dim=4", "dim=12 block-dim=5", "dim=8 epsilon=0", "dim=8 bogus=1"):
+        with pytest.raises(nnet3.Nnet3Error):
+            nnet3.Component.new("BatchNormComponent", bad)
