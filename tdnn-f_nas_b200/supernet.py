@@ -3,14 +3,15 @@
 forward-backward, backward, data-parallel reduction of the deltas and the parameter step.
 
 What runs where:
-  * the 2 x 14 TdnnDARTSV3Component instances, BatchNormTestComponent (search mode) -> the nnet3
-    component mirror (csrc/nnet3) exactly as NnetComputer would call them;
-  * ReLU / BatchNorm-train / bypass sum / the stock affine layers around them (tdnn1, prefinal,
-    output: "N4" neighbours) -> the same kernels through the C ABI (a stock TdnnComponent is the
-    DARTS GEMM with one offset and weight 1);
+  * the 2 x 14 TdnnDARTSV3Component instances (with their OnlineNaturalGradient update), BatchNormTestComponent
+    (search mode) / BatchNormComponent (pretrain mode) -> the nnet3 component mirror (csrc/nnet3) exactly as
+    NnetComputer would call them (Propagate / StoreStats / Backprop / DeleteMemo);
+  * ReLU / bypass sum / the stock affine layers around them (tdnn1, prefinal, output: "N4" neighbours) -> the same
+    kernels through the C ABI (a stock TdnnComponent is the DARTS GEMM with one offset and weight 1; their update
+    is plain SGD);
   * ComputeChainObjfAndDeriv (chain.py) -> den kernels + the generic (per-sequence FST) numerator kernel;
-    natural gradient is the identity (N1); UpdateNnetWithMaxChange is applied (host logic, one read-back);
-    L2 / orthonormal constraint are not (N2); dropout-proportion is 0.0 as in the recipe; no xent branch.
+    UpdateNnetWithMaxChange is applied (host logic, one read-back); L2 / orthonormal constraint are not (N2);
+    dropout-proportion is 0.0 as in the recipe; no xent branch.
 torch is device memory, the H2D copy, streams and torch.distributed; every kernel launched is ours.
 
 The step is compiled once into flat lists of pre-bound C calls so the per-step Python cost is a loop.
@@ -155,10 +156,10 @@ class Supernet:
 
         # ---------------- frozen batch-norm (BatchNormTestComponent) or train-mode batch-norm
         def make_bn(dim):
-            # memo of the train-mode kernels.  In search mode these are replaced, after one calibration
-            # forward pass, by BatchNormTestComponents carrying the measured statistics -- the synthetic
-            # stand-in for "pretrain the supernet, then sed BatchNormComponent -> BatchNormTestComponent".
-            return torch.zeros(5 * dim, device=dev)
+            # BatchNormComponent in training mode (the supernet pretrain stage).  In search mode these are replaced,
+            # after one calibration forward pass with StoreStats, by BatchNormTestComponents read from the `sed`-ed
+            # model text -- "pretrain the supernet, then sed BatchNormComponent -> BatchNormTestComponent".
+            return dict(comp=nnet3.Component.new("BatchNormComponent", f"dim={dim}"), memo=C.c_void_p())
 
         # ---------------- DARTS blocks
         left = ",".join(str(i) for i in range(-(n - 1), 1))
@@ -243,19 +244,19 @@ class Supernet:
             self.lib.tdnnf_nnet3_delete_memo(blk["lin"].h, blk["memo_lin"])
             self.lib.tdnnf_nnet3_delete_memo(blk["aff"].h, blk["memo_aff"])
 
-        def freeze(memo, dim, count):
-            m = memo.cpu().numpy().astype(np.float64)
-            mean, var = m[:dim], m[dim:2 * dim]
-            bn = nnet3.Component.new("BatchNormTestComponent", "")
-            bn.bn_test_set_stats(dim, dim, 1e-3, 1.0, float(count), mean * count, (var + mean * mean) * count)
-            bn.set_test_mode(True)
-            return bn
+        def freeze(bn):
+            # what the search recipe does to the pretrained model text, then test mode
+            self.lib.tdnnf_nnet3_delete_memo(bn["comp"].h, bn["memo"])
+            text = bn["comp"].write(False).replace(b"BatchNormComponent", b"BatchNormTestComponent")
+            test = nnet3.Component.read(text, False)
+            test.set_test_mode(True)
+            return test
 
-        self.t1["bn"] = freeze(self.t1["bn"], self.cfg.dim, self.t1["aff"].shape[0])
+        self.t1["bn"] = freeze(self.t1["bn"])
         for blk in self.blocks:
-            blk["bn"] = freeze(blk["bn"], self.cfg.dim, blk["aff_out"].shape[0])
-        self.head["bn1"] = freeze(self.head["bn1"], self.cfg.dim, self.head["pa"].shape[0])
-        self.head["bn2"] = freeze(self.head["bn2"], self.cfg.prefinal_small, self.head["pli"].shape[0])
+            blk["bn"] = freeze(blk["bn"])
+        self.head["bn1"] = freeze(self.head["bn1"])
+        self.head["bn2"] = freeze(self.head["bn2"])
 
     # ------------------------------------------------------------------ the step as pre-bound calls
     def _affine_fwd(self, plan, x, p, out):
@@ -283,23 +284,25 @@ class Supernet:
                  C.c_void_p(p["db"].data_ptr()) if p["db"] is not None else None, one, 1, self.zero_off, 1, lr, None)
 
     def _bn_fwd(self, plan, bn, x, out):
-        lib, h = self.lib, self.ctx.h
+        lib = self.lib
         xp, xr, xc, xs = _m(x)
         op, _, _, os_ = _m(out)
-        if isinstance(bn, nnet3.Component):
+        if isinstance(bn, nnet3.Component):  # BatchNormTestComponent (search stage)
             plan.add("nnet3", lib.tdnnf_nnet3_propagate, bn.h, None, xp, xr, xc, xs, op, xr, xc, os_, None)
-        else:
-            plan.add("abi", lib.tdnnf_batchnorm_train_fwd, h, xp, xr, xc, xs, op, os_, 1e-3, 1.0, C.c_void_p(bn.data_ptr()))
+        else:  # BatchNormComponent in training mode: Propagate returns the memo, StoreStats accumulates it
+            plan.add("nnet3", lib.tdnnf_nnet3_propagate, bn["comp"].h, None, xp, xr, xc, xs, op, xr, xc, os_, C.byref(bn["memo"]))
+            plan.add("nnet3", lib.tdnnf_nnet3_store_stats, bn["comp"].h, None, 0, 0, 0, op, xr, xc, os_, bn["memo"])
 
     def _bn_bwd(self, plan, bn, out_value, d_out, d_in):
-        lib, h = self.lib, self.ctx.h
+        lib = self.lib
         vp_, r, c, vs = _m(out_value)
         dp, _, _, ds = _m(d_out)
         ip, _, _, is_ = _m(d_in)
         if isinstance(bn, nnet3.Component):
             plan.add("nnet3", lib.tdnnf_nnet3_backprop, bn.h, None, None, r, c, 0, vp_, vs, dp, r, c, ds, None, None, ip, is_)
         else:
-            plan.add("abi", lib.tdnnf_batchnorm_train_bwd, h, vp_, vs, dp, ds, ip, is_, r, c, 1.0, C.c_void_p(bn.data_ptr()))
+            plan.add("nnet3", lib.tdnnf_nnet3_backprop, bn["comp"].h, None, None, r, c, 0, vp_, vs, dp, r, c, ds, bn["memo"], None, ip, is_)
+            plan.add("nnet3", lib.tdnnf_nnet3_delete_memo, bn["comp"].h, bn["memo"])
 
     def _compile(self):
         cfg, lib, h = self.cfg, self.lib, self.ctx.h
