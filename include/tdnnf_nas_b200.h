@@ -213,6 +213,17 @@ int tdnnf_mat_dot(tdnnf_ctx* ctx, const float* a, int a_stride, const float* b, 
 int tdnnf_mat_dot_dev(tdnnf_ctx* ctx, const float* a, int a_stride, const float* b, int b_stride, int rows,
                       int cols, double* result_dev);
 
+/* The parameter step over MANY buffers in two launches (UpdateNnetWithMaxChange, ref nnet-utils.cc:2085-2175, needs
+ * the squared norm of every component's delta, then model += factor * delta and delta = 0):
+ *   tdnnf_multi_sumsq:     out_dev[groups[i]] += sum(bufs[i]^2)   (device doubles; groups NULL = one slot per buffer)
+ *   tdnnf_multi_axpy_zero: dst[i] += factors[i] * src[i];  src[i] = 0
+ * All arrays are HOST arrays of n <= TDNNF_MULTI_MAX entries; the pointers in them are device pointers. */
+#define TDNNF_MULTI_MAX 96
+int tdnnf_multi_sumsq(tdnnf_ctx* ctx, int n, const float* const* bufs, const int32_t* rows, const int32_t* cols,
+                      const int32_t* strides, const int32_t* groups, double* out_dev);
+int tdnnf_multi_axpy_zero(tdnnf_ctx* ctx, int n, float* const* dst, const int32_t* dst_strides, float* const* src,
+                          const int32_t* src_strides, const int32_t* rows, const int32_t* cols, const float* factors);
+
 /* ------------------------------------------------------------------ stock TDNN-F neighbours - */
 /* The stock components that sit between the NAS components in a TDNN-F block, so
  * that a whole supernet step runs on this library: RectifiedLinearComponent without self-repair,

@@ -40,6 +40,8 @@ def _declare(lib):
     sig("tdnnf_ctx_gemm_timing_read", [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)])
     sig("tdnnf_ctx_gemm_timing_read_ex", [vp, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                           C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_uint64)])
+    sig("tdnnf_multi_sumsq", [vp, i, vp, vp, vp, vp, vp, vp])
+    sig("tdnnf_multi_axpy_zero", [vp, i, vp, vp, vp, vp, vp, vp, vp])
     sig("tdnnf_ctx_set_gradient_mode", [vp, i])
     sig("tdnnf_ctx_set_gemm_planes", [vp, i])
     sig("tdnnf_ctx_operand_cache_begin", [vp, C.POINTER(C.c_void_p), i])

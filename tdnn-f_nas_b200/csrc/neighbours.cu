@@ -1,5 +1,8 @@
 // Whole-parameter ops of the updatable components and the stock TDNN-F neighbours (ReLU, bypass
 // sum, BatchNorm training mode).  All bandwidth-bound, one fused pass each.
+#include <algorithm>
+#include <cstring>
+
 #include "context.h"
 
 using namespace tdnnf;
@@ -311,6 +314,126 @@ extern "C" int tdnnf_mat_dot(tdnnf_ctx* ctx, const float* a, int a_stride, const
   TDNNF_CUDA_OK(cudaMemcpyAsync(&h, acc, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   TDNNF_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   *result = (float)h;
+  return TDNNF_OK;
+}
+
+// ---- UpdateNnetWithMaxChange over many parameter buffers in two launches (utils.cc:2085-2175).  A network has
+// ~70 parameter buffers; one kernel launch (and one host call) per buffer per operation made the parameter step
+// host-bound (~200 calls).  The buffer table travels as a kernel argument.
+struct MultiBufTable {
+  const float* src[TDNNF_MULTI_MAX];
+  float* dst[TDNNF_MULTI_MAX];
+  int rows[TDNNF_MULTI_MAX], cols[TDNNF_MULTI_MAX], src_stride[TDNNF_MULTI_MAX], dst_stride[TDNNF_MULTI_MAX];
+  int group[TDNNF_MULTI_MAX];
+  float factor[TDNNF_MULTI_MAX];
+  int first_block[TDNNF_MULTI_MAX + 1];  // blocks [first_block[i], first_block[i+1]) work on buffer i
+  int n;
+};
+
+__device__ __forceinline__ int multi_find(const MultiBufTable& t, int block) {
+  int lo = 0, hi = t.n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (t.first_block[mid] <= block) lo = mid;
+    else hi = mid - 1;
+  }
+  return lo;
+}
+
+// out[group[i]] += sum of squares of buffer i
+__global__ void __launch_bounds__(256) multi_sumsq_kernel(const __grid_constant__ MultiBufTable t, double* __restrict__ out) {
+  const int i = multi_find(t, blockIdx.x);
+  const int nb = t.first_block[i + 1] - t.first_block[i], b = blockIdx.x - t.first_block[i];
+  const long long total = (long long)t.rows[i] * t.cols[i];
+  const float* src = t.src[i];
+  const int cols = t.cols[i];
+  const long long ld = t.src_stride[i];
+  double acc = 0.0;
+  for (long long idx = (long long)b * 256 + threadIdx.x; idx < total; idx += (long long)nb * 256) {
+    const float v = src[(idx / cols) * ld + idx % cols];
+    acc += (double)v * (double)v;
+  }
+  __shared__ double red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    if (s != 0.0) atomicAdd(out + t.group[i], s);
+  }
+}
+
+// dst_i += factor_i * src_i;  src_i = 0
+__global__ void __launch_bounds__(256) multi_axpy_zero_kernel(const __grid_constant__ MultiBufTable t) {
+  const int i = multi_find(t, blockIdx.x);
+  const int nb = t.first_block[i + 1] - t.first_block[i], b = blockIdx.x - t.first_block[i];
+  const long long total = (long long)t.rows[i] * t.cols[i];
+  float* src = const_cast<float*>(t.src[i]);
+  float* dst = t.dst[i];
+  const int cols = t.cols[i];
+  const long long sld = t.src_stride[i], dld = t.dst_stride[i];
+  const float f = t.factor[i];
+  for (long long idx = (long long)b * 256 + threadIdx.x; idx < total; idx += (long long)nb * 256) {
+    const long long r = idx / cols;
+    const int c = (int)(idx % cols);
+    dst[r * dld + c] += f * src[r * sld + c];
+    src[r * sld + c] = 0.f;
+  }
+}
+
+static int multi_table(tdnnf_ctx* ctx, int n, const float* const* src, float* const* dst, const int32_t* rows, const int32_t* cols,
+                       const int32_t* src_strides, const int32_t* dst_strides, const int32_t* groups, const float* factors,
+                       MultiBufTable* t, int* blocks) {
+  TDNNF_REQUIRE(ctx && src && rows && cols && src_strides, "null argument");
+  TDNNF_REQUIRE(n >= 1 && n <= TDNNF_MULTI_MAX, "buffer count out of range");
+  memset(t, 0, sizeof(*t));
+  t->n = n;
+  int nb = 0;
+  for (int i = 0; i < n; ++i) {
+    TDNNF_REQUIRE(src[i] && rows[i] > 0 && cols[i] > 0 && src_strides[i] >= cols[i], "bad buffer");
+    t->src[i] = src[i];
+    t->dst[i] = dst ? dst[i] : nullptr;
+    t->rows[i] = rows[i];
+    t->cols[i] = cols[i];
+    t->src_stride[i] = src_strides[i];
+    t->dst_stride[i] = dst_strides ? dst_strides[i] : 0;
+    t->group[i] = groups ? groups[i] : i;
+    t->factor[i] = factors ? factors[i] : 1.f;
+    t->first_block[i] = nb;
+    const long long total = (long long)rows[i] * cols[i];
+    nb += (int)std::max<long long>(1, std::min<long long>((total + 4095) / 4096, 64));
+  }
+  t->first_block[n] = nb;
+  *blocks = nb;
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_multi_sumsq(tdnnf_ctx* ctx, int n, const float* const* bufs, const int32_t* rows, const int32_t* cols,
+                                 const int32_t* strides, const int32_t* groups, double* out_dev) {
+  TDNNF_REQUIRE(out_dev != nullptr, "null argument");
+  MultiBufTable t;
+  int blocks = 0;
+  int rc = multi_table(ctx, n, bufs, nullptr, rows, cols, strides, nullptr, groups, nullptr, &t, &blocks);
+  if (rc) return rc;
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+  multi_sumsq_kernel<<<blocks, 256, 0, ctx->stream>>>(t, out_dev);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_multi_axpy_zero(tdnnf_ctx* ctx, int n, float* const* dst, const int32_t* dst_strides, float* const* src,
+                                     const int32_t* src_strides, const int32_t* rows, const int32_t* cols, const float* factors) {
+  TDNNF_REQUIRE(dst && dst_strides && factors, "null argument");
+  MultiBufTable t;
+  int blocks = 0;
+  int rc = multi_table(ctx, n, src, dst, rows, cols, src_strides, dst_strides, nullptr, factors, &t, &blocks);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) TDNNF_REQUIRE(dst[i] && dst_strides[i] >= cols[i], "bad destination buffer");
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+  multi_axpy_zero_kernel<<<blocks, 256, 0, ctx->stream>>>(t);
+  LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
 

@@ -440,18 +440,26 @@ class Supernet:
         for name, p in st.items():
             self.updatables.append(("stock", p, None, 1.5 if name == "output" else cfg.max_change))
         self.dots = torch.zeros(len(self.updatables), dtype=torch.float64, device=self.dev)
+        # every parameter buffer of the model with the matching delta buffer: (model ptr, stride, delta ptr, stride, rows, cols, group)
+        bufs = []
         for i, (kind, m, d, _) in enumerate(self.updatables):
-            slot = C.c_void_p(self.dots.data_ptr() + 8 * i)
             if kind == "comp":
-                for ptr, rows, cols, stride in d.param_buffers():
-                    upd.add("abi", lib.tdnnf_mat_dot_dev, h, C.c_void_p(ptr), stride, C.c_void_p(ptr), stride, rows, cols, slot)
+                for (mp, r, c, ms), (dp, r2, c2, ds) in zip(m.param_buffers(), d.param_buffers()):
+                    assert (r, c) == (r2, c2)
+                    bufs.append((mp, ms, dp, ds, r, c, i))
             else:
-                gp, gr, gc, gs = _m(m["dW"])
-                upd.add("abi", lib.tdnnf_mat_dot_dev, h, gp, gs, gp, gs, gr, gc, slot)
-                if m["db"] is not None:
-                    n = m["db"].numel()
-                    dbp = C.c_void_p(m["db"].data_ptr())
-                    upd.add("abi", lib.tdnnf_mat_dot_dev, h, dbp, n, dbp, n, 1, n, slot)
+                wp, wr, wc, ws = capi._mat(m["W"])
+                gp, _, _, gs = capi._mat(m["dW"])
+                bufs.append((wp, ws, gp, gs, wr, wc, i))
+                if m["b"] is not None:
+                    n = m["b"].numel()
+                    bufs.append((m["b"].data_ptr(), n, m["db"].data_ptr(), n, 1, n, i))
+        nb = len(bufs)
+        PtrArr, IntArr, FltArr = C.c_void_p * nb, C.c_int32 * nb, C.c_float * nb
+        self.upd_tab = dict(n=nb, model=PtrArr(*[b[0] for b in bufs]), model_ld=IntArr(*[b[1] for b in bufs]),
+                            delta=PtrArr(*[b[2] for b in bufs]), delta_ld=IntArr(*[b[3] for b in bufs]),
+                            rows=IntArr(*[b[4] for b in bufs]), cols=IntArr(*[b[5] for b in bufs]),
+                            group=IntArr(*[b[6] for b in bufs]), factors=FltArr(), group_list=[b[6] for b in bufs])
         # Data-parallel reduction of the deltas: ONE flat all-reduce after the backward pass.  (Per-block
         # all-reduces overlapped with the backward GEMMs were measured slower: the persistent GEMM kernels own
         # every SM (226 KB smem per CTA), so a concurrent NCCL kernel delays a whole wave of their CTAs; and ~60
@@ -535,8 +543,12 @@ class Supernet:
     def _update_with_max_change(self, scale: float = 1.0, max_change_scale: float = 1.0):
         """UpdateNnetWithMaxChange + ScaleNnet(momentum=0) (utils.cc:2085-2175, common.py:877-878)."""
         cfg, lib, h = self.cfg, self.lib, self.ctx.h
+        t = self.upd_tab
         self.dots.zero_()
-        self.upd_plan.run()
+        # squared norm of every component's delta: ONE launch over all parameter buffers
+        if lib.tdnnf_multi_sumsq(h, t["n"], t["delta"], t["rows"], t["cols"], t["delta_ld"], t["group"],
+                                 C.c_void_p(self.dots.data_ptr())) != 0:
+            raise RuntimeError(lib.tdnnf_last_error().decode())
         dots = self.dots.cpu().numpy()  # the step's second (and last) host sync
         factors = np.ones(len(dots))
         param_delta_squared = 0.0
@@ -552,17 +564,12 @@ class Supernet:
             else:
                 scale *= cfg.max_param_change * max_change_scale / param_delta
         self.last_max_change_factors = factors * scale
-        for f, (kind, m, d, _) in zip(self.last_max_change_factors, self.updatables):
-            f = float(f)
-            if kind == "comp":
-                if lib.tdnnf_nnet3_add(m.h, C.c_float(f), d.h) != 0 or lib.tdnnf_nnet3_scale(d.h, C.c_float(0.0)) != 0:
-                    self._raise_nnet3()
-            else:
-                self.ctx.mat_axpy(f, m["dW"], m["W"])
-                self.ctx.mat_set(m["dW"], 0.0)
-                if m["b"] is not None:
-                    self.ctx.mat_axpy(f, m["db"].view(1, -1), m["b"].view(1, -1))
-                    self.ctx.mat_set(m["db"].view(1, -1), 0.0)
+        # model += factor * delta, delta = 0 (ScaleNnet(momentum = 0)): ONE launch over all parameter buffers
+        for k, g in enumerate(t["group_list"]):
+            t["factors"][k] = float(self.last_max_change_factors[g])
+        if lib.tdnnf_multi_axpy_zero(h, t["n"], t["model"], t["model_ld"], t["delta"], t["delta_ld"], t["rows"], t["cols"],
+                                     t["factors"]) != 0:
+            raise RuntimeError(lib.tdnnf_last_error().decode())
 
     def _raise_nnet3(self):
         raise RuntimeError(self.lib.tdnnf_nnet3_last_error().decode())
