@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 METRIC = "TDNN-F DARTS supernet train frames/sec"
 # dram__bytes_read.sum + dram__bytes_write.sum per splice_gemm_kernel launch, from the committed `ncu --set full`
 # capture (profiles/r01_summary.md).  A tensor-bound kernel: this is context, not the roofline numerator.
-NCU_GEMM_TRAFFIC_BYTES = 108.8e6
+NCU_GEMM_TRAFFIC_BYTES = 131.2e6
 UNIT = "frames/s"
 NG_SETTLE_STEPS = 12
 # launches with fewer algorithmic FLOPs than this are the skinny natural-gradient products (H = X W^T with 20-80
@@ -320,7 +320,7 @@ def run_ours(args, cfg, rank, world, local_rank):
         gpu_launches=int(launches),
         roofline=dict(bound="tensor", kernel="splice_gemm_kernel (tcgen05, the TdnnDARTSV3 Propagate / data-gradient / parameter-gradient GEMMs)",
                       achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=NCU_GEMM_TRAFFIC_BYTES,
-                      traffic_source="profiles/r01_summary.md: mean dram__bytes_read+write per launch of the ncu --set full capture",
+                      traffic_source="profiles/r01_summary.md: mean dram__bytes_read+write over the 10 launches of the ncu --set full capture",
                       peak_source=peaks["source"] + ", bf16 sustained",
                       achieved_tensor_pipe=achieved_pipe, frac_tensor_pipe=achieved_pipe / peak,
                       launches_timed=gt["launches"], steps_timed=ROOF_STEPS, gemm_ms_per_step=gt["ms"] / ROOF_STEPS,

@@ -307,7 +307,7 @@ class Supernet:
     def _compile(self):
         cfg, lib, h = self.cfg, self.lib, self.ctx.h
         lr = cfg.learning_rate
-        fwd, bwd, upd = _Plan(), _Plan(), _Plan()
+        fwd, bwd = _Plan(), _Plan()
         st, t1, hd = self.stock, self.t1, self.head
         # ---- forward
         self._affine_fwd(fwd, self.x, st["tdnn1"], t1["aff"])
@@ -477,7 +477,7 @@ class Supernet:
             self.delta_views = views
             self.delta_flat = torch.empty(sum(v.numel() for v in views), device=self.dev, dtype=torch.float32)
             self.delta_chunks = list(torch.split(self.delta_flat, [v.numel() for v in views]))
-        self.fwd_plan, self.bwd_plan, self.upd_plan = fwd, bwd, upd
+        self.fwd_plan, self.bwd_plan = fwd, bwd
 
     def _views_of(self, deltas):
         """The parameter buffers of delta components as flat torch views (pitch padding included: it is zero)."""
