@@ -128,13 +128,26 @@ def test_chain_objf_and_deriv(ctx):
     assert objf == pytest.approx(num_lp - den_lp, rel=1e-4)
     assert l2 == pytest.approx(-0.5 * 1e-3 * float((x.astype(np.float64) ** 2).sum()), rel=1e-4)
     assert rel_err(deriv.cpu().numpy(), num_d + den_d - 1e-3 * x) < 1e-3
+    # xent branch: the numerator posteriors come back on their own (targets of the output-xent node), the total
+    # derivative is unchanged, and the cross-entropy objective / scaled derivative follow NnetChainTrainer
+    deriv_x = torch.full_like(xd, -1.0)
+    xent = torch.full_like(xd, 9.0)
+    objf_x, _, _ = obj.compute(xd, deriv_x, xent)
+    assert objf_x == pytest.approx(objf, rel=1e-6)
+    assert rel_err(xent.cpu().numpy(), num_d) < 1e-3
+    assert rel_err(deriv_x.cpu().numpy(), deriv.cpu().numpy()) < 1e-6
+    xo = torch.log_softmax(torch.from_numpy(g.standard_normal((T * S, P)).astype(np.float32)).cuda(), dim=1)
+    ref_xent_objf = float((xo.double().cpu().numpy() * num_d.astype(np.float64)).sum())
+    assert obj.xent_objf_and_deriv(xo, xent) == pytest.approx(ref_xent_objf, rel=1e-4)
+    assert rel_err(xent.cpu().numpy(), 0.1 * num_d) < 1e-3  # xent_regularize = 0.1
     # T shorter than the phone strings: no numerator path
     bad = capi.NumeratorGraph(ctx, synth.make_num_graphs(S, P, T, seed=8, min_phones=T, max_phones=T))
     obj2 = chain.ChainObjective(ctx, dg, bad, S, 4)
     x2 = torch.from_numpy(x[: 4 * S].copy()).cuda()
     d2 = torch.full_like(x2, 3.0)
-    objf2, _, w2 = obj2.compute(x2, d2)
-    assert objf2 == -10.0 * w2 and torch.all(d2 == 0)
+    x2ent = torch.full_like(x2, 3.0)
+    objf2, _, w2 = obj2.compute(x2, d2, x2ent)
+    assert objf2 == -10.0 * w2 and torch.all(d2 == 0) and torch.all(x2ent == 0)
     for o in (obj, obj2):
         o.close()
     ng.close(); bad.close(); dg.close()
