@@ -297,6 +297,10 @@ int tdnnf_ctx_operand_rowsq(tdnnf_ctx* ctx, const float* source, int rows, const
 int tdnnf_ng_gram_scale(tdnnf_ctx* ctx, const float* H, int rows, int rank, int h_stride, float* L, int l_stride,
                         const float* WWt, int w_stride, const float* rowsq, double* sumsq, int in_rows, int n,
                         const int32_t* row_offsets, int row_stride, const float* weff, float ones_rows, float* out3);
+/* W_next (rank x dim, overwritten) = A J + AC W  with A, AC rank x rank (rank <= 128) and J, W rank x dim: the update
+ * W_{t+1} = A_t (J_t + diag(c) W_t) of OnlineNaturalGradient (kaldi: ComputeWt1), in exact fp32 FMAs. */
+int tdnnf_ng_w_update(tdnnf_ctx* ctx, const float* A, int a_stride, const float* AC, int ac_stride, const float* J, int j_stride,
+                      const float* W, int w_stride, int rank, int dim, float* W_next, int out_stride);
 /* dst += alpha * (*factor1_dev) * (*factor2_dev) * src   (device scalars, either may be NULL = 1) */
 int tdnnf_mat_axpy_dev(tdnnf_ctx* ctx, float alpha, const float* factor1_dev, const float* factor2_dev,
                        const float* src, int src_stride, float* dst, int dst_stride, int rows, int cols);

@@ -271,6 +271,57 @@ __global__ void __launch_bounds__(1024) ng_gram_finish_kernel(const float* __res
   }
 }
 
+// W_next[i][d] = sum_k A[i][k] * J[k][d] + AC[i][k] * W[k][d]     (i < r <= 128, d < D)
+// The W_{t+1} = A_t (J_t + diag(c) W_t) step of OnlineNaturalGradient in exact fp32 FMAs: K = 2r is far too short for
+// the tensor-core path (it took a zero-fill, four operand splits and two 6-product GEMMs per preconditioner).
+// A small tiled SGEMM C = [A | AC] [J ; W]: block = 16 rows x 128 columns, K in chunks of 32 staged in shared memory
+// (coalesced, many loads in flight); a thread owns one column and 16 accumulators, reads the A chunk as float4.
+__global__ void __launch_bounds__(128) ng_w_update_kernel(const float* __restrict__ A, int a_ld, const float* __restrict__ AC,
+                                                          int ac_ld, const float* __restrict__ J, long long j_ld,
+                                                          const float* __restrict__ W, long long w_ld, int r, int D,
+                                                          float* __restrict__ out, long long out_ld) {
+  __shared__ __align__(16) float sA[16][32];   // rows i0..i0+15, K chunk
+  __shared__ float sB[32][128];                // K chunk, columns d0..d0+127
+  const int d0 = blockIdx.x * 128, i0 = blockIdx.y * 16;
+  const int d = d0 + threadIdx.x;
+  float acc[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) acc[u] = 0.f;
+  const int K = 2 * r;  // k < r: (A, J); k >= r: (AC, W)
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    for (int idx = threadIdx.x; idx < 16 * 32; idx += 128) {
+      const int i = i0 + idx / 32, k = k0 + idx % 32;
+      float v = 0.f;
+      if (i < r && k < K) v = k < r ? A[i * a_ld + k] : AC[i * ac_ld + (k - r)];
+      sA[idx / 32][idx % 32] = v;
+    }
+#pragma unroll 8
+    for (int kk = 0; kk < 32; ++kk) {
+      const int k = k0 + kk;
+      float v = 0.f;
+      if (d < D && k < K) v = k < r ? J[k * j_ld + d] : W[(k - r) * w_ld + d];
+      sB[kk][threadIdx.x] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 32; kk += 4) {
+      const float b0 = sB[kk][threadIdx.x], b1 = sB[kk + 1][threadIdx.x], b2 = sB[kk + 2][threadIdx.x],
+                  b3 = sB[kk + 3][threadIdx.x];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const float4 a = *reinterpret_cast<const float4*>(&sA[u][kk]);
+        acc[u] = fmaf(a.x, b0, fmaf(a.y, b1, fmaf(a.z, b2, fmaf(a.w, b3, acc[u]))));
+      }
+    }
+    __syncthreads();
+  }
+  if (d < D) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+      if (i0 + u < r) out[(long long)(i0 + u) * out_ld + d] = acc[u];
+  }
+}
+
 __global__ void mat_axpy_dev_kernel(float alpha, const float* __restrict__ f1, const float* __restrict__ f2,
                                     const float* __restrict__ src, long long ss, float* __restrict__ dst, long long ds,
                                     int rows, int cols) {
@@ -362,6 +413,20 @@ extern "C" int tdnnf_ng_gram_scale(tdnnf_ctx* ctx, const float* H, int rows, int
   ng_gram_finish_kernel<<<(rank * rank + 127) / 128, 1024, 0, ctx->stream>>>(partials, blocks, rank, L, l_stride, WWt, w_stride, sumsq,
                                                                             rowsq ? view_partials : nullptr, weff, n, ones_rows, acc,
                                                                             counter, out3);
+  ctx->launches++;
+  TDNNF_CUDA_OK(cudaGetLastError());
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_ng_w_update(tdnnf_ctx* ctx, const float* A, int a_stride, const float* AC, int ac_stride, const float* J,
+                                 int j_stride, const float* W, int w_stride, int rank, int dim, float* W_next, int out_stride) {
+  TDNNF_REQUIRE(ctx && A && AC && J && W && W_next, "null argument");
+  TDNNF_REQUIRE(rank >= 1 && rank <= 128 && dim >= 1 && a_stride >= rank && ac_stride >= rank && j_stride >= dim &&
+                    w_stride >= dim && out_stride >= dim,
+                "bad argument (rank <= 128)");
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+  ng_w_update_kernel<<<dim3((dim + 127) / 128, (rank + 15) / 16), 128, 0, ctx->stream>>>(A, a_stride, AC, ac_stride, J, j_stride, W,
+                                                                                         w_stride, rank, dim, W_next, out_stride);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   return TDNNF_OK;

@@ -686,9 +686,14 @@ void OnlineNaturalGradient::FinishPendingUpdate() {
     pending_->upload_in_flight = true;
   }
   EnsureSize(&W_next_, R, D);
-  W_next_.SetZero();
-  ProductAB(A_, J_, consts_.Data(), &W_next_);
-  ProductAB(AC_, W_t_, consts_.Data(), &W_next_);
+  if (R <= 128) {
+    CheckStatus(tdnnf_ng_w_update(CurrentContext(), A_.Data(), A_.Stride(), AC_.Data(), AC_.Stride(), J_.Data(), J_.Stride(),
+                                  W_t_.Data(), W_t_.Stride(), R, D, W_next_.Data(), W_next_.Stride()));
+  } else {
+    W_next_.SetZero();
+    ProductAB(A_, J_, consts_.Data(), &W_next_);
+    ProductAB(AC_, W_t_, consts_.Data(), &W_next_);
+  }
   W_t_.Swap(&W_next_);
   d_t_ = pending_->d_t1;
   rho_t_ = pending_->rho_t1;
