@@ -223,8 +223,9 @@ class Supernet:
         graph = synth.make_den_graph(cfg.den_states, P, cfg.den_out_degree, seed=5)
         self.den_arcs = graph["num_arcs"]
         self.den_graph = capi.DenGraph(ctx, graph)
-        # per-sequence numerator FSTs of this rank's shard (unconstrained supervision, `--constrained false`)
-        self.num_graph = capi.NumeratorGraph(ctx, synth.make_num_graphs(S, P, T, seed=60 + self.rank))
+        # per-sequence numerator FSTs of this rank's shard (unconstrained supervision, `--constrained false`): phone
+        # strings are random walks in the denominator graph, so numerator paths are denominator paths (bounded objective)
+        self.num_graph = capi.NumeratorGraph(ctx, synth.make_num_graphs(S, P, T, seed=60 + self.rank, den_graph=graph))
         self.objective = chain.ChainObjective(ctx, self.den_graph, self.num_graph, S, T,
                                               chain.ChainTrainingOptions(leaky_hmm_coefficient=cfg.leaky_hmm))
         self._compile()
@@ -525,6 +526,8 @@ class Supernet:
 
     def step(self, x_host=None, apply_update: bool = True) -> float:
         """One training step.  x_host: pinned host tensor (rows_in x feat_dim) or None to reuse device input.
+        (Prefetching the next input on a copy stream was measured: it made the step 3 ms SLOWER than this in-stream
+        copy, which costs 0.4 ms.)
         Returns the LF-MMI objective per output frame (numerator - denominator) of this rank."""
         import torch
 

@@ -68,27 +68,42 @@ def regular_row_offsets(time_offsets, start_t_in: int, start_t_out: int, num_ima
     return n, offs
 
 
-def make_num_graphs(num_seqs: int, num_pdfs: int, frames: int, seed: int = 6, min_phones: int = 3, max_phones: int = 12) -> dict:
+def make_num_graphs(num_seqs: int, num_pdfs: int, frames: int, seed: int = 6, min_phones: int = 3, max_phones: int = 12,
+                    den_graph: dict = None) -> dict:
     """Synthetic unconstrained numerator supervision: per sequence a left-to-right FST over a random "phone" string
     with the chain topology (one forward pdf consumed on entering a phone, then a self-loop pdf), plus an optional
     alternative pronunciation branch so that the FST is not a single path.  Arc lists are given twice (grouped by
-    source = forward list, then by destination = backward list) as tdnnf_num_graph_create expects."""
+    source = forward list, then by destination = backward list) as tdnnf_num_graph_create expects.
+
+    den_graph (from make_den_graph, with self-loops): the phone string is a random WALK in the denominator graph
+    (forward pdf = the pdf of the arc taken, self-loop pdf = the pdf of the destination's self-loop), so every
+    numerator path is a denominator path as in real chain supervision.  With unrelated random pdfs the LF-MMI
+    objective is unbounded above and a long training run on a fixed minibatch drives the outputs to infinity."""
     g = rng(seed)
     state_offsets = [0]
     src, dst, pdf, lp, final = [], [], [], [], []
+    if den_graph is not None:
+        d_rng, d_state, d_pdf = den_graph["fwd_ranges"], den_graph["state"], den_graph["pdf"]
     for _ in range(num_seqs):
         k = int(g.integers(min_phones, min(max_phones, frames) + 1))
         base = state_offsets[-1]
         ns = k + 1
         f = np.full(ns, -1.0e30, dtype=np.float32)
         f[k] = 0.0
+        h = int(g.integers(0, den_graph["num_states"])) if den_graph is not None else 0
         for j in range(k):
-            fwd_pdf, loop_pdf = int(g.integers(0, num_pdfs)), int(g.integers(0, num_pdfs))
+            if den_graph is not None:
+                a = int(g.integers(d_rng[h][0], d_rng[h][1]))          # an arc leaving den state h
+                fwd_pdf, h = int(d_pdf[a]), int(d_state[a])
+                loops = [b for b in range(d_rng[h][0], d_rng[h][1]) if d_state[b] == h]
+                loop_pdf = int(d_pdf[loops[0]]) if loops else fwd_pdf
+            else:
+                fwd_pdf, loop_pdf = int(g.integers(0, num_pdfs)), int(g.integers(0, num_pdfs))
             src += [base + j, base + j + 1]
             dst += [base + j + 1, base + j + 1]
             pdf += [fwd_pdf, loop_pdf]
             lp += [float(np.log(0.5)), float(np.log(0.5))]
-            if g.uniform() < 0.3:  # alternative phone on the same transition
+            if den_graph is None and g.uniform() < 0.3:  # alternative phone on the same transition
                 src.append(base + j)
                 dst.append(base + j + 1)
                 pdf.append(int(g.integers(0, num_pdfs)))
