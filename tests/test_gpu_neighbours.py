@@ -128,3 +128,89 @@ def test_fused_tail_equals_separate_components(ctx):
     ctx.relu_scale_offset_bypass_bwd(d_out, x, scale, 0.66, d_x, d_prev)
     assert torch.equal(d_x, d_relu)
     np.testing.assert_allclose(d_prev.cpu().numpy(), 0.66 * d_out.cpu().numpy(), rtol=1e-6)
+
+
+def test_multi_buffer_parameter_step(ctx):
+    """tdnnf_multi_sumsq / tdnnf_multi_axpy_zero (the two launches of UpdateNnetWithMaxChange, nnet-utils.cc:2085-2175)
+    against torch, with strided views, grouped buffers and a buffer larger than one block's share."""
+    import ctypes as C
+
+    import torch
+
+    from tdnnf_nas_b200 import capi
+
+    lib = capi.load()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    shapes = [(160, 10752, 10752), (1, 167, 167), (1536, 1120, 1124), (7, 5, 8), (300, 256, 256)]
+    groups = [0, 0, 1, 2, 2]
+    deltas = [torch.randn(r, ld, device="cuda", generator=g)[:, :c] for r, c, ld in shapes]
+    models = [torch.randn(r, ld, device="cuda", generator=g)[:, :c] for r, c, ld in shapes]
+    n = len(shapes)
+    P, I, F = C.c_void_p * n, C.c_int32 * n, C.c_float * n
+    dptr, mptr = P(*[d.data_ptr() for d in deltas]), P(*[m.data_ptr() for m in models])
+    rows, cols = I(*[s[0] for s in shapes]), I(*[s[1] for s in shapes])
+    ld = I(*[s[2] for s in shapes])
+    out = torch.zeros(3, dtype=torch.float64, device="cuda")
+    assert lib.tdnnf_multi_sumsq(ctx.h, n, dptr, rows, cols, ld, I(*groups), C.c_void_p(out.data_ptr())) == 0
+    ref = [0.0, 0.0, 0.0]
+    for d, gi in zip(deltas, groups):
+        ref[gi] += float((d.double() ** 2).sum())
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-10)
+    factors = [0.5, 0.5, -2.0, 1.0, 0.25]
+    expect = [m + f * d for m, d, f in zip(models, deltas, factors)]
+    pads = [m.clone() for m in models]
+    assert lib.tdnnf_multi_axpy_zero(ctx.h, n, mptr, ld, dptr, ld, rows, cols, F(*factors)) == 0
+    torch.cuda.synchronize()
+    for m, e, d in zip(models, expect, deltas):
+        assert torch.allclose(m, e, rtol=1e-6, atol=1e-6) and torch.all(d == 0)
+    with pytest.raises(AssertionError):
+        assert lib.tdnnf_multi_sumsq(ctx.h, 200, dptr, rows, cols, ld, None, C.c_void_p(out.data_ptr())) == 0  # > TDNNF_MULTI_MAX
+
+
+@pytest.mark.parametrize("N,r,n_views", [(5000, 80, 1), (3000, 20, 7), (130, 33, 3)])
+def test_ng_gram_scale_and_w_update(ctx, N, r, n_views):
+    """tdnnf_ng_gram_scale (L = H^T H, tr(X X^T) from per-row sums of squares, the scale) and tdnnf_ng_w_update
+    (W_next = A J + AC W) against float64 numpy."""
+    import ctypes as C
+
+    import torch
+
+    from tdnnf_nas_b200 import capi
+
+    lib = capi.load()
+    g = np.random.default_rng(N + r)
+    H = g.standard_normal((N, r)).astype(np.float32)
+    WWt = (np.eye(r) * 0.5 + 0.01 * g.standard_normal((r, r))).astype(np.float32)
+    WWt = ((WWt + WWt.T) / 2).astype(np.float32)
+    in_rows = N + 8 * (n_views - 1)
+    rowsq = g.uniform(0.5, 2.0, in_rows).astype(np.float32)
+    offs = [8 * i for i in range(n_views)]
+    weff = g.uniform(0.2, 1.0, n_views).astype(np.float32)
+    Hd, Wd, rq, wf = (torch.from_numpy(a).cuda() for a in (H, WWt, rowsq, weff))
+    L = torch.full((r, r + 3), 7.0, device="cuda")[:, :r]
+    out3 = torch.zeros(3, device="cuda")
+    sumsq = torch.zeros(16, dtype=torch.float64, device="cuda")
+    I = C.c_int32 * n_views
+    rc = lib.tdnnf_ng_gram_scale(ctx.h, C.c_void_p(Hd.data_ptr()), N, r, r, C.c_void_p(L.data_ptr()), r + 3,
+                                 C.c_void_p(Wd.data_ptr()), r, C.c_void_p(rq.data_ptr()), C.c_void_p(sumsq.data_ptr()), in_rows,
+                                 n_views, I(*offs), 1, C.c_void_p(wf.data_ptr()), C.c_float(float(N)), C.c_void_p(out3.data_ptr()))
+    assert rc == 0, lib.tdnnf_last_error()
+    H64 = H.astype(np.float64)
+    L_ref = H64.T @ H64
+    assert rel_err(L.cpu().numpy(), L_ref) < 1e-5
+    tr_xx = float(N) + sum(float(weff[i]) ** 2 * float(rowsq[offs[i]: offs[i] + N].astype(np.float64).sum()) for i in range(n_views))
+    tr_hat = tr_xx - 2 * np.trace(L_ref) + float((L_ref * WWt.astype(np.float64)).sum())
+    o = out3.cpu().numpy()
+    assert o[0] == pytest.approx(tr_xx, rel=1e-5) and o[1] == pytest.approx(tr_hat, rel=1e-3)
+    assert o[2] == pytest.approx(np.sqrt(tr_xx / tr_hat) if tr_hat > 0 else 1.0, rel=1e-3)
+    # W update
+    D = 517
+    A, AC = g.standard_normal((r, r)).astype(np.float32), g.standard_normal((r, r)).astype(np.float32)
+    J, W = g.standard_normal((r, D)).astype(np.float32), g.standard_normal((r, D)).astype(np.float32)
+    Ad, ACd, Jd, Wd2 = (torch.from_numpy(a).cuda() for a in (A, AC, J, W))
+    Wn = torch.zeros((r, D), device="cuda")
+    rc = lib.tdnnf_ng_w_update(ctx.h, C.c_void_p(Ad.data_ptr()), r, C.c_void_p(ACd.data_ptr()), r, C.c_void_p(Jd.data_ptr()), D,
+                               C.c_void_p(Wd2.data_ptr()), D, r, D, C.c_void_p(Wn.data_ptr()), D)
+    assert rc == 0, lib.tdnnf_last_error()
+    ref = A.astype(np.float64) @ J.astype(np.float64) + AC.astype(np.float64) @ W.astype(np.float64)
+    assert rel_err(Wn.cpu().numpy(), ref) < 1e-5
