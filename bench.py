@@ -221,7 +221,9 @@ def workload_config(cfg, gpus):
                 included=("natural-gradient update (OnlineNaturalGradient rank 20/80, update period 4) of all 28 TdnnDARTSV3 "
                           "components, LF-MMI numerator (per-sequence FST) and denominator, UpdateNnetWithMaxChange"),
                 ng_settle_steps=NG_SETTLE_STEPS,
-                not_included="L2 regularisation, xent branch, dropout (proportion 0 in the recipe); the orthonormal constraint does not cover TdnnDARTSV3 (utils.cc:1047-1061)")
+                not_included=("natural gradient of the 5 stock affine layers around the blocks (tdnn1, prefinal, output: plain SGD "
+                              "there; all 28 TdnnDARTSV3 components are preconditioned), L2 regularisation, xent output branch, dropout "
+                              "(proportion 0 in the recipe); the orthonormal constraint does not cover TdnnDARTSV3 (utils.cc:1047-1061)"))
 
 
 def run_ours(args, cfg, rank, world, local_rank):
