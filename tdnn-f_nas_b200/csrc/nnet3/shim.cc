@@ -12,6 +12,10 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <map>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 namespace tdnnf {
 namespace nnet3 {
@@ -29,6 +33,7 @@ tdnnf_ctx* CurrentContext() {
   return g_ctx;
 }
 void SetCurrentContext(tdnnf_ctx* c) { g_ctx = c; }
+static tdnnf_ctx* CurrentContextOrNull() { return g_ctx; }
 void CheckStatus(int rc) {
   if (rc != TDNNF_OK) KALDI_ERR << "tdnnf kernel call failed (" << rc << "): " << tdnnf_last_error();
 }
@@ -378,25 +383,87 @@ template struct Matrix<float>;
 template struct Matrix<double>;
 
 // ------------------------------------------------------------------ device buffers
-CuVector::~CuVector() { if (data_) cudaFree(data_); }
+// Size-bucketed free lists in front of cudaMalloc (the role of Kaldi's CuAllocator).  The components create small
+// device vectors every minibatch (the memo of Propagate, the s_i of UpdateNaturalGradient): a cudaFree per object
+// is a device-wide synchronisation -- 84 pipeline drains per training step of the bench supernet -- and cudaMalloc is
+// slow.  A freed block goes back to its bucket and is handed out again; reuse is ordered by the stream all the work
+// runs on.  Nothing is returned to the driver before process exit.
+namespace {
+class DevicePool {
+ public:
+  static DevicePool& Get() {
+    static DevicePool* p = new DevicePool();  // leaked on purpose: outlives every static CuVector
+    return *p;
+  }
+  void* Alloc(size_t bytes) {
+    const Key k = MakeKey(bytes);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      auto it = free_.find(k);
+      if (it != free_.end() && !it->second.empty()) {
+        void* p = it->second.back();
+        it->second.pop_back();
+        return p;
+      }
+    }
+    void* p = nullptr;
+    CudaOk(cudaMalloc(&p, k.second), "cudaMalloc");
+    return p;
+  }
+  void Free(void* p, size_t bytes) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(mu_);
+    free_[MakeKey(bytes)].push_back(p);
+  }
+
+ private:
+  typedef std::pair<int, size_t> Key;  // (device, rounded bytes)
+  static Key MakeKey(size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t r = 256;
+    while (r < bytes) r <<= 1;                           // powers of two up to 1 MiB, then 1 MiB steps
+    if (bytes > (1u << 20)) r = (bytes + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
+    return Key(dev, r);
+  }
+  std::mutex mu_;
+  std::map<Key, std::vector<void*>> free_;
+};
+
+// The stream the kernels run on (the legacy default stream when no context is selected): allocation zero-fills and
+// the copies below are ordered on it, so that a block handed out again by the pool is never touched out of order.
+cudaStream_t WorkStream() {
+  void* st = nullptr;
+  tdnnf_ctx* ctx = CurrentContextOrNull();
+  if (ctx != nullptr && tdnnf_ctx_get_stream(ctx, &st) == TDNNF_OK) return static_cast<cudaStream_t>(st);
+  return nullptr;
+}
+void ZeroFill(void* p, size_t bytes) { CudaOk(cudaMemsetAsync(p, 0, bytes, WorkStream()), "cudaMemsetAsync"); }
+}  // namespace
+
+CuVector::~CuVector() { DevicePool::Get().Free(data_, sizeof(BaseFloat) * (size_t)dim_); }
 void CuVector::Resize(int32 dim) {
-  if (data_) { cudaFree(data_); data_ = nullptr; }
+  DevicePool::Get().Free(data_, sizeof(BaseFloat) * (size_t)dim_);
+  data_ = nullptr;
   dim_ = dim;
   if (dim > 0) {
-    CudaOk(cudaMalloc(reinterpret_cast<void**>(&data_), sizeof(BaseFloat) * dim), "cudaMalloc");
-    CudaOk(cudaMemset(data_, 0, sizeof(BaseFloat) * dim), "cudaMemset");
+    data_ = static_cast<BaseFloat*>(DevicePool::Get().Alloc(sizeof(BaseFloat) * (size_t)dim));
+    ZeroFill(data_, sizeof(BaseFloat) * (size_t)dim);
   }
 }
 CuVector::CuVector(const CuVector& o) { *this = o; }
 CuVector& CuVector::operator=(const CuVector& o) {
   if (this == &o) return *this;
   Resize(o.dim_);
-  if (dim_ > 0) CudaOk(cudaMemcpy(data_, o.data_, sizeof(BaseFloat) * dim_, cudaMemcpyDeviceToDevice), "cudaMemcpy");
+  if (dim_ > 0) CudaOk(cudaMemcpyAsync(data_, o.data_, sizeof(BaseFloat) * dim_, cudaMemcpyDeviceToDevice, WorkStream()), "cudaMemcpyAsync");
   return *this;
 }
 void CuVector::CopyFromHost(const std::vector<BaseFloat>& h) {
   if ((int32)h.size() != dim_) Resize((int32)h.size());
-  if (dim_ > 0) CudaOk(cudaMemcpy(data_, h.data(), sizeof(BaseFloat) * dim_, cudaMemcpyHostToDevice), "cudaMemcpy");
+  if (dim_ > 0) {
+    CudaOk(cudaMemcpyAsync(data_, h.data(), sizeof(BaseFloat) * dim_, cudaMemcpyHostToDevice, WorkStream()), "cudaMemcpyAsync");
+    CudaOk(cudaStreamSynchronize(WorkStream()), "cudaStreamSynchronize");  // h may be a temporary
+  }
 }
 std::vector<BaseFloat> CuVector::ToHost() const {
   std::vector<BaseFloat> h(dim_);
@@ -429,29 +496,33 @@ BaseFloat VecVec(const CuVector& a, const CuVector& b) {
   return r;
 }
 
-CuMatrix::~CuMatrix() { if (data_) cudaFree(data_); }
+CuMatrix::~CuMatrix() { DevicePool::Get().Free(data_, sizeof(BaseFloat) * (size_t)num_rows_ * stride_); }
 void CuMatrix::Resize(int32 rows, int32 cols) {
-  if (data_) { cudaFree(data_); data_ = nullptr; }
+  DevicePool::Get().Free(data_, sizeof(BaseFloat) * (size_t)num_rows_ * stride_);
+  data_ = nullptr;
   num_rows_ = rows;
   num_cols_ = cols;
   stride_ = (cols + 63) / 64 * 64;  // 256-byte pitch like cudaMallocPitch
   if (rows > 0 && cols > 0) {
-    CudaOk(cudaMalloc(reinterpret_cast<void**>(&data_), sizeof(BaseFloat) * (size_t)rows * stride_), "cudaMalloc");
-    CudaOk(cudaMemset(data_, 0, sizeof(BaseFloat) * (size_t)rows * stride_), "cudaMemset");
+    data_ = static_cast<BaseFloat*>(DevicePool::Get().Alloc(sizeof(BaseFloat) * (size_t)rows * stride_));
+    ZeroFill(data_, sizeof(BaseFloat) * (size_t)rows * stride_);
   }
 }
 CuMatrix::CuMatrix(const CuMatrix& o) : CuMatrixBase<BaseFloat>() { *this = o; }
 CuMatrix& CuMatrix::operator=(const CuMatrix& o) {
   if (this == &o) return *this;
   Resize(o.num_rows_, o.num_cols_);
-  if (data_) CudaOk(cudaMemcpy2D(data_, sizeof(BaseFloat) * stride_, o.data_, sizeof(BaseFloat) * o.stride_,
-                                 sizeof(BaseFloat) * num_cols_, num_rows_, cudaMemcpyDeviceToDevice), "cudaMemcpy2D");
+  if (data_) CudaOk(cudaMemcpy2DAsync(data_, sizeof(BaseFloat) * stride_, o.data_, sizeof(BaseFloat) * o.stride_,
+                                      sizeof(BaseFloat) * num_cols_, num_rows_, cudaMemcpyDeviceToDevice, WorkStream()), "cudaMemcpy2DAsync");
   return *this;
 }
 void CuMatrix::CopyFromHost(const Matrix<BaseFloat>& h) {
   if (h.rows != num_rows_ || h.cols != num_cols_) Resize(h.rows, h.cols);
-  if (data_) CudaOk(cudaMemcpy2D(data_, sizeof(BaseFloat) * stride_, h.v.data(), sizeof(BaseFloat) * h.cols,
-                                 sizeof(BaseFloat) * h.cols, h.rows, cudaMemcpyHostToDevice), "cudaMemcpy2D");
+  if (data_) {
+    CudaOk(cudaMemcpy2DAsync(data_, sizeof(BaseFloat) * stride_, h.v.data(), sizeof(BaseFloat) * h.cols,
+                             sizeof(BaseFloat) * h.cols, h.rows, cudaMemcpyHostToDevice, WorkStream()), "cudaMemcpy2DAsync");
+    CudaOk(cudaStreamSynchronize(WorkStream()), "cudaStreamSynchronize");  // h may be a temporary
+  }
 }
 Matrix<BaseFloat> CuMatrix::ToHost() const {
   Matrix<BaseFloat> h(num_rows_, num_cols_);
