@@ -146,7 +146,7 @@ __global__ void den_alpha_first_kernel(const float* __restrict__ init, int N, in
 
 // One forward frame.  Thread = (state h, V consecutive sequences); lanes run along s, so every
 // arc is two coalesced row reads (alpha(t-1,g,:) and E(t-1,pdf,:)) plus broadcast scalars.
-template <int V>
+template <int V, int U>
 __global__ void __launch_bounds__(kDenThreads)
 den_alpha_frame_kernel(const int2* __restrict__ bwd_ranges, const float4* __restrict__ trans, const int* __restrict__ order,
                        const float* __restrict__ init, int N, int spb, int S, float leaky, const float* __restrict__ alpha_prev,
@@ -174,21 +174,21 @@ den_alpha_frame_kernel(const int2* __restrict__ bwd_ranges, const float4* __rest
       float acc[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) acc[j] = 0.f;
-      // arcs in groups of 4: all transition records first, then all row gathers, then the FMAs, so that
-      // 8 independent L2 reads are in flight per thread instead of a dependent chain
-      for (int a = rg.x; a < rg.y; a += 4) {
-        float4 tr[4];
-        Vec<V> al[4], e[4];
+      // arcs in groups of U: all transition records first, then all row gathers, then the FMAs, so that 2U independent
+      // L2 reads are in flight per thread instead of a dependent chain
+      for (int a = rg.x; a < rg.y; a += U) {
+        float4 tr[U];
+        Vec<V> al[U], e[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) tr[u] = (a + u < rg.y) ? trans[a + u] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < U; ++u) tr[u] = (a + u < rg.y) ? trans[a + u] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
           const int pdf = __float_as_int(tr[u].y), g = __float_as_int(tr[u].z);  // (0,0) for the padding arcs: valid rows, weight 0
           al[u] = Vec<V>::load(alpha_prev + (long long)g * S + s);
           e[u] = Vec<V>::load(E_prev + (long long)pdf * S + s);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < U; ++u)
 #pragma unroll
           for (int j = 0; j < V; ++j) acc[j] += ((al[u].v[j] + tr[u].w * lt[j]) * tr[u].x) * e[u].v[j];
       }
@@ -246,7 +246,7 @@ __global__ void den_beta_last_kernel(const float* __restrict__ tot_prob, int N, 
 
 // One backward frame (kaldi: BetaDashGeneralFrame + Beta): thread = (source state h, V sequences).
 //   vf = p * beta(t+1,g,s) * E(t,pdf,s);  gamma(t,pdf,s) += vf * alpha'(t,h,s)/tot(t,s);  betad(t,h,s) = sum vf / tot(t,s)
-template <int V>
+template <int V, int U>
 __global__ void __launch_bounds__(kDenThreads)
 den_beta_frame_kernel(const int2* __restrict__ fwd_ranges, const float4* __restrict__ trans, const int* __restrict__ order,
                       const float* __restrict__ init, int N, int spb, int S, float leaky, const float* __restrict__ alpha_t,
@@ -282,19 +282,19 @@ den_beta_frame_kernel(const int2* __restrict__ fwd_ranges, const float4* __restr
       float occ[V], totv[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) { occ[j] = (al.v[j] + ih * lt[j]) * inv[j]; totv[j] = 0.f; }
-      for (int a = rg.x; a < rg.y; a += 4) {
-        float4 tr[4];
-        Vec<V> b[4], e[4];
+      for (int a = rg.x; a < rg.y; a += U) {
+        float4 tr[U];
+        Vec<V> b[U], e[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) tr[u] = (a + u < rg.y) ? trans[a + u] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < U; ++u) tr[u] = (a + u < rg.y) ? trans[a + u] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
           const int pdf = __float_as_int(tr[u].y), g = __float_as_int(tr[u].z);
           b[u] = Vec<V>::load(betad_next + (long long)g * S + s);
           e[u] = Vec<V>::load(E_t + (long long)pdf * S + s);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
           if (a + u < rg.y) {
             const int pdf = __float_as_int(tr[u].y);
             float op[V];
@@ -682,6 +682,14 @@ void frame_grid(int N, int num_sms, int* blocks, int* spb) {
 }
 
 int pick_vec(int S) {
+  // V consecutive sequences per thread, lanes along s: the widest loads that still leave >= 16 lanes per state.
+  // Measured at N = 16384, S = 64, T = 50: V = 4 (4 arcs per group) 2.43 ms, V = 2 with 8 arcs per group (same bytes in
+  // flight per thread, twice the threads, 98 registers) 3.12 ms, V = 1 4.71 ms.  TDNNF_DEN_VEC overrides.
+  static const int forced = [] {
+    const char* e = getenv("TDNNF_DEN_VEC");
+    return e ? atoi(e) : 0;
+  }();
+  if ((forced == 4 || forced == 2 || forced == 1) && S % forced == 0) return forced;
   if (S % 4 == 0 && S >= 64) return 4;
   if (S % 2 == 0 && S >= 32) return 2;
   return 1;
@@ -925,11 +933,11 @@ extern "C" int tdnnf_den_forward(tdnnf_den_comp* c, const float* nnet_output, in
     float* tc = c->tot + (size_t)t * S;
     const float* Ep = c->E + (size_t)(t - 1) * P * S;
     if (V == 4)
-      den_alpha_frame_kernel<4><<<blocks, kDenThreads, 0, st>>>(g->bwd_ranges, g->trans, g->order_in, g->init, N, spb, S, c->leaky, ap, tp, Ep, ac, tc);
+      den_alpha_frame_kernel<4, 4><<<blocks, kDenThreads, 0, st>>>(g->bwd_ranges, g->trans, g->order_in, g->init, N, spb, S, c->leaky, ap, tp, Ep, ac, tc);
     else if (V == 2)
-      den_alpha_frame_kernel<2><<<blocks, kDenThreads, 0, st>>>(g->bwd_ranges, g->trans, g->order_in, g->init, N, spb, S, c->leaky, ap, tp, Ep, ac, tc);
+      den_alpha_frame_kernel<2, 4><<<blocks, kDenThreads, 0, st>>>(g->bwd_ranges, g->trans, g->order_in, g->init, N, spb, S, c->leaky, ap, tp, Ep, ac, tc);
     else
-      den_alpha_frame_kernel<1><<<blocks, kDenThreads, 0, st>>>(g->bwd_ranges, g->trans, g->order_in, g->init, N, spb, S, c->leaky, ap, tp, Ep, ac, tc);
+      den_alpha_frame_kernel<1, 4><<<blocks, kDenThreads, 0, st>>>(g->bwd_ranges, g->trans, g->order_in, g->init, N, spb, S, c->leaky, ap, tp, Ep, ac, tc);
     DEN_LAUNCH_CHECK(ctx);
   }
   den_loglike_kernel<<<1, 256, 0, st>>>(c->tot, T, S, c->leaky, g->init_sum, c->tot_prob, c->scalars);
@@ -1003,11 +1011,11 @@ extern "C" int tdnnf_den_backward(tdnnf_den_comp* c, float deriv_weight, float* 
     float* gt = c->gamma + (size_t)t * P * S;
     double* chk = (t == 0) ? c->scalars + 1 : nullptr;
     if (V == 4)
-      den_beta_frame_kernel<4><<<blocks, kDenThreads, 0, st>>>(g->fwd_ranges, g->trans, g->order_out, g->init, N, spb, S, c->leaky, at, tt, Et, bn, sn, bc, sc, gt, chk);
+      den_beta_frame_kernel<4, 4><<<blocks, kDenThreads, 0, st>>>(g->fwd_ranges, g->trans, g->order_out, g->init, N, spb, S, c->leaky, at, tt, Et, bn, sn, bc, sc, gt, chk);
     else if (V == 2)
-      den_beta_frame_kernel<2><<<blocks, kDenThreads, 0, st>>>(g->fwd_ranges, g->trans, g->order_out, g->init, N, spb, S, c->leaky, at, tt, Et, bn, sn, bc, sc, gt, chk);
+      den_beta_frame_kernel<2, 4><<<blocks, kDenThreads, 0, st>>>(g->fwd_ranges, g->trans, g->order_out, g->init, N, spb, S, c->leaky, at, tt, Et, bn, sn, bc, sc, gt, chk);
     else
-      den_beta_frame_kernel<1><<<blocks, kDenThreads, 0, st>>>(g->fwd_ranges, g->trans, g->order_out, g->init, N, spb, S, c->leaky, at, tt, Et, bn, sn, bc, sc, gt, chk);
+      den_beta_frame_kernel<1, 4><<<blocks, kDenThreads, 0, st>>>(g->fwd_ranges, g->trans, g->order_out, g->init, N, spb, S, c->leaky, at, tt, Et, bn, sn, bc, sc, gt, chk);
     DEN_LAUNCH_CHECK(ctx);
   }
   den_deriv_transpose_add_kernel<<<dim3((P + 31) / 32, (S + 31) / 32, T), dim3(32, 8), 0, st>>>(c->gamma, S, P, deriv_weight,
