@@ -113,6 +113,9 @@ int tdnnf_nnet3_component_ng(void* comp, int which, void** ng);
 /* Diagnostic switch: with 1, every PreconditionDirections call is the identity with scale 1, i.e. the components
  * accumulate the un-preconditioned gradient (what the first-level parity tests pin). */
 int tdnnf_nnet3_set_ng_identity(int enable);
+/* Host only (no GPU): the symmetric eigen-solver used by OnlineNaturalGradient's update (Householder tridiagonalisation +
+ * implicit QL, double).  a: n x n row-major symmetric; vals[n]; vecs n x n row-major with eigenvector k in COLUMN k. */
+int tdnnf_nnet3_symmetric_eigen(const double* a, int n, double* vals, double* vecs);
 
 /* ReadEditConfig subset: set-temperature-proportion, set-learning-rate{,-factor} (ref: utils.cc:1166-1415). */
 int tdnnf_nnet3_apply_edits(const char* edits, const char** names, void** comps, int n);

@@ -104,6 +104,8 @@ void SetFastGradients(bool b);
 bool FastGradients();
 // Diagnostic: PreconditionDirections == identity with scale 1 (the un-preconditioned gradient).
 void SetNaturalGradientIdentity(bool b);
+// The symmetric eigen-solver of the host half of the update (Householder + implicit QL), exposed for host tests.
+bool SymmetricEigenForTest(const double* a, int n, double* vals, double* vecs);
 bool NaturalGradientIdentity();
 
 // The six mode booleans of TdnnDARTSV3Component in their on-disk order (conv.h:243-257).

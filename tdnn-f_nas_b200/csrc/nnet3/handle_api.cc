@@ -57,6 +57,11 @@ int tdnnf_nnet3_set_dp_world_size(int g) { API_BEGIN SetDataParallelWorldSize(g)
 int tdnnf_nnet3_set_print_log_alpha(int b) { API_BEGIN SetPrintLogAlpha(b != 0); API_END }
 int tdnnf_nnet3_set_fast_gradients(int b) { API_BEGIN SetFastGradients(b != 0); API_END }
 int tdnnf_nnet3_set_ng_identity(int b) { API_BEGIN SetNaturalGradientIdentity(b != 0); API_END }
+int tdnnf_nnet3_symmetric_eigen(const double* a, int n, double* vals, double* vecs) {
+  API_BEGIN
+  if (!SymmetricEigenForTest(a, n, vals, vecs)) KALDI_ERR << "symmetric eigen-solver did not converge";
+  API_END
+}
 
 int tdnnf_nnet3_ng_new(int rank, int update_period, float num_samples_history, float alpha, void** out) {
   API_BEGIN

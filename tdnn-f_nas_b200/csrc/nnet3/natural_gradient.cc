@@ -331,6 +331,15 @@ BaseFloat Sum(const std::vector<BaseFloat>& v) {
 
 }  // namespace
 
+// Host-only entry for tests: the eigen-solver of the natural-gradient update (handle_api.cc).
+bool SymmetricEigenForTest(const double* a, int n, double* vals, double* vecs) {
+  std::vector<double> m(a, a + (size_t)n * n), va, ve;
+  const bool ok = SymmetricEigen(m, n, &va, &ve);
+  std::copy(va.begin(), va.end(), vals);
+  std::copy(ve.begin(), ve.end(), vecs);
+  return ok;
+}
+
 static bool g_ng_identity = false;
 void SetNaturalGradientIdentity(bool b) { g_ng_identity = b; }
 bool NaturalGradientIdentity() { return g_ng_identity; }

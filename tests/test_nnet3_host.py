@@ -156,3 +156,63 @@ def test_batchnorm_component_config_and_text_form():
     for bad in ("block-dim=4", "dim=12 block-dim=5", "dim=8 epsilon=0", "dim=8 bogus=1"):
         with pytest.raises(nnet3.Nnet3Error):
             nnet3.Component.new("BatchNormComponent", bad)
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 20, 80, 128])
+def test_natural_gradient_eigen_solver_matches_numpy(n):
+    """The host half of OnlineNaturalGradient's update diagonalises an R x R matrix Z_t (R = 20 / 80 in the recipes):
+    Householder + implicit QL in csrc/nnet3/natural_gradient.cc against numpy.linalg.eigh, including repeated and
+    widely spread eigenvalues (the update floors small eigenvalues to a common value)."""
+    import ctypes as C
+
+    import numpy as np
+
+    from tdnnf_nas_b200 import capi
+
+    lib = capi.load()
+    g = np.random.default_rng(n)
+    q, _ = np.linalg.qr(g.standard_normal((n, n)))
+    w = np.concatenate([np.full(n // 3, 2.5), 10.0 ** g.uniform(-8, 3, n - n // 3)])  # a repeated block + 11 decades
+    a = (q * w) @ q.T
+    a = (a + a.T) / 2
+    vals, vecs = np.zeros(n), np.zeros((n, n))
+    dp = C.POINTER(C.c_double)
+    rc = lib.tdnnf_nnet3_symmetric_eigen(np.ascontiguousarray(a).ctypes.data_as(dp), n, vals.ctypes.data_as(dp), vecs.ctypes.data_as(dp))
+    assert rc == 0
+    np.testing.assert_allclose(np.sort(vals), np.sort(np.linalg.eigvalsh(a)), rtol=1e-9, atol=1e-12 * abs(w).max())
+    assert np.abs(vecs.T @ vecs - np.eye(n)).max() < 1e-12
+    assert np.abs(a @ vecs - vecs * vals).max() < 1e-11 * abs(w).max()
+
+
+def test_synthetic_numerator_paths_lie_in_the_denominator_graph():
+    """synth.make_num_graphs(den_graph=...): every (forward pdf, self-loop pdf) pair of a numerator FST is an arc of the
+    denominator graph followed by the self-loop of its destination, so numerator paths are denominator paths."""
+    import numpy as np
+
+    from tdnnf_nas_b200 import synth
+
+    den = synth.make_den_graph(400, 90, 6.0, seed=3)
+    A = den["num_arcs"]
+    src = np.repeat(np.arange(400), den["fwd_ranges"][:, 1] - den["fwd_ranges"][:, 0])
+    arcs = {}
+    for a in range(A):
+        arcs.setdefault((int(src[a]), int(den["pdf"][a])), []).append(int(den["state"][a]))
+    loops = {int(src[a]): int(den["pdf"][a]) for a in range(A) if int(den["state"][a]) == int(src[a])}
+    num = synth.make_num_graphs(6, 90, 30, seed=9, den_graph=den)
+    nA = num["num_arcs"]
+    fr = num["fwd_ranges"]
+    for s in range(num["num_seqs"]):
+        lo, hi = num["state_offsets"][s], num["state_offsets"][s + 1]
+        cand = set(range(400))  # den states the walk may be in before the first phone
+        for st in range(lo, hi - 1):
+            fwd = [a for a in range(fr[st][0], fr[st][1]) if num["arc_state"][a] == st + 1]
+            assert len(fwd) == 1
+            pdf = int(num["arc_pdf"][fwd[0]])
+            nxt = set(d for h in cand for d in arcs.get((h, pdf), []))
+            assert nxt, "forward pdf is not on any arc leaving the walk's state"
+            loop = [a for a in range(fr[st + 1][0], fr[st + 1][1]) if num["arc_state"][a] == st + 1]
+            assert len(loop) == 1
+            nxt = {h for h in nxt if loops.get(h) == int(num["arc_pdf"][loop[0]])}
+            assert nxt, "self-loop pdf does not match the destination's self-loop"
+            cand = nxt
+    assert nA == len(num["arc_pdf"]) // 2
