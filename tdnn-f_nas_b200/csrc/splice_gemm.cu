@@ -74,7 +74,15 @@ __global__ void split_rows_kernel(const float* __restrict__ src, int R, int D, l
 #pragma unroll
       for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(v[j]));
     }
-    if (rowsq != nullptr) {
+    if (rowsq != nullptr && (kvec & 31) == 0) {
+      // every aligned group of 32 consecutive idx lies inside one row: plain warp sum, one red.add per warp
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sq = fmaf(v[j], v[j], sq);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      if (lane == 0 && valid && srow < R) atomicAdd(rowsq + srow, sq);
+    } else if (rowsq != nullptr) {
       float sq = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) sq = fmaf(v[j], v[j], sq);
