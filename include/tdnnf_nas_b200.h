@@ -265,6 +265,19 @@ int tdnnf_batchnorm_train_fwd(tdnnf_ctx* ctx, const float* in, int rows, int col
 int tdnnf_batchnorm_train_bwd(tdnnf_ctx* ctx, const float* out_value, int ov_stride, const float* out_deriv,
                               int od_stride, float* in_deriv, int id_stride, int rows, int cols, float target_rms,
                               const float* memo);
+/* NonlinearComponent statistics (ref: nnet-component-itf.cc:433-481), device doubles as the reference's CuVector<double>:
+ *   store_stats:          value_sum[c] += sum_r out[r][c];  deriv_sum[c] += #{r: out[r][c] > 0}  (deriv_sum may be NULL)
+ *   store_backprop_stats: oderiv_sumsq[c] += sum_r out_deriv[r][c]^2
+ * RectifiedLinearComponent::RepairGradients (ref: nnet-simple-component.cc:990-1074), after the thresholds were scaled by
+ * the frame count: in_deriv[r][c] += -scale * ((s[c] > lower) + (s[c] > upper) - 1), s = deriv_sum averaged over the
+ * blocks_per_row blocks of the full dimension; *num_dims_repaired += #{c: term != 0}. */
+int tdnnf_nonlinear_store_stats(tdnnf_ctx* ctx, const float* out_value, int rows, int cols, int stride, double* value_sum,
+                                double* deriv_sum);
+int tdnnf_nonlinear_store_backprop_stats(tdnnf_ctx* ctx, const float* out_deriv, int rows, int cols, int stride,
+                                         double* oderiv_sumsq);
+int tdnnf_relu_repair_gradients(tdnnf_ctx* ctx, float* in_deriv, int rows, int block_dim, int stride, int blocks_per_row,
+                                const double* deriv_sum, float lower_threshold, float upper_threshold, float scale,
+                                double* num_dims_repaired);
 /* BatchNormComponent::StoreStats (ref: norm.cc:551-589): stats[0:cols] += num_frames * mean, stats[cols:2cols] +=
  * num_frames * uvar (device doubles, as the reference's CuVector<double>), mean / uvar = rows 0 / 1 of memo. */
 int tdnnf_batchnorm_accumulate_stats(tdnnf_ctx* ctx, const float* memo, int cols, float num_frames, double* stats);

@@ -32,6 +32,7 @@ int tdnnf_nnet3_set_rand_seed(uint64_t seed);
 int tdnnf_nnet3_set_rand_counter(uint64_t counter);
 uint64_t tdnnf_nnet3_get_rand_counter(void);
 float tdnnf_nnet3_rand_uniform(void);
+int tdnnf_nnet3_rand_int(int lo, int hi); /* the RandInt the components use (advances the same counter) */
 /* Data-parallel world size: the FLOPs penalty is normalised by rows * world_size. */
 int tdnnf_nnet3_set_dp_world_size(int world_size);
 /* Re-enable the reference's per-minibatch "log_alpha" stdout print (ref: tdnn.cc:571, simple.cc:2640). */

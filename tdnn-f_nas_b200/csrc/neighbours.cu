@@ -506,6 +506,53 @@ extern "C" int tdnnf_batchnorm_train_bwd(tdnnf_ctx* ctx, const float* out_value,
   return TDNNF_OK;
 }
 
+// NonlinearComponent statistics (ref: nnet-component-itf.cc:433-481), accumulated in device doubles:
+//   MODE 0: s0[c] += sum_r x[r][c],  s1[c] += sum_r (x[r][c] > 0)      (value sum, ReLU derivative sum; s1 may be null)
+//   MODE 1: s0[c] += sum_r x[r][c]^2                                    (out_deriv sum of squares)
+template <int MODE>
+__global__ void nonlin_stats_kernel(const float* __restrict__ x, long long xs, int rows, int cols, double* __restrict__ s0,
+                                    double* __restrict__ s1) {
+  __shared__ float red0[8][33], red1[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  float a0 = 0.f, a1 = 0.f;
+  if (col < cols) {
+    for (long long r = blockIdx.y * 8 + threadIdx.y; r < rows; r += (long long)gridDim.y * 8) {
+      const float v = x[r * xs + col];
+      if (MODE == 0) { a0 += v; a1 += v > 0.f ? 1.f : 0.f; }
+      else { a0 += v * v; }
+    }
+  }
+  red0[threadIdx.y][threadIdx.x] = a0;
+  red1[threadIdx.y][threadIdx.x] = a1;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < cols) {
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { t0 += red0[i][threadIdx.x]; t1 += red1[i][threadIdx.x]; }
+    atomicAdd(s0 + col, (double)t0);
+    if (MODE == 0 && s1 != nullptr) atomicAdd(s1 + col, (double)t1);
+  }
+}
+
+// RectifiedLinearComponent::RepairGradients (ref: nnet-simple-component.cc:990-1074):
+//   in_deriv[r][c] += -scale * ((stat[c] > lower) + (stat[c] > upper) - 1),  stat = deriv_sum averaged over the blocks;
+//   *num_repaired += number of columns whose term is non-zero (block 0 of the grid only counts).
+__global__ void relu_repair_kernel(float* __restrict__ in_deriv, long long ld, int rows, int block_dim, int num_blocks_of_dim,
+                                   const double* __restrict__ deriv_sum, float lower, float upper, float scale,
+                                   double* __restrict__ num_repaired) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < (long long)rows * block_dim;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % block_dim);
+    const long long r = idx / block_dim;
+    double st = 0.0;
+    for (int b = 0; b < num_blocks_of_dim; ++b) st += deriv_sum[(long long)b * block_dim + c];
+    const float stat = (float)(st / num_blocks_of_dim);
+    const float t = (stat - lower > 0.f ? 1.f : 0.f) + (stat - upper > 0.f ? 1.f : 0.f) - 1.f;
+    if (t != 0.f) in_deriv[r * ld + c] += -scale * t;
+    if (r == 0 && t != 0.f) atomicAdd(num_repaired, 1.0);
+  }
+}
+
 // stats[i] += num_frames * mean[i], stats[cols + i] += num_frames * uvar[i]   (BatchNormComponent::StoreStats, norm.cc:583-588)
 __global__ void bn_accumulate_stats_kernel(const float* __restrict__ memo, int cols, float num_frames, double* __restrict__ stats) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -513,6 +560,37 @@ __global__ void bn_accumulate_stats_kernel(const float* __restrict__ memo, int c
     stats[i] += (double)num_frames * (double)memo[i];
     stats[cols + i] += (double)num_frames * (double)memo[cols + i];
   }
+}
+
+extern "C" int tdnnf_nonlinear_store_stats(tdnnf_ctx* ctx, const float* out_value, int rows, int cols, int stride,
+                                           double* value_sum, double* deriv_sum) {
+  PROLOGUE(out_value && value_sum && stride >= cols, "bad argument");
+  int gy = std::min(128, (rows + 255) / 256);
+  nonlin_stats_kernel<0><<<dim3((cols + 31) / 32, std::max(gy, 1)), dim3(32, 8), 0, ctx->stream>>>(out_value, stride, rows, cols,
+                                                                                                  value_sum, deriv_sum);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_nonlinear_store_backprop_stats(tdnnf_ctx* ctx, const float* out_deriv, int rows, int cols, int stride,
+                                                    double* oderiv_sumsq) {
+  PROLOGUE(out_deriv && oderiv_sumsq && stride >= cols, "bad argument");
+  int gy = std::min(128, (rows + 255) / 256);
+  nonlin_stats_kernel<1><<<dim3((cols + 31) / 32, std::max(gy, 1)), dim3(32, 8), 0, ctx->stream>>>(out_deriv, stride, rows, cols,
+                                                                                                  oderiv_sumsq, nullptr);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_relu_repair_gradients(tdnnf_ctx* ctx, float* in_deriv, int rows, int block_dim, int stride, int blocks_per_row,
+                                           const double* deriv_sum, float lower_threshold, float upper_threshold, float scale,
+                                           double* num_dims_repaired) {
+  const int cols = block_dim;
+  PROLOGUE(in_deriv && deriv_sum && num_dims_repaired && stride >= block_dim && blocks_per_row >= 1, "bad argument");
+  relu_repair_kernel<<<grid_for((long long)rows * block_dim, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
+      in_deriv, stride, rows, block_dim, blocks_per_row, deriv_sum, lower_threshold, upper_threshold, scale, num_dims_repaired);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
 }
 
 extern "C" int tdnnf_batchnorm_accumulate_stats(tdnnf_ctx* ctx, const float* memo, int cols, float num_frames, double* stats) {

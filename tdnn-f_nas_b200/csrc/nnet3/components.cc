@@ -1402,6 +1402,362 @@ void BatchNormComponent::Add(BaseFloat alpha, const Component& other_in) {  // n
   ComputeDerivedBn();
 }
 
+
+// =====================================================================================
+// NonlinearComponent / RectifiedLinearComponent (nnet-component-itf.cc:433-725, nnet-simple-component.cc:958-1094)
+// =====================================================================================
+NonlinearComponent::NonlinearComponent()
+    : dim_(-1), block_dim_(-1), stats_dev_(NULL), has_value_(false), has_deriv_(false), has_oderiv_(false), count_(0.0),
+      oderiv_count_(0.0), num_dims_processed_(0.0), self_repair_lower_threshold_(kUnsetThreshold),
+      self_repair_upper_threshold_(kUnsetThreshold), self_repair_scale_(0.0) {}
+
+NonlinearComponent::NonlinearComponent(const NonlinearComponent& other)
+    : dim_(other.dim_), block_dim_(other.block_dim_), stats_dev_(NULL), has_value_(false), has_deriv_(false), has_oderiv_(false),
+      count_(other.count_), oderiv_count_(other.oderiv_count_), num_dims_processed_(other.num_dims_processed_),
+      self_repair_lower_threshold_(other.self_repair_lower_threshold_),
+      self_repair_upper_threshold_(other.self_repair_upper_threshold_), self_repair_scale_(other.self_repair_scale_) {
+  if (other.stats_dev_ != NULL) {
+    HostStats h;
+    other.Pull(&h);
+    Push(h);
+  }
+}
+
+NonlinearComponent::~NonlinearComponent() {
+  if (stats_dev_) cudaFree(stats_dev_);
+}
+
+void NonlinearComponent::EnsureDevice() const {
+  if (stats_dev_ != NULL) return;
+  KALDI_ASSERT(dim_ > 0);
+  const size_t bytes = sizeof(double) * (3 * (size_t)dim_ + 1);
+  if (cudaMalloc(reinterpret_cast<void**>(&stats_dev_), bytes) != cudaSuccess || cudaMemset(stats_dev_, 0, bytes) != cudaSuccess)
+    KALDI_ERR << "NonlinearComponent: cudaMalloc of the statistics failed";
+}
+
+void NonlinearComponent::Pull(HostStats* h) const {
+  h->value_sum.clear();
+  h->deriv_sum.clear();
+  h->oderiv_sumsq.clear();
+  h->num_dims_self_repaired = 0.0;
+  if (stats_dev_ == NULL) return;
+  std::vector<double> all(3 * (size_t)dim_ + 1);
+  void* st = NULL;
+  CheckStatus(tdnnf_ctx_get_stream(CurrentContext(), &st));
+  if (cudaMemcpyAsync(all.data(), stats_dev_, sizeof(double) * all.size(), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(st)) != cudaSuccess ||
+      cudaStreamSynchronize(static_cast<cudaStream_t>(st)) != cudaSuccess)
+    KALDI_ERR << "NonlinearComponent: reading the statistics failed";
+  if (has_value_) h->value_sum.assign(all.begin(), all.begin() + dim_);
+  if (has_deriv_) h->deriv_sum.assign(all.begin() + dim_, all.begin() + 2 * dim_);
+  if (has_oderiv_) h->oderiv_sumsq.assign(all.begin() + 2 * dim_, all.begin() + 3 * dim_);
+  h->num_dims_self_repaired = all[3 * (size_t)dim_];
+}
+
+void NonlinearComponent::Push(const HostStats& h) {
+  EnsureDevice();
+  std::vector<double> all(3 * (size_t)dim_ + 1, 0.0);
+  has_value_ = (int32)h.value_sum.size() == dim_;
+  has_deriv_ = (int32)h.deriv_sum.size() == dim_;
+  has_oderiv_ = (int32)h.oderiv_sumsq.size() == dim_;
+  if (has_value_) std::copy(h.value_sum.begin(), h.value_sum.end(), all.begin());
+  if (has_deriv_) std::copy(h.deriv_sum.begin(), h.deriv_sum.end(), all.begin() + dim_);
+  if (has_oderiv_) std::copy(h.oderiv_sumsq.begin(), h.oderiv_sumsq.end(), all.begin() + 2 * dim_);
+  all[3 * (size_t)dim_] = h.num_dims_self_repaired;
+  void* st = NULL;
+  CheckStatus(tdnnf_ctx_get_stream(CurrentContext(), &st));
+  if (cudaMemcpyAsync(stats_dev_, all.data(), sizeof(double) * all.size(), cudaMemcpyHostToDevice, static_cast<cudaStream_t>(st)) != cudaSuccess ||
+      cudaStreamSynchronize(static_cast<cudaStream_t>(st)) != cudaSuccess)
+    KALDI_ERR << "NonlinearComponent: writing the statistics failed";
+}
+
+double NonlinearComponent::NumDimsSelfRepaired() const {
+  HostStats h;
+  Pull(&h);
+  return h.num_dims_self_repaired;
+}
+
+void NonlinearComponent::InitFromConfig(ConfigLine* cfl) {  // itf.cc:707-718
+  bool ok = cfl->GetValue("dim", &dim_);
+  block_dim_ = dim_;
+  cfl->GetValue("block-dim", &block_dim_);
+  cfl->GetValue("self-repair-lower-threshold", &self_repair_lower_threshold_);
+  cfl->GetValue("self-repair-upper-threshold", &self_repair_upper_threshold_);
+  cfl->GetValue("self-repair-scale", &self_repair_scale_);
+  if (!ok || cfl->HasUnusedValues() || dim_ <= 0 || block_dim_ <= 0 || dim_ % block_dim_ != 0)
+    KALDI_ERR << "Invalid initializer for layer of type " << Type() << ": \"" << cfl->WholeLine() << "\"";
+}
+
+void NonlinearComponent::StoreStatsInternal(const CuMatrixBase<BaseFloat>& out_value, bool with_deriv) {  // itf.cc:433-459
+  KALDI_ASSERT(out_value.NumCols() == dim_);
+  EnsureDevice();
+  void* st = NULL;
+  CheckStatus(tdnnf_ctx_get_stream(CurrentContext(), &st));
+  if (!has_value_ || (with_deriv && !has_deriv_)) {  // "Resize": a dimension change zeroes the count and the sums
+    if (!has_value_) {
+      has_value_ = true;
+      count_ = 0.0;
+      cudaMemsetAsync(ValueSum(), 0, sizeof(double) * dim_, static_cast<cudaStream_t>(st));
+    }
+    if (with_deriv && !has_deriv_) {
+      has_deriv_ = true;
+      count_ = 0.0;
+      cudaMemsetAsync(ValueSum(), 0, sizeof(double) * 2 * dim_, static_cast<cudaStream_t>(st));
+    }
+  }
+  count_ += out_value.NumRows();
+  CheckStatus(tdnnf_nonlinear_store_stats(CurrentContext(), out_value.Data(), out_value.NumRows(), dim_, out_value.Stride(),
+                                          ValueSum(), with_deriv ? DerivSum() : NULL));
+}
+
+void NonlinearComponent::StoreBackpropStats(const CuMatrixBase<BaseFloat>& out_deriv) {  // itf.cc:461-480
+  // "Only store these stats about every 4 minibatches" -- the condition is the reference's (it SKIPS on a draw of 0)
+  if (RandInt(0, 3) == 0 && oderiv_count_ != 0) return;
+  KALDI_ASSERT(out_deriv.NumCols() == dim_);
+  EnsureDevice();
+  if (!has_oderiv_) {
+    has_oderiv_ = true;
+    oderiv_count_ = 0.0;
+    void* st = NULL;
+    CheckStatus(tdnnf_ctx_get_stream(CurrentContext(), &st));
+    cudaMemsetAsync(OderivSumsq(), 0, sizeof(double) * dim_, static_cast<cudaStream_t>(st));
+  }
+  CheckStatus(tdnnf_nonlinear_store_backprop_stats(CurrentContext(), out_deriv.Data(), out_deriv.NumRows(), dim_,
+                                                   out_deriv.Stride(), OderivSumsq()));
+  oderiv_count_ += out_deriv.NumRows();
+}
+
+void NonlinearComponent::ZeroStats() {  // itf.cc:483-491
+  if (stats_dev_ != NULL) {
+    void* st = NULL;
+    CheckStatus(tdnnf_ctx_get_stream(CurrentContext(), &st));
+    cudaMemsetAsync(stats_dev_, 0, sizeof(double) * (3 * (size_t)dim_ + 1), static_cast<cudaStream_t>(st));
+  }
+  count_ = 0.0;
+  oderiv_count_ = 0.0;
+  num_dims_processed_ = 0.0;
+}
+
+std::string NonlinearComponent::Info() const {  // itf.cc:493-531
+  std::ostringstream stream;
+  HostStats h;
+  Pull(&h);
+  stream << Type() << ", dim=" << dim_;
+  if (block_dim_ != dim_) stream << ", block-dim=" << block_dim_;
+  if (self_repair_lower_threshold_ != kUnsetThreshold) stream << ", self-repair-lower-threshold=" << self_repair_lower_threshold_;
+  if (self_repair_upper_threshold_ != kUnsetThreshold) stream << ", self-repair-upper-threshold=" << self_repair_upper_threshold_;
+  if (self_repair_scale_ != 0.0) stream << ", self-repair-scale=" << self_repair_scale_;
+  if (count_ > 0 && (int32)h.value_sum.size() == dim_) {
+    stream << ", count=" << std::setprecision(3) << count_ << std::setprecision(6);
+    stream << ", self-repaired-proportion=" << (num_dims_processed_ > 0 ? h.num_dims_self_repaired / num_dims_processed_ : 0);
+    std::vector<BaseFloat> avg(dim_);
+    for (int32 i = 0; i < dim_; ++i) avg[i] = (BaseFloat)h.value_sum[i] * (BaseFloat)(1.0 / count_);
+    stream << ", value-avg=" << SummarizeVector(avg);
+    if ((int32)h.deriv_sum.size() == dim_) {
+      for (int32 i = 0; i < dim_; ++i) avg[i] = (BaseFloat)(h.deriv_sum[i] / count_);
+      stream << ", deriv-avg=" << SummarizeVector(avg);
+    }
+  }
+  if (oderiv_count_ > 0 && (int32)h.oderiv_sumsq.size() == dim_) {
+    std::vector<BaseFloat> rms(dim_);
+    for (int32 i = 0; i < dim_; ++i) rms[i] = (BaseFloat)std::sqrt(std::max(0.0, h.oderiv_sumsq[i] / oderiv_count_));
+    stream << ", oderiv-rms=" << SummarizeVector(rms) << ", oderiv-count=" << oderiv_count_;
+  }
+  return stream.str();
+}
+
+void NonlinearComponent::Scale(BaseFloat scale) {  // itf.cc:533-541
+  HostStats h;
+  Pull(&h);
+  for (double& x : h.value_sum) x *= scale;
+  for (double& x : h.deriv_sum) x *= scale;
+  for (double& x : h.oderiv_sumsq) x *= scale;
+  h.num_dims_self_repaired *= scale;
+  if (stats_dev_ != NULL) Push(h);
+  count_ *= scale;
+  oderiv_count_ *= scale;
+  num_dims_processed_ *= scale;
+}
+
+void NonlinearComponent::Add(BaseFloat alpha, const Component& other_in) {  // itf.cc:543-563
+  const NonlinearComponent* other = dynamic_cast<const NonlinearComponent*>(&other_in);
+  KALDI_ASSERT(other != NULL);
+  HostStats h, o;
+  Pull(&h);
+  other->Pull(&o);
+  auto add = [&](std::vector<double>* mine, const std::vector<double>& theirs) {
+    if (mine->empty() && !theirs.empty()) mine->assign(theirs.size(), 0.0);
+    if (!theirs.empty())
+      for (size_t i = 0; i < mine->size(); ++i) (*mine)[i] += alpha * theirs[i];
+  };
+  add(&h.value_sum, o.value_sum);
+  add(&h.deriv_sum, o.deriv_sum);
+  add(&h.oderiv_sumsq, o.oderiv_sumsq);
+  h.num_dims_self_repaired += alpha * o.num_dims_self_repaired;
+  if (!h.value_sum.empty() || !h.deriv_sum.empty() || !h.oderiv_sumsq.empty() || h.num_dims_self_repaired != 0.0) Push(h);
+  count_ += alpha * other->count_;
+  oderiv_count_ += alpha * other->oderiv_count_;
+  num_dims_processed_ += alpha * other->num_dims_processed_;
+}
+
+void NonlinearComponent::Read(std::istream& is, bool binary) {  // itf.cc:565-628
+  const std::string beg = "<" + Type() + ">", end = "</" + Type() + ">";
+  ExpectOneOrTwoTokens(is, binary, beg, "<Dim>");
+  ReadBasicType(is, binary, &dim_);
+  if (PeekToken(is, binary) == 'B') {
+    ExpectToken(is, binary, "<BlockDim>");
+    ReadBasicType(is, binary, &block_dim_);
+  } else {
+    block_dim_ = dim_;
+  }
+  HostStats h;
+  h.num_dims_self_repaired = 0.0;
+  Vector<double> v;
+  ExpectToken(is, binary, "<ValueAvg>");
+  v.Read(is, binary);
+  h.value_sum = v.v;
+  ExpectToken(is, binary, "<DerivAvg>");
+  v.Read(is, binary);
+  h.deriv_sum = v.v;
+  ExpectToken(is, binary, "<Count>");
+  ReadBasicType(is, binary, &count_);
+  if (PeekToken(is, binary) == 'O') {
+    ExpectToken(is, binary, "<OderivRms>");
+    v.Read(is, binary);
+    h.oderiv_sumsq = v.v;
+    for (double& x : h.oderiv_sumsq) x = x * x;
+    ExpectToken(is, binary, "<OderivCount>");
+    ReadBasicType(is, binary, &oderiv_count_);
+  } else {
+    oderiv_count_ = 0.0;
+  }
+  for (double& x : h.value_sum) x *= count_;
+  for (double& x : h.deriv_sum) x *= count_;
+  for (double& x : h.oderiv_sumsq) x *= oderiv_count_;
+  std::string token;
+  ReadToken(is, binary, &token);
+  if (token[0] != '<') token = '<' + token;
+  if (token == "<NumDimsSelfRepaired>") {
+    ReadBasicType(is, binary, &h.num_dims_self_repaired);
+    ReadToken(is, binary, &token);
+  }
+  if (token == "<NumDimsProcessed>") {
+    ReadBasicType(is, binary, &num_dims_processed_);
+    ReadToken(is, binary, &token);
+  }
+  if (token == "<SelfRepairLowerThreshold>") {
+    ReadBasicType(is, binary, &self_repair_lower_threshold_);
+    ReadToken(is, binary, &token);
+  }
+  if (token == "<SelfRepairUpperThreshold>") {
+    ReadBasicType(is, binary, &self_repair_upper_threshold_);
+    ReadToken(is, binary, &token);
+  }
+  if (token == "<SelfRepairScale>") {
+    ReadBasicType(is, binary, &self_repair_scale_);
+    ReadToken(is, binary, &token);
+  }
+  if (token != end) KALDI_ERR << "Expected token " << end << ", got " << token;
+  if (!h.value_sum.empty() || !h.deriv_sum.empty() || !h.oderiv_sumsq.empty() || h.num_dims_self_repaired != 0.0) Push(h);
+}
+
+void NonlinearComponent::Write(std::ostream& os, bool binary) const {  // itf.cc:630-687
+  HostStats h;
+  Pull(&h);
+  WriteToken(os, binary, "<" + Type() + ">");
+  WriteToken(os, binary, "<Dim>");
+  WriteBasicType(os, binary, dim_);
+  if (block_dim_ != dim_) {
+    WriteToken(os, binary, "<BlockDim>");
+    WriteBasicType(os, binary, block_dim_);
+  }
+  auto write_scaled = [&](const char* token, const std::vector<double>& sum, double cnt, bool rms) {
+    WriteToken(os, binary, token);
+    Vector<BaseFloat> temp((int32)sum.size());
+    for (size_t i = 0; i < sum.size(); ++i) {
+      BaseFloat x = (BaseFloat)sum[i];
+      if (cnt != 0.0) x *= (BaseFloat)(1.0 / cnt);
+      if (rms) x = std::sqrt(std::max(x, 0.0f));
+      temp.v[i] = x;
+    }
+    temp.Write(os, binary);
+  };
+  write_scaled("<ValueAvg>", h.value_sum, count_, false);
+  write_scaled("<DerivAvg>", h.deriv_sum, count_, false);
+  WriteToken(os, binary, "<Count>");
+  WriteBasicType(os, binary, count_);
+  write_scaled("<OderivRms>", h.oderiv_sumsq, oderiv_count_, true);
+  WriteToken(os, binary, "<OderivCount>");
+  WriteBasicType(os, binary, oderiv_count_);
+  WriteToken(os, binary, "<NumDimsSelfRepaired>");
+  WriteBasicType(os, binary, h.num_dims_self_repaired);
+  WriteToken(os, binary, "<NumDimsProcessed>");
+  WriteBasicType(os, binary, num_dims_processed_);
+  if (self_repair_lower_threshold_ != kUnsetThreshold) {
+    WriteToken(os, binary, "<SelfRepairLowerThreshold>");
+    WriteBasicType(os, binary, self_repair_lower_threshold_);
+  }
+  if (self_repair_upper_threshold_ != kUnsetThreshold) {
+    WriteToken(os, binary, "<SelfRepairUpperThreshold>");
+    WriteBasicType(os, binary, self_repair_upper_threshold_);
+  }
+  if (self_repair_scale_ != 0.0) {
+    WriteToken(os, binary, "<SelfRepairScale>");
+    WriteBasicType(os, binary, self_repair_scale_);
+  }
+  WriteToken(os, binary, "</" + Type() + ">");
+}
+
+void* RectifiedLinearComponent::Propagate(const ComponentPrecomputedIndexes*, const CuMatrixBase<BaseFloat>& in,
+                                          CuMatrixBase<BaseFloat>* out) const {  // simple.cc:958-966
+  KALDI_ASSERT(SameDim(in, *out));
+  CheckStatus(tdnnf_relu_fwd(CurrentContext(), in.Data(), in.NumRows(), in.NumCols(), in.Stride(), out->Data(), out->Stride()));
+  return NULL;
+}
+
+void RectifiedLinearComponent::Backprop(const std::string&, const ComponentPrecomputedIndexes*, const CuMatrixBase<BaseFloat>&,
+                                        const CuMatrixBase<BaseFloat>& out_value, const CuMatrixBase<BaseFloat>& out_deriv,
+                                        void*, Component* to_update_in, CuMatrixBase<BaseFloat>* in_deriv) const {  // simple.cc:968-987
+  if (in_deriv == NULL) return;
+  KALDI_ASSERT(SameDim(out_value, out_deriv) && SameDim(out_value, *in_deriv));
+  // in_deriv = Heaviside(out_value) .* out_deriv
+  CheckStatus(tdnnf_relu_bwd(CurrentContext(), out_value.Data(), out_value.Stride(), out_deriv.Data(), out_deriv.Stride(),
+                             in_deriv->Data(), in_deriv->Stride(), out_value.NumRows(), out_value.NumCols()));
+  RectifiedLinearComponent* to_update = dynamic_cast<RectifiedLinearComponent*>(to_update_in);
+  if (to_update != NULL) {
+    RepairGradients(in_deriv, to_update);
+    to_update->StoreBackpropStats(out_deriv);
+  }
+}
+
+void RectifiedLinearComponent::RepairGradients(CuMatrixBase<BaseFloat>* in_deriv, RectifiedLinearComponent* to_update) const {
+  // simple.cc:990-1074.  The statistics are those of `this` (the model), the counters those of to_update.
+  KALDI_ASSERT(to_update != NULL);
+  const BaseFloat default_lower_threshold = 0.05f, default_upper_threshold = 0.95f, repair_probability = 0.5f;
+  KALDI_ASSERT(in_deriv->NumCols() == dim_ || in_deriv->NumCols() == block_dim_);
+  if (self_repair_scale_ == 0.0 || count_ == 0.0 || !has_deriv_) return;
+  int32 rows = in_deriv->NumRows(), stride = in_deriv->Stride();
+  if (in_deriv->NumCols() != block_dim_) {  // the reference recurses on the reshaped matrix
+    KALDI_ASSERT(in_deriv->NumCols() == in_deriv->Stride());
+    rows *= dim_ / block_dim_;
+    stride = block_dim_;
+  }
+  if (RandUniformOpen() > repair_probability) return;
+  to_update->num_dims_processed_ += block_dim_;
+  KALDI_ASSERT(self_repair_scale_ > 0.0 && self_repair_scale_ < 0.1);
+  const BaseFloat count = (BaseFloat)count_;
+  const BaseFloat lower = (self_repair_lower_threshold_ == kUnsetThreshold ? default_lower_threshold : self_repair_lower_threshold_) * count;
+  const BaseFloat upper = (self_repair_upper_threshold_ == kUnsetThreshold ? default_upper_threshold : self_repair_upper_threshold_) * count;
+  to_update->EnsureDevice();
+  CheckStatus(tdnnf_relu_repair_gradients(CurrentContext(), in_deriv->Data(), rows, block_dim_, stride, dim_ / block_dim_, DerivSum(),
+                                          lower, upper, self_repair_scale_ / repair_probability, to_update->Repaired()));
+}
+
+void RectifiedLinearComponent::StoreStats(const CuMatrixBase<BaseFloat>&, const CuMatrixBase<BaseFloat>& out_value, void*) {
+  // simple.cc:1077-1090: about every other minibatch, but always the first one
+  if (RandInt(0, 1) == 0 && count_ != 0) return;
+  StoreStatsInternal(out_value, true);
+}
+
 // =====================================================================================
 // factories (itf.cc:56-293: the registrations the README adds) and edit directives
 // =====================================================================================
@@ -1411,6 +1767,7 @@ Component* Component::NewComponentOfType(const std::string& component_type) {
   else if (component_type == "CopyNComponent") ans = new CopyNComponent();                           // itf.cc:202-203
   else if (component_type == "BatchNormTestComponent") ans = new BatchNormTestComponent();           // itf.cc:226-227
   else if (component_type == "BatchNormComponent") ans = new BatchNormComponent();                   // itf.cc (stock)
+  else if (component_type == "RectifiedLinearComponent") ans = new RectifiedLinearComponent();       // itf.cc (stock)
   else if (component_type == "OnehotFunctionComponent") ans = new OnehotFunctionComponent();         // itf.cc:250-251
   else if (component_type == "SoftmaxFlopsComponent") ans = new SoftmaxFlopsComponent();             // itf.cc:262-263
   else if (component_type == "GumbelSoftmaxFlopsComponent") ans = new GumbelSoftmaxFlopsComponent(); // itf.cc:270-273

@@ -489,6 +489,72 @@ class BatchNormComponent : public BatchNormTestComponent {
   mutable double pending_count_;
 };
 
+// ------------------------------------------------------------------ NonlinearComponent / RectifiedLinearComponent
+// The ReLU of every TDNN-F block with its activation statistics and self-repair (nnet-component-itf.h NonlinearComponent,
+// nnet-component-itf.cc:433-725; nnet-simple-component.h:344-376, nnet-simple-component.cc:958-1094).  The statistics
+// live in device doubles (the reference's CuVector<double>) and are mirrored on the host only for I/O, Scale and Add.
+class NonlinearComponent : public Component {
+ public:
+  NonlinearComponent();
+  NonlinearComponent(const NonlinearComponent& other);
+  virtual ~NonlinearComponent();
+  virtual int32 InputDim() const { return dim_; }
+  virtual int32 OutputDim() const { return dim_; }
+  virtual void InitFromConfig(ConfigLine* cfl);
+  virtual void Read(std::istream& is, bool binary);
+  virtual void Write(std::ostream& os, bool binary) const;
+  virtual std::string Info() const;
+  virtual void ZeroStats();
+  virtual void Scale(BaseFloat scale);
+  virtual void Add(BaseFloat alpha, const Component& other);
+  double Count() const { return count_; }
+  double OderivCount() const { return oderiv_count_; }
+  double NumDimsProcessed() const { return num_dims_processed_; }
+  double NumDimsSelfRepaired() const;
+
+ protected:
+  struct HostStats {
+    std::vector<double> value_sum, deriv_sum, oderiv_sumsq;  // empty = "Dim() == 0" in the reference
+    double num_dims_self_repaired;
+  };
+  void Pull(HostStats* h) const;
+  void Push(const HostStats& h);
+  void EnsureDevice() const;
+  double* ValueSum() const { return stats_dev_; }
+  double* DerivSum() const { return stats_dev_ + dim_; }
+  double* OderivSumsq() const { return stats_dev_ + 2 * dim_; }
+  double* Repaired() const { return stats_dev_ + 3 * dim_; }
+  void StoreStatsInternal(const CuMatrixBase<BaseFloat>& out_value, bool with_deriv);  // deriv = Heaviside(out_value)
+  void StoreBackpropStats(const CuMatrixBase<BaseFloat>& out_deriv);
+  static constexpr BaseFloat kUnsetThreshold = -1000.0f;
+  int32 dim_, block_dim_;
+  mutable double* stats_dev_;  // [3 * dim + 1]: value_sum, deriv_sum, oderiv_sumsq, num_dims_self_repaired
+  bool has_value_, has_deriv_, has_oderiv_;
+  double count_, oderiv_count_, num_dims_processed_;
+  BaseFloat self_repair_lower_threshold_, self_repair_upper_threshold_, self_repair_scale_;
+};
+
+class RectifiedLinearComponent : public NonlinearComponent {
+ public:
+  RectifiedLinearComponent() {}
+  RectifiedLinearComponent(const RectifiedLinearComponent& other) : NonlinearComponent(other) {}
+  virtual std::string Type() const { return "RectifiedLinearComponent"; }
+  virtual Component* Copy() const { return new RectifiedLinearComponent(*this); }
+  virtual int32 Properties() const {
+    return kSimpleComponent | kBackpropNeedsOutput | kPropagateInPlace | kStoresStats | (block_dim_ != dim_ ? kInputContiguous : 0);
+  }
+  virtual void* Propagate(const ComponentPrecomputedIndexes* indexes, const CuMatrixBase<BaseFloat>& in,
+                          CuMatrixBase<BaseFloat>* out) const;
+  virtual void Backprop(const std::string& debug_info, const ComponentPrecomputedIndexes* indexes,
+                        const CuMatrixBase<BaseFloat>& in_value, const CuMatrixBase<BaseFloat>& out_value,
+                        const CuMatrixBase<BaseFloat>& out_deriv, void* memo, Component* to_update,
+                        CuMatrixBase<BaseFloat>* in_deriv) const;
+  virtual void StoreStats(const CuMatrixBase<BaseFloat>& in_value, const CuMatrixBase<BaseFloat>& out_value, void* memo);
+
+ private:
+  void RepairGradients(CuMatrixBase<BaseFloat>* in_deriv, RectifiedLinearComponent* to_update) const;
+};
+
 // ------------------------------------------------------------------ edit directives (utils.cc:1166-1415)
 // The subset of ReadEditConfig this path needs: set-temperature-proportion (utils.cc:1352-1405)
 // plus set-learning-rate / set-learning-rate-factor for the recipes' model surgery.

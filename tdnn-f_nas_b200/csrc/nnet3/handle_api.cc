@@ -53,6 +53,7 @@ int tdnnf_nnet3_set_rand_seed(uint64_t seed) { API_BEGIN SetRandSeed(seed); API_
 int tdnnf_nnet3_set_rand_counter(uint64_t c) { API_BEGIN SetRandCounter(c); API_END }
 uint64_t tdnnf_nnet3_get_rand_counter(void) { return GetRandCounter(); }
 float tdnnf_nnet3_rand_uniform(void) { return RandUniformOpen(); }
+int tdnnf_nnet3_rand_int(int lo, int hi) { return RandInt(lo, hi); }
 int tdnnf_nnet3_set_dp_world_size(int g) { API_BEGIN SetDataParallelWorldSize(g); API_END }
 int tdnnf_nnet3_set_print_log_alpha(int b) { API_BEGIN SetPrintLogAlpha(b != 0); API_END }
 int tdnnf_nnet3_set_fast_gradients(int b) { API_BEGIN SetFastGradients(b != 0); API_END }

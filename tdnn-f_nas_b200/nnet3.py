@@ -70,6 +70,11 @@ def rand_uniform() -> float:
     return float(_lib().tdnnf_nnet3_rand_uniform())
 
 
+def rand_int(lo: int, hi: int) -> int:
+    """The RandInt draw the components make (advances the shared counter)."""
+    return int(_lib().tdnnf_nnet3_rand_int(int(lo), int(hi)))
+
+
 def set_dp_world_size(g: int):
     _check(_lib().tdnnf_nnet3_set_dp_world_size(g))
 

@@ -356,3 +356,76 @@ def test_batchnorm_component_training_mode(nn, D, block, R):
     bn.set_test_mode(False)
     bn.zero_stats()
     assert bn.bn_count() == 0
+
+
+def test_rectified_linear_component_stats_and_self_repair(nn):
+    """RectifiedLinearComponent (nnet-simple-component.cc:958-1094, nnet-component-itf.cc:433-481): Propagate, StoreStats
+    (value / derivative sums), Backprop with the self-repair term and the out_deriv statistics, replaying the component's
+    RandInt / RandUniform draws; then the text form, a round trip, Scale / Add / ZeroStats."""
+    import torch
+
+    g = np.random.default_rng(12)
+    R, D = 300, 64
+    scale = 0.01
+    comp = nn.Component.new("RectifiedLinearComponent", f"dim={D} self-repair-scale={scale}")
+    x = g.standard_normal((R, D)).astype(np.float32)
+    x[:, :5] = -np.abs(x[:, :5]) - 0.1       # dead units: derivative average 0 <= 0.05
+    x[:, 5:9] = np.abs(x[:, 5:9]) + 0.1      # always-on units: derivative average 1 > 0.95
+    xd = torch.from_numpy(x).cuda()
+    out = torch.empty_like(xd)
+    assert comp.propagate(None, xd, out) is None
+    ref_out = np.maximum(x, 0)
+    assert np.array_equal(out.cpu().numpy(), ref_out)
+    # StoreStats: the first call always stores (count == 0), whatever RandInt(0, 1) says
+    comp.store_stats(None, out, None)
+    txt = comp.write(False).decode()
+    vec = lambda tok: np.array(txt.split(tok)[1].split("[")[1].split("]")[0].split(), dtype=np.float64)
+    np.testing.assert_allclose(vec("<ValueAvg>"), ref_out.mean(0), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(vec("<DerivAvg>"), (ref_out > 0).mean(0), rtol=1e-6)
+    assert f"<Count> {R} " in txt
+    # a second StoreStats is skipped when RandInt(0, 1) == 0
+    c0 = nn.get_rand_counter()
+    skip = nn.rand_int(0, 1) == 0
+    nn.set_rand_counter(c0)
+    comp.store_stats(None, out, None)
+    assert (f"<Count> {R} " in comp.write(False).decode()) == skip
+    # Backprop into a delta copy: self-repair uses the MODEL's statistics, the counters go to the delta
+    delta = comp.copy()
+    delta.zero_stats()
+    od = g.standard_normal((R, D)).astype(np.float32)
+    odd = torch.from_numpy(od).cuda()
+    ind = torch.zeros_like(xd)
+    c0 = nn.get_rand_counter()
+    repaired = not (nn.rand_uniform() > 0.5)     # RepairGradients: "if (RandUniform() > repair_probability) return"
+    nn.rand_int(0, 3)                            # StoreBackpropStats draws, then stores anyway (oderiv_count == 0)
+    c1 = nn.get_rand_counter()
+    nn.set_rand_counter(c0)
+    comp.backprop(None, None, out, odd, None, delta, ind)
+    assert nn.get_rand_counter() == c1
+    ref = (ref_out > 0) * od
+    if repaired:
+        ref = ref.copy()
+        ref[:, :5] += scale / 0.5                # stats <= lower threshold: push the derivative up
+        ref[:, 5:9] -= scale / 0.5               # stats > upper threshold: push it down
+    np.testing.assert_allclose(ind.cpu().numpy(), ref, rtol=1e-6, atol=1e-7)
+    dtxt = delta.write(False).decode()
+    assert f"<NumDimsProcessed> {D if repaired else 0} " in dtxt and f"<NumDimsSelfRepaired> {9 if repaired else 0} " in dtxt
+    dvec = lambda tok: np.array(dtxt.split(tok)[1].split("[")[1].split("]")[0].split(), dtype=np.float64)
+    np.testing.assert_allclose(dvec("<OderivRms>"), np.sqrt((od.astype(np.float64) ** 2).mean(0)), rtol=1e-5)
+    assert f"<OderivCount> {R} " in dtxt
+    # without to_update: the plain derivative, no draws
+    c0 = nn.get_rand_counter()
+    ind2 = torch.zeros_like(xd)
+    comp.backprop(None, None, out, odd, None, None, ind2)
+    assert nn.get_rand_counter() == c0
+    np.testing.assert_allclose(ind2.cpu().numpy(), (ref_out > 0) * od, rtol=1e-6)
+    # I/O round trip (text and binary), Add / Scale
+    back = nn.Component.read(comp.write(True), True)
+    assert back.write(False) == comp.write(False)
+    assert nn.Component.read(comp.write(False), False).write(False) == comp.write(False)
+    acc = comp.copy()
+    acc.add(1.0, comp)
+    acc.scale(0.5)
+    assert acc.write(False) == comp.write(False)
+    acc.zero_stats()
+    assert "<Count> 0 " in acc.write(False).decode()

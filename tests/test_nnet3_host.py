@@ -216,3 +216,26 @@ def test_synthetic_numerator_paths_lie_in_the_denominator_graph():
             assert nxt, "self-loop pdf does not match the destination's self-loop"
             cand = nxt
     assert nA == len(num["arc_pdf"]) // 2
+
+
+def test_rectified_linear_component_config_and_text_form():
+    """RectifiedLinearComponent (the ReLU of every TDNN-F block): config keys of NonlinearComponent::InitFromConfig
+    (nnet-component-itf.cc:707-718), Properties() (nnet-simple-component.h:351-354) and the token stream of a fresh
+    component (nnet-component-itf.cc:630-687).  No statistics yet, so no device state: runs without a GPU."""
+    from tdnnf_nas_b200 import nnet3
+
+    r = nnet3.Component.new("RectifiedLinearComponent", "dim=12 block-dim=4 self-repair-scale=1e-05 self-repair-lower-threshold=0.1")
+    assert r.type() == "RectifiedLinearComponent" and r.input_dim() == 12 and r.output_dim() == 12
+    assert r.properties() == (nnet3.kSimpleComponent | nnet3.kBackpropNeedsOutput | nnet3.kPropagateInPlace |
+                              nnet3.kStoresStats | nnet3.kInputContiguous)
+    txt = r.write(False)
+    assert txt.startswith(b"<RectifiedLinearComponent> <Dim> 12 <BlockDim> 4 <ValueAvg>  [ ]\n<DerivAvg>  [ ]\n<Count> 0 <OderivRms>  [ ]\n"
+                          b"<OderivCount> 0 <NumDimsSelfRepaired> 0 <NumDimsProcessed> 0 <SelfRepairLowerThreshold> 0.1 <SelfRepairScale> 1e-05 ")
+    assert txt.rstrip().endswith(b"</RectifiedLinearComponent>")
+    assert "self-repair-scale=1e-05" in r.info() and "block-dim=4" in r.info()
+    plain = nnet3.Component.new("RectifiedLinearComponent", "dim=8")
+    assert plain.properties() & nnet3.kInputContiguous == 0
+    assert plain.write(False).startswith(b"<RectifiedLinearComponent> <Dim> 8 <ValueAvg>")
+    for bad in ("block-dim=4", "dim=12 block-dim=5", "dim=8 bogus=1"):
+        with pytest.raises(nnet3.Nnet3Error):
+            nnet3.Component.new("RectifiedLinearComponent", bad)
