@@ -223,7 +223,8 @@ def workload_config(cfg, gpus):
                 ng_settle_steps=NG_SETTLE_STEPS,
                 not_included=("natural gradient of the 5 stock affine layers around the blocks (tdnn1, prefinal, output: plain SGD "
                               "there; all 28 TdnnDARTSV3 components are preconditioned), L2 regularisation, xent output branch, dropout "
-                              "(proportion 0 in the recipe); the orthonormal constraint does not cover TdnnDARTSV3 (utils.cc:1047-1061)"))
+                              "(GeneralDropoutComponent is upstream Kaldi and not built; the recipes' schedule 0,0@0.20,0.5@0.50,0 starts "
+                              "and ends at proportion 0); the orthonormal constraint does not cover TdnnDARTSV3 (utils.cc:1047-1061)"))
 
 
 def run_ours(args, cfg, rank, world, local_rank):
