@@ -340,6 +340,19 @@ int tdnnf_den_forward(tdnnf_den_comp* c, const float* nnet_output, int stride, f
  * *ok (HOST) = 0 when the t=0 alpha.beta check fails (the reference's return value).  Syncs. */
 int tdnnf_den_backward(tdnnf_den_comp* c, float deriv_weight, float* nnet_output_deriv, int stride, int* ok);
 
+/* ------------------------------------------------------------------ orthonormal constraint - */
+/* ConstrainOrthonormalInternal (ref: nnet-utils.cc:914-1035; called for LinearComponent / AffineComponent /
+ * TdnnComponent parameters by ConstrainOrthonormal, nnet-utils.cc:1037-1077, i.e. for the `linear` half of every
+ * TDNN-F layer of the manual and derived systems; it does NOT cover TdnnDARTSV3Component).
+ *   P = A A^T with A = M when rows <= cols and A = M^T otherwise (the reference's transposed copy, :1067-1074);
+ *   scale < 0 ("floating"): scale^2 = tr(P P^T) / tr(P), update_speed 0.125 halved for ratio > 1.02 and again > 1.1;
+ *   A <- A - 4 (update_speed / scale^2) (P - scale^2 I) A,   in place, no host synchronisation.
+ * info_dev (optional, DEVICE float[4]) <- {scale used, ratio (0 when the scale is fixed), update_speed,
+ * ||P - scale^2 I||_F}.  Where the reference asserts ratio > 0.999 the update is skipped and info_dev[1] shows why.
+ * min(rows, cols) <= 512. */
+int tdnnf_constrain_orthonormal(tdnnf_ctx* ctx, float* M, int rows, int cols, int stride, float scale,
+                                float* info_dev);
+
 /* ------------------------------------------------------------------ chain numerator ---- */
 /* GenericNumeratorComputation (kaldi: chain/chain-generic-numerator.{h,cc}; SURVEY "next" row N3): log-domain
  * forward-backward over one small FST per sequence (the unconstrained / e2e supervision the recipes train

@@ -91,6 +91,11 @@ int tdnnf_nnet3_set_actual_learning_rate(void* comp, float lrate);
 int tdnnf_nnet3_get_learning_rate(void* comp, float* lrate);
 int tdnnf_nnet3_set_test_mode(void* comp, int test_mode);
 int tdnnf_nnet3_temp_proportion(const void* comp, float* value);
+/* ConstrainOrthonormal(Nnet*) (ref: nnet-utils.cc:1037-1077), to be called after every minibatch: each component of
+ * the list that is a TdnnComponent with orthonormal-constraint != 0 is updated with probability 1/4 (RandInt(0,3),
+ * one draw per constrained component, list order); *num_updated (optional) <- how many were.  Other types are skipped. */
+int tdnnf_nnet3_constrain_orthonormal(void* const* comps, int n, int* num_updated);
+int tdnnf_nnet3_orthonormal_constraint(const void* comp, float* value);
 /* Device parameter buffers (<= 2) of an updatable component, for the all-reduce of the deltas. */
 int tdnnf_nnet3_param_buffers(void* comp, float** ptrs, int* rows, int* cols, int* strides, int* count);
 int tdnnf_nnet3_bn_test_set_stats(void* comp, int dim, int block_dim, float epsilon, float target_rms, double count,

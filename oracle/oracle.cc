@@ -348,6 +348,122 @@ int orc_tdnn_backprop(const int* time_offsets, int n, int flags, float temp_prop
                               id_stride, learning_rate, dW, dw_stride, dbias, s_out, nullptr, nullptr, nullptr);
 }
 
+// ------------------------------------------------------------------ stock TdnnComponent (BASELINE configs[1])
+// The manual / derived TDNN-F systems (NAS/run_tdnn_7q_fbk_40_manual.sh and the models generate_top_list.py emits)
+// are built from upstream Kaldi's TdnnComponent, the class TdnnDARTSV3Component was forked from: the reference's
+// method bodies minus the architecture weights (every w_i = 1), bias_params_ of dimension D_out (no alpha slots)
+// which Propagate always adds (tdnn.cc:230-241 keeps only that branch), and no memo.  upstream: kaldi
+// src/nnet3/nnet-tdnn-component.cc (absent here, unpinned); structure as in tdnn.cc:214-333, 335-431, 457-626.
+int orc_plain_tdnn_propagate(int n, const float* W, int w_stride, const float* bias, const float* in, int in_rows, int in_dim,
+                             int in_stride, float* out, int out_rows, int out_dim, int out_stride, const int* row_offsets,
+                             int row_stride) {
+  Mat in_m{const_cast<float*>(in), in_rows, in_dim, in_stride};
+  Mat out_m{out, out_rows, out_dim, out_stride};
+  Mat lin{const_cast<float*>(W), out_dim, n * in_dim, w_stride};
+  if (bias != nullptr)                                           // out->CopyRowsFromVec(bias_params_); else kPropagateAdds
+    for (int r = 0; r < out_rows; ++r)
+      for (int c = 0; c < out_dim; ++c) out_m(r, c) = bias[c];
+  for (int i = 0; i < n; ++i) {
+    Mat in_part = GetInputPart(in_m, out_rows, row_stride, row_offsets[i]);
+    AddMatMat(out_m, 1.0f, in_part, kNoTrans, lin.Range(0, out_dim, i * in_dim, in_dim), kTrans, 1.0f);
+  }
+  return 0;
+}
+
+// Backprop + UpdateSimple (natural_gradient == 0) / UpdateNaturalGradient.  dbias (D_out) may be NULL (use-bias=false).
+int orc_plain_tdnn_backprop(int n, const float* W, int w_stride, const float* in_value, int in_rows, int in_dim, int in_stride,
+                            const float* out_deriv, int out_rows, int out_dim, int od_stride, const int* row_offsets,
+                            int row_stride, float* in_deriv, int id_stride, float learning_rate, float* dW, int dw_stride,
+                            float* dbias, int natural_gradient, void* ng_in, void* ng_out, float* scales_out) {
+  Mat in_m{const_cast<float*>(in_value), in_rows, in_dim, in_stride};
+  Mat od{const_cast<float*>(out_deriv), out_rows, out_dim, od_stride};
+  Mat lin{const_cast<float*>(W), out_dim, n * in_dim, w_stride};
+  if (in_deriv != nullptr) {
+    Mat id{in_deriv, in_rows, in_dim, id_stride};
+    for (int i = 0; i < n; ++i) {
+      Mat id_part = GetInputPart(id, out_rows, row_stride, row_offsets[i]);
+      AddMatMat(id_part, 1.0f, od, kNoTrans, lin.Range(0, out_dim, i * in_dim, in_dim), kNoTrans, 1.0f);
+    }
+  }
+  if (dW == nullptr || learning_rate == 0.0f) return 0;
+  const int spliced = n * in_dim;
+  Mat dlin{dW, out_dim, spliced, dw_stride};
+  if (!natural_gradient) {                                       // UpdateSimple (the shape of tdnn.cc:433-455)
+    if (dbias != nullptr)
+      for (int c = 0; c < out_dim; ++c) {
+        double sum = 0.0;
+        for (int r = 0; r < out_rows; ++r) sum += (double)od(r, c);
+        dbias[c] += learning_rate * (BaseFloat)sum;
+      }
+    for (int i = 0; i < n; ++i) {
+      Mat in_part = GetInputPart(in_m, out_rows, row_stride, row_offsets[i]);
+      AddMatMat(dlin.Range(0, out_dim, i * in_dim, in_dim), learning_rate, od, kTrans, in_part, kNoTrans, 1.0f);
+    }
+    return 0;
+  }
+  OwnedMat in_value_temp(out_rows, spliced + 1);                 // [X_1 | ... | X_n | 1]
+  for (int r = 0; r < out_rows; ++r) in_value_temp.m(r, spliced) = 1.0f;
+  for (int i = 0; i < n; ++i) {
+    Mat in_part = GetInputPart(in_m, out_rows, row_stride, row_offsets[i]);
+    for (int r = 0; r < out_rows; ++r) memcpy(&in_value_temp.m(r, i * in_dim), &in_part(r, 0), sizeof(float) * in_dim);
+  }
+  OwnedMat out_deriv_temp(out_rows, out_dim);
+  for (int r = 0; r < out_rows; ++r) memcpy(&out_deriv_temp.m(r, 0), &od(r, 0), sizeof(float) * out_dim);
+  BaseFloat in_scale = 1.0f, out_scale = 1.0f;
+  if (ng_in) NgPrecondition(static_cast<OrcNG*>(ng_in), in_value_temp.m, &in_scale);
+  if (ng_out) NgPrecondition(static_cast<OrcNG*>(ng_out), out_deriv_temp.m, &out_scale);
+  if (scales_out) { scales_out[0] = in_scale; scales_out[1] = out_scale; }
+  const BaseFloat local_lrate = in_scale * out_scale * learning_rate;
+  if (dbias != nullptr)
+    for (int c = 0; c < out_dim; ++c) {
+      double sum = 0.0;
+      for (int r = 0; r < out_rows; ++r) sum += (double)out_deriv_temp.m(r, c) * (double)in_value_temp.m(r, spliced);
+      dbias[c] += local_lrate * (BaseFloat)sum;
+    }
+  AddMatMat(dlin, local_lrate, out_deriv_temp.m, kTrans, in_value_temp.m.Range(0, out_rows, 0, spliced), kNoTrans, 1.0f);
+  return 0;
+}
+
+// ------------------------------------------------------------------ ConstrainOrthonormalInternal (utils.cc:914-1035)
+// M (rows x cols, rows <= cols: the caller transposes otherwise, utils.cc:1067-1074) <- M - 4 alpha (M M^T - scale^2 I) M.
+// scale < 0: the "floating" scale^2 = tr(P P^T) / tr(P) with the ratio-driven slow-down of update_speed.
+// info (optional, 4): {scale used, ratio (0 if scale fixed), update_speed, Frobenius norm of P - scale^2 I}.
+// Returns -1 where the reference asserts (scale == 0, ratio <= 0.999).
+int orc_constrain_orthonormal(float scale, float* M_data, int rows, int cols, int stride, float* info) {
+  if (scale == 0.0f) return -1;
+  Mat M{M_data, rows, cols, stride};
+  OwnedMat P(rows, rows), M_update(rows, cols);
+  AddMatMat(P.m, 1.0f, M, kNoTrans, M, kTrans, 0.0f);            // SymAddMat2 + CopyLowerToUpper
+  BaseFloat update_speed = 0.125f, ratio = 0.0f;
+  if (scale < 0.0f) {
+    double tr = 0.0, tr2 = 0.0;
+    for (int i = 0; i < rows; ++i) {
+      tr += P.m(i, i);
+      for (int j = 0; j < rows; ++j) tr2 += (double)P.m(i, j) * P.m(i, j);
+    }
+    const BaseFloat trace_P = (BaseFloat)tr, trace_P_P = (BaseFloat)tr2;
+    scale = std::sqrt(trace_P_P / trace_P);
+    ratio = trace_P_P * rows / (trace_P * trace_P);
+    if (!(ratio > 0.999f)) return -1;
+    if (ratio > 1.02f) {
+      update_speed *= 0.5f;
+      if (ratio > 1.1f) update_speed *= 0.5f;
+    }
+  }
+  for (int i = 0; i < rows; ++i) P.m(i, i) -= scale * scale;     // P.AddToDiag(-scale^2)
+  if (info) {
+    double e = 0.0;
+    for (int i = 0; i < rows; ++i)
+      for (int j = 0; j < rows; ++j) e += (double)P.m(i, j) * P.m(i, j);
+    info[0] = scale; info[1] = ratio; info[2] = update_speed; info[3] = (float)std::sqrt(e);
+  }
+  const BaseFloat alpha = update_speed / (scale * scale);
+  AddMatMat(M_update.m, -4.0f * alpha, P.m, kNoTrans, M, kNoTrans, 0.0f);
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < cols; ++c) M(r, c) += M_update.m(r, c);
+  return 0;
+}
+
 // ------------------------------------------------------------------ {Gumbel}SoftmaxFlops
 // Propagate: simple.cc:10088-10113 (Gumbel, u != NULL, inv_temp = 1/T) and 9968-9981 (plain).
 void orc_softmax_flops_fwd(const float* in, int rows, int cols, int in_stride, float* out, int out_stride,

@@ -158,6 +158,42 @@ def tdnn_backprop(time_offsets, flags, temp, W, x, out_deriv, coef, row_offsets,
     return s
 
 
+def plain_tdnn_propagate(W, bias, x, out_rows, row_offsets, row_stride, out=None):
+    """Upstream TdnnComponent::Propagate (every w_i = 1; bias (D_out) or None = kPropagateAdds onto `out`)."""
+    ro = np.asarray(row_offsets, dtype=np.int32)
+    n = len(ro)
+    out_dim, in_dim = W.shape[0], W.shape[1] // n
+    if out is None:
+        out = np.zeros((out_rows, out_dim), dtype=np.float32)
+    lib().orc_plain_tdnn_propagate(n, _f(W), _stride(W), None if bias is None else _f(bias), _f(x), x.shape[0], in_dim,
+                                   _stride(x), _f(out), out_rows, out_dim, _stride(out), _i(ro), row_stride)
+    return out
+
+
+def plain_tdnn_backprop(W, x, out_deriv, row_offsets, row_stride, lr, in_deriv=None, dW=None, dbias=None,
+                        natural_gradient=True, ng_in=None, ng_out=None, scales=None):
+    """Upstream TdnnComponent::Backprop (+ UpdateSimple / UpdateNaturalGradient); in_deriv, dW, dbias added to in place."""
+    ro = np.asarray(row_offsets, dtype=np.int32)
+    n = len(ro)
+    out_dim, in_dim = W.shape[0], W.shape[1] // n
+    lib().orc_plain_tdnn_backprop(
+        n, _f(W), _stride(W), _f(x), x.shape[0], in_dim, _stride(x), _f(out_deriv), out_deriv.shape[0], out_dim,
+        _stride(out_deriv), _i(ro), row_stride, None if in_deriv is None else _f(in_deriv),
+        0 if in_deriv is None else _stride(in_deriv), C.c_float(lr), None if dW is None else _f(dW),
+        0 if dW is None else _stride(dW), None if dbias is None else _f(dbias), int(natural_gradient),
+        None if ng_in is None else ng_in.h, None if ng_out is None else ng_out.h, None if scales is None else _f(scales))
+
+
+def constrain_orthonormal(M, scale):
+    """ConstrainOrthonormalInternal (utils.cc:914-1035) on M (rows <= cols) in place; returns info
+    (scale used, ratio, update_speed, ||M M^T - scale^2 I||_F)."""
+    info = np.zeros(4, dtype=np.float32)
+    rc = lib().orc_constrain_orthonormal(C.c_float(scale), _f(M), M.shape[0], M.shape[1], _stride(M), _f(info))
+    if rc != 0:
+        raise RuntimeError("oracle: the reference asserts here (scale == 0 or ratio <= 0.999)")
+    return info
+
+
 def softmax_flops_fwd(x, u=None, temp=1.0):
     out = np.zeros_like(x)
     uu = None if u is None else np.ascontiguousarray(u, dtype=np.float32)

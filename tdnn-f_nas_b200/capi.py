@@ -80,6 +80,7 @@ def _declare(lib):
     sig("tdnnf_relu_scale_offset_bypass_bwd", [vp, vp, i, vp, i, vp, f, vp, i, vp, i, i, i])
     sig("tdnnf_batchnorm_train_fwd", [vp, vp, i, i, i, vp, i, f, f, vp])
     sig("tdnnf_batchnorm_train_bwd", [vp, vp, i, vp, i, vp, i, i, i, f, vp])
+    sig("tdnnf_constrain_orthonormal", [vp, vp, i, i, i, f, vp])
     sig("tdnnf_num_graph_create", [vp, i, c_int_p, i, c_int_p, c_int_p, c_float_p, c_int_p, c_int_p, c_float_p, C.POINTER(vp)])
     sig("tdnnf_num_graph_destroy", [vp])
     sig("tdnnf_num_forward_backward", [vp, vp, vp, i, i, f, vp, i, c_float_p, c_int_p])
@@ -336,6 +337,12 @@ class Context:
         sp, r, c, ss = _mat(src)
         dp, _, _, ds = _mat(dst)
         check(load().tdnnf_add_to_rows(self.h, alpha, sp, ss, r, c, dp, ds, row_map.data_ptr()))
+
+    def constrain_orthonormal(self, m, scale: float, info=None):
+        """ConstrainOrthonormalInternal (nnet-utils.cc:914-1035) on the device matrix m, in place; scale < 0 = floating.
+        info: optional device float[4] <- (scale used, ratio, update_speed, ||M M^T - scale^2 I||_F)."""
+        p, r, c, s = _mat(m)
+        check(load().tdnnf_constrain_orthonormal(self.h, p, r, c, s, scale, _ptr(info)))
 
     def relu_fwd(self, x, out):
         xp, r, c, xs = _mat(x)

@@ -60,7 +60,7 @@ TdnnDARTSV3Component::TdnnDARTSV3Component()  // tdnn.cc:38-40
       update_theta_(true), uniform_sample_(true), temp_proportion_(1.0), orthonormal_constraint_(0.0),
       use_natural_gradient_(true) {}
 
-TdnnDARTSV3Component::TdnnDARTSV3Component(const TdnnDARTSV3Component& other)  // tdnn.cc:43-61
+TdnnDARTSV3Component::TdnnDARTSV3Component(const TdnnDARTSV3Component& other, bool check)  // tdnn.cc:43-61
     : UpdatableComponent(other), test_mode_(other.test_mode_), use_gumbel_(other.use_gumbel_),
       use_entropy_(other.use_entropy_), free_select_(other.free_select_), update_alpha_(other.update_alpha_),
       update_theta_(other.update_theta_), uniform_sample_(other.uniform_sample_),
@@ -68,7 +68,7 @@ TdnnDARTSV3Component::TdnnDARTSV3Component(const TdnnDARTSV3Component& other)  /
       linear_params_(other.linear_params_), bias_params_(other.bias_params_),
       orthonormal_constraint_(other.orthonormal_constraint_), use_natural_gradient_(other.use_natural_gradient_),
       preconditioner_in_(other.preconditioner_in_), preconditioner_out_(other.preconditioner_out_) {
-  Check();
+  if (check) Check();
 }
 
 TdnnDARTSV3Component* TdnnDARTSV3Component::NewForIndexing(const std::vector<int32>& time_offsets) {
@@ -82,7 +82,7 @@ void TdnnDARTSV3Component::Check() const {  // tdnn.cc:64-73
                std::set<int32>(time_offsets_.begin(), time_offsets_.end()).size() == time_offsets_.size() &&
                linear_params_.NumCols() % time_offsets_.size() == 0 &&
                (bias_params_.Dim() == 0 ||
-                bias_params_.Dim() == linear_params_.NumRows() + (int32)time_offsets_.size()));
+                bias_params_.Dim() == linear_params_.NumRows() + NumAlphaSlots()));
   KALDI_ASSERT(time_offsets_.size() <= TDNNF_MAX_OFFSETS);
 }
 
@@ -290,20 +290,15 @@ void TdnnDARTSV3Component::UpdateSimple(const PrecomputedIndexes&, const CuMatri
   KALDI_ERR << "TdnnDARTSV3Component::UpdateSimple is unreachable in the reference";
 }
 
-void TdnnDARTSV3Component::UpdateNaturalGradient(const PrecomputedIndexes& indexes,
-                                                 const CuMatrixBase<BaseFloat>& in_value,
-                                                 const CuMatrixBase<BaseFloat>& out_deriv,
-                                                 const CuMatrix& linear_params_temp_, const Memo& memo,
-                                                 int32 share_offset_index_temp_, int32 model_flags,
-                                                 BaseFloat temp_proportion_temp_) {  // tdnn.cc:457-626
-  // `this` is the delta component (to_update); the model's parameters / flags arrive as arguments.
+void TdnnDARTSV3Component::PreconditionedUpdate(const PrecomputedIndexes& indexes,
+                                                const CuMatrixBase<BaseFloat>& in_value,
+                                                const CuMatrixBase<BaseFloat>& out_deriv,
+                                                const CuMatrix* model_linear_params, const BaseFloat* weff_dev,
+                                                CuVector* s) {  // tdnn.cc:476-539 (operands), 592-624
   const int32 num_offsets = (int32)time_offsets_.size();
-  KALDI_ASSERT(bias_params_.Dim() == linear_params_.NumRows() + num_offsets);
   tdnnf_ctx* ctx = CurrentContext();
   const int32 num_rows = out_deriv.NumRows(), input_dim = in_value.NumCols(), output_dim = out_deriv.NumCols(),
               spliced_input_dim = num_offsets * input_dim, augmented_input_dim = spliced_input_dim + 1;
-  const bool want_s = !(model_flags & TDNNF_DARTS_UNIFORM_SAMPLE);
-  CuVector s(num_offsets);
   if (ng_consts_.Dim() == 0) {
     ng_consts_.Resize(2);
     ng_consts_.CopyFromHost(std::vector<BaseFloat>{1.0f, -1.0f});
@@ -323,7 +318,7 @@ void TdnnDARTSV3Component::UpdateNaturalGradient(const PrecomputedIndexes& index
   x_in.n = num_offsets;
   x_in.row_offsets = indexes.row_offsets.data();
   x_in.row_stride = indexes.row_stride;
-  x_in.weff = memo.weff.Data();
+  x_in.weff = weff_dev;
   x_in.ones_col = true;
   NgProjection p_in, p_out;
   preconditioner_in_.PreconditionImplicit(x_in, &p_in);
@@ -338,11 +333,12 @@ void TdnnDARTSV3Component::UpdateNaturalGradient(const PrecomputedIndexes& index
   ng_colsum_.SetZero();
   {
     FastGradientScope fast(ctx);
+    const bool want_s = s != NULL && model_linear_params != NULL;
     CheckStatus(tdnnf_darts_backprop_params(
         ctx, in_value.Data(), in_value.NumRows(), in_value.NumCols(), in_value.Stride(), out_deriv.Data(), out_deriv.NumRows(),
-        out_deriv.NumCols(), out_deriv.Stride(), linear_params_temp_.Data(), linear_params_temp_.Stride(), ng_grad_.Data(),
-        ng_grad_.Stride(), ng_colsum_.Data(), memo.weff.Data(), num_offsets, indexes.row_offsets.data(), indexes.row_stride, 1.0f,
-        want_s ? s.Data() : NULL));
+        out_deriv.NumCols(), out_deriv.Stride(), want_s ? model_linear_params->Data() : NULL,
+        want_s ? model_linear_params->Stride() : 0, ng_grad_.Data(), ng_grad_.Stride(), ng_colsum_.Data(), weff_dev,
+        num_offsets, indexes.row_offsets.data(), indexes.row_stride, 1.0f, want_s ? s->Data() : NULL));
   }
   CheckStatus(tdnnf_mat_axpy(ctx, 1.0f, ng_colsum_.Data(), 1, ng_grad_.Data() + spliced_input_dim, ng_grad_.Stride(),
                              output_dim, 1));
@@ -374,14 +370,29 @@ void TdnnDARTSV3Component::UpdateNaturalGradient(const PrecomputedIndexes& index
   }
   // local_lrate = in_scale * out_scale * learning_rate_ (tdnn.cc:600-604), the scales read on the device:
   //   linear_params_ += local_lrate * out_deriv_hat^T X_hat[:, :n D_in]            (tdnn.cc:619-624)
-  //   bias tail      += local_lrate * out_deriv_hat^T precon_ones                  (tdnn.cc:607-617)
+  //   bias           += local_lrate * out_deriv_hat^T precon_ones                  (tdnn.cc:607-617)
   CheckStatus(tdnnf_mat_axpy_dev(ctx, learning_rate_, p_in.scale_dev, p_out.scale_dev, ng_grad_.Data(), ng_grad_.Stride(),
                                  linear_params_.Data(), linear_params_.Stride(), output_dim, spliced_input_dim));
-  CheckStatus(tdnnf_mat_axpy_dev(ctx, learning_rate_, p_in.scale_dev, p_out.scale_dev, ng_grad_.Data() + spliced_input_dim,
-                                 ng_grad_.Stride(), bias_params_.Data() + num_offsets, 1, output_dim, 1));
+  if (bias_params_.Dim() != 0)
+    CheckStatus(tdnnf_mat_axpy_dev(ctx, learning_rate_, p_in.scale_dev, p_out.scale_dev, ng_grad_.Data() + spliced_input_dim,
+                                   ng_grad_.Stride(), bias_params_.Data() + NumAlphaSlots(), 1, output_dim, 1));
+}
+
+void TdnnDARTSV3Component::UpdateNaturalGradient(const PrecomputedIndexes& indexes,
+                                                 const CuMatrixBase<BaseFloat>& in_value,
+                                                 const CuMatrixBase<BaseFloat>& out_deriv,
+                                                 const CuMatrix& linear_params_temp_, const Memo& memo,
+                                                 int32 share_offset_index_temp_, int32 model_flags,
+                                                 BaseFloat temp_proportion_temp_) {  // tdnn.cc:457-626
+  // `this` is the delta component (to_update); the model's parameters / flags arrive as arguments.
+  const int32 num_offsets = (int32)time_offsets_.size();
+  KALDI_ASSERT(bias_params_.Dim() == linear_params_.NumRows() + num_offsets);
+  const bool want_s = !(model_flags & TDNNF_DARTS_UNIFORM_SAMPLE);
+  CuVector s(num_offsets);
+  PreconditionedUpdate(indexes, in_value, out_deriv, &linear_params_temp_, memo.weff.Data(), want_s ? &s : NULL);
   // architecture weights: Jacobian products + the x5 / xlr / x10000 scalings       (tdnn.cc:541-590)
-  CheckStatus(tdnnf_darts_alpha_update(ctx, s.Data(), memo.coef.Data(), num_offsets, model_flags, temp_proportion_temp_,
-                                       share_offset_index_temp_, learning_rate_, bias_params_.Data()));
+  CheckStatus(tdnnf_darts_alpha_update(CurrentContext(), s.Data(), memo.coef.Data(), num_offsets, model_flags,
+                                       temp_proportion_temp_, share_offset_index_temp_, learning_rate_, bias_params_.Data()));
   if (g_print_log_alpha) PrintLogAlpha(bias_params_.Data(), num_offsets);  // tdnn.cc:571 (prints the MODEL's alpha there)
 }
 
@@ -635,6 +646,214 @@ void TdnnDARTSV3Component::ConsolidateMemory() {  // tdnn.cc:1007-1012
   preconditioner_in_.Swap(&temp_in);
   OnlineNaturalGradient temp_out(preconditioner_out_);
   preconditioner_out_.Swap(&temp_out);
+}
+
+// =====================================================================================
+// TdnnComponent (upstream kaldi nnet-tdnn-component.cc, the class the reference forked): see components.h
+// =====================================================================================
+TdnnComponent::TdnnComponent() {}
+TdnnComponent::TdnnComponent(const TdnnComponent& other) : TdnnDARTSV3Component(other, false) { Check(); }
+
+const BaseFloat* TdnnComponent::Ones() const {
+  const int32 n = (int32)time_offsets_.size();
+  if (ones_.Dim() != n) {
+    ones_.Resize(n);
+    ones_.CopyFromHost(std::vector<BaseFloat>(n, 1.0f));
+  }
+  return ones_.Data();
+}
+
+void TdnnComponent::InitFromConfig(ConfigLine* cfl) {  // the stock keys of tdnn.cc:109-212 (no mode flags, bias of D_out)
+  InitLearningRatesFromConfig(cfl);
+  std::string time_offsets;
+  int32 input_dim = -1, output_dim = -1;
+  bool ok = cfl->GetValue("time-offsets", &time_offsets) && cfl->GetValue("input-dim", &input_dim) &&
+            cfl->GetValue("output-dim", &output_dim);
+  if (!ok || input_dim <= 0 || output_dim <= 0 || !SplitStringToIntegers(time_offsets, ",", false, &time_offsets_) ||
+      time_offsets_.empty()) {
+    KALDI_ERR << "Bad initializer: there is a problem with time-offsets, input-dim or output-dim (not defined?): "
+              << cfl->WholeLine();
+  }
+  if (std::set<int32>(time_offsets_.begin(), time_offsets_.end()).size() != time_offsets_.size())
+    KALDI_ERR << "Bad initializer: repeated time-offsets: " << cfl->WholeLine();
+  if (time_offsets_.size() > TDNNF_MAX_OFFSETS)
+    KALDI_ERR << "Bad initializer: more than " << TDNNF_MAX_OFFSETS << " time-offsets: " << cfl->WholeLine();
+  orthonormal_constraint_ = 0.0;
+  BaseFloat param_stddev = -1, bias_mean = 0.0, bias_stddev = 1.0;
+  bool use_bias = true;
+  cfl->GetValue("param-stddev", &param_stddev);
+  cfl->GetValue("bias-stddev", &bias_stddev);
+  cfl->GetValue("bias-mean", &bias_mean);
+  cfl->GetValue("use-bias", &use_bias);
+  cfl->GetValue("orthonormal-constraint", &orthonormal_constraint_);
+  const int32 n = (int32)time_offsets_.size();
+  if (param_stddev < 0.0) param_stddev = 1.0 / std::sqrt((double)input_dim * n);
+  Matrix<BaseFloat> lin(output_dim, input_dim * n);
+  lin.v = RandnVector(lin.v.size(), param_stddev, 0.0);
+  linear_params_.CopyFromHost(lin);
+  if (use_bias) bias_params_.CopyFromHost(RandnVector(output_dim, bias_stddev, bias_mean));
+  else bias_params_.Resize(0);
+
+  use_natural_gradient_ = true;
+  int32 rank_out = -1, rank_in = -1;
+  BaseFloat alpha_out = 4.0, alpha_in = 4.0, num_samples_history = 2000.0;
+  cfl->GetValue("use-natural-gradient", &use_natural_gradient_);
+  cfl->GetValue("rank-in", &rank_in);
+  cfl->GetValue("rank-out", &rank_out);
+  cfl->GetValue("alpha-in", &alpha_in);
+  cfl->GetValue("alpha-out", &alpha_out);
+  cfl->GetValue("num-samples-history", &num_samples_history);
+  const int32 spliced_input_dim = input_dim * n;
+  if (rank_in < 0) rank_in = std::min<int32>(20, (spliced_input_dim + 1) / 2);
+  if (rank_out < 0) rank_out = std::min<int32>(80, (output_dim + 1) / 2);
+  OnlineNaturalGradient* ng[2] = {&preconditioner_in_, &preconditioner_out_};
+  const int32 rank[2] = {rank_in, rank_out};
+  const BaseFloat alpha[2] = {alpha_in, alpha_out};
+  for (int k = 0; k < 2; ++k) {
+    ng[k]->SetRank(rank[k]);
+    ng[k]->SetNumSamplesHistory(num_samples_history);
+    ng[k]->SetAlpha(alpha[k]);
+    ng[k]->SetUpdatePeriod(4);
+  }
+  if (cfl->HasUnusedValues()) KALDI_ERR << "Could not process these elements in initializer: " << cfl->UnusedValues();
+  Check();
+}
+
+void* TdnnComponent::Propagate(const ComponentPrecomputedIndexes* indexes_in, const CuMatrixBase<BaseFloat>& in,
+                               CuMatrixBase<BaseFloat>* out) const {
+  const PrecomputedIndexes* indexes = dynamic_cast<const PrecomputedIndexes*>(indexes_in);
+  KALDI_ASSERT(indexes != NULL && indexes->row_offsets.size() == time_offsets_.size());
+  KALDI_ASSERT(in.NumCols() == InputDim() && out->NumCols() == OutputDim());
+  // out->CopyRowsFromVec(bias_params_) when there is a bias, else kPropagateAdds; then one AddMatMat per offset
+  const bool has_bias = bias_params_.Dim() != 0;
+  CheckStatus(tdnnf_darts_propagate(CurrentContext(), in.Data(), in.NumRows(), in.NumCols(), in.Stride(), out->Data(),
+                                    out->NumRows(), out->NumCols(), out->Stride(), linear_params_.Data(),
+                                    linear_params_.Stride(), has_bias ? bias_params_.Data() : NULL, has_bias ? 2 : 0, Ones(),
+                                    (int32)time_offsets_.size(), indexes->row_offsets.data(), indexes->row_stride));
+  return NULL;
+}
+
+void TdnnComponent::Backprop(const std::string&, const ComponentPrecomputedIndexes* indexes_in,
+                             const CuMatrixBase<BaseFloat>& in_value, const CuMatrixBase<BaseFloat>&,
+                             const CuMatrixBase<BaseFloat>& out_deriv, void*, Component* to_update_in,
+                             CuMatrixBase<BaseFloat>* in_deriv) const {
+  const PrecomputedIndexes* indexes = dynamic_cast<const PrecomputedIndexes*>(indexes_in);
+  KALDI_ASSERT(indexes != NULL && indexes->row_offsets.size() == time_offsets_.size());
+  const int32 num_offsets = (int32)time_offsets_.size();
+  tdnnf_ctx* ctx = CurrentContext();
+  struct OperandCacheScope {  // in_value / out_deriv are split into operand planes once for all their users
+    tdnnf_ctx* ctx;
+    OperandCacheScope(tdnnf_ctx* c, const BaseFloat* a, const BaseFloat* b) : ctx(c) {
+      const float* srcs[2] = {a, b};
+      CheckStatus(tdnnf_ctx_operand_cache_begin(ctx, srcs, 2));
+    }
+    ~OperandCacheScope() { tdnnf_ctx_operand_cache_end(ctx); }
+  } cache_scope(ctx, in_value.Data(), out_deriv.Data());
+  if (in_deriv != NULL) {
+    CheckStatus(tdnnf_darts_backprop_data(ctx, out_deriv.Data(), out_deriv.NumRows(), out_deriv.NumCols(),
+                                          out_deriv.Stride(), in_deriv->Data(), in_deriv->NumRows(), in_deriv->NumCols(),
+                                          in_deriv->Stride(), linear_params_.Data(), linear_params_.Stride(), Ones(),
+                                          num_offsets, indexes->row_offsets.data(), indexes->row_stride));
+  }
+  if (to_update_in != NULL) {
+    TdnnComponent* to_update = dynamic_cast<TdnnComponent*>(to_update_in);
+    KALDI_ASSERT(to_update != NULL);
+    if (to_update->learning_rate_ == 0.0) return;
+    if (to_update->is_gradient_ || !to_update->use_natural_gradient_)
+      to_update->UpdateSimple(*indexes, in_value, out_deriv);
+    else
+      to_update->PreconditionedUpdate(*indexes, in_value, out_deriv, NULL, to_update->Ones(), NULL);
+  }
+}
+
+void TdnnComponent::UpdateSimple(const PrecomputedIndexes& indexes, const CuMatrixBase<BaseFloat>& in_value,
+                                 const CuMatrixBase<BaseFloat>& out_deriv) {
+  // bias_params_.AddRowSumMat(lr, out_deriv); linear_params_part_i.AddMatMat(lr, out_deriv^T, in_part_i) -- the form
+  // tdnn.cc:433-455 keeps (where it is unreachable: quirk Q4)
+  CheckStatus(tdnnf_darts_backprop_params(
+      CurrentContext(), in_value.Data(), in_value.NumRows(), in_value.NumCols(), in_value.Stride(), out_deriv.Data(),
+      out_deriv.NumRows(), out_deriv.NumCols(), out_deriv.Stride(), NULL, 0, linear_params_.Data(), linear_params_.Stride(),
+      bias_params_.Dim() != 0 ? bias_params_.Data() : NULL, Ones(), (int32)time_offsets_.size(), indexes.row_offsets.data(),
+      indexes.row_stride, learning_rate_, NULL));
+}
+
+void TdnnComponent::Write(std::ostream& os, bool binary) const {  // the stock token stream (tdnn.cc:659-700 minus the flags)
+  WriteUpdatableCommon(os, binary);
+  WriteToken(os, binary, "<TimeOffsets>");
+  WriteIntegerVector(os, binary, time_offsets_);
+  WriteToken(os, binary, "<LinearParams>");
+  linear_params_.Write(os, binary);
+  WriteToken(os, binary, "<BiasParams>");
+  bias_params_.Write(os, binary);
+  WriteToken(os, binary, "<OrthonormalConstraint>");
+  WriteBasicType(os, binary, orthonormal_constraint_);
+  WriteToken(os, binary, "<UseNaturalGradient>");
+  WriteBasicType(os, binary, use_natural_gradient_);
+  WriteToken(os, binary, "<NumSamplesHistory>");
+  WriteBasicType(os, binary, preconditioner_in_.GetNumSamplesHistory());
+  WriteToken(os, binary, "<AlphaInOut>");
+  WriteBasicType(os, binary, preconditioner_in_.GetAlpha());
+  WriteBasicType(os, binary, preconditioner_out_.GetAlpha());
+  WriteToken(os, binary, "<RankInOut>");
+  WriteBasicType(os, binary, preconditioner_in_.GetRank());
+  WriteBasicType(os, binary, preconditioner_out_.GetRank());
+  WriteToken(os, binary, "</TdnnComponent>");
+}
+
+void TdnnComponent::Read(std::istream& is, bool binary) {
+  ReadUpdatableCommon(is, binary);
+  ExpectToken(is, binary, "<TimeOffsets>");
+  ReadIntegerVector(is, binary, &time_offsets_);
+  ExpectToken(is, binary, "<LinearParams>");
+  linear_params_.Read(is, binary);
+  ExpectToken(is, binary, "<BiasParams>");
+  bias_params_.Read(is, binary);
+  ExpectToken(is, binary, "<OrthonormalConstraint>");
+  ReadBasicType(is, binary, &orthonormal_constraint_);
+  ExpectToken(is, binary, "<UseNaturalGradient>");
+  ReadBasicType(is, binary, &use_natural_gradient_);
+  BaseFloat history = 0, alpha[2] = {0, 0};
+  int32 rank[2] = {0, 0};
+  ExpectToken(is, binary, "<NumSamplesHistory>");
+  ReadBasicType(is, binary, &history);
+  std::string alpha_token;
+  ReadToken(is, binary, &alpha_token);
+  if (alpha_token == "<AlphaInOut>") {
+    ReadBasicType(is, binary, &alpha[0]);
+    ReadBasicType(is, binary, &alpha[1]);
+  } else {  // older models: one <Alpha> for both factors
+    KALDI_ASSERT(alpha_token == "<Alpha>");
+    ReadBasicType(is, binary, &alpha[0]);
+    alpha[1] = alpha[0];
+  }
+  ExpectToken(is, binary, "<RankInOut>");
+  ReadBasicType(is, binary, &rank[0]);
+  ReadBasicType(is, binary, &rank[1]);
+  OnlineNaturalGradient* ng[2] = {&preconditioner_in_, &preconditioner_out_};
+  for (int k = 0; k < 2; ++k) {
+    ng[k]->SetAlpha(alpha[k]);
+    ng[k]->SetRank(rank[k]);
+    ng[k]->SetNumSamplesHistory(history);
+    ng[k]->SetUpdatePeriod(4);
+  }
+  ExpectToken(is, binary, "</TdnnComponent>");
+  Check();
+}
+
+int32 ConstrainOrthonormal(const std::vector<Component*>& components) {  // utils.cc:1037-1077
+  int32 updated = 0;
+  for (Component* component : components) {
+    TdnnComponent* tc = dynamic_cast<TdnnComponent*>(component);
+    const BaseFloat orthonormal_constraint = (tc != NULL) ? tc->OrthonormalConstraint() : 0.0;
+    // "only do this every 4 or so minibatches": note the short-circuit, no draw for unconstrained components
+    if (orthonormal_constraint == 0.0 || RandInt(0, 3) != 0) continue;
+    CuMatrix& params = tc->LinearParams();
+    // rows > cols: the reference constrains a transposed copy (utils.cc:1067-1074); the kernel does that in place
+    CheckStatus(tdnnf_constrain_orthonormal(CurrentContext(), params.Data(), params.NumRows(), params.NumCols(),
+                                            params.Stride(), orthonormal_constraint, NULL));
+    ++updated;
+  }
+  return updated;
 }
 
 // =====================================================================================
@@ -1764,6 +1983,7 @@ void RectifiedLinearComponent::StoreStats(const CuMatrixBase<BaseFloat>&, const 
 Component* Component::NewComponentOfType(const std::string& component_type) {
   Component* ans = NULL;
   if (component_type == "TdnnDARTSV3Component") ans = new TdnnDARTSV3Component();                    // itf.cc:88-89
+  else if (component_type == "TdnnComponent") ans = new TdnnComponent();                             // itf.cc (stock)
   else if (component_type == "CopyNComponent") ans = new CopyNComponent();                           // itf.cc:202-203
   else if (component_type == "BatchNormTestComponent") ans = new BatchNormTestComponent();           // itf.cc:226-227
   else if (component_type == "BatchNormComponent") ans = new BatchNormComponent();                   // itf.cc (stock)

@@ -117,7 +117,7 @@ struct TdnnDARTSV3ModeFlags {
 class TdnnDARTSV3Component : public UpdatableComponent {
  public:
   TdnnDARTSV3Component();
-  TdnnDARTSV3Component(const TdnnDARTSV3Component& other);
+  TdnnDARTSV3Component(const TdnnDARTSV3Component& other) : TdnnDARTSV3Component(other, true) {}
   virtual int32 InputDim() const { return linear_params_.NumCols() / static_cast<int32>(time_offsets_.size()); }
   virtual int32 OutputDim() const { return linear_params_.NumRows(); }
   virtual std::string Info() const;
@@ -190,12 +190,24 @@ class TdnnDARTSV3Component : public UpdatableComponent {
     CuVector coef, weff;
   };
 
- private:
+ protected:
+  // check == false: a derived class runs its own Check() (NumAlphaSlots() is virtual, hence not usable from this ctor)
+  TdnnDARTSV3Component(const TdnnDARTSV3Component& other, bool check);
   int32 Flags() const;
   // share_offset_index of tdnn.cc:227-241; KALDI_ERR where the reference reads it uninitialised.
   int32 ShareOffsetIndex() const;
   static void ModifyComputationIo(time_height_convolution::ConvolutionComputationIo* io);
+  // Entries of bias_params_ in front of the real bias: the n architecture weights here (tdnn.cc:172-176), none in the
+  // stock TdnnComponent below.
+  virtual int32 NumAlphaSlots() const { return static_cast<int32>(time_offsets_.size()); }
   void Check() const;
+  // The part of UpdateNaturalGradient that the stock TdnnComponent shares (tdnn.cc:592-624): both
+  // PreconditionDirections calls on the implicit operands, the raw gradient G = out_deriv^T [w_1 X_1 | .. | w_n X_n | 1]
+  // (+ the inner products s_i when `s` is given), the rank-r corrections and the scaled accumulation into
+  // linear_params_ / the bias part of bias_params_.  `this` is the delta component.
+  void PreconditionedUpdate(const PrecomputedIndexes& indexes, const CuMatrixBase<BaseFloat>& in_value,
+                            const CuMatrixBase<BaseFloat>& out_deriv, const CuMatrix* model_linear_params,
+                            const BaseFloat* weff_dev, CuVector* s);
   void UpdateNaturalGradient(const PrecomputedIndexes& indexes, const CuMatrixBase<BaseFloat>& in_value,
                              const CuMatrixBase<BaseFloat>& out_deriv, const CuMatrix& linear_params_temp_,
                              const Memo& memo, int32 share_offset_index_temp_, int32 model_flags,
@@ -215,6 +227,49 @@ class TdnnDARTSV3Component : public UpdatableComponent {
   CuMatrix ng_grad_, ng_g1_, ng_t_;
   CuVector ng_colsum_, ng_consts_;
 };
+
+// ------------------------------------------------------------------ TdnnComponent (upstream kaldi, nnet-convolutional-component.h)
+// The stock class TdnnDARTSV3Component was forked from (conv.h:112-332 is its declaration plus the mode flags), and
+// what the manual TDNN-F system (NAS/run_tdnn_7q_fbk_40_manual.sh, BASELINE configs[1]) and every architecture the
+// search emits (NAS/scripts/generate_top_list.py) are built from: out = bias + sum_i X_i W_i^T, no architecture weights,
+// no memo; ConstrainOrthonormal covers it (utils.cc:1062-1066).  It is implemented ON the DARTS class: the same GEMM
+// kernels with every w_i = 1, the same index methods and whole-parameter ops; bias_params_ has dimension D_out.
+class TdnnComponent : public TdnnDARTSV3Component {
+ public:
+  TdnnComponent();
+  TdnnComponent(const TdnnComponent& other);
+  virtual std::string Type() const { return "TdnnComponent"; }
+  virtual int32 Properties() const {
+    return kUpdatableComponent | kReordersIndexes | kBackpropAdds | (bias_params_.Dim() == 0 ? kPropagateAdds : 0) |
+           kBackpropNeedsInput;
+  }
+  virtual void InitFromConfig(ConfigLine* cfl);
+  virtual void* Propagate(const ComponentPrecomputedIndexes* indexes, const CuMatrixBase<BaseFloat>& in,
+                          CuMatrixBase<BaseFloat>* out) const;
+  virtual void Backprop(const std::string& debug_info, const ComponentPrecomputedIndexes* indexes,
+                        const CuMatrixBase<BaseFloat>& in_value, const CuMatrixBase<BaseFloat>& out_value,
+                        const CuMatrixBase<BaseFloat>& out_deriv, void* memo, Component* to_update,
+                        CuMatrixBase<BaseFloat>* in_deriv) const;
+  virtual void DeleteMemo(void*) const {}
+  virtual void Read(std::istream& is, bool binary);
+  virtual void Write(std::ostream& os, bool binary) const;
+  virtual Component* Copy() const { return new TdnnComponent(*this); }
+
+ protected:
+  virtual int32 NumAlphaSlots() const { return 0; }
+
+ private:
+  const BaseFloat* Ones() const;  // n device ones: the effective weights of the shared GEMM kernels
+  void UpdateSimple(const PrecomputedIndexes& indexes, const CuMatrixBase<BaseFloat>& in_value,
+                    const CuMatrixBase<BaseFloat>& out_deriv);
+  mutable CuVector ones_;
+};
+
+// ConstrainOrthonormal (utils.cc:1037-1077) over a list of components: every TdnnComponent with a non-zero
+// orthonormal-constraint is updated with probability 1/4 (RandInt(0, 3) == 0, one draw per constrained component in
+// list order).  Returns how many were updated.  (LinearComponent / AffineComponent are not part of this library;
+// TdnnDARTSV3Component is deliberately not covered, utils.cc:1047-1066 -- TdnnComponent* casts only.)
+int32 ConstrainOrthonormal(const std::vector<Component*>& components);
 
 // ------------------------------------------------------------------ {Gumbel}SoftmaxFlopsComponent (simple.h:2924-3040)
 class SoftmaxFlopsComponent : public RandomComponent {

@@ -318,6 +318,23 @@ int tdnnf_nnet3_param_buffers(void* comp, float** ptrs, int* rows, int* cols, in
   }
   API_END
 }
+// ConstrainOrthonormal(Nnet*) (utils.cc:1037-1077) over the given components, in order; *num_updated (optional) <- how many
+// parameter matrices the 1-in-4 draw selected this time.
+int tdnnf_nnet3_constrain_orthonormal(void* const* comps, int n, int* num_updated) {
+  API_BEGIN
+  std::vector<Component*> list;
+  for (int i = 0; i < n; ++i) list.push_back(static_cast<Component*>(comps[i]));
+  const int32 k = ConstrainOrthonormal(list);
+  if (num_updated) *num_updated = k;
+  API_END
+}
+int tdnnf_nnet3_orthonormal_constraint(const void* comp, float* value) {
+  API_BEGIN
+  const TdnnDARTSV3Component* t = dynamic_cast<const TdnnDARTSV3Component*>(static_cast<const Component*>(comp));
+  if (!t) KALDI_ERR << "component has no orthonormal-constraint";
+  *value = t->OrthonormalConstraint();
+  API_END
+}
 int tdnnf_nnet3_temp_proportion(const void* comp, float* value) {
   API_BEGIN
   const Component* c = static_cast<const Component*>(comp);

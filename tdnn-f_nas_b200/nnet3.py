@@ -361,6 +361,11 @@ class Component:
         _check(_lib().tdnnf_nnet3_temp_proportion(self.h, C.byref(r)))
         return r.value
 
+    def orthonormal_constraint(self) -> float:
+        r = C.c_float()
+        _check(_lib().tdnnf_nnet3_orthonormal_constraint(self.h, C.byref(r)))
+        return r.value
+
     def preconditioner(self, which: int = 0) -> "NaturalGradient":
         """preconditioner_in_ (0) / preconditioner_out_ (1) of a TdnnDARTSV3Component, or preconditioner_ (0)."""
         h = vp()
@@ -399,6 +404,16 @@ class Component:
                 self.h = None
         except Exception:
             pass
+
+
+def constrain_orthonormal(components: Sequence[Component]) -> int:
+    """ConstrainOrthonormal (utils.cc:1037-1077) over the components, in order: every TdnnComponent with a non-zero
+    orthonormal-constraint is updated with probability 1/4.  Returns how many were."""
+    n = len(components)
+    comps = (C.c_void_p * max(n, 1))(*[c.h for c in components])
+    k = C.c_int()
+    _check(_lib().tdnnf_nnet3_constrain_orthonormal(comps, n, C.byref(k)))
+    return k.value
 
 
 def apply_edits(edits: str, named_components: Sequence[Tuple[str, Component]]):
