@@ -180,8 +180,12 @@ extern "C" int tdnnf_constrain_orthonormal(tdnnf_ctx* ctx, float* M, int rows, i
   int splits = std::max(1, std::min(16, K / 256));
   const int k_per_split = ((K + splits - 1) / splits + kTile - 1) / kTile * kTile;
   splits = (K + k_per_split - 1) / k_per_split;
-  ctx->ws_reset();
   const size_t nn = (size_t)n * n;
+  {
+    const int rc = ctx->ws_reserve(sizeof(float) * nn * (splits + 1) + 3 * 1024);
+    if (rc != TDNNF_OK) return rc;
+  }
+  ctx->ws_reset();
   float* partial = static_cast<float*>(ctx->ws_alloc(sizeof(float) * nn * splits));
   float* Q = static_cast<float*>(ctx->ws_alloc(sizeof(float) * nn));
   float* scal = static_cast<float*>(ctx->ws_alloc(64));
