@@ -211,6 +211,19 @@ def run_reference(args, cfg, rank, world):
 
 
 def workload_config(cfg, gpus):
+    if cfg.mode == "manual":
+        # secondary workload (python bench.py --mode manual --chunks 128): NOT the headline line, see profiles/
+        return dict(workload=("manual TDNN-F 7q fbk-40 (BASELINE.json configs[1], run_tdnn_7q_fbk_40_manual.sh): tdnn1 220->1536, 14 "
+                              "tdnnf-layers {TdnnComponent 1536->160 offsets (-s,0) orthonormal, TdnnComponent 160->1536 offsets (0,s), "
+                              "ReLU, BatchNorm (train mode), bypass 0.66} with time-strides 1,1,1,0,6x10, prefinal 256/1536, output 6008; "
+                              f"LF-MMI on a synthetic {cfg.den_states}-state den graph"),
+                    mode=cfg.mode, chunks_per_gpu=cfg.num_seqs, frames_per_eg=cfg.frames_per_eg, global_chunks=cfg.num_seqs * gpus,
+                    num_pdfs=cfg.num_pdfs, den_states=cfg.den_states, parallelism=f"dp{gpus}",
+                    cache="per-step working set exceeds the 126 MB L2: no explicit flush needed",
+                    included=("natural-gradient update of all 28 TdnnComponents, LF-MMI numerator and denominator, l2-regularize 0.01 "
+                              "(ApplyL2Regularization), UpdateNnetWithMaxChange, ConstrainOrthonormal, ScaleBatchnormStats"),
+                    ng_settle_steps=NG_SETTLE_STEPS,
+                    not_included="natural gradient of the 5 stock affine layers, xent output branch, dropout")
     return dict(workload=("context-offset DARTS TDNN-F supernet, search stage (BASELINE.json configs[2]): 14 x "
                           "{TdnnDARTSV3 1536->160 offsets -6..0, TdnnDARTSV3 160->1536 offsets 0..6, ReLU, BatchNormTest, "
                           "bypass 0.66}, tdnn1 220->1536, prefinal 256/1536, output 6008; LF-MMI denominator fwd-bwd on a "
@@ -348,7 +361,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="search", choices=["search", "pretrain"])
+    ap.add_argument("--mode", default="search", choices=["search", "pretrain", "manual"])
     ap.add_argument("--den-states", type=int, default=16384)
     ap.add_argument("--blocks", type=int, default=14)
     ap.add_argument("--chunks", type=int, default=64)
@@ -359,7 +372,8 @@ def main():
 
     from tdnnf_nas_b200.supernet import SupernetConfig
 
-    cfg = SupernetConfig(mode=args.mode, den_states=args.den_states, num_blocks=args.blocks, num_seqs=args.chunks)
+    cfg = SupernetConfig(mode=args.mode, den_states=args.den_states, num_blocks=args.blocks, num_seqs=args.chunks,
+                         l2_regularize=0.01 if args.mode == "manual" else 0.0)
     if args.impl == "reference":
         if args.steps > 3:
             args.steps = 3  # each step is ~10 s of CPU work: keep the whole run within a few minutes

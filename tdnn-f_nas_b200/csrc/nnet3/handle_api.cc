@@ -310,8 +310,11 @@ int tdnnf_nnet3_param_buffers(void* comp, float** ptrs, int* rows, int* cols, in
   *count = 0;
   if (TdnnDARTSV3Component* t = dynamic_cast<TdnnDARTSV3Component*>(c)) {
     ptrs[0] = t->LinearParams().Data(); rows[0] = t->LinearParams().NumRows(); cols[0] = t->LinearParams().NumCols(); strides[0] = t->LinearParams().Stride();
-    ptrs[1] = t->BiasParams().Data(); rows[1] = 1; cols[1] = t->BiasParams().Dim(); strides[1] = t->BiasParams().Dim();
-    *count = 2;
+    *count = 1;
+    if (t->BiasParams().Dim() != 0) {  // use-bias=false (the `linear` half of a stock tdnnf-layer): one buffer
+      ptrs[1] = t->BiasParams().Data(); rows[1] = 1; cols[1] = t->BiasParams().Dim(); strides[1] = t->BiasParams().Dim();
+      *count = 2;
+    }
   } else if (VectorFunctionComponentBase* v = dynamic_cast<VectorFunctionComponentBase*>(c)) {
     ptrs[0] = v->Output().Data(); rows[0] = 1; cols[0] = v->Output().Dim(); strides[0] = v->Output().Dim();
     *count = 1;

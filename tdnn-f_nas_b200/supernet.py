@@ -44,7 +44,11 @@ class SupernetConfig:
     den_out_degree: float = 16.0
     leaky_hmm: float = 0.1
     bypass_scale: float = 0.66
-    mode: str = "search"            # "search": use-gumbel, update-alpha, BatchNormTest; "pretrain": uniform-sample
+    mode: str = "search"            # "search": use-gumbel, update-alpha, BatchNormTest; "pretrain": uniform-sample;
+                                    # "manual": the TDNN-F 7q system of run_tdnn_7q_fbk_40_manual.sh (BASELINE configs[1])
+    strides: Optional[List[int]] = None  # manual mode: time-stride per tdnnf-layer (default 1,1,1,0 then 6: :138-151)
+    l2_regularize: float = 0.0      # per-component l2-regularize (0.01 in the manual recipe; ApplyL2Regularization)
+    batchnorm_stats_scale: float = 0.8   # ScaleBatchnormStats after every minibatch (train-mode batch-norm only)
     learning_rate: float = 2.5e-4
     darts_lr_factor: float = 1.0e-4  # <LearningRateFactor> set by the cvupdate recipe's sed (search mode only)
     max_change: float = 0.75         # per-component max-change (xconfig default of the tdnnf layers)
@@ -103,20 +107,21 @@ class Supernet:
     def _frames(self):
         cfg = self.cfg
         T = cfg.frames_per_eg // cfg.frame_subsampling
-        ctx_w = cfg.num_offsets - 1
         sub = cfg.frame_subsampling
         out_t = [sub * i for i in range(T)]
         L = cfg.num_blocks
+        lw = [-min(o) for o in self.left_offsets]   # left context of each block's `linear` half
+        rw = [max(o) for o in self.right_offsets]   # right context of its `affine` half
         # per block: t-lists of the linear output (= affine input) and affine output (= block output)
         aff_t: List[List[int]] = [None] * L
         lin_t: List[List[int]] = [None] * L
         aff_t[L - 1] = out_t
-        lin_t[L - 1] = list(range(out_t[0], out_t[-1] + ctx_w + 1))
+        lin_t[L - 1] = list(range(out_t[0], out_t[-1] + rw[L - 1] + 1))
         for b in range(L - 2, -1, -1):
-            lo, hi = lin_t[b + 1][0] - ctx_w, lin_t[b + 1][-1]
+            lo, hi = lin_t[b + 1][0] - lw[b + 1], lin_t[b + 1][-1]
             aff_t[b] = list(range(lo, hi + 1))
-            lin_t[b] = list(range(lo, hi + ctx_w + 1))
-        in_t = list(range(lin_t[0][0] - ctx_w, lin_t[0][-1] + 1))  # tdnn1 output frames
+            lin_t[b] = list(range(lo, hi + rw[b] + 1))
+        in_t = list(range(lin_t[0][0] - lw[0], lin_t[0][-1] + 1))  # tdnn1 output frames
         return T, out_t, lin_t, aff_t, in_t
 
     def _build(self):
@@ -124,6 +129,17 @@ class Supernet:
 
         cfg, dev, ctx = self.cfg, self.dev, self.ctx
         S, D, B, n = cfg.num_seqs, cfg.dim, cfg.bottleneck, cfg.num_offsets
+        manual = cfg.mode == "manual"
+        if manual:
+            # tdnnf-layer time-stride s: linear offsets (-s, 0), affine offsets (0, s); s = 0: the single offset 0
+            # (composite_layers.py:145-150)
+            strides = list(cfg.strides) if cfg.strides is not None else ([1, 1, 1, 0] + [6] * cfg.num_blocks)[:cfg.num_blocks]
+            assert len(strides) == cfg.num_blocks
+            self.left_offsets = [[-s_, 0] if s_ else [0] for s_ in strides]
+            self.right_offsets = [[0, s_] if s_ else [0] for s_ in strides]
+        else:
+            self.left_offsets = [list(range(-(n - 1), 1))] * cfg.num_blocks
+            self.right_offsets = [list(range(n))] * cfg.num_blocks
         T, out_t, lin_t, aff_t, in_t = self._frames()
         self.T, self.in_frames = T, len(in_t)
         g = synth.rng(3, stream=1)
@@ -162,13 +178,20 @@ class Supernet:
             return dict(comp=nnet3.Component.new("BatchNormComponent", f"dim={dim}"), memo=C.c_void_p())
 
         # ---------------- DARTS blocks
-        left = ",".join(str(i) for i in range(-(n - 1), 1))
-        right = ",".join(str(i) for i in range(n))
         self.blocks = []
         for b in range(cfg.num_blocks):
-            common = f"learning-rate={cfg.learning_rate * lrf} learning-rate-factor={lrf} {flags_cfg} use-bias=true"
-            lin = nnet3.Component.new("TdnnDARTSV3Component", f"input-dim={D} output-dim={B} time-offsets={left} {common}")
-            aff = nnet3.Component.new("TdnnDARTSV3Component", f"input-dim={B} output-dim={D} time-offsets={right} {common}")
+            left = ",".join(str(i) for i in self.left_offsets[b])
+            right = ",".join(str(i) for i in self.right_offsets[b])
+            if manual:
+                # the config lines XconfigTdnnfLayer emits (composite_layers.py:156-169)
+                common = (f"learning-rate={cfg.learning_rate} l2-regularize={cfg.l2_regularize} max-change={cfg.max_change}")
+                lin = nnet3.Component.new("TdnnComponent", f"input-dim={D} output-dim={B} {common} use-bias=false "
+                                                           f"time-offsets={left} orthonormal-constraint=-1.0")
+                aff = nnet3.Component.new("TdnnComponent", f"input-dim={B} output-dim={D} {common} time-offsets={right}")
+            else:
+                common = f"learning-rate={cfg.learning_rate * lrf} learning-rate-factor={lrf} {flags_cfg} use-bias=true"
+                lin = nnet3.Component.new("TdnnDARTSV3Component", f"input-dim={D} output-dim={B} time-offsets={left} {common}")
+                aff = nnet3.Component.new("TdnnDARTSV3Component", f"input-dim={B} output-dim={D} time-offsets={right} {common}")
             prev_t = in_t if b == 0 else aff_t[b - 1]
             # linear: input = previous block output (t-major), output = lin_t[b]
             li_in, li_out = lin.reorder_indexes(grid(prev_t), grid(lin_t[b]))
@@ -336,6 +359,8 @@ class Supernet:
         for blk in self.blocks:
             pp, pr, pc, ps = _m(prev)
             lp, lr_, lc, ls = _m(blk["lin_out"])
+            if cfg.mode == "manual":  # use-bias=false => kPropagateAdds: the computer hands over a zeroed matrix
+                fwd.add("abi", lib.tdnnf_mat_set, h, lp, lr_, lc, ls, 0.0)
             fwd.add("nnet3", lib.tdnnf_nnet3_propagate, blk["lin"].h, blk["lin_idx"].h, pp, pr, pc, ps, lp, lr_, lc, ls,
                     C.byref(blk["memo_lin"]))
             a_in = blk["lin_out"]
@@ -528,11 +553,14 @@ class Supernet:
     def algorithmic_flops(self) -> float:
         """fwd + dgrad + wgrad FLOPs of the TdnnDARTSV3 GEMMs per step (n_eff = n in search mode)."""
         cfg = self.cfg
-        n_eff = cfg.num_offsets if cfg.mode == "search" else 2
         tot = 0.0
-        for blk in self.blocks:
-            tot += 3 * 2.0 * blk["lin_out"].shape[0] * n_eff * cfg.dim * cfg.bottleneck
-            tot += 3 * 2.0 * blk["aff_out"].shape[0] * n_eff * cfg.bottleneck * cfg.dim
+        for b, blk in enumerate(self.blocks):
+            if cfg.mode == "manual":
+                n_lin, n_aff = len(self.left_offsets[b]), len(self.right_offsets[b])
+            else:
+                n_lin = n_aff = cfg.num_offsets if cfg.mode == "search" else 2
+            tot += 3 * 2.0 * blk["lin_out"].shape[0] * n_lin * cfg.dim * cfg.bottleneck
+            tot += 3 * 2.0 * blk["aff_out"].shape[0] * n_aff * cfg.bottleneck * cfg.dim
         return tot
 
     def make_input(self, step: int = 0):
@@ -549,17 +577,58 @@ class Supernet:
         Returns the LF-MMI objective per output frame (numerator - denominator) of this rank."""
         import torch
 
+        cfg = self.cfg
         if x_host is not None:
             self.x.copy_(x_host, non_blocking=True)
         self.fwd_plan.run()
         # ComputeChainObjfAndDeriv: denominator fwd-bwd, numerator fwd-bwd, objf = num - den (host scalars, like Kaldi)
         objf, _, weight = self.objective.compute(self.head["out"], self.head["d_out"])
         self.bwd_plan.run()
+        if cfg.l2_regularize != 0.0:
+            self._apply_l2_regularization()
         if self.world > 1:
             self._allreduce_deltas()
         if apply_update:
             self._update_with_max_change()
+            self._after_update()
         return objf / weight
+
+    def _apply_l2_regularization(self):
+        """ApplyL2Regularization (utils.cc:2223-2245): delta += -2 * l2_regularize_scale * lrate * l2 * model for every
+        updatable component, l2_regularize_scale = the number of sequences of the minibatch (NnetChainTrainer passes
+        GetNumNvalues() * l2_regularize_factor).  Each rank adds its share (its own sequences), the all-reduce sums."""
+        cfg, lib, h = self.cfg, self.lib, self.ctx.h
+        scale = -2.0 * cfg.num_seqs * cfg.learning_rate * cfg.l2_regularize
+        for blk in self.blocks:
+            for k in ("lin", "aff"):
+                blk[k + "_delta"].add(scale * blk[k].learning_rate() / cfg.learning_rate, blk[k])
+        for name, p in self.stock.items():
+            l2 = 0.002 if name == "output" else cfg.l2_regularize  # output_opts (run_tdnn_7q_fbk_40_manual.sh:123)
+            sc = -2.0 * cfg.num_seqs * cfg.learning_rate * l2
+            wp, wr, wc, ws = _m(p["W"])
+            gp, _, _, gs = _m(p["dW"])
+            if lib.tdnnf_mat_axpy(h, sc, wp, ws, gp, gs, wr, wc) != 0:
+                raise RuntimeError(lib.tdnnf_last_error().decode())
+            if p["b"] is not None:
+                nb = p["b"].numel()
+                if lib.tdnnf_mat_axpy(h, sc, C.c_void_p(p["b"].data_ptr()), nb, C.c_void_p(p["db"].data_ptr()), nb, 1, nb) != 0:
+                    raise RuntimeError(lib.tdnnf_last_error().decode())
+
+    def _after_update(self):
+        """What NnetChainTrainer::TrainInternal does after the parameter step: ConstrainOrthonormal(nnet_)
+        (utils.cc:1037-1077; touches TdnnComponents / LinearComponents with a constraint: the `linear` halves, prefinal-l and
+        the prefinal layers' linear part, in network order, each with probability 1/4) and ScaleBatchnormStats
+        (utils.cc:527-539; train-mode batch-norm only).  Identical on every rank (same RNG counter, deterministic kernels)."""
+        cfg = self.cfg
+        if cfg.mode == "manual":
+            nnet3.constrain_orthonormal([blk["lin"] for blk in self.blocks])
+            for name in ("prefinal_l", "pc_linear"):   # linear-component / prefinal-layer: orthonormal-constraint=-1.0
+                if nnet3.rand_int(0, 3) == 0:
+                    self.ctx.constrain_orthonormal(self.stock[name]["W"], -1.0)
+        if cfg.mode != "search" and cfg.batchnorm_stats_scale != 1.0:
+            for bn in [self.t1["bn"]] + [blk["bn"] for blk in self.blocks] + [self.head["bn1"], self.head["bn2"]]:
+                if isinstance(bn, dict):
+                    bn["comp"].scale(cfg.batchnorm_stats_scale)
 
     def _update_with_max_change(self, scale: float = 1.0, max_change_scale: float = 1.0):
         """UpdateNnetWithMaxChange + ScaleNnet(momentum=0) (utils.cc:2085-2175, common.py:877-878)."""

@@ -53,3 +53,40 @@ def test_fused_tail_matches_component_path():
         net.close()
     for a, b in zip(*objfs):
         assert abs(a - b) <= 1e-4 * abs(a) + 1e-6, objfs
+
+
+def test_manual_tdnnf_step_runs_learns_and_stays_semi_orthogonal():
+    """BASELINE configs[1] at a small size: the manual TDNN-F system (stock TdnnComponent halves with time-strides
+    1,0,2, train-mode batch-norm, l2-regularize, ConstrainOrthonormal and ScaleBatchnormStats after every step)."""
+    import numpy as np
+
+    from tdnnf_nas_b200.supernet import Supernet, SupernetConfig
+
+    cfg = SupernetConfig(num_seqs=8, frames_per_eg=30, dim=128, bottleneck=32, num_blocks=3, prefinal_small=64,
+                         num_pdfs=200, den_states=300, den_out_degree=6.0, mode="manual", strides=[1, 0, 2],
+                         l2_regularize=0.01, learning_rate=2e-3)
+    net = Supernet(cfg)
+    assert [b["lin"].type() for b in net.blocks] == ["TdnnComponent"] * 3
+    assert net.left_offsets == [[-1, 0], [0], [-2, 0]] and net.right_offsets == [[0, 1], [0], [0, 2]]
+    assert net.blocks[0]["lin"].orthonormal_constraint() == -1.0 and net.blocks[0]["aff"].orthonormal_constraint() == 0.0
+    assert len(net.blocks[0]["lin"].param_buffers()) == 1 and len(net.blocks[0]["aff"].param_buffers()) == 2
+
+    def ortho_error(comp):
+        M = comp.vectorize().reshape(cfg.bottleneck, -1).astype(np.float64)
+        P = M @ M.T
+        s2 = np.trace(P @ P) / np.trace(P)
+        return np.linalg.norm(P - s2 * np.eye(len(P))) / (s2 * np.sqrt(len(P)))
+
+    e0 = [ortho_error(b["lin"]) for b in net.blocks]
+    x = net.make_input(0).pin_memory()
+    objfs = [net.step(x) for _ in range(24)]
+    assert all(math.isfinite(o) for o in objfs), objfs
+    assert objfs[0] < 0 and objfs[-1] > objfs[0], objfs
+    # 24 steps x probability 1/4: every `linear` half has been pulled towards a semi-orthogonal matrix
+    e1 = [ortho_error(b["lin"]) for b in net.blocks]
+    assert all(b < 0.5 * a for a, b in zip(e0, e1)), (e0, e1)
+    # train-mode batch-norm statistics decay by 0.8 per step: count -> rows * (1 + 0.8 + ...) < 5 * rows
+    bn = net.blocks[0]["bn"]["comp"]
+    rows = net.blocks[0]["aff_out"].shape[0]
+    assert rows * 0.8 <= bn.bn_count() < 5.0 * rows
+    net.close()
