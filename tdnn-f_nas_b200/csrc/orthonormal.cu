@@ -3,8 +3,9 @@
 //   P = M M^T,  scale^2 = tr(P P^T) / tr(P) when floating,  M <- M - 4 (nu / scale^2) (P - scale^2 I) M
 // The reference runs SymAddMat2 + CopyLowerToUpper + Trace + TraceMatMat (two host syncs) + AddToDiag + AddMatMat +
 // AddMat, and a transposed copy of M in and out when rows > cols (utils.cc:1067-1074).  Here: three launches, no host
-// sync, no copy of M: (1) split-K Gram partials, (2) one CTA sums them, forms the traces, the floating scale, the
-// ratio-driven update speed and Q = P - scale^2 I, (3) M is updated IN PLACE panel by panel -- column j of the update
+// sync, no copy of M: (1) split-K Gram partials, (2) one CTA per row sums them and leaves that row's share of the two
+// traces, (3) M is updated IN PLACE panel by panel, every CTA re-deriving the floating scale and the ratio-driven
+// update speed from the row traces -- column j of the update
 // depends only on column j of M (row j when M is used transposed), so a CTA that holds a panel of 32 such vectors in
 // shared memory can overwrite it.  fp32 FMAs throughout (P is at most a few hundred squared; K = a few thousand:
 // 0.16 GFLOP per call, every fourth minibatch on average -- not tensor-core work).
@@ -64,33 +65,63 @@ __global__ void __launch_bounds__(256) ortho_gram_kernel(const float* __restrict
     }
 }
 
-// One CTA.  Q (n x n) = sum_z partial[z] (lower triangle mirrored) - scale^2 I;  scal = {coef, scale, ratio, speed, err}
-__global__ void __launch_bounds__(1024) ortho_finish_kernel(const float* __restrict__ partial, int splits, int n, float scale_in,
-                                                            float* __restrict__ Q, float* __restrict__ scal,
-                                                            float* __restrict__ info) {
-  __shared__ double red[2][32];
-  __shared__ float s_scale2;
-  const int nn = n * n;
-  double tr = 0.0, tr2 = 0.0;
-  for (int e = threadIdx.x; e < nn; e += blockDim.x) {
-    const int i = e / n, j = e % n;
-    const int src = (j <= i) ? e : j * n + i;
+// CTA i: row i of P = sum_z partial[z] (lower triangle mirrored), written with pitch np (a multiple of 4, pad = 0), and
+// this row's share of tr(P) and tr(P P^T) as doubles (summed in a fixed order by the update kernel: deterministic, so
+// data-parallel replicas that apply the constraint to identical models stay bit-identical).
+__global__ void __launch_bounds__(128) ortho_reduce_kernel(const float* __restrict__ partial, int splits, int n, int np,
+                                                           float* __restrict__ P, double* __restrict__ row_tr) {
+  __shared__ double red[4];
+  const int i = blockIdx.x;
+  const size_t plane = (size_t)n * n;
+  double tr2 = 0.0;
+  for (int j = threadIdx.x; j < np; j += blockDim.x) {
     float v = 0.f;
-    for (int z = 0; z < splits; ++z) v += partial[(size_t)z * nn + src];
-    Q[e] = v;
-    tr2 += (double)v * v;
-    if (i == j) tr += v;
+    if (j < n) {
+      const size_t src = (j <= i) ? (size_t)i * n + j : (size_t)j * n + i;
+      for (int z = 0; z < splits; ++z) v += partial[(size_t)z * plane + src];
+      tr2 += (double)v * v;
+      if (j == i) row_tr[i] = (double)v;
+    }
+    P[(size_t)i * np + j] = v;
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    tr += __shfl_xor_sync(0xffffffffu, tr, o);
-    tr2 += __shfl_xor_sync(0xffffffffu, tr2, o);
-  }
+  for (int o = 16; o > 0; o >>= 1) tr2 += __shfl_xor_sync(0xffffffffu, tr2, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tr2;
+  __syncthreads();
+  if (threadIdx.x == 0) row_tr[n + i] = (red[0] + red[1]) + (red[2] + red[3]);
+}
+
+// vectors v_j (length n): column j of M (trans == 0) or row j of M (trans == 1);
+//   v_j <- v_j + coef * (P - scale^2 I) v_j,  coef = -4 update_speed / scale^2   (utils.cc:941-1033)
+// Every CTA re-derives the scalars from the per-row traces (n <= 512 doubles: cheaper than another launch).
+__global__ void __launch_bounds__(256) ortho_update_kernel(float* __restrict__ M, long long ld, int trans, int n, int np,
+                                                           int num_vec, const float* __restrict__ P,
+                                                           const double* __restrict__ row_tr, float scale_in,
+                                                           float* __restrict__ info) {
+  extern __shared__ float V[];  // n x (kPanel + 1)
+  __shared__ double red[2][8];
+  __shared__ float s_coef, s_scale2;
+  constexpr int P1 = kPanel + 1;
+  const int j0 = blockIdx.x * kPanel;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { red[0][warp] = tr; red[1][warp] = tr2; }
+  {
+    double t = 0.0, t2 = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) { t += row_tr[i]; t2 += row_tr[n + i]; }
+    for (int o = 16; o > 0; o >>= 1) {
+      t += __shfl_xor_sync(0xffffffffu, t, o);
+      t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+    }
+    if (lane == 0) { red[0][warp] = t; red[1][warp] = t2; }
+  }
+  if (!trans) {
+    for (int k = warp; k < n; k += 8) V[k * P1 + lane] = (j0 + lane < num_vec) ? M[(long long)k * ld + j0 + lane] : 0.f;
+  } else {
+    for (int j = warp; j < kPanel; j += 8)
+      for (int k = lane; k < n; k += 32) V[k * P1 + j] = (j0 + j < num_vec) ? M[(long long)(j0 + j) * ld + k] : 0.f;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0, t2 = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { t += red[0][w]; t2 += red[1][w]; }
+    for (int w = 0; w < 8; ++w) { t += red[0][w]; t2 += red[1][w]; }
     const float trace_P = (float)t, trace_P_P = (float)t2;
     float scale = scale_in, speed = 0.125f, ratio = 0.f;
     bool ok = true;
@@ -105,8 +136,8 @@ __global__ void __launch_bounds__(1024) ortho_finish_kernel(const float* __restr
     }
     const float s2 = scale * scale;
     s_scale2 = s2;
-    scal[0] = ok ? -4.0f * (speed / s2) : 0.f;
-    if (info) {
+    s_coef = ok ? -4.0f * (speed / s2) : 0.f;
+    if (info != nullptr && blockIdx.x == 0) {
       info[0] = scale;
       info[1] = ratio;
       info[2] = speed;
@@ -116,52 +147,37 @@ __global__ void __launch_bounds__(1024) ortho_finish_kernel(const float* __restr
     }
   }
   __syncthreads();
-  const float s2 = s_scale2;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) Q[(size_t)i * n + i] -= s2;  // P.AddToDiag(-scale^2)
-}
-
-// vectors v_j (length n): column j of M (trans == 0) or row j of M (trans == 1);  v_j <- v_j + coef * Q v_j
-__global__ void __launch_bounds__(256) ortho_update_kernel(float* __restrict__ M, long long ld, int trans, int n, int num_vec,
-                                                           const float* __restrict__ Q, const float* __restrict__ scal) {
-  extern __shared__ float V[];  // n x (kPanel + 1)
-  constexpr int P1 = kPanel + 1;
-  const int j0 = blockIdx.x * kPanel;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float coef = scal[0];
-  if (!trans) {
-    for (int k = warp; k < n; k += 8) V[k * P1 + lane] = (j0 + lane < num_vec) ? M[(long long)k * ld + j0 + lane] : 0.f;
-  } else {
-    for (int j = warp; j < kPanel; j += 8)
-      for (int k = lane; k < n; k += 32) V[k * P1 + j] = (j0 + j < num_vec) ? M[(long long)(j0 + j) * ld + k] : 0.f;
-  }
-  __syncthreads();
-  // warp w owns rows i = 4 (w + 8 m) .. +3; lane = vector
-  for (int ib = warp * 4; ib < n; ib += 32) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const float* q0 = Q + (size_t)min(ib + 0, n - 1) * n;
-    const float* q1 = Q + (size_t)min(ib + 1, n - 1) * n;
-    const float* q2 = Q + (size_t)min(ib + 2, n - 1) * n;
-    const float* q3 = Q + (size_t)min(ib + 3, n - 1) * n;
-#pragma unroll 4
+  const float coef = s_coef, s2 = s_scale2;
+  // warp w owns 8 consecutive rows per pass; lane = vector.  P is symmetric: rows i..i+7 of column k are 8 consecutive
+  // floats of row k (two 16-byte broadcast loads).
+  for (int ib = warp * 8; ib < n; ib += 64) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const bool second = ib + 4 < np;
+#pragma unroll 2
     for (int k = 0; k < n; ++k) {
       const float v = V[k * P1 + lane];
-      acc[0] = fmaf(__ldg(q0 + k), v, acc[0]);
-      acc[1] = fmaf(__ldg(q1 + k), v, acc[1]);
-      acc[2] = fmaf(__ldg(q2 + k), v, acc[2]);
-      acc[3] = fmaf(__ldg(q3 + k), v, acc[3]);
+      const float4 p0 = __ldg(reinterpret_cast<const float4*>(P + (size_t)k * np + ib));
+      const float4 p1 = second ? __ldg(reinterpret_cast<const float4*>(P + (size_t)k * np + ib + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      acc[0] = fmaf(p0.x, v, acc[0]);
+      acc[1] = fmaf(p0.y, v, acc[1]);
+      acc[2] = fmaf(p0.z, v, acc[2]);
+      acc[3] = fmaf(p0.w, v, acc[3]);
+      acc[4] = fmaf(p1.x, v, acc[4]);
+      acc[5] = fmaf(p1.y, v, acc[5]);
+      acc[6] = fmaf(p1.z, v, acc[6]);
+      acc[7] = fmaf(p1.w, v, acc[7]);
     }
-    if (!trans) {
-      if (j0 + lane < num_vec)
+    if (j0 + lane < num_vec) {
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-          if (ib + a < n) M[(long long)(ib + a) * ld + j0 + lane] = V[(ib + a) * P1 + lane] + coef * acc[a];
-    } else {
-      // stage the results in registers -> written below through a second shared pass would cost a sync per block of
-      // rows; the transposed case is the rare one (rows > cols), so store directly (stride-ld scatter, 4 B each)
-      if (j0 + lane < num_vec)
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-          if (ib + a < n) M[(long long)(j0 + lane) * ld + ib + a] = V[(ib + a) * P1 + lane] + coef * acc[a];
+      for (int a = 0; a < 8; ++a) {
+        const int i = ib + a;
+        if (i < n) {
+          const float old = V[i * P1 + lane];
+          const float nv = old + coef * (acc[a] - s2 * old);  // (P - s^2 I) v
+          if (!trans) M[(long long)i * ld + j0 + lane] = nv;
+          else M[(long long)(j0 + lane) * ld + i] = nv;  // rows > cols is the rare case: plain 4-byte scatter
+        }
+      }
     }
   }
 }
@@ -181,21 +197,22 @@ extern "C" int tdnnf_constrain_orthonormal(tdnnf_ctx* ctx, float* M, int rows, i
   const int k_per_split = ((K + splits - 1) / splits + kTile - 1) / kTile * kTile;
   splits = (K + k_per_split - 1) / k_per_split;
   const size_t nn = (size_t)n * n;
+  const int np = (n + 3) & ~3;
   {
-    const int rc = ctx->ws_reserve(sizeof(float) * nn * (splits + 1) + 3 * 1024);
+    const int rc = ctx->ws_reserve(sizeof(float) * (nn * splits + (size_t)n * np) + sizeof(double) * 2 * n + 3 * 1024);
     if (rc != TDNNF_OK) return rc;
   }
   ctx->ws_reset();
   float* partial = static_cast<float*>(ctx->ws_alloc(sizeof(float) * nn * splits));
-  float* Q = static_cast<float*>(ctx->ws_alloc(sizeof(float) * nn));
-  float* scal = static_cast<float*>(ctx->ws_alloc(64));
-  if (!partial || !Q || !scal) return TDNNF_ERR_CUDA;
+  float* P = static_cast<float*>(ctx->ws_alloc(sizeof(float) * (size_t)n * np));
+  double* row_tr = static_cast<double*>(ctx->ws_alloc(sizeof(double) * 2 * n));
+  if (!partial || !P || !row_tr) return TDNNF_ERR_CUDA;
   const int tiles = (n + kTile - 1) / kTile;
-  // upper-triangle tiles exit at once and leave their partial entries unwritten: the finish kernel never reads them
+  // upper-triangle tiles exit at once and leave their partial entries unwritten: the reduce kernel never reads them
   ortho_gram_kernel<<<dim3(tiles, tiles, splits), 256, 0, ctx->stream>>>(M, stride, trans, n, K, k_per_split, partial);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
-  ortho_finish_kernel<<<1, 1024, 0, ctx->stream>>>(partial, splits, n, scale, Q, scal, info_dev);
+  ortho_reduce_kernel<<<n, 128, 0, ctx->stream>>>(partial, splits, n, np, P, row_tr);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   const size_t smem = sizeof(float) * (size_t)n * (kPanel + 1);
@@ -205,7 +222,8 @@ extern "C" int tdnnf_constrain_orthonormal(tdnnf_ctx* ctx, float* M, int rows, i
                                        (int)(sizeof(float) * kMaxDim * (kPanel + 1))));
     attr_set = true;
   }
-  ortho_update_kernel<<<(K + kPanel - 1) / kPanel, 256, smem, ctx->stream>>>(M, stride, trans, n, K, Q, scal);
+  ortho_update_kernel<<<(K + kPanel - 1) / kPanel, 256, smem, ctx->stream>>>(M, stride, trans, n, np, K, P, row_tr, scale,
+                                                                             info_dev);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   return TDNNF_OK;

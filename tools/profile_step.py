@@ -21,10 +21,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--warmup", type=int, default=14)
 ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--mode", default="search")
+ap.add_argument("--chunks", type=int, default=64)
 ap.add_argument("--phases", action="store_true", help="also time forward / objective / backward / update separately")
 args = ap.parse_args()
 
-net = Supernet(SupernetConfig(mode=args.mode), device=0)
+net = Supernet(SupernetConfig(mode=args.mode, num_seqs=args.chunks, l2_regularize=0.01 if args.mode == "manual" else 0.0), device=0)
 net.x.copy_(net.make_input(0))
 for _ in range(args.warmup):
     net.step(None)
@@ -53,7 +54,10 @@ if args.phases:
         ev[2].record()
         net.bwd_plan.run()
         ev[3].record()
+        if net.cfg.l2_regularize != 0.0:
+            net._apply_l2_regularization()
         net._update_with_max_change()
+        net._after_update()
         ev[4].record()
         torch.cuda.synchronize()
         ph.append(dict(zip(["fwd", "objf", "bwd", "update"], [ev[i].elapsed_time(ev[i + 1]) for i in range(4)])))
