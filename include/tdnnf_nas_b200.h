@@ -340,6 +340,19 @@ int tdnnf_den_forward(tdnnf_den_comp* c, const float* nnet_output, int stride, f
  * *ok (HOST) = 0 when the t=0 alpha.beta check fails (the reference's return value).  Syncs. */
 int tdnnf_den_backward(tdnnf_den_comp* c, float deriv_weight, float* nnet_output_deriv, int stride, int* ok);
 
+/* ------------------------------------------------------------------ dropout ------------ */
+/* GeneralDropoutComponent (kaldi: nnet3/nnet-general-component.cc; the `dropout` of every tdnnf-layer and
+ * relu-batchnorm-dropout-layer, driven by the `set-dropout-proportion` directive, ref: nnet-utils.cc:1297-1330).
+ * tdnnf_dropout_mask = GetMemo: element e of the mask uses draw number counter + e of the component layer's counter
+ * hash (seed, counter: tdnnf_nnet3_set_rand_seed / _get_rand_counter), u in (0,1):
+ *   continuous == 0: mask = (u > p) / (1 - p);   continuous != 0: mask = 1 - 2p + 4p u.
+ * tdnnf_mul_rows_indexed = CuMatrixBase::MulRows: out[r,:] = in[r,:] .* mask[row_index[r],:] (in may alias out;
+ * row_index: DEVICE int32[rows]); the same call is the Backprop. */
+int tdnnf_dropout_mask(tdnnf_ctx* ctx, unsigned long long seed, unsigned long long counter, float* mask, int rows,
+                       int cols, int stride, float proportion, int continuous);
+int tdnnf_mul_rows_indexed(tdnnf_ctx* ctx, const float* in, int in_stride, float* out, int out_stride, int rows,
+                           int cols, const float* mask, int mask_stride, const int32_t* row_index_dev);
+
 /* ------------------------------------------------------------------ orthonormal constraint - */
 /* ConstrainOrthonormalInternal (ref: nnet-utils.cc:914-1035; called for LinearComponent / AffineComponent /
  * TdnnComponent parameters by ConstrainOrthonormal, nnet-utils.cc:1037-1077, i.e. for the `linear` half of every

@@ -91,6 +91,7 @@ int tdnnf_nnet3_set_actual_learning_rate(void* comp, float lrate);
 int tdnnf_nnet3_get_learning_rate(void* comp, float* lrate);
 int tdnnf_nnet3_set_test_mode(void* comp, int test_mode);
 int tdnnf_nnet3_temp_proportion(const void* comp, float* value);
+int tdnnf_nnet3_dropout_proportion(const void* comp, float* value); /* GeneralDropoutComponent */
 /* ConstrainOrthonormal(Nnet*) (ref: nnet-utils.cc:1037-1077), to be called after every minibatch: each component of
  * the list that is a TdnnComponent with orthonormal-constraint != 0 is updated with probability 1/4 (RandInt(0,3),
  * one draw per constrained component, list order); *num_updated (optional) <- how many were.  Other types are skipped. */

@@ -627,3 +627,74 @@ extern "C" int tdnnf_relu_scale_offset_bypass_bwd(tdnnf_ctx* ctx, const float* d
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
+
+// ------------------------------------------------------------------ GeneralDropoutComponent (kaldi: nnet-general-component.cc)
+namespace {
+// The component layer's counter hash (csrc/nnet3/shim.cc: Mix / RandUniformOpen), evaluated on the device: element e of
+// a mask is draw number counter0 + e, so a test can replay the mask with the same host calls.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// GetMemo: u ~ U(0,1); !continuous: mask = (u > p) / (1 - p); continuous: mask = 1 - 2p + 4p u  (expected value 1)
+__global__ void dropout_mask_kernel(unsigned long long seed_mixed, unsigned long long counter0, float* __restrict__ mask,
+                                    int rows, int cols, long long stride, float p, int continuous) {
+  ELEMWISE_LOOP((long long)rows * cols) {
+    const unsigned long long r = mix64(seed_mixed ^ ((counter0 + (unsigned long long)idx) * 0xD1342543DE82EF95ull));
+    const float u = ((float)(r >> 40) + 0.5f) * (1.0f / 16777216.0f);
+    float m;
+    if (continuous) m = __fadd_rn(__fmul_rn(u, p * 4.0f), 1.0f - 2.0f * p);  // Scale(4p) then Add(1 - 2p): two roundings
+    else m = (u - p > 0.0f ? 1.0f : 0.0f) * (1.0f / (1.0f - p));
+    mask[(idx / cols) * stride + idx % cols] = m;
+  }
+}
+// CuMatrixBase::MulRows(mask, indexes): out[r,:] = in[r,:] .* mask[indexes[r],:]   (in may alias out)
+__global__ void mul_rows_indexed_kernel(const float* in, long long is, float* out, long long os, int rows, int cols4,
+                                        const float* __restrict__ mask, long long ms, const int32_t* __restrict__ index) {
+  ELEMWISE_LOOP((long long)rows * cols4) {
+    const long long r = idx / cols4;
+    const int c = (int)(idx % cols4) * 4;
+    const int m = index[r];
+    const float4 v = *reinterpret_cast<const float4*>(in + r * is + c);
+    const float4 w = *reinterpret_cast<const float4*>(mask + (long long)m * ms + c);
+    *reinterpret_cast<float4*>(out + r * os + c) = make_float4(v.x * w.x, v.y * w.y, v.z * w.z, v.w * w.w);
+  }
+}
+__global__ void mul_rows_indexed_scalar_kernel(const float* in, long long is, float* out, long long os, int rows, int cols,
+                                               const float* __restrict__ mask, long long ms, const int32_t* __restrict__ index) {
+  ELEMWISE_LOOP((long long)rows * cols) {
+    const long long r = idx / cols;
+    const int c = (int)(idx % cols);
+    out[r * os + c] = in[r * is + c] * mask[(long long)index[r] * ms + c];
+  }
+}
+}  // namespace
+
+extern "C" int tdnnf_dropout_mask(tdnnf_ctx* ctx, unsigned long long seed, unsigned long long counter, float* mask, int rows,
+                                  int cols, int stride, float proportion, int continuous) {
+  PROLOGUE(mask && rows >= 0 && cols >= 0 && stride >= cols && proportion >= 0.0f && proportion <= 1.0f, "bad argument");
+  // host side of mix64(seed): the same value for every element
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  dropout_mask_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(z, counter, mask, rows, cols,
+                                                                                                   stride, proportion, continuous);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_mul_rows_indexed(tdnnf_ctx* ctx, const float* in, int in_stride, float* out, int out_stride, int rows,
+                                      int cols, const float* mask, int mask_stride, const int32_t* row_index_dev) {
+  PROLOGUE(in && out && mask && row_index_dev && in_stride >= cols && out_stride >= cols && mask_stride >= cols, "bad matrix");
+  if (cols % 4 == 0 && in_stride % 4 == 0 && out_stride % 4 == 0 && mask_stride % 4 == 0 && al16(in) && al16(out) && al16(mask))
+    mul_rows_indexed_kernel<<<grid_for((long long)rows * cols / 4, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
+        in, in_stride, out, out_stride, rows, cols / 4, mask, mask_stride, row_index_dev);
+  else
+    mul_rows_indexed_scalar_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
+        in, in_stride, out, out_stride, rows, cols, mask, mask_stride, row_index_dev);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}

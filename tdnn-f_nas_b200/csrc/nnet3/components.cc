@@ -1980,10 +1980,207 @@ void RectifiedLinearComponent::StoreStats(const CuMatrixBase<BaseFloat>&, const 
 // =====================================================================================
 // factories (itf.cc:56-293: the registrations the README adds) and edit directives
 // =====================================================================================
+// =====================================================================================
+// GeneralDropoutComponent (upstream kaldi nnet-general-component.cc; see components.h)
+// =====================================================================================
+GeneralDropoutComponent::GeneralDropoutComponent()
+    : dim_(0), block_dim_(0), time_period_(0), dropout_proportion_(0.5), specaugment_max_proportion_(0.0), continuous_(false) {}
+
+std::string GeneralDropoutComponent::Info() const {
+  std::ostringstream stream;
+  stream << Type() << ", dim=" << dim_ << ", block-dim=" << block_dim_ << ", dropout-proportion=" << dropout_proportion_;
+  if (continuous_) stream << ", continuous=true";
+  if (time_period_ > 0) stream << ", time-period=" << time_period_;
+  if (test_mode_) stream << ", test-mode=true";
+  return stream.str();
+}
+
+void GeneralDropoutComponent::InitFromConfig(ConfigLine* cfl) {
+  dim_ = 0;
+  bool ok = cfl->GetValue("dim", &dim_);
+  if (!ok || dim_ <= 0) KALDI_ERR << "Invalid configuration (dim missing or <= 0): " << cfl->WholeLine();
+  block_dim_ = dim_;
+  cfl->GetValue("block-dim", &block_dim_);
+  if (!(block_dim_ > 0 && dim_ % block_dim_ == 0))
+    KALDI_ERR << "Invalid configuration dim=" << dim_ << ", block-dim=" << block_dim_;
+  time_period_ = 0;
+  cfl->GetValue("time-period", &time_period_);
+  dropout_proportion_ = 0.5;
+  cfl->GetValue("dropout-proportion", &dropout_proportion_);
+  continuous_ = false;
+  cfl->GetValue("continuous", &continuous_);
+  specaugment_max_proportion_ = 0.0;
+  cfl->GetValue("specaugment-max-proportion", &specaugment_max_proportion_);
+  if (specaugment_max_proportion_ != 0.0)
+    KALDI_ERR << "GeneralDropoutComponent: SpecAugment masks (specaugment-max-proportion != 0) are not built";
+  test_mode_ = false;
+  cfl->GetValue("test-mode", &test_mode_);
+  if (cfl->HasUnusedValues()) KALDI_ERR << "Could not process these elements in initializer: " << cfl->UnusedValues();
+}
+
+const int32* GeneralDropoutComponent::PrecomputedIndexes::DeviceIndexes() const {
+  if (dev_.Dim() != (int32)indexes.size()) {
+    std::vector<BaseFloat> words(indexes.size());
+    static_assert(sizeof(BaseFloat) == sizeof(int32), "bit copy");
+    if (!indexes.empty()) std::memcpy(words.data(), indexes.data(), sizeof(int32) * indexes.size());
+    dev_.Resize((int32)indexes.size());
+    dev_.CopyFromHost(words);
+  }
+  return reinterpret_cast<const int32*>(dev_.Data());
+}
+
+void GeneralDropoutComponent::MulRows(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out, const CuMatrix& mask,
+                                      const PrecomputedIndexes& indexes) const {
+  const int32 multiple = dim_ / block_dim_;
+  if (multiple > 1)  // the reshaped (rows * multiple) x block_dim view needs contiguous rows (kInputContiguous | kOutputContiguous)
+    KALDI_ASSERT(in.Stride() == in.NumCols() && out->Stride() == out->NumCols());
+  const int32 rows = in.NumRows() * multiple;
+  KALDI_ASSERT((int32)indexes.indexes.size() == rows && mask.NumRows() == indexes.num_mask_rows && mask.NumCols() == block_dim_);
+  CheckStatus(tdnnf_mul_rows_indexed(CurrentContext(), in.Data(), multiple > 1 ? block_dim_ : in.Stride(), out->Data(),
+                                     multiple > 1 ? block_dim_ : out->Stride(), rows, block_dim_, mask.Data(), mask.Stride(),
+                                     indexes.DeviceIndexes()));
+}
+
+void* GeneralDropoutComponent::Propagate(const ComponentPrecomputedIndexes* indexes_in, const CuMatrixBase<BaseFloat>& in,
+                                         CuMatrixBase<BaseFloat>* out) const {
+  KALDI_ASSERT(in.NumRows() == out->NumRows() && in.NumCols() == out->NumCols() && in.NumCols() == dim_);
+  if (test_mode_ || dropout_proportion_ == 0.0) {
+    if (out->Data() != in.Data())  // out->CopyFromMat(in); kPropagateInPlace: nothing to do when they alias
+      CheckStatus(tdnnf_add_scaled(CurrentContext(), in.Data(), in.Stride(), 1.0f, in.Data(), in.Stride(), 0.0f, out->Data(),
+                                   out->Stride(), in.NumRows(), in.NumCols()));
+    return NULL;
+  }
+  const PrecomputedIndexes* indexes = dynamic_cast<const PrecomputedIndexes*>(indexes_in);
+  KALDI_ASSERT(indexes != NULL);
+  // GetMemo(num_mask_rows): one uniform per mask element, draw number = counter + element
+  CuMatrix* mask = new CuMatrix(indexes->num_mask_rows, block_dim_);
+  const uint64_t counter = GetRandCounter();
+  CheckStatus(tdnnf_dropout_mask(CurrentContext(), GetRandSeed(), counter, mask->Data(), mask->NumRows(), mask->NumCols(),
+                                 mask->Stride(), dropout_proportion_, continuous_ ? 1 : 0));
+  SetRandCounter(counter + (uint64_t)mask->NumRows() * (uint64_t)mask->NumCols());
+  MulRows(in, out, *mask, *indexes);
+  return mask;
+}
+
+void GeneralDropoutComponent::Backprop(const std::string&, const ComponentPrecomputedIndexes* indexes_in,
+                                       const CuMatrixBase<BaseFloat>&, const CuMatrixBase<BaseFloat>&,
+                                       const CuMatrixBase<BaseFloat>& out_deriv, void* memo, Component*,
+                                       CuMatrixBase<BaseFloat>* in_deriv) const {
+  if (in_deriv == NULL) return;
+  KALDI_ASSERT(in_deriv->NumRows() == out_deriv.NumRows() && in_deriv->NumCols() == out_deriv.NumCols());
+  if (test_mode_ || dropout_proportion_ == 0.0) {
+    KALDI_ASSERT(memo == NULL);
+    if (in_deriv->Data() != out_deriv.Data())  // in_deriv->CopyFromMat(out_deriv)
+      CheckStatus(tdnnf_add_scaled(CurrentContext(), out_deriv.Data(), out_deriv.Stride(), 1.0f, out_deriv.Data(),
+                                   out_deriv.Stride(), 0.0f, in_deriv->Data(), in_deriv->Stride(), out_deriv.NumRows(),
+                                   out_deriv.NumCols()));
+    return;
+  }
+  const PrecomputedIndexes* indexes = dynamic_cast<const PrecomputedIndexes*>(indexes_in);
+  KALDI_ASSERT(indexes != NULL && memo != NULL);
+  MulRows(out_deriv, in_deriv, *static_cast<const CuMatrix*>(memo), *indexes);
+}
+
+ComponentPrecomputedIndexes* GeneralDropoutComponent::PrecomputeIndexes(const MiscComputationInfo&,
+                                                                        const std::vector<Index>& input_indexes,
+                                                                        const std::vector<Index>& output_indexes,
+                                                                        bool) const {
+  KALDI_ASSERT(input_indexes == output_indexes);
+  PrecomputedIndexes* ans = new PrecomputedIndexes();
+  // one mask row per distinct (n, x, block of time_period frames); time-period 0 = one row per (n, x) for all t
+  std::map<Index, int32> row_of;
+  std::vector<int32> rows(input_indexes.size());
+  int32 cur_row = 0;
+  for (size_t i = 0; i < input_indexes.size(); ++i) {
+    Index index = input_indexes[i];
+    if (time_period_ == 0) {
+      index.t = 0;
+    } else {  // DivideRoundingDown(t, time_period)
+      int32 q = index.t / time_period_;
+      if (index.t % time_period_ != 0 && ((index.t < 0) != (time_period_ < 0))) --q;
+      index.t = q;
+    }
+    std::map<Index, int32>::const_iterator it = row_of.find(index);
+    if (it == row_of.end()) {
+      row_of[index] = cur_row;
+      rows[i] = cur_row++;
+    } else {
+      rows[i] = it->second;
+    }
+  }
+  const int32 multiple = dim_ / block_dim_;
+  if (multiple == 1) {
+    ans->indexes = rows;
+  } else {  // each row of the input is `multiple` rows of the reshaped view, each with its own mask row
+    ans->indexes.reserve(rows.size() * multiple);
+    for (int32 r : rows)
+      for (int32 j = 0; j < multiple; ++j) ans->indexes.push_back(r * multiple + j);
+    cur_row *= multiple;
+  }
+  ans->num_mask_rows = cur_row;
+  return ans;
+}
+
+void GeneralDropoutComponent::Write(std::ostream& os, bool binary) const {
+  WriteToken(os, binary, "<GeneralDropoutComponent>");
+  WriteToken(os, binary, "<Dim>");
+  WriteBasicType(os, binary, dim_);
+  WriteToken(os, binary, "<BlockDim>");
+  WriteBasicType(os, binary, block_dim_);
+  WriteToken(os, binary, "<TimePeriod>");
+  WriteBasicType(os, binary, time_period_);
+  WriteToken(os, binary, "<DropoutProportion>");
+  WriteBasicType(os, binary, dropout_proportion_);
+  if (test_mode_) WriteToken(os, binary, "<TestMode>");
+  if (continuous_) WriteToken(os, binary, "<Continuous>");
+  WriteToken(os, binary, "</GeneralDropoutComponent>");
+}
+
+void GeneralDropoutComponent::Read(std::istream& is, bool binary) {
+  ExpectOneOrTwoTokens(is, binary, "<GeneralDropoutComponent>", "<Dim>");
+  ReadBasicType(is, binary, &dim_);
+  ExpectToken(is, binary, "<BlockDim>");
+  ReadBasicType(is, binary, &block_dim_);
+  ExpectToken(is, binary, "<TimePeriod>");
+  ReadBasicType(is, binary, &time_period_);
+  ExpectToken(is, binary, "<DropoutProportion>");
+  ReadBasicType(is, binary, &dropout_proportion_);
+  test_mode_ = false;
+  continuous_ = false;
+  specaugment_max_proportion_ = 0.0;
+  for (;;) {
+    std::string token;
+    ReadToken(is, binary, &token);
+    if (token == "<TestMode>") test_mode_ = true;
+    else if (token == "<Continuous>") continuous_ = true;
+    else if (token == "<SpecAugmentMaxProportion>")
+      KALDI_ERR << "GeneralDropoutComponent: SpecAugment masks are not built";
+    else if (token == "</GeneralDropoutComponent>") break;
+    else KALDI_ERR << "Unexpected token " << token << " in GeneralDropoutComponent";
+  }
+}
+
+void GeneralDropoutComponent::PrecomputedIndexes::Write(std::ostream& os, bool binary) const {
+  WriteToken(os, binary, "<GeneralDropoutComponentPrecomputedIndexes>");
+  WriteToken(os, binary, "<NumMaskRows>");
+  WriteBasicType(os, binary, num_mask_rows);
+  WriteToken(os, binary, "<Indexes>");
+  WriteIntegerVector(os, binary, indexes);
+  WriteToken(os, binary, "</GeneralDropoutComponentPrecomputedIndexes>");
+}
+void GeneralDropoutComponent::PrecomputedIndexes::Read(std::istream& is, bool binary) {
+  ExpectOneOrTwoTokens(is, binary, "<GeneralDropoutComponentPrecomputedIndexes>", "<NumMaskRows>");
+  ReadBasicType(is, binary, &num_mask_rows);
+  ExpectToken(is, binary, "<Indexes>");
+  ReadIntegerVector(is, binary, &indexes);
+  ExpectToken(is, binary, "</GeneralDropoutComponentPrecomputedIndexes>");
+}
+
 Component* Component::NewComponentOfType(const std::string& component_type) {
   Component* ans = NULL;
   if (component_type == "TdnnDARTSV3Component") ans = new TdnnDARTSV3Component();                    // itf.cc:88-89
   else if (component_type == "TdnnComponent") ans = new TdnnComponent();                             // itf.cc (stock)
+  else if (component_type == "GeneralDropoutComponent") ans = new GeneralDropoutComponent();         // itf.cc:194-195
   else if (component_type == "CopyNComponent") ans = new CopyNComponent();                           // itf.cc:202-203
   else if (component_type == "BatchNormTestComponent") ans = new BatchNormTestComponent();           // itf.cc:226-227
   else if (component_type == "BatchNormComponent") ans = new BatchNormComponent();                   // itf.cc (stock)
@@ -1999,6 +2196,7 @@ Component* Component::NewComponentOfType(const std::string& component_type) {
 ComponentPrecomputedIndexes* ComponentPrecomputedIndexes::NewComponentPrecomputedIndexesOfType(const std::string& cpi_type) {
   ComponentPrecomputedIndexes* ans = NULL;
   if (cpi_type == "TdnnDARTSV3ComponentPrecomputedIndexes") ans = new TdnnDARTSV3Component::PrecomputedIndexes();  // itf.cc:66-67
+  else if (cpi_type == "GeneralDropoutComponentPrecomputedIndexes") ans = new GeneralDropoutComponent::PrecomputedIndexes();  // itf.cc:78-79
   if (ans != NULL) KALDI_ASSERT(cpi_type == ans->Type());
   return ans;
 }
@@ -2047,6 +2245,22 @@ void ReadEditConfig(std::istream& edit_config_is, const std::vector<std::string>
           }
         }
         KaldiLog("Set temp proportions for " + std::to_string(num_temp_proportions_set) + " components.");
+      } else if (directive == "set-dropout-proportion") {  // utils.cc:1297-1330 (GeneralDropoutComponent branch)
+        std::string name_pattern = "*";
+        config_line.GetValue("name", &name_pattern);
+        BaseFloat proportion = -1;
+        if (!config_line.GetValue("proportion", &proportion))
+          KALDI_ERR << "In edits-config, expected proportion to be set in line: " << config_line.WholeLine();
+        int32 num_dropout_proportions_set = 0;
+        for (size_t c = 0; c < components.size(); c++) {
+          if (NameMatchesPattern(names[c].c_str(), name_pattern.c_str())) {
+            if (GeneralDropoutComponent* g = dynamic_cast<GeneralDropoutComponent*>(components[c])) {
+              g->SetDropoutProportion(proportion);
+              num_dropout_proportions_set++;
+            }
+          }
+        }
+        KaldiLog("Set dropout proportions for " + std::to_string(num_dropout_proportions_set) + " components.");
       } else if (directive == "set-learning-rate" || directive == "set-learning-rate-factor") {
         std::string name_pattern = "*";
         config_line.GetValue("name", &name_pattern);

@@ -618,5 +618,64 @@ void ReadEditConfig(std::istream& config_file, const std::vector<std::string>& n
                     const std::vector<Component*>& components);
 bool NameMatchesPattern(const char* name, const char* pattern);
 
+// ------------------------------------------------------------------ GeneralDropoutComponent (upstream kaldi, nnet-general-component.h)
+// The `dropout` node of every tdnnf-layer / relu-batchnorm-dropout-layer of the recipes (composite_layers.py; configured
+// `dropout-proportion=0.0 continuous=true`, driven per iteration by `set-dropout-proportion`, utils.cc:1297-1330, from the
+// schedule 0,0@0.20,0.5@0.50,0).  One mask row per sequence n (per block of time-period frames when time-period != 0),
+// shared by all its frames: out[r,:] = in[r,:] .* mask[indexes[r],:].  Proportion 0 / test mode: a copy, no memo.
+// SpecAugment masks (specaugment-max-proportion != 0) are not built: KALDI_ERR.
+class GeneralDropoutComponent : public RandomComponent {
+ public:
+  GeneralDropoutComponent();
+  virtual int32 InputDim() const { return dim_; }
+  virtual int32 OutputDim() const { return dim_; }
+  virtual std::string Info() const;
+  virtual void InitFromConfig(ConfigLine* cfl);
+  virtual std::string Type() const { return "GeneralDropoutComponent"; }
+  virtual int32 Properties() const {
+    return kRandomComponent | kPropagateInPlace | kBackpropInPlace | kUsesMemo |
+           (block_dim_ != dim_ ? (kInputContiguous | kOutputContiguous) : 0);
+  }
+  virtual void* Propagate(const ComponentPrecomputedIndexes* indexes, const CuMatrixBase<BaseFloat>& in,
+                          CuMatrixBase<BaseFloat>* out) const;
+  virtual void Backprop(const std::string& debug_info, const ComponentPrecomputedIndexes* indexes,
+                        const CuMatrixBase<BaseFloat>& in_value, const CuMatrixBase<BaseFloat>& out_value,
+                        const CuMatrixBase<BaseFloat>& out_deriv, void* memo, Component* to_update,
+                        CuMatrixBase<BaseFloat>* in_deriv) const;
+  virtual void DeleteMemo(void* memo) const { delete static_cast<CuMatrix*>(memo); }
+  virtual ComponentPrecomputedIndexes* PrecomputeIndexes(const MiscComputationInfo& misc_info,
+                                                         const std::vector<Index>& input_indexes,
+                                                         const std::vector<Index>& output_indexes,
+                                                         bool need_backprop) const;
+  virtual void Read(std::istream& is, bool binary);
+  virtual void Write(std::ostream& os, bool binary) const;
+  virtual Component* Copy() const { return new GeneralDropoutComponent(*this); }
+  void SetDropoutProportion(BaseFloat p) { dropout_proportion_ = p; }
+  BaseFloat DropoutProportion() const { return dropout_proportion_; }
+
+  class PrecomputedIndexes : public ComponentPrecomputedIndexes {
+   public:
+    PrecomputedIndexes() : num_mask_rows(0) {}
+    PrecomputedIndexes(const PrecomputedIndexes& other) : num_mask_rows(other.num_mask_rows), indexes(other.indexes) {}
+    virtual PrecomputedIndexes* Copy() const { return new PrecomputedIndexes(*this); }
+    virtual void Write(std::ostream& os, bool binary) const;
+    virtual void Read(std::istream& is, bool binary);
+    virtual std::string Type() const { return "GeneralDropoutComponentPrecomputedIndexes"; }
+    const int32* DeviceIndexes() const;  // uploaded on first use (CuArray<int32> upstream)
+    int32 num_mask_rows;
+    std::vector<int32> indexes;  // per (reshaped) row of the input: its mask row
+
+   private:
+    mutable CuVector dev_;  // the int32 indexes, bit-copied into device words
+  };
+
+ private:
+  void MulRows(const CuMatrixBase<BaseFloat>& in, CuMatrixBase<BaseFloat>* out, const CuMatrix& mask,
+               const PrecomputedIndexes& indexes) const;
+  int32 dim_, block_dim_, time_period_;
+  BaseFloat dropout_proportion_, specaugment_max_proportion_;
+  bool continuous_;
+};
+
 }  // namespace nnet3
 }  // namespace tdnnf

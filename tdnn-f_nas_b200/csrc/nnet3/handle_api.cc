@@ -338,6 +338,13 @@ int tdnnf_nnet3_orthonormal_constraint(const void* comp, float* value) {
   *value = t->OrthonormalConstraint();
   API_END
 }
+int tdnnf_nnet3_dropout_proportion(const void* comp, float* value) {
+  API_BEGIN
+  const GeneralDropoutComponent* g = dynamic_cast<const GeneralDropoutComponent*>(static_cast<const Component*>(comp));
+  if (!g) KALDI_ERR << "not a GeneralDropoutComponent";
+  *value = g->DropoutProportion();
+  API_END
+}
 int tdnnf_nnet3_temp_proportion(const void* comp, float* value) {
   API_BEGIN
   const Component* c = static_cast<const Component*>(comp);

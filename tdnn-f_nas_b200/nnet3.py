@@ -361,6 +361,11 @@ class Component:
         _check(_lib().tdnnf_nnet3_temp_proportion(self.h, C.byref(r)))
         return r.value
 
+    def dropout_proportion(self) -> float:
+        r = C.c_float()
+        _check(_lib().tdnnf_nnet3_dropout_proportion(self.h, C.byref(r)))
+        return r.value
+
     def orthonormal_constraint(self) -> float:
         r = C.c_float()
         _check(_lib().tdnnf_nnet3_orthonormal_constraint(self.h, C.byref(r)))
@@ -434,3 +439,48 @@ def temperature_edit_string(num_archives_processed: int, num_archives_to_process
     """get_temperature_edit_string (temperature_schedule.py:34-67): the per-iteration edit directive."""
     t = temperature_for_iteration(num_archives_processed, num_archives_to_process)
     return "set-temperature-proportion name=* proportion={0}".format(t)
+
+
+def parse_dropout_schedule(schedule: str) -> List[Tuple[float, float]]:
+    """--trainer.dropout-schedule for one name pattern, e.g. '0,0@0.20,0.5@0.50,0' -> [(data_fraction, proportion), ...]
+    ascending: the first value holds at fraction 0, the last at 1, 'p@f' in between, a bare middle value means @0.5
+    (temperature_schedule.py:119-172 keeps upstream dropout_schedule.py's parser as a comment)."""
+    parts = schedule.strip().split(",")
+    if len(parts) < 2:
+        raise ValueError("dropout proportion string must specify at least the start and end dropouts")
+    values = [(0.0, float(parts[0]))]
+    for part in parts[1:-1]:
+        pv = part.split("@")
+        if len(pv) not in (1, 2):
+            raise ValueError(f"bad dropout-schedule entry {part!r}")
+        proportion, fraction = float(pv[0]), (float(pv[1]) if len(pv) == 2 else 0.5)
+        if fraction < values[-1][0] or fraction > 1.0:
+            raise ValueError("dropout-schedule must be in increasing order of data fractions")
+        values.append((fraction, proportion))
+    values.append((1.0, float(parts[-1])))
+    for fraction, proportion in values:
+        if not (0.0 <= fraction <= 1.0 and 0.0 <= proportion <= 1.0):
+            raise ValueError("dropout-schedule values must lie in [0, 1]")
+    return values
+
+
+def dropout_proportion_for_fraction(schedule: str, data_fraction: float) -> float:
+    """Piecewise-linear interpolation of the schedule at `data_fraction` of the training data (upstream
+    _get_component_dropout)."""
+    values = parse_dropout_schedule(schedule)
+    if data_fraction <= 0.0:
+        return values[0][1]
+    if data_fraction >= 1.0:
+        return values[-1][1]
+    for (f0, p0), (f1, p1) in zip(values, values[1:]):
+        if f0 <= data_fraction <= f1:
+            if f1 == f0:
+                return p1
+            return p0 + (p1 - p0) * (data_fraction - f0) / (f1 - f0)
+    return values[-1][1]
+
+
+def dropout_edit_string(schedule: str, data_fraction: float, name_pattern: str = "*") -> str:
+    """The per-iteration edit directive upstream's get_dropout_edit_string emits (utils.cc:1297-1330 consumes it)."""
+    return "set-dropout-proportion name={0} proportion={1}".format(
+        name_pattern, dropout_proportion_for_fraction(schedule, data_fraction))

@@ -49,6 +49,8 @@ class SupernetConfig:
     strides: Optional[List[int]] = None  # manual mode: time-stride per tdnnf-layer (default 1,1,1,0 then 6: :138-151)
     l2_regularize: float = 0.0      # per-component l2-regularize (0.01 in the manual recipe; ApplyL2Regularization)
     batchnorm_stats_scale: float = 0.8   # ScaleBatchnormStats after every minibatch (train-mode batch-norm only)
+    dropout: bool = False           # build the GeneralDropoutComponent of tdnn1 and of every block (pretrain / manual);
+                                    # proportion 0 until set_dropout_proportion() (the recipes' schedule starts at 0)
     learning_rate: float = 2.5e-4
     darts_lr_factor: float = 1.0e-4  # <LearningRateFactor> set by the cvupdate recipe's sed (search mode only)
     max_change: float = 0.75         # per-component max-change (xconfig default of the tdnnf layers)
@@ -229,6 +231,8 @@ class Supernet:
                        memo_lin=C.c_void_p(), memo_aff=C.c_void_p(), rows_prev=rows_prev)
             blk["lin_delta"].scale(0.0)
             blk["aff_delta"].scale(0.0)
+            if cfg.dropout:
+                blk.update(self._make_dropout(D, grid(aff_t[b]), rows_aff, zeros))
             self.blocks.append(blk)
 
         rows_in, rows_T = len(in_t) * S, T * S
@@ -237,6 +241,9 @@ class Supernet:
         self.x_host = torch.zeros((rows_in, cfg.feat_dim), dtype=torch.float32).pin_memory()
         self.t1 = dict(aff=zeros(rows_in, D), relu=zeros(rows_in, D), out=zeros(rows_in, D), bn=make_bn(D),
                        d_out=zeros(rows_in, D), d_aff=zeros(rows_in, D))
+        if cfg.dropout:
+            assert not search, "the search stage runs the fused ReLU + BatchNormTest + bypass tail: no dropout node"
+            self.t1.update(self._make_dropout(D, grid(in_t), rows_in, zeros))
         P, Ssm = cfg.num_pdfs, cfg.prefinal_small
         self.head = dict(pl=zeros(rows_T, Ssm), pa=zeros(rows_T, D), pr=zeros(rows_T, D), pb=zeros(rows_T, D),
                          pli=zeros(rows_T, Ssm), pb2=zeros(rows_T, Ssm), out=zeros(rows_T, P), bn1=make_bn(D), bn2=make_bn(Ssm),
@@ -255,6 +262,34 @@ class Supernet:
         if search:
             self._freeze_batchnorm()
             self._compile()
+
+    def _make_dropout(self, dim, indexes, rows, zeros):
+        """`component name=X.dropout type=GeneralDropoutComponent dim=D dropout-proportion=0.0 continuous=true`
+        (composite_layers.py: tdnnf-layer / relu-batchnorm-dropout-layer with dropout-per-dim-continuous=true): one mask
+        row per sequence, shared by all its frames.  Out of place: the batch-norm backward needs its own output."""
+        comp = nnet3.Component.new("GeneralDropoutComponent", f"dim={dim} dropout-proportion=0.0 continuous=true")
+        return dict(drop=comp, drop_idx=comp.precompute_indexes(indexes, indexes), drop_memo=C.c_void_p(),
+                    drop_in=zeros(rows, dim))
+
+    def set_dropout_proportion(self, proportion: float):
+        """What the per-iteration `set-dropout-proportion name=* proportion=p` edit does (utils.cc:1297-1330)."""
+        assert self.cfg.dropout, "built without dropout nodes"
+        named = [("tdnn1.dropout", self.t1["drop"])] + [(f"tdnnf{b + 2}.dropout", blk["drop"]) for b, blk in enumerate(self.blocks)]
+        nnet3.apply_edits(f"set-dropout-proportion name=* proportion={proportion}", named)
+
+    def _dropout_fwd(self, plan, d, out):
+        """d["drop_in"] (the batch-norm output) -> out."""
+        ip, r, c, is_ = _m(d["drop_in"])
+        op, _, _, os_ = _m(out)
+        plan.add("nnet3", self.lib.tdnnf_nnet3_propagate, d["drop"].h, d["drop_idx"].h, ip, r, c, is_, op, r, c, os_,
+                 C.byref(d["drop_memo"]))
+
+    def _dropout_bwd(self, plan, d, d_out, d_in):
+        dp, r, c, ds = _m(d_out)
+        ip, _, _, is_ = _m(d_in)
+        plan.add("nnet3", self.lib.tdnnf_nnet3_backprop, d["drop"].h, d["drop_idx"].h, None, r, c, 0, None, 0, dp, r, c, ds,
+                 d["drop_memo"], None, ip, is_)
+        plan.add("nnet3", self.lib.tdnnf_nnet3_delete_memo, d["drop"].h, d["drop_memo"])
 
     def _freeze_batchnorm(self):
         """The synthetic stand-in for "pretrain the supernet, then sed BatchNormComponent -> BatchNormTestComponent":
@@ -354,7 +389,11 @@ class Supernet:
         # ---- forward
         self._affine_fwd(fwd, self.x, st["tdnn1"], t1["aff"])
         fwd.add("abi", lib.tdnnf_relu_fwd, h, *_m(t1["aff"]), _m(t1["relu"])[0], _m(t1["relu"])[3])
-        self._bn_fwd(fwd, t1["bn"], t1["relu"], t1["out"])
+        if cfg.dropout:
+            self._bn_fwd(fwd, t1["bn"], t1["relu"], t1["drop_in"])
+            self._dropout_fwd(fwd, t1, t1["out"])
+        else:
+            self._bn_fwd(fwd, t1["bn"], t1["relu"], t1["out"])
         prev = t1["out"]
         for blk in self.blocks:
             pp, pr, pc, ps = _m(prev)
@@ -388,7 +427,11 @@ class Supernet:
                         _m(src)[0], _m(src)[3], cfg.bypass_scale, _m(blk["out"])[0], _m(blk["out"])[3])
             else:
                 fwd.add("abi", lib.tdnnf_relu_fwd, h, op, orr, oc, os_, _m(blk["relu"])[0], _m(blk["relu"])[3])
-                self._bn_fwd(fwd, blk["bn"], blk["relu"], blk["bn_out"])
+                if cfg.dropout:  # batchnorm -> dropout -> noop = Sum(Scale(bypass, input), dropout)
+                    self._bn_fwd(fwd, blk["bn"], blk["relu"], blk["drop_in"])
+                    self._dropout_fwd(fwd, blk, blk["bn_out"])
+                else:
+                    self._bn_fwd(fwd, blk["bn"], blk["relu"], blk["bn_out"])
                 fwd.add("abi", lib.tdnnf_add_scaled, h, _m(src)[0], _m(src)[3], cfg.bypass_scale, _m(blk["bn_out"])[0],
                         _m(blk["bn_out"])[3], 1.0, _m(blk["out"])[0], _m(blk["out"])[3], orr, oc)
             prev = blk["out"]
@@ -446,8 +489,12 @@ class Supernet:
                     bwd.add("abi", lib.tdnnf_relu_scale_offset_bypass_bwd, h, dp_, ds, _m(blk["aff_out"])[0], _m(blk["aff_out"])[3],
                             C.c_void_p(sp), 0.0, _m(blk["d_aff"])[0], _m(blk["d_aff"])[3], _m(scratch)[0], _m(scratch)[3], dr, dc)
                 else:
-                    # batchnorm, relu
-                    self._bn_bwd(bwd, blk["bn"], blk["bn_out"], blk["d_out"], blk["d_aff"])
+                    # (dropout,) batchnorm, relu
+                    if cfg.dropout:
+                        self._dropout_bwd(bwd, blk, blk["d_out"], blk["d_aff"])
+                        self._bn_bwd(bwd, blk["bn"], blk["drop_in"], blk["d_aff"], blk["d_aff"])
+                    else:
+                        self._bn_bwd(bwd, blk["bn"], blk["bn_out"], blk["d_out"], blk["d_aff"])
                     bwd.add("abi", lib.tdnnf_relu_bwd, h, _m(blk["relu"])[0], _m(blk["relu"])[3], _m(blk["d_aff"])[0], _m(blk["d_aff"])[3],
                             _m(blk["d_aff"])[0], _m(blk["d_aff"])[3], dr, dc)
             # affine DARTS: in_deriv (kBackpropAdds) must start from zero
@@ -468,7 +515,11 @@ class Supernet:
             bwd.add("nnet3", lib.tdnnf_nnet3_backprop, blk["lin"].h, blk["lin_idx"].h, pp, pr, pc, ps, None, 0, lp, lr_, lc, ls,
                     blk["memo_lin"], blk["lin_delta"].h, qp, qs)
             bwd.add("nnet3", lib.tdnnf_nnet3_delete_memo, blk["lin"].h, blk["memo_lin"])
-        self._bn_bwd(bwd, t1["bn"], t1["out"], t1["d_out"], t1["d_out"])
+        if cfg.dropout:
+            self._dropout_bwd(bwd, t1, t1["d_out"], t1["d_out"])
+            self._bn_bwd(bwd, t1["bn"], t1["drop_in"], t1["d_out"], t1["d_out"])
+        else:
+            self._bn_bwd(bwd, t1["bn"], t1["out"], t1["d_out"], t1["d_out"])
         bwd.add("abi", lib.tdnnf_relu_bwd, h, _m(t1["relu"])[0], _m(t1["relu"])[3], _m(t1["d_out"])[0], _m(t1["d_out"])[3],
                 _m(t1["d_aff"])[0], _m(t1["d_aff"])[3], t1["relu"].shape[0], t1["relu"].shape[1])
         self._affine_bwd(bwd, self.x, st["tdnn1"], t1["d_aff"], None, lr)

@@ -90,3 +90,32 @@ def test_manual_tdnnf_step_runs_learns_and_stays_semi_orthogonal():
     rows = net.blocks[0]["aff_out"].shape[0]
     assert rows * 0.8 <= bn.bn_count() < 5.0 * rows
     net.close()
+
+
+def test_dropout_nodes_in_the_step():
+    """GeneralDropoutComponent after every batch-norm (pretrain / manual systems): proportion 0 is the identity
+    (same trajectory as a net built without the nodes); the schedule's set-dropout-proportion edit switches it on."""
+    from tdnnf_nas_b200.supernet import Supernet, SupernetConfig
+
+    def run(dropout, schedule):
+        cfg = SupernetConfig(num_seqs=8, frames_per_eg=30, dim=128, bottleneck=32, num_blocks=3, prefinal_small=64,
+                             num_pdfs=200, den_states=300, den_out_degree=6.0, mode="manual", strides=[1, 0, 2],
+                             l2_regularize=0.01, learning_rate=2e-3, dropout=dropout)
+        net = Supernet(cfg)
+        x = net.make_input(0).pin_memory()
+        objfs = []
+        for p in schedule:
+            if dropout:
+                net.set_dropout_proportion(p)
+            objfs.append(net.step(x))
+        net.close()
+        return objfs
+
+    base = run(False, [0.0] * 4)
+    zero = run(True, [0.0] * 4)
+    for a, b in zip(base, zero):
+        assert abs(a - b) <= 1e-5 * abs(a) + 1e-6, (base, zero)
+    on = run(True, [0.0, 0.0, 0.4, 0.4])
+    assert all(math.isfinite(o) for o in on)
+    assert on[:2] == zero[:2] or all(abs(a - b) <= 1e-5 * abs(a) + 1e-6 for a, b in zip(on[:2], zero[:2]))
+    assert abs(on[2] - zero[2]) > 1e-4 * abs(zero[2])  # the masks changed the forward pass

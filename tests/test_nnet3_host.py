@@ -239,3 +239,67 @@ def test_rectified_linear_component_config_and_text_form():
     for bad in ("block-dim=4", "dim=12 block-dim=5", "dim=8 bogus=1"):
         with pytest.raises(nnet3.Nnet3Error):
             nnet3.Component.new("RectifiedLinearComponent", bad)
+
+
+def test_dropout_schedule():
+    """--trainer.dropout-schedule of the recipes (run_tdnn_7q_fbk_40_manual.sh:48): piecewise linear in the data fraction."""
+    from tdnnf_nas_b200 import nnet3
+
+    sch = "0,0@0.20,0.5@0.50,0"
+    assert nnet3.parse_dropout_schedule(sch) == [(0.0, 0.0), (0.2, 0.0), (0.5, 0.5), (1.0, 0.0)]
+    for f, want in [(0.0, 0.0), (0.1, 0.0), (0.2, 0.0), (0.35, 0.25), (0.5, 0.5), (0.75, 0.25), (1.0, 0.0)]:
+        assert nnet3.dropout_proportion_for_fraction(sch, f) == pytest.approx(want, abs=1e-12)
+    assert nnet3.dropout_proportion_for_fraction("0.1,0.3,0.0", 0.25) == pytest.approx(0.2)  # bare middle value = @0.5
+    assert nnet3.dropout_edit_string(sch, 0.5) == "set-dropout-proportion name=* proportion=0.5"
+    for bad in ("0.5", "0,0.5@0.6,0.2@0.3,0", "0,1.5@0.5,0"):
+        with pytest.raises(ValueError):
+            nnet3.parse_dropout_schedule(bad)
+
+
+def _dropout_indexes(pi):
+    toks = pi.write(False).decode().split()
+    assert toks[0] == "<GeneralDropoutComponentPrecomputedIndexes>" and toks[1] == "<NumMaskRows>"
+    lo, hi = toks.index("["), toks.index("]")
+    return int(toks[2]), [int(t) for t in toks[lo + 1: hi]]
+
+
+def test_general_dropout_host_side():
+    """GeneralDropoutComponent: config, Properties, token stream, the set-dropout-proportion directive and PrecomputeIndexes
+    (one mask row per sequence; per block of time-period frames when set; block-dim reshaping) -- no device needed."""
+    from tdnnf_nas_b200 import nnet3
+
+    c = nnet3.Component.new("GeneralDropoutComponent", "dim=12 dropout-proportion=0.0 continuous=true")
+    assert c.type() == "GeneralDropoutComponent" and c.dims()[:2] == (12, 12) or c.input_dim() == 12
+    assert c.properties() == (nnet3.kRandomComponent | nnet3.kPropagateInPlace | nnet3.kBackpropInPlace | nnet3.kUsesMemo)
+    assert c.write(False).split() == b"<GeneralDropoutComponent> <Dim> 12 <BlockDim> 12 <TimePeriod> 0 <DropoutProportion> 0 <Continuous> </GeneralDropoutComponent>".split()
+    for binary in (False, True):
+        back = nnet3.Component.read(c.write(binary), binary)
+        assert back.write(binary) == c.write(binary)
+    nnet3.apply_edits("set-dropout-proportion name=tdnnf*.dropout proportion=0.25",
+                      [("tdnnf2.dropout", c), ("tdnnf2.relu", nnet3.Component.new("RectifiedLinearComponent", "dim=12"))])
+    assert c.dropout_proportion() == pytest.approx(0.25)
+    assert b"<DropoutProportion> 0.25 " in c.write(False)
+    with pytest.raises(nnet3.Nnet3Error, match="expected proportion"):
+        nnet3.apply_edits("set-dropout-proportion name=*", [("x", c)])
+    # t-major grid, 3 sequences: mask row = n
+    grid = [(n, t, 0) for t in range(-2, 5) for n in range(3)]
+    rows, idx = _dropout_indexes(c.precompute_indexes(grid, grid))
+    assert rows == 3 and idx == [n for _t in range(7) for n in range(3)]
+    # time-period 3: a new mask row per (n, floor(t / 3)), numbered in order of first appearance
+    c3 = nnet3.Component.new("GeneralDropoutComponent", "dim=12 time-period=3 dropout-proportion=0.2")
+    rows, idx = _dropout_indexes(c3.precompute_indexes(grid, grid))
+    blocks = sorted({t // 3 for t in range(-2, 5)})
+    assert rows == 3 * len(blocks)
+    assert idx == [blocks.index(t // 3) * 3 + n for t in range(-2, 5) for n in range(3)]
+    # block-dim 4 of dim 12: every input row is 3 rows of the reshaped view, each with its own mask row
+    cb = nnet3.Component.new("GeneralDropoutComponent", "dim=12 block-dim=4 dropout-proportion=0.2")
+    assert cb.properties() & (nnet3.kInputContiguous | nnet3.kOutputContiguous)
+    rows, idx = _dropout_indexes(cb.precompute_indexes(grid, grid))
+    assert rows == 9 and idx[:9] == [0, 1, 2, 3, 4, 5, 6, 7, 8] and len(idx) == 3 * len(grid)
+    pi = cb.precompute_indexes(grid, grid)
+    for binary in (False, True):
+        assert nnet3.PrecomputedIndexes.read(pi.write(binary), binary).write(binary) == pi.write(binary)
+    with pytest.raises(nnet3.Nnet3Error):
+        nnet3.Component.new("GeneralDropoutComponent", "dim=12 block-dim=5")
+    with pytest.raises(nnet3.Nnet3Error, match="SpecAugment"):
+        nnet3.Component.new("GeneralDropoutComponent", "dim=12 specaugment-max-proportion=0.5")
