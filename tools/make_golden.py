@@ -54,3 +54,33 @@ lp, deriv, ok = O.den_forward_backward(graph, xo, S, T, 0.1, deriv_weight=-1.0)
 np.savez_compressed(os.path.join(out_dir, "den_small.npz"), nnet_output=xo, S=S, T=T, leaky=0.1, logprob=lp, deriv=deriv,
                     ok=ok, **{"g_" + k: np.asarray(v) for k, v in graph.items()})
 print("wrote", sorted(os.listdir(out_dir)))
+
+# ---- stock TdnnComponent (natural-gradient update over two minibatches) and ConstrainOrthonormal
+only_new = "--only-new" in sys.argv
+g = np.random.default_rng(21)
+offsets, stride, S, t_out, din, dout = [-3, 0], 1, 4, 7, 24, 10
+n = len(offsets)
+rs, ro = synth.regular_row_offsets(offsets, min(offsets), 0, S, 1, stride)
+n_t_in = t_out + 3
+W = (g.standard_normal((dout, n * din)) / np.sqrt(n * din)).astype(np.float32)
+b = g.standard_normal(dout).astype(np.float32)
+xs = [g.standard_normal((n_t_in * S, din)).astype(np.float32) for _ in range(2)]
+ods = [(g.standard_normal((t_out * S, dout)) / (t_out * S)).astype(np.float32) for _ in range(2)]
+out = O.plain_tdnn_propagate(W, b, xs[0], t_out * S, ro, stride)
+ng_in, ng_out = O.NaturalGradient(8, 4, 2000.0, 4.0), O.NaturalGradient(5, 4, 2000.0, 4.0)
+ind, dW, db = np.zeros_like(xs[0]), np.zeros_like(W), np.zeros_like(b)
+scales = np.zeros((2, 2), np.float32)
+for k in range(2):
+    O.plain_tdnn_backprop(W, xs[k], ods[k], ro, stride, 0.02, in_deriv=ind if k == 0 else None, dW=dW, dbias=db,
+                          natural_gradient=True, ng_in=ng_in, ng_out=ng_out, scales=scales[k])
+np.savez_compressed(os.path.join(out_dir, "plain_tdnn_ng.npz"), offsets=np.array(offsets), row_offsets=np.array(ro), W=W, bias=b,
+                    x0=xs[0], x1=xs[1], od0=ods[0], od1=ods[1], lr=0.02, rank_in=8, rank_out=5, out=out, in_deriv=ind, dW=dW,
+                    dbias=db, scales=scales)
+q, _ = np.linalg.qr(g.standard_normal((40, 12)))
+M = (0.8 * q.T + 0.3 / np.sqrt(40) * g.standard_normal((12, 40))).astype(np.float32)
+fl, fx = M.copy(), M.copy()
+info_fl = O.constrain_orthonormal(fl, -1.0)
+info_fx = O.constrain_orthonormal(fx, 1.0)
+np.savez_compressed(os.path.join(out_dir, "constrain_orthonormal.npz"), M=M, floating=fl, info_floating=info_fl, fixed=fx,
+                    info_fixed=info_fx)
+print("wrote", sorted(os.listdir(out_dir)))
