@@ -340,6 +340,13 @@ int tdnnf_den_forward(tdnnf_den_comp* c, const float* nnet_output, int stride, f
  * *ok (HOST) = 0 when the t=0 alpha.beta check fails (the reference's return value).  Syncs. */
 int tdnnf_den_backward(tdnnf_den_comp* c, float deriv_weight, float* nnet_output_deriv, int stride, int* ok);
 
+/* LogSoftmaxComponent (ref: nnet-simple-component.cc:3607-3632; the `output-xent` branch of the chain recipes):
+ *   fwd  out = in - log(sum_j exp(in_j)) per row (ApplyLogSoftMaxPerRow);
+ *   bwd  in_deriv = out_deriv - exp(out_value) * rowsum(out_deriv) (DiffLogSoftmaxPerRow; in_deriv may alias out_deriv). */
+int tdnnf_log_softmax_fwd(tdnnf_ctx* ctx, const float* in, int rows, int cols, int in_stride, float* out, int out_stride);
+int tdnnf_log_softmax_bwd(tdnnf_ctx* ctx, const float* out_value, int ov_stride, const float* out_deriv, int od_stride,
+                          float* in_deriv, int id_stride, int rows, int cols);
+
 /* ------------------------------------------------------------------ dropout ------------ */
 /* GeneralDropoutComponent (kaldi: nnet3/nnet-general-component.cc; the `dropout` of every tdnnf-layer and
  * relu-batchnorm-dropout-layer, driven by the `set-dropout-proportion` directive, ref: nnet-utils.cc:1297-1330).

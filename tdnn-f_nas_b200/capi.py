@@ -81,6 +81,8 @@ def _declare(lib):
     sig("tdnnf_batchnorm_train_fwd", [vp, vp, i, i, i, vp, i, f, f, vp])
     sig("tdnnf_batchnorm_train_bwd", [vp, vp, i, vp, i, vp, i, i, i, f, vp])
     sig("tdnnf_constrain_orthonormal", [vp, vp, i, i, i, f, vp])
+    sig("tdnnf_log_softmax_fwd", [vp, vp, i, i, i, vp, i])
+    sig("tdnnf_log_softmax_bwd", [vp, vp, i, vp, i, vp, i, i, i])
     sig("tdnnf_dropout_mask", [vp, C.c_uint64, C.c_uint64, vp, i, i, i, f, i])
     sig("tdnnf_mul_rows_indexed", [vp, vp, i, vp, i, i, i, vp, i, vp])
     sig("tdnnf_num_graph_create", [vp, i, c_int_p, i, c_int_p, c_int_p, c_float_p, c_int_p, c_int_p, c_float_p, C.POINTER(vp)])

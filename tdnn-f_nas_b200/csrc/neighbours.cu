@@ -698,3 +698,64 @@ extern "C" int tdnnf_mul_rows_indexed(tdnnf_ctx* ctx, const float* in, int in_st
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
+
+// ------------------------------------------------------------------ LogSoftmaxComponent (ref: nnet-simple-component.cc:3607-3632)
+namespace {
+__device__ __forceinline__ float block_reduce_256(float v, bool is_max, float* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float other = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, other) : v + other;
+  }
+  __syncthreads();  // sh may still be read from a previous reduction
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = sh[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) r = is_max ? fmaxf(r, sh[w]) : r + sh[w];
+  return r;
+}
+// ApplyLogSoftMaxPerRow: out = x - max - log(sum exp(x - max)); one CTA of 256 threads per row (grid-stride over rows)
+__global__ void __launch_bounds__(256) log_softmax_fwd_kernel(const float* __restrict__ in, long long is, float* __restrict__ out,
+                                                              long long os, int rows, int cols) {
+  __shared__ float sh[8];
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float* x = in + r * is;
+    float m = -INFINITY;
+    for (int c = threadIdx.x; c < cols; c += 256) m = fmaxf(m, x[c]);
+    m = block_reduce_256(m, true, sh);
+    float s = 0.f;
+    for (int c = threadIdx.x; c < cols; c += 256) s += __expf(x[c] - m);
+    s = block_reduce_256(s, false, sh);
+    const float shift = m + __logf(s);
+    for (int c = threadIdx.x; c < cols; c += 256) out[r * os + c] = x[c] - shift;
+  }
+}
+// DiffLogSoftmaxPerRow: in_deriv = out_deriv - exp(out_value) * sum_row(out_deriv)   (in_deriv may alias out_deriv)
+__global__ void __launch_bounds__(256) log_softmax_bwd_kernel(const float* __restrict__ ov, long long ovs, const float* od,
+                                                              long long ods, float* id, long long ids, int rows, int cols) {
+  __shared__ float sh[8];
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    float s = 0.f;
+    for (int c = threadIdx.x; c < cols; c += 256) s += od[r * ods + c];
+    s = block_reduce_256(s, false, sh);
+    for (int c = threadIdx.x; c < cols; c += 256) id[r * ids + c] = od[r * ods + c] - __expf(ov[r * ovs + c]) * s;
+  }
+}
+}  // namespace
+
+extern "C" int tdnnf_log_softmax_fwd(tdnnf_ctx* ctx, const float* in, int rows, int cols, int in_stride, float* out,
+                                     int out_stride) {
+  PROLOGUE(in && out && in_stride >= cols && out_stride >= cols, "bad matrix");
+  log_softmax_fwd_kernel<<<std::min(rows, ctx->num_sms * 8), 256, 0, ctx->stream>>>(in, in_stride, out, out_stride, rows, cols);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+extern "C" int tdnnf_log_softmax_bwd(tdnnf_ctx* ctx, const float* out_value, int ov_stride, const float* out_deriv,
+                                     int od_stride, float* in_deriv, int id_stride, int rows, int cols) {
+  PROLOGUE(out_value && out_deriv && in_deriv && ov_stride >= cols && od_stride >= cols && id_stride >= cols, "bad matrix");
+  log_softmax_bwd_kernel<<<std::min(rows, ctx->num_sms * 8), 256, 0, ctx->stream>>>(out_value, ov_stride, out_deriv, od_stride,
+                                                                                   in_deriv, id_stride, rows, cols);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}

@@ -1948,6 +1948,27 @@ void RectifiedLinearComponent::Backprop(const std::string&, const ComponentPreco
   }
 }
 
+void* LogSoftmaxComponent::Propagate(const ComponentPrecomputedIndexes*, const CuMatrixBase<BaseFloat>& in,
+                                     CuMatrixBase<BaseFloat>* out) const {  // simple.cc:3607-3614
+  KALDI_ASSERT(SameDim(in, *out));
+  CheckStatus(tdnnf_log_softmax_fwd(CurrentContext(), in.Data(), in.NumRows(), in.NumCols(), in.Stride(), out->Data(), out->Stride()));
+  return NULL;
+}
+
+void LogSoftmaxComponent::Backprop(const std::string&, const ComponentPrecomputedIndexes*, const CuMatrixBase<BaseFloat>&,
+                                   const CuMatrixBase<BaseFloat>& out_value, const CuMatrixBase<BaseFloat>& out_deriv, void*,
+                                   Component* to_update_in, CuMatrixBase<BaseFloat>* in_deriv) const {  // simple.cc:3616-3632
+  if (to_update_in) {
+    LogSoftmaxComponent* to_update = dynamic_cast<LogSoftmaxComponent*>(to_update_in);
+    KALDI_ASSERT(to_update != NULL);
+    to_update->StoreBackpropStats(out_deriv);
+  }
+  if (in_deriv == NULL) return;
+  KALDI_ASSERT(SameDim(out_value, out_deriv) && SameDim(out_value, *in_deriv));
+  CheckStatus(tdnnf_log_softmax_bwd(CurrentContext(), out_value.Data(), out_value.Stride(), out_deriv.Data(), out_deriv.Stride(),
+                                    in_deriv->Data(), in_deriv->Stride(), out_value.NumRows(), out_value.NumCols()));
+}
+
 void RectifiedLinearComponent::RepairGradients(CuMatrixBase<BaseFloat>* in_deriv, RectifiedLinearComponent* to_update) const {
   // simple.cc:990-1074.  The statistics are those of `this` (the model), the counters those of to_update.
   KALDI_ASSERT(to_update != NULL);
@@ -2185,6 +2206,7 @@ Component* Component::NewComponentOfType(const std::string& component_type) {
   else if (component_type == "BatchNormTestComponent") ans = new BatchNormTestComponent();           // itf.cc:226-227
   else if (component_type == "BatchNormComponent") ans = new BatchNormComponent();                   // itf.cc (stock)
   else if (component_type == "RectifiedLinearComponent") ans = new RectifiedLinearComponent();       // itf.cc (stock)
+  else if (component_type == "LogSoftmaxComponent") ans = new LogSoftmaxComponent();                 // itf.cc (stock)
   else if (component_type == "OnehotFunctionComponent") ans = new OnehotFunctionComponent();         // itf.cc:250-251
   else if (component_type == "SoftmaxFlopsComponent") ans = new SoftmaxFlopsComponent();             // itf.cc:262-263
   else if (component_type == "GumbelSoftmaxFlopsComponent") ans = new GumbelSoftmaxFlopsComponent(); // itf.cc:270-273

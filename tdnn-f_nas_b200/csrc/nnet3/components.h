@@ -610,6 +610,22 @@ class RectifiedLinearComponent : public NonlinearComponent {
   void RepairGradients(CuMatrixBase<BaseFloat>* in_deriv, RectifiedLinearComponent* to_update) const;
 };
 
+// LogSoftmaxComponent (simple.h:~715-740, simple.cc:3607-3632): the non-linearity of the `output-xent` branch.
+class LogSoftmaxComponent : public NonlinearComponent {
+ public:
+  LogSoftmaxComponent() {}
+  LogSoftmaxComponent(const LogSoftmaxComponent& other) : NonlinearComponent(other) {}
+  virtual std::string Type() const { return "LogSoftmaxComponent"; }
+  virtual Component* Copy() const { return new LogSoftmaxComponent(*this); }
+  virtual int32 Properties() const { return kSimpleComponent | kBackpropNeedsOutput | kStoresStats; }
+  virtual void* Propagate(const ComponentPrecomputedIndexes* indexes, const CuMatrixBase<BaseFloat>& in,
+                          CuMatrixBase<BaseFloat>* out) const;
+  virtual void Backprop(const std::string& debug_info, const ComponentPrecomputedIndexes* indexes,
+                        const CuMatrixBase<BaseFloat>& in_value, const CuMatrixBase<BaseFloat>& out_value,
+                        const CuMatrixBase<BaseFloat>& out_deriv, void* memo, Component* to_update,
+                        CuMatrixBase<BaseFloat>* in_deriv) const;
+};
+
 // ------------------------------------------------------------------ edit directives (utils.cc:1166-1415)
 // The subset of ReadEditConfig this path needs: set-temperature-proportion (utils.cc:1352-1405)
 // plus set-learning-rate / set-learning-rate-factor for the recipes' model surgery.

@@ -49,6 +49,8 @@ class SupernetConfig:
     strides: Optional[List[int]] = None  # manual mode: time-stride per tdnnf-layer (default 1,1,1,0 then 6: :138-151)
     l2_regularize: float = 0.0      # per-component l2-regularize (0.01 in the manual recipe; ApplyL2Regularization)
     batchnorm_stats_scale: float = 0.8   # ScaleBatchnormStats after every minibatch (train-mode batch-norm only)
+    xent: bool = False              # the cross-entropy regularisation branch of the chain recipes (prefinal-xent,
+                                    # output-xent + LogSoftmaxComponent; --chain.xent-regularize 0.1)
     dropout: bool = False           # build the GeneralDropoutComponent of tdnn1 and of every block (pretrain / manual);
                                     # proportion 0 until set_dropout_proportion() (the recipes' schedule starts at 0)
     learning_rate: float = 2.5e-4
@@ -171,6 +173,9 @@ class Supernet:
         self.stock = dict(tdnn1=affine_params(cfg.feat_dim, D), prefinal_l=affine_params(D, cfg.prefinal_small, False),
                           pc_affine=affine_params(cfg.prefinal_small, D), pc_linear=affine_params(D, cfg.prefinal_small, False),
                           output=affine_params(cfg.prefinal_small, cfg.num_pdfs, zero=True))  # output-layer: param-stddev=0
+        if cfg.xent:  # prefinal-layer name=prefinal-xent input=prefinal-l; output-layer name=output-xent (log-softmax)
+            self.stock.update(px_affine=affine_params(cfg.prefinal_small, D), px_linear=affine_params(D, cfg.prefinal_small, False),
+                              output_xent=affine_params(cfg.prefinal_small, cfg.num_pdfs, zero=True))
 
         # ---------------- frozen batch-norm (BatchNormTestComponent) or train-mode batch-norm
         def make_bn(dim):
@@ -249,6 +254,11 @@ class Supernet:
                          pli=zeros(rows_T, Ssm), pb2=zeros(rows_T, Ssm), out=zeros(rows_T, P), bn1=make_bn(D), bn2=make_bn(Ssm),
                          d_out=zeros(rows_T, P), d_pb2=zeros(rows_T, Ssm), d_pli=zeros(rows_T, Ssm), d_pb=zeros(rows_T, D),
                          d_pa=zeros(rows_T, D), d_pl=zeros(rows_T, Ssm))
+        if cfg.xent:
+            self.head.update(xa=zeros(rows_T, D), xr=zeros(rows_T, D), xb=zeros(rows_T, D), xli=zeros(rows_T, Ssm),
+                             xb2=zeros(rows_T, Ssm), xo=zeros(rows_T, P), xls=zeros(rows_T, P), xbn1=make_bn(D), xbn2=make_bn(Ssm),
+                             d_xls=zeros(rows_T, P), d_xb2=zeros(rows_T, Ssm), d_xb=zeros(rows_T, D), d_xa=zeros(rows_T, D),
+                             log_softmax=nnet3.Component.new("LogSoftmaxComponent", f"dim={P}"))
         # ---------------- denominator graph + synthetic numerator alignment
         graph = synth.make_den_graph(cfg.den_states, P, cfg.den_out_degree, seed=5)
         self.den_arcs = graph["num_arcs"]
@@ -262,6 +272,10 @@ class Supernet:
         if search:
             self._freeze_batchnorm()
             self._compile()
+
+    def _all_bn(self):
+        return ([self.t1["bn"]] + [blk["bn"] for blk in self.blocks] +
+                [self.head[k] for k in ("bn1", "bn2", "xbn1", "xbn2") if k in self.head])
 
     def _make_dropout(self, dim, indexes, rows, zeros):
         """`component name=X.dropout type=GeneralDropoutComponent dim=D dropout-proportion=0.0 continuous=true`
@@ -309,7 +323,7 @@ class Supernet:
                 self.lib.tdnnf_nnet3_delete_memo(blk["lin"].h, blk["memo_lin"])
                 self.lib.tdnnf_nnet3_delete_memo(blk["aff"].h, blk["memo_aff"])
 
-        bns = [self.t1["bn"]] + [blk["bn"] for blk in self.blocks] + [self.head["bn1"], self.head["bn2"]]
+        bns = self._all_bn()
         passes = 4
         for k in range(passes):
             self.x.copy_(self.make_input(-1 - k).to(self.dev))
@@ -332,8 +346,9 @@ class Supernet:
         self.t1["bn"] = freeze(self.t1["bn"])
         for blk in self.blocks:
             blk["bn"] = freeze(blk["bn"])
-        self.head["bn1"] = freeze(self.head["bn1"])
-        self.head["bn2"] = freeze(self.head["bn2"])
+        for k in ("bn1", "bn2", "xbn1", "xbn2"):
+            if k in self.head:
+                self.head[k] = freeze(self.head[k])
 
     # ------------------------------------------------------------------ the step as pre-bound calls
     def _affine_fwd(self, plan, x, p, out):
@@ -346,7 +361,8 @@ class Supernet:
                  C.c_void_p(b.data_ptr()) if b is not None else None, 2 if b is not None else 1,
                  C.c_void_p(self.one.data_ptr()), 1, self.zero_off, 1)
 
-    def _affine_bwd(self, plan, x, p, d_out, d_in, lr):
+    def _affine_bwd(self, plan, x, p, d_out, d_in, lr, zero=True):
+        """zero=False: d_in already holds another branch's derivative (kBackpropAdds)."""
         lib, h = self.lib, self.ctx.h
         xp, xr, xc, xs = _m(x)
         dp, dr, dc, ds = _m(d_out)
@@ -355,7 +371,8 @@ class Supernet:
         one = C.c_void_p(self.one.data_ptr())
         if d_in is not None:
             ip, ir, ic, is_ = _m(d_in)
-            plan.add("abi", lib.tdnnf_mat_set, h, ip, ir, ic, is_, 0.0)
+            if zero:
+                plan.add("abi", lib.tdnnf_mat_set, h, ip, ir, ic, is_, 0.0)
             plan.add("abi", lib.tdnnf_darts_backprop_data, h, dp, dr, dc, ds, ip, ir, ic, is_, wp, ws, one, 1, self.zero_off, 1)
         plan.add("abi", lib.tdnnf_darts_backprop_params, h, xp, xr, xc, xs, dp, dr, dc, ds, None, 0, gp, gs,
                  C.c_void_p(p["db"].data_ptr()) if p["db"] is not None else None, one, 1, self.zero_off, 1, lr, None)
@@ -442,6 +459,16 @@ class Supernet:
         self._affine_fwd(fwd, hd["pb"], st["pc_linear"], hd["pli"])
         self._bn_fwd(fwd, hd["bn2"], hd["pli"], hd["pb2"])
         self._affine_fwd(fwd, hd["pb2"], st["output"], hd["out"])
+        if cfg.xent:
+            self._affine_fwd(fwd, hd["pl"], st["px_affine"], hd["xa"])
+            fwd.add("abi", lib.tdnnf_relu_fwd, h, *_m(hd["xa"]), _m(hd["xr"])[0], _m(hd["xr"])[3])
+            self._bn_fwd(fwd, hd["xbn1"], hd["xr"], hd["xb"])
+            self._affine_fwd(fwd, hd["xb"], st["px_linear"], hd["xli"])
+            self._bn_fwd(fwd, hd["xbn2"], hd["xli"], hd["xb2"])
+            self._affine_fwd(fwd, hd["xb2"], st["output_xent"], hd["xo"])
+            op, orr, oc, os_ = _m(hd["xo"])
+            fwd.add("nnet3", lib.tdnnf_nnet3_propagate, hd["log_softmax"].h, None, op, orr, oc, os_, _m(hd["xls"])[0], orr, oc,
+                    _m(hd["xls"])[3], None)
 
         # ---- backward (d_out of the output layer is filled by the objective)
         self._affine_bwd(bwd, hd["pb2"], st["output"], hd["d_out"], hd["d_pb2"], lr)
@@ -451,6 +478,19 @@ class Supernet:
         bwd.add("abi", lib.tdnnf_relu_bwd, h, _m(hd["pr"])[0], _m(hd["pr"])[3], _m(hd["d_pb"])[0], _m(hd["d_pb"])[3],
                 _m(hd["d_pa"])[0], _m(hd["d_pa"])[3], hd["pr"].shape[0], hd["pr"].shape[1])
         self._affine_bwd(bwd, hd["pl"], st["pc_affine"], hd["d_pa"], hd["d_pl"], lr)
+        if cfg.xent:
+            # output-xent: d_xls = xent_regularize * numerator posteriors (filled by the objective); its affine runs at
+            # learning-rate-factor 0.5 / xent_regularize (the recipes' `learning_rate_factor`)
+            xp_, xr_, xc_, xs_ = _m(hd["xls"])
+            bwd.add("nnet3", lib.tdnnf_nnet3_backprop, hd["log_softmax"].h, None, None, xr_, xc_, 0, xp_, xs_, _m(hd["d_xls"])[0], xr_, xc_,
+                    _m(hd["d_xls"])[3], None, None, _m(hd["d_xls"])[0], _m(hd["d_xls"])[3])
+            self._affine_bwd(bwd, hd["xb2"], st["output_xent"], hd["d_xls"], hd["d_xb2"], lr * 0.5 / self.objective.opts.xent_regularize)
+            self._bn_bwd(bwd, hd["xbn2"], hd["xb2"], hd["d_xb2"], hd["d_xb2"])
+            self._affine_bwd(bwd, hd["xb"], st["px_linear"], hd["d_xb2"], hd["d_xb"], lr)
+            self._bn_bwd(bwd, hd["xbn1"], hd["xb"], hd["d_xb"], hd["d_xb"])
+            bwd.add("abi", lib.tdnnf_relu_bwd, h, _m(hd["xr"])[0], _m(hd["xr"])[3], _m(hd["d_xb"])[0], _m(hd["d_xb"])[3],
+                    _m(hd["d_xa"])[0], _m(hd["d_xa"])[3], hd["xr"].shape[0], hd["xr"].shape[1])
+            self._affine_bwd(bwd, hd["pl"], st["px_affine"], hd["d_xa"], hd["d_pl"], lr, zero=False)
         last = self.blocks[-1]
         self._affine_bwd(bwd, last["out"], st["prefinal_l"], hd["d_pl"], last["d_out"], lr)
         for bi in range(len(self.blocks) - 1, -1, -1):
@@ -533,7 +573,7 @@ class Supernet:
             self.updatables.append(("comp", blk["lin"], blk["lin_delta"], cfg.max_change))
             self.updatables.append(("comp", blk["aff"], blk["aff_delta"], cfg.max_change))
         for name, p in st.items():
-            self.updatables.append(("stock", p, None, 1.5 if name == "output" else cfg.max_change))
+            self.updatables.append(("stock", p, None, 1.5 if name.startswith("output") else cfg.max_change))
         self.dots = torch.zeros(len(self.updatables), dtype=torch.float64, device=self.dev)
         # every parameter buffer of the model with the matching delta buffer: (model ptr, stride, delta ptr, stride, rows, cols, group)
         bufs = []
@@ -633,7 +673,12 @@ class Supernet:
             self.x.copy_(x_host, non_blocking=True)
         self.fwd_plan.run()
         # ComputeChainObjfAndDeriv: denominator fwd-bwd, numerator fwd-bwd, objf = num - den (host scalars, like Kaldi)
-        objf, _, weight = self.objective.compute(self.head["out"], self.head["d_out"])
+        if cfg.xent:
+            objf, _, weight = self.objective.compute(self.head["out"], self.head["d_out"], self.head["d_xls"])
+            # NnetChainTrainer::ProcessOutputs on output-xent: objective <log-softmax, numerator posteriors>, derivative x 0.1
+            self.last_xent_objf = self.objective.xent_objf_and_deriv(self.head["xls"], self.head["d_xls"]) / weight
+        else:
+            objf, _, weight = self.objective.compute(self.head["out"], self.head["d_out"])
         self.bwd_plan.run()
         if cfg.l2_regularize != 0.0:
             self._apply_l2_regularization()
@@ -654,7 +699,7 @@ class Supernet:
             for k in ("lin", "aff"):
                 blk[k + "_delta"].add(scale * blk[k].learning_rate() / cfg.learning_rate, blk[k])
         for name, p in self.stock.items():
-            l2 = 0.002 if name == "output" else cfg.l2_regularize  # output_opts (run_tdnn_7q_fbk_40_manual.sh:123)
+            l2 = 0.002 if name.startswith("output") else cfg.l2_regularize  # output_opts (run_tdnn_7q_fbk_40_manual.sh:123)
             sc = -2.0 * cfg.num_seqs * cfg.learning_rate * l2
             wp, wr, wc, ws = _m(p["W"])
             gp, _, _, gs = _m(p["dW"])
@@ -677,7 +722,7 @@ class Supernet:
                 if nnet3.rand_int(0, 3) == 0:
                     self.ctx.constrain_orthonormal(self.stock[name]["W"], -1.0)
         if cfg.mode != "search" and cfg.batchnorm_stats_scale != 1.0:
-            for bn in [self.t1["bn"]] + [blk["bn"] for blk in self.blocks] + [self.head["bn1"], self.head["bn2"]]:
+            for bn in self._all_bn():
                 if isinstance(bn, dict):
                     bn["comp"].scale(cfg.batchnorm_stats_scale)
 

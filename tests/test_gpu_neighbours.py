@@ -214,3 +214,40 @@ def test_ng_gram_scale_and_w_update(ctx, N, r, n_views):
     assert rc == 0, lib.tdnnf_last_error()
     ref = A.astype(np.float64) @ J.astype(np.float64) + AC.astype(np.float64) @ W.astype(np.float64)
     assert rel_err(Wn.cpu().numpy(), ref) < 1e-5
+
+
+@pytest.mark.parametrize("rows,cols,pad", [(320, 6008, 0), (17, 50, 3), (5, 1, 0), (3, 300, 1)])
+def test_log_softmax_component_vs_numpy(ctx, rows, cols, pad):
+    """LogSoftmaxComponent (nnet-simple-component.cc:3607-3632): ApplyLogSoftMaxPerRow / DiffLogSoftmaxPerRow in float64."""
+    import torch
+
+    from tdnnf_nas_b200 import nnet3
+
+    nnet3.set_context(ctx)
+    comp = nnet3.Component.new("LogSoftmaxComponent", f"dim={cols}")
+    assert comp.type() == "LogSoftmaxComponent"
+    assert comp.properties() == (nnet3.kSimpleComponent | nnet3.kBackpropNeedsOutput | nnet3.kStoresStats)
+    g = np.random.default_rng(rows + cols)
+    x = (g.standard_normal((rows, cols)) * 4.0).astype(np.float32)
+    x[0, :] += 60.0  # large offsets must not overflow (max subtraction)
+    od = g.standard_normal((rows, cols)).astype(np.float32)
+    xb = torch.full((rows, cols + pad), 9.0, device="cuda")
+    xb[:, :cols] = torch.from_numpy(x).cuda()
+    xin = xb[:, :cols]
+    out = torch.empty((rows, cols), device="cuda")
+    comp.propagate(None, xin, out)
+    x64 = x.astype(np.float64)
+    m = x64.max(1, keepdims=True)
+    ref = x64 - m - np.log(np.exp(x64 - m).sum(1, keepdims=True))
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=0, atol=2e-5)
+    np.testing.assert_allclose(np.exp(out.cpu().numpy().astype(np.float64)).sum(1), 1.0, rtol=1e-5)
+    odd = torch.from_numpy(od).cuda()
+    ind = torch.empty_like(odd)
+    comp.backprop(None, None, out, odd, None, None, ind)
+    ref_d = od.astype(np.float64) - np.exp(ref) * od.astype(np.float64).sum(1, keepdims=True)
+    assert rel_err(ind.cpu().numpy(), ref_d) < 1e-5
+    # in place (the training step feeds the derivative back through the same buffer)
+    comp.backprop(None, None, out, odd, None, None, odd)
+    assert torch.equal(odd, ind)
+    back = nnet3.Component.read(comp.write(True), True)
+    assert back.type() == "LogSoftmaxComponent" and back.input_dim() == cols

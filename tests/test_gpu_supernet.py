@@ -119,3 +119,31 @@ def test_dropout_nodes_in_the_step():
     assert all(math.isfinite(o) for o in on)
     assert on[:2] == zero[:2] or all(abs(a - b) <= 1e-5 * abs(a) + 1e-6 for a, b in zip(on[:2], zero[:2]))
     assert abs(on[2] - zero[2]) > 1e-4 * abs(zero[2])  # the masks changed the forward pass
+
+
+def test_xent_branch():
+    """--chain.xent-regularize 0.1: prefinal-xent / output-xent / LogSoftmaxComponent fed with the numerator posteriors.
+    The cross-entropy objective starts at -log(num_pdfs) (zero-initialised output layer) and improves; the chain
+    objective still improves; the shared prefinal-l layer receives both derivatives."""
+    from tdnnf_nas_b200.supernet import Supernet, SupernetConfig
+
+    def run(xent):
+        cfg = SupernetConfig(num_seqs=8, frames_per_eg=30, dim=128, bottleneck=32, num_blocks=3, prefinal_small=64,
+                             num_pdfs=200, den_states=300, den_out_degree=6.0, mode="pretrain", learning_rate=2e-3, xent=xent)
+        net = Supernet(cfg)
+        x = net.make_input(0).pin_memory()
+        objfs, xents = [], []
+        for _ in range(8):
+            objfs.append(net.step(x))
+            if xent:
+                xents.append(net.last_xent_objf)
+        net.close()
+        return objfs, xents
+
+    objfs, xents = run(True)
+    assert all(math.isfinite(o) for o in objfs + xents)
+    assert xents[0] == pytest.approx(-math.log(200.0), rel=1e-4)
+    assert xents[-1] > xents[0] and objfs[-1] > objfs[0]
+    base, _ = run(False)
+    assert objfs[0] == pytest.approx(base[0], rel=1e-5)       # same forward pass on the first step
+    assert any(abs(a - b) > 1e-6 * abs(b) for a, b in zip(objfs[1:], base[1:]))  # the xent derivative reached the shared layers
