@@ -223,19 +223,21 @@ def workload_config(cfg, gpus):
                     included=("natural-gradient update of all 28 TdnnComponents, LF-MMI numerator and denominator, l2-regularize 0.01 "
                               "(ApplyL2Regularization), UpdateNnetWithMaxChange, ConstrainOrthonormal, ScaleBatchnormStats"),
                     ng_settle_steps=NG_SETTLE_STEPS,
-                    not_included="natural gradient of the 5 stock affine layers, xent output branch, dropout")
+                    not_included="natural gradient of the stock affine layers, dropout" + ("" if cfg.xent else ", xent output branch"))
     return dict(workload=("context-offset DARTS TDNN-F supernet, search stage (BASELINE.json configs[2]): 14 x "
                           "{TdnnDARTSV3 1536->160 offsets -6..0, TdnnDARTSV3 160->1536 offsets 0..6, ReLU, BatchNormTest, "
-                          "bypass 0.66}, tdnn1 220->1536, prefinal 256/1536, output 6008; LF-MMI denominator fwd-bwd on a "
-                          f"synthetic {cfg.den_states}-state den graph"),
+                          "bypass 0.66}, tdnn1 220->1536, prefinal 256/1536, output 6008" +
+                          (", prefinal-xent / output-xent (log-softmax) with xent-regularize 0.1" if cfg.xent else "") +
+                          f"; LF-MMI denominator fwd-bwd on a synthetic {cfg.den_states}-state den graph"),
                 mode=cfg.mode, chunks_per_gpu=cfg.num_seqs, frames_per_eg=cfg.frames_per_eg, global_chunks=cfg.num_seqs * gpus,
                 num_pdfs=cfg.num_pdfs, den_states=cfg.den_states, parallelism=f"dp{gpus}",
                 cache="per-step working set (~14 GB of activations) exceeds the 126 MB L2: no explicit flush needed",
                 included=("natural-gradient update (OnlineNaturalGradient rank 20/80, update period 4) of all 28 TdnnDARTSV3 "
-                          "components, LF-MMI numerator (per-sequence FST) and denominator, UpdateNnetWithMaxChange"),
+                          "components, LF-MMI numerator (per-sequence FST) and denominator, UpdateNnetWithMaxChange" +
+                          (", the cross-entropy regularisation branch (numerator posteriors -> output-xent)" if cfg.xent else "")),
                 ng_settle_steps=NG_SETTLE_STEPS,
                 not_included=("natural gradient of the 5 stock affine layers around the blocks (tdnn1, prefinal, output: plain SGD "
-                              "there; all 28 TdnnDARTSV3 components are preconditioned), L2 regularisation, xent output branch, dropout "
+                              "there; all 28 TdnnDARTSV3 components are preconditioned), L2 regularisation, dropout "
                               "(GeneralDropoutComponent is upstream Kaldi and not built; the recipes' schedule 0,0@0.20,0.5@0.50,0 starts "
                               "and ends at proportion 0); the orthonormal constraint does not cover TdnnDARTSV3 (utils.cc:1047-1061)"))
 
@@ -365,6 +367,7 @@ def main():
     ap.add_argument("--den-states", type=int, default=16384)
     ap.add_argument("--blocks", type=int, default=14)
     ap.add_argument("--chunks", type=int, default=64)
+    ap.add_argument("--no-xent", action="store_true", help="leave out the xent-regularisation branch (prefinal-xent / output-xent)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -373,7 +376,7 @@ def main():
     from tdnnf_nas_b200.supernet import SupernetConfig
 
     cfg = SupernetConfig(mode=args.mode, den_states=args.den_states, num_blocks=args.blocks, num_seqs=args.chunks,
-                         l2_regularize=0.01 if args.mode == "manual" else 0.0)
+                         l2_regularize=0.01 if args.mode == "manual" else 0.0, xent=not args.no_xent)
     if args.impl == "reference":
         if args.steps > 3:
             args.steps = 3  # each step is ~10 s of CPU work: keep the whole run within a few minutes
