@@ -840,6 +840,30 @@ void TdnnComponent::Read(std::istream& is, bool binary) {
   Check();
 }
 
+ComponentPrecomputedIndexes* TdnnComponent::PrecomputeIndexes(const MiscComputationInfo& misc_info,
+                                                              const std::vector<Index>& input_indexes,
+                                                              const std::vector<Index>& output_indexes,
+                                                              bool need_backprop) const {
+  std::unique_ptr<ComponentPrecomputedIndexes> base(
+      TdnnDARTSV3Component::PrecomputeIndexes(misc_info, input_indexes, output_indexes, need_backprop));
+  return new PrecomputedIndexes(*static_cast<TdnnDARTSV3Component::PrecomputedIndexes*>(base.get()));
+}
+void TdnnComponent::PrecomputedIndexes::Write(std::ostream& os, bool binary) const {
+  WriteToken(os, binary, "<TdnnComponentPrecomputedIndexes>");
+  WriteToken(os, binary, "<RowStride>");
+  WriteBasicType(os, binary, row_stride);
+  WriteToken(os, binary, "<RowOffsets>");
+  WriteIntegerVector(os, binary, row_offsets);
+  WriteToken(os, binary, "</TdnnComponentPrecomputedIndexes>");
+}
+void TdnnComponent::PrecomputedIndexes::Read(std::istream& is, bool binary) {
+  ExpectOneOrTwoTokens(is, binary, "<TdnnComponentPrecomputedIndexes>", "<RowStride>");
+  ReadBasicType(is, binary, &row_stride);
+  ExpectToken(is, binary, "<RowOffsets>");
+  ReadIntegerVector(is, binary, &row_offsets);
+  ExpectToken(is, binary, "</TdnnComponentPrecomputedIndexes>");
+}
+
 int32 ConstrainOrthonormal(const std::vector<Component*>& components) {  // utils.cc:1037-1077
   int32 updated = 0;
   for (Component* component : components) {
@@ -2218,6 +2242,7 @@ Component* Component::NewComponentOfType(const std::string& component_type) {
 ComponentPrecomputedIndexes* ComponentPrecomputedIndexes::NewComponentPrecomputedIndexesOfType(const std::string& cpi_type) {
   ComponentPrecomputedIndexes* ans = NULL;
   if (cpi_type == "TdnnDARTSV3ComponentPrecomputedIndexes") ans = new TdnnDARTSV3Component::PrecomputedIndexes();  // itf.cc:66-67
+  else if (cpi_type == "TdnnComponentPrecomputedIndexes") ans = new TdnnComponent::PrecomputedIndexes();  // itf.cc (stock)
   else if (cpi_type == "GeneralDropoutComponentPrecomputedIndexes") ans = new GeneralDropoutComponent::PrecomputedIndexes();  // itf.cc:78-79
   if (ans != NULL) KALDI_ASSERT(cpi_type == ans->Type());
   return ans;

@@ -254,6 +254,21 @@ class TdnnComponent : public TdnnDARTSV3Component {
   virtual void Read(std::istream& is, bool binary);
   virtual void Write(std::ostream& os, bool binary) const;
   virtual Component* Copy() const { return new TdnnComponent(*this); }
+  virtual ComponentPrecomputedIndexes* PrecomputeIndexes(const MiscComputationInfo& misc_info,
+                                                         const std::vector<Index>& input_indexes,
+                                                         const std::vector<Index>& output_indexes,
+                                                         bool need_backprop) const;
+  // Same content as the DARTS indexes (row_stride, row_offsets); the stock on-disk tokens.
+  class PrecomputedIndexes : public TdnnDARTSV3Component::PrecomputedIndexes {
+   public:
+    PrecomputedIndexes() {}
+    explicit PrecomputedIndexes(const TdnnDARTSV3Component::PrecomputedIndexes& other)
+        : TdnnDARTSV3Component::PrecomputedIndexes(other) {}
+    virtual PrecomputedIndexes* Copy() const { return new PrecomputedIndexes(*this); }
+    virtual void Write(std::ostream& os, bool binary) const;
+    virtual void Read(std::istream& is, bool binary);
+    virtual std::string Type() const { return "TdnnComponentPrecomputedIndexes"; }
+  };
 
  protected:
   virtual int32 NumAlphaSlots() const { return 0; }

@@ -216,12 +216,9 @@ extern "C" int tdnnf_constrain_orthonormal(tdnnf_ctx* ctx, float* M, int rows, i
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   const size_t smem = sizeof(float) * (size_t)n * (kPanel + 1);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (smem > 48 * 1024)  // per device and per call: the attribute is cheap to set and contexts may live on several devices
     TDNNF_CUDA_OK(cudaFuncSetAttribute(ortho_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(sizeof(float) * kMaxDim * (kPanel + 1))));
-    attr_set = true;
-  }
   ortho_update_kernel<<<(K + kPanel - 1) / kPanel, 256, smem, ctx->stream>>>(M, stride, trans, n, np, K, P, row_tr, scale,
                                                                              info_dev);
   ctx->launches++;

@@ -700,7 +700,8 @@ class Supernet:
                 blk[k + "_delta"].add(scale * blk[k].learning_rate() / cfg.learning_rate, blk[k])
         for name, p in self.stock.items():
             l2 = 0.002 if name.startswith("output") else cfg.l2_regularize  # output_opts (run_tdnn_7q_fbk_40_manual.sh:123)
-            sc = -2.0 * cfg.num_seqs * cfg.learning_rate * l2
+            lrate = cfg.learning_rate * (0.5 / self.objective.opts.xent_regularize if name == "output_xent" else 1.0)
+            sc = -2.0 * cfg.num_seqs * lrate * l2
             wp, wr, wc, ws = _m(p["W"])
             gp, _, _, gs = _m(p["dW"])
             if lib.tdnnf_mat_axpy(h, sc, wp, ws, gp, gs, wr, wc) != 0:

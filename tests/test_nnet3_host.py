@@ -303,3 +303,16 @@ def test_general_dropout_host_side():
         nnet3.Component.new("GeneralDropoutComponent", "dim=12 block-dim=5")
     with pytest.raises(nnet3.Nnet3Error, match="SpecAugment"):
         nnet3.Component.new("GeneralDropoutComponent", "dim=12 specaugment-max-proportion=0.5")
+
+
+def test_stock_tdnn_precomputed_indexes_tokens():
+    """The stock TdnnComponent writes its indexes under upstream's own token (itf.cc: TdnnComponentPrecomputedIndexes)."""
+    from tdnnf_nas_b200 import capi, nnet3
+
+    # TdnnComponent's InitFromConfig allocates parameters, so go through a model stream read on the host? No device here:
+    # the index type itself is reachable through ComponentPrecomputedIndexes::ReadNew.
+    data = b"<TdnnComponentPrecomputedIndexes> <RowStride> 3 <RowOffsets> [ 0 7 14 ]\n</TdnnComponentPrecomputedIndexes> "
+    pi = nnet3.PrecomputedIndexes.read(data, False)
+    assert pi.row_stride_and_offsets() == (3, [0, 7, 14])
+    assert pi.write(False).split() == data.split()
+    assert nnet3.PrecomputedIndexes.read(pi.write(True), True).write(False).split() == data.split()
