@@ -22,10 +22,12 @@ ap.add_argument("--warmup", type=int, default=14)
 ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--mode", default="search")
 ap.add_argument("--chunks", type=int, default=64)
+ap.add_argument("--no-xent", action="store_true")
 ap.add_argument("--phases", action="store_true", help="also time forward / objective / backward / update separately")
 args = ap.parse_args()
 
-net = Supernet(SupernetConfig(mode=args.mode, num_seqs=args.chunks, l2_regularize=0.01 if args.mode == "manual" else 0.0), device=0)
+net = Supernet(SupernetConfig(mode=args.mode, num_seqs=args.chunks, l2_regularize=0.01 if args.mode == "manual" else 0.0,
+                              xent=not args.no_xent), device=0)
 net.x.copy_(net.make_input(0))
 for _ in range(args.warmup):
     net.step(None)
