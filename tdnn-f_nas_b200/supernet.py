@@ -719,8 +719,9 @@ class Supernet:
         cfg = self.cfg
         if cfg.mode == "manual":
             nnet3.constrain_orthonormal([blk["lin"] for blk in self.blocks])
-            for name in ("prefinal_l", "pc_linear"):   # linear-component / prefinal-layer: orthonormal-constraint=-1.0
-                if nnet3.rand_int(0, 3) == 0:
+            # linear-component prefinal-l and the `linear` part of each prefinal-layer: orthonormal-constraint=-1.0
+            for name in ("prefinal_l", "pc_linear", "px_linear"):
+                if name in self.stock and nnet3.rand_int(0, 3) == 0:
                     self.ctx.constrain_orthonormal(self.stock[name]["W"], -1.0)
         if cfg.mode != "search" and cfg.batchnorm_stats_scale != 1.0:
             for bn in self._all_bn():
