@@ -51,7 +51,8 @@ class SupernetConfig:
     batchnorm_stats_scale: float = 0.8   # ScaleBatchnormStats after every minibatch (train-mode batch-norm only)
     xent: bool = False              # the cross-entropy regularisation branch of the chain recipes (prefinal-xent,
                                     # output-xent + LogSoftmaxComponent; --chain.xent-regularize 0.1)
-    dropout: bool = False           # build the GeneralDropoutComponent of tdnn1 and of every block (pretrain / manual);
+    dropout: bool = False           # build the GeneralDropoutComponent of tdnn1 and of every block (in the search stage
+                                    # this switches the fused ReLU + BatchNormTest + bypass tail off);
                                     # proportion 0 until set_dropout_proportion() (the recipes' schedule starts at 0)
     learning_rate: float = 2.5e-4
     darts_lr_factor: float = 1.0e-4  # <LearningRateFactor> set by the cvupdate recipe's sed (search mode only)
@@ -247,7 +248,6 @@ class Supernet:
         self.t1 = dict(aff=zeros(rows_in, D), relu=zeros(rows_in, D), out=zeros(rows_in, D), bn=make_bn(D),
                        d_out=zeros(rows_in, D), d_aff=zeros(rows_in, D))
         if cfg.dropout:
-            assert not search, "the search stage runs the fused ReLU + BatchNormTest + bypass tail: no dropout node"
             self.t1.update(self._make_dropout(D, grid(in_t), rows_in, zeros))
         P, Ssm = cfg.num_pdfs, cfg.prefinal_small
         self.head = dict(pl=zeros(rows_T, Ssm), pa=zeros(rows_T, D), pr=zeros(rows_T, D), pb=zeros(rows_T, D),
@@ -428,7 +428,7 @@ class Supernet:
             op, orr, oc, os_ = _m(blk["aff_out"])
             fwd.add("nnet3", lib.tdnnf_nnet3_propagate, blk["aff"].h, blk["aff_idx"].h, ap, ar, ac, as_, op, orr, oc, os_,
                     C.byref(blk["memo_aff"]))
-            fused = cfg.fuse_tail and isinstance(blk["bn"], nnet3.Component)
+            fused = cfg.fuse_tail and isinstance(blk["bn"], nnet3.Component) and not cfg.dropout  # the fused tail has no dropout node
             # noop = Sum(Scale(0.66, prev[rows]), batchnorm(relu(affine)))
             byp = blk["bypass"]
             if byp["contiguous"]:
@@ -499,7 +499,7 @@ class Supernet:
             d_prev = self.blocks[bi - 1]["d_out"] if bi > 0 else t1["d_out"]
             dp_, dr, dc, ds = _m(blk["d_out"])
             qp, qr, qc, qs = _m(d_prev)
-            fused = cfg.fuse_tail and isinstance(blk["bn"], nnet3.Component)
+            fused = cfg.fuse_tail and isinstance(blk["bn"], nnet3.Component) and not cfg.dropout  # the fused tail has no dropout node
             byp = blk["bypass"]
             if fused and byp["contiguous"]:
                 # zero only the halo rows of d_prev; the fused kernel overwrites the matching rows with the bypass term

@@ -147,3 +147,23 @@ def test_xent_branch():
     base, _ = run(False)
     assert objfs[0] == pytest.approx(base[0], rel=1e-5)       # same forward pass on the first step
     assert any(abs(a - b) > 1e-6 * abs(b) for a, b in zip(objfs[1:], base[1:]))  # the xent derivative reached the shared layers
+
+
+def test_dropout_in_the_search_stage():
+    """With dropout nodes the search stage runs ReLU / BatchNormTest / dropout / bypass as separate components; at
+    proportion 0 the trajectory equals the fused-tail one."""
+    from tdnnf_nas_b200.supernet import Supernet, SupernetConfig
+
+    objfs = []
+    for dropout in (False, True):
+        cfg = SupernetConfig(num_seqs=8, frames_per_eg=30, dim=128, bottleneck=32, num_blocks=3, prefinal_small=64,
+                             num_pdfs=200, den_states=300, den_out_degree=6.0, mode="search", learning_rate=2e-3, dropout=dropout)
+        net = Supernet(cfg)
+        x = net.make_input(0).pin_memory()
+        objfs.append([net.step(x) for _ in range(3)])
+        if dropout:
+            net.set_dropout_proportion(0.3)
+            assert math.isfinite(net.step(x))
+        net.close()
+    for a, b in zip(*objfs):
+        assert abs(a - b) <= 1e-4 * abs(a) + 1e-6, objfs
