@@ -184,6 +184,20 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand (the contraction index k is the ROW index of the operand in shared memory), 128-byte swizzle:
+// canonical layout (cute::UMMA, Major::MN, B128) in 16-byte units  ((8, n), (8, k)) : ((1, LBO), (8, SBO)), i.e. atoms of
+// 8 k-rows x 64 contiguous MN elements (8 x 128 B = 1 KB, exactly what a TMA box of 64 elements x 8 rows writes with
+// SWIZZLE_128B); LBO = byte distance between consecutive 64-element MN chunks, SBO = between groups of 8 k-rows.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;            // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
+  return d;
+}
+
 // Instruction descriptor for kind::f16 with bf16 A/B (both K-major), fp32 D, dense.
 // c_format[4,6)=1 (f32) a_format[7,10)=1 (bf16) b_format[10,13)=1 n_dim[17,23)=N>>3 m_dim[24,29)=M>>4
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
@@ -191,8 +205,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
 }
 
 // The same with the A / B formats given separately (0 = fp16, 1 = bf16): kind::f16 mixes them freely.
-__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N, uint32_t a_fmt, uint32_t b_fmt) {
-  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+// a_major[15] / b_major[16]: 0 = K-major, 1 = MN-major.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N, uint32_t a_fmt, uint32_t b_fmt,
+                                                      uint32_t mn_major = 0) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | (mn_major << 15) | (mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 }  // namespace ptx

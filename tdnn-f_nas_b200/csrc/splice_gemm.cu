@@ -278,6 +278,21 @@ static int make_map(tdnnf_ctx* ctx, const Planes& pl, int box_rows, CUtensorMap*
   return TDNNF_OK;
 }
 
+// The same row planes seen MN-major: (64 columns, row, 64-column chunk, group, plane); a box of `chunks` chunks x
+// `box_k` rows lands in shared memory as [plane][chunk][k][64 columns], 128-byte swizzled (see umma_desc_mn_sw128).
+static int make_map_mn(tdnnf_ctx* ctx, const Planes& pl, int chunks, int box_k, CUtensorMap* out) {
+  if (pl.Kpitch % 64 != 0) return fail(TDNNF_ERR_INVALID, "MN-major planes need a pitch that is a multiple of 64");
+  cuuint64_t dims[5] = {64, (cuuint64_t)pl.rows, (cuuint64_t)(pl.Kpitch / 64), (cuuint64_t)pl.groups, (cuuint64_t)pl.np};
+  cuuint64_t strides[4] = {(cuuint64_t)pl.Kpitch * 2, 128, (cuuint64_t)pl.rows * pl.Kpitch * 2, (cuuint64_t)pl.plane_elems * 2};
+  cuuint32_t box[5] = {64, (cuuint32_t)box_k, (cuuint32_t)chunks, 1, (cuuint32_t)pl.np};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = ctx->encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, pl.base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(TDNNF_ERR_CUDA, "cuTensorMapEncodeTiled (MN-major) failed with CUresult " + std::to_string((int)r));
+  return TDNNF_OK;
+}
+
 // Cache lookup / insertion for planes of a registered source (see tdnnf_ctx_operand_cache_begin).
 static tdnnf_ctx::PlaneCacheEntry make_key(int kind, const float* src, int R, int D, long long ld, int r, int groups,
                                            int c_row_mul, int c_col_mul, const float* scale, int Q, int pitch,
@@ -473,17 +488,18 @@ static int choose_splits(int tiles, int iters_per_tile, int num_sms) {
   return best;
 }
 
-template <int BN, int NPA, int NPB>
+template <int BN, int NPA, int NPB, bool MN = false>
 static int launch_gemm_bn(tdnnf_ctx* ctx, const Planes& A, const Planes& B, const GemmParams& p, double algorithmic_flops) {
+  using Cfg = GemmCfg<BN, NPA, NPB, MN>;
   CUtensorMap tmA, tmB;
-  int rc = make_map(ctx, A, kBM, &tmA);
+  int rc = MN ? make_map_mn(ctx, A, kBM / 64, Cfg::kBKk, &tmA) : make_map(ctx, A, kBM, &tmA);
   if (rc) return rc;
-  rc = make_map(ctx, B, BN, &tmB);
+  rc = MN ? make_map_mn(ctx, B, Cfg::kBNs / 64, Cfg::kBKk, &tmB) : make_map(ctx, B, BN, &tmB);
   if (rc) return rc;
-  auto kern = splice_gemm_kernel<BN, NPA, NPB>;
+  auto kern = splice_gemm_kernel<BN, NPA, NPB, MN>;
   static bool attr_set = false;  // per template instance
   if (!attr_set) {
-    TDNNF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN, NPA, NPB>::kSmemBytes));
+    TDNNF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   const int units = p.c_tiles * p.m_tiles * p.n_tiles * p.splits;
@@ -497,7 +513,7 @@ static int launch_gemm_bn(tdnnf_ctx* ctx, const Planes& A, const Planes& B, cons
     tm.products = (NPA == 3) ? 6 : (NPA == 2 && NPB == 2 ? 3 : NPA * NPB);
     TDNNF_CUDA_OK(cudaEventRecord(tm.start, ctx->stream));
   }
-  kern<<<grid, kGemmThreads, GemmCfg<BN, NPA, NPB>::kSmemBytes, ctx->stream>>>(tmA, tmB, p);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, ctx->stream>>>(tmA, tmB, p);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   if (ctx->gemm_timing) {
@@ -546,6 +562,27 @@ static int launch_gemm(tdnnf_ctx* ctx, int bn, const Planes& A, const Planes& B,
   if (A.np == 2 && B.np == 2) return launch_gemm_np<2, 2>(ctx, bn, A, B, p, algorithmic_flops);
   if (A.np == 1 && B.np == 1) return launch_gemm_np<1, 1>(ctx, bn, A, B, p, algorithmic_flops);
   return fail(TDNNF_ERR_INVALID, "unsupported operand plane combination");
+}
+
+// Both operands MN-major (row planes, contraction over rows): the parameter gradient.
+static int launch_gemm_mn(tdnnf_ctx* ctx, int bn, const Planes& A, const Planes& B, const GemmParams& p, double fl) {
+  if (A.np == 2 && B.np == 2) {
+    switch (bn) {
+      case 64: return launch_gemm_bn<64, 2, 2, true>(ctx, A, B, p, fl);
+      case 128: return launch_gemm_bn<128, 2, 2, true>(ctx, A, B, p, fl);
+      case 160: return launch_gemm_bn<160, 2, 2, true>(ctx, A, B, p, fl);
+      case 256: return launch_gemm_bn<256, 2, 2, true>(ctx, A, B, p, fl);
+      default: break;
+    }
+  } else if (A.np == 3 && B.np == 3) {
+    switch (bn) {
+      case 64: return launch_gemm_bn<64, 3, 3, true>(ctx, A, B, p, fl);
+      case 128: return launch_gemm_bn<128, 3, 3, true>(ctx, A, B, p, fl);
+      case 160: return launch_gemm_bn<160, 3, 3, true>(ctx, A, B, p, fl);
+      default: break;
+    }
+  }
+  return fail(TDNNF_ERR_INVALID, "unsupported MN-major GEMM configuration");
 }
 
 static int check_offsets(int n, const int32_t* row_offsets, int row_stride, int out_rows, int in_rows) {
@@ -776,6 +813,83 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
 
   const int r = row_stride;
   const int Q = ceil_div(in_rows, r);
+  // ---- large operands: contract over the rows of the ROW planes (MN-major operands), which the data gradient and the
+  // natural-gradient projections of the same Backprop have already built -- no transposed pre-pass, and the per-offset
+  // shift is a row coordinate (no alignment condition).  TDNNF_WGRAD_MN=0 selects the transposed-plane path below.
+  {
+    static const bool mn_enabled = [] {
+      const char* e = getenv("TDNNF_WGRAD_MN");
+      return e ? atoi(e) != 0 : true;
+    }();
+    static const int mn_min_rows = [] {  // test knob: exercise the MN-major path on small matrices too
+      const char* e = getenv("TDNNF_WGRAD_MN_MIN_ROWS");
+      return e ? atoi(e) : 512;
+    }();
+    auto waste0 = [](int x) { return (double)round_up(x, kBM) / x; };
+    const bool m_is_in0 = waste0(in_dim) <= waste0(out_dim);
+    const int n_dim = m_is_in0 ? out_dim : in_dim;
+    const int bn0 = pick_bn(n_dim, ctx->gemm_planes);
+    const bool fast0 = ctx->grad_fast && ctx->gemm_planes == 2;
+    const bool tiles_ok = bn0 >= 64 && (bn0 % 64 == 0 || ceil_div(n_dim, bn0) == 1) && !(ctx->gemm_planes == 3 && bn0 == 256);
+    if (mn_enabled && !fast0 && tiles_ok && out_rows >= mn_min_rows && in_dim >= 64 && out_dim >= 64) {
+      if (dbias) {  // bias gradient: lr * colsum(out_deriv) (the transposed pre-pass of the other path does it on the fly)
+        rc = tdnnf_add_row_sum(ctx, out_deriv, out_rows, out_dim, od_stride, lr, dbias);
+        if (rc) return rc;
+      }
+      const int KpX = round_up(in_dim, kBK), KpO = round_up(out_dim, kBK);
+      ctx->ws_reset();
+      const size_t need = planes_bytes(ctx->gemm_planes, r, Q, KpX) + planes_bytes(ctx->gemm_planes, 1, out_rows, KpO);
+      rc = ctx->ws_reserve(need + 4096);
+      if (rc) return rc;
+      rc = ctx->cws_reserve(need);
+      if (rc) return rc;
+      Planes XR, ODR;  // the same splits as tdnnf_darts_propagate / _project (X) and tdnnf_darts_backprop_data (out_deriv)
+      rc = launch_split_rows(ctx, in_value, in_rows, in_dim, in_stride, r, r, 1, 0, nullptr, Q, KpX, &XR);
+      if (rc) return rc;
+      rc = launch_split_rows(ctx, out_deriv, out_rows, out_dim, od_stride, 1, 1, 0, 0, nullptr, out_rows, KpO, &ODR);
+      if (rc) return rc;
+      if (s) TDNNF_CUDA_OK(cudaMemsetAsync(s, 0, sizeof(float) * n, ctx->stream));
+      constexpr int kBKmn = 32;
+      GemmParams p;
+      memset(&p, 0, sizeof(p));
+      p.c_tiles = n;
+      p.kb_per_seg = ceil_div(out_rows, kBKmn);
+      p.kb_last_steps = ceil_div(out_rows - (p.kb_per_seg - 1) * kBKmn, 16);
+      p.nseg = n;
+      p.seg_weight = weff;
+      p.out = dW;
+      p.out_ld = dw_stride;
+      p.accumulate = 1;
+      p.alpha = lr;
+      p.c_scale = weff;
+      p.dot_ref = s ? W_model : nullptr;
+      p.dot_ld = w_stride;
+      p.dot_out = s;
+      for (int i = 0; i < n; ++i) {
+        (m_is_in0 ? p.seg_a_k : p.seg_b_k)[i] = row_offsets[i] / r;
+        (m_is_in0 ? p.seg_a_c : p.seg_b_c)[i] = row_offsets[i] % r;
+        p.seg_cmatch[i] = i;
+        p.m_valid[i] = m_is_in0 ? in_dim : out_dim;
+      }
+      p.row_mul = 1;
+      if (m_is_in0) {  // acc[d, o] -> dW[o, i*in_dim + d] (transposed store)
+        p.m_tiles = ceil_div(in_dim, kBM);
+        p.n_tiles = ceil_div(out_dim, bn0);
+        p.n_valid = out_dim;
+        p.transposed = 1;
+        p.row_cadd = in_dim;
+      } else {         // acc[o, d] -> dW[o, i*in_dim + d]
+        p.m_tiles = ceil_div(out_dim, kBM);
+        p.n_tiles = ceil_div(in_dim, bn0);
+        p.n_valid = in_dim;
+        p.col_cadd = in_dim;
+      }
+      p.splits = choose_splits(p.m_tiles * p.n_tiles * n, p.kb_per_seg, ctx->num_sms);
+      p.atomic = p.splits > 1;
+      const double wflops0 = 2.0 * out_rows * (double)out_dim * in_dim * n;
+      return m_is_in0 ? launch_gemm_mn(ctx, bn0, XR, ODR, p, wflops0) : launch_gemm_mn(ctx, bn0, ODR, XR, p, wflops0);
+    }
+  }
   const int Qp = round_up(Q, 8);
   const int Rp = round_up(out_rows, 8);
   // TMA needs the start of every box row 16-byte aligned: with K = the (de-interleaved) row index,

@@ -84,10 +84,16 @@ struct GemmSmemMeta {
 //          parameter gradient (1e-3 tolerance; measured 2.9e-4)
 // (Mixing a bf16 operand with an fp16 one in one kind::f16 MMA -- which would give a two-product data gradient --
 // is rejected by the hardware: "illegal instruction", measured on B200.)
-template <int BN, int NPA, int NPB>
+// MN = true: both operands are MN-major (the contraction runs over ROWS of the row planes: the parameter gradient).
+// K blocks are then 32 rows (no swizzle-width constraint on K), the B tile is whole 64-column chunks.
+template <int BN, int NPA, int NPB, bool MN = false>
 struct GemmCfg {
-  static constexpr int kABytes = NPA * kBM * kBK * 2;
-  static constexpr int kBBytes = NPB * BN * kBK * 2;
+  static constexpr int kBKk = MN ? 32 : kBK;                 // K elements per pipeline stage
+  static constexpr int kBNs = MN ? (BN + 63) / 64 * 64 : BN;  // B columns held in shared memory
+  static constexpr int kAPlane = kBM * kBKk * 2;
+  static constexpr int kBPlane = kBNs * kBKk * 2;
+  static constexpr int kABytes = NPA * kAPlane;
+  static constexpr int kBBytes = NPB * kBPlane;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kMetaBytes = 2048 + (int)sizeof(GemmSmemMeta);
   static constexpr int kStages = (232448 - 1024 - kMetaBytes) / kStageBytes >= 4
@@ -107,6 +113,17 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       :
       : "r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar)), "r"(c0),
         "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
+                                            int32_t c1, int32_t c2, int32_t c3, int32_t c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      :
+      : "r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar)), "r"(c0),
+        "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 
@@ -142,12 +159,13 @@ __device__ __forceinline__ UnitCoord decode_unit(int u, const GemmParams& p, con
   return uc;
 }
 
-template <int BN, int NPA, int NPB>
+template <int BN, int NPA, int NPB, bool MN = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN, NPA, NPB>;
+  using Cfg = GemmCfg<BN, NPA, NPB, MN>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int kBKk = Cfg::kBKk;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
@@ -225,10 +243,18 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           uint8_t* sa = tiles + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          tma_load_4d(sa, &tmA, &full_bar[stage], kb * kBK + meta->seg_a_k[g], uc.m_t * kBM + meta->seg_a_m[g],
-                      meta->seg_a_c[g], 0);
-          tma_load_4d(sb, &tmB, &full_bar[stage], kb * kBK + meta->seg_b_k[g], uc.n_t * BN + meta->seg_b_n[g],
-                      meta->seg_b_c[g], 0);
+          if constexpr (MN) {
+            // row planes as (64 columns, row = k, 64-column chunk, group, plane): smem gets [plane][chunk][k][64]
+            tma_load_5d(sa, &tmA, &full_bar[stage], 0, kb * kBKk + meta->seg_a_k[g], (uc.m_t * kBM + meta->seg_a_m[g]) >> 6,
+                        meta->seg_a_c[g], 0);
+            tma_load_5d(sb, &tmB, &full_bar[stage], 0, kb * kBKk + meta->seg_b_k[g], (uc.n_t * BN + meta->seg_b_n[g]) >> 6,
+                        meta->seg_b_c[g], 0);
+          } else {
+            tma_load_4d(sa, &tmA, &full_bar[stage], kb * kBK + meta->seg_a_k[g], uc.m_t * kBM + meta->seg_a_m[g],
+                        meta->seg_a_c[g], 0);
+            tma_load_4d(sb, &tmB, &full_bar[stage], kb * kBK + meta->seg_b_k[g], uc.n_t * BN + meta->seg_b_n[g],
+                        meta->seg_b_c[g], 0);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
           if (++j == cnt) { j = 0; ++kb; }
         }
@@ -238,7 +264,7 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // ================================================= MMA issuer
     if (lane == 0) {
       // single-plane operands are fp16 (format 0), multi-plane operands are bf16 (format 1)
-      constexpr uint32_t idesc = ptx::umma_idesc_f16(kBM, BN, NPA == 1 ? 0u : 1u, NPB == 1 ? 0u : 1u);
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(kBM, BN, NPA == 1 ? 0u : 1u, NPB == 1 ? 0u : 1u, MN ? 1u : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int acc_buf = 0;
@@ -252,22 +278,27 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int cnt = max(meta->cnt[uc.c], 1);
         int kb = uc.it0 / cnt, j = uc.it0 % cnt;  // same order as the producer: K block outer, segment inner
         for (int it = uc.it0; it < uc.it1; ++it) {
-          const int ksteps = (kb == p.kb_per_seg - 1) ? p.kb_last_steps : kBK / 16;
+          const int ksteps = (kb == p.kb_per_seg - 1) ? p.kb_last_steps : kBKk / 16;
           if (++j == cnt) { j = 0; ++kb; }
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after_sync();
           const uint32_t sa = ptx::smem_u32(tiles + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
-          const uint64_t a_hi = ptx::umma_desc_k_sw128(sa);
-          const uint64_t a_lo = ptx::umma_desc_k_sw128(sa + (NPA > 1 ? 1 : 0) * kBM * kBK * 2);
-          const uint64_t b_hi = ptx::umma_desc_k_sw128(sb);
-          const uint64_t b_lo = ptx::umma_desc_k_sw128(sb + (NPB > 1 ? 1 : 0) * BN * kBK * 2);
-          const uint64_t a_l2 = ptx::umma_desc_k_sw128(sa + (NPA - 1) * kBM * kBK * 2);  // third plane (NP == 3)
-          const uint64_t b_l2 = ptx::umma_desc_k_sw128(sb + (NPB - 1) * BN * kBK * 2);
+          // MN-major: chunks of 64 columns are kBKk rows x 128 B apart (LBO), groups of 8 k-rows 1 KB apart (SBO)
+          auto desc = [](uint32_t addr) {
+            return MN ? ptx::umma_desc_mn_sw128(addr, kBKk * 128, 1024) : ptx::umma_desc_k_sw128(addr);
+          };
+          const uint64_t a_hi = desc(sa);
+          const uint64_t a_lo = desc(sa + (NPA > 1 ? 1 : 0) * Cfg::kAPlane);
+          const uint64_t b_hi = desc(sb);
+          const uint64_t b_lo = desc(sb + (NPB > 1 ? 1 : 0) * Cfg::kBPlane);
+          const uint64_t a_l2 = desc(sa + (NPA - 1) * Cfg::kAPlane);  // third plane (NP == 3)
+          const uint64_t b_l2 = desc(sb + (NPB - 1) * Cfg::kBPlane);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
+          for (int k = 0; k < kBKk / 16; ++k) {
             if (k >= ksteps) break;
-            const uint64_t adv = (uint64_t)(k * 2);  // 16 elements = 32 B = 2 x 16 B units inside the swizzle atom
+            // K-major: 16 elements = 32 B = 2 x 16 B units inside the swizzle atom; MN-major: 16 k-rows = 2 KB = 128 units
+            const uint64_t adv = (uint64_t)(MN ? k * 128 : k * 2);
             const uint32_t first = (it > uc.it0 || k > 0) ? 1u : 0u;
             if (NPA == 3) {
               // smallest products first: (lo, hi) and (mid, mid) are ~2^-16 of (hi, hi); (mid, lo), (lo, lo) < 2^-24 dropped
