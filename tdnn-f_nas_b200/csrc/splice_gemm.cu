@@ -568,6 +568,7 @@ static int launch_gemm(tdnnf_ctx* ctx, int bn, const Planes& A, const Planes& B,
 static int launch_gemm_mn(tdnnf_ctx* ctx, int bn, const Planes& A, const Planes& B, const GemmParams& p, double fl) {
   if (A.np == 2 && B.np == 2) {
     switch (bn) {
+      case 32: return launch_gemm_bn<32, 2, 2, true>(ctx, A, B, p, fl);
       case 64: return launch_gemm_bn<64, 2, 2, true>(ctx, A, B, p, fl);
       case 128: return launch_gemm_bn<128, 2, 2, true>(ctx, A, B, p, fl);
       case 160: return launch_gemm_bn<160, 2, 2, true>(ctx, A, B, p, fl);
@@ -576,6 +577,7 @@ static int launch_gemm_mn(tdnnf_ctx* ctx, int bn, const Planes& A, const Planes&
     }
   } else if (A.np == 3 && B.np == 3) {
     switch (bn) {
+      case 32: return launch_gemm_bn<32, 3, 3, true>(ctx, A, B, p, fl);
       case 64: return launch_gemm_bn<64, 3, 3, true>(ctx, A, B, p, fl);
       case 128: return launch_gemm_bn<128, 3, 3, true>(ctx, A, B, p, fl);
       case 160: return launch_gemm_bn<160, 3, 3, true>(ctx, A, B, p, fl);
@@ -830,8 +832,10 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
     const int n_dim = m_is_in0 ? out_dim : in_dim;
     const int bn0 = pick_bn(n_dim, ctx->gemm_planes);
     const bool fast0 = ctx->grad_fast && ctx->gemm_planes == 2;
-    const bool tiles_ok = bn0 >= 64 && (bn0 % 64 == 0 || ceil_div(n_dim, bn0) == 1) && !(ctx->gemm_planes == 3 && bn0 == 256);
-    if (mn_enabled && !fast0 && tiles_ok && out_rows >= mn_min_rows && in_dim >= 64 && out_dim >= 64) {
+    // n-tiles must start on a 64-column chunk; a narrow operand (the rank-20 / rank-80 H of the natural-gradient
+    // corrections) is one tile whose chunk is zero-padded by the row split
+    const bool tiles_ok = (bn0 % 64 == 0 || ceil_div(n_dim, bn0) == 1) && !(ctx->gemm_planes == 3 && bn0 == 256);
+    if (mn_enabled && !fast0 && tiles_ok && out_rows >= mn_min_rows) {
       if (dbias) {  // bias gradient: lr * colsum(out_deriv) (the transposed pre-pass of the other path does it on the fly)
         rc = tdnnf_add_row_sum(ctx, out_deriv, out_rows, out_dim, od_stride, lr, dbias);
         if (rc) return rc;
