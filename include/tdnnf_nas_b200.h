@@ -56,6 +56,10 @@ int tdnnf_ctx_get_stream(tdnnf_ctx* ctx, void** stream);
  * per K step, results within ~5e-6 of fp32.  3: hi + mid + lo to 2^-24, six products, fp32-level results at
  * twice the tensor-pipe time -- used by the natural-gradient update, whose eigen-problem amplifies rounding. */
 int tdnnf_ctx_set_gemm_planes(tdnnf_ctx* ctx, int planes);
+/* Parameter-gradient operands with at least `min_rows` rows are contracted MN-major over the row planes (no
+ * transposed pre-pass); smaller ones, and the fp16 gradient mode, use transposed planes.  Default 512; 1 = always,
+ * a negative value = never.  (Environment: TDNNF_WGRAD_MN=0 disables, TDNNF_WGRAD_MN_MIN_ROWS overrides.) */
+int tdnnf_ctx_set_wgrad_mn_min_rows(tdnnf_ctx* ctx, int min_rows);
 /* Precision of the parameter-gradient GEMM (north-star tolerance: gradients 1e-3, forward 1e-4).
  * fast = 0 (default): three bf16 products per K step (~5e-6).
  * fast = 1: tdnnf_darts_backprop_params runs ONE product: both operands as one fp16 plane, scaled into the fp16

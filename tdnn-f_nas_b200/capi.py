@@ -80,6 +80,7 @@ def _declare(lib):
     sig("tdnnf_relu_scale_offset_bypass_bwd", [vp, vp, i, vp, i, vp, f, vp, i, vp, i, i, i])
     sig("tdnnf_batchnorm_train_fwd", [vp, vp, i, i, i, vp, i, f, f, vp])
     sig("tdnnf_batchnorm_train_bwd", [vp, vp, i, vp, i, vp, i, i, i, f, vp])
+    sig("tdnnf_ctx_set_wgrad_mn_min_rows", [vp, i])
     sig("tdnnf_constrain_orthonormal", [vp, vp, i, i, i, f, vp])
     sig("tdnnf_log_softmax_fwd", [vp, vp, i, i, i, vp, i])
     sig("tdnnf_log_softmax_bwd", [vp, vp, i, vp, i, vp, i, i, i])
@@ -341,6 +342,10 @@ class Context:
         sp, r, c, ss = _mat(src)
         dp, _, _, ds = _mat(dst)
         check(load().tdnnf_add_to_rows(self.h, alpha, sp, ss, r, c, dp, ds, row_map.data_ptr()))
+
+    def set_wgrad_mn_min_rows(self, min_rows: int):
+        """Parameter gradients of operands with >= min_rows rows use the MN-major form (default 512; 1 = always, -1 = never)."""
+        check(load().tdnnf_ctx_set_wgrad_mn_min_rows(self.h, int(min_rows)))
 
     def constrain_orthonormal(self, m, scale: float, info=None):
         """ConstrainOrthonormalInternal (nnet-utils.cc:914-1035) on the device matrix m, in place; scale < 0 = floating.

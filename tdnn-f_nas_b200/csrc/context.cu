@@ -113,7 +113,7 @@ extern "C" int tdnnf_ctx_operand_cache_stats(const tdnnf_ctx* ctx, uint64_t* hit
 
 extern "C" const char* tdnnf_last_error(void) { return g_last_error.c_str(); }
 
-extern "C" int tdnnf_abi_version(void) { return 1001; }
+extern "C" int tdnnf_abi_version(void) { return 1002; }  // 1002: orthonormal constraint, dropout, log-softmax, MN-major parameter-gradient switch
 
 extern "C" int tdnnf_ctx_create(int device, tdnnf_ctx** out) {
   TDNNF_REQUIRE(out != nullptr, "null out pointer");

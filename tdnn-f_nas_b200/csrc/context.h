@@ -116,6 +116,9 @@ struct tdnnf_ctx {
   size_t ng_scratch_bytes = 0;
   // parameter-gradient GEMM precision: false = three bf16 products; true = one fp16 x fp16 product (power-of-two scaled)
   bool grad_fast = false;
+  // parameter gradient: operands with at least this many rows take the MN-major form (row planes, no transposed
+  // pre-pass); < 0 = never.  Default 512 (TDNNF_WGRAD_MN=0 disables, TDNNF_WGRAD_MN_MIN_ROWS overrides).
+  int wgrad_mn_min_rows = 512;
   // Makes room for `bytes` more cached planes; called at the top of a public call, before any plane of that call
   // exists (growing drops every cached plane).
   int cws_reserve(size_t bytes);

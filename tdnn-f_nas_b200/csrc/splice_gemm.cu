@@ -819,14 +819,14 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
   // natural-gradient projections of the same Backprop have already built -- no transposed pre-pass, and the per-offset
   // shift is a row coordinate (no alignment condition).  TDNNF_WGRAD_MN=0 selects the transposed-plane path below.
   {
-    static const bool mn_enabled = [] {
-      const char* e = getenv("TDNNF_WGRAD_MN");
-      return e ? atoi(e) != 0 : true;
-    }();
-    static const int mn_min_rows = [] {  // test knob: exercise the MN-major path on small matrices too
+    static const int env_min_rows = [] {  // process-wide defaults from the environment; the context setting wins
+      const char* off = getenv("TDNNF_WGRAD_MN");
+      if (off && atoi(off) == 0) return -1;
       const char* e = getenv("TDNNF_WGRAD_MN_MIN_ROWS");
-      return e ? atoi(e) : 512;
+      return e ? atoi(e) : 0;
     }();
+    const int mn_min_rows = env_min_rows != 0 ? env_min_rows : ctx->wgrad_mn_min_rows;
+    const bool mn_enabled = mn_min_rows >= 0;
     auto waste0 = [](int x) { return (double)round_up(x, kBM) / x; };
     const bool m_is_in0 = waste0(in_dim) <= waste0(out_dim);
     const int n_dim = m_is_in0 ? out_dim : in_dim;
@@ -995,6 +995,12 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
 extern "C" int tdnnf_ctx_set_gemm_planes(tdnnf_ctx* ctx, int planes) {
   TDNNF_REQUIRE(ctx && (planes == 2 || planes == 3), "planes must be 2 or 3");
   ctx->gemm_planes = planes;
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_ctx_set_wgrad_mn_min_rows(tdnnf_ctx* ctx, int min_rows) {
+  TDNNF_REQUIRE(ctx, "null context");
+  ctx->wgrad_mn_min_rows = min_rows;
   return TDNNF_OK;
 }
 

@@ -242,3 +242,31 @@ def test_bad_arguments_fail_loudly(ctx):
     weff = torch.ones(2, device="cuda")
     with pytest.raises(capi.TdnnfError):  # view does not fit (ref: KALDI_ASSERT in GetInputPart, tdnn.cc:811-813)
         ctx.darts_propagate(x, out, W, None, 1, weff, [0, 5], 1)
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c[0] in ("cfg1_mirrored", "linear_1536_160", "affine_160_1536", "subsample3",
+                                                                "two_offsets", "ragged_dims")], ids=lambda c: c[0])
+def test_param_gradient_mn_major_equals_transposed_form(ctx, case):
+    """The parameter gradient contracted MN-major over the row planes (default for >= 512 rows) against the
+    transposed-plane form, on the same inputs: same products, different operand layout and K blocking."""
+    import torch
+
+    name, n, in_dim, out_dim, S, t_out, offsets, row_stride, pad = case
+    d = _setup(n, in_dim, out_dim, S, t_out, offsets, row_stride, seed=7, pad=pad)
+    x, W, od = to_cuda_view(d["x"]), to_cuda_view(d["W"]), to_cuda_view(d["od"])
+    weff = torch.from_numpy(d["rng"].uniform(0.1, 1.0, n).astype(np.float32)).cuda()
+    res = []
+    try:
+        for min_rows in (-1, 1):
+            ctx.set_wgrad_mn_min_rows(min_rows)
+            dW = torch.zeros((out_dim, n * in_dim), device="cuda")
+            db = torch.zeros(out_dim, device="cuda")
+            s = torch.zeros(n, device="cuda")
+            ctx.darts_backprop_params(x, od, W, dW, db, weff, d["row_offsets"], row_stride, 0.25, s)
+            res.append((dW.cpu().numpy(), db.cpu().numpy(), s.cpu().numpy()))
+    finally:
+        ctx.set_wgrad_mn_min_rows(512)
+    (dW0, db0, s0), (dW1, db1, s1) = res
+    assert rel_err(dW1, dW0) < 2e-5 and max_rel_to_scale(dW1, dW0) < 5e-5
+    assert rel_err(db1, db0) < 2e-5
+    assert np.abs(s1 - s0).max() <= 1e-4 * np.abs(s0).max()

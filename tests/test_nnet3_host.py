@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) > 70
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
-    assert lib.tdnnf_abi_version() == 1001
+    assert lib.tdnnf_abi_version() == 1002
 
 
 def test_no_gpu_means_loud_failure():
