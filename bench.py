@@ -156,16 +156,10 @@ def cpu_frames_per_sec(cfg, sample, total_flops, frames_per_step):
 
 
 def supernet_flops(cfg):
-    """Algorithmic DARTS GEMM FLOPs per step without building the net (same formula as Supernet.algorithmic_flops)."""
-    T = cfg.frames_per_eg // cfg.frame_subsampling
-    w = cfg.num_offsets - 1
-    n_eff = cfg.num_offsets if cfg.mode == "search" else 2
-    rows_aff = [T]
-    rows_lin = [cfg.frame_subsampling * (T - 1) + 1 + w]
-    for _ in range(cfg.num_blocks - 1):
-        rows_aff.append(rows_lin[-1] + w)
-        rows_lin.append(rows_aff[-1] + w)
-    return sum(3 * 2.0 * (rl + ra) * cfg.num_seqs * n_eff * cfg.dim * cfg.bottleneck for rl, ra in zip(rows_lin, rows_aff))
+    """Algorithmic block-GEMM FLOPs per step without building the net (Supernet.algorithmic_flops)."""
+    from tdnnf_nas_b200.supernet import algorithmic_flops
+
+    return algorithmic_flops(cfg)
 
 
 def den_report(cfg, arcs, den_ms, peaks):

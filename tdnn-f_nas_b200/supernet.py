@@ -62,6 +62,56 @@ class SupernetConfig:
     seed: int = 20221 + 3
 
 
+def block_offsets(cfg: "SupernetConfig"):
+    """(left, right): the time offsets of the `linear` and `affine` half of every block.  DARTS stages: all
+    `num_offsets` candidates (-6..0 / 0..6); manual: tdnnf-layer time-stride s gives (-s, 0) / (0, s), and the single
+    offset 0 for s = 0 (composite_layers.py:145-150; default strides 1,1,1,0 then 6: run_tdnn_7q_fbk_40_manual.sh:138-151)."""
+    n = cfg.num_offsets
+    if cfg.mode == "manual":
+        strides = list(cfg.strides) if cfg.strides is not None else ([1, 1, 1, 0] + [6] * cfg.num_blocks)[:cfg.num_blocks]
+        assert len(strides) == cfg.num_blocks
+        return [[-s_, 0] if s_ else [0] for s_ in strides], [[0, s_] if s_ else [0] for s_ in strides]
+    return [list(range(-(n - 1), 1))] * cfg.num_blocks, [list(range(n))] * cfg.num_blocks
+
+
+def frame_plan(cfg: "SupernetConfig", left_offsets, right_offsets):
+    """Which frames every layer computes for one chunk (what the nnet3 compiler derives from the output request):
+    (T, output frames, per block the frames of the linear output, per block the frames of the affine output, the frames
+    of tdnn1).  Pure host arithmetic (no device)."""
+    T = cfg.frames_per_eg // cfg.frame_subsampling
+    sub = cfg.frame_subsampling
+    out_t = [sub * i for i in range(T)]
+    L = cfg.num_blocks
+    lw = [-min(o) for o in left_offsets]   # left context of each block's `linear` half
+    rw = [max(o) for o in right_offsets]   # right context of its `affine` half
+    aff_t: List[List[int]] = [None] * L
+    lin_t: List[List[int]] = [None] * L
+    aff_t[L - 1] = out_t
+    lin_t[L - 1] = list(range(out_t[0], out_t[-1] + rw[L - 1] + 1))
+    for b in range(L - 2, -1, -1):
+        lo, hi = lin_t[b + 1][0] - lw[b + 1], lin_t[b + 1][-1]
+        aff_t[b] = list(range(lo, hi + 1))
+        lin_t[b] = list(range(lo, hi + rw[b] + 1))
+    in_t = list(range(lin_t[0][0] - lw[0], lin_t[0][-1] + 1))  # tdnn1 output frames
+    return T, out_t, lin_t, aff_t, in_t
+
+
+def algorithmic_flops(cfg: "SupernetConfig") -> float:
+    """fwd + dgrad + wgrad FLOPs of the block GEMMs per step and GPU without building the net: every
+    candidate offset in the search stage, the shared + the sampled one in the pretrain stage, the layer's own in manual."""
+    left, right = block_offsets(cfg)
+    _, _, lin_t, aff_t, _ = frame_plan(cfg, left, right)
+    tot = 0.0
+    for b in range(cfg.num_blocks):
+        if cfg.mode == "manual":
+            n_lin, n_aff = len(left[b]), len(right[b])
+        else:
+            n_lin = n_aff = cfg.num_offsets if cfg.mode == "search" else 2
+        tot += 3 * 2.0 * len(lin_t[b]) * cfg.num_seqs * n_lin * cfg.dim * cfg.bottleneck
+        tot += 3 * 2.0 * len(aff_t[b]) * cfg.num_seqs * n_aff * cfg.bottleneck * cfg.dim
+    return tot
+
+
 class _Plan:
     """A flat list of zero-argument C calls; run() checks every status."""
 
@@ -110,24 +160,7 @@ class Supernet:
 
     # ------------------------------------------------------------------ construction
     def _frames(self):
-        cfg = self.cfg
-        T = cfg.frames_per_eg // cfg.frame_subsampling
-        sub = cfg.frame_subsampling
-        out_t = [sub * i for i in range(T)]
-        L = cfg.num_blocks
-        lw = [-min(o) for o in self.left_offsets]   # left context of each block's `linear` half
-        rw = [max(o) for o in self.right_offsets]   # right context of its `affine` half
-        # per block: t-lists of the linear output (= affine input) and affine output (= block output)
-        aff_t: List[List[int]] = [None] * L
-        lin_t: List[List[int]] = [None] * L
-        aff_t[L - 1] = out_t
-        lin_t[L - 1] = list(range(out_t[0], out_t[-1] + rw[L - 1] + 1))
-        for b in range(L - 2, -1, -1):
-            lo, hi = lin_t[b + 1][0] - lw[b + 1], lin_t[b + 1][-1]
-            aff_t[b] = list(range(lo, hi + 1))
-            lin_t[b] = list(range(lo, hi + rw[b] + 1))
-        in_t = list(range(lin_t[0][0] - lw[0], lin_t[0][-1] + 1))  # tdnn1 output frames
-        return T, out_t, lin_t, aff_t, in_t
+        return frame_plan(self.cfg, self.left_offsets, self.right_offsets)
 
     def _build(self):
         import torch
@@ -135,16 +168,7 @@ class Supernet:
         cfg, dev, ctx = self.cfg, self.dev, self.ctx
         S, D, B, n = cfg.num_seqs, cfg.dim, cfg.bottleneck, cfg.num_offsets
         manual = cfg.mode == "manual"
-        if manual:
-            # tdnnf-layer time-stride s: linear offsets (-s, 0), affine offsets (0, s); s = 0: the single offset 0
-            # (composite_layers.py:145-150)
-            strides = list(cfg.strides) if cfg.strides is not None else ([1, 1, 1, 0] + [6] * cfg.num_blocks)[:cfg.num_blocks]
-            assert len(strides) == cfg.num_blocks
-            self.left_offsets = [[-s_, 0] if s_ else [0] for s_ in strides]
-            self.right_offsets = [[0, s_] if s_ else [0] for s_ in strides]
-        else:
-            self.left_offsets = [list(range(-(n - 1), 1))] * cfg.num_blocks
-            self.right_offsets = [list(range(n))] * cfg.num_blocks
+        self.left_offsets, self.right_offsets = block_offsets(cfg)
         T, out_t, lin_t, aff_t, in_t = self._frames()
         self.T, self.in_frames = T, len(in_t)
         g = synth.rng(3, stream=1)
@@ -642,17 +666,8 @@ class Supernet:
         return self.cfg.num_seqs * self.cfg.frames_per_eg
 
     def algorithmic_flops(self) -> float:
-        """fwd + dgrad + wgrad FLOPs of the TdnnDARTSV3 GEMMs per step (n_eff = n in search mode)."""
-        cfg = self.cfg
-        tot = 0.0
-        for b, blk in enumerate(self.blocks):
-            if cfg.mode == "manual":
-                n_lin, n_aff = len(self.left_offsets[b]), len(self.right_offsets[b])
-            else:
-                n_lin = n_aff = cfg.num_offsets if cfg.mode == "search" else 2
-            tot += 3 * 2.0 * blk["lin_out"].shape[0] * n_lin * cfg.dim * cfg.bottleneck
-            tot += 3 * 2.0 * blk["aff_out"].shape[0] * n_aff * cfg.bottleneck * cfg.dim
-        return tot
+        """fwd + dgrad + wgrad FLOPs of the block GEMMs per step; see the module-level function."""
+        return algorithmic_flops(self.cfg)
 
     def make_input(self, step: int = 0):
         """Synthetic egs for this rank: N(0,1) features, different per rank (its shard of the minibatch)."""

@@ -316,3 +316,30 @@ def test_stock_tdnn_precomputed_indexes_tokens():
     assert pi.row_stride_and_offsets() == (3, [0, 7, 14])
     assert pi.write(False).split() == data.split()
     assert nnet3.PrecomputedIndexes.read(pi.write(True), True).write(False).split() == data.split()
+
+
+def test_frame_plan_matches_the_survey_row_counts():
+    """SURVEY 8d, config 3 at 64 chunks x 150 frames: `.linear` outputs 19 840 (tdnnf2) ... 9 856 (tdnnf15) rows, `.affine`
+    outputs 19 456 (tdnnf2), 10 240 (tdnnf14), 3 200 (tdnnf15); 4.17 TFLOP of algorithmic GEMM work per step.  Manual
+    system: time-strides 1,1,1,0 then 6 (run_tdnn_7q_fbk_40_manual.sh:138-151)."""
+    from tdnnf_nas_b200.supernet import SupernetConfig, algorithmic_flops, block_offsets, frame_plan
+
+    cfg = SupernetConfig()
+    left, right = block_offsets(cfg)
+    assert left[0] == list(range(-6, 1)) and right[0] == list(range(0, 7))
+    T, out_t, lin_t, aff_t, in_t = frame_plan(cfg, left, right)
+    S = cfg.num_seqs
+    assert T == 50 and out_t[:3] == [0, 3, 6]
+    assert [len(t) * S for t in lin_t][0] == 19840 and [len(t) * S for t in lin_t][-1] == 9856
+    assert [len(t) * S for t in aff_t][0] == 19456 and [len(t) * S for t in aff_t][-2:] == [10240, 3200]
+    for b in range(1, cfg.num_blocks):
+        assert len(lin_t[b - 1]) - len(lin_t[b]) == 12  # each layer down adds 12 frames of context
+    assert algorithmic_flops(cfg) == pytest.approx(4.17e12, rel=2e-3)
+    pre = SupernetConfig(mode="pretrain")
+    assert algorithmic_flops(pre) == pytest.approx(algorithmic_flops(cfg) * 2 / 7, rel=1e-12)  # shared + sampled offset
+    man = SupernetConfig(mode="manual", num_seqs=128)
+    left, right = block_offsets(man)
+    assert left[:5] == [[-1, 0], [-1, 0], [-1, 0], [0], [-6, 0]] and right[3] == [0] and right[-1] == [0, 6]
+    _, _, lin_t, aff_t, in_t = frame_plan(man, left, right)
+    assert len(aff_t[-1]) == 50 and aff_t[-1][-1] == 147
+    assert lin_t[-1][-1] == 147 + 6 and in_t[0] == -(6 * 10 + 0 + 3) and in_t[-1] == 147 + 6 * 10 + 3
