@@ -1,0 +1,125 @@
+"""Fixtures produced by RUNNING the reference's own Python (tools/make_golden_ref.py -> tests/golden/ref_scripts.json):
+the per-iteration temperature directive, and the component config lines its config generators emit.  Every such line must
+be accepted by the matching component here, with the dimensions / offsets / flags it asks for -- this is the one place
+where outputs of reference code (not of the oracle) pin this library."""
+import json
+import os
+import re
+
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_scripts.json")
+HOST_TYPES = {"GumbelSoftmaxFlopsComponent", "SoftmaxFlopsComponent", "CopyNComponent", "ElementwiseProductComponent",
+              "RectifiedLinearComponent", "BatchNormComponent", "GeneralDropoutComponent"}
+DEVICE_TYPES = {"TdnnComponent", "TdnnDARTSV3Component", "ConstantFunctionComponent", "OnehotFunctionComponent"}
+GRAPH_ONLY = {"NoOpComponent"}  # descriptor plumbing of the nnet3 graph, not a component of the path
+
+
+def _fixture():
+    return json.load(open(GOLD))
+
+
+def _component_lines(lines):
+    """[(name, type, rest-of-config)] of the `component name=... type=...` lines (what nnet3-init hands to InitFromConfig)."""
+    out = []
+    for line in lines:
+        m = re.match(r"component name=(\S+) type=(\S+)\s*(.*)$", line)
+        if m:
+            out.append((m.group(1), m.group(2), m.group(3)))
+    return out
+
+
+def _kv(rest):
+    return dict(tok.split("=", 1) for tok in rest.split())
+
+
+def test_temperature_directive_matches_the_reference_schedule():
+    from tdnnf_nas_b200 import nnet3
+
+    fx = _fixture()["temperature_edits"]
+    assert len(fx) >= 20
+    comp = nnet3.Component.new("GumbelSoftmaxFlopsComponent", "dim=8 scale=0.001 temp-proportion=1.0")
+    for done, total, ref_string in fx:
+        ours = nnet3.temperature_edit_string(done, total)
+        assert "nnet3-copy --edits='" + ours + "' - - |" == ref_string  # character for character (float repr included)
+        nnet3.apply_edits(ours, [("tdnnf2.softmax", comp)])
+        assert comp.temp_proportion() == pytest.approx(float(ours.rsplit("=", 1)[1]), rel=1e-6)
+    assert fx[0][2].endswith("proportion=1.0' - - |") and "proportion=0.03' - - |" in fx[-1][2]
+
+
+def test_every_generated_component_type_is_known():
+    fx = _fixture()
+    types = set()
+    for key in ("change_config_gumbel", "change_config_softmax", "bottleneck_final_config", "supernet_final_config"):
+        types |= {t for _, t, _ in _component_lines(fx[key])}
+    assert types <= HOST_TYPES | DEVICE_TYPES | GRAPH_ONLY, types - (HOST_TYPES | DEVICE_TYPES | GRAPH_ONLY)
+    assert {"TdnnDARTSV3Component", "GumbelSoftmaxFlopsComponent", "SoftmaxFlopsComponent", "CopyNComponent",
+            "OnehotFunctionComponent", "ConstantFunctionComponent"} <= types
+
+
+def test_generated_lines_of_parameter_free_components_are_accepted():
+    """No device needed: the mixing components, CopyN, ElementwiseProduct, ReLU, BatchNorm, GeneralDropout."""
+    from tdnnf_nas_b200 import nnet3
+
+    fx = _fixture()
+    seen = set()
+    copyn_dims = {}
+    for key in ("change_config_gumbel", "change_config_softmax", "bottleneck_final_config", "supernet_final_config"):
+        for name, typ, rest in _component_lines(fx[key]):
+            if typ not in HOST_TYPES:
+                continue
+            comp = nnet3.Component.new(typ, rest)
+            kv = _kv(rest)
+            assert comp.type() == typ
+            seen.add(typ)
+            if "dim" in kv:
+                assert comp.input_dim() == comp.output_dim() == int(kv["dim"])
+            if "input-dim" in kv:
+                assert comp.input_dim() == int(kv["input-dim"]) and comp.output_dim() == int(kv["output-dim"])
+            if typ == "GumbelSoftmaxFlopsComponent":
+                assert comp.temp_proportion() == pytest.approx(float(kv["temp-proportion"]))
+                assert ("<Scale> " + kv["scale"]).encode() in comp.write(False)
+            if typ == "SoftmaxFlopsComponent":
+                assert ("<Scale> " + kv["scale"]).encode() in comp.write(False)
+            if typ == "CopyNComponent":
+                m = re.match(r"(tdnnf\d)(\d)\.copyn$", name)
+                copyn_dims.setdefault(m.group(1), []).append(comp.output_dim())
+            if typ == "GeneralDropoutComponent":
+                assert comp.dropout_proportion() == 0.0 and b"<Continuous>" in comp.write(False)
+    assert seen == HOST_TYPES
+    # the shared bottleneck candidates: blocks of 25/25/30/20/20/40/40/40 = 240
+    assert copyn_dims and all(v == [25, 25, 30, 20, 20, 40, 40, 40] for v in copyn_dims.values())
+
+
+@pytest.mark.gpu
+def test_generated_lines_of_parameterised_components_are_accepted(ctx):
+    """TdnnDARTSV3Component (context-offset supernet), TdnnComponent (bottleneck search), ConstantFunction / Onehot."""
+    from tdnnf_nas_b200 import nnet3
+
+    nnet3.set_context(ctx)
+    nnet3.set_rand_seed(3)
+    fx = _fixture()
+    seen = set()
+    for key in ("change_config_gumbel", "bottleneck_final_config", "supernet_final_config"):
+        for name, typ, rest in _component_lines(fx[key]):
+            if typ not in DEVICE_TYPES or (typ, name[-6:]) in seen:
+                continue
+            seen.add((typ, name[-6:]))
+            comp = nnet3.Component.new(typ, rest)
+            kv = _kv(rest)
+            assert comp.type() == typ
+            assert comp.input_dim() == int(kv["input-dim"]) and comp.output_dim() == int(kv["output-dim"])
+            if typ in ("TdnnComponent", "TdnnDARTSV3Component"):
+                assert "time-offsets=" + kv["time-offsets"] in comp.info()
+                assert comp.orthonormal_constraint() == float(kv.get("orthonormal-constraint", 0.0))
+            if typ == "TdnnDARTSV3Component":
+                # generate_config.py forces use-bias=true and writes all 7 candidate offsets; alpha slots + bias
+                assert "use-bias=true" in rest or "use-bias" not in rest
+                n = len(kv["time-offsets"].split(","))
+                assert n == 7
+                assert comp.num_parameters() == int(kv["output-dim"]) * n * int(kv["input-dim"]) + n + int(kv["output-dim"])
+                head = comp.write(False)[:400]  # the pretrain-stage flags of run_TDNN_DARTSV3_fbk_stride_pretrain.sh:124
+                assert b"<use-gumbel> F" in head and b"<uniform-sample> T" in head
+            if typ == "TdnnComponent" and kv.get("use-bias") == "false":
+                assert comp.num_parameters() == int(kv["output-dim"]) * len(kv["time-offsets"].split(",")) * int(kv["input-dim"])
+    assert {t for t, _ in seen} == DEVICE_TYPES
