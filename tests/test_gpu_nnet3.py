@@ -429,3 +429,20 @@ def test_rectified_linear_component_stats_and_self_repair(nn):
     assert acc.write(False) == comp.write(False)
     acc.zero_stats()
     assert "<Count> 0 " in acc.write(False).decode()
+
+
+def test_text_model_is_readable_by_generate_top_list(nn):
+    """NAS/scripts/generate_top_list.py:21-27 recovers the architecture weights from the TEXT model with
+    `line.split('[')[1].split(' ')[1:offset+1]` on every line that contains '<BiasParams>': the alpha entries must be
+    the first `offset` numbers of that one line (Kaldi's vector text form)."""
+    n, din, dout = 7, 16, 12
+    comp = nn.Component.new("TdnnDARTSV3Component", f"input-dim={din} output-dim={dout} time-offsets=0,1,2,3,4,5,6")
+    v = comp.vectorize()
+    alpha = np.array([0.25, -1.5, 3.0, 1e-5, -0.125, 2.75, 0.5], dtype=np.float32)
+    v[dout * n * din: dout * n * din + n] = alpha
+    comp.unvectorize(v)
+    text = comp.write(False).decode()
+    hits = [line.strip() for line in text.split("\n") if "<BiasParams>" in line]
+    assert len(hits) == 1
+    prob = hits[0].split("[")[1].split(" ")[1:n + 1]          # the reference's expression, offset = 7
+    np.testing.assert_allclose([float(item) for item in prob], alpha, rtol=1e-5)
