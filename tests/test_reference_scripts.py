@@ -123,3 +123,22 @@ def test_generated_lines_of_parameterised_components_are_accepted(ctx):
             if typ == "TdnnComponent" and kv.get("use-bias") == "false":
                 assert comp.num_parameters() == int(kv["output-dim"]) * len(kv["time-offsets"].split(",")) * int(kv["input-dim"])
     assert {t for t, _ in seen} == DEVICE_TYPES
+
+
+def test_flops_vector_is_the_cumulative_bottleneck_width():
+    """The hard-coded FLOPs vector of {Gumbel}SoftmaxFlopsComponent (simple.cc:10145-10152: -25 ... -240) is minus the
+    cumulative width of the shared bottleneck candidates -- the CopyN blocks the reference's config generator emits
+    (25, 25, 30, 20, 20, 40, 40, 40), and the widths bottleneckdim_search_top_model_size.py:62 lists."""
+    import numpy as np
+
+    from oracle import oracle as O
+
+    fx = _fixture()
+    dims = [int(_kv(rest)["output-dim"]) for name, typ, rest in _component_lines(fx["bottleneck_final_config"])
+            if typ == "CopyNComponent" and name.startswith("tdnnf2")]
+    widths = np.cumsum(dims).tolist()
+    assert widths == [25, 50, 80, 100, 120, 160, 200, 240]
+    # read the vector back from the oracle: out_deriv = 0, one row of 8 columns, scale = rows * cols = 8  =>  e = f
+    p = np.full((1, 8), 0.125, np.float32)
+    _, e = O.softmax_flops_bwd(p, np.zeros((1, 8), np.float32), 8.0, False, 1.0)
+    assert (-np.asarray(e).ravel()).tolist() == [float(w) for w in widths]
