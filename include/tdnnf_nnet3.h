@@ -46,6 +46,8 @@ int tdnnf_nnet3_component_new(const char* type, const char* config_line, void** 
 int tdnnf_nnet3_tdnn_darts_for_indexing(const int32_t* time_offsets, int n, void** out);
 /* Component::ReadNew / Write on memory buffers, text or binary (ref: itf.cc:106-124, tdnn.cc:659-761, ...). */
 int tdnnf_nnet3_component_read(const char* data, uint64_t len, int binary, void** out);
+/* tdnnf_nnet3_component_read that also reports the bytes consumed (to walk the component list of a raw nnet3 model). */
+int tdnnf_nnet3_component_read_ex(const char* data, uint64_t len, int binary, void** out, uint64_t* consumed);
 int tdnnf_nnet3_component_write(const void* comp, int binary, char** out, uint64_t* len);
 int tdnnf_nnet3_component_copy(const void* comp, void** out);
 int tdnnf_nnet3_component_delete(void* comp);

@@ -139,6 +139,18 @@ int tdnnf_nnet3_component_read(const char* data, uint64_t len, int binary, void*
   *out = Component::ReadNew(is, binary != 0);
   API_END
 }
+// The same, reporting how many bytes of the buffer the component occupied: lets a host walk the component list of a
+// raw nnet3 model (Nnet::Read: "<ComponentName> name <Type> ... </Type>" repeated).
+int tdnnf_nnet3_component_read_ex(const char* data, uint64_t len, int binary, void** out, uint64_t* consumed) {
+  API_BEGIN
+  std::istringstream is(std::string(data, len));
+  *out = Component::ReadNew(is, binary != 0);
+  if (consumed) {
+    const std::streampos pos = is.tellg();
+    *consumed = (pos == std::streampos(-1)) ? len : (uint64_t)pos;
+  }
+  API_END
+}
 int tdnnf_nnet3_component_write(const void* comp, int binary, char** out, uint64_t* len) {
   API_BEGIN
   std::ostringstream os;

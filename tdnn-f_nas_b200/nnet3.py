@@ -41,7 +41,7 @@ def _lib():
 
 def _check(rc):
     if rc != 0:
-        raise Nnet3Error(_lib().tdnnf_nnet3_last_error().decode())
+        raise Nnet3Error(_lib().tdnnf_nnet3_last_error().decode(errors="replace"))  # messages may quote raw stream bytes
 
 
 def _take_string(p: C.c_char_p, length: Optional[int] = None) -> bytes:
@@ -200,6 +200,14 @@ class Component:
         h = vp()
         _check(_lib().tdnnf_nnet3_component_read(data, C.c_uint64(len(data)), int(binary), C.byref(h)))
         return Component(h)
+
+    @staticmethod
+    def read_prefix(data: bytes, binary: bool = False) -> Tuple["Component", int]:
+        """Component.read from the START of `data`; also returns how many bytes the component occupied."""
+        h = vp()
+        used = C.c_uint64()
+        _check(_lib().tdnnf_nnet3_component_read_ex(data, C.c_uint64(len(data)), int(binary), C.byref(h), C.byref(used)))
+        return Component(h), int(used.value)
 
     @staticmethod
     def tdnn_darts_for_indexing(time_offsets: Sequence[int]) -> "Component":
@@ -484,3 +492,71 @@ def dropout_edit_string(schedule: str, data_fraction: float, name_pattern: str =
     """The per-iteration edit directive upstream's get_dropout_edit_string emits (utils.cc:1297-1330 consumes it)."""
     return "set-dropout-proportion name={0} proportion={1}".format(
         name_pattern, dropout_proportion_for_fraction(schedule, data_fraction))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The raw nnet3 model container (kaldi: nnet3/nnet-nnet.cc, Nnet::Write / Nnet::Read): "<Nnet3>", the config lines of the
+# graph (kept as opaque text: the graph compiler stays in Kaldi), a blank line, "<NumComponents> N", then
+# "<ComponentName> name" + the component for each, "</Nnet3>".  What `nnet3-copy --binary=false` writes, so the
+# reference's scripts that grep the text model (generate_top_list.py:21-27 on '<BiasParams>' lines,
+# bottleneckdim_search_top_model_size.py:15-18 on 'alpha <ConstantFunctionComponent>' lines) work on models written here.
+def _bin_int32(v: int) -> bytes:
+    import struct
+
+    return b"\x04" + struct.pack("<i", v)  # WriteBasicType(binary): size byte, then the value
+
+
+def write_nnet(config_lines: Sequence[str], named_components: Sequence[Tuple[str, Component]], binary: bool = False) -> bytes:
+    out = [b"<Nnet3> \n"]
+    for line in config_lines:
+        if not line.strip():
+            raise ValueError("config lines must not be empty (a blank line ends the config section)")
+        out.append(line.encode() + b"\n")
+    out.append(b"\n<NumComponents> ")
+    out.append(_bin_int32(len(named_components)) if binary else str(len(named_components)).encode() + b" \n")
+    for name, comp in named_components:
+        if not name or any(ch.isspace() for ch in name):
+            raise ValueError(f"bad component name {name!r}")
+        out.append(b"<ComponentName> " + name.encode() + b" ")
+        out.append(comp.write(binary))
+        if not binary:
+            out.append(b"\n")
+    out.append(b"</Nnet3> ")
+    return b"".join(out)
+
+
+def read_nnet(data: bytes, binary: bool = False) -> Tuple[List[str], List[Tuple[str, Component]]]:
+    def expect(pos: int, token: bytes) -> int:
+        while not binary and data[pos:pos + 1].isspace():
+            pos += 1
+        if data[pos:pos + len(token)] != token:
+            raise Nnet3Error(f"expected {token.decode()} at byte {pos}, got {data[pos:pos + 24]!r}")
+        return pos + len(token)
+
+    pos = expect(0, b"<Nnet3>")
+    end = data.index(b"\n\n", pos)  # a blank line terminates the config section
+    config_lines = [l.decode() for l in data[pos:end].split(b"\n") if l.strip()]
+    pos = expect(end + 2, b"<NumComponents> ")
+    if binary:
+        import struct
+
+        if data[pos:pos + 1] != b"\x04":
+            raise Nnet3Error("bad binary <NumComponents>")
+        n = struct.unpack("<i", data[pos + 1:pos + 5])[0]
+        pos += 5
+    else:
+        stop = pos
+        while not data[stop:stop + 1].isspace():
+            stop += 1
+        n = int(data[pos:stop])
+        pos = stop
+    comps = []
+    for _ in range(n):
+        pos = expect(pos, b"<ComponentName> ")
+        stop = data.index(b" ", pos)
+        name = data[pos:stop].decode()
+        comp, used = Component.read_prefix(data[stop + 1:], binary)
+        comps.append((name, comp))
+        pos = stop + 1 + used
+    expect(pos, b"</Nnet3>")
+    return config_lines, comps

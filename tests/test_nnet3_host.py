@@ -343,3 +343,34 @@ def test_frame_plan_matches_the_survey_row_counts():
     _, _, lin_t, aff_t, in_t = frame_plan(man, left, right)
     assert len(aff_t[-1]) == 50 and aff_t[-1][-1] == 147
     assert lin_t[-1][-1] == 147 + 6 and in_t[0] == -(6 * 10 + 0 + 3) and in_t[-1] == 147 + 6 * 10 + 3
+
+
+def test_raw_nnet_container_roundtrip():
+    """Nnet::Write / Nnet::Read framing (kaldi nnet3/nnet-nnet.cc): '<Nnet3>', config lines, blank line, '<NumComponents> N',
+    '<ComponentName> name' + component ..., '</Nnet3>'; text and binary, parameter-free components (no device here)."""
+    from tdnnf_nas_b200 import nnet3
+
+    comps = [("tdnnf2.softmax", nnet3.Component.new("GumbelSoftmaxFlopsComponent", "dim=8 scale=0.001 temp-proportion=0.5")),
+             ("tdnnf20.copyn", nnet3.Component.new("CopyNComponent", "input-dim=1 output-dim=25")),
+             ("tdnnf20.output", nnet3.Component.new("ElementwiseProductComponent", "input-dim=50 output-dim=25")),
+             ("tdnnf2.dropout", nnet3.Component.new("GeneralDropoutComponent", "dim=12 dropout-proportion=0.25 continuous=true"))]
+    cfg = ["input-node name=input dim=40", "component-node name=tdnnf2.softmax component=tdnnf2.softmax input=tdnnf2.alpha"]
+    text = nnet3.write_nnet(cfg, comps, False)
+    lines = text.decode().split("\n")
+    assert lines[0] == "<Nnet3> " and lines[1:3] == cfg and lines[3] == "" and lines[4] == "<NumComponents> 4 "
+    assert lines[5].startswith("<ComponentName> tdnnf2.softmax <GumbelSoftmaxFlopsComponent> <Dim> 8 ")
+    assert lines[-1] == "</Nnet3> "
+    for binary in (False, True):
+        data = nnet3.write_nnet(cfg, comps, binary)
+        cfg2, back = nnet3.read_nnet(data, binary)
+        assert cfg2 == cfg and [n for n, _ in back] == [n for n, _ in comps]
+        for (_, a), (_, b) in zip(comps, back):
+            assert a.type() == b.type() and a.write(binary) == b.write(binary)
+    # the edits of the training driver apply to the components read back, by name pattern
+    _, back = nnet3.read_nnet(text, False)
+    nnet3.apply_edits("set-temperature-proportion name=tdnnf*.softmax proportion=0.1; set-dropout-proportion name=* proportion=0.4", back)
+    assert back[0][1].temp_proportion() == pytest.approx(0.1) and back[3][1].dropout_proportion() == pytest.approx(0.4)
+    with pytest.raises(nnet3.Nnet3Error):
+        nnet3.read_nnet(text[:-12], False)  # truncated: no </Nnet3>
+    with pytest.raises(ValueError):
+        nnet3.write_nnet(["a", ""], comps)
