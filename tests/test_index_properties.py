@@ -85,3 +85,18 @@ def test_reorder_with_missing_frames(case, drop_seed):
             comp.reorder_indexes(inp, out)
         return
     assert comp.reorder_indexes(inp, out) == expect
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.text(alphabet="ab.-_1", min_size=1, max_size=8), st.text(alphabet="ab.-_1*", min_size=1, max_size=7))
+def test_name_patterns_of_edit_directives(name, pattern):
+    """NameMatchesPattern (kaldi nnet3/nnet-parse.cc): '*' matches any run of characters (also empty), everything else is
+    literal -- checked through set-dropout-proportion against a regular expression."""
+    import re
+
+    from tdnnf_nas_b200 import nnet3
+
+    comp = nnet3.Component.new("GeneralDropoutComponent", "dim=4 dropout-proportion=0.0")
+    nnet3.apply_edits(f"set-dropout-proportion name={pattern} proportion=0.5", [(name, comp)])
+    want = re.fullmatch(".*".join(re.escape(part) for part in pattern.split("*")), name) is not None
+    assert (comp.dropout_proportion() == 0.5) == want, (name, pattern)
