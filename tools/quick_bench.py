@@ -33,8 +33,12 @@ for name, din, dout, offsets, t_out in [("linear_1536_160", 1536, 160, list(rang
     res[name + "_fwd"] = dict(ms=t, tflops_fp32eq=flop / t / 1e9, tflops_bf16_raw=3 * flop / t / 1e9)
     t = timeit(lambda: ctx.darts_backprop_data(od, ind, W, weff, ro, 1))
     res[name + "_dgrad"] = dict(ms=t, tflops_fp32eq=flop / t / 1e9, tflops_bf16_raw=3 * flop / t / 1e9)
-    t = timeit(lambda: ctx.darts_backprop_params(x, od, W, dW, db, weff, ro, 1, 1e-3, s))
-    res[name + "_wgrad"] = dict(ms=t, tflops_fp32eq=flop / t / 1e9, tflops_bf16_raw=3 * flop / t / 1e9)
+    # parameter gradient, both operand forms (the pre-passes are inside the call: nothing is cached here)
+    for label, min_rows in (("wgrad_mn_major", 1), ("wgrad_transposed_planes", -1)):
+        ctx.set_wgrad_mn_min_rows(min_rows)
+        t = timeit(lambda: ctx.darts_backprop_params(x, od, W, dW, db, weff, ro, 1, 1e-3, s))
+        res[name + "_" + label] = dict(ms=t, tflops_fp32eq=flop / t / 1e9, tflops_bf16_raw=3 * flop / t / 1e9)
+    ctx.set_wgrad_mn_min_rows(512)
 
 for N, Sd, T in [(8192, 64, 50), (16384, 64, 50), (32768, 128, 50)]:
     P = 6008
