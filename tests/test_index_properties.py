@@ -100,3 +100,30 @@ def test_name_patterns_of_edit_directives(name, pattern):
     nnet3.apply_edits(f"set-dropout-proportion name={pattern} proportion=0.5", [(name, comp)])
     want = re.fullmatch(".*".join(re.escape(part) for part in pattern.split("*")), name) is not None
     assert (comp.dropout_proportion() == 0.5) == want, (name, pattern)
+
+
+@settings(max_examples=120, deadline=None)
+@given(st.integers(1, 4), st.integers(-9, 9), st.integers(1, 9), st.sampled_from([0, 1, 2, 3, 5]), st.sampled_from([1, 2, 3]),
+       st.integers(0, 10 ** 6))
+def test_general_dropout_precompute_indexes(S, t0, frames, time_period, multiple, seed):
+    """GeneralDropoutComponent::PrecomputeIndexes (kaldi nnet-general-component.cc): one mask row per distinct
+    (n, x, floor(t / time_period)) -- per (n, x) when time_period = 0 -- numbered in order of first appearance; with
+    block-dim < dim every input row becomes `multiple` reshaped rows with consecutive mask rows.  Any index order,
+    negative frames included (floor division)."""
+    from tdnnf_nas_b200 import nnet3
+
+    block = 4
+    comp = nnet3.Component.new("GeneralDropoutComponent",
+                               f"dim={block * multiple} block-dim={block} time-period={time_period} dropout-proportion=0.3")
+    idx = [(n, t, x) for t in range(t0, t0 + frames) for x in (0, 1) for n in range(S)]
+    random.Random(seed).shuffle(idx)
+    toks = comp.precompute_indexes(idx, idx).write(False).decode().split()
+    rows = int(toks[2])
+    got = [int(t) for t in toks[toks.index("[") + 1: toks.index("]")]]
+    seen = {}
+    want = []
+    for (n, t, x) in idx:
+        key = (n, x, 0 if time_period == 0 else t // time_period)  # Python's // floors, like DivideRoundingDown
+        r = seen.setdefault(key, len(seen))
+        want += [r * multiple + j for j in range(multiple)]
+    assert rows == len(seen) * multiple and got == want
