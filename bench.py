@@ -228,7 +228,9 @@ def workload_config(cfg, gpus):
                 cache="per-step working set (~14 GB of activations) exceeds the 126 MB L2: no explicit flush needed",
                 included=("natural-gradient update (OnlineNaturalGradient rank 20/80, update period 4) of all 28 TdnnDARTSV3 "
                           "components, LF-MMI numerator (per-sequence FST) and denominator, UpdateNnetWithMaxChange" +
-                          (", the cross-entropy regularisation branch (numerator posteriors -> output-xent)" if cfg.xent else "")),
+                          (", the cross-entropy regularisation branch (numerator posteriors -> output-xent)" if cfg.xent else "") +
+                          "; the stock affine layers (tdnn1, prefinal, output) are also trained (plain SGD) although the search recipe "
+                          "freezes them with learning-rate-factor 0 (run_TDNN_DARTSV3_fbk_stride_cvupdate.sh:129): extra work in the step"),
                 ng_settle_steps=NG_SETTLE_STEPS,
                 not_included=("natural gradient of the 5 stock affine layers around the blocks (tdnn1, prefinal, output: plain SGD "
                               "there; all 28 TdnnDARTSV3 components are preconditioned), L2 regularisation, dropout "
