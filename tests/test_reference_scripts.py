@@ -91,40 +91,6 @@ def test_generated_lines_of_parameter_free_components_are_accepted():
     assert copyn_dims and all(v == [25, 25, 30, 20, 20, 40, 40, 40] for v in copyn_dims.values())
 
 
-@pytest.mark.gpu
-def test_generated_lines_of_parameterised_components_are_accepted(ctx):
-    """TdnnDARTSV3Component (context-offset supernet), TdnnComponent (bottleneck search), ConstantFunction / Onehot."""
-    from tdnnf_nas_b200 import nnet3
-
-    nnet3.set_context(ctx)
-    nnet3.set_rand_seed(3)
-    fx = _fixture()
-    seen = set()
-    for key in ("change_config_gumbel", "bottleneck_final_config", "supernet_final_config"):
-        for name, typ, rest in _component_lines(fx[key]):
-            if typ not in DEVICE_TYPES or (typ, name[-6:]) in seen:
-                continue
-            seen.add((typ, name[-6:]))
-            comp = nnet3.Component.new(typ, rest)
-            kv = _kv(rest)
-            assert comp.type() == typ
-            assert comp.input_dim() == int(kv["input-dim"]) and comp.output_dim() == int(kv["output-dim"])
-            if typ in ("TdnnComponent", "TdnnDARTSV3Component"):
-                assert "time-offsets=" + kv["time-offsets"] in comp.info()
-                assert comp.orthonormal_constraint() == float(kv.get("orthonormal-constraint", 0.0))
-            if typ == "TdnnDARTSV3Component":
-                # generate_config.py forces use-bias=true and writes all 7 candidate offsets; alpha slots + bias
-                assert "use-bias=true" in rest or "use-bias" not in rest
-                n = len(kv["time-offsets"].split(","))
-                assert n == 7
-                assert comp.num_parameters() == int(kv["output-dim"]) * n * int(kv["input-dim"]) + n + int(kv["output-dim"])
-                head = comp.write(False)[:400]  # the pretrain-stage flags of run_TDNN_DARTSV3_fbk_stride_pretrain.sh:124
-                assert b"<use-gumbel> F" in head and b"<uniform-sample> T" in head
-            if typ == "TdnnComponent" and kv.get("use-bias") == "false":
-                assert comp.num_parameters() == int(kv["output-dim"]) * len(kv["time-offsets"].split(",")) * int(kv["input-dim"])
-    assert {t for t, _ in seen} == DEVICE_TYPES
-
-
 def test_flops_vector_is_the_cumulative_bottleneck_width():
     """The hard-coded FLOPs vector of {Gumbel}SoftmaxFlopsComponent (simple.cc:10145-10152: -25 ... -240) is minus the
     cumulative width of the shared bottleneck candidates -- the CopyN blocks the reference's config generator emits
