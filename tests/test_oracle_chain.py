@@ -68,3 +68,55 @@ def test_denominator_invariants(N, P, S, T):
     lp_p, _, _ = O.den_forward_backward(graph, x + eps * v, S, T, 0.1)
     lp_m, _, _ = O.den_forward_backward(graph, x - eps * v, S, T, 0.1)
     assert (lp_p - lp_m) / (2 * eps) == pytest.approx(float(-(d * v).sum()), rel=2e-2)
+
+
+def _den_logprob_f64(graph, x, S, T, leaky):
+    """Independent float64 statement of the leaky-HMM denominator log-probability, dense matrices:
+    alpha_0 = init;  alpha'_t = alpha_t + leaky * init * sum(alpha_t);  alpha_{t+1} = alpha'_t . (sum_pdf e_t[pdf] A[pdf]);
+    log p = sum_s log sum(alpha'_T)."""
+    N, P = int(graph["num_states"]), int(graph["num_pdfs"])
+    A = np.zeros((P, N, N))
+    fr = graph["fwd_ranges"]
+    for h in range(N):
+        for a in range(fr[h][0], fr[h][1]):
+            A[graph["pdf"][a], h, graph["state"][a]] += float(graph["prob"][a])
+    init = graph["init"].astype(np.float64)
+    total = 0.0
+    for s in range(S):
+        alpha = init.copy()
+        for t in range(T):
+            ad = alpha + leaky * init * alpha.sum()
+            alpha = ad @ np.tensordot(np.exp(x[t * S + s]), A, axes=(0, 0))
+        total += np.log((alpha + leaky * init * alpha.sum()).sum())
+    return total
+
+
+def test_denominator_backward_is_the_gradient_of_an_independent_forward():
+    """The oracle's Backward (beta recursion with the leaky-HMM terms, per-frame rescaling, posterior accumulation) against
+    the element-wise gradient of an independent float64 forward pass, on random tiny graphs: every (frame, sequence, pdf)
+    posterior, not just a directional derivative."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.integers(2, 6), st.integers(2, 4), st.integers(1, 3), st.integers(1, 4), st.sampled_from([0.1, 0.5, 1e-5]),
+           st.booleans(), st.integers(0, 10 ** 6))
+    def check(N, P, S, T, leaky, self_loops, seed):
+        graph = synth.make_den_graph(N, P, 2.0, seed=seed, self_loops=self_loops)
+        g = np.random.default_rng(seed)
+        x = g.standard_normal((T * S, P)).astype(np.float32)
+        lp, d, ok = O.den_forward_backward(graph, x, S, T, leaky, deriv_weight=-1.0)
+        assert ok
+        x64 = x.astype(np.float64)
+        assert lp == pytest.approx(_den_logprob_f64(graph, x64, S, T, leaky), rel=2e-5, abs=2e-5)
+        grad = np.zeros_like(x64)
+        eps = 1e-5
+        for i in range(x64.shape[0]):
+            for j in range(P):
+                xp, xm = x64.copy(), x64.copy()
+                xp[i, j] += eps
+                xm[i, j] -= eps
+                grad[i, j] = (_den_logprob_f64(graph, xp, S, T, leaky) - _den_logprob_f64(graph, xm, S, T, leaky)) / (2 * eps)
+        np.testing.assert_allclose(-d, grad, rtol=2e-4, atol=2e-5)
+
+    check()
