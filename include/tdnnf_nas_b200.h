@@ -228,6 +228,30 @@ int tdnnf_multi_sumsq(tdnnf_ctx* ctx, int n, const float* const* bufs, const int
 int tdnnf_multi_axpy_zero(tdnnf_ctx* ctx, int n, float* const* dst, const int32_t* dst_strides, float* const* src,
                           const int32_t* src_strides, const int32_t* rows, const int32_t* cols, const float* factors);
 
+/* UpdateNnetWithMaxChange followed by ScaleNnet(momentum, delta_nnet) (ref: nnet-utils.cc:2085-2175; kaldi:
+ * NnetChainTrainer::TrainInternal) over the n parameter buffers of a network, as ONE call for a C++ host:
+ *   dot_g = sum of squares of the delta buffers of updatable component g = groups[i]   (one launch, ONE read-back);
+ *   per-component factor = max_change[g] * max_change_scale / (sqrt(dot_g) |scale|) where that is < 1 (max_change 0 = off),
+ *   then the global max_param_change on sqrt(sum factor_g^2 dot_g) |scale|, all in BaseFloat as the reference;
+ *   model_i += factor * scale * delta_i;  delta_i *= momentum (0 stores exact zeros)                (one launch).
+ * A non-finite parameter change sets *applied = 0 ("Infinite parameter change, will not apply."): the model is left
+ * untouched (the reference returns false) and the delta is still scaled by momentum.
+ * Host arrays: model / delta (device pointers), strides, rows, cols, groups [n]; max_change [num_groups];
+ * scale_factors_out [num_groups] (optional: factor * scale actually applied), num_max_change_per_component_applied
+ * [num_groups] and num_max_change_global_applied (optional counters, incremented).  dots_dev: DEVICE double[num_groups]. */
+int tdnnf_update_with_max_change(tdnnf_ctx* ctx, int n, float* const* model, const int32_t* model_strides,
+                                 float* const* delta, const int32_t* delta_strides, const int32_t* rows,
+                                 const int32_t* cols, const int32_t* groups, int num_groups, const float* max_change,
+                                 float max_param_change, float max_change_scale, float scale, float momentum,
+                                 double* dots_dev, float* scale_factors_out, int32_t* num_max_change_per_component_applied,
+                                 int32_t* num_max_change_global_applied, int* applied);
+/* ApplyL2Regularization (ref: nnet-utils.cc:2223-2245): delta_i += -2 * l2_regularize_scale * lrate[g] * l2_regularize[g]
+ * * model_i for every buffer of an updatable component g with a non-zero product; one launch. */
+int tdnnf_apply_l2_regularization(tdnnf_ctx* ctx, int n, float* const* model, const int32_t* model_strides,
+                                  float* const* delta, const int32_t* delta_strides, const int32_t* rows,
+                                  const int32_t* cols, const int32_t* groups, int num_groups, const float* lrate,
+                                  const float* l2_regularize, float l2_regularize_scale);
+
 /* ------------------------------------------------------------------ stock TDNN-F neighbours - */
 /* The stock components that sit between the NAS components in a TDNN-F block, so
  * that a whole supernet step runs on this library: RectifiedLinearComponent without self-repair,
@@ -397,6 +421,50 @@ int tdnnf_num_graph_destroy(tdnnf_num_graph* g);
 int tdnnf_num_forward_backward(tdnnf_ctx* ctx, const tdnnf_num_graph* g, const float* nnet_output, int stride,
                                int frames_per_seq, float deriv_weight, float* nnet_output_deriv, int deriv_stride,
                                float* logprob, int* ok);
+
+/* ------------------------------------------------------------------ chain objective --- */
+/* ComputeChainObjfAndDeriv (kaldi: chain/chain-training.cc; called by NnetChainTrainer::ProcessOutputs) for the
+ * unconstrained-egs supervision the recipes train with:
+ *   weight = w * num_seqs * frames_per_seq;  deriv = 0;
+ *   den = w * Denominator.Forward();  Denominator.Backward(-w, &deriv)                     (the denominator first)
+ *   num = w * GenericNumerator: posteriors (x w) into xent_output_deriv when given (then added to deriv), else into deriv
+ *   objf = num - den;  non-finite objf or a failed denominator / numerator check: derivs zeroed, objf = -10 * weight
+ *   l2_term = -0.5 * w * l2_regularize * ||nnet_output||^2;  deriv += -w * l2_regularize * nnet_output   (when numerator ok)
+ *   out-of-range penalty: tdnnf_penalize_out_of_range with limit 30 and scale 2 * out_of_range_regularize * oor_row_step
+ *   on the rows oor_row_offset + k * oor_row_step (upstream penalises a sub-sampled set of rows; the caller draws the
+ *   offset).  out_of_range_regularize = 0 switches it off.
+ * nnet_output_deriv / xent_output_deriv may be NULL (objective only).  objf, l2_term, weight: HOST.  Synchronises. */
+int tdnnf_chain_objf_and_deriv(tdnnf_ctx* ctx, tdnnf_den_comp* den, const tdnnf_num_graph* num, const float* nnet_output,
+                               int stride, int num_seqs, int frames_per_seq, int num_pdfs, float supervision_weight,
+                               float l2_regularize, float out_of_range_regularize, int oor_row_step, int oor_row_offset,
+                               float* nnet_output_deriv, int deriv_stride, float* xent_output_deriv, int xent_stride,
+                               float* objf, float* l2_term, float* weight);
+/* PenalizeOutOfRange (kaldi: chain/chain-training.cc): on the rows r = row_offset + k * row_step (r < rows),
+ *   deriv[r][c] -= scale * (x - limit) where x > limit,  deriv[r][c] -= scale * (x + limit) where x < -limit. */
+int tdnnf_penalize_out_of_range(tdnnf_ctx* ctx, const float* nnet_output, int rows, int cols, int stride, float limit,
+                                float scale, int row_step, int row_offset, float* deriv, int deriv_stride);
+
+/* ------------------------------------------------------------------ data-parallel reduction - */
+/* SURVEY 8b capability (8): the deltas of the ranks' minibatch shards are SUMMED over NCCL (NVLink / NVSwitch): the
+ * synchronous replacement of the multi-job `nnet3-average` (ref: steps/libs/nnet3/train/common.py:144-164; learning
+ * rate x num_jobs then averaging == summing the per-job deltas).  NCCL is bound at run time (the libnccl already in
+ * the process, else libnccl.so.2).  One process per GPU:
+ *   rank 0: tdnnf_dp_unique_id(id)  -> the host ships the 128 bytes to the other ranks (MPI, a file, torch.distributed)
+ *   all:    tdnnf_dp_comm_create(ctx, nranks, rank, id, &comm)           (collective: ncclCommInitRank)
+ *   or      tdnnf_dp_comm_adopt(ctx, existing ncclComm_t, ...)           (the host set NCCL up itself)
+ *   step:   tdnnf_dp_allreduce_deltas(comm, n, bufs, counts)             in place, on the context's stream, one NCCL group
+ *   or      tdnnf_dp_allreduce_bucket_async(comm, buf, count) per bucket as the backward pass completes it (a side
+ *           stream that first waits for the work queued on the context's stream) + tdnnf_dp_allreduce_wait(comm)
+ *           before the parameter step. */
+typedef struct tdnnf_dp_comm tdnnf_dp_comm;
+int tdnnf_dp_unique_id(char* id_out, int id_bytes /* >= 128 */);
+int tdnnf_dp_comm_create(tdnnf_ctx* ctx, int nranks, int rank, const char* unique_id, tdnnf_dp_comm** out);
+int tdnnf_dp_comm_adopt(tdnnf_ctx* ctx, void* nccl_comm, int nranks, int rank, tdnnf_dp_comm** out);
+int tdnnf_dp_comm_destroy(tdnnf_dp_comm* c);
+int tdnnf_dp_allreduce_deltas(tdnnf_dp_comm* c, int n, float* const* bufs, const int64_t* counts);
+int tdnnf_dp_allreduce_bucket_async(tdnnf_dp_comm* c, float* buf, int64_t count);
+int tdnnf_dp_allreduce_wait(tdnnf_dp_comm* c);
+int tdnnf_dp_nccl_version(int* version);
 
 #ifdef __cplusplus
 }

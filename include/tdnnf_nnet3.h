@@ -27,6 +27,13 @@ void tdnnf_nnet3_free(void* p);
 
 /* The "CuDevice" of the mirror: the context the components launch on (per host thread). */
 int tdnnf_nnet3_set_context(tdnnf_ctx* ctx);
+/* Parameter arena: between begin and end every device allocation of the component layer (the parameters of the
+ * components created, read or copied meanwhile) is carved in call order, 256-byte aligned, from the caller-owned device
+ * range [base, base + bytes) (base 256-byte aligned); *used <- bytes consumed.  Creating the delta components of a network
+ * inside one arena makes all deltas ONE contiguous range: tdnnf_dp_allreduce_deltas then needs a single buffer
+ * (replaces the per-component nnet3-average of steps/libs/nnet3/train/common.py:144-164). */
+int tdnnf_nnet3_arena_begin(void* base, uint64_t bytes);
+int tdnnf_nnet3_arena_end(uint64_t* used);
 /* Counter-based host RNG behind SetRandUniform / RandInt: same seed + counter => same draws on every rank. */
 int tdnnf_nnet3_set_rand_seed(uint64_t seed);
 int tdnnf_nnet3_set_rand_counter(uint64_t counter);

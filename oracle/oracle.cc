@@ -401,8 +401,11 @@ int orc_plain_tdnn_backprop(int n, const float* W, int w_stride, const float* in
     }
     return 0;
   }
-  OwnedMat in_value_temp(out_rows, spliced + 1);                 // [X_1 | ... | X_n | 1]
-  for (int r = 0; r < out_rows; ++r) in_value_temp.m(r, spliced) = 1.0f;
+  // [X_1 | ... | X_n | 1]: the column of ones only when there is a bias (tdnn.cc:477-478: bias_params_.Dim() != 0)
+  const bool has_bias = dbias != nullptr;
+  OwnedMat in_value_temp(out_rows, spliced + (has_bias ? 1 : 0));
+  if (has_bias)
+    for (int r = 0; r < out_rows; ++r) in_value_temp.m(r, spliced) = 1.0f;
   for (int i = 0; i < n; ++i) {
     Mat in_part = GetInputPart(in_m, out_rows, row_stride, row_offsets[i]);
     for (int r = 0; r < out_rows; ++r) memcpy(&in_value_temp.m(r, i * in_dim), &in_part(r, 0), sizeof(float) * in_dim);

@@ -19,7 +19,7 @@ LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libtdnnf_nas_b200.so")
 
-CUDA_SOURCES = ["context.cu", "splice_gemm.cu", "mixing.cu", "den.cu", "num.cu", "neighbours.cu", "ng.cu", "orthonormal.cu"]
+CUDA_SOURCES = ["context.cu", "splice_gemm.cu", "mixing.cu", "den.cu", "num.cu", "neighbours.cu", "ng.cu", "orthonormal.cu", "chain_step.cu"]
 CXX_SOURCES = [
     "nnet3/shim.cc",
     "nnet3/indexes.cc",
@@ -93,7 +93,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         outs = list(ex.map(_run, jobs))
     if verbose:
         print("\n".join(outs))
-    _run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"])
+    _run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl"])
     with open(stamp, "w") as f:
         f.write(dig)
     return LIB

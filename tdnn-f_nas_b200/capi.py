@@ -95,6 +95,19 @@ def _declare(lib):
     sig("tdnnf_den_destroy", [vp])
     sig("tdnnf_den_forward", [vp, vp, i, c_float_p])
     sig("tdnnf_den_backward", [vp, f, vp, i, c_int_p])
+    sig("tdnnf_update_with_max_change", [vp, i, vp, vp, vp, vp, vp, vp, vp, i, c_float_p, f, f, f, f, vp, c_float_p, c_int_p,
+                                         c_int_p, c_int_p])
+    sig("tdnnf_apply_l2_regularization", [vp, i, vp, vp, vp, vp, vp, vp, vp, i, c_float_p, c_float_p, f])
+    sig("tdnnf_chain_objf_and_deriv", [vp, vp, vp, vp, i, i, i, i, f, f, f, i, i, vp, i, vp, i, c_float_p, c_float_p, c_float_p])
+    sig("tdnnf_penalize_out_of_range", [vp, vp, i, i, i, f, f, i, i, vp, i])
+    sig("tdnnf_dp_unique_id", [C.c_char_p, i])
+    sig("tdnnf_dp_comm_create", [vp, i, i, C.c_char_p, C.POINTER(vp)])
+    sig("tdnnf_dp_comm_adopt", [vp, vp, i, i, C.POINTER(vp)])
+    sig("tdnnf_dp_comm_destroy", [vp])
+    sig("tdnnf_dp_allreduce_deltas", [vp, i, vp, C.POINTER(C.c_int64)])
+    sig("tdnnf_dp_allreduce_bucket_async", [vp, vp, C.c_int64])
+    sig("tdnnf_dp_allreduce_wait", [vp])
+    sig("tdnnf_dp_nccl_version", [c_int_p])
 
 
 def load():
@@ -347,6 +360,11 @@ class Context:
         """Parameter gradients of operands with >= min_rows rows use the MN-major form (default 512; 1 = always, -1 = never)."""
         check(load().tdnnf_ctx_set_wgrad_mn_min_rows(self.h, int(min_rows)))
 
+    def penalize_out_of_range(self, nnet_output, deriv, limit: float, scale: float, row_step: int = 1, row_offset: int = 0):
+        xp, r, c, xs = _mat(nnet_output)
+        dp, _, _, ds = _mat(deriv)
+        check(load().tdnnf_penalize_out_of_range(self.h, xp, r, c, xs, limit, scale, row_step, row_offset, dp, ds))
+
     def constrain_orthonormal(self, m, scale: float, info=None):
         """ConstrainOrthonormalInternal (nnet-utils.cc:914-1035) on the device matrix m, in place; scale < 0 = floating.
         info: optional device float[4] <- (scale used, ratio, update_speed, ||M M^T - scale^2 I||_F)."""
@@ -395,6 +413,80 @@ class Context:
         dp, _, _, ds = _mat(out_deriv)
         ip, _, _, is_ = _mat(in_deriv)
         check(load().tdnnf_batchnorm_train_bwd(self.h, vp_, vs, dp, ds, ip, is_, r, c, target_rms, memo.data_ptr()))
+
+
+class ParamTable:
+    """The parameter buffers of a network next to their delta buffers, grouped by updatable component: the argument
+    block of tdnnf_update_with_max_change / tdnnf_apply_l2_regularization (ref: nnet-utils.cc:2085-2175, 2223-2245).
+    bufs: list of (model_ptr, model_stride, delta_ptr, delta_stride, rows, cols, group)."""
+
+    def __init__(self, ctx: "Context", bufs, max_change: Sequence[float]):
+        import torch
+
+        n = len(bufs)
+        self.ctx, self.n, self.num_groups = ctx, n, len(max_change)
+        P, I = vp * n, C.c_int32 * n
+        self.model, self.model_ld = P(*[b[0] for b in bufs]), I(*[b[1] for b in bufs])
+        self.delta, self.delta_ld = P(*[b[2] for b in bufs]), I(*[b[3] for b in bufs])
+        self.rows, self.cols, self.groups = I(*[b[4] for b in bufs]), I(*[b[5] for b in bufs]), I(*[b[6] for b in bufs])
+        self.max_change = (C.c_float * self.num_groups)(*[float(m) for m in max_change])
+        self.dots = torch.zeros(self.num_groups, dtype=torch.float64, device=torch.device("cuda", ctx.device))
+        self.factors = (C.c_float * self.num_groups)()
+        self.num_per_component = (C.c_int32 * self.num_groups)()
+        self.num_global = C.c_int32(0)
+
+    def update_with_max_change(self, max_param_change: float, max_change_scale: float = 1.0, scale: float = 1.0,
+                               momentum: float = 0.0) -> bool:
+        """Returns False where the reference returns false ("Infinite parameter change, will not apply.")."""
+        applied = C.c_int32(0)
+        check(load().tdnnf_update_with_max_change(
+            self.ctx.h, self.n, self.model, self.model_ld, self.delta, self.delta_ld, self.rows, self.cols, self.groups,
+            self.num_groups, self.max_change, max_param_change, max_change_scale, scale, momentum, vp(self.dots.data_ptr()),
+            self.factors, self.num_per_component, C.byref(self.num_global), C.byref(applied)))
+        return bool(applied.value)
+
+    def apply_l2_regularization(self, lrate: Sequence[float], l2: Sequence[float], l2_regularize_scale: float):
+        check(load().tdnnf_apply_l2_regularization(
+            self.ctx.h, self.n, self.model, self.model_ld, self.delta, self.delta_ld, self.rows, self.cols, self.groups,
+            self.num_groups, _fhost(lrate), _fhost(l2), l2_regularize_scale))
+
+
+class DataParallel:
+    """tdnnf_dp_*: the NCCL sum of the ranks' deltas through the C ABI.  `exchange` ships rank 0's 128-byte NCCL id to
+    the other ranks (e.g. a torch.distributed broadcast): plumbing, not data path."""
+
+    def __init__(self, ctx: "Context", nranks: int, rank: int, exchange):
+        self.ctx, self.nranks, self.rank = ctx, nranks, rank
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            check(load().tdnnf_dp_unique_id(buf, 128))
+        ident = exchange(bytes(buf.raw))
+        assert len(ident) == 128
+        h = vp()
+        check(load().tdnnf_dp_comm_create(ctx.h, nranks, rank, ident, C.byref(h)))
+        self.h = h
+
+    def allreduce(self, ptrs_and_counts):
+        n = len(ptrs_and_counts)
+        P, L = vp * n, C.c_int64 * n
+        check(load().tdnnf_dp_allreduce_deltas(self.h, n, P(*[p for p, _ in ptrs_and_counts]), L(*[c for _, c in ptrs_and_counts])))
+
+    def allreduce_bucket_async(self, ptr: int, count: int):
+        check(load().tdnnf_dp_allreduce_bucket_async(self.h, vp(ptr), count))
+
+    def wait(self):
+        check(load().tdnnf_dp_allreduce_wait(self.h))
+
+    @staticmethod
+    def nccl_version() -> int:
+        v = C.c_int32(0)
+        check(load().tdnnf_dp_nccl_version(C.byref(v)))
+        return int(v.value)
+
+    def close(self):
+        if getattr(self, "h", None):
+            load().tdnnf_dp_comm_destroy(self.h)
+            self.h = None
 
 
 class DenGraph:

@@ -9,13 +9,19 @@
 xent branch (xent_output_deriv != None): the numerator posteriors (x sup.weight) are returned on their own, as the
 targets of the cross-entropy output; NnetChainTrainer then takes objf_xent = <xent_output, xent_deriv> and feeds
 xent_regularize * xent_deriv back as that output's derivative (xent_objf_and_deriv below).
-The out-of-range penalty (|x| > 30, sub-sampled rows upstream) is NOT applied: its exact sub-sampling is not
-recoverable from the reference and it is inert for the bounded synthetic outputs used here.
+out-of-range penalty: PenalizeOutOfRange(limit 30, scale 2 * out_of_range_regularize) on every oor_row_step-th row
+starting at a RandInt(0, step - 1) offset drawn by the caller, the scale multiplied by the step.  Upstream's exact
+sub-sampling is not part of the reference tree (unpinned); the penalty is zero whenever |nnet_output| <= 30.
+
+The arithmetic lives in the C entry tdnnf_chain_objf_and_deriv (csrc/chain_step.cu), so that a C++ host needs no
+Python; this class only holds the handles.
 """
 from __future__ import annotations
 
 import math
 from dataclasses import dataclass
+
+import ctypes as C
 
 from . import capi
 
@@ -26,6 +32,7 @@ class ChainTrainingOptions:
     leaky_hmm_coefficient: float = 0.1    # --chain.leaky-hmm-coefficient 0.1
     xent_regularize: float = 0.1          # --chain.xent-regularize 0.1: see xent_objf_and_deriv
     out_of_range_regularize: float = 0.01
+    oor_row_step: int = 4                 # rows penalised: every 4th (upstream sub-samples; unpinned)
 
 
 class ChainObjective:
@@ -37,34 +44,19 @@ class ChainObjective:
         self.den = capi.DenominatorComputation(ctx, den_graph, num_seqs, frames_per_seq, opts.leaky_hmm_coefficient)
         self.num = num_graph
 
-    def compute(self, nnet_output, nnet_output_deriv, xent_output_deriv=None):
+    def compute(self, nnet_output, nnet_output_deriv, xent_output_deriv=None, oor_row_offset: int = 0):
         """Returns (objf, l2_term, weight); fills nnet_output_deriv (overwritten) and, if given, xent_output_deriv with
-        the numerator posteriors (overwritten)."""
-        w = self.sup_weight
-        weight = w * self.S * self.T
-        self.ctx.mat_set(nnet_output_deriv, 0.0)
-        den = w * self.den.forward(nnet_output)
-        den_ok = self.den.backward(-w, nnet_output_deriv)
-        if xent_output_deriv is not None:
-            self.ctx.mat_set(xent_output_deriv, 0.0)
-            num, num_ok = self.num.forward_backward(nnet_output, self.T, w, xent_output_deriv)
-            if num_ok:
-                self.ctx.mat_axpy(1.0, xent_output_deriv, nnet_output_deriv)
-        else:
-            num, num_ok = self.num.forward_backward(nnet_output, self.T, w, nnet_output_deriv)
-        num *= w
-        objf = num - den
-        if not math.isfinite(objf) or not den_ok or not num_ok:
-            self.ctx.mat_set(nnet_output_deriv, 0.0)
-            if xent_output_deriv is not None:
-                self.ctx.mat_set(xent_output_deriv, 0.0)
-            objf = -10.0 * weight
-        l2_term = 0.0
-        if self.opts.l2_regularize != 0.0 and num_ok:
-            scale = w * self.opts.l2_regularize
-            l2_term = -0.5 * scale * self.ctx.mat_dot(nnet_output, nnet_output)
-            self.ctx.mat_axpy(-scale, nnet_output, nnet_output_deriv)
-        return objf, l2_term, weight
+        the numerator posteriors (overwritten).  oor_row_offset: the caller's RandInt(0, oor_row_step - 1) draw."""
+        xp, rows, cols, xs = capi._mat(nnet_output)
+        assert rows == self.S * self.T
+        dp, ds = (0, 0) if nnet_output_deriv is None else (capi._mat(nnet_output_deriv)[0], capi._mat(nnet_output_deriv)[3])
+        qp, qs = (0, 0) if xent_output_deriv is None else (capi._mat(xent_output_deriv)[0], capi._mat(xent_output_deriv)[3])
+        objf, l2_term, weight = C.c_float(0), C.c_float(0), C.c_float(0)
+        capi.check(capi.load().tdnnf_chain_objf_and_deriv(
+            self.ctx.h, self.den.h, self.num.h, xp, xs, self.S, self.T, cols, self.sup_weight, self.opts.l2_regularize,
+            self.opts.out_of_range_regularize, self.opts.oor_row_step, oor_row_offset, dp, ds, qp, qs, C.byref(objf),
+            C.byref(l2_term), C.byref(weight)))
+        return float(objf.value), float(l2_term.value), float(weight.value)
 
     def xent_objf_and_deriv(self, xent_output, xent_output_deriv):
         """NnetChainTrainer::ProcessOutputs for the 'output-xent' node (kaldi: nnet3/nnet-chain-training.cc): the

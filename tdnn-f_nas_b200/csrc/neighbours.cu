@@ -1,6 +1,7 @@
 // Whole-parameter ops of the updatable components and the stock TDNN-F neighbours (ReLU, bypass
 // sum, BatchNorm training mode).  All bandwidth-bound, one fused pass each.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include "context.h"
@@ -365,8 +366,10 @@ __global__ void __launch_bounds__(256) multi_sumsq_kernel(const __grid_constant_
   }
 }
 
-// dst_i += factor_i * src_i;  src_i = 0
-__global__ void __launch_bounds__(256) multi_axpy_zero_kernel(const __grid_constant__ MultiBufTable t) {
+// dst_i += factor_i * src_i;  src_i = keep * src_i.  factor 0 adds nothing (0 * inf would be NaN: Kaldi's
+// UpdateNnetWithMaxChange leaves the model untouched on a non-finite delta); keep 0 stores exact zeros
+// (ScaleNnet(0.0) is SetZero), keep 1 leaves the source alone (ApplyL2Regularization reads the model).
+__global__ void __launch_bounds__(256) multi_axpy_zero_kernel(const __grid_constant__ MultiBufTable t, float keep) {
   const int i = multi_find(t, blockIdx.x);
   const int nb = t.first_block[i + 1] - t.first_block[i], b = blockIdx.x - t.first_block[i];
   const long long total = (long long)t.rows[i] * t.cols[i];
@@ -378,8 +381,9 @@ __global__ void __launch_bounds__(256) multi_axpy_zero_kernel(const __grid_const
   for (long long idx = (long long)b * 256 + threadIdx.x; idx < total; idx += (long long)nb * 256) {
     const long long r = idx / cols;
     const int c = (int)(idx % cols);
-    dst[r * dld + c] += f * src[r * sld + c];
-    src[r * sld + c] = 0.f;
+    if (f != 0.f) dst[r * dld + c] += f * src[r * sld + c];
+    if (keep == 0.f) src[r * sld + c] = 0.f;
+    else if (keep != 1.f) src[r * sld + c] *= keep;
   }
 }
 
@@ -432,7 +436,128 @@ extern "C" int tdnnf_multi_axpy_zero(tdnnf_ctx* ctx, int n, float* const* dst, c
   if (rc) return rc;
   for (int i = 0; i < n; ++i) TDNNF_REQUIRE(dst[i] && dst_strides[i] >= cols[i], "bad destination buffer");
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
-  multi_axpy_zero_kernel<<<blocks, 256, 0, ctx->stream>>>(t);
+  multi_axpy_zero_kernel<<<blocks, 256, 0, ctx->stream>>>(t, 0.f);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+
+// UpdateNnetWithMaxChange + ScaleNnet(momentum, delta_nnet) (ref: nnet-utils.cc:2085-2175; kaldi: NnetChainTrainer::TrainInternal)
+// as ONE entry: squared norms of every component's delta on the device (one launch), ONE read-back, the per-component /
+// global factors on the host exactly as the reference computes them, then model += factor * delta and delta *= momentum
+// (one launch).  *applied = 0 reproduces "Infinite parameter change, will not apply.": the model is untouched and the
+// delta is still scaled by momentum (the trainer calls ScaleNnet either way).
+extern "C" int tdnnf_update_with_max_change(tdnnf_ctx* ctx, int n, float* const* model, const int32_t* model_strides,
+                                            float* const* delta, const int32_t* delta_strides, const int32_t* rows,
+                                            const int32_t* cols, const int32_t* groups, int num_groups, const float* max_change,
+                                            float max_param_change, float max_change_scale, float scale, float momentum,
+                                            double* dots_dev, float* scale_factors_out, int32_t* num_max_change_per_component_applied,
+                                            int32_t* num_max_change_global_applied, int* applied) {
+  TDNNF_REQUIRE(ctx && model && model_strides && delta && delta_strides && rows && cols && groups && max_change && dots_dev && applied,
+                "null argument");
+  TDNNF_REQUIRE(num_groups >= 1 && num_groups <= TDNNF_MULTI_MAX, "group count out of range");
+  for (int i = 0; i < n; ++i) TDNNF_REQUIRE(groups[i] >= 0 && groups[i] < num_groups, "group index out of range");
+  for (int g = 0; g < num_groups; ++g) TDNNF_REQUIRE(max_change[g] >= 0.f, "max-change must be >= 0");  // KALDI_ASSERT :2112
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+  TDNNF_CUDA_OK(cudaMemsetAsync(dots_dev, 0, sizeof(double) * num_groups, ctx->stream));
+  int rc = tdnnf_multi_sumsq(ctx, n, delta, rows, cols, delta_strides, groups, dots_dev);
+  if (rc) return rc;
+  double dots[TDNNF_MULTI_MAX];
+  TDNNF_CUDA_OK(cudaMemcpyAsync(dots, dots_dev, sizeof(double) * num_groups, cudaMemcpyDeviceToHost, ctx->stream));
+  TDNNF_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  float factors[TDNNF_MULTI_MAX];
+  float param_delta_squared = 0.f;
+  for (int g = 0; g < num_groups; ++g) {  // BaseFloat arithmetic as in the reference
+    const float dot_prod = (float)dots[g];
+    const float mc = max_change[g];
+    if (mc != 0.f && std::sqrt(dot_prod) * std::fabs(scale) > mc * max_change_scale) {
+      factors[g] = mc * max_change_scale / (std::sqrt(dot_prod) * std::fabs(scale));
+      if (num_max_change_per_component_applied) num_max_change_per_component_applied[g]++;
+    } else {
+      factors[g] = 1.f;
+    }
+    param_delta_squared += factors[g] * factors[g] * dot_prod;
+  }
+  float param_delta = std::sqrt(param_delta_squared) * std::fabs(scale);
+  *applied = 1;
+  if (max_param_change != 0.f && param_delta > max_param_change * max_change_scale) {
+    if (param_delta - param_delta != 0.f) {
+      *applied = 0;  // "Infinite parameter change, will not apply."
+    } else {
+      scale *= max_param_change * max_change_scale / param_delta;
+      if (num_max_change_global_applied) (*num_max_change_global_applied)++;
+    }
+  }
+  float per_buf[TDNNF_MULTI_MAX];
+  for (int g = 0; g < num_groups; ++g) {
+    factors[g] = *applied ? factors[g] * scale : 0.f;
+    if (scale_factors_out) scale_factors_out[g] = factors[g];
+  }
+  for (int i = 0; i < n; ++i) per_buf[i] = factors[groups[i]];
+  MultiBufTable t;
+  int blocks = 0;
+  rc = multi_table(ctx, n, delta, model, rows, cols, delta_strides, model_strides, nullptr, per_buf, &t, &blocks);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) TDNNF_REQUIRE(model[i] && model_strides[i] >= cols[i], "bad model buffer");
+  multi_axpy_zero_kernel<<<blocks, 256, 0, ctx->stream>>>(t, momentum);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+
+// ApplyL2Regularization (ref: nnet-utils.cc:2223-2245): delta_g += -2 * l2_regularize_scale * lrate_g * l2_g * model_g for
+// every updatable component g with a non-zero product, in one launch.
+extern "C" int tdnnf_apply_l2_regularization(tdnnf_ctx* ctx, int n, float* const* model, const int32_t* model_strides,
+                                             float* const* delta, const int32_t* delta_strides, const int32_t* rows,
+                                             const int32_t* cols, const int32_t* groups, int num_groups, const float* lrate,
+                                             const float* l2_regularize, float l2_regularize_scale) {
+  TDNNF_REQUIRE(ctx && model && model_strides && delta && delta_strides && rows && cols && groups && lrate && l2_regularize,
+                "null argument");
+  if (l2_regularize_scale == 0.f) return TDNNF_OK;
+  float per_buf[TDNNF_MULTI_MAX];
+  bool any = false;
+  for (int i = 0; i < n && i < TDNNF_MULTI_MAX; ++i) {
+    TDNNF_REQUIRE(groups[i] >= 0 && groups[i] < num_groups, "group index out of range");
+    TDNNF_REQUIRE(lrate[groups[i]] >= 0.f && l2_regularize[groups[i]] >= 0.f, "lrate and l2-regularize must be >= 0");  // :2241
+    per_buf[i] = -2.f * l2_regularize_scale * lrate[groups[i]] * l2_regularize[groups[i]];
+    any = any || per_buf[i] != 0.f;
+  }
+  if (!any) return TDNNF_OK;
+  MultiBufTable t;
+  int blocks = 0;
+  int rc = multi_table(ctx, n, model, delta, rows, cols, model_strides, delta_strides, nullptr, per_buf, &t, &blocks);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) TDNNF_REQUIRE(delta[i] && delta_strides[i] >= cols[i], "bad delta buffer");
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+  multi_axpy_zero_kernel<<<blocks, 256, 0, ctx->stream>>>(t, 1.f);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+
+// PenalizeOutOfRange (kaldi: chain/chain-training.cc): on the rows row_offset + k * row_step,
+//   deriv[r][c] -= scale * (x - limit) for x > limit,  deriv[r][c] -= scale * (x + limit) for x < -limit.
+__global__ void penalize_out_of_range_kernel(const float* __restrict__ x, long long xs, int rows, int cols, float limit,
+                                             float scale, int row_step, int row_offset, float* __restrict__ d, long long ds) {
+  const long long total = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = (long long)row_offset + (i / cols) * row_step;
+    const int c = (int)(i % cols);
+    const float v = x[r * xs + c];
+    if (v > limit) d[r * ds + c] -= scale * (v - limit);
+    else if (v < -limit) d[r * ds + c] -= scale * (v + limit);
+  }
+}
+
+extern "C" int tdnnf_penalize_out_of_range(tdnnf_ctx* ctx, const float* nnet_output, int rows, int cols, int stride, float limit,
+                                           float scale, int row_step, int row_offset, float* deriv, int deriv_stride) {
+  TDNNF_REQUIRE(ctx && nnet_output && deriv, "null argument");
+  TDNNF_REQUIRE(limit > 0.f && scale >= 0.f && row_step >= 1 && row_offset >= 0 && row_offset < row_step, "bad argument");
+  TDNNF_REQUIRE(stride >= cols && deriv_stride >= cols, "stride < cols");
+  if (scale == 0.f || rows <= row_offset || cols == 0) return TDNNF_OK;
+  const int sub_rows = (rows - row_offset + row_step - 1) / row_step;
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+  const long long total = (long long)sub_rows * cols;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 8);
+  penalize_out_of_range_kernel<<<blocks, 256, 0, ctx->stream>>>(nnet_output, stride, sub_rows, cols, limit, scale, row_step,
+                                                               row_offset, deriv, deriv_stride);
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }

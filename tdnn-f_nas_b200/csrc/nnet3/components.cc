@@ -277,8 +277,8 @@ void TdnnDARTSV3Component::Backprop(const std::string& debug_info, const Compone
     if (to_update->is_gradient_ || !to_update->use_natural_gradient_)
       to_update->UpdateSimple(*indexes, in_value, out_deriv);
     else
-      to_update->UpdateNaturalGradient(*indexes, in_value, out_deriv, linear_params_, *memo, share_offset_index, Flags(),
-                                       temp_proportion_);
+      to_update->UpdateNaturalGradient(*indexes, in_value, out_deriv, linear_params_, bias_params_, *memo,
+                                       share_offset_index, Flags(), temp_proportion_);
   }
 }
 
@@ -298,7 +298,10 @@ void TdnnDARTSV3Component::PreconditionedUpdate(const PrecomputedIndexes& indexe
   const int32 num_offsets = (int32)time_offsets_.size();
   tdnnf_ctx* ctx = CurrentContext();
   const int32 num_rows = out_deriv.NumRows(), input_dim = in_value.NumCols(), output_dim = out_deriv.NumCols(),
-              spliced_input_dim = num_offsets * input_dim, augmented_input_dim = spliced_input_dim + 1;
+              spliced_input_dim = num_offsets * input_dim;
+  // the column of ones is appended only when there is a bias (tdnn.cc:477-478; stock TdnnComponent likewise)
+  const bool has_bias = bias_params_.Dim() != 0;
+  const int32 augmented_input_dim = spliced_input_dim + (has_bias ? 1 : 0);
   if (ng_consts_.Dim() == 0) {
     ng_consts_.Resize(2);
     ng_consts_.CopyFromHost(std::vector<BaseFloat>{1.0f, -1.0f});
@@ -319,7 +322,7 @@ void TdnnDARTSV3Component::PreconditionedUpdate(const PrecomputedIndexes& indexe
   x_in.row_offsets = indexes.row_offsets.data();
   x_in.row_stride = indexes.row_stride;
   x_in.weff = weff_dev;
-  x_in.ones_col = true;
+  x_in.ones_col = has_bias;
   NgProjection p_in, p_out;
   preconditioner_in_.PreconditionImplicit(x_in, &p_in);
   preconditioner_out_.PreconditionImplicit(NgOperand::Plain(out_deriv), &p_out);
@@ -329,19 +332,22 @@ void TdnnDARTSV3Component::PreconditionedUpdate(const PrecomputedIndexes& indexe
   if (ng_grad_.NumRows() != output_dim || ng_grad_.NumCols() != augmented_input_dim)
     ng_grad_.Resize(output_dim, augmented_input_dim);
   ng_grad_.SetZero();
-  if (ng_colsum_.Dim() != output_dim) ng_colsum_.Resize(output_dim);
-  ng_colsum_.SetZero();
+  if (has_bias) {
+    if (ng_colsum_.Dim() != output_dim) ng_colsum_.Resize(output_dim);
+    ng_colsum_.SetZero();
+  }
   {
     FastGradientScope fast(ctx);
     const bool want_s = s != NULL && model_linear_params != NULL;
     CheckStatus(tdnnf_darts_backprop_params(
         ctx, in_value.Data(), in_value.NumRows(), in_value.NumCols(), in_value.Stride(), out_deriv.Data(), out_deriv.NumRows(),
         out_deriv.NumCols(), out_deriv.Stride(), want_s ? model_linear_params->Data() : NULL,
-        want_s ? model_linear_params->Stride() : 0, ng_grad_.Data(), ng_grad_.Stride(), ng_colsum_.Data(), weff_dev,
+        want_s ? model_linear_params->Stride() : 0, ng_grad_.Data(), ng_grad_.Stride(), has_bias ? ng_colsum_.Data() : NULL, weff_dev,
         num_offsets, indexes.row_offsets.data(), indexes.row_stride, 1.0f, want_s ? s->Data() : NULL));
   }
-  CheckStatus(tdnnf_mat_axpy(ctx, 1.0f, ng_colsum_.Data(), 1, ng_grad_.Data() + spliced_input_dim, ng_grad_.Stride(),
-                             output_dim, 1));
+  if (has_bias)
+    CheckStatus(tdnnf_mat_axpy(ctx, 1.0f, ng_colsum_.Data(), 1, ng_grad_.Data() + spliced_input_dim, ng_grad_.Stride(),
+                               output_dim, 1));
   // out_deriv_hat^T X_hat = (I - W_o^T W_o) [ G - (out_deriv^T H_in) W_in ]: both projections are applied to the
   // D_out x D gradient (rank-r corrections) instead of to the R x D operands.
   if (!p_in.identity) {
@@ -373,7 +379,7 @@ void TdnnDARTSV3Component::PreconditionedUpdate(const PrecomputedIndexes& indexe
   //   bias           += local_lrate * out_deriv_hat^T precon_ones                  (tdnn.cc:607-617)
   CheckStatus(tdnnf_mat_axpy_dev(ctx, learning_rate_, p_in.scale_dev, p_out.scale_dev, ng_grad_.Data(), ng_grad_.Stride(),
                                  linear_params_.Data(), linear_params_.Stride(), output_dim, spliced_input_dim));
-  if (bias_params_.Dim() != 0)
+  if (has_bias)
     CheckStatus(tdnnf_mat_axpy_dev(ctx, learning_rate_, p_in.scale_dev, p_out.scale_dev, ng_grad_.Data() + spliced_input_dim,
                                    ng_grad_.Stride(), bias_params_.Data() + NumAlphaSlots(), 1, output_dim, 1));
 }
@@ -381,7 +387,8 @@ void TdnnDARTSV3Component::PreconditionedUpdate(const PrecomputedIndexes& indexe
 void TdnnDARTSV3Component::UpdateNaturalGradient(const PrecomputedIndexes& indexes,
                                                  const CuMatrixBase<BaseFloat>& in_value,
                                                  const CuMatrixBase<BaseFloat>& out_deriv,
-                                                 const CuMatrix& linear_params_temp_, const Memo& memo,
+                                                 const CuMatrix& linear_params_temp_,
+                                                 const CuVector& bias_params_temp_, const Memo& memo,
                                                  int32 share_offset_index_temp_, int32 model_flags,
                                                  BaseFloat temp_proportion_temp_) {  // tdnn.cc:457-626
   // `this` is the delta component (to_update); the model's parameters / flags arrive as arguments.
@@ -393,7 +400,8 @@ void TdnnDARTSV3Component::UpdateNaturalGradient(const PrecomputedIndexes& index
   // architecture weights: Jacobian products + the x5 / xlr / x10000 scalings       (tdnn.cc:541-590)
   CheckStatus(tdnnf_darts_alpha_update(CurrentContext(), s.Data(), memo.coef.Data(), num_offsets, model_flags,
                                        temp_proportion_temp_, share_offset_index_temp_, learning_rate_, bias_params_.Data()));
-  if (g_print_log_alpha) PrintLogAlpha(bias_params_.Data(), num_offsets);  // tdnn.cc:571 (prints the MODEL's alpha there)
+  // tdnn.cc:571 prints bias_params_temp_: the MODEL's log-alpha, not this delta component's scaled update
+  if (g_print_log_alpha) PrintLogAlpha(bias_params_temp_.Data(), num_offsets);
 }
 
 void TdnnDARTSV3Component::ReorderIndexes(std::vector<Index>* input_indexes, std::vector<Index>* output_indexes) const {

@@ -41,15 +41,17 @@ class OnlineNaturalGradient {
   OnlineNaturalGradient(const OnlineNaturalGradient& other);
   OnlineNaturalGradient& operator=(const OnlineNaturalGradient& other);
   ~OnlineNaturalGradient();
-  void SetRank(int32 rank) { rank_ = rank; }
-  void SetUpdatePeriod(int32 update_period) { update_period_ = update_period; }
-  void SetNumSamplesHistory(BaseFloat h) { num_samples_history_ = h; }
-  void SetAlpha(BaseFloat alpha) { alpha_ = alpha; }
+  // The setters first complete a refresh whose host half may still be running on a worker thread (it reads rank_,
+  // alpha_, d_t_, rho_t_): Read() / an edit config may call them between two minibatches.
+  void SetRank(int32 rank) { FinishPendingUpdate(); rank_ = rank; }
+  void SetUpdatePeriod(int32 update_period) { FinishPendingUpdate(); update_period_ = update_period; }
+  void SetNumSamplesHistory(BaseFloat h) { FinishPendingUpdate(); num_samples_history_ = h; }
+  void SetAlpha(BaseFloat alpha) { FinishPendingUpdate(); alpha_ = alpha; }
   int32 GetRank() const { return rank_; }
   int32 GetUpdatePeriod() const { return update_period_; }
   BaseFloat GetNumSamplesHistory() const { return num_samples_history_; }
   BaseFloat GetAlpha() const { return alpha_; }
-  void Freeze(bool frozen) { frozen_ = frozen; }
+  void Freeze(bool frozen) { FinishPendingUpdate(); frozen_ = frozen; }
   void Swap(OnlineNaturalGradient* other);
   // The upstream call: X_t <- X_hat_t, *scale on the host (synchronises the stream once).
   void PreconditionDirections(CuMatrixBase<BaseFloat>* X_t, BaseFloat* scale);
@@ -210,7 +212,8 @@ class TdnnDARTSV3Component : public UpdatableComponent {
                             const BaseFloat* weff_dev, CuVector* s);
   void UpdateNaturalGradient(const PrecomputedIndexes& indexes, const CuMatrixBase<BaseFloat>& in_value,
                              const CuMatrixBase<BaseFloat>& out_deriv, const CuMatrix& linear_params_temp_,
-                             const Memo& memo, int32 share_offset_index_temp_, int32 model_flags,
+                             const CuVector& bias_params_temp_, const Memo& memo, int32 share_offset_index_temp_,
+                             int32 model_flags,
                              BaseFloat temp_proportion_temp_);
   void UpdateSimple(const PrecomputedIndexes& indexes, const CuMatrixBase<BaseFloat>& in_value,
                     const CuMatrixBase<BaseFloat>& out_deriv);

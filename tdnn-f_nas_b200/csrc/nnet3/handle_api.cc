@@ -48,6 +48,13 @@ extern "C" {
 const char* tdnnf_nnet3_last_error(void) { return g_err.c_str(); }
 void tdnnf_nnet3_free(void* p) { std::free(p); }
 
+int tdnnf_nnet3_arena_begin(void* base, uint64_t bytes) { API_BEGIN DeviceArenaBegin(base, (size_t)bytes); API_END }
+int tdnnf_nnet3_arena_end(uint64_t* used) {
+  API_BEGIN
+  const size_t u = DeviceArenaEnd();
+  if (used) *used = u;
+  API_END
+}
 int tdnnf_nnet3_set_context(tdnnf_ctx* ctx) { API_BEGIN SetCurrentContext(ctx); API_END }
 int tdnnf_nnet3_set_rand_seed(uint64_t seed) { API_BEGIN SetRandSeed(seed); API_END }
 int tdnnf_nnet3_set_rand_counter(uint64_t c) { API_BEGIN SetRandCounter(c); API_END }

@@ -395,10 +395,34 @@ class DevicePool {
     static DevicePool* p = new DevicePool();  // leaked on purpose: outlives every static CuVector
     return *p;
   }
+  // Arena scope: between ArenaBegin and ArenaEnd every allocation of this thread is carved (256-byte aligned, in call
+  // order) from a caller-owned device range, so that e.g. the parameters of all the delta components of a network
+  // form ONE contiguous range for the data-parallel all-reduce.  Arena blocks are never recycled by the pool.
+  void ArenaBegin(void* base, size_t bytes) {
+    std::lock_guard<std::mutex> lk(mu_);
+    arena_base_ = static_cast<char*>(base);
+    arena_bytes_ = bytes;
+    arena_off_ = 0;
+    arenas_.push_back(std::make_pair(arena_base_, bytes));
+  }
+  size_t ArenaEnd() {
+    std::lock_guard<std::mutex> lk(mu_);
+    const size_t used = arena_off_;
+    arena_base_ = nullptr;
+    arena_bytes_ = arena_off_ = 0;
+    return used;
+  }
   void* Alloc(size_t bytes) {
     const Key k = MakeKey(bytes);
     {
       std::lock_guard<std::mutex> lk(mu_);
+      if (arena_base_ != nullptr) {
+        const size_t need = (bytes + 255) & ~(size_t)255;
+        if (arena_off_ + need > arena_bytes_) KALDI_ERR << "device arena exhausted (" << arena_bytes_ << " bytes)";
+        void* p = arena_base_ + arena_off_;
+        arena_off_ += need;
+        return p;
+      }
       auto it = free_.find(k);
       if (it != free_.end() && !it->second.empty()) {
         void* p = it->second.back();
@@ -413,6 +437,8 @@ class DevicePool {
   void Free(void* p, size_t bytes) {
     if (!p) return;
     std::lock_guard<std::mutex> lk(mu_);
+    for (const auto& a : arenas_)
+      if (static_cast<char*>(p) >= a.first && static_cast<char*>(p) < a.first + a.second) return;  // caller-owned
     free_[MakeKey(bytes)].push_back(p);
   }
 
@@ -428,6 +454,9 @@ class DevicePool {
   }
   std::mutex mu_;
   std::map<Key, std::vector<void*>> free_;
+  char* arena_base_ = nullptr;
+  size_t arena_bytes_ = 0, arena_off_ = 0;
+  std::vector<std::pair<char*, size_t>> arenas_;
 };
 
 // The stream the kernels run on (the legacy default stream when no context is selected): allocation zero-fills and
@@ -440,6 +469,12 @@ cudaStream_t WorkStream() {
 }
 void ZeroFill(void* p, size_t bytes) { CudaOk(cudaMemsetAsync(p, 0, bytes, WorkStream()), "cudaMemsetAsync"); }
 }  // namespace
+
+void DeviceArenaBegin(void* base, size_t bytes) {
+  KALDI_ASSERT(base != nullptr && (reinterpret_cast<uintptr_t>(base) & 255) == 0);
+  DevicePool::Get().ArenaBegin(base, bytes);
+}
+size_t DeviceArenaEnd() { return DevicePool::Get().ArenaEnd(); }
 
 CuVector::~CuVector() { DevicePool::Get().Free(data_, sizeof(BaseFloat) * (size_t)dim_); }
 void CuVector::Resize(int32 dim) {

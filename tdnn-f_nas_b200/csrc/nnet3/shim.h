@@ -159,6 +159,10 @@ class CuMatrix : public CuMatrixBase<BaseFloat> {
   void Read(std::istream& is, bool binary);
 };
 BaseFloat VecVec(const CuVector& a, const CuVector& b);
+// Between Begin and End every CuVector / CuMatrix allocation is carved, in call order and 256-byte aligned, from the
+// caller-owned device range [base, base + bytes); End returns the bytes used.  See DevicePool in shim.cc.
+void DeviceArenaBegin(void* base, size_t bytes);
+size_t DeviceArenaEnd();
 BaseFloat TraceMatMatTrans(const CuMatrix& a, const CuMatrix& b);  // TraceMatMat(a, b, kTrans)
 
 // ------------------------------------------------------------------ Kaldi token I/O (base/io-funcs.h)

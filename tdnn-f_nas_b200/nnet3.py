@@ -75,6 +75,24 @@ def rand_int(lo: int, hi: int) -> int:
     return int(_lib().tdnnf_nnet3_rand_int(int(lo), int(hi)))
 
 
+class arena:
+    """with nnet3.arena(ptr, nbytes) as a: ... components created / copied inside take their device parameters from
+    [ptr, ptr + nbytes) in creation order; a.used = bytes consumed (tdnnf_nnet3_arena_begin / _end)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.ptr, self.nbytes, self.used = ptr, nbytes, 0
+
+    def __enter__(self):
+        _check(_lib().tdnnf_nnet3_arena_begin(vp(self.ptr), C.c_uint64(self.nbytes)))
+        return self
+
+    def __exit__(self, *exc):
+        used = C.c_uint64(0)
+        _check(_lib().tdnnf_nnet3_arena_end(C.byref(used)))
+        self.used = int(used.value)
+        return False
+
+
 def set_dp_world_size(g: int):
     _check(_lib().tdnnf_nnet3_set_dp_world_size(g))
 

@@ -144,10 +144,14 @@ def _m(t):
 
 class Supernet:
     def __init__(self, cfg: SupernetConfig, device: int = 0, rank: int = 0, world_size: int = 1,
-                 process_group=None):
+                 process_group=None, dp_buckets: int = 1):
+        """dp_buckets: 1 = one in-place all-reduce of the whole delta arena after the backward pass; k > 1 = the arena is
+        cut into k buckets in backward order, each reduced on a side stream as soon as the backward pass has produced it
+        (tdnnf_dp_allreduce_bucket_async), the parameter step waits for all of them."""
         import torch
 
         self.cfg, self.rank, self.world, self.pg = cfg, rank, world_size, process_group
+        self.dp_buckets = max(1, int(dp_buckets))
         self.dev = torch.device("cuda", device)
         torch.cuda.set_device(self.dev)
         self.ctx = capi.Context(device)
@@ -189,9 +193,7 @@ class Supernet:
         def affine_params(din, dout, bias=True, zero=False):
             W = zeros(dout, din) if zero else randn(dout, din, 1.0 / np.sqrt(din))
             b = (torch.zeros(dout, device=dev) if zero else randn(1, dout, 0.1)[0]) if bias else None
-            dW = zeros(dout, din)
-            db = torch.zeros(dout, device=dev) if bias else None
-            return dict(W=W, b=b, dW=dW, db=db)
+            return dict(W=W, b=b, dW=None, db=None)  # the deltas live in the delta arena (_alloc_deltas)
 
         self.one = torch.ones(1, device=dev)
         self.zero_off = (C.c_int32 * 1)(0)
@@ -253,14 +255,12 @@ class Supernet:
                           map=None if contiguous else torch.from_numpy(by_rows).to(dev))
             rows_lin, rows_aff, rows_prev = len(lin_t[b]) * S, len(aff_t[b]) * S, len(prev_t) * S
             blk = dict(lin=lin, aff=aff, lin_idx=lin_idx, aff_idx=aff_idx, reorder=reorder, bypass=bypass,
-                       lin_delta=lin.copy(), aff_delta=aff.copy(), bn=make_bn(D),
+                       lin_delta=None, aff_delta=None, bn=make_bn(D),
                        lin_out=zeros(rows_lin, B), aff_in=zeros(reorder["rows"], B) if reorder else None,
                        aff_out=zeros(rows_aff, D), relu=zeros(rows_aff, D), bn_out=zeros(rows_aff, D), out=zeros(rows_aff, D),
                        d_out=zeros(rows_aff, D), d_aff=zeros(rows_aff, D), d_aff_in=zeros(reorder["rows"], B) if reorder else None,
                        d_lin=zeros(rows_lin, B), byp_tmp=None if contiguous else zeros(rows_aff, D),
                        memo_lin=C.c_void_p(), memo_aff=C.c_void_p(), rows_prev=rows_prev)
-            blk["lin_delta"].scale(0.0)
-            blk["aff_delta"].scale(0.0)
             if cfg.dropout:
                 blk.update(self._make_dropout(D, grid(aff_t[b]), rows_aff, zeros))
             self.blocks.append(blk)
@@ -292,10 +292,83 @@ class Supernet:
         self.num_graph = capi.NumeratorGraph(ctx, synth.make_num_graphs(S, P, T, seed=60 + self.rank, den_graph=graph))
         self.objective = chain.ChainObjective(ctx, self.den_graph, self.num_graph, S, T,
                                               chain.ChainTrainingOptions(leaky_hmm_coefficient=cfg.leaky_hmm))
+        self._alloc_deltas()
         self._compile()
         if search:
             self._freeze_batchnorm()
             self._compile()
+
+    def _backward_order(self):
+        """Updatable components in the order the backward pass finishes them (= their order in the delta arena)."""
+        head = ["output", "pc_linear", "pc_affine"] + (["output_xent", "px_linear", "px_affine"] if self.cfg.xent else []) + ["prefinal_l"]
+        order = [("stock", nm) for nm in head]
+        for b in range(len(self.blocks) - 1, -1, -1):
+            order += [("comp", (b, "aff")), ("comp", (b, "lin"))]
+        return order + [("stock", "tdnn1")]
+
+    def _alloc_deltas(self):
+        """delta_nnet_ as ONE device range (nnet3.arena): the delta copy of every updatable component, in backward order,
+        so that the data-parallel reduction is a single in-place ncclAllReduce (or a few contiguous buckets issued while
+        the backward pass is still running) instead of a gather / all-reduce / scatter."""
+        import torch
+
+        pad = lambda nbytes: (nbytes + 255) // 256 * 256
+        pitch = lambda cols: (cols + 63) // 64 * 64
+        total = 0
+        for kind, key in self._backward_order():
+            if kind == "stock":
+                p = self.stock[key]
+                total += pad(p["W"].numel() * 4) + (pad(p["b"].numel() * 4) if p["b"] is not None else 0)
+            else:
+                for _, r, c, _ in self.blocks[key[0]][key[1]].param_buffers():
+                    total += pad(r * (pitch(c) if r > 1 else c) * 4)
+        total += 4096
+        self.delta_arena = torch.zeros(total // 4, device=self.dev, dtype=torch.float32)
+        base = self.delta_arena.data_ptr()
+        assert base % 256 == 0
+        off = 0
+        self.delta_spans = []  # (kind, key, begin_float, end_float) in backward order
+        for kind, key in self._backward_order():
+            begin = off
+            if kind == "stock":
+                p = self.stock[key]
+                n = p["W"].numel()
+                p["dW"] = self.delta_arena[off // 4: off // 4 + n].view(p["W"].shape)
+                off += pad(n * 4)
+                if p["b"] is not None:
+                    nb = p["b"].numel()
+                    p["db"] = self.delta_arena[off // 4: off // 4 + nb]
+                    off += pad(nb * 4)
+            else:
+                blk = self.blocks[key[0]]
+                with nnet3.arena(base + off, total - off) as a:
+                    delta = blk[key[1]].copy()
+                delta.scale(0.0)
+                for ptr, _, _, _ in delta.param_buffers():
+                    assert base + off <= ptr < base + off + a.used, "delta parameters were not carved from the arena"
+                blk[key[1] + "_delta"] = delta
+                off += pad(a.used)
+            self.delta_spans.append((kind, key, begin // 4, off // 4))
+        self.delta_floats = off // 4
+        # buckets for the overlapped reduction: contiguous runs of spans of about equal size
+        k = min(self.dp_buckets, len(self.delta_spans))
+        self.delta_buckets = []   # (last (kind, key) of the bucket, begin_float, end_float)
+        target, start = self.delta_floats / k, 0
+        for i, (kind, key, b, e) in enumerate(self.delta_spans):
+            last = i == len(self.delta_spans) - 1
+            if last or (len(self.delta_buckets) < k - 1 and e >= target * (len(self.delta_buckets) + 1)):
+                self.delta_buckets.append(((kind, key), start, e))
+                start = e
+        self.dp = None
+        if self.world > 1:
+            import torch.distributed as dist
+
+            def exchange(ident: bytes) -> bytes:  # rank 0's NCCL id to everybody: plumbing over torch.distributed
+                t = torch.tensor(list(ident), dtype=torch.uint8, device=self.dev if dist.get_backend(self.pg) == "nccl" else "cpu")
+                dist.broadcast(t, src=0, group=self.pg)
+                return bytes(t.cpu().tolist())
+
+            self.dp = capi.DataParallel(self.ctx, self.world, self.rank, exchange)
 
     def _all_bn(self):
         return ([self.t1["bn"]] + [blk["bn"] for blk in self.blocks] +
@@ -401,6 +474,16 @@ class Supernet:
         plan.add("abi", lib.tdnnf_darts_backprop_params, h, xp, xr, xc, xs, dp, dr, dc, ds, None, 0, gp, gs,
                  C.c_void_p(p["db"].data_ptr()) if p["db"] is not None else None, one, 1, self.zero_off, 1, lr, None)
 
+    def _bucket_hook(self, plan, kind, key):
+        """Inside the backward plan: once the backward pass has finished the last component of a delta bucket, start its
+        all-reduce on the side stream (only with dp_buckets > 1 and more than one rank)."""
+        if self.dp is None or self.dp_buckets <= 1:
+            return
+        for (last, begin, end) in self.delta_buckets:
+            if last == (kind, key):
+                ptr, count = self.delta_arena.data_ptr() + 4 * begin, end - begin
+                plan.add_py(partial(self.dp.allreduce_bucket_async, ptr, count))
+
     def _bn_fwd(self, plan, bn, x, out):
         lib = self.lib
         xp, xr, xc, xs = _m(x)
@@ -496,12 +579,15 @@ class Supernet:
 
         # ---- backward (d_out of the output layer is filled by the objective)
         self._affine_bwd(bwd, hd["pb2"], st["output"], hd["d_out"], hd["d_pb2"], lr)
+        self._bucket_hook(bwd, "stock", "output")
         self._bn_bwd(bwd, hd["bn2"], hd["pb2"], hd["d_pb2"], hd["d_pb2"])
         self._affine_bwd(bwd, hd["pb"], st["pc_linear"], hd["d_pb2"], hd["d_pb"], lr)
+        self._bucket_hook(bwd, "stock", "pc_linear")
         self._bn_bwd(bwd, hd["bn1"], hd["pb"], hd["d_pb"], hd["d_pb"])
         bwd.add("abi", lib.tdnnf_relu_bwd, h, _m(hd["pr"])[0], _m(hd["pr"])[3], _m(hd["d_pb"])[0], _m(hd["d_pb"])[3],
                 _m(hd["d_pa"])[0], _m(hd["d_pa"])[3], hd["pr"].shape[0], hd["pr"].shape[1])
         self._affine_bwd(bwd, hd["pl"], st["pc_affine"], hd["d_pa"], hd["d_pl"], lr)
+        self._bucket_hook(bwd, "stock", "pc_affine")
         if cfg.xent:
             # output-xent: d_xls = xent_regularize * numerator posteriors (filled by the objective); its affine runs at
             # learning-rate-factor 0.5 / xent_regularize (the recipes' `learning_rate_factor`)
@@ -509,14 +595,18 @@ class Supernet:
             bwd.add("nnet3", lib.tdnnf_nnet3_backprop, hd["log_softmax"].h, None, None, xr_, xc_, 0, xp_, xs_, _m(hd["d_xls"])[0], xr_, xc_,
                     _m(hd["d_xls"])[3], None, None, _m(hd["d_xls"])[0], _m(hd["d_xls"])[3])
             self._affine_bwd(bwd, hd["xb2"], st["output_xent"], hd["d_xls"], hd["d_xb2"], lr * 0.5 / self.objective.opts.xent_regularize)
+            self._bucket_hook(bwd, "stock", "output_xent")
             self._bn_bwd(bwd, hd["xbn2"], hd["xb2"], hd["d_xb2"], hd["d_xb2"])
             self._affine_bwd(bwd, hd["xb"], st["px_linear"], hd["d_xb2"], hd["d_xb"], lr)
+            self._bucket_hook(bwd, "stock", "px_linear")
             self._bn_bwd(bwd, hd["xbn1"], hd["xb"], hd["d_xb"], hd["d_xb"])
             bwd.add("abi", lib.tdnnf_relu_bwd, h, _m(hd["xr"])[0], _m(hd["xr"])[3], _m(hd["d_xb"])[0], _m(hd["d_xb"])[3],
                     _m(hd["d_xa"])[0], _m(hd["d_xa"])[3], hd["xr"].shape[0], hd["xr"].shape[1])
             self._affine_bwd(bwd, hd["pl"], st["px_affine"], hd["d_xa"], hd["d_pl"], lr, zero=False)
+            self._bucket_hook(bwd, "stock", "px_affine")
         last = self.blocks[-1]
         self._affine_bwd(bwd, last["out"], st["prefinal_l"], hd["d_pl"], last["d_out"], lr)
+        self._bucket_hook(bwd, "stock", "prefinal_l")
         for bi in range(len(self.blocks) - 1, -1, -1):
             blk = self.blocks[bi]
             prev_out = self.blocks[bi - 1]["out"] if bi > 0 else t1["out"]
@@ -570,6 +660,7 @@ class Supernet:
             bwd.add("nnet3", lib.tdnnf_nnet3_backprop, blk["aff"].h, blk["aff_idx"].h, ip, ir, ic, is_, None, 0,
                     _m(blk["d_aff"])[0], dr, dc, _m(blk["d_aff"])[3], blk["memo_aff"], blk["aff_delta"].h, gp, gs)
             bwd.add("nnet3", lib.tdnnf_nnet3_delete_memo, blk["aff"].h, blk["memo_aff"])
+            self._bucket_hook(bwd, "comp", (bi, "aff"))
             if blk["reorder"]:
                 lp, lr_, lc, ls = _m(blk["d_lin"])
                 bwd.add("abi", lib.tdnnf_copy_rows, h, gp, gs, lp, ls, lr_, lc, C.c_void_p(blk["reorder"]["inv"].data_ptr()))
@@ -579,6 +670,7 @@ class Supernet:
             bwd.add("nnet3", lib.tdnnf_nnet3_backprop, blk["lin"].h, blk["lin_idx"].h, pp, pr, pc, ps, None, 0, lp, lr_, lc, ls,
                     blk["memo_lin"], blk["lin_delta"].h, qp, qs)
             bwd.add("nnet3", lib.tdnnf_nnet3_delete_memo, blk["lin"].h, blk["memo_lin"])
+            self._bucket_hook(bwd, "comp", (bi, "lin"))
         if cfg.dropout:
             self._dropout_bwd(bwd, t1, t1["d_out"], t1["d_out"])
             self._bn_bwd(bwd, t1["bn"], t1["drop_in"], t1["d_out"], t1["d_out"])
@@ -587,6 +679,7 @@ class Supernet:
         bwd.add("abi", lib.tdnnf_relu_bwd, h, _m(t1["relu"])[0], _m(t1["relu"])[3], _m(t1["d_out"])[0], _m(t1["d_out"])[3],
                 _m(t1["d_aff"])[0], _m(t1["d_aff"])[3], t1["relu"].shape[0], t1["relu"].shape[1])
         self._affine_bwd(bwd, self.x, st["tdnn1"], t1["d_aff"], None, lr)
+        self._bucket_hook(bwd, "stock", "tdnn1")
 
         # ---- parameter step (UpdateNnetWithMaxChange, utils.cc:2085-2175): squared norms of every delta on the
         # device, ONE read-back, Kaldi's per-component / global max-change factors on the host, scaled Add.
@@ -598,7 +691,6 @@ class Supernet:
             self.updatables.append(("comp", blk["aff"], blk["aff_delta"], cfg.max_change))
         for name, p in st.items():
             self.updatables.append(("stock", p, None, 1.5 if name.startswith("output") else cfg.max_change))
-        self.dots = torch.zeros(len(self.updatables), dtype=torch.float64, device=self.dev)
         # every parameter buffer of the model with the matching delta buffer: (model ptr, stride, delta ptr, stride, rows, cols, group)
         bufs = []
         for i, (kind, m, d, _) in enumerate(self.updatables):
@@ -613,51 +705,24 @@ class Supernet:
                 if m["b"] is not None:
                     n = m["b"].numel()
                     bufs.append((m["b"].data_ptr(), n, m["db"].data_ptr(), n, 1, n, i))
-        nb = len(bufs)
-        PtrArr, IntArr, FltArr = C.c_void_p * nb, C.c_int32 * nb, C.c_float * nb
-        self.upd_tab = dict(n=nb, model=PtrArr(*[b[0] for b in bufs]), model_ld=IntArr(*[b[1] for b in bufs]),
-                            delta=PtrArr(*[b[2] for b in bufs]), delta_ld=IntArr(*[b[3] for b in bufs]),
-                            rows=IntArr(*[b[4] for b in bufs]), cols=IntArr(*[b[5] for b in bufs]),
-                            group=IntArr(*[b[6] for b in bufs]), factors=FltArr(), group_list=[b[6] for b in bufs])
-        # Data-parallel reduction of the deltas: ONE flat all-reduce after the backward pass.  (Per-block
-        # all-reduces overlapped with the backward GEMMs were measured slower: the persistent GEMM kernels own
-        # every SM (226 KB smem per CTA), so a concurrent NCCL kernel delays a whole wave of their CTAs; and ~60
-        # separate 1-7 MB all-reduces are latency-bound.)
-        if self.world > 1:
-            import torch
-
-            views = []
-            for blk in self.blocks:
-                views += self._views_of([blk["aff_delta"], blk["lin_delta"]])
-            for p in st.values():
-                views.append(p["dW"].view(-1))
-                if p["db"] is not None:
-                    views.append(p["db"])
-            self.delta_views = views
-            self.delta_flat = torch.empty(sum(v.numel() for v in views), device=self.dev, dtype=torch.float32)
-            self.delta_chunks = list(torch.split(self.delta_flat, [v.numel() for v in views]))
+        self.param_table = capi.ParamTable(self.ctx, bufs, [u[3] for u in self.updatables])
+        # per updatable component: learning rate and l2-regularize of ApplyL2Regularization (utils.cc:2223-2245)
+        self.l2_lrate, self.l2_value = [], []
+        for kind, m, d, _ in self.updatables:
+            if kind == "comp":
+                self.l2_lrate.append(d.learning_rate())
+                self.l2_value.append(cfg.l2_regularize)
+        for name in st:
+            self.l2_lrate.append(cfg.learning_rate * (0.5 / self.objective.opts.xent_regularize if name == "output_xent" else 1.0))
+            self.l2_value.append(0.002 if name.startswith("output") else cfg.l2_regularize)  # output_opts (run_tdnn_7q_fbk_40_manual.sh:123)
         self.fwd_plan, self.bwd_plan = fwd, bwd
 
-    def _views_of(self, deltas):
-        """The parameter buffers of delta components as flat torch views (pitch padding included: it is zero)."""
-        import torch
-
-        class _Arr:
-            def __init__(self, ptr, nelem):
-                self.__cuda_array_interface__ = dict(shape=(nelem,), typestr="<f4", data=(ptr, False), version=2, strides=None)
-
-        views = []
-        for d in deltas:
-            for ptr, rows, cols, stride in d.param_buffers():
-                views.append(torch.as_tensor(_Arr(ptr, rows * stride), device=self.dev))
-        return views
-
     def _allreduce_deltas(self):
-        import torch
-
-        torch._foreach_copy_(self.delta_chunks, self.delta_views)      # gather (device-to-device, one multi-tensor kernel)
-        parallel.allreduce_deltas([self.delta_flat], self.pg)          # NCCL all-reduce(sum) over NVLink
-        torch._foreach_copy_(self.delta_views, self.delta_chunks)      # scatter back into the delta components
+        """Sum of the ranks' deltas (tdnnf_dp_*: NCCL over NVLink through the C ABI), in place on the delta arena."""
+        if self.dp_buckets > 1:
+            self.dp.wait()  # the buckets were issued from inside the backward plan
+        else:
+            self.dp.allreduce([(self.delta_arena.data_ptr(), self.delta_floats)])
 
     # ------------------------------------------------------------------ public API
     @property
@@ -694,9 +759,11 @@ class Supernet:
             self.last_xent_objf = self.objective.xent_objf_and_deriv(self.head["xls"], self.head["d_xls"]) / weight
         else:
             objf, _, weight = self.objective.compute(self.head["out"], self.head["d_out"])
-        self.bwd_plan.run()
         if cfg.l2_regularize != 0.0:
+            # additive and independent of the derivatives: applied before the backward pass so that the overlapped
+            # bucket reductions (dp_buckets > 1) see complete deltas
             self._apply_l2_regularization()
+        self.bwd_plan.run()
         if self.world > 1:
             self._allreduce_deltas()
         if apply_update:
@@ -708,23 +775,7 @@ class Supernet:
         """ApplyL2Regularization (utils.cc:2223-2245): delta += -2 * l2_regularize_scale * lrate * l2 * model for every
         updatable component, l2_regularize_scale = the number of sequences of the minibatch (NnetChainTrainer passes
         GetNumNvalues() * l2_regularize_factor).  Each rank adds its share (its own sequences), the all-reduce sums."""
-        cfg, lib, h = self.cfg, self.lib, self.ctx.h
-        scale = -2.0 * cfg.num_seqs * cfg.learning_rate * cfg.l2_regularize
-        for blk in self.blocks:
-            for k in ("lin", "aff"):
-                blk[k + "_delta"].add(scale * blk[k].learning_rate() / cfg.learning_rate, blk[k])
-        for name, p in self.stock.items():
-            l2 = 0.002 if name.startswith("output") else cfg.l2_regularize  # output_opts (run_tdnn_7q_fbk_40_manual.sh:123)
-            lrate = cfg.learning_rate * (0.5 / self.objective.opts.xent_regularize if name == "output_xent" else 1.0)
-            sc = -2.0 * cfg.num_seqs * lrate * l2
-            wp, wr, wc, ws = _m(p["W"])
-            gp, _, _, gs = _m(p["dW"])
-            if lib.tdnnf_mat_axpy(h, sc, wp, ws, gp, gs, wr, wc) != 0:
-                raise RuntimeError(lib.tdnnf_last_error().decode())
-            if p["b"] is not None:
-                nb = p["b"].numel()
-                if lib.tdnnf_mat_axpy(h, sc, C.c_void_p(p["b"].data_ptr()), nb, C.c_void_p(p["db"].data_ptr()), nb, 1, nb) != 0:
-                    raise RuntimeError(lib.tdnnf_last_error().decode())
+        self.param_table.apply_l2_regularization(self.l2_lrate, self.l2_value, float(self.cfg.num_seqs))
 
     def _after_update(self):
         """What NnetChainTrainer::TrainInternal does after the parameter step: ConstrainOrthonormal(nnet_)
@@ -744,35 +795,13 @@ class Supernet:
                     bn["comp"].scale(cfg.batchnorm_stats_scale)
 
     def _update_with_max_change(self, scale: float = 1.0, max_change_scale: float = 1.0):
-        """UpdateNnetWithMaxChange + ScaleNnet(momentum=0) (utils.cc:2085-2175, common.py:877-878)."""
-        cfg, lib, h = self.cfg, self.lib, self.ctx.h
-        t = self.upd_tab
-        self.dots.zero_()
-        # squared norm of every component's delta: ONE launch over all parameter buffers
-        if lib.tdnnf_multi_sumsq(h, t["n"], t["delta"], t["rows"], t["cols"], t["delta_ld"], t["group"],
-                                 C.c_void_p(self.dots.data_ptr())) != 0:
-            raise RuntimeError(lib.tdnnf_last_error().decode())
-        dots = self.dots.cpu().numpy()  # the step's second (and last) host sync
-        factors = np.ones(len(dots))
-        param_delta_squared = 0.0
-        for i, (_, _, _, mc) in enumerate(self.updatables):
-            norm = float(np.sqrt(dots[i])) * abs(scale)
-            if mc != 0.0 and norm > mc * max_change_scale:
-                factors[i] = mc * max_change_scale / norm
-            param_delta_squared += factors[i] ** 2 * dots[i]
-        param_delta = float(np.sqrt(param_delta_squared)) * abs(scale)
-        if cfg.max_param_change != 0.0 and param_delta > cfg.max_param_change * max_change_scale:
-            if not np.isfinite(param_delta):
-                factors[:] = 0.0  # "Infinite parameter change, will not apply."
-            else:
-                scale *= cfg.max_param_change * max_change_scale / param_delta
-        self.last_max_change_factors = factors * scale
-        # model += factor * delta, delta = 0 (ScaleNnet(momentum = 0)): ONE launch over all parameter buffers
-        for k, g in enumerate(t["group_list"]):
-            t["factors"][k] = float(self.last_max_change_factors[g])
-        if lib.tdnnf_multi_axpy_zero(h, t["n"], t["model"], t["model_ld"], t["delta"], t["delta_ld"], t["rows"], t["cols"],
-                                     t["factors"]) != 0:
-            raise RuntimeError(lib.tdnnf_last_error().decode())
+        """UpdateNnetWithMaxChange + ScaleNnet(momentum=0) (utils.cc:2085-2175, common.py:877-878): one C call
+        (tdnnf_update_with_max_change).  Returns False where the reference refuses an infinite parameter change (the
+        model is then untouched and the deltas are zeroed)."""
+        t = self.param_table
+        self.last_update_applied = t.update_with_max_change(self.cfg.max_param_change, max_change_scale, scale, momentum=0.0)
+        self.last_max_change_factors = np.array(list(t.factors), dtype=np.float64)
+        return self.last_update_applied
 
     def _raise_nnet3(self):
         raise RuntimeError(self.lib.tdnnf_nnet3_last_error().decode())
@@ -781,6 +810,9 @@ class Supernet:
         import torch
 
         torch.cuda.synchronize(self.dev)
+        if getattr(self, "dp", None) is not None:
+            self.dp.close()
+            self.dp = None
         self.objective.close()
         self.num_graph.close()
         self.den_graph.close()

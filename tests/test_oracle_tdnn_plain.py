@@ -67,6 +67,41 @@ def test_plain_tdnn_matches_numpy(offsets, row_stride, use_bias):
         assert rel_err(db2, db) < 2e-6
 
 
+@pytest.mark.parametrize("use_bias", [True, False])
+def test_plain_tdnn_natural_gradient_matches_float64(use_bias):
+    """UpdateNaturalGradient of the stock TdnnComponent against a float64 restatement from the equations: the input
+    operand is [X_1 | ... | X_n] with the column of ones appended ONLY when the component has a bias
+    (tdnn.cc:477-478, bias_params_.Dim() != 0; the `linear` halves of the TDNN-F layers have none)."""
+    offsets, row_stride, n, din, dout, S, t_out, lr = [-3, 0], 1, 2, 24, 18, 6, 20, 0.05
+    g, x, W, b, od, ro = _case(n, din, dout, S, t_out, offsets, row_stride, seed=11)
+    out_rows = od.shape[0]
+    rank_in, rank_out = 7, 5
+    ng_in, ng_out = O.NaturalGradient(rank_in, 4, 2000.0, 4.0), O.NaturalGradient(rank_out, 4, 2000.0, 4.0)
+    ref_in, ref_out = R.NaturalGradientF64(rank_in, 4, 2000.0, 4.0), R.NaturalGradientF64(rank_out, 4, 2000.0, 4.0)
+    dW = np.zeros_like(W)
+    db = np.zeros(dout, np.float32) if use_bias else None
+    dW_r, db_r = np.zeros(W.shape), np.zeros(dout)
+    for step in range(3):
+        xs = (x + 0.1 * step * g.standard_normal(x.shape)).astype(np.float32)
+        ods = (od * (1.0 + 0.2 * step)).astype(np.float32)
+        O.plain_tdnn_backprop(W, xs, ods, ro, row_stride, lr, dW=dW, dbias=db, natural_gradient=True, ng_in=ng_in, ng_out=ng_out)
+        cols = [xs[o: o + out_rows * row_stride: row_stride][:out_rows].astype(np.float64) for o in ro]
+        if use_bias:
+            cols.append(np.ones((out_rows, 1)))
+        X = np.concatenate(cols, axis=1)
+        assert X.shape[1] == n * din + (1 if use_bias else 0)
+        Xh, s_in = ref_in.precondition(X)
+        Dh, s_out = ref_out.precondition(ods.astype(np.float64))
+        G = lr * s_in * s_out * Dh.T @ Xh
+        dW_r += G[:, : n * din]
+        if use_bias:
+            db_r += G[:, n * din]
+        assert rel_err(dW, dW_r) < 5e-4, (step, rel_err(dW, dW_r))
+        if use_bias:
+            assert rel_err(db, db_r) < 5e-4
+    assert ng_in.state()["D"] == n * din + (1 if use_bias else 0)
+
+
 def test_plain_tdnn_is_darts_with_unit_weights():
     """TdnnDARTSV3 in uniform-sample mode with the sampled slot == the shared slot is a single-offset TdnnComponent; with
     free-select and sigmoid(alpha) -> 1 it is the all-offsets TdnnComponent (the two classes share every GEMM)."""
