@@ -361,6 +361,12 @@ int tdnnf_den_graph_destroy(tdnnf_den_graph* g);
 int tdnnf_den_create(tdnnf_ctx* ctx, const tdnnf_den_graph* g, int num_seqs, int frames_per_seq,
                      float leaky_hmm_coefficient, tdnnf_den_comp** out);
 int tdnnf_den_destroy(tdnnf_den_comp* c);
+/* Which kernels this computation runs: *path = 2 sequence-slice clusters (one launch per direction: a cluster of *cluster
+ * CTAs per slice of 8 sequences, E(t) staged in shared memory in *parts pdf ranges, *ctas CTAs in all), 0 = one launch
+ * per frame and direction (num_seqs not a multiple of 8, 8 x num_pdfs floats beyond shared memory, too few slices to
+ * fill the chip, or TDNNF_DEN_PATH=frames), 1 = the opt-in resident experiment (TDNNF_DEN_RESIDENT=1).
+ * Environment: TDNNF_DEN_PATH=frames|slices, TDNNF_DEN_PARTS=1|2, TDNNF_DEN_CLUSTER=1..16. */
+int tdnnf_den_describe(const tdnnf_den_comp* c, int* path, int* cluster, int* parts, int* ctas);
 /* Forward(): returns the total log-prob summed over sequences in *logprob (HOST; this call
  * synchronises the stream -- the reference returns the scalar the same way). */
 int tdnnf_den_forward(tdnnf_den_comp* c, const float* nnet_output, int stride, float* logprob);

@@ -19,7 +19,7 @@ LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libtdnnf_nas_b200.so")
 
-CUDA_SOURCES = ["context.cu", "splice_gemm.cu", "mixing.cu", "den.cu", "num.cu", "neighbours.cu", "ng.cu", "orthonormal.cu", "chain_step.cu"]
+CUDA_SOURCES = ["context.cu", "splice_gemm.cu", "mixing.cu", "den.cu", "den_slices.cu", "num.cu", "neighbours.cu", "ng.cu", "orthonormal.cu", "chain_step.cu"]
 CXX_SOURCES = [
     "nnet3/shim.cc",
     "nnet3/indexes.cc",

@@ -93,6 +93,7 @@ def _declare(lib):
     sig("tdnnf_den_graph_destroy", [vp])
     sig("tdnnf_den_create", [vp, vp, i, i, f, C.POINTER(vp)])
     sig("tdnnf_den_destroy", [vp])
+    sig("tdnnf_den_describe", [vp, c_int_p, c_int_p, c_int_p, c_int_p])
     sig("tdnnf_den_forward", [vp, vp, i, c_float_p])
     sig("tdnnf_den_backward", [vp, f, vp, i, c_int_p])
     sig("tdnnf_update_with_max_change", [vp, i, vp, vp, vp, vp, vp, vp, vp, i, c_float_p, f, f, f, f, vp, c_float_p, c_int_p,
@@ -530,6 +531,12 @@ class DenominatorComputation:
         h = vp()
         check(load().tdnnf_den_create(ctx.h, graph.h, num_seqs, frames_per_seq, leaky, C.byref(h)))
         self.h = h
+
+    def describe(self) -> dict:
+        """Which kernels run: path 'slices' (cluster size, E parts, CTAs), 'frames' or 'resident'."""
+        a, b, c, d = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        check(load().tdnnf_den_describe(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(path={0: "frames", 1: "resident", 2: "slices"}[a.value], cluster=b.value, parts=c.value, ctas=d.value)
 
     def forward(self, nnet_output) -> float:
         p, r, c, s = _mat(nnet_output)

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "context.h"
+#include "den_slices.h"
 
 using namespace tdnnf;
 
@@ -37,7 +38,7 @@ struct tdnnf_den_graph {
   float init_sum = 0.f;         // sum_h init[h] (host copy, fp32 sequential sum)
   // host copies for the per-computation arc plans of the resident kernels (den2_*)
   std::vector<int> h_fwd_ranges, h_bwd_ranges, h_pdf, h_state;
-  std::vector<float> h_prob;
+  std::vector<float> h_prob, h_init;
 };
 
 // One direction of the resident kernels' work list.  States are sorted by arc count and cut into warp-tasks of 32
@@ -77,6 +78,8 @@ struct tdnnf_den_comp {
   int V = 0, C = 0, state_bits = 0;
   DenPlan plan_fwd, plan_bwd;
   size_t smem_fwd = 0, smem_bwd = 0;
+  // sequence-slice path (den_slices.cu): the default wherever it applies
+  tdnnf_den_slices* slices = nullptr;
 };
 
 namespace {
@@ -734,6 +737,7 @@ extern "C" int tdnnf_den_graph_create(tdnnf_ctx* ctx, int num_states, int num_pd
   g->h_prob.assign(trans_prob, trans_prob + num_transitions);
   g->h_pdf.assign(trans_pdf, trans_pdf + num_transitions);
   g->h_state.assign(trans_state, trans_state + num_transitions);
+  g->h_init.assign(initial_probs, initial_probs + num_states);
   cudaError_t e = cudaSuccess;
   auto up = [&](void** dst, const void* src, size_t bytes) {
     if (e != cudaSuccess) return;
@@ -834,16 +838,26 @@ extern "C" int tdnnf_den_create(tdnnf_ctx* ctx, const tdnnf_den_graph* g, int nu
       }
     }
   }
+  if (!c->resident) {
+    const int rc = den_slices_create(ctx, (int)N, (int)P, (int)S, (int)T, g->h_fwd_ranges, g->h_bwd_ranges, g->h_prob, g->h_pdf,
+                                     g->h_state, g->h_init, &c->slices);
+    if (rc != TDNNF_OK) {
+      tdnnf_den_destroy(c);
+      return rc;
+    }
+  }
   cudaError_t e = cudaSuccess;
   auto al = [&](void** p, size_t bytes) {
     if (e == cudaSuccess) e = cudaMalloc(p, bytes);
   };
-  al(reinterpret_cast<void**>(&c->E), sizeof(float) * T * P * S);
-  al(reinterpret_cast<void**>(&c->alpha), sizeof(float) * (T + 1) * N * S);
+  if (!c->slices) {  // the slice path keeps E / alpha / beta / gamma in its own layouts
+    al(reinterpret_cast<void**>(&c->E), sizeof(float) * T * P * S);
+    al(reinterpret_cast<void**>(&c->alpha), sizeof(float) * (T + 1) * N * S);
+    al(reinterpret_cast<void**>(&c->betad), sizeof(float) * 2 * N * S);
+    al(reinterpret_cast<void**>(&c->gamma), sizeof(float) * T * P * S);
+  }
   al(reinterpret_cast<void**>(&c->tot), sizeof(float) * (T + 1) * S);
-  al(reinterpret_cast<void**>(&c->betad), sizeof(float) * 2 * N * S);
   al(reinterpret_cast<void**>(&c->bsum), sizeof(float) * (c->resident ? (T + 1) : 2) * S);
-  al(reinterpret_cast<void**>(&c->gamma), sizeof(float) * T * P * S);
   al(reinterpret_cast<void**>(&c->tot_prob), sizeof(float) * S);
   al(reinterpret_cast<void**>(&c->scalars), sizeof(double) * 2);
   if (e != cudaSuccess) {
@@ -866,7 +880,23 @@ extern "C" int tdnnf_den_destroy(tdnnf_den_comp* c) {
   cudaFree(c->scalars);
   c->plan_fwd.destroy();
   c->plan_bwd.destroy();
+  den_slices_destroy(c->slices);
   delete c;
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_den_describe(const tdnnf_den_comp* c, int* path, int* cluster, int* parts, int* ctas) {
+  TDNNF_REQUIRE(c && path && cluster && parts && ctas, "null argument");
+  *path = 0;
+  *cluster = *parts = *ctas = 0;
+  if (c->slices) {
+    *path = 2;
+    den_slices_describe(c->slices, cluster, parts, ctas);
+  } else if (c->resident) {
+    *path = 1;
+    *cluster = c->C;
+    *ctas = (c->S / c->V) * c->C;
+  }
   return TDNNF_OK;
 }
 
@@ -884,6 +914,18 @@ extern "C" int tdnnf_den_forward(tdnnf_den_comp* c, const float* nnet_output, in
   TDNNF_REQUIRE(stride >= P, "stride < num_pdfs");
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
+  if (c->slices) {
+    int rc = den_slices_forward(ctx, c->slices, nnet_output, stride, g->init, g->init_sum, N, P, S, T, c->leaky, c->tot);
+    if (rc) return rc;
+    den_loglike_kernel<<<1, 256, 0, st>>>(c->tot, T, S, c->leaky, g->init_sum, c->tot_prob, c->scalars);
+    DEN_LAUNCH_CHECK(ctx);
+    double lp = 0.0;
+    TDNNF_CUDA_OK(cudaMemcpyAsync(&lp, c->scalars, sizeof(double), cudaMemcpyDeviceToHost, st));
+    TDNNF_CUDA_OK(cudaStreamSynchronize(st));
+    *logprob = (float)lp;
+    c->forward_done = true;
+    return TDNNF_OK;
+  }
   if (c->resident) {
     const int V = c->V, C = c->C;
     den2_exp_kernel<<<dim3((P + 31) / 32, (S + 31) / 32, T), dim3(32, 8), 0, st>>>(nnet_output, stride, S, P, V, c->E);
@@ -959,8 +1001,18 @@ extern "C" int tdnnf_den_backward(tdnnf_den_comp* c, float deriv_weight, float* 
   TDNNF_REQUIRE(stride >= P, "stride < num_pdfs");
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  TDNNF_CUDA_OK(cudaMemsetAsync(c->gamma, 0, sizeof(float) * (size_t)T * P * S, st));
   TDNNF_CUDA_OK(cudaMemsetAsync(c->scalars + 1, 0, sizeof(double), st));
+  if (c->slices) {
+    int rc = den_slices_backward(ctx, c->slices, g->init, g->init_sum, N, P, S, T, c->leaky, c->tot, c->tot_prob, deriv_weight,
+                                 nnet_output_deriv, stride, c->scalars + 1);
+    if (rc) return rc;
+    double chk = 0.0;
+    TDNNF_CUDA_OK(cudaMemcpyAsync(&chk, c->scalars + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
+    TDNNF_CUDA_OK(cudaStreamSynchronize(st));
+    *ok = (chk == chk && fabs(chk - (double)S) <= 2.0) ? 1 : 0;
+    return TDNNF_OK;
+  }
+  TDNNF_CUDA_OK(cudaMemsetAsync(c->gamma, 0, sizeof(float) * (size_t)T * P * S, st));
   if (c->resident) {
     const int V = c->V, C = c->C;
     TDNNF_CUDA_OK(cudaMemsetAsync(c->bsum, 0, sizeof(float) * (size_t)(T + 1) * S, st));

@@ -8,17 +8,21 @@ from tests.util import rel_err
 pytestmark = pytest.mark.gpu
 
 
-def _run_gpu(ctx, graph, x, S, T, leaky, w):
+def _run_gpu(ctx, graph, x, S, T, leaky, w, want_path=None, pad=0, repeat=1):
     import torch
 
     from tdnnf_nas_b200 import capi
 
     dg = capi.DenGraph(ctx, graph)
     dc = capi.DenominatorComputation(ctx, dg, S, T, leaky)
-    xd = torch.from_numpy(x).cuda()
-    lp = dc.forward(xd)
-    deriv = torch.zeros_like(xd)
-    ok = dc.backward(w, deriv)
+    if want_path is not None:
+        assert dc.describe()["path"] == want_path, dc.describe()
+    P = x.shape[1]
+    xd = torch.from_numpy(np.pad(x, ((0, 0), (0, pad)), constant_values=99.0)).cuda()[:, :P]  # stride > cols like a CuMatrix pitch
+    for _ in range(repeat):  # a second call reuses every workspace
+        lp = dc.forward(xd)
+        deriv = torch.zeros((x.shape[0], P + pad), device="cuda")[:, :P]
+        ok = dc.backward(w, deriv)
     torch.cuda.synchronize()
     out = deriv.cpu().numpy()
     dc.close()
@@ -28,10 +32,12 @@ def _run_gpu(ctx, graph, x, S, T, leaky, w):
 
 @pytest.mark.parametrize("N,P,S,T,deg", [(40, 12, 3, 5, 3.0), (300, 50, 32, 9, 6.0), (500, 200, 64, 12, 8.0),
                                           (1000, 300, 128, 7, 16.0), (257, 33, 20, 4, 5.0)])
-def test_den_parity(ctx, N, P, S, T, deg):
+def test_den_parity(ctx, monkeypatch, N, P, S, T, deg):
+    """The per-frame kernels (any num_seqs)."""
     from oracle import oracle as O
     from tdnnf_nas_b200 import synth
 
+    monkeypatch.setenv("TDNNF_DEN_PATH", "frames")
     graph = synth.make_den_graph(N, P, deg, seed=N)
     g = np.random.default_rng(N + S)
     x = np.clip(g.standard_normal((T * S, P)) * 2.0, -30, 30).astype(np.float32)
@@ -44,6 +50,52 @@ def test_den_parity(ctx, N, P, S, T, deg):
     assert rel_err(d, d_ref) < 1e-3
     # posterior mass: -deriv sums to 1 per (t, s)
     np.testing.assert_allclose(-d.sum(axis=1), 1.0, rtol=2e-3)
+
+
+@pytest.mark.parametrize("parts", [1, 2])
+@pytest.mark.parametrize("N,P,S,T,deg,cluster", [(40, 12, 8, 5, 3.0, 1), (300, 50, 32, 9, 6.0, 16), (500, 203, 64, 12, 8.0, 16),
+                                                  (1000, 300, 128, 7, 16.0, 9), (257, 33, 16, 4, 5.0, 3), (2000, 601, 24, 6, 12.0, 8),
+                                                  (16, 7, 8, 3, 2.0, 4), (700, 90, 40, 1, 9.0, 2)])
+def test_den_slice_path_parity(ctx, monkeypatch, N, P, S, T, deg, cluster, parts):
+    """The sequence-slice cluster kernels (den_slices.cu; the default for Switchboard-sized minibatches), forced here on
+    small shapes: cluster sizes 1..16 (more CTAs than warp-tasks included), E staged in one or two pdf ranges, pdf counts
+    that are not multiples of 4, state counts that are not multiples of 16, strided matrices, T = 1, two calls."""
+    from oracle import oracle as O
+    from tdnnf_nas_b200 import synth
+
+    monkeypatch.setenv("TDNNF_DEN_PATH", "slices")
+    monkeypatch.setenv("TDNNF_DEN_PARTS", str(parts))
+    monkeypatch.setenv("TDNNF_DEN_CLUSTER", str(cluster))
+    graph = synth.make_den_graph(N, P, deg, seed=N)
+    g = np.random.default_rng(N + S)
+    x = np.clip(g.standard_normal((T * S, P)) * 2.0, -30, 30).astype(np.float32)
+    x[0, 0] = 40.0
+    x[1, 1] = -45.0
+    lp_ref, d_ref, ok_ref = O.den_forward_backward(graph, x, S, T, 0.1, deriv_weight=-1.0)
+    lp, d, ok = _run_gpu(ctx, graph, x, S, T, 0.1, -1.0, want_path="slices", pad=3, repeat=2)
+    assert ok and ok_ref
+    assert abs(lp - lp_ref) <= 1e-4 * abs(lp_ref), (lp, lp_ref)
+    assert rel_err(d, d_ref) < 1e-3
+    np.testing.assert_allclose(-d.sum(axis=1), 1.0, rtol=2e-3)
+
+
+def test_den_slice_path_matches_frame_path_at_full_size(ctx, monkeypatch):
+    """BASELINE configs[4] size (16 384 states, 6008 pdfs, 64 sequences): the default path is the slice path, and it
+    agrees with the per-frame kernels (different summation orders: 1e-5 / 1e-4)."""
+    from tdnnf_nas_b200 import synth
+
+    N, P, S, T = 16384, 6008, 64, 17
+    graph = synth.make_den_graph(N, P, 16.0, seed=12)
+    g = np.random.default_rng(1)
+    x = np.clip(g.standard_normal((T * S, P)), -30, 30).astype(np.float32)
+    monkeypatch.delenv("TDNNF_DEN_PATH", raising=False)
+    lp_s, d_s, ok_s = _run_gpu(ctx, graph, x, S, T, 0.1, -1.0, want_path="slices")
+    monkeypatch.setenv("TDNNF_DEN_PATH", "frames")
+    lp_f, d_f, ok_f = _run_gpu(ctx, graph, x, S, T, 0.1, -1.0, want_path="frames")
+    assert ok_s and ok_f
+    assert abs(lp_s - lp_f) <= 1e-5 * abs(lp_f), (lp_s, lp_f)
+    assert rel_err(d_s, d_f) < 1e-4
+    np.testing.assert_allclose(-d_s.sum(axis=1), 1.0, rtol=2e-3)
 
 
 @pytest.mark.parametrize("N,P,S,T,deg", [(300, 50, 32, 9, 6.0), (1000, 300, 128, 7, 16.0), (257, 33, 21, 4, 5.0)])
