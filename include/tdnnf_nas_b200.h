@@ -198,6 +198,19 @@ int tdnnf_elementwise_product_fwd(tdnnf_ctx* ctx, const float* in, int rows, int
 int tdnnf_elementwise_product_bwd(tdnnf_ctx* ctx, const float* in, int in_stride, const float* out_deriv,
                                   int od_stride, float* in_deriv, int id_stride, int rows, int out_cols);
 
+/* The shared-candidate mask of the bottleneck-dimension search block (ref: local/chain_NAS/scripts/
+ * generate_bottleneckCB8share_onehottrain_config.py:11-90): the descriptors dim-range / Sum(p_j, .., p_{nb-1}), the nb
+ * CopyNComponents (1 -> widths[j], `scale`), Append(copyn_j, linear_j), the nb ElementwiseProductComponents and the final
+ * Append evaluated in one pass instead of ~5 nb matrix commands:
+ *   fwd: out[r, c] = lin[r, c] * scale * sum_{k >= j(c)} p[r, k]       j(c) = the block column c belongs to
+ *   bwd: d_lin[r, c] = d_out[r, c] * scale * sum_{k >= j(c)} p[r, k]    (d_lin may be NULL)
+ *        d_p[r, k]   = scale * sum_{j <= k} sum_{c in block j} d_out[r, c] * lin[r, c]    (overwritten)
+ * Equal to running the components one by one (tests/test_gpu_bottleneck_block.py).  widths: HOST, nb <= 8 entries. */
+int tdnnf_shared_mask_fwd(tdnnf_ctx* ctx, const float* p, int rows, int nb, int p_stride, const float* lin, int cols,
+                          int lin_stride, float* out, int out_stride, const int32_t* widths, float scale);
+int tdnnf_shared_mask_bwd(tdnnf_ctx* ctx, const float* p, int p_stride, const float* lin, int lin_stride,
+                          const float* d_out, int do_stride, float* d_lin, int dl_stride, float* d_p, int dp_stride,
+                          int rows, int cols, int nb, const int32_t* widths, float scale);
 
 /* ------------------------------------------------------------------ whole-parameter ops -- */
 /* The CuMatrix/CuVector calls inside Scale / Add / DotProduct / PerturbParams / Vectorize of the
@@ -361,11 +374,11 @@ int tdnnf_den_graph_destroy(tdnnf_den_graph* g);
 int tdnnf_den_create(tdnnf_ctx* ctx, const tdnnf_den_graph* g, int num_seqs, int frames_per_seq,
                      float leaky_hmm_coefficient, tdnnf_den_comp** out);
 int tdnnf_den_destroy(tdnnf_den_comp* c);
-/* Which kernels this computation runs: *path = 2 sequence-slice clusters (one launch per direction: a cluster of *cluster
- * CTAs per slice of 8 sequences, E(t) staged in shared memory in *parts pdf ranges, *ctas CTAs in all), 0 = one launch
- * per frame and direction (num_seqs not a multiple of 8, 8 x num_pdfs floats beyond shared memory, too few slices to
- * fill the chip, or TDNNF_DEN_PATH=frames), 1 = the opt-in resident experiment (TDNNF_DEN_RESIDENT=1).
- * Environment: TDNNF_DEN_PATH=frames|slices, TDNNF_DEN_PARTS=1|2, TDNNF_DEN_CLUSTER=1..16. */
+/* Which kernels this computation runs: *path = 0 one launch per frame and direction (the default), 2 = sequence-slice
+ * clusters (opt-in, TDNNF_DEN_PATH=slices; num_seqs a multiple of 8 and 8 x num_pdfs floats within shared memory: one launch
+ * per direction, a cluster of *cluster CTAs per slice of 8 sequences, E(t) staged in shared memory in *parts pdf ranges,
+ * *ctas CTAs in all; measured slower, see den_slices.cu), 1 = the resident experiment (TDNNF_DEN_RESIDENT=1).
+ * Environment: TDNNF_DEN_PATH=slices, TDNNF_DEN_PARTS=1|2, TDNNF_DEN_CLUSTER=1..16. */
 int tdnnf_den_describe(const tdnnf_den_comp* c, int* path, int* cluster, int* parts, int* ctas);
 /* Forward(): returns the total log-prob summed over sequences in *logprob (HOST; this call
  * synchronises the stream -- the reference returns the scalar the same way). */

@@ -65,6 +65,8 @@ def _declare(lib):
     sig("tdnnf_scale_offset_rows", [vp, vp, i, i, i, vp, i, vp, vp])
     sig("tdnnf_elementwise_product_fwd", [vp, vp, i, i, i, vp, i])
     sig("tdnnf_elementwise_product_bwd", [vp, vp, i, vp, i, vp, i, i, i])
+    sig("tdnnf_shared_mask_fwd", [vp, vp, i, i, i, vp, i, i, vp, i, c_int_p, f])
+    sig("tdnnf_shared_mask_bwd", [vp, vp, i, vp, i, vp, i, vp, i, vp, i, i, i, i, c_int_p, f])
     sig("tdnnf_mat_set", [vp, vp, i, i, i, f])
     sig("tdnnf_mat_scale", [vp, vp, i, i, i, f])
     sig("tdnnf_mat_axpy", [vp, f, vp, i, vp, i, i, i])
@@ -325,6 +327,20 @@ class Context:
         ip, _, _, is_ = _mat(in_deriv)
         check(load().tdnnf_elementwise_product_bwd(self.h, xp, xs, dp, ds, ip, is_, r, oc))
 
+
+    def shared_mask_fwd(self, p, lin, out, widths, scale=1.0):
+        pp, r, nb, ps = _mat(p)
+        lp, _, c, ls = _mat(lin)
+        op, _, _, os_ = _mat(out)
+        check(load().tdnnf_shared_mask_fwd(self.h, pp, r, nb, ps, lp, c, ls, op, os_, _ihost(widths), scale))
+
+    def shared_mask_bwd(self, p, lin, d_out, d_lin, d_p, widths, scale=1.0):
+        pp, r, nb, ps = _mat(p)
+        lp, _, c, ls = _mat(lin)
+        dp, _, _, ds = _mat(d_out)
+        gp, gs = (0, 0) if d_lin is None else (_mat(d_lin)[0], _mat(d_lin)[3])
+        qp, _, _, qs = _mat(d_p)
+        check(load().tdnnf_shared_mask_bwd(self.h, pp, ps, lp, ls, dp, ds, gp, gs, qp, qs, r, c, nb, _ihost(widths), scale))
 
     # ------------------------------------------------------------------ parameter ops / neighbours
     def mat_set(self, a, value):

@@ -12,6 +12,16 @@
 //     (8 B per arc and slice, states grouped 16 to a warp with interleaved lists of equal length);
 //   * per-sequence totals: warp shuffles, then a fixed-order sum of the G CTAs' partials exchanged through
 //     distributed shared memory (bit-identical in every CTA, no atomics).
+// MEASURED (B200, N = 16384 states, 262 k arcs, P = 6008, T = 50; tools/den_sweep.py --variants, profiles/r02_den.md):
+// S = 64: 4.32 ms with E in one part, 6.04 ms in two parts, against 2.43 ms for the per-frame kernels; S = 128: 6.73 / 9.39
+// against 4.10 ms.  Parity-green (tests/test_gpu_den.py), but slower, so it is OPT-IN (TDNNF_DEN_PATH=slices).  Why: (i) with
+// 188 KB of E per CTA the occupancy API grants clusters of at most 10 (S = 64) / 6 (S = 128) CTAs, i.e. 80 / 96 of 148
+// SMs; (ii) one CTA of 512 threads per SM with 4 x 16-byte gathers in flight per thread keeps 32 KB in flight per SM
+// (the per-frame kernels: 3 CTAs x 256 threads x 128 B = 96 KB), and at ~1 us of loaded L2 latency that is 2.6 TB/s of row
+// visits over 80 SMs -- the 2.3 TB/s measured: latency-bound on memory-level parallelism, not on L2 bandwidth;
+// (iii) the second E part costs a second cluster barrier per frame and a partial-sum round trip.  The traffic saved
+// (3 row visits per arc instead of 5) is partly paid back by re-streaming the transition records per slice (8-12 B per
+// arc and slice) -- the net L2 bytes per frame pair are 249 MB against 351 MB, too small a gain to carry (i) and (ii).
 // Layouts (fp32): E3 / gamma3 [T][S/8][Ppad][8], alpha3 [T+1][S/8][N][8], betad3 [2][S/8][N][8], tot / bsum [T+1][S].
 #include <algorithm>
 #include <cstdlib>
@@ -611,9 +621,10 @@ int tdnnf::den_slices_create(tdnnf_ctx* ctx, int N, int P, int S, int T, const s
                              const std::vector<int>& bwd_ranges, const std::vector<float>& prob, const std::vector<int>& pdf,
                              const std::vector<int>& state, const std::vector<float>& init, tdnnf_den_slices** out) {
   *out = nullptr;
-  const char* env = getenv("TDNNF_DEN_PATH");  // "frames" = per-frame kernels, "slices" = this path wherever it fits
-  if (env && strcmp(env, "frames") == 0) return TDNNF_OK;
-  const bool forced = env && strcmp(env, "slices") == 0;
+  // Opt-in (TDNNF_DEN_PATH=slices): measured on B200 at N = 16384, P = 6008, T = 50 (profiles/r02_den.md) this path runs
+  // 4.3 ms (S = 64, E in one part) against 2.4 ms for the per-frame kernels: see the note at the top of the file.
+  const char* env = getenv("TDNNF_DEN_PATH");
+  if (!(env && strcmp(env, "slices") == 0)) return TDNNF_OK;
   if (S % kV != 0) return TDNNF_OK;
   const int SB = S / kV;
   int NP = 2;
@@ -640,8 +651,6 @@ int tdnnf::den_slices_create(tdnnf_ctx* ctx, int N, int P, int S, int T, const s
     if (n >= SB || (n >= 1 && G == 1)) break;
   }
   if (G < 1) return TDNNF_OK;
-  // with few slices most SMs would idle: the frame kernels spread one frame over the whole chip instead
-  if (!forced && SB * G < ctx->num_sms / 2) return TDNNF_OK;
   tdnnf_den_slices* s = new tdnnf_den_slices();
   s->G = G;
   s->NP = NP;

@@ -365,6 +365,109 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 }  // namespace
 
+// ------------------------------------------------------------------ shared-candidate bottleneck mask (configs[3])
+// The descriptor sub-graph generate_bottleneckCB8share_onehottrain_config.py:11-90 builds around every tdnnf `linear`:
+//   m_j = Sum(p_j .. p_{nb-1})  ->  CopyNComponent(1 -> b_j, scale)  ->  Append(copyn_j, linear_j)  ->
+//   ElementwiseProductComponent  ->  Append of the nb blocks
+// i.e. out[r, c] = lin[r, c] * scale * sum_{k >= j(c)} p[r, k]: candidate k keeps the first b_0 + .. + b_k bottleneck columns.
+// One warp per row (the row's nb <= 8 probabilities and its suffix sums live in registers), float4 columns.
+struct MaskBlocks {
+  int nb;
+  int end[8];  // exclusive end column of block j
+};
+__device__ __forceinline__ int mask_block_of(const MaskBlocks& b, int c) {
+  int j = 0;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) j += (k < b.nb - 1 && c >= b.end[k]) ? 1 : 0;
+  return j;
+}
+__global__ void __launch_bounds__(256) shared_mask_fwd_kernel(const float* __restrict__ p, long long ps, const float* __restrict__ lin,
+                                                              long long ls, float* __restrict__ out, long long os, int rows, int cols,
+                                                              MaskBlocks blk, float scale, bool vec) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    float m[8];
+    float run = 0.f;
+#pragma unroll
+    for (int k = 7; k >= 0; --k) {
+      if (k < blk.nb) run += p[r * ps + k];
+      m[k] = run * scale;
+    }
+    const float* src = lin + r * ls;
+    float* dst = out + r * os;
+    if (vec) {
+      for (int c = lane * 4; c < cols; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(src + c);
+        float4 o;
+        o.x = v.x * m[mask_block_of(blk, c)];
+        o.y = v.y * m[mask_block_of(blk, c + 1)];
+        o.z = v.z * m[mask_block_of(blk, c + 2)];
+        o.w = v.w * m[mask_block_of(blk, c + 3)];
+        *reinterpret_cast<float4*>(dst + c) = o;
+      }
+    } else {
+      for (int c = lane; c < cols; c += 32) dst[c] = src[c] * m[mask_block_of(blk, c)];
+    }
+  }
+}
+// d_lin[r, c] = d_out[r, c] * m_j(c);  d_p[r, k] = scale * sum_{j <= k} sum_{c in block j} d_out[r, c] lin[r, c]
+// (the transposes of ElementwiseProduct, CopyN and the Sum descriptor); d_p is overwritten.
+__global__ void __launch_bounds__(256) shared_mask_bwd_kernel(const float* __restrict__ p, long long ps, const float* __restrict__ lin,
+                                                              long long ls, const float* __restrict__ d_out, long long dos,
+                                                              float* __restrict__ d_lin, long long dls, float* __restrict__ d_p,
+                                                              long long dps, int rows, int cols, MaskBlocks blk, float scale, bool vec) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    float m[8], dm[8];
+    float run = 0.f;
+#pragma unroll
+    for (int k = 7; k >= 0; --k) {
+      if (k < blk.nb) run += p[r * ps + k];
+      m[k] = run * scale;
+      dm[k] = 0.f;
+    }
+    const float* src = lin + r * ls;
+    const float* dsrc = d_out + r * dos;
+    float* dst = d_lin ? d_lin + r * dls : nullptr;
+    auto one = [&](int c, float x, float d) -> float {
+      const int j = mask_block_of(blk, c);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dm[k] += (k == j) ? d * x : 0.f;
+      return d * m[j];
+    };
+    if (vec) {
+      for (int c = lane * 4; c < cols; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(src + c);
+        const float4 d = *reinterpret_cast<const float4*>(dsrc + c);
+        float4 o;
+        o.x = one(c, v.x, d.x); o.y = one(c + 1, v.y, d.y); o.z = one(c + 2, v.z, d.z); o.w = one(c + 3, v.w, d.w);
+        if (dst) *reinterpret_cast<float4*>(dst + c) = o;
+      }
+    } else {
+      for (int c = lane; c < cols; c += 32) {
+        const float o = one(c, src[c], dsrc[c]);
+        if (dst) dst[c] = o;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dm[k] += __shfl_xor_sync(0xffffffffu, dm[k], o);
+    if (lane == 0) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        acc += dm[k];
+        if (k < blk.nb) d_p[r * dps + k] = acc * scale;
+      }
+    }
+  }
+}
+
 #define LAUNCH_CHECK(ctx)          \
   do {                             \
     (ctx)->launches++;             \
@@ -558,6 +661,57 @@ extern "C" int tdnnf_elementwise_product_bwd(tdnnf_ctx* ctx, const float* in, in
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
   ewprod_bwd_kernel<<<grid_for((long long)rows * out_cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
       in, in_stride, out_deriv, od_stride, in_deriv, id_stride, rows, out_cols);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+
+static int mask_blocks(const int32_t* widths, int nb, int cols, MaskBlocks* b) {
+  TDNNF_REQUIRE(widths && nb >= 1 && nb <= 8, "1 to 8 candidate blocks");
+  int end = 0;
+  b->nb = nb;
+  for (int j = 0; j < 8; ++j) {
+    if (j < nb) {
+      TDNNF_REQUIRE(widths[j] > 0, "empty candidate block");
+      end += widths[j];
+    }
+    b->end[j] = end;
+  }
+  TDNNF_REQUIRE(end == cols, "block widths must add up to the bottleneck dimension");
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_shared_mask_fwd(tdnnf_ctx* ctx, const float* p, int rows, int nb, int p_stride, const float* lin, int cols,
+                                     int lin_stride, float* out, int out_stride, const int32_t* widths, float scale) {
+  TDNNF_REQUIRE(ctx && p && lin && out, "null argument");
+  TDNNF_REQUIRE(p_stride >= nb && lin_stride >= cols && out_stride >= cols, "stride < cols");
+  MaskBlocks b;
+  int rc = mask_blocks(widths, nb, cols, &b);
+  if (rc) return rc;
+  if (rows == 0) return TDNNF_OK;
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+  const bool vec = cols % 4 == 0 && lin_stride % 4 == 0 && out_stride % 4 == 0 && ((uintptr_t)lin & 15) == 0 && ((uintptr_t)out & 15) == 0;
+  const int blocks = (int)std::min<long long>(((long long)rows + 7) / 8, (long long)ctx->num_sms * 8);
+  shared_mask_fwd_kernel<<<blocks, 256, 0, ctx->stream>>>(p, p_stride, lin, lin_stride, out, out_stride, rows, cols, b, scale, vec);
+  LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_shared_mask_bwd(tdnnf_ctx* ctx, const float* p, int p_stride, const float* lin, int lin_stride,
+                                     const float* d_out, int do_stride, float* d_lin, int dl_stride, float* d_p, int dp_stride,
+                                     int rows, int cols, int nb, const int32_t* widths, float scale) {
+  TDNNF_REQUIRE(ctx && p && lin && d_out && d_p, "null argument");
+  TDNNF_REQUIRE(p_stride >= nb && dp_stride >= nb && lin_stride >= cols && do_stride >= cols && (!d_lin || dl_stride >= cols),
+                "stride < cols");
+  MaskBlocks b;
+  int rc = mask_blocks(widths, nb, cols, &b);
+  if (rc) return rc;
+  if (rows == 0) return TDNNF_OK;
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+  const bool vec = cols % 4 == 0 && lin_stride % 4 == 0 && do_stride % 4 == 0 && (!d_lin || dl_stride % 4 == 0) &&
+                   ((uintptr_t)lin & 15) == 0 && ((uintptr_t)d_out & 15) == 0 && ((uintptr_t)d_lin & 15) == 0;
+  const int blocks = (int)std::min<long long>(((long long)rows + 7) / 8, (long long)ctx->num_sms * 8);
+  shared_mask_bwd_kernel<<<blocks, 256, 0, ctx->stream>>>(p, p_stride, lin, lin_stride, d_out, do_stride, d_lin, dl_stride, d_p,
+                                                         dp_stride, rows, cols, b, scale, vec);
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }

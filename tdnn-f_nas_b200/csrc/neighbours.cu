@@ -479,13 +479,14 @@ extern "C" int tdnnf_update_with_max_change(tdnnf_ctx* ctx, int n, float* const*
   }
   float param_delta = std::sqrt(param_delta_squared) * std::fabs(scale);
   *applied = 1;
-  if (max_param_change != 0.f && param_delta > max_param_change * max_change_scale) {
-    if (param_delta - param_delta != 0.f) {
-      *applied = 0;  // "Infinite parameter change, will not apply."
-    } else {
-      scale *= max_param_change * max_change_scale / param_delta;
-      if (num_max_change_global_applied) (*num_max_change_global_applied)++;
-    }
+  if (param_delta - param_delta != 0.f) {
+    // "Infinite parameter change, will not apply."  The reference only gets here for +inf (nnet-utils.cc:2147-2150): when a
+    // per-component clip has already turned the sum into NaN (factor 0 times an infinite dot product) its test
+    // `param_delta > max` is false and it goes on to add 0 * inf = NaN into the model.  Both cases are refused here.
+    *applied = 0;
+  } else if (max_param_change != 0.f && param_delta > max_param_change * max_change_scale) {
+    scale *= max_param_change * max_change_scale / param_delta;
+    if (num_max_change_global_applied) (*num_max_change_global_applied)++;
   }
   float per_buf[TDNNF_MULTI_MAX];
   for (int g = 0; g < num_groups; ++g) {

@@ -97,3 +97,35 @@ def test_bottleneck_search_block(ctx, gumbel, scale):
     assert rel_err(d_lin.cpu().numpy(), d_out.astype(np.float64) * mask) < 1e-5
     got = delta.vectorize().astype(np.float64)
     assert np.abs(got - d_alpha).max() <= 2e-3 * np.abs(d_alpha).max() + 1e-9, (got, d_alpha)
+
+
+@pytest.mark.parametrize("R,widths,pad", [(384, BLOCKS, 0), (1001, BLOCKS, 16), (77, [3, 5, 2], 1), (50, [240], 0), (19840, BLOCKS, 0)])
+def test_shared_mask_fused_kernels(ctx, R, widths, pad):
+    """tdnnf_shared_mask_fwd / _bwd (the block's descriptor sub-graph + CopyN + ElementwiseProduct in one pass) against the
+    float64 restatement of the component chain above: same mask, same d_linear, same d_p."""
+    import torch
+
+    g = np.random.default_rng(R)
+    nb, cols = len(widths), sum(widths)
+    p = g.uniform(0.01, 1.0, (R, nb))
+    p = (p / p.sum(1, keepdims=True)).astype(np.float32)
+    lin = g.standard_normal((R, cols)).astype(np.float32)
+    d_out = g.standard_normal((R, cols)).astype(np.float32)
+    scale = 0.75
+    view = lambda a: torch.from_numpy(np.pad(a, ((0, 0), (0, pad)), constant_values=5.0)).cuda()[:, : a.shape[1]]
+    pd, ld, dd = view(p), view(lin), view(d_out)
+    out = view(np.zeros_like(lin))
+    ctx.shared_mask_fwd(pd, ld, out, widths, scale)
+    m = scale * np.cumsum(p.astype(np.float64)[:, ::-1], axis=1)[:, ::-1]            # m_j = sum_{k >= j} p_k
+    mask = np.repeat(m, widths, axis=1)
+    assert rel_err(out.cpu().numpy(), lin * mask) < 1e-6
+    d_lin = view(np.zeros_like(lin))
+    d_p = view(np.full_like(p, 3.0))
+    ctx.shared_mask_bwd(pd, ld, dd, d_lin, d_p, widths, scale)
+    ends = np.cumsum(widths)
+    dm = np.stack([(d_out.astype(np.float64) * lin)[:, e - w:e].sum(1) for e, w in zip(ends, widths)], axis=1)
+    assert rel_err(d_lin.cpu().numpy(), d_out * mask) < 1e-6
+    assert rel_err(d_p.cpu().numpy(), scale * np.cumsum(dm, axis=1)) < 1e-5
+    d_p2 = view(np.zeros_like(p))
+    ctx.shared_mask_bwd(pd, ld, dd, None, d_p2, widths, scale)                      # d_lin not wanted
+    assert torch.equal(d_p2, d_p)

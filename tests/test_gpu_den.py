@@ -57,8 +57,7 @@ def test_den_parity(ctx, monkeypatch, N, P, S, T, deg):
                                                   (1000, 300, 128, 7, 16.0, 9), (257, 33, 16, 4, 5.0, 3), (2000, 601, 24, 6, 12.0, 8),
                                                   (16, 7, 8, 3, 2.0, 4), (700, 90, 40, 1, 9.0, 2)])
 def test_den_slice_path_parity(ctx, monkeypatch, N, P, S, T, deg, cluster, parts):
-    """The sequence-slice cluster kernels (den_slices.cu; the default for Switchboard-sized minibatches), forced here on
-    small shapes: cluster sizes 1..16 (more CTAs than warp-tasks included), E staged in one or two pdf ranges, pdf counts
+    """The sequence-slice cluster kernels (den_slices.cu; opt-in, TDNNF_DEN_PATH=slices), on small shapes: cluster sizes 1..16 (more CTAs than warp-tasks included), E staged in one or two pdf ranges, pdf counts
     that are not multiples of 4, state counts that are not multiples of 16, strided matrices, T = 1, two calls."""
     from oracle import oracle as O
     from tdnnf_nas_b200 import synth
@@ -80,17 +79,17 @@ def test_den_slice_path_parity(ctx, monkeypatch, N, P, S, T, deg, cluster, parts
 
 
 def test_den_slice_path_matches_frame_path_at_full_size(ctx, monkeypatch):
-    """BASELINE configs[4] size (16 384 states, 6008 pdfs, 64 sequences): the default path is the slice path, and it
-    agrees with the per-frame kernels (different summation orders: 1e-5 / 1e-4)."""
+    """BASELINE configs[4] size (16 384 states, 6008 pdfs, 64 sequences): the opt-in slice path agrees with the default
+    per-frame kernels (different summation orders: 1e-5 / 1e-4)."""
     from tdnnf_nas_b200 import synth
 
     N, P, S, T = 16384, 6008, 64, 17
     graph = synth.make_den_graph(N, P, 16.0, seed=12)
     g = np.random.default_rng(1)
     x = np.clip(g.standard_normal((T * S, P)), -30, 30).astype(np.float32)
-    monkeypatch.delenv("TDNNF_DEN_PATH", raising=False)
+    monkeypatch.setenv("TDNNF_DEN_PATH", "slices")
     lp_s, d_s, ok_s = _run_gpu(ctx, graph, x, S, T, 0.1, -1.0, want_path="slices")
-    monkeypatch.setenv("TDNNF_DEN_PATH", "frames")
+    monkeypatch.delenv("TDNNF_DEN_PATH", raising=False)
     lp_f, d_f, ok_f = _run_gpu(ctx, graph, x, S, T, 0.1, -1.0, want_path="frames")
     assert ok_s and ok_f
     assert abs(lp_s - lp_f) <= 1e-5 * abs(lp_f), (lp_s, lp_f)

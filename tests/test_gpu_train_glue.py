@@ -52,9 +52,9 @@ def test_update_with_max_change(ctx, case):
     g = np.random.default_rng(5)
     shapes = [(160, 1536 * 2 + 3), (1, 167), (1536, 160), (1, 1536), (256, 1536)]
     groups = [0, 0, 1, 1, 2]
-    mags = dict(none=[1e-4, 1e-4, 1e-4, 1e-4, 1e-4], per_component=[1e-2, 1e-4, 1e-5, 1e-5, 1e-5], **{"global": [1e-3] * 5},
-                both=[5e-2, 1e-2, 2e-3, 2e-3, 1e-3], scaled=[1e-3] * 5)[case]
-    max_change = [0.75, 0.75, 0.0 if case == "both" else 1.5]
+    mags = dict(none=[1e-4, 1e-4, 1e-4, 1e-4, 1e-4], per_component=[1e-2, 1e-4, 1e-5, 1e-5, 1e-5], **{"global": [2e-3] * 5},
+                both=[5e-2, 1e-2, 2e-3, 2e-3, 3e-3], scaled=[3e-3] * 5)[case]
+    max_change = [1.5, 1.5, 1.5] if case == "global" else [0.75, 0.75, 0.0 if case == "both" else 1.5]
     scale, mcs = (0.5, 0.7) if case == "scaled" else (1.0, 1.0)
     models = [g.standard_normal(s).astype(np.float32) for s in shapes]
     deltas = [(g.standard_normal(s) * m).astype(np.float32) for s, m in zip(shapes, mags)]
@@ -94,6 +94,13 @@ def test_update_with_max_change_infinite_delta_leaves_model(ctx):
     assert torch.equal(model, before) and torch.equal(model2, before2)
     assert torch.all(delta == 0) and torch.all(delta2 == 0)
     assert tab.num_global.value == 0
+    # the same without a per-component max-change: the sum is +inf, the case the reference itself refuses (:2147-2150)
+    delta = torch.from_numpy(g.standard_normal((40, 33)).astype(np.float32)).cuda()
+    delta[0, 0] = float("inf")
+    delta2 = torch.ones((1, 40), device="cuda")
+    tab = _table(ctx, [model, model2], [delta, delta2], [0, 1], [0.0, 0.0])
+    assert tab.update_with_max_change(2.0) is False
+    assert torch.equal(model, before) and torch.equal(model2, before2) and torch.all(delta == 0)
     # momentum: delta *= momentum after a normal step
     delta = torch.full((40, 33), 1e-3, device="cuda")
     delta2 = torch.full((1, 40), 1e-3, device="cuda")
