@@ -27,9 +27,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "TDNN-F DARTS supernet train frames/sec"
-# dram__bytes_read.sum + dram__bytes_write.sum per splice_gemm_kernel launch, from the committed `ncu --set full`
-# capture (profiles/r01_summary.md).  A tensor-bound kernel: this is context, not the roofline numerator.
-NCU_GEMM_TRAFFIC_BYTES = 131.2e6
+# dram__bytes_read.sum + dram__bytes_write.sum per splice_gemm_kernel launch: read at run time from the committed summary of
+# the `ncu --set full` capture (profiles/gemm_traffic.json, written by tools/summarize_profile.py from the .ncu-rep).
+# A tensor-bound kernel: this is context, not the roofline numerator.
+
+
+def load_gemm_traffic():
+    path = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if not os.path.exists(path):
+        return None, "profiles/gemm_traffic.json missing"
+    d = json.load(open(path))
+    return float(d["mean_dram_bytes_per_launch"]), f"profiles/gemm_traffic.json ({d['source']}; {d['launches']} launches)"
+
 UNIT = "frames/s"
 NG_SETTLE_STEPS = 12
 # launches with fewer algorithmic FLOPs than this are the skinny natural-gradient products (H = X W^T with 20-80
@@ -175,6 +184,110 @@ def den_report(cfg, arcs, den_ms, peaks):
                 note="bound by L2 row gathers (8 B per arc, sequence and frame), ~25x the algorithmic HBM bytes")
 
 
+def mixing_kernel_report(net, peaks, reps: int = 20):
+    """Achieved HBM GB/s of the bandwidth-bound mixing kernels (algorithmic bytes = 4 x (elements read once +
+    written once)) at R = the rows of the widest layer, each launch timed alone with CUDA events on the launch stream and
+    the 126 MB L2 flushed (a 256 MB buffer is rewritten) before every launch."""
+    import torch
+
+    ctx, dev = net.ctx, net.dev
+    R, D, Bn = max(blk["lin_out"].shape[0] for blk in net.blocks), net.cfg.dim, 240
+    widths = [25, 25, 30, 20, 20, 40, 40, 40]
+    g = torch.Generator(device=dev).manual_seed(1)
+    rnd = lambda r, c: torch.randn((r, c), device=dev, generator=g)
+    flush = torch.empty(64 * 1024 * 1024, device=dev)
+    a8, p8, d8 = rnd(R, 8), torch.zeros((R, 8), device=dev), rnd(R, 8)
+    ctx.softmax_flops_fwd(a8, p8, None, 1.0)
+    x240, y240, d240 = rnd(R, Bn), torch.zeros((R, Bn), device=dev), rnd(R, Bn)
+    xD, yD, dD, prev = rnd(R, D), torch.zeros((R, D), device=dev), rnd(R, D), rnd(R, D)
+    sc, of = torch.rand(D, device=dev) + 0.5, torch.randn(D, device=dev, generator=g)
+    one, c40 = rnd(R, 1), torch.zeros((R, 40), device=dev)
+    u8 = [0.3, 0.6, 0.2, 0.9, 0.5, 0.4, 0.7, 0.1]
+    cases = [
+        ("softmax_flops_fwd (SoftmaxFlops R x 8)", 2 * R * 8 * 4, lambda: ctx.softmax_flops_fwd(a8, p8, None, 1.0)),
+        ("softmax_flops_fwd (Gumbel R x 8)", 2 * R * 8 * 4, lambda: ctx.softmax_flops_fwd(a8, p8, u8, 2.0)),
+        ("softmax_flops_bwd (R x 8)", 3 * R * 8 * 4, lambda: ctx.softmax_flops_bwd(p8, d8, d8, 1e-3 / (R * 8), 1.0, 0)),
+        ("copyn_fwd (R x 1 -> R x 40)", (R + 2 * R * 40) * 4, lambda: ctx.copyn_fwd(one, c40, 1.0)),
+        ("copyn_bwd (R x 40 -> R x 1)", (R * 40 + 2 * R) * 4, lambda: ctx.copyn_bwd(c40, one, 1.0)),
+        ("shared_mask_fwd (R x 240; Sum + 8 CopyN + 8 ElementwiseProduct fused)", (R * 8 + 2 * R * Bn) * 4,
+         lambda: ctx.shared_mask_fwd(p8, x240, y240, widths, 1.0)),
+        ("shared_mask_bwd (R x 240)", (2 * R * 8 + 3 * R * Bn) * 4, lambda: ctx.shared_mask_bwd(p8, x240, d240, y240, d8, widths, 1.0)),
+        ("scale_offset_rows (BatchNormTest fwd, R x 1536)", 2 * R * D * 4, lambda: ctx.scale_offset_rows(xD, yD, sc, of)),
+        ("scale_offset_rows (BatchNormTest bwd, R x 1536)", 2 * R * D * 4, lambda: ctx.scale_offset_rows(dD, yD, sc, None)),
+        ("tail_fwd (ReLU + BatchNormTest + bypass fused, R x 1536)", 3 * R * D * 4,
+         lambda: ctx.relu_scale_offset_bypass_fwd(xD, sc, of, prev, 0.66, yD)),
+        ("tail_bwd (R x 1536)", 4 * R * D * 4, lambda: ctx.relu_scale_offset_bypass_bwd(dD, xD, sc, 0.66, yD, prev)),
+    ]
+    out = []
+    for name, nbytes, fn in cases:
+        fn()
+        torch.cuda.synchronize(dev)
+        total = 0.0
+        for _ in range(reps):
+            flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            total += e0.elapsed_time(e1)
+        us = total / reps * 1e3
+        gbs = nbytes / (us * 1e-6) / 1e9
+        out.append(dict(kernel=name, rows=R, algorithmic_bytes=nbytes, us=round(us, 2), achieved_GBps=round(gbs, 1),
+                        frac_of_hbm=round(gbs / peaks["hbm_gbs"], 4)))
+    return out
+
+
+def dp_self_check(net, cfg, world, rank, local_rank, x_host):
+    """Data-parallel correctness on the hardware (world > 1), one un-timed step on fresh state: (1) the deltas that come out
+    of the NCCL path (tdnnf_dp_allreduce_deltas) equal the sum of the ranks' own deltas (collected with an all-gather and
+    summed in rank order); (2) rank 0 ALSO runs other ranks' shards itself (a second Supernet built as that rank: same seed,
+    that rank's input and numerator supervision) and compares with what that rank computed.  The model is not updated."""
+    import torch
+    import torch.distributed as dist
+
+    from tdnnf_nas_b200 import nnet3
+    from tdnnf_nas_b200.supernet import Supernet
+
+    n = net.delta_floats
+    net.step(x_host, apply_update=False, reduce=False)
+    own = net.delta_arena[:n].clone()
+    gathered = [torch.empty_like(own) for _ in range(world)]
+    dist.all_gather(gathered, own)
+    net._reduce_now = True
+    if net.dp_buckets > 1:  # the one-shot form of the same NCCL path
+        net.dp.allreduce([(net.delta_arena.data_ptr(), n)])
+    else:
+        net._allreduce_deltas()
+    reduced = net.delta_arena[:n].clone()
+    net.delta_arena.zero_()
+    total = torch.zeros_like(own, dtype=torch.float64)
+    for t in gathered:
+        total += t.double()
+    err_sum = float((reduced.double() - total).norm() / total.norm())
+    out = None
+    if rank == 0:
+        counter = nnet3.get_rand_counter()
+        others = sorted(set(range(1, world)) if world <= 4 else {1, world // 2, world - 1})
+        errs = {}
+        for r in others:
+            rep = Supernet(cfg, device=local_rank, rank=r, world_size=world, process_group=None, dp_buckets=1, standalone=True)
+            rep.step(rep.make_input(0).pin_memory(), apply_update=False, reduce=False)
+            mine = rep.delta_arena[:n]
+            errs[str(r)] = float((mine.double() - gathered[r].double()).norm() / gathered[r].double().norm())
+            rep.close()
+            del rep
+        nnet3.set_context(net.ctx)
+        nnet3.set_rand_counter(counter)  # the replicas re-seeded the shared RNG: put rank 0 back in step with the other ranks
+        out = dict(ok=bool(err_sum <= 1e-5 and all(e <= 1e-4 for e in errs.values())), allreduce_vs_sum_of_shards=err_sum,
+                   shards_recomputed_on_rank0=errs, delta_floats=int(n),
+                   note=("allreduce_vs_sum_of_shards: ||NCCL result - sum_r delta_r|| / ||sum||, bar 1e-5; shards_recomputed_on_rank0: "
+                         "relative error between rank r's delta and the same shard run on rank 0 (the split-K red.global.add order "
+                         "differs between runs), bar 1e-4"))
+    dist.barrier()
+    return out
+
+
 # ------------------------------------------------------------------ arms
 def run_reference(args, cfg, rank, world):
     if rank != 0:
@@ -205,6 +318,23 @@ def run_reference(args, cfg, rank, world):
 
 
 def workload_config(cfg, gpus):
+    if cfg.mode == "bottleneck":
+        soft = "GumbelSoftmaxFlopsComponent" if cfg.bottleneck_gumbel else "SoftmaxFlopsComponent"
+        return dict(workload=("bottleneck-dimension search (BASELINE.json configs[3]; generate_bottleneckCB8share_onehottrain_config.py + "
+                              "add_flopsconstraint.py + run_TDNNf_DARTS_mod_fbk_bottleneckCBshare_cvupdate_flopsconstraint.sh): tdnn1 220->1536, "
+                              "14 tdnnf-layers {TdnnComponent 1536->240, ConstantFunctionComponent alpha(8) -> " + soft +
+                              f"(scale {cfg.flops_coef}) -> Sum(p_j..p_7) -> 8 x CopyNComponent (25,25,30,20,20,40,40,40) -> 8 x "
+                              "ElementwiseProductComponent on the 240-wide bottleneck, TdnnComponent 240->1536, ReLU, BatchNormTest, bypass "
+                              "0.66} with time-strides 1,1,1,0,3x10, prefinal 256/1536, output 6008; every pre-trained component frozen "
+                              "(learning-rate-factor 0), the 14 alpha vectors trained; LF-MMI on a synthetic "
+                              f"{cfg.den_states}-state den graph"),
+                    mode=cfg.mode, chunks_per_gpu=cfg.num_seqs, frames_per_eg=cfg.frames_per_eg, global_chunks=cfg.num_seqs * gpus,
+                    num_pdfs=cfg.num_pdfs, den_states=cfg.den_states, parallelism=f"dp{gpus}", flops_coef=cfg.flops_coef,
+                    fused_mask=cfg.fuse_mask,
+                    cache="per-step working set exceeds the 126 MB L2: no explicit flush needed",
+                    included=("forward, LF-MMI numerator and denominator (+ xent branch), data gradients through every layer, the "
+                              "mask / softmax (FLOPs penalty) / alpha backward, all-reduce of the alpha deltas, UpdateNnetWithMaxChange"),
+                    not_included="parameter gradients of the frozen layers (none are computed by the reference either)")
     if cfg.mode == "manual":
         # secondary workload (python bench.py --mode manual --chunks 128): NOT the headline line, see profiles/
         return dict(workload=("manual TDNN-F 7q fbk-40 (BASELINE.json configs[1], run_tdnn_7q_fbk_40_manual.sh): tdnn1 220->1536, 14 "
@@ -229,13 +359,14 @@ def workload_config(cfg, gpus):
                 included=("natural-gradient update (OnlineNaturalGradient rank 20/80, update period 4) of all 28 TdnnDARTSV3 "
                           "components, LF-MMI numerator (per-sequence FST) and denominator, UpdateNnetWithMaxChange" +
                           (", the cross-entropy regularisation branch (numerator posteriors -> output-xent)" if cfg.xent else "") +
-                          "; the stock affine layers (tdnn1, prefinal, output) are also trained (plain SGD) although the search recipe "
-                          "freezes them with learning-rate-factor 0 (run_TDNN_DARTSV3_fbk_stride_cvupdate.sh:129): extra work in the step"),
+                          ("; tdnn1 / prefinal / output are also trained (plain SGD; --train-stock), which the search recipe does not do"
+                           if cfg.freeze_stock is False else
+                           "; everything but the TdnnDARTSV3 components is frozen (learning-rate-factor 0, "
+                           "run_TDNN_DARTSV3_fbk_stride_cvupdate.sh:129-134): no model derivatives for tdnn1 / prefinal / output, as in nnet3")),
                 ng_settle_steps=NG_SETTLE_STEPS,
-                not_included=("natural gradient of the 5 stock affine layers around the blocks (tdnn1, prefinal, output: plain SGD "
-                              "there; all 28 TdnnDARTSV3 components are preconditioned), L2 regularisation, dropout "
-                              "(GeneralDropoutComponent is upstream Kaldi and not built; the recipes' schedule 0,0@0.20,0.5@0.50,0 starts "
-                              "and ends at proportion 0); the orthonormal constraint does not cover TdnnDARTSV3 (utils.cc:1047-1061)"))
+                not_included=("L2 regularisation (the recipe's l2 applies to frozen layers only), dropout nodes (the recipes' schedule "
+                              "0,0@0.20,0.5@0.50,0 starts and ends at proportion 0; SupernetConfig.dropout builds them); the orthonormal "
+                              "constraint does not cover TdnnDARTSV3 (utils.cc:1047-1061)"))
 
 
 def run_ours(args, cfg, rank, world, local_rank):
@@ -249,9 +380,10 @@ def run_ours(args, cfg, rank, world, local_rank):
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         pg = dist.group.WORLD
-    net = Supernet(cfg, device=local_rank, rank=rank, world_size=world, process_group=pg)
+    net = Supernet(cfg, device=local_rank, rank=rank, world_size=world, process_group=pg, dp_buckets=args.dp_buckets)
     dev = net.dev
     host_inputs = [net.make_input(i).pin_memory() for i in range(2)]
+    dp_check = dp_self_check(net, cfg, world, rank, local_rank, host_inputs[0]) if world > 1 and not args.no_dp_check else None
 
     def barrier():
         if world > 1:
@@ -306,12 +438,30 @@ def run_ours(args, cfg, rank, world, local_rank):
     d1.record()
     torch.cuda.synchronize(dev)
     den_ms = d0.elapsed_time(d1) / den_reps
+    # ---- the collective on its own: the in-place all-reduce of the delta arena, CUDA events, max over ranks
+    allreduce_ms = None
+    if world > 1:
+        net.delta_arena.zero_()
+        for _ in range(2):
+            net.dp.allreduce([(net.delta_arena.data_ptr(), net.delta_floats)])
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(5):
+            net.dp.allreduce([(net.delta_arena.data_ptr(), net.delta_floats)])
+        a1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([a0.elapsed_time(a1) / 5], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        allreduce_ms = float(t.item())
+    mixing = mixing_kernel_report(net, load_peaks()) if (rank == 0 and (cfg.mode == "bottleneck" or args.mixing)) else None
     barrier()
     if rank != 0:
         net.close()
         torch.distributed.destroy_process_group()
         return
     peaks = load_peaks()
+    gemm_traffic, gemm_traffic_source = load_gemm_traffic()
     frames_all = net.frames_per_step * world
     value = frames_all * args.steps / (ms_dev / 1e3)
     e2e = frames_all * args.steps / (ms_e2e / 1e3)
@@ -333,8 +483,8 @@ def run_ours(args, cfg, rank, world, local_rank):
                  ms_per_step=ms_e2e / args.steps),
         gpu_launches=int(launches),
         roofline=dict(bound="tensor", kernel="splice_gemm_kernel (tcgen05, the TdnnDARTSV3 Propagate / data-gradient / parameter-gradient GEMMs)",
-                      achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=NCU_GEMM_TRAFFIC_BYTES,
-                      traffic_source="profiles/r01_summary.md: mean dram__bytes_read+write over the 10 launches of the ncu --set full capture",
+                      achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=gemm_traffic,
+                      traffic_source=gemm_traffic_source,
                       peak_source=peaks["source"] + ", bf16 sustained",
                       achieved_tensor_pipe=achieved_pipe, frac_tensor_pipe=achieved_pipe / peak,
                       launches_timed=gt["launches"], steps_timed=ROOF_STEPS, gemm_ms_per_step=gt["ms"] / ROOF_STEPS,
@@ -347,6 +497,14 @@ def run_ours(args, cfg, rank, world, local_rank):
                             "natural-gradient products, timed separately")),
         den=den_report(cfg, net.den_arcs, den_ms, peaks),
         cpu_baseline=cpu_line, objf_per_frame=objf, den_arcs=net.den_arcs)
+    if world > 1:
+        line["dp_check"] = dp_check
+        line["allreduce_ms"] = allreduce_ms
+        line["allreduce"] = dict(bytes=int(net.delta_floats * 4), ms=allreduce_ms, buckets=net.dp_buckets,
+                                 path="tdnnf_dp_allreduce_deltas (ncclAllReduce in place on the delta arena, NVLink)",
+                                 algbw_GBps=net.delta_floats * 4 / (allreduce_ms * 1e-3) / 1e9 if allreduce_ms else None)
+    if mixing is not None:
+        line["mixing_kernels"] = mixing
     print(json.dumps(line), flush=True)
     net.close()
     if world > 1:
@@ -359,7 +517,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="search", choices=["search", "pretrain", "manual"])
+    ap.add_argument("--mode", default="search", choices=["search", "pretrain", "manual", "bottleneck"])
+    ap.add_argument("--flops-coef", type=float, default=1e-3, help="bottleneck mode: eta of the FLOPs penalty (0, 1e-3, 1e-1)")
+    ap.add_argument("--gumbel", action="store_true", help="bottleneck mode: GumbelSoftmaxFlopsComponent instead of SoftmaxFlopsComponent")
+    ap.add_argument("--unfused-mask", action="store_true", help="bottleneck mode: CopyN / ElementwiseProduct one by one")
+    ap.add_argument("--mixing", action="store_true", help="add the per-kernel GB/s table of the mixing kernels to the line")
+    ap.add_argument("--dp-buckets", type=int, default=1, help="N > 1: delta buckets reduced while the backward pass runs")
+    ap.add_argument("--no-dp-check", action="store_true")
+    ap.add_argument("--train-stock", action="store_true", help="search mode: also train tdnn1 / prefinal / output (round-1 behaviour)")
     ap.add_argument("--den-states", type=int, default=16384)
     ap.add_argument("--blocks", type=int, default=14)
     ap.add_argument("--chunks", type=int, default=64)
@@ -372,7 +537,10 @@ def main():
     from tdnnf_nas_b200.supernet import SupernetConfig
 
     cfg = SupernetConfig(mode=args.mode, den_states=args.den_states, num_blocks=args.blocks, num_seqs=args.chunks,
-                         l2_regularize=0.01 if args.mode == "manual" else 0.0, xent=not args.no_xent)
+                         l2_regularize=0.01 if args.mode == "manual" else 0.0, xent=not args.no_xent,
+                         bottleneck=240 if args.mode == "bottleneck" else 160, flops_coef=args.flops_coef,
+                         bottleneck_gumbel=args.gumbel, fuse_mask=not args.unfused_mask,
+                         freeze_stock=False if args.train_stock else None)
     if args.impl == "reference":
         if args.steps > 3:
             args.steps = 3  # each step is ~10 s of CPU work: keep the whole run within a few minutes

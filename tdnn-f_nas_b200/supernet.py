@@ -59,6 +59,19 @@ class SupernetConfig:
     max_change: float = 0.75         # per-component max-change (xconfig default of the tdnnf layers)
     max_param_change: float = 2.0    # --trainer.max-param-change (global)
     fuse_tail: bool = True           # search mode: ReLU + BatchNormTest + bypass as one pass (else three components)
+    # "bottleneck" mode (BASELINE configs[3]; generate_bottleneckCB8share_onehottrain_config.py + add_flopsconstraint.py and
+    # run_TDNNf_DARTS_mod_fbk_bottleneckCBshare_cvupdate_flopsconstraint.sh:136-139): every tdnnf-layer is TdnnComponent
+    # 1536 -> 240 / 240 -> 1536 (time-strides 1,1,1,0,3 x 10), its bottleneck masked by the shared candidates
+    # (25,25,30,20,20,40,40,40) weighted by {Gumbel}SoftmaxFlopsComponent(alpha); all pre-trained components are frozen
+    # (learning-rate-factor 0, BatchNormTest), only the 14 alpha vectors (ConstantFunctionComponent) are trained.
+    candidate_widths: tuple = (25, 25, 30, 20, 20, 40, 40, 40)
+    flops_coef: float = 1.0e-3       # eta: the `scale` of {Gumbel}SoftmaxFlopsComponent (0, 1e-3, 1e-1 in the recipes)
+    bottleneck_gumbel: bool = False  # GumbelSoftmaxFlopsComponent (temperature schedule) instead of SoftmaxFlopsComponent
+    fuse_mask: bool = True           # the descriptor sub-graph + 8 CopyN + 8 ElementwiseProduct as one pass (else one by one)
+    # learning-rate-factor 0 on everything but the searched parameters, as the search recipes set it
+    # (run_TDNN_DARTSV3_fbk_stride_cvupdate.sh:129-134): nnet3 then computes no model derivatives for tdnn1 / prefinal /
+    # output.  None = True in the search and bottleneck stages, False otherwise.
+    freeze_stock: Optional[bool] = None
     seed: int = 20221 + 3
 
 
@@ -67,8 +80,9 @@ def block_offsets(cfg: "SupernetConfig"):
     `num_offsets` candidates (-6..0 / 0..6); manual: tdnnf-layer time-stride s gives (-s, 0) / (0, s), and the single
     offset 0 for s = 0 (composite_layers.py:145-150; default strides 1,1,1,0 then 6: run_tdnn_7q_fbk_40_manual.sh:138-151)."""
     n = cfg.num_offsets
-    if cfg.mode == "manual":
-        strides = list(cfg.strides) if cfg.strides is not None else ([1, 1, 1, 0] + [6] * cfg.num_blocks)[:cfg.num_blocks]
+    if cfg.mode in ("manual", "bottleneck"):
+        wide = 3 if cfg.mode == "bottleneck" else 6  # generate_bottleneckCB8share_onehottrain_config.py:43-55: -3,0 / 0,3
+        strides = list(cfg.strides) if cfg.strides is not None else ([1, 1, 1, 0] + [wide] * cfg.num_blocks)[:cfg.num_blocks]
         assert len(strides) == cfg.num_blocks
         return [[-s_, 0] if s_ else [0] for s_ in strides], [[0, s_] if s_ else [0] for s_ in strides]
     return [list(range(-(n - 1), 1))] * cfg.num_blocks, [list(range(n))] * cfg.num_blocks
@@ -103,12 +117,13 @@ def algorithmic_flops(cfg: "SupernetConfig") -> float:
     _, _, lin_t, aff_t, _ = frame_plan(cfg, left, right)
     tot = 0.0
     for b in range(cfg.num_blocks):
-        if cfg.mode == "manual":
+        if cfg.mode in ("manual", "bottleneck"):
             n_lin, n_aff = len(left[b]), len(right[b])
         else:
             n_lin = n_aff = cfg.num_offsets if cfg.mode == "search" else 2
-        tot += 3 * 2.0 * len(lin_t[b]) * cfg.num_seqs * n_lin * cfg.dim * cfg.bottleneck
-        tot += 3 * 2.0 * len(aff_t[b]) * cfg.num_seqs * n_aff * cfg.bottleneck * cfg.dim
+        passes = 2 if cfg.mode == "bottleneck" else 3  # frozen layers: forward + data gradient, no parameter gradient
+        tot += passes * 2.0 * len(lin_t[b]) * cfg.num_seqs * n_lin * cfg.dim * cfg.bottleneck
+        tot += passes * 2.0 * len(aff_t[b]) * cfg.num_seqs * n_aff * cfg.bottleneck * cfg.dim
     return tot
 
 
@@ -144,7 +159,7 @@ def _m(t):
 
 class Supernet:
     def __init__(self, cfg: SupernetConfig, device: int = 0, rank: int = 0, world_size: int = 1,
-                 process_group=None, dp_buckets: int = 1):
+                 process_group=None, dp_buckets: int = 1, standalone: bool = False):
         """dp_buckets: 1 = one in-place all-reduce of the whole delta arena after the backward pass; k > 1 = the arena is
         cut into k buckets in backward order, each reduced on a side stream as soon as the backward pass has produced it
         (tdnnf_dp_allreduce_bucket_async), the parameter step waits for all of them."""
@@ -152,6 +167,8 @@ class Supernet:
 
         self.cfg, self.rank, self.world, self.pg = cfg, rank, world_size, process_group
         self.dp_buckets = max(1, int(dp_buckets))
+        self._reduce_now = False
+        self.standalone = standalone  # a replica of rank `rank` of a `world_size` job built without a communicator (self-check)
         self.dev = torch.device("cuda", device)
         torch.cuda.set_device(self.dev)
         self.ctx = capi.Context(device)
@@ -171,7 +188,11 @@ class Supernet:
 
         cfg, dev, ctx = self.cfg, self.dev, self.ctx
         S, D, B, n = cfg.num_seqs, cfg.dim, cfg.bottleneck, cfg.num_offsets
-        manual = cfg.mode == "manual"
+        manual = cfg.mode in ("manual", "bottleneck")   # stock TdnnComponent layers
+        bneck = cfg.mode == "bottleneck"
+        if bneck:
+            assert sum(cfg.candidate_widths) == cfg.bottleneck, "candidate widths must add up to the bottleneck dimension"
+        self.frozen = cfg.freeze_stock if cfg.freeze_stock is not None else cfg.mode in ("search", "bottleneck")
         self.left_offsets, self.right_offsets = block_offsets(cfg)
         T, out_t, lin_t, aff_t, in_t = self._frames()
         self.T, self.in_frames = T, len(in_t)
@@ -181,6 +202,7 @@ class Supernet:
         self.keep = []  # tensors / ctypes arrays that must outlive the plans
 
         search = cfg.mode == "search"
+        self.frozen_bn = cfg.mode in ("search", "bottleneck")
         flags_cfg = ("use-gumbel=true use-entropy=false free-select=false update-alpha=true update-theta=false uniform-sample=false"
                      if search else
                      "use-gumbel=false use-entropy=false free-select=false update-alpha=false update-theta=true uniform-sample=true")
@@ -199,10 +221,11 @@ class Supernet:
         self.zero_off = (C.c_int32 * 1)(0)
         self.stock = dict(tdnn1=affine_params(cfg.feat_dim, D), prefinal_l=affine_params(D, cfg.prefinal_small, False),
                           pc_affine=affine_params(cfg.prefinal_small, D), pc_linear=affine_params(D, cfg.prefinal_small, False),
-                          output=affine_params(cfg.prefinal_small, cfg.num_pdfs, zero=True))  # output-layer: param-stddev=0
+                          # output-layer: param-stddev=0 at the start of training; a frozen (pre-trained) one is not zero
+                          output=affine_params(cfg.prefinal_small, cfg.num_pdfs, zero=not self.frozen))
         if cfg.xent:  # prefinal-layer name=prefinal-xent input=prefinal-l; output-layer name=output-xent (log-softmax)
             self.stock.update(px_affine=affine_params(cfg.prefinal_small, D), px_linear=affine_params(D, cfg.prefinal_small, False),
-                              output_xent=affine_params(cfg.prefinal_small, cfg.num_pdfs, zero=True))
+                              output_xent=affine_params(cfg.prefinal_small, cfg.num_pdfs, zero=not self.frozen))
 
         # ---------------- frozen batch-norm (BatchNormTestComponent) or train-mode batch-norm
         def make_bn(dim):
@@ -218,7 +241,7 @@ class Supernet:
             right = ",".join(str(i) for i in self.right_offsets[b])
             if manual:
                 # the config lines XconfigTdnnfLayer emits (composite_layers.py:156-169)
-                common = (f"learning-rate={cfg.learning_rate} l2-regularize={cfg.l2_regularize} max-change={cfg.max_change}")
+                common = (f"learning-rate={0.0 if bneck else cfg.learning_rate} l2-regularize={cfg.l2_regularize} max-change={cfg.max_change}")
                 lin = nnet3.Component.new("TdnnComponent", f"input-dim={D} output-dim={B} {common} use-bias=false "
                                                            f"time-offsets={left} orthonormal-constraint=-1.0")
                 aff = nnet3.Component.new("TdnnComponent", f"input-dim={B} output-dim={D} {common} time-offsets={right}")
@@ -263,6 +286,27 @@ class Supernet:
                        memo_lin=C.c_void_p(), memo_aff=C.c_void_p(), rows_prev=rows_prev)
             if cfg.dropout:
                 blk.update(self._make_dropout(D, grid(aff_t[b]), rows_aff, zeros))
+            if bneck:
+                # tdnnfK.alpha / tdnnfK.softmax (add_flopsconstraint.py:15-30) on the rows of the `linear` output, the CopyN /
+                # ElementwiseProduct components of generate_bottleneckCB8share_onehottrain_config.py:22-75
+                soft = (f"GumbelSoftmaxFlopsComponent dim=8 scale={cfg.flops_coef} temp-proportion=1.0" if cfg.bottleneck_gumbel
+                        else f"SoftmaxFlopsComponent dim=8 scale={cfg.flops_coef}").split(" ", 1)
+                nb = len(cfg.candidate_widths)
+                blk.update(alpha=nnet3.Component.new("ConstantFunctionComponent",
+                                                     f"input-dim={cfg.feat_dim} output-dim={nb} is-updatable=true use-natural-gradient=false "
+                                                     f"learning-rate={cfg.learning_rate}"),
+                           soft=nnet3.Component.new(soft[0], soft[1].replace("dim=8", f"dim={nb}")),
+                           a_rows=zeros(rows_lin, nb), p=zeros(rows_lin, nb), d_p=zeros(rows_lin, nb), d_a=zeros(rows_lin, nb),
+                           masked=zeros(rows_lin, B), d_masked=zeros(rows_lin, B), alpha_delta=None,
+                           widths=(C.c_int32 * nb)(*cfg.candidate_widths))
+                if not cfg.fuse_mask:
+                    blk.update(copyn=[nnet3.Component.new("CopyNComponent", f"input-dim=1 output-dim={w}") for w in cfg.candidate_widths],
+                               prod=[nnet3.Component.new("ElementwiseProductComponent", f"input-dim={2 * w} output-dim={w}")
+                                     for w in cfg.candidate_widths],
+                               m_in=[zeros(rows_lin, 1) for _ in cfg.candidate_widths],
+                               cn=[zeros(rows_lin, w) for w in cfg.candidate_widths],
+                               pin=[zeros(rows_lin, 2 * w) for w in cfg.candidate_widths],
+                               d_pin=[zeros(rows_lin, 2 * w) for w in cfg.candidate_widths])
             self.blocks.append(blk)
 
         rows_in, rows_T = len(in_t) * S, T * S
@@ -294,17 +338,17 @@ class Supernet:
                                               chain.ChainTrainingOptions(leaky_hmm_coefficient=cfg.leaky_hmm))
         self._alloc_deltas()
         self._compile()
-        if search:
+        if self.frozen_bn:
             self._freeze_batchnorm()
             self._compile()
 
     def _backward_order(self):
         """Updatable components in the order the backward pass finishes them (= their order in the delta arena)."""
         head = ["output", "pc_linear", "pc_affine"] + (["output_xent", "px_linear", "px_affine"] if self.cfg.xent else []) + ["prefinal_l"]
-        order = [("stock", nm) for nm in head]
+        order = [] if self.frozen else [("stock", nm) for nm in head]
         for b in range(len(self.blocks) - 1, -1, -1):
-            order += [("comp", (b, "aff")), ("comp", (b, "lin"))]
-        return order + [("stock", "tdnn1")]
+            order += [("comp", (b, "alpha"))] if self.cfg.mode == "bottleneck" else [("comp", (b, "aff")), ("comp", (b, "lin"))]
+        return order + ([] if self.frozen else [("stock", "tdnn1")])
 
     def _alloc_deltas(self):
         """delta_nnet_ as ONE device range (nnet3.arena): the delta copy of every updatable component, in backward order,
@@ -360,7 +404,7 @@ class Supernet:
                 self.delta_buckets.append(((kind, key), start, e))
                 start = e
         self.dp = None
-        if self.world > 1:
+        if self.world > 1 and not self.standalone:
             import torch.distributed as dist
 
             def exchange(ident: bytes) -> bytes:  # rank 0's NCCL id to everybody: plumbing over torch.distributed
@@ -464,15 +508,95 @@ class Supernet:
         xp, xr, xc, xs = _m(x)
         dp, dr, dc, ds = _m(d_out)
         wp, _, _, ws = _m(p["W"])
-        gp, _, _, gs = _m(p["dW"])
+        gp, gs = (_m(p["dW"])[0], _m(p["dW"])[3]) if p["dW"] is not None else (None, 0)
         one = C.c_void_p(self.one.data_ptr())
         if d_in is not None:
             ip, ir, ic, is_ = _m(d_in)
             if zero:
                 plan.add("abi", lib.tdnnf_mat_set, h, ip, ir, ic, is_, 0.0)
             plan.add("abi", lib.tdnnf_darts_backprop_data, h, dp, dr, dc, ds, ip, ir, ic, is_, wp, ws, one, 1, self.zero_off, 1)
-        plan.add("abi", lib.tdnnf_darts_backprop_params, h, xp, xr, xc, xs, dp, dr, dc, ds, None, 0, gp, gs,
-                 C.c_void_p(p["db"].data_ptr()) if p["db"] is not None else None, one, 1, self.zero_off, 1, lr, None)
+        if not self.frozen:  # learning-rate-factor 0: no model derivative (nnet3 leaves it out of the computation)
+            plan.add("abi", lib.tdnnf_darts_backprop_params, h, xp, xr, xc, xs, dp, dr, dc, ds, None, 0, gp, gs,
+                     C.c_void_p(p["db"].data_ptr()) if p["db"] is not None else None, one, 1, self.zero_off, 1, lr, None)
+
+    def _mask_fwd(self, plan, blk):
+        """tdnnfK.alpha -> tdnnfK.softmax -> Sum(p_j..) -> CopyN_j -> Append -> ElementwiseProduct_j -> Append: lin_out -> masked."""
+        cfg, lib, h = self.cfg, self.lib, self.ctx.h
+        R = blk["lin_out"].shape[0]
+        lda = self.x[:R]  # stands for the `lda` rows the graph names as input; ConstantFunctionComponent ignores its input
+        self.keep.append(lda)
+        xp, xr, xc, xs = _m(lda)
+        ap, ar, ac, as_ = _m(blk["a_rows"])
+        plan.add("nnet3", lib.tdnnf_nnet3_propagate, blk["alpha"].h, None, xp, xr, xc, xs, ap, ar, ac, as_, None)
+        pp, _, _, ps = _m(blk["p"])
+        plan.add("nnet3", lib.tdnnf_nnet3_propagate, blk["soft"].h, None, ap, ar, ac, as_, pp, ar, ac, ps, None)
+        lp, _, lc, ls = _m(blk["lin_out"])
+        mp, _, _, ms = _m(blk["masked"])
+        if cfg.fuse_mask:
+            plan.add("abi", lib.tdnnf_shared_mask_fwd, h, pp, ar, ac, ps, lp, lc, ls, mp, ms, blk["widths"], 1.0)
+            return
+        off = 0
+        for j, w in enumerate(cfg.candidate_widths):
+            # Sum(softmax_j, .., softmax_7): matrix-add commands on 1-column sub-matrices
+            m_in = blk["m_in"][j]
+            plan.add("abi", lib.tdnnf_mat_set, h, *_m(m_in), 0.0)
+            for k in range(j, ac):
+                col = blk["p"][:, k:k + 1]
+                self.keep.append(col)
+                plan.add("abi", lib.tdnnf_mat_axpy, h, 1.0, _m(col)[0], _m(col)[3], _m(m_in)[0], _m(m_in)[3], ar, 1)
+            cn = blk["cn"][j]
+            plan.add("abi", lib.tdnnf_mat_set, h, *_m(cn), 0.0)                      # kPropagateAdds
+            plan.add("nnet3", lib.tdnnf_nnet3_propagate, blk["copyn"][j].h, None, *_m(m_in), *_m(cn), None)
+            pin = blk["pin"][j]                                                      # Append(copyn_j, linear_j)
+            left, right, lin_j = pin[:, :w], pin[:, w:], blk["lin_out"][:, off:off + w]
+            self.keep += [left, right, lin_j]
+            plan.add("abi", lib.tdnnf_add_scaled, h, _m(cn)[0], _m(cn)[3], 1.0, _m(cn)[0], _m(cn)[3], 0.0, _m(left)[0], _m(left)[3], ar, w)
+            plan.add("abi", lib.tdnnf_add_scaled, h, _m(lin_j)[0], _m(lin_j)[3], 1.0, _m(lin_j)[0], _m(lin_j)[3], 0.0, _m(right)[0],
+                     _m(right)[3], ar, w)
+            out_j = blk["masked"][:, off:off + w]
+            self.keep.append(out_j)
+            plan.add("nnet3", lib.tdnnf_nnet3_propagate, blk["prod"][j].h, None, *_m(pin), *_m(out_j), None)
+            off += w
+
+    def _mask_bwd(self, plan, blk):
+        """d_masked -> d_lin (for the `linear` layer) and the alpha update (softmax backprop with the FLOPs penalty, then
+        ConstantFunctionComponent::Backprop into the delta component)."""
+        cfg, lib, h = self.cfg, self.lib, self.ctx.h
+        ar, ac = blk["p"].shape
+        pp, _, _, ps = _m(blk["p"])
+        lp, _, lc, ls = _m(blk["lin_out"])
+        dm, _, _, dms = _m(blk["d_masked"])
+        dl, _, _, dls = _m(blk["d_lin"])
+        dp, _, _, dps = _m(blk["d_p"])
+        if cfg.fuse_mask:
+            plan.add("abi", lib.tdnnf_shared_mask_bwd, h, pp, ps, lp, ls, dm, dms, dl, dls, dp, dps, ar, lc, ac, blk["widths"], 1.0)
+        else:
+            plan.add("abi", lib.tdnnf_mat_set, h, dp, ar, ac, dps, 0.0)
+            off = 0
+            for j, w in enumerate(cfg.candidate_widths):
+                d_out_j, d_pin = blk["d_masked"][:, off:off + w], blk["d_pin"][j]
+                self.keep.append(d_out_j)
+                pin = blk["pin"][j]
+                plan.add("nnet3", lib.tdnnf_nnet3_backprop, blk["prod"][j].h, None, _m(pin)[0], ar, 2 * w, _m(pin)[3], None, 0,
+                         _m(d_out_j)[0], ar, w, _m(d_out_j)[3], None, None, _m(d_pin)[0], _m(d_pin)[3])
+                left, right, d_lin_j = d_pin[:, :w], d_pin[:, w:], blk["d_lin"][:, off:off + w]
+                self.keep += [left, right, d_lin_j]
+                plan.add("abi", lib.tdnnf_add_scaled, h, _m(right)[0], _m(right)[3], 1.0, _m(right)[0], _m(right)[3], 0.0,
+                         _m(d_lin_j)[0], _m(d_lin_j)[3], ar, w)
+                d_m = blk["m_in"][j]                                                 # reused as the derivative of Sum(..)
+                plan.add("abi", lib.tdnnf_mat_set, h, *_m(d_m), 0.0)                 # kBackpropAdds
+                plan.add("nnet3", lib.tdnnf_nnet3_backprop, blk["copyn"][j].h, None, None, ar, 1, 0, None, 0, _m(left)[0], ar, w,
+                         _m(left)[3], None, None, _m(d_m)[0], _m(d_m)[3])
+                for k in range(j, ac):                                               # transpose of the Sum descriptor
+                    col = blk["d_p"][:, k:k + 1]
+                    self.keep.append(col)
+                    plan.add("abi", lib.tdnnf_mat_axpy, h, 1.0, _m(d_m)[0], _m(d_m)[3], _m(col)[0], _m(col)[3], ar, 1)
+                off += w
+        ap, _, _, as_ = _m(blk["a_rows"])
+        da, _, _, das = _m(blk["d_a"])
+        plan.add("nnet3", lib.tdnnf_nnet3_backprop, blk["soft"].h, None, ap, ar, ac, as_, pp, ps, dp, ar, ac, dps, None, None, da, das)
+        plan.add("nnet3", lib.tdnnf_nnet3_backprop, blk["alpha"].h, None, None, ar, ac, 0, None, 0, da, ar, ac, das, None,
+                 blk["alpha_delta"].h, None, 0)
 
     def _bucket_hook(self, plan, kind, key):
         """Inside the backward plan: once the backward pass has finished the last component of a delta bucket, start its
@@ -482,7 +606,11 @@ class Supernet:
         for (last, begin, end) in self.delta_buckets:
             if last == (kind, key):
                 ptr, count = self.delta_arena.data_ptr() + 4 * begin, end - begin
-                plan.add_py(partial(self.dp.allreduce_bucket_async, ptr, count))
+                plan.add_py(partial(self._bucket_reduce, ptr, count))
+
+    def _bucket_reduce(self, ptr, count):
+        if self._reduce_now:
+            self.dp.allreduce_bucket_async(ptr, count)
 
     def _bn_fwd(self, plan, bn, x, out):
         lib = self.lib
@@ -522,11 +650,15 @@ class Supernet:
         for blk in self.blocks:
             pp, pr, pc, ps = _m(prev)
             lp, lr_, lc, ls = _m(blk["lin_out"])
-            if cfg.mode == "manual":  # use-bias=false => kPropagateAdds: the computer hands over a zeroed matrix
+            if cfg.mode in ("manual", "bottleneck"):  # use-bias=false => kPropagateAdds: the computer hands over a zeroed matrix
                 fwd.add("abi", lib.tdnnf_mat_set, h, lp, lr_, lc, ls, 0.0)
             fwd.add("nnet3", lib.tdnnf_nnet3_propagate, blk["lin"].h, blk["lin_idx"].h, pp, pr, pc, ps, lp, lr_, lc, ls,
                     C.byref(blk["memo_lin"]))
             a_in = blk["lin_out"]
+            if cfg.mode == "bottleneck":
+                self._mask_fwd(fwd, blk)
+                a_in = blk["masked"]
+                lp, lr_, lc, ls = _m(a_in)
             if blk["reorder"]:
                 ip, ir, ic, is_ = _m(blk["aff_in"])
                 fwd.add("abi", lib.tdnnf_copy_rows, h, lp, ls, ip, is_, ir, ic, C.c_void_p(blk["reorder"]["fwd"].data_ptr()))
@@ -652,25 +784,39 @@ class Supernet:
                     bwd.add("abi", lib.tdnnf_relu_bwd, h, _m(blk["relu"])[0], _m(blk["relu"])[3], _m(blk["d_aff"])[0], _m(blk["d_aff"])[3],
                             _m(blk["d_aff"])[0], _m(blk["d_aff"])[3], dr, dc)
             # affine DARTS: in_deriv (kBackpropAdds) must start from zero
-            a_in = blk["aff_in"] if blk["reorder"] else blk["lin_out"]
-            d_ain = blk["d_aff_in"] if blk["reorder"] else blk["d_lin"]
+            bneck = cfg.mode == "bottleneck"
+            a_src = blk["masked"] if bneck else blk["lin_out"]
+            d_src = blk["d_masked"] if bneck else blk["d_lin"]
+            a_in = blk["aff_in"] if blk["reorder"] else a_src
+            d_ain = blk["d_aff_in"] if blk["reorder"] else d_src
             ip, ir, ic, is_ = _m(a_in)
             gp, gr, gc, gs = _m(d_ain)
+            delta_h = lambda d: d.h if d is not None else None   # frozen component: no to_update, data gradient only
             bwd.add("abi", lib.tdnnf_mat_set, h, gp, gr, gc, gs, 0.0)
             bwd.add("nnet3", lib.tdnnf_nnet3_backprop, blk["aff"].h, blk["aff_idx"].h, ip, ir, ic, is_, None, 0,
-                    _m(blk["d_aff"])[0], dr, dc, _m(blk["d_aff"])[3], blk["memo_aff"], blk["aff_delta"].h, gp, gs)
+                    _m(blk["d_aff"])[0], dr, dc, _m(blk["d_aff"])[3], blk["memo_aff"], delta_h(blk["aff_delta"]), gp, gs)
             bwd.add("nnet3", lib.tdnnf_nnet3_delete_memo, blk["aff"].h, blk["memo_aff"])
             self._bucket_hook(bwd, "comp", (bi, "aff"))
             if blk["reorder"]:
-                lp, lr_, lc, ls = _m(blk["d_lin"])
+                lp, lr_, lc, ls = _m(d_src)
                 bwd.add("abi", lib.tdnnf_copy_rows, h, gp, gs, lp, ls, lr_, lc, C.c_void_p(blk["reorder"]["inv"].data_ptr()))
-            # linear DARTS: accumulates into d_prev on top of the bypass term
+            if bneck:
+                self._mask_bwd(bwd, blk)
+                self._bucket_hook(bwd, "comp", (bi, "alpha"))
+            # linear DARTS: accumulates into d_prev on top of the bypass term.  With everything below frozen (search stages)
+            # the first block needs no input derivative.
             pp, pr, pc, ps = _m(prev_out)
             lp, lr_, lc, ls = _m(blk["d_lin"])
-            bwd.add("nnet3", lib.tdnnf_nnet3_backprop, blk["lin"].h, blk["lin_idx"].h, pp, pr, pc, ps, None, 0, lp, lr_, lc, ls,
-                    blk["memo_lin"], blk["lin_delta"].h, qp, qs)
+            want_in = not (self.frozen and bi == 0)
+            if want_in or blk["lin_delta"] is not None:
+                bwd.add("nnet3", lib.tdnnf_nnet3_backprop, blk["lin"].h, blk["lin_idx"].h, pp, pr, pc, ps, None, 0, lp, lr_, lc, ls,
+                        blk["memo_lin"], delta_h(blk["lin_delta"]), qp if want_in else None, qs)
             bwd.add("nnet3", lib.tdnnf_nnet3_delete_memo, blk["lin"].h, blk["memo_lin"])
             self._bucket_hook(bwd, "comp", (bi, "lin"))
+        if self.frozen:  # tdnn1 and everything below it: no derivative is needed
+            self.fwd_plan, self.bwd_plan = fwd, bwd
+            self._compile_update()
+            return
         if cfg.dropout:
             self._dropout_bwd(bwd, t1, t1["d_out"], t1["d_out"])
             self._bn_bwd(bwd, t1["bn"], t1["drop_in"], t1["d_out"], t1["d_out"])
@@ -681,16 +827,22 @@ class Supernet:
         self._affine_bwd(bwd, self.x, st["tdnn1"], t1["d_aff"], None, lr)
         self._bucket_hook(bwd, "stock", "tdnn1")
 
-        # ---- parameter step (UpdateNnetWithMaxChange, utils.cc:2085-2175): squared norms of every delta on the
-        # device, ONE read-back, Kaldi's per-component / global max-change factors on the host, scaled Add.
-        import torch
+        self.fwd_plan, self.bwd_plan = fwd, bwd
+        self._compile_update()
 
+    def _compile_update(self):
+        """The parameter step (UpdateNnetWithMaxChange, utils.cc:2085-2175) as a table of (model, delta) buffers."""
+        cfg, st = self.cfg, self.stock
         self.updatables = []  # (kind, model, delta, max_change)
         for blk in self.blocks:
-            self.updatables.append(("comp", blk["lin"], blk["lin_delta"], cfg.max_change))
-            self.updatables.append(("comp", blk["aff"], blk["aff_delta"], cfg.max_change))
-        for name, p in st.items():
-            self.updatables.append(("stock", p, None, 1.5 if name.startswith("output") else cfg.max_change))
+            if cfg.mode == "bottleneck":
+                self.updatables.append(("comp", blk["alpha"], blk["alpha_delta"], 0.0))  # UpdatableComponent default max-change
+            else:
+                self.updatables.append(("comp", blk["lin"], blk["lin_delta"], cfg.max_change))
+                self.updatables.append(("comp", blk["aff"], blk["aff_delta"], cfg.max_change))
+        stock_names = [] if self.frozen else list(st)
+        for name in stock_names:
+            self.updatables.append(("stock", st[name], None, 1.5 if name.startswith("output") else cfg.max_change))
         # every parameter buffer of the model with the matching delta buffer: (model ptr, stride, delta ptr, stride, rows, cols, group)
         bufs = []
         for i, (kind, m, d, _) in enumerate(self.updatables):
@@ -712,10 +864,9 @@ class Supernet:
             if kind == "comp":
                 self.l2_lrate.append(d.learning_rate())
                 self.l2_value.append(cfg.l2_regularize)
-        for name in st:
+        for name in stock_names:
             self.l2_lrate.append(cfg.learning_rate * (0.5 / self.objective.opts.xent_regularize if name == "output_xent" else 1.0))
             self.l2_value.append(0.002 if name.startswith("output") else cfg.l2_regularize)  # output_opts (run_tdnn_7q_fbk_40_manual.sh:123)
-        self.fwd_plan, self.bwd_plan = fwd, bwd
 
     def _allreduce_deltas(self):
         """Sum of the ranks' deltas (tdnnf_dp_*: NCCL over NVLink through the C ABI), in place on the delta arena."""
@@ -741,14 +892,16 @@ class Supernet:
         g = synth.rng(3, stream=100 + self.rank * 1000 + step)
         return torch.from_numpy(g.standard_normal((self.rows_in, self.cfg.feat_dim)).astype(np.float32))
 
-    def step(self, x_host=None, apply_update: bool = True) -> float:
+    def step(self, x_host=None, apply_update: bool = True, reduce: bool = True) -> float:
         """One training step.  x_host: pinned host tensor (rows_in x feat_dim) or None to reuse device input.
+        reduce=False leaves this rank's own deltas in the delta arena (no all-reduce): bench.py's data-parallel self-check.
         (Prefetching the next input on a copy stream was measured: it made the step 3 ms SLOWER than this in-stream
         copy, which costs 0.4 ms.)
         Returns the LF-MMI objective per output frame (numerator - denominator) of this rank."""
         import torch
 
         cfg = self.cfg
+        self._reduce_now = reduce and self.dp is not None
         if x_host is not None:
             self.x.copy_(x_host, non_blocking=True)
         self.fwd_plan.run()
@@ -764,7 +917,7 @@ class Supernet:
             # bucket reductions (dp_buckets > 1) see complete deltas
             self._apply_l2_regularization()
         self.bwd_plan.run()
-        if self.world > 1:
+        if self._reduce_now:
             self._allreduce_deltas()
         if apply_update:
             self._update_with_max_change()

@@ -13,7 +13,7 @@ def test_supernet_step_runs_and_learns(mode):
     from tdnnf_nas_b200.supernet import Supernet, SupernetConfig
 
     cfg = SupernetConfig(num_seqs=8, frames_per_eg=30, dim=128, bottleneck=32, num_blocks=3, prefinal_small=64,
-                         num_pdfs=200, den_states=300, den_out_degree=6.0, mode=mode, learning_rate=2e-3)
+                         num_pdfs=200, den_states=300, den_out_degree=6.0, mode=mode, learning_rate=2e-3, freeze_stock=False)
     net = Supernet(cfg)
     x = net.make_input(0).pin_memory()
     launches0 = net.ctx.launches
@@ -36,6 +36,67 @@ def test_supernet_step_runs_and_learns(mode):
         alpha = v[cfg.bottleneck * n * cfg.dim: cfg.bottleneck * n * cfg.dim + n]
         assert all(math.isfinite(float(a)) for a in alpha) and any(abs(float(a)) > 0 for a in alpha)
     net.close()
+
+
+def test_search_stage_freezes_what_the_recipe_freezes():
+    """run_TDNN_DARTSV3_fbk_stride_cvupdate.sh:129-134: learning-rate-factor 0 on everything, then back to 1e-4 on the
+    TdnnDARTSV3 components only.  The default search step therefore leaves tdnn1 / prefinal / output bit-identical, still
+    moves every alpha, and its delta arena holds the 2 x blocks TdnnDARTSV3 deltas only."""
+    import torch
+
+    from tdnnf_nas_b200.supernet import Supernet, SupernetConfig
+
+    cfg = SupernetConfig(num_seqs=8, frames_per_eg=30, dim=128, bottleneck=32, num_blocks=3, prefinal_small=64,
+                         num_pdfs=200, den_states=300, den_out_degree=6.0, mode="search", learning_rate=2e-3, xent=True)
+    net = Supernet(cfg)
+    assert net.frozen and len(net.delta_spans) == 2 * cfg.num_blocks
+    before = {k: (p["W"].clone(), None if p["b"] is None else p["b"].clone()) for k, p in net.stock.items()}
+    assert float(before["output"][0].abs().max()) > 0  # a frozen (pre-trained) output layer is not the zero initialisation
+    x = net.make_input(0).pin_memory()
+    n = cfg.num_offsets
+    a0 = [blk["lin"].vectorize()[cfg.bottleneck * n * cfg.dim: cfg.bottleneck * n * cfg.dim + n].copy() for blk in net.blocks]
+    objfs = [net.step(x) for _ in range(3)]
+    assert all(math.isfinite(o) for o in objfs)
+    for k, p in net.stock.items():
+        assert torch.equal(p["W"], before[k][0]) and (p["b"] is None or torch.equal(p["b"], before[k][1])), k
+    for blk, a in zip(net.blocks, a0):
+        a1 = blk["lin"].vectorize()[cfg.bottleneck * n * cfg.dim: cfg.bottleneck * n * cfg.dim + n]
+        assert all(math.isfinite(float(v)) for v in a1) and any(float(v) != float(w) for v, w in zip(a1, a))
+    net.close()
+
+
+@pytest.mark.parametrize("gumbel", [False, True])
+def test_bottleneck_search_step(gumbel):
+    """BASELINE configs[3] at a small size: frozen TdnnComponent layers with the shared-candidate mask on the bottleneck,
+    {Gumbel}SoftmaxFlopsComponent(alpha) with the FLOPs penalty; only the alpha vectors move.  The fused mask kernels and
+    the component-by-component graph (CopyN, ElementwiseProduct, matrix-add descriptors) give the same trajectory."""
+    import numpy as np
+    import torch
+
+    from tdnnf_nas_b200.supernet import Supernet, SupernetConfig
+
+    runs = []
+    for fuse in (True, False):
+        cfg = SupernetConfig(num_seqs=8, frames_per_eg=30, dim=128, bottleneck=24, num_blocks=3, prefinal_small=64,
+                             num_pdfs=200, den_states=300, den_out_degree=6.0, mode="bottleneck", learning_rate=2e-3,
+                             candidate_widths=(3, 5, 4, 12), flops_coef=0.1, bottleneck_gumbel=gumbel, fuse_mask=fuse,
+                             strides=[1, 0, 3])
+        net = Supernet(cfg)
+        assert net.frozen and len(net.delta_spans) == cfg.num_blocks
+        w0 = [blk["lin"].vectorize().copy() for blk in net.blocks]
+        x = net.make_input(0).pin_memory()
+        objfs = [net.step(x) for _ in range(3)]
+        alphas = np.stack([blk["alpha"].vectorize() for blk in net.blocks])
+        assert all(math.isfinite(o) for o in objfs) and np.isfinite(alphas).all()
+        assert (np.abs(alphas).max(axis=1) > 0).all()          # every layer's alpha received a gradient
+        for blk, w in zip(net.blocks, w0):
+            assert np.array_equal(blk["lin"].vectorize(), w)   # learning-rate-factor 0
+        runs.append((objfs, alphas))
+        net.close()
+    (o1, a1), (o2, a2) = runs
+    for a, b in zip(o1, o2):
+        assert abs(a - b) <= 1e-5 * abs(a) + 1e-6, (o1, o2)
+    np.testing.assert_allclose(a1, a2, rtol=2e-3, atol=1e-7)
 
 
 def test_fused_tail_matches_component_path():
