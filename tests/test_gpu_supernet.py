@@ -79,7 +79,7 @@ def test_bottleneck_search_step(gumbel):
     for fuse in (True, False):
         cfg = SupernetConfig(num_seqs=8, frames_per_eg=30, dim=128, bottleneck=24, num_blocks=3, prefinal_small=64,
                              num_pdfs=200, den_states=300, den_out_degree=6.0, mode="bottleneck", learning_rate=2e-3,
-                             candidate_widths=(3, 5, 4, 12), flops_coef=0.1, bottleneck_gumbel=gumbel, fuse_mask=fuse,
+                             candidate_widths=(2, 2, 3, 3, 2, 4, 4, 4), flops_coef=0.1, bottleneck_gumbel=gumbel, fuse_mask=fuse,
                              strides=[1, 0, 3])
         net = Supernet(cfg)
         assert net.frozen and len(net.delta_spans) == cfg.num_blocks
