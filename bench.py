@@ -104,6 +104,53 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ CPU baseline (the oracle, timed)
+CPU_REF_CHUNKS = 16  # chunks per CPU "step": a bounded sample (a quarter of the 64-chunk minibatch, every layer at full width)
+
+
+def cpu_reference_steps(cfg, steps: int, warmup: int, chunks: int = CPU_REF_CHUNKS):
+    """The search-stage training step on the host cores, WHOLE (oracle/supernet_ref.py: every layer, LF-MMI numerator and
+    denominator, TdnnDARTSV3 Backprop with both OnlineNaturalGradient preconditioners, max-change update), every AddMatMat
+    through cblas_sgemm (numpy's bundled OpenBLAS) as in a Kaldi CPU build.  Each step is a minibatch of `chunks` chunks of
+    150 frames (the GPU step has 64): nothing is extrapolated, frames/s = chunks * 150 * steps / wall time."""
+    import numpy as np
+
+    from oracle import oracle as O
+    from oracle import supernet_ref as R
+    from tdnnf_nas_b200 import synth
+
+    O.use_all_cores()
+    blas = O.enable_blas()
+    rcfg = R.RefConfig(num_seqs=chunks, frames_per_eg=cfg.frames_per_eg, frame_subsampling=cfg.frame_subsampling, feat_dim=cfg.feat_dim,
+                       dim=cfg.dim, bottleneck=cfg.bottleneck, num_blocks=cfg.num_blocks, num_offsets=cfg.num_offsets,
+                       prefinal_small=cfg.prefinal_small, num_pdfs=cfg.num_pdfs, leaky_hmm=cfg.leaky_hmm, xent=cfg.xent,
+                       learning_rate=cfg.learning_rate, darts_lr_factor=cfg.darts_lr_factor)
+    T = cfg.frames_per_eg // cfg.frame_subsampling
+    den = synth.make_den_graph(cfg.den_states, cfg.num_pdfs, cfg.den_out_degree, seed=5)
+    num = synth.make_num_graphs(chunks, cfg.num_pdfs, T, seed=60, den_graph=den)
+    net = R.CpuSupernet(rcfg, den, num)
+    g = np.random.default_rng(7)
+    x = g.standard_normal((len(net.in_t) * chunks, cfg.feat_dim)).astype(np.float32)
+    draws = lambda: [g.uniform(0.05, 0.95, cfg.num_offsets).astype(np.float32) for _ in range(2 * cfg.num_blocks)]
+    for _ in range(warmup):
+        net.step(x, draws())
+    if warmup > 0:  # like the NG_SETTLE_STEPS of the GPU arm: time the steady state (one Fisher refresh per 4 minibatches)
+        for pair in net.ng.values():
+            for ng in pair:
+                ng.skip_initial_updates()
+    t0 = time.perf_counter()
+    objf = None
+    for _ in range(steps):
+        objf = net.step(x, draws())
+    wall = time.perf_counter() - t0
+    frames = chunks * cfg.frames_per_eg
+    return dict(fps=frames * steps / wall, step_s=wall / steps, wall=wall, cores=O.num_threads(), chunks=chunks, objf=objf,
+                sample=(f"whole search-stage training step on the host (oracle/supernet_ref.py: 14 blocks at full width, LF-MMI numerator + "
+                        f"denominator on the {cfg.den_states}-state graph, TdnnDARTSV3 Backprop with both OnlineNaturalGradient "
+                        f"preconditioners, max-change update) at {chunks} chunks x {cfg.frames_per_eg} frames per step (the GPU step: "
+                        f"{cfg.num_seqs}), {steps} steps timed after {warmup} warm-up; GEMMs: {blas or 'plain OpenMP loops (no BLAS found)'}; "
+                        "measured, not extrapolated"))
+
+
 def cpu_baseline_sample(cfg, repeats: int = 1):
     """Times the oracle on a bounded sample of the workload and extrapolates to frames/sec.
     Sample: one TDNN-F block (TdnnDARTSV3 1536->160 and 160->1536, 7 offsets; Propagate + Backprop incl. the
@@ -292,6 +339,19 @@ def dp_self_check(net, cfg, world, rank, local_rank, x_host):
 def run_reference(args, cfg, rank, world):
     if rank != 0:
         return
+    if cfg.mode == "search":
+        r = cpu_reference_steps(cfg, args.steps, args.warmup)
+        line = dict(impl="reference", metric=METRIC, value=r["fps"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=r["step_s"] * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                    data="synthetic", config=workload_config(cfg, args.gpus),
+                    cpu_baseline=dict(value=r["fps"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"]),
+                    e2e=dict(value=r["fps"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                    objf_per_frame=r["objf"],
+                    note=("the reference (a patch set on upstream Kaldi) cannot be built here; this arm runs the in-repo CPU restatement "
+                          f"of its methods on one host ({r['cores']} threads, {r['chunks']} chunks per step); single-host number, does "
+                          "not scale with --gpus"))
+        print(json.dumps(line), flush=True)
+        return
     frames = cfg.num_seqs * cfg.frames_per_eg
     flops = supernet_flops(cfg)
     for _ in range(args.warmup):
@@ -470,10 +530,14 @@ def run_ours(args, cfg, rank, world, local_rank):
     peak = peaks["bf16_tflops_sustained"]
     step_ms = ms_dev / args.steps
     cpu_line = None
-    if world == 1:  # the CPU baseline is reported at N = 1 only
-        cpu = cpu_baseline_sample(cfg)
-        cpu_fps, _ = cpu_frames_per_sec(cfg, cpu, net.algorithmic_flops(), net.frames_per_step)
-        cpu_line = dict(value=cpu_fps, unit=UNIT, cores=cpu["cores"], kind="port", sample=cpu["sample"])
+    if world == 1 and not args.no_cpu_baseline:  # the CPU baseline is reported at N = 1 only
+        if cfg.mode == "search":
+            r = cpu_reference_steps(cfg, steps=2, warmup=1)
+            cpu_line = dict(value=r["fps"], unit=UNIT, cores=r["cores"], kind="port", sample=r["sample"])
+        else:
+            cpu = cpu_baseline_sample(cfg)
+            cpu_fps, _ = cpu_frames_per_sec(cfg, cpu, net.algorithmic_flops(), net.frames_per_step)
+            cpu_line = dict(value=cpu_fps, unit=UNIT, cores=cpu["cores"], kind="port", sample=cpu["sample"])
     line = dict(
         metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=step_ms,
         higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -524,6 +588,7 @@ def main():
     ap.add_argument("--mixing", action="store_true", help="add the per-kernel GB/s table of the mixing kernels to the line")
     ap.add_argument("--dp-buckets", type=int, default=1, help="N > 1: delta buckets reduced while the backward pass runs")
     ap.add_argument("--no-dp-check", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     ap.add_argument("--train-stock", action="store_true", help="search mode: also train tdnn1 / prefinal / output (round-1 behaviour)")
     ap.add_argument("--den-states", type=int, default=16384)
     ap.add_argument("--blocks", type=int, default=14)
@@ -542,9 +607,9 @@ def main():
                          bottleneck_gumbel=args.gumbel, fuse_mask=not args.unfused_mask,
                          freeze_stock=False if args.train_stock else None)
     if args.impl == "reference":
-        if args.steps > 3:
-            args.steps = 3  # each step is ~10 s of CPU work: keep the whole run within a few minutes
-        args.warmup = min(args.warmup, 1)
+        if cfg.mode != "search" and args.steps > 3:
+            args.steps = 3  # the sampled legs of the secondary workloads: ~10 s of CPU work each
+        args.warmup = min(args.warmup, 1) if cfg.mode != "search" else args.warmup
         run_reference(args, cfg, rank, world)
         return
     args.warmup = max(args.warmup, 3)

@@ -358,6 +358,9 @@ int tdnnf_ng_w_update(tdnnf_ctx* ctx, const float* A, int a_stride, const float*
 /* dst += alpha * (*factor1_dev) * (*factor2_dev) * src   (device scalars, either may be NULL = 1) */
 int tdnnf_mat_axpy_dev(tdnnf_ctx* ctx, float alpha, const float* factor1_dev, const float* factor2_dev,
                        const float* src, int src_stride, float* dst, int dst_stride, int rows, int cols);
+/* The same, and src = 0 afterwards (the gradient scratch of UpdateNaturalGradient is consumed exactly once). */
+int tdnnf_mat_axpy_dev_zero(tdnnf_ctx* ctx, float alpha, const float* factor1_dev, const float* factor2_dev, float* src,
+                            int src_stride, float* dst, int dst_stride, int rows, int cols);
 
 /* ------------------------------------------------------------------ chain denominator - */
 /* DenominatorGraph (kaldi: chain/chain-den-graph.{h,cc}).  Host arrays, copied to the device.

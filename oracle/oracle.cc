@@ -30,8 +30,20 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#include <dlfcn.h>
 
 namespace {
+
+// Optional BLAS behind AddMatMat (orc_use_blas): a Kaldi CPU build calls cblas_sgemm for every AddMatMat, so the timed
+// CPU baseline should too.  No BLAS is installed system-wide in the image; numpy ships OpenBLAS (ILP64, symbols
+// scipy_cblas_sgemm64_), bound at run time.  Without it the plain OpenMP loops below are used (the parity tests).
+typedef void (*sgemm64_fn)(int order, int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda,
+                           const float* B, int64_t ldb, float beta, float* C, int64_t ldc);
+typedef void (*sgemm32_fn)(int order, int ta, int tb, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
+                           int ldb, float beta, float* C, int ldc);
+sgemm64_fn g_sgemm64 = nullptr;
+sgemm32_fn g_sgemm32 = nullptr;
+void (*g_blas_set_threads)(int) = nullptr;
 
 typedef float BaseFloat;
 
@@ -56,6 +68,13 @@ enum Trans { kNoTrans, kTrans };
 void AddMatMat(Mat C, BaseFloat alpha, const Mat& A, Trans ta, const Mat& B, Trans tb, BaseFloat beta) {
   const int M = C.rows, N = C.cols;
   const int K = (ta == kNoTrans) ? A.cols : A.rows;
+  if ((g_sgemm64 || g_sgemm32) && M > 0 && N > 0 && K > 0 && !(ta == kTrans && tb == kTrans)) {
+    // row-major: CblasRowMajor = 101, CblasNoTrans = 111, CblasTrans = 112
+    const int cta = ta == kNoTrans ? 111 : 112, ctb = tb == kNoTrans ? 111 : 112;
+    if (g_sgemm64) g_sgemm64(101, cta, ctb, M, N, K, alpha, A.data, A.stride, B.data, B.stride, beta, C.data, C.stride);
+    else g_sgemm32(101, cta, ctb, M, N, K, alpha, A.data, A.stride, B.data, B.stride, beta, C.data, C.stride);
+    return;
+  }
   if (ta == kNoTrans && tb == kTrans) {
     // C[m,n] = sum_k A[m,k] B[n,k]
 #pragma omp parallel for schedule(static)
@@ -117,6 +136,25 @@ extern "C" {
 #define ORC_UNIFORM_SAMPLE 4
 #define ORC_USE_ENTROPY 8
 #define ORC_UPDATE_ALPHA 16
+
+// Binds cblas_sgemm from the shared library at `path` (NULL: back to the plain loops).  Returns 1 if bound.
+int orc_use_blas(const char* path) {
+  g_sgemm64 = nullptr;
+  g_sgemm32 = nullptr;
+  g_blas_set_threads = nullptr;
+  if (path == nullptr) return 0;
+  void* h = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return 0;
+  g_sgemm64 = reinterpret_cast<sgemm64_fn>(dlsym(h, "scipy_cblas_sgemm64_"));
+  if (!g_sgemm64) g_sgemm64 = reinterpret_cast<sgemm64_fn>(dlsym(h, "cblas_sgemm64_"));
+  if (!g_sgemm64) g_sgemm32 = reinterpret_cast<sgemm32_fn>(dlsym(h, "cblas_sgemm"));
+  for (const char* nm : {"scipy_openblas_set_num_threads64_", "openblas_set_num_threads64_", "openblas_set_num_threads"})
+    if (!g_blas_set_threads) g_blas_set_threads = reinterpret_cast<void (*)(int)>(dlsym(h, nm));
+#ifdef _OPENMP
+  if (g_blas_set_threads) g_blas_set_threads(omp_get_max_threads());
+#endif
+  return (g_sgemm64 || g_sgemm32) ? 1 : 0;
+}
 
 void orc_set_num_threads(int n) {
 #ifdef _OPENMP
@@ -264,6 +302,7 @@ int orc_tdnn_backprop_ng(const int* time_offsets, int n, int flags, float temp_p
   // ---- UpdateNaturalGradient, tdnn.cc:457-626
   const int spliced = n * in_dim, augmented = spliced + 1;       // bias always present (Q3)
   OwnedMat in_value_temp(out_rows, augmented);
+#pragma omp parallel for schedule(static)
   for (int r = 0; r < out_rows; ++r) in_value_temp.m(r, spliced) = 1.0f;
   const bool gumbel = flags & ORC_USE_GUMBEL, uniform = flags & ORC_UNIFORM_SAMPLE, freesel = flags & ORC_FREE_SELECT;
   for (int i = 0; i < n; ++i) {
@@ -280,11 +319,10 @@ int orc_tdnn_backprop_ng(const int* time_offsets, int n, int flags, float temp_p
       }
       continue;
     }
+#pragma omp parallel for schedule(static)
     for (int r = 0; r < out_rows; ++r) memcpy(&tpart(r, 0), &in_part(r, 0), sizeof(float) * in_dim);
-    if (freesel) {
-      for (int r = 0; r < out_rows; ++r)
-        for (int c = 0; c < in_dim; ++c) tpart(r, c) *= coef[i];
-    } else if (i != share) {
+    if (freesel || i != share) {
+#pragma omp parallel for schedule(static)
       for (int r = 0; r < out_rows; ++r)
         for (int c = 0; c < in_dim; ++c) tpart(r, c) *= coef[i];
     }
@@ -292,6 +330,7 @@ int orc_tdnn_backprop_ng(const int* time_offsets, int n, int flags, float temp_p
     AddMatMat(out_temp.m, 1.0f, in_part, kNoTrans, lin_part, kTrans, 0.0f);
     // out_temp.AddMatMatElements(1.0, out_temp, out_deriv, 0.0); out_temp.Sum()
     double sum = 0.0;  // CuMatrix::Sum() reduces in BaseFloat on the GPU; the order is unspecified
+#pragma omp parallel for schedule(static) reduction(+ : sum)
     for (int r = 0; r < out_rows; ++r)
       for (int c = 0; c < out_dim; ++c) sum += (double)(out_temp.m(r, c) * od(r, c));
     const BaseFloat s = (BaseFloat)sum;
@@ -318,6 +357,7 @@ int orc_tdnn_backprop_ng(const int* time_offsets, int n, int flags, float temp_p
 
   // CuMatrix<BaseFloat> out_deriv_temp(out_deriv); the two PreconditionDirections calls   tdnn.cc:592-604
   OwnedMat out_deriv_temp(out_rows, out_dim);
+#pragma omp parallel for schedule(static)
   for (int r = 0; r < out_rows; ++r) memcpy(&out_deriv_temp.m(r, 0), &od(r, 0), sizeof(float) * out_dim);
   BaseFloat in_scale = 1.0f, out_scale = 1.0f;
   if (ng_in) NgPrecondition(static_cast<OrcNG*>(ng_in), in_value_temp.m, &in_scale);
@@ -325,6 +365,7 @@ int orc_tdnn_backprop_ng(const int* time_offsets, int n, int flags, float temp_p
   if (scales_out) { scales_out[0] = in_scale; scales_out[1] = out_scale; }
   const BaseFloat scale = in_scale * out_scale, local_lrate = scale * learning_rate;
   // bias tail: AddMatVec(local_lrate, out_deriv_temp, kTrans, precon_ones, 1.0)   tdnn.cc:607-617
+#pragma omp parallel for schedule(static)
   for (int c = 0; c < out_dim; ++c) {
     double sum = 0.0;
     for (int r = 0; r < out_rows; ++r) sum += (double)out_deriv_temp.m(r, c) * (double)in_value_temp.m(r, spliced);

@@ -57,6 +57,27 @@ def _stride(a):
     return a.strides[0] // a.itemsize
 
 
+def enable_blas(on: bool = True) -> str:
+    """AddMatMat through cblas_sgemm (what a Kaldi CPU build calls) instead of the plain OpenMP loops: binds the OpenBLAS
+    that numpy bundles (no system BLAS exists in the image).  Returns a description of what was bound ('' if nothing)."""
+    import glob
+
+    if not on:
+        lib().orc_use_blas(None)
+        return ""
+    cands = []
+    for pkg in ("numpy", "scipy"):
+        try:
+            mod = __import__(pkg)
+            cands += sorted(glob.glob(os.path.join(os.path.dirname(os.path.dirname(mod.__file__)), pkg + ".libs", "libscipy_openblas*.so")))
+        except Exception:
+            pass
+    for path in cands:
+        if lib().orc_use_blas(path.encode()) == 1:
+            return "OpenBLAS cblas_sgemm (" + os.path.basename(path) + ", bundled with numpy/scipy)"
+    return ""
+
+
 def num_threads() -> int:
     return lib().orc_num_threads()
 
@@ -116,6 +137,10 @@ class NaturalGradient:
 
     def freeze(self, frozen=True):
         lib().orc_ng_freeze(self.h, int(frozen))
+
+    def skip_initial_updates(self):
+        """Timing aid: past the 10 initial every-call updates, into the one-in-update_period steady state."""
+        lib().orc_ng_skip_initial_updates(self.h)
 
     def state(self):
         t, rank, D, nre, nfl = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()

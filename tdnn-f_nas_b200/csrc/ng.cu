@@ -322,8 +322,9 @@ __global__ void __launch_bounds__(128) ng_w_update_kernel(const float* __restric
   }
 }
 
+template <bool ZERO>
 __global__ void mat_axpy_dev_kernel(float alpha, const float* __restrict__ f1, const float* __restrict__ f2,
-                                    const float* __restrict__ src, long long ss, float* __restrict__ dst, long long ds,
+                                    float* __restrict__ src, long long ss, float* __restrict__ dst, long long ds,
                                     int rows, int cols) {
   float a = alpha;
   if (f1) a *= *f1;
@@ -333,6 +334,7 @@ __global__ void mat_axpy_dev_kernel(float alpha, const float* __restrict__ f1, c
     const long long r = idx / cols;
     const int c = (int)(idx % cols);
     dst[r * ds + c] += a * src[r * ss + c];
+    if (ZERO) src[r * ss + c] = 0.f;
   }
 }
 
@@ -439,8 +441,22 @@ extern "C" int tdnnf_mat_axpy_dev(tdnnf_ctx* ctx, float alpha, const float* fact
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
   long long b = ((long long)rows * cols + 255) / 256;
   b = std::max(1LL, std::min(b, (long long)ctx->num_sms * 16));
-  mat_axpy_dev_kernel<<<(int)b, 256, 0, ctx->stream>>>(alpha, factor1_dev, factor2_dev, src, src_stride, dst, dst_stride,
-                                                       rows, cols);
+  mat_axpy_dev_kernel<false><<<(int)b, 256, 0, ctx->stream>>>(alpha, factor1_dev, factor2_dev, const_cast<float*>(src), src_stride, dst,
+                                                              dst_stride, rows, cols);
+  ctx->launches++;
+  TDNNF_CUDA_OK(cudaGetLastError());
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_mat_axpy_dev_zero(tdnnf_ctx* ctx, float alpha, const float* factor1_dev, const float* factor2_dev, float* src,
+                                       int src_stride, float* dst, int dst_stride, int rows, int cols) {
+  TDNNF_REQUIRE(ctx && src && dst, "null argument");
+  if (rows <= 0 || cols <= 0) return TDNNF_OK;
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+  long long b = ((long long)rows * cols + 255) / 256;
+  b = std::max(1LL, std::min(b, (long long)ctx->num_sms * 16));
+  mat_axpy_dev_kernel<true><<<(int)b, 256, 0, ctx->stream>>>(alpha, factor1_dev, factor2_dev, src, src_stride, dst, dst_stride, rows,
+                                                             cols);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   return TDNNF_OK;

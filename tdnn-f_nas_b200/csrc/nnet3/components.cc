@@ -329,9 +329,10 @@ void TdnnDARTSV3Component::PreconditionedUpdate(const PrecomputedIndexes& indexe
 
   // G = out_deriv^T [w_1 X_1 | ... | w_n X_n | 1]  (D_out x (n D_in + 1)), the un-preconditioned gradient, with
   // s_i = sum((X_i W_i^T) .* out_deriv), the out_temp.Sum() of tdnn.cc:506-507, 538-539, as an epilogue reduction.
+  // ng_grad_ is zero on entry: Resize zero-fills, and the accumulation at the end of every call zeroes what it has read
+  // (tdnnf_mat_axpy_dev_zero), which saves a zero-fill of the D_out x (n D_in + 1) matrix per minibatch.
   if (ng_grad_.NumRows() != output_dim || ng_grad_.NumCols() != augmented_input_dim)
     ng_grad_.Resize(output_dim, augmented_input_dim);
-  ng_grad_.SetZero();
   if (has_bias) {
     if (ng_colsum_.Dim() != output_dim) ng_colsum_.Resize(output_dim);
     ng_colsum_.SetZero();
@@ -348,15 +349,17 @@ void TdnnDARTSV3Component::PreconditionedUpdate(const PrecomputedIndexes& indexe
   if (has_bias)
     CheckStatus(tdnnf_mat_axpy(ctx, 1.0f, ng_colsum_.Data(), 1, ng_grad_.Data() + spliced_input_dim, ng_grad_.Stride(),
                                output_dim, 1));
-  // out_deriv_hat^T X_hat = (I - W_o^T W_o) [ G - (out_deriv^T H_in) W_in ]: both projections are applied to the
-  // D_out x D gradient (rank-r corrections) instead of to the R x D operands.
+  // out_deriv_hat^T X_hat = (I - W_o^T W_o) G (I - W_in^T W_in): both projections are applied to the D_out x D gradient
+  // (rank-r corrections) instead of to the R x D operands.  out_deriv^T H_in = (out_deriv^T X) W_in^T = G W_in^T, so the
+  // in-side correction needs no second pass over the R rows of out_deriv either.
   if (!p_in.identity) {
     const int32 r = p_in.rank;
     if (ng_g1_.NumRows() != output_dim || ng_g1_.NumCols() != r) ng_g1_.Resize(output_dim, r);
-    ng_g1_.SetZero();
-    CheckStatus(tdnnf_darts_backprop_params(ctx, p_in.H->Data(), num_rows, r, p_in.H->Stride(), out_deriv.Data(), num_rows,
-                                            output_dim, out_deriv.Stride(), NULL, 0, ng_g1_.Data(), ng_g1_.Stride(), NULL, one,
-                                            1, zero_offset, 1, 1.0f, NULL));
+    // G1 = G W_in^T   (D_out x r; the Propagate form with one offset: out = in W^T)
+    CheckStatus(tdnnf_darts_propagate(ctx, ng_grad_.Data(), output_dim, augmented_input_dim, ng_grad_.Stride(), ng_g1_.Data(),
+                                      output_dim, r, ng_g1_.Stride(), p_in.W->Data(), p_in.W->Stride(), NULL, 1, one, 1,
+                                      zero_offset, 1));
+    // G -= G1 W_in
     CheckStatus(tdnnf_darts_backprop_data(ctx, ng_g1_.Data(), output_dim, r, ng_g1_.Stride(), ng_grad_.Data(), output_dim,
                                           augmented_input_dim, ng_grad_.Stride(), p_in.W->Data(), p_in.W->Stride(), minus_one,
                                           1, zero_offset, 1));
@@ -377,11 +380,12 @@ void TdnnDARTSV3Component::PreconditionedUpdate(const PrecomputedIndexes& indexe
   // local_lrate = in_scale * out_scale * learning_rate_ (tdnn.cc:600-604), the scales read on the device:
   //   linear_params_ += local_lrate * out_deriv_hat^T X_hat[:, :n D_in]            (tdnn.cc:619-624)
   //   bias           += local_lrate * out_deriv_hat^T precon_ones                  (tdnn.cc:607-617)
-  CheckStatus(tdnnf_mat_axpy_dev(ctx, learning_rate_, p_in.scale_dev, p_out.scale_dev, ng_grad_.Data(), ng_grad_.Stride(),
-                                 linear_params_.Data(), linear_params_.Stride(), output_dim, spliced_input_dim));
+  // and ng_grad_ is left zero for the next minibatch.
+  CheckStatus(tdnnf_mat_axpy_dev_zero(ctx, learning_rate_, p_in.scale_dev, p_out.scale_dev, ng_grad_.Data(), ng_grad_.Stride(),
+                                      linear_params_.Data(), linear_params_.Stride(), output_dim, spliced_input_dim));
   if (has_bias)
-    CheckStatus(tdnnf_mat_axpy_dev(ctx, learning_rate_, p_in.scale_dev, p_out.scale_dev, ng_grad_.Data() + spliced_input_dim,
-                                   ng_grad_.Stride(), bias_params_.Data() + NumAlphaSlots(), 1, output_dim, 1));
+    CheckStatus(tdnnf_mat_axpy_dev_zero(ctx, learning_rate_, p_in.scale_dev, p_out.scale_dev, ng_grad_.Data() + spliced_input_dim,
+                                        ng_grad_.Stride(), bias_params_.Data() + NumAlphaSlots(), 1, output_dim, 1));
 }
 
 void TdnnDARTSV3Component::UpdateNaturalGradient(const PrecomputedIndexes& indexes,
