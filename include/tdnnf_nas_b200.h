@@ -466,6 +466,32 @@ int tdnnf_chain_objf_and_deriv(tdnnf_ctx* ctx, tdnnf_den_comp* den, const tdnnf_
 int tdnnf_penalize_out_of_range(tdnnf_ctx* ctx, const float* nnet_output, int rows, int cols, int stride, float limit,
                                 float scale, int row_step, int row_offset, float* deriv, int deriv_stride);
 
+/* ------------------------------------------------------------------ graph readers (host only) - */
+/* den.fst and the per-sequence numerator FSTs of an unconstrained Supervision in AT&T FSM text form (`fstprint`: one arc
+ * per line "src dst ilabel olabel [weight]", one line "state [weight]" per final state, start state = source of the
+ * first line, tropical weights = -log probability, ilabel = pdf-id + 1).  No CUDA device is needed to parse.
+ * tdnnf_den_graph_parse_fst_text = DenominatorGraph::SetTransitions + SetInitialProbs (kaldi: chain/chain-den-graph.cc;
+ * SURVEY.md B.2): forward transitions grouped by source state then backward transitions grouped by destination, and the
+ * initial probabilities as the average over 100 steps of the state distribution from the start state (every state's
+ * outgoing mass normalised together with its final probability, renormalised after each step). */
+typedef struct tdnnf_host_graph tdnnf_host_graph;
+typedef struct tdnnf_host_num_graph tdnnf_host_num_graph;
+int tdnnf_den_graph_parse_fst_text(const char* text, uint64_t len, int num_pdfs, tdnnf_host_graph** out);
+int tdnnf_host_graph_dims(const tdnnf_host_graph* g, int* num_states, int* num_pdfs, int* num_transitions);
+int tdnnf_host_graph_arrays(const tdnnf_host_graph* g, const int32_t** fwd_ranges, const int32_t** bwd_ranges, const float** prob,
+                            const int32_t** pdf, const int32_t** state, const float** initial_probs);
+int tdnnf_host_graph_free(tdnnf_host_graph* g);
+int tdnnf_den_graph_create_from_host(tdnnf_ctx* ctx, const tdnnf_host_graph* g, tdnnf_den_graph** out);
+/* One FSM text per sequence -> the arrays of tdnnf_num_graph_create (each sequence's start state first; final weights
+ * become log final probabilities, absent = not final). */
+int tdnnf_num_graph_parse_fst_texts(const char* const* texts, const uint64_t* lens, int num_seqs, int num_pdfs,
+                                    tdnnf_host_num_graph** out);
+int tdnnf_host_num_graph_arrays(const tdnnf_host_num_graph* g, int* num_seqs, int* num_arcs, const int32_t** state_offsets,
+                                const int32_t** fwd_ranges, const int32_t** bwd_ranges, const float** arc_logprob,
+                                const int32_t** arc_pdf, const int32_t** arc_state, const float** final_logprob);
+int tdnnf_host_num_graph_free(tdnnf_host_num_graph* g);
+int tdnnf_num_graph_create_from_host(tdnnf_ctx* ctx, const tdnnf_host_num_graph* g, tdnnf_num_graph** out);
+
 /* ------------------------------------------------------------------ data-parallel reduction - */
 /* SURVEY 8b capability (8): the deltas of the ranks' minibatch shards are SUMMED over NCCL (NVLink / NVSwitch): the
  * synchronous replacement of the multi-job `nnet3-average` (ref: steps/libs/nnet3/train/common.py:144-164; learning

@@ -26,6 +26,7 @@ CXX_SOURCES = [
     "nnet3/components.cc",
     "nnet3/natural_gradient.cc",
     "nnet3/handle_api.cc",
+    "chain_io.cc",
 ]
 
 NVCC_FLAGS = [

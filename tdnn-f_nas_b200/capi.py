@@ -103,6 +103,16 @@ def _declare(lib):
     sig("tdnnf_apply_l2_regularization", [vp, i, vp, vp, vp, vp, vp, vp, vp, i, c_float_p, c_float_p, f])
     sig("tdnnf_chain_objf_and_deriv", [vp, vp, vp, vp, i, i, i, i, f, f, f, i, i, vp, i, vp, i, c_float_p, c_float_p, c_float_p])
     sig("tdnnf_penalize_out_of_range", [vp, vp, i, i, i, f, f, i, i, vp, i])
+    pp_i, pp_f = C.POINTER(c_int_p), C.POINTER(c_float_p)
+    sig("tdnnf_den_graph_parse_fst_text", [C.c_char_p, C.c_uint64, i, C.POINTER(vp)])
+    sig("tdnnf_host_graph_dims", [vp, c_int_p, c_int_p, c_int_p])
+    sig("tdnnf_host_graph_arrays", [vp, pp_i, pp_i, pp_f, pp_i, pp_i, pp_f])
+    sig("tdnnf_host_graph_free", [vp])
+    sig("tdnnf_den_graph_create_from_host", [vp, vp, C.POINTER(vp)])
+    sig("tdnnf_num_graph_parse_fst_texts", [C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), i, i, C.POINTER(vp)])
+    sig("tdnnf_host_num_graph_arrays", [vp, c_int_p, c_int_p, pp_i, pp_i, pp_i, pp_f, pp_i, pp_i, pp_f])
+    sig("tdnnf_host_num_graph_free", [vp])
+    sig("tdnnf_num_graph_create_from_host", [vp, vp, C.POINTER(vp)])
     sig("tdnnf_dp_unique_id", [C.c_char_p, i])
     sig("tdnnf_dp_comm_create", [vp, i, i, C.c_char_p, C.POINTER(vp)])
     sig("tdnnf_dp_comm_adopt", [vp, vp, i, i, C.POINTER(vp)])
@@ -430,6 +440,55 @@ class Context:
         dp, _, _, ds = _mat(out_deriv)
         ip, _, _, is_ = _mat(in_deriv)
         check(load().tdnnf_batchnorm_train_bwd(self.h, vp_, vs, dp, ds, ip, is_, r, c, target_rms, memo.data_ptr()))
+
+
+def parse_den_fst_text(text: str, num_pdfs: int) -> dict:
+    """den.fst in FSM text form -> the DenominatorGraph arrays (tdnnf_den_graph_parse_fst_text: SetTransitions +
+    SetInitialProbs of kaldi chain-den-graph.cc).  Host only: no GPU needed.  Same dict layout as synth.make_den_graph."""
+    import numpy as np
+
+    data = text.encode() if isinstance(text, str) else text
+    h = vp()
+    check(load().tdnnf_den_graph_parse_fst_text(data, len(data), num_pdfs, C.byref(h)))
+    try:
+        n, p, a = C.c_int32(), C.c_int32(), C.c_int32()
+        check(load().tdnnf_host_graph_dims(h, C.byref(n), C.byref(p), C.byref(a)))
+        fr, br, pd, st = c_int_p(), c_int_p(), c_int_p(), c_int_p()
+        pr, init = c_float_p(), c_float_p()
+        check(load().tdnnf_host_graph_arrays(h, C.byref(fr), C.byref(br), C.byref(pr), C.byref(pd), C.byref(st), C.byref(init)))
+        arr = lambda ptr, count, dt: np.ctypeslib.as_array(ptr, shape=(count,)).astype(dt).copy()
+        N, A2 = n.value, a.value
+        return dict(num_states=N, num_pdfs=p.value, fwd_ranges=arr(fr, 2 * N, np.int32).reshape(N, 2),
+                    bwd_ranges=arr(br, 2 * N, np.int32).reshape(N, 2), prob=arr(pr, A2, np.float32), pdf=arr(pd, A2, np.int32),
+                    state=arr(st, A2, np.int32), init=arr(init, N, np.float32), num_arcs=A2 // 2)
+    finally:
+        load().tdnnf_host_graph_free(h)
+
+
+def parse_num_fst_texts(texts: Sequence[str], num_pdfs: int) -> dict:
+    """Per-sequence numerator FSTs in FSM text form -> the arrays of tdnnf_num_graph_create (host only).  Same dict
+    layout as synth.make_num_graphs."""
+    import numpy as np
+
+    datas = [t.encode() if isinstance(t, str) else t for t in texts]
+    k = len(datas)
+    arr_t, arr_l = (C.c_char_p * k)(*datas), (C.c_uint64 * k)(*[len(d) for d in datas])
+    h = vp()
+    check(load().tdnnf_num_graph_parse_fst_texts(arr_t, arr_l, k, num_pdfs, C.byref(h)))
+    try:
+        ns, na = C.c_int32(), C.c_int32()
+        so, fr, br, pd, st = c_int_p(), c_int_p(), c_int_p(), c_int_p(), c_int_p()
+        lp, fl = c_float_p(), c_float_p()
+        check(load().tdnnf_host_num_graph_arrays(h, C.byref(ns), C.byref(na), C.byref(so), C.byref(fr), C.byref(br), C.byref(lp),
+                                                 C.byref(pd), C.byref(st), C.byref(fl)))
+        arr = lambda ptr, count, dt: np.ctypeslib.as_array(ptr, shape=(count,)).astype(dt).copy()
+        offs = arr(so, k + 1, np.int32)
+        N, A = int(offs[-1]), na.value
+        return dict(num_seqs=k, state_offsets=offs, num_arcs=A, fwd_ranges=arr(fr, 2 * N, np.int32).reshape(N, 2),
+                    bwd_ranges=arr(br, 2 * N, np.int32).reshape(N, 2), arc_logprob=arr(lp, 2 * A, np.float32),
+                    arc_pdf=arr(pd, 2 * A, np.int32), arc_state=arr(st, 2 * A, np.int32), final_logprob=arr(fl, N, np.float32))
+    finally:
+        load().tdnnf_host_num_graph_free(h)
 
 
 class ParamTable:

@@ -121,3 +121,34 @@ def make_num_graphs(num_seqs: int, num_pdfs: int, frames: int, seed: int = 6, mi
                 fwd_ranges=np.stack([fb[:-1], fb[1:]], 1).astype(np.int32), bwd_ranges=np.stack([bb[:-1], bb[1:]], 1).astype(np.int32),
                 arc_logprob=np.concatenate([lp[of], lp[ob]]), arc_pdf=np.concatenate([pdf[of], pdf[ob]]),
                 arc_state=np.concatenate([dst[of], src[ob]]).astype(np.int32), final_logprob=np.concatenate(final))
+
+
+def den_graph_to_fst_text(graph: dict, start_first: bool = True) -> str:
+    """A DenominatorGraph as `fstprint den.fst` would show its FST: "src dst ilabel olabel weight" with ilabel = olabel =
+    pdf-id + 1 and weight = -log transition probability, every state final with weight 0 (chain den FSTs are)."""
+    A = graph["num_arcs"]
+    lines = []
+    for h in range(graph["num_states"]):
+        b, e = graph["fwd_ranges"][h]
+        for a in range(b, e):
+            lines.append(f"{h} {int(graph['state'][a])} {int(graph['pdf'][a]) + 1} {int(graph['pdf'][a]) + 1} {-np.log(float(graph['prob'][a])):.9g}")
+    assert len(lines) == A
+    return "\n".join(lines) + "\n"
+
+
+def num_graphs_to_fst_texts(graph: dict):
+    """The per-sequence numerator FSTs of make_num_graphs as FSM texts (local state numbers, start state 0)."""
+    texts = []
+    offs, A = graph["state_offsets"], graph["num_arcs"]
+    for s in range(graph["num_seqs"]):
+        lines = []
+        for st in range(offs[s], offs[s + 1]):
+            b, e = graph["fwd_ranges"][st]
+            for a in range(b, e):
+                lines.append(f"{st - offs[s]} {int(graph['arc_state'][a]) - offs[s]} {int(graph['arc_pdf'][a]) + 1} "
+                             f"{int(graph['arc_pdf'][a]) + 1} {-float(graph['arc_logprob'][a]):.9g}")
+        for st in range(offs[s], offs[s + 1]):
+            if graph["final_logprob"][st] > -1.0e29:
+                lines.append(f"{st - offs[s]} {-float(graph['final_logprob'][st]):.9g}")
+        texts.append("\n".join(lines) + "\n")
+    return texts

@@ -51,7 +51,10 @@ def test_whole_step_matches_cpu_reference(xent):
     from tdnnf_nas_b200 import nnet3, synth
     from tdnnf_nas_b200.supernet import Supernet, SupernetConfig
 
-    cfg = SupernetConfig(num_seqs=8, frames_per_eg=30, dim=128, bottleneck=32, num_blocks=3, prefinal_small=64, num_pdfs=200,
+    # the bottleneck keeps its real width: rank-out 80 of OnlineNaturalGradient must stay well below the dimension it
+    # preconditions (with 32 columns the rank is clipped to 31 and X_hat is the ill-conditioned remainder of a near-total
+    # projection: rounding differences of 1e-6 in X come out as 1e-2 in the delta)
+    cfg = SupernetConfig(num_seqs=8, frames_per_eg=30, dim=256, bottleneck=160, num_blocks=3, prefinal_small=64, num_pdfs=200,
                          den_states=300, den_out_degree=6.0, mode="search", learning_rate=2e-3, darts_lr_factor=0.05, xent=xent)
     net = Supernet(cfg)
     S, T, P, L, n = cfg.num_seqs, net.T, cfg.num_pdfs, cfg.num_blocks, cfg.num_offsets
@@ -76,15 +79,18 @@ def test_whole_step_matches_cpu_reference(xent):
         assert rel_err(net.head["d_out"].cpu().numpy(), ref.st["d_out"]) < 1e-3
         if xent:
             assert abs(net.last_xent_objf - ref.xent_objf) <= 1e-4 * abs(ref.xent_objf)
+        errs = {}
         for b, blk in enumerate(net.blocks):
-            assert rel_err(blk["d_aff"].cpu().numpy(), ref.st[b]["d_aff"]) < 1e-3, (step, b)
-            assert rel_err(blk["d_lin"].cpu().numpy(), ref.st[b]["d_lin"]) < 1e-3, (step, b)
-            for h, din, dout in (("lin", cfg.dim, cfg.bottleneck), ("aff", cfg.bottleneck, cfg.dim)):
+            errs[(b, "d_aff")] = rel_err(blk["d_aff"].cpu().numpy(), ref.st[b]["d_aff"])
+            errs[(b, "d_lin")] = rel_err(blk["d_lin"].cpu().numpy(), ref.st[b]["d_lin"])
+            for h in ("lin", "aff"):
                 dv = blk[h + "_delta"].vectorize()
                 dW, db = ref.delta[(b, h)]
-                assert rel_err(dv[: dW.size].reshape(dW.shape), dW) < 1e-3, (step, b, h, "theta")
-                assert rel_err(dv[dW.size + n:], db[n:]) < 1e-3, (step, b, h, "bias")
-                assert np.abs(dv[dW.size: dW.size + n] - db[:n]).max() <= 1e-3 * np.abs(db[:n]).max() + 1e-12, (step, b, h, "alpha")
+                errs[(b, h, "theta")] = rel_err(dv[: dW.size].reshape(dW.shape), dW)
+                errs[(b, h, "bias")] = rel_err(dv[dW.size + n:], db[n:])
+                errs[(b, h, "alpha")] = float(np.abs(dv[dW.size: dW.size + n] - db[:n]).max() / (np.abs(db[:n]).max() + 1e-30))
+        bad = {k: v for k, v in errs.items() if not v < 1e-3}
+        assert not bad, (step, bad, errs)
         # the parameter step (max-change) on both sides
         assert net._update_with_max_change() and ref.update()
         np.testing.assert_allclose(net.last_max_change_factors, ref.last_factors, rtol=1e-3)
