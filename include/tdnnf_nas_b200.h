@@ -75,6 +75,26 @@ int tdnnf_ctx_set_gradient_mode(tdnnf_ctx* ctx, int fast);
 int tdnnf_ctx_operand_cache_begin(tdnnf_ctx* ctx, const float* const* sources, int num_sources);
 int tdnnf_ctx_operand_cache_end(tdnnf_ctx* ctx);
 int tdnnf_ctx_operand_cache_stats(const tdnnf_ctx* ctx, uint64_t* hits, uint64_t* misses);
+/* Operand planes with a life of their own.  A GEMM operand (fp32 matrix) is split into bf16 hi/lo row planes before every
+ * tensor-core product; tdnnf_planes is one such split kept by the caller:
+ *   tdnnf_planes_acquire   the planes of (src, rows, cols, stride) for a component with `row_stride` (the reorder_t_in of
+ *                          its PrecomputedIndexes): an attached handle for the same matrix is returned with one more
+ *                          reference, otherwise the split runs once (one pass over src, also leaving the per-row sums of
+ *                          squares the natural gradient needs);
+ *   tdnnf_ctx_planes_attach / _detach   while attached, every tdnnf_darts_* call whose operand is that very matrix (same
+ *                          pointer, shape, stride, row stride) uses the planes instead of splitting it again.  The caller
+ *                          promises the matrix does not change while its planes are attached;
+ *   tdnnf_planes_release   drops a reference; the memory returns to the context's pool.
+ * TdnnDARTSV3Component::Propagate keeps the planes of its input in the memo and Backprop attaches them again (the
+ * reference's Backprop re-reads in_value: tdnn.cc:476-539); the fused tail kernels below hand over planes of what they
+ * have just written (tdnnf_relu_scale_offset_bypass_{fwd,bwd}_planes). */
+typedef struct tdnnf_planes tdnnf_planes;
+int tdnnf_planes_acquire(tdnnf_ctx* ctx, const float* src, int rows, int cols, int stride, int row_stride, tdnnf_planes** out);
+int tdnnf_planes_release(tdnnf_planes* p);
+int tdnnf_ctx_planes_attach(tdnnf_ctx* ctx, tdnnf_planes* p);
+int tdnnf_ctx_planes_detach(tdnnf_ctx* ctx, tdnnf_planes* p);
+/* 1 if p holds the planes of exactly this matrix */
+int tdnnf_planes_matches(const tdnnf_planes* p, const float* src, int rows, int cols, int stride);
 /* Pre-size the internal scratch arena (bf16 operand planes) so later calls never grow it. */
 int tdnnf_ctx_reserve(tdnnf_ctx* ctx, uint64_t bytes);
 /* Number of kernels this context has launched so far (for gpu_launches accounting). */
@@ -297,6 +317,16 @@ int tdnnf_relu_scale_offset_bypass_fwd(tdnnf_ctx* ctx, const float* x, int rows,
 int tdnnf_relu_scale_offset_bypass_bwd(tdnnf_ctx* ctx, const float* d_out, int do_stride, const float* x, int x_stride,
                                        const float* scale, float bypass_scale, float* d_x, int dx_stride, float* d_prev,
                                        int dp_stride, int rows, int cols);
+/* The same two kernels as producers of the next GEMM operand: besides out / d_x they write its bf16 hi/lo planes, the
+ * per-row sums of squares and (backward) the column sums of d_x, i.e. the bias gradient; *planes is a new handle
+ * (tdnnf_ctx_planes_attach it around the component call that reads the matrix, then tdnnf_planes_release).
+ * cols <= 4096. */
+int tdnnf_relu_scale_offset_bypass_fwd_planes(tdnnf_ctx* ctx, const float* x, int rows, int cols, int x_stride,
+                                              const float* scale, const float* offset, const float* prev, int prev_stride,
+                                              float bypass_scale, float* out, int out_stride, tdnnf_planes** planes);
+int tdnnf_relu_scale_offset_bypass_bwd_planes(tdnnf_ctx* ctx, const float* d_out, int do_stride, const float* x, int x_stride,
+                                              const float* scale, float bypass_scale, float* d_x, int dx_stride, float* d_prev,
+                                              int dp_stride, int rows, int cols, tdnnf_planes** planes);
 /* BatchNorm, training mode.  memo: device, 5 x cols (rows: mean, uvar, scale, -, -) as in the reference.
  *   fwd:  mean/var over rows; scale = target_rms * (var + eps)^-0.5; out = (in - mean) .* scale
  *   bwd:  x' = scale .* (z' - mean(z')) + z .* var_deriv_mod,

@@ -42,6 +42,9 @@ float tdnnf_nnet3_rand_uniform(void);
 int tdnnf_nnet3_rand_int(int lo, int hi); /* the RandInt the components use (advances the same counter) */
 /* Data-parallel world size: the FLOPs penalty is normalised by rows * world_size. */
 int tdnnf_nnet3_set_dp_world_size(int world_size);
+/* TdnnDARTSV3Component::Propagate keeps the bf16 operand planes of its input in the memo and Backprop reuses them (default
+ * 1): the input is split once per minibatch, not twice.  0 restores a split per call. */
+int tdnnf_nnet3_set_keep_planes(int enable);
 /* Re-enable the reference's per-minibatch "log_alpha" stdout print (ref: tdnn.cc:571, simple.cc:2640). */
 int tdnnf_nnet3_set_print_log_alpha(int enable);
 /* Parameter-gradient GEMM of TdnnDARTSV3Component::Backprop with one fp16 product (tdnnf_ctx_set_gradient_mode).

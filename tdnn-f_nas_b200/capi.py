@@ -80,6 +80,12 @@ def _declare(lib):
     sig("tdnnf_add_scaled", [vp, vp, i, f, vp, i, f, vp, i, i, i])
     sig("tdnnf_relu_scale_offset_bypass_fwd", [vp, vp, i, i, i, vp, vp, vp, i, f, vp, i])
     sig("tdnnf_relu_scale_offset_bypass_bwd", [vp, vp, i, vp, i, vp, f, vp, i, vp, i, i, i])
+    sig("tdnnf_relu_scale_offset_bypass_fwd_planes", [vp, vp, i, i, i, vp, vp, vp, i, f, vp, i, C.POINTER(vp)])
+    sig("tdnnf_relu_scale_offset_bypass_bwd_planes", [vp, vp, i, vp, i, vp, f, vp, i, vp, i, i, i, C.POINTER(vp)])
+    sig("tdnnf_planes_acquire", [vp, vp, i, i, i, i, C.POINTER(vp)])
+    sig("tdnnf_planes_release", [vp])
+    sig("tdnnf_ctx_planes_attach", [vp, vp])
+    sig("tdnnf_ctx_planes_detach", [vp, vp])
     sig("tdnnf_batchnorm_train_fwd", [vp, vp, i, i, i, vp, i, f, f, vp])
     sig("tdnnf_batchnorm_train_bwd", [vp, vp, i, vp, i, vp, i, i, i, f, vp])
     sig("tdnnf_ctx_set_wgrad_mn_min_rows", [vp, i])

@@ -5,6 +5,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/tdnnf_nas_b200.h"
@@ -16,6 +17,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 void set_error(const std::string& msg);
+}  // namespace tdnnf
+struct tdnnf_ctx;
+struct tdnnf_planes;
+namespace tdnnf {
+int planes_alloc_for_producer(tdnnf_ctx* ctx, const float* src, int rows, int cols, int stride, tdnnf_planes** out);
 int fail(int code, const std::string& msg);
 
 #define TDNNF_CUDA_OK(expr)                                                                        \
@@ -31,6 +37,24 @@ int fail(int code, const std::string& msg);
   } while (0)
 
 }  // namespace tdnnf
+
+// Operand planes with a life of their own (tdnnf_planes_*): the bf16 hi/lo row planes (and the per-row sums of squares /
+// column sums that come with building them) of one fp32 matrix, kept from Propagate to Backprop in the component's memo
+// or written by the kernel that produces the matrix.  While attached to the context, every split of that matrix is a hit.
+struct tdnnf_planes {
+  tdnnf_ctx* ctx = nullptr;
+  const float* src = nullptr;
+  int R = 0, D = 0, r = 1, Q = 0, Kpad = 0, np = 2;
+  long long ld = 0;
+  void* block = nullptr;      // one pooled allocation: [planes][rowsq: R floats][colsum: D floats]
+  size_t bytes = 0;
+  void* base = nullptr;       // hi plane; plane p at base + p * plane_elems (bf16)
+  long long plane_elems = 0;
+  float* rowsq = nullptr;     // [R] sum of squares of every source row
+  float* colsum = nullptr;    // [D] column sums (valid only when has_colsum)
+  bool has_colsum = false;
+  int refs = 1, attached = 0;
+};
 
 // per-offset row offsets passed by value to kernels
 struct TdnnfOffsets {
@@ -119,6 +143,15 @@ struct tdnnf_ctx {
   // parameter gradient: operands with at least this many rows take the MN-major form (row planes, no transposed
   // pre-pass); < 0 = never.  Default 512 (TDNNF_WGRAD_MN=0 disables, TDNNF_WGRAD_MN_MIN_ROWS overrides).
   int wgrad_mn_min_rows = 512;
+  // tdnnf_planes_*: attached plane sets (matched by source pointer, shape, stride and row stride) and the pool their
+  // blocks come from / return to (nothing is handed back to the driver)
+  std::vector<tdnnf_planes*> attached_planes;
+  std::vector<std::pair<size_t, void*>> planes_pool;
+  const tdnnf_planes* find_attached(const float* src, int R, int D, long long ld, int r) const {
+    for (const tdnnf_planes* p : attached_planes)
+      if (p->src == src && p->R == R && p->D == D && p->ld == ld && p->r == r) return p;
+    return nullptr;
+  }
   // Makes room for `bytes` more cached planes; called at the top of a public call, before any plane of that call
   // exists (growing drops every cached plane).
   int cws_reserve(size_t bytes);

@@ -1,5 +1,7 @@
 // Whole-parameter ops of the updatable components and the stock TDNN-F neighbours (ReLU, bypass
 // sum, BatchNorm training mode).  All bandwidth-bound, one fused pass each.
+#include <cuda_bf16.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -229,6 +231,94 @@ __global__ void tail_bwd_kernel(const float* __restrict__ dout, long long dos, c
     *reinterpret_cast<float4*>(dx + r * dxs + c) =
         make_float4(v.x > 0.f ? g.x * s.x : 0.f, v.y > 0.f ? g.y * s.y : 0.f, v.z > 0.f ? g.z * s.z : 0.f, v.w > 0.f ? g.w * s.w : 0.f);
     *reinterpret_cast<float4*>(dprev + r * dps + c) = make_float4(bs * g.x, bs * g.y, bs * g.z, bs * g.w);
+  }
+}
+
+// The fused tails as PRODUCERS of the next GEMM's operand: besides the fp32 matrix they write its bf16 hi/lo row planes
+// (the layout of split_rows_kernel with one row group), the per-row sums of squares (tr(X X^T) of the natural gradient)
+// and, in the backward form, the column sums (the bias gradient) -- the matrix is not read again by a split pass.
+// One block per row at a time, thread = 4 consecutive columns (blockDim.x = Kpad / 4 <= 1024; threads beyond cols / 4 only
+// zero the K padding of the planes).
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* hi, __nv_bfloat16* lo, long long o, float4 y) {
+  __align__(8) __nv_bfloat16 h[4];
+  __align__(8) __nv_bfloat16 l[4];
+  const float v[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j] = __float2bfloat16_rn(v[j]);
+    l[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h[j]));
+  }
+  *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(h);
+  *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(l);
+}
+__device__ __forceinline__ float block_sum(float v, float* red /* [32] */) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();  // red may still be read from the previous row
+  if ((threadIdx.x & 31) == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < nw; ++w) t += red[w];
+  return t;
+}
+__global__ void tail_fwd_planes_kernel(const float* __restrict__ x, long long xs, const float* __restrict__ scale,
+                                       const float* __restrict__ offset, const float* __restrict__ prev, long long ps, float bs,
+                                       float* __restrict__ out, long long os, int rows, int cols, int Kpad,
+                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ rowsq) {
+  __shared__ float red[32];
+  const int c = threadIdx.x * 4;
+  const bool live = c < cols;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), o = s;
+  if (live) {
+    s = *reinterpret_cast<const float4*>(scale + c);
+    o = *reinterpret_cast<const float4*>(offset + c);
+  }
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+      const float4 v = *reinterpret_cast<const float4*>(x + r * xs + c);
+      const float4 p = *reinterpret_cast<const float4*>(prev + r * ps + c);
+      y.x = fmaxf(v.x, 0.f) * s.x + o.x + bs * p.x;
+      y.y = fmaxf(v.y, 0.f) * s.y + o.y + bs * p.y;
+      y.z = fmaxf(v.z, 0.f) * s.z + o.z + bs * p.z;
+      y.w = fmaxf(v.w, 0.f) * s.w + o.w + bs * p.w;
+      *reinterpret_cast<float4*>(out + r * os + c) = y;
+    }
+    store_planes4(hi, lo, r * Kpad + c, y);
+    const float sq = block_sum(y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w, red);
+    if (threadIdx.x == 0) rowsq[r] = sq;
+  }
+}
+__global__ void tail_bwd_planes_kernel(const float* __restrict__ dout, long long dos, const float* __restrict__ x, long long xs,
+                                       const float* __restrict__ scale, float bs, float* __restrict__ dx, long long dxs,
+                                       float* __restrict__ dprev, long long dps, int rows, int cols, int Kpad,
+                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ rowsq,
+                                       float* __restrict__ colsum) {
+  __shared__ float red[32];
+  const int c = threadIdx.x * 4;
+  const bool live = c < cols;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), cs = s;
+  if (live) s = *reinterpret_cast<const float4*>(scale + c);
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+      const float4 g = *reinterpret_cast<const float4*>(dout + r * dos + c);
+      const float4 v = *reinterpret_cast<const float4*>(x + r * xs + c);
+      y = make_float4(v.x > 0.f ? g.x * s.x : 0.f, v.y > 0.f ? g.y * s.y : 0.f, v.z > 0.f ? g.z * s.z : 0.f, v.w > 0.f ? g.w * s.w : 0.f);
+      *reinterpret_cast<float4*>(dx + r * dxs + c) = y;
+      *reinterpret_cast<float4*>(dprev + r * dps + c) = make_float4(bs * g.x, bs * g.y, bs * g.z, bs * g.w);
+      cs.x += y.x; cs.y += y.y; cs.z += y.z; cs.w += y.w;
+    }
+    store_planes4(hi, lo, r * Kpad + c, y);
+    const float sq = block_sum(y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w, red);
+    if (threadIdx.x == 0) rowsq[r] = sq;
+  }
+  if (live) {
+    atomicAdd(colsum + c, cs.x);
+    atomicAdd(colsum + c + 1, cs.y);
+    atomicAdd(colsum + c + 2, cs.z);
+    atomicAdd(colsum + c + 3, cs.w);
   }
 }
 
@@ -751,6 +841,51 @@ extern "C" int tdnnf_relu_scale_offset_bypass_bwd(tdnnf_ctx* ctx, const float* d
   tail_bwd_kernel<<<grid_for((long long)rows * cols / 4, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
       d_out, do_stride, x, x_stride, scale, bypass_scale, d_x, dx_stride, d_prev, dp_stride, rows, cols);
   LAUNCH_CHECK(ctx);
+  return TDNNF_OK;
+}
+
+// The fused tails that also hand the next GEMM its operand planes (see tail_fwd_planes_kernel).  *planes: a new handle for
+// `out` / `d_x` (tdnnf_planes_release when done); attach it to the context before the component call that consumes the matrix.
+extern "C" int tdnnf_relu_scale_offset_bypass_fwd_planes(tdnnf_ctx* ctx, const float* x, int rows, int cols, int x_stride,
+                                                         const float* scale, const float* offset, const float* prev, int prev_stride,
+                                                         float bypass_scale, float* out, int out_stride, tdnnf_planes** planes) {
+  PROLOGUE(x && scale && offset && prev && out && planes && x_stride >= cols && prev_stride >= cols && out_stride >= cols, "bad matrix");
+  TDNNF_REQUIRE(cols % 4 == 0 && x_stride % 4 == 0 && prev_stride % 4 == 0 && out_stride % 4 == 0 && al16(x) && al16(prev) &&
+                    al16(out) && al16(scale) && al16(offset),
+                "fused tail needs 16-byte aligned rows (cols and strides multiples of 4)");
+  tdnnf_planes* pl = nullptr;
+  int rc = tdnnf::planes_alloc_for_producer(ctx, out, rows, cols, out_stride, &pl);
+  if (rc) return rc;
+  TDNNF_REQUIRE(pl->Kpad / 4 <= 1024, "fused tail with planes: at most 4096 columns");
+  __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(pl->base);
+  tail_fwd_planes_kernel<<<std::min(rows, ctx->num_sms * 4), pl->Kpad / 4, 0, ctx->stream>>>(
+      x, x_stride, scale, offset, prev, prev_stride, bypass_scale, out, out_stride, rows, cols, pl->Kpad, hi, hi + pl->plane_elems, pl->rowsq);
+  LAUNCH_CHECK(ctx);
+  *planes = pl;
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_relu_scale_offset_bypass_bwd_planes(tdnnf_ctx* ctx, const float* d_out, int do_stride, const float* x,
+                                                         int x_stride, const float* scale, float bypass_scale, float* d_x,
+                                                         int dx_stride, float* d_prev, int dp_stride, int rows, int cols,
+                                                         tdnnf_planes** planes) {
+  PROLOGUE(d_out && x && scale && d_x && d_prev && planes && do_stride >= cols && x_stride >= cols && dx_stride >= cols && dp_stride >= cols,
+           "bad matrix");
+  TDNNF_REQUIRE(cols % 4 == 0 && do_stride % 4 == 0 && x_stride % 4 == 0 && dx_stride % 4 == 0 && dp_stride % 4 == 0 &&
+                    al16(d_out) && al16(x) && al16(d_x) && al16(d_prev) && al16(scale),
+                "fused tail needs 16-byte aligned rows (cols and strides multiples of 4)");
+  tdnnf_planes* pl = nullptr;
+  int rc = tdnnf::planes_alloc_for_producer(ctx, d_x, rows, cols, dx_stride, &pl);
+  if (rc) return rc;
+  TDNNF_REQUIRE(pl->Kpad / 4 <= 1024, "fused tail with planes: at most 4096 columns");
+  TDNNF_CUDA_OK(cudaMemsetAsync(pl->colsum, 0, sizeof(float) * (size_t)cols, ctx->stream));
+  __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(pl->base);
+  tail_bwd_planes_kernel<<<std::min(rows, ctx->num_sms * 4), pl->Kpad / 4, 0, ctx->stream>>>(
+      d_out, do_stride, x, x_stride, scale, bypass_scale, d_x, dx_stride, d_prev, dp_stride, rows, cols, pl->Kpad, hi,
+      hi + pl->plane_elems, pl->rowsq, pl->colsum);
+  LAUNCH_CHECK(ctx);
+  pl->has_colsum = true;
+  *planes = pl;
   return TDNNF_OK;
 }
 

@@ -23,6 +23,8 @@ void SetPrintLogAlpha(bool b) { g_print_log_alpha = b; }
 // tdnnf_ctx_set_gradient_mode).  OFF by default: its 2.9e-4 error is within the 1e-3 gradient tolerance on the raw
 // gradient, but the natural-gradient projection that follows keeps only the residual of the dominant directions and
 // rescales it (in_scale x out_scale was 48 in tests/test_gpu_ng.py), which amplified it to 1.2e-2 in the delta.
+static bool g_keep_planes = true;
+void SetKeepPlanes(bool b) { g_keep_planes = b; }
 static bool g_fast_gradients = false;
 void SetFastGradients(bool b) { g_fast_gradients = b; }
 bool FastGradients() { return g_fast_gradients; }
@@ -230,10 +232,17 @@ void* TdnnDARTSV3Component::Propagate(const ComponentPrecomputedIndexes* indexes
   CheckStatus(tdnnf_darts_coef(ctx, bias_params_.Data(), num_offsets, Flags(), temp_proportion_,
                                use_gumbel_ ? u_gumbel : NULL, u_uniform, share_offset_index, memo->coef.Data(),
                                memo->weff.Data()));
-  CheckStatus(tdnnf_darts_propagate(ctx, in.Data(), in.NumRows(), in.NumCols(), in.Stride(), out->Data(), out->NumRows(),
-                                    out->NumCols(), out->Stride(), linear_params_.Data(), linear_params_.Stride(),
-                                    bias_params_.Data() + num_offsets, bias_mode, memo->weff.Data(), num_offsets,
-                                    indexes->row_offsets.data(), indexes->row_stride));
+  if (g_keep_planes && indexes->row_stride <= 16) {
+    CheckStatus(tdnnf_planes_acquire(ctx, in.Data(), in.NumRows(), in.NumCols(), in.Stride(), indexes->row_stride, &memo->in_planes));
+    CheckStatus(tdnnf_ctx_planes_attach(ctx, memo->in_planes));
+  }
+  const int rc = tdnnf_darts_propagate(ctx, in.Data(), in.NumRows(), in.NumCols(), in.Stride(), out->Data(), out->NumRows(),
+                                       out->NumCols(), out->Stride(), linear_params_.Data(), linear_params_.Stride(),
+                                       bias_params_.Data() + num_offsets, bias_mode, memo->weff.Data(), num_offsets,
+                                       indexes->row_offsets.data(), indexes->row_stride);
+  if (memo->in_planes) tdnnf_ctx_planes_detach(ctx, memo->in_planes);
+  if (rc != 0) delete memo;
+  CheckStatus(rc);
   return memo;
 }
 
@@ -263,6 +272,20 @@ void TdnnDARTSV3Component::Backprop(const std::string& debug_info, const Compone
     }
     ~OperandCacheScope() { tdnnf_ctx_operand_cache_end(ctx); }
   } cache_scope(ctx, in_value.Data(), out_deriv.Data());
+  // the input planes Propagate kept in the memo (same matrix: nnet3 hands Backprop the in_value Propagate saw)
+  struct PlanesScope {
+    tdnnf_ctx* ctx;
+    tdnnf_planes* p;
+    PlanesScope(tdnnf_ctx* c, tdnnf_planes* pl, const CuMatrixBase<BaseFloat>& m) : ctx(c), p(NULL) {
+      if (pl != NULL && tdnnf_planes_matches(pl, m.Data(), m.NumRows(), m.NumCols(), m.Stride())) {
+        p = pl;
+        CheckStatus(tdnnf_ctx_planes_attach(ctx, p));
+      }
+    }
+    ~PlanesScope() {
+      if (p) tdnnf_ctx_planes_detach(ctx, p);
+    }
+  } planes_scope(ctx, memo->in_planes, in_value);
   if (in_deriv != NULL) {
     CheckStatus(tdnnf_darts_backprop_data(ctx, out_deriv.Data(), out_deriv.NumRows(), out_deriv.NumCols(),
                                           out_deriv.Stride(), in_deriv->Data(), in_deriv->NumRows(), in_deriv->NumCols(),

@@ -101,6 +101,8 @@ int32 GetDataParallelWorldSize();
 // The reference prints "log_alpha [ ... ]" to stdout every minibatch per component (tdnn.cc:571,
 // simple.cc:2640), which costs a device->host sync each time; off by default here.
 void SetPrintLogAlpha(bool b);
+// TdnnDARTSV3Component::Propagate keeps the operand planes of its input in the memo for Backprop (default on).
+void SetKeepPlanes(bool b);
 // One fp16 tensor-core product in the parameter-gradient GEMM of TdnnDARTSV3Component (default: off, see components.cc).
 void SetFastGradients(bool b);
 bool FastGradients();
@@ -188,8 +190,13 @@ class TdnnDARTSV3Component : public UpdatableComponent {
 
   // The memo returned by Propagate: the mixing coefficients (what the reference keeps) plus the
   // effective GEMM weights derived from them; both stay on the device.
+  // in_planes: the bf16 operand planes of Propagate's input (tdnnf_planes_acquire), attached again in Backprop, whose
+  // natural-gradient projection and parameter gradient re-read in_value (tdnn.cc:476-539): the matrix is split once per
+  // minibatch instead of twice.  nnet3 keeps in_value unchanged between the two calls (kBackpropNeedsInput).
   struct Memo {
     CuVector coef, weff;
+    tdnnf_planes* in_planes = nullptr;
+    ~Memo() { tdnnf_planes_release(in_planes); }
   };
 
  protected:

@@ -62,6 +62,7 @@ uint64_t tdnnf_nnet3_get_rand_counter(void) { return GetRandCounter(); }
 float tdnnf_nnet3_rand_uniform(void) { return RandUniformOpen(); }
 int tdnnf_nnet3_rand_int(int lo, int hi) { return RandInt(lo, hi); }
 int tdnnf_nnet3_set_dp_world_size(int g) { API_BEGIN SetDataParallelWorldSize(g); API_END }
+int tdnnf_nnet3_set_keep_planes(int b) { API_BEGIN SetKeepPlanes(b != 0); API_END }
 int tdnnf_nnet3_set_print_log_alpha(int b) { API_BEGIN SetPrintLogAlpha(b != 0); API_END }
 int tdnnf_nnet3_set_fast_gradients(int b) { API_BEGIN SetFastGradients(b != 0); API_END }
 int tdnnf_nnet3_set_ng_identity(int b) { API_BEGIN SetNaturalGradientIdentity(b != 0); API_END }

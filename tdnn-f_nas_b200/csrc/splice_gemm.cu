@@ -372,6 +372,16 @@ static int launch_split_rows(tdnnf_ctx* ctx, const float* src, int R, int D, lon
   pl->groups = groups;
   pl->np = np ? np : ctx->gemm_planes;
   const int fp16 = pl->np == 1;
+  // planes that outlive this call (kept from Propagate, or written by the producer of the matrix): no split at all
+  if (scale == nullptr && !fp16 && !ctx->grad_fast && groups == r && (groups == 1 || (c_row_mul == 1 && c_col_mul == 0))) {
+    const tdnnf_planes* a = ctx->find_attached(src, R, D, ld, r);
+    if (a && a->np >= pl->np && a->Q == Q && a->Kpad == Kpad) {
+      pl->base = static_cast<__nv_bfloat16*>(a->base);
+      pl->plane_elems = a->plane_elems;
+      ctx->cache_hits++;
+      return TDNNF_OK;
+    }
+  }
   const bool cacheable = ctx->cache_registered(src);
   tdnnf_ctx::PlaneCacheEntry key;
   if (cacheable) {
@@ -837,7 +847,11 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
     const bool tiles_ok = (bn0 % 64 == 0 || ceil_div(n_dim, bn0) == 1) && !(ctx->gemm_planes == 3 && bn0 == 256);
     if (mn_enabled && !fast0 && tiles_ok && out_rows >= mn_min_rows) {
       if (dbias) {  // bias gradient: lr * colsum(out_deriv) (the transposed pre-pass of the other path does it on the fly)
-        rc = tdnnf_add_row_sum(ctx, out_deriv, out_rows, out_dim, od_stride, lr, dbias);
+        const tdnnf_planes* pa = ctx->find_attached(out_deriv, out_rows, out_dim, od_stride, 1);
+        if (pa && pa->has_colsum && !ctx->grad_fast)  // the producer of out_deriv summed its columns while writing it
+          rc = tdnnf_mat_axpy(ctx, lr, pa->colsum, out_dim, dbias, out_dim, 1, out_dim);
+        else
+          rc = tdnnf_add_row_sum(ctx, out_deriv, out_rows, out_dim, od_stride, lr, dbias);
         if (rc) return rc;
       }
       const int KpX = round_up(in_dim, kBK), KpO = round_up(out_dim, kBK);
@@ -1015,5 +1029,112 @@ extern "C" int tdnnf_ctx_operand_rowsq(tdnnf_ctx* ctx, const float* source, int 
   *rowsq = nullptr;
   const int idx = ctx->cache_source_index(source);
   if (idx >= 0 && ctx->rowsq_valid[idx] && ctx->rowsq_rows[idx] == rows) *rowsq = ctx->rowsq_dev[idx];
+  if (*rowsq == nullptr && !ctx->grad_fast)
+    for (const tdnnf_planes* p : ctx->attached_planes)
+      if (p->src == source && p->R == rows && p->rowsq) *rowsq = p->rowsq;
   return TDNNF_OK;
+}
+
+// ------------------------------------------------------------------------------------------ tdnnf_planes_*
+static int planes_new(tdnnf_ctx* ctx, const float* src, int rows, int cols, int stride, int row_stride, tdnnf_planes** out) {
+  const int r = row_stride, Q = ceil_div(rows, r), Kpad = round_up(cols, kBK);
+  const size_t pb = planes_bytes(2, r, Q, Kpad);
+  const size_t rb = ((size_t)rows * sizeof(float) + 255) & ~size_t(255), cb = ((size_t)cols * sizeof(float) + 255) & ~size_t(255);
+  const size_t bytes = pb + rb + cb;
+  void* block = nullptr;
+  for (size_t i = 0; i < ctx->planes_pool.size(); ++i) {
+    if (ctx->planes_pool[i].first == bytes) {
+      block = ctx->planes_pool[i].second;
+      ctx->planes_pool.erase(ctx->planes_pool.begin() + i);
+      break;
+    }
+  }
+  if (!block) {
+    cudaError_t e = cudaMalloc(&block, bytes);
+    if (e != cudaSuccess) return fail(TDNNF_ERR_NOMEM, std::string("cudaMalloc of operand planes failed: ") + cudaGetErrorString(e));
+  }
+  tdnnf_planes* p = new tdnnf_planes();
+  p->ctx = ctx;
+  p->src = src;
+  p->R = rows;
+  p->D = cols;
+  p->ld = stride;
+  p->r = r;
+  p->Q = Q;
+  p->Kpad = Kpad;
+  p->np = 2;
+  p->block = block;
+  p->bytes = bytes;
+  p->base = block;
+  p->plane_elems = (long long)r * Q * Kpad;
+  p->rowsq = reinterpret_cast<float*>(static_cast<char*>(block) + pb);
+  p->colsum = reinterpret_cast<float*>(static_cast<char*>(block) + pb + rb);
+  *out = p;
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_planes_acquire(tdnnf_ctx* ctx, const float* src, int rows, int cols, int stride, int row_stride,
+                                    tdnnf_planes** out) {
+  TDNNF_REQUIRE(ctx && src && out, "null argument");
+  TDNNF_REQUIRE(rows > 0 && cols > 0 && stride >= cols && row_stride >= 1 && row_stride <= kMaxSeg, "bad matrix");
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+  if (const tdnnf_planes* a = ctx->find_attached(src, rows, cols, stride, row_stride)) {
+    tdnnf_planes* p = const_cast<tdnnf_planes*>(a);
+    p->refs++;
+    *out = p;
+    return TDNNF_OK;
+  }
+  tdnnf_planes* p = nullptr;
+  int rc = planes_new(ctx, src, rows, cols, stride, row_stride, &p);
+  if (rc) return rc;
+  TDNNF_CUDA_OK(cudaMemsetAsync(p->rowsq, 0, sizeof(float) * (size_t)rows, ctx->stream));
+  __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(p->base);
+  const long long total = (long long)p->r * p->Q * (p->Kpad >> 3);
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 16));
+  split_rows_kernel<<<blocks, 256, 0, ctx->stream>>>(src, rows, cols, stride, p->r, p->r, 1, 0, nullptr, p->Q, p->Kpad, hi,
+                                                     hi + p->plane_elems, nullptr, 0, nullptr, nullptr, p->rowsq);
+  ctx->launches++;
+  TDNNF_CUDA_OK(cudaGetLastError());
+  *out = p;
+  return TDNNF_OK;
+}
+
+// Planes for a matrix whose PRODUCER fills them (the fused tail kernels): nothing is launched here.
+int tdnnf::planes_alloc_for_producer(tdnnf_ctx* ctx, const float* src, int rows, int cols, int stride, tdnnf_planes** out) {
+  return planes_new(ctx, src, rows, cols, stride, 1, out);
+}
+
+extern "C" int tdnnf_planes_release(tdnnf_planes* p) {
+  if (!p) return TDNNF_OK;
+  if (--p->refs > 0) return TDNNF_OK;
+  tdnnf_ctx* ctx = p->ctx;
+  for (size_t i = 0; i < ctx->attached_planes.size(); ++i)
+    if (ctx->attached_planes[i] == p) {
+      ctx->attached_planes.erase(ctx->attached_planes.begin() + i);
+      break;
+    }
+  ctx->planes_pool.push_back(std::make_pair(p->bytes, p->block));  // stream-ordered reuse: everything runs on the context's stream
+  delete p;
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_ctx_planes_attach(tdnnf_ctx* ctx, tdnnf_planes* p) {
+  TDNNF_REQUIRE(ctx && p && p->ctx == ctx, "bad argument");
+  if (p->attached++ == 0) ctx->attached_planes.push_back(p);
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_ctx_planes_detach(tdnnf_ctx* ctx, tdnnf_planes* p) {
+  TDNNF_REQUIRE(ctx && p && p->ctx == ctx, "bad argument");
+  if (p->attached > 0 && --p->attached == 0)
+    for (size_t i = 0; i < ctx->attached_planes.size(); ++i)
+      if (ctx->attached_planes[i] == p) {
+        ctx->attached_planes.erase(ctx->attached_planes.begin() + i);
+        break;
+      }
+  return TDNNF_OK;
+}
+
+extern "C" int tdnnf_planes_matches(const tdnnf_planes* p, const float* src, int rows, int cols, int stride) {
+  return p && p->src == src && p->R == rows && p->D == cols && p->ld == stride;
 }

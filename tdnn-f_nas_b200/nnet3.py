@@ -97,6 +97,11 @@ def set_dp_world_size(g: int):
     _check(_lib().tdnnf_nnet3_set_dp_world_size(g))
 
 
+def set_keep_planes(flag: bool):
+    """TdnnDARTSV3Component: keep the operand planes of Propagate's input in the memo for Backprop (default on)."""
+    _check(_lib().tdnnf_nnet3_set_keep_planes(int(flag)))
+
+
 def set_print_log_alpha(flag: bool):
     _check(_lib().tdnnf_nnet3_set_print_log_alpha(int(flag)))
 

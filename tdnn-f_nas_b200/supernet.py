@@ -68,6 +68,8 @@ class SupernetConfig:
     flops_coef: float = 1.0e-3       # eta: the `scale` of {Gumbel}SoftmaxFlopsComponent (0, 1e-3, 1e-1 in the recipes)
     bottleneck_gumbel: bool = False  # GumbelSoftmaxFlopsComponent (temperature schedule) instead of SoftmaxFlopsComponent
     fuse_mask: bool = True           # the descriptor sub-graph + 8 CopyN + 8 ElementwiseProduct as one pass (else one by one)
+    tail_planes: bool = True         # the fused tails also write the bf16 operand planes (+ row / column sums) of what they
+                                     # produce: the next GEMM does not split the matrix again
     # learning-rate-factor 0 on everything but the searched parameters, as the search recipes set it
     # (run_TDNN_DARTSV3_fbk_stride_cvupdate.sh:129-134): nnet3 then computes no model derivatives for tdnn1 / prefinal /
     # output.  None = True in the search and bottleneck stages, False otherwise.
@@ -598,6 +600,19 @@ class Supernet:
         plan.add("nnet3", lib.tdnnf_nnet3_backprop, blk["alpha"].h, None, None, ar, ac, 0, None, 0, da, ar, ac, das, None,
                  blk["alpha_delta"].h, None, 0)
 
+    def _with_planes(self, plan, holder, add_consumer):
+        """The consumer call(s) added by add_consumer() run with the planes handle in `holder` (a ctypes pointer filled at
+        run time by a producer kernel) attached to the context; afterwards the producer's reference is dropped (a
+        TdnnDARTSV3Component keeps its own in the memo until Backprop)."""
+        if holder is None:
+            add_consumer()
+            return
+        lib, h = self.lib, self.ctx.h
+        plan.add("abi", lib.tdnnf_ctx_planes_attach, h, holder)
+        add_consumer()
+        plan.add("abi", lib.tdnnf_ctx_planes_detach, h, holder)
+        plan.add("abi", lib.tdnnf_planes_release, holder)
+
     def _bucket_hook(self, plan, kind, key):
         """Inside the backward plan: once the backward pass has finished the last component of a delta bucket, start its
         all-reduce on the side stream (only with dp_buckets > 1 and more than one rank)."""
@@ -647,13 +662,15 @@ class Supernet:
         else:
             self._bn_fwd(fwd, t1["bn"], t1["relu"], t1["out"])
         prev = t1["out"]
+        prev_planes = None  # the planes handle of `prev` when its producer wrote them (fused tail with tail_planes)
         for blk in self.blocks:
             pp, pr, pc, ps = _m(prev)
             lp, lr_, lc, ls = _m(blk["lin_out"])
             if cfg.mode in ("manual", "bottleneck"):  # use-bias=false => kPropagateAdds: the computer hands over a zeroed matrix
                 fwd.add("abi", lib.tdnnf_mat_set, h, lp, lr_, lc, ls, 0.0)
-            fwd.add("nnet3", lib.tdnnf_nnet3_propagate, blk["lin"].h, blk["lin_idx"].h, pp, pr, pc, ps, lp, lr_, lc, ls,
-                    C.byref(blk["memo_lin"]))
+            self._with_planes(fwd, prev_planes, lambda: fwd.add(
+                "nnet3", lib.tdnnf_nnet3_propagate, blk["lin"].h, blk["lin_idx"].h, pp, pr, pc, ps, lp, lr_, lc, ls,
+                C.byref(blk["memo_lin"])))
             a_in = blk["lin_out"]
             if cfg.mode == "bottleneck":
                 self._mask_fwd(fwd, blk)
@@ -677,7 +694,14 @@ class Supernet:
                         C.c_void_p(byp["map"].data_ptr()))
                 src = blk["byp_tmp"]
             self.keep.append(src)
-            if fused:
+            prev_planes = None
+            if fused and cfg.tail_planes and oc <= 4096:
+                sp, ofp, _ = blk["bn"].bn_test_scale_offset()
+                blk["out_pl"] = C.c_void_p()
+                fwd.add("abi", lib.tdnnf_relu_scale_offset_bypass_fwd_planes, h, op, orr, oc, os_, C.c_void_p(sp), C.c_void_p(ofp),
+                        _m(src)[0], _m(src)[3], cfg.bypass_scale, _m(blk["out"])[0], _m(blk["out"])[3], C.byref(blk["out_pl"]))
+                prev_planes = blk["out_pl"]
+            elif fused:
                 sp, ofp, _ = blk["bn"].bn_test_scale_offset()
                 fwd.add("abi", lib.tdnnf_relu_scale_offset_bypass_fwd, h, op, orr, oc, os_, C.c_void_p(sp), C.c_void_p(ofp),
                         _m(src)[0], _m(src)[3], cfg.bypass_scale, _m(blk["out"])[0], _m(blk["out"])[3])
@@ -691,7 +715,7 @@ class Supernet:
                 fwd.add("abi", lib.tdnnf_add_scaled, h, _m(src)[0], _m(src)[3], cfg.bypass_scale, _m(blk["bn_out"])[0],
                         _m(blk["bn_out"])[3], 1.0, _m(blk["out"])[0], _m(blk["out"])[3], orr, oc)
             prev = blk["out"]
-        self._affine_fwd(fwd, prev, st["prefinal_l"], hd["pl"])
+        self._with_planes(fwd, prev_planes, lambda: self._affine_fwd(fwd, prev, st["prefinal_l"], hd["pl"]))
         self._affine_fwd(fwd, hd["pl"], st["pc_affine"], hd["pa"])
         fwd.add("abi", lib.tdnnf_relu_fwd, h, *_m(hd["pa"]), _m(hd["pr"])[0], _m(hd["pr"])[3])
         self._bn_fwd(fwd, hd["bn1"], hd["pr"], hd["pb"])
@@ -747,6 +771,7 @@ class Supernet:
             qp, qr, qc, qs = _m(d_prev)
             fused = cfg.fuse_tail and isinstance(blk["bn"], nnet3.Component) and not cfg.dropout  # the fused tail has no dropout node
             byp = blk["bypass"]
+            daff_planes = None  # planes of d_aff when the fused tail wrote them
             if fused and byp["contiguous"]:
                 # zero only the halo rows of d_prev; the fused kernel overwrites the matching rows with the bypass term
                 off = byp["offset"]
@@ -758,8 +783,14 @@ class Supernet:
                 dst = d_prev[off: off + dr]
                 self.keep.append(dst)
                 sp, _, _ = blk["bn"].bn_test_scale_offset()
-                bwd.add("abi", lib.tdnnf_relu_scale_offset_bypass_bwd, h, dp_, ds, _m(blk["aff_out"])[0], _m(blk["aff_out"])[3],
-                        C.c_void_p(sp), cfg.bypass_scale, _m(blk["d_aff"])[0], _m(blk["d_aff"])[3], _m(dst)[0], _m(dst)[3], dr, dc)
+                if cfg.tail_planes and dc <= 4096:
+                    daff_planes = blk["daff_pl"] = C.c_void_p()
+                    bwd.add("abi", lib.tdnnf_relu_scale_offset_bypass_bwd_planes, h, dp_, ds, _m(blk["aff_out"])[0], _m(blk["aff_out"])[3],
+                            C.c_void_p(sp), cfg.bypass_scale, _m(blk["d_aff"])[0], _m(blk["d_aff"])[3], _m(dst)[0], _m(dst)[3], dr, dc,
+                            C.byref(daff_planes))
+                else:
+                    bwd.add("abi", lib.tdnnf_relu_scale_offset_bypass_bwd, h, dp_, ds, _m(blk["aff_out"])[0], _m(blk["aff_out"])[3],
+                            C.c_void_p(sp), cfg.bypass_scale, _m(blk["d_aff"])[0], _m(blk["d_aff"])[3], _m(dst)[0], _m(dst)[3], dr, dc)
             else:
                 # d_prev = 0 everywhere, then the bypass term on the matching rows
                 bwd.add("abi", lib.tdnnf_mat_set, h, qp, qr, qc, qs, 0.0)
@@ -772,8 +803,14 @@ class Supernet:
                 if fused:
                     sp, _, _ = blk["bn"].bn_test_scale_offset()
                     scratch = blk["bn_out"]  # d_prev of the non-contiguous (last) block is handled above; discard the kernel's copy
-                    bwd.add("abi", lib.tdnnf_relu_scale_offset_bypass_bwd, h, dp_, ds, _m(blk["aff_out"])[0], _m(blk["aff_out"])[3],
-                            C.c_void_p(sp), 0.0, _m(blk["d_aff"])[0], _m(blk["d_aff"])[3], _m(scratch)[0], _m(scratch)[3], dr, dc)
+                    if cfg.tail_planes and dc <= 4096:
+                        daff_planes = blk["daff_pl"] = C.c_void_p()
+                        bwd.add("abi", lib.tdnnf_relu_scale_offset_bypass_bwd_planes, h, dp_, ds, _m(blk["aff_out"])[0],
+                                _m(blk["aff_out"])[3], C.c_void_p(sp), 0.0, _m(blk["d_aff"])[0], _m(blk["d_aff"])[3], _m(scratch)[0],
+                                _m(scratch)[3], dr, dc, C.byref(daff_planes))
+                    else:
+                        bwd.add("abi", lib.tdnnf_relu_scale_offset_bypass_bwd, h, dp_, ds, _m(blk["aff_out"])[0], _m(blk["aff_out"])[3],
+                                C.c_void_p(sp), 0.0, _m(blk["d_aff"])[0], _m(blk["d_aff"])[3], _m(scratch)[0], _m(scratch)[3], dr, dc)
                 else:
                     # (dropout,) batchnorm, relu
                     if cfg.dropout:
@@ -793,8 +830,9 @@ class Supernet:
             gp, gr, gc, gs = _m(d_ain)
             delta_h = lambda d: d.h if d is not None else None   # frozen component: no to_update, data gradient only
             bwd.add("abi", lib.tdnnf_mat_set, h, gp, gr, gc, gs, 0.0)
-            bwd.add("nnet3", lib.tdnnf_nnet3_backprop, blk["aff"].h, blk["aff_idx"].h, ip, ir, ic, is_, None, 0,
-                    _m(blk["d_aff"])[0], dr, dc, _m(blk["d_aff"])[3], blk["memo_aff"], delta_h(blk["aff_delta"]), gp, gs)
+            self._with_planes(bwd, daff_planes, lambda: bwd.add(
+                "nnet3", lib.tdnnf_nnet3_backprop, blk["aff"].h, blk["aff_idx"].h, ip, ir, ic, is_, None, 0,
+                _m(blk["d_aff"])[0], dr, dc, _m(blk["d_aff"])[3], blk["memo_aff"], delta_h(blk["aff_delta"]), gp, gs))
             bwd.add("nnet3", lib.tdnnf_nnet3_delete_memo, blk["aff"].h, blk["memo_aff"])
             self._bucket_hook(bwd, "comp", (bi, "aff"))
             if blk["reorder"]:

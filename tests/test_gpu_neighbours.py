@@ -251,3 +251,63 @@ def test_log_softmax_component_vs_numpy(ctx, rows, cols, pad):
     assert torch.equal(odd, ind)
     back = nnet3.Component.read(comp.write(True), True)
     assert back.type() == "LogSoftmaxComponent" and back.input_dim() == cols
+
+
+@pytest.mark.parametrize("rows,cols,pad", [(37, 1536, 0), (300, 160, 0), (5, 64, 4), (129, 200, 8)])
+def test_fused_tail_producers_write_the_operand_planes(ctx, rows, cols, pad):
+    """tdnnf_relu_scale_offset_bypass_{fwd,bwd}_planes: same fp32 results as the plain fused tails, and the planes they
+    hand over give the same GEMM result as splitting the matrix (tdnnf_darts_propagate with the handle attached counts a
+    cache hit and launches no split of the activation), the same bias gradient and the same row sums of squares."""
+    import ctypes as C
+
+    import torch
+
+    from tdnnf_nas_b200 import capi
+
+    lib = capi.load()
+    g = np.random.default_rng(rows + cols)
+    mk = lambda r, c: torch.from_numpy(np.pad(g.standard_normal((r, c)).astype(np.float32), ((0, 0), (0, pad)))).cuda()[:, :c]
+    x, prev, d_out = mk(rows, cols), mk(rows, cols), mk(rows, cols)
+    scale = torch.from_numpy((g.random(cols) + 0.5).astype(np.float32)).cuda()
+    offset = torch.from_numpy(g.standard_normal(cols).astype(np.float32)).cuda()
+    ref_out, out = mk(rows, cols), mk(rows, cols)
+    ctx.relu_scale_offset_bypass_fwd(x, scale, offset, prev, 0.66, ref_out)
+    pl = C.c_void_p()
+    m = capi._mat
+    capi.check(lib.tdnnf_relu_scale_offset_bypass_fwd_planes(ctx.h, m(x)[0], rows, cols, m(x)[3], scale.data_ptr(), offset.data_ptr(),
+                                                             m(prev)[0], m(prev)[3], 0.66, m(out)[0], m(out)[3], C.byref(pl)))
+    assert torch.equal(out, ref_out)
+    # a Propagate-shaped GEMM on `out`: with the producer's planes attached vs. splitting the matrix
+    W = torch.from_numpy((g.standard_normal((48, cols)) / np.sqrt(cols)).astype(np.float32)).cuda()
+    one = torch.ones(1, device="cuda")
+    y_split, y_planes = torch.zeros((rows, 48), device="cuda"), torch.zeros((rows, 48), device="cuda")
+    ctx.darts_propagate(out, y_split, W, None, 1, one, [0], 1)
+    h0, _ = ctx.operand_cache_stats()
+    capi.check(lib.tdnnf_ctx_planes_attach(ctx.h, pl))
+    ctx.darts_propagate(out, y_planes, W, None, 1, one, [0], 1)
+    capi.check(lib.tdnnf_ctx_planes_detach(ctx.h, pl))
+    assert ctx.operand_cache_stats()[0] == h0 + 1
+    assert torch.equal(y_split, y_planes)
+    capi.check(lib.tdnnf_planes_release(pl))
+    # backward producer: d_x, d_prev as the plain kernel; planes + column sums feed the parameter gradient
+    ref_dx, ref_dp, dx, dp = mk(rows, cols), mk(rows, cols), mk(rows, cols), mk(rows, cols)
+    ctx.relu_scale_offset_bypass_bwd(d_out, x, scale, 0.66, ref_dx, ref_dp)
+    pl = C.c_void_p()
+    capi.check(lib.tdnnf_relu_scale_offset_bypass_bwd_planes(ctx.h, m(d_out)[0], m(d_out)[3], m(x)[0], m(x)[3], scale.data_ptr(), 0.66,
+                                                             m(dx)[0], m(dx)[3], m(dp)[0], m(dp)[3], rows, cols, C.byref(pl)))
+    assert torch.equal(dx, ref_dx) and torch.equal(dp, ref_dp)
+    if rows >= 512 or True:
+        ctx.set_wgrad_mn_min_rows(1)  # the MN-major parameter gradient is the consumer of planes + column sums
+        try:
+            inp = mk(rows, 40)
+            dW1, db1 = torch.zeros((cols, 40), device="cuda"), torch.zeros(cols, device="cuda")
+            dW2, db2 = torch.zeros((cols, 40), device="cuda"), torch.zeros(cols, device="cuda")
+            ctx.darts_backprop_params(inp, dx, None, dW1, db1, one, [0], 1, 0.5)
+            capi.check(lib.tdnnf_ctx_planes_attach(ctx.h, pl))
+            ctx.darts_backprop_params(inp, dx, None, dW2, db2, one, [0], 1, 0.5)
+            capi.check(lib.tdnnf_ctx_planes_detach(ctx.h, pl))
+            assert rel_err(dW2.cpu().numpy(), dW1.cpu().numpy()) < 1e-6
+            assert rel_err(db2.cpu().numpy(), db1.cpu().numpy()) < 1e-5
+        finally:
+            ctx.set_wgrad_mn_min_rows(512)
+    capi.check(lib.tdnnf_planes_release(pl))

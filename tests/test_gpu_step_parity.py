@@ -43,8 +43,10 @@ def _params_of(net):
     return p
 
 
-@pytest.mark.parametrize("xent", [True, False])
-def test_whole_step_matches_cpu_reference(xent):
+@pytest.mark.parametrize("xent,planes", [(True, True), (False, True), (True, False)])
+def test_whole_step_matches_cpu_reference(xent, planes):
+    """planes: the fused tails write the operand planes of what they produce and Propagate keeps its input planes for
+    Backprop (the default); False: every GEMM call splits its operands itself."""
     import torch
 
     from oracle import supernet_ref as R
@@ -55,7 +57,9 @@ def test_whole_step_matches_cpu_reference(xent):
     # preconditions (with 32 columns the rank is clipped to 31 and X_hat is the ill-conditioned remainder of a near-total
     # projection: rounding differences of 1e-6 in X come out as 1e-2 in the delta)
     cfg = SupernetConfig(num_seqs=8, frames_per_eg=30, dim=256, bottleneck=160, num_blocks=3, prefinal_small=64, num_pdfs=200,
-                         den_states=300, den_out_degree=6.0, mode="search", learning_rate=2e-3, darts_lr_factor=0.05, xent=xent)
+                         den_states=300, den_out_degree=6.0, mode="search", learning_rate=2e-3, darts_lr_factor=0.05, xent=xent,
+                         tail_planes=planes)
+    nnet3.set_keep_planes(planes)
     net = Supernet(cfg)
     S, T, P, L, n = cfg.num_seqs, net.T, cfg.num_pdfs, cfg.num_blocks, cfg.num_offsets
     den_graph = synth.make_den_graph(cfg.den_states, P, cfg.den_out_degree, seed=5)
@@ -98,4 +102,7 @@ def test_whole_step_matches_cpu_reference(xent):
             v = blk["lin"].vectorize()
             W = ref.p[f"blk{b}.lin.W"]
             assert rel_err(v[: W.size].reshape(W.shape), W) < 1e-5
+    h0, m0 = net.ctx.operand_cache_stats()
     net.close()
+    nnet3.set_keep_planes(True)
+    assert h0 > 0
