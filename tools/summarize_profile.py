@@ -17,7 +17,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-G = os.path.join(ROOT, "gpurun_out")
+G = os.path.join(ROOT, sys.argv[2]) if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out")
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 lines = []
@@ -90,15 +90,17 @@ def full_table(rep, title, want):
 
 
 full_table(os.path.join(G, "prof_gemm.ncu-rep"),
-           "`ncu --set full --clock-control none` of the first 10 splice_gemm_kernel launches of a plain step (forward pass: tdnn1, "
-           "then TdnnDARTSV3 1536->160 / 160->1536 alternating), per launch",
+           "`ncu --set full --clock-control none` of splice_gemm_kernel launches of a plain step (round 2: 14 consecutive launches of "
+           "the backward pass of the top blocks: data gradient, natural-gradient products, the MN-major parameter gradient "
+           "`<160, 2, 2, true>`), per launch",
            ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum",
             "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
             "lts__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread"])
-full_table(os.path.join(G, "prof_den.ncu-rep"), "`ncu --set full` of denominator frame kernels (N = 16384, S = 64), per launch",
-           ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
-            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
-            "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread"])
+for den_rep in ("prof_den.ncu-rep", "prof_den_a.ncu-rep", "prof_den_b.ncu-rep"):
+  full_table(os.path.join(G, den_rep), f"`ncu --set full` of denominator kernels ({den_rep}; N = 16384, S = 64), per launch",
+            ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+             "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread"])
 bench = os.path.join(G, "bench.log")
 if os.path.exists(bench):
     try:
