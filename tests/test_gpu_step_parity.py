@@ -94,6 +94,15 @@ def test_whole_step_matches_cpu_reference(xent, planes):
                 errs[(b, h, "bias")] = rel_err(dv[dW.size + n:], db[n:])
                 errs[(b, h, "alpha")] = float(np.abs(dv[dW.size: dW.size + n] - db[:n]).max() / (np.abs(db[:n]).max() + 1e-30))
         bad = {k: v for k, v in errs.items() if not v < 1e-3}
+        if bad:  # leave the whole picture behind for the post-mortem (gpurun_out/ comes back from the GPU box)
+            import json
+            import os
+
+            os.makedirs("gpurun_out", exist_ok=True)
+            with open(f"gpurun_out/step_parity_fail_{int(xent)}{int(planes)}_{step}.json", "w") as f:
+                json.dump({"errs": {str(k): v for k, v in errs.items()}, "objf": [objf_gpu, objf_ref],
+                           "out": rel_err(net.head["out"].cpu().numpy(), ref.st["out"]),
+                           "d_out": rel_err(net.head["d_out"].cpu().numpy(), ref.st["d_out"])}, f)
         assert not bad, (step, bad, errs)
         # the parameter step (max-change) on both sides
         assert net._update_with_max_change() and ref.update()
