@@ -443,6 +443,7 @@ def run_ours(args, cfg, rank, world, local_rank):
     net = Supernet(cfg, device=local_rank, rank=rank, world_size=world, process_group=pg, dp_buckets=args.dp_buckets)
     dev = net.dev
     host_inputs = [net.make_input(i).pin_memory() for i in range(2)]
+    host_sups = [net.make_supervision(i) for i in range(2)]  # every minibatch brings its own numerator supervision
     dp_check = dp_self_check(net, cfg, world, rank, local_rank, host_inputs[0]) if world > 1 and not args.no_dp_check else None
 
     def barrier():
@@ -457,7 +458,7 @@ def run_ours(args, cfg, rank, world, local_rank):
         e0.record()
         last = None
         for i in range(n_steps):
-            last = net.step(host_inputs[i % 2] if with_copy else None)
+            last = net.step(host_inputs[i % 2], supervision=host_sups[i % 2]) if with_copy else net.step(None)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -543,8 +544,10 @@ def run_ours(args, cfg, rank, world, local_rank):
         higher_is_better=True, scaling="weak", vs_baseline=None,
         dtype="f32 (bf16 hi/lo split operands, 3 tensor-core products, fp32 accumulate)", data="synthetic",
         config=workload_config(cfg, world), clocks=clocks,
-        e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=int(net.x.numel() * 4), d2h_bytes_per_step=12,
-                 ms_per_step=ms_e2e / args.steps),
+        e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=int(net.x.numel() * 4 + getattr(net, "last_supervision_bytes", 0)),
+                 d2h_bytes_per_step=int(8 * net.param_table.num_groups + 16 + (4 if cfg.xent else 0)), ms_per_step=ms_e2e / args.steps,
+                 per_step=("pinned-host features copied in, this minibatch's numerator FSTs uploaded (tdnnf_num_graph_update), the "
+                           "LF-MMI objective (2 scalars + 2 check flags), the xent objective and the max-change norms read back")),
         gpu_launches=int(launches),
         roofline=dict(bound="tensor", kernel="splice_gemm_kernel (tcgen05, the TdnnDARTSV3 Propagate / data-gradient / parameter-gradient GEMMs)",
                       achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=gemm_traffic,

@@ -468,6 +468,12 @@ int tdnnf_num_graph_create(tdnnf_ctx* ctx, int num_seqs, const int32_t* state_of
                            const int32_t* arc_pdf, const int32_t* arc_state, const float* final_logprob,
                            tdnnf_num_graph** out);
 int tdnnf_num_graph_destroy(tdnnf_num_graph* g);
+/* The next minibatch's numerator FSTs into the same handle (every NnetChainExample carries its own supervision): a pinned
+ * staging buffer and asynchronous copies on the context's stream; no allocation or synchronisation while the new graphs
+ * fit the capacity of the largest seen so far.  */
+int tdnnf_num_graph_update(tdnnf_num_graph* g, int num_seqs, const int32_t* state_offsets, int num_arcs,
+                           const int32_t* fwd_ranges, const int32_t* bwd_ranges, const float* arc_logprob,
+                           const int32_t* arc_pdf, const int32_t* arc_state, const float* final_logprob);
 /* total log-prob summed over sequences in *logprob (HOST; synchronises).  If nnet_output_deriv != NULL:
  * nnet_output_deriv[t*num_seqs+s, pdf] += deriv_weight * posterior.  *ok = 0 if any sequence has no path. */
 int tdnnf_num_forward_backward(tdnnf_ctx* ctx, const tdnnf_num_graph* g, const float* nnet_output, int stride,

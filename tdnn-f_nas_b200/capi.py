@@ -96,6 +96,7 @@ def _declare(lib):
     sig("tdnnf_mul_rows_indexed", [vp, vp, i, vp, i, i, i, vp, i, vp])
     sig("tdnnf_num_graph_create", [vp, i, c_int_p, i, c_int_p, c_int_p, c_float_p, c_int_p, c_int_p, c_float_p, C.POINTER(vp)])
     sig("tdnnf_num_graph_destroy", [vp])
+    sig("tdnnf_num_graph_update", [vp, i, c_int_p, i, c_int_p, c_int_p, c_float_p, c_int_p, c_int_p, c_float_p])
     sig("tdnnf_num_forward_backward", [vp, vp, vp, i, i, f, vp, i, c_float_p, c_int_p])
     sig("tdnnf_den_graph_create", [vp, i, i, i, c_int_p, c_int_p, c_float_p, c_int_p, c_int_p, c_float_p, C.POINTER(vp)])
     sig("tdnnf_den_graph_destroy", [vp])
@@ -660,6 +661,26 @@ class NumeratorGraph:
                                             pd.ctypes.data_as(c_int_p), st.ctypes.data_as(c_int_p), fl.ctypes.data_as(c_float_p),
                                             C.byref(h)))
         self.h = h
+
+    @staticmethod
+    def host_arrays(graph: dict):
+        """The contiguous host arrays of a supervision dict, prepared once (what a data loader would hand over)."""
+        import numpy as np
+
+        a = lambda k, dt: np.ascontiguousarray(graph[k], dtype=dt)
+        return dict(num_seqs=int(graph["num_seqs"]), num_arcs=int(graph["num_arcs"]), so=a("state_offsets", np.int32),
+                    fr=a("fwd_ranges", np.int32), br=a("bwd_ranges", np.int32), lp=a("arc_logprob", np.float32),
+                    pd=a("arc_pdf", np.int32), st=a("arc_state", np.int32), fl=a("final_logprob", np.float32))
+
+    def update(self, h: dict) -> int:
+        """The next minibatch's supervision (host_arrays) into this handle: asynchronous copies from a pinned staging
+        buffer on the context's stream.  Returns the bytes copied."""
+        check(load().tdnnf_num_graph_update(self.h, h["num_seqs"], h["so"].ctypes.data_as(c_int_p), h["num_arcs"],
+                                            h["fr"].ctypes.data_as(c_int_p), h["br"].ctypes.data_as(c_int_p),
+                                            h["lp"].ctypes.data_as(c_float_p), h["pd"].ctypes.data_as(c_int_p),
+                                            h["st"].ctypes.data_as(c_int_p), h["fl"].ctypes.data_as(c_float_p)))
+        self.num_seqs = h["num_seqs"]
+        return sum(int(h[k].nbytes) for k in ("so", "fr", "br", "lp", "pd", "st", "fl"))
 
     def forward_backward(self, nnet_output, frames_per_seq: int, deriv_weight: float = 1.0, nnet_output_deriv=None):
         """Returns (logprob, ok); adds deriv_weight * posteriors into nnet_output_deriv if given."""

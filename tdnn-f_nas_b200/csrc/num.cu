@@ -4,8 +4,10 @@
 // per-sequence global scratch strip and each frame is one pass of "thread = state, loop over its arcs" with a
 // block barrier between frames; log-sum-exp in fp32 with a running max.  Posteriors go to nnet_output_deriv
 // with atomicAdd (a handful per frame).
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "context.h"
@@ -25,6 +27,11 @@ struct tdnnf_num_graph {
   float* alpha = nullptr;          // device scratch, grown on demand: [num_states][T+1] laid out per sequence
   size_t alpha_elems = 0;
   double* scalars = nullptr;  // [2]: total logprob, number of failed sequences
+  // tdnnf_num_graph_update: capacities of the device arrays, a pinned staging buffer and the event of its last copy
+  int cap_seqs = 0, cap_states = 0, cap_arcs = 0;
+  char* staging = nullptr;
+  size_t staging_bytes = 0;
+  cudaEvent_t staged = nullptr;
 };
 
 namespace {
@@ -142,6 +149,9 @@ extern "C" int tdnnf_num_graph_create(tdnnf_ctx* ctx, int num_seqs, const int32_
   g->num_states = num_states;
   g->num_arcs = num_arcs;
   g->max_states = max_states;
+  g->cap_seqs = num_seqs;
+  g->cap_states = num_states;
+  g->cap_arcs = num_arcs;
   cudaError_t e = cudaSuccess;
   auto up = [&](void** dst, const void* src, size_t bytes) {
     if (e != cudaSuccess) return;
@@ -175,7 +185,78 @@ extern "C" int tdnnf_num_graph_destroy(tdnnf_num_graph* g) {
   cudaFree(g->final_logprob);
   cudaFree(g->alpha);
   cudaFree(g->scalars);
+  if (g->staging) cudaFreeHost(g->staging);
+  if (g->staged) cudaEventDestroy(g->staged);
   delete g;
+  return TDNNF_OK;
+}
+
+// A new minibatch's supervision into the SAME device arrays (every minibatch brings its own numerator FSTs: kaldi
+// NnetChainExample -> Supervision::e2e_fsts): one pinned staging buffer, asynchronous copies on the context's stream,
+// no allocation and no device synchronisation as long as the new graphs fit the capacities of the first ones.
+extern "C" int tdnnf_num_graph_update(tdnnf_num_graph* g, int num_seqs, const int32_t* state_offsets, int num_arcs,
+                                      const int32_t* fwd_ranges, const int32_t* bwd_ranges, const float* arc_logprob,
+                                      const int32_t* arc_pdf, const int32_t* arc_state, const float* final_logprob) {
+  TDNNF_REQUIRE(g && state_offsets && fwd_ranges && bwd_ranges && arc_logprob && arc_pdf && arc_state && final_logprob, "null argument");
+  TDNNF_REQUIRE(num_seqs > 0 && num_arcs > 0 && state_offsets[0] == 0, "empty numerator graph");
+  const int num_states = state_offsets[num_seqs];
+  int max_states = 0;
+  for (int s = 0; s < num_seqs; ++s) {
+    TDNNF_REQUIRE(state_offsets[s + 1] > state_offsets[s], "a sequence has no states");
+    max_states = std::max(max_states, state_offsets[s + 1] - state_offsets[s]);
+  }
+  TDNNF_REQUIRE(max_states <= 12000, "numerator FST too large for the per-sequence kernel");
+  for (int h = 0; h < num_states; ++h)
+    TDNNF_REQUIRE(fwd_ranges[2 * h] <= fwd_ranges[2 * h + 1] && fwd_ranges[2 * h + 1] <= 2 * num_arcs &&
+                      bwd_ranges[2 * h] <= bwd_ranges[2 * h + 1] && bwd_ranges[2 * h + 1] <= 2 * num_arcs,
+                  "arc range out of bounds");
+  tdnnf_ctx* ctx = g->ctx;
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (num_seqs > g->cap_seqs || num_states > g->cap_states || num_arcs > g->cap_arcs) {
+    // grow (with head-room): the one path that synchronises
+    TDNNF_CUDA_OK(cudaStreamSynchronize(st));
+    const int cs = std::max(num_seqs, g->cap_seqs), cn = std::max(num_states + num_states / 4, g->cap_states),
+              ca = std::max(num_arcs + num_arcs / 4, g->cap_arcs);
+    cudaFree(g->state_offsets); cudaFree(g->fwd_ranges); cudaFree(g->bwd_ranges); cudaFree(g->arc_logprob);
+    cudaFree(g->arc_pdf); cudaFree(g->arc_state); cudaFree(g->final_logprob);
+    g->state_offsets = nullptr; g->fwd_ranges = g->bwd_ranges = nullptr; g->arc_logprob = nullptr;
+    g->arc_pdf = g->arc_state = nullptr; g->final_logprob = nullptr;
+    TDNNF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&g->state_offsets), sizeof(int) * (cs + 1)));
+    TDNNF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&g->fwd_ranges), sizeof(int2) * cn));
+    TDNNF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&g->bwd_ranges), sizeof(int2) * cn));
+    TDNNF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&g->arc_logprob), sizeof(float) * 2 * ca));
+    TDNNF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&g->arc_pdf), sizeof(int) * 2 * ca));
+    TDNNF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&g->arc_state), sizeof(int) * 2 * ca));
+    TDNNF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&g->final_logprob), sizeof(float) * cn));
+    g->cap_seqs = cs; g->cap_states = cn; g->cap_arcs = ca;
+  }
+  const size_t sizes[7] = {sizeof(int) * (size_t)(num_seqs + 1), sizeof(int2) * (size_t)num_states, sizeof(int2) * (size_t)num_states,
+                           sizeof(float) * 2 * (size_t)num_arcs, sizeof(int) * 2 * (size_t)num_arcs, sizeof(int) * 2 * (size_t)num_arcs,
+                           sizeof(float) * (size_t)num_states};
+  const void* srcs[7] = {state_offsets, fwd_ranges, bwd_ranges, arc_logprob, arc_pdf, arc_state, final_logprob};
+  void* dsts[7] = {g->state_offsets, g->fwd_ranges, g->bwd_ranges, g->arc_logprob, g->arc_pdf, g->arc_state, g->final_logprob};
+  size_t total = 0;
+  for (size_t b : sizes) total += (b + 255) & ~size_t(255);
+  if (!g->staged) TDNNF_CUDA_OK(cudaEventCreateWithFlags(&g->staged, cudaEventDisableTiming));
+  else TDNNF_CUDA_OK(cudaEventSynchronize(g->staged));  // the previous minibatch's copies have left the staging buffer
+  if (g->staging_bytes < total) {
+    if (g->staging) cudaFreeHost(g->staging);
+    g->staging = nullptr;
+    TDNNF_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&g->staging), total * 2));
+    g->staging_bytes = total * 2;
+  }
+  size_t off = 0;
+  for (int i = 0; i < 7; ++i) {
+    memcpy(g->staging + off, srcs[i], sizes[i]);
+    TDNNF_CUDA_OK(cudaMemcpyAsync(dsts[i], g->staging + off, sizes[i], cudaMemcpyHostToDevice, st));
+    off += (sizes[i] + 255) & ~size_t(255);
+  }
+  TDNNF_CUDA_OK(cudaEventRecord(g->staged, st));
+  g->num_seqs = num_seqs;
+  g->num_states = num_states;
+  g->num_arcs = num_arcs;
+  g->max_states = max_states;
   return TDNNF_OK;
 }
 

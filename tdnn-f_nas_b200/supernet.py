@@ -332,6 +332,7 @@ class Supernet:
         # ---------------- denominator graph + synthetic numerator alignment
         graph = synth.make_den_graph(cfg.den_states, P, cfg.den_out_degree, seed=5)
         self.den_arcs = graph["num_arcs"]
+        self.den_graph_host = graph
         self.den_graph = capi.DenGraph(ctx, graph)
         # per-sequence numerator FSTs of this rank's shard (unconstrained supervision, `--constrained false`): phone
         # strings are random walks in the denominator graph, so numerator paths are denominator paths (bounded objective)
@@ -930,7 +931,14 @@ class Supernet:
         g = synth.rng(3, stream=100 + self.rank * 1000 + step)
         return torch.from_numpy(g.standard_normal((self.rows_in, self.cfg.feat_dim)).astype(np.float32))
 
-    def step(self, x_host=None, apply_update: bool = True, reduce: bool = True) -> float:
+    def make_supervision(self, step: int = 0) -> dict:
+        """Host arrays of a synthetic numerator supervision for this rank's chunks (what the egs reader would deliver with
+        every minibatch); pass to step(supervision=...)."""
+        g = synth.make_num_graphs(self.cfg.num_seqs, self.cfg.num_pdfs, self.T, seed=60 + self.rank + 1000 * (step + 1),
+                                  den_graph=self.den_graph_host)
+        return capi.NumeratorGraph.host_arrays(g)
+
+    def step(self, x_host=None, apply_update: bool = True, reduce: bool = True, supervision: Optional[dict] = None) -> float:
         """One training step.  x_host: pinned host tensor (rows_in x feat_dim) or None to reuse device input.
         reduce=False leaves this rank's own deltas in the delta arena (no all-reduce): bench.py's data-parallel self-check.
         (Prefetching the next input on a copy stream was measured: it made the step 3 ms SLOWER than this in-stream
@@ -942,6 +950,8 @@ class Supernet:
         self._reduce_now = reduce and self.dp is not None
         if x_host is not None:
             self.x.copy_(x_host, non_blocking=True)
+        if supervision is not None:  # this minibatch's numerator FSTs: asynchronous upload into the resident handle
+            self.last_supervision_bytes = self.num_graph.update(supervision)
         self.fwd_plan.run()
         # ComputeChainObjfAndDeriv: denominator fwd-bwd, numerator fwd-bwd, objf = num - den (host scalars, like Kaldi)
         if cfg.xent:

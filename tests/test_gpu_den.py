@@ -202,3 +202,29 @@ def test_chain_objf_and_deriv(ctx):
     for o in (obj, obj2):
         o.close()
     ng.close(); bad.close(); dg.close()
+
+
+def test_numerator_supervision_update(ctx):
+    """tdnnf_num_graph_update: the next minibatch's numerator FSTs uploaded into the same handle give what a freshly
+    created graph gives -- smaller and larger supervisions than the first one (capacity growth included)."""
+    import torch
+
+    from tdnnf_nas_b200 import capi, synth
+
+    S, P, T = 6, 40, 14
+    g = np.random.default_rng(3)
+    x = torch.from_numpy((g.standard_normal((T * S, P)) * 2).astype(np.float32)).cuda()
+    first = synth.make_num_graphs(S, P, T, seed=1, min_phones=3, max_phones=5)
+    handle = capi.NumeratorGraph(ctx, first)
+    for seed, lo, hi in ((2, 3, 4), (3, 8, 12), (4, 3, 12), (5, 10, 12)):
+        sup = synth.make_num_graphs(S, P, T, seed=seed, min_phones=lo, max_phones=hi)
+        nbytes = handle.update(capi.NumeratorGraph.host_arrays(sup))
+        assert nbytes > 0
+        d_upd, d_new = torch.zeros_like(x), torch.zeros_like(x)
+        lp_upd, ok_upd = handle.forward_backward(x, T, 1.0, d_upd)
+        fresh = capi.NumeratorGraph(ctx, sup)
+        lp_new, ok_new = fresh.forward_backward(x, T, 1.0, d_new)
+        fresh.close()
+        assert ok_upd and ok_new and lp_upd == pytest.approx(lp_new, rel=1e-6)
+        assert rel_err(d_upd.cpu().numpy(), d_new.cpu().numpy()) < 1e-6
+    handle.close()
