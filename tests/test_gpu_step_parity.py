@@ -99,8 +99,24 @@ def test_whole_step_matches_cpu_reference(xent, planes):
             import os
 
             os.makedirs("gpurun_out", exist_ok=True)
+            # a third opinion on the top of the backward pass: float64 numpy from the CPU side's own d_out and activations
+            f64 = lambda a: np.asarray(a, dtype=np.float64)
+            pp, stt = ref.p, ref.st
+            d = f64(stt["d_out"]) @ f64(pp["output.W"])
+            d = (d * f64(pp["bn.pc2.scale"])) @ f64(pp["pc_linear.W"])
+            d_pl64 = (d * f64(pp["bn.pc1.scale"]) * (f64(stt["pc"]["a"]) > 0)) @ f64(pp["pc_affine.W"])
+            if xent:
+                dx = f64(stt["d_xls"])
+                dx = dx - np.exp(f64(stt["xls"])) * dx.sum(1, keepdims=True)
+                dx = (dx @ f64(pp["output_xent.W"]) * f64(pp["bn.px2.scale"])) @ f64(pp["px_linear.W"])
+                d_pl64 = d_pl64 + (dx * f64(pp["bn.px1.scale"]) * (f64(stt["px"]["a"]) > 0)) @ f64(pp["px_affine.W"])
+            d_last64 = d_pl64 @ f64(pp["prefinal_l.W"])
+            d_aff64 = d_last64 * f64(pp[f"bn.blk{L - 1}.scale"]) * (f64(stt[L - 1]["aff_out"]) > 0)
+            third = {"gpu_vs_f64": rel_err(net.blocks[-1]["d_aff"].cpu().numpy(), d_aff64),
+                     "cpuref_vs_f64": rel_err(stt[L - 1]["d_aff"], d_aff64),
+                     "gpu_d_pl_vs_f64": rel_err(net.head["d_pl"].cpu().numpy(), d_pl64)}
             with open(f"gpurun_out/step_parity_fail_{int(xent)}{int(planes)}_{step}.json", "w") as f:
-                json.dump({"errs": {str(k): v for k, v in errs.items()}, "objf": [objf_gpu, objf_ref],
+                json.dump({"third_opinion": third, "errs": {str(k): v for k, v in errs.items()}, "objf": [objf_gpu, objf_ref],
                            "out": rel_err(net.head["out"].cpu().numpy(), ref.st["out"]),
                            "d_out": rel_err(net.head["d_out"].cpu().numpy(), ref.st["d_out"])}, f)
         assert not bad, (step, bad, errs)
