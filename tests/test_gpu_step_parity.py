@@ -112,7 +112,13 @@ def test_whole_step_matches_cpu_reference(xent, planes):
                 d_pl64 = d_pl64 + (dx * f64(pp["bn.px1.scale"]) * (f64(stt["px"]["a"]) > 0)) @ f64(pp["px_affine.W"])
             d_last64 = d_pl64 @ f64(pp["prefinal_l.W"])
             d_aff64 = d_last64 * f64(pp[f"bn.blk{L - 1}.scale"]) * (f64(stt[L - 1]["aff_out"]) > 0)
-            third = {"gpu_vs_f64": rel_err(net.blocks[-1]["d_aff"].cpu().numpy(), d_aff64),
+            g64 = lambda t: t.cpu().numpy().astype(np.float64)
+            hd = net.head
+            stage = {}  # every GEMM of the head's backward pass re-done in float64 from the GPU's OWN operands
+            stage["output dgrad"] = rel_err(g64(hd["d_pb2"]), (g64(hd["d_out"]) @ f64(pp["output.W"])) * f64(pp["bn.pc2.scale"]))
+            stage["pc_linear dgrad"] = rel_err(g64(hd["d_pb"]), (g64(hd["d_pb2"]) @ f64(pp["pc_linear.W"])) * f64(pp["bn.pc1.scale"]))
+            stage["relu bwd"] = rel_err(g64(hd["d_pa"]), g64(hd["d_pb"]) * (g64(hd["pr"]) > 0))
+            third = {"stages": stage, "gpu_vs_f64": rel_err(net.blocks[-1]["d_aff"].cpu().numpy(), d_aff64),
                      "cpuref_vs_f64": rel_err(stt[L - 1]["d_aff"], d_aff64),
                      "gpu_d_pl_vs_f64": rel_err(net.head["d_pl"].cpu().numpy(), d_pl64)}
             with open(f"gpurun_out/step_parity_fail_{int(xent)}{int(planes)}_{step}.json", "w") as f:
