@@ -1,0 +1,19 @@
+#!/bin/bash
+# Multi-GPU check (run with gpurun --gpus N): bench at N ranks with the data-parallel self-check, one all-reduce vs overlapped
+# buckets, and the denominator sweep under torch.distributed.run.
+N=${1:-2}
+mkdir -p gpurun_out
+RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
+timeout 900 $RUN bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_${N}gpu.log 2> gpurun_out/bench_${N}gpu.err; echo "bench N=$N exit=$?"
+timeout 900 $RUN bench.py --gpus $N --steps 10 --warmup 3 --dp-buckets 4 --no-dp-check > gpurun_out/bench_${N}gpu_b4.log 2> gpurun_out/bench_${N}gpu_b4.err; echo "bench N=$N buckets=4 exit=$?"
+python - <<PY
+import json
+for f in ("gpurun_out/bench_${N}gpu.log", "gpurun_out/bench_${N}gpu_b4.log"):
+    try:
+        d = json.loads([l for l in open(f) if l.startswith("{")][-1])
+        print(f, {k: d[k] for k in ("value", "ms_per_step", "n_gpus")}, "e2e", d["e2e"]["value"], "allreduce", d.get("allreduce"), "dp_check", d.get("dp_check"))
+    except Exception as e:
+        print(f, "unreadable", e)
+PY
+tail -3 gpurun_out/bench_${N}gpu.err
+timeout 900 $RUN tools/den_sweep.py --quick > gpurun_out/den_sweep_${N}gpu.md 2> gpurun_out/den_sweep_${N}gpu.err; echo "den sweep exit=$?"; cat gpurun_out/den_sweep_${N}gpu.md
