@@ -118,6 +118,15 @@ def test_whole_step_matches_cpu_reference(xent, planes):
             stage["output dgrad"] = rel_err(g64(hd["d_pb2"]), (g64(hd["d_out"]) @ f64(pp["output.W"])) * f64(pp["bn.pc2.scale"]))
             stage["pc_linear dgrad"] = rel_err(g64(hd["d_pb"]), (g64(hd["d_pb2"]) @ f64(pp["pc_linear.W"])) * f64(pp["bn.pc1.scale"]))
             stage["relu bwd"] = rel_err(g64(hd["d_pa"]), g64(hd["d_pb"]) * (g64(hd["pr"]) > 0))
+            stage["pa fwd (gpu vs cpu)"] = rel_err(g64(hd["pa"]), f64(stt["pc"]["a"]))
+            stage["relu mask mismatches"] = int(((g64(hd["pr"]) > 0) != (f64(stt["pc"]["a"]) > 0)).sum())
+            stage["pl fwd (gpu vs cpu)"] = rel_err(g64(hd["pl"]), f64(stt["pl"]))
+            stage["last block aff_out (gpu vs cpu)"] = rel_err(g64(net.blocks[-1]["aff_out"]), f64(stt[L - 1]["aff_out"]))
+            stage["last block mask mismatches"] = int(((g64(net.blocks[-1]["aff_out"]) > 0) != (f64(stt[L - 1]["aff_out"]) > 0)).sum())
+            stage["pc_affine dgrad"] = rel_err(g64(hd["d_pl"]) if not xent else g64(hd["d_pl"]), g64(hd["d_pa"]) @ f64(pp["pc_affine.W"])
+                                               + ((g64(hd["d_xa"]) @ f64(pp["px_affine.W"])) if xent else 0.0))
+            stage["d_pa gpu vs cpu chain"] = rel_err(g64(hd["d_pa"]), d * f64(pp["bn.pc1.scale"]) * (f64(stt["pc"]["a"]) > 0))
+            stage["d_pb2 gpu vs cpu chain"] = rel_err(g64(hd["d_pb2"]), (f64(stt["d_out"]) @ f64(pp["output.W"])) * f64(pp["bn.pc2.scale"]))
             third = {"stages": stage, "gpu_vs_f64": rel_err(net.blocks[-1]["d_aff"].cpu().numpy(), d_aff64),
                      "cpuref_vs_f64": rel_err(stt[L - 1]["d_aff"], d_aff64),
                      "gpu_d_pl_vs_f64": rel_err(net.head["d_pl"].cpu().numpy(), d_pl64)}

@@ -1,5 +1,5 @@
-"""Diagnostic: are the stock-layer data-gradient GEMMs of the supernet head reproducible?  Runs the head backward of a small
-search-stage supernet many times on a fixed d_out and compares every intermediate with a float64 torch product."""
+"""Diagnostic: the parity test's flow (GPU step, then the CPU reference step in the same process) for several steps, with a
+GPU-only check of the head's data-gradient GEMMs (float64 products of the GPU's own operands) after every step."""
 import json
 import os
 import sys
@@ -9,39 +9,40 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 
-from tdnnf_nas_b200 import nnet3
+from oracle import supernet_ref as R
+from tdnnf_nas_b200 import nnet3, synth
 from tdnnf_nas_b200.supernet import Supernet, SupernetConfig
+from tests.test_gpu_step_parity import _params_of
 
+mode = sys.argv[1] if len(sys.argv) > 1 else "oracle"
 cfg = SupernetConfig(num_seqs=8, frames_per_eg=30, dim=256, bottleneck=160, num_blocks=3, prefinal_small=64, num_pdfs=200,
-                     den_states=300, den_out_degree=6.0, mode="search", learning_rate=2e-3, darts_lr_factor=0.05, xent=True)
+                     den_states=300, den_out_degree=6.0, mode="search", learning_rate=2e-3, darts_lr_factor=0.05, xent=False)
 net = Supernet(cfg)
-x = net.make_input(0).pin_memory()
-net.step(x, apply_update=False)
-net._update_with_max_change()
+S, T, P, L, n = cfg.num_seqs, net.T, cfg.num_pdfs, cfg.num_blocks, cfg.num_offsets
+den_graph = synth.make_den_graph(cfg.den_states, P, cfg.den_out_degree, seed=5)
+num_graph = synth.make_num_graphs(S, P, T, seed=60, den_graph=den_graph)
+rcfg = R.RefConfig(num_seqs=S, frames_per_eg=cfg.frames_per_eg, feat_dim=cfg.feat_dim, dim=cfg.dim, bottleneck=cfg.bottleneck,
+                   num_blocks=L, num_offsets=n, prefinal_small=cfg.prefinal_small, num_pdfs=P, xent=False,
+                   learning_rate=cfg.learning_rate, darts_lr_factor=cfg.darts_lr_factor)
+ref = R.CpuSupernet(rcfg, den_graph, num_graph, _params_of(net))
 hd, st = net.head, net.stock
-bad = 0
-worst = {}
-for it in range(int(sys.argv[1]) if len(sys.argv) > 1 else 60):
-    net.step(net.make_input(1 + it % 3).pin_memory(), apply_update=False)
+out = []
+for step in range(5):
+    x = net.make_input(step)
+    c0 = nnet3.get_rand_counter()
+    net.step(x.pin_memory(), apply_update=False)
+    nnet3.set_rand_counter(c0)
+    u = [np.array([nnet3.rand_uniform() for _ in range(n)], np.float32) for _ in range(2 * L)]
     torch.cuda.synchronize()
-    d_out = hd["d_out"].double()
-    W = {k: v["W"].double() for k, v in st.items()}
-    ref_pb2 = d_out @ W["output"]
-    e = {"d_pb2(after bn: skip)": 0.0}
-    # the chain of data gradients as float64 torch products
-    sc2 = torch.as_tensor(np.frombuffer(b"", dtype=np.float32))  # unused
-    # d_pl = branch sums; compare only the FIRST GEMM of the backward pass and the last (prefinal_l), which bracket the rest
-    got_first = None
-    e_first = float(((hd["d_pb2"].double() / 1.0)).norm())  # placeholder norm (bn scaled in place)
-    d_pl_ref = None
-    ref_last = hd["d_pl"].double() @ W["prefinal_l"]
-    got_last = net.blocks[-1]["d_out"].double()
-    err_last = float((got_last - ref_last).norm() / ref_last.norm())
-    worst["prefinal_l dgrad"] = max(worst.get("prefinal_l dgrad", 0.0), err_last)
-    # pc_affine: d_pl (before the xent branch adds) is not kept; check output-layer GEMM through d_xb2 of the xent branch instead
-    ref_x = hd["d_xls"].double() @ W["output_xent"]
-    if err_last > 1e-4:
-        bad += 1
-        print(json.dumps(dict(iter=it, err_last=err_last)), flush=True)
-print(json.dumps(dict(iters=it + 1, bad=bad, worst=worst)))
+    chk = hd["d_pa"].double() @ st["pc_affine"]["W"].double()
+    e_gpu = float((hd["d_pl"].double() - chk).norm() / chk.norm())
+    e_ref = None
+    if mode == "oracle":
+        ref.step(x.numpy(), u, apply_update=False)
+        e_ref = float(np.linalg.norm(net.blocks[-1]["d_aff"].cpu().numpy().astype(np.float64) - ref.st[L - 1]["d_aff"]) /
+                      np.linalg.norm(ref.st[L - 1]["d_aff"]))
+        ref.update()
+    net._update_with_max_change()
+    out.append(dict(step=step, pc_affine_dgrad_vs_f64=round(e_gpu, 8), d_aff_vs_cpu=None if e_ref is None else round(e_ref, 8)))
+print(json.dumps(out))
 net.close()
