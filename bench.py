@@ -289,7 +289,10 @@ def dp_self_check(net, cfg, world, rank, local_rank, x_host):
     """Data-parallel correctness on the hardware (world > 1), one un-timed step on fresh state: (1) the deltas that come out
     of the NCCL path (tdnnf_dp_allreduce_deltas) equal the sum of the ranks' own deltas (collected with an all-gather and
     summed in rank order); (2) rank 0 ALSO runs other ranks' shards itself (a second Supernet built as that rank: same seed,
-    that rank's input and numerator supervision) and compares with what that rank computed.  The model is not updated."""
+    that rank's input and numerator supervision) and compares with what that rank computed; its own shard run a second time
+    gives the run-to-run spread to read that against (split-K sums are red.global.add in arrival order, and at full size a
+    few of the 3e8 ReLU pre-activations per step lie within that rounding noise of zero: each flipped sign moves the
+    derivatives below it by ~1e-4).  The model is not updated."""
     import torch
     import torch.distributed as dist
 
@@ -317,7 +320,7 @@ def dp_self_check(net, cfg, world, rank, local_rank, x_host):
         counter = nnet3.get_rand_counter()
         others = sorted(set(range(1, world)) if world <= 4 else {1, world // 2, world - 1})
         errs = {}
-        for r in others:
+        for r in [0] + others:
             rep = Supernet(cfg, device=local_rank, rank=r, world_size=world, process_group=None, dp_buckets=1, standalone=True)
             rep.step(rep.make_input(0).pin_memory(), apply_update=False, reduce=False)
             mine = rep.delta_arena[:n]
@@ -326,11 +329,13 @@ def dp_self_check(net, cfg, world, rank, local_rank, x_host):
             del rep
         nnet3.set_context(net.ctx)
         nnet3.set_rand_counter(counter)  # the replicas re-seeded the shared RNG: put rank 0 back in step with the other ranks
-        out = dict(ok=bool(err_sum <= 1e-5 and all(e <= 1e-4 for e in errs.values())), allreduce_vs_sum_of_shards=err_sum,
-                   shards_recomputed_on_rank0=errs, delta_floats=int(n),
+        spread = errs.pop("0")
+        out = dict(ok=bool(err_sum <= 1e-5 and all(e <= 1e-3 for e in errs.values())), allreduce_vs_sum_of_shards=err_sum,
+                   shards_recomputed_on_rank0=errs, run_to_run_spread_rank0=spread, delta_floats=int(n),
                    note=("allreduce_vs_sum_of_shards: ||NCCL result - sum_r delta_r|| / ||sum||, bar 1e-5; shards_recomputed_on_rank0: "
-                         "relative error between rank r's delta and the same shard run on rank 0 (the split-K red.global.add order "
-                         "differs between runs), bar 1e-4"))
+                         "relative error between rank r's delta and the same shard run on rank 0, bar 1e-3 (the derivative tolerance); "
+                         "run_to_run_spread_rank0: rank 0's own shard run twice -- the floor of that comparison (split-K red.global.add "
+                         "order + ReLU sign ties)"))
     dist.barrier()
     return out
 

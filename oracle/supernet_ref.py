@@ -227,17 +227,33 @@ class CpuSupernet:
             st["d_xls"] = (cfg.xent_regularize * _t(num_d)).numpy()
         return objf / (S * T)
 
-    def backward(self):
+    def relu_inputs(self):
+        """The pre-activations whose sign the backward pass depends on: {'pc', 'px', block index} -> array."""
+        d = {"pc": self.st["pc"]["a"]}
+        if self.cfg.xent:
+            d["px"] = self.st["px"]["a"]
+        for b in range(self.cfg.num_blocks):
+            d[b] = self.st[b]["aff_out"]
+        return d
+
+    def backward(self, relu_masks=None):
+        """relu_masks (optional, keys as relu_inputs()): boolean arrays to use as the ReLU derivative instead of this
+        side's own (x > 0).  The derivative of ReLU is discontinuous at 0: a pre-activation within rounding of zero can
+        come out on either side in two correct implementations, and ONE such element moves every derivative below it by
+        ~1e-3 relative.  A parity check hands over the other side's masks after checking that they differ from this
+        side's only at such elements."""
         import torch
 
         cfg, p, st, S = self.cfg, self.p, self.st, self.cfg.num_seqs
         lr = cfg.learning_rate * cfg.darts_lr_factor
+        own = self.relu_inputs()
+        mask = lambda key: _t(np.ascontiguousarray(relu_masks[key])) if relu_masks is not None and key in relu_masks else (_t(own[key]) > 0)
 
         def branch_bwd(pre, bn1, bn2, out_name, d_top):
             d_b2 = torch.mm(_t(d_top), _t(p[f"{out_name}.W"]))
             d_li = d_b2 * _t(p[f"bn.{bn2}.scale"])
             d_bnd = torch.mm(d_li, _t(p[f"{pre}_linear.W"]))
-            d_a = d_bnd * _t(p[f"bn.{bn1}.scale"]) * (_t(st[pre]["a"]) > 0)
+            d_a = d_bnd * _t(p[f"bn.{bn1}.scale"]) * mask(pre)
             return torch.mm(d_a, _t(p[f"{pre}_affine.W"]))
 
         d_pl = branch_bwd("pc", "pc1", "pc2", "output", st["d_out"])
@@ -251,7 +267,7 @@ class CpuSupernet:
             d_prev = np.zeros_like(s["prev"])
             # bypass + ReLU / BatchNormTest backward
             d_prev.reshape(len(s["prev_t"]), S, -1)[s["byp_idx"]] = (cfg.bypass_scale * _t(d_out)).numpy().reshape(len(s["byp_idx"]), S, -1)
-            d_aff = (_t(d_out) * _t(p[f"bn.blk{b}.scale"]) * (_t(s["aff_out"]) > 0)).numpy()
+            d_aff = (_t(d_out) * _t(p[f"bn.blk{b}.scale"]) * mask(b)).numpy()
             dW, db = self.delta[(b, "aff")]
             d_ain = np.zeros_like(s["a_in"])
             ng_in, ng_out = self.ng[(b, "aff")]
@@ -291,10 +307,11 @@ class CpuSupernet:
         self.last_factors = [float(f * scale) for f in factors]
         return applied
 
-    def step(self, x, u_gumbel, apply_update=True):
+    def step(self, x, u_gumbel, apply_update=True, relu_masks=None):
+        """relu_masks: None, or a callable(self) -> dict evaluated after the forward pass (see backward)."""
         self.forward(x, u_gumbel)
         objf = self.objective()
-        self.backward()
+        self.backward(relu_masks(self) if callable(relu_masks) else relu_masks)
         if apply_update:
             self.update()
         return objf

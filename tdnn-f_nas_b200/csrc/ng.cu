@@ -276,50 +276,48 @@ __global__ void __launch_bounds__(1024) ng_gram_finish_kernel(const float* __res
 // the tensor-core path (it took a zero-fill, four operand splits and two 6-product GEMMs per preconditioner).
 // A small tiled SGEMM C = [A | AC] [J ; W]: block = 16 rows x 128 columns, K in chunks of 32 staged in shared memory
 // (coalesced, many loads in flight); a thread owns one column and 16 accumulators, reads the A chunk as float4.
-__global__ void __launch_bounds__(128) ng_w_update_kernel(const float* __restrict__ A, int a_ld, const float* __restrict__ AC,
-                                                          int ac_ld, const float* __restrict__ J, long long j_ld,
-                                                          const float* __restrict__ W, long long w_ld, int r, int D,
-                                                          float* __restrict__ out, long long out_ld) {
-  __shared__ __align__(16) float sA[16][32];   // rows i0..i0+15, K chunk
-  __shared__ float sB[32][128];                // K chunk, columns d0..d0+127
-  const int d0 = blockIdx.x * 128, i0 = blockIdx.y * 16;
+// out[i, d] = sum_{k < r} A[i, k] J[k, d] + sum_{k < r} AC[i, k] W[k, d]: a block owns 16 rows x 64 columns.  The 16 x 2r
+// coefficient strip goes to shared memory ONCE; every thread then streams its column of [J; W] in batches of 8
+// independent coalesced loads (no barrier inside the K loop: the first version staged 32-row chunks of [J; W] through
+// shared memory with two barriers each, five dependent global-load round trips for rank 80, and measured 57 us).
+constexpr int kWuRows = 16, kWuCols = 64;
+__global__ void __launch_bounds__(kWuCols) ng_w_update_kernel(const float* __restrict__ A, int a_ld, const float* __restrict__ AC,
+                                                              int ac_ld, const float* __restrict__ J, long long j_ld,
+                                                              const float* __restrict__ W, long long w_ld, int r, int D,
+                                                              float* __restrict__ out, long long out_ld) {
+  extern __shared__ __align__(16) float sM[];  // [kWuRows][Kp], Kp = 2r rounded up to 8
+  const int K = 2 * r, Kp = (K + 7) & ~7;
+  const int d0 = blockIdx.x * kWuCols, i0 = blockIdx.y * kWuRows;
+  for (int idx = threadIdx.x; idx < kWuRows * Kp; idx += kWuCols) {
+    const int u = idx / Kp, k = idx % Kp, i = i0 + u;
+    float v = 0.f;
+    if (i < r && k < K) v = k < r ? A[i * a_ld + k] : AC[i * ac_ld + (k - r)];
+    sM[idx] = v;
+  }
+  __syncthreads();
   const int d = d0 + threadIdx.x;
-  float acc[16];
+  if (d >= D) return;
+  float acc[kWuRows];
 #pragma unroll
-  for (int u = 0; u < 16; ++u) acc[u] = 0.f;
-  const int K = 2 * r;  // k < r: (A, J); k >= r: (AC, W)
-  for (int k0 = 0; k0 < K; k0 += 32) {
-    for (int idx = threadIdx.x; idx < 16 * 32; idx += 128) {
-      const int i = i0 + idx / 32, k = k0 + idx % 32;
-      float v = 0.f;
-      if (i < r && k < K) v = k < r ? A[i * a_ld + k] : AC[i * ac_ld + (k - r)];
-      sA[idx / 32][idx % 32] = v;
-    }
-#pragma unroll 8
-    for (int kk = 0; kk < 32; ++kk) {
+  for (int u = 0; u < kWuRows; ++u) acc[u] = 0.f;
+  for (int k0 = 0; k0 < Kp; k0 += 8) {
+    float b[8];
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
       const int k = k0 + kk;
-      float v = 0.f;
-      if (d < D && k < K) v = k < r ? J[k * j_ld + d] : W[(k - r) * w_ld + d];
-      sB[kk][threadIdx.x] = v;
+      b[kk] = k < r ? J[k * j_ld + d] : (k < K ? W[(k - r) * w_ld + d] : 0.f);
     }
-    __syncthreads();
 #pragma unroll
-    for (int kk = 0; kk < 32; kk += 4) {
-      const float b0 = sB[kk][threadIdx.x], b1 = sB[kk + 1][threadIdx.x], b2 = sB[kk + 2][threadIdx.x],
-                  b3 = sB[kk + 3][threadIdx.x];
-#pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const float4 a = *reinterpret_cast<const float4*>(&sA[u][kk]);
-        acc[u] = fmaf(a.x, b0, fmaf(a.y, b1, fmaf(a.z, b2, fmaf(a.w, b3, acc[u]))));
-      }
+    for (int u = 0; u < kWuRows; ++u) {
+      const float4 m0 = *reinterpret_cast<const float4*>(&sM[u * Kp + k0]);
+      const float4 m1 = *reinterpret_cast<const float4*>(&sM[u * Kp + k0 + 4]);
+      acc[u] = fmaf(m0.x, b[0], fmaf(m0.y, b[1], fmaf(m0.z, b[2], fmaf(m0.w, b[3], acc[u]))));
+      acc[u] = fmaf(m1.x, b[4], fmaf(m1.y, b[5], fmaf(m1.z, b[6], fmaf(m1.w, b[7], acc[u]))));
     }
-    __syncthreads();
   }
-  if (d < D) {
 #pragma unroll
-    for (int u = 0; u < 16; ++u)
-      if (i0 + u < r) out[(long long)(i0 + u) * out_ld + d] = acc[u];
-  }
+  for (int u = 0; u < kWuRows; ++u)
+    if (i0 + u < r) out[(long long)(i0 + u) * out_ld + d] = acc[u];
 }
 
 template <bool ZERO>
@@ -427,8 +425,9 @@ extern "C" int tdnnf_ng_w_update(tdnnf_ctx* ctx, const float* A, int a_stride, c
                     w_stride >= dim && out_stride >= dim,
                 "bad argument (rank <= 128)");
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
-  ng_w_update_kernel<<<dim3((dim + 127) / 128, (rank + 15) / 16), 128, 0, ctx->stream>>>(A, a_stride, AC, ac_stride, J, j_stride, W,
-                                                                                         w_stride, rank, dim, W_next, out_stride);
+  const int Kp = (2 * rank + 7) & ~7;
+  ng_w_update_kernel<<<dim3((dim + kWuCols - 1) / kWuCols, (rank + kWuRows - 1) / kWuRows), kWuCols, sizeof(float) * kWuRows * Kp,
+                       ctx->stream>>>(A, a_stride, AC, ac_stride, J, j_stride, W, w_stride, rank, dim, W_next, out_stride);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   return TDNNF_OK;

@@ -77,7 +77,23 @@ def test_whole_step_matches_cpu_reference(xent, planes):
         nnet3.set_rand_counter(c0)
         u = [np.array([nnet3.rand_uniform() for _ in range(n)], np.float32) for _ in range(2 * L)]
         assert nnet3.get_rand_counter() == c1  # exactly the draws the 2 L components made
-        objf_ref = ref.step(x.numpy(), u, apply_update=False)
+        # The derivative of ReLU jumps at 0.  With ~1e5 pre-activations per layer some lie within 1e-5 rms of zero, i.e.
+        # within the forward tolerance: the GPU (whose split-K reductions even reorder sums from run to run) and the CPU
+        # may then disagree on ONE mask element, and everything below that layer moves by ~1e-3.  So the reference uses
+        # the GPU's masks, after a check that they differ from its own only where its pre-activation is within the forward
+        # tolerance of zero (and in a handful of places at most).
+        def gpu_masks(r):
+            g = {"pc": net.head["pr"], **({"px": net.head["xr"]} if xent else {}), **{b: blk["aff_out"] for b, blk in enumerate(net.blocks)}}
+            masks = {}
+            for key, own in r.relu_inputs().items():
+                masks[key] = (g[key] > 0).cpu().numpy()
+                diff = masks[key] != (own > 0)
+                assert diff.sum() <= 4, (key, int(diff.sum()))
+                if diff.any():
+                    assert np.abs(own[diff]).max() < 1e-4 * np.sqrt((own.astype(np.float64) ** 2).mean()), key
+            return masks
+
+        objf_ref = ref.step(x.numpy(), u, apply_update=False, relu_masks=gpu_masks)
         assert rel_err(net.head["out"].cpu().numpy(), ref.st["out"]) < 1e-4
         assert abs(objf_gpu - objf_ref) <= 1e-4 * abs(objf_ref), (objf_gpu, objf_ref)
         assert rel_err(net.head["d_out"].cpu().numpy(), ref.st["d_out"]) < 1e-3
@@ -94,46 +110,6 @@ def test_whole_step_matches_cpu_reference(xent, planes):
                 errs[(b, h, "bias")] = rel_err(dv[dW.size + n:], db[n:])
                 errs[(b, h, "alpha")] = float(np.abs(dv[dW.size: dW.size + n] - db[:n]).max() / (np.abs(db[:n]).max() + 1e-30))
         bad = {k: v for k, v in errs.items() if not v < 1e-3}
-        if bad:  # leave the whole picture behind for the post-mortem (gpurun_out/ comes back from the GPU box)
-            import json
-            import os
-
-            os.makedirs("gpurun_out", exist_ok=True)
-            # a third opinion on the top of the backward pass: float64 numpy from the CPU side's own d_out and activations
-            f64 = lambda a: np.asarray(a, dtype=np.float64)
-            pp, stt = ref.p, ref.st
-            d = f64(stt["d_out"]) @ f64(pp["output.W"])
-            d = (d * f64(pp["bn.pc2.scale"])) @ f64(pp["pc_linear.W"])
-            d_pl64 = (d * f64(pp["bn.pc1.scale"]) * (f64(stt["pc"]["a"]) > 0)) @ f64(pp["pc_affine.W"])
-            if xent:
-                dx = f64(stt["d_xls"])
-                dx = dx - np.exp(f64(stt["xls"])) * dx.sum(1, keepdims=True)
-                dx = (dx @ f64(pp["output_xent.W"]) * f64(pp["bn.px2.scale"])) @ f64(pp["px_linear.W"])
-                d_pl64 = d_pl64 + (dx * f64(pp["bn.px1.scale"]) * (f64(stt["px"]["a"]) > 0)) @ f64(pp["px_affine.W"])
-            d_last64 = d_pl64 @ f64(pp["prefinal_l.W"])
-            d_aff64 = d_last64 * f64(pp[f"bn.blk{L - 1}.scale"]) * (f64(stt[L - 1]["aff_out"]) > 0)
-            g64 = lambda t: t.cpu().numpy().astype(np.float64)
-            hd = net.head
-            stage = {}  # every GEMM of the head's backward pass re-done in float64 from the GPU's OWN operands
-            stage["output dgrad"] = rel_err(g64(hd["d_pb2"]), (g64(hd["d_out"]) @ f64(pp["output.W"])) * f64(pp["bn.pc2.scale"]))
-            stage["pc_linear dgrad"] = rel_err(g64(hd["d_pb"]), (g64(hd["d_pb2"]) @ f64(pp["pc_linear.W"])) * f64(pp["bn.pc1.scale"]))
-            stage["relu bwd"] = rel_err(g64(hd["d_pa"]), g64(hd["d_pb"]) * (g64(hd["pr"]) > 0))
-            stage["pa fwd (gpu vs cpu)"] = rel_err(g64(hd["pa"]), f64(stt["pc"]["a"]))
-            stage["relu mask mismatches"] = int(((g64(hd["pr"]) > 0) != (f64(stt["pc"]["a"]) > 0)).sum())
-            stage["pl fwd (gpu vs cpu)"] = rel_err(g64(hd["pl"]), f64(stt["pl"]))
-            stage["last block aff_out (gpu vs cpu)"] = rel_err(g64(net.blocks[-1]["aff_out"]), f64(stt[L - 1]["aff_out"]))
-            stage["last block mask mismatches"] = int(((g64(net.blocks[-1]["aff_out"]) > 0) != (f64(stt[L - 1]["aff_out"]) > 0)).sum())
-            stage["pc_affine dgrad"] = rel_err(g64(hd["d_pl"]) if not xent else g64(hd["d_pl"]), g64(hd["d_pa"]) @ f64(pp["pc_affine.W"])
-                                               + ((g64(hd["d_xa"]) @ f64(pp["px_affine.W"])) if xent else 0.0))
-            stage["d_pa gpu vs cpu chain"] = rel_err(g64(hd["d_pa"]), d * f64(pp["bn.pc1.scale"]) * (f64(stt["pc"]["a"]) > 0))
-            stage["d_pb2 gpu vs cpu chain"] = rel_err(g64(hd["d_pb2"]), (f64(stt["d_out"]) @ f64(pp["output.W"])) * f64(pp["bn.pc2.scale"]))
-            third = {"stages": stage, "gpu_vs_f64": rel_err(net.blocks[-1]["d_aff"].cpu().numpy(), d_aff64),
-                     "cpuref_vs_f64": rel_err(stt[L - 1]["d_aff"], d_aff64),
-                     "gpu_d_pl_vs_f64": rel_err(net.head["d_pl"].cpu().numpy(), d_pl64)}
-            with open(f"gpurun_out/step_parity_fail_{int(xent)}{int(planes)}_{step}.json", "w") as f:
-                json.dump({"third_opinion": third, "errs": {str(k): v for k, v in errs.items()}, "objf": [objf_gpu, objf_ref],
-                           "out": rel_err(net.head["out"].cpu().numpy(), ref.st["out"]),
-                           "d_out": rel_err(net.head["d_out"].cpu().numpy(), ref.st["d_out"])}, f)
         assert not bad, (step, bad, errs)
         # the parameter step (max-change) on both sides
         assert net._update_with_max_change() and ref.update()
