@@ -498,23 +498,40 @@ static int choose_splits(int tiles, int iters_per_tile, int num_sms) {
   return best;
 }
 
-template <int BN, int NPA, int NPB, bool MN = false>
+// CTA-pair kernels (splice_gemm.cuh, PAIR): K-major two-plane GEMMs with BN = 160 / 256 and enough m-tiles.
+// TDNNF_GEMM_PAIR=0 turns them off (A/B experiments).
+static bool pair_eligible(const tdnnf_ctx* ctx, int bn, int m_tiles, int np, bool mn) {
+  static const int on = [] {
+    const char* e = getenv("TDNNF_GEMM_PAIR");
+    return e ? atoi(e) : 1;
+  }();
+  return on && !mn && np == 2 && (bn == 160 || bn == 256) && m_tiles >= 4 && ctx->num_sms >= 2;
+}
+
+// Sets p->pair and p->splits: `other_tiles` = n-tiles x groups, `iters` = K iterations of one tile.
+static void plan_units(const tdnnf_ctx* ctx, GemmParams* p, int bn, int np, bool mn, int other_tiles, int iters) {
+  p->pair = pair_eligible(ctx, bn, p->m_tiles, np, mn) ? 1 : 0;
+  if (p->pair) p->splits = choose_splits((p->m_tiles + 1) / 2 * other_tiles, iters, ctx->num_sms / 2);
+  else p->splits = choose_splits(p->m_tiles * other_tiles, iters, ctx->num_sms);
+}
+
+template <int BN, int NPA, int NPB, bool MN = false, bool PAIR = false>
 static int launch_gemm_bn(tdnnf_ctx* ctx, const Planes& A, const Planes& B, const GemmParams& p, double algorithmic_flops) {
-  using Cfg = GemmCfg<BN, NPA, NPB, MN>;
+  using Cfg = GemmCfg<BN, NPA, NPB, MN, PAIR>;
   CUtensorMap tmA, tmB;
   int rc = MN ? make_map_mn(ctx, A, kBM / 64, Cfg::kBKk, &tmA) : make_map(ctx, A, kBM, &tmA);
   if (rc) return rc;
-  rc = MN ? make_map_mn(ctx, B, Cfg::kBNs / 64, Cfg::kBKk, &tmB) : make_map(ctx, B, BN, &tmB);
+  rc = MN ? make_map_mn(ctx, B, Cfg::kBNs / 64, Cfg::kBKk, &tmB) : make_map(ctx, B, Cfg::kBNs, &tmB);
   if (rc) return rc;
-  auto kern = splice_gemm_kernel<BN, NPA, NPB, MN>;
+  auto kern = splice_gemm_kernel<BN, NPA, NPB, MN, PAIR>;
   static bool attr_set = false;  // per template instance
   if (!attr_set) {
     TDNNF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int units = p.c_tiles * p.m_tiles * p.n_tiles * p.splits;
+  const int units = p.c_tiles * (PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles * p.splits;
   if (units <= 0) return TDNNF_OK;
-  const int grid = std::min(units, ctx->num_sms);
+  const int grid = PAIR ? 2 * std::min(units, ctx->num_sms / 2) : std::min(units, ctx->num_sms);
   tdnnf_ctx::GemmTiming tm;
   if (ctx->gemm_timing) {
     TDNNF_CUDA_OK(cudaEventCreate(&tm.start));
@@ -523,7 +540,24 @@ static int launch_gemm_bn(tdnnf_ctx* ctx, const Planes& A, const Planes& B, cons
     tm.products = (NPA == 3) ? 6 : (NPA == 2 && NPB == 2 ? 3 : NPA * NPB);
     TDNNF_CUDA_OK(cudaEventRecord(tm.start, ctx->stream));
   }
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, ctx->stream>>>(tmA, tmB, p);
+  if constexpr (PAIR) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TDNNF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  } else {
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, ctx->stream>>>(tmA, tmB, p);
+  }
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   if (ctx->gemm_timing) {
@@ -559,10 +593,17 @@ static int launch_gemm_np(tdnnf_ctx* ctx, int bn, const Planes& A, const Planes&
     case 32: return launch_gemm_bn<32, NPA, NPB>(ctx, A, B, p, fl);
     case 64: return launch_gemm_bn<64, NPA, NPB>(ctx, A, B, p, fl);
     case 128: return launch_gemm_bn<128, NPA, NPB>(ctx, A, B, p, fl);
-    case 160: return launch_gemm_bn<160, NPA, NPB>(ctx, A, B, p, fl);
+    case 160:
+      if constexpr (NPA == 2)
+        if (p.pair) return launch_gemm_bn<160, NPA, NPB, false, true>(ctx, A, B, p, fl);
+      return launch_gemm_bn<160, NPA, NPB>(ctx, A, B, p, fl);
     case 256:
       if constexpr (NPA == 3) return fail(TDNNF_ERR_INVALID, "unsupported BN for 3-plane operands");
-      else return launch_gemm_bn<256, NPA, NPB>(ctx, A, B, p, fl);
+      else {
+        if constexpr (NPA == 2)
+          if (p.pair) return launch_gemm_bn<256, NPA, NPB, false, true>(ctx, A, B, p, fl);
+        return launch_gemm_bn<256, NPA, NPB>(ctx, A, B, p, fl);
+      }
     default: return fail(TDNNF_ERR_INVALID, "unsupported BN");
   }
 }
@@ -657,7 +698,7 @@ extern "C" int tdnnf_darts_propagate(tdnnf_ctx* ctx, const float* in, int in_row
   p.m_valid[0] = out_rows;
   p.n_valid = out_dim;
   p.seg_weight = weff;
-  p.splits = choose_splits(p.m_tiles * p.n_tiles, n * p.kb_per_seg, ctx->num_sms);
+  plan_units(ctx, &p, bn, A.np == B.np ? A.np : 0, false, p.n_tiles, n * p.kb_per_seg);
   p.out = out;
   p.out_ld = out_stride;
   p.row_mul = 1;
@@ -733,7 +774,7 @@ extern "C" int tdnnf_darts_project(tdnnf_ctx* ctx, const float* in, int in_rows,
     p.m_valid[c] = (in_rows - c + r - 1) / r;
   }
   p.n_valid = ncols;
-  p.splits = choose_splits(p.m_tiles * p.n_tiles * r, p.kb_per_seg, ctx->num_sms);
+  plan_units(ctx, &p, bn, A.np == B.np ? A.np : 0, false, p.n_tiles * r, p.kb_per_seg);
   p.out = Y;
   p.out_ld = ncols;
   p.row_mul = r;
@@ -799,7 +840,7 @@ extern "C" int tdnnf_darts_backprop_data(tdnnf_ctx* ctx, const float* out_deriv,
   for (int c = 0; c < r; ++c) p.m_valid[c] = (in_rows - c + r - 1) / r;
   p.n_valid = in_dim;
   p.seg_weight = weff;
-  p.splits = choose_splits(p.m_tiles * p.n_tiles * r, std::max(1, n / r) * p.kb_per_seg, ctx->num_sms);
+  plan_units(ctx, &p, bn, A.np == B.np ? A.np : 0, false, p.n_tiles * r, std::max(1, n / r) * p.kb_per_seg);
   p.out = in_deriv;
   p.out_ld = id_stride;
   p.row_mul = r;

@@ -28,6 +28,7 @@ constexpr int kAccCols = 256;  // TMEM columns per accumulator buffer
 
 struct GemmParams {
   int m_tiles, n_tiles, c_tiles, splits;
+  int pair;        // 1: CTA-pair kernel (cta_group::2): a unit is TWO consecutive m-tiles, one per CTA of a cluster of 2
   int kb_per_seg;  // K blocks (of 64) per segment
   int kb_last_steps;  // 16-wide MMA steps that hold data in the LAST K block of a segment (1..4): zero padding is skipped
   int nseg;
@@ -86,10 +87,15 @@ struct GemmSmemMeta {
 // is rejected by the hardware: "illegal instruction", measured on B200.)
 // MN = true: both operands are MN-major (the contraction runs over ROWS of the row planes: the parameter gradient).
 // K blocks are then 32 rows (no swizzle-width constraint on K), the B tile is whole 64-column chunks.
-template <int BN, int NPA, int NPB, bool MN = false>
+// PAIR = true: two CTAs of a cluster (one TPC) issue ONE tcgen05.mma.cta_group::2 of M = 256: each CTA stages its own 128
+// rows of A and HALF of the B tile, and reads the other half from its partner's shared memory.  The kernels are bound
+// by L2 -> SM bandwidth (hi + lo planes: 72-96 KB per K block of 64 at one CTA per tile, i.e. 62-75 B/clk/SM at full
+// tensor rate against ~45-50 B/clk/SM measured): the pair form stages 52-64 KB per SM for the same MMA work, and at
+// BN = 256 a third pipeline stage fits.
+template <int BN, int NPA, int NPB, bool MN = false, bool PAIR = false>
 struct GemmCfg {
   static constexpr int kBKk = MN ? 32 : kBK;                 // K elements per pipeline stage
-  static constexpr int kBNs = MN ? (BN + 63) / 64 * 64 : BN;  // B columns held in shared memory
+  static constexpr int kBNs = (MN ? (BN + 63) / 64 * 64 : BN) / (PAIR ? 2 : 1);  // B columns held in this CTA's shared memory
   static constexpr int kAPlane = kBM * kBKk * 2;
   static constexpr int kBPlane = kBNs * kBKk * 2;
   static constexpr int kABytes = NPA * kAPlane;
@@ -103,6 +109,8 @@ struct GemmCfg {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N must be a multiple of 16 in [16,256]");
   static_assert(kStages >= 2, "need at least a double buffer");
   static_assert(NPA == NPB && NPA >= 1 && NPA <= 3, "unsupported plane combination");
+  static_assert(!PAIR || (!MN && BN % 32 == 0), "pair kernels: K-major operands, N/2 a multiple of 16");
+  static constexpr int kClusterBytes = (PAIR ? 2 : 1) * kStageBytes;  // what one full barrier waits for
 };
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
@@ -125,6 +133,65 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
       : "r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar)), "r"(c0),
         "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+
+// ---- CTA-pair (cta_group::2) forms
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of `smem_addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on an mbarrier of any CTA of the cluster (address from mapa_shared)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose bytes are counted on an mbarrier of either CTA of the pair
+__device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int32_t c0,
+                                                 int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D (128 rows in each CTA's TMEM) (+)= [A_cta0; A_cta1] * [B_cta0; B_cta1]^T, issued by one thread of the leader CTA
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the mbarrier at this shared-memory offset in BOTH CTAs once the MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   ptx::smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
 }
 
 // No "memory" clobber on purpose: the reductions are fire-and-forget and nothing in the thread reads the
@@ -152,18 +219,23 @@ __device__ __forceinline__ UnitCoord decode_unit(int u, const GemmParams& p, con
   uc.n_t = u % p.n_tiles;
   u /= p.n_tiles;
   uc.split = u % p.splits;
-  uc.m_t = u / p.splits;
+  uc.m_t = u / p.splits;  // pair kernels: the pair index; the caller turns it into 2 * pair + cta rank
   const long long total = (long long)meta->cnt[uc.c] * p.kb_per_seg;
   uc.it0 = (int)((total * uc.split) / p.splits);
   uc.it1 = (int)((total * (uc.split + 1)) / p.splits);
   return uc;
 }
 
-template <int BN, int NPA, int NPB, bool MN = false>
+template <int BN, int NPA, int NPB, bool MN = false, bool PAIR = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN, NPA, NPB, MN>;
+  using Cfg = GemmCfg<BN, NPA, NPB, MN, PAIR>;
+  // pair kernels: clusters of 2 consecutive CTAs; CTA `rank` owns m-tile 2 * (pair index) + rank and rows
+  // [rank * BN / 2, +BN / 2) of the B tile; rank 0 (the leader) issues the MMAs and owns the full / tmem_empty barriers
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr int kStages = Cfg::kStages;
   constexpr int kBKk = Cfg::kBKk;
   extern __shared__ uint8_t smem_raw[];
@@ -209,28 +281,35 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tmem_full[b], 1);
-      ptx::mbar_init(&tmem_empty[b], 4);
+      ptx::mbar_init(&tmem_empty[b], PAIR ? 8 : 4);  // the epilogue warps of both CTAs release the leader's accumulator
     }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_ptr, 2 * kAccCols);
-    ptx::tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_pair(tmem_ptr, 2 * kAccCols);
+    } else {
+      ptx::tmem_alloc(tmem_ptr, 2 * kAccCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before_sync();
-  __syncthreads();
+  __syncwarp();
+  if constexpr (PAIR) cluster_sync_all();  // the partner's barriers exist before anything is signalled across
+  else __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int total_units = p.c_tiles * p.m_tiles * p.n_tiles * p.splits;
+  const int total_units = p.c_tiles * (PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles * p.splits;
 
   if (warp == 0) {
     // ================================================= TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-        const UnitCoord uc = decode_unit(u, p, meta);
+      for (int u = worker; u < total_units; u += workers) {
+        UnitCoord uc = decode_unit(u, p, meta);
+        if constexpr (PAIR) uc.m_t = 2 * uc.m_t + (int)rank;
         // Iteration order: K block outer, segment (time offset) inner.  Offset i of m-tile m and offset i-2 of m-tile
         // m+1 read the SAME activation rows; with the segment outer they did so 2*kb_per_seg iterations apart, and
         // with one unit per SM (no split-K) the ~225 MB streamed in between pushed them out of the 126 MB L2:
@@ -240,10 +319,17 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int it = uc.it0; it < uc.it1; ++it) {
           const int g = meta->list[uc.c][j];
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (!PAIR || rank == 0) ptx::mbar_expect_tx(&full_bar[stage], Cfg::kClusterBytes);
           uint8_t* sa = tiles + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          if constexpr (MN) {
+          if constexpr (PAIR) {
+            // both CTAs' bytes are counted on the LEADER's full barrier (its expect_tx may come after the partner's
+            // first complete_tx: the phase cannot end before the leader's own arrival)
+            const uint32_t bar = mapa_shared(ptx::smem_u32(&full_bar[stage]), 0);
+            tma_load_4d_pair(sa, &tmA, bar, kb * kBK + meta->seg_a_k[g], uc.m_t * kBM + meta->seg_a_m[g], meta->seg_a_c[g], 0);
+            tma_load_4d_pair(sb, &tmB, bar, kb * kBK + meta->seg_b_k[g],
+                             uc.n_t * BN + (int)rank * (BN / 2) + meta->seg_b_n[g], meta->seg_b_c[g], 0);
+          } else if constexpr (MN) {
             // row planes as (64 columns, row = k, 64-column chunk, group, plane): smem gets [plane][chunk][k][64]
             tma_load_5d(sa, &tmA, &full_bar[stage], 0, kb * kBKk + meta->seg_a_k[g], (uc.m_t * kBM + meta->seg_a_m[g]) >> 6,
                         meta->seg_a_c[g], 0);
@@ -261,15 +347,24 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ================================================= MMA issuer
-    if (lane == 0) {
+    // ================================================= MMA issuer (pair kernels: the leader CTA only)
+    if (lane == 0 && rank == 0) {
       // single-plane operands are fp16 (format 0), multi-plane operands are bf16 (format 1)
-      constexpr uint32_t idesc = ptx::umma_idesc_f16(kBM, BN, NPA == 1 ? 0u : 1u, NPB == 1 ? 0u : 1u, MN ? 1u : 0u);
+      constexpr uint32_t idesc =
+          ptx::umma_idesc_f16(PAIR ? 2 * kBM : kBM, BN, NPA == 1 ? 0u : 1u, NPB == 1 ? 0u : 1u, MN ? 1u : 0u);
+      auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+        if constexpr (PAIR) umma_bf16_pair(d, a, b, id, acc);
+        else ptx::umma_bf16(d, a, b, id, acc);
+      };
+      auto commit = [](uint64_t* bar) {
+        if constexpr (PAIR) umma_commit_pair(bar);
+        else ptx::umma_commit(bar);
+      };
       int stage = 0;
       uint32_t phase = 0;
       int acc_buf = 0;
       uint32_t acc_phase = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      for (int u = worker; u < total_units; u += workers) {
         const UnitCoord uc = decode_unit(u, p, meta);
         if (uc.it1 <= uc.it0) continue;
         ptx::mbar_wait(&tmem_empty[acc_buf], acc_phase ^ 1);
@@ -302,24 +397,24 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const uint32_t first = (it > uc.it0 || k > 0) ? 1u : 0u;
             if (NPA == 3) {
               // smallest products first: (lo, hi) and (mid, mid) are ~2^-16 of (hi, hi); (mid, lo), (lo, lo) < 2^-24 dropped
-              ptx::umma_bf16(d_tmem, a_l2 + adv, b_hi + adv, idesc, first);
-              ptx::umma_bf16(d_tmem, a_hi + adv, b_l2 + adv, idesc, 1u);
-              ptx::umma_bf16(d_tmem, a_lo + adv, b_lo + adv, idesc, 1u);
-              ptx::umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-              ptx::umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
-              ptx::umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+              mma(d_tmem, a_l2 + adv, b_hi + adv, idesc, first);
+              mma(d_tmem, a_hi + adv, b_l2 + adv, idesc, 1u);
+              mma(d_tmem, a_lo + adv, b_lo + adv, idesc, 1u);
+              mma(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+              mma(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+              mma(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
             } else if (NPA == 2 && NPB == 2) {
-              ptx::umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, first);
-              ptx::umma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-              ptx::umma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+              mma(d_tmem, a_hi + adv, b_hi + adv, idesc, first);
+              mma(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+              mma(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
             } else {  // (1,1)
-              ptx::umma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, first);
+              mma(d_tmem, a_hi + adv, b_hi + adv, idesc, first);
             }
           }
-          ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+          commit(&empty_bar[stage]);  // frees the smem stage (in both CTAs of a pair) when these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&tmem_full[acc_buf]);
+        commit(&tmem_full[acc_buf]);
         acc_buf ^= 1;
         if (acc_buf == 0) acc_phase ^= 1;
       }
@@ -335,8 +430,11 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const float descale = 1.0f / ((p.absmax_a ? pow2_scale(*p.absmax_a) : 1.0f) * (p.absmax_b ? pow2_scale(*p.absmax_b) : 1.0f));
     const bool dot_vec_ok = p.dot_ref != nullptr && ((reinterpret_cast<uintptr_t>(p.dot_ref) & 15) == 0) &&
                             ((p.dot_ld & 3) == 0) && ((p.col_cadd & 3) == 0);
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-      const UnitCoord uc = decode_unit(u, p, meta);
+    const uint32_t tmem_empty_leader[2] = {PAIR ? mapa_shared(ptx::smem_u32(&tmem_empty[0]), 0) : 0u,
+                                           PAIR ? mapa_shared(ptx::smem_u32(&tmem_empty[1]), 0) : 0u};
+    for (int u = worker; u < total_units; u += workers) {
+      UnitCoord uc = decode_unit(u, p, meta);
+      if constexpr (PAIR) uc.m_t = 2 * uc.m_t + (int)rank;
       const bool has_acc = uc.it1 > uc.it0;
       if (!has_acc && p.accumulate) continue;  // nothing to add
       if (has_acc) {
@@ -444,7 +542,10 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (has_acc) {
         ptx::tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc_buf]);
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_cluster(tmem_empty_leader[acc_buf]);
+          else ptx::mbar_arrive(&tmem_empty[acc_buf]);
+        }
         acc_buf ^= 1;
         if (acc_buf == 0) acc_phase ^= 1;
       }
@@ -453,11 +554,14 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   // ---- teardown
   ptx::tc_fence_before_sync();
-  __syncthreads();
+  __syncwarp();  // the single-lane role branches above: barrier.cluster is .aligned
+  if constexpr (PAIR) cluster_sync_all();  // the partner may still be reading this CTA's B half / signalling its barriers
+  else __syncthreads();
   if (warp == 1) {
     __syncwarp();
     ptx::tc_fence_after_sync();
-    ptx::tmem_dealloc(tmem_base, 2 * kAccCols);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, 2 * kAccCols);
+    else ptx::tmem_dealloc(tmem_base, 2 * kAccCols);
   }
 }
 
