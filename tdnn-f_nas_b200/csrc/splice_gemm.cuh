@@ -348,7 +348,13 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else if (warp == 1) {
     // ================================================= MMA issuer (pair kernels: the leader CTA only)
-    if (lane == 0 && rank == 0) {
+    // The WHOLE warp runs the loop and one elected lane issues: with the loop under `if (lane == 0)` the operands of
+    // every tcgen05.mma lived in per-thread registers and reached the instruction's uniform registers through an
+    // ELECT + 5 x R2UR.BROADCAST + branch sequence (14 SASS instructions per MMA, ~175 per K block of the MN-major
+    // kernel: the single issuing thread, not the tensor pipe or the TMA loads, bounded these kernels at 51-65 % tensor
+    // activity).  Values that every lane computes identically but that come out of shared memory are passed through
+    // __shfl_sync so that the compiler knows they are warp-uniform.
+    if (rank == 0) {
       // single-plane operands are fp16 (format 0), multi-plane operands are bf16 (format 1)
       constexpr uint32_t idesc =
           ptx::umma_idesc_f16(PAIR ? 2 * kBM : kBM, BN, NPA == 1 ? 0u : 1u, NPB == 1 ? 0u : 1u, MN ? 1u : 0u);
@@ -360,24 +366,27 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if constexpr (PAIR) umma_commit_pair(bar);
         else ptx::umma_commit(bar);
       };
+      const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t tiles_u = __shfl_sync(0xffffffffu, ptx::smem_u32(tiles), 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc_buf = 0;
       uint32_t acc_phase = 0;
       for (int u = worker; u < total_units; u += workers) {
         const UnitCoord uc = decode_unit(u, p, meta);
-        if (uc.it1 <= uc.it0) continue;
+        const int it0 = __shfl_sync(0xffffffffu, uc.it0, 0), it1 = __shfl_sync(0xffffffffu, uc.it1, 0);
+        const int cnt = max(__shfl_sync(0xffffffffu, meta->cnt[uc.c], 0), 1);
+        if (it1 <= it0) continue;
         ptx::mbar_wait(&tmem_empty[acc_buf], acc_phase ^ 1);
         ptx::tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + acc_buf * kAccCols;
-        const int cnt = max(meta->cnt[uc.c], 1);
-        int kb = uc.it0 / cnt, j = uc.it0 % cnt;  // same order as the producer: K block outer, segment inner
-        for (int it = uc.it0; it < uc.it1; ++it) {
+        const uint32_t d_tmem = tmem_base_u + acc_buf * kAccCols;
+        int kb = it0 / cnt, j = it0 % cnt;  // same order as the producer: K block outer, segment inner
+        for (int it = it0; it < it1; ++it) {
           const int ksteps = (kb == p.kb_per_seg - 1) ? p.kb_last_steps : kBKk / 16;
           if (++j == cnt) { j = 0; ++kb; }
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after_sync();
-          const uint32_t sa = ptx::smem_u32(tiles + stage * Cfg::kStageBytes);
+          const uint32_t sa = tiles_u + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
           // MN-major: chunks of 64 columns are kBKk rows x 128 B apart (LBO), groups of 8 k-rows 1 KB apart (SBO)
           auto desc = [](uint32_t addr) {
@@ -389,32 +398,36 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint64_t b_lo = desc(sb + (NPB > 1 ? 1 : 0) * Cfg::kBPlane);
           const uint64_t a_l2 = desc(sa + (NPA - 1) * Cfg::kAPlane);  // third plane (NP == 3)
           const uint64_t b_l2 = desc(sb + (NPB - 1) * Cfg::kBPlane);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBKk / 16; ++k) {
-            if (k >= ksteps) break;
-            // K-major: 16 elements = 32 B = 2 x 16 B units inside the swizzle atom; MN-major: 16 k-rows = 2 KB = 128 units
-            const uint64_t adv = (uint64_t)(MN ? k * 128 : k * 2);
-            const uint32_t first = (it > uc.it0 || k > 0) ? 1u : 0u;
-            if (NPA == 3) {
-              // smallest products first: (lo, hi) and (mid, mid) are ~2^-16 of (hi, hi); (mid, lo), (lo, lo) < 2^-24 dropped
-              mma(d_tmem, a_l2 + adv, b_hi + adv, idesc, first);
-              mma(d_tmem, a_hi + adv, b_l2 + adv, idesc, 1u);
-              mma(d_tmem, a_lo + adv, b_lo + adv, idesc, 1u);
-              mma(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-              mma(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
-              mma(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
-            } else if (NPA == 2 && NPB == 2) {
-              mma(d_tmem, a_hi + adv, b_hi + adv, idesc, first);
-              mma(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-              mma(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
-            } else {  // (1,1)
-              mma(d_tmem, a_hi + adv, b_hi + adv, idesc, first);
+            for (int k = 0; k < kBKk / 16; ++k) {
+              if (k >= ksteps) break;
+              // K-major: 16 elements = 32 B = 2 x 16 B units inside the swizzle atom; MN-major: 16 k-rows = 2 KB = 128 units
+              const uint64_t adv = (uint64_t)(MN ? k * 128 : k * 2);
+              const uint32_t first = (it > it0 || k > 0) ? 1u : 0u;
+              if (NPA == 3) {
+                // smallest products first: (lo, hi) and (mid, mid) are ~2^-16 of (hi, hi); (mid, lo), (lo, lo) < 2^-24 dropped
+                mma(d_tmem, a_l2 + adv, b_hi + adv, idesc, first);
+                mma(d_tmem, a_hi + adv, b_l2 + adv, idesc, 1u);
+                mma(d_tmem, a_lo + adv, b_lo + adv, idesc, 1u);
+                mma(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                mma(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+                mma(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+              } else if (NPA == 2 && NPB == 2) {
+                mma(d_tmem, a_hi + adv, b_hi + adv, idesc, first);
+                mma(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                mma(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+              } else {  // (1,1)
+                mma(d_tmem, a_hi + adv, b_hi + adv, idesc, first);
+              }
             }
+            commit(&empty_bar[stage]);  // frees the smem stage (in both CTAs of a pair) when these MMAs retire
           }
-          commit(&empty_bar[stage]);  // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        commit(&tmem_full[acc_buf]);
+        if (ptx::elect_one()) commit(&tmem_full[acc_buf]);
+        __syncwarp();
         acc_buf ^= 1;
         if (acc_buf == 0) acc_phase ^= 1;
       }
