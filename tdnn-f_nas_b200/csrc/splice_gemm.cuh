@@ -102,10 +102,17 @@ struct GemmCfg {
   static constexpr int kBBytes = NPB * kBPlane;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kMetaBytes = 2048 + (int)sizeof(GemmSmemMeta);
-  static constexpr int kStages = (232448 - 1024 - kMetaBytes) / kStageBytes >= 4
-                                     ? 4
-                                     : (232448 - 1024 - kMetaBytes) / kStageBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kMetaBytes + 1024;
+  static constexpr int kAvail = 232448 - 1024 - kMetaBytes;
+  static constexpr int kStagesMax = kAvail / kStageBytes >= 4 ? 4 : kAvail / kStageBytes;
+  // Epilogue staging (one 32 x 32 fp32 block per epilogue warp, rows padded to 36 floats): the accumulator leaves TMEM
+  // with one ROW per lane, so a direct st / red.global.v4 of a warp touches 32 rows x 16 B; through the staging block a
+  // warp instruction covers 4 rows x 128 B.  Only where it does not cost a pipeline stage.
+  static constexpr int kEpiPitch = 36;
+  static constexpr int kEpiWant = 4 * 32 * kEpiPitch * 4;
+  static constexpr int kStagesEpi = (kAvail - kEpiWant) / kStageBytes >= 4 ? 4 : (kAvail - kEpiWant) / kStageBytes;
+  static constexpr int kEpiBytes = (kStagesEpi == kStagesMax) ? kEpiWant : 0;
+  static constexpr int kStages = kStagesMax;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kMetaBytes + kEpiBytes + 1024;
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N must be a multiple of 16 in [16,256]");
   static_assert(kStages >= 2, "need at least a double buffer");
   static_assert(NPA == NPB && NPA >= 1 && NPA <= 3, "unsupported plane combination");
@@ -248,6 +255,7 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   GemmSmemMeta* meta = reinterpret_cast<GemmSmemMeta*>(meta_base + 2048);
+  float* epi_stage = reinterpret_cast<float*>(meta_base + Cfg::kMetaBytes);  // kEpiBytes (16-byte aligned)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -459,6 +467,74 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const long long R = (long long)m * p.row_mul + (long long)uc.c * p.row_cadd;
       const float scale = p.alpha * meta->c_scale[uc.c] * descale;
       const bool add_bias = (p.bias != nullptr) && (uc.split == 0);
+      if (Cfg::kEpiBytes > 0 && vec_ok && p.dot_ref == nullptr) {
+        // ---- staged epilogue: 32 columns at a time through this warp's staging block
+        float* stg = epi_stage + (warp - 2) * (32 * Cfg::kEpiPitch);
+        const int cq = lane & 7, rsub = lane >> 3;
+#pragma unroll 1
+        for (int g = 0; g < BN / 32; ++g) {
+          const int n = uc.n_t * BN + g * 32 + cq * 4;  // first of this lane's 4 columns in the row-major phase
+          if (uc.n_t * BN + g * 32 >= p.n_valid) break;  // warp-uniform
+          uint32_t v[32];
+          __syncwarp();  // the previous block has been read; tcgen05.ld is .sync.aligned
+          if (has_acc) {
+            ptx::tmem_ld_32x32(tmem_base + acc_buf * kAccCols + ((uint32_t)(quarter * 32) << 16) + g * 32, v);
+            ptx::tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0u;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            o.x = scale * __uint_as_float(v[j]);
+            o.y = scale * __uint_as_float(v[j + 1]);
+            o.z = scale * __uint_as_float(v[j + 2]);
+            o.w = scale * __uint_as_float(v[j + 3]);
+            *reinterpret_cast<float4*>(stg + lane * Cfg::kEpiPitch + j) = o;
+          }
+          __syncwarp();
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (add_bias && n < p.n_valid) {  // the bias tail is not 16-byte aligned in general
+            b4.x = __ldg(p.bias + n);
+            if (n + 1 < p.n_valid) b4.y = __ldg(p.bias + n + 1);
+            if (n + 2 < p.n_valid) b4.z = __ldg(p.bias + n + 2);
+            if (n + 3 < p.n_valid) b4.w = __ldg(p.bias + n + 3);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + rsub;
+            const int mm = uc.m_t * kBM + quarter * 32 + rr;
+            if (mm >= meta->m_valid[uc.c] || n >= p.n_valid) continue;
+            float4 o = *reinterpret_cast<const float4*>(stg + rr * Cfg::kEpiPitch + cq * 4);
+            o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+            float* dst = p.out + ((long long)mm * p.row_mul + (long long)uc.c * p.row_cadd) * p.out_ld + n +
+                         (long long)uc.c * p.col_cadd;
+            if (n + 4 <= p.n_valid) {
+              if (p.atomic || p.accumulate) red_add_v4_f32(dst, o.x, o.y, o.z, o.w);
+              else *reinterpret_cast<float4*>(dst) = o;
+            } else {
+              const float e[4] = {o.x, o.y, o.z, o.w};
+              for (int j = 0; j < 4 && n + j < p.n_valid; ++j) {
+                if (p.atomic || p.accumulate) red_add_f32(dst + j, e[j]);
+                else dst[j] = e[j];
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (has_acc) {
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (PAIR) mbar_arrive_cluster(tmem_empty_leader[acc_buf]);
+            else ptx::mbar_arrive(&tmem_empty[acc_buf]);
+          }
+          acc_buf ^= 1;
+          if (acc_buf == 0) acc_phase ^= 1;
+        }
+        continue;
+      }
       float dot = 0.f;
 #pragma unroll 1
       for (int chunk = 0; chunk < BN / 16; ++chunk) {
