@@ -381,6 +381,11 @@ int tdnnf_ctx_operand_rowsq(tdnnf_ctx* ctx, const float* source, int rows, const
 int tdnnf_ng_gram_scale(tdnnf_ctx* ctx, const float* H, int rows, int rank, int h_stride, float* L, int l_stride,
                         const float* WWt, int w_stride, const float* rowsq, double* sumsq, int in_rows, int n,
                         const int32_t* row_offsets, int row_stride, const float* weff, float ones_rows, float* out3);
+/* n <= 4 strided 2-D copies dst_k[r][c] = src_k[r][c] in one launch.  Either side may be page-locked host memory
+ * (cudaMallocHost / cudaHostAlloc: device-accessible under unified addressing), so small matrices reach a host thread --
+ * after an event recorded behind the call -- without the copy engine. */
+int tdnnf_copy_blocks(tdnnf_ctx* ctx, int n, const float* const* src, const int32_t* src_strides, float* const* dst,
+                      const int32_t* dst_strides, const int32_t* rows, const int32_t* cols);
 /* W_next (rank x dim, overwritten) = A J + AC W  with A, AC rank x rank (rank <= 128) and J, W rank x dim: the update
  * W_{t+1} = A_t (J_t + diag(c) W_t) of OnlineNaturalGradient (kaldi: ComputeWt1), in exact fp32 FMAs. */
 int tdnnf_ng_w_update(tdnnf_ctx* ctx, const float* A, int a_stride, const float* AC, int ac_stride, const float* J, int j_stride,

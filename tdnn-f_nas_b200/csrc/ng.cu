@@ -5,6 +5,7 @@
 #include <algorithm>
 
 #include "context.h"
+#include <cstring>
 
 using namespace tdnnf;
 
@@ -456,6 +457,50 @@ extern "C" int tdnnf_mat_axpy_dev_zero(tdnnf_ctx* ctx, float alpha, const float*
   b = std::max(1LL, std::min(b, (long long)ctx->num_sms * 16));
   mat_axpy_dev_kernel<true><<<(int)b, 256, 0, ctx->stream>>>(alpha, factor1_dev, factor2_dev, src, src_stride, dst, dst_stride, rows,
                                                              cols);
+  ctx->launches++;
+  TDNNF_CUDA_OK(cudaGetLastError());
+  return TDNNF_OK;
+}
+
+// Up to 4 strided 2-D copies in ONE launch, either side of which may be page-locked HOST memory (device-accessible
+// under unified addressing): the R x R matrices of the natural-gradient eigen-update travel device -> host -> device
+// without the copy engine.  (As cudaMemcpy2DAsync calls they were ~280 engine switches per refresh period in the middle of
+// the backward pass: the finish step ran 2 ms longer than the sum of its kernels.)
+struct CopyBlocks {
+  const float* src[4];
+  float* dst[4];
+  int src_stride[4], dst_stride[4], rows[4], cols[4];
+  int n;
+};
+__global__ void copy_blocks_kernel(const CopyBlocks b) {
+  for (int k = 0; k < b.n; ++k) {
+    const int total = b.rows[k] * b.cols[k];
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+      const int r = idx / b.cols[k], c = idx % b.cols[k];
+      b.dst[k][(long long)r * b.dst_stride[k] + c] = b.src[k][(long long)r * b.src_stride[k] + c];
+    }
+  }
+}
+
+extern "C" int tdnnf_copy_blocks(tdnnf_ctx* ctx, int n, const float* const* src, const int32_t* src_strides, float* const* dst,
+                                 const int32_t* dst_strides, const int32_t* rows, const int32_t* cols) {
+  TDNNF_REQUIRE(ctx && src && dst && src_strides && dst_strides && rows && cols && n >= 1 && n <= 4, "bad argument (1 <= n <= 4)");
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+  CopyBlocks b;
+  memset(&b, 0, sizeof(b));
+  b.n = n;
+  long long most = 0;
+  for (int k = 0; k < n; ++k) {
+    TDNNF_REQUIRE(src[k] && dst[k] && rows[k] >= 0 && cols[k] >= 0 && src_strides[k] >= cols[k] && dst_strides[k] >= cols[k],
+                  "bad block");
+    b.src[k] = src[k]; b.dst[k] = dst[k];
+    b.src_stride[k] = src_strides[k]; b.dst_stride[k] = dst_strides[k];
+    b.rows[k] = rows[k]; b.cols[k] = cols[k];
+    most = std::max(most, (long long)rows[k] * cols[k]);
+  }
+  if (most == 0) return TDNNF_OK;
+  const int blocks = (int)std::max(1LL, std::min((most + 255) / 256, 64LL));
+  copy_blocks_kernel<<<blocks, 256, 0, ctx->stream>>>(b);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   return TDNNF_OK;

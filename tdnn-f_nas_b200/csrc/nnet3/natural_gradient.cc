@@ -568,12 +568,12 @@ void OnlineNaturalGradient::Step(const NgOperand& X, bool updating) {
   }
   if (!pending_->ready) CudaCheck(cudaEventCreateWithFlags(&pending_->ready, cudaEventDisableTiming), "cudaEventCreate");
   cudaStream_t st = Stream();
-  CudaCheck(cudaMemcpy2DAsync(pending_->host, sizeof(float) * R, L_.Data(), sizeof(float) * L_.Stride(), sizeof(float) * R, R,
-                              cudaMemcpyDeviceToHost, st), "cudaMemcpy2DAsync");
-  CudaCheck(cudaMemcpy2DAsync(pending_->host + (size_t)R * R, sizeof(float) * R, K_.Data(), sizeof(float) * K_.Stride(),
-                              sizeof(float) * R, R, cudaMemcpyDeviceToHost, st), "cudaMemcpy2DAsync");
-  CudaCheck(cudaMemcpyAsync(pending_->host + (size_t)2 * R * R, scal_.Data(), sizeof(float) * 4, cudaMemcpyDeviceToHost, st),
-            "cudaMemcpyAsync");
+  {
+    const float* src[3] = {L_.Data(), K_.Data(), scal_.Data()};
+    float* dst[3] = {pending_->host, pending_->host + (size_t)R * R, pending_->host + (size_t)2 * R * R};
+    const int32_t ss[3] = {L_.Stride(), K_.Stride(), 4}, ds[3] = {R, R, 4}, rr[3] = {R, R, 1}, cc[3] = {R, R, 4};
+    CheckStatus(tdnnf_copy_blocks(ctx, 3, src, ss, dst, ds, rr, cc));
+  }
   CudaCheck(cudaEventRecord(pending_->ready, st), "cudaEventRecord");
   pending_->active = true;
   pending_->N = N;
@@ -686,10 +686,10 @@ void OnlineNaturalGradient::FinishPendingUpdate() {
   EnsureSize(&AC_, R, R);
   {
     cudaStream_t st = Stream();
-    CudaCheck(cudaMemcpy2DAsync(A_.Data(), sizeof(float) * A_.Stride(), A, sizeof(float) * R, sizeof(float) * R, R,
-                                cudaMemcpyHostToDevice, st), "cudaMemcpy2DAsync");
-    CudaCheck(cudaMemcpy2DAsync(AC_.Data(), sizeof(float) * AC_.Stride(), AC, sizeof(float) * R, sizeof(float) * R, R,
-                                cudaMemcpyHostToDevice, st), "cudaMemcpy2DAsync");
+    const float* src[2] = {A, AC};
+    float* dst[2] = {A_.Data(), AC_.Data()};
+    const int32_t ss[2] = {R, R}, ds[2] = {A_.Stride(), AC_.Stride()}, rr[2] = {R, R}, cc[2] = {R, R};
+    CheckStatus(tdnnf_copy_blocks(CurrentContext(), 2, src, ss, dst, ds, rr, cc));
     if (!pending_->uploaded) CudaCheck(cudaEventCreateWithFlags(&pending_->uploaded, cudaEventDisableTiming), "cudaEventCreate");
     CudaCheck(cudaEventRecord(pending_->uploaded, st), "cudaEventRecord");
     pending_->upload_in_flight = true;

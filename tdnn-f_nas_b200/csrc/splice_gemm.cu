@@ -249,6 +249,40 @@ __global__ void project_gather_kernel(const float* __restrict__ Y, long long y_l
   }
 }
 
+// Hs[r', i*od + j] = weff[i] * od_mat[q, j] where r' = offs[i] + q*row_stride, zero where no such q exists: the n shifted
+// copies of a NARROW out_deriv side by side (tdnnf_darts_backprop_params, stacked form)
+__global__ void stack_shift_kernel(const float* __restrict__ od_mat, long long od_ld, int out_rows, int od, int n,
+                                   GroupRowOffsets offs, int row_stride, const float* __restrict__ weff, int in_rows,
+                                   float* __restrict__ Hs, int ncols) {
+  const long long total = (long long)in_rows * ncols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % ncols);
+    const long long rp = idx / ncols;
+    const int i = c / od, j = c - i * od;
+    const long long t = rp - offs.v[i];
+    float v = 0.f;
+    if (t >= 0 && t % row_stride == 0) {
+      const long long q = t / row_stride;
+      if (q < out_rows) v = weff[i] * od_mat[q * od_ld + j];
+    }
+    Hs[idx] = v;
+  }
+}
+
+// dW[j, i*in_dim + d] += alpha * T[(i*od + j), d]
+__global__ void stack_scatter_kernel(const float* __restrict__ T, int in_dim, int od, int n, float alpha, float* __restrict__ dW,
+                                     long long dw_ld) {
+  const long long total = (long long)n * od * in_dim;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(idx % in_dim);
+    const int c = (int)(idx / in_dim);
+    const int i = c / od, j = c - i * od;
+    dW[(long long)j * dw_ld + (long long)i * in_dim + d] += alpha * T[idx];
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 struct Planes {
   __nv_bfloat16* base = nullptr;  // hi plane; lo plane follows at base + plane_elems
@@ -894,6 +928,79 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
         else
           rc = tdnnf_add_row_sum(ctx, out_deriv, out_rows, out_dim, od_stride, lr, dbias);
         if (rc) return rc;
+      }
+      // ---- stacked form for a NARROW out_deriv (the J = H^T X product of OnlineNaturalGradient on the spliced input:
+      // rank 20 against n * 1536 columns).  The per-offset form reads the activation planes once per offset into a
+      // 32-column tile (bandwidth-bound: 113 us per call).  Here the n shifted copies of out_deriv stand side by side,
+      // Hs = [w_1 S_1 od | ... | w_n S_n od] (in_rows x n*out_dim), and ONE GEMM T = Hs^T X reads every activation tile
+      // once; dW[:, i-th block] += lr * T[i-th block of rows].
+      static const int stacked_on = [] {
+        const char* e = getenv("TDNNF_WGRAD_STACKED");
+        return e ? atoi(e) : 1;
+      }();
+      const int ncols = n * out_dim;
+      const int bnS = pick_bn(ncols, ctx->gemm_planes);
+      if (stacked_on && s == nullptr && n > 1 && ncols <= 256 && ceil_div(ncols, bnS) == 1 && !(ctx->gemm_planes == 3 && bnS == 256)) {
+        const int KpX = round_up(in_dim, kBK), KpS = round_up(ncols, kBK);
+        const size_t hs_bytes = ((size_t)in_rows * ncols * sizeof(float) + 1023) & ~size_t(1023);
+        const size_t t_bytes = ((size_t)ncols * in_dim * sizeof(float) + 1023) & ~size_t(1023);
+        const size_t need = planes_bytes(ctx->gemm_planes, r, Q, KpX) + planes_bytes(ctx->gemm_planes, r, Q, KpS);
+        ctx->ws_reset();
+        rc = ctx->ws_reserve(need + hs_bytes + t_bytes + 4096);
+        if (rc) return rc;
+        rc = ctx->cws_reserve(need);
+        if (rc) return rc;
+        float* Hs = static_cast<float*>(ctx->ws_alloc(hs_bytes));
+        float* T = static_cast<float*>(ctx->ws_alloc(t_bytes));
+        if (!Hs || !T) return TDNNF_ERR_NOMEM;
+        GroupRowOffsets offs;
+        for (int i = 0; i < kMaxSeg; ++i) offs.v[i] = i < n ? row_offsets[i] : 0;
+        {
+          const long long total = (long long)in_rows * ncols;
+          const int blocks = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 16));
+          stack_shift_kernel<<<blocks, 256, 0, ctx->stream>>>(out_deriv, od_stride, out_rows, out_dim, n, offs, r, weff, in_rows, Hs,
+                                                              ncols);
+          ctx->launches++;
+          TDNNF_CUDA_OK(cudaGetLastError());
+        }
+        Planes XR, HS;
+        rc = launch_split_rows(ctx, in_value, in_rows, in_dim, in_stride, r, r, 1, 0, nullptr, Q, KpX, &XR);
+        if (rc) return rc;
+        rc = launch_split_rows(ctx, Hs, in_rows, ncols, ncols, r, r, 1, 0, nullptr, Q, KpS, &HS);
+        if (rc) return rc;
+        TDNNF_CUDA_OK(cudaMemsetAsync(T, 0, (size_t)ncols * in_dim * sizeof(float), ctx->stream));
+        constexpr int kBKmn = 32;
+        GemmParams p;
+        memset(&p, 0, sizeof(p));
+        p.c_tiles = 1;
+        p.kb_per_seg = ceil_div(Q, kBKmn);
+        p.kb_last_steps = ceil_div(Q - (p.kb_per_seg - 1) * kBKmn, 16);
+        p.nseg = r;  // one segment per row group of the planes (row_stride > 1: rows are de-interleaved)
+        for (int c = 0; c < r; ++c) {
+          p.seg_a_c[c] = c;
+          p.seg_b_c[c] = c;
+          p.seg_cmatch[c] = -1;
+        }
+        p.m_valid[0] = in_dim;
+        p.m_tiles = ceil_div(in_dim, kBM);
+        p.n_tiles = 1;
+        p.n_valid = ncols;
+        p.out = T;  // acc[d, c] -> T[c, d]
+        p.out_ld = in_dim;
+        p.transposed = 1;
+        p.row_mul = 1;
+        p.accumulate = 1;
+        p.atomic = 1;
+        p.alpha = 1.0f;
+        p.splits = choose_splits(p.m_tiles, r * p.kb_per_seg, ctx->num_sms);
+        rc = launch_gemm_mn(ctx, bnS, XR, HS, p, 2.0 * out_rows * (double)out_dim * in_dim * n);
+        if (rc) return rc;
+        const long long total = (long long)ncols * in_dim;
+        const int blocks = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 16));
+        stack_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(T, in_dim, out_dim, n, lr, dW, dw_stride);
+        ctx->launches++;
+        TDNNF_CUDA_OK(cudaGetLastError());
+        return TDNNF_OK;
       }
       const int KpX = round_up(in_dim, kBK), KpO = round_up(out_dim, kBK);
       ctx->ws_reset();
