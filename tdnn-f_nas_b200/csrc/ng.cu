@@ -104,16 +104,20 @@ __global__ void ng_scale_kernel(const double* __restrict__ sumsq, const float* _
 
 // L (r x r) += H^T H for a tall skinny H (N x r, r <= 16*TB): the Gram matrix of the natural-gradient projection
 // (kaldi: L_t = H_t^T H_t), in plain fp32 FMAs.  Thread (ti, tj) of a 16 x 16 block owns the TB x TB outputs
-// (ti*TB.., tj*TB..); rows are staged through shared memory 32 at a time; one red.add per output per CTA.
-// Replaces {zero L, two transposed operand splits of H, a split-K tensor-core GEMM}: HBM-bound on reading H once.
+// (ti*TB.., tj*TB..).  A CTA owns ONE contiguous slab of rows and stages it in shared memory in a single pass (every load
+// in flight at once: the first version staged 32 rows at a time, four dependent load -> barrier -> FMA rounds per CTA,
+// and measured 30 us at rank 80 for 0.2 GFLOP), then adds its partial into one of kGramBufs accumulation buffers with
+// red.add: chains of ~18 same-address reductions instead of 148 (all CTAs into one buffer measured 37 us), and the
+// finish kernel sums 8 buffers instead of 148 per-CTA partials.
+constexpr int kGramBufs = 8;
+constexpr int kGramSlab = 256;  // rows staged per pass (dynamic shared memory: kGramSlab x (16*TB + 1) floats)
 template <int TB>
 __global__ void __launch_bounds__(256) ng_gram_kernel(const float* __restrict__ H, int N, int r, long long ld,
                                                       float* __restrict__ partials,
                                                       const float* __restrict__ rowsq, int in_rows, int n, TdnnfOffsets offs,
                                                       int row_stride, double* __restrict__ sumsq) {
-  constexpr int kRows = 32;
   constexpr int W = 16 * TB;
-  __shared__ float tile[kRows][W + 1];
+  extern __shared__ float gram_tile[];  // [slab rows][W + 1]
   // optional second job: this CTA's share of sum over the rows of view i of rowsq[row] (view i = rows offs[i] +
   // k*row_stride, k < N) -> sumsq[blockIdx.x][i]: tr(X X^T) of the spliced operand from the per-row sums of squares
   // the operand split left behind
@@ -155,47 +159,51 @@ __global__ void __launch_bounds__(256) ng_gram_kernel(const float* __restrict__ 
   for (int a = 0; a < TB; ++a)
 #pragma unroll
     for (int b = 0; b < TB; ++b) acc[a][b] = 0.f;
-  for (long long row0 = (long long)blockIdx.x * kRows; row0 < N; row0 += (long long)gridDim.x * kRows) {
-    for (int idx = threadIdx.x; idx < kRows * W; idx += 256) {
+  const int per = (N + gridDim.x - 1) / gridDim.x;
+  const long long first = (long long)blockIdx.x * per;
+  const long long last = first + per < N ? first + per : N;
+  for (long long row0 = first; row0 < last; row0 += kGramSlab) {
+    const int rows_here = (int)(last - row0 < kGramSlab ? last - row0 : kGramSlab);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < rows_here * W; idx += 256) {
       const int rr = idx / W, c = idx % W;
-      tile[rr][c] = (row0 + rr < N && c < r) ? H[(row0 + rr) * ld + c] : 0.f;
+      gram_tile[rr * (W + 1) + c] = c < r ? H[(row0 + rr) * ld + c] : 0.f;
     }
     __syncthreads();
 #pragma unroll 4
-    for (int rr = 0; rr < kRows; ++rr) {
+    for (int rr = 0; rr < rows_here; ++rr) {
       float a[TB], b[TB];
+      const float* row = gram_tile + rr * (W + 1);
 #pragma unroll
       for (int k = 0; k < TB; ++k) {
-        a[k] = tile[rr][ti * TB + k];
-        b[k] = tile[rr][tj * TB + k];
+        a[k] = row[ti * TB + k];
+        b[k] = row[tj * TB + k];
       }
 #pragma unroll
       for (int x = 0; x < TB; ++x)
 #pragma unroll
         for (int y = 0; y < TB; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
     }
-    __syncthreads();
   }
-  // per-CTA partial (no atomics: rank^2 same-address red.adds from every CTA serialise in L2, measured 37 us at
-  // rank 80 from 117 CTAs); ng_gram_finish_kernel sums the partials
-  float* mine = partials + (size_t)blockIdx.x * r * r;
+  float* mine = partials + (size_t)(blockIdx.x % kGramBufs) * r * r;
 #pragma unroll
   for (int x = 0; x < TB; ++x)
 #pragma unroll
     for (int y = 0; y < TB; ++y) {
       const int i = ti * TB + x, j = tj * TB + y;
-      if (i < r && j < r) mine[i * r + j] = acc[x][y];
+      if (i < r && j < r && first < last) atomicAdd(mine + i * r + j, acc[x][y]);
     }
 }
 
-// L[i][j] = sum of the per-CTA partials; tr(L) and <L, W W^T> reduced across CTAs in double; the last CTA to finish
+// L[i][j] = sum of the accumulation buffers (which are zeroed again as they are read); tr(L) and <L, W W^T> reduced across CTAs in double; the last CTA to finish
 // turns them into out[0..2] = {tr(X X^T), tr(X^ X^^T), scale} exactly as ng_scale_kernel, and re-arms the scratch.
 // 1024 threads = 128 consecutive elements x 8 slices of the partials: coalesced, and only nblk/8 loads per thread.
-__global__ void __launch_bounds__(1024) ng_gram_finish_kernel(const float* __restrict__ partials, int nblk, int r,
+__global__ void __launch_bounds__(1024) ng_gram_finish_kernel(float* __restrict__ partials, int nblk, int r,
                                                               float* __restrict__ L, long long l_ld,
                                                               const float* __restrict__ WWt, long long w_ld,
                                                               const double* __restrict__ sumsq,
-                                                              const double* __restrict__ view_partials /* [nblk][16] or null */,
+                                                              const double* __restrict__ view_partials /* [nview][16] or null */,
+                                                              int nview,
                                                               const float* __restrict__ weff, int n, float ones_rows,
                                                               double* __restrict__ acc /* [2] */,
                                                               unsigned int* __restrict__ counter, float* __restrict__ out) {
@@ -208,7 +216,10 @@ __global__ void __launch_bounds__(1024) ng_gram_finish_kernel(const float* __res
   float sum = 0.f;
   if (e < r * r) {
 #pragma unroll 4
-    for (int b = slice; b < nblk; b += 8) sum += partials[(size_t)b * r * r + e];
+    for (int b = slice; b < nblk; b += 8) {
+      sum += partials[(size_t)b * r * r + e];
+      partials[(size_t)b * r * r + e] = 0.f;  // re-armed for the next call on this stream
+    }
   }
   red[slice][col] = sum;
   __syncthreads();
@@ -248,7 +259,7 @@ __global__ void __launch_bounds__(1024) ng_gram_finish_kernel(const float* __res
   if (view_partials != nullptr) {
     const int i = threadIdx.x & 15;
     double v = 0.0;
-    for (int b = threadIdx.x >> 4; b < nblk; b += 64) v += view_partials[(size_t)b * TDNNF_MAX_OFFSETS + i];
+    for (int b = threadIdx.x >> 4; b < nview; b += 64) v += view_partials[(size_t)b * TDNNF_MAX_OFFSETS + i];
     if (i < n && v != 0.0) atomicAdd(&view_sum[i], v);
   } else if (threadIdx.x < n) {
     view_sum[threadIdx.x] = sumsq[threadIdx.x];
@@ -272,53 +283,68 @@ __global__ void __launch_bounds__(1024) ng_gram_finish_kernel(const float* __res
   }
 }
 
-// W_next[i][d] = sum_k A[i][k] * J[k][d] + AC[i][k] * W[k][d]     (i < r <= 128, d < D)
+// W_next[i][d] = sum_{k < r} A[i][k] J[k][d] + sum_{k < r} AC[i][k] W[k][d]     (i < r <= 128, d < D)
 // The W_{t+1} = A_t (J_t + diag(c) W_t) step of OnlineNaturalGradient in exact fp32 FMAs: K = 2r is far too short for
 // the tensor-core path (it took a zero-fill, four operand splits and two 6-product GEMMs per preconditioner).
-// A small tiled SGEMM C = [A | AC] [J ; W]: block = 16 rows x 128 columns, K in chunks of 32 staged in shared memory
-// (coalesced, many loads in flight); a thread owns one column and 16 accumulators, reads the A chunk as float4.
-// out[i, d] = sum_{k < r} A[i, k] J[k, d] + sum_{k < r} AC[i, k] W[k, d]: a block owns 16 rows x 64 columns.  The 16 x 2r
-// coefficient strip goes to shared memory ONCE; every thread then streams its column of [J; W] in batches of 8
-// independent coalesced loads (no barrier inside the K loop: the first version staged 32-row chunks of [J; W] through
-// shared memory with two barriers each, five dependent global-load round trips for rank 80, and measured 57 us).
-constexpr int kWuRows = 16, kWuCols = 64;
-__global__ void __launch_bounds__(kWuCols) ng_w_update_kernel(const float* __restrict__ A, int a_ld, const float* __restrict__ AC,
-                                                              int ac_ld, const float* __restrict__ J, long long j_ld,
-                                                              const float* __restrict__ W, long long w_ld, int r, int D,
-                                                              float* __restrict__ out, long long out_ld) {
-  extern __shared__ __align__(16) float sM[];  // [kWuRows][Kp], Kp = 2r rounded up to 8
+// A block owns 16 rows x 64 columns and splits K over 4 thread groups (256 threads): the 16 x 2r coefficient strip goes
+// to shared memory once, every thread streams its quarter of its column of [J; W] in batches of 8 independent coalesced
+// loads, and the four partial sums meet in shared memory.  (History: 32-row chunks of [J; W] through shared memory with
+// two barriers each measured 57 us at rank 80; one thread per column over the whole K, 20 dependent load batches with 2
+// warps per SM, 26 us.)
+constexpr int kWuRows = 16, kWuCols = 64, kWuGroups = 4;
+__global__ void __launch_bounds__(kWuCols* kWuGroups)
+ng_w_update_kernel(const float* __restrict__ A, int a_ld, const float* __restrict__ AC, int ac_ld, const float* __restrict__ J,
+                   long long j_ld, const float* __restrict__ W, long long w_ld, int r, int D, float* __restrict__ out,
+                   long long out_ld) {
+  extern __shared__ __align__(16) float sM[];  // [kWuRows][Kp] coefficients, then [kWuGroups][kWuRows][kWuCols] partial sums
   const int K = 2 * r, Kp = (K + 7) & ~7;
+  float* sP = sM + kWuRows * Kp;
   const int d0 = blockIdx.x * kWuCols, i0 = blockIdx.y * kWuRows;
-  for (int idx = threadIdx.x; idx < kWuRows * Kp; idx += kWuCols) {
+  const int tx = threadIdx.x % kWuCols, grp = threadIdx.x / kWuCols;
+  for (int idx = threadIdx.x; idx < kWuRows * Kp; idx += kWuCols * kWuGroups) {
     const int u = idx / Kp, k = idx % Kp, i = i0 + u;
     float v = 0.f;
     if (i < r && k < K) v = k < r ? A[i * a_ld + k] : AC[i * ac_ld + (k - r)];
     sM[idx] = v;
   }
   __syncthreads();
-  const int d = d0 + threadIdx.x;
-  if (d >= D) return;
+  const int d = d0 + tx;
   float acc[kWuRows];
 #pragma unroll
   for (int u = 0; u < kWuRows; ++u) acc[u] = 0.f;
-  for (int k0 = 0; k0 < Kp; k0 += 8) {
-    float b[8];
+  const int kq = ((Kp / 8 + kWuGroups - 1) / kWuGroups) * 8;  // K share of one group, a multiple of 8
+  const int k_begin = grp * kq, k_end = min(k_begin + kq, Kp);
+  if (d < D) {
+    for (int k0 = k_begin; k0 < k_end; k0 += 8) {
+      float b[8];
 #pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
-      const int k = k0 + kk;
-      b[kk] = k < r ? J[k * j_ld + d] : (k < K ? W[(k - r) * w_ld + d] : 0.f);
-    }
+      for (int kk = 0; kk < 8; ++kk) {
+        const int k = k0 + kk;
+        b[kk] = k < r ? J[k * j_ld + d] : (k < K ? W[(k - r) * w_ld + d] : 0.f);
+      }
 #pragma unroll
-    for (int u = 0; u < kWuRows; ++u) {
-      const float4 m0 = *reinterpret_cast<const float4*>(&sM[u * Kp + k0]);
-      const float4 m1 = *reinterpret_cast<const float4*>(&sM[u * Kp + k0 + 4]);
-      acc[u] = fmaf(m0.x, b[0], fmaf(m0.y, b[1], fmaf(m0.z, b[2], fmaf(m0.w, b[3], acc[u]))));
-      acc[u] = fmaf(m1.x, b[4], fmaf(m1.y, b[5], fmaf(m1.z, b[6], fmaf(m1.w, b[7], acc[u]))));
+      for (int u = 0; u < kWuRows; ++u) {
+        const float4 m0 = *reinterpret_cast<const float4*>(&sM[u * Kp + k0]);
+        const float4 m1 = *reinterpret_cast<const float4*>(&sM[u * Kp + k0 + 4]);
+        acc[u] = fmaf(m0.x, b[0], fmaf(m0.y, b[1], fmaf(m0.z, b[2], fmaf(m0.w, b[3], acc[u]))));
+        acc[u] = fmaf(m1.x, b[4], fmaf(m1.y, b[5], fmaf(m1.z, b[6], fmaf(m1.w, b[7], acc[u]))));
+      }
     }
   }
 #pragma unroll
-  for (int u = 0; u < kWuRows; ++u)
-    if (i0 + u < r) out[(long long)(i0 + u) * out_ld + d] = acc[u];
+  for (int u = 0; u < kWuRows; ++u) sP[(grp * kWuRows + u) * kWuCols + tx] = acc[u];
+  __syncthreads();
+  // group g finishes rows 4g .. 4g+3
+  if (d < D) {
+#pragma unroll
+    for (int uu = 0; uu < kWuRows / kWuGroups; ++uu) {
+      const int u = grp * (kWuRows / kWuGroups) + uu;
+      float v = 0.f;
+#pragma unroll
+      for (int g = 0; g < kWuGroups; ++g) v += sP[(g * kWuRows + u) * kWuCols + tx];
+      if (i0 + u < r) out[(long long)(i0 + u) * out_ld + d] = v;
+    }
+  }
 }
 
 template <bool ZERO>
@@ -379,14 +405,15 @@ extern "C" int tdnnf_ng_gram_scale(tdnnf_ctx* ctx, const float* H, int rows, int
   const int blocks = std::max(1, std::min((rows + 63) / 64, ctx->num_sms));
   // scratch: [0,16) acc[2] doubles, [16,20) counter, [64, 64 + 128*blocks) per-CTA view sums, then the partial Gram matrices
   const size_t view_bytes = (size_t)ctx->num_sms * TDNNF_MAX_OFFSETS * sizeof(double);
-  const size_t need = 64 + view_bytes + (size_t)blocks * rank * rank * sizeof(float);
+  const size_t need = 64 + view_bytes + (size_t)kGramBufs * rank * rank * sizeof(float);
   if (ctx->ng_scratch_bytes < need) {
     if (ctx->ng_scratch) TDNNF_CUDA_OK(cudaFree(ctx->ng_scratch));  // waits for kernels still using it
     ctx->ng_scratch = nullptr;
     ctx->ng_scratch_bytes = 0;
-    const size_t want = std::max(need, 64 + view_bytes + (size_t)ctx->num_sms * 128 * 128 * sizeof(float));
+    const size_t want = std::max(need, 64 + view_bytes + (size_t)kGramBufs * 128 * 128 * sizeof(float));
     TDNNF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ctx->ng_scratch), want));
-    TDNNF_CUDA_OK(cudaMemsetAsync(ctx->ng_scratch, 0, 64, ctx->stream));  // {acc[2], counter}: self re-arming afterwards
+    // {acc[2], counter} and the accumulation buffers start at zero and re-arm themselves in the finish kernel
+    TDNNF_CUDA_OK(cudaMemsetAsync(ctx->ng_scratch, 0, want, ctx->stream));
     ctx->ng_scratch_bytes = want;
   }
   double* acc = reinterpret_cast<double*>(ctx->ng_scratch);
@@ -396,23 +423,32 @@ extern "C" int tdnnf_ng_gram_scale(tdnnf_ctx* ctx, const float* H, int rows, int
   TdnnfOffsets offs;
   for (int i = 0; i < TDNNF_MAX_OFFSETS; ++i) offs.v[i] = (rowsq && i < n) ? row_offsets[i] : 0;
   const int tb = (rank + 15) / 16;
-  auto launch = [&](auto kern) {
-    kern<<<blocks, 256, 0, ctx->stream>>>(H, rows, rank, h_stride, partials, rowsq, in_rows, n, offs, row_stride, view_partials);
+  const int per = (rows + blocks - 1) / blocks;
+  const size_t tile_bytes = (size_t)std::min(per, kGramSlab) * (16 * tb + 1) * sizeof(float);
+  auto launch = [&](auto kern) -> cudaError_t {
+    static bool attr_set = false;  // per instance
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGramSlab * (16 * 8 + 1) * (int)sizeof(float));
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    kern<<<blocks, 256, tile_bytes, ctx->stream>>>(H, rows, rank, h_stride, partials, rowsq, in_rows, n, offs, row_stride, view_partials);
+    return cudaSuccess;
   };
   switch (tb) {
-    case 1: launch(ng_gram_kernel<1>); break;
-    case 2: launch(ng_gram_kernel<2>); break;
-    case 3: launch(ng_gram_kernel<3>); break;
-    case 4: launch(ng_gram_kernel<4>); break;
-    case 5: launch(ng_gram_kernel<5>); break;
-    case 6: launch(ng_gram_kernel<6>); break;
-    case 7: launch(ng_gram_kernel<7>); break;
-    default: launch(ng_gram_kernel<8>); break;
+    case 1: TDNNF_CUDA_OK(launch(ng_gram_kernel<1>)); break;
+    case 2: TDNNF_CUDA_OK(launch(ng_gram_kernel<2>)); break;
+    case 3: TDNNF_CUDA_OK(launch(ng_gram_kernel<3>)); break;
+    case 4: TDNNF_CUDA_OK(launch(ng_gram_kernel<4>)); break;
+    case 5: TDNNF_CUDA_OK(launch(ng_gram_kernel<5>)); break;
+    case 6: TDNNF_CUDA_OK(launch(ng_gram_kernel<6>)); break;
+    case 7: TDNNF_CUDA_OK(launch(ng_gram_kernel<7>)); break;
+    default: TDNNF_CUDA_OK(launch(ng_gram_kernel<8>)); break;
   }
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
-  ng_gram_finish_kernel<<<(rank * rank + 127) / 128, 1024, 0, ctx->stream>>>(partials, blocks, rank, L, l_stride, WWt, w_stride, sumsq,
-                                                                            rowsq ? view_partials : nullptr, weff, n, ones_rows, acc,
+  ng_gram_finish_kernel<<<(rank * rank + 127) / 128, 1024, 0, ctx->stream>>>(partials, std::min(blocks, kGramBufs), rank, L, l_stride, WWt, w_stride, sumsq,
+                                                                            rowsq ? view_partials : nullptr, blocks, weff, n, ones_rows, acc,
                                                                             counter, out3);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
@@ -427,8 +463,9 @@ extern "C" int tdnnf_ng_w_update(tdnnf_ctx* ctx, const float* A, int a_stride, c
                 "bad argument (rank <= 128)");
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
   const int Kp = (2 * rank + 7) & ~7;
-  ng_w_update_kernel<<<dim3((dim + kWuCols - 1) / kWuCols, (rank + kWuRows - 1) / kWuRows), kWuCols, sizeof(float) * kWuRows * Kp,
-                       ctx->stream>>>(A, a_stride, AC, ac_stride, J, j_stride, W, w_stride, rank, dim, W_next, out_stride);
+  ng_w_update_kernel<<<dim3((dim + kWuCols - 1) / kWuCols, (rank + kWuRows - 1) / kWuRows), kWuCols * kWuGroups,
+                       sizeof(float) * (kWuRows * Kp + kWuGroups * kWuRows * kWuCols), ctx->stream>>>(
+      A, a_stride, AC, ac_stride, J, j_stride, W, w_stride, rank, dim, W_next, out_stride);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   return TDNNF_OK;
