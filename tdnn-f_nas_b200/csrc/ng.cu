@@ -111,7 +111,12 @@ __global__ void ng_scale_kernel(const double* __restrict__ sumsq, const float* _
 // finish kernel sums 8 buffers instead of 148 per-CTA partials.
 constexpr int kGramBufs = 8;
 constexpr int kGramSlab = 256;  // rows staged per pass (dynamic shared memory: kGramSlab x (16*TB + 1) floats)
-template <int TB>
+constexpr int kGramCluster = 8;
+// CL = true (launched in clusters of kGramCluster CTAs): the CTAs of a cluster leave their r x r partial sums in their own
+// shared memory, and CTA c of the cluster adds up slice c of all eight through distributed shared memory and stores it:
+// one partial per CLUSTER in global memory, plain stores, no atomics (the 6400 red.adds per CTA of the buffer scheme were
+// ~20 of the 28 us at rank 80).
+template <int TB, bool CL>
 __global__ void __launch_bounds__(256) ng_gram_kernel(const float* __restrict__ H, int N, int r, long long ld,
                                                       float* __restrict__ partials,
                                                       const float* __restrict__ rowsq, int in_rows, int n, TdnnfOffsets offs,
@@ -159,15 +164,43 @@ __global__ void __launch_bounds__(256) ng_gram_kernel(const float* __restrict__ 
   for (int a = 0; a < TB; ++a)
 #pragma unroll
     for (int b = 0; b < TB; ++b) acc[a][b] = 0.f;
+  const bool vec = (r % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(H) & 15) == 0);
   const int per = (N + gridDim.x - 1) / gridDim.x;
   const long long first = (long long)blockIdx.x * per;
   const long long last = first + per < N ? first + per : N;
   for (long long row0 = first; row0 < last; row0 += kGramSlab) {
     const int rows_here = (int)(last - row0 < kGramSlab ? last - row0 : kGramSlab);
     __syncthreads();
-    for (int idx = threadIdx.x; idx < rows_here * W; idx += 256) {
-      const int rr = idx / W, c = idx % W;
-      gram_tile[rr * (W + 1) + c] = c < r ? H[(row0 + rr) * ld + c] : 0.f;
+    if (vec) {
+      // float4 loads, four per thread in flight before the first store (a plain element loop left ~32 dependent
+      // load -> store rounds per thread: most of the 28 us this kernel took at rank 80)
+      constexpr int W4 = W / 4;
+      const int total4 = rows_here * W4;
+      for (int base = threadIdx.x; base < total4; base += 256 * 4) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + u * 256;
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (idx < total4) {
+            const int rr = idx / W4, c = (idx % W4) * 4;
+            if (c < r) v[u] = *reinterpret_cast<const float4*>(H + (row0 + rr) * ld + c);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + u * 256;
+          if (idx < total4) {
+            float* d = gram_tile + (idx / W4) * (W + 1) + (idx % W4) * 4;
+            d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
+          }
+        }
+      }
+    } else {
+      for (int idx = threadIdx.x; idx < rows_here * W; idx += 256) {
+        const int rr = idx / W, c = idx % W;
+        gram_tile[rr * (W + 1) + c] = c < r ? H[(row0 + rr) * ld + c] : 0.f;
+      }
     }
     __syncthreads();
 #pragma unroll 4
@@ -185,14 +218,48 @@ __global__ void __launch_bounds__(256) ng_gram_kernel(const float* __restrict__ 
         for (int y = 0; y < TB; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
     }
   }
-  float* mine = partials + (size_t)(blockIdx.x % kGramBufs) * r * r;
+  if constexpr (CL) {
+    __syncthreads();  // the staging tile is no longer read
+    float* part = gram_tile;  // [r * r]
 #pragma unroll
-  for (int x = 0; x < TB; ++x)
+    for (int x = 0; x < TB; ++x)
 #pragma unroll
-    for (int y = 0; y < TB; ++y) {
-      const int i = ti * TB + x, j = tj * TB + y;
-      if (i < r && j < r && first < last) atomicAdd(mine + i * r + j, acc[x][y]);
+      for (int y = 0; y < TB; ++y) {
+        const int i = ti * TB + x, j = tj * TB + y;
+        if (i < r && j < r) part[i * r + j] = acc[x][y];
+      }
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    uint32_t crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int rr2 = r * r, slice = (rr2 + kGramCluster - 1) / kGramCluster;
+    const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(part));
+    float* mine = partials + (size_t)(blockIdx.x / kGramCluster) * rr2;
+    for (int e = (int)crank * slice + threadIdx.x; e < min(((int)crank + 1) * slice, rr2); e += 256) {
+      float v = 0.f;
+#pragma unroll
+      for (int c = 0; c < kGramCluster; ++c) {
+        uint32_t remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(base + 4u * (uint32_t)e), "r"(c));
+        float t;
+        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(t) : "r"(remote));
+        v += t;
+      }
+      mine[e] = v;
     }
+    __syncthreads();
+    // nobody leaves while its shared memory is still being read
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else {
+    float* mine = partials + (size_t)(blockIdx.x % kGramBufs) * r * r;
+#pragma unroll
+    for (int x = 0; x < TB; ++x)
+#pragma unroll
+      for (int y = 0; y < TB; ++y) {
+        const int i = ti * TB + x, j = tj * TB + y;
+        if (i < r && j < r && first < last) atomicAdd(mine + i * r + j, acc[x][y]);
+      }
+  }
 }
 
 // L[i][j] = sum of the accumulation buffers (which are zeroed again as they are read); tr(L) and <L, W W^T> reduced across CTAs in double; the last CTA to finish
@@ -402,15 +469,21 @@ extern "C" int tdnnf_ng_gram_scale(tdnnf_ctx* ctx, const float* H, int rows, int
   TDNNF_REQUIRE(n >= 1 && n <= TDNNF_MAX_OFFSETS, "bad number of views");
   TDNNF_REQUIRE(rowsq == nullptr || (row_offsets && row_stride >= 1 && in_rows > 0), "bad view description");
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
-  const int blocks = std::max(1, std::min((rows + 63) / 64, ctx->num_sms));
-  // scratch: [0,16) acc[2] doubles, [16,20) counter, [64, 64 + 128*blocks) per-CTA view sums, then the partial Gram matrices
+  int blocks = std::max(1, std::min((rows + 63) / 64, ctx->num_sms));
+  const int tb = (rank + 15) / 16;
+  // wide Gram matrices from many CTAs: clusters reduce through distributed shared memory (one partial per cluster)
+  const bool clustered = tb >= 3 && blocks >= 2 * kGramCluster;
+  if (clustered) blocks = blocks / kGramCluster * kGramCluster;
+  const int nparts = clustered ? blocks / kGramCluster : std::min(blocks, kGramBufs);
+  // scratch: [0,16) acc[2] doubles, [16,20) counter, [64, 64 + 128*num_sms) per-CTA view sums, then the partial Gram matrices
   const size_t view_bytes = (size_t)ctx->num_sms * TDNNF_MAX_OFFSETS * sizeof(double);
-  const size_t need = 64 + view_bytes + (size_t)kGramBufs * rank * rank * sizeof(float);
+  const size_t max_parts = std::max(kGramBufs, ctx->num_sms / kGramCluster + 1);
+  const size_t need = 64 + view_bytes + max_parts * rank * rank * sizeof(float);
   if (ctx->ng_scratch_bytes < need) {
     if (ctx->ng_scratch) TDNNF_CUDA_OK(cudaFree(ctx->ng_scratch));  // waits for kernels still using it
     ctx->ng_scratch = nullptr;
     ctx->ng_scratch_bytes = 0;
-    const size_t want = std::max(need, 64 + view_bytes + (size_t)kGramBufs * 128 * 128 * sizeof(float));
+    const size_t want = std::max(need, 64 + view_bytes + max_parts * 128 * 128 * sizeof(float));
     TDNNF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ctx->ng_scratch), want));
     // {acc[2], counter} and the accumulation buffers start at zero and re-arm themselves in the finish kernel
     TDNNF_CUDA_OK(cudaMemsetAsync(ctx->ng_scratch, 0, want, ctx->stream));
@@ -422,32 +495,47 @@ extern "C" int tdnnf_ng_gram_scale(tdnnf_ctx* ctx, const float* H, int rows, int
   float* partials = reinterpret_cast<float*>(ctx->ng_scratch + 64 + view_bytes);
   TdnnfOffsets offs;
   for (int i = 0; i < TDNNF_MAX_OFFSETS; ++i) offs.v[i] = (rowsq && i < n) ? row_offsets[i] : 0;
-  const int tb = (rank + 15) / 16;
   const int per = (rows + blocks - 1) / blocks;
-  const size_t tile_bytes = (size_t)std::min(per, kGramSlab) * (16 * tb + 1) * sizeof(float);
-  auto launch = [&](auto kern) -> cudaError_t {
+  const size_t tile_bytes = std::max((size_t)std::min(per, kGramSlab) * (16 * tb + 1), (size_t)rank * rank) * sizeof(float);
+  auto launch = [&](auto kern, bool cl) -> cudaError_t {
     static bool attr_set = false;  // per instance
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGramSlab * (16 * 8 + 1) * (int)sizeof(float));
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
-    kern<<<blocks, 256, tile_bytes, ctx->stream>>>(H, rows, rank, h_stride, partials, rowsq, in_rows, n, offs, row_stride, view_partials);
-    return cudaSuccess;
+    if (!cl) {
+      kern<<<blocks, 256, tile_bytes, ctx->stream>>>(H, rows, rank, h_stride, partials, rowsq, in_rows, n, offs, row_stride, view_partials);
+      return cudaSuccess;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = tile_bytes;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kGramCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, H, rows, rank, (long long)h_stride, partials, rowsq, in_rows, n, offs, row_stride, view_partials);
   };
   switch (tb) {
-    case 1: TDNNF_CUDA_OK(launch(ng_gram_kernel<1>)); break;
-    case 2: TDNNF_CUDA_OK(launch(ng_gram_kernel<2>)); break;
-    case 3: TDNNF_CUDA_OK(launch(ng_gram_kernel<3>)); break;
-    case 4: TDNNF_CUDA_OK(launch(ng_gram_kernel<4>)); break;
-    case 5: TDNNF_CUDA_OK(launch(ng_gram_kernel<5>)); break;
-    case 6: TDNNF_CUDA_OK(launch(ng_gram_kernel<6>)); break;
-    case 7: TDNNF_CUDA_OK(launch(ng_gram_kernel<7>)); break;
-    default: TDNNF_CUDA_OK(launch(ng_gram_kernel<8>)); break;
+    case 1: TDNNF_CUDA_OK(launch(ng_gram_kernel<1, false>, false)); break;
+    case 2: TDNNF_CUDA_OK(launch(ng_gram_kernel<2, false>, false)); break;
+    case 3: TDNNF_CUDA_OK(clustered ? launch(ng_gram_kernel<3, true>, true) : launch(ng_gram_kernel<3, false>, false)); break;
+    case 4: TDNNF_CUDA_OK(clustered ? launch(ng_gram_kernel<4, true>, true) : launch(ng_gram_kernel<4, false>, false)); break;
+    case 5: TDNNF_CUDA_OK(clustered ? launch(ng_gram_kernel<5, true>, true) : launch(ng_gram_kernel<5, false>, false)); break;
+    case 6: TDNNF_CUDA_OK(clustered ? launch(ng_gram_kernel<6, true>, true) : launch(ng_gram_kernel<6, false>, false)); break;
+    case 7: TDNNF_CUDA_OK(clustered ? launch(ng_gram_kernel<7, true>, true) : launch(ng_gram_kernel<7, false>, false)); break;
+    default: TDNNF_CUDA_OK(clustered ? launch(ng_gram_kernel<8, true>, true) : launch(ng_gram_kernel<8, false>, false)); break;
   }
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
-  ng_gram_finish_kernel<<<(rank * rank + 127) / 128, 1024, 0, ctx->stream>>>(partials, std::min(blocks, kGramBufs), rank, L, l_stride, WWt, w_stride, sumsq,
+  ng_gram_finish_kernel<<<(rank * rank + 127) / 128, 1024, 0, ctx->stream>>>(partials, nparts, rank, L, l_stride, WWt, w_stride, sumsq,
                                                                             rowsq ? view_partials : nullptr, blocks, weff, n, ones_rows, acc,
                                                                             counter, out3);
   ctx->launches++;
