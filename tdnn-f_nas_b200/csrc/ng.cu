@@ -3,6 +3,7 @@
 // WITHOUT materialising X~ (the reference builds the R x (n*D_in+1) matrix in_value_temp, tdnn.cc:476-514),
 // the "scale" factor kept on the device (no host sync), and an axpy whose coefficient lives on the device.
 #include <algorithm>
+#include <vector>
 
 #include "context.h"
 #include <cstring>
@@ -498,11 +499,12 @@ extern "C" int tdnnf_ng_gram_scale(tdnnf_ctx* ctx, const float* H, int rows, int
   const int per = (rows + blocks - 1) / blocks;
   const size_t tile_bytes = std::max((size_t)std::min(per, kGramSlab) * (16 * tb + 1), (size_t)rank * rank) * sizeof(float);
   auto launch = [&](auto kern, bool cl) -> cudaError_t {
-    static bool attr_set = false;  // per instance
-    if (!attr_set) {
+    // every instance has the same pointer TYPE (one instantiation of this lambda): remember the functions, not a flag
+    static std::vector<const void*> attr_set;
+    if (std::find(attr_set.begin(), attr_set.end(), (const void*)kern) == attr_set.end()) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGramSlab * (16 * 8 + 1) * (int)sizeof(float));
       if (e != cudaSuccess) return e;
-      attr_set = true;
+      attr_set.push_back((const void*)kern);
     }
     if (!cl) {
       kern<<<blocks, 256, tile_bytes, ctx->stream>>>(H, rows, rank, h_stride, partials, rowsq, in_rows, n, offs, row_stride, view_partials);

@@ -167,7 +167,10 @@ def test_multi_buffer_parameter_step(ctx):
         assert lib.tdnnf_multi_sumsq(ctx.h, 200, dptr, rows, cols, ld, None, C.c_void_p(out.data_ptr())) == 0  # > TDNNF_MULTI_MAX
 
 
-@pytest.mark.parametrize("N,r,n_views", [(5000, 80, 1), (3000, 20, 7), (130, 33, 3)])
+@pytest.mark.parametrize("N,r,n_views", [(5000, 80, 1), (3000, 20, 7), (130, 33, 3),
+                                        (40000, 80, 1),   # clusters, two passes over a slab that needs > 48 KB of shared memory
+                                        (40001, 128, 2),  # the widest tile
+                                        (20000, 48, 2)])
 def test_ng_gram_scale_and_w_update(ctx, N, r, n_views):
     """tdnnf_ng_gram_scale (L = H^T H, tr(X X^T) from per-row sums of squares, the scale) and tdnnf_ng_w_update
     (W_next = A J + AC W) against float64 numpy."""
@@ -198,6 +201,13 @@ def test_ng_gram_scale_and_w_update(ctx, N, r, n_views):
     H64 = H.astype(np.float64)
     L_ref = H64.T @ H64
     assert rel_err(L.cpu().numpy(), L_ref) < 1e-5
+    # a second call finds the scratch (accumulation buffers, counters) re-armed by the first
+    L2 = torch.zeros((r, r), device="cuda")
+    rc = lib.tdnnf_ng_gram_scale(ctx.h, C.c_void_p(Hd.data_ptr()), N, r, r, C.c_void_p(L2.data_ptr()), r,
+                                 C.c_void_p(Wd.data_ptr()), r, C.c_void_p(rq.data_ptr()), C.c_void_p(sumsq.data_ptr()), in_rows,
+                                 n_views, I(*offs), 1, C.c_void_p(wf.data_ptr()), C.c_float(float(N)), C.c_void_p(out3.data_ptr()))
+    assert rc == 0, lib.tdnnf_last_error()
+    assert rel_err(L2.cpu().numpy(), L_ref) < 1e-5
     tr_xx = float(N) + sum(float(weff[i]) ** 2 * float(rowsq[offs[i]: offs[i] + N].astype(np.float64).sum()) for i in range(n_views))
     tr_hat = tr_xx - 2 * np.trace(L_ref) + float((L_ref * WWt.astype(np.float64)).sum())
     o = out3.cpu().numpy()
