@@ -381,6 +381,12 @@ int tdnnf_ctx_operand_rowsq(tdnnf_ctx* ctx, const float* source, int rows, const
 int tdnnf_ng_gram_scale(tdnnf_ctx* ctx, const float* H, int rows, int rank, int h_stride, float* L, int l_stride,
                         const float* WWt, int w_stride, const float* rowsq, double* sumsq, int in_rows, int n,
                         const int32_t* row_offsets, int row_stride, const float* weff, float ones_rows, float* out3);
+/* G <- (I - Wo^T Wo) G (I - Wi^T Wi): the rank-r projections of OnlineNaturalGradient::PreconditionDirections applied to
+ * the gradient G = out_deriv^T X (rows = D_out, cols = n D_in + 1) instead of to its operands: X_hat = X (I - Wi^T Wi) on
+ * the input side and out_deriv_hat = out_deriv (I - Wo^T Wo) on the output side (ref: tdnn.cc:598-624).  Wi: ri x cols,
+ * Wo: ro x rows (device, row-major; either may be NULL = no projection on that side), ranks <= 128.  In place, fp32. */
+int tdnnf_ng_project_gradient(tdnnf_ctx* ctx, float* G, int rows, int cols, int g_stride, const float* Wi, int ri,
+                              int wi_stride, const float* Wo, int ro, int wo_stride);
 /* n <= 4 strided 2-D copies dst_k[r][c] = src_k[r][c] in one launch.  Either side may be page-locked host memory
  * (cudaMallocHost / cudaHostAlloc: device-accessible under unified addressing), so small matrices reach a host thread --
  * after an event recorded behind the call -- without the copy engine. */

@@ -43,6 +43,7 @@ def _declare(lib):
     sig("tdnnf_ng_gram_scale", [vp, vp, i, i, i, vp, i, vp, i, vp, vp, i, i, c_int_p, i, vp, f, vp])
     sig("tdnnf_ng_w_update", [vp, vp, i, vp, i, vp, i, vp, i, i, i, vp, i])
     sig("tdnnf_copy_blocks", [vp, i, vp, vp, vp, vp, vp, vp])
+    sig("tdnnf_ng_project_gradient", [vp, vp, i, i, i, vp, i, i, vp, i, i])
     sig("tdnnf_multi_sumsq", [vp, i, vp, vp, vp, vp, vp, vp])
     sig("tdnnf_multi_axpy_zero", [vp, i, vp, vp, vp, vp, vp, vp, vp])
     sig("tdnnf_ctx_set_gradient_mode", [vp, i])

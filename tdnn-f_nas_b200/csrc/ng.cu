@@ -3,6 +3,7 @@
 // WITHOUT materialising X~ (the reference builds the R x (n*D_in+1) matrix in_value_temp, tdnn.cc:476-514),
 // the "scale" factor kept on the device (no host sync), and an axpy whose coefficient lives on the device.
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "context.h"
@@ -586,6 +587,275 @@ extern "C" int tdnnf_mat_axpy_dev_zero(tdnnf_ctx* ctx, float alpha, const float*
                                                              cols);
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
+  return TDNNF_OK;
+}
+
+// ---- G <- (I - Wo^T Wo) G (I - Wi^T Wi): the two rank-r projections of the preconditioned gradient, in fp32 FMAs.
+// As four calls of the tensor-core GEMM (G Wi^T, G -= . Wi, Wo G, G -= Wo^T .) they were 14 launches per component (eight
+// operand splits, two zero-fills) for 0.7 GFLOP: ~2.5 ms per step of fixed costs.  Three small kernels instead:
+//   ng_rt_kernel  Ht[k, o] += sum_c Wi[k, c] G[o, c]      (contraction over the columns, split over column ranges)
+//   ng_lt_kernel  T[k, c]  += sum_o Wo[k, o] G[o, c]      (contraction over the rows, split over row ranges)
+//   ng_lu_kernel  G[o, c]  -= sum_k P[k, o] Q[k, c]       (P = Ht, Q = Wi  or  P = Wo, Q = T)
+constexpr int kNgMaxRank = 128;
+constexpr int kNgBufs = 8;  // accumulation buffers of the split reductions (chains of same-address red.adds serialise in L2)
+
+// grid (o-tiles of 32 rows, column splits); 256 threads: thread (to = tid % 32, tk = tid / 32) owns Ht[tk + 8 i][o0 + to],
+// i < NK (NK = ceil(rank / 8)).  Split s adds into buffer s % kNgBufs.
+template <int NK>
+__global__ void __launch_bounds__(256) ng_rt_kernel(const float* __restrict__ G, int rows, int cols, long long g_ld,
+                                                    const float* __restrict__ Wi, int ri, long long wi_ld, int cols_per_split,
+                                                    float* __restrict__ Ht /* [kNgBufs][ri][rows] */) {
+  __shared__ float Gs[2][32][33];
+  __shared__ float Ws[2][NK * 8][33];
+  const int to = threadIdx.x & 31, tk = threadIdx.x >> 5;
+  const int o0 = blockIdx.x * 32;
+  const int c_begin = blockIdx.y * cols_per_split, c_end = min(c_begin + cols_per_split, cols);
+  float acc[NK];
+#pragma unroll
+  for (int i = 0; i < NK; ++i) acc[i] = 0.f;
+  // register-staged double buffering: the loads of chunk j + 1 are in flight while chunk j is multiplied
+  float gl[4], wl[NK];
+  auto load = [&](int c0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int o = o0 + tk + 8 * j, c = c0 + to;
+      gl[j] = (o < rows && c < c_end) ? G[(long long)o * g_ld + c] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < NK; ++i) {
+      const int k = tk + 8 * i, c = c0 + to;
+      wl[i] = (k < ri && c < c_end) ? Wi[(long long)k * wi_ld + c] : 0.f;
+    }
+  };
+  auto stash = [&](int b) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Gs[b][tk + 8 * j][to] = gl[j];
+#pragma unroll
+    for (int i = 0; i < NK; ++i) Ws[b][tk + 8 * i][to] = wl[i];
+  };
+  load(c_begin);
+  stash(0);
+  __syncthreads();
+  int buf = 0;
+  for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+    const bool more = c0 + 32 < c_end;
+    if (more) load(c0 + 32);
+#pragma unroll 8
+    for (int cc = 0; cc < 32; ++cc) {
+      const float g = Gs[buf][to][cc];
+#pragma unroll
+      for (int i = 0; i < NK; ++i) acc[i] = fmaf(Ws[buf][tk + 8 * i][cc], g, acc[i]);
+    }
+    if (more) stash(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+  const int o = o0 + to;
+  float* mine = Ht + (size_t)(blockIdx.y % kNgBufs) * ri * rows;
+  if (o < rows) {
+#pragma unroll
+    for (int i = 0; i < NK; ++i)
+      if (tk + 8 * i < ri) atomicAdd(mine + (long long)(tk + 8 * i) * rows + o, acc[i]);
+  }
+}
+
+// grid (c-tiles of 32 columns, row splits); thread (tc = tid % 32, tk = tid / 32) owns T[tk + 8 i][c0 + tc], i < NK.
+template <int NK>
+__global__ void __launch_bounds__(256) ng_lt_kernel(const float* __restrict__ G, int rows, int cols, long long g_ld,
+                                                    const float* __restrict__ Wo, int ro, long long wo_ld, int rows_per_split,
+                                                    float* __restrict__ T /* [kNgBufs][ro][cols] */) {
+  __shared__ float Gs[2][32][32];
+  __shared__ __align__(16) float Ps[2][NK * 8][36];
+  const int tc = threadIdx.x & 31, tk = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 32, c = c0 + tc;
+  const int o_begin = blockIdx.y * rows_per_split, o_end = min(o_begin + rows_per_split, rows);
+  float acc[NK];
+#pragma unroll
+  for (int i = 0; i < NK; ++i) acc[i] = 0.f;
+  float gl[4], pl[NK];
+  auto load = [&](int o0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int o = o0 + tk + 8 * j;
+      gl[j] = (o < o_end && c < cols) ? G[(long long)o * g_ld + c] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < NK; ++i) {
+      const int k = tk + 8 * i, o = o0 + tc;
+      pl[i] = (k < ro && o < o_end) ? Wo[(long long)k * wo_ld + o] : 0.f;
+    }
+  };
+  auto stash = [&](int b) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Gs[b][tk + 8 * j][tc] = gl[j];
+#pragma unroll
+    for (int i = 0; i < NK; ++i) Ps[b][tk + 8 * i][tc] = pl[i];
+  };
+  load(o_begin);
+  stash(0);
+  __syncthreads();
+  int buf = 0;
+  for (int o0 = o_begin; o0 < o_end; o0 += 32) {
+    const bool more = o0 + 32 < o_end;
+    if (more) load(o0 + 32);
+#pragma unroll 2
+    for (int oo = 0; oo < 32; oo += 4) {
+      const float g0 = Gs[buf][oo][tc], g1 = Gs[buf][oo + 1][tc], g2 = Gs[buf][oo + 2][tc], g3 = Gs[buf][oo + 3][tc];
+#pragma unroll
+      for (int i = 0; i < NK; ++i) {
+        const float4 p = *reinterpret_cast<const float4*>(&Ps[buf][tk + 8 * i][oo]);
+        acc[i] = fmaf(p.x, g0, fmaf(p.y, g1, fmaf(p.z, g2, fmaf(p.w, g3, acc[i]))));
+      }
+    }
+    if (more) stash(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+  float* mine = T + (size_t)(blockIdx.y % kNgBufs) * ro * cols;
+  if (c < cols) {
+#pragma unroll
+    for (int i = 0; i < NK; ++i)
+      if (tk + 8 * i < ro) atomicAdd(mine + (long long)(tk + 8 * i) * cols + c, acc[i]);
+  }
+}
+
+// buf[0][e] += buf[1][e] + ... + buf[n-1][e]
+__global__ void ng_sum_bufs_kernel(float* __restrict__ buf, long long elems, int n) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < elems; e += (long long)gridDim.x * blockDim.x) {
+    float v = buf[e];
+    for (int b = 1; b < n; ++b) v += buf[b * elems + e];
+    buf[e] = v;
+  }
+}
+
+// G[o, c] -= sum_k P[k, o] Q[k, c]; grid (c-tiles of 64, o-tiles of 64); thread (tc = tid % 32, to = tid / 32) owns rows
+// o0 + 8 to .. + 7 and columns c0 + tc, c0 + tc + 32 (r x 128 floats staged per 4096 outputs)
+__global__ void __launch_bounds__(256) ng_lu_kernel(float* __restrict__ G, int rows, int cols, long long g_ld,
+                                                    const float* __restrict__ P, long long p_ld, const float* __restrict__ Q,
+                                                    long long q_ld, int r) {
+  extern __shared__ __align__(16) float lu_smem[];  // Ps[r][64], Qs[r][64]
+  float* Ps = lu_smem;
+  float* Qs = lu_smem + r * 64;
+  const int tc = threadIdx.x & 31, to = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 64, o0 = blockIdx.y * 64;
+#pragma unroll 2
+  for (int k = to; k < r; k += 8) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int o = o0 + tc + 32 * h, c = c0 + tc + 32 * h;
+      Ps[k * 64 + tc + 32 * h] = o < rows ? P[(long long)k * p_ld + o] : 0.f;
+      Qs[k * 64 + tc + 32 * h] = c < cols ? Q[(long long)k * q_ld + c] : 0.f;
+    }
+  }
+  __syncthreads();
+  float acc[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.f;
+#pragma unroll 2
+  for (int k = 0; k < r; ++k) {
+    const float4 pa = *reinterpret_cast<const float4*>(&Ps[k * 64 + to * 8]);
+    const float4 pb = *reinterpret_cast<const float4*>(&Ps[k * 64 + to * 8 + 4]);
+    const float q0 = Qs[k * 64 + tc], q1 = Qs[k * 64 + tc + 32];
+    const float pv[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[j][0] = fmaf(pv[j], q0, acc[j][0]);
+      acc[j][1] = fmaf(pv[j], q1, acc[j][1]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int o = o0 + to * 8 + j;
+    if (o >= rows) continue;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = c0 + tc + 32 * h;
+      if (c < cols) G[(long long)o * g_ld + c] -= acc[j][h];
+    }
+  }
+}
+
+template <typename F>
+static bool ng_dispatch_nk(int rank, F&& f) {  // NK = ceil(rank / 8) rounded up to an instantiated value
+  const int nk = (rank + 7) / 8;
+  if (nk <= 1) f(std::integral_constant<int, 1>());
+  else if (nk <= 3) f(std::integral_constant<int, 3>());
+  else if (nk <= 5) f(std::integral_constant<int, 5>());
+  else if (nk <= 8) f(std::integral_constant<int, 8>());
+  else if (nk <= 10) f(std::integral_constant<int, 10>());
+  else if (nk <= 16) f(std::integral_constant<int, 16>());
+  else return false;
+  return true;
+}
+
+extern "C" int tdnnf_ng_project_gradient(tdnnf_ctx* ctx, float* G, int rows, int cols, int g_stride, const float* Wi, int ri,
+                                         int wi_stride, const float* Wo, int ro, int wo_stride) {
+  TDNNF_REQUIRE(ctx && G && rows > 0 && cols > 0 && g_stride >= cols, "bad gradient matrix");
+  TDNNF_REQUIRE(!Wi || (ri >= 1 && ri <= kNgMaxRank && wi_stride >= cols), "bad in-side projection (rank <= 128)");
+  TDNNF_REQUIRE(!Wo || (ro >= 1 && ro <= kNgMaxRank && wo_stride >= rows), "bad out-side projection (rank <= 128)");
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
+  const size_t ht_floats = Wi ? (size_t)kNgBufs * ri * rows : 0, t_floats = Wo ? (size_t)kNgBufs * ro * cols : 0;
+  const size_t ht_bytes = (ht_floats * sizeof(float) + 255) & ~size_t(255);
+  const size_t t_bytes = (t_floats * sizeof(float) + 255) & ~size_t(255);
+  ctx->ws_reset();
+  int rc = ctx->ws_reserve(ht_bytes + t_bytes + 1024);
+  if (rc) return rc;
+  float* scratch = static_cast<float*>(ctx->ws_alloc(ht_bytes + t_bytes));
+  if (!scratch) return TDNNF_ERR_NOMEM;
+  float* Ht = scratch;
+  float* T = scratch + ht_bytes / sizeof(float);
+  const int want_blocks = 4 * ctx->num_sms;
+  {
+    static bool lu_attr = false;
+    if (!lu_attr) {
+      TDNNF_CUDA_OK(cudaFuncSetAttribute(ng_lu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(float) * kNgMaxRank * 128));
+      lu_attr = true;
+    }
+  }
+  if (Wi) {
+    const int o_tiles = (rows + 31) / 32;
+    int splits = std::max(1, std::min(want_blocks / o_tiles, (cols + 63) / 64));
+    const int per = (((cols + splits - 1) / splits) + 31) / 32 * 32;
+    splits = (cols + per - 1) / per;
+    const int bufs = std::min(splits, kNgBufs);
+    TDNNF_CUDA_OK(cudaMemsetAsync(Ht, 0, (size_t)bufs * ri * rows * sizeof(float), ctx->stream));
+    if (!ng_dispatch_nk(ri, [&](auto nk) {
+          ng_rt_kernel<decltype(nk)::value><<<dim3(o_tiles, splits), 256, 0, ctx->stream>>>(G, rows, cols, g_stride, Wi, ri, wi_stride,
+                                                                                          per, Ht);
+        }))
+      return fail(TDNNF_ERR_INVALID, "unsupported rank");
+    if (bufs > 1) {
+      ng_sum_bufs_kernel<<<std::max(1, std::min((ri * rows + 255) / 256, ctx->num_sms * 4)), 256, 0, ctx->stream>>>(
+          Ht, (long long)ri * rows, bufs);
+      ctx->launches++;
+    }
+    ng_lu_kernel<<<dim3((cols + 63) / 64, (rows + 63) / 64), 256, sizeof(float) * ri * 128, ctx->stream>>>(G, rows, cols, g_stride, Ht,
+                                                                                                    rows, Wi, wi_stride, ri);
+    ctx->launches += 2;
+    TDNNF_CUDA_OK(cudaGetLastError());
+  }
+  if (Wo) {
+    const int c_tiles = (cols + 31) / 32;
+    int splits = std::max(1, std::min(want_blocks / c_tiles, (rows + 63) / 64));
+    const int per = (((rows + splits - 1) / splits) + 31) / 32 * 32;
+    splits = (rows + per - 1) / per;
+    const int bufs = std::min(splits, kNgBufs);
+    TDNNF_CUDA_OK(cudaMemsetAsync(T, 0, (size_t)bufs * ro * cols * sizeof(float), ctx->stream));
+    if (!ng_dispatch_nk(ro, [&](auto nk) {
+          ng_lt_kernel<decltype(nk)::value><<<dim3(c_tiles, splits), 256, 0, ctx->stream>>>(G, rows, cols, g_stride, Wo, ro, wo_stride,
+                                                                                          per, T);
+        }))
+      return fail(TDNNF_ERR_INVALID, "unsupported rank");
+    if (bufs > 1) {
+      ng_sum_bufs_kernel<<<std::max(1, std::min((ro * cols + 255) / 256, ctx->num_sms * 4)), 256, 0, ctx->stream>>>(
+          T, (long long)ro * cols, bufs);
+      ctx->launches++;
+    }
+    ng_lu_kernel<<<dim3((cols + 63) / 64, (rows + 63) / 64), 256, sizeof(float) * ro * 128, ctx->stream>>>(G, rows, cols, g_stride, Wo,
+                                                                                                    wo_stride, T, cols, ro);
+    ctx->launches += 2;
+    TDNNF_CUDA_OK(cudaGetLastError());
+  }
   return TDNNF_OK;
 }
 

@@ -375,31 +375,12 @@ void TdnnDARTSV3Component::PreconditionedUpdate(const PrecomputedIndexes& indexe
   // out_deriv_hat^T X_hat = (I - W_o^T W_o) G (I - W_in^T W_in): both projections are applied to the D_out x D gradient
   // (rank-r corrections) instead of to the R x D operands.  out_deriv^T H_in = (out_deriv^T X) W_in^T = G W_in^T, so the
   // in-side correction needs no second pass over the R rows of out_deriv either.
-  if (!p_in.identity) {
-    const int32 r = p_in.rank;
-    if (ng_g1_.NumRows() != output_dim || ng_g1_.NumCols() != r) ng_g1_.Resize(output_dim, r);
-    // G1 = G W_in^T   (D_out x r; the Propagate form with one offset: out = in W^T)
-    CheckStatus(tdnnf_darts_propagate(ctx, ng_grad_.Data(), output_dim, augmented_input_dim, ng_grad_.Stride(), ng_g1_.Data(),
-                                      output_dim, r, ng_g1_.Stride(), p_in.W->Data(), p_in.W->Stride(), NULL, 1, one, 1,
-                                      zero_offset, 1));
-    // G -= G1 W_in
-    CheckStatus(tdnnf_darts_backprop_data(ctx, ng_g1_.Data(), output_dim, r, ng_g1_.Stride(), ng_grad_.Data(), output_dim,
-                                          augmented_input_dim, ng_grad_.Stride(), p_in.W->Data(), p_in.W->Stride(), minus_one,
-                                          1, zero_offset, 1));
-  }
-  if (!p_out.identity) {
-    const int32 q = p_out.rank;
-    if (ng_t_.NumRows() != q || ng_t_.NumCols() != augmented_input_dim) ng_t_.Resize(q, augmented_input_dim);
-    ng_t_.SetZero();
-    // T = W_o G
-    CheckStatus(tdnnf_darts_backprop_data(ctx, p_out.W->Data(), q, output_dim, p_out.W->Stride(), ng_t_.Data(), q,
-                                          augmented_input_dim, ng_t_.Stride(), ng_grad_.Data(), ng_grad_.Stride(), one, 1,
-                                          zero_offset, 1));
-    // G -= W_o^T T
-    CheckStatus(tdnnf_darts_backprop_params(ctx, ng_t_.Data(), q, augmented_input_dim, ng_t_.Stride(), p_out.W->Data(), q,
-                                            output_dim, p_out.W->Stride(), NULL, 0, ng_grad_.Data(), ng_grad_.Stride(), NULL,
-                                            one, 1, zero_offset, 1, -1.0f, NULL));
-  }
+  // (three small fp32 kernels per side: tdnnf_ng_project_gradient)
+  if (!p_in.identity || !p_out.identity)
+    CheckStatus(tdnnf_ng_project_gradient(ctx, ng_grad_.Data(), output_dim, augmented_input_dim, ng_grad_.Stride(),
+                                          p_in.identity ? NULL : p_in.W->Data(), p_in.identity ? 0 : p_in.rank,
+                                          p_in.identity ? 0 : p_in.W->Stride(), p_out.identity ? NULL : p_out.W->Data(),
+                                          p_out.identity ? 0 : p_out.rank, p_out.identity ? 0 : p_out.W->Stride()));
   // local_lrate = in_scale * out_scale * learning_rate_ (tdnn.cc:600-604), the scales read on the device:
   //   linear_params_ += local_lrate * out_deriv_hat^T X_hat[:, :n D_in]            (tdnn.cc:619-624)
   //   bias           += local_lrate * out_deriv_hat^T precon_ones                  (tdnn.cc:607-617)

@@ -2,7 +2,7 @@
 # Round-2 GPU check J: ncu durations of the natural-gradient helper kernels only (one period).
 mkdir -p gpurun_out
 CMD="python tools/profile_step.py --warmup 14 --steps 4"
-ncu --profile-from-start off -k regex:'ng_|copy_blocks|stack_' --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_ng.csv $CMD > gpurun_out/ncu_launches_ng.log 2>&1
+ncu --profile-from-start off -k regex:'ng_|copy_blocks|stack_|mat_axpy_dev' --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_ng.csv $CMD > gpurun_out/ncu_launches_ng.log 2>&1
 echo "rc=$?"; python - <<'PY'
 import csv, collections
 rows = list(csv.reader(open('gpurun_out/launches_ng.csv')))
