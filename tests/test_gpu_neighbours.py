@@ -226,6 +226,42 @@ def test_ng_gram_scale_and_w_update(ctx, N, r, n_views):
     assert rel_err(Wn.cpu().numpy(), ref) < 1e-5
 
 
+@pytest.mark.parametrize("rows,cols,ri,ro", [(160, 10753, 20, 80), (1536, 1121, 20, 80), (37, 130, 5, 0), (70, 65, 0, 33),
+                                             (129, 257, 128, 128), (8, 40, 1, 3)])
+def test_ng_project_gradient(ctx, rows, cols, ri, ro):
+    """tdnnf_ng_project_gradient: G <- (I - Wo^T Wo) G (I - Wi^T Wi) (the rank-r projections of
+    OnlineNaturalGradient::PreconditionDirections applied to the gradient, tdnn.cc:598-624) against float64 numpy;
+    rank 0 = that side is the identity (NULL)."""
+    import ctypes as C
+
+    import torch
+
+    from tdnnf_nas_b200 import capi
+
+    lib = capi.load()
+    g = np.random.default_rng(rows * 7 + cols)
+    G = g.standard_normal((rows, cols)).astype(np.float32)
+    Wi = (g.standard_normal((max(ri, 1), cols)) / np.sqrt(cols)).astype(np.float32)
+    Wo = (g.standard_normal((max(ro, 1), rows)) / np.sqrt(rows)).astype(np.float32)
+    Gd = torch.full((rows, cols + 5), 3.0, device="cuda")
+    Gd[:, :cols] = torch.from_numpy(G).cuda()
+    Wid, Wod = torch.from_numpy(Wi).cuda(), torch.from_numpy(Wo).cuda()
+    rc = lib.tdnnf_ng_project_gradient(ctx.h, C.c_void_p(Gd.data_ptr()), rows, cols, cols + 5,
+                                       C.c_void_p(Wid.data_ptr()) if ri else None, ri, cols if ri else 0,
+                                       C.c_void_p(Wod.data_ptr()) if ro else None, ro, rows if ro else 0)
+    assert rc == 0, lib.tdnnf_last_error()
+    ref = G.astype(np.float64)
+    if ri:
+        W = Wi.astype(np.float64)
+        ref = ref - (ref @ W.T) @ W
+    if ro:
+        W = Wo.astype(np.float64)
+        ref = ref - W.T @ (W @ ref)
+    out = Gd.cpu().numpy()
+    assert rel_err(out[:, :cols], ref) < 2e-6
+    assert (out[:, cols:] == 3.0).all()  # the padding of the stride is not touched
+
+
 @pytest.mark.parametrize("rows,cols,pad", [(320, 6008, 0), (17, 50, 3), (5, 1, 0), (3, 300, 1)])
 def test_log_softmax_component_vs_numpy(ctx, rows, cols, pad):
     """LogSoftmaxComponent (nnet-simple-component.cc:3607-3632): ApplyLogSoftMaxPerRow / DiffLogSoftmaxPerRow in float64."""

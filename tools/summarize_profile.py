@@ -90,8 +90,8 @@ def full_table(rep, title, want):
 
 
 full_table(os.path.join(G, "prof_gemm.ncu-rep"),
-           "`ncu --set full --clock-control none` of splice_gemm_kernel launches of a plain step (round 2: 14 consecutive launches of "
-           "the backward pass of the top blocks: data gradient, natural-gradient products, the MN-major parameter gradient "
+           "`ncu --set full --clock-control none` of splice_gemm_kernel launches of a plain step (round 2 final: 16 consecutive launches of "
+           "forward and backward: CTA-pair kernels `<BN, 2, 2, false, true>`, natural-gradient products, the MN-major parameter gradient "
            "`<160, 2, 2, true>`), per launch",
            ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum",
             "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
