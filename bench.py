@@ -330,10 +330,11 @@ def dp_self_check(net, cfg, world, rank, local_rank, x_host):
         nnet3.set_context(net.ctx)
         nnet3.set_rand_counter(counter)  # the replicas re-seeded the shared RNG: put rank 0 back in step with the other ranks
         spread = errs.pop("0")
-        out = dict(ok=bool(err_sum <= 1e-5 and all(e <= 1e-3 for e in errs.values())), allreduce_vs_sum_of_shards=err_sum,
+        out = dict(ok=bool(err_sum <= 1e-5 and all(e <= 2e-3 for e in errs.values())), allreduce_vs_sum_of_shards=err_sum,
                    shards_recomputed_on_rank0=errs, run_to_run_spread_rank0=spread, delta_floats=int(n),
                    note=("allreduce_vs_sum_of_shards: ||NCCL result - sum_r delta_r|| / ||sum||, bar 1e-5; shards_recomputed_on_rank0: "
-                         "relative error between rank r's delta and the same shard run on rank 0, bar 1e-3 (the derivative tolerance); "
+                         "relative error between rank r's delta and the same shard run on rank 0, bar 2e-3 (two runs, each within the 1e-3 "
+                         "derivative tolerance of the exact result); "
                          "run_to_run_spread_rank0: rank 0's own shard run twice -- the floor of that comparison (split-K red.global.add "
                          "order + ReLU sign ties)"))
     dist.barrier()
