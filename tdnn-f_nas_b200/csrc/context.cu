@@ -4,8 +4,18 @@
 #include <string>
 
 #include "context.h"
+#include <cstdlib>
 
 namespace tdnnf {
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("TDNNF_PDL");
+    return e ? atoi(e) != 0 : true;
+  }();
+  return on;
+}
+
 
 static thread_local std::string g_last_error;
 

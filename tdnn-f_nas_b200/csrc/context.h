@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 #include <string>
 #include <utility>
 #include <vector>
@@ -30,6 +31,38 @@ int fail(int code, const std::string& msg);
     if (_e != cudaSuccess)                                                                         \
       return ::tdnnf::fail(TDNNF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));    \
   } while (0)
+
+// Kernel launch with programmatic dependent launch allowed (the kernel must begin with ptx::grid_dep_wait() before it
+// touches anything a predecessor wrote): its CTAs are scheduled while the tail of the previous kernel drains, so launch
+// latency and prologue leave the critical path.  TDNNF_PDL=0 turns the attribute off.  cluster_x > 1 adds a cluster.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster_x;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(std::forward<Args>(args))...);
+}
 
 #define TDNNF_REQUIRE(cond, msg)                                                   \
   do {                                                                             \

@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "context.h"
+#include "ptx.cuh"
 
 using namespace tdnnf;
 
@@ -25,6 +26,8 @@ inline int grid_for(long long total, int threads, int num_sms) {
        idx += (long long)gridDim.x * blockDim.x)
 
 __global__ void mat_set_kernel(float* a, int rows, int cols, long long stride, float v) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   ELEMWISE_LOOP((long long)rows * cols) a[(idx / cols) * stride + idx % cols] = v;
 }
 __global__ void copy_rows_from_vec_kernel(const float* __restrict__ vec, float* __restrict__ out, int rows, int cols,
@@ -339,7 +342,8 @@ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 extern "C" int tdnnf_mat_set(tdnnf_ctx* ctx, float* a, int rows, int cols, int stride, float value) {
   PROLOGUE(a && rows >= 0 && cols >= 0 && stride >= cols, "bad matrix");
-  mat_set_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(a, rows, cols, stride, value);
+  TDNNF_CUDA_OK(launch_pdl(mat_set_kernel, dim3(grid_for((long long)rows * cols, 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, a,
+                           rows, cols, stride, value));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }

@@ -32,6 +32,8 @@ __global__ void split_rows_kernel(const float* __restrict__ src, int R, int D, l
                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                   __nv_bfloat16* __restrict__ lo2, int fp16, const float* __restrict__ absmax_in,
                                   float* __restrict__ absmax_out, float* __restrict__ rowsq) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const int kvec = Kpad >> 3;
   const long long total = (long long)groups * Q * kvec;
   const long long total_up = (total + 31) & ~31LL;  // warp-uniform trip count (the by-products use shuffles)
@@ -152,6 +154,8 @@ split_transpose_kernel(const float* __restrict__ src, int R, int J, long long ld
                        GroupRowOffsets c_row_off, const float* __restrict__ scale, int Q, int Qp,
                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, __nv_bfloat16* __restrict__ lo2,
                        float* __restrict__ colsum, float colsum_scale, int fp16, const float* __restrict__ absmax_in) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   // 64 (q) x 64 (j) tile: 256-byte coalesced float4 reads along j, 128-byte (8 x bf16 per lane) writes along q.
   __shared__ float tile[64][65];
   const int c = blockIdx.z;
@@ -225,6 +229,8 @@ split_transpose_kernel(const float* __restrict__ src, int R, int J, long long ld
 // out[r, :] = bias (or 0) for all rows: the starting value when Propagate is split along K.
 __global__ void init_rows_kernel(float* __restrict__ out, int rows, int cols, long long ld,
                                  const float* __restrict__ bias) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const long long total = (long long)rows * cols;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -459,11 +465,10 @@ static int launch_split_rows(tdnnf_ctx* ctx, const float* src, int R, int D, lon
   const long long total = (long long)groups * Q * (Kpad >> 3);
   const int threads = 256;
   const int blocks = (int)std::min<long long>((total + threads - 1) / threads, (long long)ctx->num_sms * 16);
-  split_rows_kernel<<<std::max(blocks, 1), threads, 0, ctx->stream>>>(src, R, D, ld, r, groups, c_row_mul, c_col_mul,
-                                                                      scale, Q, Kpad, pl->base,
-                                                                      pl->base + pl->plane_elems,
-                                                                      pl->np == 3 ? pl->base + 2 * pl->plane_elems : nullptr,
-                                                                      fp16, absmax_in, absmax_out, rowsq);
+  TDNNF_CUDA_OK(launch_pdl(split_rows_kernel, dim3(std::max(blocks, 1)), dim3(threads), 0, ctx->stream, 1, src, R, D, ld, r, groups,
+                           c_row_mul, c_col_mul, scale, Q, Kpad, pl->base, pl->base + pl->plane_elems,
+                           pl->np == 3 ? pl->base + 2 * pl->plane_elems : (__nv_bfloat16*)nullptr, fp16, absmax_in, absmax_out,
+                           rowsq));
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   if (cacheable) cache_store(ctx, key, *pl);
@@ -500,10 +505,10 @@ static int launch_split_transpose(tdnnf_ctx* ctx, const float* src, int R, int J
   dim3 grid(ceil_div(Qp, 64), ceil_div(J, 64), groups), block(256);
   GroupRowOffsets gro;
   for (int i = 0; i < kMaxSeg; ++i) gro.v[i] = (group_row_offsets && i < groups) ? group_row_offsets[i] : 0;
-  split_transpose_kernel<<<grid, block, 0, ctx->stream>>>(src, R, J, ld, r, c_row_mul, c_col_mul, gro, scale, Q, Qp,
-                                                          pl->base, pl->base + pl->plane_elems,
-                                                          pl->np == 3 ? pl->base + 2 * pl->plane_elems : nullptr, colsum,
-                                                          colsum_scale, fp16, absmax_in);
+  TDNNF_CUDA_OK(launch_pdl(split_transpose_kernel, grid, block, 0, ctx->stream, 1, src, R, J, ld, r, c_row_mul, c_col_mul, gro, scale,
+                           Q, Qp, pl->base, pl->base + pl->plane_elems,
+                           pl->np == 3 ? pl->base + 2 * pl->plane_elems : (__nv_bfloat16*)nullptr, colsum, colsum_scale, fp16,
+                           absmax_in));
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   if (cacheable) cache_store(ctx, key, *pl);
@@ -511,7 +516,7 @@ static int launch_split_transpose(tdnnf_ctx* ctx, const float* src, int R, int J
 }
 
 // Split-K factor: fill the SMs in whole waves without starving a unit of K iterations.
-static int choose_splits(int tiles, int iters_per_tile, int num_sms) {
+static int choose_splits(int tiles, int iters_per_tile, int num_sms, int min_iters = 8) {
   // Skinny outputs (the natural-gradient Gram matrices H^T H, J J^T: one or two tiles, K = all rows): even 8 splits
   // leave most SMs idle, and the epilogue of an r x r tile is nothing, so spread K over every SM.  (Measured
   // before: 56 single-CTA launches of 130-175 us each per step.)
@@ -519,7 +524,7 @@ static int choose_splits(int tiles, int iters_per_tile, int num_sms) {
   int best = 1;
   double best_score = -1.0;
   for (int s = 1; s <= 8; ++s) {
-    if (s > 1 && iters_per_tile / s < 8) break;
+    if (s > 1 && iters_per_tile / s < min_iters) break;
     const double units = (double)tiles * s;
     const double waves = std::ceil(units / num_sms);
     const double eff = units / (waves * num_sms);
@@ -545,8 +550,12 @@ static bool pair_eligible(const tdnnf_ctx* ctx, int bn, int m_tiles, int np, boo
 // Sets p->pair and p->splits: `other_tiles` = n-tiles x groups, `iters` = K iterations of one tile.
 static void plan_units(const tdnnf_ctx* ctx, GemmParams* p, int bn, int np, bool mn, int other_tiles, int iters) {
   p->pair = pair_eligible(ctx, bn, p->m_tiles, np, mn) ? 1 : 0;
-  if (p->pair) p->splits = choose_splits((p->m_tiles + 1) / 2 * other_tiles, iters, ctx->num_sms / 2);
-  else p->splits = choose_splits(p->m_tiles * other_tiles, iters, ctx->num_sms);
+  // A 128 x 256 tile takes ~13 us to leave through red.global.add (the L2 atomic units, measured): a split that leaves a
+  // unit fewer than 16 K blocks (~13 us of MMAs) makes the kernel epilogue-bound -- 92 against ~80 us for the data gradient
+  // of the linear layers at 2 splits -- so wide tiles split only when K is long.
+  const int min_iters = bn >= 256 ? 16 : 8;
+  if (p->pair) p->splits = choose_splits((p->m_tiles + 1) / 2 * other_tiles, iters, ctx->num_sms / 2, min_iters);
+  else p->splits = choose_splits(p->m_tiles * other_tiles, iters, ctx->num_sms, min_iters);
 }
 
 template <int BN, int NPA, int NPB, bool MN = false, bool PAIR = false>
@@ -574,24 +583,7 @@ static int launch_gemm_bn(tdnnf_ctx* ctx, const Planes& A, const Planes& B, cons
     tm.products = (NPA == 3) ? 6 : (NPA == 2 && NPB == 2 ? 3 : NPA * NPB);
     TDNNF_CUDA_OK(cudaEventRecord(tm.start, ctx->stream));
   }
-  if constexpr (PAIR) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-    cfg.stream = ctx->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    TDNNF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
-  } else {
-    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, ctx->stream>>>(tmA, tmB, p);
-  }
+  TDNNF_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, ctx->stream, PAIR ? 2 : 1, tmA, tmB, p));
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   if (ctx->gemm_timing) {
@@ -741,8 +733,8 @@ extern "C" int tdnnf_darts_propagate(tdnnf_ctx* ctx, const float* in, int in_row
     if (bias_mode != 0) {
       const long long total = (long long)out_rows * out_dim;
       const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 16);
-      init_rows_kernel<<<blocks, 256, 0, ctx->stream>>>(out, out_rows, out_dim, out_stride,
-                                                        bias_mode == 2 ? bias : nullptr);
+      TDNNF_CUDA_OK(launch_pdl(init_rows_kernel, dim3(blocks), dim3(256), 0, ctx->stream, 1, out, out_rows, out_dim, out_stride,
+                               bias_mode == 2 ? bias : (const float*)nullptr));
       ctx->launches++;
       TDNNF_CUDA_OK(cudaGetLastError());
     }

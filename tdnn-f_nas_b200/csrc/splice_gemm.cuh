@@ -261,25 +261,7 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int lane = threadIdx.x & 31;
 
   // ---- one-time setup
-  for (int i = threadIdx.x; i < kMaxSeg; i += blockDim.x) {
-    meta->seg_a_k[i] = p.seg_a_k[i];
-    meta->seg_a_m[i] = p.seg_a_m[i];
-    meta->seg_a_c[i] = p.seg_a_c[i];
-    meta->seg_b_k[i] = p.seg_b_k[i];
-    meta->seg_b_n[i] = p.seg_b_n[i];
-    meta->seg_b_c[i] = p.seg_b_c[i];
-    meta->m_valid[i] = p.m_valid[i];
-    meta->c_scale[i] = (p.c_scale != nullptr && i < p.c_tiles) ? p.c_scale[i] : 1.0f;
-    // active segment list of group c = i
-    int n = 0;
-    if (i < p.c_tiles) {
-      for (int g = 0; g < p.nseg; ++g) {
-        const bool active = (p.seg_weight == nullptr) || (p.seg_weight[g] != 0.0f);
-        if (active && (p.seg_cmatch[g] < 0 || p.seg_cmatch[g] == i)) meta->list[i][n++] = g;
-      }
-    }
-    meta->cnt[i] = n;
-  }
+  ptx::grid_dep_launch_dependents();  // the next kernel may queue its CTAs behind ours
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
@@ -300,6 +282,27 @@ splice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       ptx::tmem_alloc(tmem_ptr, 2 * kAccCols);
       ptx::tmem_relinquish();
     }
+  }
+  // everything above is private to this CTA; what follows reads what earlier kernels wrote (seg_weight, c_scale, operands)
+  ptx::grid_dep_wait();
+  for (int i = threadIdx.x; i < kMaxSeg; i += blockDim.x) {
+    meta->seg_a_k[i] = p.seg_a_k[i];
+    meta->seg_a_m[i] = p.seg_a_m[i];
+    meta->seg_a_c[i] = p.seg_a_c[i];
+    meta->seg_b_k[i] = p.seg_b_k[i];
+    meta->seg_b_n[i] = p.seg_b_n[i];
+    meta->seg_b_c[i] = p.seg_b_c[i];
+    meta->m_valid[i] = p.m_valid[i];
+    meta->c_scale[i] = (p.c_scale != nullptr && i < p.c_tiles) ? p.c_scale[i] : 1.0f;
+    // active segment list of group c = i
+    int n = 0;
+    if (i < p.c_tiles) {
+      for (int g = 0; g < p.nseg; ++g) {
+        const bool active = (p.seg_weight == nullptr) || (p.seg_weight[g] != 0.0f);
+        if (active && (p.seg_cmatch[g] < 0 || p.seg_cmatch[g] == i)) meta->list[i][n++] = g;
+      }
+    }
+    meta->cnt[i] = n;
   }
   ptx::tc_fence_before_sync();
   __syncwarp();
