@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "context.h"
+#include "ptx.cuh"
 #include "den_slices.h"
 
 using namespace tdnnf;
@@ -121,6 +122,8 @@ constexpr int kStatesPerBlock = 32;
 
 // E[t][p][s] = exp(clamp(x[t*S+s][p])) : 32x32 tiled transpose per frame.
 __global__ void den_exp_transpose_kernel(const float* __restrict__ x, long long ld, int S, int P, float* __restrict__ E) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   __shared__ float tile[32][33];
   const int t = blockIdx.z;
   const int p0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
@@ -140,6 +143,8 @@ __global__ void den_exp_transpose_kernel(const float* __restrict__ x, long long 
 // alpha(0,h,s) = init[h]; tot(0,s) = sum_h init[h]
 __global__ void den_alpha_first_kernel(const float* __restrict__ init, int N, int S, float init_sum,
                                        float* __restrict__ alpha0, float* __restrict__ tot0) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const long long total = (long long)N * S;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
     alpha0[i] = init[i / S];
@@ -155,6 +160,8 @@ den_alpha_frame_kernel(const int2* __restrict__ bwd_ranges, const float4* __rest
                        const float* __restrict__ init, int N, int spb, int S, float leaky, const float* __restrict__ alpha_prev,
                        const float* __restrict__ tot_prev, const float* __restrict__ E_prev,
                        float* __restrict__ alpha_cur, float* __restrict__ tot_cur) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const int SV = S / V;
   const int tps = kDenThreads / SV;  // states processed concurrently by the block (SV <= 256 divides 256 or not: see host)
   const int sv = threadIdx.x % SV;
@@ -221,6 +228,8 @@ den_alpha_frame_kernel(const int2* __restrict__ bwd_ranges, const float4* __rest
 // Also seeds the backward pass: betad(T,h,s) = 1/tot_prob[s]  =>  bsum(T,s) = sum(init)/tot_prob[s].
 __global__ void den_loglike_kernel(const float* __restrict__ tot, int T, int S, float leaky, float init_sum,
                                    float* __restrict__ tot_prob, double* __restrict__ scalars) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   __shared__ double red[256];
   double acc = 0.0;
   for (int s = threadIdx.x; s < S; s += blockDim.x) {
@@ -240,6 +249,8 @@ __global__ void den_loglike_kernel(const float* __restrict__ tot, int T, int S, 
 
 __global__ void den_beta_last_kernel(const float* __restrict__ tot_prob, int N, int S, float init_sum,
                                      float* __restrict__ betad, float* __restrict__ bsum) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const long long total = (long long)N * S;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
     betad[i] = 1.0f / tot_prob[i % S];
@@ -257,6 +268,8 @@ den_beta_frame_kernel(const int2* __restrict__ fwd_ranges, const float4* __restr
                       const float* __restrict__ betad_next, const float* __restrict__ bsum_next,
                       float* __restrict__ betad_cur, float* __restrict__ bsum_cur, float* __restrict__ gamma_t,
                       double* __restrict__ check /* null unless t == 0 */) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const int SV = S / V;
   const int tps = kDenThreads / SV;
   const int sv = threadIdx.x % SV;
@@ -352,6 +365,8 @@ den_beta_frame_kernel(const int2* __restrict__ fwd_ranges, const float4* __restr
 // nnet_output_deriv[t*S+s][p] += w * gamma[t][p][s]   (32x32 tiled transpose-add)
 __global__ void den_deriv_transpose_add_kernel(const float* __restrict__ gamma, int S, int P, float w,
                                                float* __restrict__ deriv, long long ld) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   __shared__ float tile[32][33];
   const int t = blockIdx.z;
   const int p0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
@@ -387,6 +402,8 @@ constexpr int kDen2Threads = 512;
 
 // E[t][sb][p][v] = exp(clamp(x[t*S + sb*V + v][p]))
 __global__ void den2_exp_kernel(const float* __restrict__ x, long long ld, int S, int P, int V, float* __restrict__ E) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   __shared__ float tile[32][33];
   const int t = blockIdx.z;
   const int p0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
@@ -406,6 +423,8 @@ __global__ void den2_exp_kernel(const float* __restrict__ x, long long ld, int S
 // deriv[t*S + s][p] += w * gamma[t][sb][p][v]
 __global__ void den2_deriv_kernel(const float* __restrict__ gamma, int S, int P, int V, float w, float* __restrict__ deriv,
                                   long long ld) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   __shared__ float tile[32][33];
   const int t = blockIdx.z;
   const int p0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
@@ -423,6 +442,8 @@ __global__ void den2_deriv_kernel(const float* __restrict__ gamma, int S, int P,
 // alpha(0, h, :) = init[h] in the [sb][N][V] layout; tot(0, s) = sum(init)
 __global__ void den2_alpha_first_kernel(const float* __restrict__ init, int N, int S, int V, float init_sum,
                                         float* __restrict__ alpha0, float* __restrict__ tot0) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const long long total = (long long)N * S;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
     alpha0[i] = init[(i / V) % N];
@@ -917,7 +938,7 @@ extern "C" int tdnnf_den_forward(tdnnf_den_comp* c, const float* nnet_output, in
   if (c->slices) {
     int rc = den_slices_forward(ctx, c->slices, nnet_output, stride, g->init, g->init_sum, N, P, S, T, c->leaky, c->tot);
     if (rc) return rc;
-    den_loglike_kernel<<<1, 256, 0, st>>>(c->tot, T, S, c->leaky, g->init_sum, c->tot_prob, c->scalars);
+    TDNNF_CUDA_OK(launch_pdl(den_loglike_kernel, dim3(1), dim3(256), 0, st, 1, c->tot, T, S, c->leaky, g->init_sum, c->tot_prob, c->scalars));
     DEN_LAUNCH_CHECK(ctx);
     double lp = 0.0;
     TDNNF_CUDA_OK(cudaMemcpyAsync(&lp, c->scalars, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -928,10 +949,10 @@ extern "C" int tdnnf_den_forward(tdnnf_den_comp* c, const float* nnet_output, in
   }
   if (c->resident) {
     const int V = c->V, C = c->C;
-    den2_exp_kernel<<<dim3((P + 31) / 32, (S + 31) / 32, T), dim3(32, 8), 0, st>>>(nnet_output, stride, S, P, V, c->E);
+    TDNNF_CUDA_OK(launch_pdl(den2_exp_kernel, dim3((P + 31) / 32, (S + 31) / 32, T), dim3(32, 8), 0, st, 1, nnet_output, stride, S, P, V, c->E));
     DEN_LAUNCH_CHECK(ctx);
     TDNNF_CUDA_OK(cudaMemsetAsync(c->tot, 0, sizeof(float) * (size_t)(T + 1) * S, st));
-    den2_alpha_first_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(g->init, N, S, V, g->init_sum, c->alpha, c->tot);
+    TDNNF_CUDA_OK(launch_pdl(den2_alpha_first_kernel, dim3(ctx->num_sms * 4), dim3(256), 0, st, 1, g->init, N, S, V, g->init_sum, c->alpha, c->tot));
     DEN_LAUNCH_CHECK(ctx);
     const DenPlan& pl = c->plan_fwd;
     const int grid = (S / V) * C;
@@ -950,7 +971,7 @@ extern "C" int tdnnf_den_forward(tdnnf_den_comp* c, const float* nnet_output, in
                           (const float*)c->E, c->alpha, c->tot);
     TDNNF_CUDA_OK(le);
     DEN_LAUNCH_CHECK(ctx);
-    den_loglike_kernel<<<1, 256, 0, st>>>(c->tot, T, S, c->leaky, g->init_sum, c->tot_prob, c->scalars);
+    TDNNF_CUDA_OK(launch_pdl(den_loglike_kernel, dim3(1), dim3(256), 0, st, 1, c->tot, T, S, c->leaky, g->init_sum, c->tot_prob, c->scalars));
     DEN_LAUNCH_CHECK(ctx);
     double lp = 0.0;
     TDNNF_CUDA_OK(cudaMemcpyAsync(&lp, c->scalars, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -959,10 +980,10 @@ extern "C" int tdnnf_den_forward(tdnnf_den_comp* c, const float* nnet_output, in
     c->forward_done = true;
     return TDNNF_OK;
   }
-  den_exp_transpose_kernel<<<dim3((P + 31) / 32, (S + 31) / 32, T), dim3(32, 8), 0, st>>>(nnet_output, stride, S, P, c->E);
+  TDNNF_CUDA_OK(launch_pdl(den_exp_transpose_kernel, dim3((P + 31) / 32, (S + 31) / 32, T), dim3(32, 8), 0, st, 1, nnet_output, stride, S, P, c->E));
   DEN_LAUNCH_CHECK(ctx);
   TDNNF_CUDA_OK(cudaMemsetAsync(c->tot, 0, sizeof(float) * (size_t)(T + 1) * S, st));
-  den_alpha_first_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(g->init, N, S, g->init_sum, c->alpha, c->tot);
+  TDNNF_CUDA_OK(launch_pdl(den_alpha_first_kernel, dim3(ctx->num_sms * 4), dim3(256), 0, st, 1, g->init, N, S, g->init_sum, c->alpha, c->tot));
   DEN_LAUNCH_CHECK(ctx);
   const int V = pick_vec(S);
   int blocks, spb;
@@ -975,14 +996,14 @@ extern "C" int tdnnf_den_forward(tdnnf_den_comp* c, const float* nnet_output, in
     float* tc = c->tot + (size_t)t * S;
     const float* Ep = c->E + (size_t)(t - 1) * P * S;
     if (V == 4)
-      den_alpha_frame_kernel<4, 4><<<blocks, kDenThreads, 0, st>>>(g->bwd_ranges, g->trans, g->order_in, g->init, N, spb, S, c->leaky, ap, tp, Ep, ac, tc);
+      TDNNF_CUDA_OK(launch_pdl(den_alpha_frame_kernel<4, 4>, dim3(blocks), dim3(kDenThreads), 0, st, 1, g->bwd_ranges, g->trans, g->order_in, g->init, N, spb, S, c->leaky, ap, tp, Ep, ac, tc));
     else if (V == 2)
-      den_alpha_frame_kernel<2, 4><<<blocks, kDenThreads, 0, st>>>(g->bwd_ranges, g->trans, g->order_in, g->init, N, spb, S, c->leaky, ap, tp, Ep, ac, tc);
+      TDNNF_CUDA_OK(launch_pdl(den_alpha_frame_kernel<2, 4>, dim3(blocks), dim3(kDenThreads), 0, st, 1, g->bwd_ranges, g->trans, g->order_in, g->init, N, spb, S, c->leaky, ap, tp, Ep, ac, tc));
     else
-      den_alpha_frame_kernel<1, 4><<<blocks, kDenThreads, 0, st>>>(g->bwd_ranges, g->trans, g->order_in, g->init, N, spb, S, c->leaky, ap, tp, Ep, ac, tc);
+      TDNNF_CUDA_OK(launch_pdl(den_alpha_frame_kernel<1, 4>, dim3(blocks), dim3(kDenThreads), 0, st, 1, g->bwd_ranges, g->trans, g->order_in, g->init, N, spb, S, c->leaky, ap, tp, Ep, ac, tc));
     DEN_LAUNCH_CHECK(ctx);
   }
-  den_loglike_kernel<<<1, 256, 0, st>>>(c->tot, T, S, c->leaky, g->init_sum, c->tot_prob, c->scalars);
+  TDNNF_CUDA_OK(launch_pdl(den_loglike_kernel, dim3(1), dim3(256), 0, st, 1, c->tot, T, S, c->leaky, g->init_sum, c->tot_prob, c->scalars));
   DEN_LAUNCH_CHECK(ctx);
   double lp = 0.0;
   TDNNF_CUDA_OK(cudaMemcpyAsync(&lp, c->scalars, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1036,8 +1057,8 @@ extern "C" int tdnnf_den_backward(tdnnf_den_comp* c, float deriv_weight, float* 
                           c->betad, c->bsum, c->gamma, c->scalars + 1);
     TDNNF_CUDA_OK(le);
     DEN_LAUNCH_CHECK(ctx);
-    den2_deriv_kernel<<<dim3((P + 31) / 32, (S + 31) / 32, T), dim3(32, 8), 0, st>>>(c->gamma, S, P, V, deriv_weight,
-                                                                                    nnet_output_deriv, stride);
+    TDNNF_CUDA_OK(launch_pdl(den2_deriv_kernel, dim3((P + 31) / 32, (S + 31) / 32, T), dim3(32, 8), 0, st, 1, c->gamma, S, P, V, deriv_weight,
+                                                                                    nnet_output_deriv, stride));
     DEN_LAUNCH_CHECK(ctx);
     double chk = 0.0;
     TDNNF_CUDA_OK(cudaMemcpyAsync(&chk, c->scalars + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1045,8 +1066,8 @@ extern "C" int tdnnf_den_backward(tdnnf_den_comp* c, float deriv_weight, float* 
     *ok = (chk == chk && fabs(chk - (double)S) <= 2.0) ? 1 : 0;
     return TDNNF_OK;
   }
-  den_beta_last_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(c->tot_prob, N, S, g->init_sum, c->betad + (size_t)(T & 1) * N * S,
-                                                         c->bsum + (size_t)(T & 1) * S);
+  TDNNF_CUDA_OK(launch_pdl(den_beta_last_kernel, dim3(ctx->num_sms * 4), dim3(256), 0, st, 1, c->tot_prob, N, S, g->init_sum, c->betad + (size_t)(T & 1) * N * S,
+                                                         c->bsum + (size_t)(T & 1) * S));
   DEN_LAUNCH_CHECK(ctx);
   const int V = pick_vec(S);
   int blocks, spb;
@@ -1063,15 +1084,15 @@ extern "C" int tdnnf_den_backward(tdnnf_den_comp* c, float deriv_weight, float* 
     float* gt = c->gamma + (size_t)t * P * S;
     double* chk = (t == 0) ? c->scalars + 1 : nullptr;
     if (V == 4)
-      den_beta_frame_kernel<4, 4><<<blocks, kDenThreads, 0, st>>>(g->fwd_ranges, g->trans, g->order_out, g->init, N, spb, S, c->leaky, at, tt, Et, bn, sn, bc, sc, gt, chk);
+      TDNNF_CUDA_OK(launch_pdl(den_beta_frame_kernel<4, 4>, dim3(blocks), dim3(kDenThreads), 0, st, 1, g->fwd_ranges, g->trans, g->order_out, g->init, N, spb, S, c->leaky, at, tt, Et, bn, sn, bc, sc, gt, chk));
     else if (V == 2)
-      den_beta_frame_kernel<2, 4><<<blocks, kDenThreads, 0, st>>>(g->fwd_ranges, g->trans, g->order_out, g->init, N, spb, S, c->leaky, at, tt, Et, bn, sn, bc, sc, gt, chk);
+      TDNNF_CUDA_OK(launch_pdl(den_beta_frame_kernel<2, 4>, dim3(blocks), dim3(kDenThreads), 0, st, 1, g->fwd_ranges, g->trans, g->order_out, g->init, N, spb, S, c->leaky, at, tt, Et, bn, sn, bc, sc, gt, chk));
     else
-      den_beta_frame_kernel<1, 4><<<blocks, kDenThreads, 0, st>>>(g->fwd_ranges, g->trans, g->order_out, g->init, N, spb, S, c->leaky, at, tt, Et, bn, sn, bc, sc, gt, chk);
+      TDNNF_CUDA_OK(launch_pdl(den_beta_frame_kernel<1, 4>, dim3(blocks), dim3(kDenThreads), 0, st, 1, g->fwd_ranges, g->trans, g->order_out, g->init, N, spb, S, c->leaky, at, tt, Et, bn, sn, bc, sc, gt, chk));
     DEN_LAUNCH_CHECK(ctx);
   }
-  den_deriv_transpose_add_kernel<<<dim3((P + 31) / 32, (S + 31) / 32, T), dim3(32, 8), 0, st>>>(c->gamma, S, P, deriv_weight,
-                                                                                               nnet_output_deriv, stride);
+  TDNNF_CUDA_OK(launch_pdl(den_deriv_transpose_add_kernel, dim3((P + 31) / 32, (S + 31) / 32, T), dim3(32, 8), 0, st, 1, c->gamma, S, P, deriv_weight,
+                                                                                               nnet_output_deriv, stride));
   DEN_LAUNCH_CHECK(ctx);
   double chk = 0.0;
   TDNNF_CUDA_OK(cudaMemcpyAsync(&chk, c->scalars + 1, sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -4,6 +4,7 @@
 #include <cfloat>
 
 #include "context.h"
+#include "ptx.cuh"
 
 using namespace tdnnf;
 
@@ -37,6 +38,8 @@ __device__ void weff_from_coef(const float* coef, int n, int flags, int share, f
 
 __global__ void darts_coef_kernel(const float* __restrict__ alpha, int n, int flags, float temperature, Uniforms ug,
                                   float u_uniform, int share, float* __restrict__ coef, float* __restrict__ weff) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float c[TDNNF_MAX_OFFSETS];
   for (int i = 0; i < n; ++i) c[i] = alpha[i];
@@ -70,6 +73,8 @@ __global__ void darts_coef_kernel(const float* __restrict__ alpha, int n, int fl
 
 __global__ void darts_weff_kernel(const float* __restrict__ coef, int n, int flags, int share,
                                   float* __restrict__ weff) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float c[TDNNF_MAX_OFFSETS];
   for (int i = 0; i < n; ++i) c[i] = coef[i];
@@ -80,6 +85,8 @@ __global__ void darts_weff_kernel(const float* __restrict__ coef, int n, int fla
 // reference (offset by offset into the delta) is kept.
 __global__ void darts_alpha_update_kernel(const float* __restrict__ s, const float* __restrict__ coef, int n, int flags,
                                           float temperature, int share, float lr, float* __restrict__ dalpha) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float d[TDNNF_MAX_OFFSETS], c[TDNNF_MAX_OFFSETS];
   for (int i = 0; i < n; ++i) { d[i] = dalpha[i]; c[i] = coef[i]; }
@@ -112,6 +119,8 @@ template <int COLS>
 __global__ void softmax_flops_fwd_small(const float* __restrict__ in, int rows, long long in_stride,
                                         float* __restrict__ out, long long out_stride, Uniforms g, float inv_temp,
                                         bool vec) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows;
        r += (long long)gridDim.x * blockDim.x) {
     float x[COLS];
@@ -150,6 +159,8 @@ __global__ void softmax_flops_fwd_small(const float* __restrict__ in, int rows, 
 __global__ void softmax_flops_fwd_warp(const float* __restrict__ in, int rows, int cols, long long in_stride,
                                        float* __restrict__ out, long long out_stride, const float* __restrict__ noise,
                                        float inv_temp) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -174,6 +185,8 @@ template <int COLS>
 __global__ void softmax_flops_bwd_small(const float* __restrict__ out_value, long long ov_stride, float* out_deriv,
                                         long long od_stride, float* in_deriv, long long id_stride, int rows,
                                         float penalty, float inv_temp, int write_back_e, bool vec) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows;
        r += (long long)gridDim.x * blockDim.x) {
     float p[COLS], e[COLS];
@@ -223,6 +236,8 @@ __global__ void softmax_flops_bwd_small(const float* __restrict__ out_value, lon
 __global__ void softmax_flops_bwd_warp(const float* __restrict__ out_value, long long ov_stride, float* out_deriv,
                                        long long od_stride, float* in_deriv, long long id_stride, int rows, int cols,
                                        float penalty, float inv_temp, int write_back_e) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -249,6 +264,8 @@ __global__ void softmax_flops_bwd_warp(const float* __restrict__ out_value, long
 // ------------------------------------------------------------------ CopyN (AddMatBlocks)
 __global__ void copyn_fwd_kernel(const float* __restrict__ in, int rows, int in_cols, long long in_stride,
                                  float* __restrict__ out, int out_cols, long long out_stride, float scale) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const long long total = (long long)rows * out_cols;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -260,6 +277,8 @@ __global__ void copyn_fwd_kernel(const float* __restrict__ in, int rows, int in_
 
 __global__ void copyn_bwd_kernel(const float* __restrict__ od, int rows, int out_cols, long long od_stride,
                                  float* __restrict__ id, int in_cols, long long id_stride, float scale) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const long long total = (long long)rows * in_cols;
   const int nblocks = out_cols / in_cols;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -274,6 +293,8 @@ __global__ void copyn_bwd_kernel(const float* __restrict__ od, int rows, int out
 
 // ------------------------------------------------------------------ Onehot
 __global__ void onehot_fwd_kernel(float* __restrict__ out, int rows, int dim, long long stride, float u) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const long long total = (long long)rows * dim;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -286,6 +307,8 @@ __global__ void onehot_fwd_kernel(float* __restrict__ out, int rows, int dim, lo
 // ------------------------------------------------------------------ AddRowSumMat
 __global__ void add_row_sum_kernel(const float* __restrict__ mat, int rows, int cols, long long stride, float scale,
                                    float* __restrict__ vec) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   __shared__ float red[8][33];
   const int col = blockIdx.x * 32 + threadIdx.x;
   float sum = 0.f;
@@ -306,6 +329,8 @@ __global__ void add_row_sum_kernel(const float* __restrict__ mat, int rows, int 
 __global__ void scale_offset_rows_kernel(const float* __restrict__ in, int rows, int cols, long long in_stride,
                                          float* __restrict__ out, long long out_stride, const float* __restrict__ scale,
                                          const float* __restrict__ offset, bool vec) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   if (vec) {
     const int c4 = cols >> 2;
     const long long total = (long long)rows * c4;
@@ -338,6 +363,8 @@ __global__ void scale_offset_rows_kernel(const float* __restrict__ in, int rows,
 // ------------------------------------------------------------------ ElementwiseProduct
 __global__ void ewprod_fwd_kernel(const float* __restrict__ in, int rows, int D, long long in_stride,
                                   float* __restrict__ out, long long out_stride) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const long long total = (long long)rows * D;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -349,6 +376,8 @@ __global__ void ewprod_fwd_kernel(const float* __restrict__ in, int rows, int D,
 
 __global__ void ewprod_bwd_kernel(const float* __restrict__ in, long long in_stride, const float* __restrict__ od,
                                   long long od_stride, float* __restrict__ id, long long id_stride, int rows, int D) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const long long total = (long long)rows * D;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -384,6 +413,8 @@ __device__ __forceinline__ int mask_block_of(const MaskBlocks& b, int c) {
 __global__ void __launch_bounds__(256) shared_mask_fwd_kernel(const float* __restrict__ p, long long ps, const float* __restrict__ lin,
                                                               long long ls, float* __restrict__ out, long long os, int rows, int cols,
                                                               MaskBlocks blk, float scale, bool vec) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -418,6 +449,8 @@ __global__ void __launch_bounds__(256) shared_mask_bwd_kernel(const float* __res
                                                               long long ls, const float* __restrict__ d_out, long long dos,
                                                               float* __restrict__ d_lin, long long dls, float* __restrict__ d_p,
                                                               long long dps, int rows, int cols, MaskBlocks blk, float scale, bool vec) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -483,7 +516,7 @@ extern "C" int tdnnf_darts_coef(tdnnf_ctx* ctx, const float* alpha, int n, int f
   Uniforms ug;
   for (int i = 0; i < TDNNF_MAX_OFFSETS; ++i) ug.u[i] = (u_gumbel && i < n) ? u_gumbel[i] : 0.5f;
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
-  darts_coef_kernel<<<1, 32, 0, ctx->stream>>>(alpha, n, flags, temperature, ug, u_uniform, share_index, coef, weff);
+  TDNNF_CUDA_OK(launch_pdl(darts_coef_kernel, dim3(1), dim3(32), 0, ctx->stream, 1, alpha, n, flags, temperature, ug, u_uniform, share_index, coef, weff));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -493,7 +526,7 @@ extern "C" int tdnnf_darts_weff_from_coef(tdnnf_ctx* ctx, const float* coef, int
   TDNNF_REQUIRE(ctx && coef && weff, "null argument");
   TDNNF_REQUIRE(n >= 1 && n <= TDNNF_MAX_OFFSETS, "number of time offsets must be in [1,16]");
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
-  darts_weff_kernel<<<1, 32, 0, ctx->stream>>>(coef, n, flags, share_index, weff);
+  TDNNF_CUDA_OK(launch_pdl(darts_weff_kernel, dim3(1), dim3(32), 0, ctx->stream, 1, coef, n, flags, share_index, weff));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -503,7 +536,7 @@ extern "C" int tdnnf_darts_alpha_update(tdnnf_ctx* ctx, const float* s, const fl
   TDNNF_REQUIRE(ctx && s && coef && dalpha, "null argument");
   TDNNF_REQUIRE(n >= 1 && n <= TDNNF_MAX_OFFSETS, "number of time offsets must be in [1,16]");
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
-  darts_alpha_update_kernel<<<1, 32, 0, ctx->stream>>>(s, coef, n, flags, temperature, share_index, lr, dalpha);
+  TDNNF_CUDA_OK(launch_pdl(darts_alpha_update_kernel, dim3(1), dim3(32), 0, ctx->stream, 1, s, coef, n, flags, temperature, share_index, lr, dalpha));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -520,9 +553,9 @@ extern "C" int tdnnf_softmax_flops_fwd(tdnnf_ctx* ctx, const float* in, int rows
     const bool vec = aligned16(in) && aligned16(out) && (in_stride % 4 == 0) && (out_stride % 4 == 0);
     const int grid = grid_for(rows, 128, ctx->num_sms);
     if (cols == 8)
-      softmax_flops_fwd_small<8><<<grid, 128, 0, ctx->stream>>>(in, rows, in_stride, out, out_stride, g, inv_temp, vec);
+      TDNNF_CUDA_OK(launch_pdl(softmax_flops_fwd_small<8>, dim3(grid), dim3(128), 0, ctx->stream, 1, in, rows, in_stride, out, out_stride, g, inv_temp, vec));
     else
-      softmax_flops_fwd_small<16><<<grid, 128, 0, ctx->stream>>>(in, rows, in_stride, out, out_stride, g, inv_temp, vec);
+      TDNNF_CUDA_OK(launch_pdl(softmax_flops_fwd_small<16>, dim3(grid), dim3(128), 0, ctx->stream, 1, in, rows, in_stride, out, out_stride, g, inv_temp, vec));
     LAUNCH_CHECK(ctx);
     return TDNNF_OK;
   }
@@ -541,7 +574,7 @@ extern "C" int tdnnf_softmax_flops_fwd(tdnnf_ctx* ctx, const float* in, int rows
     TDNNF_CUDA_OK(cudaStreamSynchronize(ctx->stream));  // h is a pageable temporary
   }
   const int grid = grid_for((long long)rows * 32, 256, ctx->num_sms);
-  softmax_flops_fwd_warp<<<grid, 256, 0, ctx->stream>>>(in, rows, cols, in_stride, out, out_stride, noise, inv_temp);
+  TDNNF_CUDA_OK(launch_pdl(softmax_flops_fwd_warp, dim3(grid), dim3(256), 0, ctx->stream, 1, in, rows, cols, in_stride, out, out_stride, noise, inv_temp));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -560,15 +593,15 @@ extern "C" int tdnnf_softmax_flops_bwd(tdnnf_ctx* ctx, const float* out_value, i
                      (od_stride % 4 == 0) && (id_stride % 4 == 0);
     const int grid = grid_for(rows, 128, ctx->num_sms);
     if (cols == 8)
-      softmax_flops_bwd_small<8><<<grid, 128, 0, ctx->stream>>>(out_value, ov_stride, out_deriv, od_stride, in_deriv,
-                                                                 id_stride, rows, penalty, inv_temp, write_back_e, vec);
+      TDNNF_CUDA_OK(launch_pdl(softmax_flops_bwd_small<8>, dim3(grid), dim3(128), 0, ctx->stream, 1, out_value, ov_stride, out_deriv, od_stride, in_deriv,
+                                                                 id_stride, rows, penalty, inv_temp, write_back_e, vec));
     else
-      softmax_flops_bwd_small<16><<<grid, 128, 0, ctx->stream>>>(out_value, ov_stride, out_deriv, od_stride, in_deriv,
-                                                                  id_stride, rows, penalty, inv_temp, write_back_e, vec);
+      TDNNF_CUDA_OK(launch_pdl(softmax_flops_bwd_small<16>, dim3(grid), dim3(128), 0, ctx->stream, 1, out_value, ov_stride, out_deriv, od_stride, in_deriv,
+                                                                  id_stride, rows, penalty, inv_temp, write_back_e, vec));
   } else {
     const int grid = grid_for((long long)rows * 32, 256, ctx->num_sms);
-    softmax_flops_bwd_warp<<<grid, 256, 0, ctx->stream>>>(out_value, ov_stride, out_deriv, od_stride, in_deriv,
-                                                          id_stride, rows, cols, penalty, inv_temp, write_back_e);
+    TDNNF_CUDA_OK(launch_pdl(softmax_flops_bwd_warp, dim3(grid), dim3(256), 0, ctx->stream, 1, out_value, ov_stride, out_deriv, od_stride, in_deriv,
+                                                          id_stride, rows, cols, penalty, inv_temp, write_back_e));
   }
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
@@ -581,8 +614,8 @@ extern "C" int tdnnf_copyn_fwd(tdnnf_ctx* ctx, const float* in, int rows, int in
                 "CopyN: output-dim must be a multiple of input-dim");
   if (rows == 0) return TDNNF_OK;
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
-  copyn_fwd_kernel<<<grid_for((long long)rows * out_cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
-      in, rows, in_cols, in_stride, out, out_cols, out_stride, scale);
+  TDNNF_CUDA_OK(launch_pdl(copyn_fwd_kernel, dim3(grid_for((long long)rows * out_cols, 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, 
+      in, rows, in_cols, in_stride, out, out_cols, out_stride, scale));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -594,8 +627,8 @@ extern "C" int tdnnf_copyn_bwd(tdnnf_ctx* ctx, const float* out_deriv, int rows,
                 "CopyN: output-dim must be a multiple of input-dim");
   if (rows == 0) return TDNNF_OK;
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
-  copyn_bwd_kernel<<<grid_for((long long)rows * in_cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
-      out_deriv, rows, out_cols, od_stride, in_deriv, in_cols, id_stride, scale);
+  TDNNF_CUDA_OK(launch_pdl(copyn_bwd_kernel, dim3(grid_for((long long)rows * in_cols, 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, 
+      out_deriv, rows, out_cols, od_stride, in_deriv, in_cols, id_stride, scale));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -605,8 +638,8 @@ extern "C" int tdnnf_onehot_fwd(tdnnf_ctx* ctx, float* out, int rows, int dim, i
   TDNNF_REQUIRE(dim > 0 && out_stride >= dim, "bad matrix shape");
   if (rows == 0) return TDNNF_OK;
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
-  onehot_fwd_kernel<<<grid_for((long long)rows * dim, 256, ctx->num_sms), 256, 0, ctx->stream>>>(out, rows, dim,
-                                                                                                 out_stride, u);
+  TDNNF_CUDA_OK(launch_pdl(onehot_fwd_kernel, dim3(grid_for((long long)rows * dim, 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, out, rows, dim,
+                                                                                                 out_stride, u));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -620,7 +653,7 @@ extern "C" int tdnnf_add_row_sum(tdnnf_ctx* ctx, const float* mat, int rows, int
   int gy = (rows + 255) / 256;
   if (gy > 64) gy = 64;
   if (gy < 1) gy = 1;
-  add_row_sum_kernel<<<dim3((cols + 31) / 32, gy), dim3(32, 8), 0, ctx->stream>>>(mat, rows, cols, stride, scale, vec);
+  TDNNF_CUDA_OK(launch_pdl(add_row_sum_kernel, dim3((cols + 31) / 32, gy), dim3(32, 8), 0, ctx->stream, 1, mat, rows, cols, stride, scale, vec));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -634,8 +667,8 @@ extern "C" int tdnnf_scale_offset_rows(tdnnf_ctx* ctx, const float* in, int rows
   const bool vec = (cols % 4 == 0) && (in_stride % 4 == 0) && (out_stride % 4 == 0) && aligned16(in) &&
                    aligned16(out) && aligned16(scale) && (!offset || aligned16(offset));
   const long long total = vec ? (long long)rows * (cols / 4) : (long long)rows * cols;
-  scale_offset_rows_kernel<<<grid_for(total, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
-      in, rows, cols, in_stride, out, out_stride, scale, offset, vec);
+  TDNNF_CUDA_OK(launch_pdl(scale_offset_rows_kernel, dim3(grid_for(total, 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, 
+      in, rows, cols, in_stride, out, out_stride, scale, offset, vec));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -646,8 +679,8 @@ extern "C" int tdnnf_elementwise_product_fwd(tdnnf_ctx* ctx, const float* in, in
   TDNNF_REQUIRE(out_cols > 0 && in_stride >= 2 * out_cols && out_stride >= out_cols, "bad matrix shape");
   if (rows == 0) return TDNNF_OK;
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
-  ewprod_fwd_kernel<<<grid_for((long long)rows * out_cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
-      in, rows, out_cols, in_stride, out, out_stride);
+  TDNNF_CUDA_OK(launch_pdl(ewprod_fwd_kernel, dim3(grid_for((long long)rows * out_cols, 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, 
+      in, rows, out_cols, in_stride, out, out_stride));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -659,8 +692,8 @@ extern "C" int tdnnf_elementwise_product_bwd(tdnnf_ctx* ctx, const float* in, in
                 "bad matrix shape");
   if (rows == 0) return TDNNF_OK;
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
-  ewprod_bwd_kernel<<<grid_for((long long)rows * out_cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
-      in, in_stride, out_deriv, od_stride, in_deriv, id_stride, rows, out_cols);
+  TDNNF_CUDA_OK(launch_pdl(ewprod_bwd_kernel, dim3(grid_for((long long)rows * out_cols, 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, 
+      in, in_stride, out_deriv, od_stride, in_deriv, id_stride, rows, out_cols));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -691,7 +724,7 @@ extern "C" int tdnnf_shared_mask_fwd(tdnnf_ctx* ctx, const float* p, int rows, i
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
   const bool vec = cols % 4 == 0 && lin_stride % 4 == 0 && out_stride % 4 == 0 && ((uintptr_t)lin & 15) == 0 && ((uintptr_t)out & 15) == 0;
   const int blocks = (int)std::min<long long>(((long long)rows + 7) / 8, (long long)ctx->num_sms * 8);
-  shared_mask_fwd_kernel<<<blocks, 256, 0, ctx->stream>>>(p, p_stride, lin, lin_stride, out, out_stride, rows, cols, b, scale, vec);
+  TDNNF_CUDA_OK(launch_pdl(shared_mask_fwd_kernel, dim3(blocks), dim3(256), 0, ctx->stream, 1, p, p_stride, lin, lin_stride, out, out_stride, rows, cols, b, scale, vec));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -710,8 +743,8 @@ extern "C" int tdnnf_shared_mask_bwd(tdnnf_ctx* ctx, const float* p, int p_strid
   const bool vec = cols % 4 == 0 && lin_stride % 4 == 0 && do_stride % 4 == 0 && (!d_lin || dl_stride % 4 == 0) &&
                    ((uintptr_t)lin & 15) == 0 && ((uintptr_t)d_out & 15) == 0 && ((uintptr_t)d_lin & 15) == 0;
   const int blocks = (int)std::min<long long>(((long long)rows + 7) / 8, (long long)ctx->num_sms * 8);
-  shared_mask_bwd_kernel<<<blocks, 256, 0, ctx->stream>>>(p, p_stride, lin, lin_stride, d_out, do_stride, d_lin, dl_stride, d_p,
-                                                         dp_stride, rows, cols, b, scale, vec);
+  TDNNF_CUDA_OK(launch_pdl(shared_mask_bwd_kernel, dim3(blocks), dim3(256), 0, ctx->stream, 1, p, p_stride, lin, lin_stride, d_out, do_stride, d_lin, dl_stride, d_p,
+                                                         dp_stride, rows, cols, b, scale, vec));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }

@@ -32,10 +32,14 @@ __global__ void mat_set_kernel(float* a, int rows, int cols, long long stride, f
 }
 __global__ void copy_rows_from_vec_kernel(const float* __restrict__ vec, float* __restrict__ out, int rows, int cols,
                                           long long stride) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   ELEMWISE_LOOP((long long)rows * cols) out[(idx / cols) * stride + idx % cols] = vec[idx % cols];
 }
 __global__ void copy_rows_kernel(const float* __restrict__ src, long long ss, float* __restrict__ dst, long long ds,
                                  int rows, int cols, const int32_t* __restrict__ map) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   ELEMWISE_LOOP((long long)rows * cols) {
     const long long r = idx / cols;
     const int c = (int)(idx % cols);
@@ -45,6 +49,8 @@ __global__ void copy_rows_kernel(const float* __restrict__ src, long long ss, fl
 }
 __global__ void add_to_rows_kernel(float alpha, const float* __restrict__ src, long long ss, int rows, int cols,
                                    float* __restrict__ dst, long long ds, const int32_t* __restrict__ map) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   ELEMWISE_LOOP((long long)rows * cols) {
     const long long r = idx / cols;
     const int c = (int)(idx % cols);
@@ -53,10 +59,14 @@ __global__ void add_to_rows_kernel(float alpha, const float* __restrict__ src, l
   }
 }
 __global__ void mat_scale_kernel(float* a, int rows, int cols, long long stride, float s) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   ELEMWISE_LOOP((long long)rows * cols) a[(idx / cols) * stride + idx % cols] *= s;
 }
 __global__ void mat_axpy_kernel(float alpha, const float* __restrict__ src, long long ss, float* __restrict__ dst,
                                 long long ds, int rows, int cols) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   ELEMWISE_LOOP((long long)rows * cols) {
     const long long r = idx / cols;
     const int c = (int)(idx % cols);
@@ -65,6 +75,8 @@ __global__ void mat_axpy_kernel(float alpha, const float* __restrict__ src, long
 }
 __global__ void mat_dot_kernel(const float* __restrict__ a, long long as, const float* __restrict__ b, long long bs,
                                int rows, int cols, double* __restrict__ result) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   __shared__ double red[256];
   double acc = 0.0;
   ELEMWISE_LOOP((long long)rows * cols) {
@@ -83,6 +95,8 @@ __global__ void mat_dot_kernel(const float* __restrict__ a, long long as, const 
 
 __global__ void relu_fwd_kernel(const float* __restrict__ in, int rows, int cols, long long is, float* __restrict__ out,
                                 long long os, bool vec) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   if (vec) {
     const int c4 = cols >> 2;
     ELEMWISE_LOOP((long long)rows * c4) {
@@ -102,6 +116,8 @@ __global__ void relu_fwd_kernel(const float* __restrict__ in, int rows, int cols
 }
 __global__ void relu_bwd_kernel(const float* __restrict__ ov, long long vs, const float* __restrict__ od, long long ds,
                                 float* __restrict__ id, long long is, int rows, int cols, bool vec) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   if (vec) {
     const int c4 = cols >> 2;
     ELEMWISE_LOOP((long long)rows * c4) {
@@ -122,6 +138,8 @@ __global__ void relu_bwd_kernel(const float* __restrict__ ov, long long vs, cons
 }
 __global__ void add_scaled_kernel(const float* a, long long as, float alpha, const float* b, long long bs, float beta,
                                   float* out, long long os, int rows, int cols, bool vec) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   if (vec) {
     const int c4 = cols >> 2;
     ELEMWISE_LOOP((long long)rows * c4) {
@@ -147,6 +165,8 @@ __global__ void add_scaled_kernel(const float* a, long long as, float alpha, con
 template <int MODE>
 __global__ void col_stats_kernel(const float* __restrict__ a, long long as, const float* __restrict__ b, long long bs,
                                  int rows, int cols, float* __restrict__ sums /* 2 x cols */) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   __shared__ float red0[8][33], red1[8][33];
   const int col = blockIdx.x * 32 + threadIdx.x;
   float s0 = 0.f, s1 = 0.f;
@@ -171,6 +191,8 @@ __global__ void col_stats_kernel(const float* __restrict__ a, long long as, cons
 
 // memo rows: 0 mean, 1 uvar, 2 scale ; rows 3,4 scratch sums
 __global__ void bn_finalize_fwd_kernel(float* memo, int cols, int rows, float eps, float target_rms) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
   const float mean = memo[3 * cols + c] / rows;
@@ -183,6 +205,8 @@ __global__ void bn_finalize_fwd_kernel(float* memo, int cols, int rows, float ep
 }
 __global__ void bn_apply_fwd_kernel(const float* __restrict__ in, long long is, float* __restrict__ out, long long os,
                                     int rows, int cols, const float* __restrict__ memo) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   ELEMWISE_LOOP((long long)rows * cols) {
     const long long r = idx / cols;
     const int c = (int)(idx % cols);
@@ -192,6 +216,8 @@ __global__ void bn_apply_fwd_kernel(const float* __restrict__ in, long long is, 
 __global__ void bn_apply_bwd_kernel(const float* __restrict__ ov, long long vs, const float* __restrict__ od,
                                     long long ds, float* __restrict__ id, long long is, int rows, int cols,
                                     float target_rms, const float* __restrict__ memo, const float* __restrict__ sums) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   ELEMWISE_LOOP((long long)rows * cols) {
     const long long r = idx / cols;
     const int c = (int)(idx % cols);
@@ -205,6 +231,8 @@ __global__ void bn_apply_bwd_kernel(const float* __restrict__ ov, long long vs, 
 __global__ void tail_fwd_kernel(const float* __restrict__ x, long long xs, const float* __restrict__ scale,
                                 const float* __restrict__ offset, const float* __restrict__ prev, long long ps, float bs,
                                 float* __restrict__ out, long long os, int rows, int cols) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const int c4 = cols >> 2;
   ELEMWISE_LOOP((long long)rows * c4) {
     const long long r = idx / c4;
@@ -224,6 +252,8 @@ __global__ void tail_fwd_kernel(const float* __restrict__ x, long long xs, const
 __global__ void tail_bwd_kernel(const float* __restrict__ dout, long long dos, const float* __restrict__ x, long long xs,
                                 const float* __restrict__ scale, float bs, float* __restrict__ dx, long long dxs,
                                 float* __restrict__ dprev, long long dps, int rows, int cols) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const int c4 = cols >> 2;
   ELEMWISE_LOOP((long long)rows * c4) {
     const long long r = idx / c4;
@@ -269,6 +299,8 @@ __global__ void tail_fwd_planes_kernel(const float* __restrict__ x, long long xs
                                        const float* __restrict__ offset, const float* __restrict__ prev, long long ps, float bs,
                                        float* __restrict__ out, long long os, int rows, int cols, int Kpad,
                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ rowsq) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   __shared__ float red[32];
   const int c = threadIdx.x * 4;
   const bool live = c < cols;
@@ -298,6 +330,8 @@ __global__ void tail_bwd_planes_kernel(const float* __restrict__ dout, long long
                                        float* __restrict__ dprev, long long dps, int rows, int cols, int Kpad,
                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ rowsq,
                                        float* __restrict__ colsum) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   __shared__ float red[32];
   const int c = threadIdx.x * 4;
   const bool live = c < cols;
@@ -349,46 +383,46 @@ extern "C" int tdnnf_mat_set(tdnnf_ctx* ctx, float* a, int rows, int cols, int s
 }
 extern "C" int tdnnf_copy_rows_from_vec(tdnnf_ctx* ctx, const float* vec, float* out, int rows, int cols, int stride) {
   PROLOGUE(vec && out && rows >= 0 && cols >= 0 && stride >= cols, "bad matrix");
-  copy_rows_from_vec_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(vec, out, rows, cols,
-                                                                                                         stride);
+  TDNNF_CUDA_OK(launch_pdl(copy_rows_from_vec_kernel, dim3(grid_for((long long)rows * cols, 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, vec, out, rows, cols,
+                                                                                                         stride));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
 extern "C" int tdnnf_copy_rows(tdnnf_ctx* ctx, const float* src, int src_stride, float* dst, int dst_stride, int rows,
                                int cols, const int32_t* row_map) {
   PROLOGUE(src && dst && row_map && src_stride >= cols && dst_stride >= cols, "bad matrix");
-  copy_rows_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(src, src_stride, dst, dst_stride,
-                                                                                                 rows, cols, row_map);
+  TDNNF_CUDA_OK(launch_pdl(copy_rows_kernel, dim3(grid_for((long long)rows * cols, 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, src, src_stride, dst, dst_stride,
+                                                                                                 rows, cols, row_map));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
 extern "C" int tdnnf_add_to_rows(tdnnf_ctx* ctx, float alpha, const float* src, int src_stride, int rows, int cols,
                                  float* dst, int dst_stride, const int32_t* row_map) {
   PROLOGUE(src && dst && row_map && src_stride >= cols && dst_stride >= cols, "bad matrix");
-  add_to_rows_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(alpha, src, src_stride, rows,
-                                                                                                   cols, dst, dst_stride, row_map);
+  TDNNF_CUDA_OK(launch_pdl(add_to_rows_kernel, dim3(grid_for((long long)rows * cols, 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, alpha, src, src_stride, rows,
+                                                                                                   cols, dst, dst_stride, row_map));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
 extern "C" int tdnnf_mat_scale(tdnnf_ctx* ctx, float* a, int rows, int cols, int stride, float scale) {
   PROLOGUE(a && rows >= 0 && cols >= 0 && stride >= cols, "bad matrix");
-  mat_scale_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(a, rows, cols, stride, scale);
+  TDNNF_CUDA_OK(launch_pdl(mat_scale_kernel, dim3(grid_for((long long)rows * cols, 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, a, rows, cols, stride, scale));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
 extern "C" int tdnnf_mat_axpy(tdnnf_ctx* ctx, float alpha, const float* src, int src_stride, float* dst,
                               int dst_stride, int rows, int cols) {
   PROLOGUE(src && dst && src_stride >= cols && dst_stride >= cols, "bad matrix");
-  mat_axpy_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(alpha, src, src_stride, dst,
-                                                                                                dst_stride, rows, cols);
+  TDNNF_CUDA_OK(launch_pdl(mat_axpy_kernel, dim3(grid_for((long long)rows * cols, 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, alpha, src, src_stride, dst,
+                                                                                                dst_stride, rows, cols));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
 extern "C" int tdnnf_mat_dot_dev(tdnnf_ctx* ctx, const float* a, int a_stride, const float* b, int b_stride, int rows,
                                  int cols, double* result_dev) {
   PROLOGUE(a && b && result_dev && a_stride >= cols && b_stride >= cols, "bad matrix");
-  mat_dot_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(a, a_stride, b, b_stride, rows,
-                                                                                               cols, result_dev);
+  TDNNF_CUDA_OK(launch_pdl(mat_dot_kernel, dim3(grid_for((long long)rows * cols, 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, a, a_stride, b, b_stride, rows,
+                                                                                               cols, result_dev));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -437,6 +471,8 @@ __device__ __forceinline__ int multi_find(const MultiBufTable& t, int block) {
 
 // out[group[i]] += sum of squares of buffer i
 __global__ void __launch_bounds__(256) multi_sumsq_kernel(const __grid_constant__ MultiBufTable t, double* __restrict__ out) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const int i = multi_find(t, blockIdx.x);
   const int nb = t.first_block[i + 1] - t.first_block[i], b = blockIdx.x - t.first_block[i];
   const long long total = (long long)t.rows[i] * t.cols[i];
@@ -464,6 +500,8 @@ __global__ void __launch_bounds__(256) multi_sumsq_kernel(const __grid_constant_
 // UpdateNnetWithMaxChange leaves the model untouched on a non-finite delta); keep 0 stores exact zeros
 // (ScaleNnet(0.0) is SetZero), keep 1 leaves the source alone (ApplyL2Regularization reads the model).
 __global__ void __launch_bounds__(256) multi_axpy_zero_kernel(const __grid_constant__ MultiBufTable t, float keep) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const int i = multi_find(t, blockIdx.x);
   const int nb = t.first_block[i + 1] - t.first_block[i], b = blockIdx.x - t.first_block[i];
   const long long total = (long long)t.rows[i] * t.cols[i];
@@ -516,7 +554,7 @@ extern "C" int tdnnf_multi_sumsq(tdnnf_ctx* ctx, int n, const float* const* bufs
   int rc = multi_table(ctx, n, bufs, nullptr, rows, cols, strides, nullptr, groups, nullptr, &t, &blocks);
   if (rc) return rc;
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
-  multi_sumsq_kernel<<<blocks, 256, 0, ctx->stream>>>(t, out_dev);
+  TDNNF_CUDA_OK(launch_pdl(multi_sumsq_kernel, dim3(blocks), dim3(256), 0, ctx->stream, 1, t, out_dev));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -530,7 +568,7 @@ extern "C" int tdnnf_multi_axpy_zero(tdnnf_ctx* ctx, int n, float* const* dst, c
   if (rc) return rc;
   for (int i = 0; i < n; ++i) TDNNF_REQUIRE(dst[i] && dst_strides[i] >= cols[i], "bad destination buffer");
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
-  multi_axpy_zero_kernel<<<blocks, 256, 0, ctx->stream>>>(t, 0.f);
+  TDNNF_CUDA_OK(launch_pdl(multi_axpy_zero_kernel, dim3(blocks), dim3(256), 0, ctx->stream, 1, t, 0.f));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -593,7 +631,7 @@ extern "C" int tdnnf_update_with_max_change(tdnnf_ctx* ctx, int n, float* const*
   rc = multi_table(ctx, n, delta, model, rows, cols, delta_strides, model_strides, nullptr, per_buf, &t, &blocks);
   if (rc) return rc;
   for (int i = 0; i < n; ++i) TDNNF_REQUIRE(model[i] && model_strides[i] >= cols[i], "bad model buffer");
-  multi_axpy_zero_kernel<<<blocks, 256, 0, ctx->stream>>>(t, momentum);
+  TDNNF_CUDA_OK(launch_pdl(multi_axpy_zero_kernel, dim3(blocks), dim3(256), 0, ctx->stream, 1, t, momentum));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -622,7 +660,7 @@ extern "C" int tdnnf_apply_l2_regularization(tdnnf_ctx* ctx, int n, float* const
   if (rc) return rc;
   for (int i = 0; i < n; ++i) TDNNF_REQUIRE(delta[i] && delta_strides[i] >= cols[i], "bad delta buffer");
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
-  multi_axpy_zero_kernel<<<blocks, 256, 0, ctx->stream>>>(t, 1.f);
+  TDNNF_CUDA_OK(launch_pdl(multi_axpy_zero_kernel, dim3(blocks), dim3(256), 0, ctx->stream, 1, t, 1.f));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -631,6 +669,8 @@ extern "C" int tdnnf_apply_l2_regularization(tdnnf_ctx* ctx, int n, float* const
 //   deriv[r][c] -= scale * (x - limit) for x > limit,  deriv[r][c] -= scale * (x + limit) for x < -limit.
 __global__ void penalize_out_of_range_kernel(const float* __restrict__ x, long long xs, int rows, int cols, float limit,
                                              float scale, int row_step, int row_offset, float* __restrict__ d, long long ds) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const long long total = (long long)rows * cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = (long long)row_offset + (i / cols) * row_step;
@@ -651,8 +691,8 @@ extern "C" int tdnnf_penalize_out_of_range(tdnnf_ctx* ctx, const float* nnet_out
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
   const long long total = (long long)sub_rows * cols;
   const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 8);
-  penalize_out_of_range_kernel<<<blocks, 256, 0, ctx->stream>>>(nnet_output, stride, sub_rows, cols, limit, scale, row_step,
-                                                               row_offset, deriv, deriv_stride);
+  TDNNF_CUDA_OK(launch_pdl(penalize_out_of_range_kernel, dim3(blocks), dim3(256), 0, ctx->stream, 1, nnet_output, stride, sub_rows, cols, limit, scale, row_step,
+                                                               row_offset, deriv, deriv_stride));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -661,8 +701,8 @@ extern "C" int tdnnf_relu_fwd(tdnnf_ctx* ctx, const float* in, int rows, int col
                               int out_stride) {
   PROLOGUE(in && out && in_stride >= cols && out_stride >= cols, "bad matrix");
   const bool vec = cols % 4 == 0 && in_stride % 4 == 0 && out_stride % 4 == 0 && al16(in) && al16(out);
-  relu_fwd_kernel<<<grid_for((long long)rows * cols / (vec ? 4 : 1), 256, ctx->num_sms), 256, 0, ctx->stream>>>(
-      in, rows, cols, in_stride, out, out_stride, vec);
+  TDNNF_CUDA_OK(launch_pdl(relu_fwd_kernel, dim3(grid_for((long long)rows * cols / (vec ? 4 : 1), 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, 
+      in, rows, cols, in_stride, out, out_stride, vec));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -671,8 +711,8 @@ extern "C" int tdnnf_relu_bwd(tdnnf_ctx* ctx, const float* out_value, int ov_str
   PROLOGUE(out_value && out_deriv && in_deriv && ov_stride >= cols && od_stride >= cols && id_stride >= cols, "bad matrix");
   const bool vec = cols % 4 == 0 && ov_stride % 4 == 0 && od_stride % 4 == 0 && id_stride % 4 == 0 && al16(out_value) &&
                    al16(out_deriv) && al16(in_deriv);
-  relu_bwd_kernel<<<grid_for((long long)rows * cols / (vec ? 4 : 1), 256, ctx->num_sms), 256, 0, ctx->stream>>>(
-      out_value, ov_stride, out_deriv, od_stride, in_deriv, id_stride, rows, cols, vec);
+  TDNNF_CUDA_OK(launch_pdl(relu_bwd_kernel, dim3(grid_for((long long)rows * cols / (vec ? 4 : 1), 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, 
+      out_value, ov_stride, out_deriv, od_stride, in_deriv, id_stride, rows, cols, vec));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -681,8 +721,8 @@ extern "C" int tdnnf_add_scaled(tdnnf_ctx* ctx, const float* a, int a_stride, fl
   PROLOGUE(a && b && out && a_stride >= cols && b_stride >= cols && out_stride >= cols, "bad matrix");
   const bool vec = cols % 4 == 0 && a_stride % 4 == 0 && b_stride % 4 == 0 && out_stride % 4 == 0 && al16(a) && al16(b) &&
                    al16(out);
-  add_scaled_kernel<<<grid_for((long long)rows * cols / (vec ? 4 : 1), 256, ctx->num_sms), 256, 0, ctx->stream>>>(
-      a, a_stride, alpha, b, b_stride, beta, out, out_stride, rows, cols, vec);
+  TDNNF_CUDA_OK(launch_pdl(add_scaled_kernel, dim3(grid_for((long long)rows * cols / (vec ? 4 : 1), 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, 
+      a, a_stride, alpha, b, b_stride, beta, out, out_stride, rows, cols, vec));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -693,13 +733,13 @@ extern "C" int tdnnf_batchnorm_train_fwd(tdnnf_ctx* ctx, const float* in, int ro
   TDNNF_CUDA_OK(cudaMemsetAsync(memo + 3 * (size_t)cols, 0, sizeof(float) * 2 * cols, ctx->stream));
   int gy = (rows + 255) / 256;
   if (gy > 128) gy = 128;
-  col_stats_kernel<0><<<dim3((cols + 31) / 32, gy), dim3(32, 8), 0, ctx->stream>>>(in, in_stride, nullptr, 0, rows, cols,
-                                                                                memo + 3 * (size_t)cols);
+  TDNNF_CUDA_OK(launch_pdl(col_stats_kernel<0>, dim3((cols + 31) / 32, gy), dim3(32, 8), 0, ctx->stream, 1, in, in_stride, nullptr, 0, rows, cols,
+                                                                                memo + 3 * (size_t)cols));
   LAUNCH_CHECK(ctx);
-  bn_finalize_fwd_kernel<<<(cols + 255) / 256, 256, 0, ctx->stream>>>(memo, cols, rows, epsilon, target_rms);
+  TDNNF_CUDA_OK(launch_pdl(bn_finalize_fwd_kernel, dim3((cols + 255) / 256), dim3(256), 0, ctx->stream, 1, memo, cols, rows, epsilon, target_rms));
   LAUNCH_CHECK(ctx);
-  bn_apply_fwd_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(in, in_stride, out,
-                                                                                                    out_stride, rows, cols, memo);
+  TDNNF_CUDA_OK(launch_pdl(bn_apply_fwd_kernel, dim3(grid_for((long long)rows * cols, 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, in, in_stride, out,
+                                                                                                    out_stride, rows, cols, memo));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -717,11 +757,11 @@ extern "C" int tdnnf_batchnorm_train_bwd(tdnnf_ctx* ctx, const float* out_value,
   TDNNF_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * cols, ctx->stream));
   int gy = (rows + 255) / 256;
   if (gy > 128) gy = 128;
-  col_stats_kernel<1><<<dim3((cols + 31) / 32, gy), dim3(32, 8), 0, ctx->stream>>>(out_deriv, od_stride, out_value, ov_stride,
-                                                                                rows, cols, sums);
+  TDNNF_CUDA_OK(launch_pdl(col_stats_kernel<1>, dim3((cols + 31) / 32, gy), dim3(32, 8), 0, ctx->stream, 1, out_deriv, od_stride, out_value, ov_stride,
+                                                                                rows, cols, sums));
   LAUNCH_CHECK(ctx);
-  bn_apply_bwd_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
-      out_value, ov_stride, out_deriv, od_stride, in_deriv, id_stride, rows, cols, target_rms, memo, sums);
+  TDNNF_CUDA_OK(launch_pdl(bn_apply_bwd_kernel, dim3(grid_for((long long)rows * cols, 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, 
+      out_value, ov_stride, out_deriv, od_stride, in_deriv, id_stride, rows, cols, target_rms, memo, sums));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -732,6 +772,8 @@ extern "C" int tdnnf_batchnorm_train_bwd(tdnnf_ctx* ctx, const float* out_value,
 template <int MODE>
 __global__ void nonlin_stats_kernel(const float* __restrict__ x, long long xs, int rows, int cols, double* __restrict__ s0,
                                     double* __restrict__ s1) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   __shared__ float red0[8][33], red1[8][33];
   const int col = blockIdx.x * 32 + threadIdx.x;
   float a0 = 0.f, a1 = 0.f;
@@ -760,6 +802,8 @@ __global__ void nonlin_stats_kernel(const float* __restrict__ x, long long xs, i
 __global__ void relu_repair_kernel(float* __restrict__ in_deriv, long long ld, int rows, int block_dim, int num_blocks_of_dim,
                                    const double* __restrict__ deriv_sum, float lower, float upper, float scale,
                                    double* __restrict__ num_repaired) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < (long long)rows * block_dim;
        idx += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(idx % block_dim);
@@ -775,6 +819,8 @@ __global__ void relu_repair_kernel(float* __restrict__ in_deriv, long long ld, i
 
 // stats[i] += num_frames * mean[i], stats[cols + i] += num_frames * uvar[i]   (BatchNormComponent::StoreStats, norm.cc:583-588)
 __global__ void bn_accumulate_stats_kernel(const float* __restrict__ memo, int cols, float num_frames, double* __restrict__ stats) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < cols) {
     stats[i] += (double)num_frames * (double)memo[i];
@@ -786,8 +832,8 @@ extern "C" int tdnnf_nonlinear_store_stats(tdnnf_ctx* ctx, const float* out_valu
                                            double* value_sum, double* deriv_sum) {
   PROLOGUE(out_value && value_sum && stride >= cols, "bad argument");
   int gy = std::min(128, (rows + 255) / 256);
-  nonlin_stats_kernel<0><<<dim3((cols + 31) / 32, std::max(gy, 1)), dim3(32, 8), 0, ctx->stream>>>(out_value, stride, rows, cols,
-                                                                                                  value_sum, deriv_sum);
+  TDNNF_CUDA_OK(launch_pdl(nonlin_stats_kernel<0>, dim3((cols + 31) / 32, std::max(gy, 1)), dim3(32, 8), 0, ctx->stream, 1, out_value, stride, rows, cols,
+                                                                                                  value_sum, deriv_sum));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -796,8 +842,8 @@ extern "C" int tdnnf_nonlinear_store_backprop_stats(tdnnf_ctx* ctx, const float*
                                                     double* oderiv_sumsq) {
   PROLOGUE(out_deriv && oderiv_sumsq && stride >= cols, "bad argument");
   int gy = std::min(128, (rows + 255) / 256);
-  nonlin_stats_kernel<1><<<dim3((cols + 31) / 32, std::max(gy, 1)), dim3(32, 8), 0, ctx->stream>>>(out_deriv, stride, rows, cols,
-                                                                                                  oderiv_sumsq, nullptr);
+  TDNNF_CUDA_OK(launch_pdl(nonlin_stats_kernel<1>, dim3((cols + 31) / 32, std::max(gy, 1)), dim3(32, 8), 0, ctx->stream, 1, out_deriv, stride, rows, cols,
+                                                                                                  oderiv_sumsq, nullptr));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -807,8 +853,8 @@ extern "C" int tdnnf_relu_repair_gradients(tdnnf_ctx* ctx, float* in_deriv, int 
                                            double* num_dims_repaired) {
   const int cols = block_dim;
   PROLOGUE(in_deriv && deriv_sum && num_dims_repaired && stride >= block_dim && blocks_per_row >= 1, "bad argument");
-  relu_repair_kernel<<<grid_for((long long)rows * block_dim, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
-      in_deriv, stride, rows, block_dim, blocks_per_row, deriv_sum, lower_threshold, upper_threshold, scale, num_dims_repaired);
+  TDNNF_CUDA_OK(launch_pdl(relu_repair_kernel, dim3(grid_for((long long)rows * block_dim, 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, 
+      in_deriv, stride, rows, block_dim, blocks_per_row, deriv_sum, lower_threshold, upper_threshold, scale, num_dims_repaired));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -816,7 +862,7 @@ extern "C" int tdnnf_relu_repair_gradients(tdnnf_ctx* ctx, float* in_deriv, int 
 extern "C" int tdnnf_batchnorm_accumulate_stats(tdnnf_ctx* ctx, const float* memo, int cols, float num_frames, double* stats) {
   const int rows = 1;
   PROLOGUE(memo && stats && cols > 0, "bad argument");
-  bn_accumulate_stats_kernel<<<(cols + 255) / 256, 256, 0, ctx->stream>>>(memo, cols, num_frames, stats);
+  TDNNF_CUDA_OK(launch_pdl(bn_accumulate_stats_kernel, dim3((cols + 255) / 256), dim3(256), 0, ctx->stream, 1, memo, cols, num_frames, stats));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -828,8 +874,8 @@ extern "C" int tdnnf_relu_scale_offset_bypass_fwd(tdnnf_ctx* ctx, const float* x
   TDNNF_REQUIRE(cols % 4 == 0 && x_stride % 4 == 0 && prev_stride % 4 == 0 && out_stride % 4 == 0 && al16(x) && al16(prev) &&
                     al16(out) && al16(scale) && al16(offset),
                 "fused tail needs 16-byte aligned rows (cols and strides multiples of 4)");
-  tail_fwd_kernel<<<grid_for((long long)rows * cols / 4, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
-      x, x_stride, scale, offset, prev, prev_stride, bypass_scale, out, out_stride, rows, cols);
+  TDNNF_CUDA_OK(launch_pdl(tail_fwd_kernel, dim3(grid_for((long long)rows * cols / 4, 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, 
+      x, x_stride, scale, offset, prev, prev_stride, bypass_scale, out, out_stride, rows, cols));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -842,8 +888,8 @@ extern "C" int tdnnf_relu_scale_offset_bypass_bwd(tdnnf_ctx* ctx, const float* d
   TDNNF_REQUIRE(cols % 4 == 0 && do_stride % 4 == 0 && x_stride % 4 == 0 && dx_stride % 4 == 0 && dp_stride % 4 == 0 &&
                     al16(d_out) && al16(x) && al16(d_x) && al16(d_prev) && al16(scale),
                 "fused tail needs 16-byte aligned rows (cols and strides multiples of 4)");
-  tail_bwd_kernel<<<grid_for((long long)rows * cols / 4, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
-      d_out, do_stride, x, x_stride, scale, bypass_scale, d_x, dx_stride, d_prev, dp_stride, rows, cols);
+  TDNNF_CUDA_OK(launch_pdl(tail_bwd_kernel, dim3(grid_for((long long)rows * cols / 4, 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, 
+      d_out, do_stride, x, x_stride, scale, bypass_scale, d_x, dx_stride, d_prev, dp_stride, rows, cols));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -862,8 +908,8 @@ extern "C" int tdnnf_relu_scale_offset_bypass_fwd_planes(tdnnf_ctx* ctx, const f
   if (rc) return rc;
   TDNNF_REQUIRE(pl->Kpad / 4 <= 1024, "fused tail with planes: at most 4096 columns");
   __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(pl->base);
-  tail_fwd_planes_kernel<<<std::min(rows, ctx->num_sms * 4), pl->Kpad / 4, 0, ctx->stream>>>(
-      x, x_stride, scale, offset, prev, prev_stride, bypass_scale, out, out_stride, rows, cols, pl->Kpad, hi, hi + pl->plane_elems, pl->rowsq);
+  TDNNF_CUDA_OK(launch_pdl(tail_fwd_planes_kernel, dim3(std::min(rows, ctx->num_sms * 4)), dim3(pl->Kpad / 4), 0, ctx->stream, 1, 
+      x, x_stride, scale, offset, prev, prev_stride, bypass_scale, out, out_stride, rows, cols, pl->Kpad, hi, hi + pl->plane_elems, pl->rowsq));
   LAUNCH_CHECK(ctx);
   *planes = pl;
   return TDNNF_OK;
@@ -884,9 +930,9 @@ extern "C" int tdnnf_relu_scale_offset_bypass_bwd_planes(tdnnf_ctx* ctx, const f
   TDNNF_REQUIRE(pl->Kpad / 4 <= 1024, "fused tail with planes: at most 4096 columns");
   TDNNF_CUDA_OK(cudaMemsetAsync(pl->colsum, 0, sizeof(float) * (size_t)cols, ctx->stream));
   __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(pl->base);
-  tail_bwd_planes_kernel<<<std::min(rows, ctx->num_sms * 4), pl->Kpad / 4, 0, ctx->stream>>>(
+  TDNNF_CUDA_OK(launch_pdl(tail_bwd_planes_kernel, dim3(std::min(rows, ctx->num_sms * 4)), dim3(pl->Kpad / 4), 0, ctx->stream, 1, 
       d_out, do_stride, x, x_stride, scale, bypass_scale, d_x, dx_stride, d_prev, dp_stride, rows, cols, pl->Kpad, hi,
-      hi + pl->plane_elems, pl->rowsq, pl->colsum);
+      hi + pl->plane_elems, pl->rowsq, pl->colsum));
   LAUNCH_CHECK(ctx);
   pl->has_colsum = true;
   *planes = pl;
@@ -906,6 +952,8 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
 // GetMemo: u ~ U(0,1); !continuous: mask = (u > p) / (1 - p); continuous: mask = 1 - 2p + 4p u  (expected value 1)
 __global__ void dropout_mask_kernel(unsigned long long seed_mixed, unsigned long long counter0, float* __restrict__ mask,
                                     int rows, int cols, long long stride, float p, int continuous) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   ELEMWISE_LOOP((long long)rows * cols) {
     const unsigned long long r = mix64(seed_mixed ^ ((counter0 + (unsigned long long)idx) * 0xD1342543DE82EF95ull));
     const float u = ((float)(r >> 40) + 0.5f) * (1.0f / 16777216.0f);
@@ -918,6 +966,8 @@ __global__ void dropout_mask_kernel(unsigned long long seed_mixed, unsigned long
 // CuMatrixBase::MulRows(mask, indexes): out[r,:] = in[r,:] .* mask[indexes[r],:]   (in may alias out)
 __global__ void mul_rows_indexed_kernel(const float* in, long long is, float* out, long long os, int rows, int cols4,
                                         const float* __restrict__ mask, long long ms, const int32_t* __restrict__ index) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   ELEMWISE_LOOP((long long)rows * cols4) {
     const long long r = idx / cols4;
     const int c = (int)(idx % cols4) * 4;
@@ -929,6 +979,8 @@ __global__ void mul_rows_indexed_kernel(const float* in, long long is, float* ou
 }
 __global__ void mul_rows_indexed_scalar_kernel(const float* in, long long is, float* out, long long os, int rows, int cols,
                                                const float* __restrict__ mask, long long ms, const int32_t* __restrict__ index) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   ELEMWISE_LOOP((long long)rows * cols) {
     const long long r = idx / cols;
     const int c = (int)(idx % cols);
@@ -945,8 +997,8 @@ extern "C" int tdnnf_dropout_mask(tdnnf_ctx* ctx, unsigned long long seed, unsig
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   z = z ^ (z >> 31);
-  dropout_mask_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(z, counter, mask, rows, cols,
-                                                                                                   stride, proportion, continuous);
+  TDNNF_CUDA_OK(launch_pdl(dropout_mask_kernel, dim3(grid_for((long long)rows * cols, 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, z, counter, mask, rows, cols,
+                                                                                                   stride, proportion, continuous));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -955,11 +1007,11 @@ extern "C" int tdnnf_mul_rows_indexed(tdnnf_ctx* ctx, const float* in, int in_st
                                       int cols, const float* mask, int mask_stride, const int32_t* row_index_dev) {
   PROLOGUE(in && out && mask && row_index_dev && in_stride >= cols && out_stride >= cols && mask_stride >= cols, "bad matrix");
   if (cols % 4 == 0 && in_stride % 4 == 0 && out_stride % 4 == 0 && mask_stride % 4 == 0 && al16(in) && al16(out) && al16(mask))
-    mul_rows_indexed_kernel<<<grid_for((long long)rows * cols / 4, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
-        in, in_stride, out, out_stride, rows, cols / 4, mask, mask_stride, row_index_dev);
+    TDNNF_CUDA_OK(launch_pdl(mul_rows_indexed_kernel, dim3(grid_for((long long)rows * cols / 4, 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, 
+        in, in_stride, out, out_stride, rows, cols / 4, mask, mask_stride, row_index_dev));
   else
-    mul_rows_indexed_scalar_kernel<<<grid_for((long long)rows * cols, 256, ctx->num_sms), 256, 0, ctx->stream>>>(
-        in, in_stride, out, out_stride, rows, cols, mask, mask_stride, row_index_dev);
+    TDNNF_CUDA_OK(launch_pdl(mul_rows_indexed_scalar_kernel, dim3(grid_for((long long)rows * cols, 256, ctx->num_sms)), dim3(256), 0, ctx->stream, 1, 
+        in, in_stride, out, out_stride, rows, cols, mask, mask_stride, row_index_dev));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
@@ -983,6 +1035,8 @@ __device__ __forceinline__ float block_reduce_256(float v, bool is_max, float* s
 // ApplyLogSoftMaxPerRow: out = x - max - log(sum exp(x - max)); one CTA of 256 threads per row (grid-stride over rows)
 __global__ void __launch_bounds__(256) log_softmax_fwd_kernel(const float* __restrict__ in, long long is, float* __restrict__ out,
                                                               long long os, int rows, int cols) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   __shared__ float sh[8];
   for (int r = blockIdx.x; r < rows; r += gridDim.x) {
     const float* x = in + r * is;
@@ -999,6 +1053,8 @@ __global__ void __launch_bounds__(256) log_softmax_fwd_kernel(const float* __res
 // DiffLogSoftmaxPerRow: in_deriv = out_deriv - exp(out_value) * sum_row(out_deriv)   (in_deriv may alias out_deriv)
 __global__ void __launch_bounds__(256) log_softmax_bwd_kernel(const float* __restrict__ ov, long long ovs, const float* od,
                                                               long long ods, float* id, long long ids, int rows, int cols) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   __shared__ float sh[8];
   for (int r = blockIdx.x; r < rows; r += gridDim.x) {
     float s = 0.f;
@@ -1012,15 +1068,15 @@ __global__ void __launch_bounds__(256) log_softmax_bwd_kernel(const float* __res
 extern "C" int tdnnf_log_softmax_fwd(tdnnf_ctx* ctx, const float* in, int rows, int cols, int in_stride, float* out,
                                      int out_stride) {
   PROLOGUE(in && out && in_stride >= cols && out_stride >= cols, "bad matrix");
-  log_softmax_fwd_kernel<<<std::min(rows, ctx->num_sms * 8), 256, 0, ctx->stream>>>(in, in_stride, out, out_stride, rows, cols);
+  TDNNF_CUDA_OK(launch_pdl(log_softmax_fwd_kernel, dim3(std::min(rows, ctx->num_sms * 8)), dim3(256), 0, ctx->stream, 1, in, in_stride, out, out_stride, rows, cols));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }
 extern "C" int tdnnf_log_softmax_bwd(tdnnf_ctx* ctx, const float* out_value, int ov_stride, const float* out_deriv,
                                      int od_stride, float* in_deriv, int id_stride, int rows, int cols) {
   PROLOGUE(out_value && out_deriv && in_deriv && ov_stride >= cols && od_stride >= cols && id_stride >= cols, "bad matrix");
-  log_softmax_bwd_kernel<<<std::min(rows, ctx->num_sms * 8), 256, 0, ctx->stream>>>(out_value, ov_stride, out_deriv, od_stride,
-                                                                                   in_deriv, id_stride, rows, cols);
+  TDNNF_CUDA_OK(launch_pdl(log_softmax_bwd_kernel, dim3(std::min(rows, ctx->num_sms * 8)), dim3(256), 0, ctx->stream, 1, out_value, ov_stride, out_deriv, od_stride,
+                                                                                   in_deriv, id_stride, rows, cols));
   LAUNCH_CHECK(ctx);
   return TDNNF_OK;
 }

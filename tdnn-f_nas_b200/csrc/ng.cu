@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "context.h"
+#include "ptx.cuh"
 #include <cstring>
 
 using namespace tdnnf;
@@ -18,6 +19,8 @@ namespace {
 __global__ void __launch_bounds__(256)
 view_sumsq_kernel(const float* __restrict__ in, int in_rows, int in_dim, long long ld, int out_rows, int n,
                   TdnnfOffsets offs, int row_stride, double* __restrict__ sumsq) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   __shared__ double acc[TDNNF_MAX_OFFSETS];
   if (threadIdx.x < TDNNF_MAX_OFFSETS) acc[threadIdx.x] = 0.0;
   __syncthreads();
@@ -64,6 +67,8 @@ view_sumsq_kernel(const float* __restrict__ in, int in_rows, int in_dim, long lo
 __global__ void ng_scale_kernel(const double* __restrict__ sumsq, const float* __restrict__ weff, int n, float ones_rows,
                                 const float* __restrict__ L, int l_ld, const float* __restrict__ WWt, int w_ld, int r,
                                 float* __restrict__ out) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   // 1024 threads, row-strided: every thread has ~r*r/1024 independent loads in flight (the single-block version with a
   // dependent idx/r loop took 17 us at r = 80, all of it load latency)
   __shared__ double red_tr[32], red_dot[32];
@@ -125,6 +130,8 @@ __global__ void __launch_bounds__(256) ng_gram_kernel(const float* __restrict__ 
                                                       int row_stride, double* __restrict__ sumsq) {
   constexpr int W = 16 * TB;
   extern __shared__ float gram_tile[];  // [slab rows][W + 1]
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   // optional second job: this CTA's share of sum over the rows of view i of rowsq[row] (view i = rows offs[i] +
   // k*row_stride, k < N) -> sumsq[blockIdx.x][i]: tr(X X^T) of the spliced operand from the per-row sums of squares
   // the operand split left behind
@@ -276,6 +283,8 @@ __global__ void __launch_bounds__(1024) ng_gram_finish_kernel(float* __restrict_
                                                               const float* __restrict__ weff, int n, float ones_rows,
                                                               double* __restrict__ acc /* [2] */,
                                                               unsigned int* __restrict__ counter, float* __restrict__ out) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   __shared__ float red[8][128];
   __shared__ double red_tr[4], red_dot[4];
   __shared__ double view_sum[TDNNF_MAX_OFFSETS];
@@ -365,6 +374,8 @@ __global__ void __launch_bounds__(kWuCols* kWuGroups)
 ng_w_update_kernel(const float* __restrict__ A, int a_ld, const float* __restrict__ AC, int ac_ld, const float* __restrict__ J,
                    long long j_ld, const float* __restrict__ W, long long w_ld, int r, int D, float* __restrict__ out,
                    long long out_ld) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   extern __shared__ __align__(16) float sM[];  // [kWuRows][Kp] coefficients, then [kWuGroups][kWuRows][kWuCols] partial sums
   const int K = 2 * r, Kp = (K + 7) & ~7;
   float* sP = sM + kWuRows * Kp;
@@ -420,6 +431,8 @@ template <bool ZERO>
 __global__ void mat_axpy_dev_kernel(float alpha, const float* __restrict__ f1, const float* __restrict__ f2,
                                     float* __restrict__ src, long long ss, float* __restrict__ dst, long long ds,
                                     int rows, int cols) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   float a = alpha;
   if (f1) a *= *f1;
   if (f2) a *= *f2;
@@ -444,7 +457,7 @@ extern "C" int tdnnf_darts_view_sumsq(tdnnf_ctx* ctx, const float* in, int in_ro
   for (int i = 0; i < TDNNF_MAX_OFFSETS; ++i) offs.v[i] = i < n ? row_offsets[i] : 0;
   TDNNF_CUDA_OK(cudaMemsetAsync(sumsq, 0, sizeof(double) * n, ctx->stream));
   const int blocks = std::min((in_rows + 7) / 8, ctx->num_sms * 8);
-  view_sumsq_kernel<<<blocks, 256, 0, ctx->stream>>>(in, in_rows, in_dim, in_stride, out_rows, n, offs, row_stride, sumsq);
+  TDNNF_CUDA_OK(launch_pdl(view_sumsq_kernel, dim3(blocks), dim3(256), 0, ctx->stream, 1, in, in_rows, in_dim, in_stride, out_rows, n, offs, row_stride, sumsq));
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   return TDNNF_OK;
@@ -455,7 +468,7 @@ extern "C" int tdnnf_ng_scale(tdnnf_ctx* ctx, const double* sumsq, const float* 
   TDNNF_REQUIRE(ctx && sumsq && L && WWt && out3, "null argument");
   TDNNF_REQUIRE(n >= 1 && n <= TDNNF_MAX_OFFSETS && rank >= 1 && l_stride >= rank && w_stride >= rank, "bad argument");
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
-  ng_scale_kernel<<<1, 1024, 0, ctx->stream>>>(sumsq, weff, n, ones_rows, L, l_stride, WWt, w_stride, rank, out3);
+  TDNNF_CUDA_OK(launch_pdl(ng_scale_kernel, dim3(1), dim3(1024), 0, ctx->stream, 1, sumsq, weff, n, ones_rows, L, l_stride, WWt, w_stride, rank, out3));
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   return TDNNF_OK;
@@ -507,24 +520,8 @@ extern "C" int tdnnf_ng_gram_scale(tdnnf_ctx* ctx, const float* H, int rows, int
       if (e != cudaSuccess) return e;
       attr_set.push_back((const void*)kern);
     }
-    if (!cl) {
-      kern<<<blocks, 256, tile_bytes, ctx->stream>>>(H, rows, rank, h_stride, partials, rowsq, in_rows, n, offs, row_stride, view_partials);
-      return cudaSuccess;
-    }
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(blocks);
-    cfg.blockDim = dim3(256);
-    cfg.dynamicSmemBytes = tile_bytes;
-    cfg.stream = ctx->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kGramCluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, H, rows, rank, (long long)h_stride, partials, rowsq, in_rows, n, offs, row_stride, view_partials);
+    return launch_pdl(kern, dim3(blocks), dim3(256), tile_bytes, ctx->stream, cl ? kGramCluster : 1, H, rows, rank, h_stride, partials,
+                      rowsq, in_rows, n, offs, row_stride, view_partials);
   };
   switch (tb) {
     case 1: TDNNF_CUDA_OK(launch(ng_gram_kernel<1, false>, false)); break;
@@ -538,9 +535,9 @@ extern "C" int tdnnf_ng_gram_scale(tdnnf_ctx* ctx, const float* H, int rows, int
   }
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
-  ng_gram_finish_kernel<<<(rank * rank + 127) / 128, 1024, 0, ctx->stream>>>(partials, nparts, rank, L, l_stride, WWt, w_stride, sumsq,
+  TDNNF_CUDA_OK(launch_pdl(ng_gram_finish_kernel, dim3((rank * rank + 127) / 128), dim3(1024), 0, ctx->stream, 1, partials, nparts, rank, L, l_stride, WWt, w_stride, sumsq,
                                                                             rowsq ? view_partials : nullptr, blocks, weff, n, ones_rows, acc,
-                                                                            counter, out3);
+                                                                            counter, out3));
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   return TDNNF_OK;
@@ -554,9 +551,8 @@ extern "C" int tdnnf_ng_w_update(tdnnf_ctx* ctx, const float* A, int a_stride, c
                 "bad argument (rank <= 128)");
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
   const int Kp = (2 * rank + 7) & ~7;
-  ng_w_update_kernel<<<dim3((dim + kWuCols - 1) / kWuCols, (rank + kWuRows - 1) / kWuRows), kWuCols * kWuGroups,
-                       sizeof(float) * (kWuRows * Kp + kWuGroups * kWuRows * kWuCols), ctx->stream>>>(
-      A, a_stride, AC, ac_stride, J, j_stride, W, w_stride, rank, dim, W_next, out_stride);
+  TDNNF_CUDA_OK(launch_pdl(ng_w_update_kernel, dim3((dim + kWuCols - 1) / kWuCols, (rank + kWuRows - 1) / kWuRows), dim3(kWuCols * kWuGroups), sizeof(float) * (kWuRows * Kp + kWuGroups * kWuRows * kWuCols), ctx->stream, 1, 
+      A, a_stride, AC, ac_stride, J, j_stride, W, w_stride, rank, dim, W_next, out_stride));
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   return TDNNF_OK;
@@ -569,8 +565,8 @@ extern "C" int tdnnf_mat_axpy_dev(tdnnf_ctx* ctx, float alpha, const float* fact
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
   long long b = ((long long)rows * cols + 255) / 256;
   b = std::max(1LL, std::min(b, (long long)ctx->num_sms * 16));
-  mat_axpy_dev_kernel<false><<<(int)b, 256, 0, ctx->stream>>>(alpha, factor1_dev, factor2_dev, const_cast<float*>(src), src_stride, dst,
-                                                              dst_stride, rows, cols);
+  TDNNF_CUDA_OK(launch_pdl(mat_axpy_dev_kernel<false>, dim3((int)b), dim3(256), 0, ctx->stream, 1, alpha, factor1_dev, factor2_dev, const_cast<float*>(src), src_stride, dst,
+                                                              dst_stride, rows, cols));
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   return TDNNF_OK;
@@ -583,8 +579,8 @@ extern "C" int tdnnf_mat_axpy_dev_zero(tdnnf_ctx* ctx, float alpha, const float*
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
   long long b = ((long long)rows * cols + 255) / 256;
   b = std::max(1LL, std::min(b, (long long)ctx->num_sms * 16));
-  mat_axpy_dev_kernel<true><<<(int)b, 256, 0, ctx->stream>>>(alpha, factor1_dev, factor2_dev, src, src_stride, dst, dst_stride, rows,
-                                                             cols);
+  TDNNF_CUDA_OK(launch_pdl(mat_axpy_dev_kernel<true>, dim3((int)b), dim3(256), 0, ctx->stream, 1, alpha, factor1_dev, factor2_dev, src, src_stride, dst, dst_stride, rows,
+                                                             cols));
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   return TDNNF_OK;
@@ -605,6 +601,8 @@ template <int NK>
 __global__ void __launch_bounds__(256) ng_rt_kernel(const float* __restrict__ G, int rows, int cols, long long g_ld,
                                                     const float* __restrict__ Wi, int ri, long long wi_ld, int cols_per_split,
                                                     float* __restrict__ Ht /* [kNgBufs][ri][rows] */) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   __shared__ float Gs[2][32][33];
   __shared__ float Ws[2][NK * 8][33];
   const int to = threadIdx.x & 31, tk = threadIdx.x >> 5;
@@ -664,6 +662,8 @@ template <int NK>
 __global__ void __launch_bounds__(256) ng_lt_kernel(const float* __restrict__ G, int rows, int cols, long long g_ld,
                                                     const float* __restrict__ Wo, int ro, long long wo_ld, int rows_per_split,
                                                     float* __restrict__ T /* [kNgBufs][ro][cols] */) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   __shared__ float Gs[2][32][32];
   __shared__ __align__(16) float Ps[2][NK * 8][36];
   const int tc = threadIdx.x & 31, tk = threadIdx.x >> 5;
@@ -721,6 +721,8 @@ __global__ void __launch_bounds__(256) ng_lt_kernel(const float* __restrict__ G,
 
 // buf[0][e] += buf[1][e] + ... + buf[n-1][e]
 __global__ void ng_sum_bufs_kernel(float* __restrict__ buf, long long elems, int n) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < elems; e += (long long)gridDim.x * blockDim.x) {
     float v = buf[e];
     for (int b = 1; b < n; ++b) v += buf[b * elems + e];
@@ -733,6 +735,8 @@ __global__ void ng_sum_bufs_kernel(float* __restrict__ buf, long long elems, int
 __global__ void __launch_bounds__(256) ng_lu_kernel(float* __restrict__ G, int rows, int cols, long long g_ld,
                                                     const float* __restrict__ P, long long p_ld, const float* __restrict__ Q,
                                                     long long q_ld, int r) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   extern __shared__ __align__(16) float lu_smem[];  // Ps[r][64], Qs[r][64]
   float* Ps = lu_smem;
   float* Qs = lu_smem + r * 64;
@@ -819,18 +823,20 @@ extern "C" int tdnnf_ng_project_gradient(tdnnf_ctx* ctx, float* G, int rows, int
     splits = (cols + per - 1) / per;
     const int bufs = std::min(splits, kNgBufs);
     TDNNF_CUDA_OK(cudaMemsetAsync(Ht, 0, (size_t)bufs * ri * rows * sizeof(float), ctx->stream));
-    if (!ng_dispatch_nk(ri, [&](auto nk) {
-          ng_rt_kernel<decltype(nk)::value><<<dim3(o_tiles, splits), 256, 0, ctx->stream>>>(G, rows, cols, g_stride, Wi, ri, wi_stride,
-                                                                                          per, Ht);
-        }))
-      return fail(TDNNF_ERR_INVALID, "unsupported rank");
+    {
+      cudaError_t err = cudaSuccess;
+      if (!ng_dispatch_nk(ri, [&](auto nk) { err = launch_pdl(ng_rt_kernel<decltype(nk)::value>, dim3(o_tiles, splits), dim3(256), 0, ctx->stream, 1, G, rows, cols, g_stride, Wi, ri, wi_stride,
+                                                                                          per, Ht); }))
+        return fail(TDNNF_ERR_INVALID, "unsupported rank");
+      TDNNF_CUDA_OK(err);
+    }
     if (bufs > 1) {
-      ng_sum_bufs_kernel<<<std::max(1, std::min((ri * rows + 255) / 256, ctx->num_sms * 4)), 256, 0, ctx->stream>>>(
-          Ht, (long long)ri * rows, bufs);
+      TDNNF_CUDA_OK(launch_pdl(ng_sum_bufs_kernel, dim3(std::max(1, std::min((ri * rows + 255) / 256, ctx->num_sms * 4))), dim3(256), 0, ctx->stream, 1, 
+          Ht, (long long)ri * rows, bufs));
       ctx->launches++;
     }
-    ng_lu_kernel<<<dim3((cols + 63) / 64, (rows + 63) / 64), 256, sizeof(float) * ri * 128, ctx->stream>>>(G, rows, cols, g_stride, Ht,
-                                                                                                    rows, Wi, wi_stride, ri);
+    TDNNF_CUDA_OK(launch_pdl(ng_lu_kernel, dim3((cols + 63) / 64, (rows + 63) / 64), dim3(256), sizeof(float) * ri * 128, ctx->stream, 1, G, rows, cols, g_stride, Ht,
+                                                                                                    rows, Wi, wi_stride, ri));
     ctx->launches += 2;
     TDNNF_CUDA_OK(cudaGetLastError());
   }
@@ -841,18 +847,20 @@ extern "C" int tdnnf_ng_project_gradient(tdnnf_ctx* ctx, float* G, int rows, int
     splits = (rows + per - 1) / per;
     const int bufs = std::min(splits, kNgBufs);
     TDNNF_CUDA_OK(cudaMemsetAsync(T, 0, (size_t)bufs * ro * cols * sizeof(float), ctx->stream));
-    if (!ng_dispatch_nk(ro, [&](auto nk) {
-          ng_lt_kernel<decltype(nk)::value><<<dim3(c_tiles, splits), 256, 0, ctx->stream>>>(G, rows, cols, g_stride, Wo, ro, wo_stride,
-                                                                                          per, T);
-        }))
-      return fail(TDNNF_ERR_INVALID, "unsupported rank");
+    {
+      cudaError_t err = cudaSuccess;
+      if (!ng_dispatch_nk(ro, [&](auto nk) { err = launch_pdl(ng_lt_kernel<decltype(nk)::value>, dim3(c_tiles, splits), dim3(256), 0, ctx->stream, 1, G, rows, cols, g_stride, Wo, ro, wo_stride,
+                                                                                          per, T); }))
+        return fail(TDNNF_ERR_INVALID, "unsupported rank");
+      TDNNF_CUDA_OK(err);
+    }
     if (bufs > 1) {
-      ng_sum_bufs_kernel<<<std::max(1, std::min((ro * cols + 255) / 256, ctx->num_sms * 4)), 256, 0, ctx->stream>>>(
-          T, (long long)ro * cols, bufs);
+      TDNNF_CUDA_OK(launch_pdl(ng_sum_bufs_kernel, dim3(std::max(1, std::min((ro * cols + 255) / 256, ctx->num_sms * 4))), dim3(256), 0, ctx->stream, 1, 
+          T, (long long)ro * cols, bufs));
       ctx->launches++;
     }
-    ng_lu_kernel<<<dim3((cols + 63) / 64, (rows + 63) / 64), 256, sizeof(float) * ro * 128, ctx->stream>>>(G, rows, cols, g_stride, Wo,
-                                                                                                    wo_stride, T, cols, ro);
+    TDNNF_CUDA_OK(launch_pdl(ng_lu_kernel, dim3((cols + 63) / 64, (rows + 63) / 64), dim3(256), sizeof(float) * ro * 128, ctx->stream, 1, G, rows, cols, g_stride, Wo,
+                                                                                                    wo_stride, T, cols, ro));
     ctx->launches += 2;
     TDNNF_CUDA_OK(cudaGetLastError());
   }
@@ -870,6 +878,8 @@ struct CopyBlocks {
   int n;
 };
 __global__ void copy_blocks_kernel(const CopyBlocks b) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   for (int k = 0; k < b.n; ++k) {
     const int total = b.rows[k] * b.cols[k];
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -897,7 +907,7 @@ extern "C" int tdnnf_copy_blocks(tdnnf_ctx* ctx, int n, const float* const* src,
   }
   if (most == 0) return TDNNF_OK;
   const int blocks = (int)std::max(1LL, std::min((most + 255) / 256, 64LL));
-  copy_blocks_kernel<<<blocks, 256, 0, ctx->stream>>>(b);
+  TDNNF_CUDA_OK(launch_pdl(copy_blocks_kernel, dim3(blocks), dim3(256), 0, ctx->stream, 1, b));
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   return TDNNF_OK;

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "context.h"
+#include "ptx.cuh"
 
 using namespace tdnnf;
 
@@ -53,6 +54,8 @@ num_fwd_bwd_kernel(const int* __restrict__ state_offsets, const int2* __restrict
                    const float* __restrict__ final_logprob, const float* __restrict__ x, long long x_stride, int S, int T,
                    float* __restrict__ alpha_all, float deriv_weight, float* deriv, long long d_stride,
                    double* __restrict__ scalars) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   extern __shared__ float beta_sm[];  // [2][ns]
   __shared__ float red[kNumThreads];
   const int s = blockIdx.x;
@@ -284,9 +287,9 @@ extern "C" int tdnnf_num_forward_backward(tdnnf_ctx* ctx, const tdnnf_num_graph*
       set = true;
     }
   }
-  num_fwd_bwd_kernel<<<g->num_seqs, kNumThreads, smem, ctx->stream>>>(
+  TDNNF_CUDA_OK(launch_pdl(num_fwd_bwd_kernel, dim3(g->num_seqs), dim3(kNumThreads), smem, ctx->stream, 1, 
       g->state_offsets, g->fwd_ranges, g->bwd_ranges, g->arc_logprob, g->arc_pdf, g->arc_state, g->final_logprob, nnet_output,
-      stride, g->num_seqs, frames_per_seq, g->alpha, deriv_weight, nnet_output_deriv, deriv_stride, g->scalars);
+      stride, g->num_seqs, frames_per_seq, g->alpha, deriv_weight, nnet_output_deriv, deriv_stride, g->scalars));
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   double h[2] = {0, 0};

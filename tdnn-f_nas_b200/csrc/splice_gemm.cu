@@ -130,6 +130,8 @@ __global__ void split_rows_kernel(const float* __restrict__ src, int R, int D, l
 
 // max |x| over a matrix (for operands that were not row-split earlier in the cache scope).
 __global__ void absmax_kernel(const float* __restrict__ src, int R, int D, long long ld, float* __restrict__ absmax_out) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   float amax = 0.f;
   const long long total = (long long)R * D;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
@@ -244,6 +246,8 @@ __global__ void init_rows_kernel(float* __restrict__ out, int rows, int cols, lo
 __global__ void project_gather_kernel(const float* __restrict__ Y, long long y_ld, int out_rows, int rank, int n,
                                       GroupRowOffsets offs, int row_stride, const float* __restrict__ bias,
                                       float* __restrict__ out, long long out_ld) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const long long total = (long long)out_rows * rank;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -260,6 +264,8 @@ __global__ void project_gather_kernel(const float* __restrict__ Y, long long y_l
 __global__ void stack_shift_kernel(const float* __restrict__ od_mat, long long od_ld, int out_rows, int od, int n,
                                    GroupRowOffsets offs, int row_stride, const float* __restrict__ weff, int in_rows,
                                    float* __restrict__ Hs, int ncols) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const long long total = (long long)in_rows * ncols;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -279,6 +285,8 @@ __global__ void stack_shift_kernel(const float* __restrict__ od_mat, long long o
 // dW[j, i*in_dim + d] += alpha * T[(i*od + j), d]
 __global__ void stack_scatter_kernel(const float* __restrict__ T, int in_dim, int od, int n, float alpha, float* __restrict__ dW,
                                      long long dw_ld) {
+  ptx::grid_dep_launch_dependents();
+  ptx::grid_dep_wait();
   const long long total = (long long)n * od * in_dim;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -394,7 +402,7 @@ static int get_absmax(tdnnf_ctx* ctx, const float* src, int R, int D, long long 
   }
   const long long total = (long long)R * D;
   const int blocks = (int)std::max<long long>(1, std::min<long long>((total + 1023) / 1024, (long long)ctx->num_sms * 8));
-  absmax_kernel<<<blocks, 256, 0, ctx->stream>>>(src, R, D, ld, slot);
+  TDNNF_CUDA_OK(launch_pdl(absmax_kernel, dim3(blocks), dim3(256), 0, ctx->stream, 1, src, R, D, ld, slot));
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   *out = slot;
@@ -817,7 +825,7 @@ extern "C" int tdnnf_darts_project(tdnnf_ctx* ctx, const float* in, int in_rows,
   for (int i = 0; i < kMaxSeg; ++i) offs.v[i] = i < n ? row_offsets[i] : 0;
   const long long total = (long long)out_rows * rank;
   const int blocks = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 16));
-  project_gather_kernel<<<blocks, 256, 0, ctx->stream>>>(Y, ncols, out_rows, rank, n, offs, r, bias, out, out_stride);
+  TDNNF_CUDA_OK(launch_pdl(project_gather_kernel, dim3(blocks), dim3(256), 0, ctx->stream, 1, Y, ncols, out_rows, rank, n, offs, r, bias, out, out_stride));
   ctx->launches++;
   TDNNF_CUDA_OK(cudaGetLastError());
   return TDNNF_OK;
@@ -950,8 +958,8 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
         {
           const long long total = (long long)in_rows * ncols;
           const int blocks = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 16));
-          stack_shift_kernel<<<blocks, 256, 0, ctx->stream>>>(out_deriv, od_stride, out_rows, out_dim, n, offs, r, weff, in_rows, Hs,
-                                                              ncols);
+          TDNNF_CUDA_OK(launch_pdl(stack_shift_kernel, dim3(blocks), dim3(256), 0, ctx->stream, 1, out_deriv, od_stride, out_rows, out_dim, n, offs, r, weff, in_rows, Hs,
+                                                              ncols));
           ctx->launches++;
           TDNNF_CUDA_OK(cudaGetLastError());
         }
@@ -989,7 +997,7 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
         if (rc) return rc;
         const long long total = (long long)ncols * in_dim;
         const int blocks = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)ctx->num_sms * 16));
-        stack_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(T, in_dim, out_dim, n, lr, dW, dw_stride);
+        TDNNF_CUDA_OK(launch_pdl(stack_scatter_kernel, dim3(blocks), dim3(256), 0, ctx->stream, 1, T, in_dim, out_dim, n, lr, dW, dw_stride));
         ctx->launches++;
         TDNNF_CUDA_OK(cudaGetLastError());
         return TDNNF_OK;
