@@ -8,12 +8,48 @@
 
 namespace tdnnf {
 
-bool pdl_enabled() {
+// zero-fill as a kernel: unlike a memset node it takes part in programmatic dependent launch chains
+__global__ void zero_words_kernel(uint32_t* __restrict__ p, size_t n) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0u;
+}
+
+int zero_async(tdnnf_ctx* ctx, void* p, size_t bytes) {
+  if (bytes == 0) return TDNNF_OK;
+  if ((bytes & 3) != 0 || (reinterpret_cast<uintptr_t>(p) & 3) != 0) {
+    TDNNF_CUDA_OK(cudaMemsetAsync(p, 0, bytes, ctx->stream));
+    return TDNNF_OK;
+  }
+  const size_t n = bytes / 4;
+  const int blocks = (int)std::max<size_t>(1, std::min<size_t>((n + 255) / 256, (size_t)ctx->num_sms * 8));
+  TDNNF_CUDA_OK(launch_pdl(zero_words_kernel, dim3(blocks), dim3(256), 0, ctx->stream, 1, static_cast<uint32_t*>(p), n));
+  ctx->launches++;
+  return TDNNF_OK;
+}
+
+bool pdl_enabled(const char* file) {
   static const bool on = [] {
     const char* e = getenv("TDNNF_PDL");
     return e ? atoi(e) != 0 : true;
   }();
-  return on;
+  static const std::string off = [] {
+    const char* e = getenv("TDNNF_PDL_OFF");
+    return std::string(e ? e : "");
+  }();
+  if (!on) return false;
+  if (file == nullptr || off.empty()) return true;
+  const char* base = strrchr(file, '/');
+  base = base ? base + 1 : file;
+  size_t pos = 0;
+  while (pos <= off.size()) {
+    size_t comma = off.find(',', pos);
+    if (comma == std::string::npos) comma = off.size();
+    const std::string tok = off.substr(pos, comma - pos);
+    if (!tok.empty() && strstr(base, tok.c_str()) != nullptr) return false;
+    pos = comma + 1;
+  }
+  return true;
 }
 
 

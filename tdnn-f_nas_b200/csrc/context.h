@@ -35,10 +35,11 @@ int fail(int code, const std::string& msg);
 // Kernel launch with programmatic dependent launch allowed (the kernel must begin with ptx::grid_dep_wait() before it
 // touches anything a predecessor wrote): its CTAs are scheduled while the tail of the previous kernel drains, so launch
 // latency and prologue leave the critical path.  TDNNF_PDL=0 turns the attribute off.  cluster_x > 1 adds a cluster.
-bool pdl_enabled();
+bool pdl_enabled(const char* file = nullptr);  // TDNNF_PDL_OFF=<substrings of source file names, comma separated> turns it off per file
+int zero_async(tdnnf_ctx* ctx, void* p, size_t bytes);  // zero-fill on the context's stream (a kernel)
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
-                              Args&&... args) {
+inline cudaError_t launch_pdl_at(const char* file, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 int cluster_x, Args&&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
@@ -54,7 +55,7 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     attr[na].val.clusterDim.z = 1;
     ++na;
   }
-  if (pdl_enabled()) {
+  if (pdl_enabled(file)) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
@@ -63,6 +64,8 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(std::forward<Args>(args))...);
 }
+
+#define launch_pdl(...) launch_pdl_at(__FILE__, __VA_ARGS__)
 
 #define TDNNF_REQUIRE(cond, msg)                                                   \
   do {                                                                             \

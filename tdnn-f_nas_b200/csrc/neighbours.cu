@@ -928,7 +928,7 @@ extern "C" int tdnnf_relu_scale_offset_bypass_bwd_planes(tdnnf_ctx* ctx, const f
   int rc = tdnnf::planes_alloc_for_producer(ctx, d_x, rows, cols, dx_stride, &pl);
   if (rc) return rc;
   TDNNF_REQUIRE(pl->Kpad / 4 <= 1024, "fused tail with planes: at most 4096 columns");
-  TDNNF_CUDA_OK(cudaMemsetAsync(pl->colsum, 0, sizeof(float) * (size_t)cols, ctx->stream));
+  { int zrc = zero_async(ctx, pl->colsum, sizeof(float) * (size_t)cols); if (zrc) return zrc; }
   __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(pl->base);
   TDNNF_CUDA_OK(launch_pdl(tail_bwd_planes_kernel, dim3(std::min(rows, ctx->num_sms * 4)), dim3(pl->Kpad / 4), 0, ctx->stream, 1, 
       d_out, do_stride, x, x_stride, scale, bypass_scale, d_x, dx_stride, d_prev, dp_stride, rows, cols, pl->Kpad, hi,

@@ -822,7 +822,7 @@ extern "C" int tdnnf_ng_project_gradient(tdnnf_ctx* ctx, float* G, int rows, int
     const int per = (((cols + splits - 1) / splits) + 31) / 32 * 32;
     splits = (cols + per - 1) / per;
     const int bufs = std::min(splits, kNgBufs);
-    TDNNF_CUDA_OK(cudaMemsetAsync(Ht, 0, (size_t)bufs * ri * rows * sizeof(float), ctx->stream));
+    { int zrc = zero_async(ctx, Ht, (size_t)bufs * ri * rows * sizeof(float)); if (zrc) return zrc; }
     {
       cudaError_t err = cudaSuccess;
       if (!ng_dispatch_nk(ri, [&](auto nk) { err = launch_pdl(ng_rt_kernel<decltype(nk)::value>, dim3(o_tiles, splits), dim3(256), 0, ctx->stream, 1, G, rows, cols, g_stride, Wi, ri, wi_stride,
@@ -846,7 +846,7 @@ extern "C" int tdnnf_ng_project_gradient(tdnnf_ctx* ctx, float* G, int rows, int
     const int per = (((rows + splits - 1) / splits) + 31) / 32 * 32;
     splits = (rows + per - 1) / per;
     const int bufs = std::min(splits, kNgBufs);
-    TDNNF_CUDA_OK(cudaMemsetAsync(T, 0, (size_t)bufs * ro * cols * sizeof(float), ctx->stream));
+    { int zrc = zero_async(ctx, T, (size_t)bufs * ro * cols * sizeof(float)); if (zrc) return zrc; }
     {
       cudaError_t err = cudaSuccess;
       if (!ng_dispatch_nk(ro, [&](auto nk) { err = launch_pdl(ng_lt_kernel<decltype(nk)::value>, dim3(c_tiles, splits), dim3(256), 0, ctx->stream, 1, G, rows, cols, g_stride, Wo, ro, wo_stride,

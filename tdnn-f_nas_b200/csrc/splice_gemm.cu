@@ -815,7 +815,7 @@ extern "C" int tdnnf_darts_project(tdnnf_ctx* ctx, const float* in, int in_rows,
   p.row_cadd = 1;
   p.alpha = 1.0f;
   if (p.splits > 1) {
-    TDNNF_CUDA_OK(cudaMemsetAsync(Y, 0, (size_t)in_rows * ncols * sizeof(float), ctx->stream));
+    { int zrc = zero_async(ctx, Y, (size_t)in_rows * ncols * sizeof(float)); if (zrc) return zrc; }
     p.accumulate = 1;
     p.atomic = 1;
   }
@@ -968,7 +968,7 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
         if (rc) return rc;
         rc = launch_split_rows(ctx, Hs, in_rows, ncols, ncols, r, r, 1, 0, nullptr, Q, KpS, &HS);
         if (rc) return rc;
-        TDNNF_CUDA_OK(cudaMemsetAsync(T, 0, (size_t)ncols * in_dim * sizeof(float), ctx->stream));
+        { int zrc = zero_async(ctx, T, (size_t)ncols * in_dim * sizeof(float)); if (zrc) return zrc; }
         constexpr int kBKmn = 32;
         GemmParams p;
         memset(&p, 0, sizeof(p));
@@ -1014,7 +1014,7 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
       if (rc) return rc;
       rc = launch_split_rows(ctx, out_deriv, out_rows, out_dim, od_stride, 1, 1, 0, 0, nullptr, out_rows, KpO, &ODR);
       if (rc) return rc;
-      if (s) TDNNF_CUDA_OK(cudaMemsetAsync(s, 0, sizeof(float) * n, ctx->stream));
+      if (s) { int zrc = zero_async(ctx, s, sizeof(float) * n); if (zrc) return zrc; }
       constexpr int kBKmn = 32;
       GemmParams p;
       memset(&p, 0, sizeof(p));
@@ -1094,7 +1094,7 @@ extern "C" int tdnnf_darts_backprop_params(tdnnf_ctx* ctx, const float* in_value
   rc = launch_split_transpose(ctx, out_deriv, out_rows, out_dim, od_stride, 1, 1, 0, 0, nullptr, out_rows, Rp,
                               out_rows, &ODT, nullptr, dbias, lr, gnp, amax_od);
   if (rc) return rc;
-  if (s) TDNNF_CUDA_OK(cudaMemsetAsync(s, 0, sizeof(float) * n, ctx->stream));
+  if (s) { int zrc = zero_async(ctx, s, sizeof(float) * n); if (zrc) return zrc; }
 
   auto waste = [](int x) { return (double)round_up(x, kBM) / x; };
   const bool m_is_in = waste(in_dim) <= waste(out_dim);  // which dimension rides the 128-row MMA M
