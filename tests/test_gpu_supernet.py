@@ -99,7 +99,9 @@ def test_bottleneck_search_step(gumbel):
     # Two GPU trajectories over three steps: split-K sums arrive in a different order from run to run (more so with
     # programmatic dependent launch), and ONE ReLU pre-activation within rounding of zero that comes out on the other side
     # moves the smallest gradients (the alpha of the bottom block) by ~1e-2 of their size: 5 of 10 runs showed the same four
-    # elements off by 7e-6 against max |alpha| = 2.7e-3, none with TDNNF_PDL=0.  The kernel-level equivalence of the fused and
+    # elements off by 7e-6 against max |alpha| = 2.7e-3, none with TDNNF_PDL=0; tools/diag_tie_or_race.py found, in every
+    # diverging pair, exactly ONE mask mismatch, at a pre-activation of 5e-7..2e-6 (rms 1), with all activations equal to
+    # ~2e-6 (profiles/r02_pdl_sign_tie.md).  The kernel-level equivalence of the fused and
     # the component-by-component mask is tested to 1e-6 in tests/test_gpu_bottleneck_block.py; here the bar is relative to the
     # largest alpha.
     assert np.abs(a1 - a2).max() <= 1e-2 * np.abs(a2).max(), (a1, a2)
