@@ -539,6 +539,45 @@ int tdnnf_host_num_graph_arrays(const tdnnf_host_num_graph* g, int* num_seqs, in
 int tdnnf_host_num_graph_free(tdnnf_host_num_graph* g);
 int tdnnf_num_graph_create_from_host(tdnnf_ctx* ctx, const tdnnf_host_num_graph* g, tdnnf_num_graph** out);
 
+/* den.fst in the OpenFst binary form chain-make-den-fst writes (VectorFst<StdArc>, "vector"/"standard"; a
+ * "compact_acceptor" is read too): same result as tdnnf_den_graph_parse_fst_text on `fstprint den.fst`. */
+int tdnnf_den_graph_parse_fst_binary(const char* buf, uint64_t len, int num_pdfs, tdnnf_host_graph** out);
+
+/* Training examples: a Kaldi table archive of NnetChainExample (`ark:cegs.N.ark`, binary, or `ark,t:` text) -> the
+ * minibatch the step takes.  Replaces, for this path's inputs, kaldi: nnet3/nnet-chain-example.cc
+ * NnetChainExample::Read / MergeChainExamples, nnet3/nnet-example.cc NnetIo::Read, chain/chain-supervision.cc
+ * Supervision::Read (called by nnet3-chain-merge-egs | nnet3-chain-train in the recipes,
+ * ref: steps/nnet3/chain/train.py via run_TDNN_DARTSV3_fbk_stride_pretrain.sh:181-209, `--constrained false` at :195); formats in csrc/egs_io.cc.
+ * Host only; the archive is parsed from memory (the caller reads or maps the file); every count in the data is checked
+ * against the buffer, a malformed archive is TDNNF_ERR_INVALID with the example key and offset in tdnnf_last_error().
+ *   inputs: name, indexes (n, t, x per row) and the matrix expanded to dense fp32 whatever its on-disk coding;
+ *   supervision: weight, num_sequences, frames_per_seq, label_dim, the FST(s) (arcs: src, dst, ilabel = pdf-id + 1;
+ *   tropical weights), alignment pdfs, derivative weights.
+ * tdnnf_chain_egs_merge_*: examples [first, first + count) as ONE minibatch, laid out as the kernels take it: row =
+ * (rank of t within the sequence) * num_seqs + sequence (nnet3's t-major order with n fastest), sequences numbered in
+ * example order.  merge_input: out == NULL returns the dimensions only.  merge_supervision: derivative weights
+ * [frames_per_seq * num_seqs] in that order (1 where an example has none), the mean supervision weight, and the
+ * per-sequence numerator graph (unconstrained examples: their <Fsts>; constrained examples of one sequence: their FST). */
+typedef struct tdnnf_chain_egs tdnnf_chain_egs;
+int tdnnf_chain_egs_read_ark(const char* buf, uint64_t len, int max_examples /* <= 0: all */, tdnnf_chain_egs** out);
+int tdnnf_chain_egs_free(tdnnf_chain_egs* e);
+int tdnnf_chain_egs_count(const tdnnf_chain_egs* e, int* num_examples);
+int tdnnf_chain_egs_example(const tdnnf_chain_egs* e, int i, const char** key, int* binary, int* num_inputs, int* num_outputs);
+int tdnnf_chain_egs_input(const tdnnf_chain_egs* e, int i, int j, const char** name, int* rows, int* cols,
+                          const int32_t** indexes /* rows x 3 */, const float** data /* rows x cols */);
+int tdnnf_chain_egs_supervision(const tdnnf_chain_egs* e, int i, int j, const char** name, float* weight, int* num_sequences,
+                                int* frames_per_seq, int* label_dim, int* e2e, int* num_fsts, const int32_t** indexes,
+                                int* num_deriv_weights, const float** deriv_weights, int* num_alignment_pdfs,
+                                const int32_t** alignment_pdfs);
+int tdnnf_chain_egs_fst(const tdnnf_chain_egs* e, int i, int j, int k, int* start, int* num_states, int* num_arcs,
+                        const int32_t** arcs /* num_arcs x 3: src dst ilabel */, const float** arc_weights, int* num_finals,
+                        const int32_t** final_states, const float** final_weights);
+int tdnnf_chain_egs_merge_input(const tdnnf_chain_egs* e, int first, int count, const char* name, float* out, int64_t out_floats,
+                                int* num_t, int* num_seqs, int* cols, int* first_t);
+int tdnnf_chain_egs_merge_supervision(const tdnnf_chain_egs* e, int first, int count, const char* name, int num_pdfs,
+                                      float* deriv_weights, int deriv_weights_floats, int* num_seqs, int* frames_per_seq,
+                                      float* weight, tdnnf_host_num_graph** num_graph /* NULL: not built */);
+
 /* ------------------------------------------------------------------ data-parallel reduction - */
 /* SURVEY 8b capability (8): the deltas of the ranks' minibatch shards are SUMMED over NCCL (NVLink / NVSwitch): the
  * synchronous replacement of the multi-job `nnet3-average` (ref: steps/libs/nnet3/train/common.py:144-164; learning

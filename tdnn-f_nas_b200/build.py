@@ -27,6 +27,7 @@ CXX_SOURCES = [
     "nnet3/natural_gradient.cc",
     "nnet3/handle_api.cc",
     "chain_io.cc",
+    "egs_io.cc",
 ]
 
 NVCC_FLAGS = [

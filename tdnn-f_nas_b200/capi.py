@@ -122,6 +122,18 @@ def _declare(lib):
     sig("tdnnf_host_num_graph_arrays", [vp, c_int_p, c_int_p, pp_i, pp_i, pp_i, pp_f, pp_i, pp_i, pp_f])
     sig("tdnnf_host_num_graph_free", [vp])
     sig("tdnnf_num_graph_create_from_host", [vp, vp, C.POINTER(vp)])
+    sig("tdnnf_den_graph_parse_fst_binary", [C.c_char_p, C.c_uint64, i, C.POINTER(vp)])
+    pp_c = C.POINTER(C.c_char_p)
+    sig("tdnnf_chain_egs_read_ark", [C.c_char_p, C.c_uint64, i, C.POINTER(vp)])
+    sig("tdnnf_chain_egs_free", [vp])
+    sig("tdnnf_chain_egs_count", [vp, c_int_p])
+    sig("tdnnf_chain_egs_example", [vp, i, pp_c, c_int_p, c_int_p, c_int_p])
+    sig("tdnnf_chain_egs_input", [vp, i, i, pp_c, c_int_p, c_int_p, pp_i, pp_f])
+    sig("tdnnf_chain_egs_supervision", [vp, i, i, pp_c, c_float_p, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, pp_i, c_int_p, pp_f,
+                                        c_int_p, pp_i])
+    sig("tdnnf_chain_egs_fst", [vp, i, i, i, c_int_p, c_int_p, c_int_p, pp_i, pp_f, c_int_p, pp_i, pp_f])
+    sig("tdnnf_chain_egs_merge_input", [vp, i, i, C.c_char_p, vp, C.c_int64, c_int_p, c_int_p, c_int_p, c_int_p])
+    sig("tdnnf_chain_egs_merge_supervision", [vp, i, i, C.c_char_p, i, vp, i, c_int_p, c_int_p, c_float_p, C.POINTER(vp)])
     sig("tdnnf_dp_unique_id", [C.c_char_p, i])
     sig("tdnnf_dp_comm_create", [vp, i, i, C.c_char_p, C.POINTER(vp)])
     sig("tdnnf_dp_comm_adopt", [vp, vp, i, i, C.POINTER(vp)])
@@ -151,7 +163,7 @@ class TdnnfError(RuntimeError):
 
 def check(rc: int):
     if rc != 0:
-        raise TdnnfError(f"tdnnf error {rc}: {load().tdnnf_last_error().decode()}")
+        raise TdnnfError(f"tdnnf error {rc}: {load().tdnnf_last_error().decode(errors='replace')}")
 
 
 def _ptr(t) -> int:
@@ -472,6 +484,139 @@ def parse_den_fst_text(text: str, num_pdfs: int) -> dict:
                     state=arr(st, A2, np.int32), init=arr(init, N, np.float32), num_arcs=A2 // 2)
     finally:
         load().tdnnf_host_graph_free(h)
+
+
+def _host_graph_dict(h) -> dict:
+    import numpy as np
+
+    n, p, a = C.c_int32(), C.c_int32(), C.c_int32()
+    check(load().tdnnf_host_graph_dims(h, C.byref(n), C.byref(p), C.byref(a)))
+    fr, br, pd, st = c_int_p(), c_int_p(), c_int_p(), c_int_p()
+    pr, init = c_float_p(), c_float_p()
+    check(load().tdnnf_host_graph_arrays(h, C.byref(fr), C.byref(br), C.byref(pr), C.byref(pd), C.byref(st), C.byref(init)))
+    arr = lambda ptr, count, dt: np.ctypeslib.as_array(ptr, shape=(count,)).astype(dt).copy()
+    N, A2 = n.value, a.value
+    return dict(num_states=N, num_pdfs=p.value, fwd_ranges=arr(fr, 2 * N, np.int32).reshape(N, 2),
+                bwd_ranges=arr(br, 2 * N, np.int32).reshape(N, 2), prob=arr(pr, A2, np.float32), pdf=arr(pd, A2, np.int32),
+                state=arr(st, A2, np.int32), init=arr(init, N, np.float32), num_arcs=A2 // 2)
+
+
+def parse_den_fst_binary(data: bytes, num_pdfs: int) -> dict:
+    """den.fst as chain-make-den-fst writes it (OpenFst binary) -> the same dict as parse_den_fst_text.  Host only."""
+    h = vp()
+    check(load().tdnnf_den_graph_parse_fst_binary(data, len(data), num_pdfs, C.byref(h)))
+    try:
+        return _host_graph_dict(h)
+    finally:
+        load().tdnnf_host_graph_free(h)
+
+
+def _host_num_graph_dict(h) -> dict:
+    import numpy as np
+
+    ns, na = C.c_int32(), C.c_int32()
+    so, fr, br, pd, st = c_int_p(), c_int_p(), c_int_p(), c_int_p(), c_int_p()
+    lp, fl = c_float_p(), c_float_p()
+    check(load().tdnnf_host_num_graph_arrays(h, C.byref(ns), C.byref(na), C.byref(so), C.byref(fr), C.byref(br), C.byref(lp),
+                                             C.byref(pd), C.byref(st), C.byref(fl)))
+    arr = lambda ptr, count, dt: np.ctypeslib.as_array(ptr, shape=(count,)).astype(dt).copy() if count else np.zeros(0, dt)
+    k = ns.value
+    offs = arr(so, k + 1, np.int32)
+    N, A = int(offs[-1]), na.value
+    return dict(num_seqs=k, state_offsets=offs, num_arcs=A, fwd_ranges=arr(fr, 2 * N, np.int32).reshape(N, 2),
+                bwd_ranges=arr(br, 2 * N, np.int32).reshape(N, 2), arc_logprob=arr(lp, 2 * A, np.float32),
+                arc_pdf=arr(pd, 2 * A, np.int32), arc_state=arr(st, 2 * A, np.int32), final_logprob=arr(fl, N, np.float32))
+
+
+class ChainEgs:
+    """A Kaldi archive of NnetChainExample parsed on the host (tdnnf_chain_egs_*; formats in csrc/egs_io.cc).  `data` is
+    the archive's bytes (binary `ark:` or text `ark,t:`).  Examples are dicts of numpy arrays; merge_* give the minibatch
+    nnet3-chain-merge-egs would form from examples [first, first + count) in the row order the kernels take."""
+
+    def __init__(self, data: bytes, max_examples: int = 0):
+        self.h = vp()
+        check(load().tdnnf_chain_egs_read_ark(data, len(data), max_examples, C.byref(self.h)))
+        n = C.c_int32()
+        check(load().tdnnf_chain_egs_count(self.h, C.byref(n)))
+        self.count = n.value
+
+    def close(self):
+        if self.h:
+            load().tdnnf_chain_egs_free(self.h)
+            self.h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return self.count
+
+    def example(self, i: int) -> dict:
+        import numpy as np
+
+        lib = load()
+        arr = lambda ptr, shape, dt: (np.ctypeslib.as_array(ptr, shape=shape).astype(dt).copy() if int(np.prod(shape)) else np.zeros(shape, dt))
+        key, binary, ni, no = C.c_char_p(), C.c_int32(), C.c_int32(), C.c_int32()
+        check(lib.tdnnf_chain_egs_example(self.h, i, C.byref(key), C.byref(binary), C.byref(ni), C.byref(no)))
+        ex = dict(key=key.value.decode(errors="replace"), binary=bool(binary.value), inputs=[], outputs=[])
+        for j in range(ni.value):
+            name, r, c_, ix, d = C.c_char_p(), C.c_int32(), C.c_int32(), c_int_p(), c_float_p()
+            check(lib.tdnnf_chain_egs_input(self.h, i, j, C.byref(name), C.byref(r), C.byref(c_), C.byref(ix), C.byref(d)))
+            ex["inputs"].append(dict(name=name.value.decode(errors="replace"), indexes=arr(ix, (r.value, 3), np.int32),
+                                     data=arr(d, (r.value, c_.value), np.float32)))
+        for j in range(no.value):
+            name, w, ns, fps, ld, e2e, nf = C.c_char_p(), C.c_float(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+            ix, ndw, dw, nap, ap = c_int_p(), C.c_int32(), c_float_p(), C.c_int32(), c_int_p()
+            check(lib.tdnnf_chain_egs_supervision(self.h, i, j, C.byref(name), C.byref(w), C.byref(ns), C.byref(fps), C.byref(ld),
+                                                  C.byref(e2e), C.byref(nf), C.byref(ix), C.byref(ndw), C.byref(dw), C.byref(nap),
+                                                  C.byref(ap)))
+            fsts = []
+            for k in range(nf.value):
+                st, nst, na, nfin = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+                a3, aw, fs, fw = c_int_p(), c_float_p(), c_int_p(), c_float_p()
+                check(lib.tdnnf_chain_egs_fst(self.h, i, j, k, C.byref(st), C.byref(nst), C.byref(na), C.byref(a3), C.byref(aw),
+                                              C.byref(nfin), C.byref(fs), C.byref(fw)))
+                fsts.append(dict(start=st.value, num_states=nst.value, arcs=arr(a3, (na.value, 3), np.int32),
+                                 weights=arr(aw, (na.value,), np.float32), final_states=arr(fs, (nfin.value,), np.int32),
+                                 final_weights=arr(fw, (nfin.value,), np.float32)))
+            ex["outputs"].append(dict(name=name.value.decode(errors="replace"), weight=w.value, num_sequences=ns.value, frames_per_seq=fps.value,
+                                      label_dim=ld.value, e2e=bool(e2e.value), fsts=fsts,
+                                      indexes=arr(ix, (ns.value * fps.value, 3), np.int32), deriv_weights=arr(dw, (ndw.value,), np.float32),
+                                      alignment_pdfs=arr(ap, (nap.value,), np.int32)))
+        return ex
+
+    def merge_input(self, first: int, count: int, name: str):
+        """-> (array [num_t, num_seqs, dim] (row = t_rank * num_seqs + sequence), first_t)"""
+        import numpy as np
+
+        T, S, D, t0 = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        args = (self.h, first, count, name.encode())
+        check(load().tdnnf_chain_egs_merge_input(*args, None, 0, C.byref(T), C.byref(S), C.byref(D), C.byref(t0)))
+        out = np.empty((T.value, S.value, D.value), np.float32)
+        check(load().tdnnf_chain_egs_merge_input(*args, out.ctypes.data, out.size, C.byref(T), C.byref(S), C.byref(D), C.byref(t0)))
+        return out, t0.value
+
+    def merge_supervision(self, first: int, count: int, name: str, num_pdfs: int, graph: bool = True) -> dict:
+        """-> dict(num_seqs, frames_per_seq, weight, deriv_weights [frames_per_seq, num_seqs], num_graph (as parse_num_fst_texts))"""
+        import numpy as np
+
+        S, T, w = C.c_int32(), C.c_int32(), C.c_float()
+        args = (self.h, first, count, name.encode(), num_pdfs)
+        check(load().tdnnf_chain_egs_merge_supervision(*args, None, 0, C.byref(S), C.byref(T), C.byref(w), None))
+        dw = np.empty((T.value, S.value), np.float32)
+        g = vp()
+        check(load().tdnnf_chain_egs_merge_supervision(*args, dw.ctypes.data, dw.size, C.byref(S), C.byref(T), C.byref(w),
+                                                       C.byref(g) if graph else None))
+        out = dict(num_seqs=S.value, frames_per_seq=T.value, weight=w.value, deriv_weights=dw)
+        if graph:
+            try:
+                out["num_graph"] = _host_num_graph_dict(g)
+            finally:
+                load().tdnnf_host_num_graph_free(g)
+        return out
 
 
 def parse_num_fst_texts(texts: Sequence[str], num_pdfs: int) -> dict:

@@ -14,21 +14,11 @@
 #include <string>
 #include <vector>
 
-#include "context.h"
+#include "chain_io.h"
 
 using namespace tdnnf;
 
-namespace {
-
-struct FsmArc {
-  int src, dst, ilabel;
-  float weight;
-};
-struct Fsm {
-  int start = -1, num_states = 0;
-  std::vector<FsmArc> arcs;
-  std::map<int, float> finals;
-};
+namespace tdnnf {
 
 int parse_fsm(const char* text, size_t len, Fsm* f, std::string* err) {
   std::istringstream in(std::string(text, len));
@@ -92,7 +82,7 @@ int parse_fsm(const char* text, size_t len, Fsm* f, std::string* err) {
   return TDNNF_OK;
 }
 
-}  // namespace
+}  // namespace tdnnf
 
 struct tdnnf_host_graph {
   int num_states = 0, num_pdfs = 0, num_transitions = 0;  // num_transitions = forward list + backward list
@@ -112,6 +102,10 @@ extern "C" int tdnnf_den_graph_parse_fst_text(const char* text, uint64_t len, in
   std::string err;
   int rc = parse_fsm(text, (size_t)len, &f, &err);
   if (rc) return fail(rc, "den.fst: " + err);
+  return build_host_den_graph(f, num_pdfs, out);
+}
+
+int tdnnf::build_host_den_graph(const Fsm& f, int num_pdfs, tdnnf_host_graph** out) {
   const int N = f.num_states;
   const size_t A = f.arcs.size();
   TDNNF_REQUIRE(A > 0, "den.fst has no arcs");
@@ -221,18 +215,28 @@ extern "C" int tdnnf_den_graph_create_from_host(tdnnf_ctx* ctx, const tdnnf_host
 extern "C" int tdnnf_num_graph_parse_fst_texts(const char* const* texts, const uint64_t* lens, int num_seqs, int num_pdfs,
                                                tdnnf_host_num_graph** out) {
   TDNNF_REQUIRE(texts && lens && out && num_seqs > 0 && num_pdfs > 0, "bad argument");
+  std::vector<Fsm> fsms((size_t)num_seqs);
+  for (int s = 0; s < num_seqs; ++s) {
+    std::string err;
+    int rc = parse_fsm(texts[s], (size_t)lens[s], &fsms[s], &err);
+    if (rc) return fail(rc, "numerator FST " + std::to_string(s) + ": " + err);
+  }
+  return build_host_num_graph(fsms, num_pdfs, out);
+}
+
+int tdnnf::build_host_num_graph(const std::vector<Fsm>& fsms, int num_pdfs, tdnnf_host_num_graph** out) {
+  const int num_seqs = (int)fsms.size();
+  TDNNF_REQUIRE(out && num_seqs > 0 && num_pdfs > 0, "bad argument");
   tdnnf_host_num_graph* g = new tdnnf_host_num_graph();
   g->num_seqs = num_seqs;
   g->state_offsets.push_back(0);
   struct Arc { int src, dst, pdf; float lp; };
   std::vector<Arc> arcs;
   for (int s = 0; s < num_seqs; ++s) {
-    Fsm f;
-    std::string err;
-    int rc = parse_fsm(texts[s], (size_t)lens[s], &f, &err);
-    if (rc) {
+    const Fsm& f = fsms[s];
+    if (f.start < 0 || f.num_states <= 0) {
       delete g;
-      return fail(rc, "numerator FST " + std::to_string(s) + ": " + err);
+      return fail(TDNNF_ERR_INVALID, "numerator FST " + std::to_string(s) + ": empty FST");
     }
     const int base = g->state_offsets.back();
     // the start state becomes the sequence's first state (tdnnf_num_graph_create's convention)
