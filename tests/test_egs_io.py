@@ -236,3 +236,39 @@ def test_corrupted_bytes_never_crash(data):
                 egs.merge_supervision(i, 1, ex["outputs"][0]["name"], ex["outputs"][0]["label_dim"])
         except capi.TdnnfError:
             pass
+
+
+def synth_supervision_examples(rng, S, P, T, seed):
+    """One single-sequence unconstrained example per sequence of synth.make_num_graphs (the recipes' egs before merging),
+    plus the graph they came from."""
+    graph = synth.make_num_graphs(S, P, T, seed=seed)
+    exs = []
+    for s, text in enumerate(synth.num_graphs_to_fst_texts(graph)):
+        fst = dict(start=0, num_states=int(graph["state_offsets"][s + 1] - graph["state_offsets"][s]), arcs=[], finals={})
+        for line in text.splitlines():
+            f = line.split()
+            if len(f) >= 4:
+                fst["arcs"].append((int(f[0]), int(f[1]), int(f[2]), float(f[4])))
+            else:
+                fst["finals"][int(f[0])] = float(f[1])
+        ex = W.random_example(rng, f"utt{s}", frames=T, num_pdfs=P, deriv_weights=False)
+        ex["outputs"][0]["fsts"] = [fst]
+        exs.append(ex)
+    return graph, exs
+
+
+@pytest.mark.parametrize("binary", [True, False])
+def test_merged_supervision_through_the_oracle_numerator(binary):
+    """archive -> merged numerator graph -> the oracle's GenericNumeratorComputation gives what it gives on the generator's
+    own arrays (log-prob and derivative): the graph dict the reader returns is the one the numerator kernels take."""
+    from oracle import oracle as O
+
+    S, P, T = 5, 17, 9
+    rng = np.random.default_rng(21)
+    graph, exs = synth_supervision_examples(rng, S, P, T, seed=6)
+    m = capi.ChainEgs(W.ark(exs, binary)).merge_supervision(0, S, "output", P)
+    x = (rng.standard_normal((T * S, P)) * 2).astype(np.float32)
+    lp_ref, d_ref, ok_ref = O.num_forward_backward(graph, x, T, deriv_weight=1.0)
+    lp, d, ok = O.num_forward_backward(m["num_graph"], x, T, deriv_weight=1.0)
+    assert ok and ok_ref and lp == pytest.approx(lp_ref, rel=1e-6)
+    np.testing.assert_allclose(d, d_ref, rtol=1e-5, atol=1e-7)
