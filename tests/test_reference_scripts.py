@@ -108,3 +108,34 @@ def test_flops_vector_is_the_cumulative_bottleneck_width():
     p = np.full((1, 8), 0.125, np.float32)
     _, e = O.softmax_flops_bwd(p, np.zeros((1, 8), np.float32), 8.0, False, 1.0)
     assert (-np.asarray(e).ravel()).tolist() == [float(w) for w in widths]
+
+
+def test_xconfig_layer_classes_emit_the_lines_the_generators_were_fed():
+    """The reference's own xconfig layer classes (composite_layers.py: XconfigTdnnfDARTSV3Layer, XconfigTdnnfLayer), RUN on the
+    recipes' layer lines: every component they emit is a known type, the parameter-free ones are accepted as they are, and
+    the TdnnDARTSV3Component / TdnnComponent lines carry the keys InitFromConfig reads here (the device-side acceptance of
+    such lines is tests/test_zz_gpu_reference_compat.py, on the generators' output, which main() of tools/make_golden_ref.py
+    checks line for line against these)."""
+    from tdnnf_nas_b200 import nnet3
+
+    fx = _fixture()["xconfig_layers"]
+    assert len(fx) == 5
+    for layer_line, lines in fx.items():
+        comps = _component_lines(lines)
+        assert [t for _, t, _ in comps] == [("TdnnDARTSV3Component" if layer_line.startswith("tdnnfdartsv3") else "TdnnComponent")] * 2 + [
+            "RectifiedLinearComponent", "BatchNormComponent", "GeneralDropoutComponent", "NoOpComponent"]
+        stride = int(re.search(r"time-stride=(\d+)", layer_line).group(1))
+        for name, typ, rest in comps:
+            kv = _kv(rest)
+            if typ in HOST_TYPES:
+                comp = nnet3.Component.new(typ, rest)
+                assert comp.input_dim() == comp.output_dim() == 1536
+            elif typ in DEVICE_TYPES:
+                known = {"input-dim", "output-dim", "l2-regularize", "max-change", "use-bias", "time-offsets", "orthonormal-constraint",
+                         "use-gumbel", "use-entropy", "free-select", "update-alpha", "update-theta", "uniform-sample", "Temp-Proportion"}
+                assert set(kv) <= known, set(kv) - known
+                want = ("0" if stride == 0 else (f"-{stride},0" if name.endswith(".linear") else f"0,{stride}"))
+                assert kv["time-offsets"] == want
+                assert (kv.get("use-bias") == "false") == name.endswith(".linear")
+        # the bypass the step fuses into its tail kernels: Sum(Scale(0.66, input), dropout output)
+        assert lines[-1].endswith(f"input=Sum(Scale(0.66, tdnn1.dropout), {comps[0][0].split('.')[0]}.dropout)")

@@ -10,9 +10,13 @@ the output tests/golden/ref_scripts.json is committed and travels to the GPU box
   * local/chain_NAS/scripts/generate_config.py                                    -- the TdnnDARTSV3Component lines of the
     context-offset supernet (executed on a final.config_temp).
 
-The two *.config inputs are what steps/nnet3/xconfig_to_configs.py would write for the recipes' xconfig; upstream's
-xconfig package is not in the reference tree, so they are laid out here from the format strings of
-steps/libs/nnet3/xconfig/composite_layers.py:733-770 (tdnnfdartsv3-layer) and :156-190 (tdnnf-layer)."""
+  * steps/libs/nnet3/xconfig/composite_layers.py::XconfigTdnnfDARTSV3Layer / XconfigTdnnfLayer  -- the component lines
+    the xconfig layer classes emit for the recipes' `tdnnfdartsv3-layer` / `tdnnf-layer` lines (imported and run; their
+    base class XconfigLayerBase lives in upstream's basic_layers.py, which the reference does not ship, so a stub of it
+    that parses the key=value pairs and supplies the input descriptor is put on the import path).
+
+The two *.config inputs are what steps/nnet3/xconfig_to_configs.py would write for the recipes' xconfig: darts_layer() /
+stock_layer() below lay them out, and main() checks them line for line against what the reference's layer classes emit."""
 import importlib.util
 import json
 import os
@@ -74,8 +78,70 @@ def stock_layer(name, inp, stride, dim=1536, bottleneck=160):
     ]
 
 
+STUB_BASE = '''
+class XconfigLayerBase(object):
+    """Stand-in for upstream steps/libs/nnet3/xconfig/basic_layers.py (not in the reference tree): key=value parsing with
+    the defaults' types, and the descriptor of the layer's input."""
+    def __init__(self, first_token, key_to_value, prev_names=None):
+        self.layer_type = first_token
+        self.name = key_to_value["name"]
+        self.set_default_configs()
+        for k, v in key_to_value.items():
+            if k == "name":
+                continue
+            if k not in self.config:
+                raise RuntimeError("unknown option " + k)
+            d = self.config[k]
+            self.config[k] = (v.lower() == "true") if isinstance(d, bool) else int(v) if isinstance(d, int) else float(v) if isinstance(d, float) else v
+        self.descriptors = {"input": {"dim": prev_names["dim"], "final-string": prev_names["name"]}}
+        self.set_derived_configs()
+        self.check_configs()
+'''
+
+
+def xconfig_layers():
+    """Run the reference's xconfig layer classes on the recipes' layer lines."""
+    with tempfile.TemporaryDirectory() as d:
+        pkg = os.path.join(d, "libs", "nnet3", "xconfig")
+        os.makedirs(pkg)
+        for sub in ("libs", "libs/nnet3", "libs/nnet3/xconfig"):
+            open(os.path.join(d, sub, "__init__.py"), "w").close()
+        open(os.path.join(pkg, "basic_layers.py"), "w").write(STUB_BASE)
+        sys.path.insert(0, d)
+        try:
+            spec = importlib.util.spec_from_file_location(
+                "ref_composite_layers", os.path.join(REF, "steps", "libs", "nnet3", "xconfig", "composite_layers.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+        finally:
+            sys.path.remove(d)
+            for m in [m for m in sys.modules if m == "libs" or m.startswith("libs.")]:
+                del sys.modules[m]
+    # run_TDNN_DARTSV3_fbk_stride_pretrain.sh:124,143 and run_tdnn_7q_fbk_40_manual.sh (tdnnf_opts; time-stride 1 / 0 / 6)
+    darts_opts = ("l2-regularize=0.01 dropout-proportion=0.0 bypass-scale=0.66 use-gumbel=false use-entropy=false free-select=false "
+                  "update-alpha=false update-theta=true uniform-sample=true")
+    stock_opts = "l2-regularize=0.01 dropout-proportion=0.0 bypass-scale=0.66"
+    out = {}
+    for first, cls, line in (
+            ("tdnnfdartsv3-layer", mod.XconfigTdnnfDARTSV3Layer, f"name=tdnnf2 {darts_opts} dim=1536 bottleneck-dim=160 time-stride=6"),
+            ("tdnnfdartsv3-layer", mod.XconfigTdnnfDARTSV3Layer, f"name=tdnnf3 {darts_opts} dim=1536 bottleneck-dim=160 time-stride=1"),
+            ("tdnnf-layer", mod.XconfigTdnnfLayer, f"name=tdnnf2 {stock_opts} dim=1536 bottleneck-dim=160 time-stride=1"),
+            ("tdnnf-layer", mod.XconfigTdnnfLayer, f"name=tdnnf5 {stock_opts} dim=1536 bottleneck-dim=160 time-stride=0"),
+            ("tdnnf-layer", mod.XconfigTdnnfLayer, f"name=tdnnf6 {stock_opts} dim=1536 bottleneck-dim=160 time-stride=3")):
+        kv = dict(t.split("=", 1) for t in line.split())
+        layer = cls(first, kv, {"dim": 1536, "name": "tdnn1.dropout"})
+        out[first + " " + line] = [l for name, l in layer.get_full_config() if name == "final"]
+    return out
+
+
 def main():
     out = {}
+    out["xconfig_layers"] = xl = xconfig_layers()
+    # the hand-laid inputs of the config generators below are what the reference's layer classes emit
+    by_name = {k.split()[1] + "/" + k.split()[0] + "/" + [t for t in k.split() if t.startswith("time-stride")][0]: v for k, v in xl.items()}
+    assert by_name["name=tdnnf3/tdnnfdartsv3-layer/time-stride=1"] == darts_layer("tdnnf3", "tdnn1.dropout"), "darts_layer() drifted from the reference"
+    for nm, stride in (("tdnnf2", 1), ("tdnnf5", 0), ("tdnnf6", 3)):
+        assert by_name[f"name={nm}/tdnnf-layer/time-stride={stride}"] == stock_layer(nm, "tdnn1.dropout", stride), "stock_layer() drifted from the reference"
     spec = importlib.util.spec_from_file_location(
         "ref_temperature_schedule", os.path.join(REF, "steps", "libs", "nnet3", "train", "temperature_schedule.py"))
     mod = importlib.util.module_from_spec(spec)
