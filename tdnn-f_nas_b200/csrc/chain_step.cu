@@ -100,6 +100,8 @@ struct NcclApi {
 };
 constexpr int kNcclFloat = 7, kNcclSum = 0;  // ncclFloat32, ncclSum (stable enum values of nccl.h)
 
+std::string g_nccl_error = "NCCL is not loadable (libnccl.so.2)";
+
 NcclApi* nccl_api() {
   static NcclApi api;
   static bool tried = false;
@@ -112,7 +114,8 @@ NcclApi* nccl_api() {
   for (const char* nm : names)
     if (!api.handle) api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
   if (!api.handle) {
-    api.error = std::string("NCCL is not loadable: ") + (dlerror() ? dlerror() : "libnccl.so.2 not found");
+    const char* why = dlerror();
+    g_nccl_error = api.error = std::string("NCCL is not loadable: ") + (why ? why : "libnccl.so.2 not found");
     return nullptr;
   }
   bool ok = true;
@@ -133,6 +136,7 @@ NcclApi* nccl_api() {
   api.GetErrorString = reinterpret_cast<const char* (*)(int)>(sym("ncclGetErrorString"));
   api.GetVersion = reinterpret_cast<int (*)(int*)>(sym("ncclGetVersion"));
   if (!ok) {
+    g_nccl_error = api.error;
     api.handle = nullptr;
     return nullptr;
   }
@@ -159,7 +163,7 @@ struct tdnnf_dp_comm {
 extern "C" int tdnnf_dp_unique_id(char* id_out, int id_bytes) {
   TDNNF_REQUIRE(id_out && id_bytes >= 128, "id_out must hold 128 bytes");
   NcclApi* api = nccl_api();
-  if (!api) return fail(TDNNF_ERR_UNSUPPORTED, "NCCL is not loadable (libnccl.so.2)");
+  if (!api) return fail(TDNNF_ERR_UNSUPPORTED, g_nccl_error);
   NcclUniqueId id;
   TDNNF_NCCL_OK(api, api->GetUniqueId(&id));
   memcpy(id_out, id.internal, 128);
@@ -170,7 +174,7 @@ extern "C" int tdnnf_dp_comm_create(tdnnf_ctx* ctx, int nranks, int rank, const 
   TDNNF_REQUIRE(ctx && unique_id && out, "null argument");
   TDNNF_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank");
   NcclApi* api = nccl_api();
-  if (!api) return fail(TDNNF_ERR_UNSUPPORTED, "NCCL is not loadable (libnccl.so.2)");
+  if (!api) return fail(TDNNF_ERR_UNSUPPORTED, g_nccl_error);
   TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
   NcclUniqueId id;
   memcpy(id.internal, unique_id, 128);
@@ -194,14 +198,15 @@ extern "C" int tdnnf_dp_comm_create(tdnnf_ctx* ctx, int nranks, int rank, const 
 extern "C" int tdnnf_dp_comm_adopt(tdnnf_ctx* ctx, void* nccl_comm, int nranks, int rank, tdnnf_dp_comm** out) {
   TDNNF_REQUIRE(ctx && nccl_comm && out, "null argument");
   NcclApi* api = nccl_api();
-  if (!api) return fail(TDNNF_ERR_UNSUPPORTED, "NCCL is not loadable (libnccl.so.2)");
+  if (!api) return fail(TDNNF_ERR_UNSUPPORTED, g_nccl_error);
+  TDNNF_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank");
+  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
   tdnnf_dp_comm* c = new tdnnf_dp_comm();
   c->ctx = ctx;
   c->comm = static_cast<ncclComm_t>(nccl_comm);
   c->nranks = nranks;
   c->rank = rank;
   c->owned = false;
-  TDNNF_CUDA_OK(cudaSetDevice(ctx->device));
   cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming);
@@ -226,7 +231,7 @@ extern "C" int tdnnf_dp_allreduce_deltas(tdnnf_dp_comm* c, int n, float* const* 
   TDNNF_REQUIRE(c && bufs && counts && n >= 0, "bad argument");
   if (c->nranks == 1 || n == 0) return TDNNF_OK;
   NcclApi* api = nccl_api();
-  if (!api) return fail(TDNNF_ERR_UNSUPPORTED, "NCCL is not loadable (libnccl.so.2)");
+  if (!api) return fail(TDNNF_ERR_UNSUPPORTED, g_nccl_error);
   TDNNF_CUDA_OK(cudaSetDevice(c->ctx->device));
   TDNNF_NCCL_OK(api, api->GroupStart());
   for (int i = 0; i < n; ++i) {
@@ -248,7 +253,7 @@ extern "C" int tdnnf_dp_allreduce_bucket_async(tdnnf_dp_comm* c, float* buf, int
   TDNNF_REQUIRE(c && buf && count >= 0, "bad argument");
   if (c->nranks == 1 || count == 0) return TDNNF_OK;
   NcclApi* api = nccl_api();
-  if (!api) return fail(TDNNF_ERR_UNSUPPORTED, "NCCL is not loadable (libnccl.so.2)");
+  if (!api) return fail(TDNNF_ERR_UNSUPPORTED, g_nccl_error);
   TDNNF_CUDA_OK(cudaSetDevice(c->ctx->device));
   TDNNF_CUDA_OK(cudaEventRecord(c->ready, c->ctx->stream));
   TDNNF_CUDA_OK(cudaStreamWaitEvent(c->side, c->ready, 0));
@@ -268,7 +273,7 @@ extern "C" int tdnnf_dp_allreduce_wait(tdnnf_dp_comm* c) {
 extern "C" int tdnnf_dp_nccl_version(int* version) {
   TDNNF_REQUIRE(version, "null argument");
   NcclApi* api = nccl_api();
-  if (!api) return fail(TDNNF_ERR_UNSUPPORTED, "NCCL is not loadable (libnccl.so.2)");
+  if (!api) return fail(TDNNF_ERR_UNSUPPORTED, g_nccl_error);
   TDNNF_NCCL_OK(api, api->GetVersion(version));
   return TDNNF_OK;
 }

@@ -586,6 +586,7 @@ extern "C" int tdnnf_update_with_max_change(tdnnf_ctx* ctx, int n, float* const*
                                             int32_t* num_max_change_global_applied, int* applied) {
   TDNNF_REQUIRE(ctx && model && model_strides && delta && delta_strides && rows && cols && groups && max_change && dots_dev && applied,
                 "null argument");
+  TDNNF_REQUIRE(n >= 1 && n <= TDNNF_MULTI_MAX, "buffer count out of range");  // per_buf below is indexed by buffer
   TDNNF_REQUIRE(num_groups >= 1 && num_groups <= TDNNF_MULTI_MAX, "group count out of range");
   for (int i = 0; i < n; ++i) TDNNF_REQUIRE(groups[i] >= 0 && groups[i] < num_groups, "group index out of range");
   for (int g = 0; g < num_groups; ++g) TDNNF_REQUIRE(max_change[g] >= 0.f, "max-change must be >= 0");  // KALDI_ASSERT :2112
