@@ -374,3 +374,14 @@ def test_raw_nnet_container_roundtrip():
         nnet3.read_nnet(text[:-12], False)  # truncated: no </Nnet3>
     with pytest.raises(ValueError):
         nnet3.write_nnet(["a", ""], comps)
+
+
+def test_docs_name_only_declared_entry_points():
+    """Every tdnnf_* name in the documents exists in include/*.h (a `tdnnf_x_{fwd,bwd}` shorthand must be the prefix of one)."""
+    header = "".join(open(os.path.join(ROOT, "include", h)).read() for h in sorted(os.listdir(os.path.join(ROOT, "include"))))
+    declared = set(re.findall(r"\b(tdnnf_[a-z0-9_]+)\b", header))
+    for doc in ("INTEGRATION.md", "DESIGN.md", "README.md", os.path.join("profiles", "INDEX.md")):
+        names = set(re.findall(r"\b(tdnnf_[a-z0-9_]+)\b", open(os.path.join(ROOT, doc)).read()))
+        stale = sorted(n for n in names if n not in declared and not (n.endswith("_") and any(d.startswith(n) for d in declared))
+                       and n not in ("tdnnf_nas_b200", "tdnnf_nnet3"))
+        assert not stale, (doc, stale)

@@ -139,3 +139,20 @@ def test_xconfig_layer_classes_emit_the_lines_the_generators_were_fed():
                 assert (kv.get("use-bias") == "false") == name.endswith(".linear")
         # the bypass the step fuses into its tail kernels: Sum(Scale(0.66, input), dropout output)
         assert lines[-1].endswith(f"input=Sum(Scale(0.66, tdnn1.dropout), {comps[0][0].split('.')[0]}.dropout)")
+
+
+def test_dropout_directive_matches_the_reference_schedule_code():
+    """The dropout half of the per-iteration edit string (train.py:524-532): fixture from executing the dropout-schedule code
+    the reference keeps (as a comment block, un-commented mechanically) in temperature_schedule.py:68-367 -- the recipes'
+    schedule '0,0@0.20,0.5@0.50,0' (run_TDNN_DARTSV3_fbk_stride_pretrain.sh:49) and the block's own self-test forms.
+    Character for character, float repr included; the directive is then applied to a GeneralDropoutComponent."""
+    from tdnnf_nas_b200 import nnet3
+
+    fx = _fixture()["dropout_edits"]
+    assert len(fx) >= 60
+    comp = nnet3.Component.new("GeneralDropoutComponent", "dim=8 dropout-proportion=0.0 continuous=true")
+    for schedule, pattern, fraction, ref_string in fx:
+        ours = nnet3.dropout_edit_string(schedule, fraction, pattern)
+        assert "nnet3-copy --edits='" + ours + "' - - |" == ref_string
+        nnet3.apply_edits(ours, [("tdnnf2.dropout", comp)])
+        assert comp.dropout_proportion() == pytest.approx(float(ours.rsplit("=", 1)[1]), rel=1e-6, abs=1e-9)

@@ -134,8 +134,29 @@ def xconfig_layers():
     return out
 
 
+def dropout_edits():
+    """The reference keeps upstream's dropout-schedule code in temperature_schedule.py:68-367 as a comment block (its live
+    train.py:524-532 calls common_train_lib.get_dropout_edit_string, i.e. upstream's dropout_schedule.py with this very text).
+    The block is un-commented mechanically ('# ' stripped) and executed: get_dropout_edit_string(schedule, fraction, iter)."""
+    import logging
+
+    src = open(os.path.join(REF, "steps", "libs", "nnet3", "train", "temperature_schedule.py")).read().split("\n")
+    body = [(l[2:] if l.startswith("# ") else ("" if l.strip() in ("#", "") else l)) for l in src[67:]]
+    ns = {"logger": logging.getLogger("ref_dropout"), "__name__": "ref_dropout"}
+    exec(compile("\n".join(body), "temperature_schedule.py[68:] un-commented", "exec"), ns)
+    out = []
+    # run_TDNN_DARTSV3_fbk_stride_pretrain.sh:49 dropout_schedule, then the forms of the block's own _self_test()
+    for sch in ("0,0@0.20,0.5@0.50,0", "0.0,0.5,0.0", "0.0,0.3@0.25,0.0", "0.1,0.4@0.3,0.2@0.8,0.05", "0.2,0.2"):
+        for frac in (0.0, 0.1, 0.2, 0.25, 0.3, 0.35, 0.5, 0.6, 0.75, 0.8, 0.9, 1.0):
+            out.append([sch, "*", frac, ns["get_dropout_edit_string"](sch, frac, 7)])
+    for frac in (0.0, 0.4, 1.0):
+        out.append(["0,0.5,0", "tdnnf*", frac, ns["get_dropout_edit_string"]("tdnnf*=0,0.5,0", frac, 7)])
+    return out
+
+
 def main():
     out = {}
+    out["dropout_edits"] = dropout_edits()
     out["xconfig_layers"] = xl = xconfig_layers()
     # the hand-laid inputs of the config generators below are what the reference's layer classes emit
     by_name = {k.split()[1] + "/" + k.split()[0] + "/" + [t for t in k.split() if t.startswith("time-stride")][0]: v for k, v in xl.items()}
