@@ -1,5 +1,4 @@
-"""GPU test of the training-example reader feeding the chain objective (sorted last on purpose: written after the round's
-GPU budget was spent, so under `pytest -x` a failure here cannot hide the rest of the suite): a binary archive of
+"""GPU test of the training-example reader feeding the chain objective: a binary archive of
 single-sequence unconstrained examples and a binary den.fst go through tdnnf_chain_egs_* / tdnnf_den_graph_parse_fst_binary
 and the objective computed from them equals the oracle's on the generators' own arrays."""
 import numpy as np
