@@ -1,5 +1,4 @@
-"""GPU tests of compatibility with the reference's scripts and model text (sorted last on purpose: they were added after the
-round's GPU budget was spent, so a failure here must not hide the rest of the suite under `pytest -x`):
+"""GPU tests of compatibility with the reference's scripts and model text:
   * every parameterised component line the reference's config generators emit is accepted (fixture: tests/golden/ref_scripts.json);
   * the text model written here parses with the expressions of generate_top_list.py / bottleneckdim_search_top_model_size.py."""
 import numpy as np
