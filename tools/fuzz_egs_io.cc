@@ -9,7 +9,9 @@
 //   g++ -O1 -g -std=c++17 -fsanitize=address,undefined -fno-sanitize-recover=undefined -I include -I tdnn-f_nas_b200/csrc \
 //       -I /usr/local/cuda/include tools/fuzz_egs_io.cc tdnn-f_nas_b200/csrc/egs_io.cc tdnn-f_nas_b200/csrc/chain_io.cc -o /tmp/fuzz_egs_io
 //   /tmp/fuzz_egs_io /tmp/bin.ark /tmp/txt.ark /tmp/den_v.fst /tmp/den_c.fst      # 160 000 mutants, ~45 s; prints "ok N err M"
-// (round 2: one finding, a signed overflow in the index vector's one-byte t step, fixed; clean since.)
+//   (FUZZ_SEED / FUZZ_ITERS in the environment: another seed, iterations per file)
+// (round 2: one finding, a signed overflow in the index vector's one-byte t step, fixed; clean since: 160 000 + 600 000
+// mutants over seven seed files, two seeds.)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -21,7 +23,8 @@ namespace tdnnf { int fail(int code, const std::string& msg) { return code; } }
 extern "C" int tdnnf_den_graph_create(tdnnf_ctx*, int, int, int, const int32_t*, const int32_t*, const float*, const int32_t*, const int32_t*, const float*, tdnnf_den_graph**) { return 1; }
 extern "C" int tdnnf_num_graph_create(tdnnf_ctx*, int, const int32_t*, int, const int32_t*, const int32_t*, const float*, const int32_t*, const int32_t*, const float*, tdnnf_num_graph**) { return 1; }
 int main(int argc, char** argv) {
-  std::mt19937 rng(1);
+  std::mt19937 rng(getenv("FUZZ_SEED") ? atoi(getenv("FUZZ_SEED")) : 1);
+  const int iters = getenv("FUZZ_ITERS") ? atoi(getenv("FUZZ_ITERS")) : 40000;
   long ok = 0, err = 0;
   for (int a = 1; a < argc; ++a) {
     FILE* f = fopen(argv[a], "rb");
@@ -29,7 +32,7 @@ int main(int argc, char** argv) {
     size_t n = fread(base.data(), 1, base.size(), f);
     fclose(f);
     base.resize(n);
-    for (int it = 0; it < 40000; ++it) {
+    for (int it = 0; it < iters; ++it) {
       std::vector<char> b = base;
       int k = 1 + rng() % 5;
       for (int j = 0; j < k; ++j) {
