@@ -278,3 +278,17 @@ def random_example(rng, key: str, *, frames: int = 6, left: int = 3, right: int 
                e2e=e2e, fsts=[random_fst(rng, frames, num_pdfs) for _ in range(nf)], alignment_pdfs=[], dw2=dw2,
                deriv_weights=(np.round(rng.uniform(0, 1, frames * num_sequences) * 255) / 255).astype(np.float32) if deriv_weights else [])
     return dict(key=key, inputs=inputs, outputs=[sup])
+
+
+def den_graph_to_fst(graph, text: str) -> dict:
+    """The FST dict of this module from the FSM text synth.den_graph_to_fst_text(graph) writes."""
+    fst = dict(start=None, num_states=int(graph["num_states"]), arcs=[], finals={})
+    for line in text.splitlines():
+        f = line.split()
+        if len(f) >= 4:
+            fst["arcs"].append((int(f[0]), int(f[1]), int(f[2]), float(f[4]) if len(f) > 4 else 0.0))
+            if fst["start"] is None:
+                fst["start"] = int(f[0])
+        elif f:
+            fst["finals"][int(f[0])] = float(f[1]) if len(f) > 1 else 0.0
+    return fst
