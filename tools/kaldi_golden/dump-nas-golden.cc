@@ -16,6 +16,7 @@
 // in_deriv.k.txt delta.k.txt (Vectorize of to_update after Backprop, to_update zeroed before every step).
 #include <cmath>
 #include <fstream>
+#include <set>
 #include <sstream>
 
 #include "base/kaldi-common.h"
@@ -161,7 +162,7 @@ static void DumpDenominator(const std::string &in_root, const std::string &out_r
   std::string dir = out_root + "/" + case_name;
   MakeDir(dir);
   fst::StdVectorFst den_fst;
-  ReadFstKaldi(in_root + "/" + case_name + ".den.fst", &den_fst);
+  fst::ReadFstKaldi(in_root + "/" + case_name + ".den.fst", &den_fst);
   chain::DenominatorGraph graph(den_fst, num_pdfs);
   chain::ChainTrainingOptions opts;
   opts.leaky_hmm_coefficient = leaky;
