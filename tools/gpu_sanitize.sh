@@ -5,7 +5,6 @@
 #   gpurun --timeout 1500 -- 'bash tools/gpu_sanitize.sh'
 set -u
 mkdir -p gpurun_out
-SMALL="tests/test_gpu_mixing.py tests/test_gpu_dropout.py tests/test_gpu_den.py::test_den_parity tests/test_gpu_den.py::test_numerator_parity tests/test_gpu_darts.py -k 'not full'"
 run() {  # tool, log name, pytest args
   local tool=$1 log=$2; shift 2
   timeout 600 compute-sanitizer --tool "$tool" --error-exitcode 9 --print-limit 20 \
@@ -14,7 +13,7 @@ run() {  # tool, log name, pytest args
 }
 run memcheck mixing tests/test_gpu_mixing.py tests/test_gpu_dropout.py
 run memcheck den tests/test_gpu_den.py::test_den_parity tests/test_gpu_den.py::test_numerator_parity
-run memcheck darts tests/test_gpu_darts.py -k "not full"
+run memcheck darts tests/test_gpu_darts.py -k "adds_mode or mn_major or project"
 run racecheck den tests/test_gpu_den.py::test_den_parity tests/test_gpu_den.py::test_numerator_parity
 run racecheck ng tests/test_gpu_ng.py -k "precondition"
-run synccheck darts tests/test_gpu_darts.py -k "not full"
+run synccheck darts tests/test_gpu_darts.py -k "adds_mode or mn_major"
