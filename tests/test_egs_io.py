@@ -272,3 +272,36 @@ def test_merged_supervision_through_the_oracle_numerator(binary):
     lp, d, ok = O.num_forward_backward(m["num_graph"], x, T, deriv_weight=1.0)
     assert ok and ok_ref and lp == pytest.approx(lp_ref, rel=1e-6)
     np.testing.assert_allclose(d, d_ref, rtol=1e-5, atol=1e-7)
+
+
+def test_archive_drives_a_whole_cpu_training_step():
+    """Data path end to end on the host: an archive of single-sequence examples -> the merged minibatch (features in the
+    t-major / sequence-fastest row order, numerator graph) -> one whole search-stage training step of the CPU reference
+    (oracle/supernet_ref.py) gives the objective the same step gives on the generator's own arrays; with the rows left in the
+    archive's sequence-major order it does not (the layout is what is being checked)."""
+    from oracle import supernet_ref as R
+
+    cfg = R.RefConfig(num_seqs=3, frames_per_eg=12, feat_dim=10, dim=24, bottleneck=8, num_blocks=2, num_offsets=3, prefinal_small=12,
+                      num_pdfs=19, xent=False)
+    T, _, _, _, in_t = R.frame_plan(cfg)
+    rng = np.random.default_rng(40)
+    den = synth.make_den_graph(30, cfg.num_pdfs, 4.0, seed=5)
+    graph, exs = synth_supervision_examples(rng, cfg.num_seqs, cfg.num_pdfs, T, seed=9)
+    feats = rng.standard_normal((len(in_t), cfg.num_seqs, cfg.feat_dim)).astype(np.float32)     # [t, sequence, dim]
+    for s, ex in enumerate(exs):      # the recipe's shape: 'input' rows over the model's whole input context of one chunk
+        ex["inputs"] = [dict(name="input", indexes=[(0, t, 0) for t in in_t], data=feats[:, s].copy(), coding="cm2")]
+    egs = capi.ChainEgs(W.ark(exs, True))
+    x, t0 = egs.merge_input(0, cfg.num_seqs, "input")
+    sup = egs.merge_supervision(0, cfg.num_seqs, "output", cfg.num_pdfs)
+    assert t0 == in_t[0] and x.shape == feats.shape
+    np.testing.assert_allclose(x, feats, atol=float(np.ptp(feats)) / 65535 + 1e-6)     # two-byte compressed on disk
+    draws = [np.full(cfg.num_offsets, 0.5, np.float32) for _ in range(2 * cfg.num_blocks)]
+
+    def objf(rows, num_graph):
+        return R.CpuSupernet(cfg, den, num_graph).step(np.ascontiguousarray(rows), draws, apply_update=False)
+
+    want = objf(x.reshape(-1, cfg.feat_dim), graph)
+    got = objf(x.reshape(-1, cfg.feat_dim), sup["num_graph"])
+    assert got == pytest.approx(want, rel=1e-6)
+    wrong = objf(x.transpose(1, 0, 2).reshape(-1, cfg.feat_dim), sup["num_graph"])              # sequence-major rows
+    assert abs(wrong - want) > 1e-3 * abs(want)
