@@ -385,3 +385,54 @@ def test_docs_name_only_declared_entry_points():
         stale = sorted(n for n in names if n not in declared and not (n.endswith("_") and any(d.startswith(n) for d in declared))
                        and n not in ("tdnnf_nas_b200", "tdnnf_nnet3"))
         assert not stale, (doc, stale)
+
+
+def _top_level_args(text, open_paren):
+    """The argument strings of the call whose '(' is at text[open_paren]; None if the parentheses do not balance."""
+    depth, args, cur = 0, [], ""
+    for i in range(open_paren, len(text)):
+        ch = text[i]
+        if ch in "([{":
+            depth += 1
+            if depth == 1:
+                continue
+        elif ch in ")]}":
+            depth -= 1
+            if depth == 0:
+                if cur.strip():
+                    args.append(cur.strip())
+                return args
+        if depth == 1 and ch == ",":
+            args.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    return None
+
+
+def test_integration_snippets_call_the_abi_with_the_declared_number_of_arguments():
+    """Every complete tdnnf_* call inside a ```cpp block of INTEGRATION.md passes as many arguments as include/*.h declares
+    (calls abbreviated with '...' are skipped): the reference-side stubs shown to a maintainer cannot drift from the ABI."""
+    header = "".join(open(os.path.join(ROOT, "include", h)).read() for h in sorted(os.listdir(os.path.join(ROOT, "include"))))
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    header = re.sub(r"//[^\n]*", " ", header)
+    arity = {}
+    for m in re.finditer(r"\b(tdnnf_[a-z0-9_]+)\s*\(", header):
+        args = _top_level_args(header, m.end() - 1)
+        if args is not None and header[:m.start()].rstrip().split()[-1:] not in ([], ["return"]):
+            arity.setdefault(m.group(1), 0 if args == ["void"] else len(args))
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    checked, bad = 0, []
+    for block in re.findall(r"```cpp\n(.*?)```", doc, flags=re.S):
+        code = re.sub(r"//[^\n]*", " ", block)
+        code = re.sub(r"/\*.*?\*/", " ", code, flags=re.S)
+        for m in re.finditer(r"\b(tdnnf_[a-z0-9_]+)\s*\(", code):
+            name = m.group(1)
+            args = _top_level_args(code, m.end() - 1)
+            if name not in arity or args is None or any(a == "..." or a.endswith("...") for a in args):
+                continue
+            checked += 1
+            if len(args) != arity[name]:
+                bad.append((name, len(args), arity[name]))
+    assert checked >= 12, checked
+    assert not bad, bad
