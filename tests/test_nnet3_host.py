@@ -436,3 +436,39 @@ def test_integration_snippets_call_the_abi_with_the_declared_number_of_arguments
                 bad.append((name, len(args), arity[name]))
     assert checked >= 12, checked
     assert not bad, bad
+
+
+def _header_arity():
+    header = "".join(open(os.path.join(ROOT, "include", h)).read() for h in sorted(os.listdir(os.path.join(ROOT, "include"))))
+    header = re.sub(r"//[^\n]*", " ", re.sub(r"/\*.*?\*/", " ", header, flags=re.S))
+    arity = {}
+    for m in re.finditer(r"\b(tdnnf_[a-z0-9_]+)\s*\(", header):
+        args = _top_level_args(header, m.end() - 1)
+        if args is not None and header[:m.start()].rstrip().split()[-1:] not in ([], ["return"]):
+            arity.setdefault(m.group(1), 0 if args == ["void"] else len(args))
+    return arity
+
+
+def test_python_bindings_match_the_declared_arity():
+    """ctypes checks nothing against the C prototype: the argtypes lists of capi.py and every call site of the handle API in
+    nnet3.py (which declares no argtypes) are compared with the parameter counts of include/*.h."""
+    arity = _header_arity()
+    pkg = os.path.join(ROOT, "tdnn-f_nas_b200")
+    bad, sigs, calls = [], 0, 0
+    src = open(os.path.join(pkg, "capi.py")).read()
+    for m in re.finditer(r"sig\(\s*\"(tdnnf_[a-z0-9_]+)\"\s*,\s*\[", src):
+        args = _top_level_args(src, m.end() - 1)
+        sigs += 1
+        if arity.get(m.group(1)) != len(args):
+            bad.append(("capi.py sig", m.group(1), len(args), arity.get(m.group(1))))
+    for f in ("nnet3.py", "supernet.py", "chain.py", "parallel.py"):
+        src = re.sub(r"#[^\n]*", " ", open(os.path.join(pkg, f)).read())
+        for m in re.finditer(r"\.(tdnnf_nnet3_[a-z0-9_]+)\s*\(", src):
+            args = _top_level_args(src, m.end() - 1)
+            if args is None or m.group(1) not in arity or any(a.startswith("*") for a in args):
+                continue
+            calls += 1
+            if len(args) != arity[m.group(1)]:
+                bad.append((f, m.group(1), len(args), arity[m.group(1)]))
+    assert sigs > 100 and calls > 60, (sigs, calls)
+    assert not bad, bad
