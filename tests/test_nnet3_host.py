@@ -472,3 +472,38 @@ def test_python_bindings_match_the_declared_arity():
                 bad.append((f, m.group(1), len(args), arity[m.group(1)]))
     assert sigs > 100 and calls > 60, (sigs, calls)
     assert not bad, bad
+
+
+def test_capi_argtypes_match_the_declared_parameter_kinds():
+    """... and kind for kind: pointer / int / float / double / 64-bit integer (an int declared where the C side takes a float
+    goes to the wrong register without any error)."""
+    header = "".join(open(os.path.join(ROOT, "include", h)).read() for h in sorted(os.listdir(os.path.join(ROOT, "include"))))
+    header = re.sub(r"//[^\n]*", " ", re.sub(r"/\*.*?\*/", " ", header, flags=re.S))
+
+    def c_kind(p):
+        if "*" in p or "[" in p:
+            return "ptr"
+        toks = p.replace("const", "").split()
+        base = " ".join(toks[:-1]) if len(toks) > 1 else toks[0]
+        return {"float": "float", "double": "double", "int": "int", "int32_t": "int", "uint64_t": "u64", "int64_t": "i64", "size_t": "u64",
+                "unsigned long long": "u64"}[base]
+
+    def py_kind(a):
+        if a in ("vp", "c_int_p", "c_float_p", "pp_i", "pp_f", "pp_c", "C.c_char_p", "C.c_void_p") or a.startswith("C.POINTER"):
+            return "ptr"
+        return {"i": "int", "C.c_int": "int", "C.c_int32": "int", "f": "float", "C.c_float": "float", "C.c_double": "double",
+                "C.c_uint64": "u64", "C.c_int64": "i64"}[a]
+
+    proto = {}
+    for m in re.finditer(r"\b(tdnnf_[a-z0-9_]+)\s*\(", header):
+        args = _top_level_args(header, m.end() - 1)
+        if args is not None and header[:m.start()].rstrip().split()[-1:] not in ([], ["return"]):
+            proto.setdefault(m.group(1), [] if args == ["void"] else [c_kind(a) for a in args])
+    src = open(os.path.join(ROOT, "tdnn-f_nas_b200", "capi.py")).read()
+    bad, n = [], 0
+    for m in re.finditer(r"sig\(\s*\"(tdnnf_[a-z0-9_]+)\"\s*,\s*\[", src):
+        kinds = [py_kind(a.strip()) for a in _top_level_args(src, m.end() - 1)]
+        n += 1
+        if kinds != proto[m.group(1)]:
+            bad.append((m.group(1), [(k, a, b) for k, (a, b) in enumerate(zip(kinds, proto[m.group(1)])) if a != b]))
+    assert n > 100 and not bad, bad
